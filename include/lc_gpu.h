@@ -1,0 +1,258 @@
+/*
+ * lc_gpu.h — C ABI of the B200-native liquid-cache hot path.
+ *
+ * This is the drop-in boundary for ONE path of XiangpengHao/liquid-cache: the
+ * insert() transcode Arrow -> liquid, and get() / with_selection() /
+ * eval_predicate() on liquid columns, with the liquid columns resident in HBM
+ * and every array-sized loop running as a hand-written sm_100a CUDA kernel.
+ *
+ * The reference has no FFI seam; its seam is the Rust trait
+ *   trait LiquidArray            src/core/src/liquid_array/mod.rs:82-146
+ * and the cache front door
+ *   LiquidCache::{insert,get,eval_predicate}   src/core/src/cache/core.rs:122-142
+ *   Insert / Get / EvaluatePredicate builders  src/core/src/cache/builders.rs:162-356
+ * Each entry point below names the reference item it stands in for. The Rust
+ * side binding (a `GpuLiquidArray: LiquidArray` adapter) is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; arrays cross as Arrow C Data Interface
+ *     structs (borrowed on input, caller-owned on output via `release`).
+ *   - every function returns LC_OK (0) or a negative lc_status; nothing
+ *     throws or aborts. lc_last_error() gives a thread-local message.
+ *   - selections are Arrow BooleanBuffer bytes (LSB-first), bit offset 0,
+ *     `sel_len` bits long, NULL meaning "all rows".
+ *   - there is NO CPU fallback behind these calls: without a CUDA device
+ *     lc_ctx_create() fails with LC_ERR_NO_DEVICE; shapes the kernels do not
+ *     cover return LC_ERR_UNSUPPORTED_* so the caller can take the reference's
+ *     own fallback (byte_view_array/mod.rs:360-361, transcode.rs:155-159).
+ *   - one lc_ctx per process per GPU (one process per GPU); entry points are
+ *     thread-safe (serialised on the context).
+ */
+#ifndef LC_GPU_H
+#define LC_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+
+typedef struct lc_ctx lc_ctx;   /* one per process; owns the device, stream, HBM arena      */
+typedef uint64_t lc_handle;     /* device-resident liquid column (an `Arc<dyn LiquidArray>`) */
+
+typedef enum lc_status {
+  LC_OK = 0,
+  LC_ERR_INVALID = -1,           /* bad argument (length mismatch, NULL pointer ...)            */
+  LC_ERR_UNSUPPORTED_TYPE = -2,  /* mirrors transcode's Err(array): caller keeps the Arrow array */
+  LC_ERR_UNSUPPORTED_EXPR = -3,  /* mirrors try_eval_predicate -> None / LiquidExpr::try_new None */
+  LC_ERR_CACHE_FULL = -4,        /* mirrors cache/mod.rs CacheFull                              */
+  LC_ERR_NOT_FOUND = -5,         /* entry absent (reference returns Option::None)               */
+  LC_ERR_CUDA = -6,
+  LC_ERR_OOM = -7,
+  LC_ERR_NO_DEVICE = -8
+} lc_status;
+
+/* Predicate operator. Reference: ByteViewOperator (byte_view_array/operator.rs:45-52,66-82) and the
+ * Operator whitelist of LiquidExpr (cache/liquid_expr.rs:85-127). */
+typedef enum lc_op {
+  LC_OP_EQ = 0,
+  LC_OP_NE = 1,
+  LC_OP_LT = 2,
+  LC_OP_LE = 3,
+  LC_OP_GT = 4,
+  LC_OP_GE = 5,
+  LC_OP_LIKE = 6,        /* LikeExpr / LikeMatch; literal is the SQL pattern WITH its % signs */
+  LC_OP_NOT_LIKE = 7,    /* negated LikeExpr / NotLikeMatch                                    */
+  LC_OP_CONST_TRUE = 8,  /* Literal(Boolean(true))  on a byte-like column (helpers.rs:72-78)   */
+  LC_OP_CONST_FALSE = 9
+} lc_op;
+
+/* CacheExpression hint (cache/expressions.rs:38-53) — only SUBSTRING_SEARCH changes the encoding
+ * (it turns on the per-unique 32-bit fingerprints, transcode.rs:165). */
+typedef enum lc_hint { LC_HINT_NONE = 0, LC_HINT_PREDICATE = 1, LC_HINT_SUBSTRING_SEARCH = 2 } lc_hint;
+
+typedef enum lc_literal_kind { LC_LIT_I64 = 0, LC_LIT_U64 = 1, LC_LIT_BYTES = 2 } lc_literal_kind;
+
+/* `col <op> literal` after DataFusion's coercion (the reference receives the same thing inside a
+ * PhysicalExpr; src/core/src/liquid_array/mod.rs:265-280, operator.rs:134-176). */
+typedef struct lc_predicate {
+  int32_t op;            /* lc_op */
+  int32_t lit_kind;      /* lc_literal_kind */
+  int64_t lit_i64;       /* LC_LIT_I64: signed ints, Date32/64, Timestamp */
+  uint64_t lit_u64;      /* LC_LIT_U64: unsigned ints */
+  const uint8_t* lit_bytes; /* LC_LIT_BYTES: Utf8/Binary literal or LIKE pattern */
+  uint64_t lit_len;
+} lc_predicate;
+
+/* Liquid logical type, numbering of LiquidDataType (liquid_array/mod.rs:52-65). */
+typedef enum lc_liquid_type { LC_LIQUID_INTEGER = 1, LC_LIQUID_BYTE_VIEW = 4 } lc_liquid_type;
+
+typedef struct lc_stats {
+  uint64_t entries;            /* CacheStats.total_entries   (cache/core.rs:68-119) */
+  uint64_t hbm_bytes_used;     /* CacheStats.memory_usage_bytes, counted in HBM     */
+  uint64_t hbm_bytes_budget;   /* LiquidCacheBuilder::with_max_memory_bytes         */
+  uint64_t kernel_launches;    /* our CUDA kernels launched since ctx creation       */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+} lc_stats;
+
+/* ------------------------------------------------------------------ context ---- */
+
+/* LiquidCacheBuilder::new().with_max_memory_bytes(b).build()  (cache/builders.rs:50-157).
+ * device_id: CUDA ordinal. hbm_budget_bytes: 0 = no limit. */
+int lc_ctx_create(int device_id, uint64_t hbm_budget_bytes, lc_ctx** out);
+void lc_ctx_destroy(lc_ctx* ctx);
+/* Run everything on an externally owned cudaStream_t (e.g. torch's current stream) instead of the
+ * context's own stream. NULL restores the context stream. */
+int lc_ctx_set_stream(lc_ctx* ctx, void* cuda_stream);
+int lc_ctx_synchronize(lc_ctx* ctx);
+int lc_ctx_stats(lc_ctx* ctx, lc_stats* out);
+const char* lc_last_error(void);
+const char* lc_version(void);
+
+/* --------------------------------------------------- LiquidArray-level calls ---- */
+
+/* transcode_liquid_inner_with_hint (cache/transcode.rs:46-290): Arrow -> liquid, into HBM.
+ *   ints/dates/timestamps -> LiquidPrimitiveArray::from_arrow_array (primitive_array.rs:159-206)
+ *   Utf8/Binary/Utf8View/BinaryView/Dictionary<UInt16,_> -> LiquidByteViewArray (conversions.rs:260-373)
+ * compressor_scope identifies the FSST symbol table to train-or-reuse
+ * (with_fsst_compressor_or_train, transcode.rs:16-33; one table per (file,row-group,column)).
+ * Anything else returns LC_ERR_UNSUPPORTED_TYPE and the caller keeps the Arrow array. */
+int lc_encode(lc_ctx* ctx, const struct ArrowSchema* schema, const struct ArrowArray* array,
+              int32_t hint, uint64_t compressor_scope, lc_handle* out);
+void lc_release(lc_ctx* ctx, lc_handle h);
+
+uint64_t lc_len(lc_ctx* ctx, lc_handle h);           /* LiquidArray::len                      */
+uint64_t lc_memory_size(lc_ctx* ctx, lc_handle h);   /* LiquidArray::get_array_memory_size    */
+int32_t lc_data_type(lc_ctx* ctx, lc_handle h);      /* LiquidArray::data_type -> lc_liquid_type */
+/* LiquidArray::original_arrow_data_type, as an Arrow C format string copied into buf. */
+int lc_arrow_format(lc_ctx* ctx, lc_handle h, char* buf, size_t buf_len);
+
+/* LiquidArray::to_arrow_array (sel_bits == NULL) / LiquidArray::filter(&BooleanBuffer)
+ * (primitive_array.rs:350-374, byte_view_array/mod.rs:266-290,421-424). The result has the
+ * ORIGINAL arrow type, length popcount(sel), host buffers owned through `release`. */
+int lc_to_arrow(lc_ctx* ctx, lc_handle h, const uint8_t* sel_bits, uint64_t sel_len,
+                struct ArrowSchema* out_schema, struct ArrowArray* out_array);
+
+/* LiquidArray::try_eval_predicate(&LiquidExpr, &BooleanBuffer) (liquid_array/mod.rs:123-130):
+ * apply the selection, then evaluate; output is a BooleanArray of length popcount(sel):
+ *   out_values   ceil(out_len/8) bytes, LSB-first   (caller buffer of >= ceil(len/8) bytes)
+ *   out_validity same size; may be NULL if the caller does not want it
+ *   *out_null_count  nulls among the selected rows (0 => validity is all ones)
+ * Value bits under a null are written as 0 (the reference leaves them unspecified). */
+int lc_eval_predicate(lc_ctx* ctx, lc_handle h, const lc_predicate* pred, const uint8_t* sel_bits,
+                      uint64_t sel_len, uint8_t* out_values, uint8_t* out_validity, uint64_t* out_len,
+                      uint64_t* out_null_count);
+
+/* Batched forms — same semantics per element, ONE launch sequence for all entries. This is how a
+ * scan over a row group (or a whole column) should call in: 8192-row entries are too small to
+ * amortise a launch each.
+ *   sel_bits[i]   NULL = all rows of entry i (sel_bits itself may be NULL = all rows everywhere)
+ *   out_values    caller buffer; entry i's mask starts at byte out_byte_offsets[i] (the caller
+ *                 reserves ceil(len_i/8) rounded up to 4 bytes per entry; lc_mask_bytes() below)
+ *   out_validity  same layout, may be NULL
+ *   out_len[i], out_null_count[i] as above */
+uint64_t lc_mask_bytes(uint64_t n_rows);
+int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const lc_predicate* pred,
+                           const uint8_t* const* sel_bits, uint8_t* out_values, uint8_t* out_validity,
+                           const uint64_t* out_byte_offsets, uint64_t* out_len, uint64_t* out_null_count);
+
+/* Batched get-with-selection: the filtered arrays of all entries CONCATENATED into one Arrow array
+ * (in `handles` order) — what LiquidCacheReader::read_from_cache + concat produce for one column
+ * (src/datafusion/src/reader/runtime/liquid_cache_reader.rs:342-391). All handles must share the
+ * original arrow type. */
+int lc_to_arrow_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const uint8_t* const* sel_bits,
+                     struct ArrowSchema* out_schema, struct ArrowArray* out_array);
+
+/* boolean_buffer_and_then(left, right) (src/datafusion/src/utils.rs:62-236, the BMI2 PDEP routine):
+ * out bit p = left[p] & right[rank_left(p)]; right has popcount(left) bits. out has left_len bits. */
+int lc_and_then(lc_ctx* ctx, const uint8_t* left_bits, uint64_t left_len, const uint8_t* right_bits,
+                uint64_t right_len, uint8_t* out_bits);
+
+/* ---------------------------------------------------- LiquidCache-level calls ---- */
+
+/* LiquidCache::insert(entry_id, array) (cache/core.rs:122-128, builders.rs:193-204). Transcodes
+ * eagerly into HBM. LC_ERR_UNSUPPORTED_TYPE: caller keeps the array (reference keeps MemoryArrow).
+ * LC_ERR_CACHE_FULL mirrors Result<(), CacheFull>. entry_id packs file<<48|rg<<32|col<<16|batch
+ * (src/datafusion/src/cache/id.rs:15-22); the FSST table scope is entry_id with batch cleared. */
+int lc_cache_insert(lc_ctx* ctx, uint64_t entry_id, const struct ArrowSchema* schema,
+                    const struct ArrowArray* array, int32_t hint);
+int lc_cache_is_cached(lc_ctx* ctx, uint64_t entry_id);                       /* core.rs is_cached */
+int lc_cache_remove(lc_ctx* ctx, uint64_t entry_id);
+int lc_cache_reset(lc_ctx* ctx);                                              /* core.rs reset     */
+/* Resolve entry ids to handles (borrowed; valid until remove/reset). LC_ERR_NOT_FOUND if any absent. */
+int lc_cache_handles(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, lc_handle* out);
+/* cache.get(&id).with_selection(&sel)        (builders.rs:218-276, core.rs:595-634) */
+int lc_cache_get(lc_ctx* ctx, uint64_t entry_id, const uint8_t* sel_bits, uint64_t sel_len,
+                 struct ArrowSchema* out_schema, struct ArrowArray* out_array);
+/* cache.eval_predicate(&id, &expr).with_selection(&sel)   (builders.rs:314-356, core.rs:862-930) */
+int lc_cache_eval_predicate(lc_ctx* ctx, uint64_t entry_id, const lc_predicate* pred,
+                            const uint8_t* sel_bits, uint64_t sel_len, uint8_t* out_values,
+                            uint8_t* out_validity, uint64_t* out_len, uint64_t* out_null_count);
+
+/* --------------------------------------------- device-resident scan pipeline ---- */
+/* The per-batch loop of LiquidCacheReader::build_predicate_filter + read_from_cache
+ * (liquid_cache_reader.rs:297-391) for MANY batches at once, with the running selection kept in
+ * HBM between conjuncts: predicate -> nulls-to-false -> boolean_buffer_and_then all stay on device.
+ *
+ *   lc_scan_begin(n_batches, rows[i])            running selection := all rows
+ *   lc_scan_filter(scan, handles[i], pred)       selection := and_then(selection, eval(handles[i]))
+ *   lc_scan_counts(scan, counts[i])              popcount(selection_i)  (one D2H of n u32)
+ *   lc_scan_selection(scan, i, bits)             copy selection of batch i to host
+ *   lc_scan_read(scan, handles[i], out)          concatenated get().with_selection(selection_i)
+ */
+typedef struct lc_scan lc_scan;
+int lc_scan_begin(lc_ctx* ctx, uint64_t n_batches, const uint64_t* rows_per_batch, lc_scan** out);
+/* Optional: seed the running selection of batch i from host bits (RowSelection of the reader). */
+int lc_scan_set_selection(lc_scan* scan, uint64_t batch, const uint8_t* sel_bits, uint64_t sel_len);
+int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* pred);
+int lc_scan_counts(lc_scan* scan, uint64_t* out_counts, uint64_t* out_total);
+int lc_scan_selection(lc_scan* scan, uint64_t batch, uint8_t* out_bits);
+int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* out_schema,
+                 struct ArrowArray* out_array);
+/* Same as lc_scan_read but leaves the concatenated result in device memory the CALLER owns (e.g. a
+ * torch tensor) so it can be handed to NCCL without touching the host:
+ *   fixed-width: values -> d_values (out_rows * width bytes), validity bytes -> d_validity
+ *   byte-view:   offsets(int32, out_rows+1) -> d_offsets, bytes -> d_values, validity -> d_validity
+ * Call first with all pointers NULL to get the sizes. */
+int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap,
+                        void* d_offsets, void* d_validity, uint64_t* out_rows, uint64_t* out_value_bytes,
+                        uint64_t* out_null_count);
+void lc_scan_end(lc_scan* scan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LC_GPU_H */

@@ -1,0 +1,236 @@
+// host_common.h — host-side state behind the C ABI: context, HBM arena, scratch, entries.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/lc_gpu.h"
+#include "entry_layout.h"
+#include "kernels.h"
+
+namespace lc {
+
+// ---- errors ------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define LC_CUDA_OK(expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::lc::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                      cudaGetErrorString(_e));                                                 \
+      return LC_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define LC_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != LC_OK) return _rc; \
+  } while (0)
+
+inline uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// ---- HBM arena ---------------------------------------------------------------------------------
+// Entries are immutable blobs; the arena hands out 128-byte aligned ranges from large cudaMalloc'd
+// slabs (bump pointer + per-slab live count; a slab whose entries are all released is recycled).
+class DeviceArena {
+ public:
+  ~DeviceArena();
+  // returns nullptr on cudaMalloc failure
+  uint8_t* alloc(uint64_t bytes, uint32_t* slab_out);
+  void free(uint32_t slab, uint64_t bytes);
+  void reset();
+  uint64_t bytes_used() const { return used_; }
+  uint64_t bytes_reserved() const { return reserved_; }
+
+ private:
+  struct Slab {
+    uint8_t* base = nullptr;
+    uint64_t size = 0, bump = 0, live = 0;
+  };
+  static constexpr uint64_t kSlabBytes = 256ull << 20;
+  std::vector<Slab> slabs_;
+  uint64_t used_ = 0, reserved_ = 0;
+};
+
+// Growable device + pinned-host scratch, bump-allocated inside one API call.
+struct Scratch {
+  uint8_t* d = nullptr;
+  uint64_t d_cap = 0, d_off = 0;
+  uint8_t* h = nullptr;  // pinned
+  uint64_t h_cap = 0, h_off = 0;
+  ~Scratch();
+  void reset() { d_off = 0; h_off = 0; }
+  // Both return nullptr on allocation failure. Growing invalidates earlier pointers, so callers
+  // reserve() the total first.
+  int reserve(uint64_t d_bytes, uint64_t h_bytes);
+  uint8_t* dev(uint64_t bytes) {
+    uint64_t o = round_up(d_off, 256);
+    if (o + bytes > d_cap) return nullptr;
+    d_off = o + bytes;
+    return d + o;
+  }
+  uint8_t* host(uint64_t bytes) {
+    uint64_t o = round_up(h_off, 64);
+    if (o + bytes > h_cap) return nullptr;
+    h_off = o + bytes;
+    return h + o;
+  }
+};
+
+// ---- FSST symbol table (host copy + device copies), one per compressor scope --------------------
+struct FsstCodec {
+  FsstTable dec;                       // decode view (symbols + lengths)
+  std::unique_ptr<FsstEncTable> enc;   // encode lookup
+  FsstTable* d_dec = nullptr;          // device copies (cudaMalloc'd, tiny)
+  FsstEncTable* d_enc = nullptr;
+};
+// fsst_host.cc
+void fsst_train(const uint8_t* const* strs, const uint32_t* lens, size_t n, FsstCodec* out);
+size_t fsst_compress_host(const FsstCodec& c, const uint8_t* in, size_t len, uint8_t* out);
+size_t fsst_decompress_host(const FsstTable& t, const uint8_t* in, size_t len, uint8_t* out, size_t cap);
+
+// ---- entries -----------------------------------------------------------------------------------
+constexpr uint32_t kEntryMagic = 0x4C43454Eu;
+
+struct Entry {
+  uint32_t magic = kEntryMagic;
+  int32_t liquid_type = 0;  // lc_liquid_type
+  uint8_t* d_blob = nullptr;
+  uint32_t blob_bytes = 0;
+  uint32_t slab = 0;
+  uint32_t n = 0;
+  uint32_t refcount = 1;
+  std::string arrow_format;  // original arrow type as C format string (dictionary: "S" + value fmt in dict_format)
+  std::string dict_value_format;
+  IntHeader ih;   // host copies of the blob header
+  StrHeader sh;
+  std::vector<uint8_t> shared_prefix;  // byte-view: host copy (predicate planning)
+  std::shared_ptr<FsstCodec> codec;    // byte-view
+};
+
+inline Entry* entry_of(lc_handle h) {
+  Entry* e = reinterpret_cast<Entry*>(static_cast<uintptr_t>(h));
+  return (e && e->magic == kEntryMagic) ? e : nullptr;
+}
+
+}  // namespace lc
+
+struct lc_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  uint64_t budget = 0;
+  std::mutex mu;
+  lc::DeviceArena arena;
+  lc::Scratch scratch;
+  std::unordered_map<uint64_t, lc_handle> cache;                               // entry_id -> handle
+  std::unordered_map<uint64_t, std::shared_ptr<lc::FsstCodec>> codecs;         // compressor scope -> table
+  uint64_t n_entries = 0;
+  uint64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+namespace lc {
+
+// ---- Arrow C data helpers (arrow_io.cc) ---------------------------------------------------------
+struct HostBuf {  // 64-byte aligned host allocation
+  uint8_t* p = nullptr;
+  uint64_t bytes = 0;
+};
+uint8_t* host_alloc(uint64_t bytes);
+void host_free(uint8_t* p);
+
+// Parsed view of an input array (borrowed pointers).
+struct ArrowIn {
+  enum Kind { K_INT, K_BYTES, K_VIEW, K_DICT } kind;
+  uint8_t phys = 0, tbits = 0;
+  bool is_signed = false;
+  uint8_t byte_type = 0;  // ByteType of the ORIGINAL array type
+  int64_t length = 0, offset = 0, null_count = 0;
+  const uint8_t* validity = nullptr;  // bitmap with bit offset `offset`
+  const void* values = nullptr;       // ints: native values (not yet offset); bytes: int32 offsets
+  const uint8_t* data = nullptr;      // bytes: value bytes
+  const void* const* view_buffers = nullptr;  // views: variadic data buffers
+  int64_t n_view_buffers = 0;
+  // dictionary (keys must be uint16)
+  const uint16_t* dict_keys = nullptr;
+  int64_t dict_len = 0, dict_offset = 0;
+  const int32_t* dict_offsets = nullptr;
+  const uint8_t* dict_data = nullptr;
+  const uint8_t* dict_validity = nullptr;
+  std::string format, dict_value_format;
+};
+int parse_arrow_input(const ArrowSchema* schema, const ArrowArray* array, ArrowIn* out);
+inline bool bit_get(const uint8_t* bits, int64_t i) { return (bits[i >> 3] >> (i & 7)) & 1; }
+// copy `n` bits starting at bit `off` of src into dst (bit offset 0), zero padding to `dst_bytes`
+void copy_bits(const uint8_t* src, int64_t off, int64_t n, uint8_t* dst, uint64_t dst_bytes);
+uint64_t popcount_bits(const uint8_t* bits, uint64_t n);
+
+// Build caller-owned Arrow C structs around malloc'd buffers (released by the release callbacks).
+void export_schema(const std::string& format, const std::string& dict_value_format, ArrowSchema* out);
+// buffers: ownership moves into the array. dictionary may be null.
+void export_array(int64_t length, int64_t null_count, std::vector<HostBuf> buffers, ArrowArray* dictionary,
+                  ArrowArray* out);
+
+// ---- per-type host orchestration ----------------------------------------------------------------
+// int_host.cc
+int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out);
+// str_host.cc
+int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out);
+
+// Selection prepared for a launch.
+struct SelIn {
+  const uint8_t* bits = nullptr;  // host bits or nullptr
+};
+
+// scan_host.cc: batched operations over homogeneous entry lists (all int or all byte-view)
+struct PredOut {
+  uint8_t* values;            // host
+  uint8_t* validity;          // host or null
+  const uint64_t* byte_offsets;
+  uint64_t* len;
+  uint64_t* null_count;
+};
+int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
+                         const uint8_t* const* sel_bits, const PredOut& out);
+// Selections that already live in HBM (the scan pipeline): word-aligned per entry.
+struct DevSel {
+  const uint32_t* d_base;      // selection words of all batches, back to back
+  const uint64_t* word_off;    // per entry, in u32 words
+  const uint32_t* k;           // per entry popcount (host copy)
+  bool all_rows;               // no filter applied yet: every row selected
+};
+// Where a get() leaves its result.
+struct DeviceOut {             // caller-owned device buffers (lc_scan_read_device)
+  void* d_values;
+  uint64_t values_cap;
+  void* d_offsets;
+  void* d_validity;
+  uint64_t* out_rows;
+  uint64_t* out_value_bytes;
+  uint64_t* out_null_count;
+};
+int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t* const* sel_bits,
+                   const DevSel* dev_sel, ArrowSchema* out_schema, ArrowArray* out_array,
+                   const DeviceOut* dev_out = nullptr);
+
+int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred, uint32_t* d_sel_base,
+                 const uint64_t* word_off, bool all_rows, uint32_t* d_counts);
+
+// predicate planning
+// ints: (op, literal) -> unsigned-domain compare for this entry; returns LC_ERR_UNSUPPORTED_EXPR if not mappable
+int plan_int_predicate(const IntHeader& h, const lc_predicate* pred, int32_t* ucmp, uint64_t* thr);
+
+void release_entry(lc_ctx* ctx, Entry* e);
+
+}  // namespace lc

@@ -1,0 +1,294 @@
+// k_int.cu — frame-of-reference + FastLanes bit-packed integers on sm_100a.
+//
+// Reference semantics restated (all under /root/reference/src/core/src/liquid_array/):
+//   encode  LiquidPrimitiveArray::from_arrow_array   primitive_array.rs:159-206
+//           get_bit_width                            ../utils/mod.rs:24-32
+//           BitPackedArray::from_primitive           raw/bit_pack_array.rs:71-124
+//   decode  BitPackedArray::to_primitive             raw/bit_pack_array.rs:127-169
+//           LiquidPrimitiveArray::to_arrow_array     primitive_array.rs:350-368
+//   filter / try_eval_predicate                      primitive_array.rs:370-379
+//
+// Design (B200): one CTA per entry (an 8192-row batch). The CTA pulls the whole entry blob
+// (header + validity + packed chunks) into shared memory with ONE TMA bulk copy, then every lane
+// decodes "its" row straight out of the FastLanes layout (two shared loads + a funnel shift), so
+// rows come out in logical order and selection -> write-offset compaction is a warp ballot plus a
+// prefix sum over 32-bit selection words. The comparison runs in the packed domain
+// (u = v - reference against a host-precomputed threshold), never materialising the column.
+// Purely HBM-bound integer work: no tensor cores.
+#include <type_traits>
+
+#include "device_utils.cuh"
+#include "kernels.h"
+#include "scan_rows.cuh"
+
+namespace lc {
+
+// ------------------------------------------------------------------------------------------------
+// FastLanes unified transposed order (crate fastlanes 0.5.0, BitPacking::unchecked_{pack,unpack}):
+// a 1024-value block of a T-bit type has LANES = 1024/T lanes; logical index of (row r, lane l) is
+//   (r % 8) * 128 + FL_ORDER[r / 8] * 16 + l,  FL_ORDER = {0,4,2,6,1,5,3,7} = 3-bit reversal
+// lane l's W-bit fields are concatenated over rows into T-bit words, word k stored at
+// packed[LANES * k + l]. Inverting the index map gives a direct random-access decode.
+// ------------------------------------------------------------------------------------------------
+template <typename U>
+struct FL {
+  static constexpr uint32_t T = sizeof(U) * 8;
+  static constexpr uint32_t LANES = 1024 / T;
+  static constexpr uint32_t LOG_O = (T == 64) ? 3 : (T == 32) ? 2 : (T == 16) ? 1 : 0;
+};
+
+template <typename U>
+__device__ __forceinline__ U fl_get(const U* __restrict__ chunk, uint32_t j, uint32_t W) {
+  constexpr uint32_t T = FL<U>::T, LANES = FL<U>::LANES, LOG_O = FL<U>::LOG_O;
+  const uint32_t s = j >> 7, rem = j & 127u;
+  const uint32_t l = rem & (LANES - 1u);
+  const uint32_t q = rem / LANES;
+  const uint32_t o = LOG_O ? (__brev(q) >> (32u - (LOG_O ? LOG_O : 1u))) : 0u;
+  const uint32_t r = o * 8u + s;
+  const uint32_t b = r * W;
+  const uint32_t k = b / T, sh = b % T;
+  U v = static_cast<U>(chunk[LANES * k + l] >> sh);
+  if (sh + W > T) v = static_cast<U>(v | static_cast<U>(chunk[LANES * (k + 1u) + l] << (T - sh)));
+  if (W < T) v = static_cast<U>(v & static_cast<U>((static_cast<U>(1) << W) - static_cast<U>(1)));
+  return v;
+}
+
+template <typename U>
+__device__ __forceinline__ bool ucmp_eval(int32_t kind, U u, U thr) {
+  switch (kind) {
+    case UC_FALSE: return false;
+    case UC_TRUE: return true;
+    case UC_EQ: return u == thr;
+    case UC_NE: return u != thr;
+    case UC_LT: return u < thr;
+    case UC_LE: return u <= thr;
+    case UC_GT: return u > thr;
+    default: return u >= thr;
+  }
+}
+
+template <typename U, int MODE>
+__device__ __forceinline__ void int_scan_entry(const IntScanWork& w, const uint8_t* base, ScanSmem* sm) {
+  constexpr uint32_t T = FL<U>::T;
+  const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
+  const uint32_t W = h->bit_width;
+  const U ref = static_cast<U>(h->reference);
+  const U thr = static_cast<U>(w.thr);
+  const int32_t kind = w.ucmp;
+  const U* packed = reinterpret_cast<const U*>(base + h->packed_off);
+  const uint32_t* valid = h->has_nulls ? reinterpret_cast<const uint32_t*>(base + h->validity_off) : nullptr;
+  const uint32_t chunk_words = 1024u * W / T;  // in units of U
+  U* out_vals = reinterpret_cast<U*>(w.out_values);
+
+  auto value_of = [&](uint32_t row) -> U {
+    if (W == 0) return static_cast<U>(0);
+    return fl_get<U>(packed + static_cast<size_t>(row >> 10) * chunk_words, row & 1023u, W);
+  };
+  auto cmp = [&](uint32_t row) -> bool { return ucmp_eval<U>(kind, value_of(row), thr); };
+  auto emit = [&](uint32_t row, uint32_t dst) { out_vals[dst] = static_cast<U>(value_of(row) + ref); };
+  scan_entry_rows<MODE>(w.sel, h->n, valid, h->null_count, reinterpret_cast<uint32_t*>(w.out_values),
+                        w.out_validity, w.out_counts, sm, cmp, emit);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int_scan(const IntScanWork* __restrict__ works, uint32_t stage_cap) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
+  uint8_t* stage = smem_raw + kScanFixedSmem;
+
+  const IntScanWork w = works[blockIdx.x];
+  const bool staged = w.blob_bytes <= stage_cap;
+  scan_smem_init(sm);
+  if (threadIdx.x == 0 && staged) {
+    mbar_init(&sm->bar[0], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&sm->bar[0], w.blob_bytes);
+    tma_bulk_g2s(stage, w.blob, w.blob_bytes, &sm->bar[0]);  // whole entry in one bulk copy
+  }
+  __syncthreads();
+  const uint8_t* base = w.blob;
+  if (staged) {
+    mbar_wait(&sm->bar[0], 0);
+    base = stage;
+  }
+  const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
+  switch (h->tbits) {
+    case 8: int_scan_entry<uint8_t, MODE>(w, base, sm); break;
+    case 16: int_scan_entry<uint16_t, MODE>(w, base, sm); break;
+    case 32: int_scan_entry<uint32_t, MODE>(w, base, sm); break;
+    default: int_scan_entry<uint64_t, MODE>(w, base, sm); break;
+  }
+}
+
+cudaError_t launch_int_scan(int mode, const IntScanWork* d_works, uint32_t n_works, uint32_t max_blob_bytes,
+                            cudaStream_t s) {
+  if (n_works == 0) return cudaSuccess;
+  const uint32_t stage = max_blob_bytes <= kStageCap ? ((max_blob_bytes + 127u) & ~127u) : 0u;
+  const uint32_t smem = kScanFixedSmem + stage;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_int_scan<MODE_DECODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kScanFixedSmem + kStageCap);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_int_scan<MODE_PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kScanFixedSmem + kStageCap);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_int_scan<MODE_REFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kScanFixedSmem + kStageCap);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  switch (mode) {
+    case MODE_DECODE: k_int_scan<MODE_DECODE><<<n_works, 256, smem, s>>>(d_works, stage); break;
+    case MODE_PRED: k_int_scan<MODE_PRED><<<n_works, 256, smem, s>>>(d_works, stage); break;
+    default: k_int_scan<MODE_REFINE><<<n_works, 256, smem, s>>>(d_works, stage); break;
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode pass 1: min / max over valid rows (arrow aggregate min/max, primitive_array.rs:160,171)
+// ------------------------------------------------------------------------------------------------
+template <typename N, bool SIGNED>
+__device__ __forceinline__ void minmax_entry(const IntMinMaxWork& w, uint64_t* s_red) {
+  const N* v = reinterpret_cast<const N*>(w.values);
+  using Wide = typename std::conditional<SIGNED, long long, unsigned long long>::type;
+  Wide mn = SIGNED ? static_cast<Wide>(0x7fffffffffffffffLL) : static_cast<Wide>(~0ULL);
+  Wide mx = SIGNED ? static_cast<Wide>(0x8000000000000000ULL) : static_cast<Wide>(0);
+  uint32_t cnt = 0;
+  for (uint32_t i = threadIdx.x; i < w.n; i += blockDim.x) {
+    const bool ok = w.validity ? ((w.validity[i >> 5] >> (i & 31u)) & 1u) : true;
+    if (ok) {
+      const Wide x = static_cast<Wide>(v[i]);
+      mn = x < mn ? x : mn;
+      mx = x > mx ? x : mx;
+      ++cnt;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const Wide omn = static_cast<Wide>(__shfl_xor_sync(kFullMask, static_cast<unsigned long long>(mn), d));
+    const Wide omx = static_cast<Wide>(__shfl_xor_sync(kFullMask, static_cast<unsigned long long>(mx), d));
+    mn = omn < mn ? omn : mn;
+    mx = omx > mx ? omx : mx;
+    cnt += __shfl_xor_sync(kFullMask, cnt, d);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_red[warp * 3 + 0] = static_cast<uint64_t>(mn);
+    s_red[warp * 3 + 1] = static_cast<uint64_t>(mx);
+    s_red[warp * 3 + 2] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < blockDim.x / 32; ++i) {
+      const Wide omn = static_cast<Wide>(s_red[i * 3 + 0]);
+      const Wide omx = static_cast<Wide>(s_red[i * 3 + 1]);
+      mn = omn < mn ? omn : mn;
+      mx = omx > mx ? omx : mx;
+      total += s_red[i * 3 + 2];
+    }
+    w.out[0] = static_cast<uint64_t>(mn);
+    w.out[1] = static_cast<uint64_t>(mx);
+    w.out[2] = total;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_int_minmax(const IntMinMaxWork* __restrict__ works) {
+  __shared__ uint64_t s_red[8 * 3];
+  const IntMinMaxWork w = works[blockIdx.x];
+  switch (w.phys) {
+    case PT_I8: minmax_entry<int8_t, true>(w, s_red); break;
+    case PT_I16: minmax_entry<int16_t, true>(w, s_red); break;
+    case PT_I32: case PT_DATE32: minmax_entry<int32_t, true>(w, s_red); break;
+    case PT_U8: minmax_entry<uint8_t, false>(w, s_red); break;
+    case PT_U16: minmax_entry<uint16_t, false>(w, s_red); break;
+    case PT_U32: minmax_entry<uint32_t, false>(w, s_red); break;
+    case PT_U64: minmax_entry<uint64_t, false>(w, s_red); break;
+    default: minmax_entry<int64_t, true>(w, s_red); break;  // I64, DATE64, TS_*
+  }
+}
+
+cudaError_t launch_int_minmax(const IntMinMaxWork* d_works, uint32_t n_works, cudaStream_t s) {
+  if (n_works == 0) return cudaSuccess;
+  k_int_minmax<<<n_works, 256, 0, s>>>(d_works);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode pass 2: (v - reference) -> FastLanes pack, fused; one thread per OUTPUT word, gathering the
+// rows whose W-bit fields overlap it (coalesced reads across lanes, no atomics). Null slots are
+// zeroed (the reference leaves whatever the Arrow buffer held; Arrow equality ignores them).
+// ------------------------------------------------------------------------------------------------
+template <typename U>
+__device__ __forceinline__ void pack_entry(const IntPackWork& w) {
+  constexpr uint32_t T = FL<U>::T, LANES = FL<U>::LANES;
+  const IntHeader& h = w.hdr;
+  const uint32_t W = h.bit_width, n = h.n;
+  if (W == 0) return;
+  const U* in = reinterpret_cast<const U*>(w.values);
+  U* out = reinterpret_cast<U*>(w.blob + h.packed_off);
+  const U ref = static_cast<U>(h.reference);
+  const U mask = (W < T) ? static_cast<U>((static_cast<U>(1) << W) - static_cast<U>(1)) : static_cast<U>(~static_cast<U>(0));
+  const uint32_t chunk_words = 1024u * W / T;
+  const uint32_t total = h.n_chunks * chunk_words;
+  for (uint32_t g = threadIdx.x; g < total; g += blockDim.x) {
+    const uint32_t c = g / chunk_words, within = g % chunk_words;
+    const uint32_t k = within / LANES, l = within % LANES;
+    const uint32_t bit0 = k * T;
+    const uint32_t r0 = bit0 / W;
+    uint32_t r1 = (bit0 + T - 1u) / W;
+    if (r1 > T - 1u) r1 = T - 1u;
+    U word = 0;
+    for (uint32_t r = r0; r <= r1; ++r) {
+      const uint32_t idx = c * 1024u + (r & 7u) * 128u + (__brev(r >> 3) >> 29) * 16u + l;
+      U val = 0;
+      if (idx < n) {
+        const bool ok = w.validity ? ((w.validity[idx >> 5] >> (idx & 31u)) & 1u) : true;
+        if (ok) val = static_cast<U>(static_cast<U>(in[idx] - ref) & mask);
+      }
+      const uint32_t b = r * W;
+      if (b >= bit0) word = static_cast<U>(word | static_cast<U>(val << (b - bit0)));
+      else word = static_cast<U>(word | static_cast<U>(val >> (bit0 - b)));
+    }
+    out[g] = word;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_int_pack(const IntPackWork* __restrict__ works) {
+  const IntPackWork& w = works[blockIdx.x];
+  const IntHeader& h = w.hdr;
+  // header + validity
+  if (threadIdx.x < sizeof(IntHeader) / 4) {
+    reinterpret_cast<uint32_t*>(w.blob)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&h)[threadIdx.x];
+  }
+  if (h.has_nulls) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(w.blob + h.validity_off);
+    const uint32_t n_words = (h.n + 31u) >> 5;
+    const uint32_t padded = (h.packed_off - h.validity_off) / 4;
+    for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
+      uint32_t v = 0;
+      if (i < n_words) {
+        v = w.validity[i];
+        if (i == n_words - 1u && (h.n & 31u)) v &= (1u << (h.n & 31u)) - 1u;
+      }
+      dst[i] = v;
+    }
+  }
+  switch (h.tbits) {
+    case 8: pack_entry<uint8_t>(w); break;
+    case 16: pack_entry<uint16_t>(w); break;
+    case 32: pack_entry<uint32_t>(w); break;
+    default: pack_entry<uint64_t>(w); break;
+  }
+}
+
+cudaError_t launch_int_pack(const IntPackWork* d_works, uint32_t n_works, cudaStream_t s) {
+  if (n_works == 0) return cudaSuccess;
+  k_int_pack<<<n_works, 256, 0, s>>>(d_works);
+  return cudaGetLastError();
+}
+
+}  // namespace lc

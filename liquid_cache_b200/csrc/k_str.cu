@@ -1,0 +1,513 @@
+// k_str.cu — byte-view (dictionary + FSST) columns on sm_100a: predicates and get-with-selection.
+//
+// Reference semantics restated (all under /root/reference/src/core/src/liquid_array/byte_view_array/):
+//   try_eval_predicate            mod.rs:357-362, helpers.rs:44-92
+//   compare_equals / not_equals   comparisons.rs:21-90
+//   compare_with_inner (+prefix)  comparisons.rs:114-151, 351-405, 469-501
+//   compare_like_substring        comparisons.rs:159-183, 600-651; fingerprint.rs:19-36
+//   dictionary -> rows            comparisons.rs:325-347
+//   filter / to_arrow_array       mod.rs:266-290, 421-424; helpers.rs:14-64; ../raw/fsst_buffer.rs:88-119, 642-663
+//
+// Design (B200): one CTA per entry. Two TMA bulk copies are issued up front: (A) header + dictionary
+// metadata (shared prefix, 8-byte prefix keys, fingerprints, offset residuals), (B) validity + u16
+// keys. Phase 1 evaluates the predicate ONCE PER DICTIONARY ENTRY on the encoded form (prefix keys /
+// fingerprints first, FSST codes walked only for the candidates that survive) into a bitmap in shared
+// memory while copy B is still in flight; phase 2 broadcasts the bitmap through the keys with the
+// same ballot + prefix-sum selection machinery the integer path uses (scan_rows.cuh).
+#include "../../include/lc_gpu.h"
+#include "device_utils.cuh"
+#include "kernels.h"
+#include "scan_rows.cuh"
+
+namespace lc {
+
+struct StrView {
+  const StrHeader* h;
+  const uint8_t* sp;
+  const uint64_t* pk;
+  const uint32_t* fp;
+  const uint8_t* resid;
+  const uint32_t* valid;
+  const uint16_t* keys;
+  const uint8_t* fsst;  // always in global memory
+};
+
+// head: where the header + sections up to head_bytes live (shared or global); blob: global blob.
+__device__ __forceinline__ StrView make_view(const uint8_t* head, const uint8_t* blob) {
+  StrView v;
+  v.h = reinterpret_cast<const StrHeader*>(head);
+  v.sp = head + v.h->shared_prefix_off;
+  v.pk = reinterpret_cast<const uint64_t*>(head + v.h->prefix_keys_off);
+  v.fp = v.h->has_fp ? reinterpret_cast<const uint32_t*>(head + v.h->fp_off) : nullptr;
+  v.resid = head + v.h->resid_off;
+  v.valid = v.h->has_nulls ? reinterpret_cast<const uint32_t*>(head + v.h->validity_off) : nullptr;
+  v.keys = reinterpret_cast<const uint16_t*>(head + v.h->keys_off);
+  v.fsst = blob + v.h->fsst_off;
+  return v;
+}
+
+// CompactOffsets::get_offset (raw/fsst_buffer.rs:365-368)
+__device__ __forceinline__ uint32_t dict_offset(const StrView& v, uint32_t i) {
+  int32_t r;
+  const uint32_t ob = v.h->offset_bytes;
+  if (ob == 1) r = reinterpret_cast<const int8_t*>(v.resid)[i];
+  else if (ob == 2) r = reinterpret_cast<const int16_t*>(v.resid)[i];
+  else r = reinterpret_cast<const int32_t*>(v.resid)[i];
+  return static_cast<uint32_t>(v.h->slope * static_cast<int32_t>(i) + v.h->intercept + r);
+}
+
+// Sequential reader over a compressed value, 8 bytes per global load.
+struct CodeStream {
+  const uint8_t* base;
+  uint32_t p, end;
+  uint64_t cur;
+  __device__ __forceinline__ void init(const uint8_t* fsst, uint32_t start, uint32_t end_) {
+    base = fsst;
+    p = start;
+    end = end_;
+    cur = 0;
+    if (p < end) cur = *reinterpret_cast<const uint64_t*>(base + (p & ~7u));
+  }
+  __device__ __forceinline__ uint32_t next() {
+    const uint32_t b = static_cast<uint32_t>(cur >> ((p & 7u) * 8u)) & 0xffu;
+    ++p;
+    if ((p & 7u) == 0 && p < end) cur = *reinterpret_cast<const uint64_t*>(base + p);
+    return b;
+  }
+};
+
+// Walk the decoded bytes of one value (thread-serial); f(byte) returns false to stop early.
+template <typename F>
+__device__ __forceinline__ void decode_visit(const uint8_t* fsst, uint32_t start, uint32_t end,
+                                             const uint64_t* s_sym, const uint8_t* s_len, F&& f) {
+  CodeStream cs;
+  cs.init(fsst, start, end);
+  while (cs.p < cs.end) {
+    const uint32_t code = cs.next();
+    if (code == 255u) {
+      if (cs.p >= cs.end) break;
+      if (!f(cs.next())) return;
+    } else {
+      uint64_t sym = s_sym[code];
+      const uint32_t l = s_len[code];
+      for (uint32_t t = 0; t < l; ++t) {
+        if (!f(static_cast<uint32_t>(sym & 0xffu))) return;
+        sym >>= 8;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t decoded_length(const uint8_t* fsst, uint32_t start, uint32_t end,
+                                                   const uint8_t* s_len) {
+  CodeStream cs;
+  cs.init(fsst, start, end);
+  uint32_t n = 0;
+  while (cs.p < cs.end) {
+    const uint32_t code = cs.next();
+    if (code == 255u) {
+      if (cs.p >= cs.end) break;
+      cs.next();
+      ++n;
+    } else {
+      n += s_len[code];
+    }
+  }
+  return n;
+}
+
+// byte-wise lexicographic compare of the decoded value against the needle: -1 / 0 / +1
+__device__ __forceinline__ int full_compare(const StrView& v, uint32_t i, const uint64_t* s_sym,
+                                            const uint8_t* s_len, const uint8_t* nd, uint32_t m) {
+  const uint32_t start = dict_offset(v, i), end = dict_offset(v, i + 1u);
+  uint32_t pos = 0;
+  int ord = 0;
+  decode_visit(v.fsst, start, end, s_sym, s_len, [&](uint32_t b) -> bool {
+    if (pos >= m) {
+      ord = 1;  // value is longer than the needle and equal so far
+      return false;
+    }
+    const uint32_t nb = nd[pos];
+    if (b != nb) {
+      ord = b < nb ? -1 : 1;
+      return false;
+    }
+    ++pos;
+    return true;
+  });
+  if (ord == 0 && pos < m) ord = -1;  // value is a proper prefix of the needle
+  return ord;
+}
+
+// substring test with the needle's KMP failure links (exact, any needle length <= kMaxNeedle)
+__device__ __forceinline__ bool contains_needle(const StrView& v, uint32_t i, const uint64_t* s_sym,
+                                                const uint8_t* s_len, const uint8_t* nd, const uint16_t* fail,
+                                                uint32_t m) {
+  const uint32_t start = dict_offset(v, i), end = dict_offset(v, i + 1u);
+  uint32_t q = 0;
+  bool found = false;
+  decode_visit(v.fsst, start, end, s_sym, s_len, [&](uint32_t b) -> bool {
+    while (q > 0 && nd[q] != b) q = fail[q - 1u];
+    if (nd[q] == b) ++q;
+    if (q == m) {
+      found = true;
+      return false;
+    }
+    return true;
+  });
+  return found;
+}
+
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) {
+  const uint32_t lo = static_cast<uint32_t>(x), hi = static_cast<uint32_t>(x >> 32);
+  return (static_cast<uint64_t>(__byte_perm(lo, 0, 0x0123)) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+
+__device__ __forceinline__ void load_fsst_table(const FsstTable* t, uint64_t* s_sym, uint8_t* s_len) {
+  const uint64_t* gs = t->symbols;
+  for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) s_sym[i] = gs[i];
+  const uint32_t* gl = reinterpret_cast<const uint32_t*>(t->lens);
+  uint32_t* sl = reinterpret_cast<uint32_t*>(s_len);
+  for (uint32_t i = threadIdx.x; i < 64u; i += blockDim.x) sl[i] = gl[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// predicate kernel
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_str_scan(const StrScanWork* __restrict__ works, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
+  uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
+  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
+  uint8_t* s_nd = s_len + 256;
+  const uint32_t m = pred.needle_len;
+  const uint32_t nd_bytes = (m + 15u) & ~15u;
+  uint16_t* s_fail = reinterpret_cast<uint16_t*>(s_nd + nd_bytes);
+  uint32_t* s_dict = reinterpret_cast<uint32_t*>(s_nd + nd_bytes + ((2u * m + 15u) & ~15u));
+  uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_dict + dict_words);
+  uint8_t* stage = reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u);
+  stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage) + 127u) & ~static_cast<uintptr_t>(127u));
+
+  const StrScanWork w = works[blockIdx.x];
+  const bool staged = w.head_bytes <= stage_cap;
+  scan_smem_init(sm);
+  if (threadIdx.x == 0 && staged) {
+    mbar_init(&sm->bar[0], 1);
+    mbar_init(&sm->bar[1], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&sm->bar[0], w.meta_bytes);
+    tma_bulk_g2s(stage, w.blob, w.meta_bytes, &sm->bar[0]);  // header + dictionary metadata
+    const uint32_t rest = w.head_bytes - w.meta_bytes;
+    if (rest) {
+      mbar_expect_tx(&sm->bar[1], rest);
+      tma_bulk_g2s(stage + w.meta_bytes, w.blob + w.meta_bytes, rest, &sm->bar[1]);  // validity + keys
+    }
+  }
+  // needle + KMP links (shared by all entries of the launch)
+  for (uint32_t i = threadIdx.x; i < m; i += 256u) {
+    s_nd[i] = pred.needle[i];
+    s_fail[i] = reinterpret_cast<const uint16_t*>(pred.needle + ((m + 3u) & ~3u))[i];
+  }
+  for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = 0;
+  __syncthreads();
+  const uint8_t* head = w.blob;
+  if (staged) {
+    mbar_wait(&sm->bar[0], 0);
+    head = stage;
+  }
+  const StrView v = make_view(head, w.blob);
+  const uint32_t U = v.h->n_unique;
+  const int lane = threadIdx.x & 31;
+  const int32_t kind = w.kind;
+  const bool neg = (w.flags & 2u) != 0;
+  const bool needs_table = (kind == SP_EQ_LONG || kind == SP_ORD || kind == SP_LIKE);
+  if (needs_table) {
+    load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
+    __syncthreads();
+  }
+
+  // ---------------- phase 1: one decision per dictionary entry ----------------
+  if (kind == SP_CONST) {
+    const uint32_t fill = (w.flags & 1u) ? kFullMask : 0u;
+    for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = fill;
+  } else {
+    const uint32_t op = static_cast<uint32_t>(pred.op);
+    uint32_t any_cand = 0;
+    for (uint32_t i0 = (threadIdx.x & ~31u); i0 < U; i0 += 256u) {
+      const uint32_t i = i0 + lane;
+      const bool act = i < U;
+      const uint64_t key = act ? v.pk[i] : 0ull;
+      bool res = false, cand = false;
+      if (kind == SP_EQ_SHORT) {
+        res = (key == w.key_expect) != neg;
+      } else if (kind == SP_EQ_LONG) {
+        cand = (key == w.key_expect);
+        res = neg;
+      } else if (kind == SP_ORD) {
+        const uint64_t mask = ~0ull << (8u * (8u - w.cmp_len));
+        const uint64_t a = bswap64(key) & mask;
+        if (a < w.key_expect) res = (op == LC_OP_LT || op == LC_OP_LE);
+        else if (a > w.key_expect) res = (op == LC_OP_GT || op == LC_OP_GE);
+        else cand = true;
+      } else if (kind == SP_ORD_EMPTY) {
+        const bool empty = (key >> 56) == 0;
+        res = (op == LC_OP_LT) ? false : (op == LC_OP_LE) ? empty : (op == LC_OP_GT) ? !empty : true;
+      } else {  // SP_LIKE
+        cand = v.fp ? ((v.fp[i < U ? i : 0] & pred.needle_fp) == pred.needle_fp) : true;
+      }
+      res = res && act;
+      cand = cand && act;
+      const uint32_t rw = __ballot_sync(kFullMask, res);
+      const uint32_t cw = __ballot_sync(kFullMask, cand);
+      if (lane == 0) s_dict[i0 >> 5] = rw;
+      if (cw) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&sm->misc[0], __popc(cw));
+        base = __shfl_sync(kFullMask, base, 0);
+        if (cand) s_cand[base + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i);
+        any_cand = 1;
+      }
+    }
+    __syncthreads();
+    const uint32_t ncand = sm->misc[0];
+    // candidates: walk the FSST codes of the value
+    for (uint32_t c = threadIdx.x; c < ncand; c += 256u) {
+      const uint32_t i = s_cand[c];
+      bool res;
+      if (kind == SP_LIKE) {
+        res = contains_needle(v, i, s_sym, s_len, s_nd, s_fail, m);
+      } else {
+        const int ord = full_compare(v, i, s_sym, s_len, s_nd, m);
+        if (kind == SP_EQ_LONG) res = (ord == 0) != neg;
+        else res = (op == LC_OP_LT) ? ord < 0 : (op == LC_OP_LE) ? ord <= 0 : (op == LC_OP_GT) ? ord > 0 : ord >= 0;
+      }
+      if (kind == SP_EQ_LONG && neg) {
+        if (!res) atomicAnd(&s_dict[i >> 5], ~(1u << (i & 31u)));
+      } else if (res) {
+        atomicOr(&s_dict[i >> 5], 1u << (i & 31u));
+      }
+    }
+    if (kind == SP_LIKE && neg) {
+      // NOT LIKE inverts every dictionary result — but, as in the reference, only inside
+      // apply_like_match_on_candidates, i.e. only when the fingerprint gate let something through
+      // (comparisons.rs:166-180, 644-648). Without fingerprints (flags bit2) it is a plain negation.
+      __syncthreads();
+      const bool invert = (w.flags & 4u) ? true : (ncand != 0);
+      if (invert)
+        for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = ~s_dict[i];
+    }
+    (void)any_cand;
+  }
+  __syncthreads();
+  if (staged && w.head_bytes > w.meta_bytes) mbar_wait(&sm->bar[1], 0);
+
+  // ---------------- phase 2: dictionary results -> rows ----------------
+  const uint16_t* keys = v.keys;
+  auto cmp = [&](uint32_t row) -> bool {
+    const uint32_t k = keys[row];
+    return (s_dict[k >> 5] >> (k & 31u)) & 1u;
+  };
+  auto emit = [&](uint32_t, uint32_t) {};
+  scan_entry_rows<MODE>(w.sel, v.h->n, v.valid, v.h->null_count, reinterpret_cast<uint32_t*>(w.out_values),
+                        w.out_validity, w.out_counts, sm, cmp, emit);
+}
+
+static uint32_t str_scan_smem(uint32_t needle_len, uint32_t dict_words, uint32_t stage) {
+  const uint32_t nd = (needle_len + 15u) & ~15u;
+  const uint32_t fl = (2u * needle_len + 15u) & ~15u;
+  return kScanFixedSmem + 2048u + 256u + nd + fl + dict_words * 4u + (((dict_words * 64u) + 127u) & ~127u) + 128u +
+         stage;
+}
+
+cudaError_t launch_str_scan(int mode, const StrScanWork* d_works, uint32_t n_works, const StrPredDesc& pred,
+                            uint32_t max_head_bytes, uint32_t max_unique, cudaStream_t s) {
+  if (n_works == 0) return cudaSuccess;
+  const uint32_t dict_words = ((max_unique + 31u) / 32u + 3u) & ~3u;
+  constexpr uint32_t kMaxSmem = 227u * 1024u;
+  uint32_t stage = (max_head_bytes + 127u) & ~127u;
+  if (str_scan_smem(pred.needle_len, dict_words, stage) > 100u * 1024u) stage = 0;  // keep >= 2 CTAs per SM
+  const uint32_t smem = str_scan_smem(pred.needle_len, dict_words, stage);
+  if (smem > kMaxSmem) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_str_scan<MODE_PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_str_scan<MODE_REFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (mode == MODE_PRED) k_str_scan<MODE_PRED><<<n_works, 256, smem, s>>>(d_works, pred, stage, dict_words);
+  else k_str_scan<MODE_REFINE><<<n_works, 256, smem, s>>>(d_works, pred, stage, dict_words);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// get / filter, pass 1: selected keys, decoded lengths, local offsets
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_str_lengths(const StrGatherWork* __restrict__ works, uint32_t stage_cap) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
+  uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
+  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
+  uint8_t* stage = s_len + 256;
+
+  const StrGatherWork w = works[blockIdx.x];
+  const bool staged = w.head_bytes <= stage_cap;
+  scan_smem_init(sm);
+  if (threadIdx.x == 0 && staged) {
+    mbar_init(&sm->bar[0], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&sm->bar[0], w.head_bytes);
+    tma_bulk_g2s(stage, w.blob, w.head_bytes, &sm->bar[0]);
+  }
+  __syncthreads();
+  const uint8_t* head = w.blob;
+  if (staged) {
+    mbar_wait(&sm->bar[0], 0);
+    head = stage;
+  }
+  const StrView v = make_view(head, w.blob);
+  load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
+  __syncthreads();
+  const uint32_t U = v.h->n_unique, spl = v.h->shared_prefix_len;
+  const bool precomp = (w.flags & kGatherPrecompLens) != 0;
+  if (precomp) {
+    // decoded length of every unique: PrefixKey.len when < 255, else walk the codes
+    for (uint32_t i = threadIdx.x; i < U; i += 256u) {
+      const uint32_t l = static_cast<uint32_t>(v.pk[i] >> 56);
+      uint32_t len = spl + l;
+      const uint32_t start = dict_offset(v, i), end = dict_offset(v, i + 1u);
+      if (start == end) len = 0;  // empty / null dictionary value (fsst_buffer.rs:100-113)
+      else if (l == 255u) len = decoded_length(v.fsst, start, end, s_len);
+      w.ulen[i] = len;
+    }
+    __syncthreads();
+  }
+  const uint16_t* keys = v.keys;
+  const uint32_t* valid = v.valid;
+  uint32_t* row_off = w.row_off;
+  uint32_t* row_key = w.row_key;
+  auto cmp = [&](uint32_t) -> bool { return false; };
+  auto emit = [&](uint32_t row, uint32_t dst) {
+    const bool ok = valid ? ((valid[row >> 5] >> (row & 31u)) & 1u) : true;
+    uint32_t len = 0, key = 0xFFFFFFFFu;
+    if (ok) {
+      key = keys[row];
+      if (precomp) {
+        len = w.ulen[key];
+      } else {
+        const uint32_t l = static_cast<uint32_t>(v.pk[key] >> 56);
+        const uint32_t start = dict_offset(v, key), end = dict_offset(v, key + 1u);
+        if (start == end) len = 0;
+        else if (l == 255u) len = decoded_length(v.fsst, start, end, s_len);
+        else len = spl + l;
+      }
+    }
+    row_off[dst] = len;
+    row_key[dst] = key;
+  };
+  scan_entry_rows<MODE_DECODE>(w.sel, v.h->n, valid, v.h->null_count, nullptr, w.out_validity, w.out_counts, sm, cmp,
+                               emit);
+  __syncthreads();
+  // exclusive scan of the selected rows' lengths -> local offsets (in place), total bytes
+  const uint32_t k = w.out_counts[0];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < k; base += 256u) {
+    const uint32_t j = base + threadIdx.x;
+    const uint32_t len = j < k ? row_off[j] : 0u;
+    uint32_t tot;
+    const uint32_t excl = block_excl_scan_256(len, sm->warp_tot, &tot);
+    if (j < k) row_off[j] = carry + excl;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) {
+    row_off[k] = carry;
+    w.out_counts[2] = carry;
+  }
+}
+
+cudaError_t launch_str_lengths(const StrGatherWork* d_works, uint32_t n_works, uint32_t max_head_bytes,
+                               cudaStream_t s) {
+  if (n_works == 0) return cudaSuccess;
+  uint32_t stage = (max_head_bytes + 127u) & ~127u;
+  if (stage > kStageCap) stage = 0;
+  const uint32_t smem = kScanFixedSmem + 2048u + 256u + stage;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_str_lengths, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kScanFixedSmem + 2304u + kStageCap);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_str_lengths<<<n_works, 256, smem, s>>>(d_works, stage);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// get / filter, pass 2: one warp per selected row, one lane per FSST code
+// ------------------------------------------------------------------------------------------------
+// fsst-rs Decompressor::decompress_into restated for a warp: lane p looks at compressed byte p of a
+// 32-byte window; a byte is an escaped literal iff it is preceded by an odd run of unconsumed 0xFF
+// bytes (ballot + clz), otherwise it is an escape marker (0xFF) or a code whose symbol length comes
+// from the table; an exclusive scan of the produced lengths gives each lane its output position.
+__device__ __forceinline__ uint32_t warp_decode(const uint8_t* __restrict__ c, uint32_t clen,
+                                                uint8_t* __restrict__ out, const uint64_t* s_sym,
+                                                const uint8_t* s_len, int lane) {
+  uint32_t produced = 0;
+  uint32_t carry_lit = 0;
+  for (uint32_t base = 0; base < clen; base += 32u) {
+    const uint32_t idx = base + lane;
+    const bool in = idx < clen;
+    const uint32_t b = in ? c[idx] : 0u;
+    const uint32_t F = __ballot_sync(kFullMask, in && b == 255u);
+    const uint32_t Fp = carry_lit ? (F & ~1u) : F;
+    const uint32_t zeros = ~Fp & lanemask_lt();
+    const uint32_t run = zeros ? (lane - 1u - (31u - __clz(zeros))) : static_cast<uint32_t>(lane);
+    const bool lit = (lane == 0) ? (carry_lit != 0) : ((run & 1u) != 0);
+    const bool esc = in && (b == 255u) && !lit;
+    const uint32_t l = !in ? 0u : lit ? 1u : esc ? 0u : s_len[b];
+    const uint32_t incl = warp_incl_scan(l, lane);
+    if (l) {
+      uint64_t val = lit ? static_cast<uint64_t>(b) : s_sym[b];
+      uint8_t* o = out + produced + incl - l;
+      for (uint32_t t = 0; t < l; ++t) {
+        o[t] = static_cast<uint8_t>(val);
+        val >>= 8;
+      }
+    }
+    produced += __shfl_sync(kFullMask, incl, 31);
+    carry_lit = __shfl_sync(kFullMask, esc ? 1u : 0u, 31);
+  }
+  return produced;
+}
+
+__global__ void __launch_bounds__(256) k_str_decode(const StrDecodeWork* __restrict__ works) {
+  __shared__ uint64_t s_sym[256];
+  __shared__ __align__(16) uint8_t s_len[256];
+  const StrDecodeWork w = works[blockIdx.x];
+  const StrView v = make_view(w.blob, w.blob);
+  load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // final offsets of this entry's slice (the LAST entry also owns the closing offset; the host adds it)
+  for (uint32_t j = threadIdx.x; j < w.k; j += 256u)
+    w.out_offsets[j] = static_cast<int32_t>(w.byte_base + w.row_off[j]);
+  for (uint32_t j = warp; j < w.k; j += 8u) {
+    const uint32_t key = w.row_key[j];
+    if (key == 0xFFFFFFFFu) continue;
+    const uint32_t start = dict_offset(v, key), end = dict_offset(v, key + 1u);
+    if (start == end) continue;
+    warp_decode(v.fsst + start, end - start, w.out_bytes + w.byte_base + w.row_off[j], s_sym, s_len, lane);
+  }
+}
+
+cudaError_t launch_str_decode(const StrDecodeWork* d_works, uint32_t n_works, cudaStream_t s) {
+  if (n_works == 0) return cudaSuccess;
+  k_str_decode<<<n_works, 256, 0, s>>>(d_works);
+  return cudaGetLastError();
+}
+
+}  // namespace lc

@@ -1,0 +1,477 @@
+// lc_abi.cc — extern "C" entry points declared in include/lc_gpu.h.
+#include <algorithm>
+
+#include "host_common.h"
+
+using namespace lc;
+
+namespace {
+
+struct Guard {
+  lc_ctx* ctx;
+  std::unique_lock<std::mutex> lk;
+  explicit Guard(lc_ctx* c) : ctx(c), lk(c->mu) {
+    cudaSetDevice(c->device);
+    c->scratch.reset();
+  }
+};
+
+int encode_locked(lc_ctx* ctx, const ArrowSchema* schema, const ArrowArray* array, int32_t hint, uint64_t scope,
+                  Entry** out) {
+  ArrowIn in;
+  LC_TRY(parse_arrow_input(schema, array, &in));
+  if (in.kind == ArrowIn::K_INT) return int_encode(ctx, in, out);
+  return str_encode(ctx, in, hint, scope, out);
+}
+
+}  // namespace
+
+struct lc_scan {
+  lc_ctx* ctx = nullptr;
+  uint64_t n = 0;
+  std::vector<uint32_t> rows;
+  std::vector<uint64_t> word_off;
+  uint64_t total_words = 0;
+  uint32_t* d_sel = nullptr;
+  uint32_t* d_counts = nullptr;
+  bool all_rows = true;       // no filter applied yet
+  bool counts_on_device = false;
+  bool counts_cached = false;
+  std::vector<uint32_t> counts;
+};
+
+extern "C" {
+
+int lc_encode(lc_ctx* ctx, const struct ArrowSchema* schema, const struct ArrowArray* array, int32_t hint,
+              uint64_t compressor_scope, lc_handle* out) {
+  if (!ctx || !out) {
+    set_error("lc_encode: NULL argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  Entry* e = nullptr;
+  LC_TRY(encode_locked(ctx, schema, array, hint, compressor_scope, &e));
+  *out = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
+  return LC_OK;
+}
+
+void lc_release(lc_ctx* ctx, lc_handle h) {
+  if (!ctx) return;
+  Guard g(ctx);
+  release_entry(ctx, entry_of(h));
+}
+
+uint64_t lc_len(lc_ctx*, lc_handle h) {
+  Entry* e = entry_of(h);
+  return e ? e->n : 0;
+}
+
+uint64_t lc_memory_size(lc_ctx*, lc_handle h) {
+  Entry* e = entry_of(h);
+  return e ? e->blob_bytes : 0;
+}
+
+int32_t lc_data_type(lc_ctx*, lc_handle h) {
+  Entry* e = entry_of(h);
+  return e ? e->liquid_type : 0;
+}
+
+int lc_arrow_format(lc_ctx*, lc_handle h, char* buf, size_t buf_len) {
+  Entry* e = entry_of(h);
+  if (!e || !buf || buf_len == 0) return LC_ERR_INVALID;
+  std::string f = e->arrow_format;
+  if (!e->dict_value_format.empty()) f += ":" + e->dict_value_format;  // "S:u" = Dictionary<UInt16, Utf8>
+  if (f.size() + 1 > buf_len) return LC_ERR_INVALID;
+  std::memcpy(buf, f.c_str(), f.size() + 1);
+  return LC_OK;
+}
+
+uint64_t lc_mask_bytes(uint64_t n_rows) { return round_up((n_rows + 7) / 8, 16); }
+
+int lc_to_arrow_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const uint8_t* const* sel_bits,
+                     struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  if (!ctx || !handles || !out_schema || !out_array || n == 0) {
+    set_error("lc_to_arrow_many: bad argument");
+    return LC_ERR_INVALID;
+  }
+  std::vector<Entry*> es(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    es[i] = entry_of(handles[i]);
+    if (!es[i]) {
+      set_error("invalid handle at position %llu", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+  }
+  Guard g(ctx);
+  return to_arrow_batch(ctx, es.data(), n, sel_bits, nullptr, out_schema, out_array);
+}
+
+int lc_to_arrow(lc_ctx* ctx, lc_handle h, const uint8_t* sel_bits, uint64_t sel_len, struct ArrowSchema* out_schema,
+                struct ArrowArray* out_array) {
+  Entry* e = entry_of(h);
+  if (!e) {
+    set_error("invalid handle");
+    return LC_ERR_INVALID;
+  }
+  if (sel_bits && sel_len != e->n) {
+    set_error("selection has %llu bits, entry has %u rows", (unsigned long long)sel_len, e->n);
+    return LC_ERR_INVALID;
+  }
+  const uint8_t* sels[1] = {sel_bits};
+  return lc_to_arrow_many(ctx, &h, 1, sel_bits ? sels : nullptr, out_schema, out_array);
+}
+
+int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const lc_predicate* pred,
+                           const uint8_t* const* sel_bits, uint8_t* out_values, uint8_t* out_validity,
+                           const uint64_t* out_byte_offsets, uint64_t* out_len, uint64_t* out_null_count) {
+  if (!ctx || !handles || !pred || !out_values) {
+    set_error("lc_eval_predicate_many: NULL argument");
+    return LC_ERR_INVALID;
+  }
+  if (n > 1 && !out_byte_offsets) {
+    set_error("lc_eval_predicate_many: out_byte_offsets required for n > 1");
+    return LC_ERR_INVALID;
+  }
+  std::vector<Entry*> es(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    es[i] = entry_of(handles[i]);
+    if (!es[i]) {
+      set_error("invalid handle at position %llu", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+  }
+  Guard g(ctx);
+  PredOut po{out_values, out_validity, out_byte_offsets, out_len, out_null_count};
+  return eval_predicate_batch(ctx, es.data(), n, pred, sel_bits, po);
+}
+
+int lc_eval_predicate(lc_ctx* ctx, lc_handle h, const lc_predicate* pred, const uint8_t* sel_bits, uint64_t sel_len,
+                      uint8_t* out_values, uint8_t* out_validity, uint64_t* out_len, uint64_t* out_null_count) {
+  Entry* e = entry_of(h);
+  if (!e) {
+    set_error("invalid handle");
+    return LC_ERR_INVALID;
+  }
+  if (sel_bits && sel_len != e->n) {
+    set_error("selection has %llu bits, entry has %u rows", (unsigned long long)sel_len, e->n);
+    return LC_ERR_INVALID;
+  }
+  const uint8_t* sels[1] = {sel_bits};
+  const uint64_t off0 = 0;
+  return lc_eval_predicate_many(ctx, &h, 1, pred, sel_bits ? sels : nullptr, out_values, out_validity, &off0, out_len,
+                                out_null_count);
+}
+
+int lc_and_then(lc_ctx* ctx, const uint8_t* left_bits, uint64_t left_len, const uint8_t* right_bits, uint64_t right_len,
+                uint8_t* out_bits) {
+  if (!ctx || !left_bits || !out_bits || (!right_bits && right_len)) {
+    set_error("lc_and_then: NULL argument");
+    return LC_ERR_INVALID;
+  }
+  if (left_len > 0xffffffffull) {
+    set_error("lc_and_then: selection too long");
+    return LC_ERR_INVALID;
+  }
+  const uint64_t ones = popcount_bits(left_bits, left_len);
+  if (ones != right_len) {
+    // debug_assert_eq!(left.count_set_bits(), right.len())  (datafusion/src/utils.rs:63-67)
+    set_error("lc_and_then: right has %llu bits but left has %llu set bits", (unsigned long long)right_len,
+              (unsigned long long)ones);
+    return LC_ERR_INVALID;
+  }
+  if (left_len == right_len) {  // utils.rs:69-72
+    std::memcpy(out_bits, right_bits, (right_len + 7) / 8);
+    return LC_OK;
+  }
+  Guard g(ctx);
+  const uint64_t lw = round_up((left_len + 31) / 32, 4) * 4, rw = round_up((right_len + 31) / 32, 4) * 4 + 16;
+  Scratch& sc = ctx->scratch;
+  LC_TRY(sc.reserve(2 * lw + rw + 1024, 2 * lw + rw + 1024));
+  uint8_t* h_l = sc.host(lw);
+  uint8_t* h_r = sc.host(rw);
+  uint8_t* h_o = sc.host(lw);
+  uint8_t* d_l = sc.dev(lw);
+  uint8_t* d_r = sc.dev(rw);
+  uint8_t* d_o = sc.dev(lw);
+  if (!h_l || !h_r || !h_o || !d_l || !d_r || !d_o) return LC_ERR_OOM;
+  copy_bits(left_bits, 0, static_cast<int64_t>(left_len), h_l, lw);
+  copy_bits(right_bits, 0, static_cast<int64_t>(right_len), h_r, rw);
+  cudaStream_t s = ctx->stream;
+  LC_CUDA_OK(cudaMemcpyAsync(d_l, h_l, lw, cudaMemcpyHostToDevice, s));
+  LC_CUDA_OK(cudaMemcpyAsync(d_r, h_r, rw, cudaMemcpyHostToDevice, s));
+  LC_CUDA_OK(launch_and_then(reinterpret_cast<const uint32_t*>(d_l), static_cast<uint32_t>(left_len),
+                             reinterpret_cast<const uint32_t*>(d_r), reinterpret_cast<uint32_t*>(d_o), s));
+  LC_CUDA_OK(cudaMemcpyAsync(h_o, d_o, lw, cudaMemcpyDeviceToHost, s));
+  LC_CUDA_OK(cudaStreamSynchronize(s));
+  ctx->kernel_launches++;
+  ctx->h2d_bytes += lw + rw;
+  ctx->d2h_bytes += lw;
+  std::memcpy(out_bits, h_o, (left_len + 7) / 8);
+  return LC_OK;
+}
+
+/* ---------------------------------------------------- LiquidCache-level calls ---- */
+
+int lc_cache_insert(lc_ctx* ctx, uint64_t entry_id, const struct ArrowSchema* schema, const struct ArrowArray* array,
+                    int32_t hint) {
+  if (!ctx) return LC_ERR_INVALID;
+  Guard g(ctx);
+  Entry* e = nullptr;
+  // FSST table scope = (file, row group, column): entry id with the batch bits cleared (cache/id.rs:15-22)
+  const uint64_t scope = entry_id & ~0xFFFFull;
+  LC_TRY(encode_locked(ctx, schema, array, hint, scope, &e));
+  auto it = ctx->cache.find(entry_id);
+  if (it != ctx->cache.end()) release_entry(ctx, entry_of(it->second));  // overwrite (index insert replaces)
+  ctx->cache[entry_id] = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
+  return LC_OK;
+}
+
+int lc_cache_is_cached(lc_ctx* ctx, uint64_t entry_id) {
+  if (!ctx) return 0;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return ctx->cache.count(entry_id) ? 1 : 0;
+}
+
+int lc_cache_remove(lc_ctx* ctx, uint64_t entry_id) {
+  if (!ctx) return LC_ERR_INVALID;
+  Guard g(ctx);
+  auto it = ctx->cache.find(entry_id);
+  if (it == ctx->cache.end()) return LC_ERR_NOT_FOUND;
+  release_entry(ctx, entry_of(it->second));
+  ctx->cache.erase(it);
+  return LC_OK;
+}
+
+int lc_cache_reset(lc_ctx* ctx) {
+  if (!ctx) return LC_ERR_INVALID;
+  Guard g(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->cache) release_entry(ctx, entry_of(kv.second));
+  ctx->cache.clear();
+  return LC_OK;
+}
+
+int lc_cache_handles(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, lc_handle* out) {
+  if (!ctx || !entry_ids || !out) return LC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  for (uint64_t i = 0; i < n; ++i) {
+    auto it = ctx->cache.find(entry_ids[i]);
+    if (it == ctx->cache.end()) {
+      set_error("entry %llu not cached", (unsigned long long)entry_ids[i]);
+      return LC_ERR_NOT_FOUND;
+    }
+    out[i] = it->second;
+  }
+  return LC_OK;
+}
+
+int lc_cache_get(lc_ctx* ctx, uint64_t entry_id, const uint8_t* sel_bits, uint64_t sel_len,
+                 struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  lc_handle h;
+  LC_TRY(lc_cache_handles(ctx, &entry_id, 1, &h));
+  return lc_to_arrow(ctx, h, sel_bits, sel_len, out_schema, out_array);
+}
+
+int lc_cache_eval_predicate(lc_ctx* ctx, uint64_t entry_id, const lc_predicate* pred, const uint8_t* sel_bits,
+                            uint64_t sel_len, uint8_t* out_values, uint8_t* out_validity, uint64_t* out_len,
+                            uint64_t* out_null_count) {
+  lc_handle h;
+  LC_TRY(lc_cache_handles(ctx, &entry_id, 1, &h));
+  return lc_eval_predicate(ctx, h, pred, sel_bits, sel_len, out_values, out_validity, out_len, out_null_count);
+}
+
+/* --------------------------------------------- device-resident scan pipeline ---- */
+
+int lc_scan_begin(lc_ctx* ctx, uint64_t n_batches, const uint64_t* rows_per_batch, lc_scan** out) {
+  if (!ctx || !rows_per_batch || !out || n_batches == 0) {
+    set_error("lc_scan_begin: bad argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  lc_scan* sc = new lc_scan();
+  sc->ctx = ctx;
+  sc->n = n_batches;
+  sc->rows.resize(n_batches);
+  sc->word_off.resize(n_batches);
+  uint64_t w = 0;
+  for (uint64_t i = 0; i < n_batches; ++i) {
+    if (rows_per_batch[i] > 0x7fffffffull) {
+      delete sc;
+      set_error("batch too large");
+      return LC_ERR_INVALID;
+    }
+    sc->rows[i] = static_cast<uint32_t>(rows_per_batch[i]);
+    sc->word_off[i] = w;
+    w += round_up((rows_per_batch[i] + 31) / 32, 4);
+  }
+  sc->total_words = w;
+  if (cudaMalloc(reinterpret_cast<void**>(&sc->d_sel), (w + 4) * 4) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&sc->d_counts), n_batches * 8 + 16) != cudaSuccess) {
+    cudaGetLastError();
+    if (sc->d_sel) cudaFree(sc->d_sel);
+    delete sc;
+    set_error("lc_scan_begin: cudaMalloc failed");
+    return LC_ERR_OOM;
+  }
+  *out = sc;
+  return LC_OK;
+}
+
+int lc_scan_set_selection(lc_scan* scan, uint64_t batch, const uint8_t* sel_bits, uint64_t sel_len) {
+  if (!scan || batch >= scan->n || !sel_bits || sel_len != scan->rows[batch]) {
+    set_error("lc_scan_set_selection: bad argument");
+    return LC_ERR_INVALID;
+  }
+  lc_ctx* ctx = scan->ctx;
+  Guard g(ctx);
+  cudaStream_t s = ctx->stream;
+  if (scan->all_rows) {
+    LC_CUDA_OK(cudaMemsetAsync(scan->d_sel, 0xFF, scan->total_words * 4, s));
+    scan->all_rows = false;
+  }
+  const uint64_t words = round_up((sel_len + 31) / 32, 4);
+  LC_TRY(ctx->scratch.reserve(0, words * 4 + 256));
+  uint8_t* hb = ctx->scratch.host(words * 4);
+  if (!hb) return LC_ERR_OOM;
+  copy_bits(sel_bits, 0, static_cast<int64_t>(sel_len), hb, words * 4);
+  LC_CUDA_OK(cudaMemcpyAsync(scan->d_sel + scan->word_off[batch], hb, words * 4, cudaMemcpyHostToDevice, s));
+  LC_CUDA_OK(cudaStreamSynchronize(s));
+  ctx->h2d_bytes += words * 4;
+  scan->counts_on_device = false;
+  scan->counts_cached = false;
+  return LC_OK;
+}
+
+int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* pred) {
+  if (!scan || !handles || !pred) {
+    set_error("lc_scan_filter: NULL argument");
+    return LC_ERR_INVALID;
+  }
+  std::vector<Entry*> es(scan->n);
+  for (uint64_t i = 0; i < scan->n; ++i) {
+    es[i] = entry_of(handles[i]);
+    if (!es[i] || es[i]->n != scan->rows[i]) {
+      set_error("lc_scan_filter: handle %llu invalid or row count differs from the scan's", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+  }
+  lc_ctx* ctx = scan->ctx;
+  Guard g(ctx);
+  LC_TRY(refine_batch(ctx, es.data(), scan->n, pred, scan->d_sel, scan->word_off.data(), scan->all_rows, scan->d_counts));
+  scan->all_rows = false;
+  scan->counts_on_device = true;
+  scan->counts_cached = false;
+  return LC_OK;
+}
+
+static int scan_fetch_counts(lc_scan* scan) {
+  if (scan->counts_cached) return LC_OK;
+  lc_ctx* ctx = scan->ctx;
+  scan->counts.assign(scan->n, 0);
+  if (scan->all_rows) {
+    for (uint64_t i = 0; i < scan->n; ++i) scan->counts[i] = scan->rows[i];
+  } else if (scan->counts_on_device) {
+    std::vector<uint32_t> tmp(scan->n * 2);
+    LC_CUDA_OK(cudaMemcpyAsync(tmp.data(), scan->d_counts, scan->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += scan->n * 8;
+    for (uint64_t i = 0; i < scan->n; ++i) scan->counts[i] = tmp[2 * i];
+  } else {
+    // selections were seeded from the host and not filtered yet: count them from a copy
+    std::vector<uint32_t> words(scan->total_words);
+    LC_CUDA_OK(cudaMemcpyAsync(words.data(), scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += scan->total_words * 4;
+    for (uint64_t i = 0; i < scan->n; ++i)
+      scan->counts[i] = static_cast<uint32_t>(
+          popcount_bits(reinterpret_cast<const uint8_t*>(words.data() + scan->word_off[i]), scan->rows[i]));
+  }
+  scan->counts_cached = true;
+  return LC_OK;
+}
+
+int lc_scan_counts(lc_scan* scan, uint64_t* out_counts, uint64_t* out_total) {
+  if (!scan) return LC_ERR_INVALID;
+  Guard g(scan->ctx);
+  LC_TRY(scan_fetch_counts(scan));
+  uint64_t tot = 0;
+  for (uint64_t i = 0; i < scan->n; ++i) {
+    if (out_counts) out_counts[i] = scan->counts[i];
+    tot += scan->counts[i];
+  }
+  if (out_total) *out_total = tot;
+  return LC_OK;
+}
+
+int lc_scan_selection(lc_scan* scan, uint64_t batch, uint8_t* out_bits) {
+  if (!scan || batch >= scan->n || !out_bits) return LC_ERR_INVALID;
+  lc_ctx* ctx = scan->ctx;
+  Guard g(ctx);
+  const uint32_t rows = scan->rows[batch];
+  const uint64_t nbytes = (rows + 7) / 8;
+  if (scan->all_rows) {
+    std::memset(out_bits, 0xFF, nbytes);
+  } else {
+    const uint64_t words = (rows + 31) / 32;
+    std::vector<uint32_t> tmp(words + 1);
+    LC_CUDA_OK(cudaMemcpyAsync(tmp.data(), scan->d_sel + scan->word_off[batch], words * 4, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += words * 4;
+    std::memcpy(out_bits, tmp.data(), nbytes);
+  }
+  if (rows & 7) out_bits[nbytes - 1] &= static_cast<uint8_t>((1u << (rows & 7)) - 1u);
+  return LC_OK;
+}
+
+static int scan_entries(lc_scan* scan, const lc_handle* handles, std::vector<Entry*>* es) {
+  es->resize(scan->n);
+  for (uint64_t i = 0; i < scan->n; ++i) {
+    (*es)[i] = entry_of(handles[i]);
+    if (!(*es)[i] || (*es)[i]->n != scan->rows[i]) {
+      set_error("lc_scan_read: handle %llu invalid or row count differs from the scan's", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+  }
+  return LC_OK;
+}
+
+int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* out_schema,
+                 struct ArrowArray* out_array) {
+  if (!scan || !handles || !out_schema || !out_array) return LC_ERR_INVALID;
+  std::vector<Entry*> es;
+  LC_TRY(scan_entries(scan, handles, &es));
+  lc_ctx* ctx = scan->ctx;
+  Guard g(ctx);
+  LC_TRY(scan_fetch_counts(scan));
+  ctx->scratch.reset();
+  DevSel ds{scan->d_sel, scan->word_off.data(), scan->counts.data(), scan->all_rows};
+  return to_arrow_batch(ctx, es.data(), scan->n, nullptr, &ds, out_schema, out_array);
+}
+
+int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap, void* d_offsets,
+                        void* d_validity, uint64_t* out_rows, uint64_t* out_value_bytes, uint64_t* out_null_count) {
+  if (!scan || !handles) return LC_ERR_INVALID;
+  std::vector<Entry*> es;
+  LC_TRY(scan_entries(scan, handles, &es));
+  lc_ctx* ctx = scan->ctx;
+  Guard g(ctx);
+  LC_TRY(scan_fetch_counts(scan));
+  ctx->scratch.reset();
+  DevSel ds{scan->d_sel, scan->word_off.data(), scan->counts.data(), scan->all_rows};
+  DeviceOut dout{d_values, values_cap, d_offsets, d_validity, out_rows, out_value_bytes, out_null_count};
+  return to_arrow_batch(ctx, es.data(), scan->n, nullptr, &ds, nullptr, nullptr, &dout);
+}
+
+void lc_scan_end(lc_scan* scan) {
+  if (!scan) return;
+  {
+    Guard g(scan->ctx);
+    cudaStreamSynchronize(scan->ctx->stream);
+    if (scan->d_sel) cudaFree(scan->d_sel);
+    if (scan->d_counts) cudaFree(scan->d_counts);
+  }
+  delete scan;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// lc_ctx.cc — context lifecycle, HBM arena, scratch buffers, error state.
+#include "host_common.h"
+
+namespace lc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---- arena -------------------------------------------------------------------------------------
+DeviceArena::~DeviceArena() {
+  for (auto& s : slabs_)
+    if (s.base) cudaFree(s.base);
+}
+
+uint8_t* DeviceArena::alloc(uint64_t bytes, uint32_t* slab_out) {
+  bytes = round_up(bytes, 128);
+  // first fit among existing slabs (recycle empty ones)
+  for (uint32_t i = 0; i < slabs_.size(); ++i) {
+    Slab& s = slabs_[i];
+    if (!s.base) continue;
+    if (s.live == 0) s.bump = 0;
+    if (s.bump + bytes <= s.size) {
+      uint8_t* p = s.base + s.bump;
+      s.bump += bytes;
+      s.live += bytes;
+      used_ += bytes;
+      *slab_out = i;
+      return p;
+    }
+  }
+  Slab s;
+  s.size = bytes > kSlabBytes ? bytes : kSlabBytes;
+  if (cudaMalloc(reinterpret_cast<void**>(&s.base), s.size) != cudaSuccess) {
+    cudaGetLastError();
+    // retry with an exact-size slab before giving up
+    s.size = bytes;
+    if (cudaMalloc(reinterpret_cast<void**>(&s.base), s.size) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  reserved_ += s.size;
+  s.bump = bytes;
+  s.live = bytes;
+  used_ += bytes;
+  // reuse a vacated slot if any
+  for (uint32_t i = 0; i < slabs_.size(); ++i) {
+    if (!slabs_[i].base) {
+      slabs_[i] = s;
+      *slab_out = i;
+      return s.base;
+    }
+  }
+  slabs_.push_back(s);
+  *slab_out = static_cast<uint32_t>(slabs_.size() - 1);
+  return s.base;
+}
+
+void DeviceArena::free(uint32_t slab, uint64_t bytes) {
+  bytes = round_up(bytes, 128);
+  if (slab >= slabs_.size()) return;
+  Slab& s = slabs_[slab];
+  s.live -= bytes;
+  used_ -= bytes;
+  if (s.live == 0 && s.size != kSlabBytes) {  // odd-sized slab: give it back
+    cudaFree(s.base);
+    reserved_ -= s.size;
+    s = Slab();
+  }
+}
+
+void DeviceArena::reset() {
+  for (auto& s : slabs_) {
+    s.bump = 0;
+    s.live = 0;
+  }
+  used_ = 0;
+}
+
+// ---- scratch -----------------------------------------------------------------------------------
+Scratch::~Scratch() {
+  if (d) cudaFree(d);
+  if (h) cudaFreeHost(h);
+}
+
+int Scratch::reserve(uint64_t d_bytes, uint64_t h_bytes) {
+  d_bytes += 4096;
+  h_bytes += 4096;
+  if (d_bytes > d_cap) {
+    uint64_t cap = d_cap ? d_cap : (8ull << 20);
+    while (cap < d_bytes) cap *= 2;
+    if (d) cudaFree(d);
+    d = nullptr;
+    d_cap = 0;
+    if (cudaMalloc(reinterpret_cast<void**>(&d), cap) != cudaSuccess) {
+      cudaGetLastError();
+      if (cudaMalloc(reinterpret_cast<void**>(&d), d_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("scratch: cudaMalloc of %llu bytes failed", (unsigned long long)d_bytes);
+        return LC_ERR_OOM;
+      }
+      cap = d_bytes;
+    }
+    d_cap = cap;
+  }
+  if (h_bytes > h_cap) {
+    uint64_t cap = h_cap ? h_cap : (4ull << 20);
+    while (cap < h_bytes) cap *= 2;
+    if (h) cudaFreeHost(h);
+    h = nullptr;
+    h_cap = 0;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), cap, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("scratch: cudaHostAlloc of %llu bytes failed", (unsigned long long)cap);
+      return LC_ERR_OOM;
+    }
+    h_cap = cap;
+  }
+  d_off = 0;
+  h_off = 0;
+  return LC_OK;
+}
+
+void release_entry(lc_ctx* ctx, Entry* e) {
+  if (!e) return;
+  if (--e->refcount > 0) return;
+  if (e->d_blob) ctx->arena.free(e->slab, e->blob_bytes);
+  e->magic = 0;
+  ctx->n_entries--;
+  delete e;
+}
+
+}  // namespace lc
+
+using namespace lc;
+
+extern "C" {
+
+const char* lc_last_error(void) { return get_error(); }
+const char* lc_version(void) { return "liquid_cache_b200 0.1 (sm_100a)"; }
+
+int lc_ctx_create(int device_id, uint64_t hbm_budget_bytes, lc_ctx** out) {
+  if (!out) {
+    set_error("lc_ctx_create: out is NULL");
+    return LC_ERR_INVALID;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device visible (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return LC_ERR_NO_DEVICE;
+  }
+  if (device_id < 0 || device_id >= n_dev) {
+    set_error("device %d out of range (%d devices)", device_id, n_dev);
+    return LC_ERR_INVALID;
+  }
+  LC_CUDA_OK(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  LC_CUDA_OK(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library ships sm_100a code only", device_id, prop.major, prop.minor);
+    return LC_ERR_NO_DEVICE;
+  }
+  lc_ctx* ctx = new lc_ctx();
+  ctx->device = device_id;
+  ctx->budget = hbm_budget_bytes;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return LC_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return LC_OK;
+}
+
+void lc_ctx_destroy(lc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    for (auto& kv : ctx->cache) {
+      Entry* e = entry_of(kv.second);
+      if (e) release_entry(ctx, e);
+    }
+    ctx->cache.clear();
+    for (auto& kv : ctx->codecs) {
+      if (kv.second->d_dec) cudaFree(kv.second->d_dec);
+      if (kv.second->d_enc) cudaFree(kv.second->d_enc);
+      kv.second->d_dec = nullptr;
+      kv.second->d_enc = nullptr;
+    }
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int lc_ctx_set_stream(lc_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return LC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return LC_OK;
+}
+
+int lc_ctx_synchronize(lc_ctx* ctx) {
+  if (!ctx) return LC_ERR_INVALID;
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return LC_OK;
+}
+
+int lc_ctx_stats(lc_ctx* ctx, lc_stats* out) {
+  if (!ctx || !out) return LC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  out->entries = ctx->n_entries;
+  out->hbm_bytes_used = ctx->arena.bytes_used();
+  out->hbm_bytes_budget = ctx->budget;
+  out->kernel_launches = ctx->kernel_launches;
+  out->h2d_bytes = ctx->h2d_bytes;
+  out->d2h_bytes = ctx->d2h_bytes;
+  return LC_OK;
+}
+
+}  // extern "C"
