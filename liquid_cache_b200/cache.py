@@ -1,0 +1,478 @@
+"""Host-side mirror of the reference's cache front door, over the C ABI.
+
+Reference: `LiquidCacheBuilder` (/root/reference/src/core/src/cache/builders.rs:32-158),
+`LiquidCache::{insert,get,eval_predicate}` (src/core/src/cache/core.rs:122-142) and the
+`Insert` / `Get` / `EvaluatePredicate` builders (builders.rs:162-356). Same names, same argument
+meaning, same return conventions (`None` = entry absent; `CacheFull` raised where the reference
+returns `Err(CacheFull)`). The reference's builders are `IntoFuture`; here `.read()` / `.run()` play
+the part of `.await`.
+
+Everything array-sized happens in liblc_gpu.so on the GPU. This module only moves Arrow arrays across
+the Arrow C Data Interface and keeps the EntryID bookkeeping.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+import pyarrow as pa
+from pyarrow.cffi import ffi as _ffi
+
+from . import _native as N
+from .expr import CacheExpression, LiquidExpr
+
+
+class EntryID(int):
+    """`EntryID(usize)` (src/core/src/cache/utils.rs:73-88)."""
+
+    def __new__(cls, v: int):
+        return super().__new__(cls, int(v))
+
+
+def parquet_array_id(file_id: int, rg_id: int, col_id: int, batch_id: int) -> EntryID:
+    """`ParquetArrayID` packing: file<<48 | rg<<32 | col<<16 | batch (src/datafusion/src/cache/id.rs:15-22)."""
+    return EntryID((file_id << 48) | (rg_id << 32) | (col_id << 16) | batch_id)
+
+
+# ---- Arrow C Data Interface plumbing ----
+def _export(arr: pa.Array):
+    c_arr = _ffi.new("struct ArrowArray*")
+    c_sch = _ffi.new("struct ArrowSchema*")
+    arr._export_to_c(int(_ffi.cast("uintptr_t", c_arr)), int(_ffi.cast("uintptr_t", c_sch)))
+    return c_arr, c_sch
+
+
+def _ptr(cdata) -> int:
+    return int(_ffi.cast("uintptr_t", cdata))
+
+
+def _new_out():
+    return _ffi.new("struct ArrowArray*"), _ffi.new("struct ArrowSchema*")
+
+
+def _import(c_arr, c_sch) -> pa.Array:
+    return pa.Array._import_from_c(_ptr(c_arr), _ptr(c_sch))
+
+
+def selection_bits(sel) -> tuple[Optional[np.ndarray], int]:
+    """BooleanBuffer -> (LSB-first bytes at bit offset 0, length). Accepts a pyarrow BooleanArray
+    (must have no nulls: a BooleanBuffer cannot), a numpy bool array, or a list of bools."""
+    if sel is None:
+        return None, 0
+    if isinstance(sel, pa.ChunkedArray):
+        sel = sel.combine_chunks()
+    if isinstance(sel, pa.Array):
+        if sel.null_count:
+            raise ValueError("a selection is a BooleanBuffer: it cannot have nulls")
+        mask = np.asarray(sel.to_numpy(zero_copy_only=False), dtype=bool)
+    else:
+        mask = np.asarray(sel, dtype=bool)
+    n = int(mask.shape[0])
+    bits = np.packbits(mask, bitorder="little")
+    pad = (-len(bits)) % 8
+    if pad or len(bits) == 0:
+        bits = np.concatenate([bits, np.zeros(pad or 8, dtype=np.uint8)])
+    return np.ascontiguousarray(bits), n
+
+
+def _mask_to_boolean_array(values: np.ndarray, validity: Optional[np.ndarray], n: int, null_count: int) -> pa.Array:
+    vals = np.unpackbits(values, bitorder="little")[:n].astype(bool)
+    if null_count == 0 or validity is None:
+        return pa.array(vals, type=pa.bool_())
+    valid = np.unpackbits(validity, bitorder="little")[:n].astype(bool)
+    return pa.array(vals, type=pa.bool_(), mask=~valid)
+
+
+class GpuLiquidArray:
+    """`Arc<dyn LiquidArray>` whose payload lives in HBM (trait LiquidArray,
+    src/core/src/liquid_array/mod.rs:82-146)."""
+
+    def __init__(self, cache: "LiquidCache", handle: int, owned: bool = True):
+        self._cache = cache
+        self._h = handle
+        self._owned = owned
+
+    def __del__(self):
+        try:
+            if self._owned and self._h and self._cache._ctx:
+                N.lib().lc_release(self._cache._ctx, self._h)
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> int:
+        return self._h
+
+    def len(self) -> int:
+        return int(N.lib().lc_len(self._cache._ctx, self._h))
+
+    __len__ = len
+
+    def get_array_memory_size(self) -> int:
+        return int(N.lib().lc_memory_size(self._cache._ctx, self._h))
+
+    def data_type(self) -> int:
+        return int(N.lib().lc_data_type(self._cache._ctx, self._h))
+
+    def original_arrow_data_type(self) -> pa.DataType:
+        return self.to_arrow_array().type if self.len() == 0 else self._type_from_format()
+
+    def _type_from_format(self) -> pa.DataType:
+        buf = C.create_string_buffer(64)
+        N.check(N.lib().lc_arrow_format(self._cache._ctx, self._h, buf, 64))
+        return _FORMAT_TO_TYPE[buf.value.decode()]
+
+    def to_arrow_array(self) -> pa.Array:
+        return self.filter(None)
+
+    def filter(self, selection) -> pa.Array:
+        bits, n = selection_bits(selection)
+        out_a, out_s = _new_out()
+        N.check(
+            N.lib().lc_to_arrow(
+                self._cache._ctx, self._h, bits.ctypes.data if bits is not None else None, n, _ptr(out_s), _ptr(out_a)
+            )
+        )
+        return _import(out_a, out_s)
+
+    def try_eval_predicate(self, expr: LiquidExpr, selection) -> pa.Array:
+        pred = expr.to_native(self._type_from_format())
+        bits, n = selection_bits(selection)
+        rows = self.len()
+        nb = int(N.lib().lc_mask_bytes(rows))
+        vals = np.zeros(nb, dtype=np.uint8)
+        valid = np.zeros(nb, dtype=np.uint8)
+        out_len, out_nulls = C.c_uint64(0), C.c_uint64(0)
+        N.check(
+            N.lib().lc_eval_predicate(
+                self._cache._ctx,
+                self._h,
+                C.byref(pred),
+                bits.ctypes.data if bits is not None else None,
+                n,
+                vals.ctypes.data,
+                valid.ctypes.data,
+                C.byref(out_len),
+                C.byref(out_nulls),
+            )
+        )
+        return _mask_to_boolean_array(vals, valid, int(out_len.value), int(out_nulls.value))
+
+
+_FORMAT_TO_TYPE = {
+    "c": pa.int8(), "s": pa.int16(), "i": pa.int32(), "l": pa.int64(),
+    "C": pa.uint8(), "S": pa.uint16(), "I": pa.uint32(), "L": pa.uint64(),
+    "tdD": pa.date32(), "tdm": pa.date64(),
+    "tss:": pa.timestamp("s"), "tsm:": pa.timestamp("ms"), "tsu:": pa.timestamp("us"), "tsn:": pa.timestamp("ns"),
+    "u": pa.string(), "z": pa.binary(), "vu": pa.string_view(), "vz": pa.binary_view(),
+    "S:u": pa.dictionary(pa.uint16(), pa.string()), "S:z": pa.dictionary(pa.uint16(), pa.binary()),
+}
+
+
+class LiquidCacheBuilder:
+    """`LiquidCacheBuilder` (builders.rs:32-158). Options that configure the reference's CPU-side
+    policies (cache/hydration/squeeze policies, disk store) are accepted and recorded but have no
+    effect here: an HBM-resident cache never squeezes to disk."""
+
+    def __init__(self):
+        self._batch_size = 8192
+        self._max_memory_bytes = 0
+        self._device = 0
+        self._ignored = {}
+
+    @staticmethod
+    def new() -> "LiquidCacheBuilder":
+        return LiquidCacheBuilder()
+
+    def with_batch_size(self, n: int):
+        self._batch_size = int(n)
+        return self
+
+    def with_max_memory_bytes(self, n: int):
+        self._max_memory_bytes = int(n)
+        return self
+
+    def with_device(self, device: int):
+        self._device = int(device)
+        return self
+
+    def _ignore(name):  # noqa: N805
+        def f(self, *a, **k):
+            self._ignored[name] = (a, k)
+            return self
+
+        return f
+
+    with_max_disk_bytes = _ignore("max_disk_bytes")
+    with_cache_policy = _ignore("cache_policy")
+    with_hydration_policy = _ignore("hydration_policy")
+    with_squeeze_policy = _ignore("squeeze_policy")
+    with_metadata = _ignore("metadata")
+    with_store = _ignore("store")
+    with_squeeze_victims_concurrently = _ignore("squeeze_victims_concurrently")
+
+    def build(self) -> "LiquidCache":
+        return LiquidCache(self._device, self._max_memory_bytes, self._batch_size)
+
+
+class Insert:
+    """`Insert` builder (builders.rs:162-214)."""
+
+    def __init__(self, cache, entry_id, array):
+        self._cache, self._id, self._array = cache, entry_id, array
+        self._hint = None
+
+    def with_skip_gc(self):
+        return self
+
+    def with_squeeze_hint(self, hint):
+        self._hint = hint
+        return self
+
+    def run(self) -> None:
+        hint = N.HINT_SUBSTRING_SEARCH if self._hint == CacheExpression.SubstringSearch else (
+            N.HINT_PREDICATE if self._hint else N.HINT_NONE)
+        c_arr, c_sch = _export(self._array)
+        N.check(N.lib().lc_cache_insert(self._cache._ctx, int(self._id), _ptr(c_sch), _ptr(c_arr), hint))
+        self._cache._types[int(self._id)] = self._array.type
+
+
+class Get:
+    """`Get` builder (builders.rs:218-276)."""
+
+    def __init__(self, cache, entry_id):
+        self._cache, self._id = cache, entry_id
+        self._sel = None
+
+    def with_selection(self, selection):
+        self._sel = selection
+        return self
+
+    def with_expression_hint(self, _hint):
+        return self
+
+    def with_optional_expression_hint(self, _hint):
+        return self
+
+    def read(self) -> Optional[pa.Array]:
+        if not self._cache.is_cached(self._id):
+            return None
+        bits, n = selection_bits(self._sel)
+        out_a, out_s = _new_out()
+        N.check(
+            N.lib().lc_cache_get(
+                self._cache._ctx, int(self._id), bits.ctypes.data if bits is not None else None, n, _ptr(out_s), _ptr(out_a)
+            )
+        )
+        return _import(out_a, out_s)
+
+
+class EvaluatePredicate:
+    """`EvaluatePredicate` builder (builders.rs:314-356)."""
+
+    def __init__(self, cache, entry_id, expr: LiquidExpr):
+        self._cache, self._id, self._expr = cache, entry_id, expr
+        self._sel = None
+
+    def with_selection(self, selection):
+        self._sel = selection
+        return self
+
+    def read(self) -> Optional[pa.Array]:
+        if not self._cache.is_cached(self._id):
+            return None
+        arr = GpuLiquidArray(self._cache, self._cache._handle(self._id), owned=False)
+        return arr.try_eval_predicate(self._expr, self._sel)
+
+
+class LiquidCache:
+    """`LiquidCache` (core.rs:52-277) with its entries resident in the HBM of ONE device."""
+
+    def __init__(self, device: int = 0, max_memory_bytes: int = 0, batch_size: int = 8192):
+        self._ctx = None
+        ctx = C.c_void_p()
+        N.check(N.lib().lc_ctx_create(device, max_memory_bytes, C.byref(ctx)))
+        self._ctx = ctx
+        self._batch_size = batch_size
+        self._types: dict[int, pa.DataType] = {}
+
+    def close(self):
+        if self._ctx:
+            N.lib().lc_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def batch_size(self) -> int:
+        return self._batch_size
+
+    # -- reference front door --
+    def insert(self, entry_id, array: pa.Array) -> Insert:
+        return Insert(self, entry_id, array)
+
+    def get(self, entry_id) -> Get:
+        return Get(self, entry_id)
+
+    def eval_predicate(self, entry_id, expr: LiquidExpr) -> EvaluatePredicate:
+        return EvaluatePredicate(self, entry_id, expr)
+
+    def is_cached(self, entry_id) -> bool:
+        return bool(N.lib().lc_cache_is_cached(self._ctx, int(entry_id)))
+
+    def try_read_liquid(self, entry_id) -> Optional[GpuLiquidArray]:
+        if not self.is_cached(entry_id):
+            return None
+        return GpuLiquidArray(self, self._handle(entry_id), owned=False)
+
+    def reset(self) -> None:
+        N.check(N.lib().lc_cache_reset(self._ctx))
+        self._types.clear()
+
+    def stats(self) -> N.Stats:
+        s = N.Stats()
+        N.check(N.lib().lc_ctx_stats(self._ctx, C.byref(s)))
+        return s
+
+    def set_stream(self, cuda_stream: int) -> None:
+        N.check(N.lib().lc_ctx_set_stream(self._ctx, cuda_stream))
+
+    def synchronize(self) -> None:
+        N.check(N.lib().lc_ctx_synchronize(self._ctx))
+
+    # -- LiquidArray-level helpers (transcode without the index) --
+    def transcode(self, array: pa.Array, hint=None, compressor_scope: int = 0) -> GpuLiquidArray:
+        """`transcode_liquid_inner_with_hint` (src/core/src/cache/transcode.rs:46-290)."""
+        h = C.c_uint64(0)
+        c_arr, c_sch = _export(array)
+        nh = N.HINT_SUBSTRING_SEARCH if hint == CacheExpression.SubstringSearch else N.HINT_NONE
+        N.check(N.lib().lc_encode(self._ctx, _ptr(c_sch), _ptr(c_arr), nh, compressor_scope, C.byref(h)))
+        return GpuLiquidArray(self, int(h.value))
+
+    def _handle(self, entry_id) -> int:
+        ids = (C.c_uint64 * 1)(int(entry_id))
+        out = (C.c_uint64 * 1)()
+        N.check(N.lib().lc_cache_handles(self._ctx, ids, 1, out))
+        return int(out[0])
+
+    def handles(self, entry_ids: Sequence[int]) -> np.ndarray:
+        ids = np.ascontiguousarray(np.asarray(entry_ids, dtype=np.uint64))
+        out = np.zeros(len(ids), dtype=np.uint64)
+        N.check(N.lib().lc_cache_handles(self._ctx, ids.ctypes.data, len(ids), out.ctypes.data))
+        return out
+
+    # -- batched forms (one launch sequence for many entries) --
+    def eval_predicate_many(self, handles: np.ndarray, rows: np.ndarray, expr: LiquidExpr, column_type: pa.DataType,
+                            selections: Optional[Sequence[Optional[np.ndarray]]] = None):
+        """Returns (values bytes, validity bytes, byte_offsets, out_len, out_null_count) as numpy arrays."""
+        pred = expr.to_native(column_type)
+        return self._eval_many_native(handles, rows, pred, selections)
+
+    def _eval_many_native(self, handles, rows, pred, selections=None, out=None):
+        n = len(handles)
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        if out is None:
+            sizes = (((np.asarray(rows, dtype=np.uint64) + 7) // 8 + 15) // 16) * 16
+            offs = np.zeros(n, dtype=np.uint64)
+            np.cumsum(sizes[:-1], out=offs[1:])
+            total = int(sizes.sum())
+            out = (np.zeros(total, dtype=np.uint8), np.zeros(total, dtype=np.uint8), offs,
+                   np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64))
+        vals, valid, offs, out_len, out_nulls = out
+        sel_ptrs = None
+        keep = None
+        if selections is not None:
+            keep = [s for s in selections]
+            arr = (C.c_void_p * n)(*[(s.ctypes.data if s is not None else None) for s in keep])
+            sel_ptrs = arr
+        N.check(
+            N.lib().lc_eval_predicate_many(
+                self._ctx, handles.ctypes.data, n, C.byref(pred), sel_ptrs, vals.ctypes.data, valid.ctypes.data,
+                offs.ctypes.data, out_len.ctypes.data, out_nulls.ctypes.data,
+            )
+        )
+        return out
+
+    def to_arrow_many(self, handles: np.ndarray, selections: Optional[Sequence[Optional[np.ndarray]]] = None) -> pa.Array:
+        n = len(handles)
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        sel_ptrs = None
+        if selections is not None:
+            sel_ptrs = (C.c_void_p * n)(*[(s.ctypes.data if s is not None else None) for s in selections])
+        out_a, out_s = _new_out()
+        N.check(N.lib().lc_to_arrow_many(self._ctx, handles.ctypes.data, n, sel_ptrs, _ptr(out_s), _ptr(out_a)))
+        return _import(out_a, out_s)
+
+    def and_then(self, left, right) -> pa.Array:
+        """`boolean_buffer_and_then` (src/datafusion/src/utils.rs:62-83)."""
+        lb, ln = selection_bits(left)
+        rb, rn = selection_bits(right)
+        out = np.zeros(len(lb) + 8, dtype=np.uint8)
+        N.check(N.lib().lc_and_then(self._ctx, lb.ctypes.data, ln, rb.ctypes.data, rn, out.ctypes.data))
+        return pa.array(np.unpackbits(out, bitorder="little")[:ln].astype(bool))
+
+    def scan(self, rows_per_batch: Sequence[int]) -> "Scan":
+        return Scan(self, rows_per_batch)
+
+
+class Scan:
+    """The per-batch loop of `LiquidCacheReader::build_predicate_filter` + `read_from_cache`
+    (/root/reference/src/datafusion/src/reader/runtime/liquid_cache_reader.rs:297-391) for many batches at
+    once, with the running selection resident in HBM between conjuncts."""
+
+    def __init__(self, cache: LiquidCache, rows_per_batch: Sequence[int]):
+        self._cache = cache
+        self._rows = np.ascontiguousarray(np.asarray(rows_per_batch, dtype=np.uint64))
+        self._scan = C.c_void_p()
+        N.check(N.lib().lc_scan_begin(cache._ctx, len(self._rows), self._rows.ctypes.data, C.byref(self._scan)))
+
+    def close(self):
+        if self._scan:
+            N.lib().lc_scan_end(self._scan)
+            self._scan = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_selection(self, batch: int, selection) -> None:
+        bits, n = selection_bits(selection)
+        N.check(N.lib().lc_scan_set_selection(self._scan, batch, bits.ctypes.data, n))
+
+    def filter(self, handles: np.ndarray, expr: LiquidExpr, column_type: pa.DataType) -> None:
+        pred = expr.to_native(column_type)
+        self.filter_native(handles, pred)
+
+    def filter_native(self, handles: np.ndarray, pred: N.Predicate) -> None:
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        N.check(N.lib().lc_scan_filter(self._scan, handles.ctypes.data, C.byref(pred)))
+
+    def counts(self) -> tuple[np.ndarray, int]:
+        out = np.zeros(len(self._rows), dtype=np.uint64)
+        tot = C.c_uint64(0)
+        N.check(N.lib().lc_scan_counts(self._scan, out.ctypes.data, C.byref(tot)))
+        return out, int(tot.value)
+
+    def selection(self, batch: int) -> pa.Array:
+        rows = int(self._rows[batch])
+        out = np.zeros((rows + 7) // 8 + 8, dtype=np.uint8)
+        N.check(N.lib().lc_scan_selection(self._scan, batch, out.ctypes.data))
+        return pa.array(np.unpackbits(out, bitorder="little")[:rows].astype(bool))
+
+    def read(self, handles: np.ndarray) -> pa.Array:
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        out_a, out_s = _new_out()
+        N.check(N.lib().lc_scan_read(self._scan, handles.ctypes.data, _ptr(out_s), _ptr(out_a)))
+        return _import(out_a, out_s)
