@@ -139,6 +139,12 @@ void lc_ctx_destroy(lc_ctx* ctx);
 int lc_ctx_set_stream(lc_ctx* ctx, void* cuda_stream);
 int lc_ctx_synchronize(lc_ctx* ctx);
 int lc_ctx_stats(lc_ctx* ctx, lc_stats* out);
+/* Measurement aid (off by default): while enabled, the byte-view predicate kernel adds, per launch,
+ *   out[0] += dictionary entries looked at, out[1] += candidates whose FSST codes were walked,
+ *   out[2] += compressed bytes of those candidates
+ * so a benchmark can state the ALGORITHMIC bytes of a scan exactly. Costs a few atomics; never enable it in
+ * a timed region. */
+int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[4]);
 const char* lc_last_error(void);
 const char* lc_version(void);
 
@@ -235,6 +241,8 @@ int lc_cache_eval_predicate(lc_ctx* ctx, uint64_t entry_id, const lc_predicate* 
  */
 typedef struct lc_scan lc_scan;
 int lc_scan_begin(lc_ctx* ctx, uint64_t n_batches, const uint64_t* rows_per_batch, lc_scan** out);
+/* running selection := all rows again (reuse one scan object for the next query over the same batches) */
+int lc_scan_reset(lc_scan* scan);
 /* Optional: seed the running selection of batch i from host bits (RowSelection of the reader). */
 int lc_scan_set_selection(lc_scan* scan, uint64_t batch, const uint8_t* sel_bits, uint64_t sel_len);
 int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* pred);

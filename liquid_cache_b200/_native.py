@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblc_gpu.so")
+LIB_PATH = os.environ.get("LC_GPU_LIB") or os.path.join(_HERE, "lib", "liblc_gpu.so")  # LC_GPU_LIB: debug builds only
 
 LC_OK = 0
 LC_ERR_INVALID = -1
@@ -124,6 +124,8 @@ def lib() -> C.CDLL:
     l.lc_cache_get.argtypes = [vp, u64, vp, u64, vp, vp]
     l.lc_cache_eval_predicate.argtypes = [vp, u64, C.POINTER(Predicate), vp, u64, vp, vp, u64p, u64p]
     l.lc_scan_begin.argtypes = [vp, u64, vp, C.POINTER(vp)]
+    l.lc_scan_reset.argtypes = [vp]
+    l.lc_ctx_profile_counters.argtypes = [vp, C.c_int, vp]
     l.lc_scan_set_selection.argtypes = [vp, u64, vp, u64]
     l.lc_scan_filter.argtypes = [vp, vp, C.POINTER(Predicate)]
     l.lc_scan_counts.argtypes = [vp, vp, u64p]

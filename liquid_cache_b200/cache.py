@@ -338,6 +338,12 @@ class LiquidCache:
         N.check(N.lib().lc_ctx_stats(self._ctx, C.byref(s)))
         return s
 
+    def profile_counters(self, enable: bool) -> np.ndarray:
+        """Measurement aid: returns the counters accumulated so far and switches accumulation on/off."""
+        out = np.zeros(4, dtype=np.uint64)
+        N.check(N.lib().lc_ctx_profile_counters(self._ctx, 1 if enable else 0, out.ctypes.data))
+        return out
+
     def set_stream(self, cuda_stream: int) -> None:
         N.check(N.lib().lc_ctx_set_stream(self._ctx, cuda_stream))
 
@@ -446,6 +452,9 @@ class Scan:
             self.close()
         except Exception:
             pass
+
+    def reset(self) -> None:
+        N.check(N.lib().lc_scan_reset(self._scan))
 
     def set_selection(self, batch: int, selection) -> None:
         bits, n = selection_bits(selection)

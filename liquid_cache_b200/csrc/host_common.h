@@ -138,6 +138,10 @@ struct lc_ctx {
   std::unordered_map<uint64_t, std::shared_ptr<lc::FsstCodec>> codecs;         // compressor scope -> table
   uint64_t n_entries = 0;
   uint64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  uint64_t epoch = 0;            // bumped whenever an entry is released (invalidates cached entry lists)
+  uint8_t* d_needle = nullptr;   // small device buffer for predicate needles
+  unsigned long long* d_prof = nullptr;  // profile counters (lc_ctx_profile_counters)
+  bool prof_on = false;
 };
 
 namespace lc {
@@ -225,11 +229,9 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
                    const DeviceOut* dev_out = nullptr);
 
 int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred, uint32_t* d_sel_base,
-                 const uint64_t* word_off, bool all_rows, uint32_t* d_counts);
+                 const uint64_t* d_word_off, bool all_rows, uint32_t* d_counts);
+void drop_ref_cache(lc_ctx* ctx);
 
-// predicate planning
-// ints: (op, literal) -> unsigned-domain compare for this entry; returns LC_ERR_UNSUPPORTED_EXPR if not mappable
-int plan_int_predicate(const IntHeader& h, const lc_predicate* pred, int32_t* ucmp, uint64_t* thr);
 
 void release_entry(lc_ctx* ctx, Entry* e);
 

@@ -126,54 +126,4 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
   return LC_OK;
 }
 
-// (op, literal) -> compare in the unsigned packed domain u = v - reference.
-// All valid values satisfy reference <= v <= reference + (2^W - 1) in the column's own ordering, so a
-// literal outside that window folds to a constant and one inside becomes an unsigned threshold.
-int plan_int_predicate(const IntHeader& h, const lc_predicate* pred, int32_t* ucmp, uint64_t* thr) {
-  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
-    set_error("operator %d is not supported on integer columns", pred->op);
-    return LC_ERR_UNSUPPORTED_EXPR;
-  }
-  __int128 lit;
-  if (pred->lit_kind == LC_LIT_I64) lit = pred->lit_i64;
-  else if (pred->lit_kind == LC_LIT_U64) lit = static_cast<__int128>(pred->lit_u64);
-  else {
-    set_error("integer column needs an integer literal");
-    return LC_ERR_UNSUPPORTED_EXPR;
-  }
-  *thr = 0;
-  if (h.bit_width == 0) {  // all null: values never matter
-    *ucmp = UC_FALSE;
-    return LC_OK;
-  }
-  __int128 ref;
-  if (h.is_signed) {
-    const int sh = 64 - h.tbits;
-    ref = static_cast<__int128>(static_cast<int64_t>(h.reference << sh) >> sh);
-  } else {
-    ref = static_cast<__int128>(h.reference);
-  }
-  const __int128 umax = h.bit_width == 64 ? static_cast<__int128>(~0ull) : ((static_cast<__int128>(1) << h.bit_width) - 1);
-  const __int128 d = lit - ref;
-  const int op = pred->op;
-  if (d < 0) {
-    *ucmp = (op == LC_OP_NE || op == LC_OP_GT || op == LC_OP_GE) ? UC_TRUE : UC_FALSE;
-    return LC_OK;
-  }
-  if (d > umax) {
-    *ucmp = (op == LC_OP_NE || op == LC_OP_LT || op == LC_OP_LE) ? UC_TRUE : UC_FALSE;
-    return LC_OK;
-  }
-  *thr = static_cast<uint64_t>(d);
-  switch (op) {
-    case LC_OP_EQ: *ucmp = UC_EQ; break;
-    case LC_OP_NE: *ucmp = UC_NE; break;
-    case LC_OP_LT: *ucmp = UC_LT; break;
-    case LC_OP_LE: *ucmp = UC_LE; break;
-    case LC_OP_GT: *ucmp = UC_GT; break;
-    default: *ucmp = UC_GE; break;
-  }
-  return LC_OK;
-}
-
 }  // namespace lc

@@ -67,18 +67,94 @@ __device__ __forceinline__ bool ucmp_eval(int32_t kind, U u, U thr) {
   }
 }
 
+// Everything a CTA needs for its entry, resolved from ScanIo.
+struct EntryIo {
+  const uint32_t* sel;
+  void* out;
+  uint32_t* out_valid;
+  uint32_t* counts;
+};
+
+__device__ __forceinline__ EntryIo resolve_io(const ScanIo& io, uint32_t e, uint32_t elem_bytes) {
+  EntryIo r;
+  r.sel = nullptr;
+  if (io.sel_base) {
+    const uint64_t so = io.sel_off[e];
+    if (so != kNoSel) r.sel = io.sel_base + so;
+  }
+  r.out = io.out_base ? static_cast<uint8_t*>(io.out_base) + io.out_off[e] * elem_bytes : nullptr;
+  r.out_valid = io.valid_base ? io.valid_base + io.valid_off[e] : nullptr;
+  r.counts = io.counts ? io.counts + static_cast<size_t>(e) * io.counts_stride : nullptr;
+  return r;
+}
+
+// (op, literal) -> compare in the unsigned packed domain u = v - reference. All valid values satisfy
+// reference <= v <= reference + (2^W - 1) in the column's own ordering, so a literal outside that window
+// folds to a constant and one inside becomes an unsigned threshold. No 128-bit arithmetic needed:
+// once lit >= reference is known, (lit - reference) fits in 64 unsigned bits.
+__device__ __forceinline__ void plan_int_pred(const IntHeader* h, const IntPredDesc& p, int32_t* ucmp, uint64_t* thr) {
+  *thr = 0;
+  if (h->bit_width == 0) {  // all null: values never matter
+    *ucmp = UC_FALSE;
+    return;
+  }
+  const uint32_t W = h->bit_width;
+  const uint64_t umax = W == 64 ? ~0ull : ((1ull << W) - 1ull);
+  bool below, above = false;
+  uint64_t d = 0;
+  if (h->is_signed) {
+    const int sh = 64 - h->tbits;
+    const long long ref = static_cast<long long>(h->reference << sh) >> sh;
+    if (p.lit_kind == 1 /*U64*/ && p.lit_u > 0x7fffffffffffffffull) {
+      below = false;
+      above = true;
+    } else {
+      const long long lit = p.lit_kind == 1 ? static_cast<long long>(p.lit_u) : p.lit_i;
+      below = lit < ref;
+      if (!below) {
+        d = static_cast<uint64_t>(lit) - static_cast<uint64_t>(ref);
+        above = d > umax;
+      }
+    }
+  } else {
+    const uint64_t ref = h->reference;
+    if (p.lit_kind == 0 /*I64*/ && p.lit_i < 0) {
+      below = true;
+    } else {
+      const uint64_t lit = p.lit_kind == 0 ? static_cast<uint64_t>(p.lit_i) : p.lit_u;
+      below = lit < ref;
+      if (!below) {
+        d = lit - ref;
+        above = d > umax;
+      }
+    }
+  }
+  const int op = p.op;
+  if (below) {
+    *ucmp = (op == 1 || op == 4 || op == 5) ? UC_TRUE : UC_FALSE;  // NE, GT, GE
+  } else if (above) {
+    *ucmp = (op == 1 || op == 2 || op == 3) ? UC_TRUE : UC_FALSE;  // NE, LT, LE
+  } else {
+    *thr = d;
+    *ucmp = op == 0 ? UC_EQ : op == 1 ? UC_NE : op == 2 ? UC_LT : op == 3 ? UC_LE : op == 4 ? UC_GT : UC_GE;
+  }
+}
+
 template <typename U, int MODE>
-__device__ __forceinline__ void int_scan_entry(const IntScanWork& w, const uint8_t* base, ScanSmem* sm) {
+__device__ __forceinline__ void int_scan_entry(const EntryIo& w, const IntPredDesc& pred, const uint8_t* base,
+                                               ScanSmem* sm) {
   constexpr uint32_t T = FL<U>::T;
   const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
   const uint32_t W = h->bit_width;
   const U ref = static_cast<U>(h->reference);
-  const U thr = static_cast<U>(w.thr);
-  const int32_t kind = w.ucmp;
+  int32_t kind = UC_TRUE;
+  uint64_t thr64 = 0;
+  if (MODE != MODE_DECODE) plan_int_pred(h, pred, &kind, &thr64);
+  const U thr = static_cast<U>(thr64);
   const U* packed = reinterpret_cast<const U*>(base + h->packed_off);
   const uint32_t* valid = h->has_nulls ? reinterpret_cast<const uint32_t*>(base + h->validity_off) : nullptr;
   const uint32_t chunk_words = 1024u * W / T;  // in units of U
-  U* out_vals = reinterpret_cast<U*>(w.out_values);
+  U* out_vals = reinterpret_cast<U*>(w.out);
 
   auto value_of = [&](uint32_t row) -> U {
     if (W == 0) return static_cast<U>(0);
@@ -86,43 +162,44 @@ __device__ __forceinline__ void int_scan_entry(const IntScanWork& w, const uint8
   };
   auto cmp = [&](uint32_t row) -> bool { return ucmp_eval<U>(kind, value_of(row), thr); };
   auto emit = [&](uint32_t row, uint32_t dst) { out_vals[dst] = static_cast<U>(value_of(row) + ref); };
-  scan_entry_rows<MODE>(w.sel, h->n, valid, h->null_count, reinterpret_cast<uint32_t*>(w.out_values),
-                        w.out_validity, w.out_counts, sm, cmp, emit);
+  scan_entry_rows<MODE>(w.sel, h->n, valid, h->null_count, reinterpret_cast<uint32_t*>(w.out), w.out_valid,
+                        w.counts, sm, cmp, emit);
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k_int_scan(const IntScanWork* __restrict__ works, uint32_t stage_cap) {
+__global__ void __launch_bounds__(256) k_int_scan(ScanIo io, IntPredDesc pred, uint32_t stage_cap) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
   uint8_t* stage = smem_raw + kScanFixedSmem;
 
-  const IntScanWork w = works[blockIdx.x];
-  const bool staged = w.blob_bytes <= stage_cap;
+  const EntryRef ref = io.refs[blockIdx.x];
+  const bool staged = ref.blob_bytes <= stage_cap;
   scan_smem_init(sm);
   if (threadIdx.x == 0 && staged) {
     mbar_init(&sm->bar[0], 1);
     fence_mbar_init();
-    mbar_expect_tx(&sm->bar[0], w.blob_bytes);
-    tma_bulk_g2s(stage, w.blob, w.blob_bytes, &sm->bar[0]);  // whole entry in one bulk copy
+    mbar_expect_tx(&sm->bar[0], ref.blob_bytes);
+    tma_bulk_g2s(stage, ref.blob, ref.blob_bytes, &sm->bar[0]);  // whole entry in one bulk copy
   }
   __syncthreads();
-  const uint8_t* base = w.blob;
+  const uint8_t* base = ref.blob;
   if (staged) {
     mbar_wait(&sm->bar[0], 0);
     base = stage;
   }
   const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
+  const EntryIo w = resolve_io(io, blockIdx.x, MODE == MODE_DECODE ? h->tbits / 8u : 4u);
   switch (h->tbits) {
-    case 8: int_scan_entry<uint8_t, MODE>(w, base, sm); break;
-    case 16: int_scan_entry<uint16_t, MODE>(w, base, sm); break;
-    case 32: int_scan_entry<uint32_t, MODE>(w, base, sm); break;
-    default: int_scan_entry<uint64_t, MODE>(w, base, sm); break;
+    case 8: int_scan_entry<uint8_t, MODE>(w, pred, base, sm); break;
+    case 16: int_scan_entry<uint16_t, MODE>(w, pred, base, sm); break;
+    case 32: int_scan_entry<uint32_t, MODE>(w, pred, base, sm); break;
+    default: int_scan_entry<uint64_t, MODE>(w, pred, base, sm); break;
   }
 }
 
-cudaError_t launch_int_scan(int mode, const IntScanWork* d_works, uint32_t n_works, uint32_t max_blob_bytes,
-                            cudaStream_t s) {
-  if (n_works == 0) return cudaSuccess;
+cudaError_t launch_int_scan(int mode, uint32_t n_entries, const ScanIo& io, const IntPredDesc& pred,
+                            uint32_t max_blob_bytes, cudaStream_t s) {
+  if (n_entries == 0) return cudaSuccess;
   const uint32_t stage = max_blob_bytes <= kStageCap ? ((max_blob_bytes + 127u) & ~127u) : 0u;
   const uint32_t smem = kScanFixedSmem + stage;
   static bool attr_set = false;
@@ -140,9 +217,9 @@ cudaError_t launch_int_scan(int mode, const IntScanWork* d_works, uint32_t n_wor
     attr_set = true;
   }
   switch (mode) {
-    case MODE_DECODE: k_int_scan<MODE_DECODE><<<n_works, 256, smem, s>>>(d_works, stage); break;
-    case MODE_PRED: k_int_scan<MODE_PRED><<<n_works, 256, smem, s>>>(d_works, stage); break;
-    default: k_int_scan<MODE_REFINE><<<n_works, 256, smem, s>>>(d_works, stage); break;
+    case MODE_DECODE: k_int_scan<MODE_DECODE><<<n_entries, 256, smem, s>>>(io, pred, stage); break;
+    case MODE_PRED: k_int_scan<MODE_PRED><<<n_entries, 256, smem, s>>>(io, pred, stage); break;
+    default: k_int_scan<MODE_REFINE><<<n_entries, 256, smem, s>>>(io, pred, stage); break;
   }
   return cudaGetLastError();
 }

@@ -174,14 +174,101 @@ __device__ __forceinline__ void load_fsst_table(const FsstTable* t, uint64_t* s_
 // ------------------------------------------------------------------------------------------------
 // predicate kernel
 // ------------------------------------------------------------------------------------------------
+struct EntryIo {
+  const uint32_t* sel;
+  void* out;
+  uint32_t* out_valid;
+  uint32_t* counts;
+};
+
+__device__ __forceinline__ EntryIo resolve_io(const ScanIo& io, uint32_t e) {
+  EntryIo r;
+  r.sel = nullptr;
+  if (io.sel_base) {
+    const uint64_t so = io.sel_off[e];
+    if (so != kNoSel) r.sel = io.sel_base + so;
+  }
+  r.out = io.out_base ? static_cast<uint8_t*>(io.out_base) + io.out_off[e] * 4u : nullptr;
+  r.out_valid = io.valid_base ? io.valid_base + io.valid_off[e] : nullptr;
+  r.counts = io.counts ? io.counts + static_cast<size_t>(e) * io.counts_stride : nullptr;
+  return r;
+}
+
+// Per-entry plan, decided on the device from the entry's own shared prefix (thread 0, then broadcast).
+// Restates the case analysis of comparisons.rs:21-82 (equality), :351-405 + :469-501 (ordering), :159-183 (LIKE).
+struct StrPlan {
+  int32_t kind;
+  uint32_t flags;       // bit0 const result, bit1 negate, bit2 LIKE without fingerprints (plain semantics)
+  uint32_t cmp_len;
+  uint32_t pad;
+  uint64_t key_expect;
+};
+
+__device__ __forceinline__ void plan_str_pred(const StrView& v, const StrPredDesc& pred, const uint8_t* nd,
+                                              StrPlan* out) {
+  const int op = pred.op;
+  const uint32_t m = pred.needle_len, spl = v.h->shared_prefix_len;
+  StrPlan p;
+  p.kind = SP_CONST;
+  p.flags = 0;
+  p.cmp_len = 0;
+  p.pad = 0;
+  p.key_expect = 0;
+  if (op == LC_OP_CONST_TRUE || op == LC_OP_CONST_FALSE) {
+    p.flags = (op == LC_OP_CONST_TRUE) ? 1u : 0u;
+  } else if (op == LC_OP_EQ || op == LC_OP_NE) {
+    const bool neg = (op == LC_OP_NE);
+    bool has_prefix = m >= spl;
+    for (uint32_t i = 0; has_prefix && i < spl; ++i) has_prefix = nd[i] == v.sp[i];
+    if (!has_prefix) {
+      p.flags = neg ? 1u : 0u;  // no value can equal the needle
+    } else {
+      const uint32_t L = m - spl;
+      uint64_t k = 0;
+      for (uint32_t b = 0; b < (L < 7u ? L : 7u); ++b) k |= static_cast<uint64_t>(nd[spl + b]) << (8u * b);
+      k |= static_cast<uint64_t>(L >= 255u ? 255u : L) << 56;
+      p.key_expect = k;
+      p.kind = (L <= 7u) ? SP_EQ_SHORT : SP_EQ_LONG;
+      p.flags = neg ? 2u : 0u;
+    }
+  } else if (op >= LC_OP_LT && op <= LC_OP_GE) {
+    const bool less_op = (op == LC_OP_LT || op == LC_OP_LE);
+    const uint32_t c_len = m < spl ? m : spl;
+    int c = 0;
+    for (uint32_t i = 0; c == 0 && i < c_len; ++i) c = static_cast<int>(v.sp[i]) - static_cast<int>(nd[i]);
+    if (c != 0 || m < spl) {
+      // compare_with_shared_prefix: decided for the whole dictionary; a needle shorter than the shared
+      // prefix is smaller than every value
+      const bool res = (c < 0) ? less_op : !less_op;
+      p.flags = res ? 1u : 0u;
+    } else {
+      const uint32_t L7 = (m - spl) < 7u ? (m - spl) : 7u;
+      if (L7 == 0) {
+        p.kind = SP_ORD_EMPTY;
+      } else {
+        uint64_t k = 0;
+        for (uint32_t b = 0; b < L7; ++b) k |= static_cast<uint64_t>(nd[spl + b]) << (8u * (7u - b));
+        p.kind = SP_ORD;
+        p.key_expect = k;
+        p.cmp_len = L7;
+      }
+    }
+  } else {  // LIKE / NOT LIKE
+    p.kind = SP_LIKE;
+    p.flags = (op == LC_OP_NOT_LIKE ? 2u : 0u) | (v.h->has_fp ? 0u : 4u);
+  }
+  *out = p;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_str_scan(const StrScanWork* __restrict__ works, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words) {
+k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
   uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
   uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
-  uint8_t* s_nd = s_len + 256;
+  StrPlan* s_plan = reinterpret_cast<StrPlan*>(s_len + 256);
+  uint8_t* s_nd = reinterpret_cast<uint8_t*>(s_plan + 1);
   const uint32_t m = pred.needle_len;
   const uint32_t nd_bytes = (m + 15u) & ~15u;
   uint16_t* s_fail = reinterpret_cast<uint16_t*>(s_nd + nd_bytes);
@@ -190,19 +277,20 @@ k_str_scan(const StrScanWork* __restrict__ works, StrPredDesc pred, uint32_t sta
   uint8_t* stage = reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u);
   stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage) + 127u) & ~static_cast<uintptr_t>(127u));
 
-  const StrScanWork w = works[blockIdx.x];
-  const bool staged = w.head_bytes <= stage_cap;
+  const EntryRef ref = io.refs[blockIdx.x];
+  const EntryIo w = resolve_io(io, blockIdx.x);
+  const bool staged = ref.head_bytes <= stage_cap;
   scan_smem_init(sm);
   if (threadIdx.x == 0 && staged) {
     mbar_init(&sm->bar[0], 1);
     mbar_init(&sm->bar[1], 1);
     fence_mbar_init();
-    mbar_expect_tx(&sm->bar[0], w.meta_bytes);
-    tma_bulk_g2s(stage, w.blob, w.meta_bytes, &sm->bar[0]);  // header + dictionary metadata
-    const uint32_t rest = w.head_bytes - w.meta_bytes;
+    mbar_expect_tx(&sm->bar[0], ref.meta_bytes);
+    tma_bulk_g2s(stage, ref.blob, ref.meta_bytes, &sm->bar[0]);  // header + dictionary metadata
+    const uint32_t rest = ref.head_bytes - ref.meta_bytes;
     if (rest) {
       mbar_expect_tx(&sm->bar[1], rest);
-      tma_bulk_g2s(stage + w.meta_bytes, w.blob + w.meta_bytes, rest, &sm->bar[1]);  // validity + keys
+      tma_bulk_g2s(stage + ref.meta_bytes, ref.blob + ref.meta_bytes, rest, &sm->bar[1]);  // validity + keys
     }
   }
   // needle + KMP links (shared by all entries of the launch)
@@ -212,16 +300,19 @@ k_str_scan(const StrScanWork* __restrict__ works, StrPredDesc pred, uint32_t sta
   }
   for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = 0;
   __syncthreads();
-  const uint8_t* head = w.blob;
+  const uint8_t* head = ref.blob;
   if (staged) {
     mbar_wait(&sm->bar[0], 0);
     head = stage;
   }
-  const StrView v = make_view(head, w.blob);
+  const StrView v = make_view(head, ref.blob);
+  if (threadIdx.x == 0) plan_str_pred(v, pred, s_nd, s_plan);
+  __syncthreads();
+  const StrPlan plan = *s_plan;
   const uint32_t U = v.h->n_unique;
   const int lane = threadIdx.x & 31;
-  const int32_t kind = w.kind;
-  const bool neg = (w.flags & 2u) != 0;
+  const int32_t kind = plan.kind;
+  const bool neg = (plan.flags & 2u) != 0;
   const bool needs_table = (kind == SP_EQ_LONG || kind == SP_ORD || kind == SP_LIKE);
   if (needs_table) {
     load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
@@ -230,32 +321,31 @@ k_str_scan(const StrScanWork* __restrict__ works, StrPredDesc pred, uint32_t sta
 
   // ---------------- phase 1: one decision per dictionary entry ----------------
   if (kind == SP_CONST) {
-    const uint32_t fill = (w.flags & 1u) ? kFullMask : 0u;
+    const uint32_t fill = (plan.flags & 1u) ? kFullMask : 0u;
     for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = fill;
   } else {
     const uint32_t op = static_cast<uint32_t>(pred.op);
-    uint32_t any_cand = 0;
     for (uint32_t i0 = (threadIdx.x & ~31u); i0 < U; i0 += 256u) {
       const uint32_t i = i0 + lane;
       const bool act = i < U;
       const uint64_t key = act ? v.pk[i] : 0ull;
       bool res = false, cand = false;
       if (kind == SP_EQ_SHORT) {
-        res = (key == w.key_expect) != neg;
+        res = (key == plan.key_expect) != neg;
       } else if (kind == SP_EQ_LONG) {
-        cand = (key == w.key_expect);
+        cand = (key == plan.key_expect);
         res = neg;
       } else if (kind == SP_ORD) {
-        const uint64_t mask = ~0ull << (8u * (8u - w.cmp_len));
+        const uint64_t mask = ~0ull << (8u * (8u - plan.cmp_len));
         const uint64_t a = bswap64(key) & mask;
-        if (a < w.key_expect) res = (op == LC_OP_LT || op == LC_OP_LE);
-        else if (a > w.key_expect) res = (op == LC_OP_GT || op == LC_OP_GE);
+        if (a < plan.key_expect) res = (op == LC_OP_LT || op == LC_OP_LE);
+        else if (a > plan.key_expect) res = (op == LC_OP_GT || op == LC_OP_GE);
         else cand = true;
       } else if (kind == SP_ORD_EMPTY) {
         const bool empty = (key >> 56) == 0;
         res = (op == LC_OP_LT) ? false : (op == LC_OP_LE) ? empty : (op == LC_OP_GT) ? !empty : true;
       } else {  // SP_LIKE
-        cand = v.fp ? ((v.fp[i < U ? i : 0] & pred.needle_fp) == pred.needle_fp) : true;
+        cand = v.fp ? ((v.fp[act ? i : 0] & pred.needle_fp) == pred.needle_fp) : true;
       }
       res = res && act;
       cand = cand && act;
@@ -267,11 +357,20 @@ k_str_scan(const StrScanWork* __restrict__ works, StrPredDesc pred, uint32_t sta
         if (lane == 0) base = atomicAdd(&sm->misc[0], __popc(cw));
         base = __shfl_sync(kFullMask, base, 0);
         if (cand) s_cand[base + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i);
-        any_cand = 1;
       }
     }
     __syncthreads();
     const uint32_t ncand = sm->misc[0];
+    if (pred.prof) {  // measurement aid, never on in a timed run
+      unsigned long long bytes = 0;
+      for (uint32_t c = threadIdx.x; c < ncand; c += 256u)
+        bytes += dict_offset(v, s_cand[c] + 1u) - dict_offset(v, s_cand[c]);
+      if (bytes) atomicAdd(&pred.prof[2], bytes);
+      if (threadIdx.x == 0) {
+        atomicAdd(&pred.prof[0], static_cast<unsigned long long>(U));
+        atomicAdd(&pred.prof[1], static_cast<unsigned long long>(ncand));
+      }
+    }
     // candidates: walk the FSST codes of the value
     for (uint32_t c = threadIdx.x; c < ncand; c += 256u) {
       const uint32_t i = s_cand[c];
@@ -294,14 +393,13 @@ k_str_scan(const StrScanWork* __restrict__ works, StrPredDesc pred, uint32_t sta
       // apply_like_match_on_candidates, i.e. only when the fingerprint gate let something through
       // (comparisons.rs:166-180, 644-648). Without fingerprints (flags bit2) it is a plain negation.
       __syncthreads();
-      const bool invert = (w.flags & 4u) ? true : (ncand != 0);
+      const bool invert = (plan.flags & 4u) ? true : (ncand != 0);
       if (invert)
         for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = ~s_dict[i];
     }
-    (void)any_cand;
   }
   __syncthreads();
-  if (staged && w.head_bytes > w.meta_bytes) mbar_wait(&sm->bar[1], 0);
+  if (staged && ref.head_bytes > ref.meta_bytes) mbar_wait(&sm->bar[1], 0);
 
   // ---------------- phase 2: dictionary results -> rows ----------------
   const uint16_t* keys = v.keys;
@@ -310,20 +408,20 @@ k_str_scan(const StrScanWork* __restrict__ works, StrPredDesc pred, uint32_t sta
     return (s_dict[k >> 5] >> (k & 31u)) & 1u;
   };
   auto emit = [&](uint32_t, uint32_t) {};
-  scan_entry_rows<MODE>(w.sel, v.h->n, v.valid, v.h->null_count, reinterpret_cast<uint32_t*>(w.out_values),
-                        w.out_validity, w.out_counts, sm, cmp, emit);
+  scan_entry_rows<MODE>(w.sel, v.h->n, v.valid, v.h->null_count, reinterpret_cast<uint32_t*>(w.out), w.out_valid,
+                        w.counts, sm, cmp, emit);
 }
 
 static uint32_t str_scan_smem(uint32_t needle_len, uint32_t dict_words, uint32_t stage) {
   const uint32_t nd = (needle_len + 15u) & ~15u;
   const uint32_t fl = (2u * needle_len + 15u) & ~15u;
-  return kScanFixedSmem + 2048u + 256u + nd + fl + dict_words * 4u + (((dict_words * 64u) + 127u) & ~127u) + 128u +
-         stage;
+  return kScanFixedSmem + 2048u + 256u + 32u + nd + fl + dict_words * 4u + (((dict_words * 64u) + 127u) & ~127u) +
+         128u + stage;
 }
 
-cudaError_t launch_str_scan(int mode, const StrScanWork* d_works, uint32_t n_works, const StrPredDesc& pred,
+cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, const StrPredDesc& pred,
                             uint32_t max_head_bytes, uint32_t max_unique, cudaStream_t s) {
-  if (n_works == 0) return cudaSuccess;
+  if (n_entries == 0) return cudaSuccess;
   const uint32_t dict_words = ((max_unique + 31u) / 32u + 3u) & ~3u;
   constexpr uint32_t kMaxSmem = 227u * 1024u;
   uint32_t stage = (max_head_bytes + 127u) & ~127u;
@@ -338,58 +436,76 @@ cudaError_t launch_str_scan(int mode, const StrScanWork* d_works, uint32_t n_wor
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (mode == MODE_PRED) k_str_scan<MODE_PRED><<<n_works, 256, smem, s>>>(d_works, pred, stage, dict_words);
-  else k_str_scan<MODE_REFINE><<<n_works, 256, smem, s>>>(d_works, pred, stage, dict_words);
+  if (mode == MODE_PRED) k_str_scan<MODE_PRED><<<n_entries, 256, smem, s>>>(io, pred, stage, dict_words);
+  else k_str_scan<MODE_REFINE><<<n_entries, 256, smem, s>>>(io, pred, stage, dict_words);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // get / filter, pass 1: selected keys, decoded lengths, local offsets
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_str_lengths(const StrGatherWork* __restrict__ works, uint32_t stage_cap) {
+__global__ void __launch_bounds__(256) k_str_lengths(StrGatherIo g, uint32_t stage_cap) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
   uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
   uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
   uint8_t* stage = s_len + 256;
 
-  const StrGatherWork w = works[blockIdx.x];
-  const bool staged = w.head_bytes <= stage_cap;
+  const uint32_t e = blockIdx.x;
+  const EntryRef ref = g.io.refs[e];
+  const EntryIo w = resolve_io(g.io, e);
+  const bool staged = ref.head_bytes <= stage_cap;
   scan_smem_init(sm);
   if (threadIdx.x == 0 && staged) {
     mbar_init(&sm->bar[0], 1);
     fence_mbar_init();
-    mbar_expect_tx(&sm->bar[0], w.head_bytes);
-    tma_bulk_g2s(stage, w.blob, w.head_bytes, &sm->bar[0]);
+    mbar_expect_tx(&sm->bar[0], ref.head_bytes);
+    tma_bulk_g2s(stage, ref.blob, ref.head_bytes, &sm->bar[0]);
   }
   __syncthreads();
-  const uint8_t* head = w.blob;
+  const uint8_t* head = ref.blob;
   if (staged) {
     mbar_wait(&sm->bar[0], 0);
     head = stage;
   }
-  const StrView v = make_view(head, w.blob);
+  const StrView v = make_view(head, ref.blob);
   load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
-  __syncthreads();
-  const uint32_t U = v.h->n_unique, spl = v.h->shared_prefix_len;
-  const bool precomp = (w.flags & kGatherPrecompLens) != 0;
+  const uint32_t U = v.h->n_unique, spl = v.h->shared_prefix_len, n = v.h->n;
+  uint32_t* row_off = g.row_off_base + g.row_base[e] + e;
+  uint32_t* row_key = g.row_key_base + g.row_base[e];
+  uint32_t* ulen = g.ulen_base + g.ulen_off[e];
+  // how many rows are selected decides whether every unique's length is worth computing up front
+  uint32_t k_sel = n;
+  if (w.sel) {
+    uint32_t c = 0;
+    const uint32_t n_words = (n + 31u) >> 5, tail = n & 31u;
+    for (uint32_t i = threadIdx.x; i < n_words; i += 256u) {
+      uint32_t sw = w.sel[i];
+      if (i == n_words - 1u && tail) sw &= (1u << tail) - 1u;
+      c += __popc(sw);
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sm->misc[1], c);
+    __syncthreads();
+    k_sel = sm->misc[1];
+  } else {
+    __syncthreads();
+  }
+  const bool precomp = static_cast<uint64_t>(k_sel) * 4ull >= U;
   if (precomp) {
     // decoded length of every unique: PrefixKey.len when < 255, else walk the codes
     for (uint32_t i = threadIdx.x; i < U; i += 256u) {
       const uint32_t l = static_cast<uint32_t>(v.pk[i] >> 56);
       uint32_t len = spl + l;
       const uint32_t start = dict_offset(v, i), end = dict_offset(v, i + 1u);
-      if (start == end) len = 0;  // empty / null dictionary value (fsst_buffer.rs:100-113)
+      if (start == end) len = 0;  // empty value (fsst_buffer.rs:100-113)
       else if (l == 255u) len = decoded_length(v.fsst, start, end, s_len);
-      w.ulen[i] = len;
+      ulen[i] = len;
     }
     __syncthreads();
   }
   const uint16_t* keys = v.keys;
   const uint32_t* valid = v.valid;
-  uint32_t* row_off = w.row_off;
-  uint32_t* row_key = w.row_key;
   auto cmp = [&](uint32_t) -> bool { return false; };
   auto emit = [&](uint32_t row, uint32_t dst) {
     const bool ok = valid ? ((valid[row >> 5] >> (row & 31u)) & 1u) : true;
@@ -397,7 +513,7 @@ k_str_lengths(const StrGatherWork* __restrict__ works, uint32_t stage_cap) {
     if (ok) {
       key = keys[row];
       if (precomp) {
-        len = w.ulen[key];
+        len = ulen[key];
       } else {
         const uint32_t l = static_cast<uint32_t>(v.pk[key] >> 56);
         const uint32_t start = dict_offset(v, key), end = dict_offset(v, key + 1u);
@@ -409,11 +525,10 @@ k_str_lengths(const StrGatherWork* __restrict__ works, uint32_t stage_cap) {
     row_off[dst] = len;
     row_key[dst] = key;
   };
-  scan_entry_rows<MODE_DECODE>(w.sel, v.h->n, valid, v.h->null_count, nullptr, w.out_validity, w.out_counts, sm, cmp,
-                               emit);
+  scan_entry_rows<MODE_DECODE>(w.sel, n, valid, v.h->null_count, nullptr, w.out_valid, w.counts, sm, cmp, emit);
   __syncthreads();
   // exclusive scan of the selected rows' lengths -> local offsets (in place), total bytes
-  const uint32_t k = w.out_counts[0];
+  const uint32_t k = w.counts[0];
   uint32_t carry = 0;
   for (uint32_t base = 0; base < k; base += 256u) {
     const uint32_t j = base + threadIdx.x;
@@ -425,13 +540,12 @@ k_str_lengths(const StrGatherWork* __restrict__ works, uint32_t stage_cap) {
   }
   if (threadIdx.x == 0) {
     row_off[k] = carry;
-    w.out_counts[2] = carry;
+    w.counts[2] = carry;
   }
 }
 
-cudaError_t launch_str_lengths(const StrGatherWork* d_works, uint32_t n_works, uint32_t max_head_bytes,
-                               cudaStream_t s) {
-  if (n_works == 0) return cudaSuccess;
+cudaError_t launch_str_lengths(uint32_t n_entries, const StrGatherIo& g, uint32_t max_head_bytes, cudaStream_t s) {
+  if (n_entries == 0) return cudaSuccess;
   uint32_t stage = (max_head_bytes + 127u) & ~127u;
   if (stage > kStageCap) stage = 0;
   const uint32_t smem = kScanFixedSmem + 2048u + 256u + stage;
@@ -442,7 +556,7 @@ cudaError_t launch_str_lengths(const StrGatherWork* d_works, uint32_t n_works, u
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_str_lengths<<<n_works, 256, smem, s>>>(d_works, stage);
+  k_str_lengths<<<n_entries, 256, smem, s>>>(g, stage);
   return cudaGetLastError();
 }
 
@@ -484,29 +598,35 @@ __device__ __forceinline__ uint32_t warp_decode(const uint8_t* __restrict__ c, u
   return produced;
 }
 
-__global__ void __launch_bounds__(256) k_str_decode(const StrDecodeWork* __restrict__ works) {
+__global__ void __launch_bounds__(256) k_str_decode(StrGatherIo g) {
   __shared__ uint64_t s_sym[256];
   __shared__ __align__(16) uint8_t s_len[256];
-  const StrDecodeWork w = works[blockIdx.x];
-  const StrView v = make_view(w.blob, w.blob);
+  const uint32_t e = blockIdx.x;
+  const EntryRef ref = g.io.refs[e];
+  const StrView v = make_view(ref.blob, ref.blob);
   load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // final offsets of this entry's slice (the LAST entry also owns the closing offset; the host adds it)
-  for (uint32_t j = threadIdx.x; j < w.k; j += 256u)
-    w.out_offsets[j] = static_cast<int32_t>(w.byte_base + w.row_off[j]);
-  for (uint32_t j = warp; j < w.k; j += 8u) {
-    const uint32_t key = w.row_key[j];
+  const uint64_t rb = g.row_base[e];
+  const uint32_t* row_off = g.row_off_base + rb + e;
+  const uint32_t* row_key = g.row_key_base + rb;
+  const uint32_t k = g.io.counts[static_cast<size_t>(e) * g.io.counts_stride];
+  const uint32_t byte_base = static_cast<uint32_t>(g.byte_base[e]);
+  int32_t* out_offsets = g.out_offsets + rb;
+  // final offsets of this entry's slice (the closing offset of the whole array is written by the host)
+  for (uint32_t j = threadIdx.x; j < k; j += 256u) out_offsets[j] = static_cast<int32_t>(byte_base + row_off[j]);
+  for (uint32_t j = warp; j < k; j += 8u) {
+    const uint32_t key = row_key[j];
     if (key == 0xFFFFFFFFu) continue;
     const uint32_t start = dict_offset(v, key), end = dict_offset(v, key + 1u);
     if (start == end) continue;
-    warp_decode(v.fsst + start, end - start, w.out_bytes + w.byte_base + w.row_off[j], s_sym, s_len, lane);
+    warp_decode(v.fsst + start, end - start, g.out_bytes + byte_base + row_off[j], s_sym, s_len, lane);
   }
 }
 
-cudaError_t launch_str_decode(const StrDecodeWork* d_works, uint32_t n_works, cudaStream_t s) {
-  if (n_works == 0) return cudaSuccess;
-  k_str_decode<<<n_works, 256, 0, s>>>(d_works);
+cudaError_t launch_str_decode(uint32_t n_entries, const StrGatherIo& g, cudaStream_t s) {
+  if (n_entries == 0) return cudaSuccess;
+  k_str_decode<<<n_entries, 256, 0, s>>>(g);
   return cudaGetLastError();
 }
 

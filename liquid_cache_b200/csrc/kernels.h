@@ -17,18 +17,41 @@ enum ScanMode : int32_t {
   MODE_REFINE = 2,  // device pipeline: selection := selection & valid & cmp, full length, in place
 };
 
-// One entry of a batched integer scan. 64 bytes.
-struct alignas(16) IntScanWork {
-  const uint8_t* blob;      // IntHeader + sections, in HBM
-  const uint32_t* sel;      // selection words (bit i of word i/32 = row i) or nullptr = all rows
-  void* out_values;         // DECODE: native T[k]; PRED: mask words; REFINE: selection words (may alias sel)
-  uint32_t* out_validity;   // DECODE/PRED: validity words of the output, or nullptr
-  uint32_t* out_counts;     // [0] = k (selected rows / surviving rows for REFINE), [1] = nulls among selected
-  uint64_t thr;             // PRED/REFINE: threshold in the unsigned (v - reference) domain
-  int32_t ucmp;             // PRED/REFINE: UCmp
+// One entry of a batched scan: where its blob lives and how much of it to stage. Built once per handle list
+// and cached on the device; everything else a scan kernel needs is planned ON THE DEVICE from the blob header.
+struct alignas(8) EntryRef {
+  const uint8_t* blob;
   uint32_t blob_bytes;
+  uint32_t head_bytes;   // byte-view: header .. keys (what predicate kernels stage); ints: = blob_bytes
+  uint32_t meta_bytes;   // byte-view: header .. residuals
+  uint32_t rows;
 };
-static_assert(sizeof(IntScanWork) == 64, "IntScanWork must be 64 bytes");
+static_assert(sizeof(EntryRef) == 24, "EntryRef must be 24 bytes");
+
+constexpr uint64_t kNoSel = ~0ull;  // sel_off value meaning "every row of this entry is selected"
+
+// Per-launch addressing of selections and outputs. Offsets are per entry so outputs can be dense.
+struct ScanIo {
+  const EntryRef* refs;
+  const uint32_t* sel_base;   // selection words of all entries; nullptr = all rows everywhere
+  const uint64_t* sel_off;    // per entry: word offset into sel_base, or kNoSel
+  void* out_base;             // DECODE: native values; PRED: mask words; REFINE: selection words (may alias sel_base)
+  const uint64_t* out_off;    // per entry: DECODE element offset; PRED/REFINE word offset
+  uint32_t* valid_base;       // DECODE/PRED: validity words of the output (nullptr = not wanted)
+  const uint64_t* valid_off;  // per entry word offset
+  uint32_t* counts;           // per entry `counts_stride` u32: [0]=k (REFINE: survivors), [1]=nulls among selected, [2]=bytes
+  uint32_t counts_stride;
+  uint32_t pad;
+};
+
+// `col <op> literal` on an integer column, as it crossed the C ABI; lowered to the packed domain per entry
+// on the device (u = v - reference against a threshold, or a constant when the literal is outside the window).
+struct IntPredDesc {
+  int32_t op;        // lc_op EQ..GE
+  int32_t lit_kind;  // LC_LIT_I64 / LC_LIT_U64
+  int64_t lit_i;
+  uint64_t lit_u;
+};
 
 struct alignas(16) IntMinMaxWork {  // 32 bytes
   const void* values;         // native T[n] in device scratch
@@ -47,8 +70,8 @@ struct alignas(16) IntPackWork {  // 96 bytes
 };
 static_assert(sizeof(IntPackWork) == 96, "IntPackWork must be 96 bytes");
 
-cudaError_t launch_int_scan(int mode, const IntScanWork* d_works, uint32_t n_works, uint32_t max_blob_bytes,
-                            cudaStream_t s);
+cudaError_t launch_int_scan(int mode, uint32_t n_entries, const ScanIo& io, const IntPredDesc& pred,
+                            uint32_t max_blob_bytes, cudaStream_t s);
 cudaError_t launch_int_minmax(const IntMinMaxWork* d_works, uint32_t n_works, cudaStream_t s);
 cudaError_t launch_int_pack(const IntPackWork* d_works, uint32_t n_works, cudaStream_t s);
 
@@ -64,69 +87,37 @@ enum StrPredKind : int32_t {
 
 constexpr uint32_t kMaxNeedle = 1024;  // needle bytes staged into shared memory
 
-// Predicate descriptor shared by every entry of a launch whose shared prefix agrees with `sp_case`;
-// the per-entry part lives in StrScanWork.
+// Predicate on a byte-view column as it crossed the C ABI. The per-entry case analysis (shared prefix vs needle,
+// prefix-key shortcut, candidates) happens on the device, from the entry's own header.
 struct alignas(16) StrPredDesc {
   int32_t op;            // lc_op (EQ..GE, LIKE, NOT_LIKE)
   uint32_t needle_len;   // full needle (for LIKE: the inner pattern without the % signs)
   uint32_t needle_fp;    // fingerprint of the LIKE needle (fingerprint.rs:19-26)
   uint32_t pad;
   const uint8_t* needle; // device: needle bytes padded to 4, then needle_len x u16 KMP failure links
+  unsigned long long* prof;  // optional device counters {uniques, candidates, candidate bytes}; nullptr = off
 };
 
-struct alignas(16) StrScanWork {  // 80 bytes
-  const uint8_t* blob;
-  const uint32_t* sel;
-  void* out_values;        // PRED: mask words; REFINE: selection words
-  uint32_t* out_validity;
-  uint32_t* out_counts;
-  uint64_t key_expect;     // EQ_SHORT/EQ_LONG: the PrefixKey a match must equal (prefix7 | len<<56);
-                           // ORD: first min(7,len) suffix bytes of the needle, big-endian in the top bytes
-  int32_t kind;            // StrPredKind after the host looked at the entry's shared prefix
-  uint32_t flags;          // bit0 const_result, bit1 negate (NE / NOT LIKE), bit2 LIKE without fingerprints
-  uint32_t cmp_len;        // ORD: number of prefix bytes compared (1..7)
-  uint32_t blob_bytes;
-  uint32_t head_bytes;
-  uint32_t meta_bytes;
-  uint32_t pad[2];
-};
-static_assert(sizeof(StrScanWork) == 80, "StrScanWork must be 80 bytes");
-
-cudaError_t launch_str_scan(int mode, const StrScanWork* d_works, uint32_t n_works, const StrPredDesc& pred,
+cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, const StrPredDesc& pred,
                             uint32_t max_head_bytes, uint32_t max_unique, cudaStream_t s);
 
-// get()/filter() for byte-view entries: pass 1 (lengths + local offsets), host prefix sums, pass 2 (decode).
-constexpr uint32_t kGatherPrecompLens = 1u;  // compute decoded lengths of ALL long uniques up front
-
-struct alignas(16) StrGatherWork {  // 80 bytes
-  const uint8_t* blob;
-  const uint32_t* sel;       // nullptr = all rows
-  uint32_t* row_off;         // scratch, k+1: exclusive prefix of decoded lengths of the selected rows
-  uint32_t* row_key;         // scratch, k: dictionary key of each selected row (0xFFFFFFFF = null row)
-  uint32_t* ulen;            // scratch, U: decoded length per unique (kGatherPrecompLens)
-  uint32_t* out_validity;    // validity words of this entry's slice (word aligned scratch), or nullptr
-  uint32_t* out_counts;      // [0]=k, [1]=nulls among selected, [2]=sum of decoded bytes
-  uint32_t blob_bytes;
-  uint32_t head_bytes;
-  uint32_t flags;
-  uint32_t pad[3];
+// get()/filter() for byte-view entries: pass 1 (selected keys, decoded lengths, local offsets), host prefix
+// sums over the per-entry counts, pass 2 (decode, one warp per selected row).
+struct StrGatherIo {
+  ScanIo io;                 // refs / selections / validity out / counts ([0]=k,[1]=nulls,[2]=decoded bytes)
+  uint32_t* row_off_base;    // scratch: per entry k+1 local offsets at row_off_base[row_base[i] + i]
+  uint32_t* row_key_base;    // scratch: per entry k dictionary keys at row_key_base[row_base[i]]  (0xFFFFFFFF = null)
+  uint32_t* ulen_base;       // scratch: decoded length per unique at ulen_base[ulen_off[i]]
+  const uint64_t* row_base;  // per entry: rows selected before it (pass 1: an upper bound layout; pass 2: exact)
+  const uint64_t* ulen_off;  // per entry
+  // pass 2 only
+  const uint64_t* byte_base; // per entry: decoded bytes before it
+  int32_t* out_offsets;      // concatenated offsets (rows + 1)
+  uint8_t* out_bytes;        // concatenated values
 };
-static_assert(sizeof(StrGatherWork) == 80, "StrGatherWork must be 80 bytes");
 
-struct alignas(16) StrDecodeWork {  // 48 bytes
-  const uint8_t* blob;
-  const uint32_t* row_off;   // from pass 1
-  const uint32_t* row_key;
-  int32_t* out_offsets;      // this entry's first slot in the concatenated offsets buffer
-  uint8_t* out_bytes;        // concatenated value buffer (base)
-  uint32_t byte_base;        // where this entry's bytes start in out_bytes
-  uint32_t k;                // selected rows
-};
-static_assert(sizeof(StrDecodeWork) == 48, "StrDecodeWork must be 48 bytes");
-
-cudaError_t launch_str_lengths(const StrGatherWork* d_works, uint32_t n_works, uint32_t max_head_bytes,
-                               cudaStream_t s);
-cudaError_t launch_str_decode(const StrDecodeWork* d_works, uint32_t n_works, cudaStream_t s);
+cudaError_t launch_str_lengths(uint32_t n_entries, const StrGatherIo& g, uint32_t max_head_bytes, cudaStream_t s);
+cudaError_t launch_str_decode(uint32_t n_entries, const StrGatherIo& g, cudaStream_t s);
 
 // ---- FSST compression at insert ----------------------------------------------------------------
 struct alignas(16) FsstEncTable {

@@ -34,6 +34,7 @@ struct lc_scan {
   uint64_t total_words = 0;
   uint32_t* d_sel = nullptr;
   uint32_t* d_counts = nullptr;
+  uint64_t* d_word_off = nullptr;
   bool all_rows = true;       // no filter applied yet
   bool counts_on_device = false;
   bool counts_cached = false;
@@ -306,14 +307,34 @@ int lc_scan_begin(lc_ctx* ctx, uint64_t n_batches, const uint64_t* rows_per_batc
   }
   sc->total_words = w;
   if (cudaMalloc(reinterpret_cast<void**>(&sc->d_sel), (w + 4) * 4) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&sc->d_counts), n_batches * 8 + 16) != cudaSuccess) {
+      cudaMalloc(reinterpret_cast<void**>(&sc->d_counts), n_batches * 8 + 16) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&sc->d_word_off), n_batches * 8 + 16) != cudaSuccess) {
     cudaGetLastError();
     if (sc->d_sel) cudaFree(sc->d_sel);
+    if (sc->d_counts) cudaFree(sc->d_counts);
     delete sc;
     set_error("lc_scan_begin: cudaMalloc failed");
     return LC_ERR_OOM;
   }
+  if (cudaMemcpyAsync(sc->d_word_off, sc->word_off.data(), n_batches * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    set_error("lc_scan_begin: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(sc->d_sel);
+    cudaFree(sc->d_counts);
+    cudaFree(sc->d_word_off);
+    delete sc;
+    return LC_ERR_CUDA;
+  }
   *out = sc;
+  return LC_OK;
+}
+
+int lc_scan_reset(lc_scan* scan) {
+  if (!scan) return LC_ERR_INVALID;
+  Guard g(scan->ctx);
+  scan->all_rows = true;
+  scan->counts_on_device = false;
+  scan->counts_cached = false;
   return LC_OK;
 }
 
@@ -357,7 +378,7 @@ int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* 
   }
   lc_ctx* ctx = scan->ctx;
   Guard g(ctx);
-  LC_TRY(refine_batch(ctx, es.data(), scan->n, pred, scan->d_sel, scan->word_off.data(), scan->all_rows, scan->d_counts));
+  LC_TRY(refine_batch(ctx, es.data(), scan->n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
   scan->all_rows = false;
   scan->counts_on_device = true;
   scan->counts_cached = false;
@@ -470,6 +491,7 @@ void lc_scan_end(lc_scan* scan) {
     cudaStreamSynchronize(scan->ctx->stream);
     if (scan->d_sel) cudaFree(scan->d_sel);
     if (scan->d_counts) cudaFree(scan->d_counts);
+    if (scan->d_word_off) cudaFree(scan->d_word_off);
   }
   delete scan;
 }

@@ -1,7 +1,46 @@
 // lc_ctx.cc — context lifecycle, HBM arena, scratch buffers, error state.
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
+#include <cstdlib>
+
 #include "host_common.h"
 
 namespace lc {
+
+// Debugging aid (LC_DEBUG_SEGV=1): print the native stack of a crashing thread before dying.
+static void segv_handler(int sig) {
+  void* bt[96];
+  const int n = backtrace(bt, 96);
+  const char msg[] = "\n[liblc_gpu] fatal signal, native backtrace:\n";
+  ssize_t w = write(2, msg, sizeof(msg) - 1);
+  (void)w;
+  backtrace_symbols_fd(bt, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+
+static void maybe_install_segv_handler() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = std::getenv("LC_DEBUG_SEGV");
+  if (!e || e[0] != '1') return;
+  static char alt[1 << 16];
+  stack_t ss;
+  ss.ss_sp = alt;
+  ss.ss_size = sizeof(alt);
+  ss.ss_flags = 0;
+  sigaltstack(&ss, nullptr);
+  struct sigaction sa;
+  std::memset(&sa, 0, sizeof(sa));
+  sa.sa_handler = segv_handler;
+  sa.sa_flags = SA_ONSTACK;
+  sigaction(SIGSEGV, &sa, nullptr);
+  sigaction(SIGBUS, &sa, nullptr);
+  sigaction(SIGABRT, &sa, nullptr);
+}
 
 static thread_local char g_err[512] = "";
 
@@ -132,6 +171,7 @@ void release_entry(lc_ctx* ctx, Entry* e) {
   if (!e) return;
   if (--e->refcount > 0) return;
   if (e->d_blob) ctx->arena.free(e->slab, e->blob_bytes);
+  ctx->epoch++;
   e->magic = 0;
   ctx->n_entries--;
   delete e;
@@ -151,6 +191,7 @@ int lc_ctx_create(int device_id, uint64_t hbm_budget_bytes, lc_ctx** out) {
     set_error("lc_ctx_create: out is NULL");
     return LC_ERR_INVALID;
   }
+  maybe_install_segv_handler();
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev == 0) {
@@ -201,6 +242,9 @@ void lc_ctx_destroy(lc_ctx* ctx) {
       kv.second->d_enc = nullptr;
     }
   }
+  drop_ref_cache(ctx);
+  if (ctx->d_needle) cudaFree(ctx->d_needle);
+  if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -216,6 +260,29 @@ int lc_ctx_set_stream(lc_ctx* ctx, void* cuda_stream) {
 int lc_ctx_synchronize(lc_ctx* ctx) {
   if (!ctx) return LC_ERR_INVALID;
   LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return LC_OK;
+}
+
+int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[4]) {
+  if (!ctx) return LC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (!ctx->d_prof) {
+    if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_prof), 64) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc for profile counters failed");
+      return LC_ERR_OOM;
+    }
+    LC_CUDA_OK(cudaMemsetAsync(ctx->d_prof, 0, 64, ctx->stream));
+  }
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (out) {
+    unsigned long long tmp[4] = {0, 0, 0, 0};
+    LC_CUDA_OK(cudaMemcpy(tmp, ctx->d_prof, 32, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out[i] = tmp[i];
+  }
+  if (enable && !ctx->prof_on) LC_CUDA_OK(cudaMemset(ctx->d_prof, 0, 64));
+  ctx->prof_on = enable != 0;
   return LC_OK;
 }
 

@@ -78,80 +78,6 @@ void kmp_fail(const uint8_t* nd, uint32_t m, uint16_t* fail) {
 
 }  // namespace
 
-// ---- byte-view predicate planning ---------------------------------------------------------------
-// Restates the shared-prefix / length / prefix7 case analysis of
-// byte_view_array/comparisons.rs:21-82 (equality), :351-405 + :469-501 (ordering), :159-183 (LIKE).
-struct StrPlan {
-  int32_t kind;
-  uint32_t flags;
-  uint64_t key_expect;
-  uint32_t cmp_len;
-};
-
-static int plan_str_entry(const Entry* e, int op, const uint8_t* needle, uint32_t m, StrPlan* out) {
-  const uint8_t* sp = e->shared_prefix.data();
-  const uint32_t spl = static_cast<uint32_t>(e->shared_prefix.size());
-  out->flags = 0;
-  out->key_expect = 0;
-  out->cmp_len = 0;
-  if (op == LC_OP_CONST_TRUE || op == LC_OP_CONST_FALSE) {
-    out->kind = SP_CONST;
-    out->flags = (op == LC_OP_CONST_TRUE) ? 1u : 0u;
-    return LC_OK;
-  }
-  if (op == LC_OP_EQ || op == LC_OP_NE) {
-    const bool neg = (op == LC_OP_NE);
-    if (m < spl || std::memcmp(needle, sp, spl) != 0) {
-      out->kind = SP_CONST;  // no value can equal the needle
-      out->flags = neg ? 1u : 0u;
-      return LC_OK;
-    }
-    const uint8_t* s = needle + spl;
-    const uint32_t L = m - spl;
-    uint64_t k = 0;
-    for (uint32_t b = 0; b < (L < 7 ? L : 7); ++b) k |= static_cast<uint64_t>(s[b]) << (8 * b);
-    k |= static_cast<uint64_t>(L >= 255 ? 255u : L) << 56;
-    out->key_expect = k;
-    out->kind = (L <= 7) ? SP_EQ_SHORT : SP_EQ_LONG;
-    out->flags = neg ? 2u : 0u;
-    return LC_OK;
-  }
-  if (op >= LC_OP_LT && op <= LC_OP_GE) {
-    const bool less_op = (op == LC_OP_LT || op == LC_OP_LE);
-    const uint32_t c_len = m < spl ? m : spl;
-    const int c = c_len ? std::memcmp(sp, needle, c_len) : 0;
-    if (c != 0 || m < spl) {
-      // compare_with_shared_prefix: decided for the whole dictionary
-      bool res;
-      if (c < 0) res = less_op;
-      else if (c > 0) res = !less_op;
-      else res = !less_op;  // needle shorter than the shared prefix: every value is greater
-      out->kind = SP_CONST;
-      out->flags = res ? 1u : 0u;
-      return LC_OK;
-    }
-    const uint8_t* s = needle + spl;
-    const uint32_t L7 = (m - spl) < 7 ? (m - spl) : 7;
-    if (L7 == 0) {
-      out->kind = SP_ORD_EMPTY;
-      return LC_OK;
-    }
-    uint64_t k = 0;
-    for (uint32_t b = 0; b < L7; ++b) k |= static_cast<uint64_t>(s[b]) << (8 * (7 - b));
-    out->kind = SP_ORD;
-    out->key_expect = k;
-    out->cmp_len = L7;
-    return LC_OK;
-  }
-  if (op == LC_OP_LIKE || op == LC_OP_NOT_LIKE) {
-    out->kind = SP_LIKE;
-    out->flags = (op == LC_OP_NOT_LIKE ? 2u : 0u) | (e->sh.has_fp ? 0u : 4u);
-    return LC_OK;
-  }
-  set_error("unsupported operator %d on a byte-view column", op);
-  return LC_ERR_UNSUPPORTED_EXPR;
-}
-
 // substring_pattern_bytes (byte_view_array/fingerprint.rs:59-73): '%x%' with x non-empty, no % or _.
 // A backslash would make arrow's LIKE take the escape-aware regex path, so it is declined as well.
 static int like_inner(const uint8_t* pat, uint64_t len, const uint8_t** inner, uint32_t* inner_len) {
@@ -212,35 +138,158 @@ static int prepare_str_pred(const lc_predicate* pred, StrLaunch* L) {
   return LC_OK;
 }
 
+// ---- entry reference lists -----------------------------------------------------------------------
+// The device-side list of {blob, sizes} for a handle list is cached per context (keyed by a hash of the handle
+// array) so that repeated scans over the same column chunk upload nothing but a few scalars.
+struct RefList {
+  uint64_t key = 0;
+  uint64_t n = 0;
+  EntryRef* d_refs = nullptr;
+  uint32_t max_blob = 0, max_head = 0, max_unique = 1;
+  uint64_t epoch = 0;
+  uint64_t last_use = 0;
+};
+
+struct RefCache {
+  std::vector<RefList> lists;
+  uint64_t tick = 0;
+};
+
+static std::unordered_map<lc_ctx*, RefCache>& ref_caches() {
+  static std::unordered_map<lc_ctx*, RefCache> m;
+  return m;
+}
+
+void drop_ref_cache(lc_ctx* ctx) {
+  auto& m = ref_caches();
+  auto it = m.find(ctx);
+  if (it == m.end()) return;
+  for (auto& l : it->second.lists)
+    if (l.d_refs) cudaFree(l.d_refs);
+  m.erase(it);
+}
+
+static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const RefList** out) {
+  uint64_t h = 0xcbf29ce484222325ull ^ n;
+  for (uint64_t i = 0; i < n; ++i) {
+    h ^= reinterpret_cast<uintptr_t>(entries[i]);
+    h *= 0x100000001b3ull;
+    h ^= h >> 29;
+  }
+  RefCache& rc = ref_caches()[ctx];
+  rc.tick++;
+  for (auto& l : rc.lists) {
+    if (l.key == h && l.n == n && l.epoch == ctx->epoch) {
+      l.last_use = rc.tick;
+      *out = &l;
+      return LC_OK;
+    }
+  }
+  // build + upload
+  std::vector<EntryRef> refs(n);
+  RefList nl;
+  nl.key = h;
+  nl.n = n;
+  nl.epoch = ctx->epoch;
+  nl.last_use = rc.tick;
+  for (uint64_t i = 0; i < n; ++i) {
+    const Entry* e = entries[i];
+    refs[i].blob = e->d_blob;
+    refs[i].blob_bytes = e->blob_bytes;
+    refs[i].rows = e->n;
+    if (e->liquid_type == LC_LIQUID_INTEGER) {
+      refs[i].head_bytes = e->blob_bytes;
+      refs[i].meta_bytes = e->blob_bytes;
+    } else {
+      refs[i].head_bytes = e->sh.head_bytes;
+      refs[i].meta_bytes = e->sh.meta_bytes;
+      nl.max_head = std::max(nl.max_head, e->sh.head_bytes);
+      nl.max_unique = std::max(nl.max_unique, e->sh.n_unique);
+    }
+    nl.max_blob = std::max(nl.max_blob, e->blob_bytes);
+  }
+  if (cudaMalloc(reinterpret_cast<void**>(&nl.d_refs), n * sizeof(EntryRef) + 64) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc for the entry list failed");
+    return LC_ERR_OOM;
+  }
+  LC_CUDA_OK(cudaMemcpyAsync(nl.d_refs, refs.data(), n * sizeof(EntryRef), cudaMemcpyHostToDevice, ctx->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // `refs` is pageable host memory
+  ctx->h2d_bytes += n * sizeof(EntryRef);
+  // evict: stale epochs first, then least recently used beyond 16 lists
+  for (size_t i = 0; i < rc.lists.size();) {
+    if (rc.lists[i].epoch != ctx->epoch) {
+      cudaFree(rc.lists[i].d_refs);
+      rc.lists.erase(rc.lists.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+  if (rc.lists.size() >= 16) {
+    size_t lru = 0;
+    for (size_t i = 1; i < rc.lists.size(); ++i)
+      if (rc.lists[i].last_use < rc.lists[lru].last_use) lru = i;
+    cudaFree(rc.lists[lru].d_refs);
+    rc.lists.erase(rc.lists.begin() + lru);
+  }
+  rc.lists.push_back(nl);
+  *out = &rc.lists.back();
+  return LC_OK;
+}
+
+static int check_same_type(Entry* const* entries, uint64_t n, const char* who) {
+  const int32_t type = entries[0]->liquid_type;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (entries[i]->liquid_type != type) {
+      set_error("%s: entries of different liquid types in one call", who);
+      return LC_ERR_INVALID;
+    }
+  }
+  return LC_OK;
+}
+
+static int make_int_pred(const lc_predicate* pred, IntPredDesc* out) {
+  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
+    set_error("operator %d is not supported on integer columns", pred->op);
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  if (pred->lit_kind != LC_LIT_I64 && pred->lit_kind != LC_LIT_U64) {
+    set_error("integer column needs an integer literal");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  out->op = pred->op;
+  out->lit_kind = pred->lit_kind;
+  out->lit_i = pred->lit_i64;
+  out->lit_u = pred->lit_u64;
+  return LC_OK;
+}
+
 // ---- eval_predicate --------------------------------------------------------------------------------
 int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
                          const uint8_t* const* sel_bits, const PredOut& out) {
   if (n == 0) return LC_OK;
-  const int32_t type = entries[0]->liquid_type;
-  for (uint64_t i = 0; i < n; ++i) {
-    if (entries[i]->liquid_type != type) {
-      set_error("eval_predicate_many: entries of different liquid types in one call");
-      return LC_ERR_INVALID;
-    }
-  }
+  LC_TRY(check_same_type(entries, n, "eval_predicate_many"));
+  const bool is_int = (entries[0]->liquid_type == LC_LIQUID_INTEGER);
   SelPlan sp;
   plan_selection(entries, n, sel_bits, &sp);
-  const bool is_int = (type == LC_LIQUID_INTEGER);
   StrLaunch sl;
-  if (!is_int) LC_TRY(prepare_str_pred(pred, &sl));
+  IntPredDesc ip{};
+  if (is_int) LC_TRY(make_int_pred(pred, &ip));
+  else LC_TRY(prepare_str_pred(pred, &sl));
+  const RefList* rl;
+  LC_TRY(get_ref_list(ctx, entries, n, &rl));
 
-  // output layout: counts[2n] | mask words | validity words  (word aligned per entry)
-  std::vector<uint64_t> out_word_off(n);
+  // upload: sel_off[n] | out_off[n] | needle | selection words ; download: counts[2n] | mask words | validity words
+  const uint64_t up_offs = round_up(n * 16, 256);
+  const uint64_t up_needle = is_int ? 0 : round_up(sl.needle_blob.size(), 256);
+  const uint64_t up_sel = round_up(sp.sel_words * 4, 256);
+  const uint64_t up_total = up_offs + up_needle + up_sel;
   uint64_t out_words = 0;
+  std::vector<uint64_t> out_word_off(n);
   for (uint64_t i = 0; i < n; ++i) {
     out_word_off[i] = out_words;
     out_words += round_up((sp.k[i] + 31) / 32, 4);
   }
-  const uint64_t work_sz = is_int ? sizeof(IntScanWork) : sizeof(StrScanWork);
-  const uint64_t up_works = round_up(n * work_sz, 256);
-  const uint64_t up_needle = is_int ? 0 : round_up(sl.needle_blob.size(), 256);
-  const uint64_t up_sel = round_up(sp.sel_words * 4, 256);
-  const uint64_t up_total = up_works + up_needle + up_sel;
   const uint64_t dn_counts = round_up(n * 8, 256);
   const uint64_t dn_bits = round_up(out_words * 4, 256);
   const uint64_t dn_total = dn_counts + 2 * dn_bits;
@@ -254,63 +303,33 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     set_error("eval_predicate: scratch exhausted");
     return LC_ERR_OOM;
   }
-  uint32_t* d_sel = reinterpret_cast<uint32_t*>(d_up + up_works + up_needle);
-  uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_dn);
-  uint32_t* d_mask = reinterpret_cast<uint32_t*>(d_dn + dn_counts);
-  uint32_t* d_valid = reinterpret_cast<uint32_t*>(d_dn + dn_counts + dn_bits);
-  fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_works + up_needle));
-
-  uint32_t max_blob = 0, max_head = 0, max_unique = 1;
-  if (is_int) {
-    IntScanWork* w = reinterpret_cast<IntScanWork*>(h_up);
-    for (uint64_t i = 0; i < n; ++i) {
-      Entry* e = entries[i];
-      int32_t ucmp;
-      uint64_t thr;
-      LC_TRY(plan_int_predicate(e->ih, pred, &ucmp, &thr));
-      w[i].blob = e->d_blob;
-      w[i].sel = sp.bits[i] ? d_sel + sp.word_off[i] : nullptr;
-      w[i].out_values = d_mask + out_word_off[i];
-      w[i].out_validity = d_valid + out_word_off[i];
-      w[i].out_counts = d_counts + 2 * i;
-      w[i].thr = thr;
-      w[i].ucmp = ucmp;
-      w[i].blob_bytes = e->blob_bytes;
-      max_blob = std::max(max_blob, e->blob_bytes);
-    }
-  } else {
-    std::memcpy(h_up + up_works, sl.needle_blob.data(), sl.needle_blob.size());
-    sl.desc.needle = d_up + up_works;
-    StrScanWork* w = reinterpret_cast<StrScanWork*>(h_up);
-    for (uint64_t i = 0; i < n; ++i) {
-      Entry* e = entries[i];
-      StrPlan p;
-      LC_TRY(plan_str_entry(e, pred->op, sl.needle, sl.m, &p));
-      std::memset(&w[i], 0, sizeof(StrScanWork));
-      w[i].blob = e->d_blob;
-      w[i].sel = sp.bits[i] ? d_sel + sp.word_off[i] : nullptr;
-      w[i].out_values = d_mask + out_word_off[i];
-      w[i].out_validity = d_valid + out_word_off[i];
-      w[i].out_counts = d_counts + 2 * i;
-      w[i].key_expect = p.key_expect;
-      w[i].kind = p.kind;
-      w[i].flags = p.flags;
-      w[i].cmp_len = p.cmp_len;
-      w[i].blob_bytes = e->blob_bytes;
-      w[i].head_bytes = e->sh.head_bytes;
-      w[i].meta_bytes = e->sh.meta_bytes;
-      max_head = std::max(max_head, e->sh.head_bytes);
-      max_unique = std::max(max_unique, e->sh.n_unique);
-    }
+  uint64_t* h_sel_off = reinterpret_cast<uint64_t*>(h_up);
+  uint64_t* h_out_off = h_sel_off + n;
+  for (uint64_t i = 0; i < n; ++i) {
+    h_sel_off[i] = sp.bits[i] ? sp.word_off[i] : kNoSel;
+    h_out_off[i] = out_word_off[i];
   }
+  if (!is_int) std::memcpy(h_up + up_offs, sl.needle_blob.data(), sl.needle_blob.size());
+  fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_offs + up_needle));
+  ScanIo io{};
+  io.refs = rl->d_refs;
+  io.sel_base = sp.sel_words ? reinterpret_cast<const uint32_t*>(d_up + up_offs + up_needle) : nullptr;
+  io.sel_off = reinterpret_cast<const uint64_t*>(d_up);
+  io.out_base = d_dn + dn_counts;
+  io.out_off = reinterpret_cast<const uint64_t*>(d_up) + n;
+  io.valid_base = reinterpret_cast<uint32_t*>(d_dn + dn_counts + dn_bits);
+  io.valid_off = io.out_off;
+  io.counts = reinterpret_cast<uint32_t*>(d_dn);
+  io.counts_stride = 2;
   cudaStream_t s = ctx->stream;
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_total;
   if (is_int) {
-    LC_CUDA_OK(launch_int_scan(MODE_PRED, reinterpret_cast<const IntScanWork*>(d_up), static_cast<uint32_t>(n), max_blob, s));
+    LC_CUDA_OK(launch_int_scan(MODE_PRED, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
   } else {
-    LC_CUDA_OK(launch_str_scan(MODE_PRED, reinterpret_cast<const StrScanWork*>(d_up), static_cast<uint32_t>(n), sl.desc,
-                               max_head, max_unique, s));
+    sl.desc.needle = d_up + up_offs;
+    sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
+    LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(n), io, sl.desc, rl->max_head, rl->max_unique, s));
   }
   ctx->kernel_launches++;
   LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
@@ -341,85 +360,47 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
 
 // ---- device pipeline: selection := selection & valid & predicate (no host round trip of bits) ----
 int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred, uint32_t* d_sel_base,
-                 const uint64_t* word_off, bool all_rows, uint32_t* d_counts) {
+                 const uint64_t* d_word_off, bool all_rows, uint32_t* d_counts) {
   if (n == 0) return LC_OK;
-  const int32_t type = entries[0]->liquid_type;
-  for (uint64_t i = 0; i < n; ++i) {
-    if (entries[i]->liquid_type != type) {
-      set_error("scan_filter: entries of different liquid types in one call");
-      return LC_ERR_INVALID;
-    }
-  }
-  const bool is_int = (type == LC_LIQUID_INTEGER);
+  LC_TRY(check_same_type(entries, n, "scan_filter"));
+  const bool is_int = (entries[0]->liquid_type == LC_LIQUID_INTEGER);
   StrLaunch sl;
-  if (!is_int) LC_TRY(prepare_str_pred(pred, &sl));
-  const uint64_t work_sz = is_int ? sizeof(IntScanWork) : sizeof(StrScanWork);
-  const uint64_t up_works = round_up(n * work_sz, 256);
-  const uint64_t up_needle = is_int ? 0 : round_up(sl.needle_blob.size(), 256);
-  const uint64_t up_total = up_works + up_needle;
-  Scratch& sc = ctx->scratch;
-  LC_TRY(sc.reserve(up_total + 1024, up_total + 1024));
-  uint8_t* h_up = sc.host(up_total);
-  uint8_t* d_up = sc.dev(up_total);
-  if (!h_up || !d_up) {
-    set_error("scan_filter: scratch exhausted");
-    return LC_ERR_OOM;
-  }
-  uint32_t max_blob = 0, max_head = 0, max_unique = 1;
-  if (is_int) {
-    IntScanWork* w = reinterpret_cast<IntScanWork*>(h_up);
-    for (uint64_t i = 0; i < n; ++i) {
-      Entry* e = entries[i];
-      int32_t ucmp;
-      uint64_t thr;
-      LC_TRY(plan_int_predicate(e->ih, pred, &ucmp, &thr));
-      w[i].blob = e->d_blob;
-      w[i].sel = all_rows ? nullptr : d_sel_base + word_off[i];
-      w[i].out_values = d_sel_base + word_off[i];
-      w[i].out_validity = nullptr;
-      w[i].out_counts = d_counts + 2 * i;
-      w[i].thr = thr;
-      w[i].ucmp = ucmp;
-      w[i].blob_bytes = e->blob_bytes;
-      max_blob = std::max(max_blob, e->blob_bytes);
-    }
-  } else {
-    std::memcpy(h_up + up_works, sl.needle_blob.data(), sl.needle_blob.size());
-    sl.desc.needle = d_up + up_works;
-    StrScanWork* w = reinterpret_cast<StrScanWork*>(h_up);
-    for (uint64_t i = 0; i < n; ++i) {
-      Entry* e = entries[i];
-      StrPlan p;
-      LC_TRY(plan_str_entry(e, pred->op, sl.needle, sl.m, &p));
-      std::memset(&w[i], 0, sizeof(StrScanWork));
-      w[i].blob = e->d_blob;
-      w[i].sel = all_rows ? nullptr : d_sel_base + word_off[i];
-      w[i].out_values = d_sel_base + word_off[i];
-      w[i].out_validity = nullptr;
-      w[i].out_counts = d_counts + 2 * i;
-      w[i].key_expect = p.key_expect;
-      w[i].kind = p.kind;
-      w[i].flags = p.flags;
-      w[i].cmp_len = p.cmp_len;
-      w[i].blob_bytes = e->blob_bytes;
-      w[i].head_bytes = e->sh.head_bytes;
-      w[i].meta_bytes = e->sh.meta_bytes;
-      max_head = std::max(max_head, e->sh.head_bytes);
-      max_unique = std::max(max_unique, e->sh.n_unique);
-    }
-  }
+  IntPredDesc ip{};
+  if (is_int) LC_TRY(make_int_pred(pred, &ip));
+  else LC_TRY(prepare_str_pred(pred, &sl));
+  const RefList* rl;
+  LC_TRY(get_ref_list(ctx, entries, n, &rl));
+  ScanIo io{};
+  io.refs = rl->d_refs;
+  io.sel_base = all_rows ? nullptr : d_sel_base;
+  io.sel_off = d_word_off;
+  io.out_base = d_sel_base;
+  io.out_off = d_word_off;
+  io.valid_base = nullptr;
+  io.valid_off = nullptr;
+  io.counts = d_counts;
+  io.counts_stride = 2;
   cudaStream_t s = ctx->stream;
-  LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
-  ctx->h2d_bytes += up_total;
   if (is_int) {
-    LC_CUDA_OK(launch_int_scan(MODE_REFINE, reinterpret_cast<const IntScanWork*>(d_up), static_cast<uint32_t>(n), max_blob, s));
+    LC_CUDA_OK(launch_int_scan(MODE_REFINE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
   } else {
-    LC_CUDA_OK(launch_str_scan(MODE_REFINE, reinterpret_cast<const StrScanWork*>(d_up), static_cast<uint32_t>(n), sl.desc,
-                               max_head, max_unique, s));
+    // the needle is the only thing that travels: a few bytes from pageable memory (the runtime stages such
+    // copies before returning) into a small buffer the context keeps for this purpose
+    if (!ctx->d_needle) {
+      if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_needle), 2 * (kMaxNeedle + 16) * 2) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc for the needle buffer failed");
+        return LC_ERR_OOM;
+      }
+    }
+    uint8_t* d_nd = ctx->d_needle;
+    LC_CUDA_OK(cudaMemcpyAsync(d_nd, sl.needle_blob.data(), sl.needle_blob.size(), cudaMemcpyHostToDevice, s));
+    ctx->h2d_bytes += sl.needle_blob.size();
+    sl.desc.needle = d_nd;
+    sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
+    LC_CUDA_OK(launch_str_scan(MODE_REFINE, static_cast<uint32_t>(n), io, sl.desc, rl->max_head, rl->max_unique, s));
   }
   ctx->kernel_launches++;
-  // the pinned staging area is reused by the next call: wait for the upload (cheap, the kernel keeps running)
-  LC_CUDA_OK(cudaStreamSynchronize(s));
   return LC_OK;
 }
 
@@ -472,10 +453,6 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   }
   SelPlan sp;
   plan_selection(entries, n, sel_bits, &sp, dev_sel);
-  auto sel_ptr = [&](uint64_t i, uint32_t* d_upload) -> const uint32_t* {
-    if (dev_sel) return dev_sel->all_rows ? nullptr : dev_sel->d_base + dev_sel->word_off[i];
-    return sp.bits[i] ? d_upload + sp.word_off[i] : nullptr;
-  };
   if (dev_out) {
     set_error("device-resident results are not wired up for this call yet");
     return LC_ERR_INVALID;
@@ -496,15 +473,64 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     set_error("result has more than 2^31 rows");
     return LC_ERR_INVALID;
   }
+  const RefList* rl;
+  LC_TRY(get_ref_list(ctx, entries, n, &rl));
+  // upload: sel_off[n] | out_off[n] (ints: element offsets; strings: row_base) | valid_off[n] | ulen_off[n] |
+  //         byte_base[n] (strings, second upload) | selection words
+  const uint64_t up_offs = round_up(n * 8 * 5, 256);
   const uint64_t up_sel = round_up(sp.sel_words * 4, 256);
+  const uint64_t up_total = up_offs + up_sel;
   const uint64_t dn_counts = round_up(n * 16, 256);
   const uint64_t dn_valid = round_up(vwords * 4, 256);
+  const uint64_t dn_total = dn_counts + dn_valid;
+
+  auto fill_offsets = [&](uint8_t* h_up, const std::vector<uint64_t>* ulen_off) {
+    uint64_t* a = reinterpret_cast<uint64_t*>(h_up);
+    for (uint64_t i = 0; i < n; ++i) {
+      a[i] = dev_sel ? (dev_sel->all_rows ? kNoSel : dev_sel->word_off[i]) : (sp.bits[i] ? sp.word_off[i] : kNoSel);
+      a[n + i] = row_base[i];
+      a[2 * n + i] = vword_off[i];
+      a[3 * n + i] = ulen_off ? (*ulen_off)[i] : 0;
+      a[4 * n + i] = 0;
+    }
+  };
+  auto make_io = [&](uint8_t* d_up, uint8_t* d_dn, void* out_base) {
+    ScanIo io{};
+    io.refs = rl->d_refs;
+    const uint64_t* offs = reinterpret_cast<const uint64_t*>(d_up);
+    if (dev_sel) io.sel_base = dev_sel->all_rows ? nullptr : dev_sel->d_base;
+    else io.sel_base = sp.sel_words ? reinterpret_cast<const uint32_t*>(d_up + up_offs) : nullptr;
+    io.sel_off = offs;
+    io.out_base = out_base;
+    io.out_off = offs + n;
+    io.valid_base = reinterpret_cast<uint32_t*>(d_dn + dn_counts);
+    io.valid_off = offs + 2 * n;
+    io.counts = reinterpret_cast<uint32_t*>(d_dn);
+    io.counts_stride = 4;
+    return io;
+  };
+  auto build_validity = [&](const uint8_t* h_dn, uint64_t nulls, HostBuf* validity) {
+    const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
+    validity->p = nullptr;
+    validity->bytes = 0;
+    if (!nulls) return;
+    validity->bytes = (rows + 7) / 8;
+    validity->p = host_alloc(validity->bytes);
+    std::memset(validity->p, 0, round_up(validity->bytes, 64));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (h_counts[4 * i + 1] == 0) set_bits_ones(validity->p, row_base[i], sp.k[i]);
+      else concat_validity(h_dn + dn_counts + vword_off[i] * 4, sp.k[i], row_base[i], validity->p);
+    }
+  };
 
   if (is_int) {
     const uint32_t tb = proto->ih.tbits / 8;
-    const uint64_t up_works = round_up(n * sizeof(IntScanWork), 256);
-    const uint64_t up_total = up_works + up_sel;
-    const uint64_t dn_total = dn_counts + dn_valid;
+    for (uint64_t i = 1; i < n; ++i) {
+      if (entries[i]->ih.tbits != proto->ih.tbits) {
+        set_error("to_arrow_many: mixed integer widths");
+        return LC_ERR_INVALID;
+      }
+    }
     const uint64_t val_bytes = round_up(rows * tb, 256);
     LC_TRY(sc.reserve(up_total + dn_total + val_bytes + 1024, up_total + dn_total + 1024));
     uint8_t* h_up = sc.host(up_total);
@@ -516,27 +542,13 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       set_error("to_arrow: scratch exhausted");
       return LC_ERR_OOM;
     }
-    uint32_t* d_sel = reinterpret_cast<uint32_t*>(d_up + up_works);
-    uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_dn);
-    uint32_t* d_valid = reinterpret_cast<uint32_t*>(d_dn + dn_counts);
-    fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_works));
-    IntScanWork* w = reinterpret_cast<IntScanWork*>(h_up);
-    uint32_t max_blob = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-      Entry* e = entries[i];
-      w[i].blob = e->d_blob;
-      w[i].sel = sel_ptr(i, d_sel);
-      w[i].out_values = d_vals + row_base[i] * tb;
-      w[i].out_validity = d_valid + vword_off[i];
-      w[i].out_counts = d_counts + 4 * i;
-      w[i].thr = 0;
-      w[i].ucmp = UC_TRUE;
-      w[i].blob_bytes = e->blob_bytes;
-      max_blob = std::max(max_blob, e->blob_bytes);
-    }
+    fill_offsets(h_up, nullptr);
+    if (!dev_sel) fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_offs));
+    const ScanIo io = make_io(d_up, d_dn, d_vals);
+    IntPredDesc ip{};
     LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
     ctx->h2d_bytes += up_total;
-    LC_CUDA_OK(launch_int_scan(MODE_DECODE, reinterpret_cast<const IntScanWork*>(d_up), static_cast<uint32_t>(n), max_blob, s));
+    LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
     ctx->kernel_launches++;
     HostBuf values{host_alloc(rows * tb), rows * tb};
     if (!values.p) {
@@ -549,17 +561,16 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     ctx->d2h_bytes += dn_total + rows * tb;
     const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
     uint64_t nulls = 0;
-    for (uint64_t i = 0; i < n; ++i) nulls += h_counts[4 * i + 1];
-    HostBuf validity{nullptr, 0};
-    if (nulls) {
-      validity.bytes = (rows + 7) / 8;
-      validity.p = host_alloc(validity.bytes);
-      std::memset(validity.p, 0, round_up(validity.bytes, 64));
-      for (uint64_t i = 0; i < n; ++i) {
-        if (h_counts[4 * i + 1] == 0) set_bits_ones(validity.p, row_base[i], sp.k[i]);
-        else concat_validity(h_dn + dn_counts + vword_off[i] * 4, sp.k[i], row_base[i], validity.p);
+    for (uint64_t i = 0; i < n; ++i) {
+      if (h_counts[4 * i] != sp.k[i]) {
+        host_free(values.p);
+        set_error("internal: selected-row count mismatch on entry %llu", (unsigned long long)i);
+        return LC_ERR_INVALID;
       }
+      nulls += h_counts[4 * i + 1];
     }
+    HostBuf validity;
+    build_validity(h_dn, nulls, &validity);
     export_schema(proto->arrow_format, "", out_schema);
     std::vector<HostBuf> bufs;
     bufs.push_back(validity);
@@ -569,102 +580,70 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   }
 
   // ---------------- byte-view: pass 1 (lengths), host prefix sums, pass 2 (decode) ----------------
-  const uint64_t up_works = round_up(n * sizeof(StrGatherWork), 256);
-  const uint64_t up_total = up_works + up_sel;
   uint64_t ulen_words = 0;
   std::vector<uint64_t> ulen_off(n);
   for (uint64_t i = 0; i < n; ++i) {
     ulen_off[i] = ulen_words;
     ulen_words += round_up(entries[i]->sh.n_unique, 4);
   }
-  const uint64_t dv_rowoff = round_up((rows + n) * 4, 256);  // k_i + 1 per entry
-  const uint64_t dv_rowkey = round_up(rows * 4 + 4, 256);
-  const uint64_t dv_ulen = round_up(ulen_words * 4 + 4, 256);
-  const uint64_t dn_total = dn_counts + dn_valid;
-  const uint64_t up2 = round_up(n * sizeof(StrDecodeWork), 256);
-  LC_TRY(sc.reserve(up_total + dn_total + dv_rowoff + dv_rowkey + dv_ulen + up2 + 1024, up_total + dn_total + up2 + 1024));
+  const uint64_t dv_rowoff = round_up((rows + n) * 4 + 16, 256);  // k_i + 1 per entry
+  const uint64_t dv_rowkey = round_up(rows * 4 + 16, 256);
+  const uint64_t dv_ulen = round_up(ulen_words * 4 + 16, 256);
+  LC_TRY(sc.reserve(up_total + dn_total + dv_rowoff + dv_rowkey + dv_ulen + 1024, up_total + dn_total + 1024));
   uint8_t* h_up = sc.host(up_total);
   uint8_t* h_dn = sc.host(dn_total);
-  uint8_t* h_up2 = sc.host(up2);
   uint8_t* d_up = sc.dev(up_total);
   uint8_t* d_dn = sc.dev(dn_total);
   uint8_t* d_rowoff = sc.dev(dv_rowoff);
   uint8_t* d_rowkey = sc.dev(dv_rowkey);
   uint8_t* d_ulen = sc.dev(dv_ulen);
-  uint8_t* d_up2 = sc.dev(up2);
-  if (!h_up || !h_dn || !h_up2 || !d_up || !d_dn || !d_rowoff || !d_rowkey || !d_ulen || !d_up2) {
+  if (!h_up || !h_dn || !d_up || !d_dn || !d_rowoff || !d_rowkey || !d_ulen) {
     set_error("to_arrow: scratch exhausted");
     return LC_ERR_OOM;
   }
-  uint32_t* d_sel = reinterpret_cast<uint32_t*>(d_up + up_works);
-  uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_dn);
-  uint32_t* d_valid = reinterpret_cast<uint32_t*>(d_dn + dn_counts);
-  fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_works));
-  StrGatherWork* w = reinterpret_cast<StrGatherWork*>(h_up);
-  uint32_t max_head = 0;
-  for (uint64_t i = 0; i < n; ++i) {
-    Entry* e = entries[i];
-    std::memset(&w[i], 0, sizeof(StrGatherWork));
-    w[i].blob = e->d_blob;
-    w[i].sel = sel_ptr(i, d_sel);
-    w[i].row_off = reinterpret_cast<uint32_t*>(d_rowoff) + row_base[i] + i;
-    w[i].row_key = reinterpret_cast<uint32_t*>(d_rowkey) + row_base[i];
-    w[i].ulen = reinterpret_cast<uint32_t*>(d_ulen) + ulen_off[i];
-    w[i].out_validity = d_valid + vword_off[i];
-    w[i].out_counts = d_counts + 4 * i;
-    w[i].blob_bytes = e->blob_bytes;
-    w[i].head_bytes = e->sh.head_bytes;
-    // all decoded lengths up front when most of the dictionary will be touched anyway
-    w[i].flags = (static_cast<uint64_t>(sp.k[i]) * 4 >= e->sh.n_unique) ? kGatherPrecompLens : 0u;
-    max_head = std::max(max_head, e->sh.head_bytes);
-  }
+  fill_offsets(h_up, &ulen_off);
+  if (!dev_sel) fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_offs));
+  StrGatherIo g{};
+  g.io = make_io(d_up, d_dn, nullptr);
+  g.row_off_base = reinterpret_cast<uint32_t*>(d_rowoff);
+  g.row_key_base = reinterpret_cast<uint32_t*>(d_rowkey);
+  g.ulen_base = reinterpret_cast<uint32_t*>(d_ulen);
+  g.row_base = reinterpret_cast<const uint64_t*>(d_up) + n;
+  g.ulen_off = reinterpret_cast<const uint64_t*>(d_up) + 3 * n;
+  g.byte_base = reinterpret_cast<const uint64_t*>(d_up) + 4 * n;
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_total;
-  LC_CUDA_OK(launch_str_lengths(reinterpret_cast<const StrGatherWork*>(d_up), static_cast<uint32_t>(n), max_head, s));
+  LC_CUDA_OK(launch_str_lengths(static_cast<uint32_t>(n), g, rl->max_head, s));
   ctx->kernel_launches++;
   LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
   LC_CUDA_OK(cudaStreamSynchronize(s));
   ctx->d2h_bytes += dn_total;
   const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
   uint64_t nulls = 0, total_bytes = 0;
-  std::vector<uint64_t> byte_base(n);
+  uint64_t* h_byte_base = reinterpret_cast<uint64_t*>(h_up) + 4 * n;
   for (uint64_t i = 0; i < n; ++i) {
     if (h_counts[4 * i] != sp.k[i]) {
       set_error("internal: selected-row count mismatch on entry %llu", (unsigned long long)i);
       return LC_ERR_INVALID;
     }
     nulls += h_counts[4 * i + 1];
-    byte_base[i] = total_bytes;
+    h_byte_base[i] = total_bytes;
     total_bytes += h_counts[4 * i + 2];
   }
   if (total_bytes > 0x7fffffffull) {
     set_error("decoded values exceed 2 GiB (int32 offsets); split the call");
     return LC_ERR_INVALID;
   }
-  // device result buffers
   const uint64_t off_bytes = (rows + 1) * 4;
-  uint8_t* d_off = nullptr;
-  uint8_t* d_bytes = nullptr;
-  // scratch is already carved; results go to a separate temporary allocation
-  const uint64_t res_bytes = round_up(off_bytes, 256) + round_up(total_bytes + 8, 256);
+  const uint64_t res_bytes = round_up(off_bytes, 256) + round_up(total_bytes + 16, 256);
   uint8_t* d_res = nullptr;
   if (cudaMallocAsync(reinterpret_cast<void**>(&d_res), res_bytes, s) != cudaSuccess) {
     cudaGetLastError();
     set_error("cudaMallocAsync of %llu result bytes failed", (unsigned long long)res_bytes);
     return LC_ERR_OOM;
   }
-  d_off = d_res;
-  d_bytes = d_res + round_up(off_bytes, 256);
-  StrDecodeWork* w2 = reinterpret_cast<StrDecodeWork*>(h_up2);
-  for (uint64_t i = 0; i < n; ++i) {
-    w2[i].blob = entries[i]->d_blob;
-    w2[i].row_off = reinterpret_cast<uint32_t*>(d_rowoff) + row_base[i] + i;
-    w2[i].row_key = reinterpret_cast<uint32_t*>(d_rowkey) + row_base[i];
-    w2[i].out_offsets = reinterpret_cast<int32_t*>(d_off) + row_base[i];
-    w2[i].out_bytes = d_bytes;
-    w2[i].byte_base = static_cast<uint32_t>(byte_base[i]);
-    w2[i].k = sp.k[i];
-  }
+  g.out_offsets = reinterpret_cast<int32_t*>(d_res);
+  g.out_bytes = d_res + round_up(off_bytes, 256);
   HostBuf offsets{host_alloc(off_bytes), off_bytes};
   HostBuf data{host_alloc(total_bytes ? total_bytes : 1), total_bytes};
   if (!offsets.p || !data.p) {
@@ -672,10 +651,11 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     set_error("host allocation failed");
     return LC_ERR_OOM;
   }
-  cudaError_t ce = cudaMemcpyAsync(d_up2, h_up2, up2, cudaMemcpyHostToDevice, s);
-  if (ce == cudaSuccess) ce = launch_str_decode(reinterpret_cast<const StrDecodeWork*>(d_up2), static_cast<uint32_t>(n), s);
-  if (ce == cudaSuccess && rows) ce = cudaMemcpyAsync(offsets.p, d_off, rows * 4, cudaMemcpyDeviceToHost, s);
-  if (ce == cudaSuccess && total_bytes) ce = cudaMemcpyAsync(data.p, d_bytes, total_bytes, cudaMemcpyDeviceToHost, s);
+  // second (small) upload: byte_base[n]
+  cudaError_t ce = cudaMemcpyAsync(d_up + 4 * n * 8, h_byte_base, n * 8, cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = launch_str_decode(static_cast<uint32_t>(n), g, s);
+  if (ce == cudaSuccess && rows) ce = cudaMemcpyAsync(offsets.p, g.out_offsets, rows * 4, cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess && total_bytes) ce = cudaMemcpyAsync(data.p, g.out_bytes, total_bytes, cudaMemcpyDeviceToHost, s);
   cudaFreeAsync(d_res, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess) {
@@ -685,19 +665,11 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     return LC_ERR_CUDA;
   }
   ctx->kernel_launches++;
-  ctx->h2d_bytes += up2;
+  ctx->h2d_bytes += n * 8;
   ctx->d2h_bytes += rows * 4 + total_bytes;
   reinterpret_cast<int32_t*>(offsets.p)[rows] = static_cast<int32_t>(total_bytes);
-  HostBuf validity{nullptr, 0};
-  if (nulls) {
-    validity.bytes = (rows + 7) / 8;
-    validity.p = host_alloc(validity.bytes);
-    std::memset(validity.p, 0, round_up(validity.bytes, 64));
-    for (uint64_t i = 0; i < n; ++i) {
-      if (h_counts[4 * i + 1] == 0) set_bits_ones(validity.p, row_base[i], sp.k[i]);
-      else concat_validity(h_dn + dn_counts + vword_off[i] * 4, sp.k[i], row_base[i], validity.p);
-    }
-  }
+  HostBuf validity;
+  build_validity(h_dn, nulls, &validity);
   return finish_bytes_array(proto, rows, nulls, validity, offsets, data, out_schema, out_array);
 }
 

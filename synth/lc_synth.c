@@ -90,7 +90,7 @@ static uint32_t make_url(uint64_t* rng, char* dst, uint32_t cap, int with_google
 static double* g_zipf = NULL;
 static uint32_t g_zipf_n = 0;
 static void zipf_init(uint32_t pool) {
-  if (g_zipf && g_zipf_n == pool) return;
+  if (g_zipf && g_zipf_n == pool) return;  /* call lcs_init() once before generating from several threads */
   free(g_zipf);
   g_zipf = (double*)malloc(sizeof(double) * pool);
   double acc = 0;
@@ -110,6 +110,8 @@ static uint32_t zipf_draw(uint64_t* rng) {
   }
   return lo;
 }
+
+EXPORT void lcs_init(uint32_t pool) { zipf_init(pool); }
 
 /* URL column entry. offsets: rows+1 int32; data: caller buffer of data_cap bytes (rows*512 is always enough).
  * Returns bytes written. pool = size of the per-entry unique pool (8000 gives ~1 900 distinct per 8192 rows). */

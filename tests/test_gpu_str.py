@@ -77,10 +77,11 @@ def build(vals, mask, typ):
     base = typ.value_type if pa.types.is_dictionary(typ) else typ
     is_text = pa.types.is_string(base) or pa.types.is_string_view(base)
     data = [None if (mask is not None and mask[i]) else (v if is_text else v.encode()) for i, v in enumerate(vals)]
-    plain = pa.array(data, type=pa.string() if is_text else pa.binary())
     if pa.types.is_dictionary(typ):
-        return plain.dictionary_encode().cast(typ)
-    return plain.cast(typ)
+        return pa.array(data, type=pa.string() if is_text else pa.binary()).dictionary_encode().cast(typ)
+    # built directly in the target type: pyarrow 24's cast() to a view type can leave a null variadic buffer
+    # behind, which its own C-data exporter then dereferences (segfault in arrow::ExportArray)
+    return pa.array(data, type=typ)
 
 
 @pytest.mark.parametrize("typ", STRING_TYPES, ids=str)
