@@ -1,0 +1,107 @@
+"""Multi-GPU plumbing: entries shard by EntryID, one process per GPU, and the only exchange on the path is the
+gather of the final filtered Arrow batches to rank 0.
+
+torch.distributed is used for what it is good at — rendezvous and NCCL point-to-point over NVLink/NVSwitch (or
+gloo on CPU in tests); no collective touches the scan itself, which is embarrassingly parallel over entries.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import pyarrow as pa
+
+
+def shard_of(entry_id: int, world: int) -> int:
+    """Owner rank of an entry. All columns of one (file, row group, batch) land on the same GPU so the selection
+    mask never leaves the device between eval_predicate and get (column id, bits 16..31, is ignored)."""
+    file_rg = entry_id >> 32
+    batch = entry_id & 0xFFFF
+    x = (file_rg * 0x9E3779B97F4A7C15 + batch * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 29
+    return int(x % world)
+
+
+def partition_entries(entry_ids: Sequence[int], world: int) -> list[list[int]]:
+    parts: list[list[int]] = [[] for _ in range(world)]
+    for e in entry_ids:
+        parts[shard_of(int(e), world)].append(int(e))
+    return parts
+
+
+def _buffers_of(arr: pa.Array):
+    """(validity bytes | None, offsets int32 | None, data bytes) of a Utf8/Binary or primitive array, offset 0."""
+    if isinstance(arr, pa.ChunkedArray):
+        arr = arr.combine_chunks()
+    n = len(arr)
+    valid = None
+    if arr.null_count:
+        valid = np.packbits(np.asarray(arr.is_valid().to_numpy(zero_copy_only=False), dtype=bool), bitorder="little")
+    if pa.types.is_string(arr.type) or pa.types.is_binary(arr.type):
+        bufs = arr.buffers()
+        off = np.frombuffer(bufs[1], dtype=np.int32, count=n + 1 + arr.offset)[arr.offset:].astype(np.int64)
+        data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None else np.zeros(0, np.uint8)
+        data = data[int(off[0]):int(off[-1])] if n else np.zeros(0, np.uint8)
+        return valid, (off - off[0]).astype(np.int32), np.ascontiguousarray(data)
+    width = arr.type.bit_width // 8
+    bufs = arr.buffers()
+    data = np.frombuffer(bufs[1], dtype=np.uint8)[arr.offset * width:(arr.offset + n) * width] if n else np.zeros(0, np.uint8)
+    return valid, None, np.ascontiguousarray(data)
+
+
+def gather_arrow_to_rank0(arr: pa.Array, rank: int, world: int, device=None) -> Optional[pa.Array]:
+    """Variable-length gather of per-rank result arrays to rank 0: one small all_gather of sizes, then grouped
+    point-to-point transfers (NCCL has no gatherv). Returns the concatenation (rank order) on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return arr
+    backend = dist.get_backend()
+    dev = device if (backend == "nccl") else torch.device("cpu")
+    valid, off, data = _buffers_of(arr)
+    n = len(arr)
+    sizes = torch.tensor([n, 0 if valid is None else len(valid), 0 if off is None else len(off), len(data)], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [t.cpu().tolist() for t in all_sizes]
+
+    def to_t(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).copy()).to(dev)
+
+    if rank != 0:
+        ops = []
+        for a in (valid, off, data):
+            if a is not None and len(a):
+                ops.append(dist.P2POp(dist.isend, to_t(a), 0))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return None
+    parts = [arr]
+    ops, recv = [], []
+    for r in range(1, world):
+        nr, nv, no, nd = all_sizes[r]
+        bufs = []
+        for nbytes in (nv, no * 4, nd):
+            if nbytes:
+                t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                ops.append(dist.P2POp(dist.irecv, t, r))
+                bufs.append(t)
+            else:
+                bufs.append(None)
+        recv.append((nr, bufs))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    for nr, (bv, bo, bd) in recv:
+        vb = pa.py_buffer(bv.cpu().numpy().tobytes()) if bv is not None else None
+        nulls = -1 if bv is not None else 0
+        if pa.types.is_string(arr.type) or pa.types.is_binary(arr.type):
+            ob = pa.py_buffer(bo.cpu().numpy().tobytes()) if bo is not None else pa.py_buffer(np.zeros(1, np.int32).tobytes())
+            db = pa.py_buffer(bd.cpu().numpy().tobytes()) if bd is not None else pa.py_buffer(b"")
+            parts.append(pa.Array.from_buffers(arr.type, nr, [vb, ob, db], null_count=nulls))
+        else:
+            db = pa.py_buffer(bd.cpu().numpy().tobytes()) if bd is not None else pa.py_buffer(b"")
+            parts.append(pa.Array.from_buffers(arr.type, nr, [vb, db], null_count=nulls))
+    return pa.concat_arrays(parts)

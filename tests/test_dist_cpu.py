@@ -1,0 +1,76 @@
+"""CPU (gloo, world_size 2) tests of the multi-GPU host logic: EntryID sharding and the gather of filtered
+Arrow batches to rank 0. The scan itself needs no collective."""
+import os
+import socket
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from liquid_cache_b200.dist import gather_arrow_to_rank0
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        strs = pa.array([None if rng.random() < 0.2 else f"http://r{rank}/{i}" * int(rng.integers(0, 4)) for i in range(50 + 30 * rank)])
+        ints = pa.array(rng.integers(-5, 5, size=10 * (rank + 1)), pa.int64())
+        empty = pa.array([], pa.string()) if rank == 1 else pa.array(["only-rank0"])
+        out = []
+        for a in (strs, ints, empty):
+            g = gather_arrow_to_rank0(a, rank, world)
+            out.append(None if g is None else g.to_pylist())
+        q.put((rank, [strs.to_pylist(), ints.to_pylist(), empty.to_pylist()], out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_to_rank0_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        rank, local, out = q.get(timeout=120)
+        res[rank] = (local, out)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k in range(3):
+        assert res[0][1][k] == res[0][0][k] + res[1][0][k]
+        assert res[1][1][k] is None
+
+
+def test_sharding_keeps_all_columns_of_a_batch_together():
+    from liquid_cache_b200 import parquet_array_id
+    from liquid_cache_b200.dist import partition_entries, shard_of
+
+    ids = [parquet_array_id(f, rg, col, b) for f in range(2) for rg in range(5) for col in range(4) for b in range(32)]
+    for world in (1, 2, 4, 8):
+        parts = partition_entries(ids, world)
+        assert sum(len(p) for p in parts) == len(ids)
+        for f in range(2):
+            for rg in range(5):
+                for b in range(32):
+                    owners = {shard_of(parquet_array_id(f, rg, col, b), world) for col in range(4)}
+                    assert len(owners) == 1
+        if world > 1:
+            assert min(len(p) for p in parts) > 0.5 * len(ids) / world

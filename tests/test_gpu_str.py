@@ -122,7 +122,7 @@ def test_predicates_match_oracle_and_arrow(cache, with_fp, n, n_unique, prefix):
                 got = liquid.try_eval_predicate(_bin(op, needle), sel)
                 assert_masks_equal(got, oracle.try_eval_predicate(op, needle, sel), f"{op} {needle!r} vs oracle")
                 assert_masks_equal(got, fn(filt, pa.scalar(needle)), f"{op} {needle!r} vs arrow")
-        for inner in ("google", "tours", "%D0", "q", "zzzz", "://", vals[2][1:6] or "x", "2013"):
+        for inner in ("google", "tours", "D0", "q", "zzzz", "://", (vals[2][1:6] or "x").replace("%", "5").replace("_", "-"), "2013"):
             pat = f"%{inner}%"
             for negated in (False, True):
                 got = liquid.try_eval_predicate(_like(pat, negated), sel)
