@@ -65,8 +65,10 @@ struct alignas(16) StrHeader {   // 128 bytes
   int32_t slope;        // CompactOffsets header (fsst_buffer.rs:267-296)
   int32_t intercept;
   uint32_t shared_prefix_len;
-  // sections, in blob order: header | shared prefix | prefix keys | fingerprints | residuals |
-  //                          validity | keys | compressed values   (each 16-byte aligned)
+  // sections, in blob order: header | shared prefix | fingerprints | residuals | prefix keys |
+  //                          validity | keys | compressed values   (each 16-byte aligned).
+  // A LIKE scan stages [header .. residuals] + [validity, keys]; every other predicate stages
+  // [header, shared prefix] + [prefix keys] + [validity, keys].
   uint32_t validity_off;      // n bits (0 if !has_nulls)
   uint32_t keys_off;          // n x u16 (null rows hold key 0)
   uint32_t prefix_keys_off;   // U x 8 B {prefix7[7], len}
@@ -80,9 +82,10 @@ struct alignas(16) StrHeader {   // 128 bytes
   uint32_t max_value_len;     // longest decoded unique value (sizing hint)
   uint64_t uncompressed_bytes;// sum of decoded unique value lengths (RawFsstBuffer.uncompressed_bytes)
   uint64_t table_ptr;         // device pointer to this column-chunk's FsstTable
-  uint32_t head_bytes;        // bytes from blob start up to fsst_off (what predicate kernels stage)
-  uint32_t meta_bytes;        // bytes from blob start up to the validity/keys sections (dictionary metadata)
-  uint32_t pad[8];
+  uint32_t head_bytes;        // bytes from blob start up to fsst_off (everything but the compressed values)
+  uint32_t sp_end;            // end of the shared prefix section (= fp_off if has_fp else resid_off)
+  uint32_t rows_off;          // start of the per-row sections (validity if has_nulls, else keys)
+  uint32_t pad[7];
 };
 static_assert(sizeof(StrHeader) == 128, "StrHeader must be 128 bytes");
 

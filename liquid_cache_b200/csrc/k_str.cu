@@ -260,52 +260,93 @@ __device__ __forceinline__ void plan_str_pred(const StrView& v, const StrPredDes
   *out = p;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256)
-k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
-  uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
-  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
-  StrPlan* s_plan = reinterpret_cast<StrPlan*>(s_len + 256);
-  uint8_t* s_nd = reinterpret_cast<uint8_t*>(s_plan + 1);
-  const uint32_t m = pred.needle_len;
-  const uint32_t nd_bytes = (m + 15u) & ~15u;
-  uint16_t* s_fail = reinterpret_cast<uint16_t*>(s_nd + nd_bytes);
-  uint32_t* s_dict = reinterpret_cast<uint32_t*>(s_nd + nd_bytes + ((2u * m + 15u) & ~15u));
-  uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_dict + dict_words);
-  uint8_t* stage = reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u);
-  stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage) + 127u) & ~static_cast<uintptr_t>(127u));
+// ---- substring match directly on FSST codes --------------------------------------------------------
+// Shift-And over the needle (m <= 32): state bit j <=> needle[0..j] matches the text ending here; one text
+// byte b maps S -> ((S << 1) | 1) & M[b]. That map is linear over OR, so the effect of a whole symbol
+// (1..8 bytes) collapses into three masks computed once per CTA from the column chunk's symbol table:
+//     S' = ((S << L) & A) | B        and   "the needle completed inside this symbol"  <=>  (S & H) | hit0
+// One FSST code then costs one 16-byte shared-memory load and ~6 ALU ops, instead of ~8 bytes x (load,
+// compare, branch). Values are never decompressed: this IS the predicate evaluated on the encoded bytes.
+struct SymStep {
+  uint32_t A, B, H;
+  uint32_t L_hit;  // bits 0..7 symbol length, bit 8 = hit0
+};
 
-  const EntryRef ref = io.refs[blockIdx.x];
-  const EntryIo w = resolve_io(io, blockIdx.x);
-  const bool staged = ref.head_bytes <= stage_cap;
-  scan_smem_init(sm);
-  if (threadIdx.x == 0 && staged) {
-    mbar_init(&sm->bar[0], 1);
-    mbar_init(&sm->bar[1], 1);
-    fence_mbar_init();
-    mbar_expect_tx(&sm->bar[0], ref.meta_bytes);
-    tma_bulk_g2s(stage, ref.blob, ref.meta_bytes, &sm->bar[0]);  // header + dictionary metadata
-    const uint32_t rest = ref.head_bytes - ref.meta_bytes;
-    if (rest) {
-      mbar_expect_tx(&sm->bar[1], rest);
-      tma_bulk_g2s(stage + ref.meta_bytes, ref.blob + ref.meta_bytes, rest, &sm->bar[1]);  // validity + keys
+__device__ __forceinline__ void build_sym_steps(const uint64_t* s_sym, const uint8_t* s_len, const uint8_t* nd,
+                                                uint32_t m, uint32_t* s_M, SymStep* s_step) {
+  // M[b]: bit j set iff needle[j] == b
+  for (uint32_t b = threadIdx.x; b < 256u; b += blockDim.x) {
+    uint32_t bits = 0;
+    for (uint32_t j = 0; j < m; ++j) bits |= (nd[j] == b ? 1u : 0u) << j;
+    s_M[b] = bits;
+  }
+  __syncthreads();
+  const uint32_t acc = 1u << (m - 1u);
+  for (uint32_t c = threadIdx.x; c < 256u; c += blockDim.x) {
+    uint64_t sym = s_sym[c];
+    const uint32_t L = s_len[c];
+    uint32_t A = 0xffffffffu, B = 0, H = 0, hit0 = 0;
+    for (uint32_t k = 0; k < L; ++k) {
+      const uint32_t Mb = s_M[static_cast<uint32_t>(sym & 0xffu)];
+      sym >>= 8;
+      A = (A << 1) & Mb;
+      B = ((B << 1) | 1u) & Mb;
+      H |= (A & acc) >> (k + 1u);
+      hit0 |= (B & acc) ? 1u : 0u;
+    }
+    SymStep st;
+    st.A = A;
+    st.B = B;
+    st.H = H;
+    st.L_hit = L | (hit0 << 8);
+    s_step[c] = st;
+  }
+}
+
+// Lanes pull candidates from a shared queue and each walks its value's codes; a lane that finishes (or finds
+// the needle) immediately takes the next candidate, so warps stay converged however uneven the value lengths are.
+template <typename View>
+__device__ __forceinline__ void like_candidates(const View& v, const uint16_t* s_cand, uint32_t ncand,
+                                                uint32_t* queue, const uint32_t* s_M, const SymStep* s_step,
+                                                uint32_t m, uint32_t* s_dict) {
+  const uint32_t acc = 1u << (m - 1u);
+  uint32_t S = 0, hit = 0, cur = 0xffffffffu;
+  CodeStream cs;
+  cs.p = cs.end = 0;
+  cs.cur = 0;
+  cs.base = v.fsst;
+  while (true) {
+    if (cs.p >= cs.end || hit) {
+      if (hit) atomicOr(&s_dict[cur >> 5], 1u << (cur & 31u));
+      const uint32_t idx = atomicAdd(queue, 1u);
+      if (idx >= ncand) break;
+      cur = s_cand[idx];
+      cs.init(v.fsst, dict_offset(v, cur), dict_offset(v, cur + 1u));
+      S = 0;
+      hit = 0;
+      continue;
+    }
+    const uint32_t code = cs.next();
+    if (code != 255u) {
+      const SymStep st = s_step[code];
+      hit = (S & st.H) | (st.L_hit >> 8);
+      S = ((S << (st.L_hit & 0xffu)) & st.A) | st.B;
+    } else if (cs.p < cs.end) {
+      S = ((S << 1) | 1u) & s_M[cs.next()];
+      hit = S & acc;
     }
   }
-  // needle + KMP links (shared by all entries of the launch)
-  for (uint32_t i = threadIdx.x; i < m; i += 256u) {
-    s_nd[i] = pred.needle[i];
-    s_fail[i] = reinterpret_cast<const uint16_t*>(pred.needle + ((m + 3u) & ~3u))[i];
-  }
-  for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = 0;
-  __syncthreads();
-  const uint8_t* head = ref.blob;
-  if (staged) {
-    mbar_wait(&sm->bar[0], 0);
-    head = stage;
-  }
-  const StrView v = make_view(head, ref.blob);
+}
+
+// The body of the predicate kernel, instantiated per address space of the staged sections so that the
+// compiler emits LDS / LDG instead of generic loads.
+template <int MODE>
+__device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w, const StrPredDesc& pred,
+                                              ScanSmem* sm, uint64_t* s_sym, uint8_t* s_len, StrPlan* s_plan,
+                                              const uint8_t* s_nd, const uint16_t* s_fail, uint32_t* s_dict,
+                                              uint16_t* s_cand, uint32_t* s_M, SymStep* s_step, uint32_t dict_words,
+                                              uint64_t* bar_rows) {
+  const uint32_t m = pred.needle_len;
   if (threadIdx.x == 0) plan_str_pred(v, pred, s_nd, s_plan);
   __syncthreads();
   const StrPlan plan = *s_plan;
@@ -314,9 +355,11 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
   const int32_t kind = plan.kind;
   const bool neg = (plan.flags & 2u) != 0;
   const bool needs_table = (kind == SP_EQ_LONG || kind == SP_ORD || kind == SP_LIKE);
+  const bool fast_like = (kind == SP_LIKE) && m <= 32u;
   if (needs_table) {
     load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
     __syncthreads();
+    if (fast_like) build_sym_steps(s_sym, s_len, s_nd, m, s_M, s_step);
   }
 
   // ---------------- phase 1: one decision per dictionary entry ----------------
@@ -328,24 +371,26 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
     for (uint32_t i0 = (threadIdx.x & ~31u); i0 < U; i0 += 256u) {
       const uint32_t i = i0 + lane;
       const bool act = i < U;
-      const uint64_t key = act ? v.pk[i] : 0ull;
       bool res = false, cand = false;
-      if (kind == SP_EQ_SHORT) {
-        res = (key == plan.key_expect) != neg;
-      } else if (kind == SP_EQ_LONG) {
-        cand = (key == plan.key_expect);
-        res = neg;
-      } else if (kind == SP_ORD) {
-        const uint64_t mask = ~0ull << (8u * (8u - plan.cmp_len));
-        const uint64_t a = bswap64(key) & mask;
-        if (a < plan.key_expect) res = (op == LC_OP_LT || op == LC_OP_LE);
-        else if (a > plan.key_expect) res = (op == LC_OP_GT || op == LC_OP_GE);
-        else cand = true;
-      } else if (kind == SP_ORD_EMPTY) {
-        const bool empty = (key >> 56) == 0;
-        res = (op == LC_OP_LT) ? false : (op == LC_OP_LE) ? empty : (op == LC_OP_GT) ? !empty : true;
-      } else {  // SP_LIKE
+      if (kind == SP_LIKE) {
         cand = v.fp ? ((v.fp[act ? i : 0] & pred.needle_fp) == pred.needle_fp) : true;
+      } else {
+        const uint64_t key = act ? v.pk[i] : 0ull;
+        if (kind == SP_EQ_SHORT) {
+          res = (key == plan.key_expect) != neg;
+        } else if (kind == SP_EQ_LONG) {
+          cand = (key == plan.key_expect);
+          res = neg;
+        } else if (kind == SP_ORD) {
+          const uint64_t mask = ~0ull << (8u * (8u - plan.cmp_len));
+          const uint64_t a = bswap64(key) & mask;
+          if (a < plan.key_expect) res = (op == LC_OP_LT || op == LC_OP_LE);
+          else if (a > plan.key_expect) res = (op == LC_OP_GT || op == LC_OP_GE);
+          else cand = true;
+        } else {  // SP_ORD_EMPTY
+          const bool empty = (key >> 56) == 0;
+          res = (op == LC_OP_LT) ? false : (op == LC_OP_LE) ? empty : (op == LC_OP_GT) ? !empty : true;
+        }
       }
       res = res && act;
       cand = cand && act;
@@ -372,20 +417,24 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
       }
     }
     // candidates: walk the FSST codes of the value
-    for (uint32_t c = threadIdx.x; c < ncand; c += 256u) {
-      const uint32_t i = s_cand[c];
-      bool res;
-      if (kind == SP_LIKE) {
-        res = contains_needle(v, i, s_sym, s_len, s_nd, s_fail, m);
-      } else {
-        const int ord = full_compare(v, i, s_sym, s_len, s_nd, m);
-        if (kind == SP_EQ_LONG) res = (ord == 0) != neg;
-        else res = (op == LC_OP_LT) ? ord < 0 : (op == LC_OP_LE) ? ord <= 0 : (op == LC_OP_GT) ? ord > 0 : ord >= 0;
-      }
-      if (kind == SP_EQ_LONG && neg) {
-        if (!res) atomicAnd(&s_dict[i >> 5], ~(1u << (i & 31u)));
-      } else if (res) {
-        atomicOr(&s_dict[i >> 5], 1u << (i & 31u));
+    if (fast_like) {
+      like_candidates(v, s_cand, ncand, &sm->misc[1], s_M, s_step, m, s_dict);
+    } else {
+      for (uint32_t c = threadIdx.x; c < ncand; c += 256u) {
+        const uint32_t i = s_cand[c];
+        bool res;
+        if (kind == SP_LIKE) {
+          res = contains_needle(v, i, s_sym, s_len, s_nd, s_fail, m);
+        } else {
+          const int ord = full_compare(v, i, s_sym, s_len, s_nd, m);
+          if (kind == SP_EQ_LONG) res = (ord == 0) != neg;
+          else res = (op == LC_OP_LT) ? ord < 0 : (op == LC_OP_LE) ? ord <= 0 : (op == LC_OP_GT) ? ord > 0 : ord >= 0;
+        }
+        if (kind == SP_EQ_LONG && neg) {
+          if (!res) atomicAnd(&s_dict[i >> 5], ~(1u << (i & 31u)));
+        } else if (res) {
+          atomicOr(&s_dict[i >> 5], 1u << (i & 31u));
+        }
       }
     }
     if (kind == SP_LIKE && neg) {
@@ -399,7 +448,7 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
     }
   }
   __syncthreads();
-  if (staged && ref.head_bytes > ref.meta_bytes) mbar_wait(&sm->bar[1], 0);
+  if (bar_rows) mbar_wait(bar_rows, 0);
 
   // ---------------- phase 2: dictionary results -> rows ----------------
   const uint16_t* keys = v.keys;
@@ -412,11 +461,85 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
                         w.counts, sm, cmp, emit);
 }
 
+// Shared-memory map of the predicate kernel (after the fixed ScanSmem area):
+//   symbols 2048 | lengths 256 | plan 32 | M[256] 1024 | SymStep[256] 4096 | needle | KMP links | dictionary
+//   result bits | candidate list | staged entry head
+constexpr uint32_t kStrScanTables = 2048u + 256u + 32u + 1024u + 4096u;
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
+  uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
+  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
+  StrPlan* s_plan = reinterpret_cast<StrPlan*>(s_len + 256);
+  uint32_t* s_M = reinterpret_cast<uint32_t*>(s_len + 256 + 32);
+  SymStep* s_step = reinterpret_cast<SymStep*>(s_M + 256);
+  uint8_t* s_nd = reinterpret_cast<uint8_t*>(s_step + 256);
+  const uint32_t m = pred.needle_len;
+  const uint32_t nd_bytes = (m + 15u) & ~15u;
+  uint16_t* s_fail = reinterpret_cast<uint16_t*>(s_nd + nd_bytes);
+  uint32_t* s_dict = reinterpret_cast<uint32_t*>(s_nd + nd_bytes + ((2u * m + 15u) & ~15u));
+  uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_dict + dict_words);
+  uint8_t* stage = reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u);
+  stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage) + 127u) & ~static_cast<uintptr_t>(127u));
+
+  const EntryRef ref = io.refs[blockIdx.x];
+  const EntryIo w = resolve_io(io, blockIdx.x);
+  const bool staged = ref.head_bytes <= stage_cap;
+  const bool is_like = (pred.op == LC_OP_LIKE || pred.op == LC_OP_NOT_LIKE);
+  scan_smem_init(sm);
+  if (threadIdx.x == 0 && staged) {
+    mbar_init(&sm->bar[0], 1);
+    mbar_init(&sm->bar[1], 1);
+    fence_mbar_init();
+    // (A) what phase 1 needs: LIKE -> header, shared prefix, fingerprints, offset residuals (no prefix keys);
+    //     everything else -> header, shared prefix and the prefix keys (residuals stay in global memory,
+    //     only the few prefix ties ever look at them)
+    if (is_like) {
+      mbar_expect_tx(&sm->bar[0], ref.pk_off);
+      tma_bulk_g2s(stage, ref.blob, ref.pk_off, &sm->bar[0]);
+    } else {
+      const uint32_t pk_bytes = ref.rows_off - ref.pk_off;
+      mbar_expect_tx(&sm->bar[0], ref.sp_end + pk_bytes);
+      tma_bulk_g2s(stage, ref.blob, ref.sp_end, &sm->bar[0]);
+      if (pk_bytes) tma_bulk_g2s(stage + ref.pk_off, ref.blob + ref.pk_off, pk_bytes, &sm->bar[0]);
+    }
+    // (B) what phase 2 needs, in flight while phase 1 computes: validity + keys
+    const uint32_t rest = ref.head_bytes - ref.rows_off;
+    mbar_expect_tx(&sm->bar[1], rest);
+    tma_bulk_g2s(stage + ref.rows_off, ref.blob + ref.rows_off, rest, &sm->bar[1]);
+  }
+  // needle + KMP links (shared by all entries of the launch)
+  for (uint32_t i = threadIdx.x; i < m; i += 256u) {
+    s_nd[i] = pred.needle[i];
+    s_fail[i] = reinterpret_cast<const uint16_t*>(pred.needle + ((m + 3u) & ~3u))[i];
+  }
+  for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = 0;
+  __syncthreads();
+  if (staged) {
+    mbar_wait(&sm->bar[0], 0);
+    StrView v = make_view(stage, ref.blob);
+    if (is_like) v.pk = reinterpret_cast<const uint64_t*>(ref.blob + v.h->prefix_keys_off);  // not staged, not used
+    else {
+      v.resid = ref.blob + v.h->resid_off;
+      v.fp = nullptr;
+    }
+    str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
+                        &sm->bar[1]);
+  } else {
+    const StrView v = make_view(ref.blob, ref.blob);
+    str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
+                        nullptr);
+  }
+}
+
 static uint32_t str_scan_smem(uint32_t needle_len, uint32_t dict_words, uint32_t stage) {
   const uint32_t nd = (needle_len + 15u) & ~15u;
   const uint32_t fl = (2u * needle_len + 15u) & ~15u;
-  return kScanFixedSmem + 2048u + 256u + 32u + nd + fl + dict_words * 4u + (((dict_words * 64u) + 127u) & ~127u) +
-         128u + stage;
+  return kScanFixedSmem + kStrScanTables + nd + fl + dict_words * 4u + (((dict_words * 64u) + 127u) & ~127u) + 128u +
+         stage;
 }
 
 cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, const StrPredDesc& pred,
@@ -425,7 +548,7 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
   const uint32_t dict_words = ((max_unique + 31u) / 32u + 3u) & ~3u;
   constexpr uint32_t kMaxSmem = 227u * 1024u;
   uint32_t stage = (max_head_bytes + 127u) & ~127u;
-  if (str_scan_smem(pred.needle_len, dict_words, stage) > 100u * 1024u) stage = 0;  // keep >= 2 CTAs per SM
+  if (str_scan_smem(pred.needle_len, dict_words, stage) > 110u * 1024u) stage = 0;  // keep >= 2 CTAs per SM
   const uint32_t smem = str_scan_smem(pred.needle_len, dict_words, stage);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
   static bool attr_set = false;

@@ -19,14 +19,16 @@ enum ScanMode : int32_t {
 
 // One entry of a batched scan: where its blob lives and how much of it to stage. Built once per handle list
 // and cached on the device; everything else a scan kernel needs is planned ON THE DEVICE from the blob header.
-struct alignas(8) EntryRef {
+struct alignas(16) EntryRef {
   const uint8_t* blob;
   uint32_t blob_bytes;
-  uint32_t head_bytes;   // byte-view: header .. keys (what predicate kernels stage); ints: = blob_bytes
-  uint32_t meta_bytes;   // byte-view: header .. residuals
+  uint32_t head_bytes;   // byte-view: header .. keys (everything but the compressed values); ints: = blob_bytes
+  uint32_t sp_end;       // byte-view: end of header + shared prefix
+  uint32_t pk_off;       // byte-view: start of the prefix keys (= end of fingerprints + residuals)
+  uint32_t rows_off;     // byte-view: start of validity/keys
   uint32_t rows;
 };
-static_assert(sizeof(EntryRef) == 24, "EntryRef must be 24 bytes");
+static_assert(sizeof(EntryRef) == 32, "EntryRef must be 32 bytes");
 
 constexpr uint64_t kNoSel = ~0ull;  // sel_off value meaning "every row of this entry is selected"
 

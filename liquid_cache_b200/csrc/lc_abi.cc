@@ -457,6 +457,23 @@ static int scan_entries(lc_scan* scan, const lc_handle* handles, std::vector<Ent
   return LC_OK;
 }
 
+// Only batches with surviving rows are read, as LiquidCacheReader::read_from_cache does
+// (liquid_cache_reader.rs:346-349 returns early when the selection is empty).
+static void scan_nonempty(lc_scan* scan, const std::vector<Entry*>& es, std::vector<Entry*>* es2,
+                          std::vector<uint64_t>* woff2, std::vector<uint32_t>* k2) {
+  for (uint64_t i = 0; i < scan->n; ++i) {
+    if (scan->counts[i] == 0) continue;
+    es2->push_back(es[i]);
+    woff2->push_back(scan->word_off[i]);
+    k2->push_back(scan->counts[i]);
+  }
+  if (es2->empty()) {  // keep one batch so the (empty) result still carries the column's type
+    es2->push_back(es[0]);
+    woff2->push_back(scan->word_off[0]);
+    k2->push_back(scan->counts[0]);
+  }
+}
+
 int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* out_schema,
                  struct ArrowArray* out_array) {
   if (!scan || !handles || !out_schema || !out_array) return LC_ERR_INVALID;
@@ -466,8 +483,12 @@ int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* ou
   Guard g(ctx);
   LC_TRY(scan_fetch_counts(scan));
   ctx->scratch.reset();
-  DevSel ds{scan->d_sel, scan->word_off.data(), scan->counts.data(), scan->all_rows};
-  return to_arrow_batch(ctx, es.data(), scan->n, nullptr, &ds, out_schema, out_array);
+  std::vector<Entry*> es2;
+  std::vector<uint64_t> woff2;
+  std::vector<uint32_t> k2;
+  scan_nonempty(scan, es, &es2, &woff2, &k2);
+  DevSel ds{scan->d_sel, woff2.data(), k2.data(), scan->all_rows};
+  return to_arrow_batch(ctx, es2.data(), es2.size(), nullptr, &ds, out_schema, out_array);
 }
 
 int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap, void* d_offsets,

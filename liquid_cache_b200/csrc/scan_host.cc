@@ -199,10 +199,12 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
     refs[i].rows = e->n;
     if (e->liquid_type == LC_LIQUID_INTEGER) {
       refs[i].head_bytes = e->blob_bytes;
-      refs[i].meta_bytes = e->blob_bytes;
+      refs[i].sp_end = refs[i].pk_off = refs[i].rows_off = e->blob_bytes;
     } else {
       refs[i].head_bytes = e->sh.head_bytes;
-      refs[i].meta_bytes = e->sh.meta_bytes;
+      refs[i].sp_end = e->sh.sp_end;
+      refs[i].pk_off = e->sh.prefix_keys_off;
+      refs[i].rows_off = e->sh.rows_off;
       nl.max_head = std::max(nl.max_head, e->sh.head_bytes);
       nl.max_unique = std::max(nl.max_unique, e->sh.n_unique);
     }

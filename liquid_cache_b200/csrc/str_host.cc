@@ -289,13 +289,14 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   uint64_t o = sizeof(StrHeader);
   h.shared_prefix_off = static_cast<uint32_t>(o);
   o += round_up(spl, 16);
-  h.prefix_keys_off = static_cast<uint32_t>(o);
-  o += round_up(8ull * U, 16);
+  h.sp_end = static_cast<uint32_t>(o);
   h.fp_off = build_fp ? static_cast<uint32_t>(o) : 0;
   if (build_fp) o += round_up(4ull * U, 16);
   h.resid_off = static_cast<uint32_t>(o);
   o += round_up(static_cast<uint64_t>(ob) * (U + 1), 16);
-  h.meta_bytes = static_cast<uint32_t>(o);
+  h.prefix_keys_off = static_cast<uint32_t>(o);
+  o += round_up(8ull * U, 16);
+  h.rows_off = static_cast<uint32_t>(o);
   h.validity_off = h.has_nulls ? static_cast<uint32_t>(o) : 0;
   if (h.has_nulls) o += round_up((n + 7) / 8, 16);
   h.keys_off = static_cast<uint32_t>(o);
