@@ -56,7 +56,8 @@ __device__ __forceinline__ uint32_t dict_offset(const StrView& v, uint32_t i) {
   return static_cast<uint32_t>(v.h->slope * static_cast<int32_t>(i) + v.h->intercept + r);
 }
 
-// Sequential reader over a compressed value, 8 bytes per global load.
+// Sequential reader over a compressed value: one aligned 8-byte global load per 8 codes, bytes peeled off
+// with constant shifts.
 struct CodeStream {
   const uint8_t* base;
   uint32_t p, end;
@@ -66,10 +67,11 @@ struct CodeStream {
     p = start;
     end = end_;
     cur = 0;
-    if (p < end) cur = *reinterpret_cast<const uint64_t*>(base + (p & ~7u));
+    if (p < end) cur = *reinterpret_cast<const uint64_t*>(base + (p & ~7u)) >> ((p & 7u) * 8u);
   }
   __device__ __forceinline__ uint32_t next() {
-    const uint32_t b = static_cast<uint32_t>(cur >> ((p & 7u) * 8u)) & 0xffu;
+    const uint32_t b = static_cast<uint32_t>(cur) & 0xffu;
+    cur >>= 8;
     ++p;
     if ((p & 7u) == 0 && p < end) cur = *reinterpret_cast<const uint64_t*>(base + p);
     return b;
@@ -282,9 +284,11 @@ __device__ __forceinline__ void build_sym_steps(const uint64_t* s_sym, const uin
   }
   __syncthreads();
   const uint32_t acc = 1u << (m - 1u);
-  for (uint32_t c = threadIdx.x; c < 256u; c += blockDim.x) {
-    uint64_t sym = s_sym[c];
-    const uint32_t L = s_len[c];
+  // entries 0..254: FSST codes; 255: the escape marker (identity, the next byte is a literal);
+  // entries 256..511: a literal byte b (what follows an escape) = a one-byte symbol
+  for (uint32_t c = threadIdx.x; c < 512u; c += blockDim.x) {
+    uint64_t sym = c < 256u ? s_sym[c] : static_cast<uint64_t>(c - 256u);
+    const uint32_t L = c < 255u ? s_len[c] : (c == 255u ? 0u : 1u);
     uint32_t A = 0xffffffffu, B = 0, H = 0, hit0 = 0;
     for (uint32_t k = 0; k < L; ++k) {
       const uint32_t Mb = s_M[static_cast<uint32_t>(sym & 0xffu)];
@@ -303,38 +307,63 @@ __device__ __forceinline__ void build_sym_steps(const uint64_t* s_sym, const uin
   }
 }
 
-// Lanes pull candidates from a shared queue and each walks its value's codes; a lane that finishes (or finds
-// the needle) immediately takes the next candidate, so warps stay converged however uneven the value lengths are.
+// Lanes pull candidates from a shared queue and each walks its value's codes, eight codes (one aligned 8-byte
+// word of the compressed value) per trip: the next word is prefetched before the eight table steps run, the
+// steps are branch-free (an escape just switches the table half used for the following byte), and refills are
+// warp-synchronous — when at least a quarter of the lanes are out of work they all take new candidates in one
+// converged pass. Neither uneven value lengths nor escapes nor the refill split the warp.
 template <typename View>
 __device__ __forceinline__ void like_candidates(const View& v, const uint16_t* s_cand, uint32_t ncand,
-                                                uint32_t* queue, const uint32_t* s_M, const SymStep* s_step,
-                                                uint32_t m, uint32_t* s_dict) {
-  const uint32_t acc = 1u << (m - 1u);
-  uint32_t S = 0, hit = 0, cur = 0xffffffffu;
-  CodeStream cs;
-  cs.p = cs.end = 0;
-  cs.cur = 0;
-  cs.base = v.fsst;
+                                                uint32_t* queue, const SymStep* s_step, uint32_t* s_dict) {
+  const int lane = threadIdx.x & 31;
+  uint32_t S = 0, hit = 0, cur_i = 0, pending = 0;
+  uint32_t p = 0, end = 0;
+  uint64_t cur = 0;
+  bool exhausted = false;  // warp-uniform: the queue has nothing left
+  const uint8_t* base = v.fsst;
   while (true) {
-    if (cs.p >= cs.end || hit) {
-      if (hit) atomicOr(&s_dict[cur >> 5], 1u << (cur & 31u));
-      const uint32_t idx = atomicAdd(queue, 1u);
-      if (idx >= ncand) break;
-      cur = s_cand[idx];
-      cs.init(v.fsst, dict_offset(v, cur), dict_offset(v, cur + 1u));
-      S = 0;
-      hit = 0;
+    const bool idle = (p >= end) || (hit != 0);
+    const uint32_t idle_mask = __ballot_sync(kFullMask, idle);
+    if (idle_mask == kFullMask || (!exhausted && __popc(idle_mask) >= 8)) {
+      if (hit) {
+        atomicOr(&s_dict[cur_i >> 5], 1u << (cur_i & 31u));
+        hit = 0;
+        p = end;
+      }
+      if (exhausted) break;  // only reached with every lane idle
+      uint32_t qb = 0;
+      if (lane == 0) qb = atomicAdd(queue, static_cast<uint32_t>(__popc(idle_mask)));
+      qb = __shfl_sync(kFullMask, qb, 0);
+      const uint32_t idx = qb + __popc(idle_mask & lanemask_lt());
+      if (idle && idx < ncand) {
+        cur_i = s_cand[idx];
+        p = dict_offset(v, cur_i);
+        end = dict_offset(v, cur_i + 1u);
+        S = 0;
+        pending = 0;
+        if (p < end) cur = *reinterpret_cast<const uint64_t*>(base + (p & ~7u)) >> ((p & 7u) * 8u);
+      }
+      exhausted = (qb + __popc(idle_mask)) >= ncand;
       continue;
     }
-    const uint32_t code = cs.next();
-    if (code != 255u) {
-      const SymStep st = s_step[code];
-      hit = (S & st.H) | (st.L_hit >> 8);
-      S = ((S << (st.L_hit & 0xffu)) & st.A) | st.B;
-    } else if (cs.p < cs.end) {
-      S = ((S << 1) | 1u) & s_M[cs.next()];
-      hit = S & acc;
+    // one compressed word: prefetch the next one, then up to eight table steps
+    const uint32_t word_end = (p & ~7u) + 8u;
+    const uint32_t lim = word_end < end ? word_end : end;
+    uint64_t nxt = 0;
+    if (!idle && word_end < end) nxt = *reinterpret_cast<const uint64_t*>(base + word_end);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (p < lim && !hit) {
+        const uint32_t b = static_cast<uint32_t>(cur) & 0xffu;
+        cur >>= 8;
+        ++p;
+        const SymStep st = s_step[b + (pending << 8)];
+        hit = (S & st.H) | (st.L_hit >> 8);
+        S = ((S << (st.L_hit & 0xffu)) & st.A) | st.B;
+        pending = (pending == 0u && b == 255u) ? 1u : 0u;
+      }
     }
+    if (p == word_end) cur = nxt;
   }
 }
 
@@ -418,7 +447,7 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
     }
     // candidates: walk the FSST codes of the value
     if (fast_like) {
-      like_candidates(v, s_cand, ncand, &sm->misc[1], s_M, s_step, m, s_dict);
+      like_candidates(v, s_cand, ncand, &sm->misc[1], s_step, s_dict);
     } else {
       for (uint32_t c = threadIdx.x; c < ncand; c += 256u) {
         const uint32_t i = s_cand[c];
@@ -462,9 +491,9 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
 }
 
 // Shared-memory map of the predicate kernel (after the fixed ScanSmem area):
-//   symbols 2048 | lengths 256 | plan 32 | M[256] 1024 | SymStep[256] 4096 | needle | KMP links | dictionary
+//   symbols 2048 | lengths 256 | plan 32 | M[256] 1024 | SymStep[512] 8192 | needle | KMP links | dictionary
 //   result bits | candidate list | staged entry head
-constexpr uint32_t kStrScanTables = 2048u + 256u + 32u + 1024u + 4096u;
+constexpr uint32_t kStrScanTables = 2048u + 256u + 32u + 1024u + 8192u;
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 4)
@@ -476,7 +505,7 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
   StrPlan* s_plan = reinterpret_cast<StrPlan*>(s_len + 256);
   uint32_t* s_M = reinterpret_cast<uint32_t*>(s_len + 256 + 32);
   SymStep* s_step = reinterpret_cast<SymStep*>(s_M + 256);
-  uint8_t* s_nd = reinterpret_cast<uint8_t*>(s_step + 256);
+  uint8_t* s_nd = reinterpret_cast<uint8_t*>(s_step + 512);
   const uint32_t m = pred.needle_len;
   const uint32_t nd_bytes = (m + 15u) & ~15u;
   uint16_t* s_fail = reinterpret_cast<uint16_t*>(s_nd + nd_bytes);
@@ -487,8 +516,8 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
 
   const EntryRef ref = io.refs[blockIdx.x];
   const EntryIo w = resolve_io(io, blockIdx.x);
-  const bool staged = ref.head_bytes <= stage_cap;
   const bool is_like = (pred.op == LC_OP_LIKE || pred.op == LC_OP_NOT_LIKE);
+  const bool staged = (is_like ? ref.head_bytes - (ref.rows_off - ref.pk_off) : ref.head_bytes) <= stage_cap;
   scan_smem_init(sm);
   if (threadIdx.x == 0 && staged) {
     mbar_init(&sm->bar[0], 1);
@@ -506,10 +535,11 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
       tma_bulk_g2s(stage, ref.blob, ref.sp_end, &sm->bar[0]);
       if (pk_bytes) tma_bulk_g2s(stage + ref.pk_off, ref.blob + ref.pk_off, pk_bytes, &sm->bar[0]);
     }
-    // (B) what phase 2 needs, in flight while phase 1 computes: validity + keys
+    // (B) what phase 2 needs, in flight while phase 1 computes: validity + keys. For LIKE they are packed right
+    //     behind the metadata (the prefix keys are not staged, so their slot is not reserved either).
     const uint32_t rest = ref.head_bytes - ref.rows_off;
     mbar_expect_tx(&sm->bar[1], rest);
-    tma_bulk_g2s(stage + ref.rows_off, ref.blob + ref.rows_off, rest, &sm->bar[1]);
+    tma_bulk_g2s(stage + (is_like ? ref.pk_off : ref.rows_off), ref.blob + ref.rows_off, rest, &sm->bar[1]);
   }
   // needle + KMP links (shared by all entries of the launch)
   for (uint32_t i = threadIdx.x; i < m; i += 256u) {
@@ -521,8 +551,12 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
   if (staged) {
     mbar_wait(&sm->bar[0], 0);
     StrView v = make_view(stage, ref.blob);
-    if (is_like) v.pk = reinterpret_cast<const uint64_t*>(ref.blob + v.h->prefix_keys_off);  // not staged, not used
-    else {
+    if (is_like) {
+      v.pk = reinterpret_cast<const uint64_t*>(ref.blob + v.h->prefix_keys_off);  // not staged, not used
+      const uint32_t shift = ref.rows_off - ref.pk_off;                             // rows section moved down
+      v.keys = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(v.keys) - shift);
+      if (v.valid) v.valid = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(v.valid) - shift);
+    } else {
       v.resid = ref.blob + v.h->resid_off;
       v.fp = nullptr;
     }

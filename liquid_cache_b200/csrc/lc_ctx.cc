@@ -220,6 +220,14 @@ int lc_ctx_create(int device_id, uint64_t hbm_budget_bytes, lc_ctx** out) {
     return LC_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  // keep stream-ordered allocations cached in the pool across synchronisations (the default threshold of 0
+  // hands the memory back to the driver at every sync, which costs milliseconds per call)
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
   *out = ctx;
   return LC_OK;
 }

@@ -4,6 +4,8 @@
 // Reference call sites: LiquidCache::read_arrow_array / eval_predicate_internal
 // (/root/reference/src/core/src/cache/core.rs:595-634, 862-930).
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "host_common.h"
 
@@ -145,7 +147,7 @@ struct RefList {
   uint64_t key = 0;
   uint64_t n = 0;
   EntryRef* d_refs = nullptr;
-  uint32_t max_blob = 0, max_head = 0, max_unique = 1;
+  uint32_t max_blob = 0, max_head = 0, max_head_like = 0, max_unique = 1;
   uint64_t epoch = 0;
   uint64_t last_use = 0;
 };
@@ -206,6 +208,7 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
       refs[i].pk_off = e->sh.prefix_keys_off;
       refs[i].rows_off = e->sh.rows_off;
       nl.max_head = std::max(nl.max_head, e->sh.head_bytes);
+      nl.max_head_like = std::max(nl.max_head_like, e->sh.head_bytes - (e->sh.rows_off - e->sh.prefix_keys_off));
       nl.max_unique = std::max(nl.max_unique, e->sh.n_unique);
     }
     nl.max_blob = std::max(nl.max_blob, e->blob_bytes);
@@ -331,7 +334,9 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   } else {
     sl.desc.needle = d_up + up_offs;
     sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
-    LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(n), io, sl.desc, rl->max_head, rl->max_unique, s));
+    const bool like = (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
+    LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(n), io, sl.desc, like ? rl->max_head_like : rl->max_head,
+                               rl->max_unique, s));
   }
   ctx->kernel_launches++;
   LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
@@ -400,7 +405,9 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
     ctx->h2d_bytes += sl.needle_blob.size();
     sl.desc.needle = d_nd;
     sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
-    LC_CUDA_OK(launch_str_scan(MODE_REFINE, static_cast<uint32_t>(n), io, sl.desc, rl->max_head, rl->max_unique, s));
+    const bool like = (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
+    LC_CUDA_OK(launch_str_scan(MODE_REFINE, static_cast<uint32_t>(n), io, sl.desc, like ? rl->max_head_like : rl->max_head,
+                               rl->max_unique, s));
   }
   ctx->kernel_launches++;
   return LC_OK;
@@ -439,8 +446,24 @@ static void set_bits_ones(uint8_t* dst, uint64_t from, uint64_t count) {
 static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls, HostBuf validity, HostBuf offsets,
                               HostBuf data, ArrowSchema* out_schema, ArrowArray* out_array);
 
+namespace {
+struct Tracer {  // LC_TRACE=1: wall-clock split of a call, printed to stderr
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  const char* what;
+  explicit Tracer(const char* w) : on(std::getenv("LC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+  void mark(const char* stage) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[lc_trace] %s: %s %.3f ms\n", what, stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t* const* sel_bits,
                    const DevSel* dev_sel, ArrowSchema* out_schema, ArrowArray* out_array, const DeviceOut* dev_out) {
+  Tracer tr("to_arrow");
   if (n == 0) {
     set_error("to_arrow: empty entry list");
     return LC_ERR_INVALID;
@@ -477,6 +500,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   }
   const RefList* rl;
   LC_TRY(get_ref_list(ctx, entries, n, &rl));
+  tr.mark("plan + entry list");
   // upload: sel_off[n] | out_off[n] (ints: element offsets; strings: row_base) | valid_off[n] | ulen_off[n] |
   //         byte_base[n] (strings, second upload) | selection words
   const uint64_t up_offs = round_up(n * 8 * 5, 256);
@@ -615,10 +639,12 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   g.byte_base = reinterpret_cast<const uint64_t*>(d_up) + 4 * n;
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_total;
+  tr.mark("fill + upload");
   LC_CUDA_OK(launch_str_lengths(static_cast<uint32_t>(n), g, rl->max_head, s));
   ctx->kernel_launches++;
   LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
   LC_CUDA_OK(cudaStreamSynchronize(s));
+  tr.mark("lengths kernel + counts D2H");
   ctx->d2h_bytes += dn_total;
   const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
   uint64_t nulls = 0, total_bytes = 0;
@@ -644,6 +670,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     set_error("cudaMallocAsync of %llu result bytes failed", (unsigned long long)res_bytes);
     return LC_ERR_OOM;
   }
+  tr.mark("prefix sums + cudaMallocAsync");
   g.out_offsets = reinterpret_cast<int32_t*>(d_res);
   g.out_bytes = d_res + round_up(off_bytes, 256);
   HostBuf offsets{host_alloc(off_bytes), off_bytes};
@@ -666,6 +693,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     set_error("CUDA error in byte-view decode: %s", cudaGetErrorString(ce));
     return LC_ERR_CUDA;
   }
+  tr.mark("decode kernel + result D2H");
   ctx->kernel_launches++;
   ctx->h2d_bytes += n * 8;
   ctx->d2h_bytes += rows * 4 + total_bytes;
