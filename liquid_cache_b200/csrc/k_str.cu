@@ -349,20 +349,39 @@ __device__ __forceinline__ void like_candidates(const View& v, const uint16_t* s
     // one compressed word: prefetch the next one, then up to eight table steps
     const uint32_t word_end = (p & ~7u) + 8u;
     const uint32_t lim = word_end < end ? word_end : end;
+    const uint32_t cnt = idle ? 0u : lim - p;  // bytes of `cur` to consume (they sit at byte positions 0..cnt-1)
     uint64_t nxt = 0;
     if (!idle && word_end < end) nxt = *reinterpret_cast<const uint64_t*>(base + word_end);
+    const uint32_t lo = static_cast<uint32_t>(cur), hi = static_cast<uint32_t>(cur >> 32);
+    // any 0xFF byte (escape marker) among the bytes we are about to consume?  (SWAR zero-byte test on ~word)
+    const uint32_t nlo = ~lo, nhi = ~hi;
+    const uint32_t zlo = (nlo - 0x01010101u) & ~nlo & 0x80808080u, zhi = (nhi - 0x01010101u) & ~nhi & 0x80808080u;
+    const bool has_esc = (pending != 0u) || ((zlo | zhi) != 0u);
+    if (__any_sync(kFullMask, has_esc && cnt != 0u)) {
+      // general path: an escape switches the table half used for the following byte
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (p < lim && !hit) {
-        const uint32_t b = static_cast<uint32_t>(cur) & 0xffu;
-        cur >>= 8;
-        ++p;
-        const SymStep st = s_step[b + (pending << 8)];
-        hit = (S & st.H) | (st.L_hit >> 8);
-        S = ((S << (st.L_hit & 0xffu)) & st.A) | st.B;
-        pending = (pending == 0u && b == 255u) ? 1u : 0u;
+      for (int k = 0; k < 8; ++k) {
+        if (static_cast<uint32_t>(k) < cnt) {
+          const uint32_t b = ((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xffu;
+          const SymStep st = s_step[b + (pending << 8)];
+          hit |= (S & st.H) | (st.L_hit >> 8);
+          S = ((S << (st.L_hit & 0xffu)) & st.A) | st.B;
+          pending = (pending == 0u && b == 255u) ? 1u : 0u;
+        }
+      }
+    } else {
+      // fast path (no escape in any lane's word): plain table steps
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (static_cast<uint32_t>(k) < cnt) {
+          const uint32_t b = ((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xffu;
+          const SymStep st = s_step[b];
+          hit |= (S & st.H) | (st.L_hit >> 8);
+          S = ((S << (st.L_hit & 0xffu)) & st.A) | st.B;
+        }
       }
     }
+    p += cnt;
     if (p == word_end) cur = nxt;
   }
 }

@@ -289,19 +289,44 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   const uint64_t up_needle = is_int ? 0 : round_up(sl.needle_blob.size(), 256);
   const uint64_t up_sel = round_up(sp.sel_words * 4, 256);
   const uint64_t up_total = up_offs + up_needle + up_sel;
-  uint64_t out_words = 0;
+  bool any_nulls = false;
+  for (uint64_t i = 0; i < n; ++i)
+    any_nulls = any_nulls || (is_int ? entries[i]->ih.null_count : entries[i]->sh.null_count) != 0;
+  const bool want_valid = any_nulls && out.validity != nullptr;
+  // The device lays the masks out exactly as the caller's buffer is laid out (byte_offsets) whenever those
+  // offsets are word aligned and ascending, so the whole result moves with ONE copy.
   std::vector<uint64_t> out_word_off(n);
-  for (uint64_t i = 0; i < n; ++i) {
-    out_word_off[i] = out_words;
-    out_words += round_up((sp.k[i] + 31) / 32, 4);
+  uint64_t out_words = 0;
+  bool mirror = out.byte_offsets != nullptr || n == 1;
+  const uint64_t first_off = out.byte_offsets ? out.byte_offsets[0] : 0;
+  if (mirror) {
+    uint64_t prev_end = first_off;
+    for (uint64_t i = 0; i < n && mirror; ++i) {
+      const uint64_t bo = out.byte_offsets ? out.byte_offsets[i] : 0;
+      if ((bo & 3) || bo < prev_end) mirror = false;
+      out_word_off[i] = (bo - first_off) / 4;
+      prev_end = bo + static_cast<uint64_t>((sp.k[i] + 31) / 32) * 4;
+      out_words = (prev_end - first_off) / 4;
+    }
+    if (out_words * 4 > (sp.total_k / 8 + n * 64) * 4 + (64u << 20)) mirror = false;  // absurdly sparse layout
+  }
+  if (!mirror) {
+    out_words = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      out_word_off[i] = out_words;
+      out_words += round_up((sp.k[i] + 31) / 32, 4);
+    }
   }
   const uint64_t dn_counts = round_up(n * 8, 256);
-  const uint64_t dn_bits = round_up(out_words * 4, 256);
-  const uint64_t dn_total = dn_counts + 2 * dn_bits;
+  const uint64_t dn_bits = round_up(out_words * 4 + 16, 256);
+  const uint64_t dn_total = dn_counts + (want_valid ? 2 : 1) * dn_bits;
+  cudaPointerAttributes pa;
+  const bool direct = mirror && cudaPointerGetAttributes(&pa, out.values) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+  cudaGetLastError();
   Scratch& sc = ctx->scratch;
-  LC_TRY(sc.reserve(up_total + dn_total + 1024, up_total + dn_total + 1024));
+  LC_TRY(sc.reserve(up_total + dn_total + 1024, up_total + (direct ? dn_counts : dn_total) + 1024));
   uint8_t* h_up = sc.host(up_total);
-  uint8_t* h_dn = sc.host(dn_total);
+  uint8_t* h_dn = sc.host(direct ? dn_counts : dn_total);
   uint8_t* d_up = sc.dev(up_total);
   uint8_t* d_dn = sc.dev(dn_total);
   if (!h_up || !h_dn || !d_up || !d_dn) {
@@ -322,7 +347,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   io.sel_off = reinterpret_cast<const uint64_t*>(d_up);
   io.out_base = d_dn + dn_counts;
   io.out_off = reinterpret_cast<const uint64_t*>(d_up) + n;
-  io.valid_base = reinterpret_cast<uint32_t*>(d_dn + dn_counts + dn_bits);
+  io.valid_base = want_valid ? reinterpret_cast<uint32_t*>(d_dn + dn_counts + dn_bits) : nullptr;
   io.valid_off = io.out_off;
   io.counts = reinterpret_cast<uint32_t*>(d_dn);
   io.counts_stride = 2;
@@ -339,13 +364,27 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
                                rl->max_unique, s));
   }
   ctx->kernel_launches++;
-  LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
+  const uint64_t span = out_words * 4;
+  if (direct) {
+    // the caller's buffers are page-locked: results land in them straight from the device
+    LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
+    if (span) LC_CUDA_OK(cudaMemcpyAsync(out.values + first_off, d_dn + dn_counts, span, cudaMemcpyDeviceToHost, s));
+    if (want_valid && span)
+      LC_CUDA_OK(cudaMemcpyAsync(out.validity + first_off, d_dn + dn_counts + dn_bits, span, cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += dn_counts + span * (want_valid ? 2 : 1);
+  } else {
+    LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += dn_total;
+  }
   LC_CUDA_OK(cudaStreamSynchronize(s));
-  ctx->d2h_bytes += dn_total;
 
   const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
   const uint8_t* h_mask = h_dn + dn_counts;
   const uint8_t* h_valid = h_dn + dn_counts + dn_bits;
+  if (mirror && !direct && span) {
+    std::memcpy(out.values + first_off, h_mask, span);
+    if (want_valid) std::memcpy(out.validity + first_off, h_valid, span);
+  }
   for (uint64_t i = 0; i < n; ++i) {
     const uint32_t k = h_counts[2 * i], nulls = h_counts[2 * i + 1];
     if (k != sp.k[i]) {
@@ -354,13 +393,20 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     }
     const uint64_t bytes = static_cast<uint64_t>((k + 31) / 32) * 4;
     const uint64_t bo = out.byte_offsets ? out.byte_offsets[i] : 0;
-    std::memcpy(out.values + bo, h_mask + out_word_off[i] * 4, bytes);
-    if (out.validity) {
-      if (nulls == 0) std::memset(out.validity + bo, 0xFF, bytes);
-      else std::memcpy(out.validity + bo, h_valid + out_word_off[i] * 4, bytes);
+    if (!mirror) {
+      std::memcpy(out.values + bo, h_mask + out_word_off[i] * 4, bytes);
+      if (want_valid && nulls) std::memcpy(out.validity + bo, h_valid + out_word_off[i] * 4, bytes);
     }
+    if (out.validity && nulls == 0 && any_nulls) std::memset(out.validity + bo, 0xFF, bytes);
     if (out.len) out.len[i] = k;
     if (out.null_count) out.null_count[i] = nulls;
+  }
+  // no entry has nulls: validity (if the caller wants it at all) is all ones
+  if (out.validity && !any_nulls) {
+    if (mirror && span) std::memset(out.validity + first_off, 0xFF, span);
+    else
+      for (uint64_t i = 0; i < n; ++i)
+        std::memset(out.validity + (out.byte_offsets ? out.byte_offsets[i] : 0), 0xFF, static_cast<uint64_t>((sp.k[i] + 31) / 32) * 4);
   }
   return LC_OK;
 }
