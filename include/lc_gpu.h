@@ -187,13 +187,19 @@ int lc_eval_predicate(lc_ctx* ctx, lc_handle h, const lc_predicate* pred, const 
  * amortise a launch each.
  *   sel_bits[i]   NULL = all rows of entry i (sel_bits itself may be NULL = all rows everywhere)
  *   out_values    caller buffer; entry i's mask starts at byte out_byte_offsets[i] (the caller
- *                 reserves ceil(len_i/8) rounded up to 4 bytes per entry; lc_mask_bytes() below)
+ *                 reserves lc_mask_bytes(len_i) = ceil(len_i/8) rounded up to 16 bytes per entry)
  *   out_validity  same layout, may be NULL
- *   out_len[i], out_null_count[i] as above */
+ *   out_len[i], out_null_count[i] as above
+ *   out_true_count[i]  (may be NULL) set bits of mask i with nulls counted as false — what the caller's
+ *                 `count_set_bits()` early-exit (liquid_cache_reader.rs:308-311) would compute
+ * When the offsets are ascending and 4-byte aligned the call may write anywhere inside
+ * [out_byte_offsets[0], out_byte_offsets[n-1] + lc_mask_bytes(len_{n-1})): the result moves in one copy
+ * (straight from the device if the buffers are page-locked). */
 uint64_t lc_mask_bytes(uint64_t n_rows);
 int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const lc_predicate* pred,
                            const uint8_t* const* sel_bits, uint8_t* out_values, uint8_t* out_validity,
-                           const uint64_t* out_byte_offsets, uint64_t* out_len, uint64_t* out_null_count);
+                           const uint64_t* out_byte_offsets, uint64_t* out_len, uint64_t* out_null_count,
+                           uint64_t* out_true_count);
 
 /* Batched get-with-selection: the filtered arrays of all entries CONCATENATED into one Arrow array
  * (in `handles` order) — what LiquidCacheReader::read_from_cache + concat produce for one column

@@ -113,7 +113,7 @@ def lib() -> C.CDLL:
     l.lc_eval_predicate.argtypes = [vp, u64, C.POINTER(Predicate), vp, u64, vp, vp, u64p, u64p]
     l.lc_mask_bytes.argtypes = [u64]
     l.lc_mask_bytes.restype = u64
-    l.lc_eval_predicate_many.argtypes = [vp, vp, u64, C.POINTER(Predicate), vp, vp, vp, vp, vp, vp]
+    l.lc_eval_predicate_many.argtypes = [vp, vp, u64, C.POINTER(Predicate), vp, vp, vp, vp, vp, vp, vp]
     l.lc_to_arrow_many.argtypes = [vp, vp, u64, vp, vp, vp]
     l.lc_and_then.argtypes = [vp, vp, u64, vp, u64, vp]
     l.lc_cache_insert.argtypes = [vp, u64, vp, vp, i32]

@@ -374,7 +374,7 @@ class LiquidCache:
     # -- batched forms (one launch sequence for many entries) --
     def eval_predicate_many(self, handles: np.ndarray, rows: np.ndarray, expr: LiquidExpr, column_type: pa.DataType,
                             selections: Optional[Sequence[Optional[np.ndarray]]] = None):
-        """Returns (values bytes, validity bytes, byte_offsets, out_len, out_null_count) as numpy arrays."""
+        """Returns (values bytes, validity bytes, byte_offsets, out_len, out_null_count, out_true_count)."""
         pred = expr.to_native(column_type)
         return self._eval_many_native(handles, rows, pred, selections)
 
@@ -387,8 +387,9 @@ class LiquidCache:
             np.cumsum(sizes[:-1], out=offs[1:])
             total = int(sizes.sum())
             out = (np.zeros(total, dtype=np.uint8), np.zeros(total, dtype=np.uint8), offs,
-                   np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64))
-        vals, valid, offs, out_len, out_nulls = out
+                   np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64))
+        vals, valid, offs, out_len, out_nulls = out[:5]
+        true_counts = out[5] if len(out) > 5 else None
         sel_ptrs = None
         keep = None
         if selections is not None:
@@ -399,6 +400,7 @@ class LiquidCache:
             N.lib().lc_eval_predicate_many(
                 self._ctx, handles.ctypes.data, n, C.byref(pred), sel_ptrs, vals.ctypes.data, valid.ctypes.data,
                 offs.ctypes.data, out_len.ctypes.data, out_nulls.ctypes.data,
+                true_counts.ctypes.data if true_counts is not None else None,
             )
         )
         return out

@@ -204,6 +204,7 @@ struct PredOut {
   const uint64_t* byte_offsets;
   uint64_t* len;
   uint64_t* null_count;
+  uint64_t* true_count;       // optional: set bits of each mask (nulls count as false)
 };
 int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
                          const uint8_t* const* sel_bits, const PredOut& out);

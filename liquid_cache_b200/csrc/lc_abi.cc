@@ -124,7 +124,8 @@ int lc_to_arrow(lc_ctx* ctx, lc_handle h, const uint8_t* sel_bits, uint64_t sel_
 
 int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const lc_predicate* pred,
                            const uint8_t* const* sel_bits, uint8_t* out_values, uint8_t* out_validity,
-                           const uint64_t* out_byte_offsets, uint64_t* out_len, uint64_t* out_null_count) {
+                           const uint64_t* out_byte_offsets, uint64_t* out_len, uint64_t* out_null_count,
+                           uint64_t* out_true_count) {
   if (!ctx || !handles || !pred || !out_values) {
     set_error("lc_eval_predicate_many: NULL argument");
     return LC_ERR_INVALID;
@@ -142,7 +143,7 @@ int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, co
     }
   }
   Guard g(ctx);
-  PredOut po{out_values, out_validity, out_byte_offsets, out_len, out_null_count};
+  PredOut po{out_values, out_validity, out_byte_offsets, out_len, out_null_count, out_true_count};
   return eval_predicate_batch(ctx, es.data(), n, pred, sel_bits, po);
 }
 
@@ -160,7 +161,7 @@ int lc_eval_predicate(lc_ctx* ctx, lc_handle h, const lc_predicate* pred, const 
   const uint8_t* sels[1] = {sel_bits};
   const uint64_t off0 = 0;
   return lc_eval_predicate_many(ctx, &h, 1, pred, sel_bits ? sels : nullptr, out_values, out_validity, &off0, out_len,
-                                out_null_count);
+                                out_null_count, nullptr);
 }
 
 int lc_and_then(lc_ctx* ctx, const uint8_t* left_bits, uint64_t left_len, const uint8_t* right_bits, uint64_t right_len,

@@ -317,7 +317,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
       out_words += round_up((sp.k[i] + 31) / 32, 4);
     }
   }
-  const uint64_t dn_counts = round_up(n * 8, 256);
+  const uint64_t dn_counts = round_up(n * 16, 256);
   const uint64_t dn_bits = round_up(out_words * 4 + 16, 256);
   const uint64_t dn_total = dn_counts + (want_valid ? 2 : 1) * dn_bits;
   cudaPointerAttributes pa;
@@ -350,7 +350,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   io.valid_base = want_valid ? reinterpret_cast<uint32_t*>(d_dn + dn_counts + dn_bits) : nullptr;
   io.valid_off = io.out_off;
   io.counts = reinterpret_cast<uint32_t*>(d_dn);
-  io.counts_stride = 2;
+  io.counts_stride = 4;
   cudaStream_t s = ctx->stream;
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_total;
@@ -386,11 +386,12 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     if (want_valid) std::memcpy(out.validity + first_off, h_valid, span);
   }
   for (uint64_t i = 0; i < n; ++i) {
-    const uint32_t k = h_counts[2 * i], nulls = h_counts[2 * i + 1];
+    const uint32_t k = h_counts[4 * i], nulls = h_counts[4 * i + 1];
     if (k != sp.k[i]) {
       set_error("internal: selected-row count mismatch on entry %llu (%u vs %u)", (unsigned long long)i, k, sp.k[i]);
       return LC_ERR_INVALID;
     }
+    if (out.true_count) out.true_count[i] = h_counts[4 * i + 2];
     const uint64_t bytes = static_cast<uint64_t>((k + 31) / 32) * 4;
     const uint64_t bo = out.byte_offsets ? out.byte_offsets[i] : 0;
     if (!mirror) {

@@ -80,12 +80,18 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
       }
     }
     if (out_counts) {
-      if (MODE == MODE_REFINE) {
+      if (MODE != MODE_DECODE) {
         if (lane == 0 && survivors) atomicAdd(&sm->counts[0], survivors);
         __syncthreads();
         if (threadIdx.x == 0) {
-          out_counts[0] = sm->counts[0];
-          out_counts[1] = 0;
+          if (MODE == MODE_REFINE) {
+            out_counts[0] = sm->counts[0];
+            out_counts[1] = 0;
+          } else {
+            out_counts[0] = n;
+            out_counts[1] = entry_null_count;
+            out_counts[2] = sm->counts[0];  // set bits of the mask (nulls count as false)
+          }
         }
       } else if (threadIdx.x == 0) {
         out_counts[0] = n;
@@ -98,6 +104,7 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
   // ---------------- general: selection -> write offsets ----------------
   uint32_t goff = 0;      // selected rows before this tile
   uint32_t warp_acc = 0;  // lane 0: REFINE survivors, else nulls among the selected rows
+  uint32_t true_acc = 0;  // lane 0, PRED: set bits of the compact mask
   for (uint32_t tile_w0 = 0; tile_w0 < n_words; tile_w0 += 256u) {
     const uint32_t my_wi = tile_w0 + threadIdx.x;
     uint32_t sw = 0;
@@ -154,6 +161,7 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
           if (lane == 0) {
             bits_append(sm->maskbuf, pbase + off, k, b0);
             if (want_valid) bits_append(sm->validbuf, pbase + off, k, b1);
+            true_acc += __popc(b0);
           }
         }
         if (lane == 0) warp_acc += __popc(selw & ~vw);
@@ -187,6 +195,7 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
   }
   if (out_counts) {
     if (lane == 0 && warp_acc) atomicAdd(&sm->counts[1], warp_acc);
+    if (MODE == MODE_PRED && lane == 0 && true_acc) atomicAdd(&sm->counts[0], true_acc);
     __syncthreads();
     if (threadIdx.x == 0) {
       if (MODE == MODE_REFINE) {
@@ -195,6 +204,7 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
       } else {
         out_counts[0] = goff;
         out_counts[1] = sm->counts[1];
+        if (MODE == MODE_PRED) out_counts[2] = sm->counts[0];
       }
     }
   }

@@ -159,13 +159,14 @@ def test_batched_many(cache):
     sels = [np.packbits(rng.random(8192) < 0.3, bitorder="little") for _ in arrays]
     sels = [np.concatenate([s, np.zeros(8, np.uint8)]) for s in sels]
     expr = _expr(">", 3)
-    vals, valid, offs, out_len, out_nulls = cache.eval_predicate_many(handles, rows, expr, pa.int64(), sels)
+    vals, valid, offs, out_len, out_nulls, true_counts = cache.eval_predicate_many(handles, rows, expr, pa.int64(), sels)
     for i, a in enumerate(arrays):
         sel = pa.array(np.unpackbits(sels[i], bitorder="little")[:8192].astype(bool))
         want = OracleIntArray.from_arrow(a).try_eval_predicate(">", 3, sel)
         k = int(out_len[i])
         got = np.unpackbits(vals[int(offs[i]):int(offs[i]) + (k + 7) // 8], bitorder="little")[:k].astype(bool)
         assert got.tolist() == want.to_pylist()
+        assert int(true_counts[i]) == sum(1 for x in want.to_pylist() if x)
     concat = cache.to_arrow_many(handles, sels)
     want = pa.concat_arrays([a.filter(pa.array(np.unpackbits(s, bitorder="little")[:8192].astype(bool))) for a, s in zip(arrays, sels)])
     assert_arrays_equal(concat, want, "to_arrow_many")
