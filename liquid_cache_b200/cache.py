@@ -415,6 +415,14 @@ class LiquidCache:
         N.check(N.lib().lc_to_arrow_many(self._ctx, handles.ctypes.data, n, sel_ptrs, _ptr(out_s), _ptr(out_a)))
         return _import(out_a, out_s)
 
+    def to_arrow_many_ptrs(self, handles: np.ndarray, sel_ptrs: np.ndarray) -> pa.Array:
+        """to_arrow_many with the selections given as an array of host addresses (uint64; 0 = all rows)."""
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        sel_ptrs = np.ascontiguousarray(sel_ptrs, dtype=np.uint64)
+        out_a, out_s = _new_out()
+        N.check(N.lib().lc_to_arrow_many(self._ctx, handles.ctypes.data, len(handles), sel_ptrs.ctypes.data, _ptr(out_s), _ptr(out_a)))
+        return _import(out_a, out_s)
+
     def and_then(self, left, right) -> pa.Array:
         """`boolean_buffer_and_then` (src/datafusion/src/utils.rs:62-83)."""
         lb, ln = selection_bits(left)

@@ -269,10 +269,26 @@ static int make_int_pred(const lc_predicate* pred, IntPredDesc* out) {
   return LC_OK;
 }
 
+namespace {
+struct Tracer {  // LC_TRACE=1: wall-clock split of a call, printed to stderr
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  const char* what;
+  explicit Tracer(const char* w) : on(std::getenv("LC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+  void mark(const char* stage) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[lc_trace] %s: %s %.3f ms\n", what, stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 // ---- eval_predicate --------------------------------------------------------------------------------
 int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
                          const uint8_t* const* sel_bits, const PredOut& out) {
   if (n == 0) return LC_OK;
+  Tracer tr("eval_predicate");
   LC_TRY(check_same_type(entries, n, "eval_predicate_many"));
   const bool is_int = (entries[0]->liquid_type == LC_LIQUID_INTEGER);
   SelPlan sp;
@@ -352,6 +368,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   io.counts = reinterpret_cast<uint32_t*>(d_dn);
   io.counts_stride = 4;
   cudaStream_t s = ctx->stream;
+  tr.mark("plan + fill");
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_total;
   if (is_int) {
@@ -377,6 +394,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     ctx->d2h_bytes += dn_total;
   }
   LC_CUDA_OK(cudaStreamSynchronize(s));
+  tr.mark(direct ? "upload + kernel + direct D2H" : "upload + kernel + staged D2H");
 
   const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
   const uint8_t* h_mask = h_dn + dn_counts;
@@ -402,6 +420,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     if (out.len) out.len[i] = k;
     if (out.null_count) out.null_count[i] = nulls;
   }
+  tr.mark("per-entry results");
   // no entry has nulls: validity (if the caller wants it at all) is all ones
   if (out.validity && !any_nulls) {
     if (mirror && span) std::memset(out.validity + first_off, 0xFF, span);
@@ -492,21 +511,6 @@ static void set_bits_ones(uint8_t* dst, uint64_t from, uint64_t count) {
 
 static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls, HostBuf validity, HostBuf offsets,
                               HostBuf data, ArrowSchema* out_schema, ArrowArray* out_array);
-
-namespace {
-struct Tracer {  // LC_TRACE=1: wall-clock split of a call, printed to stderr
-  bool on;
-  std::chrono::steady_clock::time_point t0;
-  const char* what;
-  explicit Tracer(const char* w) : on(std::getenv("LC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
-  void mark(const char* stage) {
-    if (!on) return;
-    auto t1 = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[lc_trace] %s: %s %.3f ms\n", what, stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
-}  // namespace
 
 int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t* const* sel_bits,
                    const DevSel* dev_sel, ArrowSchema* out_schema, ArrowArray* out_array, const DeviceOut* dev_out) {
