@@ -145,6 +145,11 @@ int lc_ctx_stats(lc_ctx* ctx, lc_stats* out);
  * so a benchmark can state the ALGORITHMIC bytes of a scan exactly. Costs a few atomics; never enable it in
  * a timed region. */
 int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[4]);
+/* Measurement aid: while enabled, every predicate launch (lc_scan_filter / lc_eval_predicate*) is bracketed by a
+ * pair of CUDA events recorded on the launching stream immediately around the kernel launch.
+ * lc_ctx_last_kernel_ms waits for the most recent one and returns its duration (negative if none). */
+int lc_ctx_kernel_timing(lc_ctx* ctx, int enable);
+float lc_ctx_last_kernel_ms(lc_ctx* ctx);
 const char* lc_last_error(void);
 const char* lc_version(void);
 

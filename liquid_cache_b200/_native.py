@@ -125,6 +125,9 @@ def lib() -> C.CDLL:
     l.lc_cache_eval_predicate.argtypes = [vp, u64, C.POINTER(Predicate), vp, u64, vp, vp, u64p, u64p]
     l.lc_scan_begin.argtypes = [vp, u64, vp, C.POINTER(vp)]
     l.lc_scan_reset.argtypes = [vp]
+    l.lc_ctx_kernel_timing.argtypes = [vp, C.c_int]
+    l.lc_ctx_last_kernel_ms.argtypes = [vp]
+    l.lc_ctx_last_kernel_ms.restype = C.c_float
     l.lc_ctx_profile_counters.argtypes = [vp, C.c_int, vp]
     l.lc_scan_set_selection.argtypes = [vp, u64, vp, u64]
     l.lc_scan_filter.argtypes = [vp, vp, C.POINTER(Predicate)]

@@ -344,6 +344,13 @@ class LiquidCache:
         N.check(N.lib().lc_ctx_profile_counters(self._ctx, 1 if enable else 0, out.ctypes.data))
         return out
 
+    def kernel_timing(self, enable: bool) -> None:
+        N.check(N.lib().lc_ctx_kernel_timing(self._ctx, 1 if enable else 0))
+
+    def last_kernel_ms(self) -> float:
+        """Duration of the most recent predicate kernel (CUDA events recorded right around its launch)."""
+        return float(N.lib().lc_ctx_last_kernel_ms(self._ctx))
+
     def set_stream(self, cuda_stream: int) -> None:
         N.check(N.lib().lc_ctx_set_stream(self._ctx, cuda_stream))
 

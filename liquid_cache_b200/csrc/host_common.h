@@ -142,6 +142,9 @@ struct lc_ctx {
   uint8_t* d_needle = nullptr;   // small device buffer for predicate needles
   unsigned long long* d_prof = nullptr;  // profile counters (lc_ctx_profile_counters)
   bool prof_on = false;
+  bool timing_on = false;        // lc_ctx_kernel_timing
+  bool timing_valid = false;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 };
 
 namespace lc {

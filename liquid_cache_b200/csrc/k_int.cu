@@ -37,18 +37,48 @@ struct FL {
   static constexpr uint32_t LOG_O = (T == 64) ? 3 : (T == 32) ? 2 : (T == 16) ? 1 : 0;
 };
 
+// Storage-order walk of one 1024-row chunk by one warp: 32 steps, step j touches exactly ONE packed word per
+// lane (two when the W-bit field straddles a word) and covers the 32 consecutive logical rows of word order(j):
+//   T = 32: step j = packed row r = j, lane = FastLanes lane          -> logical word 4(r%8) + bitrev2(r/8)
+//   T = 64: 16 lanes only, so the two half-warps take rows r and r+32 (FL_ORDER[o+4] = FL_ORDER[o]+1 makes the
+//           two halves adjacent): j = 8o + s, r = 8(o + 4*half) + s   -> the same word formula
+//   T = 16: 64 lanes, two steps per row (lanes 0-31 / 32-63)          -> 4(r%8) + 2(r/8) + half
+//   T =  8: 128 lanes, four steps per row                             -> word j
+// Compared with decoding "row i" by inverting the index map this needs ~5x fewer instructions per row.
 template <typename U>
-__device__ __forceinline__ U fl_get(const U* __restrict__ chunk, uint32_t j, uint32_t W) {
-  constexpr uint32_t T = FL<U>::T, LANES = FL<U>::LANES, LOG_O = FL<U>::LOG_O;
-  const uint32_t s = j >> 7, rem = j & 127u;
-  const uint32_t l = rem & (LANES - 1u);
-  const uint32_t q = rem / LANES;
-  const uint32_t o = LOG_O ? (__brev(q) >> (32u - (LOG_O ? LOG_O : 1u))) : 0u;
-  const uint32_t r = o * 8u + s;
+struct FLOrder {
+  __device__ __forceinline__ uint32_t operator()(uint32_t j) const {
+    constexpr uint32_t T = sizeof(U) * 8;
+    if (T >= 32) return (j & 7u) * 4u + (__brev(j >> 3) >> 30);
+    if (T == 16) {
+      const uint32_t r = j >> 1;
+      return (r & 7u) * 4u + (r >> 3) * 2u + (j & 1u);
+    }
+    return j;
+  }
+};
+
+template <typename U>
+__device__ __forceinline__ U fl_step(const U* __restrict__ chunk, uint32_t j, uint32_t lane, uint32_t W) {
+  constexpr uint32_t T = FL<U>::T, LANES = FL<U>::LANES;
+  uint32_t r, L;
+  if (T == 64) {
+    r = ((j >> 3) + 4u * (lane >> 4)) * 8u + (j & 7u);
+    L = lane & 15u;
+  } else if (T == 32) {
+    r = j;
+    L = lane;
+  } else if (T == 16) {
+    r = j >> 1;
+    L = (j & 1u) * 32u + lane;
+  } else {
+    r = j >> 2;
+    L = (j & 3u) * 32u + lane;
+  }
   const uint32_t b = r * W;
   const uint32_t k = b / T, sh = b % T;
-  U v = static_cast<U>(chunk[LANES * k + l] >> sh);
-  if (sh + W > T) v = static_cast<U>(v | static_cast<U>(chunk[LANES * (k + 1u) + l] << (T - sh)));
+  U v = static_cast<U>(chunk[LANES * k + L] >> sh);
+  if (sh + W > T) v = static_cast<U>(v | static_cast<U>(chunk[LANES * (k + 1u) + L] << (T - sh)));
   if (W < T) v = static_cast<U>(v & static_cast<U>((static_cast<U>(1) << W) - static_cast<U>(1)));
   return v;
 }
@@ -156,18 +186,19 @@ __device__ __forceinline__ void int_scan_entry(const EntryIo& w, const IntPredDe
   const uint32_t chunk_words = 1024u * W / T;  // in units of U
   U* out_vals = reinterpret_cast<U*>(w.out);
 
-  auto value_of = [&](uint32_t row) -> U {
+  const uint32_t lane = threadIdx.x & 31u;
+  auto value_at = [&](uint32_t c, uint32_t j) -> U {
     if (W == 0) return static_cast<U>(0);
-    return fl_get<U>(packed + static_cast<size_t>(row >> 10) * chunk_words, row & 1023u, W);
+    return fl_step<U>(packed + static_cast<size_t>(c) * chunk_words, j, lane, W);
   };
-  auto cmp = [&](uint32_t row) -> bool { return ucmp_eval<U>(kind, value_of(row), thr); };
-  auto emit = [&](uint32_t row, uint32_t dst) { out_vals[dst] = static_cast<U>(value_of(row) + ref); };
+  auto cmp = [&](uint32_t, uint32_t c, uint32_t j) -> bool { return ucmp_eval<U>(kind, value_at(c, j), thr); };
+  auto emit = [&](uint32_t, uint32_t dst, uint32_t c, uint32_t j) { out_vals[dst] = static_cast<U>(value_at(c, j) + ref); };
   scan_entry_rows<MODE>(w.sel, h->n, valid, h->null_count, reinterpret_cast<uint32_t*>(w.out), w.out_valid,
-                        w.counts, sm, cmp, emit);
+                        w.counts, sm, cmp, emit, FLOrder<U>());
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k_int_scan(ScanIo io, IntPredDesc pred, uint32_t stage_cap) {
+__global__ void __launch_bounds__(256, 6) k_int_scan(ScanIo io, IntPredDesc pred, uint32_t stage_cap) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
   uint8_t* stage = smem_raw + kScanFixedSmem;

@@ -500,11 +500,11 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
 
   // ---------------- phase 2: dictionary results -> rows ----------------
   const uint16_t* keys = v.keys;
-  auto cmp = [&](uint32_t row) -> bool {
+  auto cmp = [&](uint32_t row, uint32_t, uint32_t) -> bool {
     const uint32_t k = keys[row];
     return (s_dict[k >> 5] >> (k & 31u)) & 1u;
   };
-  auto emit = [&](uint32_t, uint32_t) {};
+  auto emit = [&](uint32_t, uint32_t, uint32_t, uint32_t) {};
   scan_entry_rows<MODE>(w.sel, v.h->n, v.valid, v.h->null_count, reinterpret_cast<uint32_t*>(w.out), w.out_valid,
                         w.counts, sm, cmp, emit);
 }
@@ -682,8 +682,8 @@ __global__ void __launch_bounds__(256) k_str_lengths(StrGatherIo g, uint32_t sta
   }
   const uint16_t* keys = v.keys;
   const uint32_t* valid = v.valid;
-  auto cmp = [&](uint32_t) -> bool { return false; };
-  auto emit = [&](uint32_t row, uint32_t dst) {
+  auto cmp = [&](uint32_t, uint32_t, uint32_t) -> bool { return false; };
+  auto emit = [&](uint32_t row, uint32_t dst, uint32_t, uint32_t) {
     const bool ok = valid ? ((valid[row >> 5] >> (row & 31u)) & 1u) : true;
     uint32_t len = 0, key = 0xFFFFFFFFu;
     if (ok) {

@@ -39,7 +39,48 @@ struct lc_scan {
   bool counts_on_device = false;
   bool counts_cached = false;
   std::vector<uint32_t> counts;
+  // handle lists already validated against this scan (hash of the handle array -> entries), so that repeated
+  // filters over the same columns cost a hash of the array instead of 12k pointer chases
+  struct Validated {
+    uint64_t key = 0, epoch = 0;
+    std::vector<Entry*> es;
+  };
+  std::vector<Validated> validated;
 };
+
+static uint64_t hash_handles(const lc_handle* h, uint64_t n) {
+  uint64_t x = 0x9E3779B97F4A7C15ull ^ n;
+  for (uint64_t i = 0; i < n; ++i) {
+    x = (x ^ h[i]) * 0xff51afd7ed558ccdull;
+    x ^= x >> 32;
+  }
+  return x;
+}
+
+static int scan_entries_cached(lc_scan* scan, const lc_handle* handles, Entry* const** out) {
+  const uint64_t key = hash_handles(handles, scan->n);
+  for (auto& v : scan->validated) {
+    if (v.key == key && v.epoch == scan->ctx->epoch) {
+      *out = v.es.data();
+      return LC_OK;
+    }
+  }
+  lc_scan::Validated v;
+  v.key = key;
+  v.epoch = scan->ctx->epoch;
+  v.es.resize(scan->n);
+  for (uint64_t i = 0; i < scan->n; ++i) {
+    v.es[i] = entry_of(handles[i]);
+    if (!v.es[i] || v.es[i]->n != scan->rows[i]) {
+      set_error("scan: handle %llu invalid or row count differs from the scan's", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+  }
+  if (scan->validated.size() >= 8) scan->validated.erase(scan->validated.begin());
+  scan->validated.push_back(std::move(v));
+  *out = scan->validated.back().es.data();
+  return LC_OK;
+}
 
 extern "C" {
 
@@ -369,17 +410,11 @@ int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* 
     set_error("lc_scan_filter: NULL argument");
     return LC_ERR_INVALID;
   }
-  std::vector<Entry*> es(scan->n);
-  for (uint64_t i = 0; i < scan->n; ++i) {
-    es[i] = entry_of(handles[i]);
-    if (!es[i] || es[i]->n != scan->rows[i]) {
-      set_error("lc_scan_filter: handle %llu invalid or row count differs from the scan's", (unsigned long long)i);
-      return LC_ERR_INVALID;
-    }
-  }
   lc_ctx* ctx = scan->ctx;
   Guard g(ctx);
-  LC_TRY(refine_batch(ctx, es.data(), scan->n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
+  Entry* const* es = nullptr;
+  LC_TRY(scan_entries_cached(scan, handles, &es));
+  LC_TRY(refine_batch(ctx, es, scan->n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
   scan->all_rows = false;
   scan->counts_on_device = true;
   scan->counts_cached = false;

@@ -253,6 +253,8 @@ void lc_ctx_destroy(lc_ctx* ctx) {
   drop_ref_cache(ctx);
   if (ctx->d_needle) cudaFree(ctx->d_needle);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -292,6 +294,30 @@ int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[4]) {
   if (enable && !ctx->prof_on) LC_CUDA_OK(cudaMemset(ctx->d_prof, 0, 64));
   ctx->prof_on = enable != 0;
   return LC_OK;
+}
+
+int lc_ctx_kernel_timing(lc_ctx* ctx, int enable) {
+  if (!ctx) return LC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (enable && !ctx->ev_a) {
+    LC_CUDA_OK(cudaEventCreate(&ctx->ev_a));
+    LC_CUDA_OK(cudaEventCreate(&ctx->ev_b));
+  }
+  ctx->timing_on = enable != 0;
+  ctx->timing_valid = false;
+  return LC_OK;
+}
+
+float lc_ctx_last_kernel_ms(lc_ctx* ctx) {
+  if (!ctx) return -1.0f;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!ctx->timing_valid) return -1.0f;
+  cudaSetDevice(ctx->device);
+  if (cudaEventSynchronize(ctx->ev_b) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) != cudaSuccess) return -1.0f;
+  return ms;
 }
 
 int lc_ctx_stats(lc_ctx* ctx, lc_stats* out) {

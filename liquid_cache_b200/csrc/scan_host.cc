@@ -371,6 +371,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   tr.mark("plan + fill");
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_total;
+  if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
   if (is_int) {
     LC_CUDA_OK(launch_int_scan(MODE_PRED, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
   } else {
@@ -379,6 +380,10 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     const bool like = (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
     LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(n), io, sl.desc, like ? rl->max_head_like : rl->max_head,
                                rl->max_unique, s));
+  }
+  if (ctx->timing_on) {
+    cudaEventRecord(ctx->ev_b, s);
+    ctx->timing_valid = true;
   }
   ctx->kernel_launches++;
   const uint64_t span = out_words * 4;
@@ -455,6 +460,7 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
   io.counts_stride = 2;
   cudaStream_t s = ctx->stream;
   if (is_int) {
+    if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
     LC_CUDA_OK(launch_int_scan(MODE_REFINE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
   } else {
     // the needle is the only thing that travels: a few bytes from pageable memory (the runtime stages such
@@ -472,8 +478,13 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
     sl.desc.needle = d_nd;
     sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
     const bool like = (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
+    if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
     LC_CUDA_OK(launch_str_scan(MODE_REFINE, static_cast<uint32_t>(n), io, sl.desc, like ? rl->max_head_like : rl->max_head,
                                rl->max_unique, s));
+  }
+  if (ctx->timing_on) {
+    cudaEventRecord(ctx->ev_b, s);
+    ctx->timing_valid = true;
   }
   ctx->kernel_launches++;
   return LC_OK;

@@ -41,14 +41,22 @@ __device__ __forceinline__ void scan_smem_init(ScanSmem* sm) {
   }
 }
 
-// cmp(row) -> bool (only called for row < n); emit(row, dst) writes the decoded value (MODE_DECODE).
+struct IdentityOrder {
+  __device__ __forceinline__ uint32_t operator()(uint32_t j) const { return j; }
+};
+
+// cmp(row, c, j) -> bool (only called for row < n); emit(row, dst, c, j) writes the decoded value (MODE_DECODE).
+// A warp covers one 1024-row chunk c per pass in 32 steps j; step j handles the 32 rows of logical word
+// order(j) of that chunk. Byte-view columns walk the words in order; bit-packed integers walk them in FastLanes
+// STORAGE order, where step j needs exactly one packed word per lane (see k_int.cu) — the selection machinery
+// does not care, every word's write offset comes from the prefix-sum table.
 // `valid` may be nullptr (no nulls). Requires scan_smem_init + __syncthreads() before the call.
-template <int MODE, typename Cmp, typename Emit>
+template <int MODE, typename Cmp, typename Emit, typename Order = IdentityOrder>
 __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel, uint32_t n,
                                                 const uint32_t* __restrict__ valid, uint32_t entry_null_count,
                                                 uint32_t* __restrict__ out_bits, uint32_t* __restrict__ out_valid,
                                                 uint32_t* __restrict__ out_counts, ScanSmem* sm, Cmp cmp,
-                                                Emit emit) {
+                                                Emit emit, Order order = Order()) {
   const uint32_t n_words = (n + 31u) >> 5;
   const uint32_t tail = n & 31u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -58,19 +66,20 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
     // ---------------- dense: every row selected, rank == row ----------------
     uint32_t survivors = 0;
     for (uint32_t w0 = warp * 32u; w0 < n_words; w0 += 256u) {
+      const uint32_t c = w0 >> 5;
 #pragma unroll 4
       for (uint32_t j = 0; j < 32; ++j) {
-        const uint32_t wi = w0 + j;
-        if (wi >= n_words) break;
+        const uint32_t wi = w0 + order(j);
+        if (wi >= n_words) continue;
         const uint32_t row = wi * 32u + lane;
         const bool in = row < n;
         uint32_t vw = valid ? valid[wi] : kFullMask;
         if (wi == n_words - 1u && tail) vw &= (1u << tail) - 1u;
         if (MODE == MODE_DECODE) {
-          if (in) emit(row, row);
+          if (in) emit(row, row, c, j);
           if (want_valid && lane == 0) out_valid[wi] = vw;
         } else {
-          const uint32_t cw = __ballot_sync(kFullMask, in && cmp(row)) & vw;
+          const uint32_t cw = __ballot_sync(kFullMask, in && cmp(row, c, j)) & vw;
           if (lane == 0) {
             out_bits[wi] = cw;
             if (MODE == MODE_PRED && want_valid) out_valid[wi] = vw;
@@ -125,10 +134,11 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
     __syncthreads();
     const uint32_t pbase = goff & 31u;
 
+    const uint32_t c = (tile_w0 >> 5) + warp;
     for (uint32_t j = 0; j < 32; ++j) {
-      const uint32_t lw = warp * 32u + j;
+      const uint32_t lw = warp * 32u + order(j);
       const uint32_t wi = tile_w0 + lw;
-      if (wi >= n_words) break;
+      if (wi >= n_words) continue;
       const uint32_t selw = sm->sel[lw];
       if (selw == 0) {
         if (MODE == MODE_REFINE && lane == 0) out_bits[wi] = 0;
@@ -140,7 +150,7 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
       const uint32_t off = sm->off[lw];
       const bool mine = (selw >> lane) & 1u;
       if (MODE == MODE_REFINE) {
-        const uint32_t cw = __ballot_sync(kFullMask, mine && cmp(row)) & vw;
+        const uint32_t cw = __ballot_sync(kFullMask, mine && cmp(row, c, j)) & vw;
         if (lane == 0) {
           out_bits[wi] = cw;
           warp_acc += __popc(cw);
@@ -148,14 +158,14 @@ __device__ __forceinline__ void scan_entry_rows(const uint32_t* __restrict__ sel
       } else {
         const uint32_t vbit = (vw >> lane) & 1u;
         if (MODE == MODE_DECODE) {
-          if (mine) emit(row, goff + off + __popc(selw & lanemask_lt()));
+          if (mine) emit(row, goff + off + __popc(selw & lanemask_lt()), c, j);
           if (want_valid) {
             uint32_t b0, b1;
             warp_pext2(vbit, selw, lane, sm->scratch[warp], &b0, &b1);
             if (lane == 0) bits_append(sm->validbuf, pbase + off, k, b0);
           }
         } else {
-          const uint32_t cbit = (mine && cmp(row)) ? vbit : 0u;
+          const uint32_t cbit = (mine && cmp(row, c, j)) ? vbit : 0u;
           uint32_t b0, b1;
           warp_pext2(cbit | (vbit << 1), selw, lane, sm->scratch[warp], &b0, &b1);
           if (lane == 0) {
