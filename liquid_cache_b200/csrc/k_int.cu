@@ -58,43 +58,104 @@ struct FLOrder {
   }
 };
 
-template <typename U>
-__device__ __forceinline__ U fl_step(const U* __restrict__ chunk, uint32_t j, uint32_t lane, uint32_t W) {
-  constexpr uint32_t T = FL<U>::T, LANES = FL<U>::LANES;
-  uint32_t r, L;
+// One packed value for (step j, lane): rows, lanes and the W-bit field position as in the table above.
+// The lane's bit stream is read as 32-bit words and the field is cut out with one funnel shift; 64-bit
+// columns whose frame-of-reference range fits 32 bits (EventTime, dates, most ids) never touch 64-bit ALU ops.
+template <uint32_t T>
+__device__ __forceinline__ void fl_row_lane(uint32_t j, uint32_t lane, uint32_t* r, uint32_t* L) {
   if (T == 64) {
-    r = ((j >> 3) + 4u * (lane >> 4)) * 8u + (j & 7u);
-    L = lane & 15u;
+    *r = ((j >> 3) + 4u * (lane >> 4)) * 8u + (j & 7u);
+    *L = lane & 15u;
   } else if (T == 32) {
-    r = j;
-    L = lane;
+    *r = j;
+    *L = lane;
   } else if (T == 16) {
-    r = j >> 1;
-    L = (j & 1u) * 32u + lane;
+    *r = j >> 1;
+    *L = (j & 1u) * 32u + lane;
   } else {
-    r = j >> 2;
-    L = (j & 3u) * 32u + lane;
+    *r = j >> 2;
+    *L = (j & 3u) * 32u + lane;
   }
-  const uint32_t b = r * W;
-  const uint32_t k = b / T, sh = b % T;
-  U v = static_cast<U>(chunk[LANES * k + L] >> sh);
-  if (sh + W > T) v = static_cast<U>(v | static_cast<U>(chunk[LANES * (k + 1u) + L] << (T - sh)));
-  if (W < T) v = static_cast<U>(v & static_cast<U>((static_cast<U>(1) << W) - static_cast<U>(1)));
-  return v;
 }
 
-template <typename U>
-__device__ __forceinline__ bool ucmp_eval(int32_t kind, U u, U thr) {
-  switch (kind) {
-    case UC_FALSE: return false;
-    case UC_TRUE: return true;
-    case UC_EQ: return u == thr;
-    case UC_NE: return u != thr;
-    case UC_LT: return u < thr;
-    case UC_LE: return u <= thr;
-    case UC_GT: return u > thr;
-    default: return u >= thr;
+// T = 64, W <= 32: value as u32
+__device__ __forceinline__ uint32_t fl_step64_lo(const uint32_t* __restrict__ c32, uint32_t j, uint32_t lane, uint32_t W,
+                                                 uint32_t mask) {
+  uint32_t r, L;
+  fl_row_lane<64>(j, lane, &r, &L);
+  const uint32_t b = r * W, w = b >> 5, sh = b & 31u;
+  // 32-bit word w of lane L lives in 64-bit lane word w/2 (16 lanes interleaved), half w%2
+  const uint32_t i0 = ((w >> 1) * 16u + L) * 2u + (w & 1u);
+  const uint32_t lo = c32[i0];
+  uint32_t hi = 0;
+  if (sh + W > 32u) {
+    const uint32_t w1 = w + 1u;
+    hi = c32[((w1 >> 1) * 16u + L) * 2u + (w1 & 1u)];
   }
+  return __funnelshift_r(lo, hi, sh) & mask;
+}
+
+// T = 64, W > 32: value as u64 from up to three 32-bit words
+__device__ __forceinline__ uint64_t fl_step64_hi(const uint32_t* __restrict__ c32, uint32_t j, uint32_t lane, uint32_t W) {
+  uint32_t r, L;
+  fl_row_lane<64>(j, lane, &r, &L);
+  const uint32_t b = r * W, w = b >> 5, sh = b & 31u;
+  auto word = [&](uint32_t x) -> uint32_t { return c32[((x >> 1) * 16u + L) * 2u + (x & 1u)]; };
+  const uint32_t w0 = word(w), w1 = word(w + 1u);
+  const uint32_t w2 = (sh + W > 64u) ? word(w + 2u) : 0u;
+  const uint64_t v = (static_cast<uint64_t>(__funnelshift_r(w1, w2, sh)) << 32) | __funnelshift_r(w0, w1, sh);
+  return W < 64u ? (v & ((1ull << W) - 1ull)) : v;
+}
+
+// T = 32
+__device__ __forceinline__ uint32_t fl_step32(const uint32_t* __restrict__ c32, uint32_t j, uint32_t lane, uint32_t W,
+                                              uint32_t mask) {
+  const uint32_t b = j * W, k = b >> 5, sh = b & 31u;
+  const uint32_t lo = c32[32u * k + lane];
+  const uint32_t hi = (sh + W > 32u) ? c32[32u * (k + 1u) + lane] : 0u;
+  return __funnelshift_r(lo, hi, sh) & mask;
+}
+
+// T = 16 / 8: fields never exceed 16 bits, two narrow loads
+template <typename U>
+__device__ __forceinline__ uint32_t fl_step_small(const U* __restrict__ chunk, uint32_t j, uint32_t lane, uint32_t W,
+                                                  uint32_t mask) {
+  constexpr uint32_t T = FL<U>::T, LANES = FL<U>::LANES;
+  uint32_t r, L;
+  fl_row_lane<T>(j, lane, &r, &L);
+  const uint32_t b = r * W, k = b / T, sh = b % T;
+  uint32_t v = chunk[LANES * k + L];
+  if (sh + W > T) v |= static_cast<uint32_t>(chunk[LANES * (k + 1u) + L]) << (T & 31u);
+  return (v >> sh) & mask;
+}
+
+// Every comparison of the unsigned packed value against the threshold is one range test:
+//   cmp(u) = ((u - lo) <= span) != neg
+template <typename C>
+struct URange {
+  C lo, span;
+  bool neg;
+};
+
+template <typename C>
+__device__ __forceinline__ URange<C> make_range(int32_t kind, uint64_t thr64) {
+  const C mx = static_cast<C>(~static_cast<C>(0));
+  const C thr = static_cast<C>(thr64);
+  URange<C> g;
+  g.lo = 0;
+  g.span = mx;
+  g.neg = false;
+  switch (kind) {
+    case UC_FALSE: g.neg = true; break;
+    case UC_TRUE: break;
+    case UC_EQ: g.lo = thr; g.span = 0; break;
+    case UC_NE: g.lo = thr; g.span = 0; g.neg = true; break;
+    case UC_LT: if (thr == 0) g.neg = true; else g.span = static_cast<C>(thr - 1); break;
+    case UC_LE: g.span = thr; break;
+    case UC_GT: if (thr == mx) g.neg = true; else { g.lo = static_cast<C>(thr + 1); g.span = static_cast<C>(mx - g.lo); } break;
+    default: g.lo = thr; g.span = static_cast<C>(mx - thr); break;
+  }
+  return g;
 }
 
 // Everything a CTA needs for its entry, resolved from ScanIo.
@@ -170,9 +231,131 @@ __device__ __forceinline__ void plan_int_pred(const IntHeader* h, const IntPredD
   }
 }
 
+// ---- the common case without compaction ------------------------------------------------------------
+// REFINE (selection &= valid & cmp) and PRED over all rows produce FULL-LENGTH bit words, so no rank / prefix
+// sum is needed. Per entry the CTA first writes a 64-row STEP TABLE into shared memory: for storage-order step j
+// (and half-warp, for 64-bit lanes) the byte offsets of the one/two/three 32-bit words holding the W-bit field,
+// the funnel shift, and where the step's mask word lands. A warp then takes a 1024-row chunk and runs
+//   LDS.128 step | 2x LDS field words | SHF | LOP | IADD | ISETP | VOTE | STS (lane 0)
+// per 32 rows (~12 instructions; the general path is ~90, the per-step recomputation ~50), and finishes the chunk
+// with ONE coalesced pass over its 32 mask words: AND with validity / selection, store, popcount.
+// Requires the entry blob staged in shared memory (`chunk0` is a shared-memory pointer).
+struct FastStep {
+  uint32_t off0, off1, sh, ord4;  // byte offsets from the lane's base; shift; 4 * logical word of the step
+};
+
+template <typename U>
+__device__ __forceinline__ void build_fast_steps(ScanSmem* sm, uint32_t W) {
+  constexpr uint32_t T = FL<U>::T;
+  FastStep* tab = reinterpret_cast<FastStep*>(sm->sel);  // 64 x 16 B (the compaction tables are unused here)
+  uint32_t* off2 = sm->off;                              // third word, W > 32 only
+  if (threadIdx.x < 64u) {
+    const uint32_t j = threadIdx.x & 31u, hw = threadIdx.x >> 5;
+    FastStep st;
+    st.ord4 = FLOrder<U>()(j) * 4u;
+    uint32_t o2 = 0;
+    if (T >= 32) {
+      uint32_t r, L;
+      fl_row_lane<T>(j, hw * 16u, &r, &L);
+      const uint32_t b = r * W, w = b >> 5;
+      st.sh = b & 31u;
+      const uint32_t nw = (st.sh + W + 31u) >> 5;
+      // 32-bit word x of a lane: T=64 -> 64-bit lane word x/2 (16 lanes interleaved), half x%2; T=32 -> row x of 32 lanes
+      auto byte_off = [](uint32_t x) -> uint32_t { return T == 64 ? (x >> 1) * 128u + (x & 1u) * 4u : x * 128u; };
+      st.off0 = byte_off(w);
+      st.off1 = nw > 1u ? byte_off(w + 1u) : st.off0;
+      o2 = nw > 2u ? byte_off(w + 2u) : st.off1;
+    } else {
+      st.off0 = st.off1 = st.sh = 0;
+    }
+    tab[threadIdx.x] = st;
+    off2[threadIdx.x] = o2;
+  }
+}
+
+template <typename U, int MODE, typename C>
+__device__ __forceinline__ void int_bits_fast(const EntryIo& w, const IntHeader* h, const uint8_t* packed,
+                                              const uint32_t* valid, const URange<C>& g, ScanSmem* sm) {
+  constexpr uint32_t T = FL<U>::T;
+  const uint32_t n = h->n, W = h->bit_width;
+  const uint32_t n_words = (n + 31u) >> 5, n_chunks = (n + 1023u) >> 10;
+  const uint32_t chunk_bytes = 128u * W;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t* out_bits = reinterpret_cast<uint32_t*>(w.out);
+  uint32_t* out_valid = (MODE == MODE_PRED && valid) ? w.out_valid : nullptr;
+  const uint32_t* sel = w.sel;
+  const uint32_t tail = n & 31u;
+  build_fast_steps<U>(sm, W);
+  __syncthreads();
+  const FastStep* tab = reinterpret_cast<const FastStep*>(sm->sel) + (T == 64 ? (lane >> 4) * 32u : 0u);
+  const uint32_t* off2 = sm->off + (T == 64 ? (lane >> 4) * 32u : 0u);
+  uint8_t* wbuf = reinterpret_cast<uint8_t*>(sm->maskbuf + warp * 32u);  // this warp's 32 mask words
+  const uint32_t lane_off = T == 64 ? (lane & 15u) * 8u : lane * 4u;
+  const uint32_t mask32 = W >= 32u ? 0xffffffffu : ((1u << W) - 1u);
+  const uint64_t mask64 = W >= 64u ? ~0ull : ((1ull << W) - 1ull);
+  const uint32_t negmask = g.neg ? kFullMask : 0u;
+  uint32_t survivors = 0;
+  for (uint32_t c = warp; c < n_chunks; c += 8u) {
+    const uint8_t* chunk = packed + c * chunk_bytes;
+    const uint32_t lbase = smem_u32(chunk) + lane_off;  // 32-bit shared address: LDS, no 64-bit pointer math
+#pragma unroll 8
+    for (uint32_t j = 0; j < 32; ++j) {
+      const FastStep st = tab[j];
+      bool hit;
+      if (T >= 32) {
+        const uint32_t w0 = lds_u32(lbase + st.off0);
+        const uint32_t w1 = lds_u32(lbase + st.off1);
+        if (sizeof(C) == 8) {
+          const uint32_t w2 = lds_u32(lbase + off2[j]);
+          const uint64_t u =
+              ((static_cast<uint64_t>(__funnelshift_r(w1, w2, st.sh)) << 32) | __funnelshift_r(w0, w1, st.sh)) & mask64;
+          hit = (static_cast<C>(u - g.lo)) <= g.span;
+        } else {
+          const uint32_t u = __funnelshift_r(w0, w1, st.sh) & mask32;
+          hit = (static_cast<C>(u - g.lo)) <= g.span;
+        }
+      } else {
+        const uint32_t u = fl_step_small<U>(reinterpret_cast<const U*>(chunk), j, lane, W, mask32);
+        hit = (static_cast<C>(u - g.lo)) <= g.span;
+      }
+      const uint32_t cw = __ballot_sync(kFullMask, hit);
+      if (lane == 0) *reinterpret_cast<uint32_t*>(wbuf + st.ord4) = cw;
+    }
+    __syncwarp();
+    const uint32_t wi = c * 32u + lane;
+    if (wi < n_words) {
+      uint32_t cw = reinterpret_cast<const uint32_t*>(wbuf)[lane] ^ negmask;  // negated ranges flip once per word
+      uint32_t vw = valid ? valid[wi] : kFullMask;
+      if (wi == n_words - 1u && tail) vw &= (1u << tail) - 1u;  // rows past n in the padded last chunk
+      const uint32_t vo = vw;
+      if (sel) vw &= sel[wi];
+      cw &= vw;
+      out_bits[wi] = cw;
+      if (out_valid) out_valid[wi] = vo;
+      survivors += __popc(cw);
+    }
+    __syncwarp();
+  }
+  if (w.counts) {
+    survivors = warp_sum(survivors);
+    if (lane == 0 && survivors) atomicAdd(&sm->counts[0], survivors);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (MODE == MODE_REFINE) {
+        w.counts[0] = sm->counts[0];
+        w.counts[1] = 0;
+      } else {
+        w.counts[0] = n;
+        w.counts[1] = h->null_count;
+        w.counts[2] = sm->counts[0];
+      }
+    }
+  }
+}
+
 template <typename U, int MODE>
 __device__ __forceinline__ void int_scan_entry(const EntryIo& w, const IntPredDesc& pred, const uint8_t* base,
-                                               ScanSmem* sm) {
+                                               bool staged, ScanSmem* sm) {
   constexpr uint32_t T = FL<U>::T;
   const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
   const uint32_t W = h->bit_width;
@@ -180,51 +363,112 @@ __device__ __forceinline__ void int_scan_entry(const EntryIo& w, const IntPredDe
   int32_t kind = UC_TRUE;
   uint64_t thr64 = 0;
   if (MODE != MODE_DECODE) plan_int_pred(h, pred, &kind, &thr64);
-  const U thr = static_cast<U>(thr64);
-  const U* packed = reinterpret_cast<const U*>(base + h->packed_off);
+  const uint8_t* packed = base + h->packed_off;
   const uint32_t* valid = h->has_nulls ? reinterpret_cast<const uint32_t*>(base + h->validity_off) : nullptr;
-  const uint32_t chunk_words = 1024u * W / T;  // in units of U
+  const uint32_t chunk_bytes = 128u * W;
   U* out_vals = reinterpret_cast<U*>(w.out);
-
+  uint32_t* out_bits = reinterpret_cast<uint32_t*>(w.out);
   const uint32_t lane = threadIdx.x & 31u;
-  auto value_at = [&](uint32_t c, uint32_t j) -> U {
-    if (W == 0) return static_cast<U>(0);
-    return fl_step<U>(packed + static_cast<size_t>(c) * chunk_words, j, lane, W);
+  const uint32_t n = h->n, nulls = h->null_count;
+
+  if (W == 0) {  // entirely null (bit_pack_array.rs:18): nothing packed; masks are all false, values never read
+    auto cmp = [&](uint32_t, uint32_t, uint32_t) -> bool { return false; };
+    auto emit = [&](uint32_t, uint32_t dst, uint32_t, uint32_t) { out_vals[dst] = ref; };
+    scan_entry_rows<MODE>(w.sel, n, valid, nulls, out_bits, w.out_valid, w.counts, sm, cmp, emit);
+    return;
+  }
+  // full-length bit outputs from a staged entry: no compaction needed
+  const bool fast = staged && ((MODE == MODE_REFINE) || (MODE == MODE_PRED && w.sel == nullptr));
+  if (fast && MODE != MODE_DECODE) {
+    if (T == 64 && W > 32u) {
+      int_bits_fast<U, MODE, uint64_t>(w, h, packed, valid, make_range<uint64_t>(kind, thr64), sm);
+    } else {
+      int_bits_fast<U, MODE, uint32_t>(w, h, packed, valid, make_range<uint32_t>(kind, thr64), sm);
+    }
+    return;
+  }
+  if (T == 64 && W > 32u) {
+    const URange<uint64_t> g = make_range<uint64_t>(kind, thr64);
+    auto val = [&](uint32_t c, uint32_t j) -> uint64_t {
+      return fl_step64_hi(reinterpret_cast<const uint32_t*>(packed + static_cast<size_t>(c) * chunk_bytes), j, lane, W);
+    };
+    auto cmp = [&](uint32_t, uint32_t c, uint32_t j) -> bool { return ((val(c, j) - g.lo) <= g.span) != g.neg; };
+    auto emit = [&](uint32_t, uint32_t dst, uint32_t c, uint32_t j) { out_vals[dst] = static_cast<U>(val(c, j) + ref); };
+    scan_entry_rows<MODE>(w.sel, n, valid, nulls, out_bits, w.out_valid, w.counts, sm, cmp, emit, FLOrder<U>());
+    return;
+  }
+  // everything else fits 32 bits in the packed domain
+  const uint32_t mask = W >= 32u ? 0xffffffffu : ((1u << W) - 1u);
+  const URange<uint32_t> g = make_range<uint32_t>(kind, thr64);
+  auto val = [&](uint32_t c, uint32_t j) -> uint32_t {
+    const uint8_t* chunk = packed + static_cast<size_t>(c) * chunk_bytes;
+    if (T == 64) return fl_step64_lo(reinterpret_cast<const uint32_t*>(chunk), j, lane, W, mask);
+    if (T == 32) return fl_step32(reinterpret_cast<const uint32_t*>(chunk), j, lane, W, mask);
+    return fl_step_small<U>(reinterpret_cast<const U*>(chunk), j, lane, W, mask);
   };
-  auto cmp = [&](uint32_t, uint32_t c, uint32_t j) -> bool { return ucmp_eval<U>(kind, value_at(c, j), thr); };
-  auto emit = [&](uint32_t, uint32_t dst, uint32_t c, uint32_t j) { out_vals[dst] = static_cast<U>(value_at(c, j) + ref); };
-  scan_entry_rows<MODE>(w.sel, h->n, valid, h->null_count, reinterpret_cast<uint32_t*>(w.out), w.out_valid,
-                        w.counts, sm, cmp, emit, FLOrder<U>());
+  auto cmp = [&](uint32_t, uint32_t c, uint32_t j) -> bool { return ((val(c, j) - g.lo) <= g.span) != g.neg; };
+  auto emit = [&](uint32_t, uint32_t dst, uint32_t c, uint32_t j) {
+    out_vals[dst] = static_cast<U>(static_cast<U>(val(c, j)) + ref);
+  };
+  scan_entry_rows<MODE>(w.sel, n, valid, nulls, out_bits, w.out_valid, w.counts, sm, cmp, emit, FLOrder<U>());
 }
 
+// Persistent CTAs: each CTA walks entries blockIdx.x, +gridDim.x, ... with a two-deep TMA pipeline — while the
+// warps work on the entry staged in one shared-memory buffer, thread 0 has already issued the bulk copy of the
+// CTA's next entry into the other buffer (its own mbarrier, phase = use count parity). Entry fetch latency is
+// hidden behind compute instead of being paid once per 8192 rows.
 template <int MODE>
-__global__ void __launch_bounds__(256, 6) k_int_scan(ScanIo io, IntPredDesc pred, uint32_t stage_cap) {
+__global__ void __launch_bounds__(256, 4) k_int_scan(ScanIo io, IntPredDesc pred, uint32_t n_entries, uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
-  uint8_t* stage = smem_raw + kScanFixedSmem;
+  uint8_t* stage0 = smem_raw + kScanFixedSmem;
 
-  const EntryRef ref = io.refs[blockIdx.x];
-  const bool staged = ref.blob_bytes <= stage_cap;
-  scan_smem_init(sm);
-  if (threadIdx.x == 0 && staged) {
+  const uint32_t G = gridDim.x;
+  if (threadIdx.x == 0) {
     mbar_init(&sm->bar[0], 1);
+    mbar_init(&sm->bar[1], 1);
     fence_mbar_init();
-    mbar_expect_tx(&sm->bar[0], ref.blob_bytes);
-    tma_bulk_g2s(stage, ref.blob, ref.blob_bytes, &sm->bar[0]);  // whole entry in one bulk copy
+    if (stage_bytes && blockIdx.x < n_entries) {
+      const EntryRef r0 = io.refs[blockIdx.x];
+      if (r0.blob_bytes <= stage_bytes) {
+        mbar_expect_tx(&sm->bar[0], r0.blob_bytes);
+        tma_bulk_g2s(stage0, r0.blob, r0.blob_bytes, &sm->bar[0]);
+      } else {
+        mbar_arrive(&sm->bar[0]);  // oversized entry, read from global: still consume this barrier phase
+      }
+    }
   }
   __syncthreads();
-  const uint8_t* base = ref.blob;
-  if (staged) {
-    mbar_wait(&sm->bar[0], 0);
-    base = stage;
-  }
-  const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
-  const EntryIo w = resolve_io(io, blockIdx.x, MODE == MODE_DECODE ? h->tbits / 8u : 4u);
-  switch (h->tbits) {
-    case 8: int_scan_entry<uint8_t, MODE>(w, pred, base, sm); break;
-    case 16: int_scan_entry<uint16_t, MODE>(w, pred, base, sm); break;
-    case 32: int_scan_entry<uint32_t, MODE>(w, pred, base, sm); break;
-    default: int_scan_entry<uint64_t, MODE>(w, pred, base, sm); break;
+  uint32_t it = 0;
+  for (uint32_t e = blockIdx.x; e < n_entries; e += G, ++it) {
+    const uint32_t buf = it & 1u;
+    const EntryRef ref = io.refs[e];
+    const bool staged = stage_bytes && ref.blob_bytes <= stage_bytes;
+    scan_smem_init(sm);
+    if (threadIdx.x == 0 && stage_bytes && e + G < n_entries) {  // prefetch this CTA's next entry
+      const EntryRef nx = io.refs[e + G];
+      if (nx.blob_bytes <= stage_bytes) {
+        mbar_expect_tx(&sm->bar[buf ^ 1u], nx.blob_bytes);
+        tma_bulk_g2s(stage0 + (buf ^ 1u) * stage_bytes, nx.blob, nx.blob_bytes, &sm->bar[buf ^ 1u]);
+      } else {
+        mbar_arrive(&sm->bar[buf ^ 1u]);
+      }
+    }
+    __syncthreads();
+    const uint8_t* base = ref.blob;
+    if (staged) {
+      mbar_wait(&sm->bar[buf], (it >> 1) & 1u);
+      base = stage0 + buf * stage_bytes;
+    }
+    const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
+    const EntryIo w = resolve_io(io, e, MODE == MODE_DECODE ? h->tbits / 8u : 4u);
+    switch (h->tbits) {
+      case 8: int_scan_entry<uint8_t, MODE>(w, pred, base, staged, sm); break;
+      case 16: int_scan_entry<uint16_t, MODE>(w, pred, base, staged, sm); break;
+      case 32: int_scan_entry<uint32_t, MODE>(w, pred, base, staged, sm); break;
+      default: int_scan_entry<uint64_t, MODE>(w, pred, base, staged, sm); break;
+    }
+    __syncthreads();  // everyone is done with stage[buf] and the control area before the next round reuses them
   }
 }
 
@@ -232,25 +476,40 @@ cudaError_t launch_int_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
                             uint32_t max_blob_bytes, cudaStream_t s) {
   if (n_entries == 0) return cudaSuccess;
   const uint32_t stage = max_blob_bytes <= kStageCap ? ((max_blob_bytes + 127u) & ~127u) : 0u;
-  const uint32_t smem = kScanFixedSmem + stage;
+  // Two stage buffers (prefetch of the CTA's next entry) only while >= 3 CTAs still fit on an SM; wide columns
+  // (W = 64: 64 KB per entry) are better off with one buffer per CTA and more CTAs in flight.
+  const bool pipelined = stage != 0 && 3u * (kScanFixedSmem + 2u * stage + 1024u) <= 227u * 1024u;
+  const uint32_t smem = kScanFixedSmem + (pipelined ? 2u : 1u) * stage;
   static bool attr_set = false;
+  static int n_sm = 148;
   if (!attr_set) {
     cudaError_t e;
     e = cudaFuncSetAttribute(k_int_scan<MODE_DECODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kScanFixedSmem + kStageCap);
+                             kScanFixedSmem + 2 * kStageCap);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_int_scan<MODE_PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kScanFixedSmem + kStageCap);
+                             kScanFixedSmem + 2 * kStageCap);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_int_scan<MODE_REFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kScanFixedSmem + kStageCap);
+                             kScanFixedSmem + 2 * kStageCap);
     if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     attr_set = true;
   }
+  // pipelined: persistent grid, as many CTAs as fit at once (4 per SM by registers); else one CTA per entry
+  uint32_t grid = n_entries;
+  if (pipelined) {
+    uint32_t per_sm = 4;
+    while (per_sm > 1 && per_sm * (smem + 1024u) > 227u * 1024u) --per_sm;
+    grid = static_cast<uint32_t>(n_sm) * per_sm;
+    if (grid > n_entries) grid = n_entries;
+  }
   switch (mode) {
-    case MODE_DECODE: k_int_scan<MODE_DECODE><<<n_entries, 256, smem, s>>>(io, pred, stage); break;
-    case MODE_PRED: k_int_scan<MODE_PRED><<<n_entries, 256, smem, s>>>(io, pred, stage); break;
-    default: k_int_scan<MODE_REFINE><<<n_entries, 256, smem, s>>>(io, pred, stage); break;
+    case MODE_DECODE: k_int_scan<MODE_DECODE><<<grid, 256, smem, s>>>(io, pred, n_entries, stage); break;
+    case MODE_PRED: k_int_scan<MODE_PRED><<<grid, 256, smem, s>>>(io, pred, n_entries, stage); break;
+    default: k_int_scan<MODE_REFINE><<<grid, 256, smem, s>>>(io, pred, n_entries, stage); break;
   }
   return cudaGetLastError();
 }

@@ -9,7 +9,7 @@ namespace lc {
 
 // Shared-memory budget of the scan kernels: a fixed control area + the staged entry blob.
 constexpr uint32_t kScanFixedSmem = 4608;
-constexpr uint32_t kStageCap = 96 * 1024;  // entries larger than this are read straight from global
+constexpr uint32_t kStageCap = 100 * 1024;  // entries larger than this are read straight from global
 
 enum ScanMode : int32_t {
   MODE_DECODE = 0,  // to_arrow_array / filter: values (+validity) of the selected rows
