@@ -179,6 +179,26 @@ __device__ __forceinline__ EntryIo resolve_io(const ScanIo& io, uint32_t e, uint
   return r;
 }
 
+// The three per-entry offsets of ScanIo, fetched one iteration ahead by threads 0..2 of a persistent CTA so the
+// dependent global loads are off the entry's critical path.
+__device__ __forceinline__ uint64_t load_io_word(const ScanIo& io, uint32_t e, uint32_t t) {
+  if (t == 0) return io.sel_base ? io.sel_off[e] : kNoSel;
+  if (t == 1) return io.out_base ? io.out_off[e] : 0ull;
+  return io.valid_base ? io.valid_off[e] : 0ull;
+}
+__device__ __forceinline__ uint64_t load_ref_word(const ScanIo& io, uint32_t e, uint32_t t) {
+  return t == 0 ? reinterpret_cast<uint64_t>(io.refs[e].blob) : static_cast<uint64_t>(io.refs[e].blob_bytes);
+}
+__device__ __forceinline__ EntryIo resolve_io_slot(const ScanIo& io, const uint64_t* slot, uint32_t e, uint32_t elem_bytes) {
+  EntryIo r;
+  const uint64_t so = slot[0];
+  r.sel = (io.sel_base && so != kNoSel) ? io.sel_base + so : nullptr;
+  r.out = io.out_base ? static_cast<uint8_t*>(io.out_base) + slot[1] * elem_bytes : nullptr;
+  r.out_valid = io.valid_base ? io.valid_base + slot[2] : nullptr;
+  r.counts = io.counts ? io.counts + static_cast<size_t>(e) * io.counts_stride : nullptr;
+  return r;
+}
+
 // (op, literal) -> compare in the unsigned packed domain u = v - reference. All valid values satisfy
 // reference <= v <= reference + (2^W - 1) in the column's own ordering, so a literal outside that window
 // folds to a constant and one inside becomes an unsigned threshold. No 128-bit arithmetic needed:
@@ -241,7 +261,7 @@ __device__ __forceinline__ void plan_int_pred(const IntHeader* h, const IntPredD
 // with ONE coalesced pass over its 32 mask words: AND with validity / selection, store, popcount.
 // Requires the entry blob staged in shared memory (`chunk0` is a shared-memory pointer).
 struct FastStep {
-  uint32_t off0, off1, sh, ord4;  // byte offsets from the lane's base; shift; 4 * logical word of the step
+  uint32_t off0, off1, sh, pad;  // byte offsets from the lane's base; funnel shift
 };
 
 template <typename U>
@@ -252,7 +272,7 @@ __device__ __forceinline__ void build_fast_steps(ScanSmem* sm, uint32_t W) {
   if (threadIdx.x < 64u) {
     const uint32_t j = threadIdx.x & 31u, hw = threadIdx.x >> 5;
     FastStep st;
-    st.ord4 = FLOrder<U>()(j) * 4u;
+    st.pad = 0;
     uint32_t o2 = 0;
     if (T >= 32) {
       uint32_t r, L;
@@ -289,7 +309,7 @@ __device__ __forceinline__ void int_bits_fast(const EntryIo& w, const IntHeader*
   __syncthreads();
   const FastStep* tab = reinterpret_cast<const FastStep*>(sm->sel) + (T == 64 ? (lane >> 4) * 32u : 0u);
   const uint32_t* off2 = sm->off + (T == 64 ? (lane >> 4) * 32u : 0u);
-  uint8_t* wbuf = reinterpret_cast<uint8_t*>(sm->maskbuf + warp * 32u);  // this warp's 32 mask words
+  const uint32_t ordl = FLOrder<U>()(lane);  // lane j keeps the mask word of step j = logical word order(j)
   const uint32_t lane_off = T == 64 ? (lane & 15u) * 8u : lane * 4u;
   const uint32_t mask32 = W >= 32u ? 0xffffffffu : ((1u << W) - 1u);
   const uint64_t mask64 = W >= 64u ? ~0ull : ((1ull << W) - 1ull);
@@ -298,43 +318,47 @@ __device__ __forceinline__ void int_bits_fast(const EntryIo& w, const IntHeader*
   for (uint32_t c = warp; c < n_chunks; c += 8u) {
     const uint8_t* chunk = packed + c * chunk_bytes;
     const uint32_t lbase = smem_u32(chunk) + lane_off;  // 32-bit shared address: LDS, no 64-bit pointer math
-#pragma unroll 8
-    for (uint32_t j = 0; j < 32; ++j) {
-      const FastStep st = tab[j];
-      bool hit;
-      if (T >= 32) {
-        const uint32_t w0 = lds_u32(lbase + st.off0);
-        const uint32_t w1 = lds_u32(lbase + st.off1);
-        if (sizeof(C) == 8) {
-          const uint32_t w2 = lds_u32(lbase + off2[j]);
-          const uint64_t u =
-              ((static_cast<uint64_t>(__funnelshift_r(w1, w2, st.sh)) << 32) | __funnelshift_r(w0, w1, st.sh)) & mask64;
-          hit = (static_cast<C>(u - g.lo)) <= g.span;
+    const uint32_t wi = c * 32u + ordl;  // a permutation inside one 128-byte line: still one coalesced access
+    uint32_t sw = kFullMask;  // issued before the step loop: the global load overlaps the 32 steps
+    if (sel && wi < n_words) sw = sel[wi];
+    uint32_t mine = 0;
+    for (uint32_t j0 = 0; j0 < 32; j0 += 8) {
+      const uint32_t lrel = lane - j0;
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) {
+        const uint32_t j = j0 + k;
+        const FastStep st = tab[j];
+        bool hit;
+        if (T >= 32) {
+          const uint32_t w0 = lds_u32(lbase + st.off0);
+          const uint32_t w1 = lds_u32(lbase + st.off1);
+          if (sizeof(C) == 8) {
+            const uint32_t w2 = lds_u32(lbase + off2[j]);
+            const uint64_t u =
+                ((static_cast<uint64_t>(__funnelshift_r(w1, w2, st.sh)) << 32) | __funnelshift_r(w0, w1, st.sh)) & mask64;
+            hit = (static_cast<C>(u - g.lo)) <= g.span;
+          } else {
+            const uint32_t u = __funnelshift_r(w0, w1, st.sh) & mask32;
+            hit = (static_cast<C>(u - g.lo)) <= g.span;
+          }
         } else {
-          const uint32_t u = __funnelshift_r(w0, w1, st.sh) & mask32;
+          const uint32_t u = fl_step_small<U>(reinterpret_cast<const U*>(chunk), j, lane, W, mask32);
           hit = (static_cast<C>(u - g.lo)) <= g.span;
         }
-      } else {
-        const uint32_t u = fl_step_small<U>(reinterpret_cast<const U*>(chunk), j, lane, W, mask32);
-        hit = (static_cast<C>(u - g.lo)) <= g.span;
+        const uint32_t cw = __ballot_sync(kFullMask, hit);
+        if (lrel == k) mine = cw;  // no shared-memory store in the loop: the steps of a group can overlap
       }
-      const uint32_t cw = __ballot_sync(kFullMask, hit);
-      if (lane == 0) *reinterpret_cast<uint32_t*>(wbuf + st.ord4) = cw;
     }
-    __syncwarp();
-    const uint32_t wi = c * 32u + lane;
     if (wi < n_words) {
-      uint32_t cw = reinterpret_cast<const uint32_t*>(wbuf)[lane] ^ negmask;  // negated ranges flip once per word
+      uint32_t cw = mine ^ negmask;  // negated ranges flip once per word
       uint32_t vw = valid ? valid[wi] : kFullMask;
       if (wi == n_words - 1u && tail) vw &= (1u << tail) - 1u;  // rows past n in the padded last chunk
       const uint32_t vo = vw;
-      if (sel) vw &= sel[wi];
-      cw &= vw;
+      cw &= vw & sw;
       out_bits[wi] = cw;
       if (out_valid) out_valid[wi] = vo;
       survivors += __popc(cw);
     }
-    __syncwarp();
   }
   if (w.counts) {
     survivors = warp_sum(survivors);
@@ -424,50 +448,54 @@ __global__ void __launch_bounds__(256, 4) k_int_scan(ScanIo io, IntPredDesc pred
   uint8_t* stage0 = smem_raw + kScanFixedSmem;
 
   const uint32_t G = gridDim.x;
+  const bool staged = stage_bytes != 0;  // the host sizes the stage for the largest entry of the launch, or passes 0
   if (threadIdx.x == 0) {
     mbar_init(&sm->bar[0], 1);
     mbar_init(&sm->bar[1], 1);
     fence_mbar_init();
-    if (stage_bytes && blockIdx.x < n_entries) {
+    if (staged && blockIdx.x < n_entries) {
       const EntryRef r0 = io.refs[blockIdx.x];
-      if (r0.blob_bytes <= stage_bytes) {
-        mbar_expect_tx(&sm->bar[0], r0.blob_bytes);
-        tma_bulk_g2s(stage0, r0.blob, r0.blob_bytes, &sm->bar[0]);
-      } else {
-        mbar_arrive(&sm->bar[0]);  // oversized entry, read from global: still consume this barrier phase
-      }
+      mbar_expect_tx(&sm->bar[0], r0.blob_bytes);
+      tma_bulk_g2s(stage0, r0.blob, r0.blob_bytes, &sm->bar[0]);
     }
   }
+  if (threadIdx.x < 3u && blockIdx.x < n_entries) sm->io_slot[0][threadIdx.x] = load_io_word(io, blockIdx.x, threadIdx.x);
+  if (threadIdx.x - 3u < 2u && blockIdx.x + G < n_entries) sm->ref_slot[threadIdx.x - 3u] = load_ref_word(io, blockIdx.x + G, threadIdx.x - 3u);
   __syncthreads();
   uint32_t it = 0;
   for (uint32_t e = blockIdx.x; e < n_entries; e += G, ++it) {
     const uint32_t buf = it & 1u;
-    const EntryRef ref = io.refs[e];
-    const bool staged = stage_bytes && ref.blob_bytes <= stage_bytes;
+    const bool more = e + G < n_entries;
     scan_smem_init(sm);
-    if (threadIdx.x == 0 && stage_bytes && e + G < n_entries) {  // prefetch this CTA's next entry
-      const EntryRef nx = io.refs[e + G];
-      if (nx.blob_bytes <= stage_bytes) {
-        mbar_expect_tx(&sm->bar[buf ^ 1u], nx.blob_bytes);
-        tma_bulk_g2s(stage0 + (buf ^ 1u) * stage_bytes, nx.blob, nx.blob_bytes, &sm->bar[buf ^ 1u]);
-      } else {
-        mbar_arrive(&sm->bar[buf ^ 1u]);
-      }
+    if (threadIdx.x == 0 && staged && more) {  // prefetch this CTA's next entry into the other buffer
+      const uint32_t nbytes = static_cast<uint32_t>(sm->ref_slot[1]);
+      mbar_expect_tx(&sm->bar[buf ^ 1u], nbytes);
+      tma_bulk_g2s(stage0 + (buf ^ 1u) * stage_bytes, reinterpret_cast<const void*>(sm->ref_slot[0]), nbytes,
+                   &sm->bar[buf ^ 1u]);
     }
+    // threads 0..2: io offsets of the next entry; threads 3..4: blob / size of the one after. Both are consumed at
+    // the bottom of the iteration, so the global loads have the whole entry to complete.
+    uint64_t nx_io = 0;  // consumed at the bottom of the iteration: the load has the whole entry to complete
+    if (threadIdx.x < 3u && more) nx_io = load_io_word(io, e + G, threadIdx.x);
+    if (threadIdx.x - 3u < 2u && e + 2u * G < n_entries) nx_io = load_ref_word(io, e + 2u * G, threadIdx.x - 3u);
     __syncthreads();
-    const uint8_t* base = ref.blob;
+    const uint8_t* base;
     if (staged) {
       mbar_wait(&sm->bar[buf], (it >> 1) & 1u);
       base = stage0 + buf * stage_bytes;
+    } else {
+      base = io.refs[e].blob;
     }
     const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
-    const EntryIo w = resolve_io(io, e, MODE == MODE_DECODE ? h->tbits / 8u : 4u);
+    const EntryIo w = resolve_io_slot(io, sm->io_slot[buf], e, MODE == MODE_DECODE ? h->tbits / 8u : 4u);
     switch (h->tbits) {
       case 8: int_scan_entry<uint8_t, MODE>(w, pred, base, staged, sm); break;
       case 16: int_scan_entry<uint16_t, MODE>(w, pred, base, staged, sm); break;
       case 32: int_scan_entry<uint32_t, MODE>(w, pred, base, staged, sm); break;
       default: int_scan_entry<uint64_t, MODE>(w, pred, base, staged, sm); break;
     }
+    if (threadIdx.x < 3u) sm->io_slot[buf ^ 1u][threadIdx.x] = nx_io;
+    else if (threadIdx.x < 5u) sm->ref_slot[threadIdx.x - 3u] = nx_io;
     __syncthreads();  // everyone is done with stage[buf] and the control area before the next round reuses them
   }
 }

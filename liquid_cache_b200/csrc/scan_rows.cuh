@@ -27,6 +27,8 @@ struct ScanSmem {
   uint32_t maskbuf[264];
   uint32_t validbuf[264];
   uint8_t scratch[8][32];
+  uint64_t io_slot[2][4];  // persistent kernels: {sel_off, out_off, valid_off} of this / the next entry
+  uint64_t ref_slot[2];    // persistent kernels: {blob, blob_bytes} of the entry after the next one
 };
 static_assert(sizeof(ScanSmem) <= kScanFixedSmem, "fixed smem area too small");
 
