@@ -140,6 +140,10 @@ struct lc_ctx {
   uint64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   uint64_t epoch = 0;            // bumped whenever an entry is released (invalidates cached entry lists)
   uint8_t* d_needle = nullptr;   // small device buffer for predicate needles
+  cudaStream_t copy_stream = nullptr;  // results of chunk c travel to the host while chunk c+1 is computed
+  cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint8_t* sel_stage = nullptr;  // pinned staging of the caller's selection bitmaps (batched calls)
+  uint64_t sel_stage_cap = 0;
   unsigned long long* d_prof = nullptr;  // profile counters (lc_ctx_profile_counters)
   bool prof_on = false;
   bool timing_on = false;        // lc_ctx_kernel_timing

@@ -252,6 +252,10 @@ void lc_ctx_destroy(lc_ctx* ctx) {
   }
   drop_ref_cache(ctx);
   if (ctx->d_needle) cudaFree(ctx->d_needle);
+  if (ctx->sel_stage) cudaFreeHost(ctx->sel_stage);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (cudaEvent_t& e : ctx->ev_chunk)
+    if (e) cudaEventDestroy(e);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);

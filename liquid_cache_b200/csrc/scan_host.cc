@@ -8,19 +8,11 @@
 #include <cstdlib>
 
 #include "host_common.h"
+#include "host_pool.h"
 
 namespace lc {
 
 namespace {
-
-bool all_ones(const uint8_t* bits, uint64_t n) {
-  const uint64_t full = n / 8;
-  for (uint64_t i = 0; i < full; ++i)
-    if (bits[i] != 0xFF) return false;
-  const uint32_t rem = static_cast<uint32_t>(n & 7);
-  if (rem && (bits[full] & ((1u << rem) - 1u)) != ((1u << rem) - 1u)) return false;
-  return true;
-}
 
 // per-entry selection bookkeeping shared by every batched call
 struct SelPlan {
@@ -31,8 +23,12 @@ struct SelPlan {
   uint64_t total_k = 0;
 };
 
-void plan_selection(Entry* const* entries, uint64_t n, const uint8_t* const* sel_bits, SelPlan* p,
-                    const DevSel* dev = nullptr) {
+// Host selections: every bitmap is copied ONCE into the context's pinned staging area (word aligned, tail bits
+// cleared, zero padded) and counted on the way, split over the host pool — the bitmaps usually come straight out of
+// a device-to-host copy, so this walk is DRAM bound on one core. The staged words go to the device with one copy
+// (upload_selection). A selection that turns out to be all ones is treated as dense.
+int plan_selection(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t* const* sel_bits, SelPlan* p,
+                   const DevSel* dev = nullptr) {
   p->bits.assign(n, nullptr);
   p->k.assign(n, 0);
   p->word_off.assign(n, 0);
@@ -41,29 +37,62 @@ void plan_selection(Entry* const* entries, uint64_t n, const uint8_t* const* sel
       p->k[i] = dev->all_rows ? entries[i]->n : dev->k[i];
       p->total_k += p->k[i];
     }
-    return;
+    return LC_OK;
+  }
+  if (!sel_bits) {
+    for (uint64_t i = 0; i < n; ++i) {
+      p->k[i] = entries[i]->n;
+      p->total_k += p->k[i];
+    }
+    return LC_OK;
   }
   for (uint64_t i = 0; i < n; ++i) {
-    const uint32_t rows = entries[i]->n;
-    const uint8_t* b = sel_bits ? sel_bits[i] : nullptr;
-    if (b && all_ones(b, rows)) b = nullptr;
-    p->bits[i] = b;
-    p->k[i] = b ? static_cast<uint32_t>(popcount_bits(b, rows)) : rows;
-    if (b) {
+    p->bits[i] = sel_bits[i];
+    if (sel_bits[i]) {
       p->word_off[i] = p->sel_words;
-      p->sel_words += round_up((rows + 31) / 32, 4);
+      p->sel_words += round_up((entries[i]->n + 31) / 32, 4);
     }
-    p->total_k += p->k[i];
   }
+  const uint64_t need = p->sel_words * 4 + 64;
+  if (need > ctx->sel_stage_cap) {
+    if (ctx->sel_stage) cudaFreeHost(ctx->sel_stage);
+    ctx->sel_stage = nullptr;
+    ctx->sel_stage_cap = 0;
+    uint64_t cap = 1ull << 20;
+    while (cap < need) cap *= 2;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->sel_stage), cap, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("selection staging: cudaHostAlloc of %llu bytes failed", (unsigned long long)cap);
+      return LC_ERR_OOM;
+    }
+    ctx->sel_stage_cap = cap;
+  }
+  uint8_t* stage = ctx->sel_stage;
+  parallel_for(n, 64, [&](uint64_t b, uint64_t e) {
+    for (uint64_t i = b; i < e; ++i) {
+      const uint32_t rows = entries[i]->n;
+      if (!p->bits[i]) {
+        p->k[i] = rows;
+        continue;
+      }
+      const uint64_t words = round_up((rows + 31) / 32, 4);
+      uint8_t* dst = stage + p->word_off[i] * 4;
+      copy_bits(p->bits[i], 0, rows, dst, words * 4);
+      const uint32_t k = static_cast<uint32_t>(popcount_bits(dst, words * 32));  // padding is zero
+      p->k[i] = k;
+      if (k == rows) p->bits[i] = nullptr;  // dense after all: the kernels take their no-selection path
+    }
+  });
+  for (uint64_t i = 0; i < n; ++i) p->total_k += p->k[i];
+  return LC_OK;
 }
 
-void fill_selection(const SelPlan& p, Entry* const* entries, uint64_t n, uint32_t* h_sel) {
-  for (uint64_t i = 0; i < n; ++i) {
-    if (!p.bits[i]) continue;
-    const uint32_t rows = entries[i]->n;
-    const uint64_t words = round_up((rows + 31) / 32, 4);
-    copy_bits(p.bits[i], 0, rows, reinterpret_cast<uint8_t*>(h_sel + p.word_off[i]), words * 4);
-  }
+// One host-to-device copy of everything plan_selection staged.
+int upload_selection(lc_ctx* ctx, const SelPlan& p, uint8_t* d_sel, cudaStream_t s) {
+  if (p.sel_words == 0) return LC_OK;
+  LC_CUDA_OK(cudaMemcpyAsync(d_sel, ctx->sel_stage, p.sel_words * 4, cudaMemcpyHostToDevice, s));
+  ctx->h2d_bytes += p.sel_words * 4;
+  return LC_OK;
 }
 
 // KMP failure links of the LIKE needle
@@ -292,7 +321,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   LC_TRY(check_same_type(entries, n, "eval_predicate_many"));
   const bool is_int = (entries[0]->liquid_type == LC_LIQUID_INTEGER);
   SelPlan sp;
-  plan_selection(entries, n, sel_bits, &sp);
+  LC_TRY(plan_selection(ctx, entries, n, sel_bits, &sp));
   StrLaunch sl;
   IntPredDesc ip{};
   if (is_int) LC_TRY(make_int_pred(pred, &ip));
@@ -356,7 +385,6 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     h_out_off[i] = out_word_off[i];
   }
   if (!is_int) std::memcpy(h_up + up_offs, sl.needle_blob.data(), sl.needle_blob.size());
-  fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_offs + up_needle));
   ScanIo io{};
   io.refs = rl->d_refs;
   io.sel_base = sp.sel_words ? reinterpret_cast<const uint32_t*>(d_up + up_offs + up_needle) : nullptr;
@@ -369,35 +397,74 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   io.counts_stride = 4;
   cudaStream_t s = ctx->stream;
   tr.mark("plan + fill");
-  LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
-  ctx->h2d_bytes += up_total;
-  if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
-  if (is_int) {
-    LC_CUDA_OK(launch_int_scan(MODE_PRED, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
-  } else {
+  LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_offs + up_needle, cudaMemcpyHostToDevice, s));
+  ctx->h2d_bytes += up_offs + up_needle;
+  LC_TRY(upload_selection(ctx, sp, d_up + up_offs + up_needle, s));
+  // With page-locked caller buffers the launch is cut into chunks of entries: the masks of chunk c cross PCIe on
+  // the copy stream while chunk c+1 is being evaluated (mask download ~ kernel time for 1 KB per 8192 rows).
+  const uint64_t span = out_words * 4;
+  static const int chunk_pref = [] {
+    const char* e = std::getenv("LC_EVAL_CHUNKS");
+    const int v = e ? std::atoi(e) : 4;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+  }();
+  const int n_chunks = (direct && n >= 2048 && span) ? chunk_pref : 1;
+  if (n_chunks > 1 && !ctx->copy_stream) {
+    LC_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : ctx->ev_chunk) LC_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (!is_int) {
     sl.desc.needle = d_up + up_offs;
     sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
-    const bool like = (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
-    LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(n), io, sl.desc, like ? rl->max_head_like : rl->max_head,
-                               rl->max_unique, s));
+  }
+  const bool like = !is_int && (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
+  if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
+  for (int c = 0; c < n_chunks; ++c) {
+    const uint64_t c0 = n * c / n_chunks, c1 = n * (c + 1) / n_chunks;
+    ScanIo ioc = io;
+    ioc.refs += c0;
+    ioc.sel_off += c0;
+    ioc.out_off += c0;
+    ioc.valid_off += c0;
+    ioc.counts += c0 * io.counts_stride;
+    if (is_int) {
+      LC_CUDA_OK(launch_int_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, ip, rl->max_blob, s));
+    } else {
+      LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, sl.desc,
+                                 like ? rl->max_head_like : rl->max_head, rl->max_unique, s));
+    }
+    ctx->kernel_launches++;
+    if (n_chunks > 1) {
+      const uint64_t b0 = out_word_off[c0] * 4, b1 = (c1 < n ? out_word_off[c1] * 4 : span);
+      LC_CUDA_OK(cudaEventRecord(ctx->ev_chunk[c], s));
+      LC_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c], 0));
+      if (b1 > b0) {
+        LC_CUDA_OK(cudaMemcpyAsync(out.values + first_off + b0, d_dn + dn_counts + b0, b1 - b0, cudaMemcpyDeviceToHost,
+                                   ctx->copy_stream));
+        if (want_valid)
+          LC_CUDA_OK(cudaMemcpyAsync(out.validity + first_off + b0, d_dn + dn_counts + dn_bits + b0, b1 - b0,
+                                     cudaMemcpyDeviceToHost, ctx->copy_stream));
+      }
+    }
   }
   if (ctx->timing_on) {
     cudaEventRecord(ctx->ev_b, s);
     ctx->timing_valid = true;
   }
-  ctx->kernel_launches++;
-  const uint64_t span = out_words * 4;
   if (direct) {
     // the caller's buffers are page-locked: results land in them straight from the device
     LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
-    if (span) LC_CUDA_OK(cudaMemcpyAsync(out.values + first_off, d_dn + dn_counts, span, cudaMemcpyDeviceToHost, s));
-    if (want_valid && span)
-      LC_CUDA_OK(cudaMemcpyAsync(out.validity + first_off, d_dn + dn_counts + dn_bits, span, cudaMemcpyDeviceToHost, s));
+    if (n_chunks == 1) {
+      if (span) LC_CUDA_OK(cudaMemcpyAsync(out.values + first_off, d_dn + dn_counts, span, cudaMemcpyDeviceToHost, s));
+      if (want_valid && span)
+        LC_CUDA_OK(cudaMemcpyAsync(out.validity + first_off, d_dn + dn_counts + dn_bits, span, cudaMemcpyDeviceToHost, s));
+    }
     ctx->d2h_bytes += dn_counts + span * (want_valid ? 2 : 1);
   } else {
     LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
     ctx->d2h_bytes += dn_total;
   }
+  if (n_chunks > 1) LC_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));
   LC_CUDA_OK(cudaStreamSynchronize(s));
   tr.mark(direct ? "upload + kernel + direct D2H" : "upload + kernel + staged D2H");
 
@@ -538,8 +605,10 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       return LC_ERR_INVALID;
     }
   }
+  tr.mark("type check");
   SelPlan sp;
-  plan_selection(entries, n, sel_bits, &sp, dev_sel);
+  LC_TRY(plan_selection(ctx, entries, n, sel_bits, &sp, dev_sel));
+  tr.mark("stage selection");
   if (dev_out) {
     set_error("device-resident results are not wired up for this call yet");
     return LC_ERR_INVALID;
@@ -631,11 +700,11 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       return LC_ERR_OOM;
     }
     fill_offsets(h_up, nullptr);
-    if (!dev_sel) fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_offs));
     const ScanIo io = make_io(d_up, d_dn, d_vals);
     IntPredDesc ip{};
-    LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
-    ctx->h2d_bytes += up_total;
+    LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_offs, cudaMemcpyHostToDevice, s));
+    ctx->h2d_bytes += up_offs;
+    if (!dev_sel) LC_TRY(upload_selection(ctx, sp, d_up + up_offs, s));
     LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
     ctx->kernel_launches++;
     HostBuf values{host_alloc(rows * tb), rows * tb};
@@ -690,7 +759,6 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     return LC_ERR_OOM;
   }
   fill_offsets(h_up, &ulen_off);
-  if (!dev_sel) fill_selection(sp, entries, n, reinterpret_cast<uint32_t*>(h_up + up_offs));
   StrGatherIo g{};
   g.io = make_io(d_up, d_dn, nullptr);
   g.row_off_base = reinterpret_cast<uint32_t*>(d_rowoff);
@@ -699,8 +767,9 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   g.row_base = reinterpret_cast<const uint64_t*>(d_up) + n;
   g.ulen_off = reinterpret_cast<const uint64_t*>(d_up) + 3 * n;
   g.byte_base = reinterpret_cast<const uint64_t*>(d_up) + 4 * n;
-  LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_total, cudaMemcpyHostToDevice, s));
-  ctx->h2d_bytes += up_total;
+  LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_offs, cudaMemcpyHostToDevice, s));
+  ctx->h2d_bytes += up_offs;
+  if (!dev_sel) LC_TRY(upload_selection(ctx, sp, d_up + up_offs, s));
   tr.mark("fill + upload");
   LC_CUDA_OK(launch_str_lengths(static_cast<uint32_t>(n), g, rl->max_head, s));
   ctx->kernel_launches++;
