@@ -168,6 +168,12 @@ void lc_release(lc_ctx* ctx, lc_handle h);
 uint64_t lc_len(lc_ctx* ctx, lc_handle h);           /* LiquidArray::len                      */
 uint64_t lc_memory_size(lc_ctx* ctx, lc_handle h);   /* LiquidArray::get_array_memory_size    */
 int32_t lc_data_type(lc_ctx* ctx, lc_handle h);      /* LiquidArray::data_type -> lc_liquid_type */
+/* The entry's HBM image (layout: liquid_cache_b200/csrc/entry_layout.h) copied to host memory, and the FSST symbol
+ * table its byte-view sections are coded against (2320-byte lc::FsstTable; LC_ERR_INVALID for integer entries).
+ * The closest reference call is LiquidArray::to_bytes (liquid_array/mod.rs:116-121); the image is this library's own
+ * format, not LQDA. Pass out == NULL to query the size. Used by the insert-parity tests. */
+int lc_entry_image(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+int lc_entry_fsst_table(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 /* LiquidArray::original_arrow_data_type, as an Arrow C format string copied into buf. */
 int lc_arrow_format(lc_ctx* ctx, lc_handle h, char* buf, size_t buf_len);
 

@@ -115,6 +115,22 @@ class GpuLiquidArray:
     def data_type(self) -> int:
         return int(N.lib().lc_data_type(self._cache._ctx, self._h))
 
+    def entry_image(self) -> bytes:
+        """The entry's HBM image (csrc/entry_layout.h), copied to the host."""
+        nb = C.c_uint64(0)
+        N.check(N.lib().lc_entry_image(self._cache._ctx, self._h, None, 0, C.byref(nb)))
+        buf = np.zeros(nb.value, dtype=np.uint8)
+        N.check(N.lib().lc_entry_image(self._cache._ctx, self._h, buf.ctypes.data, nb.value, C.byref(nb)))
+        return buf.tobytes()
+
+    def fsst_table(self) -> bytes:
+        """The column chunk's FSST symbol table as the kernels see it (lc::FsstTable: 256 x u64 symbols, 256 x u8 lengths)."""
+        nb = C.c_uint64(0)
+        N.check(N.lib().lc_entry_fsst_table(self._cache._ctx, self._h, None, 0, C.byref(nb)))
+        buf = np.zeros(nb.value, dtype=np.uint8)
+        N.check(N.lib().lc_entry_fsst_table(self._cache._ctx, self._h, buf.ctypes.data, nb.value, C.byref(nb)))
+        return buf.tobytes()
+
     def original_arrow_data_type(self) -> pa.DataType:
         return self.to_arrow_array().type if self.len() == 0 else self._type_from_format()
 

@@ -133,16 +133,44 @@ struct alignas(16) FsstEncTable {
   uint16_t one_byte[256];     // code | 1<<8 of the 1-byte symbol for this byte, 0 = none (last-byte fallback)
 };
 
-struct alignas(16) FsstCompressWork {  // 48 bytes
-  const uint8_t* values;      // concatenated unique values (device scratch)
-  const uint32_t* offsets;    // U+1 offsets into values
-  uint8_t* out;               // worst-case 2x scratch: unique i compressed at out + 2*offsets[i]
-  uint32_t* out_lens;         // compressed length of each unique
-  const FsstEncTable* table;
+// ---- byte-view insert on the device (k_str_encode.cu) -------------------------------------------------
+// Rows arrive as (offset, length) pairs into one uploaded byte pool plus an optional validity bitmap.
+struct StrEncResult {      // read back by the host to size the entry blob (one small D2H)
   uint32_t n_unique;
+  uint32_t shared_prefix_len;
+  uint32_t null_count;
+  uint32_t max_value_len;
+  uint32_t offset_bytes;   // CompactOffsets residual width 1/2/4
+  uint32_t comp_bytes;
+  int32_t slope, intercept;
+  unsigned long long uncompressed_bytes;
+  uint32_t error;          // 1 = more than 65536 distinct values, 2 = compressed dictionary over 4 GiB
   uint32_t pad;
 };
-cudaError_t launch_fsst_compress(const FsstCompressWork* d_works, uint32_t n_works, cudaStream_t s);
+
+struct StrEncIo {
+  const uint8_t* pool;
+  const uint32_t* row_off;
+  const uint32_t* row_len;
+  const uint32_t* valid;     // n bits, nullptr = no nulls
+  uint32_t n;
+  uint32_t table_mask;       // dictionary hash table capacity - 1 (power of two >= 2n)
+  uint32_t* row_slot;        // n: hash slot of the row's value; later the unique id of leader rows
+  uint32_t* table;           // capacity: smallest row index holding the slot's value (0xFFFFFFFF = empty)
+  uint32_t* leader;          // n: first row with the same value (0xFFFFFFFF for null rows)
+  uint16_t* keys;            // n (null rows hold 0)
+  uint32_t* uniq_row;        // U: row of the unique's first occurrence, in first-occurrence order
+  uint32_t* clen;            // U compressed lengths
+  uint32_t* offsets;         // U + 1
+  unsigned long long* pkeys; // U PrefixKeys
+  uint32_t* fps;             // U fingerprints (nullptr = not requested)
+  uint8_t* comp;             // compressed values, back to back
+  uint8_t* resid;            // (U + 1) * offset_bytes
+  const FsstEncTable* enc;
+  StrEncResult* res;
+};
+// Enqueues the whole pipeline (dictionary -> keys -> compress -> offsets fit); `res` is valid once the stream drains.
+cudaError_t launch_str_encode(const StrEncIo& io, cudaStream_t s);
 
 // ---- bit utilities -----------------------------------------------------------------------------
 // boolean_buffer_and_then: out[p] = left[p] & right[rank_left(p)]  (datafusion/src/utils.rs:62-236)

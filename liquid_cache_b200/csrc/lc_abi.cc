@@ -118,6 +118,44 @@ int32_t lc_data_type(lc_ctx*, lc_handle h) {
   return e ? e->liquid_type : 0;
 }
 
+int lc_entry_image(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out_bytes) {
+    set_error("lc_entry_image: bad argument");
+    return LC_ERR_INVALID;
+  }
+  *out_bytes = e->blob_bytes;
+  if (!out) return LC_OK;
+  if (cap < e->blob_bytes) {
+    set_error("lc_entry_image: buffer of %llu bytes, entry has %u", (unsigned long long)cap, e->blob_bytes);
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  LC_CUDA_OK(cudaMemcpyAsync(out, e->d_blob, e->blob_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->d2h_bytes += e->blob_bytes;
+  return LC_OK;
+}
+
+int lc_entry_fsst_table(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out_bytes || e->liquid_type != LC_LIQUID_BYTE_VIEW || !e->codec) {
+    set_error("lc_entry_fsst_table: not a byte-view entry");
+    return LC_ERR_INVALID;
+  }
+  *out_bytes = sizeof(FsstTable);
+  if (!out) return LC_OK;
+  if (cap < sizeof(FsstTable)) {
+    set_error("lc_entry_fsst_table: buffer too small");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  // read it back from the device copy the kernels use, not from the host copy it was uploaded from
+  LC_CUDA_OK(cudaMemcpyAsync(out, e->codec->d_dec, sizeof(FsstTable), cudaMemcpyDeviceToHost, ctx->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return LC_OK;
+}
+
 int lc_arrow_format(lc_ctx*, lc_handle h, char* buf, size_t buf_len) {
   Entry* e = entry_of(h);
   if (!e || !buf || buf_len == 0) return LC_ERR_INVALID;

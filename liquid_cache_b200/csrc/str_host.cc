@@ -4,6 +4,10 @@
 //   CheckedDictionaryArray (src/core/src/utils/mod.rs:52-154), PrefixKey / CompactOffsets / fit_line
 //   (raw/fsst_buffer.rs:160-187, 267-383), StringFingerprint (byte_view_array/fingerprint.rs:19-26),
 //   with_fsst_compressor_or_train (src/core/src/cache/transcode.rs:16-33).
+// The host only turns the Arrow layout into (offset, length) pairs over uploaded buffers and sizes the blob; the
+// dictionary, compression, prefix keys, fingerprints and offset fit run on the device (k_str_encode.cu). FSST
+// training (once per column chunk, invisible in every result) is the one piece of byte work left here.
+#include <algorithm>
 #include <cmath>
 
 #include "host_common.h"
@@ -80,31 +84,9 @@ struct DictBuilder {
   }
 };
 
-// fit_line (raw/fsst_buffer.rs:267-296): least squares in f64, rounded to i32
-void fit_line(const std::vector<uint32_t>& offsets, int32_t* slope, int32_t* intercept) {
-  const size_t n = offsets.size();
-  if (n <= 1) {
-    *slope = 0;
-    *intercept = n ? static_cast<int32_t>(offsets[0]) : 0;
-    return;
-  }
-  const double nf = static_cast<double>(n);
-  const double sum_x = static_cast<double>(n * (n - 1) / 2);
-  double sum_y = 0.0, sum_xy = 0.0;
-  for (size_t i = 0; i < n; ++i) sum_y += static_cast<double>(offsets[i]);
-  for (size_t i = 0; i < n; ++i) sum_xy += static_cast<double>(i) * static_cast<double>(offsets[i]);
-  const double sum_x_sq = static_cast<double>(n * (n - 1) * (2 * n - 1) / 6);
-  const double sl = (nf * sum_xy - sum_x * sum_y) / (nf * sum_x_sq - sum_x * sum_x);
-  const double ic = (sum_y - sl * sum_x) / nf;
-  auto sat = [](double v) -> int32_t {
-    const double r = std::round(v);
-    if (!(r == r)) return 0;
-    if (r >= 2147483647.0) return 2147483647;
-    if (r <= -2147483648.0) return -2147483647 - 1;
-    return static_cast<int32_t>(r);
-  };
-  *slope = sat(sl);
-  *intercept = sat(ic);
+void set_bits_range(uint8_t* dst, uint32_t n) {  // first n bits := 1
+  std::memset(dst, 0xFF, n / 8);
+  if (n & 7) dst[n / 8] |= static_cast<uint8_t>((1u << (n & 7)) - 1u);
 }
 
 }  // namespace
@@ -132,144 +114,228 @@ static int get_codec(lc_ctx* ctx, uint64_t scope, const DictBuilder& d, std::sha
   return LC_OK;
 }
 
+// A contiguous piece of caller memory that becomes part of the device byte pool.
+struct PoolSeg {
+  const uint8_t* p;
+  uint64_t bytes;
+  uint64_t base;  // offset inside the pool
+};
+
 int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out) {
   const uint32_t n = static_cast<uint32_t>(in.length);
-  // ---- 1. rows ----
-  std::vector<RowRef> rows(n);
-  std::vector<uint8_t> inline_store;  // view arrays: inline payloads are addressed in place
-  for (uint32_t i = 0; i < n; ++i) {
-    const int64_t r = in.offset + i;
-    RowRef rr{nullptr, 0, true};
-    if (in.validity && in.null_count > 0 && !bit_get(in.validity, r)) rr.valid = false;
-    if (rr.valid) {
-      if (in.kind == ArrowIn::K_BYTES) {
-        const int32_t* off = static_cast<const int32_t*>(in.values);
-        rr.p = in.data + off[r];
-        rr.len = static_cast<uint32_t>(off[r + 1] - off[r]);
-      } else if (in.kind == ArrowIn::K_VIEW) {
-        const uint8_t* v = static_cast<const uint8_t*>(in.values) + 16 * r;
-        uint32_t len;
-        std::memcpy(&len, v, 4);
-        rr.len = len;
-        if (len <= 12) {
-          rr.p = v + 4;
-        } else {
-          uint32_t bi, bo;
-          std::memcpy(&bi, v + 8, 4);
-          std::memcpy(&bo, v + 12, 4);
-          if (static_cast<int64_t>(bi) >= in.n_view_buffers) {
-            set_error("view buffer index out of range");
-            return LC_ERR_INVALID;
-          }
-          rr.p = static_cast<const uint8_t*>(in.view_buffers[bi]) + bo;
+  // ---- 1. rows as (pool offset, length); the value bytes themselves are never touched on the host (except by the
+  //         once-per-column-chunk FSST training below) ----
+  std::vector<uint32_t> row_off(n, 0), row_len(n, 0);
+  std::vector<uint8_t> valid_bits;  // bit offset 0
+  bool has_input_nulls = in.validity && in.null_count != 0;
+  std::vector<PoolSeg> segs;
+  uint64_t pool_bytes = 0, sum_len = 0;
+  auto add_seg = [&](const uint8_t* p, uint64_t bytes) -> uint64_t {
+    const uint64_t base = pool_bytes;
+    segs.push_back(PoolSeg{p, bytes, base});
+    pool_bytes += round_up(bytes, 16);
+    return base;
+  };
+  auto is_valid = [&](uint32_t i) -> bool { return !has_input_nulls || bit_get(in.validity, in.offset + i); };
+  if (in.kind == ArrowIn::K_BYTES) {
+    const int32_t* off = static_cast<const int32_t*>(in.values) + in.offset;
+    const int64_t lo = n ? off[0] : 0, hi = n ? off[n] : 0;
+    add_seg(in.data + lo, static_cast<uint64_t>(hi - lo));
+    for (uint32_t i = 0; i < n; ++i) {
+      row_off[i] = static_cast<uint32_t>(off[i] - lo);
+      row_len[i] = static_cast<uint32_t>(off[i + 1] - off[i]);
+    }
+  } else if (in.kind == ArrowIn::K_VIEW) {
+    const uint8_t* views = static_cast<const uint8_t*>(in.values) + 16 * in.offset;
+    add_seg(views, 16ull * n);  // inline payloads are addressed in place (view bytes 4..15)
+    const int64_t nb = in.n_view_buffers;
+    std::vector<uint64_t> lo(nb > 0 ? nb : 0, ~0ull), hi(nb > 0 ? nb : 0, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+      if (!is_valid(i)) continue;
+      uint32_t len, bi, bo;
+      std::memcpy(&len, views + 16ull * i, 4);
+      if (len <= 12) continue;
+      std::memcpy(&bi, views + 16ull * i + 8, 4);
+      std::memcpy(&bo, views + 16ull * i + 12, 4);
+      if (static_cast<int64_t>(bi) >= nb) {
+        set_error("view buffer index out of range");
+        return LC_ERR_INVALID;
+      }
+      lo[bi] = std::min<uint64_t>(lo[bi], bo);
+      hi[bi] = std::max<uint64_t>(hi[bi], static_cast<uint64_t>(bo) + len);
+    }
+    std::vector<uint64_t> base(nb > 0 ? nb : 0, 0);
+    for (int64_t b = 0; b < nb; ++b)
+      if (hi[b] > lo[b] && lo[b] != ~0ull)
+        base[b] = add_seg(static_cast<const uint8_t*>(in.view_buffers[b]) + lo[b], hi[b] - lo[b]) - lo[b];
+    for (uint32_t i = 0; i < n; ++i) {
+      if (!is_valid(i)) continue;
+      uint32_t len, bi, bo;
+      std::memcpy(&len, views + 16ull * i, 4);
+      row_len[i] = len;
+      if (len <= 12) {
+        row_off[i] = 16u * i + 4u;
+      } else {
+        std::memcpy(&bi, views + 16ull * i + 8, 4);
+        std::memcpy(&bo, views + 16ull * i + 12, 4);
+        const uint64_t o = base[bi] + bo;
+        if (o > 0xFFFFFFFFull) {
+          set_error("string batch larger than 4 GiB");
+          return LC_ERR_UNSUPPORTED_TYPE;
         }
-      } else {  // K_DICT: a null dictionary value makes the row null (typed dictionary iterator)
-        const uint32_t key = in.dict_keys[r];
-        const int64_t dv = in.dict_offset + key;
-        if (static_cast<int64_t>(key) >= in.dict_len) {
-          set_error("dictionary key out of range");
-          return LC_ERR_INVALID;
-        }
-        if (in.dict_validity && !bit_get(in.dict_validity, dv)) {
-          rr.valid = false;
-        } else {
-          rr.p = in.dict_data + in.dict_offsets[dv];
-          rr.len = static_cast<uint32_t>(in.dict_offsets[dv + 1] - in.dict_offsets[dv]);
-        }
+        row_off[i] = static_cast<uint32_t>(o);
       }
     }
-    rows[i] = rr;
+  } else {  // K_DICT: a null dictionary value makes the row null (typed dictionary iterator)
+    const int32_t* doff = in.dict_offsets + in.dict_offset;
+    const int64_t lo = in.dict_len ? doff[0] : 0, hi = in.dict_len ? doff[in.dict_len] : 0;
+    add_seg(in.dict_data + lo, static_cast<uint64_t>(hi - lo));
+    bool extra_nulls = false;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (!is_valid(i)) continue;
+      const uint32_t key = in.dict_keys[in.offset + i];
+      if (static_cast<int64_t>(key) >= in.dict_len) {
+        set_error("dictionary key out of range");
+        return LC_ERR_INVALID;
+      }
+      if (in.dict_validity && !bit_get(in.dict_validity, in.dict_offset + key)) {
+        if (!extra_nulls) {  // materialise a validity bitmap that also carries the dictionary's nulls
+          valid_bits.assign(round_up((n + 7) / 8, 16), 0);
+          if (has_input_nulls) copy_bits(in.validity, in.offset, n, valid_bits.data(), valid_bits.size());
+          else set_bits_range(valid_bits.data(), n);
+          extra_nulls = true;
+        }
+        valid_bits[i >> 3] &= static_cast<uint8_t>(~(1u << (i & 7)));
+        continue;
+      }
+      row_off[i] = static_cast<uint32_t>(doff[key] - lo);
+      row_len[i] = static_cast<uint32_t>(doff[key + 1] - doff[key]);
+    }
+    if (extra_nulls) has_input_nulls = true;
   }
-
-  // ---- 2. u16 dictionary, first-occurrence order ----
-  DictBuilder dict(n < 1024 ? 1024 : n / 2);
-  std::vector<uint16_t> keys(n, 0);
-  uint32_t null_count = 0;
+  if (pool_bytes > 0xFFFFFFF0ull) {
+    set_error("string batch larger than 4 GiB");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
+  if (has_input_nulls && valid_bits.empty()) {
+    valid_bits.assign(round_up((n + 7) / 8, 16), 0);
+    copy_bits(in.validity, in.offset, n, valid_bits.data(), valid_bits.size());
+  }
+  auto row_is_valid = [&](uint32_t i) -> bool { return !has_input_nulls || bit_get(valid_bits.data(), i); };
   for (uint32_t i = 0; i < n; ++i) {
-    if (!rows[i].valid) {
-      ++null_count;
-      continue;
-    }
-    const uint32_t u = dict.add(rows[i].p ? rows[i].p : reinterpret_cast<const uint8_t*>(""), rows[i].len);
-    if (u > 65535u) {
-      // the reference's UInt16 dictionary builder overflows (panics) here; we decline the batch
-      set_error("more than 65536 distinct values in one batch");
-      return LC_ERR_UNSUPPORTED_TYPE;
-    }
-    keys[i] = static_cast<uint16_t>(u);
+    if (!row_is_valid(i)) row_off[i] = row_len[i] = 0;
+    sum_len += row_len[i];
   }
-  const uint32_t U = static_cast<uint32_t>(dict.uptr.size());
+  auto row_ptr = [&](uint32_t i) -> const uint8_t* {
+    // host address of a row's bytes: the segment that contains its pool offset
+    const uint64_t o = row_off[i];
+    for (size_t k = segs.size(); k-- > 0;)
+      if (o >= segs[k].base) return segs[k].p + (o - segs[k].base);
+    return segs[0].p;
+  };
 
-  // ---- 3. shared prefix = LCP of all unique values (conversions.rs:269-307) ----
-  uint32_t spl = 0;
-  if (U > 0) {
-    spl = dict.ulen[0];
-    for (uint32_t u = 1; u < U && spl > 0; ++u) {
-      const uint32_t m = dict.ulen[u] < spl ? dict.ulen[u] : spl;
-      uint32_t c = 0;
-      while (c < m && dict.uptr[u][c] == dict.uptr[0][c]) ++c;
-      spl = c;
-    }
-  }
-
-  // ---- 4. symbol table: train on the first batch of the scope, reuse afterwards ----
+  // ---- 2. symbol table: the first batch of a column chunk trains it (transcode.rs:16-33) on its unique values;
+  //         training is host work by design (once per chunk, never visible in any result) ----
   std::shared_ptr<FsstCodec> codec;
-  LC_TRY(get_codec(ctx, scope, dict, &codec));
-
-  // ---- 5. compress uniques, prefix keys, fingerprints ----
-  const bool build_fp = (hint == LC_HINT_SUBSTRING_SEARCH);
-  std::vector<uint32_t> offsets(U + 1, 0);
-  std::vector<uint8_t> comp;
-  uint64_t uncompressed = 0;
-  uint32_t max_len = 0;
   {
-    uint64_t total = 0;
-    for (uint32_t u = 0; u < U; ++u) total += dict.ulen[u];
-    comp.resize(2 * total + 16);
-  }
-  std::vector<uint64_t> pkeys(U);
-  std::vector<uint32_t> fps(build_fp ? U : 0);
-  uint64_t co = 0;
-  for (uint32_t u = 0; u < U; ++u) {
-    const uint8_t* p = dict.uptr[u];
-    const uint32_t len = dict.ulen[u];
-    uncompressed += len;
-    if (len > max_len) max_len = len;
-    co += fsst_compress_host(*codec, p, len, comp.data() + co);
-    if (co > 0xFFFFFFF0ull) {
-      set_error("compressed dictionary exceeds 4 GiB");
-      return LC_ERR_UNSUPPORTED_TYPE;
-    }
-    offsets[u + 1] = static_cast<uint32_t>(co);
-    // PrefixKey::new(suffix) (fsst_buffer.rs:173-187)
-    const uint32_t sl = len > spl ? len - spl : 0;
-    uint64_t k = 0;
-    const uint32_t cp = sl < 7 ? sl : 7;
-    for (uint32_t b = 0; b < cp; ++b) k |= static_cast<uint64_t>(p[spl + b]) << (8 * b);
-    k |= static_cast<uint64_t>(sl >= 255 ? 255u : sl) << 56;
-    pkeys[u] = k;
-    if (build_fp) {
-      uint32_t bits = 0;
-      for (uint32_t b = 0; b < len; ++b) bits |= 1u << (p[b] & 31u);
-      fps[u] = bits;
+    auto it = ctx->codecs.find(scope);
+    if (it != ctx->codecs.end()) {
+      codec = it->second;
+    } else {
+      DictBuilder dict(n < 1024 ? 1024 : n / 2);
+      for (uint32_t i = 0; i < n; ++i)
+        if (row_is_valid(i)) dict.add(row_len[i] ? row_ptr(i) : reinterpret_cast<const uint8_t*>(""), row_len[i]);
+      LC_TRY(get_codec(ctx, scope, dict, &codec));
     }
   }
 
-  // ---- 6. CompactOffsets (fsst_buffer.rs:298-359) ----
-  int32_t slope = 0, intercept = 0;
-  fit_line(offsets, &slope, &intercept);
-  std::vector<int32_t> resid(U + 1);
-  int32_t rmin = 2147483647, rmax = -2147483647 - 1;
-  for (uint32_t i = 0; i <= U; ++i) {
-    const uint32_t predicted = static_cast<uint32_t>(slope) * i + static_cast<uint32_t>(intercept);
-    const int32_t r = static_cast<int32_t>(offsets[i] - predicted);
-    resid[i] = r;
-    if (r < rmin) rmin = r;
-    if (r > rmax) rmax = r;
+  // ---- 3. device pipeline ----
+  const bool build_fp = (hint == LC_HINT_SUBSTRING_SEARCH);
+  uint32_t cap = 64;
+  while (cap < 2u * n) cap <<= 1;
+  cudaStream_t s = ctx->stream;
+  Scratch& sc = ctx->scratch;
+  const uint64_t vbytes = has_input_nulls ? round_up((n + 31) / 32 * 4, 16) : 0;
+  const uint64_t up_bytes = round_up(4ull * n, 256) * 2 + round_up(vbytes, 256);
+  const uint64_t comp_cap = 2 * sum_len + 64;
+  const uint64_t dev_need = round_up(pool_bytes + 64, 256) + up_bytes + round_up(4ull * cap, 256) +
+                            6 * round_up(4ull * (n + 1), 256) + round_up(2ull * n, 256) + round_up(8ull * (n + 1), 256) +
+                            round_up(comp_cap, 256) + 4096;
+  LC_TRY(sc.reserve(dev_need, up_bytes + 4096));
+  uint8_t* h_up = sc.host(up_bytes);
+  StrEncResult* h_res = reinterpret_cast<StrEncResult*>(sc.host(sizeof(StrEncResult)));
+  uint8_t* d_pool = sc.dev(pool_bytes + 64);
+  uint8_t* d_up = sc.dev(up_bytes);
+  uint32_t* d_table = reinterpret_cast<uint32_t*>(sc.dev(4ull * cap));
+  uint32_t* d_slot = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
+  uint32_t* d_leader = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
+  uint32_t* d_uniq = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
+  uint32_t* d_clen = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
+  uint32_t* d_offsets = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
+  uint32_t* d_fps = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
+  uint8_t* d_resid = sc.dev(4ull * (n + 1));
+  uint16_t* d_keys = reinterpret_cast<uint16_t*>(sc.dev(2ull * n + 16));
+  unsigned long long* d_pkeys = reinterpret_cast<unsigned long long*>(sc.dev(8ull * (n + 1)));
+  uint8_t* d_comp = sc.dev(comp_cap);
+  StrEncResult* d_res = reinterpret_cast<StrEncResult*>(sc.dev(sizeof(StrEncResult)));
+  if (!h_up || !h_res || !d_pool || !d_up || !d_table || !d_slot || !d_leader || !d_uniq || !d_clen || !d_offsets ||
+      !d_fps || !d_resid || !d_keys || !d_pkeys || !d_comp || !d_res) {
+    set_error("str_encode: scratch exhausted");
+    return LC_ERR_OOM;
   }
-  const uint32_t ob = (rmin >= -128 && rmax <= 127) ? 1u : (rmin >= -32768 && rmax <= 32767) ? 2u : 4u;
+  const uint64_t off_len = round_up(4ull * n, 256);
+  if (n) {
+    std::memcpy(h_up, row_off.data(), 4ull * n);
+    std::memcpy(h_up + off_len, row_len.data(), 4ull * n);
+  }
+  if (vbytes) {
+    std::memset(h_up + 2 * off_len, 0, vbytes);
+    std::memcpy(h_up + 2 * off_len, valid_bits.data(), (n + 7) / 8);
+  }
+  LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_bytes, cudaMemcpyHostToDevice, s));
+  for (const PoolSeg& sg : segs)
+    if (sg.bytes) LC_CUDA_OK(cudaMemcpyAsync(d_pool + sg.base, sg.p, sg.bytes, cudaMemcpyHostToDevice, s));
+  ctx->h2d_bytes += up_bytes + pool_bytes;
 
-  // ---- 7. blob ----
+  StrEncIo io{};
+  io.pool = d_pool;
+  io.row_off = reinterpret_cast<const uint32_t*>(d_up);
+  io.row_len = reinterpret_cast<const uint32_t*>(d_up + off_len);
+  io.valid = vbytes ? reinterpret_cast<const uint32_t*>(d_up + 2 * off_len) : nullptr;
+  io.n = n;
+  io.table_mask = cap - 1;
+  io.row_slot = d_slot;
+  io.table = d_table;
+  io.leader = d_leader;
+  io.keys = d_keys;
+  io.uniq_row = d_uniq;
+  io.clen = d_clen;
+  io.offsets = d_offsets;
+  io.pkeys = d_pkeys;
+  io.fps = build_fp ? d_fps : nullptr;
+  io.comp = d_comp;
+  io.resid = d_resid;
+  io.enc = codec->d_enc;
+  io.res = d_res;
+  LC_CUDA_OK(launch_str_encode(io, s));
+  ctx->kernel_launches += 5;
+  LC_CUDA_OK(cudaMemcpyAsync(h_res, d_res, sizeof(StrEncResult), cudaMemcpyDeviceToHost, s));
+  LC_CUDA_OK(cudaStreamSynchronize(s));
+  ctx->d2h_bytes += sizeof(StrEncResult);
+  if (h_res->error == 1) {
+    // the reference's UInt16 dictionary builder overflows (panics) here; we decline the batch
+    set_error("more than 65536 distinct values in one batch");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
+  if (h_res->error) {
+    set_error("compressed dictionary exceeds 4 GiB");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
+  const uint32_t U = h_res->n_unique, spl = h_res->shared_prefix_len, ob = h_res->offset_bytes;
+  const uint32_t null_count = h_res->null_count;
+  const uint64_t co = h_res->comp_bytes;
+
+  // ---- 4. blob layout (sizes are known now), sections moved device-to-device ----
   StrHeader h;
   std::memset(&h, 0, sizeof(h));
   h.magic = kMagicStr;
@@ -279,12 +345,12 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   h.offset_bytes = static_cast<uint8_t>(ob);
   h.n = n;
   h.n_unique = U;
-  h.slope = slope;
-  h.intercept = intercept;
+  h.slope = h_res->slope;
+  h.intercept = h_res->intercept;
   h.shared_prefix_len = spl;
   h.null_count = null_count;
-  h.max_value_len = max_len;
-  h.uncompressed_bytes = uncompressed;
+  h.max_value_len = h_res->max_value_len;
+  h.uncompressed_bytes = h_res->uncompressed_bytes;
   h.table_ptr = reinterpret_cast<uint64_t>(codec->d_dec);
   uint64_t o = sizeof(StrHeader);
   h.shared_prefix_off = static_cast<uint32_t>(o);
@@ -315,40 +381,31 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
               (unsigned long long)o, (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
-  Scratch& sc = ctx->scratch;
-  LC_TRY(sc.reserve(0, o + 4096));
-  uint8_t* hb = sc.host(o);
-  if (!hb) {
-    set_error("str_encode: scratch exhausted");
-    return LC_ERR_OOM;
-  }
-  std::memset(hb, 0, o);
-  std::memcpy(hb, &h, sizeof(h));
-  if (spl) std::memcpy(hb + h.shared_prefix_off, dict.uptr[0], spl);
-  if (U) std::memcpy(hb + h.prefix_keys_off, pkeys.data(), 8ull * U);
-  if (build_fp && U) std::memcpy(hb + h.fp_off, fps.data(), 4ull * U);
-  for (uint32_t i = 0; i <= U; ++i) {
-    if (ob == 1) reinterpret_cast<int8_t*>(hb + h.resid_off)[i] = static_cast<int8_t>(resid[i]);
-    else if (ob == 2) reinterpret_cast<int16_t*>(hb + h.resid_off)[i] = static_cast<int16_t>(resid[i]);
-    else reinterpret_cast<int32_t*>(hb + h.resid_off)[i] = resid[i];
-  }
-  if (h.has_nulls) {
-    uint8_t* vb = hb + h.validity_off;
-    for (uint32_t i = 0; i < n; ++i)
-      if (rows[i].valid) vb[i >> 3] |= static_cast<uint8_t>(1u << (i & 7));
-  }
-  if (n) std::memcpy(hb + h.keys_off, keys.data(), 2ull * n);
-  if (co) std::memcpy(hb + h.fsst_off, comp.data(), co);
-
   uint32_t slab = 0;
   uint8_t* d_blob = ctx->arena.alloc(o, &slab);
   if (!d_blob) {
     set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
     return LC_ERR_OOM;
   }
-  LC_CUDA_OK(cudaMemcpyAsync(d_blob, hb, o, cudaMemcpyHostToDevice, ctx->stream));
-  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  ctx->h2d_bytes += o;
+  // first valid row = unique 0 = where the shared prefix is read from
+  uint32_t first_valid = 0;
+  while (first_valid < n && !row_is_valid(first_valid)) ++first_valid;
+  LC_CUDA_OK(cudaMemsetAsync(d_blob, 0, o, s));  // padding between sections reads as zero
+  std::memcpy(h_up, &h, sizeof(h));              // h_up is pinned and idle after the sync above
+  LC_CUDA_OK(cudaMemcpyAsync(d_blob, h_up, sizeof(h), cudaMemcpyHostToDevice, s));
+  auto d2d = [&](uint32_t dst_off, const void* src, uint64_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return cudaMemcpyAsync(d_blob + dst_off, src, bytes, cudaMemcpyDeviceToDevice, s);
+  };
+  if (spl) LC_CUDA_OK(d2d(h.shared_prefix_off, d_pool + row_off[first_valid], spl));
+  if (build_fp) LC_CUDA_OK(d2d(h.fp_off, d_fps, 4ull * U));
+  LC_CUDA_OK(d2d(h.resid_off, d_resid, static_cast<uint64_t>(ob) * (U + 1)));
+  LC_CUDA_OK(d2d(h.prefix_keys_off, d_pkeys, 8ull * U));
+  if (h.has_nulls) LC_CUDA_OK(d2d(h.validity_off, d_up + 2 * off_len, (n + 7) / 8));
+  LC_CUDA_OK(d2d(h.keys_off, d_keys, 2ull * n));
+  LC_CUDA_OK(d2d(h.fsst_off, d_comp, co));
+  LC_CUDA_OK(cudaStreamSynchronize(s));
+  ctx->h2d_bytes += sizeof(h);
 
   Entry* e = new Entry();
   e->liquid_type = LC_LIQUID_BYTE_VIEW;
@@ -359,7 +416,10 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   e->arrow_format = in.format;
   e->dict_value_format = in.dict_value_format;
   e->sh = h;
-  e->shared_prefix.assign(hb + h.shared_prefix_off, hb + h.shared_prefix_off + spl);
+  if (spl) {
+    const uint8_t* p0 = row_ptr(first_valid);
+    e->shared_prefix.assign(p0, p0 + spl);
+  }
   e->codec = codec;
   ctx->n_entries++;
   *out = e;
