@@ -142,9 +142,11 @@ int lc_ctx_stats(lc_ctx* ctx, lc_stats* out);
 /* Measurement aid (off by default): while enabled, the byte-view predicate kernel adds, per launch,
  *   out[0] += dictionary entries looked at, out[1] += candidates whose FSST codes were walked,
  *   out[2] += compressed bytes of those candidates
+ *   out[4..11] += SM cycles one CTA of the string predicate kernel spent per phase (staging wait, plan, symbol
+ *                 tables, candidate gate, code walk, row-section wait, rows, total), summed over CTAs
  * so a benchmark can state the ALGORITHMIC bytes of a scan exactly. Costs a few atomics; never enable it in
  * a timed region. */
-int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[4]);
+int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[16]);
 /* Measurement aid: while enabled, every predicate launch (lc_scan_filter / lc_eval_predicate*) is bracketed by a
  * pair of CUDA events recorded on the launching stream immediately around the kernel launch.
  * lc_ctx_last_kernel_ms waits for the most recent one and returns its duration (negative if none). */

@@ -356,7 +356,7 @@ class LiquidCache:
 
     def profile_counters(self, enable: bool) -> np.ndarray:
         """Measurement aid: returns the counters accumulated so far and switches accumulation on/off."""
-        out = np.zeros(4, dtype=np.uint64)
+        out = np.zeros(16, dtype=np.uint64)
         N.check(N.lib().lc_ctx_profile_counters(self._ctx, 1 if enable else 0, out.ctypes.data))
         return out
 

@@ -263,16 +263,23 @@ __device__ __forceinline__ void plan_str_pred(const StrView& v, const StrPredDes
 }
 
 // ---- substring match directly on FSST codes --------------------------------------------------------
-// Shift-And over the needle (m <= 32): state bit j <=> needle[0..j] matches the text ending here; one text
+// Shift-And over the needle (m <= 31): state bit j <=> needle[0..j] matches the text ending here; one text
 // byte b maps S -> ((S << 1) | 1) & M[b]. That map is linear over OR, so the effect of a whole symbol
 // (1..8 bytes) collapses into three masks computed once per CTA from the column chunk's symbol table:
 //     S' = ((S << L) & A) | B        and   "the needle completed inside this symbol"  <=>  (S & H) | hit0
 // One FSST code then costs one 16-byte shared-memory load and ~6 ALU ops, instead of ~8 bytes x (load,
 // compare, branch). Values are never decompressed: this IS the predicate evaluated on the encoded bytes.
+// Bit 31 of the state is a constant 1 (needles are <= 31 bytes on this path, B always re-sets it), so "completed
+// at the symbol's first bytes regardless of the state" (hit0) is just bit 31 of H and the hit test is one AND.
 struct SymStep {
-  uint32_t A, B, H;
-  uint32_t L_hit;  // bits 0..7 symbol length, bit 8 = hit0
+  uint32_t A, B, H;  // B has bit 31 set; H bit 31 = hit0
+  uint32_t L;        // symbol length = shift
 };
+constexpr uint32_t kStateOne = 0x80000000u;
+#ifndef LC_LIKE_WARPS
+#define LC_LIKE_WARPS 8
+#endif
+constexpr uint32_t kLikeWarps = LC_LIKE_WARPS;
 
 __device__ __forceinline__ void build_sym_steps(const uint64_t* s_sym, const uint8_t* s_len, const uint8_t* nd,
                                                 uint32_t m, uint32_t* s_M, SymStep* s_step) {
@@ -300,9 +307,9 @@ __device__ __forceinline__ void build_sym_steps(const uint64_t* s_sym, const uin
     }
     SymStep st;
     st.A = A;
-    st.B = B;
-    st.H = H;
-    st.L_hit = L | (hit0 << 8);
+    st.B = B | kStateOne;
+    st.H = H | (hit0 << 31);
+    st.L = L;
     s_step[c] = st;
   }
 }
@@ -339,7 +346,7 @@ __device__ __forceinline__ void like_candidates(const View& v, const uint16_t* s
         cur_i = s_cand[idx];
         p = dict_offset(v, cur_i);
         end = dict_offset(v, cur_i + 1u);
-        S = 0;
+        S = kStateOne;
         pending = 0;
         if (p < end) cur = *reinterpret_cast<const uint64_t*>(base + (p & ~7u)) >> ((p & 7u) * 8u);
       }
@@ -364,20 +371,22 @@ __device__ __forceinline__ void like_candidates(const View& v, const uint16_t* s
         if (static_cast<uint32_t>(k) < cnt) {
           const uint32_t b = ((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xffu;
           const SymStep st = s_step[b + (pending << 8)];
-          hit |= (S & st.H) | (st.L_hit >> 8);
-          S = ((S << (st.L_hit & 0xffu)) & st.A) | st.B;
+          hit |= S & st.H;
+          S = ((S << st.L) & st.A) | st.B;
           pending = (pending == 0u && b == 255u) ? 1u : 0u;
         }
       }
     } else {
-      // fast path (no escape in any lane's word): plain table steps
+      // fast path (no escape in any lane's word): plain table steps. (Tried and dropped: an 8-word bitmap of the codes
+      // that cannot touch the match state, to skip their 16-byte rows — fewer bank conflicts, but the extra lookup
+      // cost more than it saved: 0.887 vs 0.828 ms on the same GPU.)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         if (static_cast<uint32_t>(k) < cnt) {
           const uint32_t b = ((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xffu;
           const SymStep st = s_step[b];
-          hit |= (S & st.H) | (st.L_hit >> 8);
-          S = ((S << (st.L_hit & 0xffu)) & st.A) | st.B;
+          hit |= S & st.H;
+          S = ((S << st.L) & st.A) | st.B;
         }
       }
     }
@@ -393,27 +402,103 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
                                               ScanSmem* sm, uint64_t* s_sym, uint8_t* s_len, StrPlan* s_plan,
                                               const uint8_t* s_nd, const uint16_t* s_fail, uint32_t* s_dict,
                                               uint16_t* s_cand, uint32_t* s_M, SymStep* s_step, uint32_t dict_words,
-                                              uint64_t* bar_rows) {
+                                              uint64_t* bar_rows, long long t_start) {
   const uint32_t m = pred.needle_len;
+  // measurement aid (pred.prof): thread 0 stamps the phase boundaries with the SM clock
+  long long t_prev = t_start;
+  auto stamp = [&](int slot) {
+#ifdef LC_PHASE_PROF  // build with -DLC_PHASE_PROF for the per-phase cycle split (profiles/r01_k_str_scan_phases.txt)
+    if (pred.prof && threadIdx.x == 0) {
+      const long long t = clock64();
+      atomicAdd(&pred.prof[4 + slot], static_cast<unsigned long long>(t - t_prev));
+      t_prev = t;
+    }
+#endif
+  };
+  stamp(0);  // staging wait
   if (threadIdx.x == 0) plan_str_pred(v, pred, s_nd, s_plan);
   __syncthreads();
+  stamp(1);  // plan
   const StrPlan plan = *s_plan;
   const uint32_t U = v.h->n_unique;
   const int lane = threadIdx.x & 31;
   const int32_t kind = plan.kind;
   const bool neg = (plan.flags & 2u) != 0;
   const bool needs_table = (kind == SP_EQ_LONG || kind == SP_ORD || kind == SP_LIKE);
-  const bool fast_like = (kind == SP_LIKE) && m <= 32u;
+  const bool fast_like = (kind == SP_LIKE) && m <= 31u;
   if (needs_table) {
     load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
     __syncthreads();
     if (fast_like) build_sym_steps(s_sym, s_len, s_nd, m, s_M, s_step);
   }
+  stamp(2);  // symbol tables (includes no barrier after build_sym_steps: its consumers sync later)
 
   // ---------------- phase 1: one decision per dictionary entry ----------------
   if (kind == SP_CONST) {
     const uint32_t fill = (plan.flags & 1u) ? kFullMask : 0u;
     for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = fill;
+  } else if (fast_like) {
+    // LIKE candidates (reference fingerprint gate, comparisons.rs:600-615), queued LONGEST CLASS FIRST: every warp
+    // drains its last values with most lanes idle, so the values left for the end should be the short ones. Two
+    // passes over the dictionary: count per length class, then scatter to the class's slice of the queue.
+    uint32_t* cls_cnt = sm->warp_tot;      // [0..3] totals, [4..7] running offsets (unused scratch in this phase)
+    if (threadIdx.x < 8u) cls_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+      for (uint32_t i0 = (threadIdx.x & ~31u); i0 < U; i0 += 256u) {
+        const uint32_t i = i0 + lane;
+        const bool act = i < U;
+        const bool cand = act && (v.fp ? ((v.fp[i] & pred.needle_fp) == pred.needle_fp) : true);
+        uint32_t cls = 4;
+        if (cand) {
+          const uint32_t len = dict_offset(v, i + 1u) - dict_offset(v, i);
+          cls = len >= 96u ? 0u : len >= 64u ? 1u : len >= 32u ? 2u : 3u;
+        }
+        if (pass == 0 && lane == 0) s_dict[i0 >> 5] = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < 4; ++c) {
+          const uint32_t cw = __ballot_sync(kFullMask, cls == c);
+          if (cw == 0) continue;
+          if (pass == 0) {
+            if (lane == 0) atomicAdd(&cls_cnt[c], __popc(cw));
+          } else {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&cls_cnt[4u + c], __popc(cw));
+            base = __shfl_sync(kFullMask, base, 0);
+            uint32_t start = 0;
+            for (uint32_t d = 0; d < c; ++d) start += cls_cnt[d];
+            if (cls == c) s_cand[start + base + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const uint32_t ncand = cls_cnt[0] + cls_cnt[1] + cls_cnt[2] + cls_cnt[3];
+    if (pred.prof) {  // measurement aid, never on in a timed run
+      unsigned long long bytes = 0;
+      for (uint32_t c = threadIdx.x; c < ncand; c += 256u)
+        bytes += dict_offset(v, s_cand[c] + 1u) - dict_offset(v, s_cand[c]);
+      if (bytes) atomicAdd(&pred.prof[2], bytes);
+      if (threadIdx.x == 0) {
+        atomicAdd(&pred.prof[0], static_cast<unsigned long long>(U));
+        atomicAdd(&pred.prof[1], static_cast<unsigned long long>(ncand));
+      }
+    }
+    // An entry has only a few hundred candidates: spread over all 256 lanes each lane would get 2-3 values and the
+    // pass would last as long as its LONGEST value (a value's codes are inherently sequential) with most lanes idle.
+    // Half of the warps walk the queue; the others wait at the barrier and cost no issue slots, which the SM's other
+    // resident CTAs use.
+    stamp(3);  // candidate gate
+    if ((threadIdx.x >> 5) < kLikeWarps) like_candidates(v, s_cand, ncand, &sm->misc[1], s_step, s_dict);
+    if (neg) {
+      // NOT LIKE inverts every dictionary result — but, as in the reference, only inside
+      // apply_like_match_on_candidates, i.e. only when the fingerprint gate let something through
+      // (comparisons.rs:166-180, 644-648). Without fingerprints (flags bit2) it is a plain negation.
+      __syncthreads();
+      const bool invert = (plan.flags & 4u) ? true : (ncand != 0);
+      if (invert)
+        for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = ~s_dict[i];
+    }
   } else {
     const uint32_t op = static_cast<uint32_t>(pred.op);
     for (uint32_t i0 = (threadIdx.x & ~31u); i0 < U; i0 += 256u) {
@@ -496,7 +581,9 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
     }
   }
   __syncthreads();
+  stamp(4);  // code walk (or the non-LIKE phase 1)
   if (bar_rows) mbar_wait(bar_rows, 0);
+  stamp(5);  // row sections
 
   // ---------------- phase 2: dictionary results -> rows ----------------
   const uint16_t* keys = v.keys;
@@ -507,6 +594,11 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
   auto emit = [&](uint32_t, uint32_t, uint32_t, uint32_t) {};
   scan_entry_rows<MODE>(w.sel, v.h->n, v.valid, v.h->null_count, reinterpret_cast<uint32_t*>(w.out), w.out_valid,
                         w.counts, sm, cmp, emit);
+  stamp(6);  // rows
+#ifdef LC_PHASE_PROF
+  if (pred.prof && threadIdx.x == 0) atomicAdd(&pred.prof[11], static_cast<unsigned long long>(clock64() - t_start));
+#endif
+  (void)t_prev;
 }
 
 // Shared-memory map of the predicate kernel (after the fixed ScanSmem area):
@@ -533,6 +625,11 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
   uint8_t* stage = reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u);
   stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage) + 127u) & ~static_cast<uintptr_t>(127u));
 
+#ifdef LC_PHASE_PROF
+  const long long t_start = pred.prof ? clock64() : 0;
+#else
+  const long long t_start = 0;
+#endif
   const EntryRef ref = io.refs[blockIdx.x];
   const EntryIo w = resolve_io(io, blockIdx.x);
   const bool is_like = (pred.op == LC_OP_LIKE || pred.op == LC_OP_NOT_LIKE);
@@ -580,11 +677,11 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
       v.fp = nullptr;
     }
     str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
-                        &sm->bar[1]);
+                        &sm->bar[1], t_start);
   } else {
     const StrView v = make_view(ref.blob, ref.blob);
     str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
-                        nullptr);
+                        nullptr, t_start);
   }
 }
 

@@ -277,25 +277,25 @@ int lc_ctx_synchronize(lc_ctx* ctx) {
   return LC_OK;
 }
 
-int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[4]) {
+int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[16]) {
   if (!ctx) return LC_ERR_INVALID;
   std::lock_guard<std::mutex> g(ctx->mu);
   cudaSetDevice(ctx->device);
   if (!ctx->d_prof) {
-    if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_prof), 64) != cudaSuccess) {
+    if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_prof), 128) != cudaSuccess) {
       cudaGetLastError();
       set_error("cudaMalloc for profile counters failed");
       return LC_ERR_OOM;
     }
-    LC_CUDA_OK(cudaMemsetAsync(ctx->d_prof, 0, 64, ctx->stream));
+    LC_CUDA_OK(cudaMemsetAsync(ctx->d_prof, 0, 128, ctx->stream));
   }
   LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   if (out) {
-    unsigned long long tmp[4] = {0, 0, 0, 0};
-    LC_CUDA_OK(cudaMemcpy(tmp, ctx->d_prof, 32, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 4; ++i) out[i] = tmp[i];
+    unsigned long long tmp[16] = {0};
+    LC_CUDA_OK(cudaMemcpy(tmp, ctx->d_prof, 128, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; ++i) out[i] = tmp[i];
   }
-  if (enable && !ctx->prof_on) LC_CUDA_OK(cudaMemset(ctx->d_prof, 0, 64));
+  if (enable && !ctx->prof_on) LC_CUDA_OK(cudaMemset(ctx->d_prof, 0, 128));
   ctx->prof_on = enable != 0;
   return LC_OK;
 }

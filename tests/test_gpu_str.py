@@ -134,6 +134,30 @@ def test_predicates_match_oracle_and_arrow(cache, with_fp, n, n_unique, prefix):
                     assert_masks_equal(got, pc.invert(arrow) if negated else arrow, f"like {pat} vs arrow")
 
 
+@pytest.mark.parametrize("with_fp", [False, True])
+def test_like_needle_length_boundaries(cache, with_fp):
+    """The code-domain matcher handles needles up to 31 bytes (state bit 31 is reserved); 32 and beyond take the
+    decode + KMP path. Both must agree with arrow's match_substring around the switch."""
+    rng = np.random.default_rng(31 + with_fp)
+    vals, mask = make_strings(rng, 6000, 1500, min_tokens=6, max_tokens=30)
+    arr = build(vals, mask, pa.string())
+    liquid = cache.transcode(arr, hint=_hint() if with_fp else None, compressor_scope=4400 + with_fp)
+    oracle = OracleByteViewArray.from_arrow(arr, build_fingerprints=with_fp)
+    sel = random_selection(rng, len(vals), 0.8)
+    filt = arr.filter(sel)
+    longest = sorted(set(vals), key=len, reverse=True)[:20]
+    for m in (1, 2, 7, 8, 9, 29, 30, 31, 32, 33, 64, 70):
+        for src in longest[:4]:
+            if len(src) < m + 2:
+                continue
+            inner = src[1:1 + m].replace("%", "5").replace("_", "-")
+            for needle in (inner, inner[:-1] + "~"):
+                pat = f"%{needle}%"
+                got = liquid.try_eval_predicate(_like(pat), sel)
+                assert_masks_equal(got, oracle.try_eval_predicate("like", pat, sel), f"like m={m} vs oracle")
+                assert_masks_equal(got, pc.match_substring(filt, needle), f"like m={m} vs arrow")
+
+
 def test_long_values_and_len255_path(cache):
     """byte_view_array/tests.rs:689-774: values with >= 255 byte suffixes take the len==255 gates."""
     base = "x" * 300
