@@ -50,6 +50,20 @@ def parse_args():
     return ap.parse_args()
 
 
+def recorded_traffic(rows: int, entries: int):
+    """DRAM bytes (read + write) of one k_str_scan launch from the committed `ncu --set full` capture of this exact
+    seeded workload (profiles/r01_k_str_scan_traffic.json); None when the shape differs or the file is absent.
+    A number taken under the profiler is only ever used for this field, never for a timing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k_str_scan_traffic.json")) as f:
+            t = json.load(f)
+        if t["workload"]["rows"] == rows and t["workload"]["entries"] == entries:
+            return int(t["dram__bytes_read.sum"]) + int(t["dram__bytes_write.sum"])
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -402,11 +416,18 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
     launches = int(st_b.kernel_launches - st_a.kernel_launches)
 
-    # multi-GPU: the ONE exchange step of this path — gather the filtered Arrow batches to rank 0 over NCCL
+    # multi-GPU: the ONE exchange step of this path — gather the filtered batches to rank 0 over NCCL. The result is
+    # read into device buffers (lc_scan_read_device) so values / offsets / validity go HBM -> HBM over NVLink.
     gathered_rows = result_rows[0]
     if world > 1:
-        empty = pa.array([], pa.string())
-        g = gather_arrow_to_rank0(last if last is not None else empty, rank, world, torch.device("cuda", local_rank))
+        from liquid_cache_b200.dist import gather_device_result_to_rank0
+        dev = torch.device("cuda", local_rank)
+        if result_rows[0]:
+            v, o, b, nrows, nnull = scan.read_torch(handles, dev)
+        else:
+            v, o, b, nrows, nnull = (torch.empty(0, dtype=torch.uint8, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
+                                     None, 0, 0)
+        g = gather_device_result_to_rank0(v, o, b, nrows, nnull, pa.string(), rank, world)
         if rank == 0:
             gathered_rows = len(g)
 
@@ -486,7 +507,8 @@ def main():
                     "matches_device_path": bool(e2e_ok)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_str_scan<MODE_REFINE>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": algo_bytes,
+                         "frac": achieved / peak, "traffic": recorded_traffic(rows_local, n_entries),
+                         "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel_ms": kern_ms, "peak_source": peak_src,
                          "kernel_share_of_step": kern_ms / (ms_total / args.steps)},
             "clocks": clk,

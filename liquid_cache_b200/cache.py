@@ -518,3 +518,28 @@ class Scan:
         out_a, out_s = _new_out()
         N.check(N.lib().lc_scan_read(self._scan, handles.ctypes.data, _ptr(out_s), _ptr(out_a)))
         return _import(out_a, out_s)
+
+    def read_device(self, handles: np.ndarray, d_values: int = 0, values_cap: int = 0, d_offsets: int = 0,
+                    d_validity: int = 0) -> tuple[int, int, int]:
+        """lc_scan_read_device: the concatenated result stays in CALLER-owned device memory (raw device addresses;
+        e.g. torch tensors' data_ptr()). All pointers 0 = size query. Returns (rows, value_bytes, null_count).
+        Buffers: values `value_bytes`; offsets (byte-view) `4 * (rows + 1)`; validity `4 * ceil(rows / 32)`."""
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        rows, nbytes, nulls = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        N.check(N.lib().lc_scan_read_device(self._scan, handles.ctypes.data, d_values or None, values_cap, d_offsets or None,
+                                            d_validity or None, C.byref(rows), C.byref(nbytes), C.byref(nulls)))
+        return int(rows.value), int(nbytes.value), int(nulls.value)
+
+    def read_torch(self, handles: np.ndarray, device):
+        """read_device into freshly allocated torch tensors on `device`:
+        (values u8[value_bytes], offsets i32[rows+1] | None, validity u8[4*ceil(rows/32)] | None, rows, null_count)."""
+        import torch
+
+        rows, nbytes, nulls = self.read_device(handles)
+        is_bytes = int(N.lib().lc_data_type(self._cache._ctx, int(handles[0]))) == N.LIQUID_BYTE_VIEW
+        values = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        offsets = torch.empty(rows + 1, dtype=torch.int32, device=device) if is_bytes else None
+        validity = torch.empty(4 * ((rows + 31) // 32), dtype=torch.uint8, device=device) if nulls else None
+        self.read_device(handles, values.data_ptr(), nbytes, offsets.data_ptr() if offsets is not None else 0,
+                         validity.data_ptr() if validity is not None else 0)
+        return values[:nbytes], offsets, validity, rows, nulls

@@ -46,6 +46,61 @@ __global__ void __launch_bounds__(256) k_and_then(const uint32_t* __restrict__ l
   }
 }
 
+// Concatenate per-entry validity bit strings (entry i: k_i bits starting at word valid_off[i] of valid_base, the
+// layout the DECODE kernels write) into ONE bitmap of `rows` bits on the device — the Arrow validity buffer of the
+// concatenated result, so a device-resident get() never visits the host (lc_scan_read_device).
+// One thread per output word; entries without nulls (counts[i*stride+1] == 0) read as all ones.
+__global__ void k_concat_validity(const uint32_t* __restrict__ valid_base, const uint64_t* __restrict__ valid_off,
+                                  const uint64_t* __restrict__ row_base, const uint32_t* __restrict__ counts,
+                                  uint32_t counts_stride, uint32_t n_entries, uint64_t rows, uint32_t* __restrict__ out) {
+  const uint64_t w = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t r0 = w * 32ull;
+  if (r0 >= rows) return;
+  // last entry whose first row is <= r0
+  uint32_t lo = 0, hi = n_entries;
+  while (hi - lo > 1u) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (row_base[mid] <= r0) lo = mid;
+    else hi = mid;
+  }
+  uint32_t e = lo, filled = 0, word = 0;
+  const uint32_t want = rows - r0 < 32ull ? static_cast<uint32_t>(rows - r0) : 32u;
+  while (filled < want && e < n_entries) {
+    const uint64_t b = row_base[e];
+    const uint64_t end = e + 1u < n_entries ? row_base[e + 1u] : rows;
+    const uint64_t pos = r0 + filled;
+    if (pos >= end) {
+      ++e;
+      continue;
+    }
+    const uint32_t local = static_cast<uint32_t>(pos - b);
+    const uint32_t avail = static_cast<uint32_t>(end - pos);
+    const uint32_t take = avail < want - filled ? avail : want - filled;
+    uint32_t bits = kFullMask;
+    if (counts[static_cast<size_t>(e) * counts_stride + 1u] != 0u) {
+      const uint32_t* vw = valid_base + valid_off[e];
+      const uint32_t wi = local >> 5, sh = local & 31u;
+      const uint32_t w0 = vw[wi];
+      const uint32_t w1 = (sh + take > 32u) ? vw[wi + 1u] : 0u;
+      bits = __funnelshift_r(w0, w1, sh);
+    }
+    if (take < 32u) bits &= (1u << take) - 1u;
+    word |= bits << filled;
+    filled += take;
+  }
+  out[w] = word;
+}
+
+cudaError_t launch_concat_validity(const uint32_t* d_valid_base, const uint64_t* d_valid_off, const uint64_t* d_row_base,
+                                   const uint32_t* d_counts, uint32_t counts_stride, uint32_t n_entries, uint64_t rows,
+                                   uint32_t* d_out, cudaStream_t s) {
+  if (rows == 0 || n_entries == 0) return cudaSuccess;
+  const uint64_t words = (rows + 31) / 32;
+  k_concat_validity<<<static_cast<uint32_t>((words + 127) / 128), 128, 0, s>>>(d_valid_base, d_valid_off, d_row_base,
+                                                                               d_counts, counts_stride, n_entries, rows, d_out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_and_then(const uint32_t* d_left, uint32_t left_bits, const uint32_t* d_right, uint32_t* d_out,
                             cudaStream_t s) {
   if (left_bits == 0) return cudaSuccess;

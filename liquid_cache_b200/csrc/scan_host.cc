@@ -609,10 +609,6 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   SelPlan sp;
   LC_TRY(plan_selection(ctx, entries, n, sel_bits, &sp, dev_sel));
   tr.mark("stage selection");
-  if (dev_out) {
-    set_error("device-resident results are not wired up for this call yet");
-    return LC_ERR_INVALID;
-  }
   const bool is_int = (proto->liquid_type == LC_LIQUID_INTEGER);
   cudaStream_t s = ctx->stream;
   Scratch& sc = ctx->scratch;
@@ -707,6 +703,33 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     if (!dev_sel) LC_TRY(upload_selection(ctx, sp, d_up + up_offs, s));
     LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
     ctx->kernel_launches++;
+    if (dev_out) {
+      // device-resident result: counts come back (null count), values and validity stay in HBM
+      LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
+      LC_CUDA_OK(cudaStreamSynchronize(s));
+      ctx->d2h_bytes += dn_counts;
+      const uint32_t* hc = reinterpret_cast<const uint32_t*>(h_dn);
+      uint64_t nulls = 0;
+      for (uint64_t i = 0; i < n; ++i) nulls += hc[4 * i + 1];
+      if (dev_out->out_rows) *dev_out->out_rows = rows;
+      if (dev_out->out_value_bytes) *dev_out->out_value_bytes = rows * tb;
+      if (dev_out->out_null_count) *dev_out->out_null_count = nulls;
+      if (!dev_out->d_values) return LC_OK;  // size query
+      if (dev_out->values_cap < rows * tb) {
+        set_error("read_device: values buffer of %llu bytes, need %llu", (unsigned long long)dev_out->values_cap,
+                  (unsigned long long)(rows * tb));
+        return LC_ERR_INVALID;
+      }
+      if (rows) LC_CUDA_OK(cudaMemcpyAsync(dev_out->d_values, d_vals, rows * tb, cudaMemcpyDeviceToDevice, s));
+      if (nulls && dev_out->d_validity) {
+        const uint64_t* offs = reinterpret_cast<const uint64_t*>(d_up);
+        LC_CUDA_OK(launch_concat_validity(io.valid_base, offs + 2 * n, offs + n, io.counts, 4, static_cast<uint32_t>(n), rows,
+                                          static_cast<uint32_t*>(dev_out->d_validity), s));
+        ctx->kernel_launches++;
+      }
+      LC_CUDA_OK(cudaStreamSynchronize(s));
+      return LC_OK;
+    }
     HostBuf values{host_alloc(rows * tb), rows * tb};
     if (!values.p) {
       set_error("host allocation of %llu bytes failed", (unsigned long long)(rows * tb));
@@ -792,6 +815,35 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   if (total_bytes > 0x7fffffffull) {
     set_error("decoded values exceed 2 GiB (int32 offsets); split the call");
     return LC_ERR_INVALID;
+  }
+  if (dev_out) {
+    if (dev_out->out_rows) *dev_out->out_rows = rows;
+    if (dev_out->out_value_bytes) *dev_out->out_value_bytes = total_bytes;
+    if (dev_out->out_null_count) *dev_out->out_null_count = nulls;
+    if (!dev_out->d_values && !dev_out->d_offsets) return LC_OK;  // size query
+    if (!dev_out->d_offsets || (total_bytes && !dev_out->d_values) || dev_out->values_cap < total_bytes) {
+      set_error("read_device: need an offsets buffer of %llu int32 and %llu value bytes", (unsigned long long)(rows + 1),
+                (unsigned long long)total_bytes);
+      return LC_ERR_INVALID;
+    }
+    g.out_offsets = static_cast<int32_t*>(dev_out->d_offsets);
+    g.out_bytes = static_cast<uint8_t*>(dev_out->d_values);
+    // byte_base[n] and the closing offset travel from the pinned upload area (idle since the sync above)
+    int32_t* h_last = reinterpret_cast<int32_t*>(h_up);  // sel_off[0] slot: no longer needed on the host
+    *h_last = static_cast<int32_t>(total_bytes);
+    LC_CUDA_OK(cudaMemcpyAsync(d_up + 4 * n * 8, h_byte_base, n * 8, cudaMemcpyHostToDevice, s));
+    LC_CUDA_OK(launch_str_decode(static_cast<uint32_t>(n), g, s));
+    LC_CUDA_OK(cudaMemcpyAsync(g.out_offsets + rows, h_last, 4, cudaMemcpyHostToDevice, s));
+    ctx->kernel_launches++;
+    if (nulls && dev_out->d_validity) {
+      const uint64_t* offs = reinterpret_cast<const uint64_t*>(d_up);
+      LC_CUDA_OK(launch_concat_validity(g.io.valid_base, offs + 2 * n, offs + n, g.io.counts, 4, static_cast<uint32_t>(n), rows,
+                                        static_cast<uint32_t*>(dev_out->d_validity), s));
+      ctx->kernel_launches++;
+    }
+    LC_CUDA_OK(cudaStreamSynchronize(s));
+    ctx->h2d_bytes += n * 8 + 4;
+    return LC_OK;
   }
   const uint64_t off_bytes = (rows + 1) * 4;
   const uint64_t res_bytes = round_up(off_bytes, 256) + round_up(total_bytes + 16, 256);

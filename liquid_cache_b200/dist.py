@@ -105,3 +105,52 @@ def gather_arrow_to_rank0(arr: pa.Array, rank: int, world: int, device=None) -> 
             db = pa.py_buffer(bd.cpu().numpy().tobytes()) if bd is not None else pa.py_buffer(b"")
             parts.append(pa.Array.from_buffers(arr.type, nr, [vb, db], null_count=nulls))
     return pa.concat_arrays(parts)
+
+
+def gather_device_result_to_rank0(values, offsets, validity, rows: int, nulls: int, arrow_type: pa.DataType, rank: int,
+                                  world: int) -> Optional[pa.Array]:
+    """Same exchange as gather_arrow_to_rank0, but starting from the DEVICE-resident result of
+    `Scan.read_torch` (lc_scan_read_device): the filtered values / int32 offsets / validity words go from each GPU's
+    HBM to rank 0's HBM over NCCL without visiting the host; only rank 0 copies the concatenation down once.
+    `values` u8 tensor, `offsets` i32 tensor (byte types) or None, `validity` u8 tensor or None."""
+    import torch
+    import torch.distributed as dist
+
+    is_bytes = pa.types.is_string(arrow_type) or pa.types.is_binary(arrow_type)
+
+    def host_array(v, o, b, n, nn):
+        vb = pa.py_buffer(b.cpu().numpy().tobytes()) if (b is not None and nn) else None
+        data = pa.py_buffer(v.cpu().numpy().tobytes())
+        if is_bytes:
+            return pa.Array.from_buffers(arrow_type, n, [vb, pa.py_buffer(o.cpu().numpy().tobytes()), data], null_count=nn)
+        return pa.Array.from_buffers(arrow_type, n, [vb, data], null_count=nn)
+
+    if world == 1:
+        return host_array(values, offsets, validity, rows, nulls)
+    dev = values.device
+    sizes = torch.tensor([rows, nulls, values.numel(), 0 if validity is None else validity.numel()], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [t.cpu().tolist() for t in all_sizes]
+    if rank != 0:
+        ops = [dist.P2POp(dist.isend, t.view(torch.uint8) if t.dtype != torch.uint8 else t, 0)
+               for t in (values, offsets, validity) if t is not None and t.numel()]
+        for r in (dist.batch_isend_irecv(ops) if ops else []):
+            r.wait()
+        return None
+    parts = [host_array(values, offsets, validity, rows, nulls)]
+    ops, recv = [], []
+    for r in range(1, world):
+        nr, nn, nv, nb = all_sizes[r]
+        tv = torch.empty(nv, dtype=torch.uint8, device=dev)
+        to = torch.empty((nr + 1) * 4, dtype=torch.uint8, device=dev) if is_bytes else None
+        tb = torch.empty(nb, dtype=torch.uint8, device=dev) if nb else None
+        for t in (tv, to, tb):
+            if t is not None and t.numel():
+                ops.append(dist.P2POp(dist.irecv, t, r))
+        recv.append((nr, nn, tv, to, tb))
+    for r in (dist.batch_isend_irecv(ops) if ops else []):
+        r.wait()
+    for nr, nn, tv, to, tb in recv:
+        parts.append(host_array(tv, to.view(torch.int32) if to is not None else None, tb, nr, nn))
+    return pa.concat_arrays(parts)

@@ -33,7 +33,23 @@ def _worker(rank, world, port, q):
         for a in (strs, ints, empty):
             g = gather_arrow_to_rank0(a, rank, world)
             out.append(None if g is None else g.to_pylist())
-        q.put((rank, [strs.to_pylist(), ints.to_pylist(), empty.to_pylist()], out))
+        # the device-buffer flavour (lc_scan_read_device results), here on CPU tensors over gloo
+        import torch
+
+        from liquid_cache_b200.dist import _buffers_of, gather_device_result_to_rank0
+
+        for a in (strs, ints):
+            valid, off, data = _buffers_of(a)
+            v = torch.from_numpy(data.copy())
+            o = torch.from_numpy(off.copy()) if off is not None else None
+            b = None
+            if valid is not None:
+                words = np.zeros(4 * ((len(a) + 31) // 32), dtype=np.uint8)
+                words[: len(valid)] = valid
+                b = torch.from_numpy(words)
+            g = gather_device_result_to_rank0(v, o, b, len(a), a.null_count, a.type, rank, world)
+            out.append(None if g is None else g.to_pylist())
+        q.put((rank, [strs.to_pylist(), ints.to_pylist(), empty.to_pylist(), strs.to_pylist(), ints.to_pylist()], out))
     finally:
         dist.destroy_process_group()
 
@@ -54,7 +70,7 @@ def test_gather_to_rank0_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for k in range(3):
+    for k in range(5):
         assert res[0][1][k] == res[0][0][k] + res[1][0][k]
         assert res[1][1][k] is None
 

@@ -238,3 +238,40 @@ def test_scan_pipeline_matches_per_call_path(cache):
         assert total == sum(len(x) for x in want_i)
         assert_arrays_equal(got_i, pa.concat_arrays(want_i), "scan ints")
         assert_arrays_equal(got_s, pa.concat_arrays(want_s), "scan strings")
+
+
+@pytest.mark.parametrize("with_nulls", [False, True])
+def test_scan_read_device_matches_host_read(cache, with_nulls):
+    """lc_scan_read_device: the same concatenated result as lc_scan_read, left in caller-owned device memory
+    (values / int32 offsets / validity words concatenated at bit granularity on the device)."""
+    import torch
+
+    from liquid_cache_b200.dist import gather_device_result_to_rank0
+
+    rng = np.random.default_rng(77 + with_nulls)
+    sizes = [8192, 1000, 8192, 37, 4096, 1]  # ragged batches: row bases that are not multiples of 32
+    ints, strs, li, ls = [], [], [], []
+    for rows in sizes:
+        mask = (rng.random(rows) < 0.2) if with_nulls else None
+        iv = pa.array(rng.integers(-1000, 1000, size=rows), pa.int32(), mask=mask)
+        sv, sm = make_strings(rng, rows, max(1, rows // 4), null_p=0.2 if with_nulls else 0.0)
+        ints.append(iv)
+        strs.append(build(sv, sm, pa.string()))
+        li.append(cache.transcode(iv))
+        ls.append(cache.transcode(strs[-1], compressor_scope=5151 + with_nulls))
+    hi = np.array([l.handle for l in li], dtype=np.uint64)
+    hs = np.array([l.handle for l in ls], dtype=np.uint64)
+    dev = torch.device("cuda", 0)
+    with cache.scan(sizes) as scan:
+        for pred in (None, _bin(">=", -300)):
+            if pred is not None:
+                scan.filter(hi, pred, pa.int32())
+            want_i, want_s = scan.read(hi), scan.read(hs)
+            v, o, b, rows, nulls = scan.read_torch(hi, dev)
+            assert o is None and rows == len(want_i) and nulls == want_i.null_count
+            got_i = gather_device_result_to_rank0(v, o, b, rows, nulls, pa.int32(), 0, 1)
+            assert_arrays_equal(got_i, want_i, "device ints")
+            v, o, b, rows, nulls = scan.read_torch(hs, dev)
+            assert rows == len(want_s) and nulls == want_s.null_count and int(o[-1].item()) == v.numel()
+            got_s = gather_device_result_to_rank0(v, o, b, rows, nulls, pa.string(), 0, 1)
+            assert_arrays_equal(got_s, want_s, "device strings")
