@@ -365,7 +365,8 @@ def main():
                                                       for i, nm in enumerate(names)) + f", total {tot / n_entries:.0f}", file=sys.stderr)
     # R = keys 2n + fingerprints 4U + candidate compressed bytes + offset residuals of the candidates' pairs
     #     (2 bytes typ.) ; W = selection words n/8   (SURVEY.md §8d "string predicate, fingerprint path")
-    algo_bytes = 2 * rows_local + 4 * uniques + cand_bytes + 2 * 2 * cand + rows_local // 8
+    #     + 8U: the bigram filters this build stores beside the fingerprints (read once, like them)
+    algo_bytes = 2 * rows_local + (4 + 8) * uniques + cand_bytes + 2 * 2 * cand + rows_local // 8
 
     k_start = torch.cuda.Event(enable_timing=True)
     k_stop = torch.cuda.Event(enable_timing=True)
@@ -497,7 +498,7 @@ def main():
                 "workload": "clickbench-hits URL column (FSST+dict+fingerprints) LIKE '%google%' then get-with-selection (BASELINE configs[1])",
                 "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "rows_per_entry": ROWS_PER_ENTRY,
                 "liquid_bytes_per_gpu": hbm_bytes, "liquid_bytes_per_row": hbm_bytes / rows_local,
-                "unique_values_per_entry": uniques / n_entries, "fingerprint_candidates_frac": cand / max(1, uniques),
+                "unique_values_per_entry": uniques / n_entries, "walked_candidates_frac": cand / max(1, uniques),
                 "matching_rows": int(gathered_rows), "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective; NCCL gather of the filtered batch",
                 "l2": "inputs (liquid column) larger than the 126 MB L2, no flush needed",
                 "setup_seconds": setup_s,

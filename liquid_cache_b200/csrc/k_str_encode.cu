@@ -19,6 +19,7 @@
 // The FSST matcher is the one fsst_host.cc trains with (lossy 3-byte hash for 3..8 byte symbols, 2-byte table,
 // 1-byte fallback, escape), so the compressed form only depends on the column chunk's table.
 #include "device_utils.cuh"
+#include "entry_layout.h"
 #include "kernels.h"
 
 namespace lc {
@@ -225,8 +226,13 @@ __global__ void k_uniq_pass1(StrEncIo io) {
     io.clen[u] = fsst_compress_value<false>(io.enc, p, len, nullptr);
     if (io.fps) {
       uint32_t bits = 0;
-      for (uint32_t b = 0; b < len; ++b) bits |= 1u << (p[b] & 31u);
+      unsigned long long bl = 0;
+      for (uint32_t b = 0; b < len; ++b) {
+        bits |= 1u << (p[b] & 31u);
+        if (b + 1u < len) bl |= 1ull << bigram_bit(p[b], p[b + 1u]);
+      }
       io.fps[u] = bits;
+      io.blooms[u] = bl;
     }
   }
   // length statistics: warp-reduce, one atomic per warp

@@ -151,8 +151,13 @@ static int prepare_str_pred(const lc_predicate* pred, StrLaunch* L) {
     LC_TRY(like_inner(pred->lit_bytes, pred->lit_len, &nd, &il));
     m = il;
     uint32_t fp = 0;
-    for (uint32_t i = 0; i < il; ++i) fp |= 1u << (nd[i] & 31u);
+    unsigned long long bl = 0;
+    for (uint32_t i = 0; i < il; ++i) {
+      fp |= 1u << (nd[i] & 31u);
+      if (i + 1 < il) bl |= 1ull << bigram_bit(nd[i], nd[i + 1]);
+    }
     L->desc.needle_fp = fp;
+    L->desc.needle_bloom = bl;
   }
   if (m > kMaxNeedle) {
     set_error("needle longer than %u bytes", kMaxNeedle);

@@ -21,14 +21,14 @@ from tests.test_gpu_str import make_strings
 
 pytestmark = pytest.mark.gpu
 
-STR_HDR = struct.Struct("<I4B I I i i I 11I Q Q 3I")  # up to rows_off; 128-byte header, tail is padding
+STR_HDR = struct.Struct("<I4B I I i i I 11I Q Q 4I")  # up to rows_off; 128-byte header, tail is padding
 INT_HDR = struct.Struct("<I4B I I Q 6I")
 
 
 def parse_str_image(img: bytes):
     (magic, arrow_type, has_nulls, has_fp, offset_bytes, n, n_unique, slope, intercept, spl, validity_off, keys_off,
      prefix_keys_off, fp_off, resid_off, shared_prefix_off, fsst_off, fsst_bytes, blob_bytes, null_count, max_value_len,
-     uncompressed, table_ptr, head_bytes, sp_end, rows_off) = STR_HDR.unpack_from(img, 0)
+     uncompressed, table_ptr, head_bytes, sp_end, rows_off, bloom_off) = STR_HDR.unpack_from(img, 0)
     assert magic == 0x3153514C and blob_bytes == len(img)
     h = dict(n=n, n_unique=n_unique, slope=slope, intercept=intercept, null_count=null_count, has_fp=has_fp,
              offset_bytes=offset_bytes, max_value_len=max_value_len, uncompressed=uncompressed, has_nulls=has_nulls)
@@ -42,7 +42,16 @@ def parse_str_image(img: bytes):
     dt = {1: np.int8, 2: np.int16, 4: np.int32}[offset_bytes]
     h["resid"] = np.frombuffer(img, dtype=dt, count=n_unique + 1, offset=resid_off).astype(np.int64)
     h["comp"] = img[fsst_off:fsst_off + fsst_bytes]
+    h["blooms"] = np.frombuffer(img, dtype=np.uint64, count=n_unique, offset=bloom_off).tolist() if bloom_off else None
     return h
+
+
+def bigram_bloom(b: bytes) -> int:
+    """entry_layout.h bigram_bit: the private 64-bit substring pre-filter stored beside the reference fingerprints."""
+    x = 0
+    for a, c in zip(b, b[1:]):
+        x |= 1 << ((((a << 8) | c) * 0x9E3779B1 & 0xFFFFFFFF) >> 26)
+    return x
 
 
 def fsst_decompress(table: bytes, comp: bytes) -> bytes:
@@ -76,8 +85,10 @@ def check_string_entry(cache, arr: pa.Array, hint=None, scope=0):
     assert h["prefix_keys"] == want.prefix_keys
     if hint is not None:
         assert h["fps"] == want.fingerprints
+        if want.uniques:
+            assert h["blooms"] == [bigram_bloom(u) for u in want.uniques]
     else:
-        assert h["fps"] is None
+        assert h["fps"] is None and h["blooms"] is None
     assert h["max_value_len"] == max([len(u) for u in want.uniques], default=0)
     assert h["uncompressed"] == sum(len(u) for u in want.uniques)
     # offsets: slope * i + intercept + resid[i], rebuilt and checked against the compressed stream
