@@ -444,8 +444,8 @@ template <int MODE>
 __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w, const StrPredDesc& pred,
                                               ScanSmem* sm, uint64_t* s_sym, uint8_t* s_len, StrPlan* s_plan,
                                               const uint8_t* s_nd, const uint16_t* s_fail, uint32_t* s_dict,
-                                              uint16_t* s_cand, uint32_t* s_verdict, uint32_t* s_M, SymStep* s_step,
-                                              uint32_t dict_words, uint64_t* bar_rows, long long t_start) {
+                                              uint16_t* s_cand, uint32_t* s_M, SymStep* s_step, uint32_t dict_words,
+                                              uint64_t* bar_rows, long long t_start) {
   const uint32_t m = pred.needle_len;
   // measurement aid (pred.prof): thread 0 stamps the phase boundaries with the SM clock
   long long t_prev = t_start;
@@ -481,16 +481,15 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
     const uint32_t fill = (plan.flags & 1u) ? kFullMask : 0u;
     for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = fill;
   } else if (fast_like) {
-    // LIKE candidates (reference fingerprint gate, comparisons.rs:600-615), queued LONGEST CLASS FIRST: every warp
-    // drains its last values with most lanes idle, so the values left for the end should be the short ones. Two
-    // passes over the dictionary: count per length class, then scatter to the class's slice of the queue.
-    uint32_t* cls_cnt = sm->warp_tot;      // [0..3] totals, [4..7] running offsets (unused scratch in this phase)
-    if (threadIdx.x < 8u) cls_cnt[threadIdx.x] = 0;
+    // LIKE candidates: the reference gate (byte-class fingerprints, comparisons.rs:600-615), then the private bigram
+    // filter on its survivors. Each thread owns the uniques i0 + lane of its warp's stripes; their gate inputs
+    // (fingerprint from the staged head, bigram filter from global memory) are loaded up front, eight stripes at a
+    // time, so the global loads overlap instead of each one stalling a ballot round. One ballot per stripe appends
+    // the survivors to the queue. (An earlier version also ordered the queue by length class — worth 3 % with ~700
+    // candidates per entry, nothing with the ~100 the bigram filter leaves, at the price of a second pass.)
+    uint32_t* cand_cnt = sm->warp_tot;  // [0] queue length (unused scratch in this phase)
+    if (threadIdx.x == 0) cand_cnt[0] = 0;
     __syncthreads();
-    // Each thread owns the uniques i0 + lane of its warp's stripes. Their gate inputs (fingerprint from the staged head,
-    // bigram filter from global memory) are loaded up front, eight stripes at a time, so the global loads overlap
-    // instead of each one stalling a ballot round; the per-unique verdict (length class, 4 = not a candidate) is kept
-    // in a nibble of `verdict` for the scatter pass.
     for (uint32_t g0 = (threadIdx.x & ~31u); g0 < U; g0 += 2048u) {
       unsigned long long bl[8];
       uint32_t fpv[8];
@@ -501,63 +500,29 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
         fpv[t] = (act && v.fp) ? v.fp[i] : 0u;
         bl[t] = (act && v.bloom) ? v.bloom[i] : ~0ull;
       }
-      uint32_t verdict = 0;
-#pragma unroll
-      for (uint32_t t = 0; t < 8; ++t) {
-        const uint32_t i0 = g0 + t * 256u;
-        const uint32_t i = i0 + lane;
-        const bool act = i < U;
-        // reference gate (byte-class fingerprints), then the private bigram filter on the survivors
-        const bool ref_ok = act && (v.fp ? ((fpv[t] & pred.needle_fp) == pred.needle_fp) : true);
-        const bool cand = ref_ok && ((bl[t] & pred.needle_bloom) == pred.needle_bloom);
-        uint32_t cls = 4;
-        if (cand) {
-          const uint32_t len = dict_offset(v, i + 1u) - dict_offset(v, i);
-          cls = len >= 96u ? 0u : len >= 64u ? 1u : len >= 32u ? 2u : 3u;
-        }
-        verdict |= cls << (4u * t);
-        if (i0 < U) {  // warp-uniform
-          const uint32_t rw = __ballot_sync(kFullMask, ref_ok);
-          if (lane == 0) {
-            s_dict[i0 >> 5] = 0;
-            if (rw) atomicAdd(&sm->misc[0], __popc(rw));
-          }
-#pragma unroll
-          for (uint32_t c = 0; c < 4; ++c) {
-            const uint32_t cw = __ballot_sync(kFullMask, cls == c);
-            if (cw && lane == 0) atomicAdd(&cls_cnt[c], __popc(cw));
-          }
-        }
-      }
-      // the scatter needs the class totals of the WHOLE dictionary: park the verdicts (one word per thread and batch)
-      s_verdict[(g0 >> 11) * 256u + threadIdx.x] = verdict;
-    }
-    __syncthreads();
-    for (uint32_t g0 = (threadIdx.x & ~31u); g0 < U; g0 += 2048u) {
-      const uint32_t verdict = s_verdict[(g0 >> 11) * 256u + threadIdx.x];
 #pragma unroll
       for (uint32_t t = 0; t < 8; ++t) {
         const uint32_t i0 = g0 + t * 256u;
         if (i0 >= U) break;  // warp-uniform
-        const uint32_t cls = (verdict >> (4u * t)) & 15u;
-#pragma unroll
-        for (uint32_t c = 0; c < 4; ++c) {
-          const uint32_t cw = __ballot_sync(kFullMask, cls == c);
-          if (cw == 0) continue;
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(&cls_cnt[4u + c], __popc(cw));
+        const uint32_t i = i0 + lane;
+        const bool ref_ok = (i < U) && (v.fp ? ((fpv[t] & pred.needle_fp) == pred.needle_fp) : true);
+        const bool cand = ref_ok && ((bl[t] & pred.needle_bloom) == pred.needle_bloom);
+        const uint32_t rw = __ballot_sync(kFullMask, ref_ok);
+        const uint32_t cw = __ballot_sync(kFullMask, cand);
+        uint32_t base = 0;
+        if (lane == 0) {
+          s_dict[i0 >> 5] = 0;
+          if (rw) atomicAdd(&sm->misc[0], __popc(rw));
+          if (cw) base = atomicAdd(&cand_cnt[0], __popc(cw));
+        }
+        if (cw) {
           base = __shfl_sync(kFullMask, base, 0);
-          uint32_t start = 0;
-          for (uint32_t d = 0; d < c; ++d) start += cls_cnt[d];
-          if (cls == c) {
-            s_cand[start + base + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i0 + lane);
-            // (Tried and dropped: prefetch.global.L2 of the value's first lines here — 0.762 vs 0.716 ms.)
-          }
+          if (cand) s_cand[base + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i);
         }
       }
     }
     __syncthreads();
-    const uint32_t ncand = cls_cnt[0] + cls_cnt[1] + cls_cnt[2] + cls_cnt[3];
+    const uint32_t ncand = cand_cnt[0];
     if (pred.prof) {  // measurement aid, never on in a timed run
       unsigned long long bytes = 0;
       for (uint32_t c = threadIdx.x; c < ncand; c += 256u)
@@ -675,6 +640,59 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
 
   // ---------------- phase 2: dictionary results -> rows ----------------
   const uint16_t* keys = v.keys;
+  if (MODE == MODE_REFINE || (MODE == MODE_PRED && w.sel == nullptr)) {
+    // Full-length outputs need no compaction: a warp takes a 1024-row chunk, 32 steps of key -> result bit -> ballot
+    // with lane j keeping the word of step j, then ONE coalesced pass over the chunk's 32 mask words (AND validity /
+    // selection, store, popcount). ~9 instructions per 32 rows instead of ~32 on the general path.
+    const uint32_t n = v.h->n, n_words = (n + 31u) >> 5, n_chunks = (n + 1023u) >> 10, tail = n & 31u;
+    const uint32_t warp = threadIdx.x >> 5;
+    uint32_t* out_bits = reinterpret_cast<uint32_t*>(w.out);
+    uint32_t* out_valid = (MODE == MODE_PRED && v.valid) ? w.out_valid : nullptr;
+    uint32_t survivors = 0;
+    for (uint32_t c = warp; c < n_chunks; c += 8u) {
+      const uint32_t wi = c * 32u + lane;
+      uint32_t sw = kFullMask;  // issued before the steps: the global load overlaps them
+      if (w.sel && wi < n_words) sw = w.sel[wi];
+      uint32_t mine = 0;
+      const uint32_t row0 = c * 1024u + lane;
+      const bool full = (c + 1u) * 1024u <= n;
+#pragma unroll 8
+      for (uint32_t j = 0; j < 32; ++j) {
+        const uint32_t row = row0 + j * 32u;
+        const uint32_t k = (full || row < n) ? keys[row] : 0u;
+        const uint32_t cw = __ballot_sync(kFullMask, (s_dict[k >> 5] >> (k & 31u)) & 1u);
+        if (static_cast<uint32_t>(lane) == j) mine = cw;
+      }
+      if (wi < n_words) {
+        uint32_t vw = v.valid ? v.valid[wi] : kFullMask;
+        if (wi == n_words - 1u && tail) vw &= (1u << tail) - 1u;
+        const uint32_t cw = mine & vw & sw;
+        out_bits[wi] = cw;
+        if (out_valid) out_valid[wi] = vw;
+        survivors += __popc(cw);
+      }
+    }
+    if (w.counts) {
+      survivors = warp_sum(survivors);
+      if (lane == 0 && survivors) atomicAdd(&sm->counts[0], survivors);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (MODE == MODE_REFINE) {
+          w.counts[0] = sm->counts[0];
+          w.counts[1] = 0;
+        } else {
+          w.counts[0] = n;
+          w.counts[1] = v.h->null_count;
+          w.counts[2] = sm->counts[0];
+        }
+      }
+    }
+    stamp(6);
+#ifdef LC_PHASE_PROF
+    if (pred.prof && threadIdx.x == 0) atomicAdd(&pred.prof[11], static_cast<unsigned long long>(clock64() - t_start));
+#endif
+    return;
+  }
   auto cmp = [&](uint32_t row, uint32_t, uint32_t) -> bool {
     const uint32_t k = keys[row];
     return (s_dict[k >> 5] >> (k & 31u)) & 1u;
@@ -691,10 +709,8 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
 
 // Shared-memory map of the predicate kernel (after the fixed ScanSmem area):
 //   symbols 2048 | lengths 256 | plan 32 | M[256] 1024 | SymStep[512] 8192 | needle | KMP links | dictionary
-//   result bits | candidate list | gate verdicts | staged entry head
+//   result bits | candidate list | staged entry head
 constexpr uint32_t kStrScanTables = 2048u + 256u + 32u + 1024u + 8192u;
-// LIKE gate verdicts: a nibble per dictionary value, one word per thread for every 2048 values
-__host__ __device__ constexpr uint32_t verdict_bytes(uint32_t dict_words) { return ((dict_words * 32u + 2047u) / 2048u) * 1024u; }
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 4)
@@ -712,8 +728,7 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
   uint16_t* s_fail = reinterpret_cast<uint16_t*>(s_nd + nd_bytes);
   uint32_t* s_dict = reinterpret_cast<uint32_t*>(s_nd + nd_bytes + ((2u * m + 15u) & ~15u));
   uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_dict + dict_words);
-  uint32_t* s_verdict = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u));
-  uint8_t* stage = reinterpret_cast<uint8_t*>(s_verdict) + verdict_bytes(dict_words);
+  uint8_t* stage = reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u);
   stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage) + 127u) & ~static_cast<uintptr_t>(127u));
 
 #ifdef LC_PHASE_PROF
@@ -767,20 +782,20 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
       v.resid = ref.blob + v.h->resid_off;
       v.fp = nullptr;
     }
-    str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_verdict, s_M, s_step,
-                        dict_words, &sm->bar[1], t_start);
+    str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
+                        &sm->bar[1], t_start);
   } else {
     const StrView v = make_view(ref.blob, ref.blob);
-    str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_verdict, s_M, s_step,
-                        dict_words, nullptr, t_start);
+    str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
+                        nullptr, t_start);
   }
 }
 
 static uint32_t str_scan_smem(uint32_t needle_len, uint32_t dict_words, uint32_t stage) {
   const uint32_t nd = (needle_len + 15u) & ~15u;
   const uint32_t fl = (2u * needle_len + 15u) & ~15u;
-  return kScanFixedSmem + kStrScanTables + nd + fl + dict_words * 4u + (((dict_words * 64u) + 127u) & ~127u) +
-         verdict_bytes(dict_words) + 128u + stage;
+  return kScanFixedSmem + kStrScanTables + nd + fl + dict_words * 4u + (((dict_words * 64u) + 127u) & ~127u) + 128u +
+         stage;
 }
 
 cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, const StrPredDesc& pred,
