@@ -445,7 +445,8 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
                                               ScanSmem* sm, uint64_t* s_sym, uint8_t* s_len, StrPlan* s_plan,
                                               const uint8_t* s_nd, const uint16_t* s_fail, uint32_t* s_dict,
                                               uint16_t* s_cand, uint32_t* s_M, SymStep* s_step, uint32_t dict_words,
-                                              uint64_t* bar_rows, long long t_start) {
+                                              uint64_t* bar_rows, uint32_t bar_parity, uint64_t& table_cache,
+                                              long long t_start) {
   const uint32_t m = pred.needle_len;
   // measurement aid (pred.prof): thread 0 stamps the phase boundaries with the SM clock
   long long t_prev = t_start;
@@ -469,10 +470,12 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
   const bool neg = (plan.flags & 2u) != 0;
   const bool needs_table = (kind == SP_EQ_LONG || kind == SP_ORD || kind == SP_LIKE);
   const bool fast_like = (kind == SP_LIKE) && m <= 31u;
-  if (needs_table) {
+  if (needs_table && v.h->table_ptr != table_cache) {
+    // symbol table + step table of this column chunk; a CTA walks consecutive entries, which usually share it
     load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
     __syncthreads();
     if (fast_like) build_sym_steps(s_sym, s_len, s_nd, m, s_M, s_step);
+    table_cache = v.h->table_ptr;
   }
   stamp(2);  // symbol tables (includes no barrier after build_sym_steps: its consumers sync later)
 
@@ -635,7 +638,7 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
   }
   __syncthreads();
   stamp(4);  // code walk (or the non-LIKE phase 1)
-  if (bar_rows) mbar_wait(bar_rows, 0);
+  if (bar_rows) mbar_wait(bar_rows, bar_parity);
   stamp(5);  // row sections
 
   // ---------------- phase 2: dictionary results -> rows ----------------
@@ -714,7 +717,7 @@ constexpr uint32_t kStrScanTables = 2048u + 256u + 32u + 1024u + 8192u;
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 4)
-k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words) {
+k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words, uint32_t n_entries, uint32_t per_cta) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
   uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
@@ -731,63 +734,75 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words)
   uint8_t* stage = reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u);
   stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage) + 127u) & ~static_cast<uintptr_t>(127u));
 
-#ifdef LC_PHASE_PROF
-  const long long t_start = pred.prof ? clock64() : 0;
-#else
-  const long long t_start = 0;
-#endif
-  const EntryRef ref = io.refs[blockIdx.x];
-  const EntryIo w = resolve_io(io, blockIdx.x);
   const bool is_like = (pred.op == LC_OP_LIKE || pred.op == LC_OP_NOT_LIKE);
-  const bool staged = (is_like ? ref.head_bytes - (ref.rows_off - ref.pk_off) : ref.head_bytes) <= stage_cap;
-  scan_smem_init(sm);
-  if (threadIdx.x == 0 && staged) {
+  if (threadIdx.x == 0) {
     mbar_init(&sm->bar[0], 1);
     mbar_init(&sm->bar[1], 1);
     fence_mbar_init();
-    // (A) what phase 1 needs: LIKE -> header, shared prefix, fingerprints, offset residuals (no prefix keys);
-    //     everything else -> header, shared prefix and the prefix keys (residuals stay in global memory,
-    //     only the few prefix ties ever look at them)
-    if (is_like) {
-      mbar_expect_tx(&sm->bar[0], ref.pk_off);
-      tma_bulk_g2s(stage, ref.blob, ref.pk_off, &sm->bar[0]);
-    } else {
-      const uint32_t pk_bytes = ref.rows_off - ref.pk_off;
-      mbar_expect_tx(&sm->bar[0], ref.sp_end + pk_bytes);
-      tma_bulk_g2s(stage, ref.blob, ref.sp_end, &sm->bar[0]);
-      if (pk_bytes) tma_bulk_g2s(stage + ref.pk_off, ref.blob + ref.pk_off, pk_bytes, &sm->bar[0]);
-    }
-    // (B) what phase 2 needs, in flight while phase 1 computes: validity + keys. For LIKE they are packed right
-    //     behind the metadata (the prefix keys are not staged, so their slot is not reserved either).
-    const uint32_t rest = ref.head_bytes - ref.rows_off;
-    mbar_expect_tx(&sm->bar[1], rest);
-    tma_bulk_g2s(stage + (is_like ? ref.pk_off : ref.rows_off), ref.blob + ref.rows_off, rest, &sm->bar[1]);
   }
   // needle + KMP links (shared by all entries of the launch)
   for (uint32_t i = threadIdx.x; i < m; i += 256u) {
     s_nd[i] = pred.needle[i];
     s_fail[i] = reinterpret_cast<const uint16_t*>(pred.needle + ((m + 3u) & ~3u))[i];
   }
-  for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = 0;
-  __syncthreads();
-  if (staged) {
-    mbar_wait(&sm->bar[0], 0);
-    StrView v = make_view(stage, ref.blob);
-    if (is_like) {
-      v.pk = reinterpret_cast<const uint64_t*>(ref.blob + v.h->prefix_keys_off);  // not staged, not used
-      const uint32_t shift = ref.rows_off - ref.pk_off;                             // rows section moved down
-      v.keys = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(v.keys) - shift);
-      if (v.valid) v.valid = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(v.valid) - shift);
-    } else {
-      v.resid = ref.blob + v.h->resid_off;
-      v.fp = nullptr;
+  // A CTA takes `per_cta` CONSECUTIVE entries: neighbours in a scan are batches of the same column chunk, so the
+  // FSST symbol table and the needle's step table are built once and reused (table_cache).
+  uint64_t table_cache = 0;
+  uint32_t n_staged = 0;  // uses of the two mbarriers so far -> wait parity
+  const uint32_t e_end = (blockIdx.x + 1u) * per_cta < n_entries ? (blockIdx.x + 1u) * per_cta : n_entries;
+  for (uint32_t e = blockIdx.x * per_cta; e < e_end; ++e) {
+#ifdef LC_PHASE_PROF
+    const long long t_start = pred.prof ? clock64() : 0;
+#else
+    const long long t_start = 0;
+#endif
+    const EntryRef ref = io.refs[e];
+    const EntryIo w = resolve_io(io, e);
+    const bool staged = (is_like ? ref.head_bytes - (ref.rows_off - ref.pk_off) : ref.head_bytes) <= stage_cap;
+    scan_smem_init(sm);
+    if (threadIdx.x == 0 && staged) {
+      // (A) what phase 1 needs: LIKE -> header, shared prefix, fingerprints, offset residuals (no prefix keys);
+      //     everything else -> header, shared prefix and the prefix keys (residuals stay in global memory,
+      //     only the few prefix ties ever look at them)
+      if (is_like) {
+        mbar_expect_tx(&sm->bar[0], ref.pk_off);
+        tma_bulk_g2s(stage, ref.blob, ref.pk_off, &sm->bar[0]);
+      } else {
+        const uint32_t pk_bytes = ref.rows_off - ref.pk_off;
+        mbar_expect_tx(&sm->bar[0], ref.sp_end + pk_bytes);
+        tma_bulk_g2s(stage, ref.blob, ref.sp_end, &sm->bar[0]);
+        if (pk_bytes) tma_bulk_g2s(stage + ref.pk_off, ref.blob + ref.pk_off, pk_bytes, &sm->bar[0]);
+      }
+      // (B) what phase 2 needs, in flight while phase 1 computes: validity + keys. For LIKE they are packed right
+      //     behind the metadata (the prefix keys are not staged, so their slot is not reserved either).
+      const uint32_t rest = ref.head_bytes - ref.rows_off;
+      mbar_expect_tx(&sm->bar[1], rest);
+      tma_bulk_g2s(stage + (is_like ? ref.pk_off : ref.rows_off), ref.blob + ref.rows_off, rest, &sm->bar[1]);
     }
-    str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
-                        &sm->bar[1], t_start);
-  } else {
-    const StrView v = make_view(ref.blob, ref.blob);
-    str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
-                        nullptr, t_start);
+    for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = 0;
+    __syncthreads();
+    if (staged) {
+      const uint32_t parity = n_staged & 1u;
+      ++n_staged;
+      mbar_wait(&sm->bar[0], parity);
+      StrView v = make_view(stage, ref.blob);
+      if (is_like) {
+        v.pk = reinterpret_cast<const uint64_t*>(ref.blob + v.h->prefix_keys_off);  // not staged, not used
+        const uint32_t shift = ref.rows_off - ref.pk_off;                             // rows section moved down
+        v.keys = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(v.keys) - shift);
+        if (v.valid) v.valid = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(v.valid) - shift);
+      } else {
+        v.resid = ref.blob + v.h->resid_off;
+        v.fp = nullptr;
+      }
+      str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
+                          &sm->bar[1], parity, table_cache, t_start);
+    } else {
+      const StrView v = make_view(ref.blob, ref.blob);
+      str_scan_body<MODE>(v, w, pred, sm, s_sym, s_len, s_plan, s_nd, s_fail, s_dict, s_cand, s_M, s_step, dict_words,
+                          nullptr, 0, table_cache, t_start);
+    }
+    __syncthreads();  // the staged sections and the control area are reused by the next entry
   }
 }
 
@@ -815,8 +830,12 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (mode == MODE_PRED) k_str_scan<MODE_PRED><<<n_entries, 256, smem, s>>>(io, pred, stage, dict_words);
-  else k_str_scan<MODE_REFINE><<<n_entries, 256, smem, s>>>(io, pred, stage, dict_words);
+  // consecutive entries per CTA (table reuse), as long as the grid still covers the GPU several times over
+  uint32_t per_cta = n_entries / (148u * 4u * 3u);
+  per_cta = per_cta < 1u ? 1u : (per_cta > 4u ? 4u : per_cta);
+  const uint32_t grid = (n_entries + per_cta - 1u) / per_cta;
+  if (mode == MODE_PRED) k_str_scan<MODE_PRED><<<grid, 256, smem, s>>>(io, pred, stage, dict_words, n_entries, per_cta);
+  else k_str_scan<MODE_REFINE><<<grid, 256, smem, s>>>(io, pred, stage, dict_words, n_entries, per_cta);
   return cudaGetLastError();
 }
 
