@@ -142,6 +142,7 @@ struct lc_ctx {
   uint8_t* d_needle = nullptr;   // small device buffer for predicate needles
   cudaStream_t copy_stream = nullptr;  // results of chunk c travel to the host while chunk c+1 is computed
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* ref_cache = nullptr;     // scan_host.cc: device-side entry lists cached per handle list
   uint8_t* sel_stage = nullptr;  // pinned staging of the caller's selection bitmaps (batched calls)
   uint64_t sel_stage_cap = 0;
   unsigned long long* d_prof = nullptr;  // profile counters (lc_ctx_profile_counters)

@@ -295,7 +295,8 @@ __device__ __forceinline__ void build_fast_steps(ScanSmem* sm, uint32_t W) {
 
 template <typename U, int MODE, typename C>
 __device__ __forceinline__ void int_bits_fast(const EntryIo& w, const IntHeader* h, const uint8_t* packed,
-                                              const uint32_t* valid, const URange<C>& g, ScanSmem* sm) {
+                                              const uint32_t* valid, const URange<C>& g, ScanSmem* sm, uint32_t& tab_key,
+                                              uint32_t* fast_cnt) {
   constexpr uint32_t T = FL<U>::T;
   const uint32_t n = h->n, W = h->bit_width;
   const uint32_t n_words = (n + 31u) >> 5, n_chunks = (n + 1023u) >> 10;
@@ -305,8 +306,14 @@ __device__ __forceinline__ void int_bits_fast(const EntryIo& w, const IntHeader*
   uint32_t* out_valid = (MODE == MODE_PRED && valid) ? w.out_valid : nullptr;
   const uint32_t* sel = w.sel;
   const uint32_t tail = n & 31u;
-  build_fast_steps<U>(sm, W);
-  __syncthreads();
+  // the step table only depends on (T, W): neighbouring entries of a column nearly always share it, and then
+  // neither the table nor its barrier is needed again
+  const uint32_t key = (T << 8) | W;
+  if (tab_key != key) {
+    build_fast_steps<U>(sm, W);
+    __syncthreads();
+    tab_key = key;
+  }
   const FastStep* tab = reinterpret_cast<const FastStep*>(sm->sel) + (T == 64 ? (lane >> 4) * 32u : 0u);
   const uint32_t* off2 = sm->off + (T == 64 ? (lane >> 4) * 32u : 0u);
   const uint32_t ordl = FLOrder<U>()(lane);  // lane j keeps the mask word of step j = logical word order(j)
@@ -361,25 +368,20 @@ __device__ __forceinline__ void int_bits_fast(const EntryIo& w, const IntHeader*
     }
   }
   if (w.counts) {
+    // the survivor count is flushed by thread 0 at the top of the CTA's NEXT round (after the round's closing barrier),
+    // so no barrier is spent on it here
     survivors = warp_sum(survivors);
-    if (lane == 0 && survivors) atomicAdd(&sm->counts[0], survivors);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (MODE == MODE_REFINE) {
-        w.counts[0] = sm->counts[0];
-        w.counts[1] = 0;
-      } else {
-        w.counts[0] = n;
-        w.counts[1] = h->null_count;
-        w.counts[2] = sm->counts[0];
-      }
+    if (lane == 0 && survivors) atomicAdd(fast_cnt, survivors);
+    if (MODE == MODE_PRED && threadIdx.x == 0) {
+      w.counts[0] = n;
+      w.counts[1] = h->null_count;
     }
   }
 }
 
 template <typename U, int MODE>
-__device__ __forceinline__ void int_scan_entry(const EntryIo& w, const IntPredDesc& pred, const uint8_t* base,
-                                               bool staged, ScanSmem* sm) {
+__device__ __forceinline__ bool int_scan_entry(const EntryIo& w, const IntPredDesc& pred, const uint8_t* base,
+                                               bool staged, ScanSmem* sm, uint32_t& tab_key, uint32_t* fast_cnt) {
   constexpr uint32_t T = FL<U>::T;
   const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
   const uint32_t W = h->bit_width;
@@ -398,19 +400,21 @@ __device__ __forceinline__ void int_scan_entry(const EntryIo& w, const IntPredDe
   if (W == 0) {  // entirely null (bit_pack_array.rs:18): nothing packed; masks are all false, values never read
     auto cmp = [&](uint32_t, uint32_t, uint32_t) -> bool { return false; };
     auto emit = [&](uint32_t, uint32_t dst, uint32_t, uint32_t) { out_vals[dst] = ref; };
+    tab_key = 0;
     scan_entry_rows<MODE>(w.sel, n, valid, nulls, out_bits, w.out_valid, w.counts, sm, cmp, emit);
-    return;
+    return false;
   }
   // full-length bit outputs from a staged entry: no compaction needed
   const bool fast = staged && ((MODE == MODE_REFINE) || (MODE == MODE_PRED && w.sel == nullptr));
   if (fast && MODE != MODE_DECODE) {
     if (T == 64 && W > 32u) {
-      int_bits_fast<U, MODE, uint64_t>(w, h, packed, valid, make_range<uint64_t>(kind, thr64), sm);
+      int_bits_fast<U, MODE, uint64_t>(w, h, packed, valid, make_range<uint64_t>(kind, thr64), sm, tab_key, fast_cnt);
     } else {
-      int_bits_fast<U, MODE, uint32_t>(w, h, packed, valid, make_range<uint32_t>(kind, thr64), sm);
+      int_bits_fast<U, MODE, uint32_t>(w, h, packed, valid, make_range<uint32_t>(kind, thr64), sm, tab_key, fast_cnt);
     }
-    return;
+    return w.counts != nullptr;  // count deferred
   }
+  tab_key = 0;  // the general path reuses the table's shared memory
   if (T == 64 && W > 32u) {
     const URange<uint64_t> g = make_range<uint64_t>(kind, thr64);
     auto val = [&](uint32_t c, uint32_t j) -> uint64_t {
@@ -419,7 +423,7 @@ __device__ __forceinline__ void int_scan_entry(const EntryIo& w, const IntPredDe
     auto cmp = [&](uint32_t, uint32_t c, uint32_t j) -> bool { return ((val(c, j) - g.lo) <= g.span) != g.neg; };
     auto emit = [&](uint32_t, uint32_t dst, uint32_t c, uint32_t j) { out_vals[dst] = static_cast<U>(val(c, j) + ref); };
     scan_entry_rows<MODE>(w.sel, n, valid, nulls, out_bits, w.out_valid, w.counts, sm, cmp, emit, FLOrder<U>());
-    return;
+    return false;
   }
   // everything else fits 32 bits in the packed domain
   const uint32_t mask = W >= 32u ? 0xffffffffu : ((1u << W) - 1u);
@@ -435,6 +439,7 @@ __device__ __forceinline__ void int_scan_entry(const EntryIo& w, const IntPredDe
     out_vals[dst] = static_cast<U>(static_cast<U>(val(c, j)) + ref);
   };
   scan_entry_rows<MODE>(w.sel, n, valid, nulls, out_bits, w.out_valid, w.counts, sm, cmp, emit, FLOrder<U>());
+  return false;
 }
 
 // Persistent CTAs: each CTA walks entries blockIdx.x, +gridDim.x, ... with a two-deep TMA pipeline — while the
@@ -450,6 +455,8 @@ __global__ void __launch_bounds__(256, 4) k_int_scan(ScanIo io, IntPredDesc pred
   const uint32_t G = gridDim.x;
   const bool staged = stage_bytes != 0;  // the host sizes the stage for the largest entry of the launch, or passes 0
   if (threadIdx.x == 0) {
+    sm->fcnt[0] = 0;
+    sm->fcnt[1] = 0;
     mbar_init(&sm->bar[0], 1);
     mbar_init(&sm->bar[1], 1);
     fence_mbar_init();
@@ -463,9 +470,23 @@ __global__ void __launch_bounds__(256, 4) k_int_scan(ScanIo io, IntPredDesc pred
   if (threadIdx.x - 3u < 2u && blockIdx.x + G < n_entries) sm->ref_slot[threadIdx.x - 3u] = load_ref_word(io, blockIdx.x + G, threadIdx.x - 3u);
   __syncthreads();
   uint32_t it = 0;
+  uint32_t tab_key = 0;   // (T, W) the step table in shared memory was built for; 0 = none
+  bool pending = false;   // the previous entry left its survivor count in fcnt[buf ^ 1]
+  auto flush_count = [&](uint32_t e_prev, uint32_t slot) {  // thread 0, after the round's closing barrier
+    uint32_t* c = io.counts + static_cast<size_t>(e_prev) * io.counts_stride;
+    const uint32_t v = sm->fcnt[slot];
+    sm->fcnt[slot] = 0;
+    if (MODE == MODE_REFINE) {
+      c[0] = v;
+      c[1] = 0;
+    } else {
+      c[2] = v;
+    }
+  };
   for (uint32_t e = blockIdx.x; e < n_entries; e += G, ++it) {
     const uint32_t buf = it & 1u;
     const bool more = e + G < n_entries;
+    if (pending && threadIdx.x == 0) flush_count(e - G, buf ^ 1u);
     scan_smem_init(sm);
     if (threadIdx.x == 0 && staged && more) {  // prefetch this CTA's next entry into the other buffer
       const uint32_t nbytes = static_cast<uint32_t>(sm->ref_slot[1]);
@@ -489,15 +510,16 @@ __global__ void __launch_bounds__(256, 4) k_int_scan(ScanIo io, IntPredDesc pred
     const IntHeader* h = reinterpret_cast<const IntHeader*>(base);
     const EntryIo w = resolve_io_slot(io, sm->io_slot[buf], e, MODE == MODE_DECODE ? h->tbits / 8u : 4u);
     switch (h->tbits) {
-      case 8: int_scan_entry<uint8_t, MODE>(w, pred, base, staged, sm); break;
-      case 16: int_scan_entry<uint16_t, MODE>(w, pred, base, staged, sm); break;
-      case 32: int_scan_entry<uint32_t, MODE>(w, pred, base, staged, sm); break;
-      default: int_scan_entry<uint64_t, MODE>(w, pred, base, staged, sm); break;
+      case 8: pending = int_scan_entry<uint8_t, MODE>(w, pred, base, staged, sm, tab_key, &sm->fcnt[buf]); break;
+      case 16: pending = int_scan_entry<uint16_t, MODE>(w, pred, base, staged, sm, tab_key, &sm->fcnt[buf]); break;
+      case 32: pending = int_scan_entry<uint32_t, MODE>(w, pred, base, staged, sm, tab_key, &sm->fcnt[buf]); break;
+      default: pending = int_scan_entry<uint64_t, MODE>(w, pred, base, staged, sm, tab_key, &sm->fcnt[buf]); break;
     }
     if (threadIdx.x < 3u) sm->io_slot[buf ^ 1u][threadIdx.x] = nx_io;
     else if (threadIdx.x < 5u) sm->ref_slot[threadIdx.x - 3u] = nx_io;
     __syncthreads();  // everyone is done with stage[buf] and the control area before the next round reuses them
   }
+  if (pending && threadIdx.x == 0 && it > 0) flush_count(blockIdx.x + (it - 1u) * G, (it - 1u) & 1u);
 }
 
 cudaError_t launch_int_scan(int mode, uint32_t n_entries, const ScanIo& io, const IntPredDesc& pred,

@@ -278,14 +278,8 @@ struct SymStep {
   uint32_t L;        // symbol length = shift
 };
 constexpr uint32_t kStateOne = 0x80000000u;
-#ifndef LC_LIKE_WARPS
-#define LC_LIKE_WARPS 8
-#endif
-constexpr uint32_t kLikeWarps = LC_LIKE_WARPS;
-#ifndef LC_CAND_PER_WARP
-#define LC_CAND_PER_WARP 32
-#endif
-constexpr uint32_t kCandPerWarp = LC_CAND_PER_WARP;
+constexpr uint32_t kLikeWarps = 8;     // warps of the CTA that may walk the candidate queue
+constexpr uint32_t kCandPerWarp = 32;  // ... one more warp for every 32 candidates (measured: 96 and 192 are slower)
 
 __device__ __forceinline__ void build_sym_steps(const uint64_t* s_sym, const uint8_t* s_len, const uint8_t* nd,
                                                 uint32_t m, uint32_t* s_M, SymStep* s_step) {
@@ -541,9 +535,9 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
     // Half of the warps walk the queue; the others wait at the barrier and cost no issue slots, which the SM's other
     // resident CTAs use.
     stamp(3);  // candidate gate
-    // A warp-trip costs the same whether 3 or 32 of its lanes are busy, and the pass cannot be shorter than the
-    // longest value anyway, so only as many warps walk the queue as keep their lanes reasonably full (about three
-    // values per lane); the others wait at the barrier and leave their issue slots to the SM's other CTAs.
+    // Warps beyond the number of candidates / 32 would find the queue empty: they skip the walk and wait at the
+    // barrier. (Giving each lane several values — fewer walking warps — was measured and is slower: the walk is a
+    // latency chain per lane, not an issue-slot problem.)
     const uint32_t walk_warps = ncand >= kCandPerWarp * kLikeWarps ? kLikeWarps : (ncand + kCandPerWarp - 1u) / kCandPerWarp;
     if ((threadIdx.x >> 5) < walk_warps) like_candidates(v, s_cand, ncand, &sm->misc[1], s_step, s_dict);
     if (neg) {

@@ -191,18 +191,20 @@ struct RefCache {
   uint64_t tick = 0;
 };
 
-static std::unordered_map<lc_ctx*, RefCache>& ref_caches() {
-  static std::unordered_map<lc_ctx*, RefCache> m;
-  return m;
+// The cache hangs off the context (opaque pointer in lc_ctx) and is only touched under the context's lock, so
+// contexts used from different threads never share state.
+static RefCache& ref_cache_of(lc_ctx* ctx) {
+  if (!ctx->ref_cache) ctx->ref_cache = new RefCache();
+  return *static_cast<RefCache*>(ctx->ref_cache);
 }
 
 void drop_ref_cache(lc_ctx* ctx) {
-  auto& m = ref_caches();
-  auto it = m.find(ctx);
-  if (it == m.end()) return;
-  for (auto& l : it->second.lists)
+  if (!ctx->ref_cache) return;
+  RefCache* rc = static_cast<RefCache*>(ctx->ref_cache);
+  for (auto& l : rc->lists)
     if (l.d_refs) cudaFree(l.d_refs);
-  m.erase(it);
+  delete rc;
+  ctx->ref_cache = nullptr;
 }
 
 static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const RefList** out) {
@@ -212,7 +214,7 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
     h *= 0x100000001b3ull;
     h ^= h >> 29;
   }
-  RefCache& rc = ref_caches()[ctx];
+  RefCache& rc = ref_cache_of(ctx);
   rc.tick++;
   for (auto& l : rc.lists) {
     if (l.key == h && l.n == n && l.epoch == ctx->epoch) {

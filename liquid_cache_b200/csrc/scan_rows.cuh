@@ -29,6 +29,7 @@ struct ScanSmem {
   uint8_t scratch[8][32];
   uint64_t io_slot[2][4];  // persistent kernels: {sel_off, out_off, valid_off} of this / the next entry
   uint64_t ref_slot[2];    // persistent kernels: {blob, blob_bytes} of the entry after the next one
+  uint32_t fcnt[2];        // persistent kernels: survivor count of this / the previous entry (flushed one round late)
 };
 static_assert(sizeof(ScanSmem) <= kScanFixedSmem, "fixed smem area too small");
 
