@@ -143,6 +143,15 @@ struct lc_ctx {
   cudaStream_t copy_stream = nullptr;  // results of chunk c travel to the host while chunk c+1 is computed
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
   void* ref_cache = nullptr;     // scan_host.cc: device-side entry lists cached per handle list
+  // handle arrays already validated (hash of the array -> entries) for the batched calls: a repeated call over the same
+  // column costs a hash of the array instead of one pointer chase per handle; any release bumps `epoch` and voids them
+  struct ValidatedHandles {
+    uint64_t key = 0, n = 0, epoch = 0;
+    std::vector<lc::Entry*> es;
+  };
+  std::vector<ValidatedHandles> validated;
+  uint8_t* d_pairs = nullptr;    // device buffer for sparse selection uploads ({word index, word} pairs)
+  uint64_t d_pairs_cap = 0;
   uint8_t* sel_stage = nullptr;  // pinned staging of the caller's selection bitmaps (batched calls)
   uint64_t sel_stage_cap = 0;
   unsigned long long* d_prof = nullptr;  // profile counters (lc_ctx_profile_counters)

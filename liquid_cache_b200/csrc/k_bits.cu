@@ -91,6 +91,18 @@ __global__ void k_concat_validity(const uint32_t* __restrict__ valid_base, const
   out[w] = word;
 }
 
+// Sparse selection upload: the area was zero-filled, drop the few non-zero words in ({word index << 32 | word}).
+__global__ void k_scatter_words(const unsigned long long* __restrict__ pairs, uint64_t n, uint32_t* __restrict__ base) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) base[pairs[i] >> 32] = static_cast<uint32_t>(pairs[i]);
+}
+
+cudaError_t launch_scatter_words(const unsigned long long* d_pairs, uint64_t n, uint32_t* d_base, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_scatter_words<<<static_cast<uint32_t>((n + 255) / 256), 256, 0, s>>>(d_pairs, n, d_base);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_concat_validity(const uint32_t* d_valid_base, const uint64_t* d_valid_off, const uint64_t* d_row_base,
                                    const uint32_t* d_counts, uint32_t counts_stride, uint32_t n_entries, uint64_t rows,
                                    uint32_t* d_out, cudaStream_t s) {

@@ -57,6 +57,46 @@ static uint64_t hash_handles(const lc_handle* h, uint64_t n) {
   return x;
 }
 
+// Batched calls outside a scan: same idea, cached on the context (call with the context lock held).
+static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Entry* const** out) {
+  if (n < 64) {  // short lists (the single-entry calls) are validated in place and never evict a big cached list
+    static thread_local std::vector<Entry*> small;
+    small.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      small[i] = entry_of(handles[i]);
+      if (!small[i]) {
+        set_error("invalid handle at position %llu", (unsigned long long)i);
+        return LC_ERR_INVALID;
+      }
+    }
+    *out = small.data();
+    return LC_OK;
+  }
+  const uint64_t key = hash_handles(handles, n);
+  for (auto& v : ctx->validated) {
+    if (v.key == key && v.n == n && v.epoch == ctx->epoch) {
+      *out = v.es.data();
+      return LC_OK;
+    }
+  }
+  lc_ctx::ValidatedHandles v;
+  v.key = key;
+  v.n = n;
+  v.epoch = ctx->epoch;
+  v.es.resize(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    v.es[i] = entry_of(handles[i]);
+    if (!v.es[i]) {
+      set_error("invalid handle at position %llu", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+  }
+  if (ctx->validated.size() >= 8) ctx->validated.erase(ctx->validated.begin());
+  ctx->validated.push_back(std::move(v));
+  *out = ctx->validated.back().es.data();
+  return LC_OK;
+}
+
 static int scan_entries_cached(lc_scan* scan, const lc_handle* handles, Entry* const** out) {
   const uint64_t key = hash_handles(handles, scan->n);
   for (auto& v : scan->validated) {
@@ -174,16 +214,10 @@ int lc_to_arrow_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const ui
     set_error("lc_to_arrow_many: bad argument");
     return LC_ERR_INVALID;
   }
-  std::vector<Entry*> es(n);
-  for (uint64_t i = 0; i < n; ++i) {
-    es[i] = entry_of(handles[i]);
-    if (!es[i]) {
-      set_error("invalid handle at position %llu", (unsigned long long)i);
-      return LC_ERR_INVALID;
-    }
-  }
   Guard g(ctx);
-  return to_arrow_batch(ctx, es.data(), n, sel_bits, nullptr, out_schema, out_array);
+  Entry* const* es = nullptr;
+  LC_TRY(entries_cached(ctx, handles, n, &es));
+  return to_arrow_batch(ctx, es, n, sel_bits, nullptr, out_schema, out_array);
 }
 
 int lc_to_arrow(lc_ctx* ctx, lc_handle h, const uint8_t* sel_bits, uint64_t sel_len, struct ArrowSchema* out_schema,
@@ -213,17 +247,11 @@ int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, co
     set_error("lc_eval_predicate_many: out_byte_offsets required for n > 1");
     return LC_ERR_INVALID;
   }
-  std::vector<Entry*> es(n);
-  for (uint64_t i = 0; i < n; ++i) {
-    es[i] = entry_of(handles[i]);
-    if (!es[i]) {
-      set_error("invalid handle at position %llu", (unsigned long long)i);
-      return LC_ERR_INVALID;
-    }
-  }
   Guard g(ctx);
+  Entry* const* es = nullptr;
+  LC_TRY(entries_cached(ctx, handles, n, &es));
   PredOut po{out_values, out_validity, out_byte_offsets, out_len, out_null_count, out_true_count};
-  return eval_predicate_batch(ctx, es.data(), n, pred, sel_bits, po);
+  return eval_predicate_batch(ctx, es, n, pred, sel_bits, po);
 }
 
 int lc_eval_predicate(lc_ctx* ctx, lc_handle h, const lc_predicate* pred, const uint8_t* sel_bits, uint64_t sel_len,

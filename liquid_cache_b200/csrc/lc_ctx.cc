@@ -253,6 +253,7 @@ void lc_ctx_destroy(lc_ctx* ctx) {
   drop_ref_cache(ctx);
   if (ctx->d_needle) cudaFree(ctx->d_needle);
   if (ctx->sel_stage) cudaFreeHost(ctx->sel_stage);
+  if (ctx->d_pairs) cudaFree(ctx->d_pairs);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (cudaEvent_t& e : ctx->ev_chunk)
     if (e) cudaEventDestroy(e);

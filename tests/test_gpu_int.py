@@ -172,6 +172,35 @@ def test_batched_many(cache):
     assert_arrays_equal(concat, want, "to_arrow_many")
 
 
+@pytest.mark.parametrize("density", [0.0, 0.0003, 0.02, 0.5])
+def test_batched_many_sparse_and_dense_selections(cache, density):
+    """Batched calls over enough entries to take the sparse selection upload ({word index, word} pairs, zero fill and
+    scatter on the device) when the selections are nearly empty, and the dense copy otherwise; a few entries are fully
+    selected or get no selection at all."""
+    rng = np.random.default_rng(int(density * 1e4) + 3)
+    n_entries, rows_n = 24, 8192
+    arrays = [pa.array(rng.integers(-1000, 1000, size=rows_n), pa.int32(), mask=rng.random(rows_n) < 0.05) for _ in range(n_entries)]
+    liquids = [cache.transcode(a) for a in arrays]
+    handles = np.array([l.handle for l in liquids], dtype=np.uint64)
+    rows = np.array([rows_n] * n_entries, dtype=np.uint64)
+    bools = [rng.random(rows_n) < density for _ in range(n_entries)]
+    bools[3] = np.ones(rows_n, dtype=bool)
+    sels = [np.concatenate([np.packbits(b, bitorder="little"), np.zeros(8, np.uint8)]) for b in bools]
+    sels[7] = None  # no selection = all rows
+    bools[7] = np.ones(rows_n, dtype=bool)
+    vals, valid, offs, out_len, out_nulls, true_counts = cache.eval_predicate_many(handles, rows, _expr("<", 0), pa.int32(), sels)
+    for i, a in enumerate(arrays):
+        want = OracleIntArray.from_arrow(a).try_eval_predicate("<", 0, pa.array(bools[i]))
+        k = int(out_len[i])
+        assert k == int(bools[i].sum()) and int(out_nulls[i]) == want.null_count
+        got = np.unpackbits(vals[int(offs[i]):int(offs[i]) + (k + 7) // 8], bitorder="little")[:k].astype(bool)
+        assert got.tolist() == [bool(x) if x is not None else False for x in want.to_pylist()]  # null -> false bit
+        assert int(true_counts[i]) == sum(1 for x in want.to_pylist() if x)
+    concat = cache.to_arrow_many(handles, sels)
+    want = pa.concat_arrays([a.filter(pa.array(b)) for a, b in zip(arrays, bools)])
+    assert_arrays_equal(concat, want, "to_arrow_many")
+
+
 def test_and_then(cache):
     """reader/utils/boolean_selection.rs:233-256 known answer + random equivalence (datafusion/src/utils.rs:317-408)."""
     from oracle.liquid_oracle import boolean_buffer_and_then

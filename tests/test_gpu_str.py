@@ -275,3 +275,34 @@ def test_scan_read_device_matches_host_read(cache, with_nulls):
             assert rows == len(want_s) and nulls == want_s.null_count and int(o[-1].item()) == v.numel()
             got_s = gather_device_result_to_rank0(v, o, b, rows, nulls, pa.string(), 0, 1)
             assert_arrays_equal(got_s, want_s, "device strings")
+
+
+def test_differential_spec_hypothesis_gpu(cache):
+    """fuzz/fuzz_targets/fsst_view.rs:86-117 through the C ABI: arbitrary unicode / control bytes, nulls, selections,
+    every comparison operator and LIKE, CUDA path == arrow (and == the oracle, which passes the same search on CPU)."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    text = st.text(alphabet=st.sampled_from(list("abgoleGOLE/%._-:?=&0189 \x00\x7f") + ["é", "к", "\U0001F600"]), max_size=14)
+    scope = [7000]
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(vals=st.lists(st.one_of(st.none(), text), min_size=1, max_size=40), needle=text, data=st.data())
+    def run(vals, needle, data):
+        arr = pa.array(vals, pa.string())
+        sel = pa.array(data.draw(st.lists(st.booleans(), min_size=len(vals), max_size=len(vals))))
+        filt = arr.filter(sel)
+        for fp in (False, True):
+            scope[0] += 1
+            liquid = cache.transcode(arr, hint=_hint() if fp else None, compressor_scope=scope[0])
+            assert_arrays_equal(liquid.to_arrow_array(), arr, "round trip")
+            assert_arrays_equal(liquid.filter(sel), filt, "filter")
+            for op, fn in (("=", pc.equal), ("!=", pc.not_equal), ("<", pc.less), ("<=", pc.less_equal), (">", pc.greater),
+                           (">=", pc.greater_equal)):
+                assert_masks_equal(liquid.try_eval_predicate(_bin(op, needle), sel), fn(filt, pa.scalar(needle)), f"{op} {needle!r}")
+            inner = needle.replace("%", "").replace("_", "").replace("\\", "")
+            if inner:
+                got = liquid.try_eval_predicate(_like(f"%{inner}%"), sel)
+                assert_masks_equal(got, pc.match_substring(filt, inner), f"like {inner!r} fp={fp}")
+
+    run()

@@ -108,6 +108,36 @@ def test_differential_spec_against_arrow():
             assert o.try_eval_predicate(op, needle, None).to_pylist() == fn(arr, pa.scalar(needle)).to_pylist()
 
 
+def test_differential_spec_hypothesis():
+    """Same spec, searched by hypothesis (the reference drives it with libfuzzer): arbitrary unicode / control bytes,
+    nulls, a selection, every comparison operator and LIKE '%x%' with and without fingerprints."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    text = st.text(alphabet=st.sampled_from(list("abgoleGOLE/%._-:?=&0189 \x00\x7f") + ["é", "к", "\U0001F600"]), max_size=14)
+
+    @settings(max_examples=150, deadline=None)
+    @given(vals=st.lists(st.one_of(st.none(), text), min_size=1, max_size=40), needle=text, data=st.data())
+    def run(vals, needle, data):
+        arr = pa.array(vals, pa.string())
+        sel_bits = data.draw(st.lists(st.booleans(), min_size=len(vals), max_size=len(vals)))
+        sel = pa.array(sel_bits)
+        filt = arr.filter(sel)
+        for fp in (False, True):
+            o = OracleByteViewArray.from_arrow(arr, build_fingerprints=fp)
+            assert o.to_arrow().equals(arr)
+            assert o.filter(sel).equals(filt)
+            for op, fn in (("=", pc.equal), ("!=", pc.not_equal), ("<", pc.less), ("<=", pc.less_equal), (">", pc.greater),
+                           (">=", pc.greater_equal)):
+                assert o.try_eval_predicate(op, needle, sel).to_pylist() == fn(filt, pa.scalar(needle)).to_pylist()
+            inner = needle.replace("%", "").replace("_", "").replace("\\", "")
+            if inner:
+                got = o.try_eval_predicate("like", f"%{inner}%", sel).to_pylist()
+                assert got == pc.match_substring(filt, inner).to_pylist()
+
+    run()
+
+
 def test_c_port_matches_python_oracle():
     """The timed CPU baseline (oracle/c) must agree with the oracle it is a port of."""
     from oracle import c_oracle as CO
