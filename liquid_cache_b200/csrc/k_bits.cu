@@ -97,6 +97,31 @@ __global__ void k_scatter_words(const unsigned long long* __restrict__ pairs, ui
   if (i < n) base[pairs[i] >> 32] = static_cast<uint32_t>(pairs[i]);
 }
 
+// Sparse mask download: collect the non-zero words of a mask area as {word index << 32 | word}; counter[0] counts all of
+// them, only the first `budget` are stored (the caller falls back to a dense copy when there are more).
+__global__ void k_gather_nonzero(const uint32_t* __restrict__ words, uint64_t n_words, unsigned long long* __restrict__ pairs,
+                                 uint64_t budget, unsigned long long* __restrict__ counter) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint32_t v = i < n_words ? words[i] : 0u;
+  const uint32_t m = __ballot_sync(kFullMask, v != 0u);
+  if (m == 0u) return;
+  if (v != 0u) {  // exactly the lanes of m
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, static_cast<unsigned long long>(__popc(m)));
+    base = __shfl_sync(m, base, leader);
+    const unsigned long long idx = base + __popc(m & lanemask_lt());
+    if (idx < budget) pairs[idx] = (static_cast<unsigned long long>(i) << 32) | v;
+  }
+}
+
+cudaError_t launch_gather_nonzero(const uint32_t* d_words, uint64_t n_words, unsigned long long* d_pairs, uint64_t budget,
+                                  unsigned long long* d_counter, cudaStream_t s) {
+  if (n_words == 0) return cudaSuccess;
+  k_gather_nonzero<<<static_cast<uint32_t>((n_words + 255) / 256), 256, 0, s>>>(d_words, n_words, d_pairs, budget, d_counter);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scatter_words(const unsigned long long* d_pairs, uint64_t n, uint32_t* d_base, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   k_scatter_words<<<static_cast<uint32_t>((n + 255) / 256), 256, 0, s>>>(d_pairs, n, d_base);

@@ -176,6 +176,8 @@ cudaError_t launch_str_encode(const StrEncIo& io, cudaStream_t s);
 
 // ---- bit utilities -----------------------------------------------------------------------------
 // boolean_buffer_and_then: out[p] = left[p] & right[rank_left(p)]  (datafusion/src/utils.rs:62-236)
+cudaError_t launch_gather_nonzero(const uint32_t* d_words, uint64_t n_words, unsigned long long* d_pairs, uint64_t budget,
+                                  unsigned long long* d_counter, cudaStream_t s);
 cudaError_t launch_scatter_words(const unsigned long long* d_pairs, uint64_t n, uint32_t* d_base, cudaStream_t s);
 cudaError_t launch_concat_validity(const uint32_t* d_valid_base, const uint64_t* d_valid_off, const uint64_t* d_row_base,
                                    const uint32_t* d_counts, uint32_t counts_stride, uint32_t n_entries, uint64_t rows,

@@ -247,6 +247,9 @@ struct RefList {
   std::shared_ptr<std::vector<uint32_t>> rows;      // rows per entry
   std::shared_ptr<std::vector<uint32_t>> n_unique;  // dictionary size per entry (byte views)
   bool same_liquid_type = true, same_arrow_type = true, same_width = true, any_nulls = false;
+  // did the last predicate over this list produce nearly-empty masks? (0 unknown, 1 sparse, 2 dense) — picks between
+  // the sparse mask download and the chunked dense one before the answer is known
+  mutable int mask_hint = 0;
 };
 
 struct RefCache {
@@ -481,7 +484,12 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     const int v = e ? std::atoi(e) : 4;
     return v < 1 ? 1 : (v > 4 ? 4 : v);
   }();
-  const int n_chunks = (direct && n >= 2048 && span) ? chunk_pref : 1;
+  // Nearly-empty masks (a selective predicate) are downloaded as {word index, word} pairs: the mask area is zeroed
+  // first, a gather kernel collects the non-zero words, and the host zero-fills the caller's buffer and drops them
+  // in. Whether that pays is only known afterwards, so the list remembers how the last predicate turned out.
+  const bool try_sparse = direct && !want_valid && span >= (1u << 16) && rl->mask_hint != 2;
+  const int n_chunks = (direct && n >= 2048 && span && !try_sparse) ? chunk_pref : 1;
+  if (try_sparse) LC_CUDA_OK(cudaMemsetAsync(d_dn + dn_counts, 0, span, s));
   if (n_chunks > 1 && !ctx->copy_stream) {
     LC_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (cudaEvent_t& e : ctx->ev_chunk) LC_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -524,7 +532,66 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     cudaEventRecord(ctx->ev_b, s);
     ctx->timing_valid = true;
   }
-  if (direct) {
+  bool sparse_done = false;
+  if (try_sparse) {
+    const uint64_t budget = out_words / 16;
+    const uint64_t need = 16 + budget * 8;
+    if (need > ctx->d_pairs_cap) {
+      if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+      ctx->d_pairs = nullptr;
+      ctx->d_pairs_cap = 0;
+      uint64_t cap = 1ull << 16;
+      while (cap < need) cap *= 2;
+      if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_pairs), cap) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of %llu bytes for sparse masks failed", (unsigned long long)cap);
+        return LC_ERR_OOM;
+      }
+      ctx->d_pairs_cap = cap;
+    }
+    unsigned long long* d_counter = reinterpret_cast<unsigned long long*>(ctx->d_pairs);
+    unsigned long long* d_pairs = d_counter + 2;
+    unsigned long long* h_counter = reinterpret_cast<unsigned long long*>(h_up);  // pinned, its upload is long done
+    LC_CUDA_OK(cudaMemsetAsync(d_counter, 0, 16, s));
+    LC_CUDA_OK(launch_gather_nonzero(reinterpret_cast<const uint32_t*>(d_dn + dn_counts), out_words, d_pairs, budget, d_counter, s));
+    ctx->kernel_launches++;
+    LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaMemcpyAsync(h_counter, d_counter, 8, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaStreamSynchronize(s));
+    const uint64_t found = *h_counter;
+    ctx->d2h_bytes += dn_counts + 8;
+    if (found <= budget) {
+      const uint64_t bytes = found * 8;
+      if (bytes + 64 > ctx->sel_stage_cap) {  // nothing is in flight on it after the sync above
+        if (ctx->sel_stage) cudaFreeHost(ctx->sel_stage);
+        ctx->sel_stage = nullptr;
+        ctx->sel_stage_cap = 0;
+        uint64_t cap = 1ull << 20;
+        while (cap < bytes + 64) cap *= 2;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->sel_stage), cap, cudaHostAllocDefault) != cudaSuccess) {
+          cudaGetLastError();
+          set_error("cudaHostAlloc of %llu bytes failed", (unsigned long long)cap);
+          return LC_ERR_OOM;
+        }
+        ctx->sel_stage_cap = cap;
+      }
+      if (bytes) LC_CUDA_OK(cudaMemcpyAsync(ctx->sel_stage, d_pairs, bytes, cudaMemcpyDeviceToHost, s));
+      // zero-fill the caller's mask area while the pairs travel
+      parallel_for(span, 1u << 20, [&](uint64_t b, uint64_t e) { std::memset(out.values + first_off + b, 0, e - b); });
+      LC_CUDA_OK(cudaStreamSynchronize(s));
+      const unsigned long long* hp = reinterpret_cast<const unsigned long long*>(ctx->sel_stage);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(out.values + first_off);
+      for (uint64_t i = 0; i < found; ++i) dst[hp[i] >> 32] = static_cast<uint32_t>(hp[i]);
+      ctx->d2h_bytes += bytes;
+      rl->mask_hint = 1;
+      sparse_done = true;
+    } else {
+      rl->mask_hint = 2;  // dense after all: plain download now, chunked overlap next time
+    }
+  }
+  if (sparse_done) {
+    // counts and masks are already on the host
+  } else if (direct) {
     // the caller's buffers are page-locked: results land in them straight from the device
     LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
     if (n_chunks == 1) {
@@ -548,6 +615,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     std::memcpy(out.values + first_off, h_mask, span);
     if (want_valid) std::memcpy(out.validity + first_off, h_valid, span);
   }
+  uint64_t total_true = 0;
   for (uint64_t i = 0; i < n; ++i) {
     const uint32_t k = h_counts[4 * i], nulls = h_counts[4 * i + 1];
     if (k != sp.k[i]) {
@@ -555,6 +623,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
       return LC_ERR_INVALID;
     }
     if (out.true_count) out.true_count[i] = h_counts[4 * i + 2];
+    total_true += h_counts[4 * i + 2];
     const uint64_t bytes = static_cast<uint64_t>((k + 31) / 32) * 4;
     const uint64_t bo = out.byte_offsets ? out.byte_offsets[i] : 0;
     if (!mirror) {
@@ -565,6 +634,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     if (out.len) out.len[i] = k;
     if (out.null_count) out.null_count[i] = nulls;
   }
+  if (rl->mask_hint == 2 && total_true < out_words / 32) rl->mask_hint = 0;  // selective again: retry the sparse download
   tr.mark("per-entry results");
   // no entry has nulls: validity (if the caller wants it at all) is all ones
   if (out.validity && !any_nulls) {

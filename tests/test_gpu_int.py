@@ -11,6 +11,7 @@ import zlib
 
 import numpy as np
 import pyarrow as pa
+import pyarrow.compute as pc
 import pytest
 
 from oracle.liquid_oracle import OracleIntArray
@@ -199,6 +200,40 @@ def test_batched_many_sparse_and_dense_selections(cache, density):
     concat = cache.to_arrow_many(handles, sels)
     want = pa.concat_arrays([a.filter(pa.array(b)) for a, b in zip(arrays, bools)])
     assert_arrays_equal(concat, want, "to_arrow_many")
+
+
+@pytest.mark.parametrize("with_nulls", [False, True])
+def test_batched_many_into_pinned_buffers(cache, with_nulls):
+    """Page-locked result buffers take the direct paths: nearly-empty masks come back as {word index, word} pairs
+    (zero fill + scatter on the host), dense ones through the chunked copy; the sequence sparse, dense, sparse, dense
+    also walks the per-list hint both ways."""
+    import torch
+
+    rng = np.random.default_rng(99)
+    n_entries, rows_n = 72, 8192
+    arrays = [pa.array(rng.integers(-1000, 1000, size=rows_n), pa.int32(),
+                       mask=(rng.random(rows_n) < 0.05) if (with_nulls and i % 3 == 0) else None) for i in range(n_entries)]
+    liquids = [cache.transcode(a) for a in arrays]
+    handles = np.array([l.handle for l in liquids], dtype=np.uint64)
+    rows = np.array([rows_n] * n_entries, dtype=np.uint64)
+    sizes = (((rows + 7) // 8 + 15) // 16) * 16
+    offs = np.zeros(n_entries, dtype=np.uint64)
+    np.cumsum(sizes[:-1], out=offs[1:])
+    total = int(sizes.sum())
+    pin = lambda nb: torch.full((nb,), 0xA5, dtype=torch.uint8).pin_memory().numpy()  # noqa: E731  (garbage to overwrite)
+    for lit in (-995, 0, -995, 5000):  # sparse, dense, sparse, dense (all true)
+        bufs = (pin(total), pin(total), offs, np.zeros(n_entries, np.uint64), np.zeros(n_entries, np.uint64), np.zeros(n_entries, np.uint64))
+        pred = _expr("<", lit).to_native(pa.int32())
+        vals, valid, _, out_len, out_nulls, true_counts = cache._eval_many_native(handles, rows, pred, None, bufs)
+        for i, a in enumerate(arrays):
+            want = pc.less(a, pa.scalar(lit, pa.int32())).to_pylist()  # == the oracle's answer for an all-rows selection
+            assert int(out_len[i]) == rows_n and int(out_nulls[i]) == a.null_count
+            got = np.unpackbits(vals[int(offs[i]):int(offs[i]) + rows_n // 8], bitorder="little").astype(bool)
+            assert got.tolist() == [bool(x) if x is not None else False for x in want], f"lit {lit} entry {i}"
+            assert int(true_counts[i]) == sum(1 for x in want if x)
+            if a.null_count:
+                gv = np.unpackbits(valid[int(offs[i]):int(offs[i]) + rows_n // 8], bitorder="little").astype(bool)
+                assert gv.tolist() == [x is not None for x in want]
 
 
 def test_and_then(cache):
