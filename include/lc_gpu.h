@@ -103,21 +103,34 @@ typedef enum lc_op {
  * (it turns on the per-unique 32-bit fingerprints, transcode.rs:165). */
 typedef enum lc_hint { LC_HINT_NONE = 0, LC_HINT_PREDICATE = 1, LC_HINT_SUBSTRING_SEARCH = 2 } lc_hint;
 
-typedef enum lc_literal_kind { LC_LIT_I64 = 0, LC_LIT_U64 = 1, LC_LIT_BYTES = 2 } lc_literal_kind;
+typedef enum lc_literal_kind {
+  LC_LIT_I64 = 0,
+  LC_LIT_U64 = 1,
+  LC_LIT_BYTES = 2,
+  LC_LIT_I128 = 3, /* Decimal128/256 literal, unscaled, SAME scale as the column (DataFusion coerces it):
+                      lit_u64 = low 64 bits, lit_i64 = high 64 bits (two's complement) */
+  LC_LIT_F64 = 4   /* Float32/Float64 literal: lit_u64 = IEEE bits of the value as f64 (a Float32 literal is
+                      widened exactly by the caller and narrowed back here) */
+} lc_literal_kind;
 
 /* `col <op> literal` after DataFusion's coercion (the reference receives the same thing inside a
  * PhysicalExpr; src/core/src/liquid_array/mod.rs:265-280, operator.rs:134-176). */
 typedef struct lc_predicate {
   int32_t op;            /* lc_op */
   int32_t lit_kind;      /* lc_literal_kind */
-  int64_t lit_i64;       /* LC_LIT_I64: signed ints, Date32/64, Timestamp */
-  uint64_t lit_u64;      /* LC_LIT_U64: unsigned ints */
+  int64_t lit_i64;       /* LC_LIT_I64: signed ints, Date32/64, Timestamp; LC_LIT_I128: high half */
+  uint64_t lit_u64;      /* LC_LIT_U64: unsigned ints; LC_LIT_I128: low half; LC_LIT_F64: f64 bits */
   const uint8_t* lit_bytes; /* LC_LIT_BYTES: Utf8/Binary literal or LIKE pattern */
   uint64_t lit_len;
 } lc_predicate;
 
 /* Liquid logical type, numbering of LiquidDataType (liquid_array/mod.rs:52-65). */
-typedef enum lc_liquid_type { LC_LIQUID_INTEGER = 1, LC_LIQUID_BYTE_VIEW = 4 } lc_liquid_type;
+typedef enum lc_liquid_type {
+  LC_LIQUID_INTEGER = 1,
+  LC_LIQUID_FLOAT = 2,     /* LiquidFloatArray: ALP (float_array.rs) */
+  LC_LIQUID_BYTE_VIEW = 4,
+  LC_LIQUID_DECIMAL = 6    /* LiquidDecimalArray: Decimal128/256 whose values fit u64 (decimal_array.rs) */
+} lc_liquid_type;
 
 typedef struct lc_stats {
   uint64_t entries;            /* CacheStats.total_entries   (cache/core.rs:68-119) */
@@ -159,6 +172,9 @@ const char* lc_version(void);
 
 /* transcode_liquid_inner_with_hint (cache/transcode.rs:46-290): Arrow -> liquid, into HBM.
  *   ints/dates/timestamps -> LiquidPrimitiveArray::from_arrow_array (primitive_array.rs:159-206)
+ *   Float32/Float64 -> LiquidFloatArray::from_arrow_array (ALP; float_array.rs:266-269, 609-751)
+ *   Decimal128/256 whose valid values all fit u64 -> LiquidDecimalArray (decimal_array.rs:127-178); other
+ *     decimals (the reference's FSST LiquidFixedLenByteArray) are declined
  *   Utf8/Binary/Utf8View/BinaryView/Dictionary<UInt16,_> -> LiquidByteViewArray (conversions.rs:260-373)
  * compressor_scope identifies the FSST symbol table to train-or-reuse
  * (with_fsst_compressor_or_train, transcode.rs:16-33; one table per (file,row-group,column)).

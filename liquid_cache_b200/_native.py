@@ -23,8 +23,8 @@ LC_ERR_NO_DEVICE = -8
 
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_LIKE, OP_NOT_LIKE, OP_CONST_TRUE, OP_CONST_FALSE = range(10)
 HINT_NONE, HINT_PREDICATE, HINT_SUBSTRING_SEARCH = 0, 1, 2
-LIT_I64, LIT_U64, LIT_BYTES = 0, 1, 2
-LIQUID_INTEGER, LIQUID_BYTE_VIEW = 1, 4
+LIT_I64, LIT_U64, LIT_BYTES, LIT_I128, LIT_F64 = 0, 1, 2, 3, 4
+LIQUID_INTEGER, LIQUID_FLOAT, LIQUID_BYTE_VIEW, LIQUID_DECIMAL = 1, 2, 4, 6
 
 
 class NativeError(RuntimeError):

@@ -137,7 +137,7 @@ class GpuLiquidArray:
     def _type_from_format(self) -> pa.DataType:
         buf = C.create_string_buffer(64)
         N.check(N.lib().lc_arrow_format(self._cache._ctx, self._h, buf, 64))
-        return _FORMAT_TO_TYPE[buf.value.decode()]
+        return _type_of_format(buf.value.decode())
 
     def to_arrow_array(self) -> pa.Array:
         return self.filter(None)
@@ -184,6 +184,18 @@ _FORMAT_TO_TYPE = {
     "u": pa.string(), "z": pa.binary(), "vu": pa.string_view(), "vz": pa.binary_view(),
     "S:u": pa.dictionary(pa.uint16(), pa.string()), "S:z": pa.dictionary(pa.uint16(), pa.binary()),
 }
+
+
+_FORMAT_TO_TYPE.update({"f": pa.float32(), "g": pa.float64()})
+
+
+def _type_of_format(fmt: str) -> pa.DataType:
+    """Arrow C format string -> pyarrow type; decimals carry their parameters ("d:precision,scale[,bits]")."""
+    if fmt.startswith("d:"):
+        parts = [int(x) for x in fmt[2:].split(",")]
+        bits = parts[2] if len(parts) > 2 else 128
+        return pa.decimal256(parts[0], parts[1]) if bits == 256 else pa.decimal128(parts[0], parts[1])
+    return _FORMAT_TO_TYPE[fmt]
 
 
 class LiquidCacheBuilder:

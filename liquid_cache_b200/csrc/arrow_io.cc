@@ -1,6 +1,7 @@
 // arrow_io.cc — Arrow C Data Interface import (borrowed) and export (caller-owned) helpers.
 // Accepted input types = the dtype dispatch of transcode_liquid_inner_with_hint
-// (/root/reference/src/core/src/cache/transcode.rs:46-290) restricted to the integer and byte-view rows.
+// (/root/reference/src/core/src/cache/transcode.rs:46-290): integers, dates, timestamps, floats, decimals, byte views.
+#include <cstdio>
 #include <cstdlib>
 
 #include "host_common.h"
@@ -113,6 +114,27 @@ int parse_arrow_input(const ArrowSchema* schema, const ArrowArray* array, ArrowI
     out->values = array->buffers[1];
     return LC_OK;
   }
+  if (f == "f" || f == "g") {  // Float32 / Float64 -> ALP (transcode.rs:107-112)
+    out->kind = ArrowIn::K_FLOAT;
+    out->phys = f == "f" ? PT_F32 : PT_F64;
+    out->tbits = f == "f" ? 32 : 64;
+    out->is_signed = true;
+    out->values = array->buffers[1];
+    return LC_OK;
+  }
+  if (f.size() > 2 && f[0] == 'd' && f[1] == ':') {  // "d:precision,scale[,bitwidth]" (transcode.rs:113-154)
+    int precision = 0, scale = 0, bw = 128;
+    const int got = std::sscanf(f.c_str(), "d:%d,%d,%d", &precision, &scale, &bw);
+    if (got >= 2 && (bw == 128 || bw == 256)) {
+      out->kind = ArrowIn::K_DECIMAL;
+      out->phys = PT_U64;
+      out->tbits = 64;
+      out->is_signed = false;
+      out->dec_width = static_cast<uint32_t>(bw / 8);
+      out->values = array->buffers[1];
+      return LC_OK;
+    }
+  }
   if (f == "u" || f == "z") {
     out->kind = ArrowIn::K_BYTES;
     out->byte_type = (f == "u") ? BT_UTF8 : BT_BINARY;
@@ -129,7 +151,7 @@ int parse_arrow_input(const ArrowSchema* schema, const ArrowArray* array, ArrowI
     out->view_buffers = array->buffers + 2;
     return LC_OK;
   }
-  // Boolean, floats, decimals, tz-timestamps, large types, nested ... (floats/decimals: SURVEY §8f-3)
+  // Boolean, Decimal32/64, tz-timestamps, large types, nested ...
   set_error("unsupported arrow type '%s'", f.c_str());
   return LC_ERR_UNSUPPORTED_TYPE;
 }

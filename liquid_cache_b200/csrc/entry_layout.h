@@ -50,7 +50,13 @@ struct alignas(16) IntHeader {   // 64 bytes
   uint32_t blob_bytes;    // total bytes incl. header, multiple of 16
   uint32_t null_count;
   uint32_t is_signed;     // ordering of the logical type
-  uint32_t pad[5];
+  // ALP floats only (LiquidFloatArray, liquid_array/float_array.rs:230-239): the packed words hold the ALP-encoded
+  // signed integers minus `reference`; rows the (e, f) pair cannot represent exactly are patched after decoding.
+  uint32_t alp_ef;        // Exponents: e | f << 8
+  uint32_t n_patches;
+  uint32_t patch_idx_off; // n_patches x u32 row indices, ascending (behind the packed chunks)
+  uint32_t patch_val_off; // n_patches x native float
+  uint32_t pad[1];
 };
 static_assert(sizeof(IntHeader) == 64, "IntHeader must be 64 bytes");
 

@@ -111,6 +111,7 @@ struct Entry {
   uint32_t slab = 0;
   uint32_t n = 0;
   uint32_t refcount = 1;
+  uint32_t dec_width = 0;    // decimals: bytes per Arrow value (16 = Decimal128, 32 = Decimal256)
   std::string arrow_format;  // original arrow type as C format string (dictionary: "S" + value fmt in dict_format)
   std::string dict_value_format;
   IntHeader ih;   // host copies of the blob header
@@ -118,6 +119,11 @@ struct Entry {
   std::vector<uint8_t> shared_prefix;  // byte-view: host copy (predicate planning)
   std::shared_ptr<FsstCodec> codec;    // byte-view
 };
+
+// integer-shaped blobs (IntHeader + FastLanes chunks): integers, ALP floats, u64 decimals
+inline bool is_int_blob(int32_t liquid_type) {
+  return liquid_type == LC_LIQUID_INTEGER || liquid_type == LC_LIQUID_FLOAT || liquid_type == LC_LIQUID_DECIMAL;
+}
 
 inline Entry* entry_of(lc_handle h) {
   Entry* e = reinterpret_cast<Entry*>(static_cast<uintptr_t>(h));
@@ -173,8 +179,9 @@ void host_free(uint8_t* p);
 
 // Parsed view of an input array (borrowed pointers).
 struct ArrowIn {
-  enum Kind { K_INT, K_BYTES, K_VIEW, K_DICT } kind;
+  enum Kind { K_INT, K_BYTES, K_VIEW, K_DICT, K_FLOAT, K_DECIMAL } kind;
   uint8_t phys = 0, tbits = 0;
+  uint32_t dec_width = 0;  // K_DECIMAL: 16 / 32 bytes per value
   bool is_signed = false;
   uint8_t byte_type = 0;  // ByteType of the ORIGINAL array type
   int64_t length = 0, offset = 0, null_count = 0;

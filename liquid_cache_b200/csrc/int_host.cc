@@ -1,6 +1,9 @@
-// int_host.cc — host orchestration of the integer encode (insert side) and predicate planning.
+// int_host.cc — host orchestration of the encode (insert side) of every integer-shaped entry: integers, ALP floats,
+// u64 decimals. The host only sizes the blob from a few scalars read back; every array-sized step is a kernel.
 // Reference: LiquidPrimitiveArray::from_arrow_array (/root/reference/src/core/src/liquid_array/
-// primitive_array.rs:159-206), get_bit_width (src/core/src/utils/mod.rs:24-32).
+// primitive_array.rs:159-206), get_bit_width (src/core/src/utils/mod.rs:24-32),
+// LiquidFloatArray::from_arrow_array (float_array.rs:266-269, 609-751),
+// LiquidDecimalArray::{fits_u64, from_decimal_array} (decimal_array.rs:127-178).
 #include "host_common.h"
 
 namespace lc {
@@ -12,21 +15,28 @@ static uint32_t bit_width_of(uint64_t max_value) {
 }
 
 int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
+  const bool is_float = in.kind == ArrowIn::K_FLOAT;
+  const bool is_dec = in.kind == ArrowIn::K_DECIMAL;
   const uint32_t n = static_cast<uint32_t>(in.length);
-  const uint32_t tb = in.tbits / 8;
+  const uint32_t tb = in.tbits / 8;                       // bytes of the packed integer type
+  const uint32_t raw_tb = is_dec ? in.dec_width : tb;     // bytes per Arrow value
+  const uint64_t raw_bytes = static_cast<uint64_t>(n) * raw_tb;
   const uint64_t val_bytes = static_cast<uint64_t>(n) * tb;
   const uint32_t n_words = (n + 31) / 32;
   const bool has_nulls = in.null_count > 0;
   Scratch& sc = ctx->scratch;
-  LC_TRY(sc.reserve(val_bytes + n_words * 4ull + 4096, val_bytes + n_words * 4ull + 4096));
+  const uint64_t extra_dev = is_dec ? round_up(val_bytes, 256) + 256
+                             : is_float ? 2 * round_up(val_bytes, 256) + round_up(n_words * 4ull, 256) + round_up(n * 4ull, 256) + 4096
+                                        : 0;
+  LC_TRY(sc.reserve(raw_bytes + n_words * 4ull + 4096 + extra_dev, raw_bytes + n_words * 4ull + 4096));
 
   // ---- stage values (+ validity re-aligned to bit offset 0), one H2D ----
-  uint8_t* h_vals = sc.host(round_up(val_bytes, 256));
+  uint8_t* h_vals = sc.host(round_up(raw_bytes, 256));
   uint8_t* h_valid = sc.host(round_up(n_words * 4ull, 256) + 256);
   IntMinMaxWork* h_mm = reinterpret_cast<IntMinMaxWork*>(sc.host(256));
   IntPackWork* h_pw = reinterpret_cast<IntPackWork*>(sc.host(256));
   uint64_t* h_mmout = reinterpret_cast<uint64_t*>(sc.host(256));
-  uint8_t* d_vals = sc.dev(round_up(val_bytes, 256));
+  uint8_t* d_vals = sc.dev(round_up(raw_bytes, 256));
   uint8_t* d_valid = sc.dev(round_up(n_words * 4ull, 256) + 256);
   uint8_t* d_mm = sc.dev(256);
   uint8_t* d_pw = sc.dev(256);
@@ -35,10 +45,30 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
     set_error("int_encode: scratch exhausted");
     return LC_ERR_OOM;
   }
-  if (n) std::memcpy(h_vals, static_cast<const uint8_t*>(in.values) + static_cast<uint64_t>(in.offset) * tb, val_bytes);
+  // device-only work areas of the float / decimal flavours
+  uint8_t *d_pack_src = d_vals, *d_exc = nullptr, *d_pidx = nullptr, *d_pval = nullptr, *d_sizes = nullptr;
+  if (is_dec) {
+    d_pack_src = sc.dev(round_up(val_bytes, 256) + 256);
+    if (!d_pack_src) {
+      set_error("int_encode: scratch exhausted");
+      return LC_ERR_OOM;
+    }
+  } else if (is_float) {
+    d_pack_src = sc.dev(round_up(val_bytes, 256));        // ALP-encoded integers
+    d_pval = sc.dev(round_up(val_bytes, 256));            // patch values (at most n)
+    d_exc = sc.dev(round_up(n_words * 4ull, 256));
+    d_pidx = sc.dev(round_up(n * 4ull, 256));
+    d_sizes = sc.dev(2048);                               // one u64 per (e, f) pair (<= 153), then the result struct
+    if (!d_pack_src || !d_pval || !d_exc || !d_pidx || !d_sizes) {
+      set_error("int_encode: scratch exhausted");
+      return LC_ERR_OOM;
+    }
+  }
+  if (n) std::memcpy(h_vals, static_cast<const uint8_t*>(in.values) + static_cast<uint64_t>(in.offset) * raw_tb, raw_bytes);
   if (has_nulls) copy_bits(in.validity, in.offset, n, h_valid, n_words * 4ull);
-  h_mm->values = d_vals;
-  h_mm->validity = has_nulls ? reinterpret_cast<const uint32_t*>(d_valid) : nullptr;
+  const uint32_t* d_valid_w = has_nulls ? reinterpret_cast<const uint32_t*>(d_valid) : nullptr;
+  h_mm->values = d_pack_src;
+  h_mm->validity = d_valid_w;
   h_mm->out = reinterpret_cast<uint64_t*>(d_mmout);
   h_mm->n = n;
   h_mm->phys = in.phys;
@@ -47,15 +77,6 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
   const uint64_t up_bytes = static_cast<uint64_t>(reinterpret_cast<uint8_t*>(h_mm) + 256 - h_vals);
   LC_CUDA_OK(cudaMemcpyAsync(d_vals, h_vals, up_bytes, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_bytes;
-  (void)d_mm;
-
-  // ---- pass 1: min / max / valid count ----
-  LC_CUDA_OK(launch_int_minmax(reinterpret_cast<const IntMinMaxWork*>(d_mm), 1, s));
-  ctx->kernel_launches++;
-  LC_CUDA_OK(cudaMemcpyAsync(h_mmout, d_mmout, 24, cudaMemcpyDeviceToHost, s));
-  LC_CUDA_OK(cudaStreamSynchronize(s));
-  ctx->d2h_bytes += 24;
-  const uint64_t mn = h_mmout[0], mx = h_mmout[1], n_valid = h_mmout[2];
 
   IntHeader h;
   std::memset(&h, 0, sizeof(h));
@@ -66,14 +87,71 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
   h.n_chunks = (n + 1023) / 1024;
   h.is_signed = in.is_signed;
   h.has_nulls = has_nulls;
-  h.null_count = static_cast<uint32_t>(n - n_valid);
   const uint64_t tmask = in.tbits == 64 ? ~0ull : ((1ull << in.tbits) - 1ull);
+  uint64_t mn = 0, mx = 0, n_valid = 0;
+  uint32_t n_patches = 0;
+
+  if (is_float) {
+    // ---- ALP: exponent search on the sample, encode, patch list, min/max — three launches, one 40-byte D2H ----
+    n_valid = n - static_cast<uint64_t>(in.null_count);
+    if (n_valid) {  // an all-null (or empty) array never looks at its values (float_array.rs:620-630)
+      AlpEncIo io{};
+      io.values = d_vals;
+      io.validity = d_valid_w;
+      io.n = n;
+      io.is_f64 = in.tbits == 64;
+      io.sample_step = n > 1024 ? n / 1024 : 0;  // NUM_SAMPLES (float_array.rs:58, 719-727)
+      io.sample_cnt = io.sample_step ? (n + io.sample_step - 1) / io.sample_step : n;
+      io.sizes = reinterpret_cast<unsigned long long*>(d_sizes);
+      io.res = reinterpret_cast<AlpEncResult*>(d_sizes + 1536);
+      io.enc = d_pack_src;
+      io.exc_words = reinterpret_cast<uint32_t*>(d_exc);
+      io.patch_idx = reinterpret_cast<uint32_t*>(d_pidx);
+      io.patch_val = d_pval;
+      LC_CUDA_OK(launch_alp_encode(io, s));
+      ctx->kernel_launches += 3;
+      AlpEncResult* h_res = reinterpret_cast<AlpEncResult*>(h_mmout);
+      LC_CUDA_OK(cudaMemcpyAsync(h_res, io.res, sizeof(AlpEncResult), cudaMemcpyDeviceToHost, s));
+      LC_CUDA_OK(cudaStreamSynchronize(s));
+      ctx->d2h_bytes += sizeof(AlpEncResult);
+      mn = static_cast<uint64_t>(h_res->min);
+      mx = static_cast<uint64_t>(h_res->max);
+      n_patches = h_res->n_patches;
+      h.alp_ef = (h_res->e & 0xffu) | ((h_res->f & 0xffu) << 8);
+    }
+  } else {
+    if (is_dec) {
+      // ---- Decimal128/256 -> low u64 words; a valid value outside u64 turns the whole array down ----
+      LC_CUDA_OK(cudaMemsetAsync(d_mmout, 0, 32, s));
+      LC_CUDA_OK(launch_dec_narrow(d_vals, d_valid_w, n, in.dec_width, reinterpret_cast<unsigned long long*>(d_pack_src),
+                                   reinterpret_cast<uint32_t*>(d_mmout + 24), s));
+      ctx->kernel_launches++;
+    }
+    // ---- pass 1: min / max / valid count ----
+    LC_CUDA_OK(launch_int_minmax(reinterpret_cast<const IntMinMaxWork*>(d_mm), 1, s));
+    ctx->kernel_launches++;
+    LC_CUDA_OK(cudaMemcpyAsync(h_mmout, d_mmout, 32, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += 32;
+    mn = h_mmout[0];
+    mx = h_mmout[1];
+    n_valid = h_mmout[2];
+    if (is_dec && (h_mmout[3] & 0xffffffffull)) {
+      // the reference stores such arrays as LiquidFixedLenByteArray (FSST over the 16/32-byte values,
+      // transcode.rs:118-131); not built here: the caller keeps the Arrow array
+      set_error("decimal values outside u64 (LiquidFixedLenByteArray is not supported)");
+      return LC_ERR_UNSUPPORTED_TYPE;
+    }
+  }
+
+  h.null_count = static_cast<uint32_t>(n - n_valid);
   if (n_valid == 0) {
     // entire array null (or empty): BitPackedArray::new_null_array, reference_value = 0
     h.bit_width = 0;
     h.reference = 0;
     h.has_nulls = n > 0;
     h.null_count = n;
+    h.alp_ef = 0;
   } else {
     const uint64_t sub = (mx - mn) & tmask;  // max.sub_wrapping(min) reinterpreted unsigned
     h.bit_width = static_cast<uint8_t>(bit_width_of(sub));
@@ -83,7 +161,14 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
   h.validity_off = h.has_nulls ? 64 : 0;
   h.packed_off = static_cast<uint32_t>(64 + valid_bytes);
   const uint64_t packed_bytes = static_cast<uint64_t>(h.n_chunks) * 128ull * h.bit_width;
-  const uint64_t blob_bytes = round_up(h.packed_off + packed_bytes, 16);
+  uint64_t blob_bytes = round_up(h.packed_off + packed_bytes, 16);
+  if (n_patches) {
+    h.n_patches = n_patches;
+    h.patch_idx_off = static_cast<uint32_t>(blob_bytes);
+    blob_bytes = round_up(blob_bytes + 4ull * n_patches, 16);
+    h.patch_val_off = static_cast<uint32_t>(blob_bytes);
+    blob_bytes = round_up(blob_bytes + static_cast<uint64_t>(tb) * n_patches, 16);
+  }
   if (blob_bytes > 0xFFFFFFF0ull) {
     set_error("int_encode: entry too large");
     return LC_ERR_UNSUPPORTED_TYPE;
@@ -103,22 +188,28 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
 
   // ---- pass 2: subtract reference + FastLanes pack (+ header, validity) ----
   std::memset(h_pw, 0, sizeof(*h_pw));
-  h_pw->values = d_vals;
+  h_pw->values = d_pack_src;
   // an all-null array that came without a validity buffer cannot happen (n_valid==0 implies nulls)
-  h_pw->validity = has_nulls ? reinterpret_cast<const uint32_t*>(d_valid) : nullptr;
+  h_pw->validity = d_valid_w;
   h_pw->blob = d_blob;
+  h_pw->pack_null_slots = is_float ? 1 : 0;
   h_pw->hdr = h;
   LC_CUDA_OK(cudaMemcpyAsync(d_pw, h_pw, sizeof(IntPackWork), cudaMemcpyHostToDevice, s));
   LC_CUDA_OK(launch_int_pack(reinterpret_cast<const IntPackWork*>(d_pw), 1, s));
   ctx->kernel_launches++;
+  if (n_patches) {
+    LC_CUDA_OK(cudaMemcpyAsync(d_blob + h.patch_idx_off, d_pidx, 4ull * n_patches, cudaMemcpyDeviceToDevice, s));
+    LC_CUDA_OK(cudaMemcpyAsync(d_blob + h.patch_val_off, d_pval, static_cast<uint64_t>(tb) * n_patches, cudaMemcpyDeviceToDevice, s));
+  }
   LC_CUDA_OK(cudaStreamSynchronize(s));
 
   Entry* e = new Entry();
-  e->liquid_type = LC_LIQUID_INTEGER;
+  e->liquid_type = is_float ? LC_LIQUID_FLOAT : is_dec ? LC_LIQUID_DECIMAL : LC_LIQUID_INTEGER;
   e->d_blob = d_blob;
   e->blob_bytes = h.blob_bytes;
   e->slab = slab;
   e->n = n;
+  e->dec_width = is_dec ? in.dec_width : 0;
   e->arrow_format = in.format;
   e->ih = h;
   ctx->n_entries++;

@@ -213,7 +213,10 @@ __device__ __forceinline__ void plan_int_pred(const IntHeader* h, const IntPredD
   const uint64_t umax = W == 64 ? ~0ull : ((1ull << W) - 1ull);
   bool below, above = false;
   uint64_t d = 0;
-  if (h->is_signed) {
+  if (p.lit_kind == kLitAboveAll) {  // decimal literal beyond u64::MAX (scan_host.cc make_int_pred)
+    below = false;
+    above = true;
+  } else if (h->is_signed) {
     const int sh = 64 - h->tbits;
     const long long ref = static_cast<long long>(h->reference << sh) >> sh;
     if (p.lit_kind == 1 /*U64*/ && p.lit_u > 0x7fffffffffffffffull) {
@@ -663,7 +666,7 @@ __device__ __forceinline__ void pack_entry(const IntPackWork& w) {
       const uint32_t idx = c * 1024u + (r & 7u) * 128u + (__brev(r >> 3) >> 29) * 16u + l;
       U val = 0;
       if (idx < n) {
-        const bool ok = w.validity ? ((w.validity[idx >> 5] >> (idx & 31u)) & 1u) : true;
+        const bool ok = (w.validity && !w.pack_null_slots) ? ((w.validity[idx >> 5] >> (idx & 31u)) & 1u) : true;
         if (ok) val = static_cast<U>(static_cast<U>(in[idx] - ref) & mask);
       }
       const uint32_t b = r * W;

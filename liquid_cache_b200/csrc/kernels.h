@@ -50,10 +50,11 @@ struct ScanIo {
 // on the device (u = v - reference against a threshold, or a constant when the literal is outside the window).
 struct IntPredDesc {
   int32_t op;        // lc_op EQ..GE
-  int32_t lit_kind;  // LC_LIT_I64 / LC_LIT_U64
+  int32_t lit_kind;  // LC_LIT_I64 / LC_LIT_U64 / kLitAboveAll
   int64_t lit_i;
   uint64_t lit_u;
 };
+constexpr int32_t kLitAboveAll = 7;  // decimal literal beyond u64: larger than every value of the column
 
 struct alignas(16) IntMinMaxWork {  // 32 bytes
   const void* values;         // native T[n] in device scratch
@@ -67,7 +68,8 @@ struct alignas(16) IntPackWork {  // 96 bytes
   const void* values;
   const uint32_t* validity;
   uint8_t* blob;
-  uint64_t pad;
+  uint64_t pack_null_slots;  // != 0: null slots are packed like any other value (ALP floats: the reference encodes
+                             // whatever the Arrow buffer holds there, float_array.rs:633-640); 0: they are zeroed
   IntHeader hdr;
 };
 static_assert(sizeof(IntPackWork) == 96, "IntPackWork must be 96 bytes");
@@ -76,6 +78,63 @@ cudaError_t launch_int_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
                             uint32_t max_blob_bytes, cudaStream_t s);
 cudaError_t launch_int_minmax(const IntMinMaxWork* d_works, uint32_t n_works, cudaStream_t s);
 cudaError_t launch_int_pack(const IntPackWork* d_works, uint32_t n_works, cudaStream_t s);
+
+// ---- ALP floats and u64 decimals (k_num.cu) -----------------------------------------------------
+// Both ride on the integer blob: a float entry packs its ALP-encoded signed integers (+ a patch list), a decimal
+// entry packs the low 64 bits of values known to fit u64. k_int_scan<DECODE> produces the integers of the selected
+// rows; the kernels below turn them into the column's own type or compare them.
+struct AlpEncResult {        // read back by the host to size the entry blob (one small D2H)
+  uint32_t e, f;             // chosen Exponents
+  uint32_t n_patches;
+  uint32_t first_ok;         // first row that is not a patch (0xFFFFFFFF if every row is one)
+  long long min, max;        // of the encoded integers after patched slots took the fill value
+  uint32_t pad[2];
+};
+struct AlpEncIo {
+  const void* values;        // native floats, n of them (null slots hold whatever the Arrow buffer held)
+  const uint32_t* validity;  // bit-offset-0 words or nullptr; only the sampling of get_best_exponents looks at it
+  uint32_t n;
+  uint32_t is_f64;
+  uint32_t sample_step;      // 0: n <= 1024, the whole array is the sample; else n / 1024 (float_array.rs:719-727)
+  uint32_t sample_cnt;       // sampled slots before nulls are dropped
+  unsigned long long* sizes; // one per (e, f) pair, in the reference's loop order
+  AlpEncResult* res;
+  void* enc;                 // n encoded integers (i32 / i64)
+  uint32_t* exc_words;       // ceil(n/32) words: bit = row needs a patch
+  uint32_t* patch_idx;       // up to n
+  void* patch_val;           // up to n native floats
+};
+cudaError_t launch_alp_encode(const AlpEncIo& io, cudaStream_t s);  // search + encode + patch list; res valid after the stream drains
+
+// After k_int_scan<DECODE> over float entries: integers -> floats in place, then the patches of the selected rows.
+// Uses io.refs / sel_base / sel_off / out_base / out_off (element offsets) / counts[0] = rows written per entry.
+cudaError_t launch_alp_finish(uint32_t n_entries, const ScanIo& io, uint32_t tbits, cudaStream_t s);
+
+// Float comparison over decoded values (arrow-ord total order), one CTA per entry.
+struct FloatCmpIo {
+  const EntryRef* refs;
+  const void* vals_base;        // decoded floats
+  const uint64_t* vals_off;     // per entry element offset
+  const uint32_t* vals_counts;  // counts of the decode launch: [e * vals_stride] = values of entry e (PRED only)
+  uint32_t vals_stride;
+  uint32_t refine;              // 0: PRED (compact mask over the selected rows); 1: REFINE (values cover all rows)
+  const uint32_t* and_base;     // PRED: compact validity words of the decode launch (nullptr = none)
+  const uint64_t* and_off;
+  const uint32_t* sel_base;     // REFINE: running selection, ANDed in (nullptr = all rows)
+  const uint64_t* sel_off;
+  uint32_t* out_base;           // mask words (PRED) / selection words (REFINE; may alias sel_base)
+  const uint64_t* out_off;      // per entry word offset
+  uint32_t* counts;             // PRED: [2] = set bits; REFINE: [0] = survivors, [1] = 0
+  uint32_t counts_stride;
+  int32_t op;                   // lc_op EQ..GE
+  long long lit_key;            // total-order key of the literal in the column's float type
+};
+cudaError_t launch_float_cmp(uint32_t n_entries, const FloatCmpIo& io, uint32_t tbits, cudaStream_t s);
+
+// Decimal128/256 <-> u64. narrow: out[i] = low 64 bits (0 for nulls); *flag |= 1 if a valid value is outside u64.
+cudaError_t launch_dec_narrow(const void* d_in, const uint32_t* d_validity, uint32_t n, uint32_t width_bytes,
+                              unsigned long long* d_out, uint32_t* d_flag, cudaStream_t s);
+cudaError_t launch_dec_widen(const unsigned long long* d_in, uint64_t n, uint32_t width_bytes, void* d_out, cudaStream_t s);
 
 // ---- byte-view (string) path -------------------------------------------------------------------
 enum StrPredKind : int32_t {

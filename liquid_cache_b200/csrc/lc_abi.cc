@@ -20,7 +20,7 @@ int encode_locked(lc_ctx* ctx, const ArrowSchema* schema, const ArrowArray* arra
                   Entry** out) {
   ArrowIn in;
   LC_TRY(parse_arrow_input(schema, array, &in));
-  if (in.kind == ArrowIn::K_INT) return int_encode(ctx, in, out);
+  if (in.kind == ArrowIn::K_INT || in.kind == ArrowIn::K_FLOAT || in.kind == ArrowIn::K_DECIMAL) return int_encode(ctx, in, out);
   return str_encode(ctx, in, hint, scope, out);
 }
 

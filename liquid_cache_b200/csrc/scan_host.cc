@@ -304,8 +304,8 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
     (*nl.rows)[i] = e->n;
     if (e->liquid_type != proto->liquid_type) nl.same_liquid_type = false;
     if (e->arrow_format != proto->arrow_format || e->dict_value_format != proto->dict_value_format) nl.same_arrow_type = false;
-    if (e->liquid_type == LC_LIQUID_INTEGER) {
-      if (proto->liquid_type == LC_LIQUID_INTEGER && e->ih.tbits != proto->ih.tbits) nl.same_width = false;
+    if (is_int_blob(e->liquid_type)) {
+      if (is_int_blob(proto->liquid_type) && e->ih.tbits != proto->ih.tbits) nl.same_width = false;
       nl.any_nulls = nl.any_nulls || e->ih.null_count != 0;
     } else {
       (*nl.n_unique)[i] = e->sh.n_unique;
@@ -314,7 +314,7 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
     refs[i].blob = e->d_blob;
     refs[i].blob_bytes = e->blob_bytes;
     refs[i].rows = e->n;
-    if (e->liquid_type == LC_LIQUID_INTEGER) {
+    if (is_int_blob(e->liquid_type)) {
       refs[i].head_bytes = e->blob_bytes;
       refs[i].sp_end = refs[i].pk_off = refs[i].rows_off = e->blob_bytes;
     } else {
@@ -357,19 +357,66 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
   return LC_OK;
 }
 
-static int make_int_pred(const lc_predicate* pred, IntPredDesc* out) {
+static int make_int_pred(const lc_predicate* pred, const Entry* proto, IntPredDesc* out) {
   if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
     set_error("operator %d is not supported on integer columns", pred->op);
     return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  out->op = pred->op;
+  if (proto->liquid_type == LC_LIQUID_DECIMAL) {
+    // Decimal128/256 compare as signed 128/256-bit integers; every stored value is in [0, u64::MAX], so a literal
+    // outside that window folds to a constant on either side (the literal arrives with the column's scale)
+    if (pred->lit_kind != LC_LIT_I128) {
+      set_error("decimal column needs an LC_LIT_I128 literal");
+      return LC_ERR_UNSUPPORTED_EXPR;
+    }
+    out->lit_i = 0;
+    out->lit_u = 0;
+    if (pred->lit_i64 == 0) {
+      out->lit_kind = LC_LIT_U64;
+      out->lit_u = pred->lit_u64;
+    } else if (pred->lit_i64 < 0) {
+      out->lit_kind = LC_LIT_I64;
+      out->lit_i = -1;
+    } else {
+      out->lit_kind = kLitAboveAll;
+    }
+    return LC_OK;
   }
   if (pred->lit_kind != LC_LIT_I64 && pred->lit_kind != LC_LIT_U64) {
     set_error("integer column needs an integer literal");
     return LC_ERR_UNSUPPORTED_EXPR;
   }
-  out->op = pred->op;
   out->lit_kind = pred->lit_kind;
   out->lit_i = pred->lit_i64;
   out->lit_u = pred->lit_u64;
+  return LC_OK;
+}
+
+// `float_col <op> literal`: the literal's key in arrow-ord's total order, in the column's own float type
+// (DataFusion has already coerced the literal to that type; alp_math.cuh order_key is the device twin).
+static int make_float_pred(const lc_predicate* pred, uint32_t tbits, int32_t* op, long long* key) {
+  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
+    set_error("operator %d is not supported on float columns", pred->op);
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  if (pred->lit_kind != LC_LIT_F64) {
+    set_error("float column needs an LC_LIT_F64 literal");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  *op = pred->op;
+  double d;
+  std::memcpy(&d, &pred->lit_u64, 8);
+  if (tbits == 64) {
+    int64_t b;
+    std::memcpy(&b, &d, 8);
+    *key = b ^ static_cast<int64_t>(static_cast<uint64_t>(b >> 63) >> 1);
+  } else {
+    const float f = static_cast<float>(d);
+    int32_t b;
+    std::memcpy(&b, &f, 4);
+    *key = b ^ static_cast<int32_t>(static_cast<uint32_t>(b >> 31) >> 1);
+  }
   return LC_OK;
 }
 
@@ -388,6 +435,189 @@ struct Tracer {  // LC_TRACE=1: wall-clock split of a call, printed to stderr
 };
 }  // namespace
 
+
+// ---- float columns: decode the selected rows, compare the decoded values ------------------------------
+// The reference evaluates float predicates exactly this way (trait default: filter, then DataFusion's compare on
+// the Arrow array, liquid_array/mod.rs:116-130); here the three steps are k_int_scan<DECODE> (unpack + compaction),
+// k_alp_finish (ALP integers -> floats, patches) and k_float_cmp (total-order compare, nulls -> false).
+static int eval_predicate_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, const RefList* rl, const lc_predicate* pred,
+                                const uint8_t* const* sel_bits, const PredOut& out) {
+  const uint32_t tbits = entries[0]->ih.tbits, tb = tbits / 8;
+  if (!rl->same_width) {
+    set_error("eval_predicate_many: Float32 and Float64 entries in one call");
+    return LC_ERR_INVALID;
+  }
+  int32_t op = 0;
+  long long key = 0;
+  LC_TRY(make_float_pred(pred, tbits, &op, &key));
+  SelPlan sp;
+  LC_TRY(plan_selection(ctx, rl->rows->data(), n, sel_bits, &sp));
+  std::vector<uint64_t> row_base(n), word_off(n);
+  uint64_t rows = 0, words = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    row_base[i] = rows;
+    rows += sp.k[i];
+    word_off[i] = words;
+    words += round_up((sp.k[i] + 31) / 32, 4);
+  }
+  const uint64_t up_offs = round_up(n * 8 * 3, 256);
+  const uint64_t up_sel = round_up(sp.sel_words * 4, 256);
+  const uint64_t up_total = up_offs + up_sel;
+  const uint64_t dn_counts = round_up(n * 16, 256);
+  const uint64_t dn_bits = round_up(words * 4 + 16, 256);
+  const uint64_t dn_total = dn_counts + 2 * dn_bits;
+  const uint64_t val_bytes = round_up(rows * tb + 16, 256);
+  Scratch& sc = ctx->scratch;
+  LC_TRY(sc.reserve(up_total + dn_total + val_bytes + 1024, up_total + dn_total + 1024));
+  uint8_t* h_up = sc.host(up_total);
+  uint8_t* h_dn = sc.host(dn_total);
+  uint8_t* d_up = sc.dev(up_total);
+  uint8_t* d_dn = sc.dev(dn_total);
+  uint8_t* d_vals = sc.dev(val_bytes);
+  if (!h_up || !h_dn || !d_up || !d_dn || !d_vals) {
+    set_error("eval_predicate: scratch exhausted");
+    return LC_ERR_OOM;
+  }
+  uint64_t* a = reinterpret_cast<uint64_t*>(h_up);
+  for (uint64_t i = 0; i < n; ++i) {
+    a[i] = sp.bits[i] ? sp.word_off[i] : kNoSel;
+    a[n + i] = row_base[i];
+    a[2 * n + i] = word_off[i];
+  }
+  cudaStream_t s = ctx->stream;
+  LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_offs, cudaMemcpyHostToDevice, s));
+  ctx->h2d_bytes += up_offs;
+  LC_TRY(upload_selection(ctx, sp, d_up + up_offs, s));
+  const uint64_t* offs = reinterpret_cast<const uint64_t*>(d_up);
+  ScanIo io{};
+  io.refs = rl->d_refs;
+  io.sel_base = sp.sel_words ? reinterpret_cast<const uint32_t*>(d_up + up_offs) : nullptr;
+  io.sel_off = offs;
+  io.out_base = d_vals;
+  io.out_off = offs + n;
+  io.valid_base = reinterpret_cast<uint32_t*>(d_dn + dn_counts + dn_bits);
+  io.valid_off = offs + 2 * n;
+  io.counts = reinterpret_cast<uint32_t*>(d_dn);
+  io.counts_stride = 4;
+  IntPredDesc ip{};
+  if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
+  LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
+  LC_CUDA_OK(launch_alp_finish(static_cast<uint32_t>(n), io, tbits, s));
+  FloatCmpIo c{};
+  c.refs = rl->d_refs;
+  c.vals_base = d_vals;
+  c.vals_off = offs + n;
+  c.vals_counts = io.counts;
+  c.vals_stride = 4;
+  c.refine = 0;
+  c.and_base = io.valid_base;
+  c.and_off = offs + 2 * n;
+  c.out_base = reinterpret_cast<uint32_t*>(d_dn + dn_counts);
+  c.out_off = offs + 2 * n;
+  c.counts = io.counts;
+  c.counts_stride = 4;
+  c.op = op;
+  c.lit_key = key;
+  LC_CUDA_OK(launch_float_cmp(static_cast<uint32_t>(n), c, tbits, s));
+  if (ctx->timing_on) {
+    cudaEventRecord(ctx->ev_b, s);
+    ctx->timing_valid = true;
+  }
+  ctx->kernel_launches += 3;
+  LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
+  LC_CUDA_OK(cudaStreamSynchronize(s));
+  ctx->d2h_bytes += dn_total;
+  const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
+  const uint8_t* h_mask = h_dn + dn_counts;
+  const uint8_t* h_valid = h_dn + dn_counts + dn_bits;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t k = h_counts[4 * i], nulls = h_counts[4 * i + 1];
+    if (k != sp.k[i]) {
+      set_error("internal: selected-row count mismatch on entry %llu (%u vs %u)", (unsigned long long)i, k, sp.k[i]);
+      return LC_ERR_INVALID;
+    }
+    const uint64_t bytes = static_cast<uint64_t>((k + 31) / 32) * 4;
+    const uint64_t bo = out.byte_offsets ? out.byte_offsets[i] : 0;
+    std::memcpy(out.values + bo, h_mask + word_off[i] * 4, bytes);
+    if (out.validity) {
+      if (nulls) std::memcpy(out.validity + bo, h_valid + word_off[i] * 4, bytes);
+      else std::memset(out.validity + bo, 0xFF, bytes);
+    }
+    if (out.true_count) out.true_count[i] = h_counts[4 * i + 2];
+    if (out.len) out.len[i] = k;
+    if (out.null_count) out.null_count[i] = nulls;
+  }
+  return LC_OK;
+}
+
+// Device pipeline flavour: every row is decoded (the values live in scratch for the duration of the launch), then
+// selection := selection & valid & cmp in place.
+static int refine_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, const RefList* rl, const lc_predicate* pred,
+                        uint32_t* d_sel_base, const uint64_t* d_word_off, bool all_rows, uint32_t* d_counts) {
+  const uint32_t tbits = entries[0]->ih.tbits, tb = tbits / 8;
+  if (!rl->same_width) {
+    set_error("scan_filter: Float32 and Float64 entries in one call");
+    return LC_ERR_INVALID;
+  }
+  int32_t op = 0;
+  long long key = 0;
+  LC_TRY(make_float_pred(pred, tbits, &op, &key));
+  std::vector<uint64_t> row_base(n);
+  uint64_t rows = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    row_base[i] = rows;
+    rows += (*rl->rows)[i];
+  }
+  const uint64_t b_rb = round_up(n * 8, 256), b_cnt = round_up(n * 16, 256), b_vals = round_up(rows * tb + 16, 256);
+  Scratch& sc = ctx->scratch;
+  LC_TRY(sc.reserve(b_rb + b_cnt + b_vals + 1024, 1024));
+  uint8_t* d_rb = sc.dev(b_rb);
+  uint8_t* d_cnt = sc.dev(b_cnt);
+  uint8_t* d_vals = sc.dev(b_vals);
+  if (!d_rb || !d_cnt || !d_vals) {
+    set_error("scan_filter: scratch exhausted");
+    return LC_ERR_OOM;
+  }
+  cudaStream_t s = ctx->stream;
+  // pageable source: the runtime stages it before returning, so `row_base` may go out of scope
+  LC_CUDA_OK(cudaMemcpyAsync(d_rb, row_base.data(), n * 8, cudaMemcpyHostToDevice, s));
+  ctx->h2d_bytes += n * 8;
+  ScanIo io{};
+  io.refs = rl->d_refs;
+  io.sel_base = nullptr;  // every row
+  io.sel_off = d_word_off;
+  io.out_base = d_vals;
+  io.out_off = reinterpret_cast<const uint64_t*>(d_rb);
+  io.valid_base = nullptr;
+  io.valid_off = nullptr;
+  io.counts = reinterpret_cast<uint32_t*>(d_cnt);
+  io.counts_stride = 4;
+  IntPredDesc ip{};
+  if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
+  LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
+  LC_CUDA_OK(launch_alp_finish(static_cast<uint32_t>(n), io, tbits, s));
+  FloatCmpIo c{};
+  c.refs = rl->d_refs;
+  c.vals_base = d_vals;
+  c.vals_off = io.out_off;
+  c.refine = 1;
+  c.sel_base = all_rows ? nullptr : d_sel_base;
+  c.sel_off = d_word_off;
+  c.out_base = d_sel_base;
+  c.out_off = d_word_off;
+  c.counts = d_counts;
+  c.counts_stride = 2;
+  c.op = op;
+  c.lit_key = key;
+  LC_CUDA_OK(launch_float_cmp(static_cast<uint32_t>(n), c, tbits, s));
+  if (ctx->timing_on) {
+    cudaEventRecord(ctx->ev_b, s);
+    ctx->timing_valid = true;
+  }
+  ctx->kernel_launches += 3;
+  return LC_OK;
+}
+
 // ---- eval_predicate --------------------------------------------------------------------------------
 int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
                          const uint8_t* const* sel_bits, const PredOut& out) {
@@ -399,12 +629,13 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     set_error("eval_predicate_many: entries of different liquid types in one call");
     return LC_ERR_INVALID;
   }
-  const bool is_int = (entries[0]->liquid_type == LC_LIQUID_INTEGER);
+  if (entries[0]->liquid_type == LC_LIQUID_FLOAT) return eval_predicate_float(ctx, entries, n, rl, pred, sel_bits, out);
+  const bool is_int = is_int_blob(entries[0]->liquid_type);
   SelPlan sp;
   LC_TRY(plan_selection(ctx, rl->rows->data(), n, sel_bits, &sp));
   StrLaunch sl;
   IntPredDesc ip{};
-  if (is_int) LC_TRY(make_int_pred(pred, &ip));
+  if (is_int) LC_TRY(make_int_pred(pred, entries[0], &ip));
   else LC_TRY(prepare_str_pred(pred, &sl));
 
   // upload: sel_off[n] | out_off[n] | needle | selection words ; download: counts[2n] | mask words | validity words
@@ -657,10 +888,12 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
     set_error("scan_filter: entries of different liquid types in one call");
     return LC_ERR_INVALID;
   }
-  const bool is_int = (entries[0]->liquid_type == LC_LIQUID_INTEGER);
+  if (entries[0]->liquid_type == LC_LIQUID_FLOAT)
+    return refine_float(ctx, entries, n, rl, pred, d_sel_base, d_word_off, all_rows, d_counts);
+  const bool is_int = is_int_blob(entries[0]->liquid_type);
   StrLaunch sl;
   IntPredDesc ip{};
-  if (is_int) LC_TRY(make_int_pred(pred, &ip));
+  if (is_int) LC_TRY(make_int_pred(pred, entries[0], &ip));
   else LC_TRY(prepare_str_pred(pred, &sl));
   ScanIo io{};
   io.refs = rl->d_refs;
@@ -755,7 +988,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   SelPlan sp;
   LC_TRY(plan_selection(ctx, rl->rows->data(), n, sel_bits, &sp, dev_sel));
   tr.mark("stage selection");
-  const bool is_int = (proto->liquid_type == LC_LIQUID_INTEGER);
+  const bool is_int = is_int_blob(proto->liquid_type);
   cudaStream_t s = ctx->stream;
   Scratch& sc = ctx->scratch;
 
@@ -822,18 +1055,23 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
 
   if (is_int) {
     const uint32_t tb = proto->ih.tbits / 8;
+    const bool is_float = proto->liquid_type == LC_LIQUID_FLOAT;
+    const bool is_dec = proto->liquid_type == LC_LIQUID_DECIMAL;
+    const uint32_t out_tb = is_dec ? proto->dec_width : tb;  // bytes per value of the Arrow result
     if (!rl->same_width) {
       set_error("to_arrow_many: mixed integer widths");
       return LC_ERR_INVALID;
     }
     const uint64_t val_bytes = round_up(rows * tb, 256);
-    LC_TRY(sc.reserve(up_total + dn_total + val_bytes + 1024, up_total + dn_total + 1024));
+    const uint64_t wide_bytes = is_dec ? round_up(rows * out_tb, 256) : 0;
+    LC_TRY(sc.reserve(up_total + dn_total + val_bytes + wide_bytes + 1024, up_total + dn_total + 1024));
     uint8_t* h_up = sc.host(up_total);
     uint8_t* h_dn = sc.host(dn_total);
     uint8_t* d_up = sc.dev(up_total);
     uint8_t* d_dn = sc.dev(dn_total);
     uint8_t* d_vals = sc.dev(val_bytes);
-    if (!h_up || !h_dn || !d_up || !d_dn || !d_vals) {
+    uint8_t* d_wide = is_dec ? sc.dev(wide_bytes) : nullptr;
+    if (!h_up || !h_dn || !d_up || !d_dn || !d_vals || (is_dec && !d_wide)) {
       set_error("to_arrow: scratch exhausted");
       return LC_ERR_OOM;
     }
@@ -845,6 +1083,12 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     if (!dev_sel) LC_TRY(upload_selection(ctx, sp, d_up + up_offs, s));
     LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
     ctx->kernel_launches++;
+    if (is_float) {
+      // the decode left the ALP integers of the selected rows: -> floats in place, then their patches
+      LC_CUDA_OK(launch_alp_finish(static_cast<uint32_t>(n), io, proto->ih.tbits, s));
+      ctx->kernel_launches++;
+    }
+    const uint8_t* d_result = d_vals;  // what travels: native values, or the decimals widened to 128/256 bits
     if (dev_out) {
       // device-resident result: counts come back (null count), values and validity stay in HBM
       LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
@@ -854,15 +1098,20 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       uint64_t nulls = 0;
       for (uint64_t i = 0; i < n; ++i) nulls += hc[4 * i + 1];
       if (dev_out->out_rows) *dev_out->out_rows = rows;
-      if (dev_out->out_value_bytes) *dev_out->out_value_bytes = rows * tb;
+      if (dev_out->out_value_bytes) *dev_out->out_value_bytes = rows * out_tb;
       if (dev_out->out_null_count) *dev_out->out_null_count = nulls;
       if (!dev_out->d_values) return LC_OK;  // size query
-      if (dev_out->values_cap < rows * tb) {
+      if (dev_out->values_cap < rows * out_tb) {
         set_error("read_device: values buffer of %llu bytes, need %llu", (unsigned long long)dev_out->values_cap,
-                  (unsigned long long)(rows * tb));
+                  (unsigned long long)(rows * out_tb));
         return LC_ERR_INVALID;
       }
-      if (rows) LC_CUDA_OK(cudaMemcpyAsync(dev_out->d_values, d_vals, rows * tb, cudaMemcpyDeviceToDevice, s));
+      if (is_dec) {
+        LC_CUDA_OK(launch_dec_widen(reinterpret_cast<const unsigned long long*>(d_vals), rows, out_tb, dev_out->d_values, s));
+        ctx->kernel_launches++;
+      } else if (rows) {
+        LC_CUDA_OK(cudaMemcpyAsync(dev_out->d_values, d_vals, rows * tb, cudaMemcpyDeviceToDevice, s));
+      }
       if (nulls && dev_out->d_validity) {
         const uint64_t* offs = reinterpret_cast<const uint64_t*>(d_up);
         LC_CUDA_OK(launch_concat_validity(io.valid_base, offs + 2 * n, offs + n, io.counts, 4, static_cast<uint32_t>(n), rows,
@@ -872,15 +1121,20 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       LC_CUDA_OK(cudaStreamSynchronize(s));
       return LC_OK;
     }
-    HostBuf values{host_alloc(rows * tb), rows * tb};
+    if (is_dec) {
+      LC_CUDA_OK(launch_dec_widen(reinterpret_cast<const unsigned long long*>(d_vals), rows, out_tb, d_wide, s));
+      ctx->kernel_launches++;
+      d_result = d_wide;
+    }
+    HostBuf values{host_alloc(rows * out_tb), rows * out_tb};
     if (!values.p) {
-      set_error("host allocation of %llu bytes failed", (unsigned long long)(rows * tb));
+      set_error("host allocation of %llu bytes failed", (unsigned long long)(rows * out_tb));
       return LC_ERR_OOM;
     }
     LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
-    if (rows) LC_CUDA_OK(cudaMemcpyAsync(values.p, d_vals, rows * tb, cudaMemcpyDeviceToHost, s));
+    if (rows) LC_CUDA_OK(cudaMemcpyAsync(values.p, d_result, rows * out_tb, cudaMemcpyDeviceToHost, s));
     LC_CUDA_OK(cudaStreamSynchronize(s));
-    ctx->d2h_bytes += dn_total + rows * tb;
+    ctx->d2h_bytes += dn_total + rows * out_tb;
     const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
     uint64_t nulls = 0;
     for (uint64_t i = 0; i < n; ++i) {

@@ -12,6 +12,7 @@ import datetime as _dt
 from dataclasses import dataclass
 from typing import Any, Optional
 
+import numpy as _np
 import pyarrow as pa
 
 from . import _native as N
@@ -182,6 +183,31 @@ class LiquidExpr:
                     raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "literal is not bytes-like")
                 _set_bytes(p, needle)
                 return p
+            if pa.types.is_floating(column_type):
+                # Float32/Float64 columns: the literal DataFusion hands over has the column's type; it crosses
+                # the ABI as f64 bits (exact for either width)
+                if not isinstance(e.left, Column):
+                    raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "float column under a cast")
+                v = e.right.value
+                if isinstance(v, bool) or not isinstance(v, (int, float)):
+                    raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "literal is not a float")
+                if pa.types.is_float32(column_type):
+                    v = float(_np.float32(v))
+                p.lit_kind = N.LIT_F64
+                p.lit_u64 = int(_np.array([float(v)], dtype=_np.float64).view(_np.uint64)[0])
+                return p
+            if pa.types.is_decimal(column_type):
+                # Decimal128/256: unscaled integer at the column's scale (the coerced ScalarValue::Decimal128)
+                if not isinstance(e.left, Column):
+                    raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "decimal column under a cast")
+                u = _decimal_unscaled(e.right.value, column_type.scale)
+                if u is None or not (-(1 << 127) <= u < (1 << 127)):
+                    raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "literal is not a decimal at the column's scale")
+                p.lit_kind = N.LIT_I128
+                p.lit_u64 = u & 0xFFFFFFFFFFFFFFFF
+                hi = (u >> 64) & 0xFFFFFFFFFFFFFFFF
+                p.lit_i64 = hi - (1 << 64) if hi >= (1 << 63) else hi
+                return p
             if not _cast_chain_is_integer_identity(e.left, column_type):
                 # e.g. to_timestamp_seconds(col) or a narrowing cast: the reference evaluates these with
                 # DataFusion on the decoded array; the caller keeps doing that.
@@ -208,6 +234,26 @@ def _set_bytes(p: N.Predicate, needle: bytes) -> None:
     p._keepalive = needle  # ctypes does not keep the bytes object alive by itself
     p.lit_bytes = needle
     p.lit_len = len(needle)
+
+
+def _decimal_unscaled(v, scale: int) -> Optional[int]:
+    """Unscaled integer of a decimal literal at `scale`; None when the value has more fractional digits."""
+    import decimal as _dec
+
+    if isinstance(v, bool):
+        return None
+    if isinstance(v, int):
+        d = _dec.Decimal(v)
+    elif isinstance(v, _dec.Decimal):
+        d = v
+    else:
+        return None
+    with _dec.localcontext() as cx:
+        cx.prec = 100
+        scaled = d.scaleb(scale)
+        if scaled != scaled.to_integral_value():
+            return None
+        return int(scaled)
 
 
 def _int_literal(lit: Literal) -> Optional[int]:

@@ -138,7 +138,8 @@ def test_unsupported_types_are_declined(cache):
     """transcode.rs:420-436: Boolean (and tz timestamps) stay Arrow -> Err(array)."""
     from liquid_cache_b200 import _native as N
 
-    for arr in (pa.array([True, False]), pa.array([1, 2], pa.timestamp("us", tz="UTC")), pa.array([1.5, 2.5])):
+    for arr in (pa.array([True, False]), pa.array([1, 2], pa.timestamp("us", tz="UTC")), pa.array([1.5, 2.5], pa.float16()),
+                pa.array([[1], [2]], pa.list_(pa.int32())), pa.array(["a"], pa.large_string())):
         with pytest.raises(N.UnsupportedType):
             cache.transcode(arr)
 
