@@ -6,7 +6,7 @@
 // Every product and sum below is a single correctly rounded IEEE operation issued through the _rn intrinsics, so
 // nvcc cannot contract a multiply and the following add into an FMA (the reference rounds after each step).
 // The power-of-ten tables are the reference's decimal literals (float_array.rs:135-160, 170-222) written as hex
-// floats of their correctly rounded values (generated from exact rationals; oracle/liquid_oracle.py holds the same).
+// floats of their correctly rounded values (generated from exact rationals; tests/test_oracle_num.py compares them with the checker's own).
 // Float comparisons follow arrow-ord's total order (`f64::total_cmp`, the ordering `cmp::{eq,lt,..}` of arrow-rs
 // documents for floating point arrays): sign-magnitude bits mapped to a two's complement key.
 #pragma once
