@@ -3,17 +3,89 @@
 // (/root/reference/src/core/src/cache/transcode.rs:46-290): integers, dates, timestamps, floats, decimals, byte views.
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 
 #include "host_common.h"
 
 namespace lc {
 
+// Result buffers. Small ones come from the C heap. From 1 MiB on they are PAGE-LOCKED blocks recycled through a
+// process-wide pool: a device-to-host copy into pageable memory is staged by the driver and ran at ~3 GB/s for the
+// 43 MB result of the l_shipdate scan (bench.py --workload shipdate: 16 ms per step, most of it this copy), while a
+// pinned destination takes the DMA directly. Page-locking is itself slow (~10 ms per 64 MB), hence the pool: the
+// Arrow release callback hands the block back (no CUDA call), and the next result of that size class reuses it.
+// The pool outlives every context on purpose — an exported array may be released after its lc_ctx is gone.
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::unordered_map<uint8_t*, uint64_t> live;                 // handed-out block -> capacity
+  std::unordered_map<uint64_t, std::vector<uint8_t*>> idle;    // capacity (power of two) -> blocks
+  uint64_t idle_bytes = 0;
+};
+PinnedPool& pinned_pool() {
+  static PinnedPool* p = new PinnedPool();  // never destroyed: release callbacks may run during interpreter shutdown
+  return *p;
+}
+constexpr uint64_t kPinnedMin = 1ull << 20;
+constexpr uint64_t kPinnedIdleMax = 2ull << 30;
+}  // namespace
+
 uint8_t* host_alloc(uint64_t bytes) {
+  if (bytes >= kPinnedMin) {
+    uint64_t cap = kPinnedMin;
+    while (cap < bytes) cap <<= 1;
+    PinnedPool& pool = pinned_pool();
+    {
+      std::lock_guard<std::mutex> l(pool.mu);
+      auto it = pool.idle.find(cap);
+      if (it != pool.idle.end() && !it->second.empty()) {
+        uint8_t* p = it->second.back();
+        it->second.pop_back();
+        pool.idle_bytes -= cap;
+        pool.live.emplace(p, cap);
+        return p;
+      }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) == cudaSuccess) {
+      std::lock_guard<std::mutex> l(pool.mu);
+      pool.live.emplace(static_cast<uint8_t*>(p), cap);
+      return static_cast<uint8_t*>(p);
+    }
+    cudaGetLastError();  // no page-locked memory to be had: fall through to the heap
+  }
   void* p = nullptr;
   if (posix_memalign(&p, 64, bytes ? round_up(bytes, 64) : 64) != 0) return nullptr;
   return static_cast<uint8_t*>(p);
 }
-void host_free(uint8_t* p) { std::free(p); }
+
+void host_free(uint8_t* p) {
+  if (!p) return;
+  PinnedPool& pool = pinned_pool();
+  uint64_t cap = 0;
+  {
+    std::lock_guard<std::mutex> l(pool.mu);
+    auto it = pool.live.find(p);
+    if (it == pool.live.end()) {
+      cap = 0;
+    } else {
+      cap = it->second;
+      pool.live.erase(it);
+      if (pool.idle_bytes + cap <= kPinnedIdleMax) {
+        pool.idle[cap].push_back(p);
+        pool.idle_bytes += cap;
+        return;
+      }
+    }
+  }
+  if (cap) {
+    if (cudaFreeHost(p) != cudaSuccess) cudaGetLastError();  // e.g. driver already shut down: the OS reclaims it
+  } else {
+    std::free(p);
+  }
+}
 
 void copy_bits(const uint8_t* src, int64_t off, int64_t n, uint8_t* dst, uint64_t dst_bytes) {
   std::memset(dst, 0, dst_bytes);

@@ -1075,6 +1075,13 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       set_error("to_arrow: scratch exhausted");
       return LC_ERR_OOM;
     }
+    if (dev_out && !dev_out->d_values && !rl->any_nulls) {
+      // size query over entries without nulls: everything asked for follows from the selection counts
+      if (dev_out->out_rows) *dev_out->out_rows = rows;
+      if (dev_out->out_value_bytes) *dev_out->out_value_bytes = rows * out_tb;
+      if (dev_out->out_null_count) *dev_out->out_null_count = 0;
+      return LC_OK;
+    }
     fill_offsets(h_up, nullptr);
     const ScanIo io = make_io(d_up, d_dn, d_vals);
     IntPredDesc ip{};

@@ -120,7 +120,7 @@ def test_float_reference_known_answers(cache):
 
 def test_float_minus_zero_and_nan_follow_the_reference(cache):
     nan_payload = np.array([0x7FF8000000000123], dtype=np.uint64).view(np.float64)[0]
-    x = np.array([0.0, -0.0, nan_payload, np.inf, -np.inf, 2.5, 1e300])
+    x = np.array([0.0, -0.0, nan_payload, np.inf, -np.inf, 2.5, 1e300, np.nan])
     arr = pa.array(x)
     liquid = cache.transcode(arr)
     want = x.copy()
@@ -128,9 +128,15 @@ def test_float_minus_zero_and_nan_follow_the_reference(cache):
     got = np.asarray(liquid.to_arrow_array().to_numpy(zero_copy_only=False))
     assert got.view(np.uint64).tolist() == want.view(np.uint64).tolist()
     sel = pa.array([True] * len(x))
-    assert liquid.try_eval_predicate(_expr("=", float("nan")), sel).to_pylist() == [False, False, True, False, False, False, False]
-    assert liquid.try_eval_predicate(_expr("<", 0.0), sel).to_pylist() == [False, False, False, False, True, False, False]
-    assert liquid.try_eval_predicate(_expr(">=", float("inf")), sel).to_pylist() == [False, False, True, True, False, False, False]
+    # total order: NaN equals NaN only bit for bit (the payload NaN is a different, larger value); the stored -0.0 is +0.0
+    assert liquid.try_eval_predicate(_expr("=", float("nan")), sel).to_pylist() == [False, False, False, False, False, False, False, True]
+    assert liquid.try_eval_predicate(_expr(">", float("nan")), sel).to_pylist() == [False, False, True, False, False, False, False, False]
+    assert liquid.try_eval_predicate(_expr("<", 0.0), sel).to_pylist() == [False, False, False, False, True, False, False, False]
+    assert liquid.try_eval_predicate(_expr(">=", float("inf")), sel).to_pylist() == [False, False, True, True, False, False, False, True]
+    oracle = OracleFloatArray.from_arrow(arr)
+    for op in ("=", "!=", "<", "<=", ">", ">="):
+        for lit in (float("nan"), -0.0, 0.0, 2.5, float("-inf")):
+            assert_masks_equal(liquid.try_eval_predicate(_expr(op, lit), sel), oracle.try_eval_predicate(op, lit, sel), f"{op} {lit}")
 
 
 def test_float_sliced_input_with_offset(cache):
