@@ -11,6 +11,7 @@
 #pragma once
 #include <cstdint>
 #include <stdexcept>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -55,6 +56,30 @@ struct LiquidExpr {
     e.pred.op = op;
     e.pred.lit_kind = LC_LIT_I64;
     e.pred.lit_i64 = v;
+    return e;
+  }
+  static LiquidExpr compare_u64(lc_op op, uint64_t v) {
+    LiquidExpr e;
+    e.pred.op = op;
+    e.pred.lit_kind = LC_LIT_U64;
+    e.pred.lit_u64 = v;
+    return e;
+  }
+  // Float32 / Float64 column: ScalarValue::Float32(v) is widened exactly (float_array.rs columns; arrow-ord total order)
+  static LiquidExpr compare_f64(lc_op op, double v) {
+    LiquidExpr e;
+    e.pred.op = op;
+    e.pred.lit_kind = LC_LIT_F64;
+    std::memcpy(&e.pred.lit_u64, &v, 8);
+    return e;
+  }
+  // Decimal128/256 column: unscaled value at the column's scale, two's complement halves (decimal_array.rs columns)
+  static LiquidExpr compare_decimal(lc_op op, uint64_t low, int64_t high) {
+    LiquidExpr e;
+    e.pred.op = op;
+    e.pred.lit_kind = LC_LIT_I128;
+    e.pred.lit_u64 = low;
+    e.pred.lit_i64 = high;
     return e;
   }
   static LiquidExpr compare_bytes(lc_op op, std::string v) {
