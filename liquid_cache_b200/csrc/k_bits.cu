@@ -1,4 +1,5 @@
-// k_bits.cu — boolean_buffer_and_then on the device.
+// k_bits.cu — boolean_buffer_and_then on the device, plus the small result-assembly kernels (validity concatenation,
+// sparse mask transfer, Utf8View views).
 // Reference: /root/reference/src/datafusion/src/utils.rs:17-83 (semantics), :104-236 (the BMI2 PDEP
 // routine, the only hand-written intrinsic in the reference). out bit p = left[p] AND the
 // rank_left(p)-th bit of right, where right has popcount(left) bits. On the GPU the "deposit" is a
@@ -113,6 +114,44 @@ __global__ void k_gather_nonzero(const uint32_t* __restrict__ words, uint64_t n_
     const unsigned long long idx = base + __popc(m & lanemask_lt());
     if (idx < budget) pairs[idx] = (static_cast<unsigned long long>(i) << 32) | v;
   }
+}
+
+// Utf8View / BinaryView result: one 16-byte view per row over the single data buffer the decode kernel filled
+// ({length, 12 inline bytes} up to 12 bytes, else {length, 4-byte prefix, buffer index 0, offset}); null rows get an
+// all-zero view. What arrow's cast Dictionary -> Utf8View leaves the reference's caller with (byte_view_array/mod.rs:287-290).
+__global__ void __launch_bounds__(256) k_build_views(const int32_t* __restrict__ off, uint32_t total_bytes,
+                                                     const uint8_t* __restrict__ data, const uint32_t* __restrict__ valid,
+                                                     uint64_t rows, uint4* __restrict__ views) {
+  const uint64_t r = static_cast<uint64_t>(blockIdx.x) * 256u + threadIdx.x;
+  if (r >= rows) return;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  const bool ok = valid ? ((valid[r >> 5] >> (r & 31u)) & 1u) : true;
+  if (ok) {
+    const uint32_t b = static_cast<uint32_t>(off[r]);
+    const uint32_t e = r + 1u < rows ? static_cast<uint32_t>(off[r + 1u]) : total_bytes;
+    const uint32_t len = e - b;
+    uint32_t w[3] = {0u, 0u, 0u};
+    const uint32_t take = len <= 12u ? len : 4u;
+    for (uint32_t i = 0; i < take; ++i) w[i >> 2] |= static_cast<uint32_t>(data[b + i]) << (8u * (i & 3u));
+    v.x = len;
+    v.y = w[0];
+    if (len <= 12u) {
+      v.z = w[1];
+      v.w = w[2];
+    } else {
+      v.z = 0u;  // buffer index
+      v.w = b;   // offset
+    }
+  }
+  views[r] = v;
+}
+
+cudaError_t launch_build_views(const int32_t* d_offsets, uint32_t total_bytes, const uint8_t* d_data, const uint32_t* d_validity,
+                               uint64_t rows, void* d_views, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  k_build_views<<<static_cast<uint32_t>((rows + 255) / 256), 256, 0, s>>>(d_offsets, total_bytes, d_data, d_validity, rows,
+                                                                           static_cast<uint4*>(d_views));
+  return cudaGetLastError();
 }
 
 cudaError_t launch_gather_nonzero(const uint32_t* d_words, uint64_t n_words, unsigned long long* d_pairs, uint64_t budget,

@@ -241,6 +241,8 @@ cudaError_t launch_scatter_words(const unsigned long long* d_pairs, uint64_t n, 
 cudaError_t launch_concat_validity(const uint32_t* d_valid_base, const uint64_t* d_valid_off, const uint64_t* d_row_base,
                                    const uint32_t* d_counts, uint32_t counts_stride, uint32_t n_entries, uint64_t rows,
                                    uint32_t* d_out, cudaStream_t s);
+cudaError_t launch_build_views(const int32_t* d_offsets, uint32_t total_bytes, const uint8_t* d_data, const uint32_t* d_validity,
+                               uint64_t rows, void* d_views, cudaStream_t s);
 cudaError_t launch_and_then(const uint32_t* d_left, uint32_t left_bits, const uint32_t* d_right, uint32_t* d_out,
                             cudaStream_t s);
 

@@ -938,37 +938,8 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
 }
 
 // ---- get / filter ----------------------------------------------------------------------------------
-static void concat_validity(const uint8_t* src_words, uint32_t k, uint64_t dst_bit, uint8_t* dst) {
-  // append k bits (src bit offset 0) at bit position dst_bit of dst (zero-initialised)
-  for (uint32_t i = 0; i < k;) {
-    const uint64_t d = dst_bit + i;
-    if ((d & 7) == 0 && (i & 7) == 0 && k - i >= 8) {
-      const uint32_t nb = (k - i) / 8;
-      std::memcpy(dst + d / 8, src_words + i / 8, nb);
-      i += nb * 8;
-    } else {
-      if ((src_words[i >> 3] >> (i & 7)) & 1) dst[d >> 3] |= static_cast<uint8_t>(1u << (d & 7));
-      ++i;
-    }
-  }
-}
-
-static void set_bits_ones(uint8_t* dst, uint64_t from, uint64_t count) {
-  for (uint64_t i = 0; i < count;) {
-    const uint64_t d = from + i;
-    if ((d & 7) == 0 && count - i >= 8) {
-      const uint64_t nb = (count - i) / 8;
-      std::memset(dst + d / 8, 0xFF, nb);
-      i += nb * 8;
-    } else {
-      dst[d >> 3] |= static_cast<uint8_t>(1u << (d & 7));
-      ++i;
-    }
-  }
-}
-
 static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls, HostBuf validity, HostBuf offsets,
-                              HostBuf data, ArrowSchema* out_schema, ArrowArray* out_array);
+                              HostBuf views, HostBuf data, ArrowSchema* out_schema, ArrowArray* out_array);
 
 int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t* const* sel_bits,
                    const DevSel* dev_sel, ArrowSchema* out_schema, ArrowArray* out_array, const DeviceOut* dev_out) {
@@ -1039,18 +1010,24 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     io.counts_stride = 4;
     return io;
   };
-  auto build_validity = [&](const uint8_t* h_dn, uint64_t nulls, HostBuf* validity) {
-    const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
-    validity->p = nullptr;
-    validity->bytes = 0;
-    if (!nulls) return;
+  // Validity of the concatenated result: the per-entry compact bit strings the kernels wrote are joined at bit
+  // granularity ON THE DEVICE (k_concat_validity; entries without nulls read as all ones) and the finished bitmap is
+  // copied to the host — no host loop over rows or entries.
+  const uint64_t cat_bytes = round_up(((rows + 31) / 32) * 4 + 16, 256);
+  auto concat_validity_device = [&](const ScanIo& io, uint8_t* d_up, uint8_t* d_cat, HostBuf* validity) -> int {
     validity->bytes = (rows + 7) / 8;
-    validity->p = host_alloc(validity->bytes);
-    std::memset(validity->p, 0, round_up(validity->bytes, 64));
-    for (uint64_t i = 0; i < n; ++i) {
-      if (h_counts[4 * i + 1] == 0) set_bits_ones(validity->p, row_base[i], sp.k[i]);
-      else concat_validity(h_dn + dn_counts + vword_off[i] * 4, sp.k[i], row_base[i], validity->p);
+    validity->p = host_alloc(round_up(validity->bytes, 4));
+    if (!validity->p) {
+      set_error("host allocation failed");
+      return LC_ERR_OOM;
     }
+    const uint64_t* offs = reinterpret_cast<const uint64_t*>(d_up);
+    LC_CUDA_OK(launch_concat_validity(io.valid_base, offs + 2 * n, offs + n, io.counts, 4, static_cast<uint32_t>(n), rows,
+                                      reinterpret_cast<uint32_t*>(d_cat), s));
+    ctx->kernel_launches++;
+    LC_CUDA_OK(cudaMemcpyAsync(validity->p, d_cat, round_up(validity->bytes, 4), cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += validity->bytes;
+    return LC_OK;
   };
 
   if (is_int) {
@@ -1064,14 +1041,15 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     }
     const uint64_t val_bytes = round_up(rows * tb, 256);
     const uint64_t wide_bytes = is_dec ? round_up(rows * out_tb, 256) : 0;
-    LC_TRY(sc.reserve(up_total + dn_total + val_bytes + wide_bytes + 1024, up_total + dn_total + 1024));
+    LC_TRY(sc.reserve(up_total + dn_total + val_bytes + wide_bytes + cat_bytes + 1024, up_total + dn_total + 1024));
     uint8_t* h_up = sc.host(up_total);
     uint8_t* h_dn = sc.host(dn_total);
     uint8_t* d_up = sc.dev(up_total);
     uint8_t* d_dn = sc.dev(dn_total);
     uint8_t* d_vals = sc.dev(val_bytes);
     uint8_t* d_wide = is_dec ? sc.dev(wide_bytes) : nullptr;
-    if (!h_up || !h_dn || !d_up || !d_dn || !d_vals || (is_dec && !d_wide)) {
+    uint8_t* d_cat = sc.dev(cat_bytes);
+    if (!h_up || !h_dn || !d_up || !d_dn || !d_vals || (is_dec && !d_wide) || !d_cat) {
       set_error("to_arrow: scratch exhausted");
       return LC_ERR_OOM;
     }
@@ -1138,10 +1116,10 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       set_error("host allocation of %llu bytes failed", (unsigned long long)(rows * out_tb));
       return LC_ERR_OOM;
     }
-    LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
     if (rows) LC_CUDA_OK(cudaMemcpyAsync(values.p, d_result, rows * out_tb, cudaMemcpyDeviceToHost, s));
     LC_CUDA_OK(cudaStreamSynchronize(s));
-    ctx->d2h_bytes += dn_total + rows * out_tb;
+    ctx->d2h_bytes += dn_counts + rows * out_tb;
     const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
     uint64_t nulls = 0;
     for (uint64_t i = 0; i < n; ++i) {
@@ -1153,7 +1131,18 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       nulls += h_counts[4 * i + 1];
     }
     HostBuf validity;
-    build_validity(h_dn, nulls, &validity);
+    if (nulls) {  // second, small round trip only when the result has nulls
+      int rc = concat_validity_device(io, d_up, d_cat, &validity);
+      if (rc == LC_OK && cudaStreamSynchronize(s) != cudaSuccess) {
+        set_error("CUDA error while joining validity: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = LC_ERR_CUDA;
+      }
+      if (rc != LC_OK) {
+        host_free(values.p);
+        host_free(validity.p);
+        return rc;
+      }
+    }
     export_schema(proto->arrow_format, "", out_schema);
     std::vector<HostBuf> bufs;
     bufs.push_back(validity);
@@ -1172,7 +1161,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   const uint64_t dv_rowoff = round_up((rows + n) * 4 + 16, 256);  // k_i + 1 per entry
   const uint64_t dv_rowkey = round_up(rows * 4 + 16, 256);
   const uint64_t dv_ulen = round_up(ulen_words * 4 + 16, 256);
-  LC_TRY(sc.reserve(up_total + dn_total + dv_rowoff + dv_rowkey + dv_ulen + 1024, up_total + dn_total + 1024));
+  LC_TRY(sc.reserve(up_total + dn_total + dv_rowoff + dv_rowkey + dv_ulen + cat_bytes + 1024, up_total + dn_total + 1024));
   uint8_t* h_up = sc.host(up_total);
   uint8_t* h_dn = sc.host(dn_total);
   uint8_t* d_up = sc.dev(up_total);
@@ -1180,7 +1169,8 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   uint8_t* d_rowoff = sc.dev(dv_rowoff);
   uint8_t* d_rowkey = sc.dev(dv_rowkey);
   uint8_t* d_ulen = sc.dev(dv_ulen);
-  if (!h_up || !h_dn || !d_up || !d_dn || !d_rowoff || !d_rowkey || !d_ulen) {
+  uint8_t* d_cat = sc.dev(cat_bytes);
+  if (!h_up || !h_dn || !d_up || !d_dn || !d_rowoff || !d_rowkey || !d_ulen || !d_cat) {
     set_error("to_arrow: scratch exhausted");
     return LC_ERR_OOM;
   }
@@ -1248,8 +1238,11 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     ctx->h2d_bytes += n * 8 + 4;
     return LC_OK;
   }
+  const uint8_t bt = proto->sh.arrow_type;
+  const bool want_views = bt == BT_UTF8_VIEW || bt == BT_BINARY_VIEW;
   const uint64_t off_bytes = (rows + 1) * 4;
-  const uint64_t res_bytes = round_up(off_bytes, 256) + round_up(total_bytes + 16, 256);
+  const uint64_t view_bytes = want_views ? rows * 16 : 0;
+  const uint64_t res_bytes = round_up(off_bytes, 256) + round_up(total_bytes + 16, 256) + round_up(view_bytes + 16, 256);
   uint8_t* d_res = nullptr;
   if (cudaMallocAsync(reinterpret_cast<void**>(&d_res), res_bytes, s) != cudaSuccess) {
     cudaGetLastError();
@@ -1259,34 +1252,54 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   tr.mark("prefix sums + cudaMallocAsync");
   g.out_offsets = reinterpret_cast<int32_t*>(d_res);
   g.out_bytes = d_res + round_up(off_bytes, 256);
-  HostBuf offsets{host_alloc(off_bytes), off_bytes};
+  uint8_t* d_views = g.out_bytes + round_up(total_bytes + 16, 256);
+  // view types ship 16-byte views built on the device instead of the offsets
+  HostBuf offsets{want_views ? nullptr : host_alloc(off_bytes), want_views ? 0 : off_bytes};
+  HostBuf views{want_views ? host_alloc(view_bytes + 16) : nullptr, view_bytes};
   HostBuf data{host_alloc(total_bytes ? total_bytes : 1), total_bytes};
-  if (!offsets.p || !data.p) {
+  HostBuf validity;
+  auto drop_host = [&]() {
+    host_free(offsets.p);
+    host_free(views.p);
+    host_free(data.p);
+    host_free(validity.p);
+  };
+  if ((!want_views && !offsets.p) || (want_views && !views.p) || !data.p) {
     cudaFreeAsync(d_res, s);
+    drop_host();
     set_error("host allocation failed");
     return LC_ERR_OOM;
   }
   // second (small) upload: byte_base[n]
   cudaError_t ce = cudaMemcpyAsync(d_up + 4 * n * 8, h_byte_base, n * 8, cudaMemcpyHostToDevice, s);
   if (ce == cudaSuccess) ce = launch_str_decode(static_cast<uint32_t>(n), g, s);
-  if (ce == cudaSuccess && rows) ce = cudaMemcpyAsync(offsets.p, g.out_offsets, rows * 4, cudaMemcpyDeviceToHost, s);
-  if (ce == cudaSuccess && total_bytes) ce = cudaMemcpyAsync(data.p, g.out_bytes, total_bytes, cudaMemcpyDeviceToHost, s);
+  int rc = LC_OK;
+  if (ce == cudaSuccess && nulls) rc = concat_validity_device(g.io, d_up, d_cat, &validity);
+  if (ce == cudaSuccess && rc == LC_OK && want_views) {
+    ce = launch_build_views(g.out_offsets, static_cast<uint32_t>(total_bytes), g.out_bytes,
+                            nulls ? reinterpret_cast<const uint32_t*>(d_cat) : nullptr, rows, d_views, s);
+    ctx->kernel_launches++;
+    if (ce == cudaSuccess && rows) ce = cudaMemcpyAsync(views.p, d_views, view_bytes, cudaMemcpyDeviceToHost, s);
+  } else if (ce == cudaSuccess && rc == LC_OK && rows) {
+    ce = cudaMemcpyAsync(offsets.p, g.out_offsets, rows * 4, cudaMemcpyDeviceToHost, s);
+  }
+  if (ce == cudaSuccess && rc == LC_OK && total_bytes) ce = cudaMemcpyAsync(data.p, g.out_bytes, total_bytes, cudaMemcpyDeviceToHost, s);
   cudaFreeAsync(d_res, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-  if (ce != cudaSuccess) {
-    host_free(offsets.p);
-    host_free(data.p);
-    set_error("CUDA error in byte-view decode: %s", cudaGetErrorString(ce));
-    return LC_ERR_CUDA;
+  if (ce != cudaSuccess || rc != LC_OK) {
+    drop_host();
+    if (ce != cudaSuccess) {
+      set_error("CUDA error in byte-view decode: %s", cudaGetErrorString(ce));
+      return LC_ERR_CUDA;
+    }
+    return rc;
   }
   tr.mark("decode kernel + result D2H");
   ctx->kernel_launches++;
   ctx->h2d_bytes += n * 8;
-  ctx->d2h_bytes += rows * 4 + total_bytes;
-  reinterpret_cast<int32_t*>(offsets.p)[rows] = static_cast<int32_t>(total_bytes);
-  HostBuf validity;
-  build_validity(h_dn, nulls, &validity);
-  return finish_bytes_array(proto, rows, nulls, validity, offsets, data, out_schema, out_array);
+  ctx->d2h_bytes += (want_views ? view_bytes : rows * 4) + total_bytes;
+  if (!want_views) reinterpret_cast<int32_t*>(offsets.p)[rows] = static_cast<int32_t>(total_bytes);
+  return finish_bytes_array(proto, rows, nulls, validity, offsets, views, data, out_schema, out_array);
 }
 
 // Turn (validity, int32 offsets, bytes) into the ORIGINAL arrow type of the column:
@@ -1294,7 +1307,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
 // Dictionary<UInt16,_> by re-encoding (what arrow's cast dictionary -> original type leaves the caller with,
 // byte_view_array/mod.rs:287-290).
 static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls, HostBuf validity, HostBuf offsets,
-                              HostBuf data, ArrowSchema* out_schema, ArrowArray* out_array) {
+                              HostBuf views, HostBuf data, ArrowSchema* out_schema, ArrowArray* out_array) {
   const uint8_t bt = proto->sh.arrow_type;
   const int32_t* off = reinterpret_cast<const int32_t*>(offsets.p);
   if (bt == BT_UTF8 || bt == BT_BINARY) {
@@ -1304,31 +1317,17 @@ static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls,
     return LC_OK;
   }
   if (bt == BT_UTF8_VIEW || bt == BT_BINARY_VIEW) {
-    HostBuf views{host_alloc(rows * 16 + 16), rows * 16};
+    // the views came off the device (k_build_views); only the variadic-sizes buffer is made here
     HostBuf sizes{host_alloc(8), 8};
-    if (!views.p || !sizes.p) {
+    if (!sizes.p) {
+      host_free(validity.p);
+      host_free(views.p);
+      host_free(data.p);
       set_error("host allocation failed");
       return LC_ERR_OOM;
     }
-    std::memset(views.p, 0, rows * 16 + 16);
-    for (uint64_t r = 0; r < rows; ++r) {
-      const bool ok = !validity.p || bit_get(validity.p, static_cast<int64_t>(r));
-      if (!ok) continue;
-      const uint32_t len = static_cast<uint32_t>(off[r + 1] - off[r]);
-      uint8_t* v = views.p + 16 * r;
-      std::memcpy(v, &len, 4);
-      if (len <= 12) {
-        std::memcpy(v + 4, data.p + off[r], len);
-      } else {
-        std::memcpy(v + 4, data.p + off[r], 4);
-        const uint32_t bi = 0, bo = static_cast<uint32_t>(off[r]);
-        std::memcpy(v + 8, &bi, 4);
-        std::memcpy(v + 12, &bo, 4);
-      }
-    }
     const int64_t sz = static_cast<int64_t>(data.bytes);
     std::memcpy(sizes.p, &sz, 8);
-    host_free(offsets.p);
     export_schema(bt == BT_UTF8_VIEW ? "vu" : "vz", "", out_schema);
     std::vector<HostBuf> bufs{validity, views, data, sizes};
     export_array(static_cast<int64_t>(rows), static_cast<int64_t>(nulls), std::move(bufs), nullptr, out_array);
