@@ -250,6 +250,13 @@ int lc_and_then(lc_ctx* ctx, const uint8_t* left_bits, uint64_t left_len, const 
  * (src/datafusion/src/cache/id.rs:15-22); the FSST table scope is entry_id with batch cleared. */
 int lc_cache_insert(lc_ctx* ctx, uint64_t entry_id, const struct ArrowSchema* schema,
                     const struct ArrowArray* array, int32_t hint);
+/* The same insert for a LIST of batches (e.g. every batch of a row group, one or several columns): entry_ids[i] gets
+ * arrays[i]. Integer / date / timestamp batches are transcoded in one pass (one upload, two kernels over the whole
+ * list, two synchronisations per call instead of per batch); other types are transcoded batch by batch. All or
+ * nothing: on an error no entry of the list is inserted. The reference inserts batch by batch from
+ * LiquidCacheReader (cache/core.rs:122-128); this is the batched form of that loop. */
+int lc_cache_insert_many(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, const struct ArrowSchema* const* schemas,
+                         const struct ArrowArray* const* arrays, int32_t hint);
 int lc_cache_is_cached(lc_ctx* ctx, uint64_t entry_id);                       /* core.rs is_cached */
 int lc_cache_remove(lc_ctx* ctx, uint64_t entry_id);
 int lc_cache_reset(lc_ctx* ctx);                                              /* core.rs reset     */

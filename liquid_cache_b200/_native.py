@@ -119,6 +119,7 @@ def lib() -> C.CDLL:
     l.lc_to_arrow_many.argtypes = [vp, vp, u64, vp, vp, vp]
     l.lc_and_then.argtypes = [vp, vp, u64, vp, u64, vp]
     l.lc_cache_insert.argtypes = [vp, u64, vp, vp, i32]
+    l.lc_cache_insert_many.argtypes = [vp, vp, u64, vp, vp, i32]
     l.lc_cache_is_cached.argtypes = [vp, u64]
     l.lc_cache_remove.argtypes = [vp, u64]
     l.lc_cache_reset.argtypes = [vp]

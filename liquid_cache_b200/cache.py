@@ -343,6 +343,23 @@ class LiquidCache:
     def insert(self, entry_id, array: pa.Array) -> Insert:
         return Insert(self, entry_id, array)
 
+    def insert_many(self, entry_ids: Sequence[int], arrays: Sequence[pa.Array], hint=None) -> None:
+        """`insert` for a list of batches in one call (lc_cache_insert_many): integer-like batches are transcoded in
+        one pass on the device. All or nothing."""
+        n = len(entry_ids)
+        if n != len(arrays):
+            raise ValueError("entry_ids and arrays differ in length")
+        if n == 0:
+            return
+        exported = [_export(a) for a in arrays]  # keeps the C structs alive for the duration of the call
+        ids = np.ascontiguousarray(np.asarray([int(x) for x in entry_ids], dtype=np.uint64))
+        sch = (C.c_void_p * n)(*[_ptr(s) for _a, s in exported])
+        arr = (C.c_void_p * n)(*[_ptr(a) for a, _s in exported])
+        nh = N.HINT_SUBSTRING_SEARCH if hint == CacheExpression.SubstringSearch else (N.HINT_PREDICATE if hint else N.HINT_NONE)
+        N.check(N.lib().lc_cache_insert_many(self._ctx, ids.ctypes.data, n, sch, arr, nh))
+        for i, a in zip(ids, arrays):
+            self._types[int(i)] = a.type
+
     def get(self, entry_id) -> Get:
         return Get(self, entry_id)
 

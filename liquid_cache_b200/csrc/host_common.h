@@ -213,6 +213,7 @@ void export_array(int64_t length, int64_t null_count, std::vector<HostBuf> buffe
 // ---- per-type host orchestration ----------------------------------------------------------------
 // int_host.cc
 int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out);
+int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<Entry*>* out);  // K_INT batches only
 // str_host.cc
 int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out);
 

@@ -5,6 +5,7 @@
 // LiquidFloatArray::from_arrow_array (float_array.rs:266-269, 609-751),
 // LiquidDecimalArray::{fits_u64, from_decimal_array} (decimal_array.rs:127-178).
 #include "host_common.h"
+#include "host_pool.h"
 
 namespace lc {
 
@@ -214,6 +215,168 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
   e->ih = h;
   ctx->n_entries++;
   *out = e;
+  return LC_OK;
+}
+
+// ---- batched form -----------------------------------------------------------------------------------
+// Many integer-like batches (any mix of the K_INT types) in ONE pass: every batch is copied once into the pinned
+// staging area (split over the host pool), one H2D carries values + validity + the min/max work list, k_int_minmax
+// and k_int_pack run with one CTA per batch (they take work LISTS), and the host sizes all blobs from one D2H of
+// 32 bytes per batch. Two stream synchronisations per call instead of two per batch.
+int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<Entry*>* out) {
+  const uint64_t nb = ins.size();
+  out->clear();
+  if (nb == 0) return LC_OK;
+  std::vector<uint64_t> voff(nb), moff(nb, ~0ull);
+  uint64_t cur = 0;
+  for (uint64_t i = 0; i < nb; ++i) {
+    const ArrowIn& in = ins[i];
+    if (in.kind != ArrowIn::K_INT) {
+      set_error("int_encode_many: batch %llu is not an integer-like array", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+    const uint64_t n = static_cast<uint64_t>(in.length);
+    voff[i] = cur;
+    cur += round_up(n * (in.tbits / 8), 256) + 256;
+    if (in.null_count > 0) {
+      moff[i] = cur;
+      cur += round_up(((n + 31) / 32) * 4, 256) + 256;
+    }
+  }
+  const uint64_t mm_off = cur;
+  cur += round_up(nb * sizeof(IntMinMaxWork), 256);
+  const uint64_t up_bytes = cur;
+  const uint64_t pw_off = cur;
+  cur += round_up(nb * sizeof(IntPackWork), 256);
+  const uint64_t mmout_off = cur;
+  cur += round_up(nb * 32, 256);
+  const uint64_t total = cur;
+  Scratch& sc = ctx->scratch;
+  LC_TRY(sc.reserve(total + 1024, total + 1024));
+  uint8_t* h = sc.host(total);
+  uint8_t* d = sc.dev(total);
+  if (!h || !d) {
+    set_error("int_encode_many: scratch exhausted");
+    return LC_ERR_OOM;
+  }
+  IntMinMaxWork* h_mm = reinterpret_cast<IntMinMaxWork*>(h + mm_off);
+  parallel_for(nb, 16, [&](uint64_t b, uint64_t e) {
+    for (uint64_t i = b; i < e; ++i) {
+      const ArrowIn& in = ins[i];
+      const uint64_t n = static_cast<uint64_t>(in.length);
+      const uint32_t tb = in.tbits / 8;
+      if (n) std::memcpy(h + voff[i], static_cast<const uint8_t*>(in.values) + static_cast<uint64_t>(in.offset) * tb, n * tb);
+      const bool has_nulls = moff[i] != ~0ull;
+      if (has_nulls) copy_bits(in.validity, in.offset, static_cast<int64_t>(n), h + moff[i], ((n + 31) / 32) * 4);
+      h_mm[i].values = d + voff[i];
+      h_mm[i].validity = has_nulls ? reinterpret_cast<const uint32_t*>(d + moff[i]) : nullptr;
+      h_mm[i].out = reinterpret_cast<uint64_t*>(d + mmout_off) + 4 * i;
+      h_mm[i].n = static_cast<uint32_t>(n);
+      h_mm[i].phys = in.phys;
+    }
+  });
+  cudaStream_t s = ctx->stream;
+  LC_CUDA_OK(cudaMemcpyAsync(d, h, up_bytes, cudaMemcpyHostToDevice, s));
+  ctx->h2d_bytes += up_bytes;
+  LC_CUDA_OK(launch_int_minmax(reinterpret_cast<const IntMinMaxWork*>(d + mm_off), static_cast<uint32_t>(nb), s));
+  ctx->kernel_launches++;
+  LC_CUDA_OK(cudaMemcpyAsync(h + mmout_off, d + mmout_off, nb * 32, cudaMemcpyDeviceToHost, s));
+  LC_CUDA_OK(cudaStreamSynchronize(s));
+  ctx->d2h_bytes += nb * 32;
+
+  // ---- size every blob, take arena space, write the pack work list ----
+  const uint64_t* h_mmout = reinterpret_cast<const uint64_t*>(h + mmout_off);
+  IntPackWork* h_pw = reinterpret_cast<IntPackWork*>(h + pw_off);
+  struct Taken {
+    uint8_t* blob;
+    uint32_t slab;
+    uint64_t bytes;
+  };
+  std::vector<Taken> taken;
+  taken.reserve(nb);
+  auto give_back = [&]() {
+    for (const Taken& t : taken) ctx->arena.free(t.slab, t.bytes);
+  };
+  for (uint64_t i = 0; i < nb; ++i) {
+    const ArrowIn& in = ins[i];
+    const uint32_t n = static_cast<uint32_t>(in.length);
+    const uint64_t mn = h_mmout[4 * i], mx = h_mmout[4 * i + 1], n_valid = h_mmout[4 * i + 2];
+    const bool has_nulls = moff[i] != ~0ull;
+    IntHeader hd;
+    std::memset(&hd, 0, sizeof(hd));
+    hd.magic = kMagicInt;
+    hd.phys = in.phys;
+    hd.tbits = in.tbits;
+    hd.n = n;
+    hd.n_chunks = (n + 1023) / 1024;
+    hd.is_signed = in.is_signed;
+    hd.has_nulls = has_nulls;
+    hd.null_count = static_cast<uint32_t>(n - n_valid);
+    const uint64_t tmask = in.tbits == 64 ? ~0ull : ((1ull << in.tbits) - 1ull);
+    if (n_valid == 0) {  // entire array null (or empty): BitPackedArray::new_null_array, reference_value = 0
+      hd.bit_width = 0;
+      hd.reference = 0;
+      hd.has_nulls = n > 0;
+      hd.null_count = n;
+    } else {
+      hd.bit_width = static_cast<uint8_t>(bit_width_of((mx - mn) & tmask));
+      hd.reference = mn & tmask;
+    }
+    const uint64_t valid_bytes = hd.has_nulls ? round_up((n + 7) / 8, 16) : 0;
+    hd.validity_off = hd.has_nulls ? 64 : 0;
+    hd.packed_off = static_cast<uint32_t>(64 + valid_bytes);
+    const uint64_t blob_bytes = round_up(hd.packed_off + static_cast<uint64_t>(hd.n_chunks) * 128ull * hd.bit_width, 16);
+    if (blob_bytes > 0xFFFFFFF0ull) {
+      give_back();
+      set_error("int_encode_many: entry too large");
+      return LC_ERR_UNSUPPORTED_TYPE;
+    }
+    hd.blob_bytes = static_cast<uint32_t>(blob_bytes);
+    if (ctx->budget && ctx->arena.bytes_used() + blob_bytes > ctx->budget) {
+      give_back();
+      set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(),
+                (unsigned long long)blob_bytes, (unsigned long long)ctx->budget);
+      return LC_ERR_CACHE_FULL;
+    }
+    uint32_t slab = 0;
+    uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
+    if (!d_blob) {
+      give_back();
+      set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+      return LC_ERR_OOM;
+    }
+    taken.push_back({d_blob, slab, blob_bytes});
+    std::memset(&h_pw[i], 0, sizeof(IntPackWork));
+    h_pw[i].values = d + voff[i];
+    // an all-null batch without a validity buffer cannot happen (n_valid == 0 implies nulls); an all-null batch WITH
+    // one keeps it
+    h_pw[i].validity = has_nulls ? reinterpret_cast<const uint32_t*>(d + moff[i]) : nullptr;
+    h_pw[i].blob = d_blob;
+    h_pw[i].hdr = hd;
+  }
+  cudaError_t ce = cudaMemcpyAsync(d + pw_off, h_pw, nb * sizeof(IntPackWork), cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = launch_int_pack(reinterpret_cast<const IntPackWork*>(d + pw_off), static_cast<uint32_t>(nb), s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (ce != cudaSuccess) {
+    give_back();
+    set_error("CUDA error in int_encode_many: %s", cudaGetErrorString(ce));
+    return LC_ERR_CUDA;
+  }
+  ctx->kernel_launches++;
+  ctx->h2d_bytes += nb * sizeof(IntPackWork);
+  out->reserve(nb);
+  for (uint64_t i = 0; i < nb; ++i) {
+    Entry* e = new Entry();
+    e->liquid_type = LC_LIQUID_INTEGER;
+    e->d_blob = taken[i].blob;
+    e->blob_bytes = static_cast<uint32_t>(taken[i].bytes);
+    e->slab = taken[i].slab;
+    e->n = static_cast<uint32_t>(ins[i].length);
+    e->arrow_format = ins[i].format;
+    e->ih = h_pw[i].hdr;
+    ctx->n_entries++;
+    out->push_back(e);
+  }
   return LC_OK;
 }
 

@@ -335,6 +335,45 @@ int lc_cache_insert(lc_ctx* ctx, uint64_t entry_id, const struct ArrowSchema* sc
   return LC_OK;
 }
 
+int lc_cache_insert_many(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, const struct ArrowSchema* const* schemas,
+                         const struct ArrowArray* const* arrays, int32_t hint) {
+  if (!ctx || (n && (!entry_ids || !schemas || !arrays))) {
+    set_error("lc_cache_insert_many: NULL argument");
+    return LC_ERR_INVALID;
+  }
+  if (n == 0) return LC_OK;
+  Guard g(ctx);
+  std::vector<ArrowIn> ins(n);
+  bool all_int = true;
+  for (uint64_t i = 0; i < n; ++i) {
+    LC_TRY(parse_arrow_input(schemas[i], arrays[i], &ins[i]));
+    all_int = all_int && ins[i].kind == ArrowIn::K_INT;
+  }
+  std::vector<Entry*> es;
+  if (all_int) {
+    // integer-like batches: one pass over the whole list (int_host.cc int_encode_many)
+    LC_TRY(int_encode_many(ctx, ins, &es));
+  } else {
+    // byte views, floats, decimals: batch by batch for now; all or nothing like the batched pass
+    for (uint64_t i = 0; i < n; ++i) {
+      Entry* e = nullptr;
+      ctx->scratch.reset();
+      const int rc = encode_locked(ctx, schemas[i], arrays[i], hint, entry_ids[i] & ~0xFFFFull, &e);
+      if (rc != LC_OK) {
+        for (Entry* made : es) release_entry(ctx, made);
+        return rc;
+      }
+      es.push_back(e);
+    }
+  }
+  for (uint64_t i = 0; i < n; ++i) {
+    auto it = ctx->cache.find(entry_ids[i]);
+    if (it != ctx->cache.end()) release_entry(ctx, entry_of(it->second));  // overwrite (index insert replaces)
+    ctx->cache[entry_ids[i]] = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(es[i]));
+  }
+  return LC_OK;
+}
+
 int lc_cache_is_cached(lc_ctx* ctx, uint64_t entry_id) {
   if (!ctx) return 0;
   std::lock_guard<std::mutex> g(ctx->mu);
