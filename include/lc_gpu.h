@@ -194,6 +194,16 @@ int lc_entry_image(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_
 int lc_entry_fsst_table(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 /* LiquidArray::original_arrow_data_type, as an Arrow C format string copied into buf. */
 int lc_arrow_format(lc_ctx* ctx, lc_handle h, char* buf, size_t buf_len);
+/* LiquidArray::to_bytes (liquid_array/mod.rs:116-121): the entry in the reference's serialized form, LQDA
+ * (liquid_array/ipc.rs:158-250; primitive_array.rs:603-654, float_array.rs:393-520, decimal_array.rs:180-218,
+ * raw/bit_pack_array.rs:181-252), for Integer / Float / Decimal entries — what the reference writes when it spills an
+ * entry to disk. out == NULL asks for the size. Byte-view entries: LC_ERR_UNSUPPORTED_TYPE
+ * (byte_view_array/serialization.rs is not built). */
+int lc_to_bytes(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+/* ipc::read_from_bytes (liquid_array/ipc.rs:252-283) for the same three logical types: an LQDA image becomes an
+ * HBM-resident entry (the Arrow type follows from the physical type id / the decimal header). The image is checked
+ * (section bounds, bit width, patch indices) and refused with LC_ERR_INVALID instead of panicking. */
+int lc_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, lc_handle* out);
 
 /* LiquidArray::to_arrow_array (sel_bits == NULL) / LiquidArray::filter(&BooleanBuffer)
  * (primitive_array.rs:350-374, byte_view_array/mod.rs:266-290,421-424). The result has the

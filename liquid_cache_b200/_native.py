@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
     l.lc_entry_image.argtypes = [vp, u64, vp, u64, u64p]
     l.lc_entry_fsst_table.argtypes = [vp, u64, vp, u64, u64p]
     l.lc_arrow_format.argtypes = [vp, u64, C.c_char_p, C.c_size_t]
+    l.lc_to_bytes.argtypes = [vp, u64, vp, u64, u64p]
+    l.lc_from_bytes.argtypes = [vp, vp, u64, u64p]
     l.lc_to_arrow.argtypes = [vp, u64, vp, u64, vp, vp]
     l.lc_eval_predicate.argtypes = [vp, u64, C.POINTER(Predicate), vp, u64, vp, vp, u64p, u64p]
     l.lc_mask_bytes.argtypes = [u64]

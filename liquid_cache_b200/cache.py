@@ -123,6 +123,14 @@ class GpuLiquidArray:
         N.check(N.lib().lc_entry_image(self._cache._ctx, self._h, buf.ctypes.data, nb.value, C.byref(nb)))
         return buf.tobytes()
 
+    def to_bytes(self) -> bytes:
+        """`LiquidArray::to_bytes`: the reference's LQDA image of the entry (Integer / Float / Decimal)."""
+        nb = C.c_uint64(0)
+        N.check(N.lib().lc_to_bytes(self._cache._ctx, self._h, None, 0, C.byref(nb)))
+        buf = np.zeros(max(int(nb.value), 1), dtype=np.uint8)
+        N.check(N.lib().lc_to_bytes(self._cache._ctx, self._h, buf.ctypes.data, nb.value, C.byref(nb)))
+        return buf[: int(nb.value)].tobytes()
+
     def fsst_table(self) -> bytes:
         """The column chunk's FSST symbol table as the kernels see it (lc::FsstTable: 256 x u64 symbols, 256 x u8 lengths)."""
         nb = C.c_uint64(0)
@@ -409,6 +417,13 @@ class LiquidCache:
         c_arr, c_sch = _export(array)
         nh = N.HINT_SUBSTRING_SEARCH if hint == CacheExpression.SubstringSearch else N.HINT_NONE
         N.check(N.lib().lc_encode(self._ctx, _ptr(c_sch), _ptr(c_arr), nh, compressor_scope, C.byref(h)))
+        return GpuLiquidArray(self, int(h.value))
+
+    def read_from_bytes(self, data: bytes) -> GpuLiquidArray:
+        """`ipc::read_from_bytes` (liquid_array/ipc.rs:252-283): an LQDA image becomes an HBM-resident entry."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_uint64(0)
+        N.check(N.lib().lc_from_bytes(self._ctx, buf.ctypes.data, len(buf), C.byref(h)))
         return GpuLiquidArray(self, int(h.value))
 
     def _handle(self, entry_id) -> int:

@@ -214,6 +214,9 @@ void export_array(int64_t length, int64_t null_count, std::vector<HostBuf> buffe
 // int_host.cc
 int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out);
 int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<Entry*>* out);  // K_INT batches only
+// ipc_host.cc: LQDA (the reference's serialized form) of integer-shaped entries
+int entry_to_bytes(lc_ctx* ctx, const Entry* e, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+int entry_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, Entry** out);
 // str_host.cc
 int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out);
 

@@ -435,6 +435,37 @@ __global__ void __launch_bounds__(256) k_dec_widen(const unsigned long long* __r
   }
 }
 
+// LQDA keeps patch indices as u64 (float_array.rs:483-496); the entry keeps them as u32. narrow also checks that every
+// index is a row of the entry (an index past the end would make k_alp_finish write out of bounds).
+__global__ void __launch_bounds__(256) k_widen_u32(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) out[i] = in[i];
+}
+__global__ void __launch_bounds__(256) k_narrow_u64(const unsigned long long* __restrict__ in, uint32_t n, unsigned long long limit,
+                                                    uint32_t* __restrict__ out, uint32_t* __restrict__ flag) {
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+    const unsigned long long v = in[i];
+    if (v >= limit) atomicOr(flag, 1u);
+    out[i] = static_cast<uint32_t>(v);
+  }
+}
+
+cudaError_t launch_widen_u32(const uint32_t* d_in, uint32_t n, unsigned long long* d_out, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  uint32_t grid = (n + 255u) / 256u;
+  if (grid > 1184u) grid = 1184u;
+  k_widen_u32<<<grid, 256, 0, s>>>(d_in, n, d_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_narrow_u64(const unsigned long long* d_in, uint32_t n, unsigned long long limit, uint32_t* d_out, uint32_t* d_flag,
+                              cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  uint32_t grid = (n + 255u) / 256u;
+  if (grid > 1184u) grid = 1184u;
+  k_narrow_u64<<<grid, 256, 0, s>>>(d_in, n, limit, d_out, d_flag);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_dec_narrow(const void* d_in, const uint32_t* d_validity, uint32_t n, uint32_t width_bytes,
                               unsigned long long* d_out, uint32_t* d_flag, cudaStream_t s) {
   if (n == 0) return cudaSuccess;

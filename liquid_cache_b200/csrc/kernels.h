@@ -136,6 +136,11 @@ cudaError_t launch_dec_narrow(const void* d_in, const uint32_t* d_validity, uint
                               unsigned long long* d_out, uint32_t* d_flag, cudaStream_t s);
 cudaError_t launch_dec_widen(const unsigned long long* d_in, uint64_t n, uint32_t width_bytes, void* d_out, cudaStream_t s);
 
+// LQDA patch indices: u32 in the entry, u64 in the file; narrow raises *flag when an index is >= limit.
+cudaError_t launch_widen_u32(const uint32_t* d_in, uint32_t n, unsigned long long* d_out, cudaStream_t s);
+cudaError_t launch_narrow_u64(const unsigned long long* d_in, uint32_t n, unsigned long long limit, uint32_t* d_out, uint32_t* d_flag,
+                              cudaStream_t s);
+
 // ---- byte-view (string) path -------------------------------------------------------------------
 enum StrPredKind : int32_t {
   SP_CONST = 0,     // every unique gets `const_result`

@@ -196,6 +196,28 @@ int lc_entry_fsst_table(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, ui
   return LC_OK;
 }
 
+int lc_to_bytes(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out_bytes) {
+    set_error("lc_to_bytes: bad argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  return entry_to_bytes(ctx, e, out, cap, out_bytes);
+}
+
+int lc_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, lc_handle* out) {
+  if (!ctx || !bytes || !out) {
+    set_error("lc_from_bytes: NULL argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  Entry* e = nullptr;
+  LC_TRY(entry_from_bytes(ctx, bytes, len, &e));
+  *out = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
+  return LC_OK;
+}
+
 int lc_arrow_format(lc_ctx*, lc_handle h, char* buf, size_t buf_len) {
   Entry* e = entry_of(h);
   if (!e || !buf || buf_len == 0) return LC_ERR_INVALID;

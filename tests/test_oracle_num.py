@@ -148,3 +148,33 @@ def test_decimal_known_answers():
     assert transcode(pa.array([decimal.Decimal(2**64)], pa.decimal128(38, 0))) is None
     big = pa.array([decimal.Decimal(2**64 - 1), None], pa.decimal256(50, 0))
     assert transcode(big).to_arrow().equals(big)
+
+
+# ---- LQDA (the reference's serialized form) -------------------------------------------------------------------
+def test_lqda_known_answers_and_round_trips():
+    """ipc.rs:308-418: header fields of a serialized Int32 array, round trips incl. all-null / no-null / single / empty /
+    sparse-null arrays; the same for floats (float_array.rs:1058-1124 run every case through to_bytes/from_bytes) and
+    decimals (decimal_array.rs:656-668)."""
+    arr = pa.array([10, 20, 30, None, 50], pa.int32())
+    b = O.to_bytes(O.OracleIntArray.from_arrow(arr))
+    assert b[0:4] == (0x4C514441).to_bytes(4, "little") and int.from_bytes(b[4:6], "little") == 1
+    assert int.from_bytes(b[6:8], "little") == 1 and int.from_bytes(b[8:10], "little") == 2  # Integer, Int32
+    assert len(b) > 100 and len(b) == 24 + 24 + 768  # header+ref pad 8 | bit-pack header + 1 null byte pad 8 | 1024 x 6 bits
+    assert O.read_from_bytes(b).to_arrow().equals(arr)
+    cases = [pa.array([None] * 1000, pa.int32()), pa.array(list(range(1000)), pa.int32()), pa.array([42], pa.int32()),
+             pa.array([], pa.int32()), pa.array([None if i in (1000, 5000, 9000) else i for i in range(10000)], pa.int32()),
+             pa.array([1, 2, 3], pa.timestamp("us")), pa.array([-5, 2**62], pa.int64()), pa.array([1, None, 2**64 - 1], pa.uint64()),
+             pa.array([8036, 10556, None], pa.date32())]
+    for a in cases:
+        assert O.read_from_bytes(O.to_bytes(O.OracleIntArray.from_arrow(a))).to_arrow().equals(a), a.type
+    for typ in FLOAT_TYPES:
+        for values in ([-1.0, 1.0, 0.0], [-1.0, 1.0, 0.0, None], [None] * 4, [], [0.1, float("nan"), 1e30, 2.5]):
+            a = pa.array(values, typ)
+            o = OracleFloatArray.from_arrow(a)
+            r = O.read_from_bytes(O.to_bytes(o))
+            assert (r.e, r.f, r.bit_width) == (o.e, o.f, o.bit_width)
+            assert_float_bits_equal(r.to_arrow(), o.to_arrow(), f"{typ} {values}")
+    d = pa.array([decimal.Decimal("12.345"), decimal.Decimal("67.890")], pa.decimal128(12, 3))
+    b = O.to_bytes(OracleDecimalArray.from_arrow(d))
+    assert int.from_bytes(b[6:8], "little") == 6 and int.from_bytes(b[8:10], "little") == 7 and list(b[16:19]) == [0, 12, 3]
+    assert O.read_from_bytes(b).to_arrow().equals(d)
