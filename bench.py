@@ -45,9 +45,10 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows PER GPU (weak scaling)")
     ap.add_argument("--cpu-sample-entries", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate"], default="url_like",
+    ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep"], default="url_like",
                     help="url_like = BASELINE configs[1] (the bench line the driver records); int_filter = configs[2]; "
-                         "shipdate = configs[3] (TPC-H SF100 l_shipdate range, one GPU's shard of the 8-way split per rank)")
+                         "shipdate = configs[3] (TPC-H SF100 l_shipdate range, one GPU's shard of the 8-way split per rank); "
+                         "clickbench_sweep = configs[4] (scan stage of the 43 ClickBench queries, bench_sweep.py)")
     return ap.parse_args()
 
 
@@ -485,6 +486,11 @@ def main():
         return
     if args.workload == "shipdate":
         run_shipdate(args, rank, world, local_rank)
+        return
+    if args.workload == "clickbench_sweep":
+        import bench_sweep
+
+        bench_sweep.main(args, rank, world, local_rank)
         return
 
     import numpy as np
