@@ -161,8 +161,46 @@ def cpu_baseline(sample_entries: int, threads: int, first_entry: int = 0, target
             "ms_per_pass": dt / reps * 1e3, "rows_per_pass": rows}
 
 
+def run_reference_shipdate(args):
+    """--impl reference --workload shipdate: the CPU port on the l_shipdate range (configs[3]), same JSON shape."""
+    import datetime as dt
+
+    import synth
+    from oracle import c_oracle as CO
+
+    threads = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    CO.lib(rebuild=True)
+    entries = [CO.CIntArray(synth.int_entry("l_shipdate", i, seed=synth.SEED_TPCH)) for i in range(args.cpu_sample_entries)]
+    d0 = dt.date(1970, 1, 1)
+    l1, l2 = (dt.date(1994, 1, 1) - d0).days, (dt.date(1995, 1, 1) - d0).days
+    for _ in range(max(1, args.warmup)):
+        CO.scan(entries, 1, b"", 5, l1, 2, l2, nthreads=threads)
+    t0 = time.perf_counter()
+    rows = 0
+    for _ in range(steps):
+        _m, r = CO.scan(entries, 1, b"", 5, l1, 2, l2, nthreads=threads)
+        rows += r
+    dt_s = time.perf_counter() - t0
+    val = rows / dt_s / 1e6
+    sample = (f"{args.cpu_sample_entries} entries x {ROWS_PER_ENTRY} rows per step (bounded sample of one GPU's 75 M-row shard); "
+              f"C port of the reference's CPU path, {threads} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC.replace("URL LIKE '%google%'", "l_shipdate range"), "value": val, "unit": "Mrows/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt_s / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "TPC-H SF100 lineitem l_shipdate range (configs[3])", "rows_per_step": rows // steps,
+                   "rows_per_entry": ROWS_PER_ENTRY},
+        "cpu_baseline": {"value": val, "unit": "Mrows/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mrows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
+        return
+    if args.workload == "shipdate":
+        run_reference_shipdate(args)
         return
     threads = os.cpu_count() or 1
     steps = max(1, args.steps)
