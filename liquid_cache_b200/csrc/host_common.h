@@ -219,6 +219,7 @@ int entry_to_bytes(lc_ctx* ctx, const Entry* e, uint8_t* out, uint64_t cap, uint
 int entry_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, Entry** out);
 // str_host.cc
 int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out);
+int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, const uint64_t* scopes, std::vector<Entry*>* out);
 
 // Selection prepared for a launch.
 struct SelIn {

@@ -237,6 +237,9 @@ struct StrEncIo {
 };
 // Enqueues the whole pipeline (dictionary -> keys -> compress -> offsets fit); `res` is valid once the stream drains.
 cudaError_t launch_str_encode(const StrEncIo& io, cudaStream_t s);
+// The same five stages over a list of batches (one work item per batch in device memory); see k_str_encode.cu.
+cudaError_t launch_str_encode_many(const StrEncIo* d_ios, uint32_t n_batches, uint32_t max_n, uint32_t* d_tables,
+                                   size_t table_words, cudaStream_t s);
 
 // ---- bit utilities -----------------------------------------------------------------------------
 // boolean_buffer_and_then: out[p] = left[p] & right[rank_left(p)]  (datafusion/src/utils.rs:62-236)

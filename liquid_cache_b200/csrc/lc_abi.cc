@@ -371,12 +371,20 @@ int lc_cache_insert_many(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, con
     LC_TRY(parse_arrow_input(schemas[i], arrays[i], &ins[i]));
     all_int = all_int && ins[i].kind == ArrowIn::K_INT;
   }
+  bool all_bytes = true;
+  for (uint64_t i = 0; i < n; ++i)
+    all_bytes = all_bytes && (ins[i].kind == ArrowIn::K_BYTES || ins[i].kind == ArrowIn::K_VIEW || ins[i].kind == ArrowIn::K_DICT);
   std::vector<Entry*> es;
   if (all_int) {
     // integer-like batches: one pass over the whole list (int_host.cc int_encode_many)
     LC_TRY(int_encode_many(ctx, ins, &es));
+  } else if (all_bytes) {
+    // byte-view batches: the five encode stages once over the whole list (str_host.cc str_encode_many)
+    std::vector<uint64_t> scopes(n);
+    for (uint64_t i = 0; i < n; ++i) scopes[i] = entry_ids[i] & ~0xFFFFull;
+    LC_TRY(str_encode_many(ctx, ins, hint, scopes.data(), &es));
   } else {
-    // byte views, floats, decimals: batch by batch for now; all or nothing like the batched pass
+    // floats, decimals, mixed lists: batch by batch; all or nothing like the batched passes
     for (uint64_t i = 0; i < n; ++i) {
       Entry* e = nullptr;
       ctx->scratch.reset();
