@@ -593,8 +593,8 @@ def main():
                                                       for i, nm in enumerate(names)) + f", total {tot / n_entries:.0f}", file=sys.stderr)
     # R = keys 2n + fingerprints 4U + candidate compressed bytes + offset residuals of the candidates' pairs
     #     (2 bytes typ.) ; W = selection words n/8   (SURVEY.md §8d "string predicate, fingerprint path")
-    #     + 8U: the bigram filters this build stores beside the fingerprints (read once, like them)
-    algo_bytes = 2 * rows_local + (4 + 8) * uniques + cand_bytes + 2 * 2 * cand + rows_local // 8
+    #     + 32U: the 256-bit trigram filters this build stores beside the fingerprints (read once, like them)
+    algo_bytes = 2 * rows_local + (4 + 32) * uniques + cand_bytes + 2 * 2 * cand + rows_local // 8
 
     k_start = torch.cuda.Event(enable_timing=True)
     k_stop = torch.cuda.Event(enable_timing=True)

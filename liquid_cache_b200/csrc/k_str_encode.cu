@@ -226,13 +226,18 @@ __device__ __forceinline__ void k_uniq_pass1_body(const StrEncIo& io, uint32_t b
     io.clen[u] = fsst_compress_value<false>(io.enc, p, len, nullptr);
     if (io.fps) {
       uint32_t bits = 0;
-      unsigned long long bl = 0;
+      unsigned long long bl[kBloomWords] = {0ull, 0ull, 0ull, 0ull};
       for (uint32_t b = 0; b < len; ++b) {
         bits |= 1u << (p[b] & 31u);
-        if (b + 1u < len) bl |= 1ull << bigram_bit(p[b], p[b + 1u]);
+        if (b + 2u < len) {
+          const uint32_t t = trigram_bit(p[b], p[b + 1u], p[b + 2u]);
+          bl[t >> 6] |= 1ull << (t & 63u);
+        }
       }
       io.fps[u] = bits;
-      io.blooms[u] = bl;
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(io.blooms + static_cast<size_t>(u) * kBloomWords);
+      dst[0] = make_ulonglong2(bl[0], bl[1]);
+      dst[1] = make_ulonglong2(bl[2], bl[3]);
     }
   }
   // length statistics: warp-reduce, one atomic per warp

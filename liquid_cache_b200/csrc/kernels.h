@@ -160,7 +160,7 @@ struct alignas(16) StrPredDesc {
   uint32_t needle_len;   // full needle (for LIKE: the inner pattern without the % signs)
   uint32_t needle_fp;    // fingerprint of the LIKE needle (fingerprint.rs:19-26)
   uint32_t pad;
-  unsigned long long needle_bloom;  // bigram bits of the LIKE needle (entry_layout.h bigram_bit); 0 for 1-byte needles
+  unsigned long long needle_bloom[4];  // trigram bits of the LIKE needle (entry_layout.h trigram_bit); all zero below 3 bytes
   const uint8_t* needle; // device: needle bytes padded to 4, then needle_len x u16 KMP failure links
   unsigned long long* prof;  // optional device counters {uniques, candidates, candidate bytes}; nullptr = off
 };
@@ -229,7 +229,7 @@ struct StrEncIo {
   uint32_t* offsets;         // U + 1
   unsigned long long* pkeys; // U PrefixKeys
   uint32_t* fps;             // U fingerprints (nullptr = not requested)
-  unsigned long long* blooms;// U bigram filters, built together with the fingerprints
+  unsigned long long* blooms;// U x kBloomWords trigram filters, built together with the fingerprints
   uint8_t* comp;             // compressed values, back to back
   uint8_t* resid;            // (U + 1) * offset_bytes
   const FsstEncTable* enc;

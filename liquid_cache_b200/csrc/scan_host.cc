@@ -209,13 +209,14 @@ static int prepare_str_pred(const lc_predicate* pred, StrLaunch* L) {
     LC_TRY(like_inner(pred->lit_bytes, pred->lit_len, &nd, &il));
     m = il;
     uint32_t fp = 0;
-    unsigned long long bl = 0;
     for (uint32_t i = 0; i < il; ++i) {
       fp |= 1u << (nd[i] & 31u);
-      if (i + 1 < il) bl |= 1ull << bigram_bit(nd[i], nd[i + 1]);
+      if (i + 2 < il) {
+        const uint32_t t = trigram_bit(nd[i], nd[i + 1], nd[i + 2]);
+        L->desc.needle_bloom[t >> 6] |= 1ull << (t & 63u);
+      }
     }
     L->desc.needle_fp = fp;
-    L->desc.needle_bloom = bl;
   }
   if (m > kMaxNeedle) {
     set_error("needle longer than %u bytes", kMaxNeedle);

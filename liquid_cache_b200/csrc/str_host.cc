@@ -291,7 +291,8 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   const uint64_t up_bytes = round_up(4ull * n, 256) * 2 + round_up(vbytes, 256);
   const uint64_t comp_cap = 2 * sum_len + 64;
   const uint64_t dev_need = round_up(pool_bytes + 64, 256) + up_bytes + round_up(4ull * cap, 256) +
-                            6 * round_up(4ull * (n + 1), 256) + round_up(2ull * n, 256) + 2 * round_up(8ull * (n + 1), 256) +
+                            6 * round_up(4ull * (n + 1), 256) + round_up(2ull * n, 256) + round_up(8ull * (n + 1), 256) +
+                            round_up(8ull * kBloomWords * (n + 1), 256) +
                             round_up(comp_cap, 256) + 4096;
   LC_TRY(sc.reserve(dev_need, up_bytes + 4096));
   uint8_t* h_up = sc.host(up_bytes);
@@ -305,7 +306,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   uint32_t* d_clen = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
   uint32_t* d_offsets = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
   uint32_t* d_fps = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
-  unsigned long long* d_blooms = reinterpret_cast<unsigned long long*>(sc.dev(8ull * (n + 1)));
+  unsigned long long* d_blooms = reinterpret_cast<unsigned long long*>(sc.dev(8ull * kBloomWords * (n + 1)));
   uint8_t* d_resid = sc.dev(4ull * (n + 1));
   uint16_t* d_keys = reinterpret_cast<uint16_t*>(sc.dev(2ull * n + 16));
   unsigned long long* d_pkeys = reinterpret_cast<unsigned long long*>(sc.dev(8ull * (n + 1)));
@@ -403,7 +404,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   o += round_up(2ull * n, 16);
   h.head_bytes = static_cast<uint32_t>(o);
   h.bloom_off = (build_fp && U) ? static_cast<uint32_t>(o) : 0;
-  if (h.bloom_off) o += round_up(8ull * U, 16);
+  if (h.bloom_off) o += round_up(8ull * kBloomWords * U, 16);
   h.fsst_off = static_cast<uint32_t>(o);
   h.fsst_bytes = static_cast<uint32_t>(co);
   o += round_up(co, 16) + 16;
@@ -435,7 +436,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   };
   if (spl) LC_CUDA_OK(d2d(h.shared_prefix_off, d_pool + row_off[first_valid], spl));
   if (build_fp) LC_CUDA_OK(d2d(h.fp_off, d_fps, 4ull * U));
-  if (h.bloom_off) LC_CUDA_OK(d2d(h.bloom_off, d_blooms, 8ull * U));
+  if (h.bloom_off) LC_CUDA_OK(d2d(h.bloom_off, d_blooms, 8ull * kBloomWords * U));
   LC_CUDA_OK(d2d(h.resid_off, d_resid, static_cast<uint64_t>(ob) * (U + 1)));
   LC_CUDA_OK(d2d(h.prefix_keys_off, d_pkeys, 8ull * U));
   if (h.has_nulls) LC_CUDA_OK(d2d(h.validity_off, d_up + 2 * off_len, (n + 7) / 8));
