@@ -571,7 +571,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       o.clen = take(4 * n1);
       o.offsets = take(4 * n1);
       o.fps = take(4 * n1);
-      o.blooms = take(8 * n1);
+      o.blooms = take(8ull * kBloomWords * n1);
       o.resid = take(4 * n1);
       o.keys = take(2ull * pl.n + 16);
       o.pkeys = take(8 * n1);
@@ -689,7 +689,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       o += round_up(2ull * n, 16);
       hd.head_bytes = static_cast<uint32_t>(o);
       hd.bloom_off = (build_fp && U) ? static_cast<uint32_t>(o) : 0;
-      if (hd.bloom_off) o += round_up(8ull * U, 16);
+      if (hd.bloom_off) o += round_up(8ull * kBloomWords * U, 16);
       hd.fsst_off = static_cast<uint32_t>(o);
       hd.fsst_bytes = static_cast<uint32_t>(co);
       o += round_up(co, 16) + 16;
@@ -723,7 +723,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       };
       if (spl) d2d(hd.shared_prefix_off, d + of.pool + pl.row_off[first_valid], spl);
       if (build_fp) d2d(hd.fp_off, d + of.fps, 4ull * U);
-      if (hd.bloom_off) d2d(hd.bloom_off, d + of.blooms, 8ull * U);
+      if (hd.bloom_off) d2d(hd.bloom_off, d + of.blooms, 8ull * kBloomWords * U);
       d2d(hd.resid_off, d + of.resid, static_cast<uint64_t>(ob) * (U + 1));
       d2d(hd.prefix_keys_off, d + of.pkeys, 8ull * U);
       if (hd.has_nulls) d2d(hd.validity_off, d + of.up + 2 * of.off_len, (n + 7) / 8);
