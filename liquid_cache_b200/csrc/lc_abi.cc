@@ -616,18 +616,6 @@ int lc_scan_selection(lc_scan* scan, uint64_t batch, uint8_t* out_bits) {
   return LC_OK;
 }
 
-static int scan_entries(lc_scan* scan, const lc_handle* handles, std::vector<Entry*>* es) {
-  es->resize(scan->n);
-  for (uint64_t i = 0; i < scan->n; ++i) {
-    (*es)[i] = entry_of(handles[i]);
-    if (!(*es)[i] || (*es)[i]->n != scan->rows[i]) {
-      set_error("lc_scan_read: handle %llu invalid or row count differs from the scan's", (unsigned long long)i);
-      return LC_ERR_INVALID;
-    }
-  }
-  return LC_OK;
-}
-
 // Only batches with surviving rows are read, as LiquidCacheReader::read_from_cache does
 // (liquid_cache_reader.rs:346-349 returns early when the selection is empty).
 static void scan_nonempty(lc_scan* scan, const std::vector<Entry*>& es, std::vector<Entry*>* es2,
@@ -648,10 +636,13 @@ static void scan_nonempty(lc_scan* scan, const std::vector<Entry*>& es, std::vec
 int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* out_schema,
                  struct ArrowArray* out_array) {
   if (!scan || !handles || !out_schema || !out_array) return LC_ERR_INVALID;
-  std::vector<Entry*> es;
-  LC_TRY(scan_entries(scan, handles, &es));
   lc_ctx* ctx = scan->ctx;
   Guard g(ctx);
+  // the handle list of a column is validated once per scan (hash of the array), not once per read: 12 k pointer chases
+  // per call were ~0.05-0.1 ms of every get of the bench step
+  Entry* const* esp = nullptr;
+  LC_TRY(scan_entries_cached(scan, handles, &esp));
+  const std::vector<Entry*> es(esp, esp + scan->n);
   LC_TRY(scan_fetch_counts(scan));
   ctx->scratch.reset();
   std::vector<Entry*> es2;
@@ -665,15 +656,15 @@ int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* ou
 int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap, void* d_offsets,
                         void* d_validity, uint64_t* out_rows, uint64_t* out_value_bytes, uint64_t* out_null_count) {
   if (!scan || !handles) return LC_ERR_INVALID;
-  std::vector<Entry*> es;
-  LC_TRY(scan_entries(scan, handles, &es));
   lc_ctx* ctx = scan->ctx;
   Guard g(ctx);
+  Entry* const* esp = nullptr;
+  LC_TRY(scan_entries_cached(scan, handles, &esp));
   LC_TRY(scan_fetch_counts(scan));
   ctx->scratch.reset();
   DevSel ds{scan->d_sel, scan->word_off.data(), scan->counts.data(), scan->all_rows};
   DeviceOut dout{d_values, values_cap, d_offsets, d_validity, out_rows, out_value_bytes, out_null_count};
-  return to_arrow_batch(ctx, es.data(), scan->n, nullptr, &ds, nullptr, nullptr, &dout);
+  return to_arrow_batch(ctx, esp, scan->n, nullptr, &ds, nullptr, nullptr, &dout);
 }
 
 void lc_scan_end(lc_scan* scan) {
