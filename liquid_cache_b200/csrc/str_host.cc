@@ -489,19 +489,42 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       set_error("batch %llu: %s", (unsigned long long)i, errs[i].c_str());
       return rcs[i];
     }
+  // Symbol tables: every column chunk without one is trained on ITS first batch of this list (what the one-batch path would
+  // have done in the same order). Training is ~2 ms of host work per chunk (measured: 1 695 URL values), so the chunks are
+  // trained side by side on the host pool; the tables are uploaded afterwards with one synchronisation.
   std::vector<std::shared_ptr<FsstCodec>> codecs(nb_all);
-  for (uint64_t i = 0; i < nb_all; ++i) {
-    auto it = ctx->codecs.find(scopes[i]);
-    if (it != ctx->codecs.end()) {
-      codecs[i] = it->second;
-      continue;
-    }
-    const RowPlan& pl = plans[i];
-    DictBuilder dict(pl.n < 1024 ? 1024 : pl.n / 2);
-    for (uint32_t r = 0; r < pl.n; ++r)
-      if (pl.row_is_valid(r)) dict.add(pl.row_len[r] ? pl.row_ptr(r) : reinterpret_cast<const uint8_t*>(""), pl.row_len[r]);
-    LC_TRY(get_codec(ctx, scopes[i], dict, &codecs[i]));
+  std::vector<uint64_t> train_first;  // index of the first batch of every scope that needs a table
+  {
+    std::unordered_map<uint64_t, uint64_t> seen;
+    for (uint64_t i = 0; i < nb_all; ++i)
+      if (!ctx->codecs.count(scopes[i]) && seen.emplace(scopes[i], i).second) train_first.push_back(i);
   }
+  std::vector<std::shared_ptr<FsstCodec>> trained(train_first.size());
+  parallel_for(train_first.size(), 1, [&](uint64_t b, uint64_t e) {
+    for (uint64_t t = b; t < e; ++t) {
+      const RowPlan& pl = plans[train_first[t]];
+      DictBuilder dict(pl.n < 1024 ? 1024 : pl.n / 2);
+      for (uint32_t r = 0; r < pl.n; ++r)
+        if (pl.row_is_valid(r)) dict.add(pl.row_len[r] ? pl.row_ptr(r) : reinterpret_cast<const uint8_t*>(""), pl.row_len[r]);
+      auto codec = std::make_shared<FsstCodec>();
+      fsst_train(dict.uptr.data(), dict.ulen.data(), dict.uptr.size(), codec.get());
+      trained[t] = codec;
+    }
+  });
+  for (uint64_t t = 0; t < train_first.size(); ++t) {
+    std::shared_ptr<FsstCodec>& codec = trained[t];
+    if (cudaMalloc(reinterpret_cast<void**>(&codec->d_dec), sizeof(FsstTable)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&codec->d_enc), sizeof(FsstEncTable)) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc for FSST tables failed");
+      return LC_ERR_OOM;
+    }
+    LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!train_first.empty()) LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // the sources are pageable host memory
+  for (uint64_t t = 0; t < train_first.size(); ++t) ctx->codecs[scopes[train_first[t]]] = trained[t];
+  for (uint64_t i = 0; i < nb_all; ++i) codecs[i] = ctx->codecs[scopes[i]];
   const bool build_fp = (hint == LC_HINT_SUBSTRING_SEARCH);
   cudaStream_t s = ctx->stream;
   Scratch& sc = ctx->scratch;
