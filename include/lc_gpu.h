@@ -197,13 +197,19 @@ int lc_arrow_format(lc_ctx* ctx, lc_handle h, char* buf, size_t buf_len);
 /* LiquidArray::to_bytes (liquid_array/mod.rs:116-121): the entry in the reference's serialized form, LQDA
  * (liquid_array/ipc.rs:158-250; primitive_array.rs:603-654, float_array.rs:393-520, decimal_array.rs:180-218,
  * raw/bit_pack_array.rs:181-252), for Integer / Float / Decimal entries — what the reference writes when it spills an
- * entry to disk. out == NULL asks for the size. Byte-view entries: LC_ERR_UNSUPPORTED_TYPE
- * (byte_view_array/serialization.rs is not built). */
+ * entry to disk; byte-view entries in the layout of byte_view_array/serialization.rs:87-220. out == NULL asks for the size. */
 int lc_to_bytes(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 /* ipc::read_from_bytes (liquid_array/ipc.rs:252-283) for the same three logical types: an LQDA image becomes an
  * HBM-resident entry (the Arrow type follows from the physical type id / the decimal header). The image is checked
  * (section bounds, bit width, patch indices) and refused with LC_ERR_INVALID instead of panicking. */
 int lc_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, lc_handle* out);
+/* Byte-view images (byte_view_array/serialization.rs:87-325) need the symbol table of their column chunk, which the
+ * reference passes in LiquidIPCContext (ipc.rs:238-249): the table registered under `compressor_scope` is used. */
+int lc_from_bytes_scoped(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, uint64_t compressor_scope, lc_handle* out);
+/* save_symbol_table / load_symbol_table (raw/fsst_buffer.rs:854-932): count u8, symbol lengths, symbols as u64 LE.
+ * load registers the table under a scope that has none yet. */
+int lc_ctx_save_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8_t* bytes, uint64_t len);
 
 /* LiquidArray::to_arrow_array (sel_bits == NULL) / LiquidArray::filter(&BooleanBuffer)
  * (primitive_array.rs:350-374, byte_view_array/mod.rs:266-290,421-424). The result has the

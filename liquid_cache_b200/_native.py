@@ -113,6 +113,9 @@ def lib() -> C.CDLL:
     l.lc_arrow_format.argtypes = [vp, u64, C.c_char_p, C.c_size_t]
     l.lc_to_bytes.argtypes = [vp, u64, vp, u64, u64p]
     l.lc_from_bytes.argtypes = [vp, vp, u64, u64p]
+    l.lc_from_bytes_scoped.argtypes = [vp, vp, u64, u64, u64p]
+    l.lc_ctx_save_symbol_table.argtypes = [vp, u64, vp, u64, u64p]
+    l.lc_ctx_load_symbol_table.argtypes = [vp, u64, vp, u64]
     l.lc_to_arrow.argtypes = [vp, u64, vp, u64, vp, vp]
     l.lc_eval_predicate.argtypes = [vp, u64, C.POINTER(Predicate), vp, u64, vp, vp, u64p, u64p]
     l.lc_mask_bytes.argtypes = [u64]

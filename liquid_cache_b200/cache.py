@@ -419,12 +419,29 @@ class LiquidCache:
         N.check(N.lib().lc_encode(self._ctx, _ptr(c_sch), _ptr(c_arr), nh, compressor_scope, C.byref(h)))
         return GpuLiquidArray(self, int(h.value))
 
-    def read_from_bytes(self, data: bytes) -> GpuLiquidArray:
-        """`ipc::read_from_bytes` (liquid_array/ipc.rs:252-283): an LQDA image becomes an HBM-resident entry."""
+    def read_from_bytes(self, data: bytes, compressor_scope: Optional[int] = None) -> GpuLiquidArray:
+        """`ipc::read_from_bytes` (liquid_array/ipc.rs:252-283): an LQDA image becomes an HBM-resident entry. Byte-view
+        images need the scope whose symbol table they were compressed with (LiquidIPCContext)."""
         buf = np.frombuffer(data, dtype=np.uint8)
         h = C.c_uint64(0)
-        N.check(N.lib().lc_from_bytes(self._ctx, buf.ctypes.data, len(buf), C.byref(h)))
+        if compressor_scope is None:
+            N.check(N.lib().lc_from_bytes(self._ctx, buf.ctypes.data, len(buf), C.byref(h)))
+        else:
+            N.check(N.lib().lc_from_bytes_scoped(self._ctx, buf.ctypes.data, len(buf), int(compressor_scope), C.byref(h)))
         return GpuLiquidArray(self, int(h.value))
+
+    def save_symbol_table(self, compressor_scope: int) -> bytes:
+        """`save_symbol_table` (raw/fsst_buffer.rs:854-883) of the scope's FSST table."""
+        nb = C.c_uint64(0)
+        N.check(N.lib().lc_ctx_save_symbol_table(self._ctx, int(compressor_scope), None, 0, C.byref(nb)))
+        buf = np.zeros(int(nb.value), dtype=np.uint8)
+        N.check(N.lib().lc_ctx_save_symbol_table(self._ctx, int(compressor_scope), buf.ctypes.data, nb.value, C.byref(nb)))
+        return buf.tobytes()
+
+    def load_symbol_table(self, compressor_scope: int, data: bytes) -> None:
+        """`load_symbol_table` (raw/fsst_buffer.rs:886-932): registers the table under a scope that has none."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        N.check(N.lib().lc_ctx_load_symbol_table(self._ctx, int(compressor_scope), buf.ctypes.data, len(buf)))
 
     def _handle(self, entry_id) -> int:
         ids = (C.c_uint64 * 1)(int(entry_id))

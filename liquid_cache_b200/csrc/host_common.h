@@ -97,6 +97,7 @@ struct FsstCodec {
 };
 // fsst_host.cc
 void fsst_train(const uint8_t* const* strs, const uint32_t* lens, size_t n, FsstCodec* out);
+void fsst_from_symbols(const uint64_t* vals, const uint8_t* lens, size_t n, FsstCodec* out);
 size_t fsst_compress_host(const FsstCodec& c, const uint8_t* in, size_t len, uint8_t* out);
 size_t fsst_decompress_host(const FsstTable& t, const uint8_t* in, size_t len, uint8_t* out, size_t cap);
 
@@ -216,7 +217,10 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out);
 int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<Entry*>* out);  // K_INT batches only
 // ipc_host.cc: LQDA (the reference's serialized form) of integer-shaped entries
 int entry_to_bytes(lc_ctx* ctx, const Entry* e, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
-int entry_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, Entry** out);
+int entry_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, const std::shared_ptr<FsstCodec>& codec, Entry** out);
+int symbol_table_to_bytes(const FsstCodec& c, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+int symbol_table_from_bytes(const uint8_t* bytes, uint64_t len, FsstCodec* out);
+int register_codec(lc_ctx* ctx, uint64_t scope, const std::shared_ptr<FsstCodec>& codec);  // str_host.cc: device copies + ctx->codecs
 // str_host.cc
 int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out);
 int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, const uint64_t* scopes, std::vector<Entry*>* out);

@@ -213,9 +213,45 @@ int lc_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, lc_handle* ou
   }
   Guard g(ctx);
   Entry* e = nullptr;
-  LC_TRY(entry_from_bytes(ctx, bytes, len, &e));
+  LC_TRY(entry_from_bytes(ctx, bytes, len, nullptr, &e));
   *out = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
   return LC_OK;
+}
+
+int lc_from_bytes_scoped(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, uint64_t compressor_scope, lc_handle* out) {
+  if (!ctx || !bytes || !out) {
+    set_error("lc_from_bytes_scoped: NULL argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  auto it = ctx->codecs.find(compressor_scope);
+  Entry* e = nullptr;
+  LC_TRY(entry_from_bytes(ctx, bytes, len, it == ctx->codecs.end() ? nullptr : it->second, &e));
+  *out = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
+  return LC_OK;
+}
+
+int lc_ctx_save_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
+  if (!ctx || !out_bytes) return LC_ERR_INVALID;
+  Guard g(ctx);
+  auto it = ctx->codecs.find(compressor_scope);
+  if (it == ctx->codecs.end()) {
+    set_error("no symbol table for scope %llu", (unsigned long long)compressor_scope);
+    return LC_ERR_NOT_FOUND;
+  }
+  return symbol_table_to_bytes(*it->second, out, cap, out_bytes);
+}
+
+int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8_t* bytes, uint64_t len) {
+  if (!ctx || !bytes) return LC_ERR_INVALID;
+  Guard g(ctx);
+  if (ctx->codecs.count(compressor_scope)) {
+    set_error("scope %llu already has a symbol table", (unsigned long long)compressor_scope);
+    return LC_ERR_INVALID;
+  }
+  auto codec = std::make_shared<FsstCodec>();
+  LC_TRY(symbol_table_from_bytes(bytes, len, codec.get()));
+  return register_codec(ctx, compressor_scope, codec);
 }
 
 int lc_arrow_format(lc_ctx*, lc_handle h, char* buf, size_t buf_len) {

@@ -115,6 +115,21 @@ static int get_codec(lc_ctx* ctx, uint64_t scope, const DictBuilder& d, std::sha
   return LC_OK;
 }
 
+// A codec that came from a stored symbol table (lc_ctx_load_symbol_table): device copies, then the scope's entry.
+int register_codec(lc_ctx* ctx, uint64_t scope, const std::shared_ptr<FsstCodec>& codec) {
+  if (cudaMalloc(reinterpret_cast<void**>(&codec->d_dec), sizeof(FsstTable)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&codec->d_enc), sizeof(FsstEncTable)) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc for FSST tables failed");
+    return LC_ERR_OOM;
+  }
+  LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->stream));
+  LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->codecs[scope] = codec;
+  return LC_OK;
+}
+
 // A contiguous piece of caller memory that becomes part of the device byte pool.
 struct PoolSeg {
   const uint8_t* p;
