@@ -211,6 +211,26 @@ int lc_from_bytes_scoped(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, uint64
 int lc_ctx_save_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8_t* bytes, uint64_t len);
 
+/* ---- squeezed integer entries --------------------------------------------------------------------------------------
+ * LiquidArray::squeeze (liquid_array/mod.rs, primitive_array.rs:389-499): when HBM is the scarce tier an integer entry is
+ * replaced by its half-width codes (LiquidPrimitiveClampedArray / LiquidPrimitiveQuantizedArray,
+ * hybrid_primitive_array.rs) while the full LQDA image moves behind the caller's SqueezeIoHandler (mod.rs:282-…): host
+ * memory or disk. lc_to_arrow / lc_eval_predicate on the squeezed handle answer from the codes when those decide and read
+ * the image back (one `read` call for the whole range, like hydrate_full_arrow) when they cannot; the result is always
+ * the full entry's. The batched and scan calls take full entries only. */
+typedef int (*lc_backing_read)(void* user, uint64_t offset, uint64_t len, uint8_t* dst); /* 0 = ok; SqueezeIoHandler::read */
+typedef enum lc_squeeze_policy { LC_SQUEEZE_CLAMP = 0, LC_SQUEEZE_QUANTIZE = 1 } lc_squeeze_policy; /* IntegerSqueezePolicy */
+/* Returns the pair of LiquidArray::squeeze: the full bytes (written to bytes_out, *out_bytes long) and the squeezed entry.
+ * *out_squeezed == 0 and *out_bytes == 0 is the reference's None: no hint, a Date32 / Timestamp column (those squeeze to a
+ * date component, squeezed_date32_array.rs — not built), an all-null column or one narrower than 8 bits, or a logical type
+ * other than Integer. bytes_out == NULL asks for the size only. `h` stays valid; the caller releases it once the bytes
+ * are stored (the reference swaps the cache entry). `read` is called under the context lock, on the calling thread. */
+int lc_squeeze(lc_ctx* ctx, lc_handle h, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
+               uint64_t cap, uint64_t* out_bytes, lc_handle* out_squeezed);
+/* out[0] = 0 for a full entry, else policy + 1; out[1] = bit width of the codes; out[2] = bucket width (quantize);
+ * out[3] = length of the backing image; out[4], out[5] = backing reads / calls answered from the codes, context-wide. */
+int lc_squeezed_info(lc_ctx* ctx, lc_handle h, uint64_t out[6]);
+
 /* LiquidArray::to_arrow_array (sel_bits == NULL) / LiquidArray::filter(&BooleanBuffer)
  * (primitive_array.rs:350-374, byte_view_array/mod.rs:266-290,421-424). The result has the
  * ORIGINAL arrow type, length popcount(sel), host buffers owned through `release`. */

@@ -131,6 +131,37 @@ class GpuLiquidArray:
         N.check(N.lib().lc_to_bytes(self._cache._ctx, self._h, buf.ctypes.data, nb.value, C.byref(nb)))
         return buf[: int(nb.value)].tobytes()
 
+    def squeeze(self, io, expression_hint, policy: str = "clamp"):
+        """`LiquidArray::squeeze(io, expression_hint)` (liquid_array/primitive_array.rs:389-499) under
+        `IntegerSqueezePolicy::{Clamp, Quantize}`: returns `(squeezed array, full LQDA bytes)` or None when the
+        reference would not squeeze. `io` mirrors `SqueezeIoHandler`: `io.read((start, end)) -> bytes` is called when the
+        half-width codes cannot answer; the caller stores the returned bytes where `io` will find them."""
+        pol = {"clamp": N.SQUEEZE_CLAMP, "quantize": N.SQUEEZE_QUANTIZE}[policy]
+        hint = N.HINT_NONE if expression_hint is None else (
+            N.HINT_SUBSTRING_SEARCH if expression_hint == CacheExpression.SubstringSearch else N.HINT_PREDICATE)
+        nb, sq = C.c_uint64(0), C.c_uint64(0)
+        ctx = self._cache._ctx
+        N.check(N.lib().lc_squeeze(ctx, self._h, pol, hint, None, None, None, 0, C.byref(nb), C.byref(sq)))
+        if nb.value == 0:
+            return None
+
+        def _read(_user, offset, length, dst):
+            try:
+                data = io.read((int(offset), int(offset + length)))
+                if len(data) != length:
+                    return 2
+                C.memmove(dst, data, length)
+                return 0
+            except Exception:  # the C side reports the failed read
+                return 1
+
+        cb = N.BACKING_READ(_read)
+        buf = np.zeros(int(nb.value), dtype=np.uint8)
+        N.check(N.lib().lc_squeeze(ctx, self._h, pol, hint, cb, None, buf.ctypes.data, nb.value, C.byref(nb), C.byref(sq)))
+        squeezed = GpuSqueezedArray(self._cache, int(sq.value))
+        squeezed._keepalive = (cb, io)  # the C side calls back for as long as the entry lives
+        return squeezed, buf[: int(nb.value)].tobytes()
+
     def fsst_table(self) -> bytes:
         """The column chunk's FSST symbol table as the kernels see it (lc::FsstTable: 256 x u64 symbols, 256 x u8 lengths)."""
         nb = C.c_uint64(0)
@@ -182,6 +213,32 @@ class GpuLiquidArray:
             )
         )
         return _mask_to_boolean_array(vals, valid, int(out_len.value), int(out_nulls.value))
+
+
+class GpuSqueezedArray(GpuLiquidArray):
+    """`LiquidSqueezedArray` (liquid_array/mod.rs:209-263) for the two integer forms: `to_arrow_array`, `filter` and
+    `try_eval_predicate` keep their meaning, reading the backing bytes through `io` when the codes cannot answer."""
+
+    def _info(self):
+        out = (C.c_uint64 * 6)()
+        N.check(N.lib().lc_squeezed_info(self._cache._ctx, self._h, out))
+        return [int(x) for x in out]
+
+    def policy(self) -> str:
+        return {1: "clamp", 2: "quantize"}[self._info()[0]]
+
+    def bit_width(self) -> int:
+        return self._info()[1]
+
+    def bucket_width(self) -> int:
+        return self._info()[2]
+
+    def disk_backing(self) -> int:
+        """`SqueezedBacking::Liquid(len)`: bytes of the image behind `io`."""
+        return self._info()[3]
+
+    def to_bytes(self) -> bytes:
+        raise N.UnsupportedType("a squeezed array has no serialized form; its full image is the backing")
 
 
 _FORMAT_TO_TYPE = {

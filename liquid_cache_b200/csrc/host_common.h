@@ -119,6 +119,13 @@ struct Entry {
   StrHeader sh;
   std::vector<uint8_t> shared_prefix;  // byte-view: host copy (predicate planning)
   std::shared_ptr<FsstCodec> codec;    // byte-view
+  // squeezed integers (LiquidPrimitiveClampedArray / LiquidPrimitiveQuantizedArray): the blob holds half-width codes,
+  // the full LQDA image sits behind the caller's read function
+  int32_t squeeze_kind = 0;            // 0 = a full entry, else lc_squeeze_policy + 1
+  uint64_t bucket_width = 0;           // quantize
+  lc_backing_read backing_read = nullptr;
+  void* backing_user = nullptr;
+  uint64_t backing_len = 0;            // disk_range = 0..backing_len
 };
 
 // integer-shaped blobs (IntHeader + FastLanes chunks): integers, ALP floats, u64 decimals
@@ -146,6 +153,8 @@ struct lc_ctx {
   uint64_t n_entries = 0;
   uint64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   uint64_t epoch = 0;            // bumped whenever an entry is released (invalidates cached entry lists)
+  bool squeeze_internal = false; // squeeze_host.cc is driving the batch functions (they refuse squeezed entries otherwise)
+  uint64_t squeeze_reads = 0, squeeze_saved = 0;  // backing reads / calls answered from the half-width codes
   uint8_t* d_needle = nullptr;   // small device buffer for predicate needles
   cudaStream_t copy_stream = nullptr;  // results of chunk c travel to the host while chunk c+1 is computed
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -261,6 +270,12 @@ struct DeviceOut {             // caller-owned device buffers (lc_scan_read_devi
 int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t* const* sel_bits,
                    const DevSel* dev_sel, ArrowSchema* out_schema, ArrowArray* out_array,
                    const DeviceOut* dev_out = nullptr);
+
+// squeeze_host.cc
+int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
+                  uint64_t cap, uint64_t* out_bytes, Entry** out);
+int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, const uint8_t* sel_bits, const PredOut& out);
+int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSchema* out_schema, ArrowArray* out_array);
 
 int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred, uint32_t* d_sel_base,
                  const uint64_t* d_word_off, bool all_rows, uint32_t* d_counts);

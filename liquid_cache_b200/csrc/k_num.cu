@@ -449,6 +449,40 @@ __global__ void __launch_bounds__(256) k_narrow_u64(const unsigned long long* __
   }
 }
 
+// Squeeze (LiquidPrimitiveArray::squeeze, liquid_array/primitive_array.rs:419-496): the decoded values of a full entry
+// become `reference + code`, code = the offset clamped at the sentinel (Clamp, :427-438) or its bucket index
+// (Quantize, :472-481), ready for k_int_pack at the halved width. In place, one value per thread, wrapping arithmetic on
+// the unsigned twin like the reference's add_wrapping / sub_wrapping.
+template <typename U>
+__global__ void __launch_bounds__(256) k_squeeze_map(U* __restrict__ vals, uint32_t n, U ref, uint32_t quantize, unsigned long long limit,
+                                                     unsigned long long bucket_width) {
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+    const unsigned long long off = static_cast<unsigned long long>(static_cast<U>(vals[i] - ref));
+    unsigned long long code;
+    if (quantize) {
+      code = off / bucket_width;
+      if (code > limit) code = limit;  // limit = bucket_count - 1
+    } else {
+      code = off >= limit ? limit : off;  // limit = sentinel
+    }
+    vals[i] = static_cast<U>(ref + static_cast<U>(code));
+  }
+}
+
+cudaError_t launch_squeeze_map(void* d_vals, uint32_t n, uint32_t tbits, unsigned long long ref, uint32_t quantize,
+                               unsigned long long limit, unsigned long long bucket_width, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  uint32_t grid = (n + 255u) / 256u;
+  if (grid > 1184u) grid = 1184u;
+  switch (tbits) {
+    case 8: k_squeeze_map<uint8_t><<<grid, 256, 0, s>>>(static_cast<uint8_t*>(d_vals), n, static_cast<uint8_t>(ref), quantize, limit, bucket_width); break;
+    case 16: k_squeeze_map<uint16_t><<<grid, 256, 0, s>>>(static_cast<uint16_t*>(d_vals), n, static_cast<uint16_t>(ref), quantize, limit, bucket_width); break;
+    case 32: k_squeeze_map<uint32_t><<<grid, 256, 0, s>>>(static_cast<uint32_t*>(d_vals), n, static_cast<uint32_t>(ref), quantize, limit, bucket_width); break;
+    default: k_squeeze_map<unsigned long long><<<grid, 256, 0, s>>>(static_cast<unsigned long long*>(d_vals), n, ref, quantize, limit, bucket_width); break;
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_widen_u32(const uint32_t* d_in, uint32_t n, unsigned long long* d_out, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   uint32_t grid = (n + 255u) / 256u;

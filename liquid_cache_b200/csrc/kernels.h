@@ -137,6 +137,10 @@ cudaError_t launch_dec_narrow(const void* d_in, const uint32_t* d_validity, uint
 cudaError_t launch_dec_widen(const unsigned long long* d_in, uint64_t n, uint32_t width_bytes, void* d_out, cudaStream_t s);
 
 // LQDA patch indices: u32 in the entry, u64 in the file; narrow raises *flag when an index is >= limit.
+// squeeze: decoded values -> reference + (clamped offset | bucket index), in place (quantize: limit = bucket_count - 1,
+// else limit = sentinel)
+cudaError_t launch_squeeze_map(void* d_vals, uint32_t n, uint32_t tbits, unsigned long long ref, uint32_t quantize,
+                               unsigned long long limit, unsigned long long bucket_width, cudaStream_t s);
 cudaError_t launch_widen_u32(const uint32_t* d_in, uint32_t n, unsigned long long* d_out, cudaStream_t s);
 cudaError_t launch_narrow_u64(const unsigned long long* d_in, uint32_t n, unsigned long long limit, uint32_t* d_out, uint32_t* d_flag,
                               cudaStream_t s);

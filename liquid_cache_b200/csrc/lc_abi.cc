@@ -202,6 +202,10 @@ int lc_to_bytes(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* 
     set_error("lc_to_bytes: bad argument");
     return LC_ERR_INVALID;
   }
+  if (e->squeeze_kind) {
+    set_error("lc_to_bytes: a squeezed entry has no serialized form (its full image is the backing)");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
   Guard g(ctx);
   return entry_to_bytes(ctx, e, out, cap, out_bytes);
 }
@@ -289,8 +293,47 @@ int lc_to_arrow(lc_ctx* ctx, lc_handle h, const uint8_t* sel_bits, uint64_t sel_
     set_error("selection has %llu bits, entry has %u rows", (unsigned long long)sel_len, e->n);
     return LC_ERR_INVALID;
   }
+  if (e->squeeze_kind) {
+    if (!ctx || !out_schema || !out_array) {
+      set_error("lc_to_arrow: bad argument");
+      return LC_ERR_INVALID;
+    }
+    Guard g(ctx);
+    return squeezed_to_arrow(ctx, e, sel_bits, out_schema, out_array);
+  }
   const uint8_t* sels[1] = {sel_bits};
   return lc_to_arrow_many(ctx, &h, 1, sel_bits ? sels : nullptr, out_schema, out_array);
+}
+
+int lc_squeeze(lc_ctx* ctx, lc_handle h, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
+               uint64_t cap, uint64_t* out_bytes, lc_handle* out_squeezed) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out_bytes || !out_squeezed) {
+    set_error("lc_squeeze: bad argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  Entry* sq = nullptr;
+  *out_squeezed = 0;
+  LC_TRY(squeeze_entry(ctx, e, policy, hint, read, user, bytes_out, cap, out_bytes, &sq));
+  *out_squeezed = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(sq));
+  return LC_OK;
+}
+
+int lc_squeezed_info(lc_ctx* ctx, lc_handle h, uint64_t out[6]) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out) {
+    set_error("lc_squeezed_info: bad argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  out[0] = static_cast<uint64_t>(e->squeeze_kind);
+  out[1] = e->liquid_type == LC_LIQUID_INTEGER ? e->ih.bit_width : 0;
+  out[2] = e->bucket_width;
+  out[3] = e->backing_len;
+  out[4] = ctx->squeeze_reads;
+  out[5] = ctx->squeeze_saved;
+  return LC_OK;
 }
 
 int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const lc_predicate* pred,
@@ -325,6 +368,15 @@ int lc_eval_predicate(lc_ctx* ctx, lc_handle h, const lc_predicate* pred, const 
   }
   const uint8_t* sels[1] = {sel_bits};
   const uint64_t off0 = 0;
+  if (e->squeeze_kind) {
+    if (!ctx || !pred || !out_values) {
+      set_error("lc_eval_predicate: NULL argument");
+      return LC_ERR_INVALID;
+    }
+    Guard g(ctx);
+    PredOut po{out_values, out_validity, &off0, out_len, out_null_count, nullptr};
+    return squeezed_eval_predicate(ctx, e, pred, sel_bits, po);
+  }
   return lc_eval_predicate_many(ctx, &h, 1, pred, sel_bits ? sels : nullptr, out_values, out_validity, &off0, out_len,
                                 out_null_count, nullptr);
 }

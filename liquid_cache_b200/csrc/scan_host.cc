@@ -302,6 +302,10 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
   const Entry* proto = entries[0];
   for (uint64_t i = 0; i < n; ++i) {
     const Entry* e = entries[i];
+    if (e->squeeze_kind && !ctx->squeeze_internal) {
+      set_error("entry %llu of the list is squeezed: squeezed entries answer through lc_to_arrow / lc_eval_predicate", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
     (*nl.rows)[i] = e->n;
     if (e->liquid_type != proto->liquid_type) nl.same_liquid_type = false;
     if (e->arrow_format != proto->arrow_format || e->dict_value_format != proto->dict_value_format) nl.same_arrow_type = false;

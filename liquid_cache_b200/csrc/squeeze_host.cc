@@ -1,0 +1,379 @@
+// squeeze_host.cc — squeezed integer entries: half-width codes in HBM, the full LQDA image behind the caller's read
+// function (host memory or disk, the caller's choice).
+// Reference: LiquidPrimitiveArray::squeeze (/root/reference/src/core/src/liquid_array/primitive_array.rs:389-499),
+// LiquidPrimitiveClampedArray / LiquidPrimitiveQuantizedArray (liquid_array/hybrid_primitive_array.rs:72-790),
+// LiquidSqueezedArray (liquid_array/mod.rs:209-263), SqueezeIoHandler (mod.rs:282-…).
+//
+// A squeezed entry is an ordinary integer blob (IntHeader + FastLanes chunks) whose packed words are the codes at
+// bit_width / 2 and whose reference is the full entry's: decoding it gives `reference + code`. Both policies then reduce
+// to the integer scan kernels that exist already:
+//   Clamp     code = min(offset, sentinel). `reference + code` IS the value below the sentinel, and a sentinel row stands
+//             for "some value >= reference + sentinel": when the literal sits below that bound (the reference's
+//             resolves_on_sentinel) the plain comparison of `reference + code` with the literal gives exactly the constants
+//             of hybrid_primitive_array.rs:232-240; otherwise a selected sentinel row makes the call read the backing.
+//   Quantize  code = offset / bucket_width. b < q / b > q decide, b == q decides only at a bucket edge (:566-598): the same
+//             operator against `reference + q` is the answer whenever no selected row sits in bucket q.
+// "Is there a selected, valid row with code c" is one more run of the scan kernel (`= reference + c`, true count).
+// When the codes cannot decide, the image is read back through the caller's function, becomes a temporary full entry
+// (entry_from_bytes) and the call runs on that — what hydrate_full_arrow + arrow's kernels do in the reference.
+#include <vector>
+
+#include "host_common.h"
+
+namespace lc {
+
+namespace {
+
+struct SqueezeScope {  // lets the batch functions accept a squeezed entry while this file drives them
+  lc_ctx* ctx;
+  bool prev;
+  explicit SqueezeScope(lc_ctx* c) : ctx(c), prev(c->squeeze_internal) { c->squeeze_internal = true; }
+  ~SqueezeScope() { ctx->squeeze_internal = prev; }
+};
+
+__int128 reference_of(const Entry* e) {
+  const uint32_t tbits = e->ih.tbits;
+  if (!e->ih.is_signed) return static_cast<__int128>(e->ih.reference);
+  const uint64_t sign = 1ull << (tbits - 1);
+  const uint64_t raw = e->ih.reference;  // zero-extended raw bits
+  return static_cast<__int128>(static_cast<int64_t>((raw ^ sign) - sign));
+}
+
+// T::Native::from_i64 / from_u64 (hybrid_primitive_array.rs:167-184): the literal as a value of the column's type
+bool literal_of(const Entry* e, const lc_predicate* pred, __int128* k) {
+  __int128 v;
+  if (pred->lit_kind == LC_LIT_I64) v = pred->lit_i64;
+  else if (pred->lit_kind == LC_LIT_U64) v = static_cast<__int128>(pred->lit_u64);
+  else return false;
+  const uint32_t tbits = e->ih.tbits;
+  const __int128 one = 1;
+  const __int128 lo = e->ih.is_signed ? -(one << (tbits - 1)) : 0;
+  const __int128 hi = e->ih.is_signed ? (one << (tbits - 1)) - 1 : (one << tbits) - 1;
+  if (v < lo || v > hi) return false;
+  *k = v;
+  return true;
+}
+
+lc_predicate int_predicate(const Entry* e, int32_t op, __int128 lit) {
+  lc_predicate p{};
+  p.op = op;
+  if (e->ih.is_signed) {
+    p.lit_kind = LC_LIT_I64;
+    p.lit_i64 = static_cast<int64_t>(lit);
+  } else {
+    p.lit_kind = LC_LIT_U64;
+    p.lit_u64 = static_cast<uint64_t>(lit);
+  }
+  return p;
+}
+
+// selected, valid rows of `sq` whose decoded value equals `value`
+int count_equal(lc_ctx* ctx, Entry* sq, __int128 value, const uint8_t* sel_bits, uint64_t* count) {
+  const lc_predicate p = int_predicate(sq, LC_OP_EQ, value);
+  std::vector<uint8_t> vals(round_up((static_cast<uint64_t>(sq->n) + 7) / 8, 16) + 16);
+  uint64_t len = 0, nulls = 0, trues = 0;
+  const uint64_t off0 = 0;
+  PredOut po{vals.data(), nullptr, &off0, &len, &nulls, &trues};
+  const uint8_t* sels[1] = {sel_bits};
+  Entry* list[1] = {sq};
+  ctx->scratch.reset();
+  LC_TRY(eval_predicate_batch(ctx, list, 1, &p, sel_bits ? sels : nullptr, po));
+  *count = trues;
+  return LC_OK;
+}
+
+// hydrate_full_arrow (hybrid_primitive_array.rs:116-127): the backing bytes as a temporary full entry
+int hydrate(lc_ctx* ctx, const Entry* sq, Entry** full) {
+  std::vector<uint8_t> image(sq->backing_len);
+  ctx->squeeze_reads++;
+  const int rc = sq->backing_read ? sq->backing_read(sq->backing_user, 0, sq->backing_len, image.data()) : -1;
+  if (rc != 0) {
+    set_error("squeezed entry: reading %llu backing bytes failed (%d)", (unsigned long long)sq->backing_len, rc);
+    return LC_ERR_INVALID;
+  }
+  ctx->scratch.reset();
+  LC_TRY(entry_from_bytes(ctx, image.data(), image.size(), nullptr, full));
+  if ((*full)->n != sq->n || (*full)->liquid_type != LC_LIQUID_INTEGER || (*full)->arrow_format != sq->arrow_format) {
+    release_entry(ctx, *full);
+    *full = nullptr;
+    set_error("squeezed entry: the backing bytes are not the image this entry was squeezed from");
+    return LC_ERR_INVALID;
+  }
+  return LC_OK;
+}
+
+}  // namespace
+
+int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
+                  uint64_t cap, uint64_t* out_bytes, Entry** out) {
+  *out = nullptr;
+  *out_bytes = 0;
+  if (policy != LC_SQUEEZE_CLAMP && policy != LC_SQUEEZE_QUANTIZE) {
+    set_error("lc_squeeze: unknown policy %d", policy);
+    return LC_ERR_INVALID;
+  }
+  // None in the reference: no hint (:394); Date32 / Timestamp columns squeeze to a date component and want a field hint
+  // (:399-411, squeezed_date32_array.rs — not built); no bit width (all null) or fewer than 8 bits (:414-417). Floats,
+  // decimals and byte views have squeezed forms of their own in the reference; none of them is built here.
+  if (full->liquid_type != LC_LIQUID_INTEGER || full->squeeze_kind != 0 || hint == LC_HINT_NONE) return LC_OK;
+  if (full->arrow_format == "tdD" || full->arrow_format.rfind("ts", 0) == 0) return LC_OK;
+  const IntHeader& fh = full->ih;
+  if (fh.bit_width < 8) return LC_OK;
+
+  uint64_t image_len = 0;
+  LC_TRY(entry_to_bytes(ctx, full, nullptr, 0, &image_len));
+  *out_bytes = image_len;
+  if (!bytes_out) return LC_OK;  // size query
+  if (cap < image_len) {
+    set_error("lc_squeeze: buffer of %llu bytes, the full image needs %llu", (unsigned long long)cap, (unsigned long long)image_len);
+    return LC_ERR_INVALID;
+  }
+  if (!read) {
+    set_error("lc_squeeze: a squeezed entry needs a read function for its backing bytes");
+    return LC_ERR_INVALID;
+  }
+  ctx->scratch.reset();
+  LC_TRY(entry_to_bytes(ctx, full, bytes_out, cap, &image_len));  // full bytes (original format) are what goes to disk (:396)
+
+  const uint32_t n = full->n, tb = fh.tbits / 8;
+  const uint32_t new_bw = fh.bit_width / 2;  // >= 4
+  const uint64_t tmask = fh.tbits == 64 ? ~0ull : ((1ull << fh.tbits) - 1ull);
+  cudaStream_t s = ctx->stream;
+
+  // ---- the full entry's values, decoded into a work area of their own (k_int_scan<DECODE>) ----
+  const uint64_t work_bytes = round_up(static_cast<uint64_t>(n) * tb, 256) + 256;
+  uint32_t wslab = 0;
+  uint8_t* d_vals = ctx->arena.alloc(work_bytes, &wslab);
+  if (!d_vals) {
+    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)work_bytes);
+    return LC_ERR_OOM;
+  }
+  struct Work {  // returned to the arena on every way out
+    lc_ctx* ctx;
+    uint32_t slab;
+    uint64_t bytes;
+    ~Work() { ctx->arena.free(slab, bytes); }
+  } work{ctx, wslab, work_bytes};
+  {
+    uint64_t rows = 0, vbytes = 0, nulls = 0;
+    DeviceOut dout{d_vals, static_cast<uint64_t>(n) * tb, nullptr, nullptr, &rows, &vbytes, &nulls};
+    Entry* list[1] = {full};
+    ctx->scratch.reset();
+    LC_TRY(to_arrow_batch(ctx, list, 1, nullptr, nullptr, nullptr, nullptr, &dout));
+  }
+  ctx->scratch.reset();
+  Scratch& sc = ctx->scratch;
+  LC_TRY(sc.reserve(2048, 2048));
+  IntMinMaxWork* h_mm = reinterpret_cast<IntMinMaxWork*>(sc.host(256));
+  IntPackWork* h_pw = reinterpret_cast<IntPackWork*>(sc.host(256));
+  uint64_t* h_mmout = reinterpret_cast<uint64_t*>(sc.host(256));
+  uint8_t* d_mm = sc.dev(256);
+  uint8_t* d_pw = sc.dev(256);
+  uint8_t* d_mmout = sc.dev(256);
+  if (!h_mm || !h_pw || !h_mmout || !d_mm || !d_pw || !d_mmout) {
+    set_error("lc_squeeze: scratch exhausted");
+    return LC_ERR_OOM;
+  }
+  const uint32_t* d_valid = fh.has_nulls ? reinterpret_cast<const uint32_t*>(full->d_blob + fh.validity_off) : nullptr;
+
+  uint64_t limit = (1ull << new_bw) - 1ull;  // the sentinel, or the last bucket
+  uint64_t bucket_width = 0;
+  if (policy == LC_SQUEEZE_QUANTIZE) {
+    // max offset -> bucket width = ceil((max_offset + 1) / bucket_count), at least 1 (:457-470). Null slots hold offset 0
+    // in an entry built here, so the maximum over the valid rows is the maximum over all of them.
+    h_mm->values = d_vals;
+    h_mm->validity = d_valid;
+    h_mm->out = reinterpret_cast<uint64_t*>(d_mmout);
+    h_mm->n = n;
+    h_mm->phys = fh.phys;
+    LC_CUDA_OK(cudaMemcpyAsync(d_mm, h_mm, sizeof(IntMinMaxWork), cudaMemcpyHostToDevice, s));
+    LC_CUDA_OK(launch_int_minmax(reinterpret_cast<const IntMinMaxWork*>(d_mm), 1, s));
+    ctx->kernel_launches++;
+    LC_CUDA_OK(cudaMemcpyAsync(h_mmout, d_mmout, 32, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaStreamSynchronize(s));
+    const uint64_t max_off = (h_mmout[1] - fh.reference) & tmask;
+    const uint64_t range = max_off == ~0ull ? ~0ull : max_off + 1;  // saturating_add(1)
+    const uint64_t buckets = 1ull << new_bw;
+    bucket_width = range / buckets + (range % buckets ? 1 : 0);
+    if (bucket_width == 0) bucket_width = 1;
+  }
+  LC_CUDA_OK(launch_squeeze_map(d_vals, n, fh.tbits, fh.reference, policy == LC_SQUEEZE_QUANTIZE, limit, bucket_width, s));
+  ctx->kernel_launches++;
+
+  // ---- the squeezed blob: same header and validity, packed at half the width ----
+  IntHeader h = fh;
+  h.bit_width = static_cast<uint8_t>(new_bw);
+  const uint64_t packed_bytes = static_cast<uint64_t>(h.n_chunks) * 128ull * new_bw;
+  const uint64_t blob_bytes = round_up(h.packed_off + packed_bytes, 16);
+  h.blob_bytes = static_cast<uint32_t>(blob_bytes);
+  if (ctx->budget && ctx->arena.bytes_used() + blob_bytes > ctx->budget) {
+    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(), (unsigned long long)blob_bytes,
+              (unsigned long long)ctx->budget);
+    return LC_ERR_CACHE_FULL;
+  }
+  uint32_t slab = 0;
+  uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
+  if (!d_blob) {
+    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return LC_ERR_OOM;
+  }
+  std::memset(h_pw, 0, sizeof(*h_pw));
+  h_pw->values = d_vals;
+  h_pw->validity = d_valid;
+  h_pw->blob = d_blob;
+  h_pw->pack_null_slots = 0;
+  h_pw->hdr = h;
+  cudaError_t ce = cudaMemcpyAsync(d_pw, h_pw, sizeof(IntPackWork), cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = launch_int_pack(reinterpret_cast<const IntPackWork*>(d_pw), 1, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (ce != cudaSuccess) {
+    ctx->arena.free(slab, blob_bytes);
+    set_error("CUDA error in lc_squeeze: %s", cudaGetErrorString(ce));
+    return LC_ERR_CUDA;
+  }
+  ctx->kernel_launches++;
+
+  Entry* e = new Entry();
+  e->liquid_type = LC_LIQUID_INTEGER;
+  e->d_blob = d_blob;
+  e->blob_bytes = h.blob_bytes;
+  e->slab = slab;
+  e->n = n;
+  e->arrow_format = full->arrow_format;
+  e->ih = h;
+  e->squeeze_kind = policy + 1;
+  e->bucket_width = bucket_width;
+  e->backing_read = read;
+  e->backing_user = user;
+  e->backing_len = image_len;
+  ctx->n_entries++;
+  *out = e;
+  return LC_OK;
+}
+
+namespace {
+
+enum class Decide { Codes, Backing };
+
+// What the half-width codes can say about `col <op> k` (try_eval_predicate_inner of either array): the predicate to run
+// on the squeezed entry, and the decoded value whose presence among the selected rows sends the call to the backing.
+struct Lowered {
+  lc_predicate pred;
+  bool has_ambiguous = false;
+  __int128 ambiguous = 0;
+};
+
+Lowered lower_clamped(const Entry* sq, int32_t op, __int128 k) {
+  const __int128 ref = reference_of(sq);
+  const __int128 sent_abs = ref + ((static_cast<__int128>(1) << sq->ih.bit_width) - 1);
+  // Eq, NotEq, Gt, LtEq resolve when k < sentinel value; Lt, GtEq when k <= it (hybrid_primitive_array.rs:196-219)
+  const bool strict = op == LC_OP_EQ || op == LC_OP_NE || op == LC_OP_GT || op == LC_OP_LE;
+  const bool resolves = strict ? k < sent_abs : k <= sent_abs;
+  Lowered l;
+  l.pred = int_predicate(sq, op, k);
+  l.has_ambiguous = !resolves;
+  l.ambiguous = sent_abs;
+  return l;
+}
+
+Lowered lower_quantized(const Entry* sq, int32_t op, __int128 k) {
+  const __int128 ref = reference_of(sq);
+  const bool above = op == LC_OP_NE || op == LC_OP_GT || op == LC_OP_GE;  // the answer for a value known to be > k
+  const bool below = op == LC_OP_NE || op == LC_OP_LT || op == LC_OP_LE;  // ... known to be < k
+  Lowered l;
+  // every decoded value is >= ref: `>= ref` is the constant true, `< ref` the constant false (nulls stay null)
+  auto constant = [&](bool v) { return int_predicate(sq, v ? LC_OP_GE : LC_OP_LT, ref); };
+  if (k < ref) {  // below the minimum (:537-560)
+    l.pred = constant(above);
+    return l;
+  }
+  const unsigned __int128 rel = static_cast<unsigned __int128>(k - ref);
+  const uint64_t bw = sq->bucket_width;
+  const unsigned __int128 q = rel / bw;
+  const uint64_t r = static_cast<uint64_t>(rel % bw);
+  const uint64_t last = (1ull << sq->ih.bit_width) - 1ull;
+  if (q > last) {  // every bucket index is below q
+    l.pred = constant(below);
+    return l;
+  }
+  bool known = false;
+  switch (op) {  // on_equal_bucket (:599-631)
+    case LC_OP_LT: case LC_OP_GE: known = r == 0; break;
+    case LC_OP_LE: case LC_OP_GT: known = r + 1 == bw; break;
+    default: break;
+  }
+  // with no row in bucket q, or at an edge where bucket q falls on the side the operator's own boundary puts it,
+  // `reference + b <op> reference + q` is the answer: b < q -> less side, b > q -> greater side, b == q -> Lt false /
+  // LtEq true / Gt false / GtEq true
+  l.pred = int_predicate(sq, op, ref + static_cast<__int128>(q));
+  l.has_ambiguous = !known;
+  l.ambiguous = ref + static_cast<__int128>(q);
+  return l;
+}
+
+}  // namespace
+
+int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, const uint8_t* sel_bits, const PredOut& out) {
+  SqueezeScope scope(ctx);
+  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
+    set_error("operator %d is not supported on integer columns", pred->op);
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  const uint8_t* sels[1] = {sel_bits};
+  __int128 k = 0;
+  Decide way = Decide::Backing;  // a literal outside the column's type (Ok(None)) goes the long way round
+  Lowered l;
+  if (literal_of(sq, pred, &k)) {
+    l = sq->squeeze_kind == LC_SQUEEZE_CLAMP + 1 ? lower_clamped(sq, pred->op, k) : lower_quantized(sq, pred->op, k);
+    way = Decide::Codes;
+    if (l.has_ambiguous) {
+      uint64_t hits = 0;
+      LC_TRY(count_equal(ctx, sq, l.ambiguous, sel_bits, &hits));
+      if (hits) way = Decide::Backing;  // Err(NeedsBacking)
+    }
+  }
+  Entry* list[1] = {sq};
+  if (way == Decide::Codes) {
+    ctx->squeeze_saved++;  // io.trace_io_saved()
+    ctx->scratch.reset();
+    return eval_predicate_batch(ctx, list, 1, &l.pred, sel_bits ? sels : nullptr, out);
+  }
+  Entry* full = nullptr;
+  LC_TRY(hydrate(ctx, sq, &full));
+  list[0] = full;
+  ctx->scratch.reset();
+  const int rc = eval_predicate_batch(ctx, list, 1, pred, sel_bits ? sels : nullptr, out);
+  release_entry(ctx, full);
+  return rc;
+}
+
+int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSchema* out_schema, ArrowArray* out_array) {
+  SqueezeScope scope(ctx);
+  const uint8_t* sels[1] = {sel_bits};
+  Entry* list[1] = {sq};
+  bool from_codes = false;
+  if (sq->squeeze_kind == LC_SQUEEZE_CLAMP + 1) {
+    // to_arrow_known_only (:129-157) / filter (:324-335): below the sentinel `reference + code` is the value itself
+    if (sel_bits && popcount_bits(sel_bits, sq->n) == 0) {
+      from_codes = true;  // new_empty_array
+    } else {
+      const __int128 sent_abs = reference_of(sq) + ((static_cast<__int128>(1) << sq->ih.bit_width) - 1);
+      uint64_t hits = 0;
+      LC_TRY(count_equal(ctx, sq, sent_abs, sel_bits, &hits));
+      from_codes = hits == 0;
+    }
+  }
+  if (from_codes) {
+    ctx->scratch.reset();
+    return to_arrow_batch(ctx, list, 1, sel_bits ? sels : nullptr, nullptr, out_schema, out_array);
+  }
+  Entry* full = nullptr;  // Quantize always (:684-686), Clamp when a selected row sits at the sentinel
+  LC_TRY(hydrate(ctx, sq, &full));
+  list[0] = full;
+  ctx->scratch.reset();
+  const int rc = to_arrow_batch(ctx, list, 1, sel_bits ? sels : nullptr, nullptr, out_schema, out_array);
+  release_entry(ctx, full);
+  return rc;
+}
+
+}  // namespace lc

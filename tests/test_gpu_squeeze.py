@@ -1,0 +1,255 @@
+"""GPU parity of squeezed integer entries: LiquidArray::squeeze under IntegerSqueezePolicy::{Clamp, Quantize} and the
+LiquidSqueezedArray calls on the result.
+
+Reference: liquid_array/primitive_array.rs:389-499 (squeeze), liquid_array/hybrid_primitive_array.rs:72-790 (the two
+arrays) and its tests :870-1291, liquid_array/mod.rs:209-263 (trait), cache/io_context.rs:144-180 (TestSqueezeIo) — all
+under /root/reference/src/core/src.
+Checked against the CPU restatement (oracle/liquid_oracle.py, pinned on the same reference tests in
+tests/test_oracle_squeeze.py): which columns squeeze at all; the full bytes handed back; the half-width codes word for word
+(FastLanes order), their bit width and the bucket width; every mask and every materialized array; and WHEN the backing
+bytes are read — zero reads for the literals the reference lists as resolvable, a read for the unresolvable ones, the same
+decision as the restatement everywhere else.
+Columns with nulls are built with the column minimum in their null slots: the reference clamps / quantizes whatever the
+Arrow buffer holds there and takes the quantize maximum over those slots too, this build over the valid rows only.
+"""
+import struct
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+from liquid_cache_b200 import BinaryExpr, CacheExpression, Column, LiquidExpr, Literal
+from liquid_cache_b200 import _native as N
+from oracle import liquid_oracle as O
+from tests.util import assert_arrays_equal, assert_masks_equal
+
+pytestmark = pytest.mark.gpu
+
+INT_HDR = struct.Struct("<I4B I I Q 6I")
+HINT = CacheExpression.PredicateColumn
+OPS = ["=", "!=", "<", "<=", ">", ">="]
+
+
+class CountingIo:
+    """TestSqueezeIo (cache/io_context.rs:144-180)"""
+
+    def __init__(self):
+        self.bytes = None
+        self.reads = 0
+
+    def set_bytes(self, b):
+        self.bytes = b
+
+    def reset_reads(self):
+        self.reads = 0
+
+    def read(self, rng):
+        self.reads += 1
+        return self.bytes[rng[0]:rng[1]]
+
+
+def make_array(typ, n, base_min, span, null_prob, seed):
+    rng = np.random.default_rng(seed)
+    vals = [base_min + int(d) for d in rng.integers(0, span, size=n, endpoint=True)]
+    nulls = rng.random(n) < null_prob
+    nulls[0] = False
+    mn = min(v for v, m in zip(vals, nulls) if not m)
+    np_vals = np.array([mn if m else v for v, m in zip(vals, nulls)], dtype=typ.to_pandas_dtype())
+    return pa.array(np_vals, type=typ, mask=nulls if nulls.any() else None)
+
+
+def boundary_of(arr):
+    mn, mx = pc.min_max(arr)["min"].as_py(), pc.min_max(arr)["max"].as_py()
+    half = O.get_bit_width(mx - mn) // 2
+    return mn + ((1 << half) - 1 if half else 0)
+
+
+def expr_of(op, k):
+    return LiquidExpr.new_unchecked(BinaryExpr(Column("col", 0), op, Literal(k)))
+
+
+def squeeze_both(cache, arr, policy):
+    io, oio = CountingIo(), O.OracleSqueezeIo()
+    full = cache.transcode(arr)
+    got = full.squeeze(io, HINT, policy)
+    want = O.squeeze_int(O.OracleIntArray.from_arrow(arr), oio, "PredicateColumn", policy)
+    assert (got is None) == (want is None)
+    if got is None:
+        return None
+    (sq, image), (osq, oimage) = got, want
+    assert image == oimage == full.to_bytes()
+    io.set_bytes(image)
+    oio.set_bytes(oimage)
+    return sq, io, osq, oio, full
+
+
+CASES = [(pa.int32(), 200, -1_000_000, 1 << 16, 0.2, 0x5173), (pa.uint32(), 180, 1_000_000, 1 << 16, 0.15, 0x5174),
+         (pa.int64(), 8192, -(2**40), 1 << 20, 0.1, 7), (pa.uint16(), 2500, 100, 1 << 12, 0.0, 8), (pa.int8(), 300, -128, 255, 0.3, 9),
+         (pa.uint64(), 1500, 2**63, 1 << 16, 0.05, 10), (pa.int16(), 5000, -20000, 1 << 15, 0.0, 11), (pa.int64(), 3000, -(2**62), 2**62, 0.1, 12)]
+
+
+def test_columns_the_reference_does_not_squeeze(cache):
+    io = CountingIo()
+    narrow = cache.transcode(make_array(pa.int32(), 64, 10_000, 100, 0.1, 0x5171))       # clamp_unsqueezable_small_range
+    assert narrow.squeeze(io, HINT, "clamp") is None and narrow.squeeze(io, HINT, "quantize") is None
+    wide = cache.transcode(make_array(pa.int32(), 64, 10_000, 1 << 12, 0.1, 0x5171))
+    assert wide.squeeze(io, None, "clamp") is None                                         # no hint
+    assert wide.squeeze(io, HINT, "clamp") is not None
+    assert cache.transcode(pa.array([None] * 50, pa.int32())).squeeze(io, HINT) is None    # no bit width
+    assert cache.transcode(pa.array(list(range(100)), pa.int32())).squeeze(io, HINT) is None   # width 7
+    assert cache.transcode(pa.array(list(range(200)), pa.int32())).squeeze(io, HINT) is not None   # width 8
+    dates = pa.array(list(range(8036, 10556)), pa.int32()).cast(pa.date32())
+    assert cache.transcode(dates).squeeze(io, HINT) is None                                # wants a date-field hint
+    stamps = pa.array([i * 1_000_000 for i in range(3000)], pa.int64()).cast(pa.timestamp("us"))
+    assert cache.transcode(stamps).squeeze(io, HINT) is None
+    assert cache.transcode(pa.array([0.5 * i for i in range(3000)])).squeeze(io, HINT) is None      # floats: not built
+    assert cache.transcode(pa.array([f"s{i}" for i in range(300)])).squeeze(io, HINT) is None      # byte views: not built
+
+
+@pytest.mark.parametrize("policy", ["clamp", "quantize"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-{c[1]}")
+def test_squeezed_codes_match_the_restatement(cache, policy, case):
+    typ, n, base, span, null_p, seed = case
+    arr = make_array(typ, n, base, span, null_p, seed)
+    sq, io, osq, oio, full = squeeze_both(cache, arr, policy)
+    assert sq.policy() == policy and sq.len() == len(arr) and sq.original_arrow_data_type() == arr.type
+    assert sq.bit_width() == osq.bit_width == O.OracleIntArray.from_arrow(arr).bit_width // 2
+    assert sq.disk_backing() == len(io.bytes)
+    if policy == "quantize":
+        assert sq.bucket_width() == osq.bucket_width
+    img = sq.entry_image()
+    magic, phys, tbits, bit_width, has_nulls, nn, n_chunks, reference, validity_off, packed_off, blob_bytes, null_count, \
+        is_signed, _ = INT_HDR.unpack_from(img, 0)
+    assert (nn, bit_width, null_count) == (len(arr), osq.bit_width, arr.null_count)
+    assert reference == osq.reference & ((1 << tbits) - 1)
+    words = np.frombuffer(img, dtype=osq.packed.dtype, count=len(osq.packed), offset=packed_off)
+    assert np.array_equal(words, osq.packed), "half-width codes differ from the restatement's"
+    assert sq.get_array_memory_size() < full.get_array_memory_size()
+    with pytest.raises(N.NativeError):
+        sq.to_bytes()
+    with pytest.raises(N.NativeError):  # the batched calls take full entries only
+        cache.to_arrow_many(np.array([sq.handle], dtype=np.uint64), None)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-{c[1]}")
+def test_clamp_predicates_resolvable_and_unresolvable(cache, case):
+    """clamp_predicate_eval_{i32,u32}_resolvable_and_unresolvable (:935-1110)"""
+    typ, n, base, span, null_p, seed = case
+    arr = make_array(typ, n, base, span, null_p, seed)
+    sq, io, osq, oio, _full = squeeze_both(cache, arr, "clamp")
+    boundary = boundary_of(arr)
+    sel = pa.array(np.random.default_rng(seed + 1).random(n) < 0.5)
+    resolvable = [("=", boundary - 1), ("!=", boundary - 1), ("<", boundary), ("<=", boundary - 1), (">", boundary - 1), (">=", boundary)]
+    unresolvable = [("=", boundary), ("!=", boundary), ("<", boundary + 1), ("<=", boundary), (">", boundary + 1), (">=", boundary + 1)]
+    for cases, reads in ((resolvable, False), (unresolvable, True)):
+        for op, k in cases:
+            io.reset_reads()
+            oio.reset_reads()
+            got = sq.try_eval_predicate(expr_of(op, k), sel)
+            want = osq.try_eval_predicate(op, k, sel)
+            assert_masks_equal(got, want, f"clamp {typ} {op} {k}")
+            assert_masks_equal(got, O._PC_CMP[op](pc.filter(arr, sel), pa.scalar(k, arr.type)), f"clamp {typ} {op} {k} vs arrow")
+            assert (io.reads > 0) == reads == (oio.reads > 0), (op, k, io.reads, oio.reads)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-{c[1]}")
+def test_quantize_predicates_resolvable_and_unresolvable(cache, case):
+    """quantize_predicate_eval_{u32,i32}_resolvable_and_unresolvable (:1112-1276)"""
+    typ, n, base, span, null_p, seed = case
+    arr = make_array(typ, n, base, span, null_p, seed)
+    sq, io, osq, oio, _full = squeeze_both(cache, arr, "quantize")
+    mn = pc.min_max(arr)["min"].as_py()
+    info = np.iinfo(typ.to_pandas_dtype())
+    lo = max(mn - 1, info.min)  # min.saturating_sub(1)
+    sel = pa.array([True] * n)
+    consts = [("=", lo, False), ("!=", lo, True), ("<", mn, False), ("<=", lo, False), (">", lo, True), (">=", mn, True)]
+    for op, k, const in consts:
+        if k == mn and op in ("=", "!=", "<=", ">"):
+            continue  # the column starts at the type's minimum: min - 1 saturates onto a present value
+        io.reset_reads()
+        got = sq.try_eval_predicate(expr_of(op, k), sel)
+        want = pa.array([None if v is None else const for v in arr.to_pylist()], pa.bool_())
+        assert_masks_equal(got, want, f"quantize {typ} {op} {k}")
+        assert io.reads == 0, (op, k)
+    k_present = next(v for v in arr.to_pylist() if v is not None)
+    io.reset_reads()
+    got = sq.try_eval_predicate(expr_of("=", k_present), sel)
+    assert_masks_equal(got, pc.equal(arr, pa.scalar(k_present, arr.type)), "quantize = present value")
+    assert io.reads > 0
+
+
+@pytest.mark.parametrize("policy", ["clamp", "quantize"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-{c[1]}")
+def test_every_answer_and_every_read_decision_matches(cache, policy, case):
+    typ, n, base, span, null_p, seed = case
+    arr = make_array(typ, n, base, span, null_p, seed)
+    sq, io, osq, oio, _full = squeeze_both(cache, arr, policy)
+    rng = np.random.default_rng(seed + 2)
+    info = np.iinfo(typ.to_pandas_dtype())
+    mn, mx = pc.min_max(arr)["min"].as_py(), pc.min_max(arr)["max"].as_py()
+    bw, b = getattr(osq, "bucket_width", 1), boundary_of(arr)
+    lits = {mn - 1, mn, mn + 1, mx - 1, mx, mx + 1, b - 1, b, b + 1, mn + bw - 1, mn + bw, mn + 5 * bw, mn + 5 * bw + 1, mn + 6 * bw - 1,
+            info.min, info.max}
+    lits |= {int(v) for v in rng.choice([v for v in arr.to_pylist() if v is not None], 5)}
+    for sel in (pa.array(rng.random(n) < 0.6), pa.array([True] * n), pa.array(rng.random(n) < 0.01)):
+        for k in sorted(x for x in lits if info.min <= x <= info.max):
+            for op in OPS:
+                io.reset_reads()
+                oio.reset_reads()
+                got = sq.try_eval_predicate(expr_of(op, k), sel)
+                want = osq.try_eval_predicate(op, k, sel)
+                assert_masks_equal(got, want, f"{policy} {typ} {op} {k}")
+                assert io.reads == oio.reads, (policy, op, k, io.reads, oio.reads)
+
+
+@pytest.mark.parametrize("case", CASES[:4], ids=lambda c: f"{c[0]}-{c[1]}")
+def test_materializing_a_squeezed_entry(cache, case):
+    """clamp_squeeze_full_read_roundtrip_i32 (:886-932), quantize_to_arrow_is_err (:1278-1291)"""
+    typ, n, base, span, null_p, seed = case
+    arr = make_array(typ, n, base, span, null_p, seed)
+    sq, io, osq, oio, _full = squeeze_both(cache, arr, "clamp")
+    boundary = boundary_of(arr)
+    known = pa.array([True if v is None else v < boundary for v in arr.to_pylist()])
+    io.reset_reads()
+    assert_arrays_equal(sq.filter(known), pc.filter(arr, known), "rows below the boundary")
+    assert io.reads == 0
+    io.reset_reads()
+    assert_arrays_equal(sq.to_arrow_array(), arr, "everything")
+    assert io.reads > 0
+    io.reset_reads()
+    assert len(sq.filter(pa.array([False] * n))) == 0 and io.reads == 0
+    sel = pa.array(np.random.default_rng(seed).random(n) < 0.3)
+    oio.reset_reads()
+    io.reset_reads()
+    assert_arrays_equal(sq.filter(sel), osq.filter(sel), "random selection")
+    assert io.reads == oio.reads
+    q, qio, oq, oqio, _ = squeeze_both(cache, arr, "quantize")
+    qio.reset_reads()
+    assert_arrays_equal(q.to_arrow_array(), arr, "quantize: to_arrow")
+    assert qio.reads > 0
+    qio.reset_reads()
+    assert_arrays_equal(q.filter(sel), pc.filter(arr, sel), "quantize: filter")
+    assert qio.reads > 0
+
+
+def test_a_failing_or_wrong_backing_is_reported(cache):
+    arr = make_array(pa.int32(), 4000, -5000, 1 << 16, 0.1, 3)
+    full = cache.transcode(arr)
+
+    class Broken(CountingIo):
+        def read(self, rng):
+            self.reads += 1
+            raise OSError("gone")
+
+    sq, _bytes = full.squeeze(Broken(), HINT, "quantize")
+    with pytest.raises(N.NativeError):
+        sq.to_arrow_array()
+    other = cache.transcode(make_array(pa.int32(), 3000, 9, 1 << 16, 0.0, 4)).to_bytes()
+    io = CountingIo()
+    sq2, image = full.squeeze(io, HINT, "quantize")
+    io.set_bytes(other.ljust(len(image), b"\0"))  # a well-formed image of another column (3000 rows, not 4000)
+    with pytest.raises(N.NativeError):
+        sq2.to_arrow_array()
+    io.set_bytes(image)
+    assert_arrays_equal(sq2.to_arrow_array(), arr, "with the right bytes again")
