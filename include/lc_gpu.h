@@ -101,7 +101,11 @@ typedef enum lc_op {
 
 /* CacheExpression hint (cache/expressions.rs:38-53) — only SUBSTRING_SEARCH changes the encoding
  * (it turns on the per-unique 32-bit fingerprints, transcode.rs:165). */
-typedef enum lc_hint { LC_HINT_NONE = 0, LC_HINT_PREDICATE = 1, LC_HINT_SUBSTRING_SEARCH = 2 } lc_hint;
+typedef enum lc_hint {
+  LC_HINT_NONE = 0, LC_HINT_PREDICATE = 1, LC_HINT_SUBSTRING_SEARCH = 2,
+  /* CacheExpression::ExtractDate32 { field } (expressions.rs:40-44, Date32Field): only lc_squeeze looks at these */
+  LC_HINT_EXTRACT_YEAR = 3, LC_HINT_EXTRACT_MONTH = 4, LC_HINT_EXTRACT_DAY = 5, LC_HINT_EXTRACT_DAY_OF_WEEK = 6
+} lc_hint;
 
 typedef enum lc_literal_kind {
   LC_LIT_I64 = 0,
@@ -221,15 +225,23 @@ int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8
 typedef int (*lc_backing_read)(void* user, uint64_t offset, uint64_t len, uint8_t* dst); /* 0 = ok; SqueezeIoHandler::read */
 typedef enum lc_squeeze_policy { LC_SQUEEZE_CLAMP = 0, LC_SQUEEZE_QUANTIZE = 1 } lc_squeeze_policy; /* IntegerSqueezePolicy */
 /* Returns the pair of LiquidArray::squeeze: the full bytes (written to bytes_out, *out_bytes long) and the squeezed entry.
- * *out_squeezed == 0 and *out_bytes == 0 is the reference's None: no hint, a Date32 / Timestamp column (those squeeze to a
- * date component, squeezed_date32_array.rs — not built), an all-null column or one narrower than 8 bits, or a logical type
- * other than Integer. bytes_out == NULL asks for the size only. `h` stays valid; the caller releases it once the bytes
+ * *out_squeezed == 0 and *out_bytes == 0 is the reference's None: no hint, a Date32 / Timestamp column under a hint
+ * that names no date field, an all-null column or one narrower than 8 bits, or a logical type other than Integer. bytes_out == NULL asks for the size only. `h` stays valid; the caller releases it once the bytes
  * are stored (the reference swaps the cache entry). `read` is called under the context lock, on the calling thread. */
 int lc_squeeze(lc_ctx* ctx, lc_handle h, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
                uint64_t cap, uint64_t* out_bytes, lc_handle* out_squeezed);
-/* out[0] = 0 for a full entry, else policy + 1; out[1] = bit width of the codes; out[2] = bucket width (quantize);
- * out[3] = length of the backing image; out[4], out[5] = backing reads / calls answered from the codes, context-wide. */
+/* out[0] = 0 for a full entry, 1 clamp, 2 quantize, 3 date component; out[1] = bit width of the codes; out[2] = bucket
+ * width (quantize) or the date field (0 year, 1 month, 2 day, 3 day of week); out[3] = length of the backing image;
+ * out[4], out[5] = backing reads / calls answered from the codes, context-wide. */
 int lc_squeezed_info(lc_ctx* ctx, lc_handle h, uint64_t out[6]);
+/* Date32 / Timestamp columns squeeze — only under an LC_HINT_EXTRACT_* hint — to the one date component the hint names
+ * (SqueezedDate32Array, liquid_array/squeezed_date32_array.rs:44-223; `policy` is ignored). lc_to_arrow and
+ * lc_eval_predicate on such a handle always read the backing (:430-486). What the codes give without a read:
+ *   lossy != 0  SqueezedDate32Array::to_component_array (:276-282): an array of the column's own type whose date has the
+ *               stored component (Year -> y-01-01, Month -> 1970-m-01, Day -> 1970-01-d, DayOfWeek -> 1970-01-04 + dow;
+ *               timestamps at midnight), so the query's date_part over it gives the component back
+ *   lossy == 0  to_component_date32 (:286-294): the component values themselves, typed Date32 */
+int lc_squeezed_component(lc_ctx* ctx, lc_handle h, int32_t lossy, struct ArrowSchema* out_schema, struct ArrowArray* out_array);
 
 /* LiquidArray::to_arrow_array (sel_bits == NULL) / LiquidArray::filter(&BooleanBuffer)
  * (primitive_array.rs:350-374, byte_view_array/mod.rs:266-290,421-424). The result has the

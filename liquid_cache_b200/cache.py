@@ -137,7 +137,8 @@ class GpuLiquidArray:
         reference would not squeeze. `io` mirrors `SqueezeIoHandler`: `io.read((start, end)) -> bytes` is called when the
         half-width codes cannot answer; the caller stores the returned bytes where `io` will find them."""
         pol = {"clamp": N.SQUEEZE_CLAMP, "quantize": N.SQUEEZE_QUANTIZE}[policy]
-        hint = N.HINT_NONE if expression_hint is None else (
+        field = CacheExpression.as_date32_field(expression_hint)
+        hint = N.HINT_NONE if expression_hint is None else N.HINT_EXTRACT[field] if field else (
             N.HINT_SUBSTRING_SEARCH if expression_hint == CacheExpression.SubstringSearch else N.HINT_PREDICATE)
         nb, sq = C.c_uint64(0), C.c_uint64(0)
         ctx = self._cache._ctx
@@ -225,7 +226,26 @@ class GpuSqueezedArray(GpuLiquidArray):
         return [int(x) for x in out]
 
     def policy(self) -> str:
-        return {1: "clamp", 2: "quantize"}[self._info()[0]]
+        return {1: "clamp", 2: "quantize", 3: "date32"}[self._info()[0]]
+
+    def field(self) -> str:
+        """`SqueezedDate32Array::field` (squeezed_date32_array.rs:270-272)"""
+        assert self._info()[0] == 3
+        return ("Year", "Month", "Day", "DayOfWeek")[self._info()[2]]
+
+    def _component(self, lossy: int) -> pa.Array:
+        out_a, out_s = _new_out()
+        N.check(N.lib().lc_squeezed_component(self._cache._ctx, self._h, lossy, _ptr(out_s), _ptr(out_a)))
+        return _import(out_a, out_s)
+
+    def to_component_array(self) -> pa.Array:
+        """`SqueezedDate32Array::to_component_array` (:276-282): the column's own type, dates whose component is the
+        stored one — no backing read."""
+        return self._component(1)
+
+    def to_component_date32(self) -> pa.Array:
+        """`to_component_date32` (:286-294): the component values themselves, typed Date32."""
+        return self._component(0)
 
     def bit_width(self) -> int:
         return self._info()[1]

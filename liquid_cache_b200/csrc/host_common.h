@@ -121,8 +121,10 @@ struct Entry {
   std::shared_ptr<FsstCodec> codec;    // byte-view
   // squeezed integers (LiquidPrimitiveClampedArray / LiquidPrimitiveQuantizedArray): the blob holds half-width codes,
   // the full LQDA image sits behind the caller's read function
-  int32_t squeeze_kind = 0;            // 0 = a full entry, else lc_squeeze_policy + 1
+  int32_t squeeze_kind = 0;            // 0 = a full entry, 1 clamp, 2 quantize, 3 date component (SqueezedDate32Array)
   uint64_t bucket_width = 0;           // quantize
+  uint32_t date_field = 0;             // date component: 0 year, 1 month, 2 day, 3 day of week
+  std::string orig_format;             // date component: the column's own arrow type (the blob itself reads as Date32)
   lc_backing_read backing_read = nullptr;
   void* backing_user = nullptr;
   uint64_t backing_len = 0;            // disk_range = 0..backing_len
@@ -276,6 +278,7 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
                   uint64_t cap, uint64_t* out_bytes, Entry** out);
 int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, const uint8_t* sel_bits, const PredOut& out);
 int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSchema* out_schema, ArrowArray* out_array);
+int squeezed_component_array(lc_ctx* ctx, Entry* sq, int32_t lossy, ArrowSchema* out_schema, ArrowArray* out_array);
 
 int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred, uint32_t* d_sel_base,
                  const uint64_t* d_word_off, bool all_rows, uint32_t* d_counts);

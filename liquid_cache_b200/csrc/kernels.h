@@ -141,6 +141,12 @@ cudaError_t launch_dec_widen(const unsigned long long* d_in, uint64_t n, uint32_
 // else limit = sentinel)
 cudaError_t launch_squeeze_map(void* d_vals, uint32_t n, uint32_t tbits, unsigned long long ref, uint32_t quantize,
                                unsigned long long limit, unsigned long long bucket_width, cudaStream_t s);
+// date-component squeeze: decoded Date32 days (in_bits 32) or Timestamp ticks (in_bits 64, ticks_per_day of the unit) ->
+// int32 component per row (field 0 year, 1 month, 2 day, 3 day of week); and back to a date / timestamp with that component
+cudaError_t launch_date_component(const void* d_in, uint32_t n, uint32_t in_bits, uint32_t field, long long ticks_per_day,
+                                  int32_t* d_out, cudaStream_t s);
+cudaError_t launch_date_lossy(const int32_t* d_comp, const uint32_t* d_valid, uint32_t n, uint32_t field, long long ticks_per_day,
+                              void* d_out, cudaStream_t s);
 cudaError_t launch_widen_u32(const uint32_t* d_in, uint32_t n, unsigned long long* d_out, cudaStream_t s);
 cudaError_t launch_narrow_u64(const unsigned long long* d_in, uint32_t n, unsigned long long limit, uint32_t* d_out, uint32_t* d_flag,
                               cudaStream_t s);

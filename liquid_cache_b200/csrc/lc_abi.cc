@@ -261,7 +261,7 @@ int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8
 int lc_arrow_format(lc_ctx*, lc_handle h, char* buf, size_t buf_len) {
   Entry* e = entry_of(h);
   if (!e || !buf || buf_len == 0) return LC_ERR_INVALID;
-  std::string f = e->arrow_format;
+  std::string f = e->orig_format.empty() ? e->arrow_format : e->orig_format;  // a date-component entry reports its column's type
   if (!e->dict_value_format.empty()) f += ":" + e->dict_value_format;  // "S:u" = Dictionary<UInt16, Utf8>
   if (f.size() + 1 > buf_len) return LC_ERR_INVALID;
   std::memcpy(buf, f.c_str(), f.size() + 1);
@@ -320,6 +320,16 @@ int lc_squeeze(lc_ctx* ctx, lc_handle h, int32_t policy, int32_t hint, lc_backin
   return LC_OK;
 }
 
+int lc_squeezed_component(lc_ctx* ctx, lc_handle h, int32_t lossy, struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out_schema || !out_array) {
+    set_error("lc_squeezed_component: bad argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  return squeezed_component_array(ctx, e, lossy, out_schema, out_array);
+}
+
 int lc_squeezed_info(lc_ctx* ctx, lc_handle h, uint64_t out[6]) {
   Entry* e = entry_of(h);
   if (!ctx || !e || !out) {
@@ -329,7 +339,7 @@ int lc_squeezed_info(lc_ctx* ctx, lc_handle h, uint64_t out[6]) {
   Guard g(ctx);
   out[0] = static_cast<uint64_t>(e->squeeze_kind);
   out[1] = e->liquid_type == LC_LIQUID_INTEGER ? e->ih.bit_width : 0;
-  out[2] = e->bucket_width;
+  out[2] = e->squeeze_kind == 3 ? e->date_field : e->bucket_width;
   out[3] = e->backing_len;
   out[4] = ctx->squeeze_reads;
   out[5] = ctx->squeeze_saved;

@@ -93,7 +93,8 @@ int hydrate(lc_ctx* ctx, const Entry* sq, Entry** full) {
   }
   ctx->scratch.reset();
   LC_TRY(entry_from_bytes(ctx, image.data(), image.size(), nullptr, full));
-  if ((*full)->n != sq->n || (*full)->liquid_type != LC_LIQUID_INTEGER || (*full)->arrow_format != sq->arrow_format) {
+  const std::string& want_format = sq->orig_format.empty() ? sq->arrow_format : sq->orig_format;
+  if ((*full)->n != sq->n || (*full)->liquid_type != LC_LIQUID_INTEGER || (*full)->arrow_format != want_format) {
     release_entry(ctx, *full);
     *full = nullptr;
     set_error("squeezed entry: the backing bytes are not the image this entry was squeezed from");
@@ -104,19 +105,179 @@ int hydrate(lc_ctx* ctx, const Entry* sq, Entry** full) {
 
 }  // namespace
 
+namespace {
+
+long long ticks_per_day_of(const std::string& format) {  // 0 for Date32
+  if (format.rfind("tss", 0) == 0) return 86400ll;
+  if (format.rfind("tsm", 0) == 0) return 86400000ll;
+  if (format.rfind("tsu", 0) == 0) return 86400000000ll;
+  if (format.rfind("tsn", 0) == 0) return 86400000000000ll;
+  return 0;
+}
+
+struct ArenaWork {  // a work area borrowed from the arena, handed back on every way out
+  lc_ctx* ctx;
+  uint8_t* p = nullptr;
+  uint32_t slab = 0;
+  uint64_t bytes = 0;
+  ArenaWork(lc_ctx* c, uint64_t b) : ctx(c), bytes(b) { p = c->arena.alloc(b, &slab); }
+  ~ArenaWork() {
+    if (p) ctx->arena.free(slab, bytes);
+  }
+  ArenaWork(const ArenaWork&) = delete;
+  ArenaWork& operator=(const ArenaWork&) = delete;
+};
+
+// SqueezedDate32Array::from_liquid_date32 / from_liquid_timestamp (squeezed_date32_array.rs:63-223): decode, one component
+// per row, its min / max over the valid rows, offsets from the min packed as a 32-bit column. The blob is an ordinary
+// Int32-shaped entry (reference = smallest component), so decoding it gives to_component_date32.
+int squeeze_date_entry(lc_ctx* ctx, Entry* full, uint32_t field, lc_backing_read read, void* user, uint64_t image_len, Entry** out) {
+  const IntHeader& fh = full->ih;
+  const uint32_t n = full->n, tb = fh.tbits / 8;
+  cudaStream_t s = ctx->stream;
+  ArenaWork vals(ctx, round_up(static_cast<uint64_t>(n) * tb, 256) + 256), comp(ctx, round_up(static_cast<uint64_t>(n) * 4, 256) + 256);
+  if (!vals.p || !comp.p) {
+    set_error("HBM arena: cudaMalloc failed for the squeeze work areas");
+    return LC_ERR_OOM;
+  }
+  if (n) {
+    uint64_t rows = 0, vbytes = 0, nulls = 0;
+    DeviceOut dout{vals.p, static_cast<uint64_t>(n) * tb, nullptr, nullptr, &rows, &vbytes, &nulls};
+    Entry* list[1] = {full};
+    ctx->scratch.reset();
+    LC_TRY(to_arrow_batch(ctx, list, 1, nullptr, nullptr, nullptr, nullptr, &dout));
+  }
+  ctx->scratch.reset();
+  Scratch& sc = ctx->scratch;
+  LC_TRY(sc.reserve(2048, 2048));
+  IntMinMaxWork* h_mm = reinterpret_cast<IntMinMaxWork*>(sc.host(256));
+  IntPackWork* h_pw = reinterpret_cast<IntPackWork*>(sc.host(256));
+  uint64_t* h_mmout = reinterpret_cast<uint64_t*>(sc.host(256));
+  uint8_t* d_mm = sc.dev(256);
+  uint8_t* d_pw = sc.dev(256);
+  uint8_t* d_mmout = sc.dev(256);
+  if (!h_mm || !h_pw || !h_mmout || !d_mm || !d_pw || !d_mmout) {
+    set_error("lc_squeeze: scratch exhausted");
+    return LC_ERR_OOM;
+  }
+  const uint32_t* d_valid = fh.has_nulls ? reinterpret_cast<const uint32_t*>(full->d_blob + fh.validity_off) : nullptr;
+  LC_CUDA_OK(launch_date_component(vals.p, n, fh.tbits, field, ticks_per_day_of(full->arrow_format), reinterpret_cast<int32_t*>(comp.p), s));
+  ctx->kernel_launches++;
+  h_mm->values = comp.p;
+  h_mm->validity = d_valid;
+  h_mm->out = reinterpret_cast<uint64_t*>(d_mmout);
+  h_mm->n = n;
+  h_mm->phys = PT_I32;
+  h_mmout[0] = h_mmout[1] = h_mmout[2] = 0;
+  if (n) {
+    LC_CUDA_OK(cudaMemcpyAsync(d_mm, h_mm, sizeof(IntMinMaxWork), cudaMemcpyHostToDevice, s));
+    LC_CUDA_OK(launch_int_minmax(reinterpret_cast<const IntMinMaxWork*>(d_mm), 1, s));
+    ctx->kernel_launches++;
+    LC_CUDA_OK(cudaMemcpyAsync(h_mmout, d_mmout, 32, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  const int64_t mn = static_cast<int64_t>(h_mmout[0]), mx = static_cast<int64_t>(h_mmout[1]);
+  const uint64_t n_valid = h_mmout[2];
+
+  IntHeader h;
+  std::memset(&h, 0, sizeof(h));
+  h.magic = kMagicInt;
+  h.phys = PT_I32;
+  h.tbits = 32;
+  h.n = n;
+  h.n_chunks = (n + 1023) / 1024;
+  h.is_signed = 1;
+  h.has_nulls = fh.has_nulls;
+  h.null_count = fh.null_count;
+  if (n_valid == 0) {  // BitPackedArray::new_null_array, reference_value 0 (:78-90, :116-124)
+    h.bit_width = 0;
+    h.reference = 0;
+    h.has_nulls = n > 0;
+    h.null_count = n;
+  } else {
+    const uint64_t span = static_cast<uint64_t>(mx - mn);
+    h.bit_width = static_cast<uint8_t>(span == 0 ? 1u : 64u - static_cast<uint32_t>(__builtin_clzll(span)));
+    h.reference = static_cast<uint64_t>(mn) & 0xffffffffull;
+  }
+  const uint64_t valid_bytes = h.has_nulls ? round_up((static_cast<uint64_t>(n) + 7) / 8, 16) : 0;
+  h.validity_off = h.has_nulls ? 64 : 0;
+  h.packed_off = static_cast<uint32_t>(64 + valid_bytes);
+  const uint64_t blob_bytes = round_up(h.packed_off + static_cast<uint64_t>(h.n_chunks) * 128ull * h.bit_width, 16);
+  h.blob_bytes = static_cast<uint32_t>(blob_bytes);
+  if (ctx->budget && ctx->arena.bytes_used() + blob_bytes > ctx->budget) {
+    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(), (unsigned long long)blob_bytes,
+              (unsigned long long)ctx->budget);
+    return LC_ERR_CACHE_FULL;
+  }
+  uint32_t slab = 0;
+  uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
+  if (!d_blob) {
+    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return LC_ERR_OOM;
+  }
+  std::memset(h_pw, 0, sizeof(*h_pw));
+  h_pw->values = comp.p;
+  h_pw->validity = d_valid;  // an entirely null column: every validity bit of the full entry is clear already
+  h_pw->blob = d_blob;
+  h_pw->pack_null_slots = 0;
+  h_pw->hdr = h;
+  cudaError_t ce = cudaMemcpyAsync(d_pw, h_pw, sizeof(IntPackWork), cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = launch_int_pack(reinterpret_cast<const IntPackWork*>(d_pw), 1, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (ce != cudaSuccess) {
+    ctx->arena.free(slab, blob_bytes);
+    set_error("CUDA error in lc_squeeze: %s", cudaGetErrorString(ce));
+    return LC_ERR_CUDA;
+  }
+  ctx->kernel_launches++;
+  Entry* e = new Entry();
+  e->liquid_type = LC_LIQUID_INTEGER;
+  e->d_blob = d_blob;
+  e->blob_bytes = h.blob_bytes;
+  e->slab = slab;
+  e->n = n;
+  e->arrow_format = "tdD";  // what the blob decodes to: the component values typed Date32 (to_component_date32)
+  e->orig_format = full->arrow_format;
+  e->ih = h;
+  e->squeeze_kind = 3;
+  e->date_field = field;
+  e->backing_read = read;
+  e->backing_user = user;
+  e->backing_len = image_len;
+  ctx->n_entries++;
+  *out = e;
+  return LC_OK;
+}
+
+}  // namespace
+
 int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
                   uint64_t cap, uint64_t* out_bytes, Entry** out) {
   *out = nullptr;
   *out_bytes = 0;
+  const bool is_date = full->arrow_format == "tdD" || full->arrow_format.rfind("ts", 0) == 0;
+  if (is_date && full->liquid_type == LC_LIQUID_INTEGER && full->squeeze_kind == 0) {
+    // Date32 / Timestamp: only a hint that names a date field squeezes (primitive_array.rs:399-411)
+    if (hint < LC_HINT_EXTRACT_YEAR || hint > LC_HINT_EXTRACT_DAY_OF_WEEK) return LC_OK;
+    uint64_t image_len = 0;
+    LC_TRY(entry_to_bytes(ctx, full, nullptr, 0, &image_len));
+    *out_bytes = image_len;
+    if (!bytes_out) return LC_OK;  // size query
+    if (cap < image_len || !read) {
+      set_error("lc_squeeze: needs a buffer of %llu bytes and a read function", (unsigned long long)image_len);
+      return LC_ERR_INVALID;
+    }
+    ctx->scratch.reset();
+    LC_TRY(entry_to_bytes(ctx, full, bytes_out, cap, &image_len));
+    return squeeze_date_entry(ctx, full, static_cast<uint32_t>(hint - LC_HINT_EXTRACT_YEAR), read, user, image_len, out);
+  }
   if (policy != LC_SQUEEZE_CLAMP && policy != LC_SQUEEZE_QUANTIZE) {
     set_error("lc_squeeze: unknown policy %d", policy);
     return LC_ERR_INVALID;
   }
-  // None in the reference: no hint (:394); Date32 / Timestamp columns squeeze to a date component and want a field hint
-  // (:399-411, squeezed_date32_array.rs — not built); no bit width (all null) or fewer than 8 bits (:414-417). Floats,
-  // decimals and byte views have squeezed forms of their own in the reference; none of them is built here.
-  if (full->liquid_type != LC_LIQUID_INTEGER || full->squeeze_kind != 0 || hint == LC_HINT_NONE) return LC_OK;
-  if (full->arrow_format == "tdD" || full->arrow_format.rfind("ts", 0) == 0) return LC_OK;
+  // None in the reference: no hint (:394); no bit width (all null) or fewer than 8 bits (:414-417). Floats, decimals and
+  // byte views have squeezed forms of their own in the reference; none of them is built here.
+  if (full->liquid_type != LC_LIQUID_INTEGER || full->squeeze_kind != 0 || hint == LC_HINT_NONE || is_date) return LC_OK;
   const IntHeader& fh = full->ih;
   if (fh.bit_width < 8) return LC_OK;
 
@@ -315,6 +476,24 @@ Lowered lower_quantized(const Entry* sq, int32_t op, __int128 k) {
 
 int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, const uint8_t* sel_bits, const PredOut& out) {
   SqueezeScope scope(ctx);
+  if (sq->squeeze_kind == 3) {
+    // SqueezedDate32Array::try_eval_predicate (:478-485): filter (which reads the backing unless nothing is selected),
+    // then the predicate on the filtered rows
+    if (sel_bits && popcount_bits(sel_bits, sq->n) == 0) {
+      if (out.len) out.len[0] = 0;
+      if (out.null_count) out.null_count[0] = 0;
+      if (out.true_count) out.true_count[0] = 0;
+      return LC_OK;
+    }
+    Entry* full = nullptr;
+    LC_TRY(hydrate(ctx, sq, &full));
+    const uint8_t* sels1[1] = {sel_bits};
+    Entry* list1[1] = {full};
+    ctx->scratch.reset();
+    const int rc = eval_predicate_batch(ctx, list1, 1, pred, sel_bits ? sels1 : nullptr, out);
+    release_entry(ctx, full);
+    return rc;
+  }
   if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
     set_error("operator %d is not supported on integer columns", pred->op);
     return LC_ERR_UNSUPPORTED_EXPR;
@@ -352,6 +531,14 @@ int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSche
   const uint8_t* sels[1] = {sel_bits};
   Entry* list[1] = {sq};
   bool from_codes = false;
+  if (sq->squeeze_kind == 3 && sel_bits && popcount_bits(sel_bits, sq->n) == 0) {
+    // new_empty_array(original type) without a read (:465-468)
+    export_schema(sq->orig_format, "", out_schema);
+    std::vector<HostBuf> bufs(2);
+    bufs[1] = HostBuf{host_alloc(8), 0};  // a zero-length values buffer that is still a buffer
+    export_array(0, 0, std::move(bufs), nullptr, out_array);
+    return LC_OK;
+  }
   if (sq->squeeze_kind == LC_SQUEEZE_CLAMP + 1) {
     // to_arrow_known_only (:129-157) / filter (:324-335): below the sentinel `reference + code` is the value itself
     if (sel_bits && popcount_bits(sel_bits, sq->n) == 0) {
@@ -374,6 +561,65 @@ int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSche
   const int rc = to_arrow_batch(ctx, list, 1, sel_bits ? sels : nullptr, nullptr, out_schema, out_array);
   release_entry(ctx, full);
   return rc;
+}
+
+// SqueezedDate32Array::to_component_array (:276-282, lossy) / to_component_date32 (:286-294): no backing read
+int squeezed_component_array(lc_ctx* ctx, Entry* sq, int32_t lossy, ArrowSchema* out_schema, ArrowArray* out_array) {
+  SqueezeScope scope(ctx);
+  if (sq->squeeze_kind != 3) {
+    set_error("lc_squeezed_component: not a date-component entry");
+    return LC_ERR_INVALID;
+  }
+  Entry* list[1] = {sq};
+  ctx->scratch.reset();
+  if (!lossy) return to_arrow_batch(ctx, list, 1, nullptr, nullptr, out_schema, out_array);
+  const uint32_t n = sq->n;
+  const long long ticks = ticks_per_day_of(sq->orig_format);
+  const uint32_t out_tb = ticks ? 8 : 4;
+  const uint64_t vwords = (static_cast<uint64_t>(n) + 31) / 32;
+  ArenaWork comp(ctx, round_up(static_cast<uint64_t>(n) * 4, 256) + 256), res(ctx, round_up(static_cast<uint64_t>(n) * out_tb, 256) + 256),
+      val(ctx, round_up(vwords * 4, 256) + 256);
+  if (!comp.p || !res.p || !val.p) {
+    set_error("HBM arena: cudaMalloc failed for the component work areas");
+    return LC_ERR_OOM;
+  }
+  cudaStream_t s = ctx->stream;
+  uint64_t rows = 0, vbytes = 0, nulls = 0;
+  if (n) {
+    DeviceOut dout{comp.p, static_cast<uint64_t>(n) * 4, nullptr, val.p, &rows, &vbytes, &nulls};
+    LC_TRY(to_arrow_batch(ctx, list, 1, nullptr, nullptr, nullptr, nullptr, &dout));  // k_int_scan<DECODE> (+ validity)
+  }
+  LC_CUDA_OK(launch_date_lossy(reinterpret_cast<const int32_t*>(comp.p), nulls ? reinterpret_cast<const uint32_t*>(val.p) : nullptr, n,
+                               sq->date_field, ticks, res.p, s));
+  ctx->kernel_launches++;
+  HostBuf values{host_alloc(static_cast<uint64_t>(n) * out_tb), static_cast<uint64_t>(n) * out_tb};
+  HostBuf validity;
+  if (nulls) {
+    validity.bytes = (static_cast<uint64_t>(n) + 7) / 8;
+    validity.p = host_alloc(round_up(validity.bytes, 4));
+  }
+  if ((n && !values.p) || (nulls && !validity.p)) {
+    host_free(values.p);
+    host_free(validity.p);
+    set_error("host allocation failed");
+    return LC_ERR_OOM;
+  }
+  cudaError_t ce = n ? cudaMemcpyAsync(values.p, res.p, static_cast<uint64_t>(n) * out_tb, cudaMemcpyDeviceToHost, s) : cudaSuccess;
+  if (ce == cudaSuccess && nulls) ce = cudaMemcpyAsync(validity.p, val.p, round_up(validity.bytes, 4), cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (ce != cudaSuccess) {
+    host_free(values.p);
+    host_free(validity.p);
+    set_error("CUDA error in lc_squeezed_component: %s", cudaGetErrorString(ce));
+    return LC_ERR_CUDA;
+  }
+  ctx->d2h_bytes += values.bytes + validity.bytes;
+  export_schema(sq->orig_format, "", out_schema);
+  std::vector<HostBuf> bufs;
+  bufs.push_back(validity);
+  bufs.push_back(values);
+  export_array(static_cast<int64_t>(n), static_cast<int64_t>(nulls), std::move(bufs), nullptr, out_array);
+  return LC_OK;
 }
 
 }  // namespace lc

@@ -79,6 +79,17 @@ class CacheExpression:
     def substring_search():
         return CacheExpression.SubstringSearch
 
+    @staticmethod
+    def extract_date32(field: str):
+        """`CacheExpression::extract_date32(Date32Field)` (expressions.rs:82-84); field in Year / Month / Day / DayOfWeek."""
+        assert field in ("Year", "Month", "Day", "DayOfWeek")
+        return ("ExtractDate32", field)
+
+    @staticmethod
+    def as_date32_field(hint):
+        """`as_date32_field` (expressions.rs:133-138)"""
+        return hint[1] if isinstance(hint, tuple) and hint[0] == "ExtractDate32" else None
+
 
 _CMP_OPS = {"=": N.OP_EQ, "!=": N.OP_NE, "<": N.OP_LT, "<=": N.OP_LE, ">": N.OP_GT, ">=": N.OP_GE}
 

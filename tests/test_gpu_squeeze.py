@@ -253,3 +253,72 @@ def test_a_failing_or_wrong_backing_is_reported(cache):
         sq2.to_arrow_array()
     io.set_bytes(image)
     assert_arrays_equal(sq2.to_arrow_array(), arr, "with the right bytes again")
+
+
+# ---- Date32 / Timestamp columns: one date component (liquid_array/squeezed_date32_array.rs) ----
+FIELDS = ["Year", "Month", "Day", "DayOfWeek"]
+D = O.ymd_to_epoch_days
+
+
+def _date_cases():
+    rng = np.random.default_rng(404)
+    days = rng.integers(-30_000, 60_000, size=8192).astype(np.int32)
+    out = [pa.array(days, pa.int32(), mask=rng.random(8192) < 0.1).cast(pa.date32()),
+           pa.array([D(1969, 12, 31), D(1970, 1, 1), D(1970, 1, 31), D(1970, 2, 1), D(1971, 7, 15), None], pa.int32()).cast(pa.date32()),
+           pa.array([D(1970, 1, 1), D(1971, 7, 15), D(1999, 12, 31), D(2024, 2, 29), D(4709, 11, 24), None], pa.int32()).cast(pa.date32()),
+           pa.array([-1, 0, D(1971, 7, 15), None, -719_468, -800_000], pa.int32()).cast(pa.date32()),   # both sides of the civil epoch
+           pa.array([None, None, None], pa.int32()).cast(pa.date32()), pa.array([D(2000, 2, 29)] * 1500, pa.int32()).cast(pa.date32()),
+           pa.array([1_609_459_200_000_000, 1_640_995_200_000_000, None, -1, 0], pa.int64()).cast(pa.timestamp("us"))]
+    for unit in ("s", "ms", "us", "ns"):
+        t = O._TICKS_PER_DAY[unit]
+        ticks = days[:5000].astype(np.int64) * t + rng.integers(0, t, size=5000)
+        out.append(pa.array(ticks, pa.int64(), mask=rng.random(5000) < 0.05).cast(pa.timestamp(unit)))
+    return out
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_date_component_squeeze_matches_the_restatement(cache, field):
+    for ci, arr in enumerate(_date_cases()):
+        io, oio = CountingIo(), O.OracleSqueezeIo()
+        full = cache.transcode(arr)
+        assert full.squeeze(io, HINT) is None and full.squeeze(io, None) is None  # only a date-field hint squeezes these
+        hint = CacheExpression.extract_date32(field)
+        sq, image = full.squeeze(io, hint)
+        osq, oimage = O.squeeze_int(O.OracleIntArray.from_arrow(arr), oio, hint)
+        assert len(image) == len(oimage)
+        io.set_bytes(image)
+        what = f"{arr.type} case {ci} {field}"
+        assert sq.policy() == "date32" and sq.field() == field and sq.len() == len(arr) and sq.original_arrow_data_type() == arr.type
+        assert sq.bit_width() == (osq.bit_width or 0) and sq.disk_backing() == len(image)
+        img = sq.entry_image()
+        magic, phys, tbits, bit_width, has_nulls, nn, n_chunks, reference, *_ = INT_HDR.unpack_from(img, 0)
+        assert tbits == 32 and reference == osq.reference & 0xFFFFFFFF, what
+        if osq.bit_width is not None:
+            packed_off = INT_HDR.unpack_from(img, 0)[9]
+            words = np.frombuffer(img, dtype=np.uint32, count=len(osq.packed), offset=packed_off)
+            assert np.array_equal(words, osq.packed), what + ": packed component offsets"
+        io.reset_reads()
+        assert_arrays_equal(sq.to_component_date32(), osq.to_component_date32(), what + ": to_component_date32")
+        comp = sq.to_component_array()
+        assert comp.type == arr.type
+        assert_arrays_equal(comp, osq.to_component_array(), what + ": to_component_array")
+        assert io.reads == 0
+        raw = arr.cast(pa.int32() if pa.types.is_date32(arr.type) else pa.int64())  # raw day / tick counts
+        per_day = O._TICKS_PER_DAY[arr.type.unit] if pa.types.is_timestamp(arr.type) else 1
+        if arr.null_count < len(arr) and pc.min(raw).as_py() > -700_000 * per_day:  # arrow's calendar starts at year 1
+            f = {"Year": pc.year, "Month": pc.month, "Day": pc.day,
+                 "DayOfWeek": lambda a: pc.day_of_week(a, count_from_zero=True, week_start=7)}[field]
+            assert f(comp).equals(f(arr)), what + ": date_part over the component array"
+        # everything else reads the backing bytes
+        assert_arrays_equal(sq.to_arrow_array(), arr, what + ": to_arrow")
+        assert io.reads == 1
+        sel = pa.array(np.random.default_rng(ci).random(len(arr)) < 0.4)
+        assert_arrays_equal(sq.filter(sel), pc.filter(arr, sel), what + ": filter")
+        before = io.reads
+        empty = sq.filter(pa.array([False] * len(arr)))
+        assert len(empty) == 0 and empty.type == arr.type and io.reads == before
+        lit = next((v for v in raw.to_pylist() if v is not None), None)
+        if lit is not None and pc.any(sel).as_py():
+            got = sq.try_eval_predicate(expr_of(">=", lit), sel)
+            assert_masks_equal(got, pc.greater_equal(pc.filter(raw, sel), pa.scalar(lit, raw.type)), what + ": >=")
+            assert io.reads == before + 1

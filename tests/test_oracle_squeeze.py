@@ -161,3 +161,113 @@ def test_all_null_and_narrow_arrays_do_not_squeeze():
     assert O.squeeze_int(O.OracleIntArray.from_arrow(pa.array([None] * 50, pa.int32())), io, HINT) is None  # no bit width
     assert O.squeeze_int(O.OracleIntArray.from_arrow(pa.array(list(range(100)), pa.int32())), io, HINT) is None  # width 7
     assert O.squeeze_int(O.OracleIntArray.from_arrow(pa.array(list(range(200)), pa.int32())), io, HINT) is not None  # width 8
+
+
+# ---- Date32 / Timestamp columns: one date component (liquid_array/squeezed_date32_array.rs:489-747) ----
+D = O.ymd_to_epoch_days
+
+
+def _dates(vals):
+    return pa.array(vals, pa.int32()).cast(pa.date32())
+
+
+def _squeezed(field, vals):
+    return O.OracleSqueezedDate32Array.from_liquid(O.OracleIntArray.from_arrow(_dates(vals)), field)
+
+
+def test_date_arithmetic_matches_the_calendar():
+    import datetime
+
+    epoch = datetime.date(1970, 1, 1)
+    for y, m, d in [(1970, 1, 1), (1969, 12, 31), (2000, 2, 29), (1900, 3, 1), (2024, 2, 29), (1, 1, 1), (9999, 12, 31), (1600, 2, 29)]:
+        days = (datetime.date(y, m, d) - epoch).days
+        assert D(y, m, d) == days
+        yy, mm, dd = O.ymd_from_epoch_days(np.array([days]))
+        assert (int(yy[0]), int(mm[0]), int(dd[0])) == (y, m, d)
+        assert int(O.component_from_days("DayOfWeek", np.array([days]))[0]) == (datetime.date(y, m, d).weekday() + 1) % 7
+    rng = np.random.default_rng(5)
+    days = rng.integers(-800_000, 2_900_000, size=20_000)  # years -220 .. 9900, both sides of the civil epoch
+    y, m, d = O.ymd_from_epoch_days(days)
+    back = np.array([D(int(a), int(b), int(c)) for a, b, c in zip(y[:2000], m[:2000], d[:2000])])
+    assert np.array_equal(back, days[:2000])
+    got = pc.year(pa.array(days[(days > -719_000)].astype(np.int32), pa.int32()).cast(pa.date32()))  # arrow's calendar from year 1 on
+    assert np.array_equal(np.asarray(got), y[days > -719_000])
+
+
+def test_extraction_correctness():
+    """:510-562"""
+    assert _squeezed("Year", [-1, 0, D(1971, 7, 15), None]).to_component_date32().equals(_dates([1969, 1970, 1971, None]))
+    assert _squeezed("Month", [D(1970, 1, 31), D(1970, 2, 1), D(1970, 12, 31), None]).to_component_date32().equals(_dates([1, 2, 12, None]))
+    assert _squeezed("Day", [D(1970, 1, 1), D(1970, 1, 31), D(1970, 2, 1), None]).to_component_date32().equals(_dates([1, 31, 1, None]))
+    assert _squeezed("DayOfWeek", [D(1970, 1, 4), D(1970, 1, 5), D(1970, 1, 10), None]).to_component_date32().equals(_dates([0, 1, 6, None]))
+
+
+def test_lossy_reconstruction_mapping():
+    """:565-616"""
+    assert _squeezed("Year", [D(1999, 12, 31), D(2000, 6, 1), None]).to_arrow_date32_lossy().equals(_dates([D(1999, 1, 1), D(2000, 1, 1), None]))
+    assert _squeezed("Month", [D(1980, 3, 14), D(1977, 12, 5), None]).to_arrow_date32_lossy().equals(_dates([D(1970, 3, 1), D(1970, 12, 1), None]))
+    assert _squeezed("Day", [D(1980, 3, 14), D(1977, 12, 5), None]).to_arrow_date32_lossy().equals(_dates([D(1970, 1, 14), D(1970, 1, 5), None]))
+    assert _squeezed("DayOfWeek", [D(2020, 5, 17), D(2020, 5, 18), None]).to_arrow_date32_lossy().equals(_dates([D(1970, 1, 4), D(1970, 1, 5), None]))
+
+
+def test_roundtrip_idempotence_and_all_nulls():
+    """:619-662"""
+    vals = [D(1969, 12, 31), D(1970, 1, 1), D(1970, 1, 31), D(1970, 2, 1), D(1971, 7, 15), None]
+    for field in O.DATE32_FIELDS:
+        comp1 = _squeezed(field, vals).to_component_date32()
+        lossy = _squeezed(field, vals).to_arrow_date32_lossy()
+        comp2 = O.OracleSqueezedDate32Array.from_liquid(O.OracleIntArray.from_arrow(lossy), field).to_component_date32()
+        assert comp1.equals(comp2), field
+        nulls = _squeezed(field, [None, None, None])
+        assert nulls.bit_width is None
+        assert nulls.to_component_date32().equals(_dates([None] * 3)) and nulls.to_arrow_date32_lossy().equals(_dates([None] * 3))
+
+
+def test_to_component_array_round_trips_through_extract():
+    """:672-709, :712-746"""
+    vals = [D(1970, 1, 1), D(1971, 7, 15), D(1999, 12, 31), D(2024, 2, 29), D(4709, 11, 24), None]
+    comp = _squeezed("Year", vals).to_component_array()
+    assert comp.type == pa.date32()
+    want = [None if v is None else int(O.component_from_days("Year", np.array([v]))[0]) for v in vals]
+    got = [None if v is None else int(O.component_from_days("Year", np.array([v]))[0]) for v in comp.cast(pa.int32()).to_pylist()]
+    assert got == want == [1970, 1971, 1999, 2024, 4709, None]
+    stamps = pa.array([1_609_459_200_000_000, 1_640_995_200_000_000, None], pa.int64()).cast(pa.timestamp("us"))
+    sq = O.OracleSqueezedDate32Array.from_liquid(O.OracleIntArray.from_arrow(stamps), "Year")
+    out = sq.to_component_array()
+    assert out.type == pa.timestamp("us")
+    assert out.cast(pa.int64()).to_pylist() == [D(2021, 1, 1) * 86_400_000_000, D(2022, 1, 1) * 86_400_000_000, None]
+    assert sq.to_component_date32().cast(pa.int32()).to_pylist() == [2021, 2022, None]
+
+
+@pytest.mark.parametrize("field", O.DATE32_FIELDS)
+def test_components_agree_with_arrow_on_random_columns(field):
+    rng = np.random.default_rng(len(field))
+    days = rng.integers(-30_000, 60_000, size=5000).astype(np.int32)  # 1887 .. 2134
+    arr = pa.array(days, pa.int32(), mask=rng.random(5000) < 0.1).cast(pa.date32())
+    f = {"Year": pc.year, "Month": pc.month, "Day": pc.day, "DayOfWeek": lambda a: pc.day_of_week(a, count_from_zero=True, week_start=7)}[field]
+    sq = O.OracleSqueezedDate32Array.from_liquid(O.OracleIntArray.from_arrow(arr), field)
+    assert sq.to_component_date32().cast(pa.int32()).cast(pa.int64()).equals(f(arr))
+    assert f(sq.to_component_array()).equals(f(arr))  # date_part over the lossy array gives the component back
+    for unit in ("s", "ms", "us", "ns"):
+        ts = pa.array(days.astype(np.int64) * O._TICKS_PER_DAY[unit] + rng.integers(0, O._TICKS_PER_DAY[unit], size=5000), pa.int64(),
+                      mask=rng.random(5000) < 0.1).cast(pa.timestamp(unit))
+        sqt = O.OracleSqueezedDate32Array.from_liquid(O.OracleIntArray.from_arrow(ts), field)
+        assert sqt.to_component_date32().cast(pa.int32()).cast(pa.int64()).equals(f(ts)), unit
+        assert f(sqt.to_component_array()).equals(f(ts)), unit
+
+
+def test_date_columns_squeeze_only_under_a_date_field_hint():
+    arr = _dates(list(range(8036, 10556)) + [None])
+    liq = O.OracleIntArray.from_arrow(arr)
+    io = O.OracleSqueezeIo()
+    assert O.squeeze_int(liq, io, HINT) is None and O.squeeze_int(liq, io, None) is None
+    sq, full = O.squeeze_int(liq, io, ("ExtractDate32", "Month"))
+    io.set_bytes(full)
+    assert full == O.to_bytes(liq) and sq.bit_width == 4 and sq.reference == 1 and len(sq) == len(arr)
+    assert io.reads == 0 and sq.to_component_array().type == pa.date32() and io.reads == 0
+    assert sq.to_arrow().equals(arr) and io.reads == 1
+    sel = pa.array([i % 7 == 0 for i in range(len(arr))])
+    assert sq.filter(sel).equals(pc.filter(arr, sel)) and io.reads == 2
+    assert len(sq.filter(pa.array([False] * len(arr)))) == 0 and io.reads == 2
+    got = sq.try_eval_predicate(">=", pa.scalar(9000, pa.int32()).cast(pa.date32()), sel)
+    assert got.equals(pc.greater_equal(pc.filter(arr, sel), pa.scalar(9000, pa.int32()).cast(pa.date32()))) and io.reads == 3
