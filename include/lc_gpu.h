@@ -132,6 +132,9 @@ typedef struct lc_predicate {
 typedef enum lc_liquid_type {
   LC_LIQUID_INTEGER = 1,
   LC_LIQUID_FLOAT = 2,     /* LiquidFloatArray: ALP (float_array.rs) */
+  LC_LIQUID_FIXED_LEN_BYTE_ARRAY = 3, /* LiquidFixedLenByteArray: Decimal128/256 with values outside u64, u16 dictionary +
+                              FSST over the 16 / 32-byte values (fix_len_byte_array.rs); get / filter only — it has no
+                              predicate of its own in the reference either (LiquidArray default: decode, then compare) */
   LC_LIQUID_BYTE_VIEW = 4,
   LC_LIQUID_DECIMAL = 6    /* LiquidDecimalArray: Decimal128/256 whose values fit u64 (decimal_array.rs) */
 } lc_liquid_type;

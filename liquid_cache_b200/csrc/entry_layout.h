@@ -34,6 +34,8 @@ enum PhysType : uint8_t {
 // ArrowByteType numbering (byte_view_array/mod.rs:113-122).
 enum ByteType : uint8_t {
   BT_UTF8 = 0, BT_UTF8_VIEW = 1, BT_DICT16_BINARY = 2, BT_DICT16_UTF8 = 3, BT_BINARY = 4, BT_BINARY_VIEW = 5,
+  // not ArrowByteType: LiquidFixedLenByteArray (fix_len_byte_array.rs:26-36), every value 16 / 32 bytes
+  BT_DECIMAL128 = 6, BT_DECIMAL256 = 7,
 };
 
 struct alignas(16) IntHeader {   // 64 bytes

@@ -128,7 +128,12 @@ struct Entry {
   lc_backing_read backing_read = nullptr;
   void* backing_user = nullptr;
   uint64_t backing_len = 0;            // disk_range = 0..backing_len
+  uint32_t fixed_width = 0;            // LiquidFixedLenByteArray (decimals outside u64): bytes per value, else 0
 };
+
+// int_encode's answer for a decimal array with values outside u64: the caller stores it as LiquidFixedLenByteArray
+// (str_encode over the 16 / 32-byte values) under the column chunk's compressor scope
+constexpr int LC_INTERNAL_FIXED_LEN = 1000;
 
 // integer-shaped blobs (IntHeader + FastLanes chunks): integers, ALP floats, u64 decimals
 inline bool is_int_blob(int32_t liquid_type) {

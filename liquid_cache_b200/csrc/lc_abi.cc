@@ -20,7 +20,15 @@ int encode_locked(lc_ctx* ctx, const ArrowSchema* schema, const ArrowArray* arra
                   Entry** out) {
   ArrowIn in;
   LC_TRY(parse_arrow_input(schema, array, &in));
-  if (in.kind == ArrowIn::K_INT || in.kind == ArrowIn::K_FLOAT || in.kind == ArrowIn::K_DECIMAL) return int_encode(ctx, in, out);
+  if (in.kind == ArrowIn::K_INT || in.kind == ArrowIn::K_FLOAT || in.kind == ArrowIn::K_DECIMAL) {
+    const int rc = int_encode(ctx, in, out);
+    if (rc != LC_INTERNAL_FIXED_LEN) return rc;
+    // LiquidFixedLenByteArray::from_decimal_array (fix_len_byte_array.rs:274-323): u16 dictionary over the 16 / 32-byte
+    // values, FSST-compressed under the column chunk's compressor (with_fsst_compressor_or_train, transcode.rs:118-131)
+    in.byte_type = in.dec_width == 16 ? BT_DECIMAL128 : BT_DECIMAL256;
+    ctx->scratch.reset();
+    return str_encode(ctx, in, LC_HINT_NONE, scope, out);
+  }
   return str_encode(ctx, in, hint, scope, out);
 }
 
@@ -155,6 +163,7 @@ uint64_t lc_memory_size(lc_ctx*, lc_handle h) {
 
 int32_t lc_data_type(lc_ctx*, lc_handle h) {
   Entry* e = entry_of(h);
+  if (e && e->fixed_width) return LC_LIQUID_FIXED_LEN_BYTE_ARRAY;  // a byte-view blob inside, LiquidFixedLenByteArray outside
   return e ? e->liquid_type : 0;
 }
 
@@ -204,6 +213,10 @@ int lc_to_bytes(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* 
   }
   if (e->squeeze_kind) {
     set_error("lc_to_bytes: a squeezed entry has no serialized form (its full image is the backing)");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
+  if (e->fixed_width) {
+    set_error("lc_to_bytes: the LQDA form of LiquidFixedLenByteArray (fix_len_byte_array.rs:116-270) is not built");
     return LC_ERR_UNSUPPORTED_TYPE;
   }
   Guard g(ctx);

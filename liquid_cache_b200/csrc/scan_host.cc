@@ -247,7 +247,7 @@ struct RefList {
   // instead of chasing 10^4 Entry pointers (each a cache miss)
   std::shared_ptr<std::vector<uint32_t>> rows;      // rows per entry
   std::shared_ptr<std::vector<uint32_t>> n_unique;  // dictionary size per entry (byte views)
-  bool same_liquid_type = true, same_arrow_type = true, same_width = true, any_nulls = false;
+  bool same_liquid_type = true, same_arrow_type = true, same_width = true, any_nulls = false, any_fixed = false;
   // did the last predicate over this list produce nearly-empty masks? (0 unknown, 1 sparse, 2 dense) — picks between
   // the sparse mask download and the chunked dense one before the answer is known
   mutable int mask_hint = 0;
@@ -307,6 +307,7 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
       return LC_ERR_INVALID;
     }
     (*nl.rows)[i] = e->n;
+    nl.any_fixed = nl.any_fixed || e->fixed_width != 0;
     if (e->liquid_type != proto->liquid_type) nl.same_liquid_type = false;
     if (e->arrow_format != proto->arrow_format || e->dict_value_format != proto->dict_value_format) nl.same_arrow_type = false;
     if (is_int_blob(e->liquid_type)) {
@@ -634,6 +635,12 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     set_error("eval_predicate_many: entries of different liquid types in one call");
     return LC_ERR_INVALID;
   }
+  if (rl->any_fixed) {
+    // LiquidFixedLenByteArray has no predicate of its own (the LiquidArray default: decode, filter, DataFusion evaluate,
+    // liquid_array/mod.rs:123-130): the caller reads the rows (lc_to_arrow) and compares them as it would there
+    set_error("predicates on decimals outside u64 (LiquidFixedLenByteArray) are evaluated by the caller on the decoded rows");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
   if (entries[0]->liquid_type == LC_LIQUID_FLOAT) return eval_predicate_float(ctx, entries, n, rl, pred, sel_bits, out);
   const bool is_int = is_int_blob(entries[0]->liquid_type);
   SelPlan sp;
@@ -892,6 +899,10 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
   if (!rl->same_liquid_type) {
     set_error("scan_filter: entries of different liquid types in one call");
     return LC_ERR_INVALID;
+  }
+  if (rl->any_fixed) {
+    set_error("predicates on decimals outside u64 (LiquidFixedLenByteArray) are evaluated by the caller on the decoded rows");
+    return LC_ERR_UNSUPPORTED_EXPR;
   }
   if (entries[0]->liquid_type == LC_LIQUID_FLOAT)
     return refine_float(ctx, entries, n, rl, pred, d_sel_base, d_word_off, all_rows, d_counts);
@@ -1214,6 +1225,10 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     set_error("decoded values exceed 2 GiB (int32 offsets); split the call");
     return LC_ERR_INVALID;
   }
+  if (dev_out && proto->fixed_width) {
+    set_error("read_device: decimals outside u64 (LiquidFixedLenByteArray) are read through lc_to_arrow / lc_scan_read");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
   if (dev_out) {
     if (dev_out->out_rows) *dev_out->out_rows = rows;
     if (dev_out->out_value_bytes) *dev_out->out_value_bytes = total_bytes;
@@ -1244,9 +1259,12 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     return LC_OK;
   }
   const uint8_t bt = proto->sh.arrow_type;
-  const bool want_views = bt == BT_UTF8_VIEW || bt == BT_BINARY_VIEW;
+  // Utf8View / BinaryView ship 16-byte views, LiquidFixedLenByteArray ships the values at their fixed stride: both are
+  // built on the device from the decoded (offsets, bytes) and take the place of the offsets in the download
+  const uint32_t fixed_w = proto->fixed_width;
+  const bool want_views = bt == BT_UTF8_VIEW || bt == BT_BINARY_VIEW || fixed_w != 0;
   const uint64_t off_bytes = (rows + 1) * 4;
-  const uint64_t view_bytes = want_views ? rows * 16 : 0;
+  const uint64_t view_bytes = fixed_w ? rows * fixed_w : want_views ? rows * 16 : 0;
   const uint64_t res_bytes = round_up(off_bytes, 256) + round_up(total_bytes + 16, 256) + round_up(view_bytes + 16, 256);
   uint8_t* d_res = nullptr;
   if (cudaMallocAsync(reinterpret_cast<void**>(&d_res), res_bytes, s) != cudaSuccess) {
@@ -1281,14 +1299,17 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   int rc = LC_OK;
   if (ce == cudaSuccess && nulls) rc = concat_validity_device(g.io, d_up, d_cat, &validity);
   if (ce == cudaSuccess && rc == LC_OK && want_views) {
-    ce = launch_build_views(g.out_offsets, static_cast<uint32_t>(total_bytes), g.out_bytes,
-                            nulls ? reinterpret_cast<const uint32_t*>(d_cat) : nullptr, rows, d_views, s);
+    ce = fixed_w ? launch_fixed_from_var(g.out_offsets, static_cast<uint32_t>(total_bytes), g.out_bytes,
+                                         nulls ? reinterpret_cast<const uint32_t*>(d_cat) : nullptr, rows, fixed_w, d_views, s)
+                 : launch_build_views(g.out_offsets, static_cast<uint32_t>(total_bytes), g.out_bytes,
+                                      nulls ? reinterpret_cast<const uint32_t*>(d_cat) : nullptr, rows, d_views, s);
     ctx->kernel_launches++;
     if (ce == cudaSuccess && rows) ce = cudaMemcpyAsync(views.p, d_views, view_bytes, cudaMemcpyDeviceToHost, s);
   } else if (ce == cudaSuccess && rc == LC_OK && rows) {
     ce = cudaMemcpyAsync(offsets.p, g.out_offsets, rows * 4, cudaMemcpyDeviceToHost, s);
   }
-  if (ce == cudaSuccess && rc == LC_OK && total_bytes) ce = cudaMemcpyAsync(data.p, g.out_bytes, total_bytes, cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess && rc == LC_OK && total_bytes && !fixed_w)
+    ce = cudaMemcpyAsync(data.p, g.out_bytes, total_bytes, cudaMemcpyDeviceToHost, s);
   cudaFreeAsync(d_res, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess || rc != LC_OK) {
@@ -1302,7 +1323,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   tr.mark("decode kernel + result D2H");
   ctx->kernel_launches++;
   ctx->h2d_bytes += n * 8;
-  ctx->d2h_bytes += (want_views ? view_bytes : rows * 4) + total_bytes;
+  ctx->d2h_bytes += (want_views ? view_bytes : rows * 4) + (fixed_w ? 0 : total_bytes);
   if (!want_views) reinterpret_cast<int32_t*>(offsets.p)[rows] = static_cast<int32_t>(total_bytes);
   return finish_bytes_array(proto, rows, nulls, validity, offsets, views, data, out_schema, out_array);
 }
@@ -1315,6 +1336,15 @@ static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls,
                               HostBuf views, HostBuf data, ArrowSchema* out_schema, ArrowArray* out_array) {
   const uint8_t bt = proto->sh.arrow_type;
   const int32_t* off = reinterpret_cast<const int32_t*>(offsets.p);
+  if (bt == BT_DECIMAL128 || bt == BT_DECIMAL256) {
+    // LiquidFixedLenByteArray::to_arrow_array (fix_len_byte_array.rs:87-95): the decimal array itself; `views` holds the
+    // values at their fixed stride (null slots zero)
+    host_free(data.p);
+    export_schema(proto->arrow_format, "", out_schema);
+    std::vector<HostBuf> bufs{validity, views};
+    export_array(static_cast<int64_t>(rows), static_cast<int64_t>(nulls), std::move(bufs), nullptr, out_array);
+    return LC_OK;
+  }
   if (bt == BT_UTF8 || bt == BT_BINARY) {
     export_schema(bt == BT_UTF8 ? "u" : "z", "", out_schema);
     std::vector<HostBuf> bufs{validity, offsets, data};

@@ -184,6 +184,14 @@ static int build_row_plan(const ArrowIn& in, RowPlan* plan) {
       row_off[i] = static_cast<uint32_t>(off[i] - lo);
       row_len[i] = static_cast<uint32_t>(off[i + 1] - off[i]);
     }
+  } else if (in.kind == ArrowIn::K_DECIMAL) {
+    // fixed-width values (Decimal128 / Decimal256 little-endian words): row i is bytes [i*w, (i+1)*w) of the values buffer
+    const uint32_t w = in.dec_width;
+    add_seg(static_cast<const uint8_t*>(in.values) + static_cast<uint64_t>(in.offset) * w, static_cast<uint64_t>(n) * w);
+    for (uint32_t i = 0; i < n; ++i) {
+      row_off[i] = i * w;
+      row_len[i] = w;
+    }
   } else if (in.kind == ArrowIn::K_VIEW) {
     const uint8_t* views = static_cast<const uint8_t*>(in.values) + 16 * in.offset;
     add_seg(views, 16ull * n);  // inline payloads are addressed in place (view bytes 4..15)
@@ -474,6 +482,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
     e->shared_prefix.assign(p0, p0 + spl);
   }
   e->codec = codec;
+  e->fixed_width = (in.byte_type == BT_DECIMAL128 || in.byte_type == BT_DECIMAL256) ? in.dec_width : 0;
   ctx->n_entries++;
   *out = e;
   return LC_OK;
