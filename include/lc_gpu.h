@@ -112,7 +112,8 @@ typedef enum lc_literal_kind {
   LC_LIT_U64 = 1,
   LC_LIT_BYTES = 2,
   LC_LIT_I128 = 3, /* Decimal128/256 literal, unscaled, SAME scale as the column (DataFusion coerces it):
-                      lit_u64 = low 64 bits, lit_i64 = high 64 bits (two's complement) */
+                      lit_u64 = low 64 bits, lit_i64 = high 64 bits (two's complement). A Decimal256 literal that needs more
+                      than 128 bits travels as LC_LIT_BYTES: the 32 little-endian bytes of the unscaled integer */
   LC_LIT_F64 = 4   /* Float32/Float64 literal: lit_u64 = IEEE bits of the value as f64 (a Float32 literal is
                       widened exactly by the caller and narrowed back here) */
 } lc_literal_kind;
@@ -133,8 +134,9 @@ typedef enum lc_liquid_type {
   LC_LIQUID_INTEGER = 1,
   LC_LIQUID_FLOAT = 2,     /* LiquidFloatArray: ALP (float_array.rs) */
   LC_LIQUID_FIXED_LEN_BYTE_ARRAY = 3, /* LiquidFixedLenByteArray: Decimal128/256 with values outside u64, u16 dictionary +
-                              FSST over the 16 / 32-byte values (fix_len_byte_array.rs); get / filter only — it has no
-                              predicate of its own in the reference either (LiquidArray default: decode, then compare) */
+                              FSST over the 16 / 32-byte values (fix_len_byte_array.rs). The values are kept in
+                              order-preserving byte form, so `col <op> LC_LIT_I128` runs on the dictionary like a byte-view
+                              comparison (the reference decodes, filters and compares: LiquidArray default) */
   LC_LIQUID_BYTE_VIEW = 4,
   LC_LIQUID_DECIMAL = 6    /* LiquidDecimalArray: Decimal128/256 whose values fit u64 (decimal_array.rs) */
 } lc_liquid_type;

@@ -146,8 +146,30 @@ __global__ void __launch_bounds__(256) k_build_views(const int32_t* __restrict__
   views[r] = v;
 }
 
-// LiquidFixedLenByteArray result: the decoded values (variable-length form: offsets + bytes, null rows empty) laid out at
-// their fixed stride, null slots zero. One thread per 4 bytes of output.
+// LiquidFixedLenByteArray keeps its 16 / 32-byte values in ORDER-PRESERVING form: the little-endian two's complement
+// integer byte-reversed (big-endian) with the sign bit flipped, so that unsigned lexicographic byte order — what the
+// byte-view comparison kernels implement — is the numeric order of the decimals. In place, one thread per value.
+__global__ void __launch_bounds__(256) k_fixed_to_ordered(uint8_t* __restrict__ pool, uint32_t n, uint32_t width) {
+  const uint32_t r = blockIdx.x * 256u + threadIdx.x;
+  if (r >= n) return;
+  uint8_t* p = pool + static_cast<size_t>(r) * width;
+  for (uint32_t i = 0; i < width / 2u; ++i) {
+    const uint8_t a = p[i], b = p[width - 1u - i];
+    p[i] = b;
+    p[width - 1u - i] = a;
+  }
+  p[0] ^= 0x80u;
+}
+
+cudaError_t launch_fixed_to_ordered(uint8_t* d_pool, uint32_t n, uint32_t width, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_fixed_to_ordered<<<(n + 255u) / 256u, 256, 0, s>>>(d_pool, n, width);
+  return cudaGetLastError();
+}
+
+// LiquidFixedLenByteArray result: the decoded values (variable-length form: offsets + bytes, null rows empty; order-preserving
+// form, see k_fixed_to_ordered) back as little-endian integers at their fixed stride, null slots zero. One thread per 4
+// bytes of output.
 __global__ void __launch_bounds__(256) k_fixed_from_var(const int32_t* __restrict__ off, uint32_t total_bytes,
                                                         const uint8_t* __restrict__ data, const uint32_t* __restrict__ valid,
                                                         uint64_t rows, uint32_t width, uint32_t* __restrict__ out) {
@@ -162,9 +184,11 @@ __global__ void __launch_bounds__(256) k_fixed_from_var(const int32_t* __restric
     const uint32_t b = static_cast<uint32_t>(off[r]);
     const uint32_t e = r + 1u < rows ? static_cast<uint32_t>(off[r + 1u]) : total_bytes;
     if (e - b == width) {  // always, for an entry built from fixed-width values
-      const uint8_t* p = data + b + 4u * wdx;
-      v = static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) | (static_cast<uint32_t>(p[2]) << 16) |
-          (static_cast<uint32_t>(p[3]) << 24);
+      // output bytes 4*wdx .. 4*wdx+3 (little-endian) are stored bytes width-1-4*wdx .. width-4-4*wdx (big-endian)
+      const uint8_t* p = data + b + (width - 4u - 4u * wdx);
+      v = static_cast<uint32_t>(p[3]) | (static_cast<uint32_t>(p[2]) << 8) | (static_cast<uint32_t>(p[1]) << 16) |
+          (static_cast<uint32_t>(p[0]) << 24);
+      if (wdx == words_per_row - 1u) v ^= 0x80000000u;  // the sign bit lives in stored byte 0 = the top output byte
     }
   }
   out[t] = v;

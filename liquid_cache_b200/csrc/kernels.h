@@ -262,6 +262,8 @@ cudaError_t launch_concat_validity(const uint32_t* d_valid_base, const uint64_t*
 cudaError_t launch_build_views(const int32_t* d_offsets, uint32_t total_bytes, const uint8_t* d_data, const uint32_t* d_validity,
                                uint64_t rows, void* d_views, cudaStream_t s);
 // LiquidFixedLenByteArray results: decoded (offsets, bytes) -> values at a fixed stride of `width` bytes, null slots zero
+// LiquidFixedLenByteArray insert: n little-endian values of `width` bytes at the start of the pool -> order-preserving form
+cudaError_t launch_fixed_to_ordered(uint8_t* d_pool, uint32_t n, uint32_t width, cudaStream_t s);
 cudaError_t launch_fixed_from_var(const int32_t* d_offsets, uint32_t total_bytes, const uint8_t* d_data, const uint32_t* d_validity,
                                   uint64_t rows, uint32_t width, void* d_out, cudaStream_t s);
 cudaError_t launch_and_then(const uint32_t* d_left, uint32_t left_bits, const uint32_t* d_right, uint32_t* d_out,

@@ -185,6 +185,45 @@ static int like_inner(const uint8_t* pat, uint64_t len, const uint8_t** inner, u
   return LC_OK;
 }
 
+// `decimal_col <op> literal` on LiquidFixedLenByteArray entries. The reference has no predicate for this type (the
+// LiquidArray default decodes, filters and lets DataFusion compare, liquid_array/mod.rs:116-130); here the values are stored
+// in order-preserving byte form (k_bits.cu k_fixed_to_ordered), so the comparison IS the byte-view comparison
+// (comparisons.rs:21-151 semantics: equality on prefix keys + compressed bytes, ordering byte-wise) against the literal
+// in the same form. The literal arrives as LC_LIT_I128 at the column's scale; a Decimal256 column sign-extends it.
+struct FixedNeedle {
+  lc_predicate pred{};
+  uint8_t bytes[32];
+};
+static int lower_fixed_pred(Entry* const* entries, uint64_t n, const lc_predicate* pred, FixedNeedle* out) {
+  const uint32_t w = entries[0]->fixed_width;
+  for (uint64_t i = 0; i < n; ++i)
+    if (entries[i]->fixed_width != w || entries[i]->arrow_format != entries[0]->arrow_format) {
+      set_error("eval_predicate_many: fixed-length decimal entries of different types (or mixed with other entries) in one call");
+      return LC_ERR_INVALID;
+    }
+  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
+    set_error("operator %d is not supported on decimal columns", pred->op);
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  uint8_t le[32];
+  if (pred->lit_kind == LC_LIT_BYTES && pred->lit_len == w) {
+    std::memcpy(le, pred->lit_bytes, w);  // the literal as the column's own little-endian integer
+  } else if (pred->lit_kind == LC_LIT_I128) {
+    std::memcpy(le, &pred->lit_u64, 8);
+    std::memcpy(le + 8, &pred->lit_i64, 8);
+    std::memset(le + 16, pred->lit_i64 < 0 ? 0xFF : 0x00, 16);
+  } else {
+    set_error("decimal column needs an LC_LIT_I128 literal (or its little-endian bytes)");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  fixed_to_ordered(le, w, out->bytes);
+  out->pred = *pred;
+  out->pred.lit_kind = LC_LIT_BYTES;
+  out->pred.lit_bytes = out->bytes;
+  out->pred.lit_len = w;
+  return LC_OK;
+}
+
 // Everything a predicate launch over byte-view entries needs, built on the host.
 struct StrLaunch {
   StrPredDesc desc;
@@ -372,12 +411,29 @@ static int make_int_pred(const lc_predicate* pred, const Entry* proto, IntPredDe
   if (proto->liquid_type == LC_LIQUID_DECIMAL) {
     // Decimal128/256 compare as signed 128/256-bit integers; every stored value is in [0, u64::MAX], so a literal
     // outside that window folds to a constant on either side (the literal arrives with the column's scale)
-    if (pred->lit_kind != LC_LIT_I128) {
-      set_error("decimal column needs an LC_LIT_I128 literal");
-      return LC_ERR_UNSUPPORTED_EXPR;
-    }
     out->lit_i = 0;
     out->lit_u = 0;
+    if (pred->lit_kind == LC_LIT_BYTES && (pred->lit_len == 16 || pred->lit_len == 32) && pred->lit_len == proto->dec_width) {
+      // the literal as the column's own little-endian integer (Decimal256 literals beyond 128 bits travel like this)
+      const uint8_t* b = pred->lit_bytes;
+      const bool negative = (b[pred->lit_len - 1] & 0x80u) != 0;
+      bool upper = false;
+      for (uint64_t i = 8; i < pred->lit_len; ++i) upper = upper || b[i] != 0;
+      if (negative) {
+        out->lit_kind = LC_LIT_I64;
+        out->lit_i = -1;
+      } else if (upper) {
+        out->lit_kind = kLitAboveAll;
+      } else {
+        out->lit_kind = LC_LIT_U64;
+        std::memcpy(&out->lit_u, b, 8);
+      }
+      return LC_OK;
+    }
+    if (pred->lit_kind != LC_LIT_I128) {
+      set_error("decimal column needs an LC_LIT_I128 literal (or its little-endian bytes)");
+      return LC_ERR_UNSUPPORTED_EXPR;
+    }
     if (pred->lit_i64 == 0) {
       out->lit_kind = LC_LIT_U64;
       out->lit_u = pred->lit_u64;
@@ -635,11 +691,10 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     set_error("eval_predicate_many: entries of different liquid types in one call");
     return LC_ERR_INVALID;
   }
+  FixedNeedle fixed;
   if (rl->any_fixed) {
-    // LiquidFixedLenByteArray has no predicate of its own (the LiquidArray default: decode, filter, DataFusion evaluate,
-    // liquid_array/mod.rs:123-130): the caller reads the rows (lc_to_arrow) and compares them as it would there
-    set_error("predicates on decimals outside u64 (LiquidFixedLenByteArray) are evaluated by the caller on the decoded rows");
-    return LC_ERR_UNSUPPORTED_EXPR;
+    LC_TRY(lower_fixed_pred(entries, n, pred, &fixed));
+    pred = &fixed.pred;
   }
   if (entries[0]->liquid_type == LC_LIQUID_FLOAT) return eval_predicate_float(ctx, entries, n, rl, pred, sel_bits, out);
   const bool is_int = is_int_blob(entries[0]->liquid_type);
@@ -900,9 +955,10 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
     set_error("scan_filter: entries of different liquid types in one call");
     return LC_ERR_INVALID;
   }
+  FixedNeedle fixed;
   if (rl->any_fixed) {
-    set_error("predicates on decimals outside u64 (LiquidFixedLenByteArray) are evaluated by the caller on the decoded rows");
-    return LC_ERR_UNSUPPORTED_EXPR;
+    LC_TRY(lower_fixed_pred(entries, n, pred, &fixed));
+    pred = &fixed.pred;
   }
   if (entries[0]->liquid_type == LC_LIQUID_FLOAT)
     return refine_float(ctx, entries, n, rl, pred, d_sel_base, d_word_off, all_rows, d_counts);

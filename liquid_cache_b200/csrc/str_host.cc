@@ -298,8 +298,19 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
       codec = it->second;
     } else {
       DictBuilder dict(n < 1024 ? 1024 : n / 2);
-      for (uint32_t i = 0; i < n; ++i)
-        if (row_is_valid(i)) dict.add(row_len[i] ? row_ptr(i) : reinterpret_cast<const uint8_t*>(""), row_len[i]);
+      std::vector<uint8_t> ordered;  // fixed-width values are compressed in their order-preserving form: train on that
+      if (in.kind == ArrowIn::K_DECIMAL) {
+        const uint32_t w = in.dec_width;
+        ordered.resize(static_cast<size_t>(n) * w);
+        for (uint32_t i = 0; i < n; ++i) {
+          if (!row_is_valid(i)) continue;
+          fixed_to_ordered(row_ptr(i), w, ordered.data() + static_cast<size_t>(i) * w);
+          dict.add(ordered.data() + static_cast<size_t>(i) * w, w);
+        }
+      } else {
+        for (uint32_t i = 0; i < n; ++i)
+          if (row_is_valid(i)) dict.add(row_len[i] ? row_ptr(i) : reinterpret_cast<const uint8_t*>(""), row_len[i]);
+      }
       LC_TRY(get_codec(ctx, scope, dict, &codec));
     }
   }
@@ -353,6 +364,10 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   for (const PoolSeg& sg : segs)
     if (sg.bytes) LC_CUDA_OK(cudaMemcpyAsync(d_pool + sg.base, sg.p, sg.bytes, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_bytes + pool_bytes;
+  if (in.kind == ArrowIn::K_DECIMAL) {  // the one segment holds the n values back to back
+    LC_CUDA_OK(launch_fixed_to_ordered(d_pool, n, in.dec_width, s));
+    ctx->kernel_launches++;
+  }
 
   StrEncIo io{};
   io.pool = d_pool;
@@ -479,7 +494,13 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   e->sh = h;
   if (spl) {
     const uint8_t* p0 = row_ptr(first_valid);
-    e->shared_prefix.assign(p0, p0 + spl);
+    if (in.kind == ArrowIn::K_DECIMAL) {  // the blob holds the order-preserving form
+      uint8_t tmp[32];
+      fixed_to_ordered(p0, in.dec_width, tmp);
+      e->shared_prefix.assign(tmp, tmp + spl);
+    } else {
+      e->shared_prefix.assign(p0, p0 + spl);
+    }
   }
   e->codec = codec;
   e->fixed_width = (in.byte_type == BT_DECIMAL128 || in.byte_type == BT_DECIMAL256) ? in.dec_width : 0;
