@@ -58,8 +58,25 @@ struct alignas(16) IntHeader {   // 64 bytes
   uint32_t n_patches;
   uint32_t patch_idx_off; // n_patches x u32 row indices, ascending (behind the packed chunks)
   uint32_t patch_val_off; // n_patches x native float
-  uint32_t pad[1];
+  // squeezed integer entries only (LiquidPrimitiveClampedArray / LiquidPrimitiveQuantizedArray, hybrid_primitive_array.rs):
+  // the packed words are half-width CODES — min(offset, sentinel) under Clamp, offset / bucket_width under Quantize. The
+  // predicate planner of k_int_scan reads these to compare in the right domain; a quantized entry keeps its bucket width
+  // in the two patch offset words above (an integer entry has no patches).
+  uint8_t squeeze_kind;   // 0 = a full entry, 1 clamp, 2 quantize
+  uint8_t pad8[3];
 };
+#ifdef __CUDACC__
+#define LC_HD __host__ __device__
+#else
+#define LC_HD
+#endif
+LC_HD inline unsigned long long int_bucket_width(const IntHeader& h) {
+  return static_cast<unsigned long long>(h.patch_idx_off) | (static_cast<unsigned long long>(h.patch_val_off) << 32);
+}
+inline void set_int_bucket_width(IntHeader* h, unsigned long long bw) {
+  h->patch_idx_off = static_cast<uint32_t>(bw);
+  h->patch_val_off = static_cast<uint32_t>(bw >> 32);
+}
 static_assert(sizeof(IntHeader) == 64, "IntHeader must be 64 bytes");
 
 struct alignas(16) StrHeader {   // 128 bytes

@@ -55,6 +55,7 @@ struct IntPredDesc {
   uint64_t lit_u;
 };
 constexpr int32_t kLitAboveAll = 7;  // decimal literal beyond u64: larger than every value of the column
+constexpr int32_t kLitSentinel = 8;  // squeezed (clamp) entries: "code == all ones of the entry's width", whatever the op says
 
 struct alignas(16) IntMinMaxWork {  // 32 bytes
   const void* values;         // native T[n] in device scratch

@@ -375,6 +375,9 @@ int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, co
   Entry* const* es = nullptr;
   LC_TRY(entries_cached(ctx, handles, n, &es));
   PredOut po{out_values, out_validity, out_byte_offsets, out_len, out_null_count, out_true_count};
+  bool any_squeezed = false;
+  for (uint64_t i = 0; i < n && !any_squeezed; ++i) any_squeezed = es[i]->squeeze_kind != 0;
+  if (any_squeezed) return squeezed_eval_predicate_many(ctx, es, n, pred, sel_bits, po);  // probes + backing reads where needed
   return eval_predicate_batch(ctx, es, n, pred, sel_bits, po);
 }
 

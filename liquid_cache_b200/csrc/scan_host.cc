@@ -445,6 +445,13 @@ static int make_int_pred(const lc_predicate* pred, const Entry* proto, IntPredDe
     }
     return LC_OK;
   }
+  if (pred->lit_kind == kLitSentinelPublic) {  // squeeze_host.cc only: rows of a clamped entry at the sentinel
+    out->op = LC_OP_EQ;
+    out->lit_kind = kLitSentinel;
+    out->lit_i = 0;
+    out->lit_u = 0;
+    return LC_OK;
+  }
   if (pred->lit_kind != LC_LIT_I64 && pred->lit_kind != LC_LIT_U64) {
     set_error("integer column needs an integer literal");
     return LC_ERR_UNSUPPORTED_EXPR;

@@ -364,6 +364,8 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
   // ---- the squeezed blob: same header and validity, packed at half the width ----
   IntHeader h = fh;
   h.bit_width = static_cast<uint8_t>(new_bw);
+  h.squeeze_kind = static_cast<uint8_t>(policy + 1);  // the scan kernel's planner compares codes accordingly (k_int.cu)
+  set_int_bucket_width(&h, bucket_width);
   const uint64_t packed_bytes = static_cast<uint64_t>(h.n_chunks) * 128ull * new_bw;
   const uint64_t blob_bytes = round_up(h.packed_off + packed_bytes, 16);
   h.blob_bytes = static_cast<uint32_t>(blob_bytes);
@@ -414,68 +416,64 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
 
 namespace {
 
-enum class Decide { Codes, Backing };
-
-// What the half-width codes can say about `col <op> k` (try_eval_predicate_inner of either array): the predicate to run
-// on the squeezed entry, and the decoded value whose presence among the selected rows sends the call to the backing.
-struct Lowered {
-  lc_predicate pred;
-  bool has_ambiguous = false;
-  __int128 ambiguous = 0;
+// What the half-width codes can say about `col <op> k` (try_eval_predicate_inner of either array). The predicate itself
+// runs on the squeezed entry unchanged — k_int_scan's planner compares `reference + code` (Clamp) or bucket indices
+// (Quantize, from the header's squeeze_kind / bucket width). What is decided here is whether the codes MAY not decide, and
+// which probe finds the rows that make them fail:
+//   Clamp     resolves_on_sentinel (hybrid_primitive_array.rs:196-219) false -> rows at the sentinel (kLitSentinelPublic)
+//   Quantize  on_equal_bucket (:599-631) unknown -> rows in the literal's bucket: `= k`, which the planner turns into b == q
+struct Doubt {
+  bool possible = false;
+  lc_predicate probe{};
 };
 
-Lowered lower_clamped(const Entry* sq, int32_t op, __int128 k) {
+Doubt doubt_of(const Entry* sq, int32_t op, __int128 k) {
+  Doubt d;
   const __int128 ref = reference_of(sq);
-  const __int128 sent_abs = ref + ((static_cast<__int128>(1) << sq->ih.bit_width) - 1);
-  // Eq, NotEq, Gt, LtEq resolve when k < sentinel value; Lt, GtEq when k <= it (hybrid_primitive_array.rs:196-219)
-  const bool strict = op == LC_OP_EQ || op == LC_OP_NE || op == LC_OP_GT || op == LC_OP_LE;
-  const bool resolves = strict ? k < sent_abs : k <= sent_abs;
-  Lowered l;
-  l.pred = int_predicate(sq, op, k);
-  l.has_ambiguous = !resolves;
-  l.ambiguous = sent_abs;
-  return l;
-}
-
-Lowered lower_quantized(const Entry* sq, int32_t op, __int128 k) {
-  const __int128 ref = reference_of(sq);
-  const bool above = op == LC_OP_NE || op == LC_OP_GT || op == LC_OP_GE;  // the answer for a value known to be > k
-  const bool below = op == LC_OP_NE || op == LC_OP_LT || op == LC_OP_LE;  // ... known to be < k
-  Lowered l;
-  // every decoded value is >= ref: `>= ref` is the constant true, `< ref` the constant false (nulls stay null)
-  auto constant = [&](bool v) { return int_predicate(sq, v ? LC_OP_GE : LC_OP_LT, ref); };
-  if (k < ref) {  // below the minimum (:537-560)
-    l.pred = constant(above);
-    return l;
+  const uint64_t last = (1ull << sq->ih.bit_width) - 1ull;  // the sentinel / the last bucket
+  if (sq->squeeze_kind == LC_SQUEEZE_CLAMP + 1) {
+    const __int128 sent_abs = ref + static_cast<__int128>(last);
+    const bool strict = op == LC_OP_EQ || op == LC_OP_NE || op == LC_OP_GT || op == LC_OP_LE;
+    d.possible = !(strict ? k < sent_abs : k <= sent_abs);
+    d.probe.op = LC_OP_EQ;
+    d.probe.lit_kind = kLitSentinelPublic;
+    return d;
   }
+  if (k < ref) return d;  // below the minimum: constants (:537-560)
   const unsigned __int128 rel = static_cast<unsigned __int128>(k - ref);
   const uint64_t bw = sq->bucket_width;
-  const unsigned __int128 q = rel / bw;
+  if (rel / bw > last) return d;  // every bucket index is below the literal's
   const uint64_t r = static_cast<uint64_t>(rel % bw);
-  const uint64_t last = (1ull << sq->ih.bit_width) - 1ull;
-  if (q > last) {  // every bucket index is below q
-    l.pred = constant(below);
-    return l;
-  }
   bool known = false;
-  switch (op) {  // on_equal_bucket (:599-631)
+  switch (op) {
     case LC_OP_LT: case LC_OP_GE: known = r == 0; break;
     case LC_OP_LE: case LC_OP_GT: known = r + 1 == bw; break;
     default: break;
   }
-  // with no row in bucket q, or at an edge where bucket q falls on the side the operator's own boundary puts it,
-  // `reference + b <op> reference + q` is the answer: b < q -> less side, b > q -> greater side, b == q -> Lt false /
-  // LtEq true / Gt false / GtEq true
-  l.pred = int_predicate(sq, op, ref + static_cast<__int128>(q));
-  l.has_ambiguous = !known;
-  l.ambiguous = ref + static_cast<__int128>(q);
-  return l;
+  d.possible = !known;
+  d.probe = int_predicate(sq, LC_OP_EQ, k);
+  return d;
+}
+
+// selected, valid rows of `sq` that the probe finds
+int count_probe(lc_ctx* ctx, Entry* sq, const lc_predicate& probe, const uint8_t* sel_bits, uint64_t* count) {
+  std::vector<uint8_t> vals(round_up((static_cast<uint64_t>(sq->n) + 7) / 8, 16) + 16);
+  uint64_t len = 0, nulls = 0, trues = 0;
+  const uint64_t off0 = 0;
+  PredOut po{vals.data(), nullptr, &off0, &len, &nulls, &trues};
+  const uint8_t* sels[1] = {sel_bits};
+  Entry* list[1] = {sq};
+  ctx->scratch.reset();
+  LC_TRY(eval_predicate_batch(ctx, list, 1, &probe, sel_bits ? sels : nullptr, po));
+  *count = trues;
+  return LC_OK;
 }
 
 }  // namespace
 
 int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, const uint8_t* sel_bits, const PredOut& out) {
   SqueezeScope scope(ctx);
+  const uint8_t* sels[1] = {sel_bits};
   if (sq->squeeze_kind == 3) {
     // SqueezedDate32Array::try_eval_predicate (:478-485): filter (which reads the backing unless nothing is selected),
     // then the predicate on the filtered rows
@@ -487,10 +485,9 @@ int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, co
     }
     Entry* full = nullptr;
     LC_TRY(hydrate(ctx, sq, &full));
-    const uint8_t* sels1[1] = {sel_bits};
     Entry* list1[1] = {full};
     ctx->scratch.reset();
-    const int rc = eval_predicate_batch(ctx, list1, 1, pred, sel_bits ? sels1 : nullptr, out);
+    const int rc = eval_predicate_batch(ctx, list1, 1, pred, sel_bits ? sels : nullptr, out);
     release_entry(ctx, full);
     return rc;
   }
@@ -498,24 +495,22 @@ int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, co
     set_error("operator %d is not supported on integer columns", pred->op);
     return LC_ERR_UNSUPPORTED_EXPR;
   }
-  const uint8_t* sels[1] = {sel_bits};
   __int128 k = 0;
-  Decide way = Decide::Backing;  // a literal outside the column's type (Ok(None)) goes the long way round
-  Lowered l;
+  bool from_codes = false;  // a literal outside the column's type (Ok(None)) goes the long way round
   if (literal_of(sq, pred, &k)) {
-    l = sq->squeeze_kind == LC_SQUEEZE_CLAMP + 1 ? lower_clamped(sq, pred->op, k) : lower_quantized(sq, pred->op, k);
-    way = Decide::Codes;
-    if (l.has_ambiguous) {
+    from_codes = true;
+    const Doubt d = doubt_of(sq, pred->op, k);
+    if (d.possible) {
       uint64_t hits = 0;
-      LC_TRY(count_equal(ctx, sq, l.ambiguous, sel_bits, &hits));
-      if (hits) way = Decide::Backing;  // Err(NeedsBacking)
+      LC_TRY(count_probe(ctx, sq, d.probe, sel_bits, &hits));
+      if (hits) from_codes = false;  // Err(NeedsBacking)
     }
   }
   Entry* list[1] = {sq};
-  if (way == Decide::Codes) {
+  if (from_codes) {
     ctx->squeeze_saved++;  // io.trace_io_saved()
     ctx->scratch.reset();
-    return eval_predicate_batch(ctx, list, 1, &l.pred, sel_bits ? sels : nullptr, out);
+    return eval_predicate_batch(ctx, list, 1, pred, sel_bits ? sels : nullptr, out);
   }
   Entry* full = nullptr;
   LC_TRY(hydrate(ctx, sq, &full));
@@ -524,6 +519,82 @@ int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, co
   const int rc = eval_predicate_batch(ctx, list, 1, pred, sel_bits ? sels : nullptr, out);
   release_entry(ctx, full);
   return rc;
+}
+
+// The same over a LIST of entries — any mix of full and squeezed (clamp / quantize) integer entries of one column — in a
+// few launches for the whole list: one probe pass per squeeze form that has entries in doubt, one pass of the predicate
+// itself, then only the entries whose probe found a row go back to their backing bytes one by one.
+int squeezed_eval_predicate_many(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
+                                 const uint8_t* const* sel_bits, const PredOut& out_in) {
+  SqueezeScope scope(ctx);
+  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
+    set_error("operator %d is not supported on integer columns", pred->op);
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  const uint64_t zero_off = 0;
+  PredOut out = out_in;
+  if (!out.byte_offsets) {
+    if (n > 1) {
+      set_error("eval_predicate_many: out_byte_offsets required for n > 1");
+      return LC_ERR_INVALID;
+    }
+    out.byte_offsets = &zero_off;
+  }
+  std::vector<uint8_t> doubt(n, 0), backing(n, 0);  // doubt: 1 clamp probe, 2 quantize probe
+  lc_predicate probes[3] = {};
+  uint64_t n_doubt[3] = {0, 0, 0};
+  for (uint64_t i = 0; i < n; ++i) {
+    Entry* e = entries[i];
+    if (e->squeeze_kind == 3 || (e->squeeze_kind && e->liquid_type != LC_LIQUID_INTEGER)) {
+      set_error("eval_predicate_many: entry %llu is a date-component entry; those answer through lc_eval_predicate", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+    if (!e->squeeze_kind) continue;
+    __int128 k = 0;
+    if (!literal_of(e, pred, &k)) {
+      backing[i] = 1;
+      continue;
+    }
+    const Doubt d = doubt_of(e, pred->op, k);
+    if (!d.possible) continue;
+    doubt[i] = static_cast<uint8_t>(e->squeeze_kind);
+    probes[e->squeeze_kind] = d.probe;  // the same for every entry of that form: the sentinel probe / `= k`
+    n_doubt[e->squeeze_kind]++;
+  }
+  // ---- probe passes: true counts per entry; masks land in a scratch area laid out like the caller's ----
+  if (n_doubt[1] || n_doubt[2]) {
+    uint64_t span = 0;
+    for (uint64_t i = 0; i < n; ++i) span = std::max<uint64_t>(span, out.byte_offsets[i] + round_up((static_cast<uint64_t>(entries[i]->n) + 7) / 8, 16));
+    std::vector<uint8_t> tmp(span + 64);
+    std::vector<uint64_t> len(n), nulls(n), trues(n);
+    for (int form = 1; form <= 2; ++form) {
+      if (!n_doubt[form]) continue;
+      PredOut po{tmp.data(), nullptr, out.byte_offsets, len.data(), nulls.data(), trues.data()};
+      ctx->scratch.reset();
+      LC_TRY(eval_predicate_batch(ctx, entries, n, &probes[form], sel_bits, po));
+      for (uint64_t i = 0; i < n; ++i)
+        if (doubt[i] == form && trues[i]) backing[i] = 1;  // Err(NeedsBacking)
+    }
+  }
+  // ---- the predicate over the whole list ----
+  ctx->scratch.reset();
+  LC_TRY(eval_predicate_batch(ctx, entries, n, pred, sel_bits, out));
+  // ---- entries the codes could not decide: their slots are overwritten with the full entry's answer ----
+  for (uint64_t i = 0; i < n; ++i) {
+    if (entries[i]->squeeze_kind && !backing[i]) ctx->squeeze_saved++;
+    if (!backing[i]) continue;
+    Entry* full = nullptr;
+    LC_TRY(hydrate(ctx, entries[i], &full));
+    Entry* list[1] = {full};
+    const uint8_t* sels[1] = {sel_bits ? sel_bits[i] : nullptr};
+    PredOut po{out.values, out.validity, out.byte_offsets + i, out.len ? out.len + i : nullptr, out.null_count ? out.null_count + i : nullptr,
+               out.true_count ? out.true_count + i : nullptr};
+    ctx->scratch.reset();
+    const int rc = eval_predicate_batch(ctx, list, 1, pred, sels[0] ? sels : nullptr, po);
+    release_entry(ctx, full);
+    LC_TRY(rc);
+  }
+  return LC_OK;
 }
 
 int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSchema* out_schema, ArrowArray* out_array) {

@@ -128,7 +128,7 @@ def test_squeezed_codes_match_the_restatement(cache, policy, case):
     assert sq.get_array_memory_size() < full.get_array_memory_size()
     with pytest.raises(N.NativeError):
         sq.to_bytes()
-    with pytest.raises(N.NativeError):  # the batched calls take full entries only
+    with pytest.raises(N.NativeError):  # batched reads and the scan calls take full entries only
         cache.to_arrow_many(np.array([sq.handle], dtype=np.uint64), None)
 
 
@@ -322,3 +322,60 @@ def test_date_component_squeeze_matches_the_restatement(cache, field):
             got = sq.try_eval_predicate(expr_of(">=", lit), sel)
             assert_masks_equal(got, pc.greater_equal(pc.filter(raw, sel), pa.scalar(lit, raw.type)), what + ": >=")
             assert io.reads == before + 1
+
+
+# ---- one call over a list of entries: full, clamped and quantized batches of one column ----
+def _mask_of(vals, valid, off, length, nulls):
+    bits = np.unpackbits(vals[off:off + (length + 7) // 8], bitorder="little")[:length].astype(bool)
+    if nulls == 0:
+        return pa.array(bits, pa.bool_())
+    ok = np.unpackbits(valid[off:off + (length + 7) // 8], bitorder="little")[:length].astype(bool)
+    return pa.array(bits & ok, pa.bool_(), mask=~ok)
+
+
+@pytest.mark.parametrize("typ,base,span", [(pa.int64(), -(2**40), 1 << 20), (pa.uint32(), 1_000_000, 1 << 16), (pa.int16(), -20000, 1 << 15)], ids=str)
+def test_batched_predicates_over_full_and_squeezed_entries(cache, typ, base, span):
+    rng = np.random.default_rng(span)
+    arrays, handles, ios, oracles, keep = [], [], [], [], []
+    for b in range(12):
+        arr = make_array(typ, int(rng.integers(900, 8193)), base + int(rng.integers(0, span // 4)), span, 0.1 if b % 3 else 0.0, 100 + b)
+        full = cache.transcode(arr)
+        form = ("full", "clamp", "quantize")[b % 3]
+        if form == "full":
+            entry, io, osq = full, None, None
+        else:
+            io, oio = CountingIo(), O.OracleSqueezeIo()
+            entry, image = full.squeeze(io, HINT, form)
+            osq, oimage = O.squeeze_int(O.OracleIntArray.from_arrow(arr), oio, "PredicateColumn", form)
+            io.set_bytes(image)
+            oio.set_bytes(oimage)
+            osq._io = oio
+        arrays.append(arr)
+        handles.append(entry.handle)
+        ios.append(io)
+        oracles.append(osq)
+        keep.append((full, entry))
+    rows = np.array([len(a) for a in arrays], dtype=np.uint64)
+    hs = np.array(handles, dtype=np.uint64)
+    all_vals = np.concatenate([np.asarray(a.drop_null().cast(pa.int64() if typ != pa.uint64() else pa.uint64())) for a in arrays])
+    lits = sorted({int(all_vals.min()) - 1, int(all_vals.min()), int(np.median(all_vals)), int(all_vals.max()), int(all_vals.max()) + 1,
+                   boundary_of(arrays[1]), boundary_of(arrays[1]) - 1, int(all_vals[7]), int(all_vals[-3])})
+    info = np.iinfo(typ.to_pandas_dtype())
+    for sel_p in (None, 0.5, 0.01):
+        sels = None if sel_p is None else [np.packbits(rng.random(len(a)) < sel_p, bitorder="little") for a in arrays]
+        for k in (x for x in lits if info.min <= x <= info.max):
+            for op in OPS:
+                for io in ios:
+                    if io is not None:
+                        io.reset_reads()
+                vals, valid, offs, out_len, out_nulls, out_true = cache.eval_predicate_many(hs, rows, expr_of(op, k), typ, sels)
+                for i, arr in enumerate(arrays):
+                    sel = pa.array([True] * len(arr)) if sels is None else pa.array(np.unpackbits(sels[i], bitorder="little")[:len(arr)].astype(bool))
+                    want = O._PC_CMP[op](pc.filter(arr, sel), pa.scalar(k, typ))
+                    got = _mask_of(vals, valid, int(offs[i]), int(out_len[i]), int(out_nulls[i]))
+                    assert_masks_equal(got, want, f"{typ} batch {i} {op} {k} sel={sel_p}")
+                    assert int(out_true[i]) == pc.sum(pc.fill_null(want, False)).as_py() or (int(out_true[i]) == 0 and not pc.any(pc.fill_null(want, False)).as_py())
+                    if oracles[i] is not None:  # the backing is read exactly when the restatement reads it
+                        oracles[i]._io.reset_reads()
+                        oracles[i].try_eval_predicate(op, k, sel)
+                        assert ios[i].reads == oracles[i]._io.reads, (i, op, k, sel_p, ios[i].reads, oracles[i]._io.reads)
