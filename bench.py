@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows PER GPU (weak scaling)")
     ap.add_argument("--cpu-sample-entries", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep"], default="url_like",
+    ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep", "squeeze"], default="url_like",
                     help="url_like = BASELINE configs[1] (the bench line the driver records); int_filter = configs[2]; "
                          "shipdate = configs[3] (TPC-H SF100 l_shipdate range, one GPU's shard of the 8-way split per rank); "
                          "clickbench_sweep = configs[4] (scan stage of the 43 ClickBench queries, bench_sweep.py)")
@@ -335,6 +335,99 @@ def run_int_filter(args, rank, world, local_rank):
     cache.close()
 
 
+def run_squeeze(args, rank, world, local_rank):
+    """`UserID = k` over the UserID column (Int64, W = 64) with every entry SQUEEZED to half-width codes
+    (IntegerSqueezePolicy::Quantize, the reference's default: 32-bit bucket indices, full LQDA images in host memory behind
+    the read callback), through lc_eval_predicate_many — against the same call over the full entries. Reports rows/s of
+    both, HBM bytes of both, and how many entries had to read their backing. Secondary workload: prints its own JSON line."""
+    import numpy as np
+    import pyarrow as pa
+    import torch
+
+    import synth
+    from liquid_cache_b200 import BinaryExpr, CacheExpression, Column, EntryID, LiquidCacheBuilder, LiquidExpr, Literal, parquet_array_id
+
+    torch.cuda.set_device(local_rank)
+    cache = LiquidCacheBuilder.new().with_device(local_rank).build()
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    cache.set_stream(stream.cuda_stream)
+    n_entries = max(1, args.rows // ROWS_PER_ENTRY)
+    ids = [parquet_array_id(0, i // 32, 9, i % 32) for i in range(n_entries)]
+    for g0 in range(0, n_entries, 1024):
+        part = range(g0, min(n_entries, g0 + 1024))
+        cache.insert_many([EntryID(int(ids[i])) for i in part], [synth.int_entry("UserID", rank * n_entries + i) for i in part])
+    hbm_full = int(cache.stats().hbm_bytes_used)
+
+    class Store:  # the "disk": one image per entry in host memory
+        def __init__(self):
+            self.image, self.reads = b"", 0
+
+        def read(self, rng):
+            self.reads += 1
+            return self.image[rng[0]:rng[1]]
+
+    policy = os.environ.get("LC_SQUEEZE_POLICY", "quantize")
+    t0 = time.perf_counter()
+    full, squeezed, stores = [], [], []
+    for i in range(n_entries):
+        la = cache.try_read_liquid(EntryID(int(ids[i])))
+        st = Store()
+        sq, st.image = la.squeeze(st, CacheExpression.PredicateColumn, policy)
+        full.append(la)
+        squeezed.append(sq)
+        stores.append(st)
+    squeeze_s = time.perf_counter() - t0
+    hbm_both = int(cache.stats().hbm_bytes_used)
+    h_full = np.array([a.handle for a in full], dtype=np.uint64)
+    h_sq = np.array([a.handle for a in squeezed], dtype=np.uint64)
+    rows = np.full(n_entries, ROWS_PER_ENTRY, dtype=np.uint64)
+    rows_local = n_entries * ROWS_PER_ENTRY
+    uid = int(synth.int_entry("UserID", rank * n_entries)[17].as_py())
+    pred = LiquidExpr.new_unchecked(BinaryExpr(Column("c", 0), "=", Literal(uid))).to_native(pa.int64())
+    out = None
+
+    def step(handles):
+        nonlocal out
+        out = cache._eval_many_native(handles, rows, pred, None, out)
+        return int(out[5].sum())
+
+    def timed(handles):
+        for _ in range(max(3, args.warmup)):
+            step(handles)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            hits = step(handles)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, hits
+
+    ms_full, hits_full = timed(h_full)
+    for st in stores:
+        st.reads = 0
+    ms_sq, hits_sq = timed(h_sq)
+    reads = sum(st.reads for st in stores) / (args.steps + max(3, args.warmup))
+    peak, peak_src = measured_peak_gbs()
+    width = squeezed[0].bit_width()
+    line = {
+        "metric": METRIC.replace("URL LIKE '%google%'", "UserID = k on squeezed entries"), "value": rows_local / (ms_sq / 1e3) / 1e6, "unit": "Mrows/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_sq, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"clickbench-hits UserID = k through lc_eval_predicate_many, entries squeezed ({policy}) to {width}-bit codes (SURVEY 8f-4)",
+                   "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "matching_rows": hits_sq, "matches_full_entries": hits_sq == hits_full,
+                   "full_entries": {"Mrows_per_s": rows_local / (ms_full / 1e3) / 1e6, "ms_per_step": ms_full, "hbm_bytes": hbm_full},
+                   "squeezed_hbm_bytes": hbm_both - hbm_full, "backing_reads_per_step": reads, "backing_bytes_host": sum(len(st.image) for st in stores),
+                   "squeeze_seconds": squeeze_s,
+                   "note": "masks come back to host buffers in both arms (sparse download); times are end to end per call"},
+        "roofline": {"bound": "hbm", "kernel": "lc_eval_predicate_many over squeezed entries (whole call)", "achieved": rows_local * width / 8 / (ms_sq / 1e3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": rows_local * width / 8 / (ms_sq / 1e3) / 1e9 / peak, "peak_source": peak_src},
+    }
+    print(json.dumps(line))
+    cache.close()
+
+
 def run_shipdate(args, rank, world, local_rank):
     """BASELINE configs[3]: TPC-H SF100 lineitem `l_shipdate >= 1994-01-01 AND l_shipdate < 1995-01-01` (q6's date
     range; Date32, W = 12), entries sharded across 8 B200: every rank holds one eighth of the 600 037 902 rows
@@ -524,6 +617,9 @@ def main():
         return
     if args.workload == "shipdate":
         run_shipdate(args, rank, world, local_rank)
+        return
+    if args.workload == "squeeze":
+        run_squeeze(args, rank, world, local_rank)
         return
     if args.workload == "clickbench_sweep":
         import bench_sweep
