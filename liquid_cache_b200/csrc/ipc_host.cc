@@ -203,7 +203,7 @@ int symbol_table_to_bytes(const FsstCodec& c, uint8_t* out, uint64_t cap, uint64
 }
 
 int symbol_table_from_bytes(const uint8_t* b, uint64_t len, FsstCodec* out) {
-  if (len < 1 || b[0] > 255 || len < 1ull + b[0] + 8ull * b[0]) {
+  if (len < 1 || len < 1ull + b[0] + 8ull * b[0]) {
     set_error("symbol table: truncated");
     return LC_ERR_INVALID;
   }
