@@ -561,8 +561,15 @@ int squeezed_eval_predicate_many(lc_ctx* ctx, Entry* const* entries, uint64_t n,
     probes[e->squeeze_kind] = d.probe;  // the same for every entry of that form: the sentinel probe / `= k`
     n_doubt[e->squeeze_kind]++;
   }
+  // `= k` over quantized entries is its own probe: the predicate pass below tells which entries have a row in bucket q
+  const bool self_probe = pred->op == LC_OP_EQ && n_doubt[2] && !n_doubt[1];
+  std::vector<uint64_t> own_trues;
+  if (self_probe && !out.true_count) {
+    own_trues.assign(n, 0);
+    out.true_count = own_trues.data();
+  }
   // ---- probe passes: true counts per entry; masks land in a scratch area laid out like the caller's ----
-  if (n_doubt[1] || n_doubt[2]) {
+  if ((n_doubt[1] || n_doubt[2]) && !self_probe) {
     uint64_t span = 0;
     for (uint64_t i = 0; i < n; ++i) span = std::max<uint64_t>(span, out.byte_offsets[i] + round_up((static_cast<uint64_t>(entries[i]->n) + 7) / 8, 16));
     std::vector<uint8_t> tmp(span + 64);
@@ -579,6 +586,9 @@ int squeezed_eval_predicate_many(lc_ctx* ctx, Entry* const* entries, uint64_t n,
   // ---- the predicate over the whole list ----
   ctx->scratch.reset();
   LC_TRY(eval_predicate_batch(ctx, entries, n, pred, sel_bits, out));
+  if (self_probe)
+    for (uint64_t i = 0; i < n; ++i)
+      if (doubt[i] == 2 && out.true_count[i]) backing[i] = 1;  // Err(NeedsBacking)
   // ---- entries the codes could not decide: their slots are overwritten with the full entry's answer ----
   for (uint64_t i = 0; i < n; ++i) {
     if (entries[i]->squeeze_kind && !backing[i]) ctx->squeeze_saved++;
