@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "alp_math.cuh"
+#include "squeeze_math.cuh"
 #include "device_utils.cuh"
 #include "kernels.h"
 
@@ -458,14 +459,7 @@ __global__ void __launch_bounds__(256) k_squeeze_map(U* __restrict__ vals, uint3
                                                      unsigned long long bucket_width) {
   for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
     const unsigned long long off = static_cast<unsigned long long>(static_cast<U>(vals[i] - ref));
-    unsigned long long code;
-    if (quantize) {
-      code = off / bucket_width;
-      if (code > limit) code = limit;  // limit = bucket_count - 1
-    } else {
-      code = off >= limit ? limit : off;  // limit = sentinel
-    }
-    vals[i] = static_cast<U>(ref + static_cast<U>(code));
+    vals[i] = static_cast<U>(ref + static_cast<U>(squeeze_code(off, quantize, limit, bucket_width)));
   }
 }
 
@@ -483,55 +477,15 @@ cudaError_t launch_squeeze_map(void* d_vals, uint32_t n, uint32_t tbits, unsigne
   return cudaGetLastError();
 }
 
-// ---- Date32 / Timestamp columns squeezed to one date component (liquid_array/squeezed_date32_array.rs) ----
-// ymd_from_epoch_days (:360-379) / ymd_to_epoch_days (:416-427): Hinnant's civil_from_days / days_from_civil in 64-bit
-// integers, `/` truncating like Rust's.
-__device__ __forceinline__ void civil_from_days(int32_t days, long long* y, long long* m, long long* d) {
-  const long long z = static_cast<long long>(days) + 719468ll;
-  const long long era = (z >= 0 ? z : z - 146096ll) / 146097ll;
-  const long long doe = z - era * 146097ll;
-  const long long yoe = (doe - doe / 1460ll + doe / 36524ll - doe / 146096ll) / 365ll;
-  const long long doy = doe - (365ll * yoe + yoe / 4ll - yoe / 100ll);
-  const long long mp = (5ll * doy + 2ll) / 153ll;
-  *d = doy - (153ll * mp + 2ll) / 5ll + 1ll;
-  *m = mp + (mp < 10 ? 3ll : -9ll);
-  *y = yoe + era * 400ll + (*m <= 2 ? 1ll : 0ll);
-}
-__device__ __forceinline__ int32_t days_from_civil(long long year, long long m, long long d) {
-  const long long y = year - (m <= 2 ? 1ll : 0ll);
-  const long long era = (y >= 0 ? y : y - 399ll) / 400ll;
-  const long long yoe = y - era * 400ll;
-  const long long mp = m + (m > 2 ? -3ll : 9ll);
-  const long long doy = (153ll * mp + 2ll) / 5ll + d - 1ll;
-  const long long doe = yoe * 365ll + yoe / 4ll - yoe / 100ll + doy;
-  return static_cast<int32_t>(static_cast<unsigned long long>(era * 146097ll + doe - 719468ll));  // `as i32`
-}
-// component_from_days (:381-393); field: 0 year, 1 month, 2 day, 3 day of week (Sunday = 0)
-__device__ __forceinline__ int32_t date_component(uint32_t field, int32_t days) {
-  if (field == 3u) {
-    const int32_t r = static_cast<int32_t>((static_cast<long long>(days) + 4ll) % 7ll);
-    return r < 0 ? r + 7 : r;  // rem_euclid
-  }
-  long long y, m, d;
-  civil_from_days(days, &y, &m, &d);
-  return static_cast<int32_t>(field == 0u ? y : field == 1u ? m : d);
-}
-
+// ---- Date32 / Timestamp columns squeezed to one date component (liquid_array/squeezed_date32_array.rs); the per-value
+// arithmetic lives in squeeze_math.cuh ----
 // from_liquid_date32 (:63-141) / from_liquid_timestamp (:144-223): decoded days (T = int32, ticks_per_day = 0) or
 // timestamp ticks (T = int64; div_euclid by the unit's ticks per day, `as i32`) -> the component of every row
 template <typename T>
 __global__ void __launch_bounds__(256) k_date_component(const T* __restrict__ in, uint32_t n, uint32_t field, long long ticks_per_day,
                                                         int32_t* __restrict__ out) {
   for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-    int32_t days;
-    if (ticks_per_day) {
-      const long long v = static_cast<long long>(in[i]);
-      long long q = v / ticks_per_day;
-      if (v % ticks_per_day < 0) --q;
-      days = static_cast<int32_t>(static_cast<unsigned long long>(q));
-    } else {
-      days = static_cast<int32_t>(in[i]);
-    }
+    const int32_t days = ticks_per_day ? days_of_ticks(static_cast<long long>(in[i]), ticks_per_day) : static_cast<int32_t>(in[i]);
     out[i] = date_component(field, days);
   }
 }
@@ -543,17 +497,7 @@ __global__ void __launch_bounds__(256) k_date_lossy(const int32_t* __restrict__ 
                                                     uint32_t field, long long ticks_per_day, void* __restrict__ out) {
   for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
     const bool ok = valid ? ((valid[i >> 5] >> (i & 31u)) & 1u) : true;
-    int32_t days = 0;
-    if (ok) {
-      const int32_t c = comp[i];
-      if (field == 0u) days = days_from_civil(c, 1, 1);
-      else if (field == 1u) days = days_from_civil(1970, static_cast<long long>(static_cast<uint32_t>(c)), 1);
-      else if (field == 2u) days = days_from_civil(1970, 1, static_cast<long long>(static_cast<uint32_t>(c)));
-      else {
-        const long long t = 3ll + static_cast<long long>(c);  // 1970-01-04 is day 3
-        days = t > 2147483647ll ? 2147483647 : t < -2147483648ll ? static_cast<int32_t>(-2147483647 - 1) : static_cast<int32_t>(t);
-      }
-    }
+    const int32_t days = ok ? lossy_days(field, comp[i]) : 0;
     if (ticks_per_day) static_cast<long long*>(out)[i] = static_cast<long long>(days) * ticks_per_day;
     else static_cast<int32_t*>(out)[i] = days;
   }
