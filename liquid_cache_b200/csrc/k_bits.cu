@@ -5,6 +5,7 @@
 // rank_left(p)-th bit of right, where right has popcount(left) bits. On the GPU the "deposit" is a
 // rank computed from a prefix sum of per-word popcounts plus __popc(word & lanemask_lt).
 #include "device_utils.cuh"
+#include "fixed_math.cuh"
 #include "kernels.h"
 
 namespace lc {
@@ -152,13 +153,7 @@ __global__ void __launch_bounds__(256) k_build_views(const int32_t* __restrict__
 __global__ void __launch_bounds__(256) k_fixed_to_ordered(uint8_t* __restrict__ pool, uint32_t n, uint32_t width) {
   const uint32_t r = blockIdx.x * 256u + threadIdx.x;
   if (r >= n) return;
-  uint8_t* p = pool + static_cast<size_t>(r) * width;
-  for (uint32_t i = 0; i < width / 2u; ++i) {
-    const uint8_t a = p[i], b = p[width - 1u - i];
-    p[i] = b;
-    p[width - 1u - i] = a;
-  }
-  p[0] ^= 0x80u;
+  fixed_to_ordered_inplace(pool + static_cast<size_t>(r) * width, width);
 }
 
 cudaError_t launch_fixed_to_ordered(uint8_t* d_pool, uint32_t n, uint32_t width, cudaStream_t s) {
@@ -184,11 +179,7 @@ __global__ void __launch_bounds__(256) k_fixed_from_var(const int32_t* __restric
     const uint32_t b = static_cast<uint32_t>(off[r]);
     const uint32_t e = r + 1u < rows ? static_cast<uint32_t>(off[r + 1u]) : total_bytes;
     if (e - b == width) {  // always, for an entry built from fixed-width values
-      // output bytes 4*wdx .. 4*wdx+3 (little-endian) are stored bytes width-1-4*wdx .. width-4-4*wdx (big-endian)
-      const uint8_t* p = data + b + (width - 4u - 4u * wdx);
-      v = static_cast<uint32_t>(p[3]) | (static_cast<uint32_t>(p[2]) << 8) | (static_cast<uint32_t>(p[1]) << 16) |
-          (static_cast<uint32_t>(p[0]) << 24);
-      if (wdx == words_per_row - 1u) v ^= 0x80000000u;  // the sign bit lives in stored byte 0 = the top output byte
+      v = fixed_le_word(data + b, width, wdx);
     }
   }
   out[t] = v;
