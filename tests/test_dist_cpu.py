@@ -29,10 +29,20 @@ def _worker(rank, world, port, q):
         strs = pa.array([None if rng.random() < 0.2 else f"http://r{rank}/{i}" * int(rng.integers(0, 4)) for i in range(50 + 30 * rank)])
         ints = pa.array(rng.integers(-5, 5, size=10 * (rank + 1)), pa.int64())
         empty = pa.array([], pa.string()) if rank == 1 else pa.array(["only-rank0"])
+        import decimal
+
+        floats = pa.array([None if rng.random() < 0.3 else float(rng.standard_normal()) for _ in range(20 + 7 * rank)], pa.float64())
+        decs = pa.array([decimal.Decimal(int(x)).scaleb(-2) for x in rng.integers(0, 10**6, size=5 + rank)], pa.decimal128(15, 2))
+        dates = pa.array(rng.integers(8036, 10556, size=9 * (rank + 1)), pa.int32()).cast(pa.date32())
         out = []
         for a in (strs, ints, empty):
             g = gather_arrow_to_rank0(a, rank, world)
             out.append(None if g is None else g.to_pylist())
+        extra_local, extra_out = [], []
+        for a in (floats, decs, dates):  # every fixed-width result type of the path travels the same way
+            g = gather_arrow_to_rank0(a, rank, world)
+            extra_local.append(a.to_pylist())
+            extra_out.append(None if g is None else g.to_pylist())
         # the device-buffer flavour (lc_scan_read_device results), here on CPU tensors over gloo
         import torch
 
@@ -49,7 +59,7 @@ def _worker(rank, world, port, q):
                 b = torch.from_numpy(words)
             g = gather_device_result_to_rank0(v, o, b, len(a), a.null_count, a.type, rank, world)
             out.append(None if g is None else g.to_pylist())
-        q.put((rank, [strs.to_pylist(), ints.to_pylist(), empty.to_pylist(), strs.to_pylist(), ints.to_pylist()], out))
+        q.put((rank, [strs.to_pylist(), ints.to_pylist(), empty.to_pylist(), strs.to_pylist(), ints.to_pylist()] + extra_local, out + extra_out))
     finally:
         dist.destroy_process_group()
 
@@ -70,8 +80,8 @@ def test_gather_to_rank0_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for k in range(5):
-        assert res[0][1][k] == res[0][0][k] + res[1][0][k]
+    for k in range(8):
+        assert res[0][1][k] == res[0][0][k] + res[1][0][k], k
         assert res[1][1][k] is None
 
 
