@@ -356,6 +356,25 @@ static int str_entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, con
     set_error("from_bytes: dictionary sections run past the image");
     return LC_ERR_INVALID;
   }
+  // the offsets the decode kernels will follow: slope * i + intercept + residual[i] (CompactOffsets::get_offset,
+  // fsst_buffer.rs:360-383) must start at 0, never step back, and stay inside the compressed values
+  if (n_resid) {
+    uint64_t prev = 0;
+    for (uint32_t i = 0; i < n_resid; ++i) {
+      int64_t r = 0;
+      const uint8_t* rp = b + resid_src + static_cast<uint64_t>(i) * ob;
+      if (ob == 1) r = static_cast<int8_t>(rp[0]);
+      else if (ob == 2) r = static_cast<int16_t>(get_u16(rp));
+      else r = static_cast<int32_t>(get_u32(rp));
+      // the kernels' arithmetic (k_str.cu dict_offset): 32-bit wrapping sum, read as unsigned
+      const uint64_t off = static_cast<uint32_t>(static_cast<uint32_t>(slope) * i + static_cast<uint32_t>(intercept) + static_cast<uint32_t>(r));
+      if ((i == 0 && off != 0) || off < prev || off > comp_bytes) {
+        set_error("from_bytes: dictionary offset %u does not fit the compressed values", i);
+        return LC_ERR_INVALID;
+      }
+      prev = off;
+    }
+  }
   // every key must name a dictionary value (W = 16: the packed words ARE the keys, transposed)
   {
     const uint64_t n_keys = kvals_len / 2;

@@ -151,7 +151,11 @@ def test_damaged_byte_view_images_are_refused(cache):
     bad_offs = bytearray(good)
     co_start = ((keys_start + keys_size) + 7) & ~7
     bad_offs[co_start + 8] = 3                                        # residual width 3
-    for bad in (good[:30], bytes(bad_key), bytes(bad_width), bytes(bad_sizes), bytes(bad_offs), good[:-(fp_size // 2)]):
+    bad_resid = bytearray(good)
+    ob = good[co_start + 8]
+    last = co_start + 9 + (len(o.uniques)) * ob   # the closing offset: pushed past the compressed values
+    bad_resid[last:last + ob] = (2 ** (8 * ob - 1) - 1).to_bytes(ob, "little")
+    for bad in (good[:30], bytes(bad_key), bytes(bad_width), bytes(bad_sizes), bytes(bad_offs), bytes(bad_resid), good[:-(fp_size // 2)]):
         with pytest.raises(N.NativeError):
             cache.read_from_bytes(bad, compressor_scope=3000)
     # nothing leaked: the good image still loads afterwards
