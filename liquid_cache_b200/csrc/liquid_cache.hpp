@@ -51,6 +51,14 @@ struct BooleanBuffer {
 struct LiquidExpr {
   lc_predicate pred{};
   std::string bytes;  // owns the literal for byte-like columns
+  // the native form with the literal pointer taken from THIS object's bytes (copies and moves of a LiquidExpr stay valid)
+  const lc_predicate* native() {
+    if (pred.lit_kind == LC_LIT_BYTES) {
+      pred.lit_bytes = reinterpret_cast<const uint8_t*>(bytes.data());
+      pred.lit_len = bytes.size();
+    }
+    return &pred;
+  }
   static LiquidExpr compare_i64(lc_op op, int64_t v) {
     LiquidExpr e;
     e.pred.op = op;
@@ -180,7 +188,7 @@ inline bool EvaluatePredicate::read(BooleanArray* out) {
   const uint64_t nb = lc_mask_bytes(lc_len(c_->raw(), h));
   out->values.assign(nb, 0);
   out->validity.assign(nb, 0);
-  check(lc_cache_eval_predicate(c_->raw(), id_, &e_.pred, sel_.bits, sel_.len, out->values.data(), out->validity.data(),
+  check(lc_cache_eval_predicate(c_->raw(), id_, e_.native(), sel_.bits, sel_.len, out->values.data(), out->validity.data(),
                                 &out->len, &out->null_count));
   return true;
 }

@@ -119,3 +119,15 @@ QUICK_START = {
     "string_selection": [True, True, False, True, True],
     "eq_apple_selected": [True, False, True, False],
 }
+
+# Multi-column OR over cached columns (src/datafusion/src/cache/mod.rs:433-639): (columns, conjuncts, rows that match)
+MULTI_COLUMN_OR_CASES = [
+    # evaluate_or_on_cached_columns: a = 3 OR b = 20
+    ([("int32", [1, 2, 3, 4]), ("int32", [10, 20, 30, 40])], [("=", 3), ("=", 20)], [1, 2]),
+    # evaluate_three_column_or: a = 2 OR b = 40 OR c = 600
+    ([("int32", [1, 2, 3, 4, 5, 6, 7, 8]), ("int32", [10, 20, 30, 40, 50, 60, 70, 80]), ("int32", [100, 200, 300, 400, 500, 600, 700, 800])],
+     [("=", 2), ("=", 40), ("=", 600)], [1, 3, 5]),
+    # evaluate_string_column_or: name = 'Bob' OR city = 'Tokyo' (Utf8View columns)
+    ([("string_view", ["Alice", "Bob", "Charlie", "David", "Eve", "Frank", "Grace", "Henry"]),
+      ("string_view", ["New York", "London", "Paris", "Tokyo", "Berlin", "Sydney", "Madrid", "Rome"])], [("=", "Bob"), ("=", "Tokyo")], [1, 3]),
+]

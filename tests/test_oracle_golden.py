@@ -171,3 +171,21 @@ def test_c_port_matches_python_oracle():
     l = rng.random(5000) < 0.3
     r = rng.random(int(l.sum())) < 0.5
     assert CO.and_then(l, r).tolist() == boolean_buffer_and_then(pa.array(l), pa.array(r)).to_pylist()
+
+
+def test_multi_column_or_known_answers():
+    """src/datafusion/src/cache/mod.rs:433-639: per-column masks under one selection, joined with or_kleene"""
+    from oracle.liquid_oracle import evaluate_multi_column_or, transcode
+    from tests.golden_cases import MULTI_COLUMN_OR_CASES
+
+    types = {"int32": pa.int32(), "string_view": pa.string_view()}
+    for cols, conjuncts, want_rows in MULTI_COLUMN_OR_CASES:
+        n = len(cols[0][1])
+        liquid = [transcode(pa.array(vals, types[t])) for t, vals in cols]
+        got = evaluate_multi_column_or([(la, op, lit) for la, (op, lit) in zip(liquid, conjuncts)], pa.array([True] * n))
+        assert got.to_pylist() == [i in want_rows for i in range(n)]
+    # nulls follow Kleene logic: NULL OR TRUE = TRUE, NULL OR FALSE = NULL
+    a = transcode(pa.array([1, None, None, 4], pa.int32()))
+    b = transcode(pa.array([10, 20, 30, None], pa.int32()))
+    got = evaluate_multi_column_or([(a, "=", 1), (b, "=", 20)], pa.array([True] * 4))
+    assert got.to_pylist() == [True, True, None, None]

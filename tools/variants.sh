@@ -48,6 +48,9 @@ case "$cmd" in
           timeout 300 python bench.py --steps 20 --warmup 5 > "$o/bench_url_like.json" 2> "$o/bench_url_like.err"
           timeout 300 python bench.py --workload int_filter --steps 20 --warmup 5 > "$o/bench_int_filter.json" 2> "$o/bench_int_filter.err"
           timeout 300 python bench.py --workload shipdate --steps 10 --warmup 3 > "$o/bench_shipdate.json" 2> "$o/bench_shipdate.err"
+          if python bench.py --help | grep -q squeeze; then
+            timeout 300 python bench.py --workload squeeze --rows 20000000 --steps 10 --warmup 3 > "$o/bench_squeeze.json" 2> "$o/bench_squeeze.err"
+          fi
         fi
       )
       verdict="$(tail -n 2 "$o/pytest.log" | tr '\n' ' ')"
@@ -55,7 +58,7 @@ case "$cmd" in
 import json, sys, os
 o = sys.argv[1]
 parts = []
-for name in ("bench_url_like", "bench_int_filter", "bench_shipdate"):
+for name in ("bench_url_like", "bench_int_filter", "bench_shipdate", "bench_squeeze"):
     p = os.path.join(o, name + ".json")
     try:
         j = json.loads(open(p).read().strip().splitlines()[-1])
