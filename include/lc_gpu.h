@@ -228,7 +228,9 @@ int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8
  * the image back (one `read` call for the whole range, like hydrate_full_arrow) when they cannot; the result is always
  * the full entry's. lc_eval_predicate_many takes any mix of full and squeezed (clamp / quantize) entries of one column: a
  * probe pass per squeeze form finds the entries whose codes cannot decide, one pass evaluates the predicate over the whole
- * list, and only those entries are read back and re-evaluated. lc_to_arrow_many and the scan calls take full entries only. */
+ * list, and only those entries are read back and re-evaluated. lc_scan_filter does the same on the device-resident selection
+ * (probes run on a copy of it). lc_to_arrow_many and lc_scan_read* take full entries only: rows are read from a squeezed
+ * column through lc_to_arrow, entry by entry. */
 typedef int (*lc_backing_read)(void* user, uint64_t offset, uint64_t len, uint8_t* dst); /* 0 = ok; SqueezeIoHandler::read */
 typedef enum lc_squeeze_policy { LC_SQUEEZE_CLAMP = 0, LC_SQUEEZE_QUANTIZE = 1 } lc_squeeze_policy; /* IntegerSqueezePolicy */
 /* Returns the pair of LiquidArray::squeeze: the full bytes (written to bytes_out, *out_bytes long) and the squeezed entry.

@@ -288,6 +288,8 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
 constexpr int32_t kLitSentinelPublic = 1000;  // lc_predicate.lit_kind used by squeeze_host.cc alone (-> kLitSentinel)
 int squeezed_eval_predicate_many(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
                                  const uint8_t* const* sel_bits, const PredOut& out);
+int squeeze_doubt(const Entry* e, const lc_predicate* pred, lc_predicate* probe);
+int squeeze_hydrate(lc_ctx* ctx, const Entry* sq, Entry** full);
 int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
                   uint64_t cap, uint64_t* out_bytes, Entry** out);
 int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, const uint8_t* sel_bits, const PredOut& out);

@@ -43,6 +43,10 @@ struct lc_scan {
   uint32_t* d_sel = nullptr;
   uint32_t* d_counts = nullptr;
   uint64_t* d_word_off = nullptr;
+  // squeezed entries only (scan_filter_squeezed), allocated on first use: probe copy / snapshot of the selection, probe counts
+  uint32_t* d_probe = nullptr;
+  uint32_t* d_save = nullptr;
+  uint32_t* d_pcounts = nullptr;
   bool all_rows = true;       // no filter applied yet
   bool counts_on_device = false;
   bool counts_cached = false;
@@ -654,6 +658,92 @@ int lc_scan_set_selection(lc_scan* scan, uint64_t batch, const uint8_t* sel_bits
   return LC_OK;
 }
 
+// lc_scan_filter over a list with squeezed (clamp / quantize) entries: selection &= valid & cmp stays one pass over the
+// whole list — the kernel's planner compares codes the way each header asks for — around two cheap extras:
+//   before  a probe pass per squeeze form in doubt, on a COPY of the selection, tells which entries have a selected row the
+//           codes cannot decide (hybrid_primitive_array.rs: Err(NeedsBacking));
+//   after   only those entries get their selection words back, read their LQDA image through the caller's function,
+//           and are refined again as full entries.
+static int scan_filter_squeezed(lc_scan* scan, Entry* const* es, const lc_predicate* pred) {
+  lc_ctx* ctx = scan->ctx;
+  const uint64_t n = scan->n;
+  struct Internal {  // the batch functions refuse squeezed entries unless squeeze code drives them
+    lc_ctx* c;
+    bool prev;
+    explicit Internal(lc_ctx* x) : c(x), prev(x->squeeze_internal) { x->squeeze_internal = true; }
+    ~Internal() { c->squeeze_internal = prev; }
+  } internal(ctx);
+  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
+    set_error("operator %d is not supported on integer columns", pred->op);
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  std::vector<uint8_t> doubt(n, 0);
+  lc_predicate probes[3] = {};
+  uint64_t n_doubt[4] = {0, 0, 0, 0};
+  for (uint64_t i = 0; i < n; ++i) {
+    if (es[i]->squeeze_kind == 3) {
+      set_error("lc_scan_filter: entry %llu is a date-component entry; those answer through lc_eval_predicate", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+    lc_predicate probe{};
+    const int d = squeeze_doubt(es[i], pred, &probe);
+    doubt[i] = static_cast<uint8_t>(d);
+    n_doubt[d]++;
+    if (d == 1 || d == 2) probes[d] = probe;
+  }
+  std::vector<uint8_t> backing(n, 0);
+  for (uint64_t i = 0; i < n; ++i) backing[i] = doubt[i] == 3;
+  const bool any_doubt = n_doubt[1] || n_doubt[2] || n_doubt[3];
+  cudaStream_t s = ctx->stream;
+  // work areas kept with the scan: a copy of the selection for the probes, one to restore from, probe counts
+  const uint64_t sel_bytes = scan->total_words * 4 + 64;
+  if (any_doubt && !scan->d_probe) {
+    if (cudaMalloc(reinterpret_cast<void**>(&scan->d_probe), sel_bytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&scan->d_save), sel_bytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&scan->d_pcounts), n * 8 + 16) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("lc_scan_filter: cudaMalloc for the probe selection failed");
+      return LC_ERR_OOM;  // lc_scan_end frees whatever was allocated
+    }
+  }
+  uint32_t* d_probe = scan->d_probe;
+  uint32_t* d_save = scan->d_save;
+  uint32_t* d_pcounts = scan->d_pcounts;
+  if (any_doubt && !scan->all_rows)
+    LC_CUDA_OK(cudaMemcpyAsync(d_save, scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToDevice, s));
+  std::vector<uint32_t> pc(n * 2);
+  for (int form = 1; form <= 2; ++form) {
+    if (!n_doubt[form]) continue;
+    if (!scan->all_rows) LC_CUDA_OK(cudaMemcpyAsync(d_probe, scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToDevice, s));
+    ctx->scratch.reset();
+    LC_TRY(refine_batch(ctx, es, n, &probes[form], d_probe, scan->d_word_off, scan->all_rows, d_pcounts));
+    LC_CUDA_OK(cudaMemcpyAsync(pc.data(), d_pcounts, n * 8, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += n * 8;
+    for (uint64_t i = 0; i < n; ++i)
+      if (doubt[i] == form && pc[2 * i]) backing[i] = 1;
+  }
+  // ---- the predicate over the whole list ----
+  ctx->scratch.reset();
+  LC_TRY(refine_batch(ctx, es, n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
+  // ---- entries the codes could not decide ----
+  for (uint64_t i = 0; i < n; ++i) {
+    if (es[i]->squeeze_kind && !backing[i]) ctx->squeeze_saved++;
+    if (!backing[i]) continue;
+    const uint64_t words = (static_cast<uint64_t>(scan->rows[i]) + 31) / 32;
+    if (!scan->all_rows)
+      LC_CUDA_OK(cudaMemcpyAsync(scan->d_sel + scan->word_off[i], d_save + scan->word_off[i], words * 4, cudaMemcpyDeviceToDevice, s));
+    Entry* full = nullptr;
+    LC_TRY(squeeze_hydrate(ctx, es[i], &full));
+    Entry* one[1] = {full};
+    ctx->scratch.reset();
+    const int rc = refine_batch(ctx, one, 1, pred, scan->d_sel, scan->d_word_off + i, scan->all_rows, scan->d_counts + 2 * i);
+    release_entry(ctx, full);
+    LC_TRY(rc);
+  }
+  return LC_OK;
+}
+
 int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* pred) {
   if (!scan || !handles || !pred) {
     set_error("lc_scan_filter: NULL argument");
@@ -663,7 +753,10 @@ int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* 
   Guard g(ctx);
   Entry* const* es = nullptr;
   LC_TRY(scan_entries_cached(scan, handles, &es));
-  LC_TRY(refine_batch(ctx, es, scan->n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
+  bool any_squeezed = false;
+  for (uint64_t i = 0; i < scan->n && !any_squeezed; ++i) any_squeezed = es[i]->squeeze_kind != 0;
+  if (any_squeezed) LC_TRY(scan_filter_squeezed(scan, es, pred));
+  else LC_TRY(refine_batch(ctx, es, scan->n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
   scan->all_rows = false;
   scan->counts_on_device = true;
   scan->counts_cached = false;
@@ -787,6 +880,9 @@ void lc_scan_end(lc_scan* scan) {
     Guard g(scan->ctx);
     cudaStreamSynchronize(scan->ctx->stream);
     if (scan->d_sel) cudaFree(scan->d_sel);
+    if (scan->d_probe) cudaFree(scan->d_probe);
+    if (scan->d_save) cudaFree(scan->d_save);
+    if (scan->d_pcounts) cudaFree(scan->d_pcounts);
     if (scan->d_counts) cudaFree(scan->d_counts);
     if (scan->d_word_off) cudaFree(scan->d_word_off);
   }

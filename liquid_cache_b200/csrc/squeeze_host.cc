@@ -521,6 +521,21 @@ int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, co
   return rc;
 }
 
+// For the scan pipeline (lc_abi.cc lc_scan_filter): what the codes of ONE entry can say about the predicate.
+//   returns 0: they decide (or the entry is a full one); 1 / 2: they decide unless the clamp / quantize probe finds a
+//   selected row (*probe is that probe); 3: the backing is needed whatever the rows (literal outside the column's type)
+int squeeze_doubt(const Entry* e, const lc_predicate* pred, lc_predicate* probe) {
+  if (!e->squeeze_kind) return 0;
+  __int128 k = 0;
+  if (!literal_of(e, pred, &k)) return 3;
+  const Doubt d = doubt_of(e, pred->op, k);
+  if (!d.possible) return 0;
+  *probe = d.probe;
+  return e->squeeze_kind;
+}
+
+int squeeze_hydrate(lc_ctx* ctx, const Entry* sq, Entry** full) { return hydrate(ctx, sq, full); }
+
 // The same over a LIST of entries — any mix of full and squeezed (clamp / quantize) integer entries of one column — in a
 // few launches for the whole list: one probe pass per squeeze form that has entries in doubt, one pass of the predicate
 // itself, then only the entries whose probe found a row go back to their backing bytes one by one.

@@ -379,3 +379,48 @@ def test_batched_predicates_over_full_and_squeezed_entries(cache, typ, base, spa
                         oracles[i]._io.reset_reads()
                         oracles[i].try_eval_predicate(op, k, sel)
                         assert ios[i].reads == oracles[i]._io.reads, (i, op, k, sel_p, ios[i].reads, oracles[i]._io.reads)
+
+
+# ---- the device-resident scan pipeline over squeezed entries (lc_scan_filter) ----
+@pytest.mark.parametrize("typ,base,span", [(pa.int64(), -(2**40), 1 << 20), (pa.uint32(), 1_000_000, 1 << 16)], ids=str)
+def test_scan_filter_over_full_and_squeezed_entries(cache, typ, base, span):
+    rng = np.random.default_rng(span + 1)
+    arrays, mixed, fulls, ios, keep = [], [], [], [], []
+    for b in range(9):
+        arr = make_array(typ, int(rng.integers(900, 8193)), base + int(rng.integers(0, span // 4)), span, 0.1 if b % 3 else 0.0, 300 + b)
+        full = cache.transcode(arr)
+        form = ("full", "clamp", "quantize")[b % 3]
+        io = None
+        entry = full
+        if form != "full":
+            io = CountingIo()
+            entry, image = full.squeeze(io, HINT, form)
+            io.set_bytes(image)
+        arrays.append(arr)
+        fulls.append(full.handle)
+        mixed.append(entry.handle)
+        ios.append(io)
+        keep.append((full, entry))
+    rows = [len(a) for a in arrays]
+    h_full, h_mixed = np.array(fulls, dtype=np.uint64), np.array(mixed, dtype=np.uint64)
+    all_vals = np.concatenate([np.asarray(a.drop_null().cast(pa.int64())) for a in arrays])
+    lo, hi, present = int(np.quantile(all_vals, 0.3)), int(np.quantile(all_vals, 0.8)), int(all_vals[11])
+    conjunct_sets = [[(">=", lo), ("<", hi)], [("=", present)], [("!=", present), ("<=", hi), (">", lo)], [("<", int(all_vals.min()))],
+                     [(">=", boundary_of(arrays[1])), ("<", boundary_of(arrays[1]) + 3)]]
+    for seeded in (False, True):
+        for conjuncts in conjunct_sets:
+            with cache.scan(rows) as want_scan, cache.scan(rows) as got_scan:
+                if seeded:  # a selection seeded from the host, then refined on the device
+                    for b, a in enumerate(arrays):
+                        sel = pa.array(np.random.default_rng(b).random(len(a)) < 0.5)
+                        want_scan.set_selection(b, sel)
+                        got_scan.set_selection(b, sel)
+                for op, k in conjuncts:
+                    want_scan.filter(h_full, expr_of(op, k), typ)
+                    got_scan.filter(h_mixed, expr_of(op, k), typ)
+                    wc, wt = want_scan.counts()
+                    gc, gt = got_scan.counts()
+                    assert gt == wt and np.array_equal(gc, wc), (seeded, conjuncts, op, k)
+                for b in range(len(arrays)):
+                    assert_masks_equal(got_scan.selection(b), want_scan.selection(b), f"batch {b} after {conjuncts} seeded={seeded}")
+    assert any(io is not None and io.reads for io in ios)  # some conjunct did go back to the backing bytes
