@@ -409,20 +409,46 @@ def run_squeeze(args, rank, world, local_rank):
         st.reads = 0
     ms_sq, hits_sq = timed(h_sq)
     reads = sum(st.reads for st in stores) / (args.steps + max(3, args.warmup))
+    # the device-resident pipeline (selection stays in HBM, only the survivor counts come back): lc_scan_filter
+    scan = cache.scan(rows)
+
+    def scan_step(handles):
+        scan.reset()
+        scan.filter_native(handles, pred)
+        return int(scan.counts()[1])
+
+    def scan_timed(handles):
+        for _ in range(max(3, args.warmup)):
+            scan_step(handles)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            hits = scan_step(handles)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, hits
+
+    scan_ms_full, scan_hits_full = scan_timed(h_full)
+    scan_ms_sq, scan_hits_sq = scan_timed(h_sq)
+    scan.close()
     peak, peak_src = measured_peak_gbs()
     width = squeezed[0].bit_width()
     line = {
-        "metric": METRIC.replace("URL LIKE '%google%'", "UserID = k on squeezed entries"), "value": rows_local / (ms_sq / 1e3) / 1e6, "unit": "Mrows/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_sq, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC.replace("URL LIKE '%google%'", "UserID = k on squeezed entries"), "value": rows_local / (scan_ms_sq / 1e3) / 1e6, "unit": "Mrows/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": scan_ms_sq, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": f"clickbench-hits UserID = k through lc_eval_predicate_many, entries squeezed ({policy}) to {width}-bit codes (SURVEY 8f-4)",
                    "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "matching_rows": hits_sq, "matches_full_entries": hits_sq == hits_full,
-                   "full_entries": {"Mrows_per_s": rows_local / (ms_full / 1e3) / 1e6, "ms_per_step": ms_full, "hbm_bytes": hbm_full},
+                   "matches_full_entries_scan": scan_hits_sq == scan_hits_full == hits_full,
+                   "full_entries": {"scan_Mrows_per_s": rows_local / (scan_ms_full / 1e3) / 1e6, "scan_ms_per_step": scan_ms_full,
+                                    "eval_many_Mrows_per_s": rows_local / (ms_full / 1e3) / 1e6, "eval_many_ms_per_step": ms_full, "hbm_bytes": hbm_full},
                    "squeezed_hbm_bytes": hbm_both - hbm_full, "backing_reads_per_step": reads, "backing_bytes_host": sum(len(st.image) for st in stores),
                    "squeeze_seconds": squeeze_s,
-                   "note": "masks come back to host buffers in both arms (sparse download); times are end to end per call"},
-        "roofline": {"bound": "hbm", "kernel": "lc_eval_predicate_many over squeezed entries (whole call)", "achieved": rows_local * width / 8 / (ms_sq / 1e3) / 1e9,
-                     "peak": peak, "unit": "GB/s", "frac": rows_local * width / 8 / (ms_sq / 1e3) / 1e9 / peak, "peak_source": peak_src},
+                   "note": "value: lc_scan_filter (selection stays in HBM, counts come back); e2e: lc_eval_predicate_many (masks to host buffers)"},
+        "e2e": {"value": rows_local / (ms_sq / 1e3) / 1e6, "unit": "Mrows/s", "ms_per_step": ms_sq},
+        "roofline": {"bound": "hbm", "kernel": "lc_scan_filter over squeezed entries (whole call)", "achieved": rows_local * width / 8 / (scan_ms_sq / 1e3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": rows_local * width / 8 / (scan_ms_sq / 1e3) / 1e9 / peak, "peak_source": peak_src},
     }
     print(json.dumps(line))
     cache.close()
