@@ -258,7 +258,7 @@ class GpuSqueezedArray(GpuLiquidArray):
         return self._info()[3]
 
     def to_bytes(self) -> bytes:
-        raise N.UnsupportedType("a squeezed array has no serialized form; its full image is the backing")
+        raise N.UnsupportedType(N.LC_ERR_UNSUPPORTED_TYPE, "a squeezed array has no serialized form; its full image is the backing")
 
 
 _FORMAT_TO_TYPE = {
