@@ -249,7 +249,7 @@ def test_decimal_round_trip_filter_predicate(cache, typ, n, null_p):
 
 
 def test_decimal_outside_u64_takes_the_fixed_length_form(cache):
-    """transcode.rs:118-131: such arrays become LiquidFixedLenByteArray (tests/test_gpu_fixed_len.py has the rest).
+    """transcode.rs:118-131: such arrays become LiquidFixedLenByteArray (tests/test_gpu_zy_fixed_len.py has the rest).
     Null slots do not count (decimal_array.rs:127-132)."""
     for arr in (_dec_array([5, -1, 7], pa.decimal128(10, 2)), _dec_array([2**64], pa.decimal128(38, 0)),
                 _dec_array([1, 2**70], pa.decimal256(60, 0))):
