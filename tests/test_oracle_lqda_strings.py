@@ -1,7 +1,7 @@
 """The byte-view half of LQDA in the CPU oracle (byte_view_array/serialization.rs:87-325): round trips of every section
 for the four original Arrow types, with and without fingerprints, including empty and entirely null arrays — the cases of
 the reference's own serialization tests (byte_view_array/tests.rs round trips through to_bytes/from_bytes). The device
-side of the same format is checked against this in tests/test_gpu_ipc_strings.py."""
+side of the same format is checked against this in tests/test_gpu_zy_ipc_strings.py."""
 import pyarrow as pa
 import pytest
 
