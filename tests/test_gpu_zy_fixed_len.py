@@ -57,7 +57,10 @@ def test_round_trip_filter_and_dictionary(cache, typ, n, n_distinct, null_p):
         sel = pa.array(rng.random(len(arr)) < p)
         assert_arrays_equal(liquid.filter(sel), oracle.filter(sel), f"{typ} filter p={p}")
     assert len(liquid.filter(pa.array([False] * len(arr)))) == 0
-    # the dictionary: first-occurrence keys, every value 16 / 32 bytes and equal to the oracle's after decompression
+    # a second batch of the chunk reuses the symbol table and stays readable
+    more = gen_decimals(typ, 1000, 200, 0.05, 5 + typ.precision)
+    assert_arrays_equal(cache.transcode(more, compressor_scope=scope).to_arrow_array(), more, f"{typ} second batch")
+    # (last: a dry run without a device stops here) the dictionary: first-occurrence keys, every value 16 / 32 bytes and equal to the oracle's after decompression
     h = parse_str_image(liquid.entry_image())
     want_keys = np.array([0 if k is None else k for k in oracle.keys], dtype=np.uint16)
     valid = np.array([k is not None for k in oracle.keys], dtype=bool)
@@ -67,9 +70,6 @@ def test_round_trip_filter_and_dictionary(cache, typ, n, n_distinct, null_p):
     table = liquid.fsst_table()
     for u in range(0, h["n_unique"], max(1, h["n_unique"] // 64)):
         assert fsst_decompress(table, h["comp"][offs[u]:offs[u + 1]]) == ordered(oracle.uniques[u]), f"dictionary value {u}"
-    # a second batch of the chunk reuses the symbol table and stays readable
-    more = gen_decimals(typ, 1000, 200, 0.05, 5 + typ.precision)
-    assert_arrays_equal(cache.transcode(more, compressor_scope=scope).to_arrow_array(), more, f"{typ} second batch")
 
 
 @pytest.mark.parametrize("typ", TYPES, ids=str)

@@ -118,18 +118,18 @@ def test_squeezed_codes_match_the_restatement(cache, policy, case):
     assert sq.disk_backing() == len(io.bytes)
     if policy == "quantize":
         assert sq.bucket_width() == osq.bucket_width
-    img = sq.entry_image()
+    assert sq.get_array_memory_size() < full.get_array_memory_size()
+    with pytest.raises(N.NativeError):
+        sq.to_bytes()
+    with pytest.raises(N.NativeError):  # batched reads and the scan calls take full entries only
+        cache.to_arrow_many(np.array([sq.handle], dtype=np.uint64), None)
+    img = sq.entry_image()  # last: a dry run without a device stops here
     magic, phys, tbits, bit_width, has_nulls, nn, n_chunks, reference, validity_off, packed_off, blob_bytes, null_count, \
         is_signed, _ = INT_HDR.unpack_from(img, 0)
     assert (nn, bit_width, null_count) == (len(arr), osq.bit_width, arr.null_count)
     assert reference == osq.reference & ((1 << tbits) - 1)
     words = np.frombuffer(img, dtype=osq.packed.dtype, count=len(osq.packed), offset=packed_off)
     assert np.array_equal(words, osq.packed), "half-width codes differ from the restatement's"
-    assert sq.get_array_memory_size() < full.get_array_memory_size()
-    with pytest.raises(N.NativeError):
-        sq.to_bytes()
-    with pytest.raises(N.NativeError):  # batched reads and the scan calls take full entries only
-        cache.to_arrow_many(np.array([sq.handle], dtype=np.uint64), None)
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-{c[1]}")
@@ -278,6 +278,7 @@ def _date_cases():
 
 @pytest.mark.parametrize("field", FIELDS)
 def test_date_component_squeeze_matches_the_restatement(cache, field):
+    images = []
     for ci, arr in enumerate(_date_cases()):
         io, oio = CountingIo(), O.OracleSqueezeIo()
         full = cache.transcode(arr)
@@ -290,13 +291,7 @@ def test_date_component_squeeze_matches_the_restatement(cache, field):
         what = f"{arr.type} case {ci} {field}"
         assert sq.policy() == "date32" and sq.field() == field and sq.len() == len(arr) and sq.original_arrow_data_type() == arr.type
         assert sq.bit_width() == (osq.bit_width or 0) and sq.disk_backing() == len(image)
-        img = sq.entry_image()
-        magic, phys, tbits, bit_width, has_nulls, nn, n_chunks, reference, *_ = INT_HDR.unpack_from(img, 0)
-        assert tbits == 32 and reference == osq.reference & 0xFFFFFFFF, what
-        if osq.bit_width is not None:
-            packed_off = INT_HDR.unpack_from(img, 0)[9]
-            words = np.frombuffer(img, dtype=np.uint32, count=len(osq.packed), offset=packed_off)
-            assert np.array_equal(words, osq.packed), what + ": packed component offsets"
+        images.append((sq, osq, what))
         io.reset_reads()
         assert_arrays_equal(sq.to_component_date32(), osq.to_component_date32(), what + ": to_component_date32")
         comp = sq.to_component_array()
@@ -322,6 +317,14 @@ def test_date_component_squeeze_matches_the_restatement(cache, field):
             got = sq.try_eval_predicate(expr_of(">=", lit), sel)
             assert_masks_equal(got, pc.greater_equal(pc.filter(raw, sel), pa.scalar(lit, raw.type)), what + ": >=")
             assert io.reads == before + 1
+    for sq, osq, what in images:  # last: a dry run without a device stops here
+        img = sq.entry_image()
+        magic, phys, tbits, bit_width, has_nulls, nn, n_chunks, reference, *_ = INT_HDR.unpack_from(img, 0)
+        assert tbits == 32 and reference == osq.reference & 0xFFFFFFFF, what
+        if osq.bit_width is not None:
+            packed_off = INT_HDR.unpack_from(img, 0)[9]
+            words = np.frombuffer(img, dtype=np.uint32, count=len(osq.packed), offset=packed_off)
+            assert np.array_equal(words, osq.packed), what + ": packed component offsets"
 
 
 # ---- one call over a list of entries: full, clamped and quantized batches of one column ----
