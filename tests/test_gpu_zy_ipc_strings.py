@@ -54,7 +54,7 @@ def _oracle_parts(o):
 def test_device_image_parses_like_the_restatement(cache, typ, fp):
     for ci, vals in enumerate(_cases()):
         arr = _build(vals, typ)
-        scope = 1000 + ci
+        scope = 1000 + 100 * TYPES.index(typ) + 20 * int(fp) + ci
         liquid = cache.transcode(arr, hint=CacheExpression.SubstringSearch if fp else None, compressor_scope=scope)
         image = liquid.to_bytes()
         assert image[0:4] == O.LQDA_MAGIC and int.from_bytes(image[4:6], "little") == 1
@@ -82,7 +82,7 @@ def test_restatement_image_becomes_an_entry(cache, typ, fp):
         arr = _build(vals, typ)
         o = O.OracleByteViewArray.from_arrow(arr, build_fingerprints=fp)
         image = O.byte_view_to_bytes(o)
-        scope = 2000 + ci
+        scope = 2000 + 100 * TYPES.index(typ) + 20 * int(fp) + ci  # one scope per image: a scope takes one table, once
         cache.load_symbol_table(scope, O.save_symbol_table(o.fsst))
         assert cache.save_symbol_table(scope) == O.save_symbol_table(o.fsst)
         entry = cache.read_from_bytes(image, compressor_scope=scope)
