@@ -156,7 +156,8 @@ def test_string_insert_rejects_more_than_65536_uniques(cache):
 
 
 @pytest.mark.parametrize("np_dt,lo,hi,n", [(np.int64, -5000, 10**12, 8192), (np.uint64, 10, 16, 6), (np.int32, -7, 8, 3000),
-                                           (np.int16, -300, 300, 1024), (np.uint8, 0, 256, 2500), (np.int64, 77, 78, 1500)])
+                                           (np.int16, -300, 300, 1024), (np.uint8, 0, 256, 2500), (np.int64, 77, 78, 1500),
+                                           (np.uint16, 0, 65536, 5000)])  # W = T = 16: how byte-view LQDA packs its dictionary keys
 def test_int_insert_layout_matches_oracle_packing(cache, np_dt, lo, hi, n):
     """Reference value, bit width and the FastLanes words themselves (fastlanes 0.5.0 unified transposed order as the
     oracle restates it) — the device packer and the oracle must agree word for word when there are no nulls."""
