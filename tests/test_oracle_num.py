@@ -178,3 +178,45 @@ def test_lqda_known_answers_and_round_trips():
     b = O.to_bytes(OracleDecimalArray.from_arrow(d))
     assert int.from_bytes(b[6:8], "little") == 6 and int.from_bytes(b[8:10], "little") == 7 and list(b[16:19]) == [0, 12, 3]
     assert O.read_from_bytes(b).to_arrow().equals(d)
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.sampled_from([pa.int8(), pa.int16(), pa.int32(), pa.int64(), pa.uint8(), pa.uint16(), pa.uint32(), pa.uint64(), pa.date32(),
+                        pa.timestamp("ms")]),
+       st.lists(st.one_of(st.none(), st.integers(min_value=-(2**63), max_value=2**64 - 1)), min_size=0, max_size=400), st.data())
+def test_integer_oracle_properties(typ, raw, data):
+    """For any integer-like column: the LQDA image reads back as the array (ipc.rs round-trip tests generalised), and
+    the oracle's predicate on a random selection equals Arrow's compare on the filtered array."""
+    import pyarrow.compute as pc
+
+    store = pa.int32() if pa.types.is_date32(typ) else (pa.int64() if pa.types.is_timestamp(typ) else typ)
+    info = np.iinfo(store.to_pandas_dtype())
+    span = int(info.max) - int(info.min) + 1
+    vals = [None if v is None else (int(v) - int(info.min)) % span + int(info.min) for v in raw]
+    arr = pa.array(vals, store).cast(typ)
+    o = O.OracleIntArray.from_arrow(arr)
+    assert o.to_arrow().equals(arr)
+    assert O.read_from_bytes(O.to_bytes(o)).to_arrow().equals(arr)
+    if len(arr):
+        sel = pa.array(data.draw(st.lists(st.booleans(), min_size=len(arr), max_size=len(arr))))
+        lit_i = data.draw(st.sampled_from([v for v in vals if v is not None] or [0]))
+        lit = pa.scalar(lit_i, store).cast(typ)
+        for op, fn in (("=", pc.equal), ("<", pc.less), (">=", pc.greater_equal), ("!=", pc.not_equal)):
+            want = fn(arr.filter(sel), lit)
+            assert o.try_eval_predicate(op, lit, sel).to_pylist() == want.to_pylist()
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.one_of(st.none(), st.integers(min_value=0, max_value=2**64 - 1)), min_size=0, max_size=200),
+       st.sampled_from([pa.decimal128(38, 0), pa.decimal128(20, 3), pa.decimal256(50, 4)]))
+def test_decimal_oracle_properties(raw, typ):
+    with decimal.localcontext() as cx:
+        cx.prec = 100
+        vals = [None if v is None else decimal.Decimal(v).scaleb(-typ.scale) for v in raw]
+        fits = all(v is None or abs(v.scaleb(typ.scale)) < 10**typ.precision for v in vals)
+    if not fits:
+        return
+    arr = pa.array(vals, typ)
+    o = OracleDecimalArray.from_arrow(arr)
+    assert o is not None and o.to_arrow().equals(arr)
+    assert O.read_from_bytes(O.to_bytes(o)).to_arrow().equals(arr)
