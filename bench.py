@@ -538,7 +538,6 @@ def main():
 
     from liquid_cache_b200 import (CacheExpression, Column, LikeExpr, LiquidCacheBuilder, LiquidExpr, Literal,
                                    parquet_array_id)
-    from liquid_cache_b200.dist import gather_arrow_to_rank0
 
     torch.cuda.set_device(local_rank)
     if world > 1:

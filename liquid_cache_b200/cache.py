@@ -13,7 +13,7 @@ the Arrow C Data Interface and keeps the EntryID bookkeeping.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Iterable, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import pyarrow as pa
