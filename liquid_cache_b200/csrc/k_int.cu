@@ -20,6 +20,7 @@
 #include "device_utils.cuh"
 #include "kernels.h"
 #include "int_plan.cuh"
+#include "wspec_math.cuh"
 #include "scan_rows.cuh"
 
 namespace lc {
@@ -322,39 +323,19 @@ __device__ __forceinline__ void int_bits_fast_w(const EntryIo& w, const IntHeade
   uint32_t* out_valid = (MODE == MODE_PRED && valid) ? w.out_valid : nullptr;
   const uint32_t* sel = w.sel;
   const uint32_t tail = n & 31u;
-  const uint32_t ordl = FLOrder<U>()(lane);
-  constexpr uint32_t mask32 = W >= 32u ? 0xffffffffu : ((1u << (W & 31u)) - 1u);
+  const uint32_t ordl = wspec_out_word(lane);  // = FLOrder<U>()(lane) for T >= 32
   const uint32_t negmask = g.neg ? kFullMask : 0u;
-  const uint32_t half = T == 64 ? (lane >> 4) : 0u;
-  // byte distance of "W 32-bit words further down the lane's stream" for an even / an odd word index (T = 64 only)
-  constexpr uint32_t dE = (W % 2u == 0u) ? (W / 2u) * 128u : ((W - 1u) / 2u) * 128u + 4u;
-  constexpr uint32_t dO = (W % 2u == 0u) ? (W / 2u) * 128u : ((W + 1u) / 2u) * 128u - 4u;
   uint32_t survivors = 0;
   for (uint32_t c = warp; c < n_chunks; c += 8u) {
     const uint8_t* chunk = packed + c * chunk_bytes;
-    const uint32_t lbase = smem_u32(chunk) + (T == 64 ? (lane & 15u) * 8u : lane * 4u);
-    const uint32_t baseE = lbase + (half ? dE : 0u), baseO = lbase + (half ? dO : 0u);
+    const WspecBases<T, W> bs = wspec_bases<T, W>(smem_u32(chunk), lane);  // wspec_math.cuh: checked on the CPU for every (T, W)
     const uint32_t wi = c * 32u + ordl;
     uint32_t sw = kFullMask;
     if (sel && wi < n_words) sw = sel[wi];
     uint32_t mine = 0;
 #pragma unroll
     for (uint32_t j = 0; j < 32; ++j) {
-      const uint32_t r = T == 64 ? ((j >> 3) * 8u + (j & 7u)) : j;  // half-warp 0's packed row of this step
-      const uint32_t b = r * W, x = b >> 5, sh = b & 31u;
-      const bool two = sh + W > 32u;
-      auto addr = [&](uint32_t y) -> uint32_t {
-        if (T == 64) return ((y & 1u) ? baseO : baseE) + (y >> 1) * 128u + (y & 1u) * 4u;
-        return lbase + y * 128u;
-      };
-      const uint32_t w0 = lds_u32(addr(x));
-      uint32_t u;
-      if (two) {
-        const uint32_t w1 = lds_u32(addr(x + 1u));
-        u = __funnelshift_r(w0, w1, sh) & mask32;
-      } else {
-        u = (w0 >> sh) & mask32;
-      }
+      const uint32_t u = wspec_value<T, W>(bs, j, [](uint32_t a) { return lds_u32(a); });
       const bool hit = (u - g.lo) <= g.span;
       const uint32_t cw = __ballot_sync(kFullMask, hit);
       if (lane == j) mine = cw;
