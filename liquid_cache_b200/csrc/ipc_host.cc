@@ -21,6 +21,7 @@
 
 #include "host_common.h"
 #include "host_pool.h"
+#include "lqda_layout.h"
 
 namespace lc {
 
@@ -75,37 +76,6 @@ Layout layout_of(int32_t liquid_type, uint32_t tb, uint32_t n, uint32_t width, b
 }  // namespace
 
 namespace {
-struct StrImage {  // byte offsets inside the LQDA image of a byte-view entry
-  uint64_t fsst_off, keys_off, keys_nulls_off, keys_values_off, co_off, pk_off, sp_off, fp_off, total;
-  uint32_t fsst_raw_size, keys_size, nulls_len, keys_values_len, co_size, sp_size, fp_size;
-};
-StrImage str_image_of(const StrHeader& h) {
-  StrImage L{};
-  uint64_t cur = pad8(36);
-  L.fsst_off = cur;
-  L.fsst_raw_size = 12 + h.fsst_bytes;
-  cur = pad8(cur + L.fsst_raw_size);
-  L.keys_off = cur;
-  L.nulls_len = h.has_nulls ? (h.n + 7) / 8 : 0;
-  L.keys_values_len = ((h.n + 1023) / 1024) * 2048;
-  L.keys_nulls_off = cur + 16;
-  L.keys_values_off = cur + pad8(16ull + L.nulls_len);
-  L.keys_size = static_cast<uint32_t>(L.keys_values_off + L.keys_values_len - L.keys_off);
-  cur = pad8(L.keys_off + L.keys_size);
-  L.co_off = cur;
-  L.co_size = 9 + (h.n_unique + 1) * h.offset_bytes;
-  cur = pad8(cur + L.co_size);
-  L.pk_off = cur;
-  cur = pad8(cur + 8ull * h.n_unique);
-  L.sp_off = cur;
-  L.sp_size = h.shared_prefix_len;
-  cur = pad8(cur + L.sp_size);
-  L.fp_off = cur;
-  L.fp_size = h.has_fp ? 4 * h.n_unique : 0;
-  L.total = cur + L.fp_size;
-  return L;
-}
-
 int str_entry_to_bytes(lc_ctx* ctx, const Entry* e, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
   const StrHeader& h = e->sh;
   const StrImage L = str_image_of(h);
@@ -292,89 +262,18 @@ static int str_entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, con
     set_error("from_bytes: a byte-view image needs its column chunk's symbol table (lc_from_bytes_scoped)");
     return LC_ERR_INVALID;
   }
-  const uint32_t bt = get_u16(b + 8);
-  if (len < 36 || bt > BT_BINARY_VIEW) {
-    set_error("from_bytes: bad byte-view header");
+  StrImageIn in;
+  if (const char* why = parse_str_image(b, len, &in)) {
+    set_error("from_bytes: %s", why);
     return LC_ERR_INVALID;
   }
-  const uint32_t keys_size = get_u32(b + 16), co_size = get_u32(b + 20), sp_size = get_u32(b + 24), fsst_size = get_u32(b + 28),
-                 fp_size = get_u32(b + 32);
-  uint64_t cur = pad8(36);
-  if (fsst_size < 12 || len < cur + fsst_size) {
-    set_error("from_bytes: FSST section runs past the image");
-    return LC_ERR_INVALID;
-  }
-  const uint64_t uncompressed = get_u64(b + cur);
-  const uint32_t comp_bytes = get_u32(b + cur + 8);
-  const uint64_t comp_off = cur + 12;
-  if (12ull + comp_bytes > fsst_size) {
-    set_error("from_bytes: FSST values longer than their section");
-    return LC_ERR_INVALID;
-  }
-  cur = pad8(cur + fsst_size);
-  if (keys_size < 16 || len < cur + keys_size) {
-    set_error("from_bytes: keys section runs past the image");
-    return LC_ERR_INVALID;
-  }
-  const uint8_t* kb = b + cur;
-  const uint32_t n = get_u32(kb);
-  const bool file_nulls = kb[5] != 0;
-  const uint32_t nulls_len = get_u32(kb + 6), kvals_len = get_u32(kb + 10);
-  const uint64_t knulls_off = cur + 16, kvals_off = cur + pad8(16ull + (file_nulls ? nulls_len : 0));
-  const uint32_t n_chunks = (n + 1023) / 1024;
-  if (n > 0x7fffffffu || (n && kb[4] != 16) || kvals_len != n_chunks * 2048u || kvals_off + kvals_len > cur + keys_size ||
-      (file_nulls && nulls_len < (n + 7) / 8)) {
-    set_error("from_bytes: keys are not %u rows bit-packed at width 16", n);
-    return LC_ERR_INVALID;
-  }
-  cur = pad8(cur + keys_size);
-  if (len < cur + co_size || (co_size && co_size < 9)) {
-    set_error("from_bytes: offsets section runs past the image");
-    return LC_ERR_INVALID;
-  }
-  int32_t slope = 0, intercept = 0;
-  uint32_t ob = 1, n_resid = 0;
-  const uint64_t resid_src = cur + 9;
-  if (co_size) {
-    std::memcpy(&slope, b + cur, 4);
-    std::memcpy(&intercept, b + cur + 4, 4);
-    ob = b[cur + 8];
-    if ((ob != 1 && ob != 2 && ob != 4) || (co_size - 9) % ob) {
-      set_error("from_bytes: bad CompactOffsets header");
-      return LC_ERR_INVALID;
-    }
-    n_resid = (co_size - 9) / ob;
-  }
-  const uint32_t U = n_resid ? n_resid - 1 : 0;
-  cur = pad8(cur + co_size);
-  const uint64_t pk_src = cur;
-  cur = pad8(cur + 8ull * U);
-  const uint64_t sp_src = cur;
-  cur = pad8(cur + sp_size);
-  const uint64_t fp_src = cur;
-  if (U > 65536 || len < fp_src + fp_size || (fp_size && fp_size != 4 * U)) {
-    set_error("from_bytes: dictionary sections run past the image");
-    return LC_ERR_INVALID;
-  }
-  // the offsets the decode kernels will follow: slope * i + intercept + residual[i] (CompactOffsets::get_offset,
-  // fsst_buffer.rs:360-383) must start at 0, never step back, and stay inside the compressed values
-  if (n_resid) {
-    uint64_t prev = 0;
-    for (uint32_t i = 0; i < n_resid; ++i) {
-      int64_t r = 0;
-      const uint8_t* rp = b + resid_src + static_cast<uint64_t>(i) * ob;
-      if (ob == 1) r = static_cast<int8_t>(rp[0]);
-      else if (ob == 2) r = static_cast<int16_t>(get_u16(rp));
-      else r = static_cast<int32_t>(get_u32(rp));
-      // the kernels' arithmetic (k_str.cu dict_offset): 32-bit wrapping sum, read as unsigned
-      const uint64_t off = static_cast<uint32_t>(static_cast<uint32_t>(slope) * i + static_cast<uint32_t>(intercept) + static_cast<uint32_t>(r));
-      if ((i == 0 && off != 0) || off < prev || off > comp_bytes) {
-        set_error("from_bytes: dictionary offset %u does not fit the compressed values", i);
-        return LC_ERR_INVALID;
-      }
-      prev = off;
-    }
-  }
+  const uint32_t bt = in.bt, n = in.n, U = in.n_unique, ob = in.offset_bytes, sp_size = in.sp_size, fp_size = in.fp_size, n_resid = in.n_resid,
+                 comp_bytes = in.comp_bytes, kvals_len = in.kvals_len, n_chunks = (in.n + 1023) / 1024;
+  const int32_t slope = in.slope, intercept = in.intercept;
+  const bool file_nulls = in.file_nulls;
+  const uint64_t uncompressed = in.uncompressed, comp_off = in.comp_off, knulls_off = in.knulls_off, kvals_off = in.kvals_off,
+                 resid_src = in.resid_src, pk_src = in.pk_src, sp_src = in.sp_src, fp_src = in.fp_src;
+  (void)n_chunks;
   // every key must name a dictionary value (W = 16: the packed words ARE the keys, transposed)
   {
     const uint64_t n_keys = kvals_len / 2;
