@@ -14,6 +14,7 @@
 
 #include "../../include/lc_gpu.h"
 #include "entry_layout.h"
+#include "squeeze_plan.h"
 #include "kernels.h"
 
 namespace lc {
@@ -285,7 +286,6 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
                    const DeviceOut* dev_out = nullptr);
 
 // squeeze_host.cc
-constexpr int32_t kLitSentinelPublic = 1000;  // lc_predicate.lit_kind used by squeeze_host.cc alone (-> kLitSentinel)
 int squeezed_eval_predicate_many(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
                                  const uint8_t* const* sel_bits, const PredOut& out);
 int squeeze_doubt(const Entry* e, const lc_predicate* pred, lc_predicate* probe);

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "host_common.h"
+#include "squeeze_plan.h"
 
 namespace lc {
 
@@ -31,41 +32,11 @@ struct SqueezeScope {  // lets the batch functions accept a squeezed entry while
   ~SqueezeScope() { ctx->squeeze_internal = prev; }
 };
 
-__int128 reference_of(const Entry* e) {
-  const uint32_t tbits = e->ih.tbits;
-  if (!e->ih.is_signed) return static_cast<__int128>(e->ih.reference);
-  const uint64_t sign = 1ull << (tbits - 1);
-  const uint64_t raw = e->ih.reference;  // zero-extended raw bits
-  return static_cast<__int128>(static_cast<int64_t>((raw ^ sign) - sign));
-}
-
-// T::Native::from_i64 / from_u64 (hybrid_primitive_array.rs:167-184): the literal as a value of the column's type
-bool literal_of(const Entry* e, const lc_predicate* pred, __int128* k) {
-  __int128 v;
-  if (pred->lit_kind == LC_LIT_I64) v = pred->lit_i64;
-  else if (pred->lit_kind == LC_LIT_U64) v = static_cast<__int128>(pred->lit_u64);
-  else return false;
-  const uint32_t tbits = e->ih.tbits;
-  const __int128 one = 1;
-  const __int128 lo = e->ih.is_signed ? -(one << (tbits - 1)) : 0;
-  const __int128 hi = e->ih.is_signed ? (one << (tbits - 1)) - 1 : (one << tbits) - 1;
-  if (v < lo || v > hi) return false;
-  *k = v;
-  return true;
-}
-
-lc_predicate int_predicate(const Entry* e, int32_t op, __int128 lit) {
-  lc_predicate p{};
-  p.op = op;
-  if (e->ih.is_signed) {
-    p.lit_kind = LC_LIT_I64;
-    p.lit_i64 = static_cast<int64_t>(lit);
-  } else {
-    p.lit_kind = LC_LIT_U64;
-    p.lit_u64 = static_cast<uint64_t>(lit);
-  }
-  return p;
-}
+SqueezeFacts facts_of(const Entry* e) { return SqueezeFacts{e->ih, e->squeeze_kind, e->bucket_width}; }
+__int128 reference_of(const Entry* e) { const SqueezeFacts f = facts_of(e); return reference_of(&f); }
+bool literal_of(const Entry* e, const lc_predicate* pred, __int128* k) { const SqueezeFacts f = facts_of(e); return literal_of(&f, pred, k); }
+lc_predicate int_predicate(const Entry* e, int32_t op, __int128 lit) { const SqueezeFacts f = facts_of(e); return int_predicate(&f, op, lit); }
+Doubt doubt_of(const Entry* e, int32_t op, __int128 k) { const SqueezeFacts f = facts_of(e); return doubt_of(&f, op, k); }
 
 // selected, valid rows of `sq` whose decoded value equals `value`
 int count_equal(lc_ctx* ctx, Entry* sq, __int128 value, const uint8_t* sel_bits, uint64_t* count) {
@@ -422,39 +393,6 @@ namespace {
 // which probe finds the rows that make them fail:
 //   Clamp     resolves_on_sentinel (hybrid_primitive_array.rs:196-219) false -> rows at the sentinel (kLitSentinelPublic)
 //   Quantize  on_equal_bucket (:599-631) unknown -> rows in the literal's bucket: `= k`, which the planner turns into b == q
-struct Doubt {
-  bool possible = false;
-  lc_predicate probe{};
-};
-
-Doubt doubt_of(const Entry* sq, int32_t op, __int128 k) {
-  Doubt d;
-  const __int128 ref = reference_of(sq);
-  const uint64_t last = (1ull << sq->ih.bit_width) - 1ull;  // the sentinel / the last bucket
-  if (sq->squeeze_kind == LC_SQUEEZE_CLAMP + 1) {
-    const __int128 sent_abs = ref + static_cast<__int128>(last);
-    const bool strict = op == LC_OP_EQ || op == LC_OP_NE || op == LC_OP_GT || op == LC_OP_LE;
-    d.possible = !(strict ? k < sent_abs : k <= sent_abs);
-    d.probe.op = LC_OP_EQ;
-    d.probe.lit_kind = kLitSentinelPublic;
-    return d;
-  }
-  if (k < ref) return d;  // below the minimum: constants (:537-560)
-  const unsigned __int128 rel = static_cast<unsigned __int128>(k - ref);
-  const uint64_t bw = sq->bucket_width;
-  if (rel / bw > last) return d;  // every bucket index is below the literal's
-  const uint64_t r = static_cast<uint64_t>(rel % bw);
-  bool known = false;
-  switch (op) {
-    case LC_OP_LT: case LC_OP_GE: known = r == 0; break;
-    case LC_OP_LE: case LC_OP_GT: known = r + 1 == bw; break;
-    default: break;
-  }
-  d.possible = !known;
-  d.probe = int_predicate(sq, LC_OP_EQ, k);
-  return d;
-}
-
 // selected, valid rows of `sq` that the probe finds
 int count_probe(lc_ctx* ctx, Entry* sq, const lc_predicate& probe, const uint8_t* sel_bits, uint64_t* count) {
   std::vector<uint8_t> vals(round_up((static_cast<uint64_t>(sq->n) + 7) / 8, 16) + 16);
