@@ -33,4 +33,26 @@ LC_FX_HD uint32_t fixed_le_word(const uint8_t* stored, uint32_t width, uint32_t 
   return v;
 }
 
+// out of place (the host's twin of fixed_to_ordered_inplace)
+LC_FX_HD void fixed_to_ordered(const uint8_t* le, uint32_t width, uint8_t* out) {
+  for (uint32_t i = 0; i < width; ++i) out[i] = le[width - 1u - i];
+  out[0] ^= 0x80u;
+}
+
+// The needle of `decimal_col <op> literal` on a LiquidFixedLenByteArray entry: the literal — LC_LIT_I128 halves (sign-extended
+// to the column's width) or, when `le` is given, the column's own little-endian integer — in order-preserving form.
+LC_FX_HD void fixed_needle(uint64_t lit_u64, int64_t lit_i64, const uint8_t* le, uint32_t width, uint8_t* out) {
+  uint8_t tmp[32];
+  if (le) {
+    for (uint32_t i = 0; i < width; ++i) tmp[i] = le[i];
+  } else {
+    for (uint32_t i = 0; i < 8; ++i) {
+      tmp[i] = static_cast<uint8_t>(lit_u64 >> (8u * i));
+      tmp[8 + i] = static_cast<uint8_t>(static_cast<uint64_t>(lit_i64) >> (8u * i));
+    }
+    for (uint32_t i = 16; i < 32; ++i) tmp[i] = lit_i64 < 0 ? 0xFFu : 0x00u;
+  }
+  fixed_to_ordered(tmp, width, out);
+}
+
 }  // namespace lc

@@ -15,6 +15,7 @@
 #include "../../include/lc_gpu.h"
 #include "entry_layout.h"
 #include "squeeze_plan.h"
+#include "fixed_math.cuh"
 #include "kernels.h"
 
 namespace lc {
@@ -135,12 +136,7 @@ struct Entry {
 // int_encode's answer for a decimal array with values outside u64: the caller stores it as LiquidFixedLenByteArray
 // (str_encode over the 16 / 32-byte values) under the column chunk's compressor scope
 constexpr int LC_INTERNAL_FIXED_LEN = 1000;
-// order-preserving form of a little-endian two's complement integer of `width` bytes: big-endian, sign bit flipped
-// (k_bits.cu k_fixed_to_ordered is the device twin)
-inline void fixed_to_ordered(const uint8_t* le, uint32_t width, uint8_t* out) {
-  for (uint32_t i = 0; i < width; ++i) out[i] = le[width - 1u - i];
-  out[0] ^= 0x80u;
-}
+// order-preserving form of fixed-width decimals: fixed_math.cuh (host + device)
 
 // integer-shaped blobs (IntHeader + FastLanes chunks): integers, ALP floats, u64 decimals
 inline bool is_int_blob(int32_t liquid_type) {

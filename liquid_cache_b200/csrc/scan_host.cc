@@ -205,18 +205,14 @@ static int lower_fixed_pred(Entry* const* entries, uint64_t n, const lc_predicat
     set_error("operator %d is not supported on decimal columns", pred->op);
     return LC_ERR_UNSUPPORTED_EXPR;
   }
-  uint8_t le[32];
   if (pred->lit_kind == LC_LIT_BYTES && pred->lit_len == w) {
-    std::memcpy(le, pred->lit_bytes, w);  // the literal as the column's own little-endian integer
+    fixed_needle(0, 0, pred->lit_bytes, w, out->bytes);  // the literal as the column's own little-endian integer
   } else if (pred->lit_kind == LC_LIT_I128) {
-    std::memcpy(le, &pred->lit_u64, 8);
-    std::memcpy(le + 8, &pred->lit_i64, 8);
-    std::memset(le + 16, pred->lit_i64 < 0 ? 0xFF : 0x00, 16);
+    fixed_needle(pred->lit_u64, pred->lit_i64, nullptr, w, out->bytes);
   } else {
     set_error("decimal column needs an LC_LIT_I128 literal (or its little-endian bytes)");
     return LC_ERR_UNSUPPORTED_EXPR;
   }
-  fixed_to_ordered(le, w, out->bytes);
   out->pred = *pred;
   out->pred.lit_kind = LC_LIT_BYTES;
   out->pred.lit_bytes = out->bytes;

@@ -13,6 +13,10 @@ void fx_to_ordered(const uint8_t* le, uint32_t n, uint32_t width, uint8_t* out) 
   for (uint32_t i = 0; i < n; ++i) lc::fixed_to_ordered_inplace(out + static_cast<size_t>(i) * width, width);
 }
 
+void fx_needle(uint64_t lit_u64, int64_t lit_i64, const uint8_t* le, uint32_t width, uint8_t* out) {
+  lc::fixed_needle(lit_u64, lit_i64, le, width, out);
+}
+
 void fx_from_ordered(const uint8_t* stored, uint32_t n, uint32_t width, uint32_t* out) {
   const uint32_t wpr = width / 4;
   for (uint32_t i = 0; i < n; ++i)

@@ -39,3 +39,20 @@ def test_ordered_form_sorts_numerically_and_reads_back(lib, width):
     back = np.zeros(n * width // 4, dtype=np.uint32)
     lib.fx_from_ordered(stored.ctypes.data_as(C.c_void_p), n, width, back.ctypes.data_as(C.c_void_p))
     assert back.tobytes() == le.tobytes()
+
+
+@pytest.mark.parametrize("width", [16, 32])
+def test_literal_needles(lib, width):
+    """the needle of a comparison: LC_LIT_I128 halves sign-extended to the column's width, or the column's own bytes"""
+    rng = np.random.default_rng(width + 1)
+    bits = 8 * width
+    lib.fx_needle.argtypes = [C.c_uint64, C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p]
+    for _ in range(2000):
+        v = int.from_bytes(rng.bytes(16), "little", signed=True) >> int(rng.integers(0, 127))
+        out = (C.c_uint8 * width)()
+        lib.fx_needle(v & (2**64 - 1), v >> 64, None, width, out)
+        assert bytes(out) == (v + (1 << (bits - 1))).to_bytes(width, "big"), v
+        w = int.from_bytes(rng.bytes(width), "little", signed=True) >> int(rng.integers(0, bits - 1))
+        le = w.to_bytes(width, "little", signed=True)
+        lib.fx_needle(0, 0, le, width, out)
+        assert bytes(out) == (w + (1 << (bits - 1))).to_bytes(width, "big"), w
