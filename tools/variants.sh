@@ -8,7 +8,8 @@
 #
 # `run` writes gpurun_out/variants/<branch>/{pytest.log,bench_*.json,smoke.log} and a one-line verdict per variant in
 # gpurun_out/variants/SUMMARY.txt. variants/ is git-ignored (it still travels with the snapshot).
-# Environment for `run`: VARIANTS="a b" restricts the set; PYTEST_ARGS (default: -m gpu -x -q); BENCH=0 skips the bench lines;
+# Environment for `run`: VARIANTS="a b" restricts the set; PYTEST_ARGS (default: -m gpu -q — every failure of a first run in
+# one call, no -x); BENCH=0 skips the bench lines;
 # PER_VARIANT_TIMEOUT seconds per pytest run (default 600).
 set -u
 root="$(cd "$(dirname "$0")/.." && pwd)"
@@ -41,7 +42,7 @@ case "$cmd" in
       mkdir -p "$o"
       (
         cd "$d" || exit 1
-        timeout "${PER_VARIANT_TIMEOUT:-600}" python -m pytest tests ${PYTEST_ARGS:--m gpu -x -q} -p no:cacheprovider > "$o/pytest.log" 2>&1
+        timeout "${PER_VARIANT_TIMEOUT:-600}" python -m pytest tests ${PYTEST_ARGS:--m gpu -q} -p no:cacheprovider > "$o/pytest.log" 2>&1
         echo "pytest exit $?" >> "$o/pytest.log"
         timeout 120 python __graft_entry__.py smoke > "$o/smoke.log" 2>&1
         if [ "${BENCH:-1}" != "0" ]; then
