@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows PER GPU (weak scaling)")
     ap.add_argument("--cpu-sample-entries", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep"], default="url_like",
+    ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep", "squeeze"], default="url_like",
                     help="url_like = BASELINE configs[1] (the bench line the driver records); int_filter = configs[2]; "
                          "shipdate = configs[3] (TPC-H SF100 l_shipdate range, one GPU's shard of the 8-way split per rank); "
                          "clickbench_sweep = configs[4] (scan stage of the 43 ClickBench queries, bench_sweep.py)")
@@ -335,6 +335,125 @@ def run_int_filter(args, rank, world, local_rank):
     cache.close()
 
 
+def run_squeeze(args, rank, world, local_rank):
+    """`UserID = k` over the UserID column (Int64, W = 64) with every entry SQUEEZED to half-width codes
+    (IntegerSqueezePolicy::Quantize, the reference's default: 32-bit bucket indices, full LQDA images in host memory behind
+    the read callback), through lc_eval_predicate_many — against the same call over the full entries. Reports rows/s of
+    both, HBM bytes of both, and how many entries had to read their backing. Secondary workload: prints its own JSON line."""
+    import numpy as np
+    import pyarrow as pa
+    import torch
+
+    import synth
+    from liquid_cache_b200 import BinaryExpr, CacheExpression, Column, EntryID, LiquidCacheBuilder, LiquidExpr, Literal, parquet_array_id
+
+    torch.cuda.set_device(local_rank)
+    cache = LiquidCacheBuilder.new().with_device(local_rank).build()
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    cache.set_stream(stream.cuda_stream)
+    n_entries = max(1, args.rows // ROWS_PER_ENTRY)
+    ids = [parquet_array_id(0, i // 32, 9, i % 32) for i in range(n_entries)]
+    for g0 in range(0, n_entries, 1024):
+        part = range(g0, min(n_entries, g0 + 1024))
+        cache.insert_many([EntryID(int(ids[i])) for i in part], [synth.int_entry("UserID", rank * n_entries + i) for i in part])
+    hbm_full = int(cache.stats().hbm_bytes_used)
+
+    class Store:  # the "disk": one image per entry in host memory
+        def __init__(self):
+            self.image, self.reads = b"", 0
+
+        def read(self, rng):
+            self.reads += 1
+            return self.image[rng[0]:rng[1]]
+
+    policy = os.environ.get("LC_SQUEEZE_POLICY", "quantize")
+    t0 = time.perf_counter()
+    full, squeezed, stores = [], [], []
+    for i in range(n_entries):
+        la = cache.try_read_liquid(EntryID(int(ids[i])))
+        st = Store()
+        sq, st.image = la.squeeze(st, CacheExpression.PredicateColumn, policy)
+        full.append(la)
+        squeezed.append(sq)
+        stores.append(st)
+    squeeze_s = time.perf_counter() - t0
+    hbm_both = int(cache.stats().hbm_bytes_used)
+    h_full = np.array([a.handle for a in full], dtype=np.uint64)
+    h_sq = np.array([a.handle for a in squeezed], dtype=np.uint64)
+    rows = np.full(n_entries, ROWS_PER_ENTRY, dtype=np.uint64)
+    rows_local = n_entries * ROWS_PER_ENTRY
+    uid = int(synth.int_entry("UserID", rank * n_entries)[17].as_py())
+    pred = LiquidExpr.new_unchecked(BinaryExpr(Column("c", 0), "=", Literal(uid))).to_native(pa.int64())
+    out = None
+
+    def step(handles):
+        nonlocal out
+        out = cache._eval_many_native(handles, rows, pred, None, out)
+        return int(out[5].sum())
+
+    def timed(handles):
+        for _ in range(max(3, args.warmup)):
+            step(handles)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            hits = step(handles)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, hits
+
+    ms_full, hits_full = timed(h_full)
+    for st in stores:
+        st.reads = 0
+    ms_sq, hits_sq = timed(h_sq)
+    reads = sum(st.reads for st in stores) / (args.steps + max(3, args.warmup))
+    # the device-resident pipeline (selection stays in HBM, only the survivor counts come back): lc_scan_filter
+    scan = cache.scan(rows)
+
+    def scan_step(handles):
+        scan.reset()
+        scan.filter_native(handles, pred)
+        return int(scan.counts()[1])
+
+    def scan_timed(handles):
+        for _ in range(max(3, args.warmup)):
+            scan_step(handles)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            hits = scan_step(handles)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, hits
+
+    scan_ms_full, scan_hits_full = scan_timed(h_full)
+    scan_ms_sq, scan_hits_sq = scan_timed(h_sq)
+    scan.close()
+    peak, peak_src = measured_peak_gbs()
+    width = squeezed[0].bit_width()
+    line = {
+        "metric": METRIC.replace("URL LIKE '%google%'", "UserID = k on squeezed entries"), "value": rows_local / (scan_ms_sq / 1e3) / 1e6, "unit": "Mrows/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": scan_ms_sq, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"clickbench-hits UserID = k through lc_eval_predicate_many, entries squeezed ({policy}) to {width}-bit codes (SURVEY 8f-4)",
+                   "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "matching_rows": hits_sq, "matches_full_entries": hits_sq == hits_full,
+                   "matches_full_entries_scan": scan_hits_sq == scan_hits_full == hits_full,
+                   "full_entries": {"scan_Mrows_per_s": rows_local / (scan_ms_full / 1e3) / 1e6, "scan_ms_per_step": scan_ms_full,
+                                    "eval_many_Mrows_per_s": rows_local / (ms_full / 1e3) / 1e6, "eval_many_ms_per_step": ms_full, "hbm_bytes": hbm_full},
+                   "squeezed_hbm_bytes": hbm_both - hbm_full, "backing_reads_per_step": reads, "backing_bytes_host": sum(len(st.image) for st in stores),
+                   "squeeze_seconds": squeeze_s,
+                   "note": "value: lc_scan_filter (selection stays in HBM, counts come back); e2e: lc_eval_predicate_many (masks to host buffers)"},
+        "e2e": {"value": rows_local / (ms_sq / 1e3) / 1e6, "unit": "Mrows/s", "ms_per_step": ms_sq},
+        "roofline": {"bound": "hbm", "kernel": "lc_scan_filter over squeezed entries (whole call)", "achieved": rows_local * width / 8 / (scan_ms_sq / 1e3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": rows_local * width / 8 / (scan_ms_sq / 1e3) / 1e9 / peak, "peak_source": peak_src},
+    }
+    print(json.dumps(line))
+    cache.close()
+
+
 def run_shipdate(args, rank, world, local_rank):
     """BASELINE configs[3]: TPC-H SF100 lineitem `l_shipdate >= 1994-01-01 AND l_shipdate < 1995-01-01` (q6's date
     range; Date32, W = 12), entries sharded across 8 B200: every rank holds one eighth of the 600 037 902 rows
@@ -528,6 +647,9 @@ def main():
     if args.workload == "shipdate":
         run_shipdate(args, rank, world, local_rank)
         return
+    if args.workload == "squeeze":
+        run_squeeze(args, rank, world, local_rank)
+        return
     if args.workload == "clickbench_sweep":
         import bench_sweep
 
@@ -560,14 +682,27 @@ def main():
     ids = []
     insert_s, arrow_bytes = 0.0, 0
     workers = max(2, min(32, (os.cpu_count() or 8) // max(1, world)))
+    pend_ids, pend_arrs = [], []
+
+    def flush():
+        nonlocal insert_s
+        if pend_ids:
+            t_i = time.perf_counter()
+            cache.insert_many(pend_ids, pend_arrs, hint=CacheExpression.SubstringSearch)
+            insert_s += time.perf_counter() - t_i  # transcode on the device, 256 batches (8 row groups) per call (untimed setup)
+            pend_ids.clear()
+            pend_arrs.clear()
+
     for i, arr in generate_entries(first, n_entries, workers):
         # 32 batches per row group, column id 13 (= URL in hits); the FSST table is per (file, row group, column)
         eid = parquet_array_id(0, i // 32, 13, i % 32)
-        t_i = time.perf_counter()
-        cache.insert(eid, arr).with_squeeze_hint(CacheExpression.SubstringSearch).run()
-        insert_s += time.perf_counter() - t_i  # insert() = transcode on the device, one batch per call (untimed setup)
+        pend_ids.append(eid)
+        pend_arrs.append(arr)
         arrow_bytes += arr.nbytes
         ids.append(int(eid))
+        if len(pend_ids) == 256:
+            flush()
+    flush()
     handles = cache.handles(ids)
     rows_local = n_entries * ROWS_PER_ENTRY
     setup_s = time.perf_counter() - t_setup
@@ -595,8 +730,8 @@ def main():
                                                       for i, nm in enumerate(names)) + f", total {tot / n_entries:.0f}", file=sys.stderr)
     # R = keys 2n + fingerprints 4U + candidate compressed bytes + offset residuals of the candidates' pairs
     #     (2 bytes typ.) ; W = selection words n/8   (SURVEY.md §8d "string predicate, fingerprint path")
-    #     + 8U: the bigram filters this build stores beside the fingerprints (read once, like them)
-    algo_bytes = 2 * rows_local + (4 + 8) * uniques + cand_bytes + 2 * 2 * cand + rows_local // 8
+    #     + 32U: the 256-bit trigram filters this build stores beside the fingerprints (read once, like them)
+    algo_bytes = 2 * rows_local + (4 + 32) * uniques + cand_bytes + 2 * 2 * cand + rows_local // 8
 
     k_start = torch.cuda.Event(enable_timing=True)
     k_stop = torch.cuda.Event(enable_timing=True)
@@ -733,7 +868,7 @@ def main():
                 "l2": "inputs (liquid column) larger than the 126 MB L2, no flush needed",
                 "setup_seconds": setup_s,
                 "insert": {"Mrows_per_s": rows_local / insert_s / 1e6, "arrow_GB_per_s": arrow_bytes / insert_s / 1e9,
-                           "note": "one lc_cache_insert call per 8192-row batch, host Arrow in, device transcode (k_str_encode.cu), single stream"},
+                           "note": "lc_cache_insert_many, 256 batches of 8192 rows per call, host Arrow in, device transcode (k_str_encode.cu *_many), single stream"},
             },
             "e2e": {"value": e2e_val, "unit": "Mrows/s", "h2d_bytes_per_step": int((st_d.h2d_bytes - st_c.h2d_bytes) / e2e_steps),
                     "d2h_bytes_per_step": int((st_d.d2h_bytes - st_c.d2h_bytes) / e2e_steps), "ms_per_step": e2e_ms / e2e_steps,

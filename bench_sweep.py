@@ -162,8 +162,8 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
             eids = [parquet_array_id(3, (first + g0 + i) // 32, col_id[c], (first + g0 + i) % 32) for i in range(nb)]
             t0 = time.perf_counter()
             if pa.types.is_string(types[c]):
-                for eid, arr in zip(eids, batches[c]):  # every string column is cached under the SubstringSearch hint
-                    cache.insert(eid, arr).with_squeeze_hint(CacheExpression.SubstringSearch).run()
+                # every string column is cached under the SubstringSearch hint; the whole group in one call
+                cache.insert_many(eids, batches[c], hint=CacheExpression.SubstringSearch)
                 insert_s["str"] += time.perf_counter() - t0
             else:
                 cache.insert_many(eids, batches[c])

@@ -101,14 +101,19 @@ typedef enum lc_op {
 
 /* CacheExpression hint (cache/expressions.rs:38-53) — only SUBSTRING_SEARCH changes the encoding
  * (it turns on the per-unique 32-bit fingerprints, transcode.rs:165). */
-typedef enum lc_hint { LC_HINT_NONE = 0, LC_HINT_PREDICATE = 1, LC_HINT_SUBSTRING_SEARCH = 2 } lc_hint;
+typedef enum lc_hint {
+  LC_HINT_NONE = 0, LC_HINT_PREDICATE = 1, LC_HINT_SUBSTRING_SEARCH = 2,
+  /* CacheExpression::ExtractDate32 { field } (expressions.rs:40-44, Date32Field): only lc_squeeze looks at these */
+  LC_HINT_EXTRACT_YEAR = 3, LC_HINT_EXTRACT_MONTH = 4, LC_HINT_EXTRACT_DAY = 5, LC_HINT_EXTRACT_DAY_OF_WEEK = 6
+} lc_hint;
 
 typedef enum lc_literal_kind {
   LC_LIT_I64 = 0,
   LC_LIT_U64 = 1,
   LC_LIT_BYTES = 2,
   LC_LIT_I128 = 3, /* Decimal128/256 literal, unscaled, SAME scale as the column (DataFusion coerces it):
-                      lit_u64 = low 64 bits, lit_i64 = high 64 bits (two's complement) */
+                      lit_u64 = low 64 bits, lit_i64 = high 64 bits (two's complement). A Decimal256 literal that needs more
+                      than 128 bits travels as LC_LIT_BYTES: the 32 little-endian bytes of the unscaled integer */
   LC_LIT_F64 = 4   /* Float32/Float64 literal: lit_u64 = IEEE bits of the value as f64 (a Float32 literal is
                       widened exactly by the caller and narrowed back here) */
 } lc_literal_kind;
@@ -128,6 +133,10 @@ typedef struct lc_predicate {
 typedef enum lc_liquid_type {
   LC_LIQUID_INTEGER = 1,
   LC_LIQUID_FLOAT = 2,     /* LiquidFloatArray: ALP (float_array.rs) */
+  LC_LIQUID_FIXED_LEN_BYTE_ARRAY = 3, /* LiquidFixedLenByteArray: Decimal128/256 with values outside u64, u16 dictionary +
+                              FSST over the 16 / 32-byte values (fix_len_byte_array.rs). The values are kept in
+                              order-preserving byte form, so `col <op> LC_LIT_I128` runs on the dictionary like a byte-view
+                              comparison (the reference decodes, filters and compares: LiquidArray default) */
   LC_LIQUID_BYTE_VIEW = 4,
   LC_LIQUID_DECIMAL = 6    /* LiquidDecimalArray: Decimal128/256 whose values fit u64 (decimal_array.rs) */
 } lc_liquid_type;
@@ -197,13 +206,51 @@ int lc_arrow_format(lc_ctx* ctx, lc_handle h, char* buf, size_t buf_len);
 /* LiquidArray::to_bytes (liquid_array/mod.rs:116-121): the entry in the reference's serialized form, LQDA
  * (liquid_array/ipc.rs:158-250; primitive_array.rs:603-654, float_array.rs:393-520, decimal_array.rs:180-218,
  * raw/bit_pack_array.rs:181-252), for Integer / Float / Decimal entries — what the reference writes when it spills an
- * entry to disk. out == NULL asks for the size. Byte-view entries: LC_ERR_UNSUPPORTED_TYPE
- * (byte_view_array/serialization.rs is not built). */
+ * entry to disk; byte-view entries in the layout of byte_view_array/serialization.rs:87-220. out == NULL asks for the size. */
 int lc_to_bytes(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
 /* ipc::read_from_bytes (liquid_array/ipc.rs:252-283) for the same three logical types: an LQDA image becomes an
  * HBM-resident entry (the Arrow type follows from the physical type id / the decimal header). The image is checked
  * (section bounds, bit width, patch indices) and refused with LC_ERR_INVALID instead of panicking. */
 int lc_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, lc_handle* out);
+/* Byte-view images (byte_view_array/serialization.rs:87-325) need the symbol table of their column chunk, which the
+ * reference passes in LiquidIPCContext (ipc.rs:238-249): the table registered under `compressor_scope` is used. */
+int lc_from_bytes_scoped(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, uint64_t compressor_scope, lc_handle* out);
+/* save_symbol_table / load_symbol_table (raw/fsst_buffer.rs:854-932): count u8, symbol lengths, symbols as u64 LE.
+ * load registers the table under a scope that has none yet. */
+int lc_ctx_save_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8_t* bytes, uint64_t len);
+
+/* ---- squeezed integer entries --------------------------------------------------------------------------------------
+ * LiquidArray::squeeze (liquid_array/mod.rs, primitive_array.rs:389-499): when HBM is the scarce tier an integer entry is
+ * replaced by its half-width codes (LiquidPrimitiveClampedArray / LiquidPrimitiveQuantizedArray,
+ * hybrid_primitive_array.rs) while the full LQDA image moves behind the caller's SqueezeIoHandler (mod.rs:282-…): host
+ * memory or disk. lc_to_arrow / lc_eval_predicate on the squeezed handle answer from the codes when those decide and read
+ * the image back (one `read` call for the whole range, like hydrate_full_arrow) when they cannot; the result is always
+ * the full entry's. lc_eval_predicate_many takes any mix of full and squeezed (clamp / quantize) entries of one column: a
+ * probe pass per squeeze form finds the entries whose codes cannot decide, one pass evaluates the predicate over the whole
+ * list, and only those entries are read back and re-evaluated. lc_scan_filter does the same on the device-resident selection
+ * (probes run on a copy of it). lc_to_arrow_many and lc_scan_read* take full entries only: rows are read from a squeezed
+ * column through lc_to_arrow, entry by entry. */
+typedef int (*lc_backing_read)(void* user, uint64_t offset, uint64_t len, uint8_t* dst); /* 0 = ok; SqueezeIoHandler::read */
+typedef enum lc_squeeze_policy { LC_SQUEEZE_CLAMP = 0, LC_SQUEEZE_QUANTIZE = 1 } lc_squeeze_policy; /* IntegerSqueezePolicy */
+/* Returns the pair of LiquidArray::squeeze: the full bytes (written to bytes_out, *out_bytes long) and the squeezed entry.
+ * *out_squeezed == 0 and *out_bytes == 0 is the reference's None: no hint, a Date32 / Timestamp column under a hint
+ * that names no date field, an all-null column or one narrower than 8 bits, or a logical type other than Integer. bytes_out == NULL asks for the size only. `h` stays valid; the caller releases it once the bytes
+ * are stored (the reference swaps the cache entry). `read` is called under the context lock, on the calling thread. */
+int lc_squeeze(lc_ctx* ctx, lc_handle h, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
+               uint64_t cap, uint64_t* out_bytes, lc_handle* out_squeezed);
+/* out[0] = 0 for a full entry, 1 clamp, 2 quantize, 3 date component; out[1] = bit width of the codes; out[2] = bucket
+ * width (quantize) or the date field (0 year, 1 month, 2 day, 3 day of week); out[3] = length of the backing image;
+ * out[4], out[5] = backing reads / calls answered from the codes, context-wide. */
+int lc_squeezed_info(lc_ctx* ctx, lc_handle h, uint64_t out[6]);
+/* Date32 / Timestamp columns squeeze — only under an LC_HINT_EXTRACT_* hint — to the one date component the hint names
+ * (SqueezedDate32Array, liquid_array/squeezed_date32_array.rs:44-223; `policy` is ignored). lc_to_arrow and
+ * lc_eval_predicate on such a handle always read the backing (:430-486). What the codes give without a read:
+ *   lossy != 0  SqueezedDate32Array::to_component_array (:276-282): an array of the column's own type whose date has the
+ *               stored component (Year -> y-01-01, Month -> 1970-m-01, Day -> 1970-01-d, DayOfWeek -> 1970-01-04 + dow;
+ *               timestamps at midnight), so the query's date_part over it gives the component back
+ *   lossy == 0  to_component_date32 (:286-294): the component values themselves, typed Date32 */
+int lc_squeezed_component(lc_ctx* ctx, lc_handle h, int32_t lossy, struct ArrowSchema* out_schema, struct ArrowArray* out_array);
 
 /* LiquidArray::to_arrow_array (sel_bits == NULL) / LiquidArray::filter(&BooleanBuffer)
  * (primitive_array.rs:350-374, byte_view_array/mod.rs:266-290,421-424). The result has the

@@ -23,7 +23,11 @@ LC_ERR_NO_DEVICE = -8
 
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_LIKE, OP_NOT_LIKE, OP_CONST_TRUE, OP_CONST_FALSE = range(10)
 HINT_NONE, HINT_PREDICATE, HINT_SUBSTRING_SEARCH = 0, 1, 2
+HINT_EXTRACT = {"Year": 3, "Month": 4, "Day": 5, "DayOfWeek": 6}  # CacheExpression::ExtractDate32 { field }
 LIT_I64, LIT_U64, LIT_BYTES, LIT_I128, LIT_F64 = 0, 1, 2, 3, 4
+SQUEEZE_CLAMP, SQUEEZE_QUANTIZE = 0, 1
+# lc_backing_read: int (*)(void* user, uint64_t offset, uint64_t len, uint8_t* dst)
+BACKING_READ = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p)
 LIQUID_INTEGER, LIQUID_FLOAT, LIQUID_BYTE_VIEW, LIQUID_DECIMAL = 1, 2, 4, 6
 
 
@@ -113,6 +117,12 @@ def lib() -> C.CDLL:
     l.lc_arrow_format.argtypes = [vp, u64, C.c_char_p, C.c_size_t]
     l.lc_to_bytes.argtypes = [vp, u64, vp, u64, u64p]
     l.lc_from_bytes.argtypes = [vp, vp, u64, u64p]
+    l.lc_from_bytes_scoped.argtypes = [vp, vp, u64, u64, u64p]
+    l.lc_ctx_save_symbol_table.argtypes = [vp, u64, vp, u64, u64p]
+    l.lc_ctx_load_symbol_table.argtypes = [vp, u64, vp, u64]
+    l.lc_squeeze.argtypes = [vp, u64, C.c_int32, C.c_int32, BACKING_READ, vp, vp, u64, u64p, u64p]
+    l.lc_squeezed_info.argtypes = [vp, u64, C.POINTER(u64)]
+    l.lc_squeezed_component.argtypes = [vp, u64, C.c_int32, vp, vp]
     l.lc_to_arrow.argtypes = [vp, u64, vp, u64, vp, vp]
     l.lc_eval_predicate.argtypes = [vp, u64, C.POINTER(Predicate), vp, u64, vp, vp, u64p, u64p]
     l.lc_mask_bytes.argtypes = [u64]

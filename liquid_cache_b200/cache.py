@@ -131,6 +131,38 @@ class GpuLiquidArray:
         N.check(N.lib().lc_to_bytes(self._cache._ctx, self._h, buf.ctypes.data, nb.value, C.byref(nb)))
         return buf[: int(nb.value)].tobytes()
 
+    def squeeze(self, io, expression_hint, policy: str = "clamp"):
+        """`LiquidArray::squeeze(io, expression_hint)` (liquid_array/primitive_array.rs:389-499) under
+        `IntegerSqueezePolicy::{Clamp, Quantize}`: returns `(squeezed array, full LQDA bytes)` or None when the
+        reference would not squeeze. `io` mirrors `SqueezeIoHandler`: `io.read((start, end)) -> bytes` is called when the
+        half-width codes cannot answer; the caller stores the returned bytes where `io` will find them."""
+        pol = {"clamp": N.SQUEEZE_CLAMP, "quantize": N.SQUEEZE_QUANTIZE}[policy]
+        field = CacheExpression.as_date32_field(expression_hint)
+        hint = N.HINT_NONE if expression_hint is None else N.HINT_EXTRACT[field] if field else (
+            N.HINT_SUBSTRING_SEARCH if expression_hint == CacheExpression.SubstringSearch else N.HINT_PREDICATE)
+        nb, sq = C.c_uint64(0), C.c_uint64(0)
+        ctx = self._cache._ctx
+        N.check(N.lib().lc_squeeze(ctx, self._h, pol, hint, None, None, None, 0, C.byref(nb), C.byref(sq)))
+        if nb.value == 0:
+            return None
+
+        def _read(_user, offset, length, dst):
+            try:
+                data = io.read((int(offset), int(offset + length)))
+                if len(data) != length:
+                    return 2
+                C.memmove(dst, data, length)
+                return 0
+            except Exception:  # the C side reports the failed read
+                return 1
+
+        cb = N.BACKING_READ(_read)
+        buf = np.zeros(int(nb.value), dtype=np.uint8)
+        N.check(N.lib().lc_squeeze(ctx, self._h, pol, hint, cb, None, buf.ctypes.data, nb.value, C.byref(nb), C.byref(sq)))
+        squeezed = GpuSqueezedArray(self._cache, int(sq.value))
+        squeezed._keepalive = (cb, io)  # the C side calls back for as long as the entry lives
+        return squeezed, buf[: int(nb.value)].tobytes()
+
     def fsst_table(self) -> bytes:
         """The column chunk's FSST symbol table as the kernels see it (lc::FsstTable: 256 x u64 symbols, 256 x u8 lengths)."""
         nb = C.c_uint64(0)
@@ -182,6 +214,51 @@ class GpuLiquidArray:
             )
         )
         return _mask_to_boolean_array(vals, valid, int(out_len.value), int(out_nulls.value))
+
+
+class GpuSqueezedArray(GpuLiquidArray):
+    """`LiquidSqueezedArray` (liquid_array/mod.rs:209-263) for the two integer forms: `to_arrow_array`, `filter` and
+    `try_eval_predicate` keep their meaning, reading the backing bytes through `io` when the codes cannot answer."""
+
+    def _info(self):
+        out = (C.c_uint64 * 6)()
+        N.check(N.lib().lc_squeezed_info(self._cache._ctx, self._h, out))
+        return [int(x) for x in out]
+
+    def policy(self) -> str:
+        return {1: "clamp", 2: "quantize", 3: "date32"}[self._info()[0]]
+
+    def field(self) -> str:
+        """`SqueezedDate32Array::field` (squeezed_date32_array.rs:270-272)"""
+        assert self._info()[0] == 3
+        return ("Year", "Month", "Day", "DayOfWeek")[self._info()[2]]
+
+    def _component(self, lossy: int) -> pa.Array:
+        out_a, out_s = _new_out()
+        N.check(N.lib().lc_squeezed_component(self._cache._ctx, self._h, lossy, _ptr(out_s), _ptr(out_a)))
+        return _import(out_a, out_s)
+
+    def to_component_array(self) -> pa.Array:
+        """`SqueezedDate32Array::to_component_array` (:276-282): the column's own type, dates whose component is the
+        stored one — no backing read."""
+        return self._component(1)
+
+    def to_component_date32(self) -> pa.Array:
+        """`to_component_date32` (:286-294): the component values themselves, typed Date32."""
+        return self._component(0)
+
+    def bit_width(self) -> int:
+        return self._info()[1]
+
+    def bucket_width(self) -> int:
+        return self._info()[2]
+
+    def disk_backing(self) -> int:
+        """`SqueezedBacking::Liquid(len)`: bytes of the image behind `io`."""
+        return self._info()[3]
+
+    def to_bytes(self) -> bytes:
+        raise N.UnsupportedType(N.LC_ERR_UNSUPPORTED_TYPE, "a squeezed array has no serialized form; its full image is the backing")
 
 
 _FORMAT_TO_TYPE = {
@@ -419,12 +496,29 @@ class LiquidCache:
         N.check(N.lib().lc_encode(self._ctx, _ptr(c_sch), _ptr(c_arr), nh, compressor_scope, C.byref(h)))
         return GpuLiquidArray(self, int(h.value))
 
-    def read_from_bytes(self, data: bytes) -> GpuLiquidArray:
-        """`ipc::read_from_bytes` (liquid_array/ipc.rs:252-283): an LQDA image becomes an HBM-resident entry."""
+    def read_from_bytes(self, data: bytes, compressor_scope: Optional[int] = None) -> GpuLiquidArray:
+        """`ipc::read_from_bytes` (liquid_array/ipc.rs:252-283): an LQDA image becomes an HBM-resident entry. Byte-view
+        images need the scope whose symbol table they were compressed with (LiquidIPCContext)."""
         buf = np.frombuffer(data, dtype=np.uint8)
         h = C.c_uint64(0)
-        N.check(N.lib().lc_from_bytes(self._ctx, buf.ctypes.data, len(buf), C.byref(h)))
+        if compressor_scope is None:
+            N.check(N.lib().lc_from_bytes(self._ctx, buf.ctypes.data, len(buf), C.byref(h)))
+        else:
+            N.check(N.lib().lc_from_bytes_scoped(self._ctx, buf.ctypes.data, len(buf), int(compressor_scope), C.byref(h)))
         return GpuLiquidArray(self, int(h.value))
+
+    def save_symbol_table(self, compressor_scope: int) -> bytes:
+        """`save_symbol_table` (raw/fsst_buffer.rs:854-883) of the scope's FSST table."""
+        nb = C.c_uint64(0)
+        N.check(N.lib().lc_ctx_save_symbol_table(self._ctx, int(compressor_scope), None, 0, C.byref(nb)))
+        buf = np.zeros(int(nb.value), dtype=np.uint8)
+        N.check(N.lib().lc_ctx_save_symbol_table(self._ctx, int(compressor_scope), buf.ctypes.data, nb.value, C.byref(nb)))
+        return buf.tobytes()
+
+    def load_symbol_table(self, compressor_scope: int, data: bytes) -> None:
+        """`load_symbol_table` (raw/fsst_buffer.rs:886-932): registers the table under a scope that has none."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        N.check(N.lib().lc_ctx_load_symbol_table(self._ctx, int(compressor_scope), buf.ctypes.data, len(buf)))
 
     def _handle(self, entry_id) -> int:
         ids = (C.c_uint64 * 1)(int(entry_id))

@@ -126,6 +126,18 @@ static void build_enc(const std::vector<Sym>& syms, FsstCodec* out) {
   }
 }
 
+// A codec from a stored symbol table (load_symbol_table, raw/fsst_buffer.rs:886-932). The decode view is exact; the encode
+// lookup keeps one symbol per 3-byte hash bucket like the trained tables do (a table written by fsst-rs may have more, which
+// only costs compression of LATER inserts under this scope, never a result).
+void fsst_from_symbols(const uint64_t* vals, const uint8_t* lens, size_t n, FsstCodec* out) {
+  std::vector<Sym> syms(n);
+  for (size_t i = 0; i < n; ++i) {
+    syms[i].len = lens[i];
+    syms[i].val = vals[i] & len_mask(lens[i]);
+  }
+  build_enc(syms, out);
+}
+
 void fsst_train(const uint8_t* const* strs, const uint32_t* lens, size_t n, FsstCodec* out) {
   // ---- sample (~16 KiB, evenly strided over the input) ----
   constexpr size_t kSampleTarget = 16384;

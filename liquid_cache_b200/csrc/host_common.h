@@ -14,6 +14,8 @@
 
 #include "../../include/lc_gpu.h"
 #include "entry_layout.h"
+#include "squeeze_plan.h"
+#include "fixed_math.cuh"
 #include "kernels.h"
 
 namespace lc {
@@ -97,6 +99,7 @@ struct FsstCodec {
 };
 // fsst_host.cc
 void fsst_train(const uint8_t* const* strs, const uint32_t* lens, size_t n, FsstCodec* out);
+void fsst_from_symbols(const uint64_t* vals, const uint8_t* lens, size_t n, FsstCodec* out);
 size_t fsst_compress_host(const FsstCodec& c, const uint8_t* in, size_t len, uint8_t* out);
 size_t fsst_decompress_host(const FsstTable& t, const uint8_t* in, size_t len, uint8_t* out, size_t cap);
 
@@ -118,7 +121,22 @@ struct Entry {
   StrHeader sh;
   std::vector<uint8_t> shared_prefix;  // byte-view: host copy (predicate planning)
   std::shared_ptr<FsstCodec> codec;    // byte-view
+  // squeezed integers (LiquidPrimitiveClampedArray / LiquidPrimitiveQuantizedArray): the blob holds half-width codes,
+  // the full LQDA image sits behind the caller's read function
+  int32_t squeeze_kind = 0;            // 0 = a full entry, 1 clamp, 2 quantize, 3 date component (SqueezedDate32Array)
+  uint64_t bucket_width = 0;           // quantize
+  uint32_t date_field = 0;             // date component: 0 year, 1 month, 2 day, 3 day of week
+  std::string orig_format;             // date component: the column's own arrow type (the blob itself reads as Date32)
+  lc_backing_read backing_read = nullptr;
+  void* backing_user = nullptr;
+  uint64_t backing_len = 0;            // disk_range = 0..backing_len
+  uint32_t fixed_width = 0;            // LiquidFixedLenByteArray (decimals outside u64): bytes per value, else 0
 };
+
+// int_encode's answer for a decimal array with values outside u64: the caller stores it as LiquidFixedLenByteArray
+// (str_encode over the 16 / 32-byte values) under the column chunk's compressor scope
+constexpr int LC_INTERNAL_FIXED_LEN = 1000;
+// order-preserving form of fixed-width decimals: fixed_math.cuh (host + device)
 
 // integer-shaped blobs (IntHeader + FastLanes chunks): integers, ALP floats, u64 decimals
 inline bool is_int_blob(int32_t liquid_type) {
@@ -145,6 +163,8 @@ struct lc_ctx {
   uint64_t n_entries = 0;
   uint64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   uint64_t epoch = 0;            // bumped whenever an entry is released (invalidates cached entry lists)
+  bool squeeze_internal = false; // squeeze_host.cc is driving the batch functions (they refuse squeezed entries otherwise)
+  uint64_t squeeze_reads = 0, squeeze_saved = 0;  // backing reads / calls answered from the half-width codes
   uint8_t* d_needle = nullptr;   // small device buffer for predicate needles
   cudaStream_t copy_stream = nullptr;  // results of chunk c travel to the host while chunk c+1 is computed
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -216,9 +236,13 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out);
 int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<Entry*>* out);  // K_INT batches only
 // ipc_host.cc: LQDA (the reference's serialized form) of integer-shaped entries
 int entry_to_bytes(lc_ctx* ctx, const Entry* e, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
-int entry_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, Entry** out);
+int entry_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, const std::shared_ptr<FsstCodec>& codec, Entry** out);
+int symbol_table_to_bytes(const FsstCodec& c, uint8_t* out, uint64_t cap, uint64_t* out_bytes);
+int symbol_table_from_bytes(const uint8_t* bytes, uint64_t len, FsstCodec* out);
+int register_codec(lc_ctx* ctx, uint64_t scope, const std::shared_ptr<FsstCodec>& codec);  // str_host.cc: device copies + ctx->codecs
 // str_host.cc
 int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out);
+int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, const uint64_t* scopes, std::vector<Entry*>* out);
 
 // Selection prepared for a launch.
 struct SelIn {
@@ -256,6 +280,17 @@ struct DeviceOut {             // caller-owned device buffers (lc_scan_read_devi
 int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t* const* sel_bits,
                    const DevSel* dev_sel, ArrowSchema* out_schema, ArrowArray* out_array,
                    const DeviceOut* dev_out = nullptr);
+
+// squeeze_host.cc
+int squeezed_eval_predicate_many(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred,
+                                 const uint8_t* const* sel_bits, const PredOut& out);
+int squeeze_doubt(const Entry* e, const lc_predicate* pred, lc_predicate* probe);
+int squeeze_hydrate(lc_ctx* ctx, const Entry* sq, Entry** full);
+int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
+                  uint64_t cap, uint64_t* out_bytes, Entry** out);
+int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, const uint8_t* sel_bits, const PredOut& out);
+int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSchema* out_schema, ArrowArray* out_array);
+int squeezed_component_array(lc_ctx* ctx, Entry* sq, int32_t lossy, ArrowSchema* out_schema, ArrowArray* out_array);
 
 int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred, uint32_t* d_sel_base,
                  const uint64_t* d_word_off, bool all_rows, uint32_t* d_counts);

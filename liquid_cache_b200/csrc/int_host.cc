@@ -138,10 +138,9 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
     mx = h_mmout[1];
     n_valid = h_mmout[2];
     if (is_dec && (h_mmout[3] & 0xffffffffull)) {
-      // the reference stores such arrays as LiquidFixedLenByteArray (FSST over the 16/32-byte values,
-      // transcode.rs:118-131); not built here: the caller keeps the Arrow array
-      set_error("decimal values outside u64 (LiquidFixedLenByteArray is not supported)");
-      return LC_ERR_UNSUPPORTED_TYPE;
+      // the reference stores such arrays as LiquidFixedLenByteArray (dictionary + FSST over the 16/32-byte values,
+      // transcode.rs:118-131): the byte-view insert path takes over (lc_abi.cc encode_locked)
+      return LC_INTERNAL_FIXED_LEN;
     }
   }
 

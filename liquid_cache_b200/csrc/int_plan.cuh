@@ -1,6 +1,6 @@
 // int_plan.cuh — how `col <op> literal` becomes a test on the unsigned PACKED value of an integer entry: the planner and the
 // range form every scan loop of k_int.cu evaluates. Host + device, so that the same code is exercised on the CPU against
-// plain comparisons (tests/cpp/int_plan_host.cc, tests/test_int_plan_cpu.py).
+// plain comparisons and the squeezed-array oracle (tests/cpp/int_plan_host.cc, tests/test_int_plan_cpu.py).
 #pragma once
 #include <cstdint>
 
@@ -56,6 +56,11 @@ LC_PL_HD void plan_int_pred(const IntHeader* h, const IntPredDesc& p, int32_t* u
   }
   const uint32_t W = h->bit_width;
   const uint64_t umax = W == 64 ? ~0ull : ((1ull << W) - 1ull);
+  if (p.lit_kind == kLitSentinel) {  // which rows of a clamped entry sit at the sentinel (squeeze_host.cc)
+    *thr = umax;
+    *ucmp = UC_EQ;
+    return;
+  }
   bool below, above = false;
   uint64_t d = 0;
   if (p.lit_kind == kLitAboveAll) {  // decimal literal beyond u64::MAX (scan_host.cc make_int_pred)
@@ -87,6 +92,15 @@ LC_PL_HD void plan_int_pred(const IntHeader* h, const IntPredDesc& p, int32_t* u
         above = d > umax;
       }
     }
+  }
+  if (h->squeeze_kind == 2 && !below && p.lit_kind != kLitAboveAll) {
+    // quantized entry (hybrid_primitive_array.rs:564-650): the words are bucket indices b = offset / bucket_width; compare
+    // them with the literal's bucket q. b < q / b > q are the operator's two sides, exactly what `b <op> q` gives; inside
+    // bucket q the same expression is right whenever the host let the call through (the literal sits on the bucket edge
+    // that decides the operator, or no selected row is in bucket q — squeeze_host.cc checks that first with `= literal`,
+    // which lands here as b == q).
+    d = d / int_bucket_width(*h);  // d was the literal's offset from the reference
+    above = d > umax;              // (the test above compared that offset with the code range: redo it for the bucket)
   }
   const int op = p.op;
   if (below) {

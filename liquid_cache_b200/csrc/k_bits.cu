@@ -5,6 +5,7 @@
 // rank_left(p)-th bit of right, where right has popcount(left) bits. On the GPU the "deposit" is a
 // rank computed from a prefix sum of per-word popcounts plus __popc(word & lanemask_lt).
 #include "device_utils.cuh"
+#include "fixed_math.cuh"
 #include "kernels.h"
 
 namespace lc {
@@ -144,6 +145,53 @@ __global__ void __launch_bounds__(256) k_build_views(const int32_t* __restrict__
     }
   }
   views[r] = v;
+}
+
+// LiquidFixedLenByteArray keeps its 16 / 32-byte values in ORDER-PRESERVING form: the little-endian two's complement
+// integer byte-reversed (big-endian) with the sign bit flipped, so that unsigned lexicographic byte order — what the
+// byte-view comparison kernels implement — is the numeric order of the decimals. In place, one thread per value.
+__global__ void __launch_bounds__(256) k_fixed_to_ordered(uint8_t* __restrict__ pool, uint32_t n, uint32_t width) {
+  const uint32_t r = blockIdx.x * 256u + threadIdx.x;
+  if (r >= n) return;
+  fixed_to_ordered_inplace(pool + static_cast<size_t>(r) * width, width);
+}
+
+cudaError_t launch_fixed_to_ordered(uint8_t* d_pool, uint32_t n, uint32_t width, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_fixed_to_ordered<<<(n + 255u) / 256u, 256, 0, s>>>(d_pool, n, width);
+  return cudaGetLastError();
+}
+
+// LiquidFixedLenByteArray result: the decoded values (variable-length form: offsets + bytes, null rows empty; order-preserving
+// form, see k_fixed_to_ordered) back as little-endian integers at their fixed stride, null slots zero. One thread per 4
+// bytes of output.
+__global__ void __launch_bounds__(256) k_fixed_from_var(const int32_t* __restrict__ off, uint32_t total_bytes,
+                                                        const uint8_t* __restrict__ data, const uint32_t* __restrict__ valid,
+                                                        uint64_t rows, uint32_t width, uint32_t* __restrict__ out) {
+  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * 256u + threadIdx.x;
+  const uint32_t words_per_row = width >> 2;
+  const uint64_t r = t / words_per_row;
+  if (r >= rows) return;
+  const uint32_t wdx = static_cast<uint32_t>(t % words_per_row);
+  const bool ok = valid ? ((valid[r >> 5] >> (r & 31u)) & 1u) : true;
+  uint32_t v = 0;
+  if (ok) {
+    const uint32_t b = static_cast<uint32_t>(off[r]);
+    const uint32_t e = r + 1u < rows ? static_cast<uint32_t>(off[r + 1u]) : total_bytes;
+    if (e - b == width) {  // always, for an entry built from fixed-width values
+      v = fixed_le_word(data + b, width, wdx);
+    }
+  }
+  out[t] = v;
+}
+
+cudaError_t launch_fixed_from_var(const int32_t* d_offsets, uint32_t total_bytes, const uint8_t* d_data, const uint32_t* d_validity,
+                                  uint64_t rows, uint32_t width, void* d_out, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  const uint64_t threads = rows * (width >> 2);
+  k_fixed_from_var<<<static_cast<uint32_t>((threads + 255) / 256), 256, 0, s>>>(d_offsets, total_bytes, d_data, d_validity, rows, width,
+                                                                               static_cast<uint32_t*>(d_out));
+  return cudaGetLastError();
 }
 
 cudaError_t launch_build_views(const int32_t* d_offsets, uint32_t total_bytes, const uint8_t* d_data, const uint32_t* d_validity,

@@ -20,6 +20,7 @@
 #include "device_utils.cuh"
 #include "kernels.h"
 #include "int_plan.cuh"
+#include "wspec_math.cuh"
 #include "scan_rows.cuh"
 
 namespace lc {
@@ -299,6 +300,79 @@ __device__ __forceinline__ void int_bits_fast(const EntryIo& w, const IntHeader*
   }
 }
 
+// ---- width-specialised variant of int_bits_fast -------------------------------------------------------------------
+// With the bit width a template parameter the 32 storage-order steps unroll into straight-line code whose word offsets,
+// funnel shifts and masks are immediates: no step table in shared memory, no LDS.128 of a table row, no address IADDs,
+// and the second field word is only loaded by the steps whose field actually straddles a word. Per 32 rows that is
+// ~7.5 instructions (W = 17: 2 LDS on 16 of 32 steps, 1 on the rest) where the table version issues 11-12.
+// Geometry (see FLOrder / fl_row_lane): T = 32: step j = packed row j, word k = j*W/32 of lane `lane` at byte 128*k + 4*lane.
+// T = 64: 16 lanes of 64-bit words; half-warp h takes row r + 32, i.e. the same shift and 32-bit word index x + W. 32-bit
+// word x of lane L sits at byte (x/2)*128 + (x%2)*4 + 8*L, so moving by W words is a constant byte distance when W is even
+// and one of two constants (by the parity of x) when W is odd: two per-lane bases cover both.
+template <typename U, int MODE, uint32_t W>
+__device__ __forceinline__ void int_bits_fast_w(const EntryIo& w, const IntHeader* h, const uint8_t* packed,
+                                                const uint32_t* valid, const URange<uint32_t>& g, uint32_t* fast_cnt) {
+  constexpr uint32_t T = FL<U>::T;
+  static_assert(T == 32 || T == 64, "width-specialised path: 32- and 64-bit columns");
+  static_assert(W >= 1 && W <= 32, "width-specialised path: fields of at most 32 bits");
+  const uint32_t n = h->n;
+  const uint32_t n_words = (n + 31u) >> 5, n_chunks = (n + 1023u) >> 10;
+  constexpr uint32_t chunk_bytes = 128u * W;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t* out_bits = reinterpret_cast<uint32_t*>(w.out);
+  uint32_t* out_valid = (MODE == MODE_PRED && valid) ? w.out_valid : nullptr;
+  const uint32_t* sel = w.sel;
+  const uint32_t tail = n & 31u;
+  const uint32_t ordl = wspec_out_word(lane);  // = FLOrder<U>()(lane) for T >= 32
+  const uint32_t negmask = g.neg ? kFullMask : 0u;
+  uint32_t survivors = 0;
+  for (uint32_t c = warp; c < n_chunks; c += 8u) {
+    const uint8_t* chunk = packed + c * chunk_bytes;
+    const WspecBases<T, W> bs = wspec_bases<T, W>(smem_u32(chunk), lane);  // wspec_math.cuh: checked on the CPU for every (T, W)
+    const uint32_t wi = c * 32u + ordl;
+    uint32_t sw = kFullMask;
+    if (sel && wi < n_words) sw = sel[wi];
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) {
+      const uint32_t u = wspec_value<T, W>(bs, j, [](uint32_t a) { return lds_u32(a); });
+      const bool hit = (u - g.lo) <= g.span;
+      const uint32_t cw = __ballot_sync(kFullMask, hit);
+      if (lane == j) mine = cw;
+    }
+    if (wi < n_words) {
+      uint32_t cw = mine ^ negmask;
+      uint32_t vw = valid ? valid[wi] : kFullMask;
+      if (wi == n_words - 1u && tail) vw &= (1u << tail) - 1u;
+      const uint32_t vo = vw;
+      cw &= vw & sw;
+      out_bits[wi] = cw;
+      if (out_valid) out_valid[wi] = vo;
+      survivors += __popc(cw);
+    }
+  }
+  if (w.counts) {
+    survivors = warp_sum(survivors);
+    if (lane == 0 && survivors) atomicAdd(fast_cnt, survivors);
+    if (MODE == MODE_PRED && threadIdx.x == 0) {
+      w.counts[0] = n;
+      w.counts[1] = h->null_count;
+    }
+  }
+}
+
+template <typename U, int MODE>
+__device__ __forceinline__ void int_bits_fast_w_dispatch(uint32_t W, const EntryIo& w, const IntHeader* h, const uint8_t* packed,
+                                                         const uint32_t* valid, const URange<uint32_t>& g, uint32_t* fast_cnt) {
+  switch (W) {
+#define LC_W(k) case k: int_bits_fast_w<U, MODE, k>(w, h, packed, valid, g, fast_cnt); break;
+    LC_W(1) LC_W(2) LC_W(3) LC_W(4) LC_W(5) LC_W(6) LC_W(7) LC_W(8) LC_W(9) LC_W(10) LC_W(11) LC_W(12) LC_W(13) LC_W(14) LC_W(15) LC_W(16)
+    LC_W(17) LC_W(18) LC_W(19) LC_W(20) LC_W(21) LC_W(22) LC_W(23) LC_W(24) LC_W(25) LC_W(26) LC_W(27) LC_W(28) LC_W(29) LC_W(30) LC_W(31)
+    default: int_bits_fast_w<U, MODE, 32>(w, h, packed, valid, g, fast_cnt); break;
+#undef LC_W
+  }
+}
+
 template <typename U, int MODE>
 __device__ __forceinline__ bool int_scan_entry(const EntryIo& w, const IntPredDesc& pred, const uint8_t* base,
                                                bool staged, ScanSmem* sm, uint32_t& tab_key, uint32_t* fast_cnt) {
@@ -330,7 +404,13 @@ __device__ __forceinline__ bool int_scan_entry(const EntryIo& w, const IntPredDe
     if (T == 64 && W > 32u) {
       int_bits_fast<U, MODE, uint64_t>(w, h, packed, valid, make_range<uint64_t>(kind, thr64), sm, tab_key, fast_cnt);
     } else {
-      int_bits_fast<U, MODE, uint32_t>(w, h, packed, valid, make_range<uint32_t>(kind, thr64), sm, tab_key, fast_cnt);
+      if constexpr (T >= 32) {
+        // 32- and 64-bit columns with fields of at most 32 bits: straight-line code per width (no step table)
+        int_bits_fast_w_dispatch<U, (MODE == MODE_DECODE ? MODE_PRED : MODE)>(W, w, h, packed, valid, make_range<uint32_t>(kind, thr64),
+                                                                              fast_cnt);
+      } else {
+        int_bits_fast<U, MODE, uint32_t>(w, h, packed, valid, make_range<uint32_t>(kind, thr64), sm, tab_key, fast_cnt);
+      }
     }
     return w.counts != nullptr;  // count deferred
   }

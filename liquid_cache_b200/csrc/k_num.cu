@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "alp_math.cuh"
+#include "squeeze_math.cuh"
 #include "device_utils.cuh"
 #include "kernels.h"
 
@@ -447,6 +448,78 @@ __global__ void __launch_bounds__(256) k_narrow_u64(const unsigned long long* __
     if (v >= limit) atomicOr(flag, 1u);
     out[i] = static_cast<uint32_t>(v);
   }
+}
+
+// Squeeze (LiquidPrimitiveArray::squeeze, liquid_array/primitive_array.rs:419-496): the decoded values of a full entry
+// become `reference + code`, code = the offset clamped at the sentinel (Clamp, :427-438) or its bucket index
+// (Quantize, :472-481), ready for k_int_pack at the halved width. In place, one value per thread, wrapping arithmetic on
+// the unsigned twin like the reference's add_wrapping / sub_wrapping.
+template <typename U>
+__global__ void __launch_bounds__(256) k_squeeze_map(U* __restrict__ vals, uint32_t n, U ref, uint32_t quantize, unsigned long long limit,
+                                                     unsigned long long bucket_width) {
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+    const unsigned long long off = static_cast<unsigned long long>(static_cast<U>(vals[i] - ref));
+    vals[i] = static_cast<U>(ref + static_cast<U>(squeeze_code(off, quantize, limit, bucket_width)));
+  }
+}
+
+cudaError_t launch_squeeze_map(void* d_vals, uint32_t n, uint32_t tbits, unsigned long long ref, uint32_t quantize,
+                               unsigned long long limit, unsigned long long bucket_width, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  uint32_t grid = (n + 255u) / 256u;
+  if (grid > 1184u) grid = 1184u;
+  switch (tbits) {
+    case 8: k_squeeze_map<uint8_t><<<grid, 256, 0, s>>>(static_cast<uint8_t*>(d_vals), n, static_cast<uint8_t>(ref), quantize, limit, bucket_width); break;
+    case 16: k_squeeze_map<uint16_t><<<grid, 256, 0, s>>>(static_cast<uint16_t*>(d_vals), n, static_cast<uint16_t>(ref), quantize, limit, bucket_width); break;
+    case 32: k_squeeze_map<uint32_t><<<grid, 256, 0, s>>>(static_cast<uint32_t*>(d_vals), n, static_cast<uint32_t>(ref), quantize, limit, bucket_width); break;
+    default: k_squeeze_map<unsigned long long><<<grid, 256, 0, s>>>(static_cast<unsigned long long*>(d_vals), n, ref, quantize, limit, bucket_width); break;
+  }
+  return cudaGetLastError();
+}
+
+// ---- Date32 / Timestamp columns squeezed to one date component (liquid_array/squeezed_date32_array.rs); the per-value
+// arithmetic lives in squeeze_math.cuh ----
+// from_liquid_date32 (:63-141) / from_liquid_timestamp (:144-223): decoded days (T = int32, ticks_per_day = 0) or
+// timestamp ticks (T = int64; div_euclid by the unit's ticks per day, `as i32`) -> the component of every row
+template <typename T>
+__global__ void __launch_bounds__(256) k_date_component(const T* __restrict__ in, uint32_t n, uint32_t field, long long ticks_per_day,
+                                                        int32_t* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+    const int32_t days = ticks_per_day ? days_of_ticks(static_cast<long long>(in[i]), ticks_per_day) : static_cast<int32_t>(in[i]);
+    out[i] = date_component(field, days);
+  }
+}
+
+// to_arrow_date32_lossy (:326-356) / to_arrow_timestamp_lossy (:299-321): a date whose component is the stored one —
+// Year -> (y,1,1), Month -> (1970,m,1), Day -> (1970,1,d), DayOfWeek -> 1970-01-04 + dow (saturating); null rows hold 0.
+// ticks_per_day = 0 writes int32 days, otherwise int64 ticks at midnight of that date.
+__global__ void __launch_bounds__(256) k_date_lossy(const int32_t* __restrict__ comp, const uint32_t* __restrict__ valid, uint32_t n,
+                                                    uint32_t field, long long ticks_per_day, void* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+    const bool ok = valid ? ((valid[i >> 5] >> (i & 31u)) & 1u) : true;
+    const int32_t days = ok ? lossy_days(field, comp[i]) : 0;
+    if (ticks_per_day) static_cast<long long*>(out)[i] = static_cast<long long>(days) * ticks_per_day;
+    else static_cast<int32_t*>(out)[i] = days;
+  }
+}
+
+cudaError_t launch_date_component(const void* d_in, uint32_t n, uint32_t in_bits, uint32_t field, long long ticks_per_day,
+                                  int32_t* d_out, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  uint32_t grid = (n + 255u) / 256u;
+  if (grid > 1184u) grid = 1184u;
+  if (in_bits == 64) k_date_component<long long><<<grid, 256, 0, s>>>(static_cast<const long long*>(d_in), n, field, ticks_per_day, d_out);
+  else k_date_component<int32_t><<<grid, 256, 0, s>>>(static_cast<const int32_t*>(d_in), n, field, 0, d_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_date_lossy(const int32_t* d_comp, const uint32_t* d_valid, uint32_t n, uint32_t field, long long ticks_per_day,
+                              void* d_out, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  uint32_t grid = (n + 255u) / 256u;
+  if (grid > 1184u) grid = 1184u;
+  k_date_lossy<<<grid, 256, 0, s>>>(d_comp, d_valid, n, field, ticks_per_day, d_out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_widen_u32(const uint32_t* d_in, uint32_t n, unsigned long long* d_out, cudaStream_t s) {

@@ -478,32 +478,44 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
     const uint32_t fill = (plan.flags & 1u) ? kFullMask : 0u;
     for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = fill;
   } else if (fast_like) {
-    // LIKE candidates: the reference gate (byte-class fingerprints, comparisons.rs:600-615), then the private bigram
+    // LIKE candidates: the reference gate (byte-class fingerprints, comparisons.rs:600-615), then the private trigram
     // filter on its survivors. Each thread owns the uniques i0 + lane of its warp's stripes; their gate inputs
-    // (fingerprint from the staged head, bigram filter from global memory) are loaded up front, eight stripes at a
+    // (fingerprint from the staged head, trigram filter from global memory) are loaded up front, four stripes at a
     // time, so the global loads overlap instead of each one stalling a ballot round. One ballot per stripe appends
     // the survivors to the queue. (An earlier version also ordered the queue by length class — worth 3 % with ~700
-    // candidates per entry, nothing with the ~100 the bigram filter leaves, at the price of a second pass.)
+    // candidates per entry, nothing with the handful the trigram filter leaves, at the price of a second pass.)
     uint32_t* cand_cnt = sm->warp_tot;  // [0] queue length (unused scratch in this phase)
     if (threadIdx.x == 0) cand_cnt[0] = 0;
     __syncthreads();
-    for (uint32_t g0 = (threadIdx.x & ~31u); g0 < U; g0 += 2048u) {
-      unsigned long long bl[8];
-      uint32_t fpv[8];
+    for (uint32_t g0 = (threadIdx.x & ~31u); g0 < U; g0 += 1024u) {
+      // four stripes in flight: fingerprint (staged head) + the value's 256-bit trigram set (two 16-byte loads from
+      // global memory, 1 KB per warp and stripe, coalesced)
+      ulonglong2 blo[4], bhi[4];
+      uint32_t fpv[4];
 #pragma unroll
-      for (uint32_t t = 0; t < 8; ++t) {
+      for (uint32_t t = 0; t < 4; ++t) {
         const uint32_t i = g0 + t * 256u + lane;
         const bool act = i < U;
         fpv[t] = (act && v.fp) ? v.fp[i] : 0u;
-        bl[t] = (act && v.bloom) ? v.bloom[i] : ~0ull;
+        if (act && v.bloom) {
+          const ulonglong2* src = reinterpret_cast<const ulonglong2*>(v.bloom + static_cast<size_t>(i) * kBloomWords);
+          blo[t] = src[0];
+          bhi[t] = src[1];
+        } else {
+          blo[t] = make_ulonglong2(~0ull, ~0ull);
+          bhi[t] = make_ulonglong2(~0ull, ~0ull);
+        }
       }
 #pragma unroll
-      for (uint32_t t = 0; t < 8; ++t) {
+      for (uint32_t t = 0; t < 4; ++t) {
         const uint32_t i0 = g0 + t * 256u;
         if (i0 >= U) break;  // warp-uniform
         const uint32_t i = i0 + lane;
         const bool ref_ok = (i < U) && (v.fp ? ((fpv[t] & pred.needle_fp) == pred.needle_fp) : true);
-        const bool cand = ref_ok && ((bl[t] & pred.needle_bloom) == pred.needle_bloom);
+        const bool cand = ref_ok && ((blo[t].x & pred.needle_bloom[0]) == pred.needle_bloom[0]) &&
+                          ((blo[t].y & pred.needle_bloom[1]) == pred.needle_bloom[1]) &&
+                          ((bhi[t].x & pred.needle_bloom[2]) == pred.needle_bloom[2]) &&
+                          ((bhi[t].y & pred.needle_bloom[3]) == pred.needle_bloom[3]);
         const uint32_t rw = __ballot_sync(kFullMask, ref_ok);
         const uint32_t cw = __ballot_sync(kFullMask, cand);
         uint32_t base = 0;

@@ -49,8 +49,8 @@ __device__ __forceinline__ bool bytes_equal(const uint8_t* a, const uint8_t* b, 
   return true;
 }
 
-__global__ void k_dict_insert(StrEncIo io) {
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < io.n; r += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void k_dict_insert_body(const StrEncIo& io, uint32_t bx, uint32_t gx) {
+  for (uint32_t r = bx * blockDim.x + threadIdx.x; r < io.n; r += gx * blockDim.x) {
     if (!row_valid(io, r)) {
       io.row_slot[r] = kEmpty;
       continue;
@@ -79,7 +79,7 @@ __global__ void k_dict_insert(StrEncIo io) {
 }
 
 // One CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) k_dict_finish(StrEncIo io) {
+__device__ __forceinline__ void k_dict_finish_body(const StrEncIo& io, uint32_t bx, uint32_t gx) {
   __shared__ uint32_t warp_tot[32];
   __shared__ uint32_t carry, nulls;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -205,11 +205,11 @@ __device__ __forceinline__ uint32_t fsst_compress_value(const FsstEncTable* __re
   return o;
 }
 
-__global__ void k_uniq_pass1(StrEncIo io) {
+__device__ __forceinline__ void k_uniq_pass1_body(const StrEncIo& io, uint32_t bx, uint32_t gx) {
   StrEncResult* res = io.res;
   const uint32_t U = res->n_unique;
   if (res->error) return;
-  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t u = bx * blockDim.x + threadIdx.x;
   uint32_t len = 0;
   if (u < U) {
     const uint32_t r = io.uniq_row[u];
@@ -226,13 +226,18 @@ __global__ void k_uniq_pass1(StrEncIo io) {
     io.clen[u] = fsst_compress_value<false>(io.enc, p, len, nullptr);
     if (io.fps) {
       uint32_t bits = 0;
-      unsigned long long bl = 0;
+      unsigned long long bl[kBloomWords] = {0ull, 0ull, 0ull, 0ull};
       for (uint32_t b = 0; b < len; ++b) {
         bits |= 1u << (p[b] & 31u);
-        if (b + 1u < len) bl |= 1ull << bigram_bit(p[b], p[b + 1u]);
+        if (b + 2u < len) {
+          const uint32_t t = trigram_bit(p[b], p[b + 1u], p[b + 2u]);
+          bl[t >> 6] |= 1ull << (t & 63u);
+        }
       }
       io.fps[u] = bits;
-      io.blooms[u] = bl;
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(io.blooms + static_cast<size_t>(u) * kBloomWords);
+      dst[0] = make_ulonglong2(bl[0], bl[1]);
+      dst[1] = make_ulonglong2(bl[2], bl[3]);
     }
   }
   // length statistics: warp-reduce, one atomic per warp
@@ -251,7 +256,7 @@ __global__ void k_uniq_pass1(StrEncIo io) {
 }
 
 // One CTA of 1024 threads: offsets, line fit, residuals.
-__global__ void __launch_bounds__(1024) k_offsets(StrEncIo io) {
+__device__ __forceinline__ void k_offsets_body(const StrEncIo& io, uint32_t bx, uint32_t gx) {
   __shared__ uint32_t warp_tot[32];
   __shared__ unsigned long long carry64;
   __shared__ int32_t s_slope, s_intercept, s_min, s_max;
@@ -357,11 +362,11 @@ __global__ void __launch_bounds__(1024) k_offsets(StrEncIo io) {
   }
 }
 
-__global__ void k_uniq_pass2(StrEncIo io) {
+__device__ __forceinline__ void k_uniq_pass2_body(const StrEncIo& io, uint32_t bx, uint32_t gx) {
   const StrEncResult* res = io.res;
   if (res->error) return;
   const uint32_t U = res->n_unique;
-  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t u = bx * blockDim.x + threadIdx.x;
   if (u >= U) return;
   const uint32_t r = io.uniq_row[u];
   const uint8_t* p = io.pool + io.row_off[r];
@@ -376,6 +381,19 @@ __global__ void k_uniq_pass2(StrEncIo io) {
   k |= static_cast<unsigned long long>(sl >= 255u ? 255u : sl) << 56;
   io.pkeys[u] = k;
 }
+
+// Every stage exists twice: for ONE batch (work item passed by value) and for a LIST of batches (blockIdx.y, or blockIdx.x
+// for the one-CTA stages, picks the work item), so a whole row group runs through the same five launches.
+__global__ void k_dict_insert(StrEncIo io) { k_dict_insert_body(io, blockIdx.x, gridDim.x); }
+__global__ void k_dict_insert_many(const StrEncIo* __restrict__ ios) { k_dict_insert_body(ios[blockIdx.y], blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(1024) k_dict_finish(StrEncIo io) { k_dict_finish_body(io, 0, 1); }
+__global__ void __launch_bounds__(1024) k_dict_finish_many(const StrEncIo* __restrict__ ios) { k_dict_finish_body(ios[blockIdx.x], 0, 1); }
+__global__ void k_uniq_pass1(StrEncIo io) { k_uniq_pass1_body(io, blockIdx.x, gridDim.x); }
+__global__ void k_uniq_pass1_many(const StrEncIo* __restrict__ ios) { k_uniq_pass1_body(ios[blockIdx.y], blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(1024) k_offsets(StrEncIo io) { k_offsets_body(io, 0, 1); }
+__global__ void __launch_bounds__(1024) k_offsets_many(const StrEncIo* __restrict__ ios) { k_offsets_body(ios[blockIdx.x], 0, 1); }
+__global__ void k_uniq_pass2(StrEncIo io) { k_uniq_pass2_body(io, blockIdx.x, gridDim.x); }
+__global__ void k_uniq_pass2_many(const StrEncIo* __restrict__ ios) { k_uniq_pass2_body(ios[blockIdx.y], blockIdx.x, gridDim.x); }
 
 }  // namespace
 
@@ -392,6 +410,26 @@ cudaError_t launch_str_encode(const StrEncIo& io, cudaStream_t s) {
   k_uniq_pass1<<<ugrid, 128, 0, s>>>(io);
   k_offsets<<<1, 1024, 0, s>>>(io);
   k_uniq_pass2<<<ugrid, 128, 0, s>>>(io);
+  return cudaGetLastError();
+}
+
+// The same pipeline over a list of batches: `d_ios` holds one work item per batch (device memory), `d_tables` is the
+// contiguous range of all their hash tables (filled with the empty marker here), `max_n` the largest row count.
+cudaError_t launch_str_encode_many(const StrEncIo* d_ios, uint32_t n_batches, uint32_t max_n, uint32_t* d_tables,
+                                   size_t table_words, cudaStream_t s) {
+  if (n_batches == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(d_tables, 0xFF, table_words * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  if (max_n) {
+    uint32_t gx = (max_n + 255u) / 256u;
+    if (gx > 64u) gx = 64u;  // rows beyond are covered by the grid-stride loop
+    k_dict_insert_many<<<dim3(gx, n_batches), 256, 0, s>>>(d_ios);
+  }
+  k_dict_finish_many<<<n_batches, 1024, 0, s>>>(d_ios);
+  const uint32_t ugrid = max_n ? (max_n + 127u) / 128u : 1u;
+  k_uniq_pass1_many<<<dim3(ugrid, n_batches), 128, 0, s>>>(d_ios);
+  k_offsets_many<<<n_batches, 1024, 0, s>>>(d_ios);
+  k_uniq_pass2_many<<<dim3(ugrid, n_batches), 128, 0, s>>>(d_ios);
   return cudaGetLastError();
 }
 

@@ -55,6 +55,7 @@ struct IntPredDesc {
   uint64_t lit_u;
 };
 constexpr int32_t kLitAboveAll = 7;  // decimal literal beyond u64: larger than every value of the column
+constexpr int32_t kLitSentinel = 8;  // squeezed (clamp) entries: "code == all ones of the entry's width", whatever the op says
 
 struct alignas(16) IntMinMaxWork {  // 32 bytes
   const void* values;         // native T[n] in device scratch
@@ -137,6 +138,16 @@ cudaError_t launch_dec_narrow(const void* d_in, const uint32_t* d_validity, uint
 cudaError_t launch_dec_widen(const unsigned long long* d_in, uint64_t n, uint32_t width_bytes, void* d_out, cudaStream_t s);
 
 // LQDA patch indices: u32 in the entry, u64 in the file; narrow raises *flag when an index is >= limit.
+// squeeze: decoded values -> reference + (clamped offset | bucket index), in place (quantize: limit = bucket_count - 1,
+// else limit = sentinel)
+cudaError_t launch_squeeze_map(void* d_vals, uint32_t n, uint32_t tbits, unsigned long long ref, uint32_t quantize,
+                               unsigned long long limit, unsigned long long bucket_width, cudaStream_t s);
+// date-component squeeze: decoded Date32 days (in_bits 32) or Timestamp ticks (in_bits 64, ticks_per_day of the unit) ->
+// int32 component per row (field 0 year, 1 month, 2 day, 3 day of week); and back to a date / timestamp with that component
+cudaError_t launch_date_component(const void* d_in, uint32_t n, uint32_t in_bits, uint32_t field, long long ticks_per_day,
+                                  int32_t* d_out, cudaStream_t s);
+cudaError_t launch_date_lossy(const int32_t* d_comp, const uint32_t* d_valid, uint32_t n, uint32_t field, long long ticks_per_day,
+                              void* d_out, cudaStream_t s);
 cudaError_t launch_widen_u32(const uint32_t* d_in, uint32_t n, unsigned long long* d_out, cudaStream_t s);
 cudaError_t launch_narrow_u64(const unsigned long long* d_in, uint32_t n, unsigned long long limit, uint32_t* d_out, uint32_t* d_flag,
                               cudaStream_t s);
@@ -160,7 +171,7 @@ struct alignas(16) StrPredDesc {
   uint32_t needle_len;   // full needle (for LIKE: the inner pattern without the % signs)
   uint32_t needle_fp;    // fingerprint of the LIKE needle (fingerprint.rs:19-26)
   uint32_t pad;
-  unsigned long long needle_bloom;  // bigram bits of the LIKE needle (entry_layout.h bigram_bit); 0 for 1-byte needles
+  unsigned long long needle_bloom[4];  // trigram bits of the LIKE needle (entry_layout.h trigram_bit); all zero below 3 bytes
   const uint8_t* needle; // device: needle bytes padded to 4, then needle_len x u16 KMP failure links
   unsigned long long* prof;  // optional device counters {uniques, candidates, candidate bytes}; nullptr = off
 };
@@ -229,7 +240,7 @@ struct StrEncIo {
   uint32_t* offsets;         // U + 1
   unsigned long long* pkeys; // U PrefixKeys
   uint32_t* fps;             // U fingerprints (nullptr = not requested)
-  unsigned long long* blooms;// U bigram filters, built together with the fingerprints
+  unsigned long long* blooms;// U x kBloomWords trigram filters, built together with the fingerprints
   uint8_t* comp;             // compressed values, back to back
   uint8_t* resid;            // (U + 1) * offset_bytes
   const FsstEncTable* enc;
@@ -237,6 +248,9 @@ struct StrEncIo {
 };
 // Enqueues the whole pipeline (dictionary -> keys -> compress -> offsets fit); `res` is valid once the stream drains.
 cudaError_t launch_str_encode(const StrEncIo& io, cudaStream_t s);
+// The same five stages over a list of batches (one work item per batch in device memory); see k_str_encode.cu.
+cudaError_t launch_str_encode_many(const StrEncIo* d_ios, uint32_t n_batches, uint32_t max_n, uint32_t* d_tables,
+                                   size_t table_words, cudaStream_t s);
 
 // ---- bit utilities -----------------------------------------------------------------------------
 // boolean_buffer_and_then: out[p] = left[p] & right[rank_left(p)]  (datafusion/src/utils.rs:62-236)
@@ -248,6 +262,11 @@ cudaError_t launch_concat_validity(const uint32_t* d_valid_base, const uint64_t*
                                    uint32_t* d_out, cudaStream_t s);
 cudaError_t launch_build_views(const int32_t* d_offsets, uint32_t total_bytes, const uint8_t* d_data, const uint32_t* d_validity,
                                uint64_t rows, void* d_views, cudaStream_t s);
+// LiquidFixedLenByteArray results: decoded (offsets, bytes) -> values at a fixed stride of `width` bytes, null slots zero
+// LiquidFixedLenByteArray insert: n little-endian values of `width` bytes at the start of the pool -> order-preserving form
+cudaError_t launch_fixed_to_ordered(uint8_t* d_pool, uint32_t n, uint32_t width, cudaStream_t s);
+cudaError_t launch_fixed_from_var(const int32_t* d_offsets, uint32_t total_bytes, const uint8_t* d_data, const uint32_t* d_validity,
+                                  uint64_t rows, uint32_t width, void* d_out, cudaStream_t s);
 cudaError_t launch_and_then(const uint32_t* d_left, uint32_t left_bits, const uint32_t* d_right, uint32_t* d_out,
                             cudaStream_t s);
 

@@ -20,7 +20,15 @@ int encode_locked(lc_ctx* ctx, const ArrowSchema* schema, const ArrowArray* arra
                   Entry** out) {
   ArrowIn in;
   LC_TRY(parse_arrow_input(schema, array, &in));
-  if (in.kind == ArrowIn::K_INT || in.kind == ArrowIn::K_FLOAT || in.kind == ArrowIn::K_DECIMAL) return int_encode(ctx, in, out);
+  if (in.kind == ArrowIn::K_INT || in.kind == ArrowIn::K_FLOAT || in.kind == ArrowIn::K_DECIMAL) {
+    const int rc = int_encode(ctx, in, out);
+    if (rc != LC_INTERNAL_FIXED_LEN) return rc;
+    // LiquidFixedLenByteArray::from_decimal_array (fix_len_byte_array.rs:274-323): u16 dictionary over the 16 / 32-byte
+    // values, FSST-compressed under the column chunk's compressor (with_fsst_compressor_or_train, transcode.rs:118-131)
+    in.byte_type = in.dec_width == 16 ? BT_DECIMAL128 : BT_DECIMAL256;
+    ctx->scratch.reset();
+    return str_encode(ctx, in, LC_HINT_NONE, scope, out);
+  }
   return str_encode(ctx, in, hint, scope, out);
 }
 
@@ -35,6 +43,10 @@ struct lc_scan {
   uint32_t* d_sel = nullptr;
   uint32_t* d_counts = nullptr;
   uint64_t* d_word_off = nullptr;
+  // squeezed entries only (scan_filter_squeezed), allocated on first use: probe copy / snapshot of the selection, probe counts
+  uint32_t* d_probe = nullptr;
+  uint32_t* d_save = nullptr;
+  uint32_t* d_pcounts = nullptr;
   bool all_rows = true;       // no filter applied yet
   bool counts_on_device = false;
   bool counts_cached = false;
@@ -155,6 +167,7 @@ uint64_t lc_memory_size(lc_ctx*, lc_handle h) {
 
 int32_t lc_data_type(lc_ctx*, lc_handle h) {
   Entry* e = entry_of(h);
+  if (e && e->fixed_width) return LC_LIQUID_FIXED_LEN_BYTE_ARRAY;  // a byte-view blob inside, LiquidFixedLenByteArray outside
   return e ? e->liquid_type : 0;
 }
 
@@ -202,6 +215,14 @@ int lc_to_bytes(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_t* 
     set_error("lc_to_bytes: bad argument");
     return LC_ERR_INVALID;
   }
+  if (e->squeeze_kind) {
+    set_error("lc_to_bytes: a squeezed entry has no serialized form (its full image is the backing)");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
+  if (e->fixed_width) {
+    set_error("lc_to_bytes: the LQDA form of LiquidFixedLenByteArray (fix_len_byte_array.rs:116-270) is not built");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
   Guard g(ctx);
   return entry_to_bytes(ctx, e, out, cap, out_bytes);
 }
@@ -213,15 +234,51 @@ int lc_from_bytes(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, lc_handle* ou
   }
   Guard g(ctx);
   Entry* e = nullptr;
-  LC_TRY(entry_from_bytes(ctx, bytes, len, &e));
+  LC_TRY(entry_from_bytes(ctx, bytes, len, nullptr, &e));
   *out = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
   return LC_OK;
+}
+
+int lc_from_bytes_scoped(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, uint64_t compressor_scope, lc_handle* out) {
+  if (!ctx || !bytes || !out) {
+    set_error("lc_from_bytes_scoped: NULL argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  auto it = ctx->codecs.find(compressor_scope);
+  Entry* e = nullptr;
+  LC_TRY(entry_from_bytes(ctx, bytes, len, it == ctx->codecs.end() ? nullptr : it->second, &e));
+  *out = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
+  return LC_OK;
+}
+
+int lc_ctx_save_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
+  if (!ctx || !out_bytes) return LC_ERR_INVALID;
+  Guard g(ctx);
+  auto it = ctx->codecs.find(compressor_scope);
+  if (it == ctx->codecs.end()) {
+    set_error("no symbol table for scope %llu", (unsigned long long)compressor_scope);
+    return LC_ERR_NOT_FOUND;
+  }
+  return symbol_table_to_bytes(*it->second, out, cap, out_bytes);
+}
+
+int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8_t* bytes, uint64_t len) {
+  if (!ctx || !bytes) return LC_ERR_INVALID;
+  Guard g(ctx);
+  if (ctx->codecs.count(compressor_scope)) {
+    set_error("scope %llu already has a symbol table", (unsigned long long)compressor_scope);
+    return LC_ERR_INVALID;
+  }
+  auto codec = std::make_shared<FsstCodec>();
+  LC_TRY(symbol_table_from_bytes(bytes, len, codec.get()));
+  return register_codec(ctx, compressor_scope, codec);
 }
 
 int lc_arrow_format(lc_ctx*, lc_handle h, char* buf, size_t buf_len) {
   Entry* e = entry_of(h);
   if (!e || !buf || buf_len == 0) return LC_ERR_INVALID;
-  std::string f = e->arrow_format;
+  std::string f = e->orig_format.empty() ? e->arrow_format : e->orig_format;  // a date-component entry reports its column's type
   if (!e->dict_value_format.empty()) f += ":" + e->dict_value_format;  // "S:u" = Dictionary<UInt16, Utf8>
   if (f.size() + 1 > buf_len) return LC_ERR_INVALID;
   std::memcpy(buf, f.c_str(), f.size() + 1);
@@ -253,8 +310,57 @@ int lc_to_arrow(lc_ctx* ctx, lc_handle h, const uint8_t* sel_bits, uint64_t sel_
     set_error("selection has %llu bits, entry has %u rows", (unsigned long long)sel_len, e->n);
     return LC_ERR_INVALID;
   }
+  if (e->squeeze_kind) {
+    if (!ctx || !out_schema || !out_array) {
+      set_error("lc_to_arrow: bad argument");
+      return LC_ERR_INVALID;
+    }
+    Guard g(ctx);
+    return squeezed_to_arrow(ctx, e, sel_bits, out_schema, out_array);
+  }
   const uint8_t* sels[1] = {sel_bits};
   return lc_to_arrow_many(ctx, &h, 1, sel_bits ? sels : nullptr, out_schema, out_array);
+}
+
+int lc_squeeze(lc_ctx* ctx, lc_handle h, int32_t policy, int32_t hint, lc_backing_read read, void* user, uint8_t* bytes_out,
+               uint64_t cap, uint64_t* out_bytes, lc_handle* out_squeezed) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out_bytes || !out_squeezed) {
+    set_error("lc_squeeze: bad argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  Entry* sq = nullptr;
+  *out_squeezed = 0;
+  LC_TRY(squeeze_entry(ctx, e, policy, hint, read, user, bytes_out, cap, out_bytes, &sq));
+  *out_squeezed = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(sq));
+  return LC_OK;
+}
+
+int lc_squeezed_component(lc_ctx* ctx, lc_handle h, int32_t lossy, struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out_schema || !out_array) {
+    set_error("lc_squeezed_component: bad argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  return squeezed_component_array(ctx, e, lossy, out_schema, out_array);
+}
+
+int lc_squeezed_info(lc_ctx* ctx, lc_handle h, uint64_t out[6]) {
+  Entry* e = entry_of(h);
+  if (!ctx || !e || !out) {
+    set_error("lc_squeezed_info: bad argument");
+    return LC_ERR_INVALID;
+  }
+  Guard g(ctx);
+  out[0] = static_cast<uint64_t>(e->squeeze_kind);
+  out[1] = e->liquid_type == LC_LIQUID_INTEGER ? e->ih.bit_width : 0;
+  out[2] = e->squeeze_kind == 3 ? e->date_field : e->bucket_width;
+  out[3] = e->backing_len;
+  out[4] = ctx->squeeze_reads;
+  out[5] = ctx->squeeze_saved;
+  return LC_OK;
 }
 
 int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, const lc_predicate* pred,
@@ -273,6 +379,9 @@ int lc_eval_predicate_many(lc_ctx* ctx, const lc_handle* handles, uint64_t n, co
   Entry* const* es = nullptr;
   LC_TRY(entries_cached(ctx, handles, n, &es));
   PredOut po{out_values, out_validity, out_byte_offsets, out_len, out_null_count, out_true_count};
+  bool any_squeezed = false;
+  for (uint64_t i = 0; i < n && !any_squeezed; ++i) any_squeezed = es[i]->squeeze_kind != 0;
+  if (any_squeezed) return squeezed_eval_predicate_many(ctx, es, n, pred, sel_bits, po);  // probes + backing reads where needed
   return eval_predicate_batch(ctx, es, n, pred, sel_bits, po);
 }
 
@@ -289,6 +398,15 @@ int lc_eval_predicate(lc_ctx* ctx, lc_handle h, const lc_predicate* pred, const 
   }
   const uint8_t* sels[1] = {sel_bits};
   const uint64_t off0 = 0;
+  if (e->squeeze_kind) {
+    if (!ctx || !pred || !out_values) {
+      set_error("lc_eval_predicate: NULL argument");
+      return LC_ERR_INVALID;
+    }
+    Guard g(ctx);
+    PredOut po{out_values, out_validity, &off0, out_len, out_null_count, nullptr};
+    return squeezed_eval_predicate(ctx, e, pred, sel_bits, po);
+  }
   return lc_eval_predicate_many(ctx, &h, 1, pred, sel_bits ? sels : nullptr, out_values, out_validity, &off0, out_len,
                                 out_null_count, nullptr);
 }
@@ -371,12 +489,20 @@ int lc_cache_insert_many(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, con
     LC_TRY(parse_arrow_input(schemas[i], arrays[i], &ins[i]));
     all_int = all_int && ins[i].kind == ArrowIn::K_INT;
   }
+  bool all_bytes = true;
+  for (uint64_t i = 0; i < n; ++i)
+    all_bytes = all_bytes && (ins[i].kind == ArrowIn::K_BYTES || ins[i].kind == ArrowIn::K_VIEW || ins[i].kind == ArrowIn::K_DICT);
   std::vector<Entry*> es;
   if (all_int) {
     // integer-like batches: one pass over the whole list (int_host.cc int_encode_many)
     LC_TRY(int_encode_many(ctx, ins, &es));
+  } else if (all_bytes) {
+    // byte-view batches: the five encode stages once over the whole list (str_host.cc str_encode_many)
+    std::vector<uint64_t> scopes(n);
+    for (uint64_t i = 0; i < n; ++i) scopes[i] = entry_ids[i] & ~0xFFFFull;
+    LC_TRY(str_encode_many(ctx, ins, hint, scopes.data(), &es));
   } else {
-    // byte views, floats, decimals: batch by batch for now; all or nothing like the batched pass
+    // floats, decimals, mixed lists: batch by batch; all or nothing like the batched passes
     for (uint64_t i = 0; i < n; ++i) {
       Entry* e = nullptr;
       ctx->scratch.reset();
@@ -532,6 +658,92 @@ int lc_scan_set_selection(lc_scan* scan, uint64_t batch, const uint8_t* sel_bits
   return LC_OK;
 }
 
+// lc_scan_filter over a list with squeezed (clamp / quantize) entries: selection &= valid & cmp stays one pass over the
+// whole list — the kernel's planner compares codes the way each header asks for — around two cheap extras:
+//   before  a probe pass per squeeze form in doubt, on a COPY of the selection, tells which entries have a selected row the
+//           codes cannot decide (hybrid_primitive_array.rs: Err(NeedsBacking));
+//   after   only those entries get their selection words back, read their LQDA image through the caller's function,
+//           and are refined again as full entries.
+static int scan_filter_squeezed(lc_scan* scan, Entry* const* es, const lc_predicate* pred) {
+  lc_ctx* ctx = scan->ctx;
+  const uint64_t n = scan->n;
+  struct Internal {  // the batch functions refuse squeezed entries unless squeeze code drives them
+    lc_ctx* c;
+    bool prev;
+    explicit Internal(lc_ctx* x) : c(x), prev(x->squeeze_internal) { x->squeeze_internal = true; }
+    ~Internal() { c->squeeze_internal = prev; }
+  } internal(ctx);
+  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
+    set_error("operator %d is not supported on integer columns", pred->op);
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  std::vector<uint8_t> doubt(n, 0);
+  lc_predicate probes[3] = {};
+  uint64_t n_doubt[4] = {0, 0, 0, 0};
+  for (uint64_t i = 0; i < n; ++i) {
+    if (es[i]->squeeze_kind == 3) {
+      set_error("lc_scan_filter: entry %llu is a date-component entry; those answer through lc_eval_predicate", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
+    lc_predicate probe{};
+    const int d = squeeze_doubt(es[i], pred, &probe);
+    doubt[i] = static_cast<uint8_t>(d);
+    n_doubt[d]++;
+    if (d == 1 || d == 2) probes[d] = probe;
+  }
+  std::vector<uint8_t> backing(n, 0);
+  for (uint64_t i = 0; i < n; ++i) backing[i] = doubt[i] == 3;
+  const bool any_doubt = n_doubt[1] || n_doubt[2] || n_doubt[3];
+  cudaStream_t s = ctx->stream;
+  // work areas kept with the scan: a copy of the selection for the probes, one to restore from, probe counts
+  const uint64_t sel_bytes = scan->total_words * 4 + 64;
+  if (any_doubt && !scan->d_probe) {
+    if (cudaMalloc(reinterpret_cast<void**>(&scan->d_probe), sel_bytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&scan->d_save), sel_bytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&scan->d_pcounts), n * 8 + 16) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("lc_scan_filter: cudaMalloc for the probe selection failed");
+      return LC_ERR_OOM;  // lc_scan_end frees whatever was allocated
+    }
+  }
+  uint32_t* d_probe = scan->d_probe;
+  uint32_t* d_save = scan->d_save;
+  uint32_t* d_pcounts = scan->d_pcounts;
+  if (any_doubt && !scan->all_rows)
+    LC_CUDA_OK(cudaMemcpyAsync(d_save, scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToDevice, s));
+  std::vector<uint32_t> pc(n * 2);
+  for (int form = 1; form <= 2; ++form) {
+    if (!n_doubt[form]) continue;
+    if (!scan->all_rows) LC_CUDA_OK(cudaMemcpyAsync(d_probe, scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToDevice, s));
+    ctx->scratch.reset();
+    LC_TRY(refine_batch(ctx, es, n, &probes[form], d_probe, scan->d_word_off, scan->all_rows, d_pcounts));
+    LC_CUDA_OK(cudaMemcpyAsync(pc.data(), d_pcounts, n * 8, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += n * 8;
+    for (uint64_t i = 0; i < n; ++i)
+      if (doubt[i] == form && pc[2 * i]) backing[i] = 1;
+  }
+  // ---- the predicate over the whole list ----
+  ctx->scratch.reset();
+  LC_TRY(refine_batch(ctx, es, n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
+  // ---- entries the codes could not decide ----
+  for (uint64_t i = 0; i < n; ++i) {
+    if (es[i]->squeeze_kind && !backing[i]) ctx->squeeze_saved++;
+    if (!backing[i]) continue;
+    const uint64_t words = (static_cast<uint64_t>(scan->rows[i]) + 31) / 32;
+    if (!scan->all_rows)
+      LC_CUDA_OK(cudaMemcpyAsync(scan->d_sel + scan->word_off[i], d_save + scan->word_off[i], words * 4, cudaMemcpyDeviceToDevice, s));
+    Entry* full = nullptr;
+    LC_TRY(squeeze_hydrate(ctx, es[i], &full));
+    Entry* one[1] = {full};
+    ctx->scratch.reset();
+    const int rc = refine_batch(ctx, one, 1, pred, scan->d_sel, scan->d_word_off + i, scan->all_rows, scan->d_counts + 2 * i);
+    release_entry(ctx, full);
+    LC_TRY(rc);
+  }
+  return LC_OK;
+}
+
 int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* pred) {
   if (!scan || !handles || !pred) {
     set_error("lc_scan_filter: NULL argument");
@@ -541,7 +753,10 @@ int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* 
   Guard g(ctx);
   Entry* const* es = nullptr;
   LC_TRY(scan_entries_cached(scan, handles, &es));
-  LC_TRY(refine_batch(ctx, es, scan->n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
+  bool any_squeezed = false;
+  for (uint64_t i = 0; i < scan->n && !any_squeezed; ++i) any_squeezed = es[i]->squeeze_kind != 0;
+  if (any_squeezed) LC_TRY(scan_filter_squeezed(scan, es, pred));
+  else LC_TRY(refine_batch(ctx, es, scan->n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
   scan->all_rows = false;
   scan->counts_on_device = true;
   scan->counts_cached = false;
@@ -608,18 +823,6 @@ int lc_scan_selection(lc_scan* scan, uint64_t batch, uint8_t* out_bits) {
   return LC_OK;
 }
 
-static int scan_entries(lc_scan* scan, const lc_handle* handles, std::vector<Entry*>* es) {
-  es->resize(scan->n);
-  for (uint64_t i = 0; i < scan->n; ++i) {
-    (*es)[i] = entry_of(handles[i]);
-    if (!(*es)[i] || (*es)[i]->n != scan->rows[i]) {
-      set_error("lc_scan_read: handle %llu invalid or row count differs from the scan's", (unsigned long long)i);
-      return LC_ERR_INVALID;
-    }
-  }
-  return LC_OK;
-}
-
 // Only batches with surviving rows are read, as LiquidCacheReader::read_from_cache does
 // (liquid_cache_reader.rs:346-349 returns early when the selection is empty).
 static void scan_nonempty(lc_scan* scan, const std::vector<Entry*>& es, std::vector<Entry*>* es2,
@@ -640,10 +843,13 @@ static void scan_nonempty(lc_scan* scan, const std::vector<Entry*>& es, std::vec
 int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* out_schema,
                  struct ArrowArray* out_array) {
   if (!scan || !handles || !out_schema || !out_array) return LC_ERR_INVALID;
-  std::vector<Entry*> es;
-  LC_TRY(scan_entries(scan, handles, &es));
   lc_ctx* ctx = scan->ctx;
   Guard g(ctx);
+  // the handle list of a column is validated once per scan (hash of the array), not once per read: 12 k pointer chases
+  // per call were ~0.05-0.1 ms of every get of the bench step
+  Entry* const* esp = nullptr;
+  LC_TRY(scan_entries_cached(scan, handles, &esp));
+  const std::vector<Entry*> es(esp, esp + scan->n);
   LC_TRY(scan_fetch_counts(scan));
   ctx->scratch.reset();
   std::vector<Entry*> es2;
@@ -657,15 +863,15 @@ int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* ou
 int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap, void* d_offsets,
                         void* d_validity, uint64_t* out_rows, uint64_t* out_value_bytes, uint64_t* out_null_count) {
   if (!scan || !handles) return LC_ERR_INVALID;
-  std::vector<Entry*> es;
-  LC_TRY(scan_entries(scan, handles, &es));
   lc_ctx* ctx = scan->ctx;
   Guard g(ctx);
+  Entry* const* esp = nullptr;
+  LC_TRY(scan_entries_cached(scan, handles, &esp));
   LC_TRY(scan_fetch_counts(scan));
   ctx->scratch.reset();
   DevSel ds{scan->d_sel, scan->word_off.data(), scan->counts.data(), scan->all_rows};
   DeviceOut dout{d_values, values_cap, d_offsets, d_validity, out_rows, out_value_bytes, out_null_count};
-  return to_arrow_batch(ctx, es.data(), scan->n, nullptr, &ds, nullptr, nullptr, &dout);
+  return to_arrow_batch(ctx, esp, scan->n, nullptr, &ds, nullptr, nullptr, &dout);
 }
 
 void lc_scan_end(lc_scan* scan) {
@@ -674,6 +880,9 @@ void lc_scan_end(lc_scan* scan) {
     Guard g(scan->ctx);
     cudaStreamSynchronize(scan->ctx->stream);
     if (scan->d_sel) cudaFree(scan->d_sel);
+    if (scan->d_probe) cudaFree(scan->d_probe);
+    if (scan->d_save) cudaFree(scan->d_save);
+    if (scan->d_pcounts) cudaFree(scan->d_pcounts);
     if (scan->d_counts) cudaFree(scan->d_counts);
     if (scan->d_word_off) cudaFree(scan->d_word_off);
   }

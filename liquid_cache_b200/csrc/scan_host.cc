@@ -185,6 +185,41 @@ static int like_inner(const uint8_t* pat, uint64_t len, const uint8_t** inner, u
   return LC_OK;
 }
 
+// `decimal_col <op> literal` on LiquidFixedLenByteArray entries. The reference has no predicate for this type (the
+// LiquidArray default decodes, filters and lets DataFusion compare, liquid_array/mod.rs:116-130); here the values are stored
+// in order-preserving byte form (k_bits.cu k_fixed_to_ordered), so the comparison IS the byte-view comparison
+// (comparisons.rs:21-151 semantics: equality on prefix keys + compressed bytes, ordering byte-wise) against the literal
+// in the same form. The literal arrives as LC_LIT_I128 at the column's scale; a Decimal256 column sign-extends it.
+struct FixedNeedle {
+  lc_predicate pred{};
+  uint8_t bytes[32];
+};
+static int lower_fixed_pred(Entry* const* entries, uint64_t n, const lc_predicate* pred, FixedNeedle* out) {
+  const uint32_t w = entries[0]->fixed_width;
+  for (uint64_t i = 0; i < n; ++i)
+    if (entries[i]->fixed_width != w || entries[i]->arrow_format != entries[0]->arrow_format) {
+      set_error("eval_predicate_many: fixed-length decimal entries of different types (or mixed with other entries) in one call");
+      return LC_ERR_INVALID;
+    }
+  if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
+    set_error("operator %d is not supported on decimal columns", pred->op);
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  if (pred->lit_kind == LC_LIT_BYTES && pred->lit_len == w) {
+    fixed_needle(0, 0, pred->lit_bytes, w, out->bytes);  // the literal as the column's own little-endian integer
+  } else if (pred->lit_kind == LC_LIT_I128) {
+    fixed_needle(pred->lit_u64, pred->lit_i64, nullptr, w, out->bytes);
+  } else {
+    set_error("decimal column needs an LC_LIT_I128 literal (or its little-endian bytes)");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  out->pred = *pred;
+  out->pred.lit_kind = LC_LIT_BYTES;
+  out->pred.lit_bytes = out->bytes;
+  out->pred.lit_len = w;
+  return LC_OK;
+}
+
 // Everything a predicate launch over byte-view entries needs, built on the host.
 struct StrLaunch {
   StrPredDesc desc;
@@ -209,13 +244,14 @@ static int prepare_str_pred(const lc_predicate* pred, StrLaunch* L) {
     LC_TRY(like_inner(pred->lit_bytes, pred->lit_len, &nd, &il));
     m = il;
     uint32_t fp = 0;
-    unsigned long long bl = 0;
     for (uint32_t i = 0; i < il; ++i) {
       fp |= 1u << (nd[i] & 31u);
-      if (i + 1 < il) bl |= 1ull << bigram_bit(nd[i], nd[i + 1]);
+      if (i + 2 < il) {
+        const uint32_t t = trigram_bit(nd[i], nd[i + 1], nd[i + 2]);
+        L->desc.needle_bloom[t >> 6] |= 1ull << (t & 63u);
+      }
     }
     L->desc.needle_fp = fp;
-    L->desc.needle_bloom = bl;
   }
   if (m > kMaxNeedle) {
     set_error("needle longer than %u bytes", kMaxNeedle);
@@ -246,7 +282,7 @@ struct RefList {
   // instead of chasing 10^4 Entry pointers (each a cache miss)
   std::shared_ptr<std::vector<uint32_t>> rows;      // rows per entry
   std::shared_ptr<std::vector<uint32_t>> n_unique;  // dictionary size per entry (byte views)
-  bool same_liquid_type = true, same_arrow_type = true, same_width = true, any_nulls = false;
+  bool same_liquid_type = true, same_arrow_type = true, same_width = true, any_nulls = false, any_fixed = false;
   // did the last predicate over this list produce nearly-empty masks? (0 unknown, 1 sparse, 2 dense) — picks between
   // the sparse mask download and the chunked dense one before the answer is known
   mutable int mask_hint = 0;
@@ -301,7 +337,12 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
   const Entry* proto = entries[0];
   for (uint64_t i = 0; i < n; ++i) {
     const Entry* e = entries[i];
+    if (e->squeeze_kind && !ctx->squeeze_internal) {
+      set_error("entry %llu of the list is squeezed: squeezed entries answer through lc_to_arrow / lc_eval_predicate", (unsigned long long)i);
+      return LC_ERR_INVALID;
+    }
     (*nl.rows)[i] = e->n;
+    nl.any_fixed = nl.any_fixed || e->fixed_width != 0;
     if (e->liquid_type != proto->liquid_type) nl.same_liquid_type = false;
     if (e->arrow_format != proto->arrow_format || e->dict_value_format != proto->dict_value_format) nl.same_arrow_type = false;
     if (is_int_blob(e->liquid_type)) {
@@ -366,12 +407,29 @@ static int make_int_pred(const lc_predicate* pred, const Entry* proto, IntPredDe
   if (proto->liquid_type == LC_LIQUID_DECIMAL) {
     // Decimal128/256 compare as signed 128/256-bit integers; every stored value is in [0, u64::MAX], so a literal
     // outside that window folds to a constant on either side (the literal arrives with the column's scale)
-    if (pred->lit_kind != LC_LIT_I128) {
-      set_error("decimal column needs an LC_LIT_I128 literal");
-      return LC_ERR_UNSUPPORTED_EXPR;
-    }
     out->lit_i = 0;
     out->lit_u = 0;
+    if (pred->lit_kind == LC_LIT_BYTES && (pred->lit_len == 16 || pred->lit_len == 32) && pred->lit_len == proto->dec_width) {
+      // the literal as the column's own little-endian integer (Decimal256 literals beyond 128 bits travel like this)
+      const uint8_t* b = pred->lit_bytes;
+      const bool negative = (b[pred->lit_len - 1] & 0x80u) != 0;
+      bool upper = false;
+      for (uint64_t i = 8; i < pred->lit_len; ++i) upper = upper || b[i] != 0;
+      if (negative) {
+        out->lit_kind = LC_LIT_I64;
+        out->lit_i = -1;
+      } else if (upper) {
+        out->lit_kind = kLitAboveAll;
+      } else {
+        out->lit_kind = LC_LIT_U64;
+        std::memcpy(&out->lit_u, b, 8);
+      }
+      return LC_OK;
+    }
+    if (pred->lit_kind != LC_LIT_I128) {
+      set_error("decimal column needs an LC_LIT_I128 literal (or its little-endian bytes)");
+      return LC_ERR_UNSUPPORTED_EXPR;
+    }
     if (pred->lit_i64 == 0) {
       out->lit_kind = LC_LIT_U64;
       out->lit_u = pred->lit_u64;
@@ -381,6 +439,13 @@ static int make_int_pred(const lc_predicate* pred, const Entry* proto, IntPredDe
     } else {
       out->lit_kind = kLitAboveAll;
     }
+    return LC_OK;
+  }
+  if (pred->lit_kind == kLitSentinelPublic) {  // squeeze_host.cc only: rows of a clamped entry at the sentinel
+    out->op = LC_OP_EQ;
+    out->lit_kind = kLitSentinel;
+    out->lit_i = 0;
+    out->lit_u = 0;
     return LC_OK;
   }
   if (pred->lit_kind != LC_LIT_I64 && pred->lit_kind != LC_LIT_U64) {
@@ -628,6 +693,11 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   if (!rl->same_liquid_type) {
     set_error("eval_predicate_many: entries of different liquid types in one call");
     return LC_ERR_INVALID;
+  }
+  FixedNeedle fixed;
+  if (rl->any_fixed) {
+    LC_TRY(lower_fixed_pred(entries, n, pred, &fixed));
+    pred = &fixed.pred;
   }
   if (entries[0]->liquid_type == LC_LIQUID_FLOAT) return eval_predicate_float(ctx, entries, n, rl, pred, sel_bits, out);
   const bool is_int = is_int_blob(entries[0]->liquid_type);
@@ -887,6 +957,11 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
   if (!rl->same_liquid_type) {
     set_error("scan_filter: entries of different liquid types in one call");
     return LC_ERR_INVALID;
+  }
+  FixedNeedle fixed;
+  if (rl->any_fixed) {
+    LC_TRY(lower_fixed_pred(entries, n, pred, &fixed));
+    pred = &fixed.pred;
   }
   if (entries[0]->liquid_type == LC_LIQUID_FLOAT)
     return refine_float(ctx, entries, n, rl, pred, d_sel_base, d_word_off, all_rows, d_counts);
@@ -1209,6 +1284,10 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     set_error("decoded values exceed 2 GiB (int32 offsets); split the call");
     return LC_ERR_INVALID;
   }
+  if (dev_out && proto->fixed_width) {
+    set_error("read_device: decimals outside u64 (LiquidFixedLenByteArray) are read through lc_to_arrow / lc_scan_read");
+    return LC_ERR_UNSUPPORTED_TYPE;
+  }
   if (dev_out) {
     if (dev_out->out_rows) *dev_out->out_rows = rows;
     if (dev_out->out_value_bytes) *dev_out->out_value_bytes = total_bytes;
@@ -1239,9 +1318,12 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     return LC_OK;
   }
   const uint8_t bt = proto->sh.arrow_type;
-  const bool want_views = bt == BT_UTF8_VIEW || bt == BT_BINARY_VIEW;
+  // Utf8View / BinaryView ship 16-byte views, LiquidFixedLenByteArray ships the values at their fixed stride: both are
+  // built on the device from the decoded (offsets, bytes) and take the place of the offsets in the download
+  const uint32_t fixed_w = proto->fixed_width;
+  const bool want_views = bt == BT_UTF8_VIEW || bt == BT_BINARY_VIEW || fixed_w != 0;
   const uint64_t off_bytes = (rows + 1) * 4;
-  const uint64_t view_bytes = want_views ? rows * 16 : 0;
+  const uint64_t view_bytes = fixed_w ? rows * fixed_w : want_views ? rows * 16 : 0;
   const uint64_t res_bytes = round_up(off_bytes, 256) + round_up(total_bytes + 16, 256) + round_up(view_bytes + 16, 256);
   uint8_t* d_res = nullptr;
   if (cudaMallocAsync(reinterpret_cast<void**>(&d_res), res_bytes, s) != cudaSuccess) {
@@ -1276,14 +1358,17 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   int rc = LC_OK;
   if (ce == cudaSuccess && nulls) rc = concat_validity_device(g.io, d_up, d_cat, &validity);
   if (ce == cudaSuccess && rc == LC_OK && want_views) {
-    ce = launch_build_views(g.out_offsets, static_cast<uint32_t>(total_bytes), g.out_bytes,
-                            nulls ? reinterpret_cast<const uint32_t*>(d_cat) : nullptr, rows, d_views, s);
+    ce = fixed_w ? launch_fixed_from_var(g.out_offsets, static_cast<uint32_t>(total_bytes), g.out_bytes,
+                                         nulls ? reinterpret_cast<const uint32_t*>(d_cat) : nullptr, rows, fixed_w, d_views, s)
+                 : launch_build_views(g.out_offsets, static_cast<uint32_t>(total_bytes), g.out_bytes,
+                                      nulls ? reinterpret_cast<const uint32_t*>(d_cat) : nullptr, rows, d_views, s);
     ctx->kernel_launches++;
     if (ce == cudaSuccess && rows) ce = cudaMemcpyAsync(views.p, d_views, view_bytes, cudaMemcpyDeviceToHost, s);
   } else if (ce == cudaSuccess && rc == LC_OK && rows) {
     ce = cudaMemcpyAsync(offsets.p, g.out_offsets, rows * 4, cudaMemcpyDeviceToHost, s);
   }
-  if (ce == cudaSuccess && rc == LC_OK && total_bytes) ce = cudaMemcpyAsync(data.p, g.out_bytes, total_bytes, cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess && rc == LC_OK && total_bytes && !fixed_w)
+    ce = cudaMemcpyAsync(data.p, g.out_bytes, total_bytes, cudaMemcpyDeviceToHost, s);
   cudaFreeAsync(d_res, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess || rc != LC_OK) {
@@ -1297,7 +1382,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   tr.mark("decode kernel + result D2H");
   ctx->kernel_launches++;
   ctx->h2d_bytes += n * 8;
-  ctx->d2h_bytes += (want_views ? view_bytes : rows * 4) + total_bytes;
+  ctx->d2h_bytes += (want_views ? view_bytes : rows * 4) + (fixed_w ? 0 : total_bytes);
   if (!want_views) reinterpret_cast<int32_t*>(offsets.p)[rows] = static_cast<int32_t>(total_bytes);
   return finish_bytes_array(proto, rows, nulls, validity, offsets, views, data, out_schema, out_array);
 }
@@ -1310,6 +1395,15 @@ static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls,
                               HostBuf views, HostBuf data, ArrowSchema* out_schema, ArrowArray* out_array) {
   const uint8_t bt = proto->sh.arrow_type;
   const int32_t* off = reinterpret_cast<const int32_t*>(offsets.p);
+  if (bt == BT_DECIMAL128 || bt == BT_DECIMAL256) {
+    // LiquidFixedLenByteArray::to_arrow_array (fix_len_byte_array.rs:87-95): the decimal array itself; `views` holds the
+    // values at their fixed stride (null slots zero)
+    host_free(data.p);
+    export_schema(proto->arrow_format, "", out_schema);
+    std::vector<HostBuf> bufs{validity, views};
+    export_array(static_cast<int64_t>(rows), static_cast<int64_t>(nulls), std::move(bufs), nullptr, out_array);
+    return LC_OK;
+  }
   if (bt == BT_UTF8 || bt == BT_BINARY) {
     export_schema(bt == BT_UTF8 ? "u" : "z", "", out_schema);
     std::vector<HostBuf> bufs{validity, offsets, data};

@@ -11,6 +11,7 @@
 #include <cmath>
 
 #include "host_common.h"
+#include "host_pool.h"
 
 namespace lc {
 
@@ -114,6 +115,21 @@ static int get_codec(lc_ctx* ctx, uint64_t scope, const DictBuilder& d, std::sha
   return LC_OK;
 }
 
+// A codec that came from a stored symbol table (lc_ctx_load_symbol_table): device copies, then the scope's entry.
+int register_codec(lc_ctx* ctx, uint64_t scope, const std::shared_ptr<FsstCodec>& codec) {
+  if (cudaMalloc(reinterpret_cast<void**>(&codec->d_dec), sizeof(FsstTable)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&codec->d_enc), sizeof(FsstEncTable)) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc for FSST tables failed");
+    return LC_ERR_OOM;
+  }
+  LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->stream));
+  LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->codecs[scope] = codec;
+  return LC_OK;
+}
+
 // A contiguous piece of caller memory that becomes part of the device byte pool.
 struct PoolSeg {
   const uint8_t* p;
@@ -121,15 +137,38 @@ struct PoolSeg {
   uint64_t base;  // offset inside the pool
 };
 
-int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out) {
-  const uint32_t n = static_cast<uint32_t>(in.length);
-  // ---- 1. rows as (pool offset, length); the value bytes themselves are never touched on the host (except by the
-  //         once-per-column-chunk FSST training below) ----
-  std::vector<uint32_t> row_off(n, 0), row_len(n, 0);
+// Step 1 of an insert, shared by the one-batch and the batched form: rows as (pool offset, length) over the caller's
+// buffers (segments that will become the device byte pool), validity re-aligned to bit offset 0.
+struct RowPlan {
+  uint32_t n = 0;
+  std::vector<uint32_t> row_off, row_len;
   std::vector<uint8_t> valid_bits;  // bit offset 0
-  bool has_input_nulls = in.validity && in.null_count != 0;
+  bool has_input_nulls = false;
   std::vector<PoolSeg> segs;
   uint64_t pool_bytes = 0, sum_len = 0;
+  bool row_is_valid(uint32_t i) const { return !has_input_nulls || bit_get(valid_bits.data(), i); }
+  const uint8_t* row_ptr(uint32_t i) const {
+    // host address of a row's bytes: the segment that contains its pool offset
+    const uint64_t o = row_off[i];
+    for (size_t k = segs.size(); k-- > 0;)
+      if (o >= segs[k].base) return segs[k].p + (o - segs[k].base);
+    return segs[0].p;
+  }
+};
+
+static int build_row_plan(const ArrowIn& in, RowPlan* plan) {
+  const uint32_t n = static_cast<uint32_t>(in.length);
+  plan->n = n;
+  std::vector<uint32_t>& row_off = plan->row_off;
+  std::vector<uint32_t>& row_len = plan->row_len;
+  row_off.assign(n, 0);
+  row_len.assign(n, 0);
+  std::vector<uint8_t>& valid_bits = plan->valid_bits;
+  bool& has_input_nulls = plan->has_input_nulls;
+  has_input_nulls = in.validity && in.null_count != 0;
+  std::vector<PoolSeg>& segs = plan->segs;
+  uint64_t& pool_bytes = plan->pool_bytes;
+  uint64_t& sum_len = plan->sum_len;
   auto add_seg = [&](const uint8_t* p, uint64_t bytes) -> uint64_t {
     const uint64_t base = pool_bytes;
     segs.push_back(PoolSeg{p, bytes, base});
@@ -144,6 +183,14 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
     for (uint32_t i = 0; i < n; ++i) {
       row_off[i] = static_cast<uint32_t>(off[i] - lo);
       row_len[i] = static_cast<uint32_t>(off[i + 1] - off[i]);
+    }
+  } else if (in.kind == ArrowIn::K_DECIMAL) {
+    // fixed-width values (Decimal128 / Decimal256 little-endian words): row i is bytes [i*w, (i+1)*w) of the values buffer
+    const uint32_t w = in.dec_width;
+    add_seg(static_cast<const uint8_t*>(in.values) + static_cast<uint64_t>(in.offset) * w, static_cast<uint64_t>(n) * w);
+    for (uint32_t i = 0; i < n; ++i) {
+      row_off[i] = i * w;
+      row_len[i] = w;
     }
   } else if (in.kind == ArrowIn::K_VIEW) {
     const uint8_t* views = static_cast<const uint8_t*>(in.values) + 16 * in.offset;
@@ -221,18 +268,26 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
     valid_bits.assign(round_up((n + 7) / 8, 16), 0);
     copy_bits(in.validity, in.offset, n, valid_bits.data(), valid_bits.size());
   }
-  auto row_is_valid = [&](uint32_t i) -> bool { return !has_input_nulls || bit_get(valid_bits.data(), i); };
+  auto row_is_valid = [&](uint32_t i) -> bool { return plan->row_is_valid(i); };
   for (uint32_t i = 0; i < n; ++i) {
     if (!row_is_valid(i)) row_off[i] = row_len[i] = 0;
     sum_len += row_len[i];
   }
-  auto row_ptr = [&](uint32_t i) -> const uint8_t* {
-    // host address of a row's bytes: the segment that contains its pool offset
-    const uint64_t o = row_off[i];
-    for (size_t k = segs.size(); k-- > 0;)
-      if (o >= segs[k].base) return segs[k].p + (o - segs[k].base);
-    return segs[0].p;
-  };
+  return LC_OK;
+}
+
+int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Entry** out) {
+  const uint32_t n = static_cast<uint32_t>(in.length);
+  RowPlan plan;
+  LC_TRY(build_row_plan(in, &plan));
+  const std::vector<uint32_t>& row_off = plan.row_off;
+  const std::vector<uint32_t>& row_len = plan.row_len;
+  const std::vector<uint8_t>& valid_bits = plan.valid_bits;
+  const bool has_input_nulls = plan.has_input_nulls;
+  const std::vector<PoolSeg>& segs = plan.segs;
+  const uint64_t pool_bytes = plan.pool_bytes, sum_len = plan.sum_len;
+  auto row_is_valid = [&](uint32_t i) -> bool { return plan.row_is_valid(i); };
+  auto row_ptr = [&](uint32_t i) -> const uint8_t* { return plan.row_ptr(i); };
 
   // ---- 2. symbol table: the first batch of a column chunk trains it (transcode.rs:16-33) on its unique values;
   //         training is host work by design (once per chunk, never visible in any result) ----
@@ -243,8 +298,19 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
       codec = it->second;
     } else {
       DictBuilder dict(n < 1024 ? 1024 : n / 2);
-      for (uint32_t i = 0; i < n; ++i)
-        if (row_is_valid(i)) dict.add(row_len[i] ? row_ptr(i) : reinterpret_cast<const uint8_t*>(""), row_len[i]);
+      std::vector<uint8_t> ordered;  // fixed-width values are compressed in their order-preserving form: train on that
+      if (in.kind == ArrowIn::K_DECIMAL) {
+        const uint32_t w = in.dec_width;
+        ordered.resize(static_cast<size_t>(n) * w);
+        for (uint32_t i = 0; i < n; ++i) {
+          if (!row_is_valid(i)) continue;
+          fixed_to_ordered(row_ptr(i), w, ordered.data() + static_cast<size_t>(i) * w);
+          dict.add(ordered.data() + static_cast<size_t>(i) * w, w);
+        }
+      } else {
+        for (uint32_t i = 0; i < n; ++i)
+          if (row_is_valid(i)) dict.add(row_len[i] ? row_ptr(i) : reinterpret_cast<const uint8_t*>(""), row_len[i]);
+      }
       LC_TRY(get_codec(ctx, scope, dict, &codec));
     }
   }
@@ -259,7 +325,8 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   const uint64_t up_bytes = round_up(4ull * n, 256) * 2 + round_up(vbytes, 256);
   const uint64_t comp_cap = 2 * sum_len + 64;
   const uint64_t dev_need = round_up(pool_bytes + 64, 256) + up_bytes + round_up(4ull * cap, 256) +
-                            6 * round_up(4ull * (n + 1), 256) + round_up(2ull * n, 256) + 2 * round_up(8ull * (n + 1), 256) +
+                            6 * round_up(4ull * (n + 1), 256) + round_up(2ull * n, 256) + round_up(8ull * (n + 1), 256) +
+                            round_up(8ull * kBloomWords * (n + 1), 256) +
                             round_up(comp_cap, 256) + 4096;
   LC_TRY(sc.reserve(dev_need, up_bytes + 4096));
   uint8_t* h_up = sc.host(up_bytes);
@@ -273,7 +340,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   uint32_t* d_clen = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
   uint32_t* d_offsets = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
   uint32_t* d_fps = reinterpret_cast<uint32_t*>(sc.dev(4ull * (n + 1)));
-  unsigned long long* d_blooms = reinterpret_cast<unsigned long long*>(sc.dev(8ull * (n + 1)));
+  unsigned long long* d_blooms = reinterpret_cast<unsigned long long*>(sc.dev(8ull * kBloomWords * (n + 1)));
   uint8_t* d_resid = sc.dev(4ull * (n + 1));
   uint16_t* d_keys = reinterpret_cast<uint16_t*>(sc.dev(2ull * n + 16));
   unsigned long long* d_pkeys = reinterpret_cast<unsigned long long*>(sc.dev(8ull * (n + 1)));
@@ -297,6 +364,10 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   for (const PoolSeg& sg : segs)
     if (sg.bytes) LC_CUDA_OK(cudaMemcpyAsync(d_pool + sg.base, sg.p, sg.bytes, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_bytes + pool_bytes;
+  if (in.kind == ArrowIn::K_DECIMAL) {  // the one segment holds the n values back to back
+    LC_CUDA_OK(launch_fixed_to_ordered(d_pool, n, in.dec_width, s));
+    ctx->kernel_launches++;
+  }
 
   StrEncIo io{};
   io.pool = d_pool;
@@ -371,7 +442,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   o += round_up(2ull * n, 16);
   h.head_bytes = static_cast<uint32_t>(o);
   h.bloom_off = (build_fp && U) ? static_cast<uint32_t>(o) : 0;
-  if (h.bloom_off) o += round_up(8ull * U, 16);
+  if (h.bloom_off) o += round_up(8ull * kBloomWords * U, 16);
   h.fsst_off = static_cast<uint32_t>(o);
   h.fsst_bytes = static_cast<uint32_t>(co);
   o += round_up(co, 16) + 16;
@@ -403,7 +474,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   };
   if (spl) LC_CUDA_OK(d2d(h.shared_prefix_off, d_pool + row_off[first_valid], spl));
   if (build_fp) LC_CUDA_OK(d2d(h.fp_off, d_fps, 4ull * U));
-  if (h.bloom_off) LC_CUDA_OK(d2d(h.bloom_off, d_blooms, 8ull * U));
+  if (h.bloom_off) LC_CUDA_OK(d2d(h.bloom_off, d_blooms, 8ull * kBloomWords * U));
   LC_CUDA_OK(d2d(h.resid_off, d_resid, static_cast<uint64_t>(ob) * (U + 1)));
   LC_CUDA_OK(d2d(h.prefix_keys_off, d_pkeys, 8ull * U));
   if (h.has_nulls) LC_CUDA_OK(d2d(h.validity_off, d_up + 2 * off_len, (n + 7) / 8));
@@ -423,11 +494,339 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   e->sh = h;
   if (spl) {
     const uint8_t* p0 = row_ptr(first_valid);
-    e->shared_prefix.assign(p0, p0 + spl);
+    if (in.kind == ArrowIn::K_DECIMAL) {  // the blob holds the order-preserving form
+      uint8_t tmp[32];
+      fixed_to_ordered(p0, in.dec_width, tmp);
+      e->shared_prefix.assign(tmp, tmp + spl);
+    } else {
+      e->shared_prefix.assign(p0, p0 + spl);
+    }
   }
   e->codec = codec;
+  e->fixed_width = (in.byte_type == BT_DECIMAL128 || in.byte_type == BT_DECIMAL256) ? in.dec_width : 0;
   ctx->n_entries++;
   *out = e;
+  return LC_OK;
+}
+
+// ---- batched form -----------------------------------------------------------------------------------------------
+// A list of byte-view batches (a row group's worth, one or several columns) in one pass: the row plans are built and the
+// value bytes copied into pinned staging by the host pool, ONE upload carries every batch's rows + byte pool, the five
+// encode stages run once over the whole list (k_str_encode.cu *_many), ONE download returns the 48-byte results, and the
+// sections of every blob are moved device-to-device. Two stream synchronisations per group of batches instead of three
+// per batch. Symbol tables are trained first, on the first batch of every column chunk that has none yet
+// (transcode.rs:16-33), exactly as the one-batch path would have done in the same order.
+int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, const uint64_t* scopes, std::vector<Entry*>* out) {
+  const uint64_t nb_all = ins.size();
+  out->clear();
+  if (nb_all == 0) return LC_OK;
+  std::vector<RowPlan> plans(nb_all);
+  std::vector<int> rcs(nb_all, LC_OK);
+  std::vector<std::string> errs(nb_all);
+  parallel_for(nb_all, 4, [&](uint64_t b, uint64_t e) {
+    for (uint64_t i = b; i < e; ++i) {
+      rcs[i] = build_row_plan(ins[i], &plans[i]);
+      if (rcs[i] != LC_OK) errs[i] = get_error();  // the message is thread-local
+    }
+  });
+  for (uint64_t i = 0; i < nb_all; ++i)
+    if (rcs[i] != LC_OK) {
+      set_error("batch %llu: %s", (unsigned long long)i, errs[i].c_str());
+      return rcs[i];
+    }
+  // Symbol tables: every column chunk without one is trained on ITS first batch of this list (what the one-batch path would
+  // have done in the same order). Training is ~2 ms of host work per chunk (measured: 1 695 URL values), so the chunks are
+  // trained side by side on the host pool; the tables are uploaded afterwards with one synchronisation.
+  std::vector<std::shared_ptr<FsstCodec>> codecs(nb_all);
+  std::vector<uint64_t> train_first;  // index of the first batch of every scope that needs a table
+  {
+    std::unordered_map<uint64_t, uint64_t> seen;
+    for (uint64_t i = 0; i < nb_all; ++i)
+      if (!ctx->codecs.count(scopes[i]) && seen.emplace(scopes[i], i).second) train_first.push_back(i);
+  }
+  std::vector<std::shared_ptr<FsstCodec>> trained(train_first.size());
+  parallel_for(train_first.size(), 1, [&](uint64_t b, uint64_t e) {
+    for (uint64_t t = b; t < e; ++t) {
+      const RowPlan& pl = plans[train_first[t]];
+      DictBuilder dict(pl.n < 1024 ? 1024 : pl.n / 2);
+      for (uint32_t r = 0; r < pl.n; ++r)
+        if (pl.row_is_valid(r)) dict.add(pl.row_len[r] ? pl.row_ptr(r) : reinterpret_cast<const uint8_t*>(""), pl.row_len[r]);
+      auto codec = std::make_shared<FsstCodec>();
+      fsst_train(dict.uptr.data(), dict.ulen.data(), dict.uptr.size(), codec.get());
+      trained[t] = codec;
+    }
+  });
+  for (uint64_t t = 0; t < train_first.size(); ++t) {
+    std::shared_ptr<FsstCodec>& codec = trained[t];
+    if (cudaMalloc(reinterpret_cast<void**>(&codec->d_dec), sizeof(FsstTable)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&codec->d_enc), sizeof(FsstEncTable)) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc for FSST tables failed");
+      return LC_ERR_OOM;
+    }
+    LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!train_first.empty()) LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // the sources are pageable host memory
+  for (uint64_t t = 0; t < train_first.size(); ++t) ctx->codecs[scopes[train_first[t]]] = trained[t];
+  for (uint64_t i = 0; i < nb_all; ++i) codecs[i] = ctx->codecs[scopes[i]];
+  const bool build_fp = (hint == LC_HINT_SUBSTRING_SEARCH);
+  cudaStream_t s = ctx->stream;
+  Scratch& sc = ctx->scratch;
+  struct Taken {
+    uint8_t* blob;
+    uint32_t slab;
+    uint64_t bytes;
+  };
+  std::vector<Taken> taken;
+  auto give_back = [&]() {
+    for (const Taken& t : taken) ctx->arena.free(t.slab, t.bytes);
+    for (Entry* e : *out) delete e;
+    out->clear();
+  };
+  constexpr uint64_t kGroup = 256;
+  for (uint64_t g0 = 0; g0 < nb_all; g0 += kGroup) {
+    const uint64_t nb = std::min<uint64_t>(kGroup, nb_all - g0);
+    // ---- per-batch offsets: upload block [row_off | row_len | validity | pool] mirrored host/device, then work areas ----
+    struct Off {
+      uint64_t up, off_len, vbytes, pool, table, slot, leader, uniq, clen, offsets, fps, blooms, resid, keys, pkeys, comp, res;
+      uint32_t cap;
+    };
+    std::vector<Off> offs(nb);
+    uint64_t cur = 0, max_n = 0;
+    for (uint64_t i = 0; i < nb; ++i) {
+      const RowPlan& pl = plans[g0 + i];
+      Off& o = offs[i];
+      o.off_len = round_up(4ull * pl.n, 256);
+      o.vbytes = pl.has_input_nulls ? round_up((pl.n + 31) / 32 * 4, 16) : 0;
+      o.up = cur;
+      cur += 2 * o.off_len + round_up(o.vbytes, 256);
+      o.pool = cur;
+      cur += round_up(pl.pool_bytes + 64, 256);
+      max_n = std::max<uint64_t>(max_n, pl.n);
+    }
+    const uint64_t up_bytes = cur;
+    const uint64_t ios_off = cur;
+    cur += round_up(nb * sizeof(StrEncIo), 256);
+    const uint64_t hdr_off = cur;  // host only: blob headers staged for their uploads
+    const uint64_t res_off = cur;  // device: results (the header staging area on the host side is reused after the sync)
+    cur += round_up(nb * std::max(sizeof(StrEncResult), sizeof(StrHeader)), 256);
+    const uint64_t host_total = cur;
+    const uint64_t table_off = cur;  // all hash tables back to back: one memset
+    uint64_t table_words = 0;
+    for (uint64_t i = 0; i < nb; ++i) {
+      const RowPlan& pl = plans[g0 + i];
+      uint32_t cap = 64;
+      while (cap < 2u * pl.n) cap <<= 1;
+      offs[i].cap = cap;
+      offs[i].table = cur;
+      cur += 4ull * cap;
+      table_words += cap;
+    }
+    cur = round_up(cur, 256);
+    for (uint64_t i = 0; i < nb; ++i) {
+      const RowPlan& pl = plans[g0 + i];
+      Off& o = offs[i];
+      auto take = [&](uint64_t bytes) {
+        const uint64_t at = cur;
+        cur += round_up(bytes, 256);
+        return at;
+      };
+      const uint64_t n1 = pl.n + 1ull;
+      o.slot = take(4 * n1);
+      o.leader = take(4 * n1);
+      o.uniq = take(4 * n1);
+      o.clen = take(4 * n1);
+      o.offsets = take(4 * n1);
+      o.fps = take(4 * n1);
+      o.blooms = take(8ull * kBloomWords * n1);
+      o.resid = take(4 * n1);
+      o.keys = take(2ull * pl.n + 16);
+      o.pkeys = take(8 * n1);
+      o.comp = take(2 * pl.sum_len + 64);
+    }
+    const uint64_t dev_total = cur;
+    LC_TRY(sc.reserve(dev_total + 1024, host_total + 1024));
+    uint8_t* h = sc.host(host_total);
+    uint8_t* d = sc.dev(dev_total);
+    if (!h || !d) {
+      give_back();
+      set_error("str_encode_many: scratch exhausted");
+      return LC_ERR_OOM;
+    }
+    StrEncIo* h_ios = reinterpret_cast<StrEncIo*>(h + ios_off);
+    parallel_for(nb, 2, [&](uint64_t b, uint64_t e) {
+      for (uint64_t i = b; i < e; ++i) {
+        const RowPlan& pl = plans[g0 + i];
+        const Off& o = offs[i];
+        if (pl.n) {
+          std::memcpy(h + o.up, pl.row_off.data(), 4ull * pl.n);
+          std::memcpy(h + o.up + o.off_len, pl.row_len.data(), 4ull * pl.n);
+        }
+        if (o.vbytes) {
+          std::memset(h + o.up + 2 * o.off_len, 0, o.vbytes);
+          std::memcpy(h + o.up + 2 * o.off_len, pl.valid_bits.data(), (pl.n + 7) / 8);
+        }
+        for (const PoolSeg& sg : pl.segs)
+          if (sg.bytes) std::memcpy(h + o.pool + sg.base, sg.p, sg.bytes);
+        StrEncIo io{};
+        io.pool = d + o.pool;
+        io.row_off = reinterpret_cast<const uint32_t*>(d + o.up);
+        io.row_len = reinterpret_cast<const uint32_t*>(d + o.up + o.off_len);
+        io.valid = o.vbytes ? reinterpret_cast<const uint32_t*>(d + o.up + 2 * o.off_len) : nullptr;
+        io.n = pl.n;
+        io.table_mask = o.cap - 1;
+        io.row_slot = reinterpret_cast<uint32_t*>(d + o.slot);
+        io.table = reinterpret_cast<uint32_t*>(d + o.table);
+        io.leader = reinterpret_cast<uint32_t*>(d + o.leader);
+        io.keys = reinterpret_cast<uint16_t*>(d + o.keys);
+        io.uniq_row = reinterpret_cast<uint32_t*>(d + o.uniq);
+        io.clen = reinterpret_cast<uint32_t*>(d + o.clen);
+        io.offsets = reinterpret_cast<uint32_t*>(d + o.offsets);
+        io.pkeys = reinterpret_cast<unsigned long long*>(d + o.pkeys);
+        io.fps = build_fp ? reinterpret_cast<uint32_t*>(d + o.fps) : nullptr;
+        io.blooms = reinterpret_cast<unsigned long long*>(d + o.blooms);
+        io.comp = d + o.comp;
+        io.resid = d + o.resid;
+        io.enc = codecs[g0 + i]->d_enc;
+        io.res = reinterpret_cast<StrEncResult*>(d + res_off) + i;
+        h_ios[i] = io;
+      }
+    });
+    cudaError_t ce = cudaMemcpyAsync(d, h, ios_off + nb * sizeof(StrEncIo), cudaMemcpyHostToDevice, s);
+    if (ce == cudaSuccess)
+      ce = launch_str_encode_many(reinterpret_cast<const StrEncIo*>(d + ios_off), static_cast<uint32_t>(nb), static_cast<uint32_t>(max_n),
+                                  reinterpret_cast<uint32_t*>(d + table_off), table_words, s);
+    StrEncResult* h_res = reinterpret_cast<StrEncResult*>(h + hdr_off);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_res, d + res_off, nb * sizeof(StrEncResult), cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) {
+      give_back();
+      set_error("CUDA error in str_encode_many: %s", cudaGetErrorString(ce));
+      return LC_ERR_CUDA;
+    }
+    ctx->kernel_launches += 5;
+    ctx->h2d_bytes += up_bytes + nb * sizeof(StrEncIo);
+    ctx->d2h_bytes += nb * sizeof(StrEncResult);
+    // ---- blob layout per batch (sizes are known now), sections moved device-to-device ----
+    std::vector<StrEncResult> results(h_res, h_res + nb);  // the pinned area is reused for the headers below
+    StrHeader* h_hdr = reinterpret_cast<StrHeader*>(h + hdr_off);
+    for (uint64_t i = 0; i < nb; ++i) {
+      const StrEncResult& r = results[i];
+      const RowPlan& pl = plans[g0 + i];
+      const ArrowIn& in = ins[g0 + i];
+      const Off& of = offs[i];
+      if (r.error) {
+        give_back();
+        set_error(r.error == 1 ? "batch %llu: more than 65536 distinct values in one batch" : "batch %llu: compressed dictionary exceeds 4 GiB",
+                  (unsigned long long)(g0 + i));
+        return LC_ERR_UNSUPPORTED_TYPE;
+      }
+      const uint32_t n = pl.n, U = r.n_unique, spl = r.shared_prefix_len, ob = r.offset_bytes;
+      const uint64_t co = r.comp_bytes;
+      StrHeader hd;
+      std::memset(&hd, 0, sizeof(hd));
+      hd.magic = kMagicStr;
+      hd.arrow_type = in.byte_type;
+      hd.has_nulls = r.null_count > 0;
+      hd.has_fp = build_fp;
+      hd.offset_bytes = static_cast<uint8_t>(ob);
+      hd.n = n;
+      hd.n_unique = U;
+      hd.slope = r.slope;
+      hd.intercept = r.intercept;
+      hd.shared_prefix_len = spl;
+      hd.null_count = r.null_count;
+      hd.max_value_len = r.max_value_len;
+      hd.uncompressed_bytes = r.uncompressed_bytes;
+      hd.table_ptr = reinterpret_cast<uint64_t>(codecs[g0 + i]->d_dec);
+      uint64_t o = sizeof(StrHeader);
+      hd.shared_prefix_off = static_cast<uint32_t>(o);
+      o += round_up(spl, 16);
+      hd.sp_end = static_cast<uint32_t>(o);
+      hd.fp_off = build_fp ? static_cast<uint32_t>(o) : 0;
+      if (build_fp) o += round_up(4ull * U, 16);
+      hd.resid_off = static_cast<uint32_t>(o);
+      o += round_up(static_cast<uint64_t>(ob) * (U + 1), 16);
+      hd.prefix_keys_off = static_cast<uint32_t>(o);
+      o += round_up(8ull * U, 16);
+      hd.rows_off = static_cast<uint32_t>(o);
+      hd.validity_off = hd.has_nulls ? static_cast<uint32_t>(o) : 0;
+      if (hd.has_nulls) o += round_up((n + 7) / 8, 16);
+      hd.keys_off = static_cast<uint32_t>(o);
+      o += round_up(2ull * n, 16);
+      hd.head_bytes = static_cast<uint32_t>(o);
+      hd.bloom_off = (build_fp && U) ? static_cast<uint32_t>(o) : 0;
+      if (hd.bloom_off) o += round_up(8ull * kBloomWords * U, 16);
+      hd.fsst_off = static_cast<uint32_t>(o);
+      hd.fsst_bytes = static_cast<uint32_t>(co);
+      o += round_up(co, 16) + 16;
+      if (o > 0xFFFFFFF0ull) {
+        give_back();
+        set_error("byte-view entry too large");
+        return LC_ERR_UNSUPPORTED_TYPE;
+      }
+      hd.blob_bytes = static_cast<uint32_t>(o);
+      if (ctx->budget && ctx->arena.bytes_used() + o > ctx->budget) {
+        give_back();
+        set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(), (unsigned long long)o,
+                  (unsigned long long)ctx->budget);
+        return LC_ERR_CACHE_FULL;
+      }
+      uint32_t slab = 0;
+      uint8_t* d_blob = ctx->arena.alloc(o, &slab);
+      if (!d_blob) {
+        give_back();
+        set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
+        return LC_ERR_OOM;
+      }
+      taken.push_back({d_blob, slab, o});
+      uint32_t first_valid = 0;
+      while (first_valid < n && !pl.row_is_valid(first_valid)) ++first_valid;
+      h_hdr[i] = hd;
+      ce = cudaMemsetAsync(d_blob, 0, o, s);  // padding between sections reads as zero
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_blob, &h_hdr[i], sizeof(StrHeader), cudaMemcpyHostToDevice, s);
+      auto d2d = [&](uint32_t dst_off, const void* src, uint64_t bytes) {
+        if (bytes && ce == cudaSuccess) ce = cudaMemcpyAsync(d_blob + dst_off, src, bytes, cudaMemcpyDeviceToDevice, s);
+      };
+      if (spl) d2d(hd.shared_prefix_off, d + of.pool + pl.row_off[first_valid], spl);
+      if (build_fp) d2d(hd.fp_off, d + of.fps, 4ull * U);
+      if (hd.bloom_off) d2d(hd.bloom_off, d + of.blooms, 8ull * kBloomWords * U);
+      d2d(hd.resid_off, d + of.resid, static_cast<uint64_t>(ob) * (U + 1));
+      d2d(hd.prefix_keys_off, d + of.pkeys, 8ull * U);
+      if (hd.has_nulls) d2d(hd.validity_off, d + of.up + 2 * of.off_len, (n + 7) / 8);
+      d2d(hd.keys_off, d + of.keys, 2ull * n);
+      d2d(hd.fsst_off, d + of.comp, co);
+      if (ce != cudaSuccess) {
+        give_back();
+        set_error("CUDA error in str_encode_many: %s", cudaGetErrorString(ce));
+        return LC_ERR_CUDA;
+      }
+      Entry* e = new Entry();
+      e->liquid_type = LC_LIQUID_BYTE_VIEW;
+      e->d_blob = d_blob;
+      e->blob_bytes = hd.blob_bytes;
+      e->slab = slab;
+      e->n = n;
+      e->arrow_format = in.format;
+      e->dict_value_format = in.dict_value_format;
+      e->sh = hd;
+      if (spl) {
+        const uint8_t* p0 = pl.row_ptr(first_valid);
+        e->shared_prefix.assign(p0, p0 + spl);
+      }
+      e->codec = codecs[g0 + i];
+      out->push_back(e);
+    }
+    ce = cudaStreamSynchronize(s);  // the group's scratch is reused by the next group
+    if (ce != cudaSuccess) {
+      give_back();
+      set_error("CUDA error in str_encode_many: %s", cudaGetErrorString(ce));
+      return LC_ERR_CUDA;
+    }
+    ctx->h2d_bytes += nb * sizeof(StrHeader);
+  }
+  ctx->n_entries += out->size();
   return LC_OK;
 }
 

@@ -79,6 +79,17 @@ class CacheExpression:
     def substring_search():
         return CacheExpression.SubstringSearch
 
+    @staticmethod
+    def extract_date32(field: str):
+        """`CacheExpression::extract_date32(Date32Field)` (expressions.rs:82-84); field in Year / Month / Day / DayOfWeek."""
+        assert field in ("Year", "Month", "Day", "DayOfWeek")
+        return ("ExtractDate32", field)
+
+    @staticmethod
+    def as_date32_field(hint):
+        """`as_date32_field` (expressions.rs:133-138)"""
+        return hint[1] if isinstance(hint, tuple) and hint[0] == "ExtractDate32" else None
+
 
 _CMP_OPS = {"=": N.OP_EQ, "!=": N.OP_NE, "<": N.OP_LT, "<=": N.OP_LE, ">": N.OP_GT, ">=": N.OP_GE}
 
@@ -201,6 +212,9 @@ class LiquidExpr:
                 if not isinstance(e.left, Column):
                     raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "decimal column under a cast")
                 u = _decimal_unscaled(e.right.value, column_type.scale)
+                if u is not None and pa.types.is_decimal256(column_type) and not (-(1 << 127) <= u < (1 << 127)) and -(1 << 255) <= u < (1 << 255):
+                    _set_bytes(p, (u & ((1 << 256) - 1)).to_bytes(32, "little"))  # the column's own little-endian integer
+                    return p
                 if u is None or not (-(1 << 127) <= u < (1 << 127)):
                     raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "literal is not a decimal at the column's scale")
                 p.lit_kind = N.LIT_I128

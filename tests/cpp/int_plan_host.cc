@@ -8,9 +8,8 @@
 
 extern "C" {
 
-// header fields: tbits, bit_width, is_signed, reference (raw bits, zero extended); squeeze_kind / bucket_width are accepted and
-// ignored here (the squeezed forms live on a branch)
-// predicate: op (lc_op EQ..GE), lit_kind (0 I64, 1 U64, 7 above-all), lit_i, lit_u
+// header fields: tbits, bit_width, is_signed, reference (raw bits, zero extended), squeeze_kind, bucket_width
+// predicate: op (lc_op EQ..GE), lit_kind (0 I64, 1 U64, 7 above-all, 8 sentinel), lit_i, lit_u
 // packed[n] -> out[n] (0 / 1); returns the UCmp kind the planner chose, *thr_out its threshold
 int ip_eval(uint32_t tbits, uint32_t bit_width, uint32_t is_signed, uint64_t reference, uint32_t squeeze_kind, uint64_t bucket_width,
             int32_t op, int32_t lit_kind, int64_t lit_i, uint64_t lit_u, const uint64_t* packed, uint32_t n, uint8_t* out, uint64_t* thr_out) {
@@ -20,8 +19,8 @@ int ip_eval(uint32_t tbits, uint32_t bit_width, uint32_t is_signed, uint64_t ref
   h.bit_width = static_cast<uint8_t>(bit_width);
   h.is_signed = is_signed;
   h.reference = reference;
-  (void)squeeze_kind;
-  (void)bucket_width;
+  h.squeeze_kind = static_cast<uint8_t>(squeeze_kind);
+  lc::set_int_bucket_width(&h, bucket_width);
   lc::IntPredDesc p{op, lit_kind, lit_i, lit_u};
   int32_t kind = 0;
   uint64_t thr = 0;

@@ -83,7 +83,7 @@ class FakeCache:
     def insert(self, eid, arr):
         return _Insert(self, eid, arr)
 
-    def insert_many(self, eids, arrays):
+    def insert_many(self, eids, arrays, hint=None):
         for e, a in zip(eids, arrays):
             self.store[int(e)] = a
 

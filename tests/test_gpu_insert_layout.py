@@ -42,16 +42,17 @@ def parse_str_image(img: bytes):
     dt = {1: np.int8, 2: np.int16, 4: np.int32}[offset_bytes]
     h["resid"] = np.frombuffer(img, dtype=dt, count=n_unique + 1, offset=resid_off).astype(np.int64)
     h["comp"] = img[fsst_off:fsst_off + fsst_bytes]
-    h["blooms"] = np.frombuffer(img, dtype=np.uint64, count=n_unique, offset=bloom_off).tolist() if bloom_off else None
+    h["blooms"] = np.frombuffer(img, dtype=np.uint64, count=4 * n_unique, offset=bloom_off).tolist() if bloom_off else None
     return h
 
 
-def bigram_bloom(b: bytes) -> int:
-    """entry_layout.h bigram_bit: the private 64-bit substring pre-filter stored beside the reference fingerprints."""
+def trigram_bloom(b: bytes) -> list:
+    """entry_layout.h trigram_bit: the private 256-bit substring pre-filter stored beside the reference fingerprints,
+    as its four u64 words."""
     x = 0
-    for a, c in zip(b, b[1:]):
-        x |= 1 << ((((a << 8) | c) * 0x9E3779B1 & 0xFFFFFFFF) >> 26)
-    return x
+    for a, c, d in zip(b, b[1:], b[2:]):
+        x |= 1 << ((((a << 16) | (c << 8) | d) * 0x9E3779B1 & 0xFFFFFFFF) >> 24)
+    return [(x >> (64 * w)) & (2**64 - 1) for w in range(4)]
 
 
 def fsst_decompress(table: bytes, comp: bytes) -> bytes:
@@ -86,7 +87,7 @@ def check_string_entry(cache, arr: pa.Array, hint=None, scope=0):
     if hint is not None:
         assert h["fps"] == want.fingerprints
         if want.uniques:
-            assert h["blooms"] == [bigram_bloom(u) for u in want.uniques]
+            assert h["blooms"] == [w for u in want.uniques for w in trigram_bloom(u)]
     else:
         assert h["fps"] is None and h["blooms"] is None
     assert h["max_value_len"] == max([len(u) for u in want.uniques], default=0)
@@ -155,7 +156,8 @@ def test_string_insert_rejects_more_than_65536_uniques(cache):
 
 
 @pytest.mark.parametrize("np_dt,lo,hi,n", [(np.int64, -5000, 10**12, 8192), (np.uint64, 10, 16, 6), (np.int32, -7, 8, 3000),
-                                           (np.int16, -300, 300, 1024), (np.uint8, 0, 256, 2500), (np.int64, 77, 78, 1500)])
+                                           (np.int16, -300, 300, 1024), (np.uint8, 0, 256, 2500), (np.int64, 77, 78, 1500),
+                                           (np.uint16, 0, 65536, 5000)])  # W = T = 16: how byte-view LQDA packs its dictionary keys
 def test_int_insert_layout_matches_oracle_packing(cache, np_dt, lo, hi, n):
     """Reference value, bit width and the FastLanes words themselves (fastlanes 0.5.0 unified transposed order as the
     oracle restates it) — the device packer and the oracle must agree word for word when there are no nulls."""

@@ -99,3 +99,41 @@ def test_insert_many_mixed_kinds_take_the_per_batch_path(cache):
     cache.insert_many(ids, arrays)
     for eid, arr in zip(ids, arrays):
         assert_arrays_equal(cache.get(eid).read(), arr, str(arr.type))
+
+
+@pytest.mark.parametrize("typ", [pa.string(), pa.binary(), pa.string_view(), pa.dictionary(pa.uint16(), pa.string())], ids=str)
+@pytest.mark.parametrize("hinted", [False, True])
+def test_insert_many_byte_views_equal_single_inserts(cache, typ, hinted):
+    """The batched byte-view insert (five encode stages over the whole list) must produce the entry the one-batch insert
+    produces under the same symbol table: same HBM image, same answers."""
+    import zlib
+
+    from liquid_cache_b200 import CacheExpression, EntryID
+    from oracle.liquid_oracle import OracleByteViewArray
+    from tests.test_gpu_str import build, make_strings
+
+    tag = zlib.crc32(repr((str(typ), hinted)).encode())
+    rng = np.random.default_rng(tag)
+    hint = CacheExpression.SubstringSearch if hinted else None
+    file_id = 12 + tag % 997
+    arrays, ids = [], []
+    for rg in range(2):           # two column chunks = two symbol tables, each trained on its chunk's first batch
+        for b, n in enumerate((8192, 1, 500, 8192, 3000)):
+            vals, mask = make_strings(rng, n, max(1, n // 4), null_p=0.1 if b % 2 else 0.0)
+            arrays.append(build(vals, mask, typ))
+            ids.append(EntryID((file_id << 48) | (rg << 32) | (5 << 16) | b))
+    arrays.append(build(["x"] * 40, np.ones(40, dtype=bool), typ))  # entirely null
+    ids.append(EntryID((file_id << 48) | (1 << 32) | (5 << 16) | 9))
+    cache.insert_many(ids, arrays, hint=hint)
+    for eid, arr in zip(ids, arrays):
+        liquid = cache.try_read_liquid(eid)
+        single = cache.transcode(arr, hint=hint, compressor_scope=int(eid) & ~0xFFFF)  # the chunk's table exists by now
+        assert liquid.entry_image() == single.entry_image(), f"{typ} n={len(arr)}: HBM image differs from the one-batch insert"
+        assert_arrays_equal(cache.get(eid).read(), arr, f"{typ} n={len(arr)}")
+    eid, arr = ids[3], arrays[3]
+    oracle = OracleByteViewArray.from_arrow(arr, build_fingerprints=hinted)
+    sel = random_selection(rng, len(arr), 0.5)
+    plain = arr.cast(arr.type.value_type) if pa.types.is_dictionary(arr.type) else arr
+    needle = next(v for v in plain.to_pylist() if v is not None)
+    got = cache.eval_predicate(eid, _expr("<=", needle)).with_selection(sel).read()
+    assert_masks_equal(got, oracle.try_eval_predicate("<=", needle, sel), "<= after the batched insert")

@@ -248,15 +248,14 @@ def test_decimal_round_trip_filter_predicate(cache, typ, n, null_p):
                 assert_masks_equal(got, want, f"{typ} n={n} {op} {u} p={p}")
 
 
-def test_decimal_outside_u64_is_declined(cache):
-    """transcode.rs:118-131: such arrays become LiquidFixedLenByteArray in the reference; this build declines them
-    (the caller keeps the Arrow array). Null slots do not count (decimal_array.rs:127-132)."""
-    from liquid_cache_b200 import _native as N
-
+def test_decimal_outside_u64_takes_the_fixed_length_form(cache):
+    """transcode.rs:118-131: such arrays become LiquidFixedLenByteArray (tests/test_gpu_zy_fixed_len.py has the rest).
+    Null slots do not count (decimal_array.rs:127-132)."""
     for arr in (_dec_array([5, -1, 7], pa.decimal128(10, 2)), _dec_array([2**64], pa.decimal128(38, 0)),
                 _dec_array([1, 2**70], pa.decimal256(60, 0))):
-        with pytest.raises(N.UnsupportedType):
-            cache.transcode(arr)
+        liquid = cache.transcode(arr)
+        assert liquid.data_type() == 3
+        assert_arrays_equal(liquid.to_arrow_array(), arr, "decimal outside u64")
     # a null slot whose payload is negative is fine
     arr = pa.array([decimal.Decimal("-1.00"), decimal.Decimal("2.00")], pa.decimal128(10, 2))
     arr = pa.Array.from_buffers(arr.type, 2, [pa.py_buffer(bytes([0b10])), arr.buffers()[1]], null_count=1)

@@ -1,14 +1,18 @@
 """k_int_scan's predicate planner (liquid_cache_b200/csrc/int_plan.cuh) on the CPU: the (comparison kind, threshold) it
 derives from an entry header and `col <op> literal`, applied to packed values exactly as the scan loops apply it, must
-give the plain comparison for entries of every integer type, literal kind and position of the literal relative to the
-entry's value window (below it, inside, above, outside the type, across the signed / unsigned boundary)."""
+give (1) the plain comparison for full entries of every integer type, literal kind and position of the literal relative
+to the entry's value window, and (2) for squeezed entries the answer of the restated reference arrays
+(oracle/liquid_oracle.py OracleClampedArray / OracleQuantizedArray) whenever those decide from the codes — which is all the
+host lets through (squeeze_host.cc) — plus the two probes that find the rows they cannot decide."""
 import ctypes as C
 import os
 import subprocess
 
 import numpy as np
+import pyarrow as pa
 import pytest
 
+from oracle import liquid_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OPS = ["=", "!=", "<", "<=", ">", ">="]
@@ -63,3 +67,44 @@ def test_full_entries_compare_like_the_values(lib, np_dt):
                     got = plan_eval(lib, tbits, width, signed, reference, op, k, offs)
                     want = np.array([PY[op](v, k) for v in values])
                     assert np.array_equal(got, want), (np.dtype(np_dt).name, width, reference, op, k)
+
+
+@pytest.mark.parametrize("typ,base,span", [(pa.int32(), -1_000_000, 1 << 16), (pa.uint32(), 1_000_000, 1 << 16), (pa.int64(), -(2**40), 1 << 20),
+                                           (pa.uint16(), 100, 1 << 12), (pa.int64(), -(2**62), 2**62), (pa.uint64(), 2**63, 1 << 20), (pa.int8(), -128, 255)], ids=str)
+@pytest.mark.parametrize("policy", ["clamp", "quantize"])
+def test_squeezed_entries_answer_like_the_reference_arrays(lib, typ, base, span, policy):
+    rng = np.random.default_rng(span % 1000 + typ.bit_width)
+    vals = [base + int(d) for d in rng.integers(0, span, size=3000, endpoint=True)]
+    arr = pa.array(vals, typ)
+    full = O.OracleIntArray.from_arrow(arr)
+    sq, _image = O.squeeze_int(full, O.OracleSqueezeIo(), "PredicateColumn", policy)
+    codes = sq._codes()
+    valid = np.ones(len(codes), dtype=bool)
+    info = np.iinfo(typ.to_pandas_dtype())
+    signed = info.min < 0
+    kind = 1 if policy == "clamp" else 2
+    bw = getattr(sq, "bucket_width", 0)
+    mn, mx = min(vals), max(vals)
+    last = (1 << sq.bit_width) - 1
+    lits = {mn - 1, mn, mn + 1, mx, mx + 1, mn + last - 1, mn + last, mn + last + 1, info.min, info.max, mn + (bw or 1), mn + (bw or 1) - 1,
+            mn + 5 * (bw or 1), mn + 5 * (bw or 1) + 1, mn + 6 * (bw or 1) - 1} | {int(v) for v in rng.choice(vals, 8)}
+    decided = doubted = 0
+    for k in sorted(x for x in lits if info.min <= x <= info.max):
+        for op in OPS:
+            got = plan_eval(lib, typ.bit_width, sq.bit_width, signed, sq.reference, op, k, codes, squeeze_kind=kind, bucket_width=bw)
+            try:
+                want = sq._eval_inner(op, k, codes, valid)
+            except O.NeedsBacking:
+                # the host never lets such a call through; what it runs first is the probe, which must find the rows in doubt
+                doubted += 1
+                if policy == "clamp":
+                    probe = plan_eval(lib, typ.bit_width, sq.bit_width, signed, sq.reference, "=", 0, codes, squeeze_kind=kind, bucket_width=bw, lit_kind=8)
+                    assert np.array_equal(probe, codes == last) and probe.any()
+                else:
+                    probe = plan_eval(lib, typ.bit_width, sq.bit_width, signed, sq.reference, "=", k, codes, squeeze_kind=kind, bucket_width=bw)
+                    q = (k - sq.reference) // bw
+                    assert np.array_equal(probe, codes.astype(np.uint64) == np.uint64(q)) and probe.any()
+                continue
+            decided += 1
+            assert np.array_equal(got, np.asarray(want.to_numpy(zero_copy_only=False), dtype=bool)), (policy, str(typ), op, k)
+    assert decided > 0 and doubted > 0

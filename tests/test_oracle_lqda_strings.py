@@ -1,7 +1,7 @@
 """The byte-view half of LQDA in the CPU oracle (byte_view_array/serialization.rs:87-325): round trips of every section
 for the four original Arrow types, with and without fingerprints, including empty and entirely null arrays — the cases of
 the reference's own serialization tests (byte_view_array/tests.rs round trips through to_bytes/from_bytes). The device
-build does not write this form yet (lc_to_bytes declines byte views); the oracle pins the layout for when it does."""
+side of the same format is checked against this in tests/test_gpu_zy_ipc_strings.py."""
 import pyarrow as pa
 import pytest
 
@@ -44,3 +44,10 @@ def test_symbol_table_save_format():
     n = blob[0]
     assert n == len(o.fsst.symbols) and len(blob) == 1 + n + 8 * n  # count, lengths, u64 symbols (fsst_buffer.rs:854-883)
     assert list(blob[1:1 + n]) == [len(s) for s in o.fsst.symbols]
+
+
+def test_symbol_table_load_is_the_inverse_of_save():
+    o = O.OracleByteViewArray.from_arrow(pa.array([f"https://shop{i % 31}.example/item?id={i}" for i in range(900)]))
+    back = O.load_symbol_table(O.save_symbol_table(o.fsst))
+    assert back.symbols == o.fsst.symbols
+    assert back.decompress(o.fsst.compress(b"https://shop7.example/item?id=12")) == b"https://shop7.example/item?id=12"

@@ -143,9 +143,11 @@ def test_decimal_known_answers():
     d = pa.array([decimal.Decimal("1.00"), decimal.Decimal("2.00"), None, decimal.Decimal("3.00")], pa.decimal128(10, 2))
     lit = pa.scalar(decimal.Decimal("1.00"), pa.decimal128(10, 2))
     assert transcode(d).try_eval_predicate(">=", lit, pa.array([True] * 4)).to_pylist() == [True, True, None, True]
-    # values outside u64 (negative, or >= 2^64) are not LiquidDecimalArray material (decimal_array.rs:127-132)
-    assert transcode(pa.array([decimal.Decimal("-0.01")], pa.decimal128(10, 2))) is None
-    assert transcode(pa.array([decimal.Decimal(2**64)], pa.decimal128(38, 0))) is None
+    # values outside u64 (negative, or >= 2^64) are not LiquidDecimalArray material (decimal_array.rs:127-132): they take
+    # the LiquidFixedLenByteArray form (transcode.rs:118-153, tests/test_oracle_fixed_len.py)
+    from oracle.liquid_oracle import OracleFixedLenByteArray
+    for outside in (pa.array([decimal.Decimal("-0.01")], pa.decimal128(10, 2)), pa.array([decimal.Decimal(2**64)], pa.decimal128(38, 0))):
+        assert isinstance(transcode(outside), OracleFixedLenByteArray) and transcode(outside).to_arrow().equals(outside)
     big = pa.array([decimal.Decimal(2**64 - 1), None], pa.decimal256(50, 0))
     assert transcode(big).to_arrow().equals(big)
 
