@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows PER GPU (weak scaling)")
-    ap.add_argument("--cpu-sample-entries", type=int, default=1024)
+    ap.add_argument("--cpu-sample-entries", type=int, default=0,
+                    help="entries per CPU-arm pass; 0 = max(8192, 64 per host thread), bounded by the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep", "squeeze"], default="url_like",
                     help="url_like = BASELINE configs[1] (the bench line the driver records); int_filter = configs[2]; "
@@ -131,109 +132,84 @@ def generate_entries(first: int, count: int, workers: int):
             yield i, arr
 
 
-def cpu_baseline(sample_entries: int, threads: int, first_entry: int = 0, target_s: float = 8.0):
-    """C port of the reference's CPU path (oracle/c): LIKE over every sampled entry + get of the hits."""
-    import pyarrow as pa
+def cpu_sample_entries(args, threads: int, cap: int) -> int:
+    import bench_cpu
 
-    from oracle import c_oracle as CO
-
-    CO.lib(rebuild=True)  # -march=native: build on the machine that is timed
-    entries = []
-    fsst = None
-    for _i, arr in generate_entries(first_entry, sample_entries, min(32, threads)):
-        if fsst is None:
-            fsst = CO.CFsst(arr)  # one symbol table per column chunk, trained on the first batch
-        entries.append(CO.CStrArray(arr, fsst, build_fingerprints=True))
-    needle = PATTERN.strip("%").encode()
-    CO.scan(entries, 3, needle, nthreads=threads)  # warm-up
-    reps, t0 = 0, time.perf_counter()
-    matched = rows = 0
-    while True:
-        matched, rows = CO.scan(entries, 3, needle, nthreads=threads)
-        reps += 1
-        dt = time.perf_counter() - t0
-        if dt >= target_s or reps >= 20000:
-            break
-    return {"value": rows * reps / dt / 1e6, "unit": "Mrows/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_entries} entries x {ROWS_PER_ENTRY} rows of the same synthetic URL column, {reps} passes in {dt:.1f} s, "
-                      f"{matched} rows matched per pass; C restatement of the reference path (oracle/c/lc_oracle.c), "
-                      f"entries round-robin over {threads} threads",
-            "ms_per_pass": dt / reps * 1e3, "rows_per_pass": rows}
+    return min(cap, args.cpu_sample_entries) if args.cpu_sample_entries > 0 else bench_cpu.default_sample_entries(threads, cap)
 
 
-def run_reference_shipdate(args):
-    """--impl reference --workload shipdate: the CPU port on the l_shipdate range (configs[3]), same JSON shape."""
+def cpu_baseline(sample_entries: int, threads: int, target_s: float = 8.0):
+    """C port of the reference's CPU path (oracle/c) on a persistent thread pool: LIKE over every sampled entry + get of
+    the hits (bench_cpu.py says how the arm is driven and why)."""
+    import bench_cpu
+
+    return bench_cpu.cpu_baseline_line("url_like", sample_entries, threads, target_s=target_s)
+
+
+def shipdate_params():
     import datetime as dt
 
-    import synth
-    from oracle import c_oracle as CO
-
-    threads = os.cpu_count() or 1
-    steps = max(1, args.steps)
-    CO.lib(rebuild=True)
-    entries = [CO.CIntArray(synth.int_entry("l_shipdate", i, seed=synth.SEED_TPCH)) for i in range(args.cpu_sample_entries)]
     d0 = dt.date(1970, 1, 1)
-    l1, l2 = (dt.date(1994, 1, 1) - d0).days, (dt.date(1995, 1, 1) - d0).days
-    for _ in range(max(1, args.warmup)):
-        CO.scan(entries, 1, b"", 5, l1, 2, l2, nthreads=threads)
-    t0 = time.perf_counter()
-    rows = 0
-    for _ in range(steps):
-        _m, r = CO.scan(entries, 1, b"", 5, l1, 2, l2, nthreads=threads)
-        rows += r
-    dt_s = time.perf_counter() - t0
-    val = rows / dt_s / 1e6
-    sample = (f"{args.cpu_sample_entries} entries x {ROWS_PER_ENTRY} rows per step (bounded sample of one GPU's 75 M-row shard); "
-              f"C port of the reference's CPU path, {threads} threads")
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC.replace("URL LIKE '%google%'", "l_shipdate range"), "value": val, "unit": "Mrows/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt_s / steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "TPC-H SF100 lineitem l_shipdate range (configs[3])", "rows_per_step": rows // steps,
-                   "rows_per_entry": ROWS_PER_ENTRY},
-        "cpu_baseline": {"value": val, "unit": "Mrows/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "Mrows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    return {"lo_days": (dt.date(1994, 1, 1) - d0).days, "hi_days": (dt.date(1995, 1, 1) - d0).days}
+
+
+def int_filter_params(first_entry: int = 0):
+    import synth
+
+    return {"lo": 1373832014 + 20000, "hi": 1373832014 + 28640,  # 10 % of the 86 400 s window
+            "uid": int(synth.int_entry("UserID", first_entry)[17].as_py())}
+
+
+REFERENCE_WORKLOADS = {
+    "url_like": ("clickbench-hits URL LIKE '%google%' + get-with-selection (configs[1])", "u8", METRIC, 100_000_000),
+    "shipdate": ("TPC-H SF100 lineitem l_shipdate range + get of the survivors (configs[3])", "int32",
+                 METRIC.replace("URL LIKE '%google%'", "l_shipdate range"), 600_037_902 // 8),
+    "int_filter": ("clickbench-hits EventTime>=lo AND EventTime<hi AND UserID=k, then get(UserID, EventTime) (configs[2])", "int64",
+                   METRIC.replace("URL LIKE '%google%'", "EventTime range AND UserID ="), 100_000_000),
+}
 
 
 def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU implementation of the path (its C port; no Rust toolchain here) on the host
+    cores — one step = one pass over a bounded sample of the workload on a persistent pool of all host threads."""
     if rank != 0:
         return
-    if args.workload == "shipdate":
-        run_reference_shipdate(args)
+    import bench_cpu
+
+    if args.workload not in REFERENCE_WORKLOADS:
+        print(json.dumps({"impl": "reference", "unavailable": f"no CPU arm for workload {args.workload}"}))
         return
+    name, dtype, metric, rows_cap = REFERENCE_WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
     steps = max(1, args.steps)
-    # each step = one pass over a bounded sample of the workload
-    import pyarrow as pa  # noqa: F401
-
-    from oracle import c_oracle as CO
-
-    CO.lib(rebuild=True)
-    entries, fsst = [], None
-    for _i, arr in generate_entries(0, args.cpu_sample_entries, min(32, threads)):
-        if fsst is None:
-            fsst = CO.CFsst(arr)
-        entries.append(CO.CStrArray(arr, fsst, build_fingerprints=True))
-    needle = PATTERN.strip("%").encode()
-    for _ in range(max(1, args.warmup)):
-        CO.scan(entries, 3, needle, nthreads=threads)
-    t0 = time.perf_counter()
-    rows = 0
-    for _ in range(steps):
-        _m, r = CO.scan(entries, 3, needle, nthreads=threads)
-        rows += r
-    dt = time.perf_counter() - t0
-    val = rows / dt / 1e6
-    sample = (f"{args.cpu_sample_entries} entries x {ROWS_PER_ENTRY} rows per step (bounded sample of the 100 M-row column); "
-              f"C port of the reference's CPU path, {threads} threads")
+    n = cpu_sample_entries(args, threads, max(1, min(args.rows, rows_cap) // ROWS_PER_ENTRY))
+    params = {"url_like": lambda: None, "shipdate": shipdate_params, "int_filter": int_filter_params}[args.workload]()
+    arm = bench_cpu.CpuArm(args.workload, n, threads, params=params)
+    try:
+        single = arm.single_thread_mrows()
+        for _ in range(max(3, args.warmup)):
+            arm.one_pass()
+        t0 = time.perf_counter()
+        rows = 0
+        matched = 0
+        for _ in range(steps):
+            matched, r = arm.one_pass()
+            rows += r
+        dt = time.perf_counter() - t0
+        val = rows / dt / 1e6
+        sample = (f"{n} entries x {ROWS_PER_ENTRY} rows per step (bounded sample of one GPU's shard of the workload), {matched} rows "
+                  f"matched per step; C port of the reference's CPU path (oracle/c/lc_oracle.c), persistent pool of {threads} threads")
+        base = {"value": val, "unit": "Mrows/s", "cores": threads, "kind": "port", "sample": sample}
+        base.update(arm.describe(single, val))
+    finally:
+        arm.close()
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrows/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "clickbench-hits URL LIKE '%google%' + get-with-selection (configs[1])",
-                   "rows_per_step": rows // steps, "rows_per_entry": ROWS_PER_ENTRY},
-        "cpu_baseline": {"value": val, "unit": "Mrows/s", "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric, "value": val, "unit": "Mrows/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(3, args.warmup), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": name, "rows_per_step": rows // steps, "rows_per_entry": ROWS_PER_ENTRY,
+                   "same_config": "same generator, seeds, predicate and per-batch reader loop as the GPU arm; a bounded sample of its rows"},
+        "cpu_baseline": base,
         "e2e": {"value": val, "unit": "Mrows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -599,7 +575,7 @@ def run_shipdate(args, rank, world, local_rank):
             "peak_source": peak_src, "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_shipdate(args.cpu_sample_entries, os.cpu_count() or 1, lo, hi)
+            line["cpu_baseline"] = cpu_baseline_shipdate(cpu_sample_entries(args, os.cpu_count() or 1, n_entries), os.cpu_count() or 1)
         print(json.dumps(line))
     scan.close()
     if world > 1:
@@ -608,29 +584,12 @@ def run_shipdate(args, rank, world, local_rank):
     cache.close()
 
 
-def cpu_baseline_shipdate(sample_entries: int, threads: int, lo, hi, target_s: float = 6.0):
+def cpu_baseline_shipdate(sample_entries: int, threads: int, target_s: float = 6.0):
     """C port of the reference's CPU path on the same column: two conjuncts (decode, filter, compare) joined by
-    boolean_buffer_and_then per entry, entries round-robin over all host threads."""
-    import datetime as dt
+    boolean_buffer_and_then per entry, then the get of the survivors; persistent pool of all host threads."""
+    import bench_cpu
 
-    import synth
-    from oracle import c_oracle as CO
-
-    CO.lib(rebuild=True)
-    entries = [CO.CIntArray(synth.int_entry("l_shipdate", i, seed=synth.SEED_TPCH)) for i in range(sample_entries)]
-    d0 = dt.date(1970, 1, 1)
-    l1, l2 = (lo - d0).days, (hi - d0).days
-    CO.scan(entries, 1, b"", 5, l1, 2, l2, nthreads=threads)  # ops: lc_op numbering, 5 = GE, 2 = LT
-    reps, t0 = 0, time.perf_counter()
-    while True:
-        matched, rows = CO.scan(entries, 1, b"", 5, l1, 2, l2, nthreads=threads)
-        reps += 1
-        dt_s = time.perf_counter() - t0
-        if dt_s >= target_s or reps >= 20000:
-            break
-    return {"value": rows * reps / dt_s / 1e6, "unit": "Mrows/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_entries} entries x {ROWS_PER_ENTRY} rows of the same l_shipdate column, {reps} passes in {dt_s:.1f} s, "
-                      f"{matched} rows matched per pass; C restatement of the reference path (oracle/c/lc_oracle.c)"}
+    return bench_cpu.cpu_baseline_line("shipdate", sample_entries, threads, params=shipdate_params(), target_s=target_s)
 
 
 def main():
@@ -882,7 +841,7 @@ def main():
             "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_sample_entries, os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_baseline(cpu_sample_entries(args, os.cpu_count() or 1, n_entries), os.cpu_count() or 1)
         print(json.dumps(line))
     scan.close()
     if world > 1:

@@ -713,83 +713,209 @@ EXPORT void lco_and_then(const uint8_t* left, uint64_t left_len, const uint8_t* 
 }
 
 /* ------------------------------------------------------------------ threaded scan drivers ---- */
-/* Round-robin partition of the entries over T threads, as DataFusion partitions would be; each thread runs
- * the per-entry path above on its entries. Returns the number of rows whose mask bit is set. */
+/* The shape being matched: DataFusion partition tasks over LiquidCacheReader
+ * (src/datafusion/src/reader/runtime/liquid_cache_reader.rs:297-391) — a fixed set of worker threads created ONCE
+ * (the tokio runtime), each taking batches of a scan and running the per-entry path above on them. So the pool
+ * below is persistent: threads are created by lco_pool_create, outside every timed region, and a pass only wakes
+ * them. Entries are handed out dynamically in grains of a few entries (kinder to the CPU than a static split: no
+ * tail imbalance), and every worker keeps its scratch buffers across passes. */
 typedef struct {
-  const void* const* entries; uint32_t n_entries; uint32_t tid, nthreads;
-  int kind; /* 0 str like, 1 int range (two conjuncts + and_then), 2 int decode, 3 str like + get */
+  const void* const* entries; uint32_t n_entries;
+  int kind; /* 0 str like, 1 int range (two conjuncts + and_then), 2 int decode, 3 str like + get,
+               5 = 1 + get of the column with the final selection,
+               4 two-column batch: range on column A (two conjuncts), third conjunct on column B, get(B, A) */
   const uint8_t* needle; uint32_t m;
   int op1, op2; int64_t lit1, lit2;
-  uint64_t matched; uint64_t rows;
-} scan_arg;
+  uint32_t grain;
+  const void* const* entries2; int op3; int64_t lit3;  /* kind 4: second column of the batch and its conjunct */
+} scan_job;
 
-static void* scan_thread(void* p) {
-  scan_arg* a = (scan_arg*)p;
-  uint64_t matched = 0, rows = 0;
-  uint8_t *mask = NULL, *valid = NULL, *mask2 = NULL, *sel = NULL;
-  size_t cap = 0;
-  for (uint32_t i = a->tid; i < a->n_entries; i += a->nthreads) {
-    const uint32_t n = a->kind == 1 || a->kind == 2 ? ((const lco_int*)a->entries[i])->n : ((const lco_str*)a->entries[i])->n;
-    if ((size_t)n / 8 + 64 > cap) {
-      cap = (size_t)n / 8 + 64;
-      mask = (uint8_t*)realloc(mask, cap); valid = (uint8_t*)realloc(valid, cap);
-      mask2 = (uint8_t*)realloc(mask2, cap); sel = (uint8_t*)realloc(sel, cap);
-    }
-    uint32_t nulls = 0;
-    rows += n;
-    if (a->kind == 0 || a->kind == 3) {
-      const lco_str* e = (const lco_str*)a->entries[i];
-      const uint32_t k = lco_str_like(e, NULL, a->needle, a->m, 0, mask, valid, &nulls);
-      if (nulls) for (uint32_t b = 0; b < (k + 7) / 8; ++b) mask[b] &= valid[b];  /* prep_null_mask_filter */
-      uint64_t hit = 0;
-      for (uint32_t b = 0; b < (k + 7) / 8; ++b) hit += (uint64_t)__builtin_popcount(mask[b]);
-      matched += hit;
-      if (a->kind == 3 && hit) {
-        int32_t* off = (int32_t*)malloc((size_t)(hit + 1) * 4);
-        uint64_t bytes = 0;
-        uint8_t* data = (uint8_t*)malloc(e->uncompressed_bytes + 16 > 1 << 20 ? e->uncompressed_bytes + 16 : 1 << 20);
-        lco_str_filter(e, mask, off, data, valid, &nulls, &bytes);
-        free(off); free(data);
-      }
-    } else if (a->kind == 1) {
-      const lco_int* e = (const lco_int*)a->entries[i];
-      uint32_t k = lco_int_eval(e, NULL, a->op1, a->lit1, (uint64_t)a->lit1, mask, valid, &nulls);
-      if (nulls) for (uint32_t b = 0; b < (k + 7) / 8; ++b) mask[b] &= valid[b];
-      memcpy(sel, mask, (k + 7) / 8);
-      /* second conjunct under the running selection, then boolean_buffer_and_then */
-      const uint32_t k2 = lco_int_eval(e, sel, a->op2, a->lit2, (uint64_t)a->lit2, mask2, valid, &nulls);
-      if (nulls) for (uint32_t b = 0; b < (k2 + 7) / 8; ++b) mask2[b] &= valid[b];
-      lco_and_then(sel, n, mask2, k2, mask);
-      for (uint32_t b = 0; b < (n + 7) / 8; ++b) matched += (uint64_t)__builtin_popcount(mask[b]);
-    } else {
-      const lco_int* e = (const lco_int*)a->entries[i];
-      void* vals = malloc((size_t)(n ? n : 1) * (e->tbits / 8));
-      matched += lco_int_filter(e, NULL, vals, valid, &nulls);
-      free(vals);
-    }
+typedef struct {
+  uint8_t *mask, *valid, *mask2, *sel; size_t cap;       /* per-entry bitmaps */
+  int32_t* off; size_t off_cap; uint8_t* data; size_t data_cap; void* vals; size_t vals_cap; /* get outputs */
+} scan_scratch;
+
+static void scratch_free(scan_scratch* s) {
+  free(s->mask); free(s->valid); free(s->mask2); free(s->sel); free(s->off); free(s->data); free(s->vals);
+  memset(s, 0, sizeof *s);
+}
+
+/* the reference's per-batch work on entry i of the job; returns rows whose final mask bit is set */
+static uint64_t scan_one(const scan_job* a, uint32_t i, scan_scratch* s, uint64_t* rows) {
+  uint64_t matched = 0;
+  const uint32_t n = a->kind == 1 || a->kind == 2 || a->kind == 4 || a->kind == 5 ? ((const lco_int*)a->entries[i])->n : ((const lco_str*)a->entries[i])->n;
+  if ((size_t)n / 8 + 64 > s->cap) {
+    s->cap = (size_t)n / 8 + 64;
+    s->mask = (uint8_t*)realloc(s->mask, s->cap); s->valid = (uint8_t*)realloc(s->valid, s->cap);
+    s->mask2 = (uint8_t*)realloc(s->mask2, s->cap); s->sel = (uint8_t*)realloc(s->sel, s->cap);
   }
-  free(mask); free(valid); free(mask2); free(sel);
-  a->matched = matched;
-  a->rows = rows;
+  uint8_t *mask = s->mask, *valid = s->valid, *mask2 = s->mask2, *sel = s->sel;
+  uint32_t nulls = 0;
+  *rows += n;
+  if (a->kind == 0 || a->kind == 3) {
+    const lco_str* e = (const lco_str*)a->entries[i];
+    const uint32_t k = lco_str_like(e, NULL, a->needle, a->m, 0, mask, valid, &nulls);
+    if (nulls) for (uint32_t b = 0; b < (k + 7) / 8; ++b) mask[b] &= valid[b];  /* prep_null_mask_filter */
+    uint64_t hit = 0;
+    for (uint32_t b = 0; b < (k + 7) / 8; ++b) hit += (uint64_t)__builtin_popcount(mask[b]);
+    matched += hit;
+    if (a->kind == 3 && hit) {
+      const size_t need_off = (size_t)(hit + 1) * 4;
+      const size_t need_data = e->uncompressed_bytes + 16 > 1 << 20 ? e->uncompressed_bytes + 16 : 1 << 20;
+      if (need_off > s->off_cap) { s->off_cap = need_off; s->off = (int32_t*)realloc(s->off, need_off); }
+      if (need_data > s->data_cap) { s->data_cap = need_data; s->data = (uint8_t*)realloc(s->data, need_data); }
+      uint64_t bytes = 0;
+      lco_str_filter(e, mask, s->off, s->data, valid, &nulls, &bytes);
+    }
+  } else if (a->kind == 1 || a->kind == 5) {
+    const lco_int* e = (const lco_int*)a->entries[i];
+    uint32_t k = lco_int_eval(e, NULL, a->op1, a->lit1, (uint64_t)a->lit1, mask, valid, &nulls);
+    if (nulls) for (uint32_t b = 0; b < (k + 7) / 8; ++b) mask[b] &= valid[b];
+    memcpy(sel, mask, (k + 7) / 8);
+    /* second conjunct under the running selection, then boolean_buffer_and_then */
+    const uint32_t k2 = lco_int_eval(e, sel, a->op2, a->lit2, (uint64_t)a->lit2, mask2, valid, &nulls);
+    if (nulls) for (uint32_t b = 0; b < (k2 + 7) / 8; ++b) mask2[b] &= valid[b];
+    lco_and_then(sel, n, mask2, k2, mask);
+    uint64_t hit = 0;
+    for (uint32_t b = 0; b < (n + 7) / 8; ++b) hit += (uint64_t)__builtin_popcount(mask[b]);
+    matched += hit;
+    if (a->kind == 5 && hit) {  /* read_from_cache: the projected column with the final selection */
+      const size_t need = (size_t)(n ? n : 1) * (e->tbits / 8);
+      if (need > s->vals_cap) { s->vals_cap = need; s->vals = realloc(s->vals, need); }
+      lco_int_filter(e, mask, s->vals, valid, &nulls);
+    }
+  } else if (a->kind == 4) {
+    /* the reader's loop for one batch (liquid_cache_reader.rs:297-391): each conjunct under the running selection,
+     * nulls->false, boolean_buffer_and_then; then every projected column read with the final selection */
+    const lco_int* ea = (const lco_int*)a->entries[i];
+    const lco_int* eb = (const lco_int*)a->entries2[i];
+    uint32_t k = lco_int_eval(ea, NULL, a->op1, a->lit1, (uint64_t)a->lit1, mask, valid, &nulls);
+    if (nulls) for (uint32_t b = 0; b < (k + 7) / 8; ++b) mask[b] &= valid[b];
+    memcpy(sel, mask, (k + 7) / 8);
+    k = lco_int_eval(ea, sel, a->op2, a->lit2, (uint64_t)a->lit2, mask2, valid, &nulls);
+    if (nulls) for (uint32_t b = 0; b < (k + 7) / 8; ++b) mask2[b] &= valid[b];
+    lco_and_then(sel, n, mask2, k, mask);
+    memcpy(sel, mask, ((size_t)n + 7) / 8);
+    k = lco_int_eval(eb, sel, a->op3, a->lit3, (uint64_t)a->lit3, mask2, valid, &nulls);
+    if (nulls) for (uint32_t b = 0; b < (k + 7) / 8; ++b) mask2[b] &= valid[b];
+    lco_and_then(sel, n, mask2, k, mask);
+    uint64_t hit = 0;
+    for (uint32_t b = 0; b < (n + 7) / 8; ++b) hit += (uint64_t)__builtin_popcount(mask[b]);
+    matched += hit;
+    const size_t need = (size_t)(n ? n : 1) * 8;
+    if (need > s->vals_cap) { s->vals_cap = need; s->vals = realloc(s->vals, need); }
+    if (hit) {
+      lco_int_filter(eb, mask, s->vals, valid, &nulls);
+      lco_int_filter(ea, mask, s->vals, valid, &nulls);
+    }
+  } else {
+    const lco_int* e = (const lco_int*)a->entries[i];
+    const size_t need = (size_t)(n ? n : 1) * (e->tbits / 8);
+    if (need > s->vals_cap) { s->vals_cap = need; s->vals = realloc(s->vals, need); }
+    matched += lco_int_filter(e, NULL, s->vals, valid, &nulls);
+  }
+  return matched;
+}
+
+typedef struct lco_pool {
+  pthread_t* th; uint32_t nthreads;
+  pthread_mutex_t mu; pthread_cond_t cv_go, cv_done;
+  uint64_t generation; uint32_t running; int stop;
+  scan_job job;
+  const void* const* entries2; int op3; int64_t lit3;   /* lco_pool_set_second */
+  volatile uint32_t next;            /* next entry to hand out (atomic fetch-add) */
+  uint64_t matched, rows;            /* totals of the current pass (under mu) */
+} lco_pool;
+
+static void* pool_worker(void* p) {
+  lco_pool* pool = (lco_pool*)p;
+  scan_scratch s; memset(&s, 0, sizeof s);
+  uint64_t seen = 0;
+  for (;;) {
+    pthread_mutex_lock(&pool->mu);
+    while (!pool->stop && pool->generation == seen) pthread_cond_wait(&pool->cv_go, &pool->mu);
+    if (pool->stop) { pthread_mutex_unlock(&pool->mu); break; }
+    seen = pool->generation;
+    const scan_job job = pool->job;
+    pthread_mutex_unlock(&pool->mu);
+    uint64_t matched = 0, rows = 0;
+    for (;;) {
+      const uint32_t b = __atomic_fetch_add(&pool->next, job.grain, __ATOMIC_RELAXED);
+      if (b >= job.n_entries) break;
+      const uint32_t e = b + job.grain < job.n_entries ? b + job.grain : job.n_entries;
+      for (uint32_t i = b; i < e; ++i) matched += scan_one(&job, i, &s, &rows);
+    }
+    pthread_mutex_lock(&pool->mu);
+    pool->matched += matched; pool->rows += rows;
+    if (--pool->running == 0) pthread_cond_signal(&pool->cv_done);
+    pthread_mutex_unlock(&pool->mu);
+  }
+  scratch_free(&s);
   return NULL;
 }
 
+EXPORT lco_pool* lco_pool_create(uint32_t nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  lco_pool* pool = (lco_pool*)calloc(1, sizeof(lco_pool));
+  pool->nthreads = nthreads;
+  pool->th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  pthread_mutex_init(&pool->mu, NULL);
+  pthread_cond_init(&pool->cv_go, NULL); pthread_cond_init(&pool->cv_done, NULL);
+  for (uint32_t t = 0; t < nthreads; ++t) pthread_create(&pool->th[t], NULL, pool_worker, pool);
+  return pool;
+}
+
+EXPORT void lco_pool_destroy(lco_pool* pool) {
+  if (!pool) return;
+  pthread_mutex_lock(&pool->mu);
+  pool->stop = 1;
+  pthread_cond_broadcast(&pool->cv_go);
+  pthread_mutex_unlock(&pool->mu);
+  for (uint32_t t = 0; t < pool->nthreads; ++t) pthread_join(pool->th[t], NULL);
+  pthread_mutex_destroy(&pool->mu); pthread_cond_destroy(&pool->cv_go); pthread_cond_destroy(&pool->cv_done);
+  free(pool->th); free(pool);
+}
+
+/* kind 4 only: the batch's second column (same length as the entry list) and the conjunct evaluated on it */
+EXPORT void lco_pool_set_second(lco_pool* pool, const void* const* entries2, int op3, int64_t lit3) {
+  pool->entries2 = entries2; pool->op3 = op3; pool->lit3 = lit3;
+}
+
+/* One pass of the scan over all entries on the pool's threads. Nothing is created or joined here. */
+EXPORT uint64_t lco_pool_scan(lco_pool* pool, const void* const* entries, uint32_t n_entries, int kind, const uint8_t* needle,
+                              uint32_t m, int op1, int64_t lit1, int op2, int64_t lit2, uint32_t grain, uint64_t* out_rows) {
+  pthread_mutex_lock(&pool->mu);
+  pool->job = (scan_job){entries, n_entries, kind, needle, m, op1, op2, lit1, lit2, grain ? grain : 4,
+                         pool->entries2, pool->op3, pool->lit3};
+  pool->next = 0; pool->matched = 0; pool->rows = 0;
+  pool->running = pool->nthreads;
+  pool->generation++;
+  pthread_cond_broadcast(&pool->cv_go);
+  while (pool->running) pthread_cond_wait(&pool->cv_done, &pool->mu);
+  const uint64_t matched = pool->matched;
+  if (out_rows) *out_rows = pool->rows;
+  pthread_mutex_unlock(&pool->mu);
+  return matched;
+}
+
+/* Single pass on the calling thread (no pool): the single-thread figure reported next to the pooled one. */
+EXPORT uint64_t lco_scan_serial(const void* const* entries, uint32_t n_entries, int kind, const uint8_t* needle, uint32_t m,
+                                int op1, int64_t lit1, int op2, int64_t lit2, uint64_t* out_rows) {
+  const scan_job job = {entries, n_entries, kind, needle, m, op1, op2, lit1, lit2, 1, NULL, 0, 0};
+  if (kind == 4) return 0; /* two-column batches go through a pool (one thread if need be) */
+  scan_scratch s; memset(&s, 0, sizeof s);
+  uint64_t matched = 0, rows = 0;
+  for (uint32_t i = 0; i < n_entries; ++i) matched += scan_one(&job, i, &s, &rows);
+  scratch_free(&s);
+  if (out_rows) *out_rows = rows;
+  return matched;
+}
+
+/* Convenience for the tests: a throw-away pool around one pass. NOT used by any timed path. */
 EXPORT uint64_t lco_scan(const void* const* entries, uint32_t n_entries, int kind, const uint8_t* needle, uint32_t m,
                          int op1, int64_t lit1, int op2, int64_t lit2, uint32_t nthreads, uint64_t* out_rows) {
-  if (nthreads < 1) nthreads = 1;
-  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
-  scan_arg* args = (scan_arg*)calloc(nthreads, sizeof(scan_arg));
-  for (uint32_t t = 0; t < nthreads; ++t) {
-    args[t] = (scan_arg){entries, n_entries, t, nthreads, kind, needle, m, op1, op2, lit1, lit2, 0, 0};
-    pthread_create(&th[t], NULL, scan_thread, &args[t]);
-  }
-  uint64_t matched = 0, rows = 0;
-  for (uint32_t t = 0; t < nthreads; ++t) {
-    pthread_join(th[t], NULL);
-    matched += args[t].matched;
-    rows += args[t].rows;
-  }
-  if (out_rows) *out_rows = rows;
-  free(th); free(args);
+  lco_pool* pool = lco_pool_create(nthreads);
+  const uint64_t matched = lco_pool_scan(pool, entries, n_entries, kind, needle, m, op1, lit1, op2, lit2, 4, out_rows);
+  lco_pool_destroy(pool);
   return matched;
 }

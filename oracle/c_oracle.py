@@ -54,6 +54,14 @@ def lib(rebuild: bool = False) -> C.CDLL:
         l.lco_and_then.argtypes = [vp, u64, vp, u64, vp]
         l.lco_scan.restype = u64
         l.lco_scan.argtypes = [vp, u32, C.c_int, vp, u32, C.c_int, i64, C.c_int, i64, u32, C.POINTER(u64)]
+        l.lco_scan_serial.restype = u64
+        l.lco_scan_serial.argtypes = [vp, u32, C.c_int, vp, u32, C.c_int, i64, C.c_int, i64, C.POINTER(u64)]
+        l.lco_pool_create.restype = vp
+        l.lco_pool_create.argtypes = [u32]
+        l.lco_pool_destroy.argtypes = [vp]
+        l.lco_pool_set_second.argtypes = [vp, vp, C.c_int, i64]
+        l.lco_pool_scan.restype = u64
+        l.lco_pool_scan.argtypes = [vp, vp, u32, C.c_int, vp, u32, C.c_int, i64, C.c_int, i64, u32, C.POINTER(u64)]
         _LIB = l
     return _LIB
 
@@ -208,3 +216,55 @@ def scan(entries: list, kind: int, needle: bytes = b"", op1: int = 0, lit1: int 
     rows = C.c_uint64(0)
     matched = lib().lco_scan(ptrs, len(entries), kind, needle, len(needle), op1, lit1, op2, lit2, nthreads, C.byref(rows))
     return int(matched), int(rows.value)
+
+
+class ScanPool:
+    """Persistent worker threads for the timed CPU arm (created once, outside every timed region), standing in for the
+    reference's tokio partition tasks. `bind(entries)` fixes the entry list so that a pass is one C call with no Python
+    work inside the clock."""
+
+    def __init__(self, nthreads: int):
+        self.nthreads = max(1, int(nthreads))
+        self.ptr = lib().lco_pool_create(self.nthreads)
+        self._ptrs = None
+        self._n = 0
+
+    def bind(self, entries: list) -> "ScanPool":
+        self._keep = entries
+        self._n = len(entries)
+        self._ptrs = (C.c_void_p * self._n)(*[e.ptr for e in entries])
+        return self
+
+    def bind_second(self, entries2: list, op3: int, lit3: int) -> "ScanPool":
+        """kind 4: the second column of every batch (same order as the bound list) and the conjunct on it."""
+        assert len(entries2) == self._n
+        self._keep2 = entries2
+        self._ptrs2 = (C.c_void_p * self._n)(*[e.ptr for e in entries2])
+        lib().lco_pool_set_second(self.ptr, self._ptrs2, op3, lit3)
+        return self
+
+    def scan(self, kind: int, needle: bytes = b"", op1: int = 0, lit1: int = 0, op2: int = 0, lit2: int = 0, grain: int = 4):
+        rows = C.c_uint64(0)
+        matched = lib().lco_pool_scan(self.ptr, self._ptrs, self._n, kind, needle, len(needle), op1, lit1, op2, lit2, grain,
+                                      C.byref(rows))
+        return int(matched), int(rows.value)
+
+    def scan_serial(self, kind: int, needle: bytes = b"", op1: int = 0, lit1: int = 0, op2: int = 0, lit2: int = 0,
+                    first: int = 0, count=None):
+        """The same pass on the calling thread over entries [first, first+count) — the single-thread figure."""
+        count = self._n - first if count is None else min(count, self._n - first)
+        sub = (C.c_void_p * count)(*[self._ptrs[first + i] for i in range(count)])
+        rows = C.c_uint64(0)
+        matched = lib().lco_scan_serial(sub, count, kind, needle, len(needle), op1, lit1, op2, lit2, C.byref(rows))
+        return int(matched), int(rows.value)
+
+    def close(self):
+        if self.ptr:
+            lib().lco_pool_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
