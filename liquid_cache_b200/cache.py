@@ -142,7 +142,7 @@ class GpuLiquidArray:
             N.HINT_SUBSTRING_SEARCH if expression_hint == CacheExpression.SubstringSearch else N.HINT_PREDICATE)
         nb, sq = C.c_uint64(0), C.c_uint64(0)
         ctx = self._cache._ctx
-        N.check(N.lib().lc_squeeze(ctx, self._h, pol, hint, None, None, None, 0, C.byref(nb), C.byref(sq)))
+        N.check(N.lib().lc_squeeze(ctx, self._h, pol, hint, N.BACKING_READ(), None, None, 0, C.byref(nb), C.byref(sq)))  # size query: no reader yet
         if nb.value == 0:
             return None
 

@@ -226,7 +226,7 @@ class LiquidExpr:
                 # e.g. to_timestamp_seconds(col) or a narrowing cast: the reference evaluates these with
                 # DataFusion on the decoded array; the caller keeps doing that.
                 raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "column side is not an integer-preserving cast chain")
-            v = _int_literal(e.right)
+            v = _int_literal(e.right, _outermost_type(e.left, column_type))
             if v is None:
                 raise N.UnsupportedExpr(N.LC_ERR_UNSUPPORTED_EXPR, "literal is not an integer/date/timestamp")
             if v < 0 or v <= 0x7FFFFFFFFFFFFFFF:
@@ -270,7 +270,10 @@ def _decimal_unscaled(v, scale: int) -> Optional[int]:
         return int(scaled)
 
 
-def _int_literal(lit: Literal) -> Optional[int]:
+def _int_literal(lit: Literal, compared_type: Optional[pa.DataType] = None) -> Optional[int]:
+    """The literal in the integer domain of `compared_type` (the column's type, or the outermost cast's): a
+    `datetime.date` is a day count against Date32 and milliseconds against Date64 — the two physical units the reference's
+    Date32 / Date64 primitive arrays hold (primitive_array.rs:55-68)."""
     v = lit.value
     if isinstance(v, bool):
         return None
@@ -279,23 +282,54 @@ def _int_literal(lit: Literal) -> Optional[int]:
     if isinstance(v, _dt.datetime):
         return None
     if isinstance(v, _dt.date):
-        return (v - _dt.date(1970, 1, 1)).days
+        days = (v - _dt.date(1970, 1, 1)).days
+        if compared_type is not None and pa.types.is_date64(compared_type):
+            return days * 86_400_000
+        if compared_type is None or pa.types.is_date32(compared_type) or pa.types.is_integer(compared_type):
+            return days
+        return None  # a date against a timestamp column: DataFusion would have coerced it to a timestamp literal
     return None
 
 
+def _int_range(t: pa.DataType):
+    """Value range of an integer-like type in its own integer domain, None when casts from/to it rescale."""
+    if pa.types.is_integer(t):
+        bits = t.bit_width
+        return (-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if pa.types.is_signed_integer(t) else (0, (1 << bits) - 1)
+    if pa.types.is_date32(t):
+        return (-(1 << 31), (1 << 31) - 1)
+    return None
+
+
+def _outermost_type(e, column_type: pa.DataType) -> pa.DataType:
+    return e.cast_type if isinstance(e, CastExpr) and e.cast_type is not None else column_type
+
+
 def _cast_chain_is_integer_identity(e, column_type: pa.DataType) -> bool:
-    """Column possibly under casts between integer-like types that keep the integer value
-    (e.g. UInt16 -> Int32 -> Date32 for ClickBench's "EventDate"::INT::DATE)."""
+    """Column possibly under casts that keep the integer value for EVERY value of the source type (e.g. UInt16 -> Int32 ->
+    Date32 for ClickBench's "EventDate"::INT::DATE). A narrowing or sign-changing cast (Int64 -> Int8, UInt64 -> Int64) is
+    not one: DataFusion's cast gives an error or a null for the values that do not fit, so the caller keeps evaluating
+    those on the decoded array, like every cast that rescales (Date64 -> Date32, timestamps)."""
+    chain = []
     while isinstance(e, CastExpr):
-        t = e.cast_type
-        if t is not None and not (pa.types.is_integer(t) or pa.types.is_date32(t)):
-            return False
+        chain.append(e.cast_type)
         e = e.expr
-    return isinstance(e, Column) and (
-        pa.types.is_integer(column_type)
-        or pa.types.is_date(column_type)
-        or (pa.types.is_timestamp(column_type) and column_type.tz is None)
-    )
+    if not isinstance(e, Column):
+        return False
+    if not chain:
+        return (pa.types.is_integer(column_type) or pa.types.is_date(column_type)
+                or (pa.types.is_timestamp(column_type) and column_type.tz is None))
+    src = _int_range(column_type)
+    if src is None:
+        return False
+    for t in reversed(chain):  # innermost cast first
+        if t is None:
+            continue
+        dst = _int_range(t)
+        if dst is None or dst[0] > src[0] or dst[1] < src[1]:
+            return False
+        src = dst
+    return True
 
 
 def _supports_expr(expr, data_type, hint) -> bool:

@@ -134,6 +134,20 @@ def test_dates_and_timestamps(cache):
     assert_arrays_equal(cache.transcode(d64).to_arrow_array(), d64, "date64")
 
 
+def test_date64_predicate_compares_milliseconds(cache):
+    """A `datetime.date` literal against a Date64 column is compared in milliseconds (the column's physical unit), checked
+    against Arrow's own comparison."""
+    days = [dt.date(2019, 12, 30) + dt.timedelta(days=i) for i in range(400)]
+    d64 = pa.array([None if i % 11 == 0 else d for i, d in enumerate(days)], pa.date64())
+    liquid = cache.transcode(d64)
+    sel = pa.array([i % 3 != 0 for i in range(len(days))])
+    lit = dt.date(2020, 1, 1)
+    for op, fn in ((">=", pc.greater_equal), ("<", pc.less), ("=", pc.equal), ("!=", pc.not_equal)):
+        got = liquid.try_eval_predicate(_expr(op, lit), sel)
+        want = fn(d64.filter(sel), pa.scalar(lit, pa.date64()))
+        assert_masks_equal(got, want, f"date64 {op}")
+
+
 def test_unsupported_types_are_declined(cache):
     """transcode.rs:420-436: Boolean (and tz timestamps) stay Arrow -> Err(array)."""
     from liquid_cache_b200 import _native as N
