@@ -687,10 +687,21 @@ def main():
         tot = float(prof[11])
         print("[phase cycles per CTA] " + ", ".join(f"{nm} {float(prof[4 + i]) / n_entries:.0f} ({100 * float(prof[4 + i]) / tot:.1f}%)"
                                                       for i, nm in enumerate(names)) + f", total {tot / n_entries:.0f}", file=sys.stderr)
-    # R = keys 2n + fingerprints 4U + candidate compressed bytes + offset residuals of the candidates' pairs
-    #     (2 bytes typ.) ; W = selection words n/8   (SURVEY.md §8d "string predicate, fingerprint path")
-    #     + 32U: the 256-bit trigram filters this build stores beside the fingerprints (read once, like them)
-    algo_bytes = 2 * rows_local + (4 + 32) * uniques + cand_bytes + 2 * 2 * cand + rows_local // 8
+    # Algorithmic bytes of one predicate launch, SURVEY.md §8d "string predicate, fingerprint path", counted by the kernel's
+    # own counters in the untimed launch above:  R = keys 2n + staged head (header, shared prefix, fingerprints 4U, ALL offset
+    # residuals (U+1)*res_bytes) + compressed bytes of the walked candidates;  W = selection words n/8.
+    # That is the reference's data for this predicate; roofline.achieved is quoted on it. Two more figures say what THIS
+    # build moves: `with_private_filter` adds the 32-byte trigram set of every value the reference gate lets through (the
+    # only ones whose set is fetched), and `kernel_reads` replaces the 2n of keys by the keys of the batches whose
+    # dictionary had a match (the others are answered without their keys: k_str.cu, k_str_like).
+    ref_pass, meta_bytes, rows_phase_entries = int(prof[12]), int(prof[13]), int(prof[3])
+    if meta_bytes == 0:  # the launch did not take the streaming LIKE kernel
+        meta_bytes = 4 * uniques + 2 * uniques
+        ref_pass = uniques
+        rows_phase_entries = n_entries
+    algo_bytes = 2 * rows_local + meta_bytes + cand_bytes + rows_local // 8
+    algo_bytes_private = algo_bytes + 32 * ref_pass
+    kernel_reads = meta_bytes + 32 * ref_pass + cand_bytes + rows_phase_entries * 2 * ROWS_PER_ENTRY + rows_local // 8
 
     k_start = torch.cuda.Event(enable_timing=True)
     k_stop = torch.cuda.Event(enable_timing=True)
@@ -833,9 +844,14 @@ def main():
                     "d2h_bytes_per_step": int((st_d.d2h_bytes - st_c.d2h_bytes) / e2e_steps), "ms_per_step": e2e_ms / e2e_steps,
                     "matches_device_path": bool(e2e_ok)},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_str_scan<MODE_REFINE>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_str_like<MODE_REFINE>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic(rows_local, n_entries),
                          "algorithmic_bytes_per_launch": algo_bytes,
+                         "algorithmic_bytes_with_private_filter": algo_bytes_private,
+                         "bytes_this_kernel_must_move": kernel_reads,
+                         "achieved_on_bytes_moved": kernel_reads / (kern_ms / 1e3) / 1e9,
+                         "reference_gate_pass_frac": ref_pass / max(1, uniques),
+                         "batches_with_a_match_frac": rows_phase_entries / n_entries,
                          "kernel_ms": kern_ms, "peak_source": peak_src,
                          "kernel_share_of_step": kern_ms / (ms_total / args.steps)},
             "clocks": clk,

@@ -320,6 +320,11 @@ int lc_cache_reset(lc_ctx* ctx);                                              /*
 /* Resolve entry ids to handles (borrowed; valid until remove/reset). LC_ERR_NOT_FOUND if any absent. */
 int lc_cache_handles(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, lc_handle* out);
 /* cache.get(&id).with_selection(&sel)        (builders.rs:218-276, core.rs:595-634) */
+/* Arc<dyn LiquidArray> out of the cache (`LiquidCache::try_read_liquid`, cache/core.rs:243-252): the entry's handle with
+ * ONE MORE reference, resolved under the cache lock. The handle stays valid — and keeps answering for the entry as it was
+ * when retained — after the id is re-inserted, removed or the cache is reset; give it back with lc_release.
+ * (lc_cache_handles returns BORROWED handles for the duration of a scan over entries the caller keeps cached.) */
+int lc_cache_retain(lc_ctx* ctx, uint64_t entry_id, lc_handle* out);
 int lc_cache_get(lc_ctx* ctx, uint64_t entry_id, const uint8_t* sel_bits, uint64_t sel_len,
                  struct ArrowSchema* out_schema, struct ArrowArray* out_array);
 /* cache.eval_predicate(&id, &expr).with_selection(&sel)   (builders.rs:314-356, core.rs:862-930) */

@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
     l.lc_ctx_synchronize.argtypes = [vp]
     l.lc_ctx_stats.argtypes = [vp, C.POINTER(Stats)]
     l.lc_encode.argtypes = [vp, vp, vp, i32, u64, u64p]
+    l.lc_cache_retain.argtypes = [vp, u64, u64p]
     l.lc_release.argtypes = [vp, u64]
     l.lc_release.restype = None
     for f in (l.lc_len, l.lc_memory_size):

@@ -395,7 +395,9 @@ class EvaluatePredicate:
     def read(self) -> Optional[pa.Array]:
         if not self._cache.is_cached(self._id):
             return None
-        arr = GpuLiquidArray(self._cache, self._cache._handle(self._id), owned=False)
+        arr = self._cache.try_read_liquid(self._id)  # holds its own reference for the duration of the call
+        if arr is None:
+            return None
         return arr.try_eval_predicate(self._expr, self._sel)
 
 
@@ -455,9 +457,14 @@ class LiquidCache:
         return bool(N.lib().lc_cache_is_cached(self._ctx, int(entry_id)))
 
     def try_read_liquid(self, entry_id) -> Optional[GpuLiquidArray]:
-        if not self.is_cached(entry_id):
+        # the reference hands out an Arc: the array stays alive (and unchanged) if the id is re-inserted, removed or the
+        # cache reset while the caller holds it
+        h = C.c_uint64(0)
+        rc = N.lib().lc_cache_retain(self._ctx, int(entry_id), C.byref(h))
+        if rc == N.LC_ERR_NOT_FOUND:
             return None
-        return GpuLiquidArray(self, self._handle(entry_id), owned=False)
+        N.check(rc)
+        return GpuLiquidArray(self, int(h.value), owned=True)
 
     def reset(self) -> None:
         N.check(N.lib().lc_cache_reset(self._ctx))

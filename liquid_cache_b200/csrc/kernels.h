@@ -177,7 +177,7 @@ struct alignas(16) StrPredDesc {
 };
 
 cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, const StrPredDesc& pred,
-                            uint32_t max_head_bytes, uint32_t max_unique, cudaStream_t s);
+                            uint32_t max_head_bytes, uint32_t max_unique, uint32_t max_meta_bytes, cudaStream_t s);
 
 // get()/filter() for byte-view entries: pass 1 (selected keys, decoded lengths, local offsets), host prefix
 // sums over the per-entry counts, pass 2 (decode, one warp per selected row).

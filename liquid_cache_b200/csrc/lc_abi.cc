@@ -155,17 +155,25 @@ void lc_release(lc_ctx* ctx, lc_handle h) {
   release_entry(ctx, entry_of(h));
 }
 
-uint64_t lc_len(lc_ctx*, lc_handle h) {
+// The three getters dereference the handle under the context lock, like every other call: a handle being released on
+// another thread is either still whole or already refused by entry_of's magic check.
+uint64_t lc_len(lc_ctx* ctx, lc_handle h) {
+  std::unique_lock<std::mutex> g;
+  if (ctx) g = std::unique_lock<std::mutex>(ctx->mu);
   Entry* e = entry_of(h);
   return e ? e->n : 0;
 }
 
-uint64_t lc_memory_size(lc_ctx*, lc_handle h) {
+uint64_t lc_memory_size(lc_ctx* ctx, lc_handle h) {
+  std::unique_lock<std::mutex> g;
+  if (ctx) g = std::unique_lock<std::mutex>(ctx->mu);
   Entry* e = entry_of(h);
   return e ? e->blob_bytes : 0;
 }
 
-int32_t lc_data_type(lc_ctx*, lc_handle h) {
+int32_t lc_data_type(lc_ctx* ctx, lc_handle h) {
+  std::unique_lock<std::mutex> g;
+  if (ctx) g = std::unique_lock<std::mutex>(ctx->mu);
   Entry* e = entry_of(h);
   if (e && e->fixed_width) return LC_LIQUID_FIXED_LEN_BYTE_ARRAY;  // a byte-view blob inside, LiquidFixedLenByteArray outside
   return e ? e->liquid_type : 0;
@@ -558,6 +566,21 @@ int lc_cache_handles(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, lc_hand
     }
     out[i] = it->second;
   }
+  return LC_OK;
+}
+
+int lc_cache_retain(lc_ctx* ctx, uint64_t entry_id, lc_handle* out) {
+  if (!ctx || !out) return LC_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->cache.find(entry_id);
+  if (it == ctx->cache.end()) {
+    set_error("entry %llu not cached", (unsigned long long)entry_id);
+    return LC_ERR_NOT_FOUND;
+  }
+  Entry* e = entry_of(it->second);
+  if (!e) return LC_ERR_INVALID;
+  e->refcount++;
+  *out = it->second;
   return LC_OK;
 }
 

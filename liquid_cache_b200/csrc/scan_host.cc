@@ -275,7 +275,7 @@ struct RefList {
   uint64_t key = 0;
   uint64_t n = 0;
   EntryRef* d_refs = nullptr;
-  uint32_t max_blob = 0, max_head = 0, max_head_like = 0, max_unique = 1;
+  uint32_t max_blob = 0, max_head = 0, max_head_like = 0, max_unique = 1, max_meta = 0;  // max_meta: header .. offset residuals
   uint64_t epoch = 0;
   uint64_t last_use = 0;
   // host-side facts about the list, gathered once when it is built so that the per-call loops walk plain arrays
@@ -366,6 +366,7 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
       nl.max_head = std::max(nl.max_head, e->sh.head_bytes);
       nl.max_head_like = std::max(nl.max_head_like, e->sh.head_bytes - (e->sh.rows_off - e->sh.prefix_keys_off));
       nl.max_unique = std::max(nl.max_unique, e->sh.n_unique);
+      nl.max_meta = std::max(nl.max_meta, e->sh.prefix_keys_off);
     }
     nl.max_blob = std::max(nl.max_blob, e->blob_bytes);
   }
@@ -813,7 +814,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
       LC_CUDA_OK(launch_int_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, ip, rl->max_blob, s));
     } else {
       LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, sl.desc,
-                                 like ? rl->max_head_like : rl->max_head, rl->max_unique, s));
+                                 like ? rl->max_head_like : rl->max_head, rl->max_unique, rl->max_meta, s));
     }
     ctx->kernel_launches++;
     if (n_chunks > 1) {
@@ -1002,7 +1003,7 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
     const bool like = (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
     if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
     LC_CUDA_OK(launch_str_scan(MODE_REFINE, static_cast<uint32_t>(n), io, sl.desc, like ? rl->max_head_like : rl->max_head,
-                               rl->max_unique, s));
+                               rl->max_unique, rl->max_meta, s));
   }
   if (ctx->timing_on) {
     cudaEventRecord(ctx->ev_b, s);

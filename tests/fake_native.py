@@ -342,6 +342,12 @@ class FakeLib:
                 C.c_uint64.from_address(_addr(out) + 8 * i).value = self.caches[int(ids_v[i])]
         return self._guard(run)
 
+    def lc_cache_retain(self, ctx, eid, out):
+        if int(eid) not in self.caches:
+            return -5
+        _set(out, self._new(self._entry(self.caches[int(eid)])))  # a second handle on the same entry: its own reference
+        return 0
+
     def lc_cache_get(self, ctx, eid, sel, sel_len, out_s, out_a):
         return self.lc_to_arrow(ctx, self.caches[int(eid)], sel, sel_len, out_s, out_a)
 
