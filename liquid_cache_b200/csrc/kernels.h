@@ -77,6 +77,12 @@ static_assert(sizeof(IntPackWork) == 96, "IntPackWork must be 96 bytes");
 
 cudaError_t launch_int_scan(int mode, uint32_t n_entries, const ScanIo& io, const IntPredDesc& pred,
                             uint32_t max_blob_bytes, cudaStream_t s);
+// Full-length integer predicates (REFINE, PRED over all rows) on lists whose entries all have fields of at most 32 bits:
+// register-resident FastLanes unpack, one warp per chunk (k_int_bits.cu). `io.counts`, if set, must be zeroed on the
+// stream before the launch; max_rows = rows of the longest entry of the list.
+cudaError_t launch_int_bits(int mode, uint32_t n_entries, const ScanIo& io, const IntPredDesc& pred, uint32_t max_rows,
+                            cudaStream_t s);
+
 cudaError_t launch_int_minmax(const IntMinMaxWork* d_works, uint32_t n_works, cudaStream_t s);
 cudaError_t launch_int_pack(const IntPackWork* d_works, uint32_t n_works, cudaStream_t s);
 

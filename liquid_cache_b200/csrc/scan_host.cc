@@ -276,6 +276,8 @@ struct RefList {
   uint64_t n = 0;
   EntryRef* d_refs = nullptr;
   uint32_t max_blob = 0, max_head = 0, max_head_like = 0, max_unique = 1, max_meta = 0;  // max_meta: header .. offset residuals
+  uint32_t max_rows = 0;
+  bool int_bits_ok = true;  // integer lists: every entry has fields of at most 32 bits (k_int_bits covers the list)
   uint64_t epoch = 0;
   uint64_t last_use = 0;
   // host-side facts about the list, gathered once when it is built so that the per-call loops walk plain arrays
@@ -342,6 +344,8 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
       return LC_ERR_INVALID;
     }
     (*nl.rows)[i] = e->n;
+    nl.max_rows = std::max(nl.max_rows, e->n);
+    if (!is_int_blob(e->liquid_type) || e->ih.bit_width > 32) nl.int_bits_ok = false;
     nl.any_fixed = nl.any_fixed || e->fixed_width != 0;
     if (e->liquid_type != proto->liquid_type) nl.same_liquid_type = false;
     if (e->arrow_format != proto->arrow_format || e->dict_value_format != proto->dict_value_format) nl.same_arrow_type = false;
@@ -801,6 +805,9 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
   }
   const bool like = !is_int && (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
+  // all rows of narrow integer entries: the register-resident kernel (its true-counts are added per chunk: zero them first)
+  const bool int_bits = is_int && rl->int_bits_ok && io.sel_base == nullptr;
+  if (int_bits) LC_CUDA_OK(cudaMemsetAsync(d_dn, 0, n * 16, s));
   if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
   for (int c = 0; c < n_chunks; ++c) {
     const uint64_t c0 = n * c / n_chunks, c1 = n * (c + 1) / n_chunks;
@@ -810,7 +817,9 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     ioc.out_off += c0;
     ioc.valid_off += c0;
     ioc.counts += c0 * io.counts_stride;
-    if (is_int) {
+    if (is_int && int_bits) {
+      LC_CUDA_OK(launch_int_bits(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, ip, rl->max_rows, s));
+    } else if (is_int) {
       LC_CUDA_OK(launch_int_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, ip, rl->max_blob, s));
     } else {
       LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, sl.desc,
@@ -983,8 +992,10 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
   io.counts_stride = 2;
   cudaStream_t s = ctx->stream;
   if (is_int) {
+    if (rl->int_bits_ok && d_counts) LC_CUDA_OK(cudaMemsetAsync(d_counts, 0, n * 8, s));  // k_int_bits adds per chunk
     if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
-    LC_CUDA_OK(launch_int_scan(MODE_REFINE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
+    if (rl->int_bits_ok) LC_CUDA_OK(launch_int_bits(MODE_REFINE, static_cast<uint32_t>(n), io, ip, rl->max_rows, s));
+    else LC_CUDA_OK(launch_int_scan(MODE_REFINE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
   } else {
     // the needle is the only thing that travels: a few bytes from pageable memory (the runtime stages such
     // copies before returning) into a small buffer the context keeps for this purpose
