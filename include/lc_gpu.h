@@ -148,6 +148,7 @@ typedef struct lc_stats {
   uint64_t kernel_launches;    /* our CUDA kernels launched since ctx creation       */
   uint64_t h2d_bytes;
   uint64_t d2h_bytes;
+  uint64_t hbm_bytes_reserved; /* what the arena holds from cudaMalloc (live entries + reusable holes): the figure the budget bounds */
 } lc_stats;
 
 /* ------------------------------------------------------------------ context ---- */

@@ -68,6 +68,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("hbm_bytes_reserved", C.c_uint64),
     ]
 
 

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -44,13 +45,17 @@ inline uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 // ---- HBM arena ---------------------------------------------------------------------------------
 // Entries are immutable blobs; the arena hands out 128-byte aligned ranges from large cudaMalloc'd
-// slabs (bump pointer + per-slab live count; a slab whose entries are all released is recycled).
+// slabs: bump pointer per slab, freed ranges kept as coalesced holes and reused first-fit (a range freed at the top of
+// a slab rolls the bump pointer back), so insert / replace / remove churn recycles HBM instead of growing the
+// reservation. `limit` caps the RESERVATION (what cudaMalloc has handed out), which is what with_max_memory_bytes bounds.
 class DeviceArena {
  public:
   ~DeviceArena();
-  // returns nullptr on cudaMalloc failure
+  // returns nullptr on cudaMalloc failure, or when a new slab would take the reservation past `limit` (0 = no limit)
   uint8_t* alloc(uint64_t bytes, uint32_t* slab_out);
-  void free(uint32_t slab, uint64_t bytes);
+  void free(uint32_t slab, uint8_t* p, uint64_t bytes);
+  void set_limit(uint64_t limit) { limit_ = limit; }
+  bool at_limit() const { return hit_limit_; }  // did the last failed alloc() stop at the limit (rather than at cudaMalloc)?
   void reset();
   uint64_t bytes_used() const { return used_; }
   uint64_t bytes_reserved() const { return reserved_; }
@@ -59,7 +64,10 @@ class DeviceArena {
   struct Slab {
     uint8_t* base = nullptr;
     uint64_t size = 0, bump = 0, live = 0;
+    std::map<uint64_t, uint64_t> holes;  // offset -> bytes, below `bump`, coalesced
   };
+  uint64_t limit_ = 0;
+  bool hit_limit_ = false;
   static constexpr uint64_t kSlabBytes = 256ull << 20;
   std::vector<Slab> slabs_;
   uint64_t used_ = 0, reserved_ = 0;

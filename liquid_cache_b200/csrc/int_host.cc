@@ -182,8 +182,8 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
   uint32_t slab = 0;
   uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
   if (!d_blob) {
-    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-    return LC_ERR_OOM;
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
 
   // ---- pass 2: subtract reference + FastLanes pack (+ header, validity) ----
@@ -294,7 +294,7 @@ int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<En
   std::vector<Taken> taken;
   taken.reserve(nb);
   auto give_back = [&]() {
-    for (const Taken& t : taken) ctx->arena.free(t.slab, t.bytes);
+    for (const Taken& t : taken) ctx->arena.free(t.slab, t.blob, t.bytes);
   };
   for (uint64_t i = 0; i < nb; ++i) {
     const ArrowIn& in = ins[i];
@@ -341,8 +341,8 @@ int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<En
     uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
     if (!d_blob) {
       give_back();
-      set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-      return LC_ERR_OOM;
+      set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+      return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
     }
     taken.push_back({d_blob, slab, blob_bytes});
     std::memset(&h_pw[i], 0, sizeof(IntPackWork));

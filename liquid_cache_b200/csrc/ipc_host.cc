@@ -349,9 +349,9 @@ static int str_entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, con
   const uint64_t tmp_bytes = 64ull + kvals_len;
   uint8_t* d_tmp = n ? ctx->arena.alloc(tmp_bytes, &tslab) : nullptr;
   if (!d_blob || (n && !d_tmp)) {
-    if (d_blob) ctx->arena.free(slab, o);
-    set_error("HBM arena: cudaMalloc failed");
-    return LC_ERR_OOM;
+    if (d_blob) ctx->arena.free(slab, d_blob, o);
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget" : "HBM arena: cudaMalloc failed");
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   cudaStream_t s = ctx->stream;
   std::memset(h_stage, 0, stage_bytes);
@@ -411,8 +411,8 @@ static int str_entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, con
     d_tmp = nullptr;
   }
   if (rc != LC_OK) {
-    ctx->arena.free(slab, o);
-    if (d_tmp) ctx->arena.free(tslab, tmp_bytes);
+    ctx->arena.free(slab, d_blob, o);
+    if (d_tmp) ctx->arena.free(tslab, d_tmp, tmp_bytes);
     return rc;
   }
   ctx->h2d_bytes += o;
@@ -562,8 +562,8 @@ int entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, const std::sha
   uint32_t slab = 0;
   uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
   if (!d_blob) {
-    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-    return LC_ERR_OOM;
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   std::memset(h_head, 0, head_bytes);
   std::memcpy(h_head, &h, sizeof(h));
@@ -588,7 +588,7 @@ int entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, const std::sha
   }
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess || *h_flag) {
-    ctx->arena.free(slab, blob_bytes);
+    ctx->arena.free(slab, d_blob, blob_bytes);
     if (ce != cudaSuccess) {
       set_error("CUDA error in from_bytes: %s", cudaGetErrorString(ce));
       return LC_ERR_CUDA;

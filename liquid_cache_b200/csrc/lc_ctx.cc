@@ -59,12 +59,27 @@ DeviceArena::~DeviceArena() {
 }
 
 uint8_t* DeviceArena::alloc(uint64_t bytes, uint32_t* slab_out) {
-  bytes = round_up(bytes, 128);
-  // first fit among existing slabs (recycle empty ones)
+  bytes = round_up(bytes ? bytes : 1, 128);
+  hit_limit_ = false;
+  // 1. first fit among the holes left by released entries
   for (uint32_t i = 0; i < slabs_.size(); ++i) {
     Slab& s = slabs_[i];
     if (!s.base) continue;
-    if (s.live == 0) s.bump = 0;
+    for (auto it = s.holes.begin(); it != s.holes.end(); ++it) {
+      if (it->second < bytes) continue;
+      const uint64_t off = it->first, rest = it->second - bytes;
+      s.holes.erase(it);
+      if (rest) s.holes.emplace(off + bytes, rest);
+      s.live += bytes;
+      used_ += bytes;
+      *slab_out = i;
+      return s.base + off;
+    }
+  }
+  // 2. bump inside an existing slab
+  for (uint32_t i = 0; i < slabs_.size(); ++i) {
+    Slab& s = slabs_[i];
+    if (!s.base) continue;
     if (s.bump + bytes <= s.size) {
       uint8_t* p = s.base + s.bump;
       s.bump += bytes;
@@ -74,8 +89,16 @@ uint8_t* DeviceArena::alloc(uint64_t bytes, uint32_t* slab_out) {
       return p;
     }
   }
+  // 3. a new slab, as long as the reservation stays within the limit
   Slab s;
   s.size = bytes > kSlabBytes ? bytes : kSlabBytes;
+  if (limit_ && reserved_ + s.size > limit_) {
+    if (reserved_ + bytes > limit_) {  // the reservation is what the budget bounds
+      hit_limit_ = true;
+      return nullptr;
+    }
+    s.size = limit_ - reserved_;                       // the last slab takes what is left of it
+  }
   if (cudaMalloc(reinterpret_cast<void**>(&s.base), s.size) != cudaSuccess) {
     cudaGetLastError();
     // retry with an exact-size slab before giving up
@@ -102,23 +125,48 @@ uint8_t* DeviceArena::alloc(uint64_t bytes, uint32_t* slab_out) {
   return s.base;
 }
 
-void DeviceArena::free(uint32_t slab, uint64_t bytes) {
-  bytes = round_up(bytes, 128);
-  if (slab >= slabs_.size()) return;
+void DeviceArena::free(uint32_t slab, uint8_t* p, uint64_t bytes) {
+  bytes = round_up(bytes ? bytes : 1, 128);
+  if (slab >= slabs_.size() || !p) return;
   Slab& s = slabs_[slab];
+  if (!s.base || p < s.base || p + bytes > s.base + s.size) return;
   s.live -= bytes;
   used_ -= bytes;
-  if (s.live == 0 && s.size != kSlabBytes) {  // odd-sized slab: give it back
-    cudaFree(s.base);
-    reserved_ -= s.size;
-    s = Slab();
+  if (s.live == 0) {
+    if (s.size != kSlabBytes) {  // odd-sized slab: give it back
+      cudaFree(s.base);
+      reserved_ -= s.size;
+      s = Slab();
+    } else {
+      s.bump = 0;
+      s.holes.clear();
+    }
+    return;
   }
+  uint64_t off = static_cast<uint64_t>(p - s.base), len = bytes;
+  // coalesce with the neighbours
+  auto next = s.holes.lower_bound(off);
+  if (next != s.holes.begin()) {
+    auto prev = std::prev(next);
+    if (prev->first + prev->second == off) {
+      off = prev->first;
+      len += prev->second;
+      s.holes.erase(prev);
+    }
+  }
+  if (next != s.holes.end() && off + len == next->first) {
+    len += next->second;
+    s.holes.erase(next);
+  }
+  if (off + len == s.bump) s.bump = off;  // the top of the slab: roll the bump pointer back
+  else s.holes.emplace(off, len);
 }
 
 void DeviceArena::reset() {
   for (auto& s : slabs_) {
     s.bump = 0;
     s.live = 0;
+    s.holes.clear();
   }
   used_ = 0;
 }
@@ -170,7 +218,7 @@ int Scratch::reserve(uint64_t d_bytes, uint64_t h_bytes) {
 void release_entry(lc_ctx* ctx, Entry* e) {
   if (!e) return;
   if (--e->refcount > 0) return;
-  if (e->d_blob) ctx->arena.free(e->slab, e->blob_bytes);
+  if (e->d_blob) ctx->arena.free(e->slab, e->d_blob, e->blob_bytes);
   ctx->epoch++;
   e->magic = 0;
   ctx->n_entries--;
@@ -214,6 +262,7 @@ int lc_ctx_create(int device_id, uint64_t hbm_budget_bytes, lc_ctx** out) {
   lc_ctx* ctx = new lc_ctx();
   ctx->device = device_id;
   ctx->budget = hbm_budget_bytes;
+  ctx->arena.set_limit(hbm_budget_bytes ? round_up(hbm_budget_bytes, 2ull << 20) : 0);
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
@@ -334,6 +383,7 @@ int lc_ctx_stats(lc_ctx* ctx, lc_stats* out) {
   out->kernel_launches = ctx->kernel_launches;
   out->h2d_bytes = ctx->h2d_bytes;
   out->d2h_bytes = ctx->d2h_bytes;
+  out->hbm_bytes_reserved = ctx->arena.bytes_reserved();
   return LC_OK;
 }
 

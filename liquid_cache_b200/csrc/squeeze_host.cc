@@ -93,7 +93,7 @@ struct ArenaWork {  // a work area borrowed from the arena, handed back on every
   uint64_t bytes = 0;
   ArenaWork(lc_ctx* c, uint64_t b) : ctx(c), bytes(b) { p = c->arena.alloc(b, &slab); }
   ~ArenaWork() {
-    if (p) ctx->arena.free(slab, bytes);
+    if (p) ctx->arena.free(slab, p, bytes);
   }
   ArenaWork(const ArenaWork&) = delete;
   ArenaWork& operator=(const ArenaWork&) = delete;
@@ -108,8 +108,8 @@ int squeeze_date_entry(lc_ctx* ctx, Entry* full, uint32_t field, lc_backing_read
   cudaStream_t s = ctx->stream;
   ArenaWork vals(ctx, round_up(static_cast<uint64_t>(n) * tb, 256) + 256), comp(ctx, round_up(static_cast<uint64_t>(n) * 4, 256) + 256);
   if (!vals.p || !comp.p) {
-    set_error("HBM arena: cudaMalloc failed for the squeeze work areas");
-    return LC_ERR_OOM;
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for the squeeze work areas" : "HBM arena: cudaMalloc failed for the squeeze work areas");
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   if (n) {
     uint64_t rows = 0, vbytes = 0, nulls = 0;
@@ -183,8 +183,8 @@ int squeeze_date_entry(lc_ctx* ctx, Entry* full, uint32_t field, lc_backing_read
   uint32_t slab = 0;
   uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
   if (!d_blob) {
-    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-    return LC_ERR_OOM;
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   std::memset(h_pw, 0, sizeof(*h_pw));
   h_pw->values = comp.p;
@@ -196,7 +196,7 @@ int squeeze_date_entry(lc_ctx* ctx, Entry* full, uint32_t field, lc_backing_read
   if (ce == cudaSuccess) ce = launch_int_pack(reinterpret_cast<const IntPackWork*>(d_pw), 1, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess) {
-    ctx->arena.free(slab, blob_bytes);
+    ctx->arena.free(slab, d_blob, blob_bytes);
     set_error("CUDA error in lc_squeeze: %s", cudaGetErrorString(ce));
     return LC_ERR_CUDA;
   }
@@ -277,15 +277,16 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
   uint32_t wslab = 0;
   uint8_t* d_vals = ctx->arena.alloc(work_bytes, &wslab);
   if (!d_vals) {
-    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)work_bytes);
-    return LC_ERR_OOM;
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)work_bytes);
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   struct Work {  // returned to the arena on every way out
     lc_ctx* ctx;
     uint32_t slab;
+    uint8_t* p;
     uint64_t bytes;
-    ~Work() { ctx->arena.free(slab, bytes); }
-  } work{ctx, wslab, work_bytes};
+    ~Work() { ctx->arena.free(slab, p, bytes); }
+  } work{ctx, wslab, d_vals, work_bytes};
   {
     uint64_t rows = 0, vbytes = 0, nulls = 0;
     DeviceOut dout{d_vals, static_cast<uint64_t>(n) * tb, nullptr, nullptr, &rows, &vbytes, &nulls};
@@ -348,8 +349,8 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
   uint32_t slab = 0;
   uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
   if (!d_blob) {
-    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-    return LC_ERR_OOM;
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   std::memset(h_pw, 0, sizeof(*h_pw));
   h_pw->values = d_vals;
@@ -361,7 +362,7 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
   if (ce == cudaSuccess) ce = launch_int_pack(reinterpret_cast<const IntPackWork*>(d_pw), 1, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess) {
-    ctx->arena.free(slab, blob_bytes);
+    ctx->arena.free(slab, d_blob, blob_bytes);
     set_error("CUDA error in lc_squeeze: %s", cudaGetErrorString(ce));
     return LC_ERR_CUDA;
   }
@@ -614,8 +615,8 @@ int squeezed_component_array(lc_ctx* ctx, Entry* sq, int32_t lossy, ArrowSchema*
   ArenaWork comp(ctx, round_up(static_cast<uint64_t>(n) * 4, 256) + 256), res(ctx, round_up(static_cast<uint64_t>(n) * out_tb, 256) + 256),
       val(ctx, round_up(vwords * 4, 256) + 256);
   if (!comp.p || !res.p || !val.p) {
-    set_error("HBM arena: cudaMalloc failed for the component work areas");
-    return LC_ERR_OOM;
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for the component work areas" : "HBM arena: cudaMalloc failed for the component work areas");
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   cudaStream_t s = ctx->stream;
   uint64_t rows = 0, vbytes = 0, nulls = 0;

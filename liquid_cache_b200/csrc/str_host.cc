@@ -459,8 +459,8 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   uint32_t slab = 0;
   uint8_t* d_blob = ctx->arena.alloc(o, &slab);
   if (!d_blob) {
-    set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
-    return LC_ERR_OOM;
+    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
+    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   // first valid row = unique 0 = where the shared prefix is read from
   uint32_t first_valid = 0;
@@ -580,7 +580,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
   };
   std::vector<Taken> taken;
   auto give_back = [&]() {
-    for (const Taken& t : taken) ctx->arena.free(t.slab, t.bytes);
+    for (const Taken& t : taken) ctx->arena.free(t.slab, t.blob, t.bytes);
     for (Entry* e : *out) delete e;
     out->clear();
   };
@@ -777,8 +777,8 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       uint8_t* d_blob = ctx->arena.alloc(o, &slab);
       if (!d_blob) {
         give_back();
-        set_error("HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
-        return LC_ERR_OOM;
+        set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
+        return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
       }
       taken.push_back({d_blob, slab, o});
       uint32_t first_valid = 0;

@@ -46,4 +46,4 @@ def test_struct_layouts_match_header():
     from liquid_cache_b200 import _native as N
 
     assert ctypes.sizeof(N.Predicate) == 40
-    assert ctypes.sizeof(N.Stats) == 48
+    assert ctypes.sizeof(N.Stats) == 56

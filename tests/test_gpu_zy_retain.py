@@ -44,3 +44,35 @@ def test_absent_entries_read_as_none():
         assert cache.eval_predicate(EntryID(1), _gt(0)).read() is None
     finally:
         cache.close()
+
+
+def test_churn_under_a_budget_recycles_hbm():
+    """with_max_memory_bytes bounds what the arena RESERVES: replacing and removing entries over and over reuses the freed
+    ranges instead of growing the reservation, and an insert that cannot fit reports CacheFull (cache/budget.rs:37-53)."""
+    import numpy as np
+
+    from liquid_cache_b200 import _native as N
+
+    budget = 8 << 20
+    cache = LiquidCacheBuilder.new().with_max_memory_bytes(budget).build()
+    try:
+        rng = np.random.default_rng(3)
+        for round_ in range(40):
+            for i in range(24):
+                # 8192 x u64 at W = 64: ~64 KB per entry; 24 live entries ~1.6 MB, far below the budget
+                arr = pa.array(rng.integers(0, 1 << 63, size=8192, dtype=np.int64), pa.int64())
+                cache.insert(EntryID(i), arr).run()
+            st = cache.stats()
+            assert st.hbm_bytes_used <= budget
+            assert st.hbm_bytes_reserved <= budget, (round_, st.hbm_bytes_reserved)
+        last = pa.array(rng.integers(0, 1 << 63, size=8192, dtype=np.int64), pa.int64())
+        cache.insert(EntryID(3), last).run()
+        assert cache.get(EntryID(3)).read().equals(last)
+        # fill up until the cache says it is full; the reservation never passes the budget
+        with pytest.raises(N.CacheFull):
+            for i in range(100, 400):
+                cache.insert(EntryID(i), pa.array(rng.integers(0, 1 << 63, size=8192, dtype=np.int64), pa.int64())).run()
+        assert cache.stats().hbm_bytes_reserved <= budget
+        assert cache.get(EntryID(3)).read().equals(last)
+    finally:
+        cache.close()
