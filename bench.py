@@ -180,7 +180,7 @@ def run_reference(args, rank: int, world: int):
         print(json.dumps({"impl": "reference", "unavailable": f"no CPU arm for workload {args.workload}"}))
         return
     name, dtype, metric, rows_cap = REFERENCE_WORKLOADS[args.workload]
-    threads = os.cpu_count() or 1
+    threads, _host = bench_cpu.usable_cpus()
     steps = max(1, args.steps)
     n = cpu_sample_entries(args, threads, max(1, min(args.rows, rows_cap) // ROWS_PER_ENTRY))
     params = {"url_like": lambda: None, "shipdate": shipdate_params, "int_filter": int_filter_params}[args.workload]()
@@ -575,7 +575,10 @@ def run_shipdate(args, rank, world, local_rank):
             "peak_source": peak_src, "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_shipdate(cpu_sample_entries(args, os.cpu_count() or 1, n_entries), os.cpu_count() or 1)
+            import bench_cpu
+
+            cpu_threads, _h = bench_cpu.usable_cpus()
+            line["cpu_baseline"] = cpu_baseline_shipdate(cpu_sample_entries(args, cpu_threads, n_entries), cpu_threads)
         print(json.dumps(line))
     scan.close()
     if world > 1:
@@ -857,7 +860,10 @@ def main():
             "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(cpu_sample_entries(args, os.cpu_count() or 1, n_entries), os.cpu_count() or 1)
+            import bench_cpu
+
+            cpu_threads, _h = bench_cpu.usable_cpus()
+            line["cpu_baseline"] = cpu_baseline(cpu_sample_entries(args, cpu_threads, n_entries), cpu_threads)
         print(json.dumps(line))
     scan.close()
     if world > 1:

@@ -25,6 +25,29 @@ def physical_cores() -> int:
         return os.cpu_count() or 1
 
 
+def usable_cpus() -> tuple[int, dict]:
+    """Threads the CPU arm should run: the logical CPUs this process may use, capped by the container's CPU quota
+    (cgroup v2 cpu.max / v1 cfs quota). Measured on the round-2 GPU box (profiles/r02_cpu_scaling_url_like.json): 128
+    logical CPUs visible, cpu.max = 16 CPUs — the port scales 15.8x on 16 threads and gets THROTTLED beyond (128 threads:
+    10x), so asking for more threads than the quota makes the baseline slower, not faster."""
+    logical = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    threads = logical if quota is None else max(1, min(logical, int(quota + 0.5)))
+    return threads, {"logical_cpus": logical, "cgroup_cpu_quota": quota, "threads_used": threads}
+
+
 def default_sample_entries(threads: int, cap: int) -> int:
     """>= 64 entries per thread per pass, bounded by the workload's own size."""
     return max(64, min(cap, max(8192, 64 * threads)))
@@ -121,9 +144,12 @@ class CpuArm:
 
     def describe(self, single: float, pooled: float) -> dict:
         phys = physical_cores()
-        return {"threads": self.threads, "threads_physical": phys, "single_thread_Mrows_per_s": single,
-                "threads_x_single": single * self.threads, "physical_x_single": single * phys,
-                "pooled_over_physical_x_single": pooled / (single * phys) if single else None,
+        _t, host = usable_cpus()
+        # the ceiling the pooled figure is checked against: what the process can actually get (quota), not what it can see
+        ceil_cores = min(self.threads, phys) if host["cgroup_cpu_quota"] is None else min(self.threads, host["cgroup_cpu_quota"])
+        return {"threads": self.threads, "threads_physical": phys, "host": host, "single_thread_Mrows_per_s": single,
+                "threads_x_single": single * self.threads, "usable_cores_x_single": single * ceil_cores,
+                "pooled_over_usable_cores_x_single": pooled / (single * ceil_cores) if single else None,
                 "entries_per_thread_per_pass": self.n / self.threads, "entries_per_pass": self.n,
                 "pool": "persistent pthreads created once outside the clock, entries handed out 4 at a time "
                         "(oracle/c/lc_oracle.c lco_pool_*)"}

@@ -12,9 +12,8 @@
 //   T = 32  thread = lane L, step s = row s                        -> W coalesced 4-byte loads (one 128-byte row each)
 //   T = 64  16 lanes: threads 0-15 take rows 0..31, threads 16-31 rows 32..63 of lane L = lane%16 (FL_ORDER[o+4] =
 //           FL_ORDER[o]+1 makes the two halves the low / high 16 bits of one word). Rows 0..31 are bits [0, 32W) of the
-//           lane's stream, rows 32..63 bits [32W, 64W): EXACTLY W 32-bit words each, fetched as ceil(W/2) 8-byte loads
-//           (128 contiguous bytes per half-warp); for odd W the upper half's stream starts in the high half of its first
-//           8-byte word, which is a one-register shift of the loaded array.
+//           lane's stream, rows 32..63 bits [32W, 64W): EXACTLY W 32-bit words each, one 4-byte load per word (a warp
+//           instruction covers the even or the odd words of two 128-byte lines; its pair fetches the other half from L1).
 //   T = 16  64 lanes: thread takes lanes `lane` and 32+lane (sub-lanes 0, 1), 16 rows each, step s = row s/2, sub s%2
 //   T = 8   128 lanes: four sub-lanes, 8 rows each, step s = row s/4, sub s%4
 // Every index below is a compile-time constant once the step loop is unrolled, so the stream lives in registers.
@@ -60,24 +59,21 @@ LC_BR_HD uint32_t breg_out_word(uint32_t s) {
 
 // Loader: ld8/ld16/ld32(byte offset) -> uint32_t, ld64(byte offset, &lo, &hi)
 template <uint32_t T, uint32_t W, typename Loader>
-LC_BR_HD void breg_load(uint32_t lane, uint32_t (&a)[BregGeom<T, W>::SUB][BregGeom<T, W>::NW + 1u], Loader ld) {
+LC_BR_HD void breg_load(uint32_t lane, uint32_t (&a)[BregGeom<T, W>::SUB][BregGeom<T, W>::NW], Loader ld) {
   using G = BregGeom<T, W>;
   if (T == 32) {
 LC_BR_UNROLL
     for (uint32_t k = 0; k < W; ++k) a[0][k] = ld.ld32(128u * k + 4u * lane);
-    a[0][G::NW] = 0;
   } else if (T == 64) {
-    constexpr uint32_t NQ = (W + 1u) / 2u;
+    // 32-bit word x of lane l sits at byte (x/2)*128 + (x%2)*4 + 8*l. The lower half-warp needs x = i, the upper x = W + i
+    // (i = 0..W-1): a constant byte distance for even W, and one of two constants (by the parity of i) for odd W — two
+    // per-thread bases make every load `[base + immediate]`.
+    constexpr uint32_t dE = (W % 2u == 0u) ? (W / 2u) * 128u : ((W - 1u) / 2u) * 128u + 4u;
+    constexpr uint32_t dO = (W % 2u == 0u) ? (W / 2u) * 128u : ((W + 1u) / 2u) * 128u - 4u;
     const uint32_t hh = lane >> 4, l = lane & 15u;
-    const uint32_t q0 = hh ? (W >> 1) : 0u;
-    uint32_t raw[2u * NQ + 1u];
+    const uint32_t base_e = 8u * l + (hh ? dE : 0u), base_o = 8u * l + (hh ? dO : 0u);
 LC_BR_UNROLL
-    for (uint32_t i = 0; i < NQ; ++i) ld.ld64(128u * (q0 + i) + 8u * l, &raw[2u * i], &raw[2u * i + 1u]);
-    raw[2u * NQ] = 0;
-    const bool shift = (W & 1u) && hh;
-LC_BR_UNROLL
-    for (uint32_t i = 0; i < W; ++i) a[0][i] = ((W & 1u) && shift) ? raw[i + 1u] : raw[i];
-    a[0][G::NW] = 0;
+    for (uint32_t i = 0; i < W; ++i) a[0][i] = ld.ld32(((i & 1u) ? base_o : base_e) + (i >> 1) * 128u + (i & 1u) * 4u);
   } else if (T == 16) {
 LC_BR_UNROLL
     for (uint32_t h = 0; h < 2u; ++h) {
@@ -87,7 +83,6 @@ LC_BR_UNROLL
         if (2u * i + 1u < W) v |= ld.ld16(128u * (2u * i + 1u) + 2u * (32u * h + lane)) << 16;
         a[h][i] = v;
       }
-      a[h][G::NW] = 0;
     }
   } else {
 LC_BR_UNROLL
@@ -100,21 +95,20 @@ LC_BR_UNROLL
           if (4u * i + b < W) v |= ld.ld8(128u * (4u * i + b) + (32u * h + lane)) << (8u * b);
         a[h][i] = v;
       }
-      a[h][G::NW] = 0;
     }
   }
 }
 
 // the packed value this thread holds at step s (s a compile-time constant in the unrolled loop)
 template <uint32_t T, uint32_t W>
-LC_BR_HD uint32_t breg_value(const uint32_t (&a)[BregGeom<T, W>::SUB][BregGeom<T, W>::NW + 1u], uint32_t s) {
+LC_BR_HD uint32_t breg_value(const uint32_t (&a)[BregGeom<T, W>::SUB][BregGeom<T, W>::NW], uint32_t s) {
   constexpr uint32_t mask32 = W >= 32u ? 0xffffffffu : ((1u << (W & 31u)) - 1u);
   const uint32_t h = T >= 32 ? 0u : (T == 16 ? (s & 1u) : (s & 3u));
   const uint32_t rr = T >= 32 ? s : (T == 16 ? (s >> 1) : (s >> 2));
   const uint32_t b = rr * W, k = b >> 5, sh = b & 31u;
   const uint32_t w0 = a[h][k];
   if (sh + W > 32u) {
-    const uint32_t w1 = a[h][k + 1u];
+    const uint32_t w1 = a[h][k + 1u < BregGeom<T, W>::NW ? k + 1u : k];  // a field that straddles never sits in the last word
 #ifdef __CUDA_ARCH__
     return __funnelshift_r(w0, w1, sh) & mask32;
 #else

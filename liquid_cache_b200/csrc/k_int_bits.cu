@@ -37,28 +37,75 @@ struct GlobalLoader {
   }
 };
 
-// the mask word of step == lane for one chunk: bit b = ((u_b - lo) <= span) of row 32 * out_word(lane) + b
+// chunks a warp keeps in flight for a W-bit field of a T-bit column: as many as fit ~40 registers of packed words
 template <uint32_t T, uint32_t W>
-__device__ __forceinline__ uint32_t bits_chunk(const uint8_t* chunk, uint32_t lane, uint32_t lo, uint32_t span) {
+__host__ __device__ constexpr uint32_t chunks_in_flight() {
+  constexpr uint32_t regs = BregGeom<T, W>::SUB * BregGeom<T, W>::NW;
+  return regs <= 10u ? 4u : (regs <= 20u ? 2u : 1u);
+}
+
+// One group of up to four chunks [c0, c1) of an entry: every chunk's mask word is finished (negation, validity,
+// selection, tail), stored, and its survivors counted. Returns the survivors of the group (per lane, to be summed).
+// A group that ends inside a CH-wide step (entries whose chunk count is not a multiple of CH) re-reads its last chunk
+// in the surplus slots and drops their words.
+template <uint32_t T, uint32_t W>
+__device__ __forceinline__ uint32_t bits_group(const uint8_t* packed, uint32_t c0, uint32_t c1, uint32_t lane, uint32_t ordl,
+                                               const URange<uint32_t>& g, uint32_t n, const uint32_t* sel, const uint32_t* valid,
+                                               uint32_t* out_bits, uint32_t* out_valid) {
+  constexpr uint32_t CH = chunks_in_flight<T, W>();
   using G = BregGeom<T, W>;
-  uint32_t a[G::SUB][G::NW + 1u];
-  breg_load<T, W>(lane, a, GlobalLoader{chunk});
-  uint32_t mine = 0;
+  const uint32_t n_words = (n + 31u) >> 5;
+  uint32_t survivors = 0;
+  for (uint32_t c = c0; c < c1; c += CH) {
+    // selection / validity words of the CH chunks: requested before the packed data, consumed after it
+    uint32_t sw[CH], vw[CH];
 #pragma unroll
-  for (uint32_t s = 0; s < 32; ++s) {
-    const uint32_t u = breg_value<T, W>(a, s);
-    const uint32_t cw = __ballot_sync(kFullMask, (u - lo) <= span);
-    if (lane == s) mine = cw;
+    for (uint32_t q = 0; q < CH; ++q) {
+      const uint32_t wi = (c + q) * 32u + ordl;
+      sw[q] = kFullMask;
+      vw[q] = kFullMask;
+      if (c + q < c1 && wi < n_words) {
+        if (sel) sw[q] = sel[wi];
+        if (valid) vw[q] = __ldg(valid + wi);
+      }
+    }
+    uint32_t a[CH][G::SUB][G::NW];
+#pragma unroll
+    for (uint32_t q = 0; q < CH; ++q) {
+      const uint32_t cq = c + q < c1 ? c + q : c1 - 1u;
+      breg_load<T, W>(lane, a[q], GlobalLoader{packed + static_cast<size_t>(cq) * (128u * W)});
+    }
+#pragma unroll
+    for (uint32_t q = 0; q < CH; ++q) {
+      uint32_t mine = 0;
+#pragma unroll
+      for (uint32_t s = 0; s < 32; ++s) {
+        const uint32_t u = breg_value<T, W>(a[q], s);
+        const uint32_t cw = __ballot_sync(kFullMask, (u - g.lo) <= g.span);
+        if (lane == s) mine = cw;
+      }
+      const uint32_t wi = (c + q) * 32u + ordl;
+      if (c + q < c1 && wi < n_words) {
+        uint32_t v = vw[q];
+        if (wi == n_words - 1u && (n & 31u)) v &= (1u << (n & 31u)) - 1u;  // rows past n in the padded last chunk
+        const uint32_t cw = (g.neg ? ~mine : mine) & v & sw[q];
+        out_bits[wi] = cw;
+        if (out_valid) out_valid[wi] = v;
+        survivors += __popc(cw);
+      }
+    }
   }
-  return mine;
+  return survivors;
 }
 
 template <uint32_t T>
-__device__ __forceinline__ uint32_t bits_chunk_w(uint32_t W, const uint8_t* chunk, uint32_t lane, uint32_t lo, uint32_t span) {
+__device__ __forceinline__ uint32_t bits_group_w(uint32_t W, const uint8_t* packed, uint32_t c0, uint32_t c1, uint32_t lane,
+                                                 uint32_t ordl, const URange<uint32_t>& g, uint32_t n, const uint32_t* sel,
+                                                 const uint32_t* valid, uint32_t* out_bits, uint32_t* out_valid) {
   switch (W) {
 #define LC_W(k) \
   case k:       \
-    if constexpr (k <= T) return bits_chunk<T, k>(chunk, lane, lo, span); \
+    if constexpr (k <= T) return bits_group<T, k>(packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); \
     break;
     LC_W(1) LC_W(2) LC_W(3) LC_W(4) LC_W(5) LC_W(6) LC_W(7) LC_W(8) LC_W(9) LC_W(10) LC_W(11) LC_W(12) LC_W(13) LC_W(14) LC_W(15) LC_W(16)
     LC_W(17) LC_W(18) LC_W(19) LC_W(20) LC_W(21) LC_W(22) LC_W(23) LC_W(24) LC_W(25) LC_W(26) LC_W(27) LC_W(28) LC_W(29) LC_W(30) LC_W(31) LC_W(32)
@@ -95,47 +142,42 @@ static_assert(offsetof(IntHeader, n) == 8 && offsetof(IntHeader, reference) == 1
                   offsetof(IntHeader, patch_val_off) == 56 && offsetof(IntHeader, squeeze_kind) == 60,
               "k_int_bits reads the header by word offset");
 
-// Tasks: (entry e, chunk c) = (t / cpe, t % cpe) for t = global warp id, + total warps, ...; cpe = chunks of the longest
-// entry of the list (8 for 8192-row batches), shorter entries simply have idle tasks. The 8 warps of a CTA take 8
-// consecutive tasks, i.e. normally the 8 chunks of ONE entry: its header is fetched from DRAM once and found in L1 after.
-template <int MODE>
-__global__ void __launch_bounds__(256, 4) k_int_bits(ScanIo io, IntPredDesc pred, uint32_t n_entries, uint32_t cpe) {
+// Tasks: (entry e, group g of four chunks) = (t >> gshift, t & (gpe - 1)) for t = global warp id, + total warps, ...;
+// gpe = groups of the longest entry of the list rounded up to a power of two (2 for 8192-row batches), shorter entries
+// have idle tasks. The warps of a CTA take consecutive tasks, i.e. the groups of neighbouring entries. Per task the
+// header is read once and the predicate planned once; the header of the warp's next task and the blob pointer of the
+// one after are already in flight (software pipeline in registers).
+__global__ void __launch_bounds__(256, 3) k_int_bits(ScanIo io, IntPredDesc pred, uint32_t n_entries, uint32_t gshift, int mode) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps_total = gridDim.x * 8u;
-  const uint32_t n_tasks = n_entries * cpe;
+  const uint32_t n_tasks = n_entries << gshift;
+  const uint32_t gmask = (1u << gshift) - 1u;
   uint32_t t = blockIdx.x * 8u + (threadIdx.x >> 5);
   if (t >= n_tasks) return;
-  // software pipeline: blob pointer two tasks ahead, header one task ahead
-  const uint8_t* blob0 = io.refs[t / cpe].blob;
+  const uint8_t* blob0 = io.refs[t >> gshift].blob;
   HdrRegs h0;
   load_hdr(blob0, h0);
-  const uint8_t* blob1 = (t + warps_total < n_tasks) ? io.refs[(t + warps_total) / cpe].blob : nullptr;
+  const uint8_t* blob1 = (t + warps_total < n_tasks) ? io.refs[(t + warps_total) >> gshift].blob : nullptr;
   for (; t < n_tasks; t += warps_total) {
-    const uint32_t e = t / cpe, c = t % cpe;
+    const uint32_t e = t >> gshift, grp = t & gmask;
     const uint32_t t1 = t + warps_total, t2 = t1 + warps_total;
     HdrRegs h1 = h0;
-    if (t1 < n_tasks) load_hdr(blob1, h1);                                         // arrives while this chunk is worked on
-    const uint8_t* blob2 = (t2 < n_tasks) ? io.refs[t2 / cpe].blob : nullptr;
+    if (t1 < n_tasks) load_hdr(blob1, h1);                                         // arrives while this group is worked on
+    const uint8_t* blob2 = (t2 < n_tasks) ? io.refs[t2 >> gshift].blob : nullptr;
 
     const uint32_t tbits = (h0.w1 >> 8) & 0xffu, W = (h0.w1 >> 16) & 0xffu, n = h0.n;
-    const uint32_t n_words = (n + 31u) >> 5, n_chunks = (n + 1023u) >> 10;
-    if (c < n_chunks) {
-      // per-entry io: broadcast loads, issued before the chunk's data so they overlap it
+    const uint32_t n_chunks = (n + 1023u) >> 10;
+    const uint32_t c0 = grp * 4u, c1 = c0 + 4u < n_chunks ? c0 + 4u : n_chunks;
+    if (c0 < n_chunks) {
       const uint32_t ordl = tbits >= 32u ? breg_out_word<32>(lane) : (tbits == 16u ? breg_out_word<16>(lane) : lane);
-      const uint32_t wi = c * 32u + ordl;
       const uint32_t* sel = nullptr;
       if (io.sel_base) {
         const uint64_t so = io.sel_off[e];
         if (so != kNoSel) sel = io.sel_base + so;
       }
       uint32_t* out_bits = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(io.out_base) + io.out_off[e] * 4u);
-      uint32_t* out_valid = (MODE == MODE_PRED && io.valid_base && (h0.w1 >> 24)) ? io.valid_base + io.valid_off[e] : nullptr;
+      uint32_t* out_valid = (mode == MODE_PRED && io.valid_base && (h0.w1 >> 24)) ? io.valid_base + io.valid_off[e] : nullptr;
       const uint32_t* valid = (h0.w1 >> 24) ? reinterpret_cast<const uint32_t*>(blob0 + h0.validity_off) : nullptr;
-      uint32_t sw = kFullMask, vw = kFullMask;
-      if (wi < n_words) {
-        if (sel) sw = sel[wi];
-        if (valid) vw = __ldg(valid + wi);
-      }
       // plan: (op, literal) in the packed domain of THIS entry (the same for all lanes)
       IntHeader hh{};
       hh.tbits = static_cast<uint8_t>(tbits);
@@ -149,33 +191,37 @@ __global__ void __launch_bounds__(256, 4) k_int_bits(ScanIo io, IntPredDesc pred
       uint64_t thr64 = 0;
       plan_int_pred(&hh, pred, &kind, &thr64);
       const URange<uint32_t> g = make_range<uint32_t>(kind, thr64);
-      uint32_t mine = 0;
-      if (W != 0u) {  // W == 0: entirely null, nothing packed (bit_pack_array.rs:18)
-        const uint8_t* chunk = blob0 + h0.packed_off + static_cast<size_t>(c) * (128u * W);
-        switch (tbits) {
-          case 8: mine = bits_chunk_w<8>(W, chunk, lane, g.lo, g.span); break;
-          case 16: mine = bits_chunk_w<16>(W, chunk, lane, g.lo, g.span); break;
-          case 32: mine = bits_chunk_w<32>(W, chunk, lane, g.lo, g.span); break;
-          default: mine = bits_chunk_w<64>(W, chunk, lane, g.lo, g.span); break;
-        }
-        if (g.neg) mine = ~mine;
-      }
       uint32_t survivors = 0;
-      if (wi < n_words) {
-        if (wi == n_words - 1u && (n & 31u)) vw &= (1u << (n & 31u)) - 1u;  // rows past n in the padded last chunk
-        const uint32_t cw = mine & vw & sw;
-        out_bits[wi] = cw;
-        if (out_valid) out_valid[wi] = vw;
-        survivors = __popc(cw);
+      if (W != 0u) {
+        const uint8_t* packed = blob0 + h0.packed_off;
+        switch (tbits) {
+          case 8: survivors = bits_group_w<8>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); break;
+          case 16: survivors = bits_group_w<16>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); break;
+          case 32: survivors = bits_group_w<32>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); break;
+          default: survivors = bits_group_w<64>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); break;
+        }
+      } else {  // W == 0: entirely null, nothing packed (bit_pack_array.rs:18): every mask bit is false
+        const uint32_t n_words = (n + 31u) >> 5;
+        for (uint32_t c = c0; c < c1; ++c) {
+          const uint32_t wi = c * 32u + lane;
+          if (wi < n_words) {
+            out_bits[wi] = 0;
+            if (out_valid) {
+              uint32_t v = valid ? __ldg(valid + wi) : kFullMask;
+              if (wi == n_words - 1u && (n & 31u)) v &= (1u << (n & 31u)) - 1u;
+              out_valid[wi] = v;
+            }
+          }
+        }
       }
       if (io.counts) {  // zeroed by the host before the launch
         survivors = warp_sum(survivors);
         uint32_t* cnt = io.counts + static_cast<size_t>(e) * io.counts_stride;
         if (lane == 0) {
-          if (MODE == MODE_REFINE) {
+          if (mode == MODE_REFINE) {
             if (survivors) atomicAdd(cnt, survivors);
           } else {
-            if (c == 0) {
+            if (grp == 0) {
               cnt[0] = n;
               cnt[1] = h0.null_count;
             }
@@ -202,21 +248,20 @@ cudaError_t launch_int_bits(int mode, uint32_t n_entries, const ScanIo& io, cons
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
   const uint32_t cpe = max_rows ? (max_rows + 1023u) / 1024u : 1u;
-  const uint64_t n_tasks = static_cast<uint64_t>(n_entries) * cpe;
-  if (n_tasks > 0xffffffffull) return cudaErrorInvalidValue;
-  static int per_sm[2] = {0, 0};
-  const int mi = mode == MODE_PRED ? 0 : 1;
-  if (!per_sm[mi]) {
-    cudaError_t e = mode == MODE_PRED ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[mi], k_int_bits<MODE_PRED>, 256, 0)
-                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[mi], k_int_bits<MODE_REFINE>, 256, 0);
+  uint32_t gshift = 0;
+  while ((4u << gshift) < cpe) ++gshift;  // groups of four chunks per entry, a power of two
+  const uint64_t n_tasks = static_cast<uint64_t>(n_entries) << gshift;
+  if (n_tasks > 0x7fffffffull) return cudaErrorInvalidValue;
+  static int per_sm = 0;
+  if (!per_sm) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_int_bits, 256, 0);
     if (e != cudaSuccess) return e;
-    if (per_sm[mi] < 1) per_sm[mi] = 1;
+    if (per_sm < 1) per_sm = 1;
   }
-  uint32_t grid = static_cast<uint32_t>(n_sm * per_sm[mi]);  // persistent: every resident warp loops over the tasks
+  uint32_t grid = static_cast<uint32_t>(n_sm * per_sm);  // persistent: every resident warp loops over the tasks
   const uint32_t need = static_cast<uint32_t>((n_tasks + 7u) / 8u);
   if (grid > need) grid = need;
-  if (mode == MODE_PRED) k_int_bits<MODE_PRED><<<grid, 256, 0, s>>>(io, pred, n_entries, cpe);
-  else k_int_bits<MODE_REFINE><<<grid, 256, 0, s>>>(io, pred, n_entries, cpe);
+  k_int_bits<<<grid, 256, 0, s>>>(io, pred, n_entries, gshift, mode);
   return cudaGetLastError();
 }
 

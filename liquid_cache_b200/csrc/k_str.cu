@@ -816,100 +816,141 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words,
 // LIKE / NOT LIKE '%needle%' (needle <= 31 bytes) with full-length outputs: the streaming form of the scan.
 //
 // What an entry costs is decided by what its DICTIONARY says, not by its rows:
-//   gate     fingerprint (staged head) -> trigram filter (global, loaded only by lanes the fingerprint let through,
-//            one 32-byte sector each) -> the few survivors are walked on their FSST codes (like_candidates)
+//   gate     fingerprint -> trigram filter (loaded only by lanes the fingerprint let through, one 32-byte sector each)
+//            -> the few survivors are matched exactly on their FSST codes (Shift-And over the decoded bytes)
 //   result   no dictionary value matched  => every row is false: the mask words are written as zeros and the u16 keys
-//            are NEVER READ (the common case of a selective predicate: ~97 % of the batches of the bench column);
+//            are NEVER READ (the common case of a selective predicate);
 //            NOT LIKE with no match       => every valid selected row is true: validity AND selection, keys not read;
-//            otherwise                    => dictionary bits are broadcast through the keys (read from global, coalesced)
+//            otherwise                    => dictionary bits are broadcast through the keys (coalesced reads)
 // Results are the reference's (comparisons.rs:159-183, 325-347, 600-651) bit for bit: a row's answer is its dictionary
 // value's answer, and both shortcuts are that rule applied to a dictionary whose answers are all equal.
-// Persistent CTAs take CONTIGUOUS runs of entries (neighbours share the column chunk's symbol table, so the Shift-And
-// step table is rebuilt once per row group, and only when an entry has a candidate at all) and keep the NEXT entry's head
-// (header, shared prefix, fingerprints, offset residuals: ref.pk_off bytes) in flight by TMA while the current one is
-// gated; the per-entry io offsets are fetched one iteration ahead as in k_int_scan.
+//
+// One WARP per entry, no block-wide phase: an entry is a chain of short dependent steps (header -> gate loads -> a
+// handful of code walks -> 1 KB of output), and a CTA that takes them together waits at every barrier for its slowest
+// lane (ncu r02, the CTA-per-entry form: `No Eligible` 66 %, a third of all samples at the barrier behind the walk,
+// DRAM 31 %). Independent warps keep 8 x as many entries in flight per SM and a walking lane stalls only its own warp.
+// The CTA's warps take neighbouring entries (one column chunk = one FSST symbol table, read through L1), each
+// warp prefetches the next entry's header word and the blob pointer of the one after (registers), fingerprints and
+// trigram sets stream from global memory with coalesced / sector-sized loads, four stripes of 32 values in flight.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t like_io_word(const ScanIo& io, uint32_t e, uint32_t t) {
-  if (t == 0) return io.sel_base ? io.sel_off[e] : kNoSel;
-  if (t == 1) return io.out_base ? io.out_off[e] : 0ull;
-  return io.valid_base ? io.valid_off[e] : 0ull;
+constexpr uint32_t kLikeCandCap = 512;  // per-warp candidate list (u16); a full list is walked and reused
+
+static_assert(offsetof(StrHeader, n) == 8 && offsetof(StrHeader, n_unique) == 12 && offsetof(StrHeader, slope) == 16 &&
+                  offsetof(StrHeader, intercept) == 20 && offsetof(StrHeader, validity_off) == 28 &&
+                  offsetof(StrHeader, keys_off) == 32 && offsetof(StrHeader, fp_off) == 40 && offsetof(StrHeader, resid_off) == 44 &&
+                  offsetof(StrHeader, fsst_off) == 52 && offsetof(StrHeader, null_count) == 64 &&
+                  offsetof(StrHeader, table_ptr) == 80 && offsetof(StrHeader, bloom_off) == 100,
+              "k_str_like reads the header by word offset");
+
+// exact substring test of dictionary value i on its FSST codes: Shift-And over the decoded bytes (state bit j <=> needle[0..j]
+// matches the text ending here), symbols straight from the column chunk's table (L1-resident)
+__device__ __forceinline__ bool like_value(const uint8_t* blob, uint32_t hw_lo, uint32_t resid_off, int32_t slope, int32_t intercept,
+                                           uint32_t fsst_off, const FsstTable* tab, const uint32_t* s_M, uint32_t acc, uint32_t i) {
+  const uint32_t ob = hw_lo >> 24;  // offset_bytes
+  auto off = [&](uint32_t k) -> uint32_t {
+    int32_t r;
+    const uint8_t* rs = blob + resid_off;
+    if (ob == 1) r = reinterpret_cast<const int8_t*>(rs)[k];
+    else if (ob == 2) r = reinterpret_cast<const int16_t*>(rs)[k];
+    else r = reinterpret_cast<const int32_t*>(rs)[k];
+    return static_cast<uint32_t>(slope * static_cast<int32_t>(k) + intercept + r);
+  };
+  const uint32_t start = off(i), end = off(i + 1u);
+  uint32_t S = 0;
+  bool found = false;
+  decode_visit(blob + fsst_off, start, end, tab->symbols, tab->lens, [&](uint32_t b) -> bool {
+    S = ((S << 1) | 1u) & s_M[b];
+    if (S & acc) {
+      found = true;
+      return false;
+    }
+    return true;
+  });
+  return found;
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 4)
-k_str_like(ScanIo io, StrPredDesc pred, uint32_t meta_cap, uint32_t dict_words, uint32_t n_entries, uint32_t per_cta) {
+k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries, uint32_t per_cta) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
-  uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
-  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
-  uint32_t* s_M = reinterpret_cast<uint32_t*>(s_len + 256 + 32);
-  SymStep* s_step = reinterpret_cast<SymStep*>(s_M + 256);
-  uint8_t* s_nd = reinterpret_cast<uint8_t*>(s_step + 512);
-  uint32_t* s_dict = reinterpret_cast<uint32_t*>(s_nd + 32);
+  uint32_t* s_M = reinterpret_cast<uint32_t*>(smem_raw);  // [256]: bit j set iff needle[j] == b
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint32_t* s_dict = s_M + 256 + warp * (dict_words + kLikeCandCap / 2u);
   uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_dict + dict_words);
-  uint8_t* stage0 = reinterpret_cast<uint8_t*>(s_cand) + (((dict_words * 64u) + 127u) & ~127u);
-  stage0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage0) + 127u) & ~static_cast<uintptr_t>(127u));
+  const uint32_t m = pred.needle_len;
+  const bool neg = pred.op == LC_OP_NOT_LIKE;
+  {
+    const uint32_t b = threadIdx.x;  // 256 threads, 256 byte values
+    uint32_t bits = 0;
+    for (uint32_t j = 0; j < m; ++j) bits |= (pred.needle[j] == b ? 1u : 0u) << j;
+    s_M[b] = bits;
+  }
+  for (uint32_t i = lane; i < dict_words; i += 32u) s_dict[i] = 0;
+  __syncthreads();  // the only block-wide barrier of the kernel
+  const uint32_t acc = 1u << (m - 1u);
 
   const uint32_t e0 = blockIdx.x * per_cta;
   const uint32_t e_end = e0 + per_cta < n_entries ? e0 + per_cta : n_entries;
-  if (e0 >= e_end) return;
-  const uint32_t m = pred.needle_len;
-  const bool neg = pred.op == LC_OP_NOT_LIKE;
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = threadIdx.x >> 5;
-  // control words: misc[0] = passes of the REFERENCE gate (NOT LIKE's inversion rule), misc[1] = walk queue head,
-  // warp_tot[0] = candidates, counts[0] = survivors (only touched when rows are true)
-  EntryRef rnext{};  // thread 0: the CTA's next entry, loaded one iteration ahead
-  if (threadIdx.x == 0) {
-    mbar_init(&sm->bar[0], 1);
-    mbar_init(&sm->bar[1], 1);
-    fence_mbar_init();
-    const EntryRef r0 = io.refs[e0];
-    mbar_expect_tx(&sm->bar[0], r0.pk_off);
-    tma_bulk_g2s(stage0, r0.blob, r0.pk_off, &sm->bar[0]);
-    sm->ref_slot[0] = reinterpret_cast<uint64_t>(r0.blob);
-    if (e0 + 1u < e_end) rnext = io.refs[e0 + 1u];
-    sm->counts[0] = 0;
-    sm->misc[0] = 0;
-    sm->misc[1] = 0;
-    sm->warp_tot[0] = 0;
-  }
-  if (threadIdx.x < 3u) sm->io_slot[0][threadIdx.x] = like_io_word(io, e0, threadIdx.x);
-  if (threadIdx.x < m) s_nd[threadIdx.x] = pred.needle[threadIdx.x];
-  for (uint32_t i = threadIdx.x; i < dict_words; i += 256u) s_dict[i] = 0;
-  __syncthreads();
+  uint32_t e = e0 + warp;
+  if (e >= e_end) return;
+  // software pipeline: header word of the next entry, blob pointer of the one after
+  const uint8_t* blob0 = io.refs[e].blob;
+  uint32_t hw0 = __ldg(reinterpret_cast<const uint32_t*>(blob0) + lane);
+  const uint8_t* blob1 = (e + 8u < e_end) ? io.refs[e + 8u].blob : nullptr;
+  for (; e < e_end; e += 8u) {
+    uint32_t hw1 = hw0;
+    if (e + 8u < e_end) hw1 = __ldg(reinterpret_cast<const uint32_t*>(blob1) + lane);
+    const uint8_t* blob2 = (e + 16u < e_end) ? io.refs[e + 16u].blob : nullptr;
+    // per-entry io (broadcast loads, consumed after the gate)
+    const uint64_t so = io.sel_base ? io.sel_off[e] : kNoSel;
+    const uint64_t oo = io.out_off[e];
+    const uint64_t vo = (MODE == MODE_PRED && io.valid_base) ? io.valid_off[e] : 0ull;
 
-  uint64_t table_cache = 0;
-  uint32_t it = 0;
-  for (uint32_t e = e0; e < e_end; ++e, ++it) {
-    const uint32_t buf = it & 1u;
-    const bool more = e + 1u < e_end;
-    if (threadIdx.x == 0 && more) {  // stage[buf ^ 1] was released by the closing barrier of the previous round
-      mbar_expect_tx(&sm->bar[buf ^ 1u], rnext.pk_off);
-      tma_bulk_g2s(stage0 + (buf ^ 1u) * meta_cap, rnext.blob, rnext.pk_off, &sm->bar[buf ^ 1u]);
-      sm->ref_slot[buf ^ 1u] = reinterpret_cast<uint64_t>(rnext.blob);
-      if (e + 2u < e_end) rnext = io.refs[e + 2u];
-    }
-    uint64_t nx_io = 0;  // consumed at the bottom of the round
-    if (threadIdx.x < 3u && more) nx_io = like_io_word(io, e + 1u, threadIdx.x);
-    mbar_wait(&sm->bar[buf], (it >> 1) & 1u);
-    const uint8_t* head = stage0 + buf * meta_cap;
-    const uint8_t* blob = reinterpret_cast<const uint8_t*>(sm->ref_slot[buf]);
-    const StrHeader* h = reinterpret_cast<const StrHeader*>(head);
-    const uint32_t U = h->n_unique, n = h->n;
-    const uint32_t* fp = h->has_fp ? reinterpret_cast<const uint32_t*>(head + h->fp_off) : nullptr;
-    const unsigned long long* bloom =
-        h->bloom_off ? reinterpret_cast<const unsigned long long*>(blob + h->bloom_off) : nullptr;
+    const uint8_t* blob = blob0;
+    const uint32_t hw_lo = __shfl_sync(kFullMask, hw0, 1);  // arrow_type | has_nulls << 8 | has_fp << 16 | offset_bytes << 24
+    const uint32_t n = __shfl_sync(kFullMask, hw0, 2), U = __shfl_sync(kFullMask, hw0, 3);
+    const int32_t slope = static_cast<int32_t>(__shfl_sync(kFullMask, hw0, 4));
+    const int32_t intercept = static_cast<int32_t>(__shfl_sync(kFullMask, hw0, 5));
+    const uint32_t validity_off = __shfl_sync(kFullMask, hw0, 7), keys_off = __shfl_sync(kFullMask, hw0, 8);
+    const uint32_t fp_off = __shfl_sync(kFullMask, hw0, 10), resid_off = __shfl_sync(kFullMask, hw0, 11);
+    const uint32_t fsst_off = __shfl_sync(kFullMask, hw0, 13), null_count = __shfl_sync(kFullMask, hw0, 16);
+    const uint64_t table_ptr = static_cast<uint64_t>(__shfl_sync(kFullMask, hw0, 20)) |
+                               (static_cast<uint64_t>(__shfl_sync(kFullMask, hw0, 21)) << 32);
+    const uint32_t bloom_off = __shfl_sync(kFullMask, hw0, 25);
+    const bool has_nulls = (hw_lo >> 8) & 0xffu, has_fp = (hw_lo >> 16) & 0xffu;
+    const uint32_t* fp = has_fp ? reinterpret_cast<const uint32_t*>(blob + fp_off) : nullptr;
+    const unsigned long long* bloom = bloom_off ? reinterpret_cast<const unsigned long long*>(blob + bloom_off) : nullptr;
+    const FsstTable* tab = reinterpret_cast<const FsstTable*>(table_ptr);
 
-    // ---- gate: one decision per dictionary value; four stripes of 32 values in flight per warp ----
-    uint32_t ref_pass = 0;
-    for (uint32_t g0 = (threadIdx.x & ~31u); g0 < U; g0 += 1024u) {
+    // ---- gate + walk ----
+    uint32_t ncand = 0, n_ref = 0, walked = 0;
+    unsigned long long walked_bytes = 0;
+    bool any = false;
+    auto walk = [&]() {  // match the listed candidates exactly; lanes take one value each
+      for (uint32_t c = lane; c < ncand; c += 32u) {
+        const uint32_t i = s_cand[c];
+        if (like_value(blob, hw_lo, resid_off, slope, intercept, fsst_off, tab, s_M, acc, i)) {
+          atomicOr(&s_dict[i >> 5], 1u << (i & 31u));
+          any = true;
+        }
+      }
+      walked += ncand;
+      ncand = 0;
+      __syncwarp();
+    };
+    for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
       ulonglong2 blo[4], bhi[4];
       bool ok[4];
+      uint32_t fpv[4];
 #pragma unroll
       for (uint32_t t = 0; t < 4; ++t) {
-        const uint32_t i = g0 + t * 256u + lane;
-        ok[t] = (i < U) && (fp ? ((fp[i] & pred.needle_fp) == pred.needle_fp) : true);
+        const uint32_t i = g0 + t * 32u + lane;
+        fpv[t] = (fp && i < U) ? __ldg(fp + i) : 0xffffffffu;
+      }
+#pragma unroll
+      for (uint32_t t = 0; t < 4; ++t) {
+        const uint32_t i = g0 + t * 32u + lane;
+        ok[t] = (i < U) && ((fpv[t] & pred.needle_fp) == pred.needle_fp);
         if (ok[t] && bloom) {  // one 32-byte sector per surviving value; lanes the fingerprint rejected fetch nothing
           const ulonglong2* src = reinterpret_cast<const ulonglong2*>(bloom + static_cast<size_t>(i) * kBloomWords);
           blo[t] = __ldg(src);
@@ -921,102 +962,82 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t meta_cap, uint32_t dict_words, 
       }
 #pragma unroll
       for (uint32_t t = 0; t < 4; ++t) {
-        const uint32_t i0 = g0 + t * 256u;
+        const uint32_t i0 = g0 + t * 32u;
         if (i0 >= U) break;  // warp-uniform
         const bool cand = ok[t] && ((blo[t].x & pred.needle_bloom[0]) == pred.needle_bloom[0]) &&
                           ((blo[t].y & pred.needle_bloom[1]) == pred.needle_bloom[1]) &&
                           ((bhi[t].x & pred.needle_bloom[2]) == pred.needle_bloom[2]) &&
                           ((bhi[t].y & pred.needle_bloom[3]) == pred.needle_bloom[3]);
         const uint32_t cw = __ballot_sync(kFullMask, cand);
-        if (neg || pred.prof) ref_pass += __popc(__ballot_sync(kFullMask, ok[t]));
-        if (cw) {  // rare: one shared atomic per stripe that has a survivor at all
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(&sm->warp_tot[0], __popc(cw));
-          base = __shfl_sync(kFullMask, base, 0);
-          if (cand) s_cand[base + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i0 + lane);
+        if (neg || pred.prof) n_ref += __popc(__ballot_sync(kFullMask, ok[t]));
+        if (cw) {
+          if (ncand + 32u > kLikeCandCap) walk();
+          if (cand) s_cand[ncand + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i0 + lane);
+          ncand += __popc(cw);
+          __syncwarp();
         }
       }
     }
-    if ((neg || pred.prof) && lane == 0 && ref_pass) atomicAdd(&sm->misc[0], ref_pass);
-    __syncthreads();
-    const uint32_t ncand = sm->warp_tot[0];
-    const uint32_t n_ref = sm->misc[0];
-    StrView v = make_view(head, blob);
     if (pred.prof) {  // measurement aid, never on in a timed run
       unsigned long long bytes = 0;
-      for (uint32_t c = threadIdx.x; c < ncand; c += 256u)
+      const StrHeader* hg = reinterpret_cast<const StrHeader*>(blob);
+      for (uint32_t c = lane; c < ncand; c += 32u) {
+        StrView v{};
+        v.h = hg;
+        v.resid = blob + resid_off;
         bytes += dict_offset(v, s_cand[c] + 1u) - dict_offset(v, s_cand[c]);
-      if (bytes) atomicAdd(&pred.prof[2], bytes);
-      if (threadIdx.x == 0) {
-        atomicAdd(&pred.prof[0], static_cast<unsigned long long>(U));
-        atomicAdd(&pred.prof[1], static_cast<unsigned long long>(ncand));
-        atomicAdd(&pred.prof[12], static_cast<unsigned long long>(n_ref));
-        atomicAdd(&pred.prof[13], static_cast<unsigned long long>(h->prefix_keys_off));  // staged head bytes
       }
+      for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(kFullMask, bytes, d);
+      walked_bytes = bytes;
     }
-    // ---- walk the survivors' FSST codes (Shift-And over the codes, no decompression) ----
-    bool any = false;
-    if (ncand) {  // CTA-uniform
-      if (h->table_ptr != table_cache) {
-        load_fsst_table(reinterpret_cast<const FsstTable*>(h->table_ptr), s_sym, s_len);
-        __syncthreads();
-        build_sym_steps(s_sym, s_len, s_nd, m, s_M, s_step);
-        __syncthreads();
-        table_cache = h->table_ptr;
-      }
-      const uint32_t walk_warps = ncand >= kCandPerWarp * kLikeWarps ? kLikeWarps : (ncand + kCandPerWarp - 1u) / kCandPerWarp;
-      if (warp < walk_warps) like_candidates(v, s_cand, ncand, &sm->misc[1], s_step, s_dict);
-      __syncthreads();
-      uint32_t mine = 0;
-      for (uint32_t i = threadIdx.x; i < ((U + 31u) >> 5); i += 256u) mine |= s_dict[i];
-      any = __syncthreads_or(mine != 0u) != 0;
+    if (ncand) walk();
+    any = __any_sync(kFullMask, any);
+    if (pred.prof && lane == 0) {
+      atomicAdd(&pred.prof[0], static_cast<unsigned long long>(U));
+      atomicAdd(&pred.prof[1], static_cast<unsigned long long>(walked));
+      atomicAdd(&pred.prof[2], walked_bytes);
+      atomicAdd(&pred.prof[12], static_cast<unsigned long long>(n_ref));
+      // what the reference's data for this predicate is besides the keys: header, fingerprints, all offset residuals
+      atomicAdd(&pred.prof[13], static_cast<unsigned long long>(128u + (has_fp ? 4u * U : 0u) + (hw_lo >> 24) * (U + 1u)));
+      if (any) atomicAdd(&pred.prof[3], 1ull);
     }
     // NOT LIKE inverts every dictionary answer — but, as in the reference, only inside apply_like_match_on_candidates,
     // i.e. only when the fingerprint gate let something through (comparisons.rs:166-180, 644-648). Without
     // fingerprints it is a plain negation.
-    const bool invert = neg && (fp == nullptr || n_ref != 0u);
+    const bool invert = neg && (!has_fp || n_ref != 0u);
 
-    const EntryIo w = [&] {
-      EntryIo r;
-      const uint64_t so = sm->io_slot[buf][0];
-      r.sel = (io.sel_base && so != kNoSel) ? io.sel_base + so : nullptr;
-      r.out = io.out_base ? static_cast<uint8_t*>(io.out_base) + sm->io_slot[buf][1] * 4u : nullptr;
-      r.out_valid = io.valid_base ? io.valid_base + sm->io_slot[buf][2] : nullptr;
-      r.counts = io.counts ? io.counts + static_cast<size_t>(e) * io.counts_stride : nullptr;
-      return r;
-    }();
+    const uint32_t* sel = (io.sel_base && so != kNoSel) ? io.sel_base + so : nullptr;
+    uint32_t* out_bits = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(io.out_base) + oo * 4u);
+    const uint32_t* valid = has_nulls ? reinterpret_cast<const uint32_t*>(blob + validity_off) : nullptr;
+    uint32_t* out_valid = (MODE == MODE_PRED && valid && io.valid_base) ? io.valid_base + vo : nullptr;
     const uint32_t n_words = (n + 31u) >> 5, tail = n & 31u;
-    uint32_t* out_bits = reinterpret_cast<uint32_t*>(w.out);
-    const uint32_t* valid = h->has_nulls ? reinterpret_cast<const uint32_t*>(blob + h->validity_off) : nullptr;
-    uint32_t* out_valid = (MODE == MODE_PRED && valid) ? w.out_valid : nullptr;
     uint32_t survivors = 0;
     if (!any) {
       // every dictionary value has the same answer: the rows need no keys
       const bool all_true = invert;
-      for (uint32_t wi = threadIdx.x; wi < n_words; wi += 256u) {
+      for (uint32_t wi = lane; wi < n_words; wi += 32u) {
         uint32_t vw = kFullMask;
         if (all_true || out_valid) {
-          vw = valid ? valid[wi] : kFullMask;
+          vw = valid ? __ldg(valid + wi) : kFullMask;
           if (wi == n_words - 1u && tail) vw &= (1u << tail) - 1u;
         }
         uint32_t cw = 0;
-        if (all_true) cw = vw & (w.sel ? w.sel[wi] : kFullMask);
+        if (all_true) cw = vw & (sel ? sel[wi] : kFullMask);
         out_bits[wi] = cw;
         if (out_valid) out_valid[wi] = vw;
         survivors += __popc(cw);
       }
     } else {
-      if (invert) {
-        for (uint32_t i = threadIdx.x; i < ((U + 31u) >> 5); i += 256u) s_dict[i] = ~s_dict[i];
-        __syncthreads();
-      }
-      if (pred.prof && threadIdx.x == 0) atomicAdd(&pred.prof[3], 1ull);
-      const uint16_t* keys = reinterpret_cast<const uint16_t*>(blob + h->keys_off);
+      const uint32_t flip = invert ? kFullMask : 0u;
+      const uint16_t* keys = reinterpret_cast<const uint16_t*>(blob + keys_off);
       const uint32_t n_chunks = (n + 1023u) >> 10;
-      for (uint32_t c = warp; c < n_chunks; c += 8u) {
+      for (uint32_t c = 0; c < n_chunks; ++c) {
         const uint32_t wi = c * 32u + lane;
-        uint32_t sw = kFullMask;
-        if (w.sel && wi < n_words) sw = w.sel[wi];
+        uint32_t sw = kFullMask, vw = kFullMask;
+        if (wi < n_words) {
+          if (sel) sw = sel[wi];
+          if (valid) vw = __ldg(valid + wi);
+        }
         uint32_t mine = 0;
         const uint32_t row0 = c * 1024u + lane;
         const bool full = (c + 1u) * 1024u <= n;
@@ -1025,55 +1046,41 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t meta_cap, uint32_t dict_words, 
           const uint32_t row = row0 + j * 32u;
           const uint32_t k = (full || row < n) ? __ldg(keys + row) : 0u;
           const uint32_t cw = __ballot_sync(kFullMask, (s_dict[k >> 5] >> (k & 31u)) & 1u);
-          if (static_cast<uint32_t>(lane) == j) mine = cw;
+          if (lane == j) mine = cw;
         }
         if (wi < n_words) {
-          uint32_t vw = valid ? valid[wi] : kFullMask;
           if (wi == n_words - 1u && tail) vw &= (1u << tail) - 1u;
-          const uint32_t cw = mine & vw & sw;
+          const uint32_t cw = (mine ^ flip) & vw & sw;
           out_bits[wi] = cw;
           if (out_valid) out_valid[wi] = vw;
           survivors += __popc(cw);
         }
       }
+      __syncwarp();
+      for (uint32_t i = lane; i < ((U + 31u) >> 5); i += 32u) s_dict[i] = 0;  // the bits this entry set
+      __syncwarp();
     }
-    // counts: only entries with true rows need the block-wide sum
-    const bool maybe_true = any || invert;
-    if (w.counts) {
-      if (maybe_true) {
-        survivors = warp_sum(survivors);
-        if (lane == 0 && survivors) atomicAdd(&sm->counts[0], survivors);
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) {
-        const uint32_t tot = maybe_true ? sm->counts[0] : 0u;
+    if (io.counts) {
+      survivors = warp_sum(survivors);
+      if (lane == 0) {
+        uint32_t* cnt = io.counts + static_cast<size_t>(e) * io.counts_stride;
         if (MODE == MODE_REFINE) {
-          w.counts[0] = tot;
-          w.counts[1] = 0;
+          cnt[0] = survivors;
+          cnt[1] = 0;
         } else {
-          w.counts[0] = n;
-          w.counts[1] = h->null_count;
-          w.counts[2] = tot;
+          cnt[0] = n;
+          cnt[1] = null_count;
+          cnt[2] = survivors;
         }
       }
     }
-    // reset the control words and the dictionary bits this entry touched; hand the next entry its io offsets
-    if (ncand)
-      for (uint32_t i = threadIdx.x; i < ((U + 31u) >> 5); i += 256u) s_dict[i] = 0;
-    if (threadIdx.x == 0) {
-      sm->counts[0] = 0;
-      sm->misc[0] = 0;
-      sm->misc[1] = 0;
-      sm->warp_tot[0] = 0;
-    }
-    if (threadIdx.x < 3u) sm->io_slot[buf ^ 1u][threadIdx.x] = nx_io;
-    __syncthreads();
+    hw0 = hw1;
+    blob0 = blob1;
+    blob1 = blob2;
   }
 }
 
-static uint32_t str_like_smem(uint32_t dict_words, uint32_t meta_cap) {
-  return kScanFixedSmem + kStrScanTables + 32u + dict_words * 4u + (((dict_words * 64u) + 127u) & ~127u) + 128u + 2u * meta_cap;
-}
+static uint32_t str_like_smem(uint32_t dict_words) { return 1024u + 8u * (dict_words * 4u + kLikeCandCap * 2u); }
 
 static uint32_t str_scan_smem(uint32_t needle_len, uint32_t dict_words, uint32_t stage) {
   const uint32_t nd = (needle_len + 15u) & ~15u;
@@ -1098,9 +1105,8 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
   const bool like_op = pred.op == LC_OP_LIKE || pred.op == LC_OP_NOT_LIKE;
   const bool full_len = mode == MODE_REFINE || (mode == MODE_PRED && io.sel_base == nullptr);
   if (like_op && full_len && pred.needle_len >= 1u && pred.needle_len <= 31u && max_meta_bytes != 0u) {
-    const uint32_t meta_cap = (max_meta_bytes + 127u) & ~127u;
-    const uint32_t smem = str_like_smem(dict_words, meta_cap);
-    if (smem <= 110u * 1024u) {
+    const uint32_t smem = str_like_smem(dict_words);
+    if (smem <= 100u * 1024u) {
       static bool like_attr = false;
       if (!like_attr) {
         cudaError_t e = cudaFuncSetAttribute(k_str_like<MODE_PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -1109,14 +1115,18 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
         if (e != cudaSuccess) return e;
         like_attr = true;
       }
-      uint32_t per_sm = 4;
-      while (per_sm > 1u && per_sm * (smem + 1024u) > kMaxSmem) --per_sm;
-      uint32_t grid = static_cast<uint32_t>(n_sm) * per_sm;
-      if (grid > n_entries) grid = n_entries;
-      const uint32_t per_cta = (n_entries + grid - 1u) / grid;
+      int occ = 0;
+      cudaError_t e = mode == MODE_PRED ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_str_like<MODE_PRED>, 256, smem)
+                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_str_like<MODE_REFINE>, 256, smem);
+      if (e != cudaSuccess) return e;
+      if (occ < 1) occ = 1;
+      // every resident warp takes entries; a CTA's 8 warps share a run of neighbouring entries (same symbol table)
+      uint32_t grid = static_cast<uint32_t>(n_sm * occ);
+      uint32_t per_cta = (n_entries + grid - 1u) / grid;
+      per_cta = (per_cta + 7u) & ~7u;  // whole rounds of the CTA's 8 warps
       grid = (n_entries + per_cta - 1u) / per_cta;
-      if (mode == MODE_PRED) k_str_like<MODE_PRED><<<grid, 256, smem, s>>>(io, pred, meta_cap, dict_words, n_entries, per_cta);
-      else k_str_like<MODE_REFINE><<<grid, 256, smem, s>>>(io, pred, meta_cap, dict_words, n_entries, per_cta);
+      if (mode == MODE_PRED) k_str_like<MODE_PRED><<<grid, 256, smem, s>>>(io, pred, dict_words, n_entries, per_cta);
+      else k_str_like<MODE_REFINE><<<grid, 256, smem, s>>>(io, pred, dict_words, n_entries, per_cta);
       return cudaGetLastError();
     }
   }

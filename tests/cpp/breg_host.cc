@@ -29,7 +29,7 @@ template <uint32_t T, uint32_t W>
 void run(const uint8_t* chunk, uint32_t* values, uint32_t* out_word) {
   using G = lc::BregGeom<T, W>;
   for (uint32_t lane = 0; lane < 32; ++lane) {
-    uint32_t a[G::SUB][G::NW + 1u];
+    uint32_t a[G::SUB][G::NW];
     lc::breg_load<T, W>(lane, a, HostLoader{chunk});
     for (uint32_t s = 0; s < 32; ++s) values[s * 32 + lane] = lc::breg_value<T, W>(a, s);
   }
