@@ -32,9 +32,9 @@ constexpr uint64_t kPinnedMin = 1ull << 20;
 constexpr uint64_t kPinnedIdleMax = 2ull << 30;
 }  // namespace
 
-uint8_t* host_alloc(uint64_t bytes) {
-  if (bytes >= kPinnedMin) {
-    uint64_t cap = kPinnedMin;
+uint8_t* host_alloc(uint64_t bytes, bool force_pinned) {
+  if (bytes >= kPinnedMin || force_pinned) {
+    uint64_t cap = force_pinned ? 4096 : kPinnedMin;  // asynchronous downloads need a page-locked destination whatever its size
     while (cap < bytes) cap <<= 1;
     PinnedPool& pool = pinned_pool();
     {

@@ -202,7 +202,7 @@ struct HostBuf {  // 64-byte aligned host allocation
   uint8_t* p = nullptr;
   uint64_t bytes = 0;
 };
-uint8_t* host_alloc(uint64_t bytes);
+uint8_t* host_alloc(uint64_t bytes, bool force_pinned = false);  // force_pinned: a page-locked block even below 1 MiB
 void host_free(uint8_t* p);
 
 // Parsed view of an input array (borrowed pointers).
@@ -299,6 +299,22 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
 int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, const uint8_t* sel_bits, const PredOut& out);
 int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSchema* out_schema, ArrowArray* out_array);
 int squeezed_component_array(lc_ctx* ctx, Entry* sq, int32_t lossy, ArrowSchema* out_schema, ArrowArray* out_array);
+
+// Device-planned reads of a scan (scan_host.cc scan_read_fused): sizes of the previous read of the same scan (they size the
+// capacities and the speculative download of the next one) and the buffers kept between calls.
+constexpr int LC_INTERNAL_FALLBACK = 1001;
+struct FusedRead {
+  bool have_spec = false;
+  uint64_t spec_rows = 0, spec_bytes = 0, spec_ulen = 0;
+  uint8_t* d_buf = nullptr;
+  uint64_t d_cap = 0;
+  ScanPlanHdr* h_hdr = nullptr;  // pinned
+  uint64_t fused_reads = 0, fallbacks = 0;
+};
+int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t n, const uint32_t* d_sel, const uint64_t* d_word_off,
+                    const uint32_t* d_counts2, uint64_t total_rows_in, ArrowSchema* out_schema, ArrowArray* out_array);
+void fused_read_learn(FusedRead* fr, const ArrowArray* arr, int64_t value_bytes, uint64_t ulen_words);
+void fused_read_free(FusedRead* fr);
 
 int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predicate* pred, uint32_t* d_sel_base,
                  const uint64_t* d_word_off, bool all_rows, uint32_t* d_counts);

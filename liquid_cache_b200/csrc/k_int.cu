@@ -452,6 +452,7 @@ __global__ void __launch_bounds__(256, 4) k_int_scan(ScanIo io, IntPredDesc pred
   ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
   uint8_t* stage0 = smem_raw + kScanFixedSmem;
 
+  if (io.abort_flag && *io.abort_flag) return;  // device-planned read whose capacities were short (k_scan_plan.cu)
   const uint32_t G = gridDim.x;
   const bool staged = stage_bytes != 0;  // the host sizes the stage for the largest entry of the launch, or passes 0
   if (threadIdx.x == 0) {

@@ -51,13 +51,21 @@ __host__ __device__ constexpr uint32_t chunks_in_flight() {
 template <uint32_t T, uint32_t W>
 __device__ __forceinline__ uint32_t bits_group(const uint8_t* packed, uint32_t c0, uint32_t c1, uint32_t lane, uint32_t ordl,
                                                const URange<uint32_t>& g, uint32_t n, const uint32_t* sel, const uint32_t* valid,
-                                               uint32_t* out_bits, uint32_t* out_valid) {
+                                               uint32_t* out_bits, uint32_t* out_valid, uint32_t* strip) {
   constexpr uint32_t CH = chunks_in_flight<T, W>();
   using G = BregGeom<T, W>;
   const uint32_t n_words = (n + 31u) >> 5;
   uint32_t survivors = 0;
   for (uint32_t c = c0; c < c1; c += CH) {
-    // selection / validity words of the CH chunks: requested before the packed data, consumed after it
+    // the packed words of the CH chunks first: nothing they need is still in flight (the header came one task ahead) ...
+    uint32_t a[CH][G::SUB][G::NW];
+#pragma unroll
+    for (uint32_t q = 0; q < CH; ++q) {
+      const uint32_t cq = c + q < c1 ? c + q : c1 - 1u;
+      breg_load<T, W>(lane, a[q], GlobalLoader{packed + static_cast<size_t>(cq) * (128u * W)});
+    }
+    // ... then their selection / validity words (`sel` hangs off a per-entry offset that may itself still be arriving);
+    // both are consumed after the 32 steps
     uint32_t sw[CH], vw[CH];
 #pragma unroll
     for (uint32_t q = 0; q < CH; ++q) {
@@ -69,21 +77,19 @@ __device__ __forceinline__ uint32_t bits_group(const uint8_t* packed, uint32_t c
         if (valid) vw[q] = __ldg(valid + wi);
       }
     }
-    uint32_t a[CH][G::SUB][G::NW];
 #pragma unroll
     for (uint32_t q = 0; q < CH; ++q) {
-      const uint32_t cq = c + q < c1 ? c + q : c1 - 1u;
-      breg_load<T, W>(lane, a[q], GlobalLoader{packed + static_cast<size_t>(cq) * (128u * W)});
-    }
-#pragma unroll
-    for (uint32_t q = 0; q < CH; ++q) {
-      uint32_t mine = 0;
+      // step s's ballot is mask word out_word(s): lane 0 parks it in the warp's 32-word strip of shared memory and lane s
+      // picks it up afterwards (one predicated store per step instead of a compare + select per step in every lane)
 #pragma unroll
       for (uint32_t s = 0; s < 32; ++s) {
         const uint32_t u = breg_value<T, W>(a[q], s);
         const uint32_t cw = __ballot_sync(kFullMask, (u - g.lo) <= g.span);
-        if (lane == s) mine = cw;
+        if (lane == 0) strip[s] = cw;
       }
+      __syncwarp();
+      const uint32_t mine = strip[lane];
+      __syncwarp();
       const uint32_t wi = (c + q) * 32u + ordl;
       if (c + q < c1 && wi < n_words) {
         uint32_t v = vw[q];
@@ -101,11 +107,11 @@ __device__ __forceinline__ uint32_t bits_group(const uint8_t* packed, uint32_t c
 template <uint32_t T>
 __device__ __forceinline__ uint32_t bits_group_w(uint32_t W, const uint8_t* packed, uint32_t c0, uint32_t c1, uint32_t lane,
                                                  uint32_t ordl, const URange<uint32_t>& g, uint32_t n, const uint32_t* sel,
-                                                 const uint32_t* valid, uint32_t* out_bits, uint32_t* out_valid) {
+                                                 const uint32_t* valid, uint32_t* out_bits, uint32_t* out_valid, uint32_t* strip) {
   switch (W) {
 #define LC_W(k) \
   case k:       \
-    if constexpr (k <= T) return bits_group<T, k>(packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); \
+    if constexpr (k <= T) return bits_group<T, k>(packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid, strip); \
     break;
     LC_W(1) LC_W(2) LC_W(3) LC_W(4) LC_W(5) LC_W(6) LC_W(7) LC_W(8) LC_W(9) LC_W(10) LC_W(11) LC_W(12) LC_W(13) LC_W(14) LC_W(15) LC_W(16)
     LC_W(17) LC_W(18) LC_W(19) LC_W(20) LC_W(21) LC_W(22) LC_W(23) LC_W(24) LC_W(25) LC_W(26) LC_W(27) LC_W(28) LC_W(29) LC_W(30) LC_W(31) LC_W(32)
@@ -148,7 +154,9 @@ static_assert(offsetof(IntHeader, n) == 8 && offsetof(IntHeader, reference) == 1
 // header is read once and the predicate planned once; the header of the warp's next task and the blob pointer of the
 // one after are already in flight (software pipeline in registers).
 __global__ void __launch_bounds__(256, 3) k_int_bits(ScanIo io, IntPredDesc pred, uint32_t n_entries, uint32_t gshift, int mode) {
+  __shared__ uint32_t s_strip[8][32];  // per warp: the 32 ballots of a chunk, transposed through shared memory
   const uint32_t lane = threadIdx.x & 31u;
+  uint32_t* strip = s_strip[threadIdx.x >> 5];
   const uint32_t warps_total = gridDim.x * 8u;
   const uint32_t n_tasks = n_entries << gshift;
   const uint32_t gmask = (1u << gshift) - 1u;
@@ -195,10 +203,10 @@ __global__ void __launch_bounds__(256, 3) k_int_bits(ScanIo io, IntPredDesc pred
       if (W != 0u) {
         const uint8_t* packed = blob0 + h0.packed_off;
         switch (tbits) {
-          case 8: survivors = bits_group_w<8>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); break;
-          case 16: survivors = bits_group_w<16>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); break;
-          case 32: survivors = bits_group_w<32>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); break;
-          default: survivors = bits_group_w<64>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid); break;
+          case 8: survivors = bits_group_w<8>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid, strip); break;
+          case 16: survivors = bits_group_w<16>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid, strip); break;
+          case 32: survivors = bits_group_w<32>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid, strip); break;
+          default: survivors = bits_group_w<64>(W, packed, c0, c1, lane, ordl, g, n, sel, valid, out_bits, out_valid, strip); break;
         }
       } else {  // W == 0: entirely null, nothing packed (bit_pack_array.rs:18): every mask bit is false
         const uint32_t n_words = (n + 31u) >> 5;

@@ -842,52 +842,51 @@ static_assert(offsetof(StrHeader, n) == 8 && offsetof(StrHeader, n_unique) == 12
                   offsetof(StrHeader, table_ptr) == 80 && offsetof(StrHeader, bloom_off) == 100,
               "k_str_like reads the header by word offset");
 
-// exact substring test of dictionary value i on its FSST codes: Shift-And over the decoded bytes (state bit j <=> needle[0..j]
-// matches the text ending here), symbols straight from the column chunk's table (L1-resident)
-__device__ __forceinline__ bool like_value(const uint8_t* blob, uint32_t hw_lo, uint32_t resid_off, int32_t slope, int32_t intercept,
-                                           uint32_t fsst_off, const FsstTable* tab, const uint32_t* s_M, uint32_t acc, uint32_t i) {
-  const uint32_t ob = hw_lo >> 24;  // offset_bytes
-  auto off = [&](uint32_t k) -> uint32_t {
-    int32_t r;
-    const uint8_t* rs = blob + resid_off;
-    if (ob == 1) r = reinterpret_cast<const int8_t*>(rs)[k];
-    else if (ob == 2) r = reinterpret_cast<const int16_t*>(rs)[k];
-    else r = reinterpret_cast<const int32_t*>(rs)[k];
-    return static_cast<uint32_t>(slope * static_cast<int32_t>(k) + intercept + r);
-  };
-  const uint32_t start = off(i), end = off(i + 1u);
-  uint32_t S = 0;
-  bool found = false;
-  decode_visit(blob + fsst_off, start, end, tab->symbols, tab->lens, [&](uint32_t b) -> bool {
-    S = ((S << 1) | 1u) & s_M[b];
-    if (S & acc) {
-      found = true;
-      return false;
-    }
-    return true;
-  });
-  return found;
+// The needle's Shift-And step table for each FSST symbol table of the list, written to global memory once per launch:
+// the walk of a candidate then costs one 16-byte (L1-resident) load and ~6 ALU ops per FSST code instead of ~25
+// instructions per decoded byte.
+__global__ void __launch_bounds__(256) k_like_steps(const uint64_t* __restrict__ tables, StrPredDesc pred, SymStep* __restrict__ out) {
+  __shared__ uint64_t s_sym[256];
+  __shared__ __align__(16) uint8_t s_len[256];
+  __shared__ uint32_t s_M[256];
+  __shared__ SymStep s_step[512];
+  __shared__ uint8_t s_nd[32];
+  if (threadIdx.x < pred.needle_len) s_nd[threadIdx.x] = pred.needle[threadIdx.x];
+  load_fsst_table(reinterpret_cast<const FsstTable*>(tables[blockIdx.x]), s_sym, s_len);
+  __syncthreads();
+  build_sym_steps(s_sym, s_len, s_nd, pred.needle_len, s_M, s_step);
+  __syncthreads();
+  SymStep* dst = out + static_cast<size_t>(blockIdx.x) * 512u;
+  for (uint32_t c = threadIdx.x; c < 512u; c += 256u) dst[c] = s_step[c];
+}
+
+cudaError_t launch_like_steps(const uint64_t* d_tables, uint32_t n_tables, const StrPredDesc& pred, void* d_steps, cudaStream_t s) {
+  if (n_tables == 0) return cudaSuccess;
+  k_like_steps<<<n_tables, 256, 0, s>>>(d_tables, pred, static_cast<SymStep*>(d_steps));
+  return cudaGetLastError();
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 4)
 k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries, uint32_t per_cta) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint32_t* s_M = reinterpret_cast<uint32_t*>(smem_raw);  // [256]: bit j set iff needle[j] == b
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  uint32_t* s_dict = s_M + 256 + warp * (dict_words + kLikeCandCap / 2u);
+  // per warp: walk queue head (4 words) | dictionary answer bits | candidate list
+  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem_raw) + warp * (4u + dict_words + kLikeCandCap / 2u);
+  uint32_t* s_dict = s_queue + 4;
   uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_dict + dict_words);
-  const uint32_t m = pred.needle_len;
   const bool neg = pred.op == LC_OP_NOT_LIKE;
-  {
-    const uint32_t b = threadIdx.x;  // 256 threads, 256 byte values
-    uint32_t bits = 0;
-    for (uint32_t j = 0; j < m; ++j) bits |= (pred.needle[j] == b ? 1u : 0u) << j;
-    s_M[b] = bits;
-  }
+  const SymStep* steps_all = static_cast<const SymStep*>(pred.like_steps);
   for (uint32_t i = lane; i < dict_words; i += 32u) s_dict[i] = 0;
-  __syncthreads();  // the only block-wide barrier of the kernel
-  const uint32_t acc = 1u << (m - 1u);
+  if (lane == 0) s_queue[0] = 0;
+  __syncwarp();
+  // the 256 trigram bits of the needle as eight 32-bit words (a value passes when it has them all)
+  uint32_t nb[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    nb[2 * q] = static_cast<uint32_t>(pred.needle_bloom[q]);
+    nb[2 * q + 1] = static_cast<uint32_t>(pred.needle_bloom[q] >> 32);
+  }
 
   const uint32_t e0 = blockIdx.x * per_cta;
   const uint32_t e_end = e0 + per_cta < n_entries ? e0 + per_cta : n_entries;
@@ -920,21 +919,26 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
     const bool has_nulls = (hw_lo >> 8) & 0xffu, has_fp = (hw_lo >> 16) & 0xffu;
     const uint32_t* fp = has_fp ? reinterpret_cast<const uint32_t*>(blob + fp_off) : nullptr;
     const unsigned long long* bloom = bloom_off ? reinterpret_cast<const unsigned long long*>(blob + bloom_off) : nullptr;
-    const FsstTable* tab = reinterpret_cast<const FsstTable*>(table_ptr);
+    (void)table_ptr;
+    (void)slope;
+    (void)intercept;
+    const SymStep* steps = steps_all + static_cast<size_t>(pred.entry_table[e]) * 512u;
+    StrView v{};  // what the walk needs: header (slope / intercept / residual width), residuals, compressed values
+    v.h = reinterpret_cast<const StrHeader*>(blob);
+    v.resid = blob + resid_off;
+    v.fsst = blob + fsst_off;
 
     // ---- gate + walk ----
     uint32_t ncand = 0, n_ref = 0, walked = 0;
     unsigned long long walked_bytes = 0;
-    bool any = false;
-    auto walk = [&]() {  // match the listed candidates exactly; lanes take one value each
-      for (uint32_t c = lane; c < ncand; c += 32u) {
-        const uint32_t i = s_cand[c];
-        if (like_value(blob, hw_lo, resid_off, slope, intercept, fsst_off, tab, s_M, acc, i)) {
-          atomicOr(&s_dict[i >> 5], 1u << (i & 31u));
-          any = true;
-        }
-      }
+    bool walked_any = false;
+    auto walk = [&]() {  // match the listed candidates exactly on their FSST codes (Shift-And, one table step per code)
+      __syncwarp();
+      like_candidates(v, s_cand, ncand, s_queue, steps, s_dict);
+      __syncwarp();
+      if (lane == 0) s_queue[0] = 0;
       walked += ncand;
+      walked_any = true;
       ncand = 0;
       __syncwarp();
     };
@@ -964,10 +968,12 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
       for (uint32_t t = 0; t < 4; ++t) {
         const uint32_t i0 = g0 + t * 32u;
         if (i0 >= U) break;  // warp-uniform
-        const bool cand = ok[t] && ((blo[t].x & pred.needle_bloom[0]) == pred.needle_bloom[0]) &&
-                          ((blo[t].y & pred.needle_bloom[1]) == pred.needle_bloom[1]) &&
-                          ((bhi[t].x & pred.needle_bloom[2]) == pred.needle_bloom[2]) &&
-                          ((bhi[t].y & pred.needle_bloom[3]) == pred.needle_bloom[3]);
+        // needle bits the value lacks, over the eight words (one LOP3 each)
+        const uint32_t miss = (~static_cast<uint32_t>(blo[t].x) & nb[0]) | (~static_cast<uint32_t>(blo[t].x >> 32) & nb[1]) |
+                              (~static_cast<uint32_t>(blo[t].y) & nb[2]) | (~static_cast<uint32_t>(blo[t].y >> 32) & nb[3]) |
+                              (~static_cast<uint32_t>(bhi[t].x) & nb[4]) | (~static_cast<uint32_t>(bhi[t].x >> 32) & nb[5]) |
+                              (~static_cast<uint32_t>(bhi[t].y) & nb[6]) | (~static_cast<uint32_t>(bhi[t].y >> 32) & nb[7]);
+        const bool cand = ok[t] && miss == 0u;
         const uint32_t cw = __ballot_sync(kFullMask, cand);
         if (neg || pred.prof) n_ref += __popc(__ballot_sync(kFullMask, ok[t]));
         if (cw) {
@@ -980,18 +986,17 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
     }
     if (pred.prof) {  // measurement aid, never on in a timed run
       unsigned long long bytes = 0;
-      const StrHeader* hg = reinterpret_cast<const StrHeader*>(blob);
-      for (uint32_t c = lane; c < ncand; c += 32u) {
-        StrView v{};
-        v.h = hg;
-        v.resid = blob + resid_off;
-        bytes += dict_offset(v, s_cand[c] + 1u) - dict_offset(v, s_cand[c]);
-      }
+      for (uint32_t c = lane; c < ncand; c += 32u) bytes += dict_offset(v, s_cand[c] + 1u) - dict_offset(v, s_cand[c]);
       for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(kFullMask, bytes, d);
       walked_bytes = bytes;
     }
     if (ncand) walk();
-    any = __any_sync(kFullMask, any);
+    bool any = false;
+    if (walked_any) {  // did any candidate match? (the walk set its bit)
+      uint32_t acc_bits = 0;
+      for (uint32_t i = lane; i < ((U + 31u) >> 5); i += 32u) acc_bits |= s_dict[i];
+      any = __any_sync(kFullMask, acc_bits != 0u);
+    }
     if (pred.prof && lane == 0) {
       atomicAdd(&pred.prof[0], static_cast<unsigned long long>(U));
       atomicAdd(&pred.prof[1], static_cast<unsigned long long>(walked));
@@ -1080,7 +1085,7 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
   }
 }
 
-static uint32_t str_like_smem(uint32_t dict_words) { return 1024u + 8u * (dict_words * 4u + kLikeCandCap * 2u); }
+static uint32_t str_like_smem(uint32_t dict_words) { return 8u * (16u + dict_words * 4u + kLikeCandCap * 2u); }
 
 static uint32_t str_scan_smem(uint32_t needle_len, uint32_t dict_words, uint32_t stage) {
   const uint32_t nd = (needle_len + 15u) & ~15u;
@@ -1104,7 +1109,7 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
   // at least two CTAs per SM with both stage buffers
   const bool like_op = pred.op == LC_OP_LIKE || pred.op == LC_OP_NOT_LIKE;
   const bool full_len = mode == MODE_REFINE || (mode == MODE_PRED && io.sel_base == nullptr);
-  if (like_op && full_len && pred.needle_len >= 1u && pred.needle_len <= 31u && max_meta_bytes != 0u) {
+  if (like_op && full_len && pred.needle_len >= 1u && pred.needle_len <= 31u && max_meta_bytes != 0u && pred.like_steps) {
     const uint32_t smem = str_like_smem(dict_words);
     if (smem <= 100u * 1024u) {
       static bool like_attr = false;
@@ -1120,11 +1125,12 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
                                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_str_like<MODE_REFINE>, 256, smem);
       if (e != cudaSuccess) return e;
       if (occ < 1) occ = 1;
-      // every resident warp takes entries; a CTA's 8 warps share a run of neighbouring entries (same symbol table)
-      uint32_t grid = static_cast<uint32_t>(n_sm * occ);
-      uint32_t per_cta = (n_entries + grid - 1u) / grid;
+      // A CTA's 8 warps share a run of neighbouring entries (same symbol table -> same step table in L1). Runs are short —
+      // about four waves of CTAs — so that the hardware's CTA scheduler evens out entries that cost more (walks, rows).
+      const uint32_t resident = static_cast<uint32_t>(n_sm * occ);
+      uint32_t per_cta = (n_entries + 4u * resident - 1u) / (4u * resident);
       per_cta = (per_cta + 7u) & ~7u;  // whole rounds of the CTA's 8 warps
-      grid = (n_entries + per_cta - 1u) / per_cta;
+      const uint32_t grid = (n_entries + per_cta - 1u) / per_cta;
       if (mode == MODE_PRED) k_str_like<MODE_PRED><<<grid, 256, smem, s>>>(io, pred, dict_words, n_entries, per_cta);
       else k_str_like<MODE_REFINE><<<grid, 256, smem, s>>>(io, pred, dict_words, n_entries, per_cta);
       return cudaGetLastError();
@@ -1162,6 +1168,7 @@ __global__ void __launch_bounds__(256) k_str_lengths(StrGatherIo g, uint32_t sta
   uint8_t* stage = s_len + 256;
 
   const uint32_t e = blockIdx.x;
+  if (g.k_hint && (g.k_hint[2u * e] == 0u || g.plan->overflow)) return;  // device-planned read: nothing selected here
   const EntryRef ref = g.io.refs[e];
   const EntryIo w = resolve_io(g.io, e);
   const bool staged = ref.head_bytes <= stage_cap;
@@ -1312,6 +1319,8 @@ __global__ void __launch_bounds__(256) k_str_decode(StrGatherIo g) {
   __shared__ uint64_t s_sym[256];
   __shared__ __align__(16) uint8_t s_len[256];
   const uint32_t e = blockIdx.x;
+  const uint32_t k = g.io.counts[static_cast<size_t>(e) * g.io.counts_stride];
+  if (g.k_hint && (k == 0u || g.plan->overflow)) return;  // device-planned read: nothing selected here (counts zeroed first)
   const EntryRef ref = g.io.refs[e];
   const StrView v = make_view(ref.blob, ref.blob);
   load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
@@ -1320,7 +1329,6 @@ __global__ void __launch_bounds__(256) k_str_decode(StrGatherIo g) {
   const uint64_t rb = g.row_base[e];
   const uint32_t* row_off = g.row_off_base + rb + e;
   const uint32_t* row_key = g.row_key_base + rb;
-  const uint32_t k = g.io.counts[static_cast<size_t>(e) * g.io.counts_stride];
   const uint32_t byte_base = static_cast<uint32_t>(g.byte_base[e]);
   int32_t* out_offsets = g.out_offsets + rb;
   // final offsets of this entry's slice (the closing offset of the whole array is written by the host)

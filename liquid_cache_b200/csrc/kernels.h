@@ -44,6 +44,7 @@ struct ScanIo {
   uint32_t* counts;           // per entry `counts_stride` u32: [0]=k (REFINE: survivors), [1]=nulls among selected, [2]=bytes
   uint32_t counts_stride;
   uint32_t pad;
+  const uint32_t* abort_flag; // device-planned reads: non-zero = a capacity is short, the kernel must not write (nullptr = none)
 };
 
 // `col <op> literal` on an integer column, as it crossed the C ABI; lowered to the packed domain per entry
@@ -180,10 +181,30 @@ struct alignas(16) StrPredDesc {
   unsigned long long needle_bloom[4];  // trigram bits of the LIKE needle (entry_layout.h trigram_bit); all zero below 3 bytes
   const uint8_t* needle; // device: needle bytes padded to 4, then needle_len x u16 KMP failure links
   unsigned long long* prof;  // optional device counters {uniques, candidates, candidate bytes}; nullptr = off
+  // streaming LIKE kernel (k_str_like): the needle's Shift-And step table of every FSST symbol table the list uses
+  // (512 x 16 bytes each, built per launch by k_like_steps) and each entry's index into them; nullptr = not prepared
+  const void* like_steps;
+  const uint32_t* entry_table;
 };
+// One step table per distinct FSST symbol table of the list: d_tables[t] -> d_steps + t * 512 entries of 16 bytes.
+cudaError_t launch_like_steps(const uint64_t* d_tables, uint32_t n_tables, const StrPredDesc& pred, void* d_steps, cudaStream_t s);
 
 cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, const StrPredDesc& pred,
                             uint32_t max_head_bytes, uint32_t max_unique, uint32_t max_meta_bytes, cudaStream_t s);
+
+// Device-side bookkeeping of a get over a device-resident selection (k_scan_plan.cu): totals the host reads back with
+// the result, and the refusal flag the decode kernels honour when a capacity chosen before the counts were known is short.
+struct alignas(16) ScanPlanHdr {  // 64 bytes
+  uint32_t n_hit;      // entries with surviving rows
+  uint32_t overflow;   // 0 ok, 1 rows / dictionary scratch over capacity, 2 bytes over capacity (or past int32 offsets)
+  uint64_t rows, bytes, nulls, ulen_words, vwords;
+  uint64_t pad;
+};
+static_assert(sizeof(ScanPlanHdr) == 64, "ScanPlanHdr must be 64 bytes");
+cudaError_t launch_scan_plan_rows(const uint32_t* d_counts2, const uint32_t* d_n_unique, uint32_t n, uint64_t cap_rows, uint64_t cap_ulen,
+                                  uint64_t* d_row_base, uint64_t* d_vword_off, uint64_t* d_ulen_off, ScanPlanHdr* d_hdr, cudaStream_t s);
+cudaError_t launch_scan_plan_bytes(const uint32_t* d_counts4, uint32_t n, uint64_t cap_bytes, uint64_t* d_byte_base,
+                                   int32_t* d_out_offsets, ScanPlanHdr* d_hdr, cudaStream_t s);
 
 // get()/filter() for byte-view entries: pass 1 (selected keys, decoded lengths, local offsets), host prefix
 // sums over the per-entry counts, pass 2 (decode, one warp per selected row).
@@ -194,6 +215,10 @@ struct StrGatherIo {
   uint32_t* ulen_base;       // scratch: decoded length per unique at ulen_base[ulen_off[i]]
   const uint64_t* row_base;  // per entry: rows selected before it (pass 1: an upper bound layout; pass 2: exact)
   const uint64_t* ulen_off;  // per entry
+  // device-planned reads (k_scan_plan.cu): rows that survived per entry (stride 2; entries with none are skipped) and the
+  // plan header whose overflow flag makes every CTA return at once. Both nullptr on the host-planned path.
+  const uint32_t* k_hint;
+  const ScanPlanHdr* plan;
   // pass 2 only
   const uint64_t* byte_base; // per entry: decoded bytes before it
   int32_t* out_offsets;      // concatenated offsets (rows + 1)

@@ -58,6 +58,7 @@ struct lc_scan {
     std::vector<Entry*> es;
   };
   std::vector<Validated> validated;
+  FusedRead fused;  // device-planned reads: what the previous read of this scan looked like
 };
 
 static uint64_t hash_handles(const lc_handle* h, uint64_t n) {
@@ -872,6 +873,16 @@ int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* ou
   // per call were ~0.05-0.1 ms of every get of the bench step
   Entry* const* esp = nullptr;
   LC_TRY(scan_entries_cached(scan, handles, &esp));
+  // After a filter the counts are on the device: read with device-side bookkeeping and one synchronisation
+  // (scan_read_fused), sized by the previous read of this scan; the first read, and shapes that path does not cover, are
+  // planned on the host below.
+  if (scan->counts_on_device && !scan->all_rows) {
+    uint64_t total_in = 0;
+    for (uint32_t r : scan->rows) total_in += r;
+    const int rc = scan_read_fused(ctx, &scan->fused, esp, scan->n, scan->d_sel, scan->d_word_off, scan->d_counts, total_in,
+                                   out_schema, out_array);
+    if (rc != LC_INTERNAL_FALLBACK) return rc;
+  }
   const std::vector<Entry*> es(esp, esp + scan->n);
   LC_TRY(scan_fetch_counts(scan));
   ctx->scratch.reset();
@@ -880,7 +891,17 @@ int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* ou
   std::vector<uint32_t> k2;
   scan_nonempty(scan, es, &es2, &woff2, &k2);
   DevSel ds{scan->d_sel, woff2.data(), k2.data(), scan->all_rows};
-  return to_arrow_batch(ctx, es2.data(), es2.size(), nullptr, &ds, out_schema, out_array);
+  LC_TRY(to_arrow_batch(ctx, es2.data(), es2.size(), nullptr, &ds, out_schema, out_array));
+  // teach the next read of this scan its sizes: rows, value bytes (byte views: the data buffer), dictionary scratch
+  int64_t value_bytes = 0;
+  uint64_t ulen = 0;
+  if (out_array->n_buffers == 3 && out_array->buffers[1]) {
+    const int32_t* off = static_cast<const int32_t*>(out_array->buffers[1]);
+    value_bytes = off[out_array->length] - off[0];
+    for (Entry* e : es2) ulen += (e->sh.n_unique + 3u) & ~3u;
+  }
+  fused_read_learn(&scan->fused, out_array, value_bytes, ulen);
+  return LC_OK;
 }
 
 int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap, void* d_offsets,
@@ -908,6 +929,7 @@ void lc_scan_end(lc_scan* scan) {
     if (scan->d_pcounts) cudaFree(scan->d_pcounts);
     if (scan->d_counts) cudaFree(scan->d_counts);
     if (scan->d_word_off) cudaFree(scan->d_word_off);
+    fused_read_free(&scan->fused);
   }
   delete scan;
 }

@@ -275,6 +275,13 @@ struct RefList {
   uint64_t key = 0;
   uint64_t n = 0;
   EntryRef* d_refs = nullptr;
+  uint32_t* d_n_unique = nullptr;  // byte views: dictionary size per entry, behind d_refs in the same allocation
+  // byte views: the distinct FSST symbol tables of the list, each entry's index into them, and room for one LIKE step table
+  // (8 KB) per symbol table — k_like_steps fills it for the needle of a launch (same allocation as d_refs)
+  uint64_t* d_tables = nullptr;
+  uint32_t* d_entry_table = nullptr;
+  uint8_t* d_like_steps = nullptr;
+  uint32_t n_tables = 0;
   uint32_t max_blob = 0, max_head = 0, max_head_like = 0, max_unique = 1, max_meta = 0;  // max_meta: header .. offset residuals
   uint32_t max_rows = 0;
   bool int_bits_ok = true;  // integer lists: every entry has fields of at most 32 bits (k_int_bits covers the list)
@@ -374,12 +381,41 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
     }
     nl.max_blob = std::max(nl.max_blob, e->blob_bytes);
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&nl.d_refs), n * sizeof(EntryRef) + 64) != cudaSuccess) {
+  // distinct symbol tables (entries of one column chunk share theirs)
+  std::vector<uint64_t> tables;
+  std::vector<uint32_t> entry_table(n, 0);
+  if (!is_int_blob(proto->liquid_type)) {
+    std::unordered_map<uint64_t, uint32_t> seen;
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t t = entries[i]->sh.table_ptr;
+      auto it = seen.find(t);
+      if (it == seen.end()) {
+        it = seen.emplace(t, static_cast<uint32_t>(tables.size())).first;
+        tables.push_back(t);
+      }
+      entry_table[i] = it->second;
+    }
+  }
+  nl.n_tables = static_cast<uint32_t>(tables.size());
+  const uint64_t o_nu = round_up(n * sizeof(EntryRef) + 64, 256), o_tab = o_nu + round_up(n * 4, 256);
+  const uint64_t o_et = o_tab + round_up(tables.size() * 8 + 8, 256), o_steps = o_et + round_up(n * 4, 256);
+  const uint64_t total = o_steps + tables.size() * 8192ull + 256;
+  if (cudaMalloc(reinterpret_cast<void**>(&nl.d_refs), total) != cudaSuccess) {
     cudaGetLastError();
     set_error("cudaMalloc for the entry list failed");
     return LC_ERR_OOM;
   }
+  uint8_t* base = reinterpret_cast<uint8_t*>(nl.d_refs);
   LC_CUDA_OK(cudaMemcpyAsync(nl.d_refs, refs.data(), n * sizeof(EntryRef), cudaMemcpyHostToDevice, ctx->stream));
+  nl.d_n_unique = reinterpret_cast<uint32_t*>(base + o_nu);
+  LC_CUDA_OK(cudaMemcpyAsync(nl.d_n_unique, nl.n_unique->data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  nl.d_tables = reinterpret_cast<uint64_t*>(base + o_tab);
+  nl.d_entry_table = reinterpret_cast<uint32_t*>(base + o_et);
+  nl.d_like_steps = base + o_steps;
+  if (!tables.empty()) {
+    LC_CUDA_OK(cudaMemcpyAsync(nl.d_tables, tables.data(), tables.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(nl.d_entry_table, entry_table.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
   LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // `refs` is pageable host memory
   ctx->h2d_bytes += n * sizeof(EntryRef);
   // evict: stale epochs first, then least recently used beyond 16 lists
@@ -805,6 +841,13 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
   }
   const bool like = !is_int && (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
+  if (like && sl.desc.needle_len >= 1 && sl.desc.needle_len <= 31 && rl->n_tables) {
+    // the streaming LIKE kernel walks candidates through one Shift-And step table per FSST symbol table of the list
+    LC_CUDA_OK(launch_like_steps(rl->d_tables, rl->n_tables, sl.desc, rl->d_like_steps, s));
+    ctx->kernel_launches++;
+    sl.desc.like_steps = rl->d_like_steps;
+    sl.desc.entry_table = rl->d_entry_table;
+  }
   // all rows of narrow integer entries: the register-resident kernel (its true-counts are added per chunk: zero them first)
   const bool int_bits = is_int && rl->int_bits_ok && io.sel_base == nullptr;
   if (int_bits) LC_CUDA_OK(cudaMemsetAsync(d_dn, 0, n * 16, s));
@@ -822,7 +865,9 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     } else if (is_int) {
       LC_CUDA_OK(launch_int_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, ip, rl->max_blob, s));
     } else {
-      LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, sl.desc,
+      StrPredDesc dc = sl.desc;
+      if (dc.entry_table) dc.entry_table += c0;
+      LC_CUDA_OK(launch_str_scan(MODE_PRED, static_cast<uint32_t>(c1 - c0), ioc, dc,
                                  like ? rl->max_head_like : rl->max_head, rl->max_unique, rl->max_meta, s));
     }
     ctx->kernel_launches++;
@@ -1012,6 +1057,12 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
     sl.desc.needle = d_nd;
     sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
     const bool like = (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
+    if (like && sl.desc.needle_len >= 1 && sl.desc.needle_len <= 31 && rl->n_tables) {
+      LC_CUDA_OK(launch_like_steps(rl->d_tables, rl->n_tables, sl.desc, rl->d_like_steps, s));
+      ctx->kernel_launches++;
+      sl.desc.like_steps = rl->d_like_steps;
+      sl.desc.entry_table = rl->d_entry_table;
+    }
     if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
     LC_CUDA_OK(launch_str_scan(MODE_REFINE, static_cast<uint32_t>(n), io, sl.desc, like ? rl->max_head_like : rl->max_head,
                                rl->max_unique, rl->max_meta, s));
@@ -1397,6 +1448,201 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   ctx->d2h_bytes += (want_views ? view_bytes : rows * 4) + (fixed_w ? 0 : total_bytes);
   if (!want_views) reinterpret_cast<int32_t*>(offsets.p)[rows] = static_cast<int32_t>(total_bytes);
   return finish_bytes_array(proto, rows, nulls, validity, offsets, views, data, out_schema, out_array);
+}
+
+// ---- get over a device-resident selection with ONE host synchronisation ----------------------------------------
+// lc_scan_read used to cost three round trips: the survivor counts (to size everything), the decoded lengths (to size
+// the bytes), the result. Here the two sizing steps are prefix sums on the device (k_scan_plan.cu) and the kernels run
+// back to back against capacities taken from the previous read of the same scan; the host downloads a 64-byte header
+// together with a speculative prefix of the result (again sized by the previous read) and only goes back for more when
+// this read turned out larger. A capacity that is too small makes the kernels return at once (ScanPlanHdr.overflow) and
+// the call falls back to the host-planned path, which also teaches the next call its sizes.
+// Covers Utf8 / Binary byte views and plain integers without nulls; everything else takes the host-planned path.
+int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t n, const uint32_t* d_sel, const uint64_t* d_word_off,
+                    const uint32_t* d_counts2, uint64_t total_rows_in, ArrowSchema* out_schema, ArrowArray* out_array) {
+  if (!fr->have_spec) return LC_INTERNAL_FALLBACK;
+  const RefList* rl;
+  LC_TRY(get_ref_list(ctx, entries, n, &rl));
+  const Entry* proto = entries[0];
+  if (!rl->same_liquid_type || !rl->same_arrow_type || rl->any_nulls || rl->any_fixed) return LC_INTERNAL_FALLBACK;
+  const bool is_int = proto->liquid_type == LC_LIQUID_INTEGER;
+  const bool is_str = proto->liquid_type == LC_LIQUID_BYTE_VIEW &&
+                      (proto->sh.arrow_type == BT_UTF8 || proto->sh.arrow_type == BT_BINARY);
+  if (!is_int && !is_str) return LC_INTERNAL_FALLBACK;
+  if (is_int && !rl->same_width) return LC_INTERNAL_FALLBACK;
+  // integers decode through the staged scan kernel, which reads every entry of the list: only worth it when a fair share
+  // of the rows survives (the host-planned path reads just the batches with survivors)
+  if (is_int && fr->spec_rows * 64 < total_rows_in) return LC_INTERNAL_FALLBACK;
+  const uint32_t tb = is_int ? proto->ih.tbits / 8 : 0;
+  cudaStream_t s = ctx->stream;
+  Tracer tr("scan_read_fused");
+
+  const uint64_t cap_rows = fr->spec_rows + fr->spec_rows / 2 + 4096;
+  const uint64_t cap_bytes = is_int ? 0 : fr->spec_bytes + fr->spec_bytes / 2 + (64u << 10);
+  const uint64_t cap_ulen = is_int ? 0 : fr->spec_ulen + fr->spec_ulen / 2 + (64u << 10);
+  // one device allocation, carved: header | 4 offset arrays | counts4 | scratch | result
+  uint64_t o = 0;
+  auto take = [&](uint64_t bytes) { const uint64_t at = o; o += round_up(bytes, 256); return at; };
+  const uint64_t o_hdr = take(256), o_rowb = take(n * 8), o_vw = take(n * 8), o_ul = take(n * 8), o_bb = take(n * 8);
+  const uint64_t o_cnt = take(n * 16);
+  const uint64_t o_rowoff = is_str ? take((cap_rows + n) * 4 + 16) : 0, o_rowkey = is_str ? take(cap_rows * 4 + 16) : 0;
+  const uint64_t o_ulen = is_str ? take(cap_ulen * 4 + 16) : 0;
+  const uint64_t o_off = is_str ? take((cap_rows + 1) * 4) : 0;
+  const uint64_t o_val = take(is_int ? cap_rows * tb + 16 : cap_bytes + 16);
+  if (o > fr->d_cap) {
+    if (fr->d_buf) {
+      LC_CUDA_OK(cudaStreamSynchronize(s));
+      cudaFree(fr->d_buf);
+      fr->d_buf = nullptr;
+      fr->d_cap = 0;
+    }
+    const uint64_t want = o + o / 4;
+    if (cudaMalloc(reinterpret_cast<void**>(&fr->d_buf), want) != cudaSuccess) {
+      cudaGetLastError();
+      return LC_INTERNAL_FALLBACK;
+    }
+    fr->d_cap = want;
+  }
+  if (!fr->h_hdr && cudaHostAlloc(reinterpret_cast<void**>(&fr->h_hdr), 256, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return LC_INTERNAL_FALLBACK;
+  }
+  uint8_t* d = fr->d_buf;
+  ScanPlanHdr* d_hdr = reinterpret_cast<ScanPlanHdr*>(d + o_hdr);
+  uint64_t* d_rowb = reinterpret_cast<uint64_t*>(d + o_rowb);
+  uint64_t* d_vw = reinterpret_cast<uint64_t*>(d + o_vw);
+  uint64_t* d_ul = reinterpret_cast<uint64_t*>(d + o_ul);
+  uint64_t* d_bb = reinterpret_cast<uint64_t*>(d + o_bb);
+  uint32_t* d_cnt = reinterpret_cast<uint32_t*>(d + o_cnt);
+  LC_CUDA_OK(cudaMemsetAsync(d_cnt, 0, n * 16, s));
+  LC_CUDA_OK(launch_scan_plan_rows(d_counts2, is_str ? rl->d_n_unique : nullptr, static_cast<uint32_t>(n), cap_rows, cap_ulen, d_rowb,
+                                   d_vw, d_ul, d_hdr, s));
+  ctx->kernel_launches++;
+  ScanIo io{};
+  io.refs = rl->d_refs;
+  io.sel_base = d_sel;
+  io.sel_off = d_word_off;
+  io.out_off = d_rowb;
+  io.valid_base = nullptr;
+  io.valid_off = d_vw;
+  io.counts = d_cnt;
+  io.counts_stride = 4;
+  HostBuf values, offsets;
+  const uint64_t spec_rows = fr->spec_rows + fr->spec_rows / 8 + 64;
+  const uint64_t spec_bytes = fr->spec_bytes + fr->spec_bytes / 8 + 4096;
+  if (is_int) {
+    io.out_base = d + o_val;
+    IntPredDesc ip{};
+    io.abort_flag = &d_hdr->overflow;  // survivors beyond the capacity: the kernel returns without writing
+    LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
+    ctx->kernel_launches++;
+    values = HostBuf{host_alloc(spec_rows * tb + 64, true), spec_rows * tb};
+    if (!values.p) return LC_ERR_OOM;
+    LC_CUDA_OK(cudaMemcpyAsync(fr->h_hdr, d_hdr, sizeof(ScanPlanHdr), cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaMemcpyAsync(values.p, d + o_val, std::min(spec_rows, cap_rows) * tb, cudaMemcpyDeviceToHost, s));
+  } else {
+    StrGatherIo g{};
+    g.io = io;
+    g.row_off_base = reinterpret_cast<uint32_t*>(d + o_rowoff);
+    g.row_key_base = reinterpret_cast<uint32_t*>(d + o_rowkey);
+    g.ulen_base = reinterpret_cast<uint32_t*>(d + o_ulen);
+    g.row_base = d_rowb;
+    g.ulen_off = d_ul;
+    g.byte_base = d_bb;
+    g.k_hint = d_counts2;
+    g.plan = d_hdr;
+    g.out_offsets = reinterpret_cast<int32_t*>(d + o_off);
+    g.out_bytes = d + o_val;
+    LC_CUDA_OK(launch_str_lengths(static_cast<uint32_t>(n), g, rl->max_head, s));
+    LC_CUDA_OK(launch_scan_plan_bytes(d_cnt, static_cast<uint32_t>(n), cap_bytes, d_bb, g.out_offsets, d_hdr, s));
+    LC_CUDA_OK(launch_str_decode(static_cast<uint32_t>(n), g, s));
+    ctx->kernel_launches += 3;
+    offsets = HostBuf{host_alloc((spec_rows + 1) * 4 + 64, true), (spec_rows + 1) * 4};
+    values = HostBuf{host_alloc(spec_bytes + 64, true), spec_bytes};
+    if (!offsets.p || !values.p) {
+      host_free(offsets.p);
+      host_free(values.p);
+      return LC_ERR_OOM;
+    }
+    LC_CUDA_OK(cudaMemcpyAsync(fr->h_hdr, d_hdr, sizeof(ScanPlanHdr), cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaMemcpyAsync(offsets.p, g.out_offsets, (std::min(spec_rows, cap_rows) + 1) * 4, cudaMemcpyDeviceToHost, s));
+    LC_CUDA_OK(cudaMemcpyAsync(values.p, g.out_bytes, std::min(spec_bytes, cap_bytes), cudaMemcpyDeviceToHost, s));
+  }
+  tr.mark("launches");
+  cudaError_t ce = cudaStreamSynchronize(s);
+  tr.mark("the one synchronisation");
+  const ScanPlanHdr hdr = *fr->h_hdr;
+  auto drop = [&]() {
+    host_free(offsets.p);
+    host_free(values.p);
+  };
+  if (ce != cudaSuccess) {
+    drop();
+    set_error("CUDA error in the device-planned read: %s", cudaGetErrorString(ce));
+    return LC_ERR_CUDA;
+  }
+  if (hdr.overflow) {  // a capacity was short: the kernels did nothing; let the host-planned path answer and re-teach the sizes
+    drop();
+    fr->have_spec = false;
+    fr->fallbacks++;
+    return LC_INTERNAL_FALLBACK;
+  }
+  const uint64_t rows = hdr.rows, bytes = is_int ? rows * tb : hdr.bytes;
+  ctx->d2h_bytes += sizeof(ScanPlanHdr) + (is_int ? std::min(spec_rows, cap_rows) * tb
+                                                  : (std::min(spec_rows, cap_rows) + 1) * 4 + std::min(spec_bytes, cap_bytes));
+  if (rows > spec_rows || (!is_int && bytes > spec_bytes)) {
+    // this read is larger than the speculative download: fetch it whole (a second round trip, rare)
+    drop();
+    if (is_int) {
+      values = HostBuf{host_alloc(rows * tb + 64, true), rows * tb};
+      if (!values.p) return LC_ERR_OOM;
+      LC_CUDA_OK(cudaMemcpyAsync(values.p, d + o_val, rows * tb, cudaMemcpyDeviceToHost, s));
+    } else {
+      offsets = HostBuf{host_alloc((rows + 1) * 4 + 64, true), (rows + 1) * 4};
+      values = HostBuf{host_alloc(bytes + 64, true), bytes};
+      if (!offsets.p || !values.p) {
+        drop();
+        return LC_ERR_OOM;
+      }
+      LC_CUDA_OK(cudaMemcpyAsync(offsets.p, d + o_off, (rows + 1) * 4, cudaMemcpyDeviceToHost, s));
+      LC_CUDA_OK(cudaMemcpyAsync(values.p, d + o_val, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    LC_CUDA_OK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += (is_int ? 0 : (rows + 1) * 4) + bytes;
+    tr.mark("second download");
+  }
+  fr->spec_rows = rows;
+  fr->spec_bytes = is_int ? 0 : bytes;
+  fr->spec_ulen = hdr.ulen_words;
+  fr->fused_reads++;
+  export_schema(proto->arrow_format, "", out_schema);
+  std::vector<HostBuf> bufs;
+  bufs.push_back(HostBuf{});  // no validity: the list has no nulls
+  if (is_int) {
+    values.bytes = rows * tb;
+    bufs.push_back(values);
+  } else {
+    reinterpret_cast<int32_t*>(offsets.p)[rows] = static_cast<int32_t>(bytes);
+    offsets.bytes = (rows + 1) * 4;
+    values.bytes = bytes;
+    bufs.push_back(offsets);
+    bufs.push_back(values);
+  }
+  export_array(static_cast<int64_t>(rows), 0, std::move(bufs), nullptr, out_array);
+  return LC_OK;
+}
+
+void fused_read_learn(FusedRead* fr, const ArrowArray* arr, int64_t value_bytes, uint64_t ulen_words) {
+  fr->spec_rows = static_cast<uint64_t>(arr->length);
+  fr->spec_bytes = value_bytes > 0 ? static_cast<uint64_t>(value_bytes) : 0;
+  fr->spec_ulen = std::max<uint64_t>(fr->spec_ulen, ulen_words);
+  fr->have_spec = true;
+}
+
+void fused_read_free(FusedRead* fr) {
+  if (fr->d_buf) cudaFree(fr->d_buf);
+  if (fr->h_hdr) cudaFreeHost(fr->h_hdr);
+  *fr = FusedRead();
 }
 
 // Turn (validity, int32 offsets, bytes) into the ORIGINAL arrow type of the column:
