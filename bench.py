@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-entries", type=int, default=0,
                     help="entries per CPU-arm pass; 0 = max(8192, 64 per host thread), bounded by the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep", "squeeze"], default="url_like",
+    ap.add_argument("--no-secondary", action="store_true", help="url_like at one GPU: skip the configs[2] / configs[3] runs that are "
+                                                               "reported under config.secondary")
+    ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep", "squeeze", "insert"], default="url_like",
                     help="url_like = BASELINE configs[1] (the bench line the driver records); int_filter = configs[2]; "
                          "shipdate = configs[3] (TPC-H SF100 l_shipdate range, one GPU's shard of the 8-way split per rank); "
                          "clickbench_sweep = configs[4] (scan stage of the 43 ClickBench queries, bench_sweep.py)")
@@ -109,6 +111,27 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pin_to_gpu_numa(local_rank: int):
+    """Run this rank (and the library's host threads it spawns) on the CPUs of its GPU's NUMA node: the readbacks of a
+    step land in that node's memory (8 unpinned ranks, GPU4-7 on node 1). Returns what was done for the record."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = ((os.cpu_count() or 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {i for i in range(os.cpu_count() or 1) if (int(mask[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if want:
+            os.sched_setaffinity(0, want)
+            return {"pinned_cpus": len(want), "first": min(want), "last": max(want)}
+    except Exception as e:  # no NVML / not permitted: run unpinned
+        return {"pinned_cpus": 0, "why": str(e)[:80]}
+    return {"pinned_cpus": 0}
 
 
 def generate_entries(first: int, count: int, workers: int):
@@ -214,9 +237,10 @@ def run_reference(args, rank: int, world: int):
     }))
 
 
-def run_int_filter(args, rank, world, local_rank):
+def run_int_filter(args, rank, world, local_rank, emit=True):
     """BASELINE configs[2]: EventTime range (two conjuncts) AND UserID equality on bit-packed Int64 columns, then
-    get-with-selection of both columns. Secondary workload: prints its own JSON line (not the driver's bench line)."""
+    get-with-selection of both columns. Secondary workload: its own JSON line when run by itself, an object under
+    `config.secondary` of the driver's bench line otherwise."""
     import numpy as np
     import pyarrow as pa
     import torch
@@ -305,9 +329,32 @@ def run_int_filter(args, rank, world, local_rank):
         ],
         "peak_source": peak_src,
     }
-    print(json.dumps(line))
+    # e2e: the same step through the public scan API by the host's clock (predicate literals go up, the two filtered Arrow
+    # arrays come down every step); the device-timed `value` above uses CUDA events around the same calls
+    torch.cuda.synchronize()
+    st_c = cache.stats()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        total, a, b = step(False)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    st_d = cache.stats()
+    line["e2e"] = {"value": rows_local / (e2e_ms / 1e3) / 1e6, "unit": "Mrows/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int((st_d.h2d_bytes - st_c.h2d_bytes) / e2e_steps),
+                   "d2h_bytes_per_step": int((st_d.d2h_bytes - st_c.d2h_bytes) / e2e_steps),
+                   "note": "lc_scan_filter x3 + lc_scan_read x2 (host Arrow results), wall clock"}
+    if not args.no_cpu_baseline:
+        import bench_cpu
+
+        cpu_threads, _h = bench_cpu.usable_cpus()
+        line["cpu_baseline"] = bench_cpu.cpu_baseline_line("int_filter", cpu_sample_entries(args, cpu_threads, n_entries), cpu_threads,
+                                                           params=int_filter_params(), target_s=6.0)
+    if emit:
+        print(json.dumps(line))
     scan.close()
     cache.close()
+    return line
 
 
 def run_squeeze(args, rank, world, local_rank):
@@ -429,7 +476,7 @@ def run_squeeze(args, rank, world, local_rank):
     cache.close()
 
 
-def run_shipdate(args, rank, world, local_rank):
+def run_shipdate(args, rank, world, local_rank, emit=True):
     """BASELINE configs[3]: TPC-H SF100 lineitem `l_shipdate >= 1994-01-01 AND l_shipdate < 1995-01-01` (q6's date
     range; Date32, W = 12), entries sharded across 8 B200: every rank holds one eighth of the 600 037 902 rows
     (weak scaling: at --gpus 8 the job is the whole table). Step = both conjuncts over every entry + get-with-selection
@@ -480,7 +527,15 @@ def run_shipdate(args, rank, world, local_rank):
     k_ms = [[], []]
     cache.kernel_timing(True)
 
-    def step(timed, to_host):
+    from liquid_cache_b200.dist import StepGather
+
+    pin = pin_to_gpu_numa(local_rank)
+    gather = StepGather(pa.date32(), rank, world, dev) if world > 1 else None
+
+    def step(timed):
+        """Both conjuncts over every entry of this rank, then the filtered batch delivered to rank 0's HOST memory: at one
+        GPU lc_scan_read (device-planned, one synchronisation); at N > 1 every rank leaves its survivors in HBM
+        (lc_scan_read_borrowed) and the NCCL gather over NVLink — the one exchange of the path — runs inside the step."""
         scan.reset()
         scan.filter_native(handles, p_ge)
         if timed:
@@ -488,11 +543,15 @@ def run_shipdate(args, rank, world, local_rank):
         scan.filter_native(handles, p_lt)
         if timed:
             k_ms[1].append(cache.last_kernel_ms())
-        if to_host:
+        if world == 1:
             res = scan.read(handles)
             return len(res), res
-        _counts, total = scan.counts()
-        return total, scan.read_torch(handles, dev)
+        r = scan.read_torch_borrowed(handles, dev)
+        if r is None:
+            v, _o, _b, rows, _nn = scan.read_torch(handles, dev)
+        else:
+            v, _o, rows = r
+        return rows, gather.gather(v, None, rows)
 
     def barrier():
         torch.cuda.synchronize()
@@ -500,8 +559,9 @@ def run_shipdate(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_res = None
     for _ in range(max(3, args.warmup)):
-        step(False, False)
+        total, host_res = step(False)  # the previous result stays alive like in the timed loops: both result blocks exist
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -510,31 +570,32 @@ def run_shipdate(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        total, dev_res = step(True, False)
+        total, host_res = step(True)
     e1.record(stream)
     barrier()
     st_b = cache.stats()
     ms = e0.elapsed_time(e1)
-    # e2e: filtered Arrow array on the host every step (D2H inside the timed region)
-    # warm-up keeps the previous result alive exactly like the timed loop does, so that BOTH page-locked result buffers the
-    # loop alternates between exist before the clock starts (the first use of each is a cudaHostAlloc of tens of MB)
-    host_res = None
-    for _ in range(3):
-        total_h, host_res = step(False, True)
-    barrier()
+    # e2e: the same step by the host's clock (predicates up, the filtered Arrow array down to rank 0 every step)
     e2e_steps = max(3, args.steps // 2)
     st_c = cache.stats()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        total_h, host_res = step(False, True)
+        total_h, host_res = step(False)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     st_d = cache.stats()
-    # parity inside the bench: the host result against pyarrow on the regenerated first entries, and device == host rows
+    # parity inside the bench: rank 0's result against pyarrow on its regenerated first entries; row counts add up
     import pyarrow.compute as pc
-    chk = pa.concat_arrays([synth.int_entry("l_shipdate", rank * n_entries + i, seed=synth.SEED_TPCH) for i in range(min(4, n_entries))])
-    want = chk.filter(pc.and_(pc.greater_equal(chk, pa.scalar(lo)), pc.less(chk, pa.scalar(hi))))
-    ok = host_res.slice(0, len(want)).equals(want) and int(dev_res[3]) == len(host_res) == int(total)
+    ok = True
+    if rank == 0:
+        chk = pa.concat_arrays([synth.int_entry("l_shipdate", i, seed=synth.SEED_TPCH) for i in range(min(4, n_entries))])
+        want = chk.filter(pc.and_(pc.greater_equal(chk, pa.scalar(lo)), pc.less(chk, pa.scalar(hi))))
+        ok = host_res.slice(0, len(want)).equals(want)
+    tot_t = torch.tensor([float(total)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot_t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ok = ok and len(host_res) == int(tot_t.item())
     t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -555,7 +616,9 @@ def run_shipdate(args, rank, world, local_rank):
                                    "(BASELINE configs[3]); each rank holds 1/8 of the 600 037 902 rows",
                        "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "matching_rows_per_gpu": int(total),
                        "selectivity": int(total) / rows_local, "liquid_bytes_per_gpu": int(cache.stats().hbm_bytes_used),
-                       "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective",
+                       "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective; the filtered batches "
+                                      "are gathered to rank 0 over NCCL INSIDE every timed step" if world > 1 else "one GPU",
+                       "gathered_rows_on_rank0": len(host_res), "numa": pin,
                        "l2": "packed column (113 MB) + selections do not fit the L2 together with the 44 MB result; no flush",
                        "setup_seconds": setup_s, "result_matches_arrow": bool(ok),
                        "insert": {"Mrows_per_s": rows_local / insert_s / 1e6, "arrow_GB_per_s": rows_local * 4 / insert_s / 1e9,
@@ -579,12 +642,14 @@ def run_shipdate(args, rank, world, local_rank):
 
             cpu_threads, _h = bench_cpu.usable_cpus()
             line["cpu_baseline"] = cpu_baseline_shipdate(cpu_sample_entries(args, cpu_threads, n_entries), cpu_threads)
-        print(json.dumps(line))
+        if emit:
+            print(json.dumps(line))
     scan.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     cache.close()
+    return line if rank == 0 else None
 
 
 def cpu_baseline_shipdate(sample_entries: int, threads: int, target_s: float = 6.0):
@@ -612,6 +677,11 @@ def main():
     if args.workload == "squeeze":
         run_squeeze(args, rank, world, local_rank)
         return
+    if args.workload == "insert":
+        import bench_insert
+
+        bench_insert.main(args, rank, world, local_rank)
+        return
     if args.workload == "clickbench_sweep":
         import bench_sweep
 
@@ -627,6 +697,7 @@ def main():
                                    parquet_array_id)
 
     torch.cuda.set_device(local_rank)
+    pin = pin_to_gpu_numa(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -713,25 +784,36 @@ def main():
 
     trace = os.environ.get("LC_BENCH_TRACE") == "1"
 
+    from liquid_cache_b200.dist import StepGather
+
+    dev = torch.device("cuda", local_rank)
+    gather = StepGather(pa.string(), rank, world, dev) if world > 1 else None
+
     def step(time_kernel: bool):
+        """LIKE over every entry of this rank, then the filtered batch delivered to rank 0's HOST memory. One GPU: lc_scan_read
+        (survivor counts, row / byte offsets and the decode all happen on the device; one synchronisation). N > 1: every rank
+        leaves its survivors in HBM (lc_scan_read_borrowed) and the NCCL gather over NVLink — the one exchange of the path —
+        runs inside the step; rank 0 downloads the concatenation."""
         t0 = time.perf_counter()
         scan.reset()
         scan.filter_native(handles, pred)
         t1 = time.perf_counter()
-        t2 = t1
-        # get-with-selection of the survivors: survivor counts, row / byte offsets and the decode all happen on the device,
-        # the host synchronises once and receives the Arrow array (lc_scan_read -> scan_read_fused)
-        out = scan.read(handles)
+        if world == 1:
+            out = scan.read(handles)
+            total = len(out)
+        else:
+            r = scan.read_torch_borrowed(handles, dev)
+            if r is None:
+                v, o, _b, total, _nn = scan.read_torch(handles, dev)
+            else:
+                v, o, total = r
+            out = gather.gather(v, o, total)
         t3 = time.perf_counter()
-        total = len(out)
-        if total == 0:
-            out = None
         result_rows[0] = total
         if time_kernel:
             kernel_ms.append(cache.last_kernel_ms())  # events recorded by the library right around the launch
         if trace and rank == 0:
-            print(f"[trace] filter(launch) {1e3*(t1-t0):.3f} ms, counts {1e3*(t2-t1):.3f} ms, read {1e3*(t3-t2):.3f} ms",
-                  file=sys.stderr)
+            print(f"[trace] filter(launch) {1e3*(t1-t0):.3f} ms, read (+ gather) {1e3*(t3-t1):.3f} ms", file=sys.stderr)
         return out
 
     def barrier():
@@ -740,8 +822,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    last = None
     for _ in range(max(3, args.warmup)):
-        step(False)
+        last = step(False)
     cache.kernel_timing(True)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -750,7 +833,6 @@ def main():
     st_a = cache.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    last = None
     for _ in range(args.steps):
         last = step(True)
     ev1.record(stream)
@@ -758,21 +840,9 @@ def main():
     st_b = cache.stats()
     ms_total = ev0.elapsed_time(ev1)
     launches = int(st_b.kernel_launches - st_a.kernel_launches)
-
-    # multi-GPU: the ONE exchange step of this path — gather the filtered batches to rank 0 over NCCL. The result is
-    # read into device buffers (lc_scan_read_device) so values / offsets / validity go HBM -> HBM over NVLink.
-    gathered_rows = result_rows[0]
-    if world > 1:
-        from liquid_cache_b200.dist import gather_device_result_to_rank0
-        dev = torch.device("cuda", local_rank)
-        if result_rows[0]:
-            v, o, b, nrows, nnull = scan.read_torch(handles, dev)
-        else:
-            v, o, b, nrows, nnull = (torch.empty(0, dtype=torch.uint8, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
-                                     None, 0, 0)
-        g = gather_device_result_to_rank0(v, o, b, nrows, nnull, pa.string(), rank, world)
-        if rank == 0:
-            gathered_rows = len(g)
+    gathered_rows = len(last) if (rank == 0 and last is not None) else result_rows[0]
+    # what the e2e arm below is compared with: THIS rank's own filtered batch
+    local_last = last if world == 1 else None
 
     # ---- e2e: the same pass through the host-buffer C ABI (H2D + D2H inside the timed region) ----
     # host result buffers, allocated once and page-locked (the reference-side caller would own these)
@@ -817,7 +887,7 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t0
     st_d = cache.stats()
-    e2e_ok = (e2e_out is None and result_rows[0] == 0) or (e2e_out is not None and last is not None and e2e_out.equals(last))
+    e2e_ok = (e2e_out is None and result_rows[0] == 0) or (e2e_out is not None and (len(e2e_out) == result_rows[0]) and (local_last is None or e2e_out.equals(local_last)))
 
     # max over ranks
     t = torch.tensor([ms_total, e2e_wall * 1e3, float(sum(kernel_ms) / max(1, len(kernel_ms)))], device="cuda", dtype=torch.float64)
@@ -841,7 +911,7 @@ def main():
                 "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "rows_per_entry": ROWS_PER_ENTRY,
                 "liquid_bytes_per_gpu": hbm_bytes, "liquid_bytes_per_row": hbm_bytes / rows_local,
                 "unique_values_per_entry": uniques / n_entries, "walked_candidates_frac": cand / max(1, uniques),
-                "matching_rows": int(gathered_rows), "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective; NCCL gather of the filtered batch",
+                "matching_rows": int(gathered_rows), "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective; the filtered batches are gathered to rank 0 over NCCL inside every timed step" if world > 1 else "one GPU", "numa": pin,
                 "l2": "inputs (liquid column) larger than the 126 MB L2, no flush needed",
                 "setup_seconds": setup_s,
                 "insert": {"Mrows_per_s": rows_local / insert_s / 1e6, "arrow_GB_per_s": arrow_bytes / insert_s / 1e9,
@@ -868,12 +938,27 @@ def main():
 
             cpu_threads, _h = bench_cpu.usable_cpus()
             line["cpu_baseline"] = cpu_baseline(cpu_sample_entries(args, cpu_threads, n_entries), cpu_threads)
-        print(json.dumps(line))
     scan.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     cache.close()
+    if rank == 0:
+        if world == 1 and not args.no_secondary:
+            # BASELINE configs[2] and [3] measured in the SAME run, so that their rooflines sit in the driver's bench line
+            #  — each is also a workload of its own (--workload int_filter / shipdate)
+            sec = {}
+            for name, fn in (("int_filter", run_int_filter), ("shipdate", run_shipdate)):
+                try:
+                    sub = fn(args, 0, 1, local_rank, emit=False)
+                    sec[name] = {k: sub[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "cpu_baseline", "gpu_launches")
+                                 if k in sub}
+                    sec[name]["workload"] = sub["config"]["workload"]
+                    sec[name]["rows_per_gpu"] = sub["config"]["rows_per_gpu"]
+                except Exception as e:  # a secondary workload must not take the headline line down with it
+                    sec[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            line["config"]["secondary"] = sec
+        print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -363,6 +363,14 @@ int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* ou
 int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap,
                         void* d_offsets, void* d_validity, uint64_t* out_rows, uint64_t* out_value_bytes,
                         uint64_t* out_null_count);
+/* lc_scan_read for a consumer ON THE DEVICE (the NCCL gather of the filtered batches to rank 0): the
+ * concatenated result of the column stays in the scan's own device buffer — *d_values (value bytes; integers: native
+ * values), *d_offsets (byte views: int32[rows + 1]; integers: NULL) — valid until the next read on this scan. Planned on
+ * the device like lc_scan_read (one synchronisation, a 64-byte header is all that crosses PCIe). Returns
+ * LC_ERR_UNSUPPORTED_EXPR when this read cannot be planned on the device (the first read of a scan, nulls, other types,
+ * a result that outgrew the capacities): use lc_scan_read_device then. */
+int lc_scan_read_borrowed(lc_scan* scan, const lc_handle* handles, void** d_values, void** d_offsets, uint64_t* out_rows,
+                          uint64_t* out_value_bytes);
 void lc_scan_end(lc_scan* scan);
 
 #ifdef __cplusplus

@@ -675,6 +675,30 @@ class Scan:
                                             d_validity or None, C.byref(rows), C.byref(nbytes), C.byref(nulls)))
         return int(rows.value), int(nbytes.value), int(nulls.value)
 
+    def read_torch_borrowed(self, handles: np.ndarray, device):
+        """The filtered column as torch tensors over the scan's OWN device buffer (lc_scan_read_borrowed: planned on the
+        device, one synchronisation, nothing but a 64-byte header crosses PCIe): `(values u8[value_bytes], offsets
+        i32[rows+1] | None, rows)`, valid until the next read on this scan. None when this read cannot be planned on the
+        device (first read of a scan, nulls, unsupported type): use `read_torch`."""
+        import torch
+
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        dv, do = C.c_void_p(), C.c_void_p()
+        rows, nbytes = C.c_uint64(0), C.c_uint64(0)
+        rc = N.lib().lc_scan_read_borrowed(self._scan, handles.ctypes.data, C.byref(dv), C.byref(do), C.byref(rows), C.byref(nbytes))
+        if rc == N.LC_ERR_UNSUPPORTED_EXPR:
+            return None
+        N.check(rc)
+
+        class _Dev:  # __cuda_array_interface__ over a raw device range: torch.as_tensor wraps it without copying
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        nb, nr = int(nbytes.value), int(rows.value)
+        values = torch.as_tensor(_Dev(dv.value, nb, "|u1"), device=device) if nb else torch.empty(0, dtype=torch.uint8, device=device)
+        offsets = torch.as_tensor(_Dev(do.value, nr + 1, "<i4"), device=device) if do.value else None
+        return values, offsets, nr
+
     def read_torch(self, handles: np.ndarray, device):
         """read_device into freshly allocated torch tensors on `device`:
         (values u8[value_bytes], offsets i32[rows+1] | None, validity u8[4*ceil(rows/32)] | None, rows, null_count)."""

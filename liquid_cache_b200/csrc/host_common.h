@@ -311,8 +311,14 @@ struct FusedRead {
   ScanPlanHdr* h_hdr = nullptr;  // pinned
   uint64_t fused_reads = 0, fallbacks = 0;
 };
+struct FusedDeviceOut {  // lc_scan_read_borrowed: the concatenated result left in the scan's own device buffer
+  void* d_values = nullptr;
+  void* d_offsets = nullptr;  // byte views: int32[rows + 1] (the closing offset included); integers: nullptr
+  uint64_t rows = 0, value_bytes = 0;
+};
 int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t n, const uint32_t* d_sel, const uint64_t* d_word_off,
-                    const uint32_t* d_counts2, uint64_t total_rows_in, ArrowSchema* out_schema, ArrowArray* out_array);
+                    const uint32_t* d_counts2, uint64_t total_rows_in, ArrowSchema* out_schema, ArrowArray* out_array,
+                    FusedDeviceOut* dev_out = nullptr);
 void fused_read_learn(FusedRead* fr, const ArrowArray* arr, int64_t value_bytes, uint64_t ulen_words);
 void fused_read_free(FusedRead* fr);
 

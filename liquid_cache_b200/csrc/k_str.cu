@@ -14,6 +14,8 @@
 // fingerprints first, FSST codes walked only for the candidates that survive) into a bitmap in shared
 // memory while copy B is still in flight; phase 2 broadcasts the bitmap through the keys with the
 // same ballot + prefix-sum selection machinery the integer path uses (scan_rows.cuh).
+#include <cstdlib>
+
 #include "../../include/lc_gpu.h"
 #include "device_utils.cuh"
 #include "kernels.h"
@@ -866,8 +868,8 @@ cudaError_t launch_like_steps(const uint64_t* d_tables, uint32_t n_tables, const
   return cudaGetLastError();
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256, 4)
+template <int MODE, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries, uint32_t per_cta) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -887,6 +889,17 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
     nb[2 * q] = static_cast<uint32_t>(pred.needle_bloom[q]);
     nb[2 * q + 1] = static_cast<uint32_t>(pred.needle_bloom[q] >> 32);
   }
+  // ... and the words that carry a bit at all (at most four for needles of up to six bytes: the pipelined gate fetches just those)
+  uint32_t nw = 0, widx[4] = {0, 0, 0, 0}, wbits[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (uint32_t q = 0; q < 8; ++q)
+    if (nb[q]) {
+      if (nw < 4u) {
+        widx[nw] = q;
+        wbits[nw] = nb[q];
+      }
+      ++nw;
+    }
 
   const uint32_t e0 = blockIdx.x * per_cta;
   const uint32_t e_end = e0 + per_cta < n_entries ? e0 + per_cta : n_entries;
@@ -942,45 +955,106 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
       ncand = 0;
       __syncwarp();
     };
-    for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
-      ulonglong2 blo[4], bhi[4];
-      bool ok[4];
-      uint32_t fpv[4];
-#pragma unroll
-      for (uint32_t t = 0; t < 4; ++t) {
-        const uint32_t i = g0 + t * 32u + lane;
-        fpv[t] = (fp && i < U) ? __ldg(fp + i) : 0xffffffffu;
+    auto append = [&](bool cand, bool ok, uint32_t i0) {  // survivors of one stripe join the candidate list
+      const uint32_t cw = __ballot_sync(kFullMask, cand);
+      if (neg || pred.prof) n_ref += __popc(__ballot_sync(kFullMask, ok));
+      if (cw) {
+        if (ncand + 32u > kLikeCandCap) walk();
+        if (cand) s_cand[ncand + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i0 + lane);
+        ncand += __popc(cw);
+        __syncwarp();
       }
+    };
+    if (nw <= 4u) {
+      // The needle's trigram bits sit in at most four of the filter's eight 32-bit words (every needle of up to six bytes):
+      // only those words are fetched — still one 32-byte sector per surviving value, but four registers per stripe instead
+      // of eight, which is what lets the gate run as a software pipeline: while the four stripes of group g are tested,
+      // the filter words of group g+1 and the fingerprints of group g+2 are already in flight.
+      const uint32_t* bloom32 = reinterpret_cast<const uint32_t*>(bloom);
+      auto load_fp = [&](uint32_t g0, uint32_t (&f)[4]) {
 #pragma unroll
-      for (uint32_t t = 0; t < 4; ++t) {
-        const uint32_t i = g0 + t * 32u + lane;
-        ok[t] = (i < U) && ((fpv[t] & pred.needle_fp) == pred.needle_fp);
-        if (ok[t] && bloom) {  // one 32-byte sector per surviving value; lanes the fingerprint rejected fetch nothing
-          const ulonglong2* src = reinterpret_cast<const ulonglong2*>(bloom + static_cast<size_t>(i) * kBloomWords);
-          blo[t] = __ldg(src);
-          bhi[t] = __ldg(src + 1);
-        } else {
-          blo[t] = make_ulonglong2(~0ull, ~0ull);
-          bhi[t] = make_ulonglong2(~0ull, ~0ull);
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i = g0 + t * 32u + lane;
+          f[t] = (fp && i < U) ? __ldg(fp + i) : 0xffffffffu;
+        }
+      };
+      auto issue = [&](uint32_t g0, const uint32_t (&f)[4], uint32_t (&bl)[4][4], bool (&ok)[4]) {
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i = g0 + t * 32u + lane;
+          ok[t] = (i < U) && ((f[t] & pred.needle_fp) == pred.needle_fp);
+          if (ok[t] && bloom32) {  // lanes the fingerprint rejected fetch nothing
+            const uint32_t* src = bloom32 + static_cast<size_t>(i) * (2u * kBloomWords);
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) bl[t][q] = __ldg(src + widx[q]);
+          } else {
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) bl[t][q] = 0xffffffffu;
+          }
+        }
+      };
+      auto test = [&](uint32_t g0, const uint32_t (&bl)[4][4], const bool (&ok)[4]) {
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i0 = g0 + t * 32u;
+          if (i0 >= U) break;  // warp-uniform
+          const uint32_t miss = (~bl[t][0] & wbits[0]) | (~bl[t][1] & wbits[1]) | (~bl[t][2] & wbits[2]) | (~bl[t][3] & wbits[3]);
+          append(ok[t] && miss == 0u, ok[t], i0);
+        }
+      };
+      uint32_t fA[4], fB[4], blA[4][4], blB[4][4];
+      bool okA[4], okB[4];
+      load_fp(0, fA);
+      issue(0, fA, blA, okA);
+      load_fp(128u, fB);
+      for (uint32_t g0 = 0; g0 < U; g0 += 256u) {
+        const bool more1 = g0 + 128u < U, more2 = g0 + 256u < U;
+        if (more1) {
+          issue(g0 + 128u, fB, blB, okB);
+          load_fp(g0 + 256u, fA);
+        }
+        test(g0, blA, okA);
+        if (more1) {
+          if (more2) {
+            issue(g0 + 256u, fA, blA, okA);
+            load_fp(g0 + 384u, fB);
+          }
+          test(g0 + 128u, blB, okB);
         }
       }
+    } else {
+      for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
+        ulonglong2 blo[4], bhi[4];
+        bool ok[4];
+        uint32_t fpv[4];
 #pragma unroll
-      for (uint32_t t = 0; t < 4; ++t) {
-        const uint32_t i0 = g0 + t * 32u;
-        if (i0 >= U) break;  // warp-uniform
-        // needle bits the value lacks, over the eight words (one LOP3 each)
-        const uint32_t miss = (~static_cast<uint32_t>(blo[t].x) & nb[0]) | (~static_cast<uint32_t>(blo[t].x >> 32) & nb[1]) |
-                              (~static_cast<uint32_t>(blo[t].y) & nb[2]) | (~static_cast<uint32_t>(blo[t].y >> 32) & nb[3]) |
-                              (~static_cast<uint32_t>(bhi[t].x) & nb[4]) | (~static_cast<uint32_t>(bhi[t].x >> 32) & nb[5]) |
-                              (~static_cast<uint32_t>(bhi[t].y) & nb[6]) | (~static_cast<uint32_t>(bhi[t].y >> 32) & nb[7]);
-        const bool cand = ok[t] && miss == 0u;
-        const uint32_t cw = __ballot_sync(kFullMask, cand);
-        if (neg || pred.prof) n_ref += __popc(__ballot_sync(kFullMask, ok[t]));
-        if (cw) {
-          if (ncand + 32u > kLikeCandCap) walk();
-          if (cand) s_cand[ncand + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i0 + lane);
-          ncand += __popc(cw);
-          __syncwarp();
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i = g0 + t * 32u + lane;
+          fpv[t] = (fp && i < U) ? __ldg(fp + i) : 0xffffffffu;
+        }
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i = g0 + t * 32u + lane;
+          ok[t] = (i < U) && ((fpv[t] & pred.needle_fp) == pred.needle_fp);
+          if (ok[t] && bloom) {  // one 32-byte sector per surviving value; lanes the fingerprint rejected fetch nothing
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(bloom + static_cast<size_t>(i) * kBloomWords);
+            blo[t] = __ldg(src);
+            bhi[t] = __ldg(src + 1);
+          } else {
+            blo[t] = make_ulonglong2(~0ull, ~0ull);
+            bhi[t] = make_ulonglong2(~0ull, ~0ull);
+          }
+        }
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i0 = g0 + t * 32u;
+          if (i0 >= U) break;  // warp-uniform
+          // needle bits the value lacks, over the eight words (one LOP3 each)
+          const uint32_t miss = (~static_cast<uint32_t>(blo[t].x) & nb[0]) | (~static_cast<uint32_t>(blo[t].x >> 32) & nb[1]) |
+                                (~static_cast<uint32_t>(blo[t].y) & nb[2]) | (~static_cast<uint32_t>(blo[t].y >> 32) & nb[3]) |
+                                (~static_cast<uint32_t>(bhi[t].x) & nb[4]) | (~static_cast<uint32_t>(bhi[t].x >> 32) & nb[5]) |
+                                (~static_cast<uint32_t>(bhi[t].y) & nb[6]) | (~static_cast<uint32_t>(bhi[t].y >> 32) & nb[7]);
+          append(ok[t] && miss == 0u, ok[t], i0);
         }
       }
     }
@@ -1046,10 +1120,16 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
         uint32_t mine = 0;
         const uint32_t row0 = c * 1024u + lane;
         const bool full = (c + 1u) * 1024u <= n;
-#pragma unroll 8
+        // the chunk's 1024 keys are requested up front (32 coalesced 64-byte loads in flight per warp), then looked up
+        uint32_t kk[32];
+#pragma unroll
         for (uint32_t j = 0; j < 32; ++j) {
           const uint32_t row = row0 + j * 32u;
-          const uint32_t k = (full || row < n) ? __ldg(keys + row) : 0u;
+          kk[j] = (full || row < n) ? __ldg(keys + row) : 0u;
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < 32; ++j) {
+          const uint32_t k = kk[j];
           const uint32_t cw = __ballot_sync(kFullMask, (s_dict[k >> 5] >> (k & 31u)) & 1u);
           if (lane == j) mine = cw;
         }
@@ -1112,17 +1192,25 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
   if (like_op && full_len && pred.needle_len >= 1u && pred.needle_len <= 31u && max_meta_bytes != 0u && pred.like_steps) {
     const uint32_t smem = str_like_smem(dict_words);
     if (smem <= 100u * 1024u) {
+      // register budget: 4 CTAs per SM (64 registers) by default; LC_LIKE_OCC=3 selects the 80-register build (experiments)
+      static const int occ_pref = [] {
+        const char* e = std::getenv("LC_LIKE_OCC");
+        return (e && e[0] == '3') ? 3 : 4;
+      }();
+      auto kern = [&](int md) -> void (*)(ScanIo, StrPredDesc, uint32_t, uint32_t, uint32_t) {
+        if (occ_pref == 3) return md == MODE_PRED ? k_str_like<MODE_PRED, 3> : k_str_like<MODE_REFINE, 3>;
+        return md == MODE_PRED ? k_str_like<MODE_PRED, 4> : k_str_like<MODE_REFINE, 4>;
+      };
       static bool like_attr = false;
       if (!like_attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_str_like<MODE_PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_str_like<MODE_REFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-        if (e != cudaSuccess) return e;
+        for (int md : {static_cast<int>(MODE_PRED), static_cast<int>(MODE_REFINE)}) {
+          cudaError_t e = cudaFuncSetAttribute(kern(md), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+          if (e != cudaSuccess) return e;
+        }
         like_attr = true;
       }
       int occ = 0;
-      cudaError_t e = mode == MODE_PRED ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_str_like<MODE_PRED>, 256, smem)
-                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_str_like<MODE_REFINE>, 256, smem);
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern(mode), 256, smem);
       if (e != cudaSuccess) return e;
       if (occ < 1) occ = 1;
       // A CTA's 8 warps share a run of neighbouring entries (same symbol table -> same step table in L1). Runs are short —
@@ -1131,8 +1219,7 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
       uint32_t per_cta = (n_entries + 4u * resident - 1u) / (4u * resident);
       per_cta = (per_cta + 7u) & ~7u;  // whole rounds of the CTA's 8 warps
       const uint32_t grid = (n_entries + per_cta - 1u) / per_cta;
-      if (mode == MODE_PRED) k_str_like<MODE_PRED><<<grid, 256, smem, s>>>(io, pred, dict_words, n_entries, per_cta);
-      else k_str_like<MODE_REFINE><<<grid, 256, smem, s>>>(io, pred, dict_words, n_entries, per_cta);
+      kern(mode)<<<grid, 256, smem, s>>>(io, pred, dict_words, n_entries, per_cta);
       return cudaGetLastError();
     }
   }

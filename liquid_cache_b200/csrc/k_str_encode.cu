@@ -433,4 +433,37 @@ cudaError_t launch_str_encode_many(const StrEncIo* d_ios, uint32_t n_batches, ui
   return cudaGetLastError();
 }
 
+// Entry blob of one batch from the pipeline's work areas (see StrAsmWork). 16-byte copies where source and length allow.
+__global__ void __launch_bounds__(256) k_str_assemble(const StrAsmWork* __restrict__ works) {
+  const StrAsmWork& w = works[blockIdx.x];
+  uint8_t* blob = w.blob;
+  if (threadIdx.x < sizeof(StrHeader) / 4) reinterpret_cast<uint32_t*>(blob)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&w.hdr)[threadIdx.x];
+  uint32_t prev_end = sizeof(StrHeader);
+  for (uint32_t q = 0; q <= w.n_segs; ++q) {
+    const bool last = q == w.n_segs;
+    const uint32_t dst = last ? w.blob_bytes : w.segs[q].dst_off;
+    // zero the gap [prev_end, dst): section padding reads as zero
+    for (uint32_t o = prev_end + threadIdx.x; o < dst; o += 256u) blob[o] = 0;
+    if (last) break;
+    const uint8_t* src = w.segs[q].src;
+    const uint32_t bytes = w.segs[q].bytes;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      const uint32_t v16 = bytes >> 4;
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(blob + dst);
+      for (uint32_t i = threadIdx.x; i < v16; i += 256u) d4[i] = s4[i];
+      for (uint32_t o = (v16 << 4) + threadIdx.x; o < bytes; o += 256u) blob[dst + o] = src[o];
+    } else {
+      for (uint32_t o = threadIdx.x; o < bytes; o += 256u) blob[dst + o] = src[o];
+    }
+    prev_end = dst + bytes;
+  }
+}
+
+cudaError_t launch_str_assemble(const StrAsmWork* d_works, uint32_t n_batches, cudaStream_t s) {
+  if (n_batches == 0) return cudaSuccess;
+  k_str_assemble<<<n_batches, 256, 0, s>>>(d_works);
+  return cudaGetLastError();
+}
+
 }  // namespace lc

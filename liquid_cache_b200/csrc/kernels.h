@@ -283,6 +283,23 @@ cudaError_t launch_str_encode(const StrEncIo& io, cudaStream_t s);
 cudaError_t launch_str_encode_many(const StrEncIo* d_ios, uint32_t n_batches, uint32_t max_n, uint32_t* d_tables,
                                    size_t table_words, cudaStream_t s);
 
+// Laying out the entry blobs of a batched insert: one work item per batch, up to 9 sections copied from the encode
+// pipeline's work areas into the blob (dst offsets 16-byte aligned), the gap behind each section zero-filled up to the
+// next one, the 128-byte header written from the work item. One launch instead of ten async calls per batch.
+struct alignas(16) StrAsmSeg {
+  const uint8_t* src;
+  uint32_t dst_off;
+  uint32_t bytes;
+};
+struct alignas(16) StrAsmWork {
+  uint8_t* blob;
+  uint32_t blob_bytes;
+  uint32_t n_segs;
+  StrHeader hdr;
+  StrAsmSeg segs[9];  // ascending dst_off
+};
+cudaError_t launch_str_assemble(const StrAsmWork* d_works, uint32_t n_batches, cudaStream_t s);
+
 // ---- bit utilities -----------------------------------------------------------------------------
 // boolean_buffer_and_then: out[p] = left[p] & right[rank_left(p)]  (datafusion/src/utils.rs:62-236)
 cudaError_t launch_gather_nonzero(const uint32_t* d_words, uint64_t n_words, unsigned long long* d_pairs, uint64_t budget,

@@ -918,6 +918,34 @@ int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values,
   return to_arrow_batch(ctx, esp, scan->n, nullptr, &ds, nullptr, nullptr, &dout);
 }
 
+int lc_scan_read_borrowed(lc_scan* scan, const lc_handle* handles, void** d_values, void** d_offsets, uint64_t* out_rows,
+                          uint64_t* out_value_bytes) {
+  if (!scan || !handles || !d_values || !d_offsets || !out_rows || !out_value_bytes) return LC_ERR_INVALID;
+  lc_ctx* ctx = scan->ctx;
+  Guard g(ctx);
+  Entry* const* esp = nullptr;
+  LC_TRY(scan_entries_cached(scan, handles, &esp));
+  if (!scan->counts_on_device || scan->all_rows) {
+    set_error("lc_scan_read_borrowed: no filter has run on this scan yet");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  uint64_t total_in = 0;
+  for (uint32_t r : scan->rows) total_in += r;
+  FusedDeviceOut out;
+  const int rc = scan_read_fused(ctx, &scan->fused, esp, scan->n, scan->d_sel, scan->d_word_off, scan->d_counts, total_in, nullptr,
+                                 nullptr, &out);
+  if (rc == LC_INTERNAL_FALLBACK) {
+    set_error("lc_scan_read_borrowed: this read is not planned on the device (first read of the scan, nulls, or capacities outgrown)");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  LC_TRY(rc);
+  *d_values = out.d_values;
+  *d_offsets = out.d_offsets;
+  *out_rows = out.rows;
+  *out_value_bytes = out.value_bytes;
+  return LC_OK;
+}
+
 void lc_scan_end(lc_scan* scan) {
   if (!scan) return;
   {

@@ -1459,7 +1459,8 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
 // the call falls back to the host-planned path, which also teaches the next call its sizes.
 // Covers Utf8 / Binary byte views and plain integers without nulls; everything else takes the host-planned path.
 int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t n, const uint32_t* d_sel, const uint64_t* d_word_off,
-                    const uint32_t* d_counts2, uint64_t total_rows_in, ArrowSchema* out_schema, ArrowArray* out_array) {
+                    const uint32_t* d_counts2, uint64_t total_rows_in, ArrowSchema* out_schema, ArrowArray* out_array,
+                    FusedDeviceOut* dev_out) {
   if (!fr->have_spec) return LC_INTERNAL_FALLBACK;
   const RefList* rl;
   LC_TRY(get_ref_list(ctx, entries, n, &rl));
@@ -1536,10 +1537,12 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
     io.abort_flag = &d_hdr->overflow;  // survivors beyond the capacity: the kernel returns without writing
     LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
     ctx->kernel_launches++;
-    values = HostBuf{host_alloc(spec_rows * tb + 64, true), spec_rows * tb};
-    if (!values.p) return LC_ERR_OOM;
     LC_CUDA_OK(cudaMemcpyAsync(fr->h_hdr, d_hdr, sizeof(ScanPlanHdr), cudaMemcpyDeviceToHost, s));
-    LC_CUDA_OK(cudaMemcpyAsync(values.p, d + o_val, std::min(spec_rows, cap_rows) * tb, cudaMemcpyDeviceToHost, s));
+    if (!dev_out) {
+      values = HostBuf{host_alloc(spec_rows * tb + 64, true), spec_rows * tb};
+      if (!values.p) return LC_ERR_OOM;
+      LC_CUDA_OK(cudaMemcpyAsync(values.p, d + o_val, std::min(spec_rows, cap_rows) * tb, cudaMemcpyDeviceToHost, s));
+    }
   } else {
     StrGatherIo g{};
     g.io = io;
@@ -1557,16 +1560,18 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
     LC_CUDA_OK(launch_scan_plan_bytes(d_cnt, static_cast<uint32_t>(n), cap_bytes, d_bb, g.out_offsets, d_hdr, s));
     LC_CUDA_OK(launch_str_decode(static_cast<uint32_t>(n), g, s));
     ctx->kernel_launches += 3;
-    offsets = HostBuf{host_alloc((spec_rows + 1) * 4 + 64, true), (spec_rows + 1) * 4};
-    values = HostBuf{host_alloc(spec_bytes + 64, true), spec_bytes};
-    if (!offsets.p || !values.p) {
-      host_free(offsets.p);
-      host_free(values.p);
-      return LC_ERR_OOM;
-    }
     LC_CUDA_OK(cudaMemcpyAsync(fr->h_hdr, d_hdr, sizeof(ScanPlanHdr), cudaMemcpyDeviceToHost, s));
-    LC_CUDA_OK(cudaMemcpyAsync(offsets.p, g.out_offsets, (std::min(spec_rows, cap_rows) + 1) * 4, cudaMemcpyDeviceToHost, s));
-    LC_CUDA_OK(cudaMemcpyAsync(values.p, g.out_bytes, std::min(spec_bytes, cap_bytes), cudaMemcpyDeviceToHost, s));
+    if (!dev_out) {
+      offsets = HostBuf{host_alloc((spec_rows + 1) * 4 + 64, true), (spec_rows + 1) * 4};
+      values = HostBuf{host_alloc(spec_bytes + 64, true), spec_bytes};
+      if (!offsets.p || !values.p) {
+        host_free(offsets.p);
+        host_free(values.p);
+        return LC_ERR_OOM;
+      }
+      LC_CUDA_OK(cudaMemcpyAsync(offsets.p, g.out_offsets, (std::min(spec_rows, cap_rows) + 1) * 4, cudaMemcpyDeviceToHost, s));
+      LC_CUDA_OK(cudaMemcpyAsync(values.p, g.out_bytes, std::min(spec_bytes, cap_bytes), cudaMemcpyDeviceToHost, s));
+    }
   }
   tr.mark("launches");
   cudaError_t ce = cudaStreamSynchronize(s);
@@ -1588,6 +1593,18 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
     return LC_INTERNAL_FALLBACK;
   }
   const uint64_t rows = hdr.rows, bytes = is_int ? rows * tb : hdr.bytes;
+  if (dev_out) {  // the result stays in the scan's device buffer (valid until the next read of this scan)
+    ctx->d2h_bytes += sizeof(ScanPlanHdr);
+    fr->spec_rows = rows;
+    fr->spec_bytes = is_int ? 0 : bytes;
+    fr->spec_ulen = hdr.ulen_words;
+    fr->fused_reads++;
+    dev_out->d_values = d + o_val;
+    dev_out->d_offsets = is_int ? nullptr : d + o_off;
+    dev_out->rows = rows;
+    dev_out->value_bytes = bytes;
+    return LC_OK;
+  }
   ctx->d2h_bytes += sizeof(ScanPlanHdr) + (is_int ? std::min(spec_rows, cap_rows) * tb
                                                   : (std::min(spec_rows, cap_rows) + 1) * 4 + std::min(spec_bytes, cap_bytes));
   if (rows > spec_rows || (!is_int && bytes > spec_bytes)) {

@@ -10,6 +10,9 @@
 #include <algorithm>
 #include <cmath>
 
+#include <chrono>
+#include <cstdlib>
+
 #include "host_common.h"
 #include "host_pool.h"
 
@@ -516,7 +519,22 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
 // sections of every blob are moved device-to-device. Two stream synchronisations per group of batches instead of three
 // per batch. Symbol tables are trained first, on the first batch of every column chunk that has none yet
 // (transcode.rs:16-33), exactly as the one-batch path would have done in the same order.
+namespace {
+struct EncTracer {  // LC_TRACE=1: wall-clock split of a batched insert, printed to stderr
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  EncTracer() : on(std::getenv("LC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* stage) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[lc_trace] str_encode_many: %s %.3f ms\n", stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, const uint64_t* scopes, std::vector<Entry*>* out) {
+  EncTracer tr;
   const uint64_t nb_all = ins.size();
   out->clear();
   if (nb_all == 0) return LC_OK;
@@ -534,6 +552,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       set_error("batch %llu: %s", (unsigned long long)i, errs[i].c_str());
       return rcs[i];
     }
+  tr.mark("row plans");
   // Symbol tables: every column chunk without one is trained on ITS first batch of this list (what the one-batch path would
   // have done in the same order). Training is ~2 ms of host work per chunk (measured: 1 695 URL values), so the chunks are
   // trained side by side on the host pool; the tables are uploaded afterwards with one synchronisation.
@@ -556,6 +575,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       trained[t] = codec;
     }
   });
+  tr.mark("fsst training");
   for (uint64_t t = 0; t < train_first.size(); ++t) {
     std::shared_ptr<FsstCodec>& codec = trained[t];
     if (cudaMalloc(reinterpret_cast<void**>(&codec->d_dec), sizeof(FsstTable)) != cudaSuccess ||
@@ -589,11 +609,12 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
     const uint64_t nb = std::min<uint64_t>(kGroup, nb_all - g0);
     // ---- per-batch offsets: upload block [row_off | row_len | validity | pool] mirrored host/device, then work areas ----
     struct Off {
-      uint64_t up, off_len, vbytes, pool, table, slot, leader, uniq, clen, offsets, fps, blooms, resid, keys, pkeys, comp, res;
+      uint64_t up, off_len, vbytes, pool, pool_staged_end = 0, table, slot, leader, uniq, clen, offsets, fps, blooms, resid, keys, pkeys, comp, res;
       uint32_t cap;
     };
     std::vector<Off> offs(nb);
     uint64_t cur = 0, max_n = 0;
+    // per-row (offset, length) pairs and validity of every batch first, the work items behind them (one upload) ...
     for (uint64_t i = 0; i < nb; ++i) {
       const RowPlan& pl = plans[g0 + i];
       Off& o = offs[i];
@@ -601,16 +622,41 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       o.vbytes = pl.has_input_nulls ? round_up((pl.n + 31) / 32 * 4, 16) : 0;
       o.up = cur;
       cur += 2 * o.off_len + round_up(o.vbytes, 256);
-      o.pool = cur;
-      cur += round_up(pl.pool_bytes + 64, 256);
       max_n = std::max<uint64_t>(max_n, pl.n);
     }
-    const uint64_t up_bytes = cur;
     const uint64_t ios_off = cur;
     cur += round_up(nb * sizeof(StrEncIo), 256);
+    // ... then the value bytes. A batch whose Arrow buffers are PAGE-LOCKED is uploaded straight from them (no staging
+    // copy on the host: the caller's memory is the DMA source); pageable batches are staged into pinned scratch first.
+    std::vector<uint8_t> direct(nb, 0);
+    for (uint64_t i = 0; i < nb; ++i) {
+      const RowPlan& pl = plans[g0 + i];
+      bool pinned = !pl.segs.empty();
+      for (const PoolSeg& sg : pl.segs) {
+        if (!sg.bytes) continue;
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, sg.p) != cudaSuccess || pa.type != cudaMemoryTypeHost) pinned = false;
+      }
+      cudaGetLastError();
+      direct[i] = pinned;
+    }
+    const uint64_t pool_begin = cur;
+    for (int pass = 0; pass < 2; ++pass)  // staged pools first (they travel with the upload block), direct ones behind
+      for (uint64_t i = 0; i < nb; ++i) {
+        if ((direct[i] != 0) != (pass == 1)) continue;
+        offs[i].pool = cur;
+        cur += round_up(plans[g0 + i].pool_bytes + 64, 256);
+        if (pass == 0) offs[i].pool_staged_end = cur;
+      }
+    uint64_t staged_end = pool_begin;
+    for (uint64_t i = 0; i < nb; ++i)
+      if (!direct[i]) staged_end = std::max(staged_end, offs[i].pool_staged_end);
+    const uint64_t up_bytes = cur;
     const uint64_t hdr_off = cur;  // host only: blob headers staged for their uploads
     const uint64_t res_off = cur;  // device: results (the header staging area on the host side is reused after the sync)
     cur += round_up(nb * std::max(sizeof(StrEncResult), sizeof(StrHeader)), 256);
+    const uint64_t asm_off = cur;  // blob assembly work items (host staging + device copy)
+    cur += round_up(nb * sizeof(StrAsmWork), 256);
     const uint64_t host_total = cur;
     const uint64_t table_off = cur;  // all hash tables back to back: one memset
     uint64_t table_words = 0;
@@ -667,8 +713,9 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
           std::memset(h + o.up + 2 * o.off_len, 0, o.vbytes);
           std::memcpy(h + o.up + 2 * o.off_len, pl.valid_bits.data(), (pl.n + 7) / 8);
         }
-        for (const PoolSeg& sg : pl.segs)
-          if (sg.bytes) std::memcpy(h + o.pool + sg.base, sg.p, sg.bytes);
+        if (!direct[i])
+          for (const PoolSeg& sg : pl.segs)
+            if (sg.bytes) std::memcpy(h + o.pool + sg.base, sg.p, sg.bytes);
         StrEncIo io{};
         io.pool = d + o.pool;
         io.row_off = reinterpret_cast<const uint32_t*>(d + o.up);
@@ -693,7 +740,13 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
         h_ios[i] = io;
       }
     });
-    cudaError_t ce = cudaMemcpyAsync(d, h, ios_off + nb * sizeof(StrEncIo), cudaMemcpyHostToDevice, s);
+    tr.mark("stage into pinned memory");
+    cudaError_t ce = cudaMemcpyAsync(d, h, staged_end, cudaMemcpyHostToDevice, s);
+    for (uint64_t i = 0; i < nb && ce == cudaSuccess; ++i) {
+      if (!direct[i]) continue;
+      for (const PoolSeg& sg : plans[g0 + i].segs)
+        if (sg.bytes && ce == cudaSuccess) ce = cudaMemcpyAsync(d + offs[i].pool + sg.base, sg.p, sg.bytes, cudaMemcpyHostToDevice, s);
+    }
     if (ce == cudaSuccess)
       ce = launch_str_encode_many(reinterpret_cast<const StrEncIo*>(d + ios_off), static_cast<uint32_t>(nb), static_cast<uint32_t>(max_n),
                                   reinterpret_cast<uint32_t*>(d + table_off), table_words, s);
@@ -705,12 +758,13 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       set_error("CUDA error in str_encode_many: %s", cudaGetErrorString(ce));
       return LC_ERR_CUDA;
     }
+    tr.mark("upload + 5 kernels + results");
     ctx->kernel_launches += 5;
     ctx->h2d_bytes += up_bytes + nb * sizeof(StrEncIo);
     ctx->d2h_bytes += nb * sizeof(StrEncResult);
     // ---- blob layout per batch (sizes are known now), sections moved device-to-device ----
     std::vector<StrEncResult> results(h_res, h_res + nb);  // the pinned area is reused for the headers below
-    StrHeader* h_hdr = reinterpret_cast<StrHeader*>(h + hdr_off);
+    StrAsmWork* h_asm = reinterpret_cast<StrAsmWork*>(h + asm_off);
     for (uint64_t i = 0; i < nb; ++i) {
       const StrEncResult& r = results[i];
       const RowPlan& pl = plans[g0 + i];
@@ -783,25 +837,25 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       taken.push_back({d_blob, slab, o});
       uint32_t first_valid = 0;
       while (first_valid < n && !pl.row_is_valid(first_valid)) ++first_valid;
-      h_hdr[i] = hd;
-      ce = cudaMemsetAsync(d_blob, 0, o, s);  // padding between sections reads as zero
-      if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_blob, &h_hdr[i], sizeof(StrHeader), cudaMemcpyHostToDevice, s);
-      auto d2d = [&](uint32_t dst_off, const void* src, uint64_t bytes) {
-        if (bytes && ce == cudaSuccess) ce = cudaMemcpyAsync(d_blob + dst_off, src, bytes, cudaMemcpyDeviceToDevice, s);
+      // the blob is laid out by ONE kernel for the whole group (k_str_assemble): sections from the pipeline's work areas,
+      // gaps zeroed, header written — instead of a memset and nine device-to-device copies per batch
+      StrAsmWork& aw = h_asm[i];
+      aw.blob = d_blob;
+      aw.blob_bytes = hd.blob_bytes;
+      aw.hdr = hd;
+      aw.n_segs = 0;
+      auto seg = [&](uint32_t dst_off, const void* src, uint64_t bytes) {
+        if (!bytes) return;
+        aw.segs[aw.n_segs++] = StrAsmSeg{static_cast<const uint8_t*>(src), dst_off, static_cast<uint32_t>(bytes)};
       };
-      if (spl) d2d(hd.shared_prefix_off, d + of.pool + pl.row_off[first_valid], spl);
-      if (build_fp) d2d(hd.fp_off, d + of.fps, 4ull * U);
-      if (hd.bloom_off) d2d(hd.bloom_off, d + of.blooms, 8ull * kBloomWords * U);
-      d2d(hd.resid_off, d + of.resid, static_cast<uint64_t>(ob) * (U + 1));
-      d2d(hd.prefix_keys_off, d + of.pkeys, 8ull * U);
-      if (hd.has_nulls) d2d(hd.validity_off, d + of.up + 2 * of.off_len, (n + 7) / 8);
-      d2d(hd.keys_off, d + of.keys, 2ull * n);
-      d2d(hd.fsst_off, d + of.comp, co);
-      if (ce != cudaSuccess) {
-        give_back();
-        set_error("CUDA error in str_encode_many: %s", cudaGetErrorString(ce));
-        return LC_ERR_CUDA;
-      }
+      if (spl) seg(hd.shared_prefix_off, d + of.pool + pl.row_off[first_valid], spl);
+      if (build_fp) seg(hd.fp_off, d + of.fps, 4ull * U);
+      seg(hd.resid_off, d + of.resid, static_cast<uint64_t>(ob) * (U + 1));
+      seg(hd.prefix_keys_off, d + of.pkeys, 8ull * U);
+      if (hd.has_nulls) seg(hd.validity_off, d + of.up + 2 * of.off_len, (n + 7) / 8);
+      seg(hd.keys_off, d + of.keys, 2ull * n);
+      if (hd.bloom_off) seg(hd.bloom_off, d + of.blooms, 8ull * kBloomWords * U);
+      seg(hd.fsst_off, d + of.comp, co);
       Entry* e = new Entry();
       e->liquid_type = LC_LIQUID_BYTE_VIEW;
       e->d_blob = d_blob;
@@ -818,13 +872,18 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       e->codec = codecs[g0 + i];
       out->push_back(e);
     }
-    ce = cudaStreamSynchronize(s);  // the group's scratch is reused by the next group
+    ce = cudaMemcpyAsync(d + asm_off, h_asm, nb * sizeof(StrAsmWork), cudaMemcpyHostToDevice, s);
+    if (ce == cudaSuccess) ce = launch_str_assemble(reinterpret_cast<const StrAsmWork*>(d + asm_off), static_cast<uint32_t>(nb), s);
+    ctx->kernel_launches++;
+    tr.mark("blob layout + assembly launched");
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);  // the group's scratch is reused by the next group
     if (ce != cudaSuccess) {
       give_back();
       set_error("CUDA error in str_encode_many: %s", cudaGetErrorString(ce));
       return LC_ERR_CUDA;
     }
-    ctx->h2d_bytes += nb * sizeof(StrHeader);
+    tr.mark("section copies done");
+    ctx->h2d_bytes += nb * sizeof(StrAsmWork);
   }
   ctx->n_entries += out->size();
   return LC_OK;

@@ -154,3 +154,100 @@ def gather_device_result_to_rank0(values, offsets, validity, rows: int, nulls: i
     for nr, nn, tv, to, tb in recv:
         parts.append(host_array(tv, to.view(torch.int32) if to is not None else None, tb, nr, nn))
     return pa.concat_arrays(parts)
+
+
+class StepGather:
+    """The gather of `gather_device_result_to_rank0`, shaped for use INSIDE a timed loop: buffers are allocated once and
+    grown geometrically, the per-rank sizes travel in one small all_gather, every part lands at its final position in rank
+    0's buffers (no per-part host bounce), string offsets are rebased on the device, and rank 0 downloads the finished
+    Arrow buffers once into page-locked memory that the returned array references directly.
+
+    One host synchronisation on every rank (the sizes), one more on rank 0 (the result)."""
+
+    def __init__(self, arrow_type: pa.DataType, rank: int, world: int, device):
+        import torch
+
+        self.t, self.rank, self.world, self.dev = arrow_type, rank, world, device
+        self.is_bytes = pa.types.is_string(arrow_type) or pa.types.is_binary(arrow_type)
+        self.width = 0 if self.is_bytes else arrow_type.bit_width // 8
+        self.torch = torch
+        self.sizes = torch.zeros(2, dtype=torch.int64, device=device)
+        self.all_sizes = torch.zeros(2 * world, dtype=torch.int64, device=device)
+        self.vals = self.offs = self.offs_packed = None
+        self.h_vals = self.h_offs = None
+        self.pin = device.type == "cuda"
+
+    def _grow(self, name: str, n: int, dtype, host: bool):
+        cur = getattr(self, name)
+        if cur is None or cur.numel() < n:
+            cap = max(n + n // 2, 1 << 16)
+            t = (self.torch.empty(cap, dtype=dtype, pin_memory=self.pin) if host
+                 else self.torch.empty(cap, dtype=dtype, device=self.dev))
+            setattr(self, name, t)
+        return getattr(self, name)
+
+    def gather(self, values, offsets, rows: int) -> Optional[pa.Array]:
+        """values: u8 tensor of this rank's value bytes (ints: rows * width bytes); offsets: i32 tensor [rows + 1] for byte
+        types, else None. No nulls (the bench columns have none). Returns the concatenation on rank 0."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        nbytes = int(values.numel())
+        if self.world == 1:
+            all_sizes = [rows, nbytes]
+        else:
+            self.sizes[0] = rows
+            self.sizes[1] = nbytes
+            dist.all_gather_into_tensor(self.all_sizes, self.sizes)
+            all_sizes = self.all_sizes.cpu().tolist()  # the one synchronisation every rank pays
+        rows_r = [int(all_sizes[2 * r]) for r in range(self.world)]
+        bytes_r = [int(all_sizes[2 * r + 1]) for r in range(self.world)]
+        if self.rank != 0:
+            ops = []
+            if nbytes:
+                ops.append(dist.P2POp(dist.isend, values, 0))
+            if self.is_bytes and rows:
+                ops.append(dist.P2POp(dist.isend, offsets[: rows + 1].view(torch.uint8), 0))
+            for w in (dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+            return None
+        tot_rows, tot_bytes = sum(rows_r), sum(bytes_r)
+        vals = self._grow("vals", max(tot_bytes, 1), torch.uint8, False)
+        vals[:nbytes].copy_(values, non_blocking=True)
+        offs = None
+        if self.is_bytes:
+            offs = self._grow("offs", tot_rows + self.world + 1, torch.int32, False)
+            offs[: rows + 1].copy_(offsets[: rows + 1], non_blocking=True)
+        ops, places = [], []
+        vb, ob = nbytes, rows + 1
+        for r in range(1, self.world):
+            if bytes_r[r]:
+                ops.append(dist.P2POp(dist.irecv, vals[vb: vb + bytes_r[r]], r))
+            if self.is_bytes and rows_r[r]:
+                # each part arrives with its own rows + 1 offsets; they are rebased and packed below
+                ops.append(dist.P2POp(dist.irecv, offs[ob: ob + rows_r[r] + 1].view(torch.uint8), r))
+            places.append((r, vb, ob))
+            vb += bytes_r[r]
+            ob += rows_r[r] + 1
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        h_vals = self._grow("h_vals", max(tot_bytes, 1), torch.uint8, True)
+        if self.is_bytes:
+            # pack the offsets: part r's rows start at byte vb_r of the concatenation; its first offset (0) is dropped
+            packed = self._grow("offs_packed", tot_rows + 1, torch.int32, False)
+            packed[: rows + 1].copy_(offs[: rows + 1])
+            at = rows + 1
+            for r, vb_r, ob_r in places:
+                if rows_r[r]:
+                    packed[at: at + rows_r[r]] = offs[ob_r + 1: ob_r + 1 + rows_r[r]] + vb_r
+                    at += rows_r[r]
+            h_offs = self._grow("h_offs", tot_rows + 1, torch.int32, True)
+            h_offs[: tot_rows + 1].copy_(packed[: tot_rows + 1], non_blocking=True)
+        h_vals[:tot_bytes].copy_(vals[:tot_bytes], non_blocking=True)
+        if self.pin:
+            torch.cuda.current_stream().synchronize()
+        data = pa.foreign_buffer(h_vals.data_ptr(), tot_bytes, base=h_vals)
+        if self.is_bytes:
+            ofb = pa.foreign_buffer(h_offs.data_ptr(), (tot_rows + 1) * 4, base=h_offs)
+            return pa.Array.from_buffers(self.t, tot_rows, [None, ofb, data], null_count=0)
+        return pa.Array.from_buffers(self.t, tot_rows, [None, data], null_count=0)

@@ -100,3 +100,61 @@ def test_sharding_keeps_all_columns_of_a_batch_together():
                     assert len(owners) == 1
         if world > 1:
             assert min(len(p) for p in parts) > 0.5 * len(ids) / world
+
+
+def _step_gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from liquid_cache_b200.dist import StepGather, _buffers_of
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dev = torch.device("cpu")
+        gs = StepGather(pa.string(), rank, world, dev)
+        gi = StepGather(pa.int32(), rank, world, dev)
+        local, got = [], []
+        for step in range(4):  # sizes change from step to step, one rank is empty in step 2: buffers are reused / grown
+            rng = np.random.default_rng(1000 * step + rank)
+            n = 0 if (step == 2 and rank == 1) else int(rng.integers(1, 200)) * (step + 1)
+            strs = pa.array([f"http://r{rank}/s{step}/{i}" * int(rng.integers(1, 4)) for i in range(n)], pa.string())
+            ints = pa.array(rng.integers(-1000, 1000, size=n).astype(np.int32), pa.int32())
+            _v, off, data = _buffers_of(strs)
+            v = torch.from_numpy(data.copy()) if len(data) else torch.zeros(0, dtype=torch.uint8)
+            o = torch.from_numpy(off.copy()) if n else torch.zeros(1, dtype=torch.int32)
+            g = gs.gather(v, o, n)
+            _v, _o, idata = _buffers_of(ints)
+            iv = torch.from_numpy(idata.copy()) if n else torch.zeros(0, dtype=torch.uint8)
+            h = gi.gather(iv, None, n)
+            local.append((strs.to_pylist(), ints.to_pylist()))
+            got.append((None if g is None else g.to_pylist(), None if h is None else h.to_pylist()))
+        q.put((rank, local, got))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_step_gather_world2_matches_concatenation():
+    """StepGather (the gather bench.py times inside its step at N > 1): every step's concatenation on rank 0 equals the
+    ranks' arrays in rank order, with buffers reused across steps."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_step_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        rank, local, got = q.get(timeout=120)
+        res[rank] = (local, got)
+    for p in procs:
+        p.join(timeout=60)
+    for step in range(4):
+        want_s = res[0][0][step][0] + res[1][0][step][0]
+        want_i = res[0][0][step][1] + res[1][0][step][1]
+        assert res[0][1][step][0] == want_s
+        assert res[0][1][step][1] == want_i
+        assert res[1][1][step] == (None, None)
