@@ -697,7 +697,7 @@ def main():
                                    parquet_array_id)
 
     torch.cuda.set_device(local_rank)
-    pin = pin_to_gpu_numa(local_rank)
+    numa_pin = pin_to_gpu_numa(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -774,8 +774,8 @@ def main():
         ref_pass = uniques
         rows_phase_entries = n_entries
     algo_bytes = 2 * rows_local + meta_bytes + cand_bytes + rows_local // 8
-    algo_bytes_private = algo_bytes + 32 * ref_pass
-    kernel_reads = meta_bytes + 32 * ref_pass + cand_bytes + rows_phase_entries * 2 * ROWS_PER_ENTRY + rows_local // 8
+    algo_bytes_private = algo_bytes + 32 * uniques
+    kernel_reads = meta_bytes + 32 * uniques + cand_bytes + rows_phase_entries * 2 * ROWS_PER_ENTRY + rows_local // 8  # every value's filter is fetched
 
     k_start = torch.cuda.Event(enable_timing=True)
     k_stop = torch.cuda.Event(enable_timing=True)
@@ -911,7 +911,7 @@ def main():
                 "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "rows_per_entry": ROWS_PER_ENTRY,
                 "liquid_bytes_per_gpu": hbm_bytes, "liquid_bytes_per_row": hbm_bytes / rows_local,
                 "unique_values_per_entry": uniques / n_entries, "walked_candidates_frac": cand / max(1, uniques),
-                "matching_rows": int(gathered_rows), "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective; the filtered batches are gathered to rank 0 over NCCL inside every timed step" if world > 1 else "one GPU", "numa": pin,
+                "matching_rows": int(gathered_rows), "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective; the filtered batches are gathered to rank 0 over NCCL inside every timed step" if world > 1 else "one GPU", "numa": numa_pin,
                 "l2": "inputs (liquid column) larger than the 126 MB L2, no flush needed",
                 "setup_seconds": setup_s,
                 "insert": {"Mrows_per_s": rows_local / insert_s / 1e6, "arrow_GB_per_s": arrow_bytes / insert_s / 1e9,

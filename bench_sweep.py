@@ -133,7 +133,7 @@ def arrow_mask(arr, op, literal):
 
 
 def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: int = 1, device=None, check_batches: int = 64,
-              timer=None, log=None):
+              timer=None, log=None, peak_gbs: float = 0.0):
     """Inserts the shard, runs every query `warmup + steps` times, returns the result dict (rank-local; the caller
     reduces over ranks). `timer()` returns a callable pair (start, stop->ms) — CUDA events in bench.py, perf_counter in tests."""
     import numpy as np
@@ -151,7 +151,14 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
     first = rank * n_entries
     ids = {c: [] for c in cols}
     types = {c: sample.cols[c].type for c in cols}
-    keep = {c: [] for c in cols}  # the first `check_batches` batches stay on the host for the parity check
+    def conjunct_literal(lit):
+        return lits[lit] if isinstance(lit, str) and lit.startswith("@") else lit
+
+    distinct_conj = {}
+    for _q, conj, _proj in QUERIES:
+        if conj:
+            distinct_conj.setdefault(repr(conj), conj)
+    expected = {k: np.zeros(n_entries, dtype=np.int64) for k in distinct_conj}
     t_setup = time.perf_counter()
     insert_s = {"int": 0.0, "str": 0.0}
     group = 512
@@ -169,17 +176,23 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
                 cache.insert_many(eids, batches[c])
                 insert_s["int"] += time.perf_counter() - t0
             ids[c].extend(int(e) for e in eids)
-            if g0 < check_batches:
-                keep[c].extend(batches[c][: max(0, check_batches - g0)])
+        # parity data: Arrow's survivor counts per batch for every distinct conjunct list, computed on the very arrays that were
+        # inserted, while they are at hand (check_batches >= the shard = every batch of the shard is checked)
+        m = min(nb, max(0, check_batches - g0))
+        if m:
+            for key, conj in distinct_conj.items():
+                want = np.ones((m, ROWS_PER_ENTRY), dtype=bool)
+                for column, op, lit in conj:
+                    mk = arrow_mask(pa.concat_arrays(batches[column][:m]), op, conjunct_literal(lit))
+                    want &= np.asarray(mk.fill_null(False).to_numpy(zero_copy_only=False), dtype=bool).reshape(m, ROWS_PER_ENTRY)
+                expected[key][g0:g0 + m] = want.sum(axis=1)
     setup_s = time.perf_counter() - t_setup
     handles = {c: cache.handles(ids[c]) for c in cols}
+    col_bytes = {c: (sum(int(N.lib().lc_memory_size(cache._ctx, int(h))) for h in handles[c]) if hasattr(cache, "_ctx") else 0) for c in cols}
     rows_local = n_entries * ROWS_PER_ENTRY
     rows_arr = np.full(n_entries, ROWS_PER_ENTRY, dtype=np.uint64)
     scan = cache.scan(rows_arr)
     n_check = min(check_batches, n_entries)
-
-    def conjunct_literal(lit):
-        return lits[lit] if isinstance(lit, str) and lit.startswith("@") else lit
 
     def host_fallback(column, op, lit):
         """column.rs:143-151: decode the selected rows of every batch, evaluate with Arrow, write the selection back."""
@@ -195,7 +208,7 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
             pos += k
             scan.set_selection(b, new)
 
-    def run_query(conj, proj, to_host):
+    def run_query(conj, proj, to_host, want_counts=False):
         scan.reset()
         for column, op, lit in conj:
             lit = conjunct_literal(lit)
@@ -204,11 +217,20 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
                 continue
             expr = LiquidExpr.try_new(make_expr(column, op, lit, types[column]), types[column], CacheExpression.SubstringSearch)
             scan.filter(handles[column], expr, types[column])
-        counts, total = scan.counts()
         out = []
-        if total or not conj:
+        counts, total = None, None
+        if want_counts or not proj or not conj:
+            counts, total = scan.counts()  # COUNT(*)-shaped queries need the survivor count itself; so does the parity check
+        if not conj or total is None or total:
             for c in proj:
-                out.append(scan.read(handles[c]) if to_host else scan.read_torch(handles[c], device))
+                if to_host or not conj:
+                    out.append(scan.read(handles[c]))  # after a filter: planned on the device, one synchronisation
+                else:
+                    r = scan.read_torch_borrowed(handles[c], device)
+                    out.append(r if r is not None else scan.read_torch(handles[c], device))
+        if total is None:
+            first_out = out[0]
+            total = len(first_out) if (to_host or not isinstance(first_out, tuple)) else int(first_out[2] if len(first_out) == 3 else first_out[3])
         return counts, total, out
 
     def safe(fn):
@@ -223,7 +245,7 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
         if not conj and not proj:
             results.append({"q": q, "ms": 0.0, "e2e_ms": 0.0, "rows_out": rows_local, "note": "no column touched"})
             continue
-        first, err = safe(lambda: run_query(conj, proj, False))
+        first, err = safe(lambda: run_query(conj, proj, False, want_counts=True))
         if err:
             results.append({"q": q, "ms": 0.0, "e2e_ms": 0.0, "rows_out": 0, "note": "not run: " + err})
             continue
@@ -231,11 +253,9 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
             run_query(conj, proj, False)
         counts, total, _ = first
         # parity on the first batches: survivor counts against Arrow on the very arrays that were inserted
-        want = np.ones((n_check, ROWS_PER_ENTRY), dtype=bool)
-        for column, op, lit in conj:
-            m = arrow_mask(pa.concat_arrays(keep[column][:n_check]), op, conjunct_literal(lit))
-            want &= np.asarray(m.fill_null(False).to_numpy(zero_copy_only=False), dtype=bool).reshape(n_check, ROWS_PER_ENTRY)
-        ok = bool(np.array_equal(np.asarray(counts[:n_check], dtype=np.int64), want.sum(axis=1)))
+        ok = True
+        if conj:
+            ok = bool(np.array_equal(np.asarray(counts[:n_check], dtype=np.int64), expected[repr(conj)][:n_check]))
         ms = []
         for _ in range(steps):
             start, stop = timer()
@@ -247,9 +267,24 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
             t0 = time.perf_counter()
             run_query(conj, proj, True)
             e2e.append((time.perf_counter() - t0) * 1e3)
-        pred_bytes = sum(int(N.lib().lc_memory_size(cache._ctx, int(h))) for column, _o, _l in conj for h in handles[column]) if hasattr(cache, "_ctx") else 0
-        r = {"q": q, "ms": float(np.median(ms)), "e2e_ms": float(np.median(e2e)), "rows_out": int(total), "selectivity": int(total) / rows_local,
-             "conjuncts": len(conj), "projected": len(proj), "counts_match_arrow": ok, "predicate_column_bytes": pred_bytes}
+        pred_cols = []
+        for column, _o, _l in conj:
+            if column not in pred_cols:
+                pred_cols.append(column)
+        pred_bytes = sum(col_bytes[c] for c in pred_cols)
+        # projected columns are read only where rows survive: batches without survivors are never touched
+        hit_frac = float(np.count_nonzero(np.asarray(counts)) / n_entries) if conj else 1.0
+        proj_bytes = int(sum(col_bytes[c] for c in proj) * hit_frac) if (total or not conj) else 0
+        sel_bytes = (rows_local // 8) * max(0, 2 * len(conj) - 1)  # running selection: written by the first conjunct, read + written after
+        med_ms = float(np.median(ms))
+        touched = pred_bytes + proj_bytes + sel_bytes
+        r = {"q": q, "ms": med_ms, "e2e_ms": float(np.median(e2e)), "rows_out": int(total), "selectivity": int(total) / rows_local,
+             "conjuncts": len(conj), "projected": len(proj), "counts_match_arrow": ok, "batches_checked": n_check,
+             "predicate_column_bytes": pred_bytes, "projected_column_bytes_read": proj_bytes,
+             "roofline": {"bound": "hbm", "algorithmic_bytes": touched, "achieved": touched / (med_ms / 1e3) / 1e9 if med_ms else 0.0,
+                          "unit": "GB/s", "peak": peak_gbs, "frac": (touched / (med_ms / 1e3) / 1e9 / peak_gbs) if (med_ms and peak_gbs) else None,
+                          "note": "liquid bytes of the predicate columns + of the projected columns in batches with survivors + the "
+                                  "running selection, over the query's device time (all launches, host gaps included)"}}
         if q in NOTES:
             r["note"] = NOTES[q]
         results.append(r)
@@ -298,7 +333,10 @@ def main(args, rank, world, local_rank):
     clocks = bench.ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    peak0, _src0 = bench.measured_peak_gbs()
+    check = 1 << 30 if os.environ.get("LC_SWEEP_CHECK_ALL") == "1" else 64  # every batch of the shard, or the first 64
     res = run_sweep(cache, rows, max(3, args.steps // 4), max(3, args.warmup), rank, world, torch.device("cuda", local_rank), timer=timer,
+                    check_batches=check, peak_gbs=peak0,
                     log=(lambda s: print(s, file=sys.stderr)) if rank == 0 and os.environ.get("LC_BENCH_TRACE") == "1" else None)
     t = torch.tensor([res["sweep_ms"], res["sweep_e2e_ms"]], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -319,6 +357,7 @@ def main(args, rank, world, local_rank):
                        "rows_per_gpu": res["rows_local"], "entries_per_gpu_per_column": res["n_entries"], "columns": len(columns_used()),
                        "liquid_bytes_per_gpu": int(cache.stats().hbm_bytes_used), "setup_seconds": res["setup_seconds"],
                        "insert_seconds": res["insert_seconds"], "all_counts_match_arrow": res["all_counts_match_arrow"],
+                       "batches_checked_against_arrow": min(check, res["n_entries"]),
                        "literals_from_sample": res["literals_from_sample"], "slowest_queries": [{"q": r["q"], "ms": r["ms"]} for r in slow],
                        "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective"},
             "e2e": {"value": scanned / (sweep_e2e / 1e3) / 1e6, "unit": "Mrows/s", "ms_per_step": sweep_e2e},

@@ -72,6 +72,9 @@ class FakeScan:
     def read_torch(self, handles, device):
         return self.read(handles)
 
+    def read_torch_borrowed(self, handles, device):
+        return None  # the double has no device: the sweep falls back to read_torch
+
     def close(self):
         pass
 
