@@ -223,10 +223,10 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
             counts, total = scan.counts()  # COUNT(*)-shaped queries need the survivor count itself; so does the parity check
         if not conj or total is None or total:
             for c in proj:
-                if to_host or not conj:
+                if to_host:
                     out.append(scan.read(handles[c]))  # after a filter: planned on the device, one synchronisation
                 else:
-                    r = scan.read_torch_borrowed(handles[c], device)
+                    r = scan.read_torch_borrowed(handles[c], device) if conj else None  # no filter: a plain full-column decode
                     out.append(r if r is not None else scan.read_torch(handles[c], device))
         if total is None:
             first_out = out[0]

@@ -29,7 +29,7 @@ PinnedPool& pinned_pool() {
   return *p;
 }
 constexpr uint64_t kPinnedMin = 1ull << 20;
-constexpr uint64_t kPinnedIdleMax = 2ull << 30;
+constexpr uint64_t kPinnedIdleMax = 8ull << 30;  // full-column string reads of the sweep are > 1 GiB each
 }  // namespace
 
 uint8_t* host_alloc(uint64_t bytes, bool force_pinned) {

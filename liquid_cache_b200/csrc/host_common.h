@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -121,7 +122,7 @@ struct Entry {
   uint32_t blob_bytes = 0;
   uint32_t slab = 0;
   uint32_t n = 0;
-  uint32_t refcount = 1;
+  std::atomic<uint32_t> refcount{1};
   uint32_t dec_width = 0;    // decimals: bytes per Arrow value (16 = Decimal128, 32 = Decimal256)
   std::string arrow_format;  // original arrow type as C format string (dictionary: "S" + value fmt in dict_format)
   std::string dict_value_format;
@@ -158,21 +159,15 @@ inline Entry* entry_of(lc_handle h) {
 
 }  // namespace lc
 
-struct lc_ctx {
-  int device = 0;
+// Everything one call mutates besides the shared cache state: stream, scratch, staging buffers, the per-list device caches.
+// One per CALLING THREAD (created on the thread's first call into a context, owned by the context), so calls from
+// different threads never share mutable state and need no lock while they run — the reference's `Arc<LiquidCache>` is hit by
+// every DataFusion partition task at once (cache/core.rs:52-63, index.rs:12-60). The first lane carries the context's own
+// stream (or the caller's, lc_ctx_set_stream applies to the calling thread's lane).
+struct lc_lane {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  uint64_t budget = 0;
-  std::mutex mu;
-  lc::DeviceArena arena;
   lc::Scratch scratch;
-  std::unordered_map<uint64_t, lc_handle> cache;                               // entry_id -> handle
-  std::unordered_map<uint64_t, std::shared_ptr<lc::FsstCodec>> codecs;         // compressor scope -> table
-  uint64_t n_entries = 0;
-  uint64_t kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-  uint64_t epoch = 0;            // bumped whenever an entry is released (invalidates cached entry lists)
-  bool squeeze_internal = false; // squeeze_host.cc is driving the batch functions (they refuse squeezed entries otherwise)
-  uint64_t squeeze_reads = 0, squeeze_saved = 0;  // backing reads / calls answered from the half-width codes
   uint8_t* d_needle = nullptr;   // small device buffer for predicate needles
   cudaStream_t copy_stream = nullptr;  // results of chunk c travel to the host while chunk c+1 is computed
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -188,11 +183,44 @@ struct lc_ctx {
   uint64_t d_pairs_cap = 0;
   uint8_t* sel_stage = nullptr;  // pinned staging of the caller's selection bitmaps (batched calls)
   uint64_t sel_stage_cap = 0;
-  unsigned long long* d_prof = nullptr;  // profile counters (lc_ctx_profile_counters)
-  bool prof_on = false;
   bool timing_on = false;        // lc_ctx_kernel_timing
   bool timing_valid = false;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  bool squeeze_internal = false; // squeeze_host.cc is driving the batch functions (they refuse squeezed entries otherwise)
+};
+
+struct lc_ctx {
+  int device = 0;
+  uint64_t budget = 0;
+  uint64_t uid = 0;              // process-unique: keys the calling threads' lane lookup
+  // SHARED state. `mu` is held only around the short operations on it (arena alloc / free, cache map, codec map, lane list)
+  // — never across a kernel launch or a synchronisation.
+  std::mutex mu;
+  lc::DeviceArena arena;
+  std::unordered_map<uint64_t, lc_handle> cache;                               // entry_id -> handle
+  struct CodecSlot {             // one per compressor scope: trained once, by whoever gets there first
+    std::mutex mu;
+    std::shared_ptr<lc::FsstCodec> codec;
+  };
+  std::unordered_map<uint64_t, std::shared_ptr<CodecSlot>> codecs;             // compressor scope -> table
+  std::vector<std::unique_ptr<lc_lane>> lanes;
+  std::atomic<uint64_t> n_entries{0};
+  std::atomic<uint64_t> kernel_launches{0}, h2d_bytes{0}, d2h_bytes{0};
+  std::atomic<uint64_t> epoch{0};           // bumped whenever an entry is released (invalidates cached entry lists)
+  std::atomic<uint64_t> squeeze_reads{0}, squeeze_saved{0};  // backing reads / calls answered from the half-width codes
+  unsigned long long* d_prof = nullptr;  // profile counters (lc_ctx_profile_counters; measurement aid, shared)
+  bool prof_on = false;
+
+  // the calling thread's lane (set by the entry point's Guard for the duration of the call)
+  lc_lane* L() const;
+  // arena under the lock; the budget is checked inside, with the allocation
+  uint8_t* arena_alloc(uint64_t bytes, uint32_t* slab_out);
+  void arena_free(uint32_t slab, uint8_t* p, uint64_t bytes);
+  uint64_t arena_used();
+  bool arena_at_limit() const;   // did the calling thread's last failed arena_alloc stop at the budget?
+  // codec of a compressor scope, or null; and the slot to train under
+  std::shared_ptr<lc::FsstCodec> codec_of(uint64_t scope);
+  std::shared_ptr<CodecSlot> codec_slot(uint64_t scope);
 };
 
 namespace lc {
@@ -328,5 +356,11 @@ void drop_ref_cache(lc_ctx* ctx);
 
 
 void release_entry(lc_ctx* ctx, Entry* e);
+// lanes (lc_ctx.cc)
+lc_lane* lane_of_thread(lc_ctx* ctx);
+lc_lane* lane_enter(lc_ctx* ctx);     // makes the calling thread's lane current; returns the previous current lane
+void lane_leave(lc_lane* prev);
+void lane_set_current(lc_lane* l);
+void sync_all_lanes(lc_ctx* ctx);
 
 }  // namespace lc

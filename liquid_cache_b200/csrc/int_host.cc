@@ -25,7 +25,7 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
   const uint64_t val_bytes = static_cast<uint64_t>(n) * tb;
   const uint32_t n_words = (n + 31) / 32;
   const bool has_nulls = in.null_count > 0;
-  Scratch& sc = ctx->scratch;
+  Scratch& sc = ctx->L()->scratch;
   const uint64_t extra_dev = is_dec ? round_up(val_bytes, 256) + 256
                              : is_float ? 2 * round_up(val_bytes, 256) + round_up(n_words * 4ull, 256) + round_up(n * 4ull, 256) + 4096
                                         : 0;
@@ -73,7 +73,7 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
   h_mm->out = reinterpret_cast<uint64_t*>(d_mmout);
   h_mm->n = n;
   h_mm->phys = in.phys;
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   // the staging areas are contiguous in both scratch spaces: one copy covers values, validity, work
   const uint64_t up_bytes = static_cast<uint64_t>(reinterpret_cast<uint8_t*>(h_mm) + 256 - h_vals);
   LC_CUDA_OK(cudaMemcpyAsync(d_vals, h_vals, up_bytes, cudaMemcpyHostToDevice, s));
@@ -174,16 +174,16 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
     return LC_ERR_UNSUPPORTED_TYPE;
   }
   h.blob_bytes = static_cast<uint32_t>(blob_bytes);
-  if (ctx->budget && ctx->arena.bytes_used() + blob_bytes > ctx->budget) {
-    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(),
+  if (ctx->budget && ctx->arena_used() + blob_bytes > ctx->budget) {
+    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena_used(),
               (unsigned long long)blob_bytes, (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
   uint32_t slab = 0;
-  uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
+  uint8_t* d_blob = ctx->arena_alloc(blob_bytes, &slab);
   if (!d_blob) {
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
 
   // ---- pass 2: subtract reference + FastLanes pack (+ header, validity) ----
@@ -250,7 +250,7 @@ int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<En
   const uint64_t mmout_off = cur;
   cur += round_up(nb * 32, 256);
   const uint64_t total = cur;
-  Scratch& sc = ctx->scratch;
+  Scratch& sc = ctx->L()->scratch;
   LC_TRY(sc.reserve(total + 1024, total + 1024));
   uint8_t* h = sc.host(total);
   uint8_t* d = sc.dev(total);
@@ -274,7 +274,7 @@ int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<En
       h_mm[i].phys = in.phys;
     }
   });
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   LC_CUDA_OK(cudaMemcpyAsync(d, h, up_bytes, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_bytes;
   LC_CUDA_OK(launch_int_minmax(reinterpret_cast<const IntMinMaxWork*>(d + mm_off), static_cast<uint32_t>(nb), s));
@@ -294,7 +294,7 @@ int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<En
   std::vector<Taken> taken;
   taken.reserve(nb);
   auto give_back = [&]() {
-    for (const Taken& t : taken) ctx->arena.free(t.slab, t.blob, t.bytes);
+    for (const Taken& t : taken) ctx->arena_free(t.slab, t.blob, t.bytes);
   };
   for (uint64_t i = 0; i < nb; ++i) {
     const ArrowIn& in = ins[i];
@@ -331,18 +331,18 @@ int int_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, std::vector<En
       return LC_ERR_UNSUPPORTED_TYPE;
     }
     hd.blob_bytes = static_cast<uint32_t>(blob_bytes);
-    if (ctx->budget && ctx->arena.bytes_used() + blob_bytes > ctx->budget) {
+    if (ctx->budget && ctx->arena_used() + blob_bytes > ctx->budget) {
       give_back();
-      set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(),
+      set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena_used(),
                 (unsigned long long)blob_bytes, (unsigned long long)ctx->budget);
       return LC_ERR_CACHE_FULL;
     }
     uint32_t slab = 0;
-    uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
+    uint8_t* d_blob = ctx->arena_alloc(blob_bytes, &slab);
     if (!d_blob) {
       give_back();
-      set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-      return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+      set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+      return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
     }
     taken.push_back({d_blob, slab, blob_bytes});
     std::memset(&h_pw[i], 0, sizeof(IntPackWork));

@@ -111,7 +111,7 @@ int str_entry_to_bytes(lc_ctx* ctx, const Entry* e, uint8_t* out, uint64_t cap, 
   std::memcpy(co, &h.slope, 4);
   std::memcpy(co + 4, &h.intercept, 4);
   co[8] = h.offset_bytes;
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   const uint8_t* blob = e->d_blob;
   auto d2h = [&](uint64_t dst, uint32_t src_off, uint64_t bytes) -> cudaError_t {
     return bytes ? cudaMemcpyAsync(out + dst, blob + src_off, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess;
@@ -124,7 +124,7 @@ int str_entry_to_bytes(lc_ctx* ctx, const Entry* e, uint8_t* out, uint64_t cap, 
   LC_CUDA_OK(d2h(L.fp_off, h.fp_off, L.fp_size));
   if (h.n) {
     // keys: FastLanes transposition at W = 16 = what k_int_pack does for a 16-bit column of width 16 with reference 0
-    Scratch& sc = ctx->scratch;
+    Scratch& sc = ctx->L()->scratch;
     const uint64_t tmp_bytes = 64ull + L.keys_values_len;
     LC_TRY(sc.reserve(tmp_bytes + 1024, 1024));
     IntPackWork* h_pw = reinterpret_cast<IntPackWork*>(sc.host(256));
@@ -220,13 +220,13 @@ int entry_to_bytes(lc_ctx* ctx, const Entry* e, uint8_t* out, uint64_t cap, uint
     out[18] = static_cast<uint8_t>(static_cast<int8_t>(scale));
   }
   std::memcpy(out + L.ref_off, &h.reference, e->liquid_type == LC_LIQUID_DECIMAL ? 8 : tb);  // little-endian host
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   if (e->liquid_type == LC_LIQUID_FLOAT) {
     out[L.exp_off] = static_cast<uint8_t>(h.alp_ef & 0xffu);
     out[L.exp_off + 1] = static_cast<uint8_t>((h.alp_ef >> 8) & 0xffu);
     put_u64(out + L.exp_off + 8, h.n_patches);
     if (h.n_patches) {
-      Scratch& sc = ctx->scratch;
+      Scratch& sc = ctx->L()->scratch;
       LC_TRY(sc.reserve(8ull * h.n_patches + 1024, 1024));
       uint8_t* d_wide = sc.dev(8ull * h.n_patches);
       if (!d_wide) {
@@ -330,12 +330,12 @@ static int str_entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, con
     return LC_ERR_UNSUPPORTED_TYPE;
   }
   h.blob_bytes = static_cast<uint32_t>(o);
-  if (ctx->budget && ctx->arena.bytes_used() + o > ctx->budget) {
-    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(), (unsigned long long)o,
+  if (ctx->budget && ctx->arena_used() + o > ctx->budget) {
+    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena_used(), (unsigned long long)o,
               (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
-  Scratch& sc = ctx->scratch;
+  Scratch& sc = ctx->L()->scratch;
   const uint64_t stage_bytes = round_up(sizeof(StrHeader) + 64 + round_up((n + 7) / 8, 16) + 64, 256);
   LC_TRY(sc.reserve(1024, stage_bytes + 1024));
   uint8_t* h_stage = sc.host(stage_bytes);
@@ -344,16 +344,16 @@ static int str_entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, con
     return LC_ERR_OOM;
   }
   uint32_t slab = 0, tslab = 0;
-  uint8_t* d_blob = ctx->arena.alloc(o, &slab);
+  uint8_t* d_blob = ctx->arena_alloc(o, &slab);
   // the keys come back through a temporary 16-bit integer entry of width 16: its packed chunks are the image's key words
   const uint64_t tmp_bytes = 64ull + kvals_len;
-  uint8_t* d_tmp = n ? ctx->arena.alloc(tmp_bytes, &tslab) : nullptr;
+  uint8_t* d_tmp = n ? ctx->arena_alloc(tmp_bytes, &tslab) : nullptr;
   if (!d_blob || (n && !d_tmp)) {
-    if (d_blob) ctx->arena.free(slab, d_blob, o);
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget" : "HBM arena: cudaMalloc failed");
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    if (d_blob) ctx->arena_free(slab, d_blob, o);
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget" : "HBM arena: cudaMalloc failed");
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   std::memset(h_stage, 0, stage_bytes);
   std::memcpy(h_stage, &h, sizeof(h));
   IntHeader ih;
@@ -411,8 +411,8 @@ static int str_entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, con
     d_tmp = nullptr;
   }
   if (rc != LC_OK) {
-    ctx->arena.free(slab, d_blob, o);
-    if (d_tmp) ctx->arena.free(tslab, d_tmp, tmp_bytes);
+    ctx->arena_free(slab, d_blob, o);
+    if (d_tmp) ctx->arena_free(tslab, d_tmp, tmp_bytes);
     return rc;
   }
   ctx->h2d_bytes += o;
@@ -543,12 +543,12 @@ int entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, const std::sha
     return LC_ERR_UNSUPPORTED_TYPE;
   }
   h.blob_bytes = static_cast<uint32_t>(blob_bytes);
-  if (ctx->budget && ctx->arena.bytes_used() + blob_bytes > ctx->budget) {
-    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(),
+  if (ctx->budget && ctx->arena_used() + blob_bytes > ctx->budget) {
+    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena_used(),
               (unsigned long long)blob_bytes, (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
-  Scratch& sc = ctx->scratch;
+  Scratch& sc = ctx->L()->scratch;
   const uint64_t head_bytes = 64 + valid_bytes;
   LC_TRY(sc.reserve(8ull * n_patches + 1024, head_bytes + 1024));
   uint8_t* h_head = sc.host(head_bytes);
@@ -560,10 +560,10 @@ int entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, const std::sha
     return LC_ERR_OOM;
   }
   uint32_t slab = 0;
-  uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
+  uint8_t* d_blob = ctx->arena_alloc(blob_bytes, &slab);
   if (!d_blob) {
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   std::memset(h_head, 0, head_bytes);
   std::memcpy(h_head, &h, sizeof(h));
@@ -571,7 +571,7 @@ int entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, const std::sha
     std::memcpy(h_head + 64, b + nulls_off, (n + 7) / 8);
     if (n & 7) h_head[64 + (n + 7) / 8 - 1] &= static_cast<uint8_t>((1u << (n & 7)) - 1u);  // bits past n stay zero in the entry
   }
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   cudaError_t ce = cudaMemcpyAsync(d_blob, h_head, head_bytes, cudaMemcpyHostToDevice, s);
   if (ce == cudaSuccess && width) ce = cudaMemcpyAsync(d_blob + h.packed_off, b + values_off, values_len, cudaMemcpyHostToDevice, s);
   *h_flag = 0;
@@ -588,7 +588,7 @@ int entry_from_bytes(lc_ctx* ctx, const uint8_t* b, uint64_t len, const std::sha
   }
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess || *h_flag) {
-    ctx->arena.free(slab, d_blob, blob_bytes);
+    ctx->arena_free(slab, d_blob, blob_bytes);
     if (ce != cudaSuccess) {
       set_error("CUDA error in from_bytes: %s", cudaGetErrorString(ce));
       return LC_ERR_CUDA;

@@ -7,14 +7,48 @@ using namespace lc;
 
 namespace {
 
+// An entry point's frame: the calling thread's lane becomes current (stream, scratch, staging buffers — nothing another
+// thread touches), the device is selected. NO context-wide lock is held while the call runs: shared state (arena, entry map,
+// codec map) is locked inside the few operations that touch it.
 struct Guard {
   lc_ctx* ctx;
-  std::unique_lock<std::mutex> lk;
-  explicit Guard(lc_ctx* c) : ctx(c), lk(c->mu) {
+  lc_lane* prev;
+  explicit Guard(lc_ctx* c) : ctx(c), prev(lane_enter(c)) {
     cudaSetDevice(c->device);
-    c->scratch.reset();
+    if (c->L()) c->L()->scratch.reset();
   }
+  ~Guard() { lane_leave(prev); }
+  Guard(const Guard&) = delete;
+  Guard& operator=(const Guard&) = delete;
 };
+#define LC_LANE_OK(ctx)                                           \
+  do {                                                            \
+    if (!(ctx)->L()) {                                            \
+      set_error("could not create a CUDA stream for this thread"); \
+      return LC_ERR_CUDA;                                         \
+    }                                                             \
+  } while (0)
+
+// Make freshly encoded entries visible under their ids: their kernels have finished (other threads read them on their own
+// streams), the map is updated under the lock, whatever they replace is released outside it.
+int publish_entries(lc_ctx* ctx, const uint64_t* ids, Entry* const* es, uint64_t n) {
+  const cudaError_t ce = cudaStreamSynchronize(ctx->L()->stream);
+  std::vector<Entry*> old;
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    for (uint64_t i = 0; i < n; ++i) {
+      auto it = ctx->cache.find(ids[i]);
+      if (it != ctx->cache.end()) old.push_back(entry_of(it->second));  // overwrite (index insert replaces)
+      ctx->cache[ids[i]] = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(es[i]));
+    }
+  }
+  for (Entry* e : old) release_entry(ctx, e);
+  if (ce != cudaSuccess) {
+    set_error("CUDA error while finishing an insert: %s", cudaGetErrorString(ce));
+    return LC_ERR_CUDA;
+  }
+  return LC_OK;
+}
 
 int encode_locked(lc_ctx* ctx, const ArrowSchema* schema, const ArrowArray* array, int32_t hint, uint64_t scope,
                   Entry** out) {
@@ -26,7 +60,7 @@ int encode_locked(lc_ctx* ctx, const ArrowSchema* schema, const ArrowArray* arra
     // LiquidFixedLenByteArray::from_decimal_array (fix_len_byte_array.rs:274-323): u16 dictionary over the 16 / 32-byte
     // values, FSST-compressed under the column chunk's compressor (with_fsst_compressor_or_train, transcode.rs:118-131)
     in.byte_type = in.dec_width == 16 ? BT_DECIMAL128 : BT_DECIMAL256;
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     return str_encode(ctx, in, LC_HINT_NONE, scope, out);
   }
   return str_encode(ctx, in, hint, scope, out);
@@ -59,6 +93,20 @@ struct lc_scan {
   };
   std::vector<Validated> validated;
   FusedRead fused;  // device-planned reads: what the previous read of this scan looked like
+  // A scan is driven by one thread at a time (its device state is ordered by that thread's stream); if another thread
+  // continues it, the previous thread's stream is drained first.
+  std::mutex mu;
+  lc_lane* last_lane = nullptr;
+};
+
+struct ScanGuard {
+  std::unique_lock<std::mutex> lk;
+  Guard g;
+  explicit ScanGuard(lc_scan* sc) : lk(sc->mu), g(sc->ctx) {
+    lc_lane* cur = sc->ctx->L();
+    if (sc->last_lane && sc->last_lane != cur) cudaStreamSynchronize(sc->last_lane->stream);
+    sc->last_lane = cur;
+  }
 };
 
 static uint64_t hash_handles(const lc_handle* h, uint64_t n) {
@@ -86,13 +134,13 @@ static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Ent
     return LC_OK;
   }
   const uint64_t key = hash_handles(handles, n);
-  for (auto& v : ctx->validated) {
+  for (auto& v : ctx->L()->validated) {
     if (v.key == key && v.n == n && v.epoch == ctx->epoch) {
       *out = v.es.data();
       return LC_OK;
     }
   }
-  lc_ctx::ValidatedHandles v;
+  lc_lane::ValidatedHandles v;
   v.key = key;
   v.n = n;
   v.epoch = ctx->epoch;
@@ -104,9 +152,9 @@ static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Ent
       return LC_ERR_INVALID;
     }
   }
-  if (ctx->validated.size() >= 8) ctx->validated.erase(ctx->validated.begin());
-  ctx->validated.push_back(std::move(v));
-  *out = ctx->validated.back().es.data();
+  if (ctx->L()->validated.size() >= 8) ctx->L()->validated.erase(ctx->L()->validated.begin());
+  ctx->L()->validated.push_back(std::move(v));
+  *out = ctx->L()->validated.back().es.data();
   return LC_OK;
 }
 
@@ -193,8 +241,8 @@ int lc_entry_image(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, uint64_
     return LC_ERR_INVALID;
   }
   Guard g(ctx);
-  LC_CUDA_OK(cudaMemcpyAsync(out, e->d_blob, e->blob_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  LC_CUDA_OK(cudaMemcpyAsync(out, e->d_blob, e->blob_bytes, cudaMemcpyDeviceToHost, ctx->L()->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
   ctx->d2h_bytes += e->blob_bytes;
   return LC_OK;
 }
@@ -213,8 +261,8 @@ int lc_entry_fsst_table(lc_ctx* ctx, lc_handle h, uint8_t* out, uint64_t cap, ui
   }
   Guard g(ctx);
   // read it back from the device copy the kernels use, not from the host copy it was uploaded from
-  LC_CUDA_OK(cudaMemcpyAsync(out, e->codec->d_dec, sizeof(FsstTable), cudaMemcpyDeviceToHost, ctx->stream));
-  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  LC_CUDA_OK(cudaMemcpyAsync(out, e->codec->d_dec, sizeof(FsstTable), cudaMemcpyDeviceToHost, ctx->L()->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
   return LC_OK;
 }
 
@@ -254,9 +302,9 @@ int lc_from_bytes_scoped(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, uint64
     return LC_ERR_INVALID;
   }
   Guard g(ctx);
-  auto it = ctx->codecs.find(compressor_scope);
+  LC_LANE_OK(ctx);
   Entry* e = nullptr;
-  LC_TRY(entry_from_bytes(ctx, bytes, len, it == ctx->codecs.end() ? nullptr : it->second, &e));
+  LC_TRY(entry_from_bytes(ctx, bytes, len, ctx->codec_of(compressor_scope), &e));
   *out = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
   return LC_OK;
 }
@@ -264,18 +312,19 @@ int lc_from_bytes_scoped(lc_ctx* ctx, const uint8_t* bytes, uint64_t len, uint64
 int lc_ctx_save_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, uint8_t* out, uint64_t cap, uint64_t* out_bytes) {
   if (!ctx || !out_bytes) return LC_ERR_INVALID;
   Guard g(ctx);
-  auto it = ctx->codecs.find(compressor_scope);
-  if (it == ctx->codecs.end()) {
+  std::shared_ptr<FsstCodec> codec = ctx->codec_of(compressor_scope);
+  if (!codec) {
     set_error("no symbol table for scope %llu", (unsigned long long)compressor_scope);
     return LC_ERR_NOT_FOUND;
   }
-  return symbol_table_to_bytes(*it->second, out, cap, out_bytes);
+  return symbol_table_to_bytes(*codec, out, cap, out_bytes);
 }
 
 int lc_ctx_load_symbol_table(lc_ctx* ctx, uint64_t compressor_scope, const uint8_t* bytes, uint64_t len) {
   if (!ctx || !bytes) return LC_ERR_INVALID;
   Guard g(ctx);
-  if (ctx->codecs.count(compressor_scope)) {
+  LC_LANE_OK(ctx);
+  if (ctx->codec_of(compressor_scope)) {
     set_error("scope %llu already has a symbol table", (unsigned long long)compressor_scope);
     return LC_ERR_INVALID;
   }
@@ -443,7 +492,7 @@ int lc_and_then(lc_ctx* ctx, const uint8_t* left_bits, uint64_t left_len, const 
   }
   Guard g(ctx);
   const uint64_t lw = round_up((left_len + 31) / 32, 4) * 4, rw = round_up((right_len + 31) / 32, 4) * 4 + 16;
-  Scratch& sc = ctx->scratch;
+  Scratch& sc = ctx->L()->scratch;
   LC_TRY(sc.reserve(2 * lw + rw + 1024, 2 * lw + rw + 1024));
   uint8_t* h_l = sc.host(lw);
   uint8_t* h_r = sc.host(rw);
@@ -454,7 +503,7 @@ int lc_and_then(lc_ctx* ctx, const uint8_t* left_bits, uint64_t left_len, const 
   if (!h_l || !h_r || !h_o || !d_l || !d_r || !d_o) return LC_ERR_OOM;
   copy_bits(left_bits, 0, static_cast<int64_t>(left_len), h_l, lw);
   copy_bits(right_bits, 0, static_cast<int64_t>(right_len), h_r, rw);
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   LC_CUDA_OK(cudaMemcpyAsync(d_l, h_l, lw, cudaMemcpyHostToDevice, s));
   LC_CUDA_OK(cudaMemcpyAsync(d_r, h_r, rw, cudaMemcpyHostToDevice, s));
   LC_CUDA_OK(launch_and_then(reinterpret_cast<const uint32_t*>(d_l), static_cast<uint32_t>(left_len),
@@ -478,10 +527,7 @@ int lc_cache_insert(lc_ctx* ctx, uint64_t entry_id, const struct ArrowSchema* sc
   // FSST table scope = (file, row group, column): entry id with the batch bits cleared (cache/id.rs:15-22)
   const uint64_t scope = entry_id & ~0xFFFFull;
   LC_TRY(encode_locked(ctx, schema, array, hint, scope, &e));
-  auto it = ctx->cache.find(entry_id);
-  if (it != ctx->cache.end()) release_entry(ctx, entry_of(it->second));  // overwrite (index insert replaces)
-  ctx->cache[entry_id] = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(e));
-  return LC_OK;
+  return publish_entries(ctx, &entry_id, &e, 1);
 }
 
 int lc_cache_insert_many(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, const struct ArrowSchema* const* schemas,
@@ -514,7 +560,7 @@ int lc_cache_insert_many(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, con
     // floats, decimals, mixed lists: batch by batch; all or nothing like the batched passes
     for (uint64_t i = 0; i < n; ++i) {
       Entry* e = nullptr;
-      ctx->scratch.reset();
+      ctx->L()->scratch.reset();
       const int rc = encode_locked(ctx, schemas[i], arrays[i], hint, entry_ids[i] & ~0xFFFFull, &e);
       if (rc != LC_OK) {
         for (Entry* made : es) release_entry(ctx, made);
@@ -523,12 +569,7 @@ int lc_cache_insert_many(lc_ctx* ctx, const uint64_t* entry_ids, uint64_t n, con
       es.push_back(e);
     }
   }
-  for (uint64_t i = 0; i < n; ++i) {
-    auto it = ctx->cache.find(entry_ids[i]);
-    if (it != ctx->cache.end()) release_entry(ctx, entry_of(it->second));  // overwrite (index insert replaces)
-    ctx->cache[entry_ids[i]] = static_cast<lc_handle>(reinterpret_cast<uintptr_t>(es[i]));
-  }
-  return LC_OK;
+  return publish_entries(ctx, entry_ids, es.data(), n);
 }
 
 int lc_cache_is_cached(lc_ctx* ctx, uint64_t entry_id) {
@@ -540,19 +581,30 @@ int lc_cache_is_cached(lc_ctx* ctx, uint64_t entry_id) {
 int lc_cache_remove(lc_ctx* ctx, uint64_t entry_id) {
   if (!ctx) return LC_ERR_INVALID;
   Guard g(ctx);
-  auto it = ctx->cache.find(entry_id);
-  if (it == ctx->cache.end()) return LC_ERR_NOT_FOUND;
-  release_entry(ctx, entry_of(it->second));
-  ctx->cache.erase(it);
+  Entry* e = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->cache.find(entry_id);
+    if (it == ctx->cache.end()) return LC_ERR_NOT_FOUND;
+    e = entry_of(it->second);
+    ctx->cache.erase(it);
+  }
+  release_entry(ctx, e);
   return LC_OK;
 }
 
 int lc_cache_reset(lc_ctx* ctx) {
   if (!ctx) return LC_ERR_INVALID;
   Guard g(ctx);
-  cudaStreamSynchronize(ctx->stream);
-  for (auto& kv : ctx->cache) release_entry(ctx, entry_of(kv.second));
-  ctx->cache.clear();
+  LC_LANE_OK(ctx);
+  cudaStreamSynchronize(ctx->L()->stream);
+  std::vector<Entry*> held;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& kv : ctx->cache) held.push_back(entry_of(kv.second));
+    ctx->cache.clear();
+  }
+  for (Entry* e : held) release_entry(ctx, e);
   return LC_OK;
 }
 
@@ -588,16 +640,20 @@ int lc_cache_retain(lc_ctx* ctx, uint64_t entry_id, lc_handle* out) {
 int lc_cache_get(lc_ctx* ctx, uint64_t entry_id, const uint8_t* sel_bits, uint64_t sel_len,
                  struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
   lc_handle h;
-  LC_TRY(lc_cache_handles(ctx, &entry_id, 1, &h));
-  return lc_to_arrow(ctx, h, sel_bits, sel_len, out_schema, out_array);
+  LC_TRY(lc_cache_retain(ctx, entry_id, &h));  // the entry cannot go away under the call (another thread may replace the id)
+  const int rc = lc_to_arrow(ctx, h, sel_bits, sel_len, out_schema, out_array);
+  lc_release(ctx, h);
+  return rc;
 }
 
 int lc_cache_eval_predicate(lc_ctx* ctx, uint64_t entry_id, const lc_predicate* pred, const uint8_t* sel_bits,
                             uint64_t sel_len, uint8_t* out_values, uint8_t* out_validity, uint64_t* out_len,
                             uint64_t* out_null_count) {
   lc_handle h;
-  LC_TRY(lc_cache_handles(ctx, &entry_id, 1, &h));
-  return lc_eval_predicate(ctx, h, pred, sel_bits, sel_len, out_values, out_validity, out_len, out_null_count);
+  LC_TRY(lc_cache_retain(ctx, entry_id, &h));
+  const int rc = lc_eval_predicate(ctx, h, pred, sel_bits, sel_len, out_values, out_validity, out_len, out_null_count);
+  lc_release(ctx, h);
+  return rc;
 }
 
 /* --------------------------------------------- device-resident scan pipeline ---- */
@@ -635,8 +691,8 @@ int lc_scan_begin(lc_ctx* ctx, uint64_t n_batches, const uint64_t* rows_per_batc
     set_error("lc_scan_begin: cudaMalloc failed");
     return LC_ERR_OOM;
   }
-  if (cudaMemcpyAsync(sc->d_word_off, sc->word_off.data(), n_batches * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+  if (cudaMemcpyAsync(sc->d_word_off, sc->word_off.data(), n_batches * 8, cudaMemcpyHostToDevice, ctx->L()->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->L()->stream) != cudaSuccess) {
     set_error("lc_scan_begin: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(sc->d_sel);
     cudaFree(sc->d_counts);
@@ -650,7 +706,7 @@ int lc_scan_begin(lc_ctx* ctx, uint64_t n_batches, const uint64_t* rows_per_batc
 
 int lc_scan_reset(lc_scan* scan) {
   if (!scan) return LC_ERR_INVALID;
-  Guard g(scan->ctx);
+  ScanGuard g(scan);
   scan->all_rows = true;
   scan->counts_on_device = false;
   scan->counts_cached = false;
@@ -663,15 +719,15 @@ int lc_scan_set_selection(lc_scan* scan, uint64_t batch, const uint8_t* sel_bits
     return LC_ERR_INVALID;
   }
   lc_ctx* ctx = scan->ctx;
-  Guard g(ctx);
-  cudaStream_t s = ctx->stream;
+  ScanGuard g(scan);
+  cudaStream_t s = ctx->L()->stream;
   if (scan->all_rows) {
     LC_CUDA_OK(cudaMemsetAsync(scan->d_sel, 0xFF, scan->total_words * 4, s));
     scan->all_rows = false;
   }
   const uint64_t words = round_up((sel_len + 31) / 32, 4);
-  LC_TRY(ctx->scratch.reserve(0, words * 4 + 256));
-  uint8_t* hb = ctx->scratch.host(words * 4);
+  LC_TRY(ctx->L()->scratch.reserve(0, words * 4 + 256));
+  uint8_t* hb = ctx->L()->scratch.host(words * 4);
   if (!hb) return LC_ERR_OOM;
   copy_bits(sel_bits, 0, static_cast<int64_t>(sel_len), hb, words * 4);
   LC_CUDA_OK(cudaMemcpyAsync(scan->d_sel + scan->word_off[batch], hb, words * 4, cudaMemcpyHostToDevice, s));
@@ -694,8 +750,8 @@ static int scan_filter_squeezed(lc_scan* scan, Entry* const* es, const lc_predic
   struct Internal {  // the batch functions refuse squeezed entries unless squeeze code drives them
     lc_ctx* c;
     bool prev;
-    explicit Internal(lc_ctx* x) : c(x), prev(x->squeeze_internal) { x->squeeze_internal = true; }
-    ~Internal() { c->squeeze_internal = prev; }
+    explicit Internal(lc_ctx* x) : c(x), prev(x->L()->squeeze_internal) { x->L()->squeeze_internal = true; }
+    ~Internal() { c->L()->squeeze_internal = prev; }
   } internal(ctx);
   if (pred->op < LC_OP_EQ || pred->op > LC_OP_GE) {
     set_error("operator %d is not supported on integer columns", pred->op);
@@ -718,7 +774,7 @@ static int scan_filter_squeezed(lc_scan* scan, Entry* const* es, const lc_predic
   std::vector<uint8_t> backing(n, 0);
   for (uint64_t i = 0; i < n; ++i) backing[i] = doubt[i] == 3;
   const bool any_doubt = n_doubt[1] || n_doubt[2] || n_doubt[3];
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   // work areas kept with the scan: a copy of the selection for the probes, one to restore from, probe counts
   const uint64_t sel_bytes = scan->total_words * 4 + 64;
   if (any_doubt && !scan->d_probe) {
@@ -739,7 +795,7 @@ static int scan_filter_squeezed(lc_scan* scan, Entry* const* es, const lc_predic
   for (int form = 1; form <= 2; ++form) {
     if (!n_doubt[form]) continue;
     if (!scan->all_rows) LC_CUDA_OK(cudaMemcpyAsync(d_probe, scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToDevice, s));
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     LC_TRY(refine_batch(ctx, es, n, &probes[form], d_probe, scan->d_word_off, scan->all_rows, d_pcounts));
     LC_CUDA_OK(cudaMemcpyAsync(pc.data(), d_pcounts, n * 8, cudaMemcpyDeviceToHost, s));
     LC_CUDA_OK(cudaStreamSynchronize(s));
@@ -748,7 +804,7 @@ static int scan_filter_squeezed(lc_scan* scan, Entry* const* es, const lc_predic
       if (doubt[i] == form && pc[2 * i]) backing[i] = 1;
   }
   // ---- the predicate over the whole list ----
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   LC_TRY(refine_batch(ctx, es, n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
   // ---- entries the codes could not decide ----
   for (uint64_t i = 0; i < n; ++i) {
@@ -760,7 +816,7 @@ static int scan_filter_squeezed(lc_scan* scan, Entry* const* es, const lc_predic
     Entry* full = nullptr;
     LC_TRY(squeeze_hydrate(ctx, es[i], &full));
     Entry* one[1] = {full};
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     const int rc = refine_batch(ctx, one, 1, pred, scan->d_sel, scan->d_word_off + i, scan->all_rows, scan->d_counts + 2 * i);
     release_entry(ctx, full);
     LC_TRY(rc);
@@ -774,7 +830,7 @@ int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* 
     return LC_ERR_INVALID;
   }
   lc_ctx* ctx = scan->ctx;
-  Guard g(ctx);
+  ScanGuard g(scan);
   Entry* const* es = nullptr;
   LC_TRY(scan_entries_cached(scan, handles, &es));
   bool any_squeezed = false;
@@ -795,15 +851,15 @@ static int scan_fetch_counts(lc_scan* scan) {
     for (uint64_t i = 0; i < scan->n; ++i) scan->counts[i] = scan->rows[i];
   } else if (scan->counts_on_device) {
     std::vector<uint32_t> tmp(scan->n * 2);
-    LC_CUDA_OK(cudaMemcpyAsync(tmp.data(), scan->d_counts, scan->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(tmp.data(), scan->d_counts, scan->n * 8, cudaMemcpyDeviceToHost, ctx->L()->stream));
+    LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
     ctx->d2h_bytes += scan->n * 8;
     for (uint64_t i = 0; i < scan->n; ++i) scan->counts[i] = tmp[2 * i];
   } else {
     // selections were seeded from the host and not filtered yet: count them from a copy
     std::vector<uint32_t> words(scan->total_words);
-    LC_CUDA_OK(cudaMemcpyAsync(words.data(), scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(words.data(), scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToHost, ctx->L()->stream));
+    LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
     ctx->d2h_bytes += scan->total_words * 4;
     for (uint64_t i = 0; i < scan->n; ++i)
       scan->counts[i] = static_cast<uint32_t>(
@@ -815,7 +871,7 @@ static int scan_fetch_counts(lc_scan* scan) {
 
 int lc_scan_counts(lc_scan* scan, uint64_t* out_counts, uint64_t* out_total) {
   if (!scan) return LC_ERR_INVALID;
-  Guard g(scan->ctx);
+  ScanGuard g(scan);
   LC_TRY(scan_fetch_counts(scan));
   uint64_t tot = 0;
   for (uint64_t i = 0; i < scan->n; ++i) {
@@ -829,7 +885,7 @@ int lc_scan_counts(lc_scan* scan, uint64_t* out_counts, uint64_t* out_total) {
 int lc_scan_selection(lc_scan* scan, uint64_t batch, uint8_t* out_bits) {
   if (!scan || batch >= scan->n || !out_bits) return LC_ERR_INVALID;
   lc_ctx* ctx = scan->ctx;
-  Guard g(ctx);
+  ScanGuard g(scan);
   const uint32_t rows = scan->rows[batch];
   const uint64_t nbytes = (rows + 7) / 8;
   if (scan->all_rows) {
@@ -838,8 +894,8 @@ int lc_scan_selection(lc_scan* scan, uint64_t batch, uint8_t* out_bits) {
     const uint64_t words = (rows + 31) / 32;
     std::vector<uint32_t> tmp(words + 1);
     LC_CUDA_OK(cudaMemcpyAsync(tmp.data(), scan->d_sel + scan->word_off[batch], words * 4, cudaMemcpyDeviceToHost,
-                               ctx->stream));
-    LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+                               ctx->L()->stream));
+    LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
     ctx->d2h_bytes += words * 4;
     std::memcpy(out_bits, tmp.data(), nbytes);
   }
@@ -868,7 +924,7 @@ int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* ou
                  struct ArrowArray* out_array) {
   if (!scan || !handles || !out_schema || !out_array) return LC_ERR_INVALID;
   lc_ctx* ctx = scan->ctx;
-  Guard g(ctx);
+  ScanGuard g(scan);
   // the handle list of a column is validated once per scan (hash of the array), not once per read: 12 k pointer chases
   // per call were ~0.05-0.1 ms of every get of the bench step
   Entry* const* esp = nullptr;
@@ -885,7 +941,7 @@ int lc_scan_read(lc_scan* scan, const lc_handle* handles, struct ArrowSchema* ou
   }
   const std::vector<Entry*> es(esp, esp + scan->n);
   LC_TRY(scan_fetch_counts(scan));
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   std::vector<Entry*> es2;
   std::vector<uint64_t> woff2;
   std::vector<uint32_t> k2;
@@ -908,11 +964,11 @@ int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values,
                         void* d_validity, uint64_t* out_rows, uint64_t* out_value_bytes, uint64_t* out_null_count) {
   if (!scan || !handles) return LC_ERR_INVALID;
   lc_ctx* ctx = scan->ctx;
-  Guard g(ctx);
+  ScanGuard g(scan);
   Entry* const* esp = nullptr;
   LC_TRY(scan_entries_cached(scan, handles, &esp));
   LC_TRY(scan_fetch_counts(scan));
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   DevSel ds{scan->d_sel, scan->word_off.data(), scan->counts.data(), scan->all_rows};
   DeviceOut dout{d_values, values_cap, d_offsets, d_validity, out_rows, out_value_bytes, out_null_count};
   return to_arrow_batch(ctx, esp, scan->n, nullptr, &ds, nullptr, nullptr, &dout);
@@ -922,7 +978,7 @@ int lc_scan_read_borrowed(lc_scan* scan, const lc_handle* handles, void** d_valu
                           uint64_t* out_value_bytes) {
   if (!scan || !handles || !d_values || !d_offsets || !out_rows || !out_value_bytes) return LC_ERR_INVALID;
   lc_ctx* ctx = scan->ctx;
-  Guard g(ctx);
+  ScanGuard g(scan);
   Entry* const* esp = nullptr;
   LC_TRY(scan_entries_cached(scan, handles, &esp));
   if (!scan->counts_on_device || scan->all_rows) {
@@ -949,8 +1005,8 @@ int lc_scan_read_borrowed(lc_scan* scan, const lc_handle* handles, void** d_valu
 void lc_scan_end(lc_scan* scan) {
   if (!scan) return;
   {
-    Guard g(scan->ctx);
-    cudaStreamSynchronize(scan->ctx->stream);
+    ScanGuard g(scan);
+    cudaStreamSynchronize(scan->ctx->L()->stream);
     if (scan->d_sel) cudaFree(scan->d_sel);
     if (scan->d_probe) cudaFree(scan->d_probe);
     if (scan->d_save) cudaFree(scan->d_save);

@@ -215,10 +215,74 @@ int Scratch::reserve(uint64_t d_bytes, uint64_t h_bytes) {
   return LC_OK;
 }
 
+// ---- lanes -------------------------------------------------------------------------------------
+namespace {
+thread_local lc_lane* g_cur_lane = nullptr;        // set by the entry point (lane_enter) for the duration of a call
+thread_local bool g_arena_hit_limit = false;
+struct LaneKey {
+  uint64_t uid;
+  lc_lane* lane;
+};
+thread_local std::vector<LaneKey> g_my_lanes;      // this thread's lane in every context it has called into
+std::atomic<uint64_t> g_ctx_uid{1};
+}  // namespace
+
+uint64_t next_ctx_uid() { return g_ctx_uid.fetch_add(1); }
+
+// The calling thread's lane of `ctx`, created on first use (its own non-blocking stream). Returns nullptr on CUDA failure.
+lc_lane* lane_of_thread(lc_ctx* ctx) {
+  for (const LaneKey& k : g_my_lanes)
+    if (k.uid == ctx->uid) return k.lane;
+  auto lane = std::make_unique<lc_lane>();
+  if (cudaStreamCreateWithFlags(&lane->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  lane->stream = lane->own_stream;
+  lc_lane* raw = lane.get();
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->lanes.push_back(std::move(lane));
+  }
+  g_my_lanes.push_back({ctx->uid, raw});
+  return raw;
+}
+
+lc_lane* lane_enter(lc_ctx* ctx) {
+  lc_lane* prev = g_cur_lane;
+  g_cur_lane = lane_of_thread(ctx);
+  if (!g_cur_lane) {  // no stream to be had for this thread: share the context's first lane rather than fail the call
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->lanes.empty()) g_cur_lane = ctx->lanes[0].get();
+  }
+  return prev;
+}
+void lane_leave(lc_lane* prev) { g_cur_lane = prev; }
+void lane_set_current(lc_lane* l) { g_cur_lane = l; }
+
+// Entries published by one thread are read by others on their own streams: wait for this lane's work before an entry
+// becomes visible, and for EVERY lane's work before an entry's HBM range is handed back to the arena.
+void sync_all_lanes(lc_ctx* ctx) {
+  std::vector<cudaStream_t> streams;
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    for (auto& l : ctx->lanes) streams.push_back(l->stream);
+  }
+  for (cudaStream_t st : streams) cudaStreamSynchronize(st);
+}
+
 void release_entry(lc_ctx* ctx, Entry* e) {
   if (!e) return;
-  if (--e->refcount > 0) return;
-  if (e->d_blob) ctx->arena.free(e->slab, e->d_blob, e->blob_bytes);
+  if (e->refcount.fetch_sub(1) > 1) return;
+  if (e->d_blob) {
+    bool many;
+    {
+      std::lock_guard<std::mutex> g(ctx->mu);
+      many = ctx->lanes.size() > 1;
+    }
+    if (many) sync_all_lanes(ctx);  // another thread's scan may still be reading the blob on its stream
+    ctx->arena_free(e->slab, e->d_blob, e->blob_bytes);
+  }
   ctx->epoch++;
   e->magic = 0;
   ctx->n_entries--;
@@ -228,6 +292,46 @@ void release_entry(lc_ctx* ctx, Entry* e) {
 }  // namespace lc
 
 using namespace lc;
+
+lc_lane* lc_ctx::L() const { return g_cur_lane; }
+
+uint8_t* lc_ctx::arena_alloc(uint64_t bytes, uint32_t* slab_out) {
+  std::lock_guard<std::mutex> g(mu);
+  g_arena_hit_limit = false;
+  if (budget && arena.bytes_used() + round_up(bytes ? bytes : 1, 128) > budget) {  // the budget is checked with the allocation
+    g_arena_hit_limit = true;
+    return nullptr;
+  }
+  uint8_t* p = arena.alloc(bytes, slab_out);
+  if (!p) g_arena_hit_limit = arena.at_limit();
+  return p;
+}
+void lc_ctx::arena_free(uint32_t slab, uint8_t* p, uint64_t bytes) {
+  std::lock_guard<std::mutex> g(mu);
+  arena.free(slab, p, bytes);
+}
+uint64_t lc_ctx::arena_used() {
+  std::lock_guard<std::mutex> g(mu);
+  return arena.bytes_used();
+}
+bool lc_ctx::arena_at_limit() const { return g_arena_hit_limit; }
+std::shared_ptr<FsstCodec> lc_ctx::codec_of(uint64_t scope) {
+  std::shared_ptr<CodecSlot> slot;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = codecs.find(scope);
+    if (it == codecs.end()) return nullptr;
+    slot = it->second;
+  }
+  std::lock_guard<std::mutex> g(slot->mu);  // a table being trained right now: wait for it
+  return slot->codec;
+}
+std::shared_ptr<lc_ctx::CodecSlot> lc_ctx::codec_slot(uint64_t scope) {
+  std::lock_guard<std::mutex> g(mu);
+  auto& slot = codecs[scope];
+  if (!slot) slot = std::make_shared<CodecSlot>();
+  return slot;
+}
 
 extern "C" {
 
@@ -262,13 +366,13 @@ int lc_ctx_create(int device_id, uint64_t hbm_budget_bytes, lc_ctx** out) {
   lc_ctx* ctx = new lc_ctx();
   ctx->device = device_id;
   ctx->budget = hbm_budget_bytes;
+  ctx->uid = next_ctx_uid();
   ctx->arena.set_limit(hbm_budget_bytes ? round_up(hbm_budget_bytes, 2ull << 20) : 0);
-  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (!lane_of_thread(ctx)) {  // the creating thread's lane: the context's first stream
     set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return LC_ERR_CUDA;
   }
-  ctx->stream = ctx->own_stream;
   // keep stream-ordered allocations cached in the pool across synchronisations (the default threshold of 0
   // hands the memory back to the driver at every sync, which costs milliseconds per call)
   cudaMemPool_t pool;
@@ -284,52 +388,70 @@ int lc_ctx_create(int device_id, uint64_t hbm_budget_bytes, lc_ctx** out) {
 void lc_ctx_destroy(lc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  sync_all_lanes(ctx);
+  lc_lane* prev = lane_enter(ctx);
+  std::vector<Entry*> held;
   {
     std::lock_guard<std::mutex> g(ctx->mu);
-    for (auto& kv : ctx->cache) {
-      Entry* e = entry_of(kv.second);
-      if (e) release_entry(ctx, e);
-    }
+    for (auto& kv : ctx->cache)
+      if (Entry* e = entry_of(kv.second)) held.push_back(e);
     ctx->cache.clear();
-    for (auto& kv : ctx->codecs) {
-      if (kv.second->d_dec) cudaFree(kv.second->d_dec);
-      if (kv.second->d_enc) cudaFree(kv.second->d_enc);
-      kv.second->d_dec = nullptr;
-      kv.second->d_enc = nullptr;
-    }
   }
-  drop_ref_cache(ctx);
-  if (ctx->d_needle) cudaFree(ctx->d_needle);
-  if (ctx->sel_stage) cudaFreeHost(ctx->sel_stage);
-  if (ctx->d_pairs) cudaFree(ctx->d_pairs);
-  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-  for (cudaEvent_t& e : ctx->ev_chunk)
-    if (e) cudaEventDestroy(e);
+  for (Entry* e : held) release_entry(ctx, e);
+  for (auto& kv : ctx->codecs) {
+    auto& c = kv.second->codec;
+    if (!c) continue;
+    if (c->d_dec) cudaFree(c->d_dec);
+    if (c->d_enc) cudaFree(c->d_enc);
+    c->d_dec = nullptr;
+    c->d_enc = nullptr;
+  }
+  for (auto& lp : ctx->lanes) {
+    lc_lane* l = lp.get();
+    lane_set_current(l);
+    drop_ref_cache(ctx);
+    if (l->d_needle) cudaFree(l->d_needle);
+    if (l->sel_stage) cudaFreeHost(l->sel_stage);
+    if (l->d_pairs) cudaFree(l->d_pairs);
+    if (l->copy_stream) cudaStreamDestroy(l->copy_stream);
+    for (cudaEvent_t& e : l->ev_chunk)
+      if (e) cudaEventDestroy(e);
+    if (l->ev_a) cudaEventDestroy(l->ev_a);
+    if (l->ev_b) cudaEventDestroy(l->ev_b);
+    if (l->own_stream) cudaStreamDestroy(l->own_stream);
+  }
   if (ctx->d_prof) cudaFree(ctx->d_prof);
-  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
-  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-  delete ctx;
+  lane_leave(prev);
+  delete ctx;  // threads that called into this context keep a stale (uid-keyed, never matched again) lane pointer
 }
 
-int lc_ctx_set_stream(lc_ctx* ctx, void* cuda_stream) {
+int lc_ctx_set_stream(lc_ctx* ctx, void* cuda_stream) {  // the calling thread's lane
   if (!ctx) return LC_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
-  cudaStreamSynchronize(ctx->stream);
-  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  lc_lane* l = lane_of_thread(ctx);
+  if (!l) return LC_ERR_CUDA;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(l->stream);
+  l->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : l->own_stream;
   return LC_OK;
 }
 
-int lc_ctx_synchronize(lc_ctx* ctx) {
+int lc_ctx_synchronize(lc_ctx* ctx) {  // the calling thread's work
   if (!ctx) return LC_ERR_INVALID;
-  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  lc_lane* l = lane_of_thread(ctx);
+  if (!l) return LC_ERR_CUDA;
+  cudaSetDevice(ctx->device);
+  LC_CUDA_OK(cudaStreamSynchronize(l->stream));
   return LC_OK;
 }
 
 int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[16]) {
   if (!ctx) return LC_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  lc_lane* prev = lane_enter(ctx);
+  struct Leave {
+    lc_lane* p;
+    ~Leave() { lane_leave(p); }
+  } leave{prev};
+  if (!ctx->L()) return LC_ERR_CUDA;
   cudaSetDevice(ctx->device);
   if (!ctx->d_prof) {
     if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_prof), 128) != cudaSuccess) {
@@ -337,9 +459,9 @@ int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[16]) {
       set_error("cudaMalloc for profile counters failed");
       return LC_ERR_OOM;
     }
-    LC_CUDA_OK(cudaMemsetAsync(ctx->d_prof, 0, 128, ctx->stream));
+    LC_CUDA_OK(cudaMemsetAsync(ctx->d_prof, 0, 128, ctx->L()->stream));
   }
-  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
   if (out) {
     unsigned long long tmp[16] = {0};
     LC_CUDA_OK(cudaMemcpy(tmp, ctx->d_prof, 128, cudaMemcpyDeviceToHost));
@@ -350,35 +472,44 @@ int lc_ctx_profile_counters(lc_ctx* ctx, int enable, uint64_t out[16]) {
   return LC_OK;
 }
 
-int lc_ctx_kernel_timing(lc_ctx* ctx, int enable) {
+int lc_ctx_kernel_timing(lc_ctx* ctx, int enable) {  // the calling thread's lane
   if (!ctx) return LC_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  lc_lane* prev = lane_enter(ctx);
+  struct Leave {
+    lc_lane* p;
+    ~Leave() { lane_leave(p); }
+  } leave{prev};
+  if (!ctx->L()) return LC_ERR_CUDA;
   cudaSetDevice(ctx->device);
-  if (enable && !ctx->ev_a) {
-    LC_CUDA_OK(cudaEventCreate(&ctx->ev_a));
-    LC_CUDA_OK(cudaEventCreate(&ctx->ev_b));
+  if (enable && !ctx->L()->ev_a) {
+    LC_CUDA_OK(cudaEventCreate(&ctx->L()->ev_a));
+    LC_CUDA_OK(cudaEventCreate(&ctx->L()->ev_b));
   }
-  ctx->timing_on = enable != 0;
-  ctx->timing_valid = false;
+  ctx->L()->timing_on = enable != 0;
+  ctx->L()->timing_valid = false;
   return LC_OK;
 }
 
 float lc_ctx_last_kernel_ms(lc_ctx* ctx) {
   if (!ctx) return -1.0f;
-  std::lock_guard<std::mutex> g(ctx->mu);
-  if (!ctx->timing_valid) return -1.0f;
+  lc_lane* prev = lane_enter(ctx);
+  struct Leave {
+    lc_lane* p;
+    ~Leave() { lane_leave(p); }
+  } leave{prev};
+  if (!ctx->L() || !ctx->L()->timing_valid) return -1.0f;
   cudaSetDevice(ctx->device);
-  if (cudaEventSynchronize(ctx->ev_b) != cudaSuccess) return -1.0f;
+  if (cudaEventSynchronize(ctx->L()->ev_b) != cudaSuccess) return -1.0f;
   float ms = -1.0f;
-  if (cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, ctx->L()->ev_a, ctx->L()->ev_b) != cudaSuccess) return -1.0f;
   return ms;
 }
 
 int lc_ctx_stats(lc_ctx* ctx, lc_stats* out) {
   if (!ctx || !out) return LC_ERR_INVALID;
-  std::lock_guard<std::mutex> g(ctx->mu);
   out->entries = ctx->n_entries;
-  out->hbm_bytes_used = ctx->arena.bytes_used();
+  out->hbm_bytes_used = ctx->arena_used();
+  std::lock_guard<std::mutex> g(ctx->mu);
   out->hbm_bytes_budget = ctx->budget;
   out->kernel_launches = ctx->kernel_launches;
   out->h2d_bytes = ctx->h2d_bytes;

@@ -58,20 +58,20 @@ int plan_selection(lc_ctx* ctx, const uint32_t* entry_rows, uint64_t n, const ui
     }
   }
   const uint64_t need = p->sel_words * 4 + 64 + (p->sel_words / 16) * 8 + 128;  // dense words + room for sparse pairs
-  if (need > ctx->sel_stage_cap) {
-    if (ctx->sel_stage) cudaFreeHost(ctx->sel_stage);
-    ctx->sel_stage = nullptr;
-    ctx->sel_stage_cap = 0;
+  if (need > ctx->L()->sel_stage_cap) {
+    if (ctx->L()->sel_stage) cudaFreeHost(ctx->L()->sel_stage);
+    ctx->L()->sel_stage = nullptr;
+    ctx->L()->sel_stage_cap = 0;
     uint64_t cap = 1ull << 20;
     while (cap < need) cap *= 2;
-    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->sel_stage), cap, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->L()->sel_stage), cap, cudaHostAllocDefault) != cudaSuccess) {
       cudaGetLastError();
       set_error("selection staging: cudaHostAlloc of %llu bytes failed", (unsigned long long)cap);
       return LC_ERR_OOM;
     }
-    ctx->sel_stage_cap = cap;
+    ctx->L()->sel_stage_cap = cap;
   }
-  uint8_t* stage = ctx->sel_stage;
+  uint8_t* stage = ctx->L()->sel_stage;
   // While staging, every range of entries also notes its non-zero words. Selections that come out of a selective
   // predicate are nearly all zero (config 2: ~1.6 set bits per 8192-bit bitmap), and then only the {word index, word}
   // pairs cross PCIe (a few KB instead of MBs); the device zero-fills the area and scatters them.
@@ -112,7 +112,7 @@ int plan_selection(lc_ctx* ctx, const uint32_t* entry_rows, uint64_t n, const ui
   if (!too_many.load() && pairs.size() <= pair_budget && p->sel_words >= 4096) {
     // park the pairs behind the dense words in the pinned staging area
     const uint64_t off = round_up(p->sel_words * 4, 64);
-    if (off + pairs.size() * 8 + 64 <= ctx->sel_stage_cap) {
+    if (off + pairs.size() * 8 + 64 <= ctx->L()->sel_stage_cap) {
       if (!pairs.empty()) std::memcpy(stage + off, pairs.data(), pairs.size() * 8);
       p->sparse = true;
       p->sparse_pairs = pairs.size();
@@ -126,29 +126,29 @@ int upload_selection(lc_ctx* ctx, const SelPlan& p, uint8_t* d_sel, cudaStream_t
   if (p.sel_words == 0) return LC_OK;
   if (p.sparse) {
     const uint64_t bytes = p.sparse_pairs * 8;
-    if (bytes > ctx->d_pairs_cap) {
-      if (ctx->d_pairs) cudaFree(ctx->d_pairs);
-      ctx->d_pairs = nullptr;
-      ctx->d_pairs_cap = 0;
+    if (bytes > ctx->L()->d_pairs_cap) {
+      if (ctx->L()->d_pairs) cudaFree(ctx->L()->d_pairs);
+      ctx->L()->d_pairs = nullptr;
+      ctx->L()->d_pairs_cap = 0;
       uint64_t cap = 1ull << 16;
       while (cap < bytes) cap *= 2;
-      if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_pairs), cap) != cudaSuccess) {
+      if (cudaMalloc(reinterpret_cast<void**>(&ctx->L()->d_pairs), cap) != cudaSuccess) {
         cudaGetLastError();
         set_error("cudaMalloc of %llu bytes for sparse selections failed", (unsigned long long)cap);
         return LC_ERR_OOM;
       }
-      ctx->d_pairs_cap = cap;
+      ctx->L()->d_pairs_cap = cap;
     }
     LC_CUDA_OK(cudaMemsetAsync(d_sel, 0, p.sel_words * 4, s));
     if (bytes == 0) return LC_OK;
-    LC_CUDA_OK(cudaMemcpyAsync(ctx->d_pairs, ctx->sel_stage + round_up(p.sel_words * 4, 64), bytes, cudaMemcpyHostToDevice, s));
-    LC_CUDA_OK(launch_scatter_words(reinterpret_cast<const unsigned long long*>(ctx->d_pairs), p.sparse_pairs,
+    LC_CUDA_OK(cudaMemcpyAsync(ctx->L()->d_pairs, ctx->L()->sel_stage + round_up(p.sel_words * 4, 64), bytes, cudaMemcpyHostToDevice, s));
+    LC_CUDA_OK(launch_scatter_words(reinterpret_cast<const unsigned long long*>(ctx->L()->d_pairs), p.sparse_pairs,
                                     reinterpret_cast<uint32_t*>(d_sel), s));
     ctx->kernel_launches++;
     ctx->h2d_bytes += bytes;
     return LC_OK;
   }
-  LC_CUDA_OK(cudaMemcpyAsync(d_sel, ctx->sel_stage, p.sel_words * 4, cudaMemcpyHostToDevice, s));
+  LC_CUDA_OK(cudaMemcpyAsync(d_sel, ctx->L()->sel_stage, p.sel_words * 4, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += p.sel_words * 4;
   return LC_OK;
 }
@@ -305,17 +305,17 @@ struct RefCache {
 // The cache hangs off the context (opaque pointer in lc_ctx) and is only touched under the context's lock, so
 // contexts used from different threads never share state.
 static RefCache& ref_cache_of(lc_ctx* ctx) {
-  if (!ctx->ref_cache) ctx->ref_cache = new RefCache();
-  return *static_cast<RefCache*>(ctx->ref_cache);
+  if (!ctx->L()->ref_cache) ctx->L()->ref_cache = new RefCache();
+  return *static_cast<RefCache*>(ctx->L()->ref_cache);
 }
 
 void drop_ref_cache(lc_ctx* ctx) {
-  if (!ctx->ref_cache) return;
-  RefCache* rc = static_cast<RefCache*>(ctx->ref_cache);
+  if (!ctx->L()->ref_cache) return;
+  RefCache* rc = static_cast<RefCache*>(ctx->L()->ref_cache);
   for (auto& l : rc->lists)
     if (l.d_refs) cudaFree(l.d_refs);
   delete rc;
-  ctx->ref_cache = nullptr;
+  ctx->L()->ref_cache = nullptr;
 }
 
 static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const RefList** out) {
@@ -346,7 +346,7 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
   const Entry* proto = entries[0];
   for (uint64_t i = 0; i < n; ++i) {
     const Entry* e = entries[i];
-    if (e->squeeze_kind && !ctx->squeeze_internal) {
+    if (e->squeeze_kind && !ctx->L()->squeeze_internal) {
       set_error("entry %llu of the list is squeezed: squeezed entries answer through lc_to_arrow / lc_eval_predicate", (unsigned long long)i);
       return LC_ERR_INVALID;
     }
@@ -406,17 +406,17 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
     return LC_ERR_OOM;
   }
   uint8_t* base = reinterpret_cast<uint8_t*>(nl.d_refs);
-  LC_CUDA_OK(cudaMemcpyAsync(nl.d_refs, refs.data(), n * sizeof(EntryRef), cudaMemcpyHostToDevice, ctx->stream));
+  LC_CUDA_OK(cudaMemcpyAsync(nl.d_refs, refs.data(), n * sizeof(EntryRef), cudaMemcpyHostToDevice, ctx->L()->stream));
   nl.d_n_unique = reinterpret_cast<uint32_t*>(base + o_nu);
-  LC_CUDA_OK(cudaMemcpyAsync(nl.d_n_unique, nl.n_unique->data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  LC_CUDA_OK(cudaMemcpyAsync(nl.d_n_unique, nl.n_unique->data(), n * 4, cudaMemcpyHostToDevice, ctx->L()->stream));
   nl.d_tables = reinterpret_cast<uint64_t*>(base + o_tab);
   nl.d_entry_table = reinterpret_cast<uint32_t*>(base + o_et);
   nl.d_like_steps = base + o_steps;
   if (!tables.empty()) {
-    LC_CUDA_OK(cudaMemcpyAsync(nl.d_tables, tables.data(), tables.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    LC_CUDA_OK(cudaMemcpyAsync(nl.d_entry_table, entry_table.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(nl.d_tables, tables.data(), tables.size() * 8, cudaMemcpyHostToDevice, ctx->L()->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(nl.d_entry_table, entry_table.data(), n * 4, cudaMemcpyHostToDevice, ctx->L()->stream));
   }
-  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // `refs` is pageable host memory
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));  // `refs` is pageable host memory
   ctx->h2d_bytes += n * sizeof(EntryRef);
   // evict: stale epochs first, then least recently used beyond 16 lists
   for (size_t i = 0; i < rc.lists.size();) {
@@ -573,7 +573,7 @@ static int eval_predicate_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, 
   const uint64_t dn_bits = round_up(words * 4 + 16, 256);
   const uint64_t dn_total = dn_counts + 2 * dn_bits;
   const uint64_t val_bytes = round_up(rows * tb + 16, 256);
-  Scratch& sc = ctx->scratch;
+  Scratch& sc = ctx->L()->scratch;
   LC_TRY(sc.reserve(up_total + dn_total + val_bytes + 1024, up_total + dn_total + 1024));
   uint8_t* h_up = sc.host(up_total);
   uint8_t* h_dn = sc.host(dn_total);
@@ -590,7 +590,7 @@ static int eval_predicate_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, 
     a[n + i] = row_base[i];
     a[2 * n + i] = word_off[i];
   }
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_offs, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_offs;
   LC_TRY(upload_selection(ctx, sp, d_up + up_offs, s));
@@ -606,7 +606,7 @@ static int eval_predicate_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, 
   io.counts = reinterpret_cast<uint32_t*>(d_dn);
   io.counts_stride = 4;
   IntPredDesc ip{};
-  if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
+  if (ctx->L()->timing_on) cudaEventRecord(ctx->L()->ev_a, s);
   LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
   LC_CUDA_OK(launch_alp_finish(static_cast<uint32_t>(n), io, tbits, s));
   FloatCmpIo c{};
@@ -625,9 +625,9 @@ static int eval_predicate_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, 
   c.op = op;
   c.lit_key = key;
   LC_CUDA_OK(launch_float_cmp(static_cast<uint32_t>(n), c, tbits, s));
-  if (ctx->timing_on) {
-    cudaEventRecord(ctx->ev_b, s);
-    ctx->timing_valid = true;
+  if (ctx->L()->timing_on) {
+    cudaEventRecord(ctx->L()->ev_b, s);
+    ctx->L()->timing_valid = true;
   }
   ctx->kernel_launches += 3;
   LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
@@ -675,7 +675,7 @@ static int refine_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
     rows += (*rl->rows)[i];
   }
   const uint64_t b_rb = round_up(n * 8, 256), b_cnt = round_up(n * 16, 256), b_vals = round_up(rows * tb + 16, 256);
-  Scratch& sc = ctx->scratch;
+  Scratch& sc = ctx->L()->scratch;
   LC_TRY(sc.reserve(b_rb + b_cnt + b_vals + 1024, 1024));
   uint8_t* d_rb = sc.dev(b_rb);
   uint8_t* d_cnt = sc.dev(b_cnt);
@@ -684,7 +684,7 @@ static int refine_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
     set_error("scan_filter: scratch exhausted");
     return LC_ERR_OOM;
   }
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   // pageable source: the runtime stages it before returning, so `row_base` may go out of scope
   LC_CUDA_OK(cudaMemcpyAsync(d_rb, row_base.data(), n * 8, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += n * 8;
@@ -699,7 +699,7 @@ static int refine_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
   io.counts = reinterpret_cast<uint32_t*>(d_cnt);
   io.counts_stride = 4;
   IntPredDesc ip{};
-  if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
+  if (ctx->L()->timing_on) cudaEventRecord(ctx->L()->ev_a, s);
   LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
   LC_CUDA_OK(launch_alp_finish(static_cast<uint32_t>(n), io, tbits, s));
   FloatCmpIo c{};
@@ -716,9 +716,9 @@ static int refine_float(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
   c.op = op;
   c.lit_key = key;
   LC_CUDA_OK(launch_float_cmp(static_cast<uint32_t>(n), c, tbits, s));
-  if (ctx->timing_on) {
-    cudaEventRecord(ctx->ev_b, s);
-    ctx->timing_valid = true;
+  if (ctx->L()->timing_on) {
+    cudaEventRecord(ctx->L()->ev_b, s);
+    ctx->L()->timing_valid = true;
   }
   ctx->kernel_launches += 3;
   return LC_OK;
@@ -786,7 +786,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   cudaPointerAttributes pa;
   const bool direct = mirror && cudaPointerGetAttributes(&pa, out.values) == cudaSuccess && pa.type == cudaMemoryTypeHost;
   cudaGetLastError();
-  Scratch& sc = ctx->scratch;
+  Scratch& sc = ctx->L()->scratch;
   LC_TRY(sc.reserve(up_total + dn_total + 1024, up_total + (direct ? dn_counts : dn_total) + 1024));
   uint8_t* h_up = sc.host(up_total);
   uint8_t* h_dn = sc.host(direct ? dn_counts : dn_total);
@@ -813,7 +813,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   io.valid_off = io.out_off;
   io.counts = reinterpret_cast<uint32_t*>(d_dn);
   io.counts_stride = 4;
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   tr.mark("plan + fill");
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_offs + up_needle, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_offs + up_needle;
@@ -832,9 +832,9 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   const bool try_sparse = direct && !want_valid && span >= (1u << 16) && rl->mask_hint != 2;
   const int n_chunks = (direct && n >= 2048 && span && !try_sparse) ? chunk_pref : 1;
   if (try_sparse) LC_CUDA_OK(cudaMemsetAsync(d_dn + dn_counts, 0, span, s));
-  if (n_chunks > 1 && !ctx->copy_stream) {
-    LC_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t& e : ctx->ev_chunk) LC_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (n_chunks > 1 && !ctx->L()->copy_stream) {
+    LC_CUDA_OK(cudaStreamCreateWithFlags(&ctx->L()->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : ctx->L()->ev_chunk) LC_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   if (!is_int) {
     sl.desc.needle = d_up + up_offs;
@@ -851,7 +851,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   // all rows of narrow integer entries: the register-resident kernel (its true-counts are added per chunk: zero them first)
   const bool int_bits = is_int && rl->int_bits_ok && io.sel_base == nullptr;
   if (int_bits) LC_CUDA_OK(cudaMemsetAsync(d_dn, 0, n * 16, s));
-  if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
+  if (ctx->L()->timing_on) cudaEventRecord(ctx->L()->ev_a, s);
   for (int c = 0; c < n_chunks; ++c) {
     const uint64_t c0 = n * c / n_chunks, c1 = n * (c + 1) / n_chunks;
     ScanIo ioc = io;
@@ -873,39 +873,39 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     ctx->kernel_launches++;
     if (n_chunks > 1) {
       const uint64_t b0 = out_word_off[c0] * 4, b1 = (c1 < n ? out_word_off[c1] * 4 : span);
-      LC_CUDA_OK(cudaEventRecord(ctx->ev_chunk[c], s));
-      LC_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c], 0));
+      LC_CUDA_OK(cudaEventRecord(ctx->L()->ev_chunk[c], s));
+      LC_CUDA_OK(cudaStreamWaitEvent(ctx->L()->copy_stream, ctx->L()->ev_chunk[c], 0));
       if (b1 > b0) {
         LC_CUDA_OK(cudaMemcpyAsync(out.values + first_off + b0, d_dn + dn_counts + b0, b1 - b0, cudaMemcpyDeviceToHost,
-                                   ctx->copy_stream));
+                                   ctx->L()->copy_stream));
         if (want_valid)
           LC_CUDA_OK(cudaMemcpyAsync(out.validity + first_off + b0, d_dn + dn_counts + dn_bits + b0, b1 - b0,
-                                     cudaMemcpyDeviceToHost, ctx->copy_stream));
+                                     cudaMemcpyDeviceToHost, ctx->L()->copy_stream));
       }
     }
   }
-  if (ctx->timing_on) {
-    cudaEventRecord(ctx->ev_b, s);
-    ctx->timing_valid = true;
+  if (ctx->L()->timing_on) {
+    cudaEventRecord(ctx->L()->ev_b, s);
+    ctx->L()->timing_valid = true;
   }
   bool sparse_done = false;
   if (try_sparse) {
     const uint64_t budget = out_words / 16;
     const uint64_t need = 16 + budget * 8;
-    if (need > ctx->d_pairs_cap) {
-      if (ctx->d_pairs) cudaFree(ctx->d_pairs);
-      ctx->d_pairs = nullptr;
-      ctx->d_pairs_cap = 0;
+    if (need > ctx->L()->d_pairs_cap) {
+      if (ctx->L()->d_pairs) cudaFree(ctx->L()->d_pairs);
+      ctx->L()->d_pairs = nullptr;
+      ctx->L()->d_pairs_cap = 0;
       uint64_t cap = 1ull << 16;
       while (cap < need) cap *= 2;
-      if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_pairs), cap) != cudaSuccess) {
+      if (cudaMalloc(reinterpret_cast<void**>(&ctx->L()->d_pairs), cap) != cudaSuccess) {
         cudaGetLastError();
         set_error("cudaMalloc of %llu bytes for sparse masks failed", (unsigned long long)cap);
         return LC_ERR_OOM;
       }
-      ctx->d_pairs_cap = cap;
+      ctx->L()->d_pairs_cap = cap;
     }
-    unsigned long long* d_counter = reinterpret_cast<unsigned long long*>(ctx->d_pairs);
+    unsigned long long* d_counter = reinterpret_cast<unsigned long long*>(ctx->L()->d_pairs);
     unsigned long long* d_pairs = d_counter + 2;
     unsigned long long* h_counter = reinterpret_cast<unsigned long long*>(h_up);  // pinned, its upload is long done
     LC_CUDA_OK(cudaMemsetAsync(d_counter, 0, 16, s));
@@ -918,24 +918,24 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     ctx->d2h_bytes += dn_counts + 8;
     if (found <= budget) {
       const uint64_t bytes = found * 8;
-      if (bytes + 64 > ctx->sel_stage_cap) {  // nothing is in flight on it after the sync above
-        if (ctx->sel_stage) cudaFreeHost(ctx->sel_stage);
-        ctx->sel_stage = nullptr;
-        ctx->sel_stage_cap = 0;
+      if (bytes + 64 > ctx->L()->sel_stage_cap) {  // nothing is in flight on it after the sync above
+        if (ctx->L()->sel_stage) cudaFreeHost(ctx->L()->sel_stage);
+        ctx->L()->sel_stage = nullptr;
+        ctx->L()->sel_stage_cap = 0;
         uint64_t cap = 1ull << 20;
         while (cap < bytes + 64) cap *= 2;
-        if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->sel_stage), cap, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->L()->sel_stage), cap, cudaHostAllocDefault) != cudaSuccess) {
           cudaGetLastError();
           set_error("cudaHostAlloc of %llu bytes failed", (unsigned long long)cap);
           return LC_ERR_OOM;
         }
-        ctx->sel_stage_cap = cap;
+        ctx->L()->sel_stage_cap = cap;
       }
-      if (bytes) LC_CUDA_OK(cudaMemcpyAsync(ctx->sel_stage, d_pairs, bytes, cudaMemcpyDeviceToHost, s));
+      if (bytes) LC_CUDA_OK(cudaMemcpyAsync(ctx->L()->sel_stage, d_pairs, bytes, cudaMemcpyDeviceToHost, s));
       // zero-fill the caller's mask area while the pairs travel
       parallel_for(span, 1u << 20, [&](uint64_t b, uint64_t e) { std::memset(out.values + first_off + b, 0, e - b); });
       LC_CUDA_OK(cudaStreamSynchronize(s));
-      const unsigned long long* hp = reinterpret_cast<const unsigned long long*>(ctx->sel_stage);
+      const unsigned long long* hp = reinterpret_cast<const unsigned long long*>(ctx->L()->sel_stage);
       uint32_t* dst = reinterpret_cast<uint32_t*>(out.values + first_off);
       for (uint64_t i = 0; i < found; ++i) dst[hp[i] >> 32] = static_cast<uint32_t>(hp[i]);
       ctx->d2h_bytes += bytes;
@@ -960,7 +960,7 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_total, cudaMemcpyDeviceToHost, s));
     ctx->d2h_bytes += dn_total;
   }
-  if (n_chunks > 1) LC_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));
+  if (n_chunks > 1) LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->copy_stream));
   LC_CUDA_OK(cudaStreamSynchronize(s));
   tr.mark(direct ? "upload + kernel + direct D2H" : "upload + kernel + staged D2H");
 
@@ -1035,23 +1035,23 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
   io.valid_off = nullptr;
   io.counts = d_counts;
   io.counts_stride = 2;
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   if (is_int) {
     if (rl->int_bits_ok && d_counts) LC_CUDA_OK(cudaMemsetAsync(d_counts, 0, n * 8, s));  // k_int_bits adds per chunk
-    if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
+    if (ctx->L()->timing_on) cudaEventRecord(ctx->L()->ev_a, s);
     if (rl->int_bits_ok) LC_CUDA_OK(launch_int_bits(MODE_REFINE, static_cast<uint32_t>(n), io, ip, rl->max_rows, s));
     else LC_CUDA_OK(launch_int_scan(MODE_REFINE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
   } else {
     // the needle is the only thing that travels: a few bytes from pageable memory (the runtime stages such
     // copies before returning) into a small buffer the context keeps for this purpose
-    if (!ctx->d_needle) {
-      if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_needle), 2 * (kMaxNeedle + 16) * 2) != cudaSuccess) {
+    if (!ctx->L()->d_needle) {
+      if (cudaMalloc(reinterpret_cast<void**>(&ctx->L()->d_needle), 2 * (kMaxNeedle + 16) * 2) != cudaSuccess) {
         cudaGetLastError();
         set_error("cudaMalloc for the needle buffer failed");
         return LC_ERR_OOM;
       }
     }
-    uint8_t* d_nd = ctx->d_needle;
+    uint8_t* d_nd = ctx->L()->d_needle;
     LC_CUDA_OK(cudaMemcpyAsync(d_nd, sl.needle_blob.data(), sl.needle_blob.size(), cudaMemcpyHostToDevice, s));
     ctx->h2d_bytes += sl.needle_blob.size();
     sl.desc.needle = d_nd;
@@ -1063,13 +1063,13 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
       sl.desc.like_steps = rl->d_like_steps;
       sl.desc.entry_table = rl->d_entry_table;
     }
-    if (ctx->timing_on) cudaEventRecord(ctx->ev_a, s);
+    if (ctx->L()->timing_on) cudaEventRecord(ctx->L()->ev_a, s);
     LC_CUDA_OK(launch_str_scan(MODE_REFINE, static_cast<uint32_t>(n), io, sl.desc, like ? rl->max_head_like : rl->max_head,
                                rl->max_unique, rl->max_meta, s));
   }
-  if (ctx->timing_on) {
-    cudaEventRecord(ctx->ev_b, s);
-    ctx->timing_valid = true;
+  if (ctx->L()->timing_on) {
+    cudaEventRecord(ctx->L()->ev_b, s);
+    ctx->L()->timing_valid = true;
   }
   ctx->kernel_launches++;
   return LC_OK;
@@ -1098,8 +1098,8 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   LC_TRY(plan_selection(ctx, rl->rows->data(), n, sel_bits, &sp, dev_sel));
   tr.mark("stage selection");
   const bool is_int = is_int_blob(proto->liquid_type);
-  cudaStream_t s = ctx->stream;
-  Scratch& sc = ctx->scratch;
+  cudaStream_t s = ctx->L()->stream;
+  Scratch& sc = ctx->L()->scratch;
 
   std::vector<uint64_t> vword_off(n), row_base(n);
   uint64_t vwords = 0, rows = 0;
@@ -1475,7 +1475,7 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
   // of the rows survives (the host-planned path reads just the batches with survivors)
   if (is_int && fr->spec_rows * 64 < total_rows_in) return LC_INTERNAL_FALLBACK;
   const uint32_t tb = is_int ? proto->ih.tbits / 8 : 0;
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   Tracer tr("scan_read_fused");
 
   const uint64_t cap_rows = fr->spec_rows + fr->spec_rows / 2 + 4096;

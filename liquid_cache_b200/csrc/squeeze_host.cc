@@ -28,8 +28,8 @@ namespace {
 struct SqueezeScope {  // lets the batch functions accept a squeezed entry while this file drives them
   lc_ctx* ctx;
   bool prev;
-  explicit SqueezeScope(lc_ctx* c) : ctx(c), prev(c->squeeze_internal) { c->squeeze_internal = true; }
-  ~SqueezeScope() { ctx->squeeze_internal = prev; }
+  explicit SqueezeScope(lc_ctx* c) : ctx(c), prev(c->L()->squeeze_internal) { c->L()->squeeze_internal = true; }
+  ~SqueezeScope() { ctx->L()->squeeze_internal = prev; }
 };
 
 SqueezeFacts facts_of(const Entry* e) { return SqueezeFacts{e->ih, e->squeeze_kind, e->bucket_width}; }
@@ -47,7 +47,7 @@ int count_equal(lc_ctx* ctx, Entry* sq, __int128 value, const uint8_t* sel_bits,
   PredOut po{vals.data(), nullptr, &off0, &len, &nulls, &trues};
   const uint8_t* sels[1] = {sel_bits};
   Entry* list[1] = {sq};
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   LC_TRY(eval_predicate_batch(ctx, list, 1, &p, sel_bits ? sels : nullptr, po));
   *count = trues;
   return LC_OK;
@@ -62,7 +62,7 @@ int hydrate(lc_ctx* ctx, const Entry* sq, Entry** full) {
     set_error("squeezed entry: reading %llu backing bytes failed (%d)", (unsigned long long)sq->backing_len, rc);
     return LC_ERR_INVALID;
   }
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   LC_TRY(entry_from_bytes(ctx, image.data(), image.size(), nullptr, full));
   const std::string& want_format = sq->orig_format.empty() ? sq->arrow_format : sq->orig_format;
   if ((*full)->n != sq->n || (*full)->liquid_type != LC_LIQUID_INTEGER || (*full)->arrow_format != want_format) {
@@ -91,9 +91,9 @@ struct ArenaWork {  // a work area borrowed from the arena, handed back on every
   uint8_t* p = nullptr;
   uint32_t slab = 0;
   uint64_t bytes = 0;
-  ArenaWork(lc_ctx* c, uint64_t b) : ctx(c), bytes(b) { p = c->arena.alloc(b, &slab); }
+  ArenaWork(lc_ctx* c, uint64_t b) : ctx(c), bytes(b) { p = c->arena_alloc(b, &slab); }
   ~ArenaWork() {
-    if (p) ctx->arena.free(slab, p, bytes);
+    if (p) ctx->arena_free(slab, p, bytes);
   }
   ArenaWork(const ArenaWork&) = delete;
   ArenaWork& operator=(const ArenaWork&) = delete;
@@ -105,21 +105,21 @@ struct ArenaWork {  // a work area borrowed from the arena, handed back on every
 int squeeze_date_entry(lc_ctx* ctx, Entry* full, uint32_t field, lc_backing_read read, void* user, uint64_t image_len, Entry** out) {
   const IntHeader& fh = full->ih;
   const uint32_t n = full->n, tb = fh.tbits / 8;
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   ArenaWork vals(ctx, round_up(static_cast<uint64_t>(n) * tb, 256) + 256), comp(ctx, round_up(static_cast<uint64_t>(n) * 4, 256) + 256);
   if (!vals.p || !comp.p) {
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for the squeeze work areas" : "HBM arena: cudaMalloc failed for the squeeze work areas");
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for the squeeze work areas" : "HBM arena: cudaMalloc failed for the squeeze work areas");
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   if (n) {
     uint64_t rows = 0, vbytes = 0, nulls = 0;
     DeviceOut dout{vals.p, static_cast<uint64_t>(n) * tb, nullptr, nullptr, &rows, &vbytes, &nulls};
     Entry* list[1] = {full};
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     LC_TRY(to_arrow_batch(ctx, list, 1, nullptr, nullptr, nullptr, nullptr, &dout));
   }
-  ctx->scratch.reset();
-  Scratch& sc = ctx->scratch;
+  ctx->L()->scratch.reset();
+  Scratch& sc = ctx->L()->scratch;
   LC_TRY(sc.reserve(2048, 2048));
   IntMinMaxWork* h_mm = reinterpret_cast<IntMinMaxWork*>(sc.host(256));
   IntPackWork* h_pw = reinterpret_cast<IntPackWork*>(sc.host(256));
@@ -175,16 +175,16 @@ int squeeze_date_entry(lc_ctx* ctx, Entry* full, uint32_t field, lc_backing_read
   h.packed_off = static_cast<uint32_t>(64 + valid_bytes);
   const uint64_t blob_bytes = round_up(h.packed_off + static_cast<uint64_t>(h.n_chunks) * 128ull * h.bit_width, 16);
   h.blob_bytes = static_cast<uint32_t>(blob_bytes);
-  if (ctx->budget && ctx->arena.bytes_used() + blob_bytes > ctx->budget) {
-    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(), (unsigned long long)blob_bytes,
+  if (ctx->budget && ctx->arena_used() + blob_bytes > ctx->budget) {
+    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena_used(), (unsigned long long)blob_bytes,
               (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
   uint32_t slab = 0;
-  uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
+  uint8_t* d_blob = ctx->arena_alloc(blob_bytes, &slab);
   if (!d_blob) {
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   std::memset(h_pw, 0, sizeof(*h_pw));
   h_pw->values = comp.p;
@@ -196,7 +196,7 @@ int squeeze_date_entry(lc_ctx* ctx, Entry* full, uint32_t field, lc_backing_read
   if (ce == cudaSuccess) ce = launch_int_pack(reinterpret_cast<const IntPackWork*>(d_pw), 1, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess) {
-    ctx->arena.free(slab, d_blob, blob_bytes);
+    ctx->arena_free(slab, d_blob, blob_bytes);
     set_error("CUDA error in lc_squeeze: %s", cudaGetErrorString(ce));
     return LC_ERR_CUDA;
   }
@@ -238,7 +238,7 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
       set_error("lc_squeeze: needs a buffer of %llu bytes and a read function", (unsigned long long)image_len);
       return LC_ERR_INVALID;
     }
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     LC_TRY(entry_to_bytes(ctx, full, bytes_out, cap, &image_len));
     return squeeze_date_entry(ctx, full, static_cast<uint32_t>(hint - LC_HINT_EXTRACT_YEAR), read, user, image_len, out);
   }
@@ -264,38 +264,38 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
     set_error("lc_squeeze: a squeezed entry needs a read function for its backing bytes");
     return LC_ERR_INVALID;
   }
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   LC_TRY(entry_to_bytes(ctx, full, bytes_out, cap, &image_len));  // full bytes (original format) are what goes to disk (:396)
 
   const uint32_t n = full->n, tb = fh.tbits / 8;
   const uint32_t new_bw = fh.bit_width / 2;  // >= 4
   const uint64_t tmask = fh.tbits == 64 ? ~0ull : ((1ull << fh.tbits) - 1ull);
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
 
   // ---- the full entry's values, decoded into a work area of their own (k_int_scan<DECODE>) ----
   const uint64_t work_bytes = round_up(static_cast<uint64_t>(n) * tb, 256) + 256;
   uint32_t wslab = 0;
-  uint8_t* d_vals = ctx->arena.alloc(work_bytes, &wslab);
+  uint8_t* d_vals = ctx->arena_alloc(work_bytes, &wslab);
   if (!d_vals) {
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)work_bytes);
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)work_bytes);
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   struct Work {  // returned to the arena on every way out
     lc_ctx* ctx;
     uint32_t slab;
     uint8_t* p;
     uint64_t bytes;
-    ~Work() { ctx->arena.free(slab, p, bytes); }
+    ~Work() { ctx->arena_free(slab, p, bytes); }
   } work{ctx, wslab, d_vals, work_bytes};
   {
     uint64_t rows = 0, vbytes = 0, nulls = 0;
     DeviceOut dout{d_vals, static_cast<uint64_t>(n) * tb, nullptr, nullptr, &rows, &vbytes, &nulls};
     Entry* list[1] = {full};
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     LC_TRY(to_arrow_batch(ctx, list, 1, nullptr, nullptr, nullptr, nullptr, &dout));
   }
-  ctx->scratch.reset();
-  Scratch& sc = ctx->scratch;
+  ctx->L()->scratch.reset();
+  Scratch& sc = ctx->L()->scratch;
   LC_TRY(sc.reserve(2048, 2048));
   IntMinMaxWork* h_mm = reinterpret_cast<IntMinMaxWork*>(sc.host(256));
   IntPackWork* h_pw = reinterpret_cast<IntPackWork*>(sc.host(256));
@@ -341,16 +341,16 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
   const uint64_t packed_bytes = static_cast<uint64_t>(h.n_chunks) * 128ull * new_bw;
   const uint64_t blob_bytes = round_up(h.packed_off + packed_bytes, 16);
   h.blob_bytes = static_cast<uint32_t>(blob_bytes);
-  if (ctx->budget && ctx->arena.bytes_used() + blob_bytes > ctx->budget) {
-    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(), (unsigned long long)blob_bytes,
+  if (ctx->budget && ctx->arena_used() + blob_bytes > ctx->budget) {
+    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena_used(), (unsigned long long)blob_bytes,
               (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
   uint32_t slab = 0;
-  uint8_t* d_blob = ctx->arena.alloc(blob_bytes, &slab);
+  uint8_t* d_blob = ctx->arena_alloc(blob_bytes, &slab);
   if (!d_blob) {
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   std::memset(h_pw, 0, sizeof(*h_pw));
   h_pw->values = d_vals;
@@ -362,7 +362,7 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
   if (ce == cudaSuccess) ce = launch_int_pack(reinterpret_cast<const IntPackWork*>(d_pw), 1, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess) {
-    ctx->arena.free(slab, d_blob, blob_bytes);
+    ctx->arena_free(slab, d_blob, blob_bytes);
     set_error("CUDA error in lc_squeeze: %s", cudaGetErrorString(ce));
     return LC_ERR_CUDA;
   }
@@ -402,7 +402,7 @@ int count_probe(lc_ctx* ctx, Entry* sq, const lc_predicate& probe, const uint8_t
   PredOut po{vals.data(), nullptr, &off0, &len, &nulls, &trues};
   const uint8_t* sels[1] = {sel_bits};
   Entry* list[1] = {sq};
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   LC_TRY(eval_predicate_batch(ctx, list, 1, &probe, sel_bits ? sels : nullptr, po));
   *count = trues;
   return LC_OK;
@@ -425,7 +425,7 @@ int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, co
     Entry* full = nullptr;
     LC_TRY(hydrate(ctx, sq, &full));
     Entry* list1[1] = {full};
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     const int rc = eval_predicate_batch(ctx, list1, 1, pred, sel_bits ? sels : nullptr, out);
     release_entry(ctx, full);
     return rc;
@@ -448,13 +448,13 @@ int squeezed_eval_predicate(lc_ctx* ctx, Entry* sq, const lc_predicate* pred, co
   Entry* list[1] = {sq};
   if (from_codes) {
     ctx->squeeze_saved++;  // io.trace_io_saved()
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     return eval_predicate_batch(ctx, list, 1, pred, sel_bits ? sels : nullptr, out);
   }
   Entry* full = nullptr;
   LC_TRY(hydrate(ctx, sq, &full));
   list[0] = full;
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   const int rc = eval_predicate_batch(ctx, list, 1, pred, sel_bits ? sels : nullptr, out);
   release_entry(ctx, full);
   return rc;
@@ -531,14 +531,14 @@ int squeezed_eval_predicate_many(lc_ctx* ctx, Entry* const* entries, uint64_t n,
     for (int form = 1; form <= 2; ++form) {
       if (!n_doubt[form]) continue;
       PredOut po{tmp.data(), nullptr, out.byte_offsets, len.data(), nulls.data(), trues.data()};
-      ctx->scratch.reset();
+      ctx->L()->scratch.reset();
       LC_TRY(eval_predicate_batch(ctx, entries, n, &probes[form], sel_bits, po));
       for (uint64_t i = 0; i < n; ++i)
         if (doubt[i] == form && trues[i]) backing[i] = 1;  // Err(NeedsBacking)
     }
   }
   // ---- the predicate over the whole list ----
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   LC_TRY(eval_predicate_batch(ctx, entries, n, pred, sel_bits, out));
   if (self_probe)
     for (uint64_t i = 0; i < n; ++i)
@@ -553,7 +553,7 @@ int squeezed_eval_predicate_many(lc_ctx* ctx, Entry* const* entries, uint64_t n,
     const uint8_t* sels[1] = {sel_bits ? sel_bits[i] : nullptr};
     PredOut po{out.values, out.validity, out.byte_offsets + i, out.len ? out.len + i : nullptr, out.null_count ? out.null_count + i : nullptr,
                out.true_count ? out.true_count + i : nullptr};
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     const int rc = eval_predicate_batch(ctx, list, 1, pred, sels[0] ? sels : nullptr, po);
     release_entry(ctx, full);
     LC_TRY(rc);
@@ -586,13 +586,13 @@ int squeezed_to_arrow(lc_ctx* ctx, Entry* sq, const uint8_t* sel_bits, ArrowSche
     }
   }
   if (from_codes) {
-    ctx->scratch.reset();
+    ctx->L()->scratch.reset();
     return to_arrow_batch(ctx, list, 1, sel_bits ? sels : nullptr, nullptr, out_schema, out_array);
   }
   Entry* full = nullptr;  // Quantize always (:684-686), Clamp when a selected row sits at the sentinel
   LC_TRY(hydrate(ctx, sq, &full));
   list[0] = full;
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   const int rc = to_arrow_batch(ctx, list, 1, sel_bits ? sels : nullptr, nullptr, out_schema, out_array);
   release_entry(ctx, full);
   return rc;
@@ -606,7 +606,7 @@ int squeezed_component_array(lc_ctx* ctx, Entry* sq, int32_t lossy, ArrowSchema*
     return LC_ERR_INVALID;
   }
   Entry* list[1] = {sq};
-  ctx->scratch.reset();
+  ctx->L()->scratch.reset();
   if (!lossy) return to_arrow_batch(ctx, list, 1, nullptr, nullptr, out_schema, out_array);
   const uint32_t n = sq->n;
   const long long ticks = ticks_per_day_of(sq->orig_format);
@@ -615,10 +615,10 @@ int squeezed_component_array(lc_ctx* ctx, Entry* sq, int32_t lossy, ArrowSchema*
   ArenaWork comp(ctx, round_up(static_cast<uint64_t>(n) * 4, 256) + 256), res(ctx, round_up(static_cast<uint64_t>(n) * out_tb, 256) + 256),
       val(ctx, round_up(vwords * 4, 256) + 256);
   if (!comp.p || !res.p || !val.p) {
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for the component work areas" : "HBM arena: cudaMalloc failed for the component work areas");
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for the component work areas" : "HBM arena: cudaMalloc failed for the component work areas");
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->L()->stream;
   uint64_t rows = 0, vbytes = 0, nulls = 0;
   if (n) {
     DeviceOut dout{comp.p, static_cast<uint64_t>(n) * 4, nullptr, val.p, &rows, &vbytes, &nulls};

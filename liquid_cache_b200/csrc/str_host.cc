@@ -96,9 +96,12 @@ void set_bits_range(uint8_t* dst, uint32_t n) {  // first n bits := 1
 }  // namespace
 
 static int get_codec(lc_ctx* ctx, uint64_t scope, const DictBuilder& d, std::shared_ptr<FsstCodec>* out) {
-  auto it = ctx->codecs.find(scope);
-  if (it != ctx->codecs.end()) {
-    *out = it->second;
+  // one table per scope, trained by whoever gets here first; a second thread inserting the chunk's next batch waits on the
+  // slot and finds the table (with_fsst_compressor_or_train holds a RwLock around the same decision, utils.rs:90-130)
+  std::shared_ptr<lc_ctx::CodecSlot> slot = ctx->codec_slot(scope);
+  std::lock_guard<std::mutex> train_lock(slot->mu);
+  if (slot->codec) {
+    *out = slot->codec;
     return LC_OK;
   }
   // first batch of this column chunk trains (transcode.rs:16-33); training input = the unique values
@@ -110,10 +113,10 @@ static int get_codec(lc_ctx* ctx, uint64_t scope, const DictBuilder& d, std::sha
     set_error("cudaMalloc for FSST tables failed");
     return LC_ERR_OOM;
   }
-  LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->stream));
-  LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->stream));
-  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  ctx->codecs[scope] = codec;
+  LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->L()->stream));
+  LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->L()->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
+  slot->codec = codec;
   *out = codec;
   return LC_OK;
 }
@@ -126,10 +129,12 @@ int register_codec(lc_ctx* ctx, uint64_t scope, const std::shared_ptr<FsstCodec>
     set_error("cudaMalloc for FSST tables failed");
     return LC_ERR_OOM;
   }
-  LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->stream));
-  LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->stream));
-  LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  ctx->codecs[scope] = codec;
+  LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->L()->stream));
+  LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->L()->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
+  std::shared_ptr<lc_ctx::CodecSlot> slot = ctx->codec_slot(scope);
+  std::lock_guard<std::mutex> g(slot->mu);
+  slot->codec = codec;
   return LC_OK;
 }
 
@@ -296,10 +301,8 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   //         training is host work by design (once per chunk, never visible in any result) ----
   std::shared_ptr<FsstCodec> codec;
   {
-    auto it = ctx->codecs.find(scope);
-    if (it != ctx->codecs.end()) {
-      codec = it->second;
-    } else {
+    codec = ctx->codec_of(scope);
+    if (!codec) {
       DictBuilder dict(n < 1024 ? 1024 : n / 2);
       std::vector<uint8_t> ordered;  // fixed-width values are compressed in their order-preserving form: train on that
       if (in.kind == ArrowIn::K_DECIMAL) {
@@ -322,8 +325,8 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   const bool build_fp = (hint == LC_HINT_SUBSTRING_SEARCH);
   uint32_t cap = 64;
   while (cap < 2u * n) cap <<= 1;
-  cudaStream_t s = ctx->stream;
-  Scratch& sc = ctx->scratch;
+  cudaStream_t s = ctx->L()->stream;
+  Scratch& sc = ctx->L()->scratch;
   const uint64_t vbytes = has_input_nulls ? round_up((n + 31) / 32 * 4, 16) : 0;
   const uint64_t up_bytes = round_up(4ull * n, 256) * 2 + round_up(vbytes, 256);
   const uint64_t comp_cap = 2 * sum_len + 64;
@@ -454,16 +457,16 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
     return LC_ERR_UNSUPPORTED_TYPE;
   }
   h.blob_bytes = static_cast<uint32_t>(o);
-  if (ctx->budget && ctx->arena.bytes_used() + o > ctx->budget) {
-    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(),
+  if (ctx->budget && ctx->arena_used() + o > ctx->budget) {
+    set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena_used(),
               (unsigned long long)o, (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
   uint32_t slab = 0;
-  uint8_t* d_blob = ctx->arena.alloc(o, &slab);
+  uint8_t* d_blob = ctx->arena_alloc(o, &slab);
   if (!d_blob) {
-    set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
-    return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+    set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
+    return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
   }
   // first valid row = unique 0 = where the shared prefix is read from
   uint32_t first_valid = 0;
@@ -558,11 +561,27 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
   // trained side by side on the host pool; the tables are uploaded afterwards with one synchronisation.
   std::vector<std::shared_ptr<FsstCodec>> codecs(nb_all);
   std::vector<uint64_t> train_first;  // index of the first batch of every scope that needs a table
+  std::vector<std::shared_ptr<lc_ctx::CodecSlot>> train_slot;
   {
     std::unordered_map<uint64_t, uint64_t> seen;
-    for (uint64_t i = 0; i < nb_all; ++i)
-      if (!ctx->codecs.count(scopes[i]) && seen.emplace(scopes[i], i).second) train_first.push_back(i);
+    for (uint64_t i = 0; i < nb_all; ++i) {
+      if (!seen.emplace(scopes[i], i).second) continue;
+      std::shared_ptr<lc_ctx::CodecSlot> slot = ctx->codec_slot(scopes[i]);
+      slot->mu.lock();  // held until the table is in place: another thread inserting into the same chunk waits for it
+      if (slot->codec) {
+        slot->mu.unlock();
+      } else {
+        train_first.push_back(i);
+        train_slot.push_back(slot);
+      }
+    }
   }
+  struct Unlock {  // whatever happens below, the slots are released
+    std::vector<std::shared_ptr<lc_ctx::CodecSlot>>* v;
+    ~Unlock() {
+      for (auto& sl : *v) sl->mu.unlock();
+    }
+  } unlock{&train_slot};
   std::vector<std::shared_ptr<FsstCodec>> trained(train_first.size());
   parallel_for(train_first.size(), 1, [&](uint64_t b, uint64_t e) {
     for (uint64_t t = b; t < e; ++t) {
@@ -584,15 +603,17 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       set_error("cudaMalloc for FSST tables failed");
       return LC_ERR_OOM;
     }
-    LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->stream));
-    LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(codec->d_dec, &codec->dec, sizeof(FsstTable), cudaMemcpyHostToDevice, ctx->L()->stream));
+    LC_CUDA_OK(cudaMemcpyAsync(codec->d_enc, codec->enc.get(), sizeof(FsstEncTable), cudaMemcpyHostToDevice, ctx->L()->stream));
   }
-  if (!train_first.empty()) LC_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // the sources are pageable host memory
-  for (uint64_t t = 0; t < train_first.size(); ++t) ctx->codecs[scopes[train_first[t]]] = trained[t];
-  for (uint64_t i = 0; i < nb_all; ++i) codecs[i] = ctx->codecs[scopes[i]];
+  if (!train_first.empty()) LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));  // the sources are pageable host memory
+  for (uint64_t t = 0; t < train_first.size(); ++t) train_slot[t]->codec = trained[t];
+  for (auto& sl : train_slot) sl->mu.unlock();
+  train_slot.clear();
+  for (uint64_t i = 0; i < nb_all; ++i) codecs[i] = ctx->codec_of(scopes[i]);
   const bool build_fp = (hint == LC_HINT_SUBSTRING_SEARCH);
-  cudaStream_t s = ctx->stream;
-  Scratch& sc = ctx->scratch;
+  cudaStream_t s = ctx->L()->stream;
+  Scratch& sc = ctx->L()->scratch;
   struct Taken {
     uint8_t* blob;
     uint32_t slab;
@@ -600,7 +621,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
   };
   std::vector<Taken> taken;
   auto give_back = [&]() {
-    for (const Taken& t : taken) ctx->arena.free(t.slab, t.blob, t.bytes);
+    for (const Taken& t : taken) ctx->arena_free(t.slab, t.blob, t.bytes);
     for (Entry* e : *out) delete e;
     out->clear();
   };
@@ -821,18 +842,18 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
         return LC_ERR_UNSUPPORTED_TYPE;
       }
       hd.blob_bytes = static_cast<uint32_t>(o);
-      if (ctx->budget && ctx->arena.bytes_used() + o > ctx->budget) {
+      if (ctx->budget && ctx->arena_used() + o > ctx->budget) {
         give_back();
-        set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena.bytes_used(), (unsigned long long)o,
+        set_error("cache full: %llu + %llu > budget %llu", (unsigned long long)ctx->arena_used(), (unsigned long long)o,
                   (unsigned long long)ctx->budget);
         return LC_ERR_CACHE_FULL;
       }
       uint32_t slab = 0;
-      uint8_t* d_blob = ctx->arena.alloc(o, &slab);
+      uint8_t* d_blob = ctx->arena_alloc(o, &slab);
       if (!d_blob) {
         give_back();
-        set_error(ctx->arena.at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
-        return ctx->arena.at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
+        set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
+        return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
       }
       taken.push_back({d_blob, slab, o});
       uint32_t first_valid = 0;
