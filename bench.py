@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-entries", type=int, default=0,
                     help="entries per CPU-arm pass; 0 = max(8192, 64 per host thread), bounded by the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--url-source", choices=["synthetic", "sample"], default="synthetic",
+                    help="url_like: the synthetic URL generator, or URLs resampled from the reference's ClickBench sample")
     ap.add_argument("--no-secondary", action="store_true", help="url_like at one GPU: skip the configs[2] / configs[3] runs that are "
                                                                "reported under config.secondary")
     ap.add_argument("--workload", choices=["url_like", "int_filter", "shipdate", "clickbench_sweep", "squeeze", "insert"], default="url_like",
@@ -134,9 +136,19 @@ def pin_to_gpu_numa(local_rank: int):
     return {"pinned_cpus": 0}
 
 
-def generate_entries(first: int, count: int, workers: int):
+def generate_entries(first: int, count: int, workers: int, source: str = "synthetic"):
     """Yield (entry_index, pyarrow URL batch) in order, generated by a thread pool (the C generator drops the GIL)."""
     import synth
+
+    if source == "sample":
+        from synth.hits import HitsSample
+
+        sample = HitsSample()
+        for g0 in range(first, first + count, 256):
+            nb = min(256, first + count - g0)
+            for k, arr in enumerate(sample.batches(["URL"], g0, nb)["URL"]):
+                yield g0 + k, arr
+        return
 
     synth.lib().lcs_init(synth.URL_POOL)
     with cf.ThreadPoolExecutor(max_workers=workers) as ex:
@@ -687,7 +699,14 @@ def main():
 
         bench_sweep.main(args, rank, world, local_rank)
         return
+    run_url_like(args, rank, world, local_rank)
 
+
+def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=None, secondary=True):
+    """BASELINE configs[1] — the driver's bench line. `source`: "synthetic" (synth/lc_synth.c: the 100 M-row column the
+    metric is quoted on) or "sample" (URLs resampled from the reference's 24 586-row ClickBench sample, synth/hits.py: the
+    real column's dictionary sizes, lengths and compressibility; reported beside it under config.secondary)."""
+    source = source or args.url_source
     import numpy as np
     import pyarrow as pa
     import torch
@@ -709,7 +728,7 @@ def main():
     cache.set_stream(stream.cuda_stream)
 
     # ---- setup (untimed): this rank's shard of the column, transcoded into HBM ----
-    n_entries = max(1, args.rows // ROWS_PER_ENTRY)
+    n_entries = max(1, (rows or args.rows) // ROWS_PER_ENTRY)
     first = rank * n_entries  # entries shard by EntryID (file, row group, batch): rank r owns [r*E, (r+1)*E)
     t_setup = time.perf_counter()
     ids = []
@@ -726,7 +745,7 @@ def main():
             pend_ids.clear()
             pend_arrs.clear()
 
-    for i, arr in generate_entries(first, n_entries, workers):
+    for i, arr in generate_entries(first, n_entries, workers, source):
         # 32 batches per row group, column id 13 (= URL in hits); the FSST table is per (file, row group, column)
         eid = parquet_array_id(0, i // 32, 13, i % 32)
         pend_ids.append(eid)
@@ -907,7 +926,9 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
-                "workload": "clickbench-hits URL column (FSST+dict+fingerprints) LIKE '%google%' then get-with-selection (BASELINE configs[1])",
+                "workload": "clickbench-hits URL column (FSST+dict+fingerprints) LIKE '%google%' then get-with-selection (BASELINE configs[1])"
+                            + ("" if source == "synthetic" else "; URLs resampled from the reference's ClickBench sample (synth/hits.py)"),
+                "url_source": source,
                 "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "rows_per_entry": ROWS_PER_ENTRY,
                 "liquid_bytes_per_gpu": hbm_bytes, "liquid_bytes_per_row": hbm_bytes / rows_local,
                 "unique_values_per_entry": uniques / n_entries, "walked_candidates_frac": cand / max(1, uniques),
@@ -933,7 +954,7 @@ def main():
                          "kernel_share_of_step": kern_ms / (ms_total / args.steps)},
             "clocks": clk,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and source == "synthetic":
             import bench_cpu
 
             cpu_threads, _h = bench_cpu.usable_cpus()
@@ -944,10 +965,20 @@ def main():
         dist.destroy_process_group()
     cache.close()
     if rank == 0:
-        if world == 1 and not args.no_secondary:
+        if world == 1 and not args.no_secondary and secondary:
             # BASELINE configs[2] and [3] measured in the SAME run, so that their rooflines sit in the driver's bench line
             #  — each is also a workload of its own (--workload int_filter / shipdate)
             sec = {}
+            if source == "synthetic":
+                # the same step on URLs resampled from the real table's sample (16.8 M rows): what the synthetic column's
+                # higher compressibility hides
+                try:
+                    sub = run_url_like(args, 0, 1, local_rank, emit=False, source="sample", rows=16_777_216, secondary=False)
+                    sec["url_like_clickbench_sample"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "e2e", "roofline", "gpu_launches")}
+                    sec["url_like_clickbench_sample"].update({k: sub["config"][k] for k in (
+                        "rows_per_gpu", "liquid_bytes_per_row", "unique_values_per_entry", "walked_candidates_frac", "matching_rows", "insert")})
+                except Exception as e:
+                    sec["url_like_clickbench_sample"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             for name, fn in (("int_filter", run_int_filter), ("shipdate", run_shipdate)):
                 try:
                     sub = fn(args, 0, 1, local_rank, emit=False)
@@ -958,7 +989,10 @@ def main():
                 except Exception as e:  # a secondary workload must not take the headline line down with it
                     sec[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
             line["config"]["secondary"] = sec
-        print(json.dumps(line))
+        if emit:
+            print(json.dumps(line))
+        return line
+    return None
 
 
 if __name__ == "__main__":
