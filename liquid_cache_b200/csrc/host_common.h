@@ -225,6 +225,25 @@ struct lc_ctx {
 
 namespace lc {
 
+// An arena range that goes back to the arena unless an Entry took it over (early returns after a CUDA error).
+struct ArenaBlock {
+  lc_ctx* ctx;
+  uint8_t* p = nullptr;
+  uint32_t slab = 0;
+  uint64_t bytes = 0;
+  ArenaBlock(lc_ctx* c, uint64_t b) : ctx(c), bytes(b) { p = c->arena_alloc(b, &slab); }
+  ~ArenaBlock() {
+    if (p) ctx->arena_free(slab, p, bytes);
+  }
+  uint8_t* release() {  // ownership moves to an Entry
+    uint8_t* r = p;
+    p = nullptr;
+    return r;
+  }
+  ArenaBlock(const ArenaBlock&) = delete;
+  ArenaBlock& operator=(const ArenaBlock&) = delete;
+};
+
 // ---- Arrow C data helpers (arrow_io.cc) ---------------------------------------------------------
 struct HostBuf {  // 64-byte aligned host allocation
   uint8_t* p = nullptr;

@@ -5,6 +5,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <mutex>
+#include <pthread.h>
 #include <thread>
 #include <vector>
 
@@ -91,9 +92,18 @@ class Pool {
   std::atomic<int> pending_{0};
 };
 
+// Worker threads do not survive fork(): the child gets a pool object whose workers are gone and would wait for them for
+// ever. The child therefore starts over with a fresh pool on its first parallel_for (the parent's object is leaked there).
+Pool* g_pool = nullptr;
+std::once_flag g_atfork_once;
+void forget_pool_in_child() { g_pool = nullptr; }
+
 Pool& pool() {
-  static Pool* p = new Pool();  // leaked on purpose: worker threads must not be joined from a static destructor
-  return *p;
+  std::call_once(g_atfork_once, [] { pthread_atfork(nullptr, nullptr, forget_pool_in_child); });
+  static std::mutex make_mu;
+  std::lock_guard<std::mutex> l(make_mu);
+  if (!g_pool) g_pool = new Pool();  // leaked on purpose: worker threads must not be joined from a static destructor
+  return *g_pool;
 }
 
 }  // namespace

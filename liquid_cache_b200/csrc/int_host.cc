@@ -179,8 +179,9 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
               (unsigned long long)blob_bytes, (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
-  uint32_t slab = 0;
-  uint8_t* d_blob = ctx->arena_alloc(blob_bytes, &slab);
+  ArenaBlock block(ctx, blob_bytes);  // handed back on every early return below
+  uint8_t* d_blob = block.p;
+  const uint32_t slab = block.slab;
   if (!d_blob) {
     set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)blob_bytes);
     return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
@@ -205,7 +206,7 @@ int int_encode(lc_ctx* ctx, const ArrowIn& in, Entry** out) {
 
   Entry* e = new Entry();
   e->liquid_type = is_float ? LC_LIQUID_FLOAT : is_dec ? LC_LIQUID_DECIMAL : LC_LIQUID_INTEGER;
-  e->d_blob = d_blob;
+  e->d_blob = block.release();
   e->blob_bytes = h.blob_bytes;
   e->slab = slab;
   e->n = n;

@@ -1254,9 +1254,16 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
       set_error("host allocation of %llu bytes failed", (unsigned long long)(rows * out_tb));
       return LC_ERR_OOM;
     }
-    LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
-    if (rows) LC_CUDA_OK(cudaMemcpyAsync(values.p, d_result, rows * out_tb, cudaMemcpyDeviceToHost, s));
-    LC_CUDA_OK(cudaStreamSynchronize(s));
+    {
+      cudaError_t ce = cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s);
+      if (ce == cudaSuccess && rows) ce = cudaMemcpyAsync(values.p, d_result, rows * out_tb, cudaMemcpyDeviceToHost, s);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+      if (ce != cudaSuccess) {
+        host_free(values.p);  // the result buffer goes back on the error path too
+        set_error("CUDA error in integer get: %s", cudaGetErrorString(ce));
+        return LC_ERR_CUDA;
+      }
+    }
     ctx->d2h_bytes += dn_counts + rows * out_tb;
     const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
     uint64_t nulls = 0;
@@ -1705,8 +1712,18 @@ static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls,
   // Dictionary<UInt16, Utf8|Binary>: first-occurrence re-encode of the decoded rows
   std::unordered_map<std::string, uint16_t> seen;
   std::vector<std::string> order;
+  // this function owns validity / offsets / data from here on: every way out releases what the result does not keep
+  auto drop_inputs = [&]() {
+    host_free(validity.p);
+    host_free(offsets.p);
+    host_free(data.p);
+  };
   HostBuf keys{host_alloc(rows * 2 + 2), rows * 2};
-  if (!keys.p) return LC_ERR_OOM;
+  if (!keys.p) {
+    drop_inputs();
+    set_error("host allocation failed");
+    return LC_ERR_OOM;
+  }
   std::memset(keys.p, 0, rows * 2 + 2);
   for (uint64_t r = 0; r < rows; ++r) {
     const bool ok = !validity.p || bit_get(validity.p, static_cast<int64_t>(r));
@@ -1717,6 +1734,7 @@ static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls,
     if (it == seen.end()) {
       if (order.size() >= 65536) {
         host_free(keys.p);
+        drop_inputs();
         set_error("more than 65536 distinct values in a dictionary result");
         return LC_ERR_UNSUPPORTED_TYPE;
       }
@@ -1732,6 +1750,14 @@ static int finish_bytes_array(const Entry* proto, uint64_t rows, uint64_t nulls,
   for (auto& sv : order) dbytes += sv.size();
   HostBuf doff{host_alloc((order.size() + 1) * 4), (order.size() + 1) * 4};
   HostBuf ddata{host_alloc(dbytes ? dbytes : 1), dbytes};
+  if (!doff.p || !ddata.p) {
+    host_free(doff.p);
+    host_free(ddata.p);
+    host_free(keys.p);
+    drop_inputs();
+    set_error("host allocation failed");
+    return LC_ERR_OOM;
+  }
   int32_t* dof = reinterpret_cast<int32_t*>(doff.p);
   uint64_t p = 0;
   for (size_t i = 0; i < order.size(); ++i) {

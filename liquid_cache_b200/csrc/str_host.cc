@@ -462,8 +462,9 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
               (unsigned long long)o, (unsigned long long)ctx->budget);
     return LC_ERR_CACHE_FULL;
   }
-  uint32_t slab = 0;
-  uint8_t* d_blob = ctx->arena_alloc(o, &slab);
+  ArenaBlock block(ctx, o);  // handed back on every early return below
+  uint8_t* d_blob = block.p;
+  const uint32_t slab = block.slab;
   if (!d_blob) {
     set_error(ctx->arena_at_limit() ? "cache full: the HBM reservation has reached the budget for %llu bytes" : "HBM arena: cudaMalloc failed for %llu bytes", (unsigned long long)o);
     return ctx->arena_at_limit() ? LC_ERR_CACHE_FULL : LC_ERR_OOM;
@@ -491,7 +492,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
 
   Entry* e = new Entry();
   e->liquid_type = LC_LIQUID_BYTE_VIEW;
-  e->d_blob = d_blob;
+  e->d_blob = block.release();
   e->blob_bytes = h.blob_bytes;
   e->slab = slab;
   e->n = n;
