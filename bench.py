@@ -794,7 +794,7 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
         rows_phase_entries = n_entries
     algo_bytes = 2 * rows_local + meta_bytes + cand_bytes + rows_local // 8
     algo_bytes_private = algo_bytes + 32 * uniques
-    kernel_reads = meta_bytes + 32 * uniques + cand_bytes + rows_phase_entries * 2 * ROWS_PER_ENTRY + rows_local // 8  # every value's filter is fetched
+    kernel_reads = meta_bytes + 32 * ref_pass + cand_bytes + rows_phase_entries * 2 * ROWS_PER_ENTRY + rows_local // 8
 
     k_start = torch.cuda.Event(enable_timing=True)
     k_stop = torch.cuda.Event(enable_timing=True)

@@ -466,6 +466,16 @@ class LiquidCache:
         N.check(rc)
         return GpuLiquidArray(self, int(h.value), owned=True)
 
+    def remove(self, entry_id) -> bool:
+        """Drop one entry (what eviction does to an in-memory entry, cache/core.rs:371-420); False when it was not cached.
+        Arrays a caller still holds (`try_read_liquid`) keep working."""
+        rc = N.lib().lc_cache_remove(self._ctx, int(entry_id))
+        if rc == N.LC_ERR_NOT_FOUND:
+            return False
+        N.check(rc)
+        self._types.pop(int(entry_id), None)
+        return True
+
     def reset(self) -> None:
         N.check(N.lib().lc_cache_reset(self._ctx))
         self._types.clear()

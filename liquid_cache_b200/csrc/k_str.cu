@@ -889,6 +889,18 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
     nb[2 * q] = static_cast<uint32_t>(pred.needle_bloom[q]);
     nb[2 * q + 1] = static_cast<uint32_t>(pred.needle_bloom[q] >> 32);
   }
+  // ... and the words that carry a bit at all (at most four for needles of up to six bytes: the pipelined gate fetches just those)
+  uint32_t nw = 0, widx[4] = {0, 0, 0, 0}, wbits[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (uint32_t q = 0; q < 8; ++q)
+    if (nb[q]) {
+      if (nw < 4u) {
+        widx[nw] = q;
+        wbits[nw] = nb[q];
+      }
+      ++nw;
+    }
+
   const uint32_t e0 = blockIdx.x * per_cta;
   const uint32_t e_end = e0 + per_cta < n_entries ? e0 + per_cta : n_entries;
   uint32_t e = e0 + warp;
@@ -943,59 +955,106 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
       ncand = 0;
       __syncwarp();
     };
-    // The gate streams the dictionary's fingerprints and trigram sets with FULLY COALESCED loads: two lanes per value, the
-    // even lane holding words 0-3 of its 32-byte set and the odd lane words 4-7, so one 16-byte load per lane covers 512
-    // contiguous bytes (16 values) per warp instruction — 16 sectors per request instead of one sector per lane (ncu r02 v5:
-    // with a lane per value the L1/LSU sector rate, not DRAM, bounded the kernel: 43 % of the samples at the set loads).
-    // Nothing depends on anything else, so two groups of 64 values are kept in flight (software pipeline in registers).
-    const bool odd = lane & 1u;
-    uint32_t nbh[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) nbh[q] = odd ? nb[4 + q] : nb[q];
-    const uint4* bloom128 = reinterpret_cast<const uint4*>(bloom);
-    auto issue = [&](uint32_t g0, uint32_t (&f)[4], uint4 (&bl)[4]) {
-#pragma unroll
-      for (uint32_t t = 0; t < 4; ++t) {
-        const uint32_t u = g0 + t * 16u + (lane >> 1);
-        f[t] = 0xffffffffu;
-        bl[t] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (u < U) {
-          if (fp) f[t] = __ldg(fp + u);
-          if (bloom128) bl[t] = __ldg(bloom128 + static_cast<size_t>(u) * 2u + (odd ? 1u : 0u));
-        }
+    auto append = [&](bool cand, bool ok, uint32_t i0) {  // survivors of one stripe join the candidate list
+      const uint32_t cw = __ballot_sync(kFullMask, cand);
+      if (neg || pred.prof) n_ref += __popc(__ballot_sync(kFullMask, ok));
+      if (cw) {
+        if (ncand + 32u > kLikeCandCap) walk();
+        if (cand) s_cand[ncand + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i0 + lane);
+        ncand += __popc(cw);
+        __syncwarp();
       }
     };
-    auto test = [&](uint32_t g0, const uint32_t (&f)[4], const uint4 (&bl)[4]) {
+    if (nw <= 4u) {
+      // The needle's trigram bits sit in at most four of the filter's eight 32-bit words (every needle of up to six bytes):
+      // only those words are fetched — still one 32-byte sector per surviving value, but four registers per stripe instead
+      // of eight, which is what lets the gate run as a software pipeline: while the four stripes of group g are tested,
+      // the filter words of group g+1 and the fingerprints of group g+2 are already in flight.
+      const uint32_t* bloom32 = reinterpret_cast<const uint32_t*>(bloom);
+      auto load_fp = [&](uint32_t g0, uint32_t (&f)[4]) {
 #pragma unroll
-      for (uint32_t t = 0; t < 4; ++t) {
-        const uint32_t u0 = g0 + t * 16u;
-        if (u0 >= U) break;  // warp-uniform
-        const uint32_t u = u0 + (lane >> 1);
-        const bool ok = (u < U) && ((f[t] & pred.needle_fp) == pred.needle_fp);
-        uint32_t miss = (~bl[t].x & nbh[0]) | (~bl[t].y & nbh[1]) | (~bl[t].z & nbh[2]) | (~bl[t].w & nbh[3]);  // this half
-        miss |= __shfl_xor_sync(kFullMask, miss, 1);                                                           // + the other
-        const bool cand = ok && miss == 0u;
-        const uint32_t cw = __ballot_sync(kFullMask, cand) & 0x55555555u;  // one bit per value (the even lane's)
-        if (neg || pred.prof) n_ref += __popc(__ballot_sync(kFullMask, ok) & 0x55555555u);
-        if (cw) {
-          if (ncand + 16u > kLikeCandCap) walk();
-          if (cand && !odd) s_cand[ncand + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(u);
-          ncand += __popc(cw);
-          __syncwarp();
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i = g0 + t * 32u + lane;
+          f[t] = (fp && i < U) ? __ldg(fp + i) : 0xffffffffu;
         }
-      }
-    };
-    {
-      uint32_t fA[4], fB[4];
-      uint4 blA[4], blB[4];
-      issue(0, fA, blA);
-      for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
-        const bool more1 = g0 + 64u < U, more2 = g0 + 128u < U;
-        if (more1) issue(g0 + 64u, fB, blB);
-        test(g0, fA, blA);
+      };
+      auto issue = [&](uint32_t g0, const uint32_t (&f)[4], uint32_t (&bl)[4][4], bool (&ok)[4]) {
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i = g0 + t * 32u + lane;
+          ok[t] = (i < U) && ((f[t] & pred.needle_fp) == pred.needle_fp);
+          if (ok[t] && bloom32) {  // lanes the fingerprint rejected fetch nothing
+            const uint32_t* src = bloom32 + static_cast<size_t>(i) * (2u * kBloomWords);
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) bl[t][q] = __ldg(src + widx[q]);
+          } else {
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) bl[t][q] = 0xffffffffu;
+          }
+        }
+      };
+      auto test = [&](uint32_t g0, const uint32_t (&bl)[4][4], const bool (&ok)[4]) {
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i0 = g0 + t * 32u;
+          if (i0 >= U) break;  // warp-uniform
+          const uint32_t miss = (~bl[t][0] & wbits[0]) | (~bl[t][1] & wbits[1]) | (~bl[t][2] & wbits[2]) | (~bl[t][3] & wbits[3]);
+          append(ok[t] && miss == 0u, ok[t], i0);
+        }
+      };
+      uint32_t fA[4], fB[4], blA[4][4], blB[4][4];
+      bool okA[4], okB[4];
+      load_fp(0, fA);
+      issue(0, fA, blA, okA);
+      load_fp(128u, fB);
+      for (uint32_t g0 = 0; g0 < U; g0 += 256u) {
+        const bool more1 = g0 + 128u < U, more2 = g0 + 256u < U;
         if (more1) {
-          if (more2) issue(g0 + 128u, fA, blA);
-          test(g0 + 64u, fB, blB);
+          issue(g0 + 128u, fB, blB, okB);
+          load_fp(g0 + 256u, fA);
+        }
+        test(g0, blA, okA);
+        if (more1) {
+          if (more2) {
+            issue(g0 + 256u, fA, blA, okA);
+            load_fp(g0 + 384u, fB);
+          }
+          test(g0 + 128u, blB, okB);
+        }
+      }
+    } else {
+      for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
+        ulonglong2 blo[4], bhi[4];
+        bool ok[4];
+        uint32_t fpv[4];
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i = g0 + t * 32u + lane;
+          fpv[t] = (fp && i < U) ? __ldg(fp + i) : 0xffffffffu;
+        }
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i = g0 + t * 32u + lane;
+          ok[t] = (i < U) && ((fpv[t] & pred.needle_fp) == pred.needle_fp);
+          if (ok[t] && bloom) {  // one 32-byte sector per surviving value; lanes the fingerprint rejected fetch nothing
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(bloom + static_cast<size_t>(i) * kBloomWords);
+            blo[t] = __ldg(src);
+            bhi[t] = __ldg(src + 1);
+          } else {
+            blo[t] = make_ulonglong2(~0ull, ~0ull);
+            bhi[t] = make_ulonglong2(~0ull, ~0ull);
+          }
+        }
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+          const uint32_t i0 = g0 + t * 32u;
+          if (i0 >= U) break;  // warp-uniform
+          // needle bits the value lacks, over the eight words (one LOP3 each)
+          const uint32_t miss = (~static_cast<uint32_t>(blo[t].x) & nb[0]) | (~static_cast<uint32_t>(blo[t].x >> 32) & nb[1]) |
+                                (~static_cast<uint32_t>(blo[t].y) & nb[2]) | (~static_cast<uint32_t>(blo[t].y >> 32) & nb[3]) |
+                                (~static_cast<uint32_t>(bhi[t].x) & nb[4]) | (~static_cast<uint32_t>(bhi[t].x >> 32) & nb[5]) |
+                                (~static_cast<uint32_t>(bhi[t].y) & nb[6]) | (~static_cast<uint32_t>(bhi[t].y >> 32) & nb[7]);
+          append(ok[t] && miss == 0u, ok[t], i0);
         }
       }
     }
@@ -1157,7 +1216,12 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
       // A CTA's 8 warps share a run of neighbouring entries (same symbol table -> same step table in L1). Runs are short —
       // about four waves of CTAs — so that the hardware's CTA scheduler evens out entries that cost more (walks, rows).
       const uint32_t resident = static_cast<uint32_t>(n_sm * occ);
-      uint32_t per_cta = (n_entries + 4u * resident - 1u) / (4u * resident);
+      static const uint32_t waves = [] {  // LC_LIKE_WAVES: CTA waves the list is cut into (experiments; default 4)
+        const char* e = std::getenv("LC_LIKE_WAVES");
+        const int v = e ? std::atoi(e) : 4;
+        return static_cast<uint32_t>(v < 1 ? 1 : (v > 16 ? 16 : v));
+      }();
+      uint32_t per_cta = (n_entries + waves * resident - 1u) / (waves * resident);
       per_cta = (per_cta + 7u) & ~7u;  // whole rounds of the CTA's 8 warps
       const uint32_t grid = (n_entries + per_cta - 1u) / per_cta;
       kern(mode)<<<grid, 256, smem, s>>>(io, pred, dict_words, n_entries, per_cta);
