@@ -793,7 +793,7 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
         ref_pass = uniques
         rows_phase_entries = n_entries
     algo_bytes = 2 * rows_local + meta_bytes + cand_bytes + rows_local // 8
-    algo_bytes_private = algo_bytes + 32 * uniques
+    algo_bytes_private = algo_bytes + 32 * ref_pass
     kernel_reads = meta_bytes + 32 * ref_pass + cand_bytes + rows_phase_entries * 2 * ROWS_PER_ENTRY + rows_local // 8
 
     k_start = torch.cuda.Event(enable_timing=True)
