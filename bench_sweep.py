@@ -195,18 +195,29 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
     n_check = min(check_batches, n_entries)
 
     def host_fallback(column, op, lit):
-        """column.rs:143-151: decode the selected rows of every batch, evaluate with Arrow, write the selection back."""
-        counts, _total = scan.counts()
-        vals = scan.read(handles[column])
+        """column.rs:143-151: decode the selected rows of every batch, evaluate with Arrow, write the selection back — one
+        download of the running selection, one get, one upload (lc_scan_store_selections / lc_scan_load_selections)."""
+        if not hasattr(scan, "store_selections"):  # the CPU test double
+            counts, _total = scan.counts()
+            vals = scan.read(handles[column])
+            mask = np.asarray(arrow_mask(vals, op, lit).fill_null(False).to_numpy(zero_copy_only=False), dtype=bool)
+            pos = 0
+            for b in range(n_entries):
+                k = int(counts[b])
+                sel = np.asarray(scan.selection(b).to_numpy(zero_copy_only=False), dtype=bool)
+                new = np.zeros(ROWS_PER_ENTRY, dtype=bool)
+                new[np.flatnonzero(sel)] = mask[pos:pos + k]
+                pos += k
+                scan.set_selection(b, new)
+            return
+        words = scan.store_selections()
+        vals = scan.read(handles[column])  # rows in batch order, then row order: the order of the set bits below
         mask = np.asarray(arrow_mask(vals, op, lit).fill_null(False).to_numpy(zero_copy_only=False), dtype=bool)
-        pos = 0
-        for b in range(n_entries):
-            k = int(counts[b])
-            sel = np.asarray(scan.selection(b).to_numpy(zero_copy_only=False), dtype=bool)
-            new = np.zeros(ROWS_PER_ENTRY, dtype=bool)
-            new[np.flatnonzero(sel)] = mask[pos:pos + k]
-            pos += k
-            scan.set_selection(b, new)
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")
+        set_pos = np.flatnonzero(bits)
+        assert len(set_pos) == len(mask)
+        bits[set_pos[~mask]] = 0
+        scan.load_selections(np.packbits(bits, bitorder="little").view(np.uint32))
 
     def run_query(conj, proj, to_host, want_counts=False):
         scan.reset()

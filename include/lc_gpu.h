@@ -350,6 +350,13 @@ int lc_scan_begin(lc_ctx* ctx, uint64_t n_batches, const uint64_t* rows_per_batc
 int lc_scan_reset(lc_scan* scan);
 /* Optional: seed the running selection of batch i from host bits (RowSelection of the reader). */
 int lc_scan_set_selection(lc_scan* scan, uint64_t batch, const uint8_t* sel_bits, uint64_t sel_len);
+/* The running selection of ALL batches in one copy each way, for conjuncts the caller evaluates itself (the reference's
+ * fallback for shapes LiquidExpr::try_new does not admit, e.g. IN lists: src/datafusion/src/cache/column.rs:143-151).
+ * Layout: batch i's bits start at 32-bit word word_offsets[i] (LSB first; padding bits are ignored on load and zero on
+ * store); lc_scan_selection_layout reports the offsets (n_batches values) and the total word count. */
+int lc_scan_selection_layout(lc_scan* scan, uint64_t* word_offsets, uint64_t* total_words);
+int lc_scan_store_selections(lc_scan* scan, uint32_t* out_words, uint64_t n_words);
+int lc_scan_load_selections(lc_scan* scan, const uint32_t* words, uint64_t n_words);
 int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* pred);
 int lc_scan_counts(lc_scan* scan, uint64_t* out_counts, uint64_t* out_total);
 int lc_scan_selection(lc_scan* scan, uint64_t batch, uint8_t* out_bits);

@@ -648,6 +648,24 @@ class Scan:
         bits, n = selection_bits(selection)
         N.check(N.lib().lc_scan_set_selection(self._scan, batch, bits.ctypes.data, n))
 
+    def selection_layout(self) -> tuple[np.ndarray, int]:
+        """(word offset of every batch, total words) of the running selection as store / load move it."""
+        offs = np.zeros(len(self._rows), dtype=np.uint64)
+        tot = C.c_uint64(0)
+        N.check(N.lib().lc_scan_selection_layout(self._scan, offs.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(tot)))
+        return offs, int(tot.value)
+
+    def store_selections(self) -> np.ndarray:
+        """The running selection of every batch in one download (uint32 words, LSB first, layout: selection_layout)."""
+        _offs, tot = self.selection_layout()
+        out = np.zeros(tot, dtype=np.uint32)
+        N.check(N.lib().lc_scan_store_selections(self._scan, out.ctypes.data, tot))
+        return out
+
+    def load_selections(self, words: np.ndarray) -> None:
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        N.check(N.lib().lc_scan_load_selections(self._scan, words.ctypes.data, len(words)))
+
     def filter(self, handles: np.ndarray, expr: LiquidExpr, column_type: pa.DataType) -> None:
         pred = expr.to_native(column_type)
         self.filter_native(handles, pred)

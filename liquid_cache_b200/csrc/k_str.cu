@@ -837,6 +837,7 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words,
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kLikeCandCap = 512;  // per-warp candidate list (u16); a full list is walked and reused
 
+static_assert(offsetof(StrHeader, shared_prefix_len) == 24 && offsetof(StrHeader, prefix_keys_off) == 36, "header words");
 static_assert(offsetof(StrHeader, n) == 8 && offsetof(StrHeader, n_unique) == 12 && offsetof(StrHeader, slope) == 16 &&
                   offsetof(StrHeader, intercept) == 20 && offsetof(StrHeader, validity_off) == 28 &&
                   offsetof(StrHeader, keys_off) == 32 && offsetof(StrHeader, fp_off) == 40 && offsetof(StrHeader, resid_off) == 44 &&
@@ -1260,7 +1261,10 @@ __global__ void __launch_bounds__(256) k_str_lengths(StrGatherIo g, uint32_t sta
   uint8_t* stage = s_len + 256;
 
   const uint32_t e = blockIdx.x;
-  if (g.k_hint && (g.k_hint[2u * e] == 0u || g.plan->overflow)) return;  // device-planned read: nothing selected here
+  if (g.k_hint) {  // device-planned read: nothing selected here, or few enough rows for k_str_lengths_sparse
+    const uint32_t kh = g.k_hint[2u * e];
+    if (kh == 0u || kh <= g.sparse_max || g.plan->overflow) return;
+  }
   const EntryRef ref = g.io.refs[e];
   const EntryIo w = resolve_io(g.io, e);
   const bool staged = ref.head_bytes <= stage_cap;
@@ -1351,6 +1355,90 @@ __global__ void __launch_bounds__(256) k_str_lengths(StrGatherIo g, uint32_t sta
     row_off[k] = carry;
     w.counts[2] = carry;
   }
+}
+
+// A selective scan leaves one or two rows in most of the batches it leaves any in (the bench column: 3 971 rows in 3 400 of
+// 12 207 batches). Staging 30 KB of entry head and synchronising a CTA for that is all overhead (k_str_lengths: 81 us for
+// those 3 400 entries), so such entries get ONE WARP each, reading only what the rows need: the selection words, the key,
+// its PrefixKey (length byte) and its two offsets. Lists without nulls only (the device-planned read's precondition).
+__global__ void __launch_bounds__(256) k_str_lengths_sparse(StrGatherIo g, uint32_t n_entries) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t e = blockIdx.x * 8u + (threadIdx.x >> 5);
+  if (e >= n_entries) return;
+  const uint32_t k = g.k_hint[2u * e];
+  if (k == 0u || k > g.sparse_max || g.plan->overflow) return;
+  const uint8_t* blob = g.io.refs[e].blob;
+  const uint32_t hw = __ldg(reinterpret_cast<const uint32_t*>(blob) + lane);
+  const uint32_t n = __shfl_sync(kFullMask, hw, 2), spl = __shfl_sync(kFullMask, hw, 6);
+  const uint32_t keys_off = __shfl_sync(kFullMask, hw, 8), pk_off = __shfl_sync(kFullMask, hw, 9);
+  const uint32_t resid_off = __shfl_sync(kFullMask, hw, 11), fsst_off = __shfl_sync(kFullMask, hw, 13);
+  const uint64_t table_ptr = static_cast<uint64_t>(__shfl_sync(kFullMask, hw, 20)) | (static_cast<uint64_t>(__shfl_sync(kFullMask, hw, 21)) << 32);
+  StrView v{};
+  v.h = reinterpret_cast<const StrHeader*>(blob);
+  v.resid = blob + resid_off;
+  v.fsst = blob + fsst_off;
+  const uint16_t* keys = reinterpret_cast<const uint16_t*>(blob + keys_off);
+  const uint64_t* pk = reinterpret_cast<const uint64_t*>(blob + pk_off);
+  const uint8_t* s_len = reinterpret_cast<const FsstTable*>(table_ptr)->lens;
+  const uint32_t* sel = g.io.sel_base + g.io.sel_off[e];
+  const uint64_t rb = g.row_base[e];
+  uint32_t* row_off = g.row_off_base + rb + e;
+  uint32_t* row_key = g.row_key_base + rb;
+  // lane L owns the selection words [L * per, (L + 1) * per): set bits in order = rows in order
+  const uint32_t n_words = (n + 31u) >> 5, per = (n_words + 31u) / 32u, tail = n & 31u;
+  uint32_t cnt = 0;
+  for (uint32_t q = 0; q < per; ++q) {
+    const uint32_t wi = lane * per + q;
+    if (wi >= n_words) break;
+    uint32_t sw = sel[wi];
+    if (wi == n_words - 1u && tail) sw &= (1u << tail) - 1u;
+    cnt += __popc(sw);
+  }
+  uint32_t dst = warp_incl_scan(cnt, static_cast<int>(lane)) - cnt;
+  if (cnt) {
+    for (uint32_t q = 0; q < per; ++q) {
+      const uint32_t wi = lane * per + q;
+      if (wi >= n_words) break;
+      uint32_t sw = sel[wi];
+      if (wi == n_words - 1u && tail) sw &= (1u << tail) - 1u;
+      while (sw) {
+        const uint32_t b = __ffs(sw) - 1u;
+        sw &= sw - 1u;
+        const uint32_t key = keys[wi * 32u + b];
+        const uint32_t l = static_cast<uint32_t>(pk[key] >> 56);
+        const uint32_t start = dict_offset(v, key), end = dict_offset(v, key + 1u);
+        uint32_t len = spl + l;
+        if (start == end) len = 0;  // empty value (fsst_buffer.rs:100-113)
+        else if (l == 255u) len = decoded_length(v.fsst, start, end, s_len);
+        row_off[dst] = len;
+        row_key[dst] = key;
+        ++dst;
+      }
+    }
+  }
+  __syncwarp();
+  // exclusive scan of the k lengths (k <= sparse_max, a few warp rounds), total bytes
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < k; base += 32u) {
+    const uint32_t j = base + lane;
+    const uint32_t len = j < k ? row_off[j] : 0u;
+    const uint32_t incl = warp_incl_scan(len, static_cast<int>(lane));
+    if (j < k) row_off[j] = carry + incl - len;
+    carry += __shfl_sync(kFullMask, incl, 31);
+  }
+  if (lane == 0) {
+    row_off[k] = carry;
+    uint32_t* cnt4 = g.io.counts + static_cast<size_t>(e) * g.io.counts_stride;
+    cnt4[0] = k;
+    cnt4[1] = 0;
+    cnt4[2] = carry;
+  }
+}
+
+cudaError_t launch_str_lengths_sparse(uint32_t n_entries, const StrGatherIo& g, cudaStream_t s) {
+  if (n_entries == 0 || g.sparse_max == 0) return cudaSuccess;
+  k_str_lengths_sparse<<<(n_entries + 7u) / 8u, 256, 0, s>>>(g, n_entries);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_str_lengths(uint32_t n_entries, const StrGatherIo& g, uint32_t max_head_bytes, cudaStream_t s) {

@@ -219,6 +219,8 @@ struct StrGatherIo {
   // plan header whose overflow flag makes every CTA return at once. Both nullptr on the host-planned path.
   const uint32_t* k_hint;
   const ScanPlanHdr* plan;
+  uint32_t sparse_max;       // device-planned reads: entries with 1..sparse_max survivors take k_str_lengths_sparse (0 = none do)
+  uint32_t pad_sparse;
   // pass 2 only
   const uint64_t* byte_base; // per entry: decoded bytes before it
   int32_t* out_offsets;      // concatenated offsets (rows + 1)
@@ -227,6 +229,9 @@ struct StrGatherIo {
 
 cudaError_t launch_str_lengths(uint32_t n_entries, const StrGatherIo& g, uint32_t max_head_bytes, cudaStream_t s);
 cudaError_t launch_str_decode(uint32_t n_entries, const StrGatherIo& g, cudaStream_t s);
+// pass 1 for entries with a handful of survivors (device-planned reads of lists without nulls): one warp per entry, straight
+// from global memory — no staging of the entry's head for one or two rows
+cudaError_t launch_str_lengths_sparse(uint32_t n_entries, const StrGatherIo& g, cudaStream_t s);
 
 // ---- FSST compression at insert ----------------------------------------------------------------
 struct alignas(16) FsstEncTable {

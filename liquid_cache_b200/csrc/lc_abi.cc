@@ -843,6 +843,54 @@ int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* 
   return LC_OK;
 }
 
+int lc_scan_selection_layout(lc_scan* scan, uint64_t* word_offsets, uint64_t* total_words) {
+  if (!scan) return LC_ERR_INVALID;
+  if (word_offsets)
+    for (uint64_t i = 0; i < scan->n; ++i) word_offsets[i] = scan->word_off[i];
+  if (total_words) *total_words = scan->total_words;
+  return LC_OK;
+}
+
+int lc_scan_store_selections(lc_scan* scan, uint32_t* out_words, uint64_t n_words) {
+  if (!scan || !out_words || n_words < scan->total_words) {
+    set_error("lc_scan_store_selections: need room for %llu words", (unsigned long long)(scan ? scan->total_words : 0));
+    return LC_ERR_INVALID;
+  }
+  lc_ctx* ctx = scan->ctx;
+  ScanGuard g(scan);
+  if (scan->all_rows) {
+    for (uint64_t i = 0; i < scan->n; ++i) {
+      const uint64_t words = (scan->rows[i] + 31) / 32, padded = round_up(words, 4);
+      uint32_t* w = out_words + scan->word_off[i];
+      for (uint64_t k = 0; k < padded; ++k) w[k] = k < words ? 0xffffffffu : 0u;
+      if (scan->rows[i] & 31) w[words - 1] = (1u << (scan->rows[i] & 31)) - 1u;
+    }
+    return LC_OK;
+  }
+  LC_CUDA_OK(cudaMemcpyAsync(out_words, scan->d_sel, scan->total_words * 4, cudaMemcpyDeviceToHost, ctx->L()->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));
+  ctx->d2h_bytes += scan->total_words * 4;
+  for (uint64_t i = 0; i < scan->n; ++i)  // rows past the batch's length carry no meaning
+    if (scan->rows[i] & 31) out_words[scan->word_off[i] + (scan->rows[i] + 31) / 32 - 1] &= (1u << (scan->rows[i] & 31)) - 1u;
+  return LC_OK;
+}
+
+int lc_scan_load_selections(lc_scan* scan, const uint32_t* words, uint64_t n_words) {
+  if (!scan || !words || n_words < scan->total_words) {
+    set_error("lc_scan_load_selections: need %llu words", (unsigned long long)(scan ? scan->total_words : 0));
+    return LC_ERR_INVALID;
+  }
+  lc_ctx* ctx = scan->ctx;
+  ScanGuard g(scan);
+  LC_CUDA_OK(cudaMemcpyAsync(scan->d_sel, words, scan->total_words * 4, cudaMemcpyHostToDevice, ctx->L()->stream));
+  LC_CUDA_OK(cudaStreamSynchronize(ctx->L()->stream));  // `words` is the caller's memory
+  ctx->h2d_bytes += scan->total_words * 4;
+  scan->all_rows = false;
+  scan->counts_on_device = false;
+  scan->counts_cached = false;
+  return LC_OK;
+}
+
 static int scan_fetch_counts(lc_scan* scan) {
   if (scan->counts_cached) return LC_OK;
   lc_ctx* ctx = scan->ctx;

@@ -1561,12 +1561,14 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
     g.byte_base = d_bb;
     g.k_hint = d_counts2;
     g.plan = d_hdr;
+    g.sparse_max = 64;  // entries with up to 64 survivors: one warp each, no staging (k_str_lengths_sparse)
     g.out_offsets = reinterpret_cast<int32_t*>(d + o_off);
     g.out_bytes = d + o_val;
+    LC_CUDA_OK(launch_str_lengths_sparse(static_cast<uint32_t>(n), g, s));
     LC_CUDA_OK(launch_str_lengths(static_cast<uint32_t>(n), g, rl->max_head, s));
     LC_CUDA_OK(launch_scan_plan_bytes(d_cnt, static_cast<uint32_t>(n), cap_bytes, d_bb, g.out_offsets, d_hdr, s));
     LC_CUDA_OK(launch_str_decode(static_cast<uint32_t>(n), g, s));
-    ctx->kernel_launches += 3;
+    ctx->kernel_launches += 4;
     LC_CUDA_OK(cudaMemcpyAsync(fr->h_hdr, d_hdr, sizeof(ScanPlanHdr), cudaMemcpyDeviceToHost, s));
     if (!dev_out) {
       offsets = HostBuf{host_alloc((spec_rows + 1) * 4 + 64, true), (spec_rows + 1) * 4};
