@@ -883,25 +883,20 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
   for (uint32_t i = lane; i < dict_words; i += 32u) s_dict[i] = 0;
   if (lane == 0) s_queue[0] = 0;
   __syncwarp();
-  // the 256 trigram bits of the needle as eight 32-bit words (a value passes when it has them all)
-  uint32_t nb[8];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    nb[2 * q] = static_cast<uint32_t>(pred.needle_bloom[q]);
-    nb[2 * q + 1] = static_cast<uint32_t>(pred.needle_bloom[q] >> 32);
-  }
-  // ... and the words that carry a bit at all (at most four for needles of up to six bytes: the pipelined gate fetches just those)
+  // The needle's 256 trigram bits as eight 32-bit words; the words that carry a bit at all (at most four for needles of up to
+  // six bytes) are what the gate fetches and tests.
   uint32_t nw = 0, widx[4] = {0, 0, 0, 0}, wbits[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (uint32_t q = 0; q < 8; ++q)
-    if (nb[q]) {
+  for (uint32_t q = 0; q < 8; ++q) {
+    const uint32_t bits = static_cast<uint32_t>(pred.needle_bloom[q >> 1] >> ((q & 1u) * 32u));
+    if (bits) {
       if (nw < 4u) {
         widx[nw] = q;
-        wbits[nw] = nb[q];
+        wbits[nw] = bits;
       }
       ++nw;
     }
-
+  }
   const uint32_t e0 = blockIdx.x * per_cta;
   const uint32_t e_end = e0 + per_cta < n_entries ? e0 + per_cta : n_entries;
   uint32_t e = e0 + warp;
@@ -914,33 +909,15 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
     uint32_t hw1 = hw0;
     if (e + 8u < e_end) hw1 = __ldg(reinterpret_cast<const uint32_t*>(blob1) + lane);
     const uint8_t* blob2 = (e + 16u < e_end) ? io.refs[e + 16u].blob : nullptr;
-    // per-entry io (broadcast loads, consumed after the gate)
-    const uint64_t so = io.sel_base ? io.sel_off[e] : kNoSel;
-    const uint64_t oo = io.out_off[e];
-    const uint64_t vo = (MODE == MODE_PRED && io.valid_base) ? io.valid_off[e] : 0ull;
-
     const uint8_t* blob = blob0;
+    // Header words are pulled out of hw0 (one register, lane i = word i) where they are needed rather than all up front:
+    // the gate loop is where registers are scarce.
     const uint32_t hw_lo = __shfl_sync(kFullMask, hw0, 1);  // arrow_type | has_nulls << 8 | has_fp << 16 | offset_bytes << 24
-    const uint32_t n = __shfl_sync(kFullMask, hw0, 2), U = __shfl_sync(kFullMask, hw0, 3);
-    const int32_t slope = static_cast<int32_t>(__shfl_sync(kFullMask, hw0, 4));
-    const int32_t intercept = static_cast<int32_t>(__shfl_sync(kFullMask, hw0, 5));
-    const uint32_t validity_off = __shfl_sync(kFullMask, hw0, 7), keys_off = __shfl_sync(kFullMask, hw0, 8);
-    const uint32_t fp_off = __shfl_sync(kFullMask, hw0, 10), resid_off = __shfl_sync(kFullMask, hw0, 11);
-    const uint32_t fsst_off = __shfl_sync(kFullMask, hw0, 13), null_count = __shfl_sync(kFullMask, hw0, 16);
-    const uint64_t table_ptr = static_cast<uint64_t>(__shfl_sync(kFullMask, hw0, 20)) |
-                               (static_cast<uint64_t>(__shfl_sync(kFullMask, hw0, 21)) << 32);
+    const uint32_t U = __shfl_sync(kFullMask, hw0, 3);
+    const bool has_fp = (hw_lo >> 16) & 0xffu;
     const uint32_t bloom_off = __shfl_sync(kFullMask, hw0, 25);
-    const bool has_nulls = (hw_lo >> 8) & 0xffu, has_fp = (hw_lo >> 16) & 0xffu;
-    const uint32_t* fp = has_fp ? reinterpret_cast<const uint32_t*>(blob + fp_off) : nullptr;
+    const uint32_t* fp = has_fp ? reinterpret_cast<const uint32_t*>(blob + __shfl_sync(kFullMask, hw0, 10)) : nullptr;
     const unsigned long long* bloom = bloom_off ? reinterpret_cast<const unsigned long long*>(blob + bloom_off) : nullptr;
-    (void)table_ptr;
-    (void)slope;
-    (void)intercept;
-    const SymStep* steps = steps_all + static_cast<size_t>(pred.entry_table[e]) * 512u;
-    StrView v{};  // what the walk needs: header (slope / intercept / residual width), residuals, compressed values
-    v.h = reinterpret_cast<const StrHeader*>(blob);
-    v.resid = blob + resid_off;
-    v.fsst = blob + fsst_off;
 
     // ---- gate + walk ----
     uint32_t ncand = 0, n_ref = 0, walked = 0;
@@ -948,6 +925,11 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
     bool walked_any = false;
     auto walk = [&]() {  // match the listed candidates exactly on their FSST codes (Shift-And, one table step per code)
       __syncwarp();
+      StrView v{};  // what the walk needs: header (slope / intercept / residual width), residuals, compressed values
+      v.h = reinterpret_cast<const StrHeader*>(blob);
+      v.resid = blob + __shfl_sync(kFullMask, hw0, 11);
+      v.fsst = blob + __shfl_sync(kFullMask, hw0, 13);
+      const SymStep* steps = steps_all + static_cast<size_t>(pred.entry_table[e]) * 512u;
       like_candidates(v, s_cand, ncand, s_queue, steps, s_dict);
       __syncwarp();
       if (lane == 0) s_queue[0] = 0;
@@ -1003,25 +985,16 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
           append(ok[t] && miss == 0u, ok[t], i0);
         }
       };
-      uint32_t fA[4], fB[4], blA[4][4], blB[4][4];
-      bool okA[4], okB[4];
-      load_fp(0, fA);
-      issue(0, fA, blA, okA);
-      load_fp(128u, fB);
-      for (uint32_t g0 = 0; g0 < U; g0 += 256u) {
-        const bool more1 = g0 + 128u < U, more2 = g0 + 256u < U;
-        if (more1) {
-          issue(g0 + 128u, fB, blB, okB);
-          load_fp(g0 + 256u, fA);
-        }
-        test(g0, blA, okA);
-        if (more1) {
-          if (more2) {
-            issue(g0 + 256u, fA, blA, okA);
-            load_fp(g0 + 384u, fB);
-          }
-          test(g0 + 128u, blB, okB);
-        }
+      // fingerprints run one group ahead of the filter words that hang off them
+      uint32_t fc[4], fn[4], bl[4][4];
+      bool ok[4];
+      load_fp(0, fc);
+      for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
+        issue(g0, fc, bl, ok);
+        if (g0 + 128u < U) load_fp(g0 + 128u, fn);
+        test(g0, bl, ok);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) fc[t] = fn[t];
       }
     } else {
       for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
@@ -1051,6 +1024,12 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
           const uint32_t i0 = g0 + t * 32u;
           if (i0 >= U) break;  // warp-uniform
           // needle bits the value lacks, over the eight words (one LOP3 each)
+          uint32_t nb[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            nb[2 * q] = static_cast<uint32_t>(pred.needle_bloom[q]);
+            nb[2 * q + 1] = static_cast<uint32_t>(pred.needle_bloom[q] >> 32);
+          }
           const uint32_t miss = (~static_cast<uint32_t>(blo[t].x) & nb[0]) | (~static_cast<uint32_t>(blo[t].x >> 32) & nb[1]) |
                                 (~static_cast<uint32_t>(blo[t].y) & nb[2]) | (~static_cast<uint32_t>(blo[t].y >> 32) & nb[3]) |
                                 (~static_cast<uint32_t>(bhi[t].x) & nb[4]) | (~static_cast<uint32_t>(bhi[t].x >> 32) & nb[5]) |
@@ -1061,6 +1040,9 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
     }
     if (pred.prof) {  // measurement aid, never on in a timed run
       unsigned long long bytes = 0;
+      StrView v{};
+      v.h = reinterpret_cast<const StrHeader*>(blob);
+      v.resid = blob + __shfl_sync(kFullMask, hw0, 11);
       for (uint32_t c = lane; c < ncand; c += 32u) bytes += dict_offset(v, s_cand[c] + 1u) - dict_offset(v, s_cand[c]);
       for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(kFullMask, bytes, d);
       walked_bytes = bytes;
@@ -1086,6 +1068,14 @@ k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries,
     // fingerprints it is a plain negation.
     const bool invert = neg && (!has_fp || n_ref != 0u);
 
+    // per-entry io and the header words of the output phase
+    const uint64_t so = io.sel_base ? io.sel_off[e] : kNoSel;
+    const uint64_t oo = io.out_off[e];
+    const uint64_t vo = (MODE == MODE_PRED && io.valid_base) ? io.valid_off[e] : 0ull;
+    const uint32_t n = __shfl_sync(kFullMask, hw0, 2);
+    const uint32_t validity_off = __shfl_sync(kFullMask, hw0, 7), keys_off = __shfl_sync(kFullMask, hw0, 8);
+    const uint32_t null_count = __shfl_sync(kFullMask, hw0, 16);
+    const bool has_nulls = (hw_lo >> 8) & 0xffu;
     const uint32_t* sel = (io.sel_base && so != kNoSel) ? io.sel_base + so : nullptr;
     uint32_t* out_bits = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(io.out_base) + oo * 4u);
     const uint32_t* valid = has_nulls ? reinterpret_cast<const uint32_t*>(blob + validity_off) : nullptr;
