@@ -1503,6 +1503,38 @@ __global__ void __launch_bounds__(256) k_str_decode(StrGatherIo g) {
   int32_t* out_offsets = g.out_offsets + rb;
   // final offsets of this entry's slice (the closing offset of the whole array is written by the host)
   for (uint32_t j = threadIdx.x; j < k; j += 256u) out_offsets[j] = static_cast<int32_t>(byte_base + row_off[j]);
+  if (g.dict_scratch && g.dict_base[e] != ~0ull) {
+    // Dense get: decode every dictionary value once (the FSST work: ~35 codes per URL), then the rows are plain copies out
+    // of the decoded dictionary — 8192 rows over ~1 750 values means 4-5 x less decoding than a decode per row.
+    __shared__ uint32_t s_wtot[8];
+    const uint32_t U = v.h->n_unique;
+    uint32_t* ulen = g.ulen_base + g.ulen_off[e];  // pass 1 left every value's decoded length here: lengths -> offsets, in place
+    uint32_t total = 0;
+    for (uint32_t base = 0; base < U; base += 256u) {
+      const uint32_t i = base + threadIdx.x;
+      const uint32_t len = i < U ? ulen[i] : 0u;
+      uint32_t tile;
+      const uint32_t excl = block_excl_scan_256(len, s_wtot, &tile);
+      if (i < U) ulen[i] = total + excl;
+      total += tile;
+    }
+    __syncthreads();
+    uint8_t* dict = g.dict_scratch + g.dict_base[e];
+    for (uint32_t u = warp; u < U; u += 8u) {
+      const uint32_t start = dict_offset(v, u), end = dict_offset(v, u + 1u);
+      if (start != end) warp_decode(v.fsst + start, end - start, dict + ulen[u], s_sym, s_len, lane);
+    }
+    __syncthreads();
+    for (uint32_t j = warp; j < k; j += 8u) {
+      const uint32_t key = row_key[j];
+      if (key == 0xFFFFFFFFu) continue;
+      const uint32_t o0 = ulen[key], o1 = key + 1u < U ? ulen[key + 1u] : total;
+      const uint8_t* src = dict + o0;
+      uint8_t* dst = g.out_bytes + byte_base + row_off[j];
+      for (uint32_t b = lane; b < o1 - o0; b += 32u) dst[b] = src[b];
+    }
+    return;
+  }
   for (uint32_t j = warp; j < k; j += 8u) {
     const uint32_t key = row_key[j];
     if (key == 0xFFFFFFFFu) continue;

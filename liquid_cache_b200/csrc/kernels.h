@@ -222,6 +222,11 @@ struct StrGatherIo {
   uint32_t sparse_max;       // device-planned reads: entries with 1..sparse_max survivors take k_str_lengths_sparse (0 = none do)
   uint32_t pad_sparse;
   // pass 2 only
+  // entries of which at least as many rows are selected as the dictionary has values: the dictionary is decoded ONCE into
+  // dict_scratch + dict_base[e] and the rows copy from there (the reference's to_dict_arrow + cast, byte_view_array/
+  // helpers.rs:14-64); dict_base[e] == ~0 (or dict_scratch == nullptr): every selected row decodes its own value
+  const uint64_t* dict_base;
+  uint8_t* dict_scratch;
   const uint64_t* byte_base; // per entry: decoded bytes before it
   int32_t* out_offsets;      // concatenated offsets (rows + 1)
   uint8_t* out_bytes;        // concatenated values

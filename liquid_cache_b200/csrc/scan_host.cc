@@ -1116,7 +1116,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   tr.mark("plan");
   // upload: sel_off[n] | out_off[n] (ints: element offsets; strings: row_base) | valid_off[n] | ulen_off[n] |
   //         byte_base[n] (strings, second upload) | selection words
-  const uint64_t up_offs = round_up(n * 8 * 5, 256);
+  const uint64_t up_offs = round_up(n * 8 * 6, 256);
   const uint64_t up_sel = round_up(sp.sel_words * 4, 256);
   const uint64_t up_total = up_offs + up_sel;
   const uint64_t dn_counts = round_up(n * 16, 256);
@@ -1328,6 +1328,7 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   g.row_base = reinterpret_cast<const uint64_t*>(d_up) + n;
   g.ulen_off = reinterpret_cast<const uint64_t*>(d_up) + 3 * n;
   g.byte_base = reinterpret_cast<const uint64_t*>(d_up) + 4 * n;
+  g.dict_base = reinterpret_cast<const uint64_t*>(d_up) + 5 * n;
   LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_offs, cudaMemcpyHostToDevice, s));
   ctx->h2d_bytes += up_offs;
   if (!dev_sel) LC_TRY(upload_selection(ctx, sp, d_up + up_offs, s));
@@ -1341,6 +1342,9 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
   const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(h_dn);
   uint64_t nulls = 0, total_bytes = 0;
   uint64_t* h_byte_base = reinterpret_cast<uint64_t*>(h_up) + 4 * n;
+  uint64_t* h_dict_base = reinterpret_cast<uint64_t*>(h_up) + 5 * n;  // adjacent: one upload carries both
+  uint64_t dict_bytes = 0;
+  constexpr uint64_t kDictScratchMax = 1ull << 30;
   for (uint64_t i = 0; i < n; ++i) {
     if (h_counts[4 * i] != sp.k[i]) {
       set_error("internal: selected-row count mismatch on entry %llu", (unsigned long long)i);
@@ -1349,6 +1353,14 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     nulls += h_counts[4 * i + 1];
     h_byte_base[i] = total_bytes;
     total_bytes += h_counts[4 * i + 2];
+    // dense entries (as many rows selected as there are dictionary values, or more) decode their dictionary once
+    const uint64_t ub = round_up(entries[i]->sh.uncompressed_bytes + 16, 256);
+    if (sp.k[i] >= (*rl->n_unique)[i] && (*rl->n_unique)[i] > 0 && dict_bytes + ub <= kDictScratchMax) {
+      h_dict_base[i] = dict_bytes;
+      dict_bytes += ub;
+    } else {
+      h_dict_base[i] = ~0ull;
+    }
   }
   if (total_bytes > 0x7fffffffull) {
     set_error("decoded values exceed 2 GiB (int32 offsets); split the call");
@@ -1373,8 +1385,15 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     // byte_base[n] and the closing offset travel from the pinned upload area (idle since the sync above)
     int32_t* h_last = reinterpret_cast<int32_t*>(h_up);  // sel_off[0] slot: no longer needed on the host
     *h_last = static_cast<int32_t>(total_bytes);
-    LC_CUDA_OK(cudaMemcpyAsync(d_up + 4 * n * 8, h_byte_base, n * 8, cudaMemcpyHostToDevice, s));
+    uint8_t* d_dict = nullptr;
+    if (dict_bytes && cudaMallocAsync(reinterpret_cast<void**>(&d_dict), dict_bytes, s) != cudaSuccess) {
+      cudaGetLastError();
+      d_dict = nullptr;  // no room for decoded dictionaries: every row decodes its own value
+    }
+    g.dict_scratch = d_dict;
+    LC_CUDA_OK(cudaMemcpyAsync(d_up + 4 * n * 8, h_byte_base, 2 * n * 8, cudaMemcpyHostToDevice, s));
     LC_CUDA_OK(launch_str_decode(static_cast<uint32_t>(n), g, s));
+    if (d_dict) cudaFreeAsync(d_dict, s);
     LC_CUDA_OK(cudaMemcpyAsync(g.out_offsets + rows, h_last, 4, cudaMemcpyHostToDevice, s));
     ctx->kernel_launches++;
     if (nulls && dev_out->d_validity) {
@@ -1422,9 +1441,16 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     set_error("host allocation failed");
     return LC_ERR_OOM;
   }
-  // second (small) upload: byte_base[n]
-  cudaError_t ce = cudaMemcpyAsync(d_up + 4 * n * 8, h_byte_base, n * 8, cudaMemcpyHostToDevice, s);
+  // second (small) upload: byte_base[n] and dict_base[n]
+  uint8_t* d_dict = nullptr;
+  if (dict_bytes && cudaMallocAsync(reinterpret_cast<void**>(&d_dict), dict_bytes, s) != cudaSuccess) {
+    cudaGetLastError();
+    d_dict = nullptr;  // no room for decoded dictionaries: every row decodes its own value
+  }
+  g.dict_scratch = d_dict;
+  cudaError_t ce = cudaMemcpyAsync(d_up + 4 * n * 8, h_byte_base, 2 * n * 8, cudaMemcpyHostToDevice, s);
   if (ce == cudaSuccess) ce = launch_str_decode(static_cast<uint32_t>(n), g, s);
+  if (d_dict) cudaFreeAsync(d_dict, s);
   int rc = LC_OK;
   if (ce == cudaSuccess && nulls) rc = concat_validity_device(g.io, d_up, d_cat, &validity);
   if (ce == cudaSuccess && rc == LC_OK && want_views) {
