@@ -58,11 +58,11 @@ def parse_args():
 
 
 def recorded_traffic(rows: int, entries: int):
-    """DRAM bytes (read + write) of one k_str_scan launch from the committed `ncu --set full` capture of this exact
-    seeded workload (profiles/r01_k_str_scan_traffic.json); None when the shape differs or the file is absent.
-    A number taken under the profiler is only ever used for this field, never for a timing."""
+    """DRAM bytes (read + write) of one k_str_like launch, REPLAYED from the committed `ncu --set full` capture of this
+    exact seeded workload (profiles/r02_k_str_like_traffic.json) — not measured in this run; None when the shape differs
+    or the file is absent. A number taken under the profiler is only ever used for this field, never for a timing."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_k_str_scan_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_k_str_like_traffic.json")) as f:
             t = json.load(f)
         if t["workload"]["rows"] == rows and t["workload"]["entries"] == entries:
             return int(t["dram__bytes_read.sum"]) + int(t["dram__bytes_write.sum"])
@@ -943,7 +943,8 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
                     "matches_device_path": bool(e2e_ok)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_str_like<MODE_REFINE>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": recorded_traffic(rows_local, n_entries),
+                         "frac": achieved / peak, "traffic": recorded_traffic(rows_local, n_entries) if source == "synthetic" else None,
+                         "traffic_source": "replayed from profiles/r02_k_str_like_traffic.json (ncu --set full of this seeded workload), not measured in this run",
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "algorithmic_bytes_with_private_filter": algo_bytes_private,
                          "bytes_this_kernel_must_move": kernel_reads,

@@ -41,7 +41,7 @@ struct GlobalLoader {
 template <uint32_t T, uint32_t W>
 __host__ __device__ constexpr uint32_t chunks_in_flight() {
   constexpr uint32_t regs = BregGeom<T, W>::SUB * BregGeom<T, W>::NW;
-  return regs <= 12u ? 4u : (regs <= 20u ? 2u : 1u);
+  return regs <= 10u ? 4u : (regs <= 20u ? 2u : 1u);
 }
 
 // One group of up to four chunks [c0, c1) of an entry: every chunk's mask word is finished (negation, validity,

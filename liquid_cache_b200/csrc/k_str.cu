@@ -869,16 +869,20 @@ cudaError_t launch_like_steps(const uint64_t* d_tables, uint32_t n_tables, const
   return cudaGetLastError();
 }
 
-template <int MODE, int OCC>
+// AUX = the launch also counts (NOT LIKE's inversion rule needs the passes of the reference gate; the untimed measurement
+// launch feeds the profile counters). The plain LIKE launch carries none of that state through the gate loop.
+template <int MODE, int OCC, bool AUX>
 __global__ void __launch_bounds__(256, OCC)
-k_str_like(ScanIo io, StrPredDesc pred, uint32_t dict_words, uint32_t n_entries, uint32_t per_cta) {
+k_str_like(ScanIo io, StrPredDesc pred_in, uint32_t dict_words, uint32_t n_entries, uint32_t per_cta) {
+  StrPredDesc pred = pred_in;
+  if (!AUX) pred.prof = nullptr;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   // per warp: walk queue head (4 words) | dictionary answer bits | candidate list
   uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem_raw) + warp * (4u + dict_words + kLikeCandCap / 2u);
   uint32_t* s_dict = s_queue + 4;
   uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_dict + dict_words);
-  const bool neg = pred.op == LC_OP_NOT_LIKE;
+  const bool neg = AUX && pred.op == LC_OP_NOT_LIKE;
   const SymStep* steps_all = static_cast<const SymStep*>(pred.like_steps);
   for (uint32_t i = lane; i < dict_words; i += 32u) s_dict[i] = 0;
   if (lane == 0) s_queue[0] = 0;
@@ -1188,16 +1192,23 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
         const char* e = std::getenv("LC_LIKE_OCC");
         return (e && e[0] == '3') ? 3 : 4;
       }();
-      auto kern = [&](int md) -> void (*)(ScanIo, StrPredDesc, uint32_t, uint32_t, uint32_t) {
-        if (occ_pref == 3) return md == MODE_PRED ? k_str_like<MODE_PRED, 3> : k_str_like<MODE_REFINE, 3>;
-        return md == MODE_PRED ? k_str_like<MODE_PRED, 4> : k_str_like<MODE_REFINE, 4>;
+      const bool aux = pred.op == LC_OP_NOT_LIKE || pred.prof != nullptr;
+      auto kern3 = [&](int md, bool ax) -> void (*)(ScanIo, StrPredDesc, uint32_t, uint32_t, uint32_t) {
+        if (occ_pref == 3) {
+          if (ax) return md == MODE_PRED ? k_str_like<MODE_PRED, 3, true> : k_str_like<MODE_REFINE, 3, true>;
+          return md == MODE_PRED ? k_str_like<MODE_PRED, 3, false> : k_str_like<MODE_REFINE, 3, false>;
+        }
+        if (ax) return md == MODE_PRED ? k_str_like<MODE_PRED, 4, true> : k_str_like<MODE_REFINE, 4, true>;
+        return md == MODE_PRED ? k_str_like<MODE_PRED, 4, false> : k_str_like<MODE_REFINE, 4, false>;
       };
+      auto kern = [&](int md) { return kern3(md, aux); };
       static bool like_attr = false;
       if (!like_attr) {
-        for (int md : {static_cast<int>(MODE_PRED), static_cast<int>(MODE_REFINE)}) {
-          cudaError_t e = cudaFuncSetAttribute(kern(md), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-          if (e != cudaSuccess) return e;
-        }
+        for (int md : {static_cast<int>(MODE_PRED), static_cast<int>(MODE_REFINE)})
+          for (bool ax : {false, true}) {
+            cudaError_t e = cudaFuncSetAttribute(kern3(md, ax), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            if (e != cudaSuccess) return e;
+          }
         like_attr = true;
       }
       int occ = 0;
