@@ -17,6 +17,7 @@
 // Per-entry header words and the next task's blob pointer are fetched one / two tasks ahead (software pipeline in
 // registers), so the only exposed latency per chunk is its own data.
 #include <cstddef>
+#include <cstdlib>
 
 #include "breg_math.cuh"
 #include "device_utils.cuh"
@@ -153,7 +154,8 @@ static_assert(offsetof(IntHeader, n) == 8 && offsetof(IntHeader, reference) == 1
 // have idle tasks. The warps of a CTA take consecutive tasks, i.e. the groups of neighbouring entries. Per task the
 // header is read once and the predicate planned once; the header of the warp's next task and the blob pointer of the
 // one after are already in flight (software pipeline in registers).
-__global__ void __launch_bounds__(256, 3) k_int_bits(ScanIo io, IntPredDesc pred, uint32_t n_entries, uint32_t gshift, int mode) {
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC) k_int_bits(ScanIo io, IntPredDesc pred, uint32_t n_entries, uint32_t gshift, int mode) {
   __shared__ uint32_t s_strip[8][32];  // per warp: the 32 ballots of a chunk, transposed through shared memory
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t* strip = s_strip[threadIdx.x >> 5];
@@ -260,16 +262,23 @@ cudaError_t launch_int_bits(int mode, uint32_t n_entries, const ScanIo& io, cons
   while ((4u << gshift) < cpe) ++gshift;  // groups of four chunks per entry, a power of two
   const uint64_t n_tasks = static_cast<uint64_t>(n_entries) << gshift;
   if (n_tasks > 0x7fffffffull) return cudaErrorInvalidValue;
+  // register budget: 3 CTAs per SM (80 registers) by default; LC_INT_OCC=4 selects the 64-register build (experiments)
+  static const int occ_pref = [] {
+    const char* e = std::getenv("LC_INT_OCC");
+    return (e && e[0] == '4') ? 4 : 3;
+  }();
   static int per_sm = 0;
   if (!per_sm) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_int_bits, 256, 0);
+    cudaError_t e = occ_pref == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_int_bits<4>, 256, 0)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_int_bits<3>, 256, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
   }
   uint32_t grid = static_cast<uint32_t>(n_sm * per_sm);  // persistent: every resident warp loops over the tasks
   const uint32_t need = static_cast<uint32_t>((n_tasks + 7u) / 8u);
   if (grid > need) grid = need;
-  k_int_bits<<<grid, 256, 0, s>>>(io, pred, n_entries, gshift, mode);
+  if (occ_pref == 4) k_int_bits<4><<<grid, 256, 0, s>>>(io, pred, n_entries, gshift, mode);
+  else k_int_bits<3><<<grid, 256, 0, s>>>(io, pred, n_entries, gshift, mode);
   return cudaGetLastError();
 }
 
