@@ -39,7 +39,7 @@ METRIC = "filtered-scan Mrows/s (URL LIKE '%google%' + get-with-selection, hot c
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)  # a step is ~0.5 ms: 100 keep one host hiccup from deciding the mean
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows PER GPU (weak scaling)")
@@ -89,6 +89,8 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        if os.environ.get("LC_BENCH_NO_CLOCKS") == "1":  # diagnosis only: is the sampler perturbing the steps?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -539,15 +541,12 @@ def run_shipdate(args, rank, world, local_rank, emit=True):
     k_ms = [[], []]
     cache.kernel_timing(True)
 
-    from liquid_cache_b200.dist import StepGather
+    from liquid_cache_b200.dist import DeviceGather
 
     pin = pin_to_gpu_numa(local_rank)
-    gather = StepGather(pa.date32(), rank, world, dev) if world > 1 else None
+    gather = DeviceGather(pa.date32(), rank, world, dev, rows_cap=rows_local // 4)
 
-    def step(timed):
-        """Both conjuncts over every entry of this rank, then the filtered batch delivered to rank 0's HOST memory: at one
-        GPU lc_scan_read (device-planned, one synchronisation); at N > 1 every rank leaves its survivors in HBM
-        (lc_scan_read_borrowed) and the NCCL gather over NVLink — the one exchange of the path — runs inside the step."""
+    def filters(timed):
         scan.reset()
         scan.filter_native(handles, p_ge)
         if timed:
@@ -555,15 +554,26 @@ def run_shipdate(args, rank, world, local_rank, emit=True):
         scan.filter_native(handles, p_lt)
         if timed:
             k_ms[1].append(cache.last_kernel_ms())
-        if world == 1:
-            res = scan.read(handles)
-            return len(res), res
-        r = scan.read_torch_borrowed(handles, dev)
-        if r is None:
-            v, _o, _b, rows, _nn = scan.read_torch(handles, dev)
-        else:
-            v, _o, rows = r
-        return rows, gather.gather(v, None, rows)
+
+    def step(timed):
+        """Both conjuncts over every entry of this rank, then get-with-selection of the survivors as Arrow-layout buffers in
+        HBM (lc_scan_read_async writes straight into this rank's gather slot); at N > 1 ONE NCCL all_gather — the one exchange
+        of the path — delivers every rank's batch into rank 0's HBM. One host synchronisation per step (the 64-byte headers)."""
+        for _ in range(16):
+            filters(timed)
+            if not scan.read_async(handles, *gather.addresses()):
+                raise RuntimeError("l_shipdate must be readable by the device-planned path")
+            hdrs = gather.exchange()
+            if not gather.overflowed():
+                return hdrs
+            gather.grow()
+        raise RuntimeError("gather slot capacities did not settle")
+
+    def e2e_step():
+        """The same filters, the result as a HOST Arrow array on every rank (lc_scan_read: one synchronisation, the download
+        inside it) — what a reference-side caller holding host buffers gets."""
+        filters(False)
+        return scan.read(handles)
 
     def barrier():
         torch.cuda.synchronize()
@@ -571,43 +581,48 @@ def run_shipdate(args, rank, world, local_rank, emit=True):
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_res = None
     for _ in range(max(3, args.warmup)):
-        total, host_res = step(False)  # the previous result stays alive like in the timed loops: both result blocks exist
+        hdrs = step(False)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     barrier()
     st_a = cache.stats()
+    grows_before = gather.grows
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        total, host_res = step(True)
+        hdrs = step(True)
     e1.record(stream)
     barrier()
     st_b = cache.stats()
     ms = e0.elapsed_time(e1)
-    # e2e: the same step by the host's clock (predicates up, the filtered Arrow array down to rank 0 every step)
+    grows_in_timed = gather.grows - grows_before
+    total = hdrs[rank][0]
+    gathered_rows = sum(h[0] for h in hdrs)
+    device_res = gather.to_arrow([rank])  # this rank's batch as it sits in the gathered slots, downloaded for the checks
+    # e2e: the same filters by the host's clock, the filtered Arrow array delivered to every rank's host memory each step
     e2e_steps = max(3, args.steps // 2)
+    host_res = None
+    for _ in range(3):
+        host_res = e2e_step()  # the previous result stays alive like in the timed loop: both result blocks exist
+    barrier()
     st_c = cache.stats()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        total_h, host_res = step(False)
+        host_res = e2e_step()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     st_d = cache.stats()
-    # parity inside the bench: rank 0's result against pyarrow on its regenerated first entries; row counts add up
+    # parity inside the bench: the device-resident and the host results agree, and match pyarrow on regenerated entries
     import pyarrow.compute as pc
-    ok = True
-    if rank == 0:
-        chk = pa.concat_arrays([synth.int_entry("l_shipdate", i, seed=synth.SEED_TPCH) for i in range(min(4, n_entries))])
-        want = chk.filter(pc.and_(pc.greater_equal(chk, pa.scalar(lo)), pc.less(chk, pa.scalar(hi))))
-        ok = host_res.slice(0, len(want)).equals(want)
-    tot_t = torch.tensor([float(total)], device="cuda", dtype=torch.float64)
+    chk = pa.concat_arrays([synth.int_entry("l_shipdate", rank * n_entries + i, seed=synth.SEED_TPCH) for i in range(min(4, n_entries))])
+    want = chk.filter(pc.and_(pc.greater_equal(chk, pa.scalar(lo)), pc.less(chk, pa.scalar(hi))))
+    ok = host_res.slice(0, len(want)).equals(want) and device_res.equals(host_res) and len(host_res) == total
+    ok_t = torch.tensor([1.0 if ok else 0.0], device="cuda", dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(tot_t, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        ok = ok and len(host_res) == int(tot_t.item())
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    ok = bool(ok_t.item() == 1.0)
     t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -628,9 +643,11 @@ def run_shipdate(args, rank, world, local_rank, emit=True):
                                    "(BASELINE configs[3]); each rank holds 1/8 of the 600 037 902 rows",
                        "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "matching_rows_per_gpu": int(total),
                        "selectivity": int(total) / rows_local, "liquid_bytes_per_gpu": int(cache.stats().hbm_bytes_used),
-                       "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective; the filtered batches "
-                                      "are gathered to rank 0 over NCCL INSIDE every timed step" if world > 1 else "one GPU",
-                       "gathered_rows_on_rank0": len(host_res), "numa": pin,
+                       "parallelism": f"entries sharded by EntryID over {world} GPU(s), no collective in the scan; every step ends with ONE "
+                                      "NCCL all_gather of the filtered batches (HBM to HBM) inside the clock" if world > 1 else "one GPU",
+                       "result": "Arrow-layout buffers in HBM (lc_scan_read_async): value; host Arrow arrays (lc_scan_read): e2e",
+                       "gathered_rows": int(gathered_rows), "host_syncs_per_step": 1, "gather_slot_bytes": gather.slot,
+                       "slot_regrown_in_timed_steps": grows_in_timed, "numa": pin,
                        "l2": "packed column (113 MB) + selections do not fit the L2 together with the 44 MB result; no flush",
                        "setup_seconds": setup_s, "result_matches_arrow": bool(ok),
                        "insert": {"Mrows_per_s": rows_local / insert_s / 1e6, "arrow_GB_per_s": rows_local * 4 / insert_s / 1e9,
@@ -803,37 +820,35 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
 
     trace = os.environ.get("LC_BENCH_TRACE") == "1"
 
-    from liquid_cache_b200.dist import StepGather
+    from liquid_cache_b200.dist import DeviceGather
 
     dev = torch.device("cuda", local_rank)
-    gather = StepGather(pa.string(), rank, world, dev) if world > 1 else None
+    gather = DeviceGather(pa.string(), rank, world, dev)
 
     def step(time_kernel: bool):
-        """LIKE over every entry of this rank, then the filtered batch delivered to rank 0's HOST memory. One GPU: lc_scan_read
-        (survivor counts, row / byte offsets and the decode all happen on the device; one synchronisation). N > 1: every rank
-        leaves its survivors in HBM (lc_scan_read_borrowed) and the NCCL gather over NVLink — the one exchange of the path —
-        runs inside the step; rank 0 downloads the concatenation."""
+        """LIKE over every entry of this rank, then get-with-selection of the survivors, delivered as Arrow-layout buffers in
+        HBM: lc_scan_read_async plans rows / bytes on the device and decodes straight into this rank's gather slot; at N > 1
+        ONE all_gather over NVLink — the one exchange of the path — puts every rank's batch into rank 0's HBM. The only host
+        synchronisation of the step is the download of the 64-byte headers (DeviceGather.exchange)."""
         t0 = time.perf_counter()
-        scan.reset()
-        scan.filter_native(handles, pred)
-        t1 = time.perf_counter()
-        if world == 1:
-            out = scan.read(handles)
-            total = len(out)
+        for _ in range(16):
+            scan.reset()
+            scan.filter_native(handles, pred)
+            if not scan.read_async(handles, *gather.addresses()):
+                raise RuntimeError("the URL column must be readable by the device-planned path")
+            hdrs = gather.exchange()
+            if not gather.overflowed():
+                break
+            gather.grow()  # warm-up only: capacities settle on the first steps
         else:
-            r = scan.read_torch_borrowed(handles, dev)
-            if r is None:
-                v, o, _b, total, _nn = scan.read_torch(handles, dev)
-            else:
-                v, o, total = r
-            out = gather.gather(v, o, total)
+            raise RuntimeError("gather slot capacities did not settle")
         t3 = time.perf_counter()
-        result_rows[0] = total
+        result_rows[0] = hdrs[rank][0]
         if time_kernel:
             kernel_ms.append(cache.last_kernel_ms())  # events recorded by the library right around the launch
         if trace and rank == 0:
-            print(f"[trace] filter(launch) {1e3*(t1-t0):.3f} ms, read (+ gather) {1e3*(t3-t1):.3f} ms", file=sys.stderr)
-        return out
+            print(f"[trace] step (filter + read + exchange) {1e3*(t3-t0):.3f} ms", file=sys.stderr)
+        return hdrs
 
     def barrier():
         torch.cuda.synchronize()
@@ -850,18 +865,46 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
         clocks.start()
     barrier()
     st_a = cache.stats()
+    grows_before = gather.grows
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+
+    gc.disable()  # a collection inside a 0.5 ms step is a visible spike; re-enabled after the timed loops
     ev0.record(stream)
+    step_wall = []
     for _ in range(args.steps):
+        w0 = time.perf_counter()
         last = step(True)
+        step_wall.append((time.perf_counter() - w0) * 1e3)  # every step ends synchronised: host wall == device time
     ev1.record(stream)
     barrier()
+    gc.enable()
     st_b = cache.stats()
     ms_total = ev0.elapsed_time(ev1)
     launches = int(st_b.kernel_launches - st_a.kernel_launches)
-    gathered_rows = len(last) if (rank == 0 and last is not None) else result_rows[0]
-    # what the e2e arm below is compared with: THIS rank's own filtered batch
-    local_last = last if world == 1 else None
+    gathered_rows = sum(h[0] for h in last)
+    grows_in_timed = gather.grows - grows_before
+    # what the e2e arm below is compared with: THIS rank's own filtered batch, downloaded from the gathered slots
+    local_last = gather.to_arrow([rank])
+
+    # where a step's time goes (untimed, after the measurement): device events between the three calls of a step
+    ph = [[], [], [], []]
+    for _ in range(5):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        w0 = time.perf_counter()
+        evs[0].record(stream)
+        scan.reset()
+        scan.filter_native(handles, pred)
+        evs[1].record(stream)
+        scan.read_async(handles, *gather.addresses())
+        evs[2].record(stream)
+        gather.exchange()
+        evs[3].record(stream)
+        stream.synchronize()
+        ph[3].append((time.perf_counter() - w0) * 1e3)
+        for i in range(3):
+            ph[i].append(evs[i].elapsed_time(evs[i + 1]))
+    step_phases = {k: float(np.median(v)) for k, v in zip(("filter_ms", "read_async_ms", "exchange_ms", "host_wall_ms"), ph)}
 
     # ---- e2e: the same pass through the host-buffer C ABI (H2D + D2H inside the timed region) ----
     # host result buffers, allocated once and page-locked (the reference-side caller would own these)
@@ -906,7 +949,7 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
     barrier()
     e2e_wall = time.perf_counter() - t0
     st_d = cache.stats()
-    e2e_ok = (e2e_out is None and result_rows[0] == 0) or (e2e_out is not None and (len(e2e_out) == result_rows[0]) and (local_last is None or e2e_out.equals(local_last)))
+    e2e_ok = (e2e_out is None and result_rows[0] == 0) or (e2e_out is not None and len(e2e_out) == result_rows[0] and e2e_out.equals(local_last))
 
     # max over ranks
     t = torch.tensor([ms_total, e2e_wall * 1e3, float(sum(kernel_ms) / max(1, len(kernel_ms)))], device="cuda", dtype=torch.float64)
@@ -932,7 +975,12 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
                 "rows_per_gpu": rows_local, "entries_per_gpu": n_entries, "rows_per_entry": ROWS_PER_ENTRY,
                 "liquid_bytes_per_gpu": hbm_bytes, "liquid_bytes_per_row": hbm_bytes / rows_local,
                 "unique_values_per_entry": uniques / n_entries, "walked_candidates_frac": cand / max(1, uniques),
-                "matching_rows": int(gathered_rows), "parallelism": f"entries sharded by EntryID over {world} GPU(s), no data-path collective; the filtered batches are gathered to rank 0 over NCCL inside every timed step" if world > 1 else "one GPU", "numa": numa_pin,
+                "matching_rows": int(gathered_rows),
+                "parallelism": f"entries sharded by EntryID over {world} GPU(s), no collective in the scan; every step ends with ONE NCCL all_gather of the filtered batches (HBM to HBM) inside the clock" if world > 1 else "one GPU",
+                "result": "Arrow-layout buffers in HBM (lc_scan_read_async): value; host Arrow arrays through the host-buffer ABI: e2e",
+                "host_syncs_per_step": 1, "gather_slot_bytes": gather.slot, "slot_regrown_in_timed_steps": grows_in_timed,
+                "step_phases": step_phases,
+                "step_ms_rank0": {"min": min(step_wall), "median": float(np.median(step_wall)), "max": max(step_wall)}, "numa": numa_pin,
                 "l2": "inputs (liquid column) larger than the 126 MB L2, no flush needed",
                 "setup_seconds": setup_s,
                 "insert": {"Mrows_per_s": rows_local / insert_s / 1e6, "arrow_GB_per_s": arrow_bytes / insert_s / 1e9,

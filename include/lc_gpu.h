@@ -378,6 +378,21 @@ int lc_scan_read_device(lc_scan* scan, const lc_handle* handles, void* d_values,
  * a result that outgrew the capacities): use lc_scan_read_device then. */
 int lc_scan_read_borrowed(lc_scan* scan, const lc_handle* handles, void** d_values, void** d_offsets, uint64_t* out_rows,
                           uint64_t* out_value_bytes);
+/* lc_scan_read for a consumer on the device, WITHOUT any host synchronisation: the concatenated result is written into
+ * caller-owned device buffers of the stated capacities — d_values (value bytes; integers: native values), d_offsets (byte
+ * views: int32[rows + 1], closing offset included; integers: may be NULL) — and a 64-byte lc_read_header into d_header
+ * (device memory). Everything is enqueued on the calling thread's stream and the call returns; the caller reads the header
+ * after its own synchronisation. overflow != 0 means a capacity was short and NOTHING was written besides the header
+ * (rows is still valid: retry with larger buffers). Returns LC_ERR_UNSUPPORTED_EXPR for shapes this path does not plan on
+ * the device (nulls, views, dictionaries, floats, decimals). */
+typedef struct lc_read_header {
+  uint32_t batches_with_rows;
+  uint32_t overflow;       /* 0 ok, 1 rows over rows_cap (or internal scratch), 2 bytes over values_cap / 2 GiB */
+  uint64_t rows, value_bytes, nulls;
+  uint64_t reserved[4];
+} lc_read_header;
+int lc_scan_read_async(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap, void* d_offsets,
+                       uint64_t rows_cap, void* d_header);
 void lc_scan_end(lc_scan* scan);
 
 #ifdef __cplusplus

@@ -155,6 +155,7 @@ def lib() -> C.CDLL:
     l.lc_scan_selection_layout.argtypes = [vp, u64p, u64p]
     l.lc_scan_store_selections.argtypes = [vp, vp, u64]
     l.lc_scan_load_selections.argtypes = [vp, vp, u64]
+    l.lc_scan_read_async.argtypes = [vp, vp, vp, u64, vp, u64, vp]
     l.lc_scan_read_borrowed.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), u64p, u64p]
     l.lc_scan_end.argtypes = [vp]
     l.lc_scan_end.restype = None

@@ -703,6 +703,17 @@ class Scan:
                                             d_validity or None, C.byref(rows), C.byref(nbytes), C.byref(nulls)))
         return int(rows.value), int(nbytes.value), int(nulls.value)
 
+    def read_async(self, handles: np.ndarray, d_values: int, values_cap: int, d_offsets: int, rows_cap: int, d_header: int) -> bool:
+        """lc_scan_read_async: enqueue the device-planned read of the column into caller-owned device buffers (raw device
+        addresses) and return without synchronising; the 64-byte header (rows at byte 8, value bytes at 16, overflow at 4)
+        lands at `d_header`. False when this column is not read by the device-planned path."""
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        rc = N.lib().lc_scan_read_async(self._scan, handles.ctypes.data, d_values, values_cap, d_offsets or None, rows_cap, d_header)
+        if rc == N.LC_ERR_UNSUPPORTED_EXPR:
+            return False
+        N.check(rc)
+        return True
+
     def read_torch_borrowed(self, handles: np.ndarray, device):
         """The filtered column as torch tensors over the scan's OWN device buffer (lc_scan_read_borrowed: planned on the
         device, one synchronisation, nothing but a 64-byte header crosses PCIe): `(values u8[value_bytes], offsets

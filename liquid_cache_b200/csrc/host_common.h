@@ -164,6 +164,23 @@ inline Entry* entry_of(lc_handle h) {
 // different threads never share mutable state and need no lock while they run — the reference's `Arc<LiquidCache>` is hit by
 // every DataFusion partition task at once (cache/core.rs:52-63, index.rs:12-60). The first lane carries the context's own
 // stream (or the caller's, lc_ctx_set_stream applies to the calling thread's lane).
+// Key of a cached list of handles / entry pointers. Four independent lanes so that a 12 k-element list hashes in a few
+// microseconds (a single multiply chain is latency-bound: ~20 us per call, paid by every filter of a scan).
+inline uint64_t hash_words(const uint64_t* p, uint64_t n) {
+  uint64_t a = 0x9E3779B97F4A7C15ull ^ n, b = 0xC2B2AE3D27D4EB4Full, c = 0x165667B19E3779F9ull, d = 0x27D4EB2F165667C5ull;
+  uint64_t i = 0;
+  for (; i + 4 <= n; i += 4) {
+    a = (a ^ p[i]) * 0xff51afd7ed558ccdull;
+    b = (b ^ p[i + 1]) * 0xc4ceb9fe1a85ec53ull;
+    c = (c ^ p[i + 2]) * 0x9fb21c651e98df25ull;
+    d = (d ^ p[i + 3]) * 0xd6e8feb86659fd93ull;
+  }
+  for (; i < n; ++i) a = (a ^ p[i]) * 0xff51afd7ed558ccdull;
+  uint64_t x = a ^ (b >> 17) ^ (c << 23) ^ (d >> 31) ^ (b << 41);
+  x ^= x >> 32;
+  return x;
+}
+
 struct lc_lane {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
@@ -176,6 +193,7 @@ struct lc_lane {
   // column costs a hash of the array instead of one pointer chase per handle; any release bumps `epoch` and voids them
   struct ValidatedHandles {
     uint64_t key = 0, n = 0, epoch = 0;
+    std::vector<lc_handle> handles;  // the list itself: the key only pre-filters, the match is exact
     std::vector<lc::Entry*> es;
   };
   std::vector<ValidatedHandles> validated;
@@ -355,6 +373,8 @@ struct FusedRead {
   uint64_t spec_rows = 0, spec_bytes = 0, spec_ulen = 0;
   uint8_t* d_buf = nullptr;
   uint64_t d_cap = 0;
+  uint8_t* a_buf = nullptr;      // scratch of the asynchronous form (scan_read_async)
+  uint64_t a_cap = 0;
   ScanPlanHdr* h_hdr = nullptr;  // pinned
   uint64_t fused_reads = 0, fallbacks = 0;
 };
@@ -366,6 +386,8 @@ struct FusedDeviceOut {  // lc_scan_read_borrowed: the concatenated result left 
 int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t n, const uint32_t* d_sel, const uint64_t* d_word_off,
                     const uint32_t* d_counts2, uint64_t total_rows_in, ArrowSchema* out_schema, ArrowArray* out_array,
                     FusedDeviceOut* dev_out = nullptr);
+int scan_read_async(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t n, const uint32_t* d_sel, const uint64_t* d_word_off,
+                    const uint32_t* d_counts2, void* d_values, uint64_t values_cap, void* d_offsets, uint64_t rows_cap, void* d_header);
 void fused_read_learn(FusedRead* fr, const ArrowArray* arr, int64_t value_bytes, uint64_t ulen_words);
 void fused_read_free(FusedRead* fr);
 

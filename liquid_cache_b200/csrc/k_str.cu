@@ -1254,36 +1254,30 @@ cudaError_t launch_str_scan(int mode, uint32_t n_entries, const ScanIo& io, cons
 // ------------------------------------------------------------------------------------------------
 // get / filter, pass 1: selected keys, decoded lengths, local offsets
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_str_lengths(StrGatherIo g, uint32_t stage_cap) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
-  uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
-  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
-  uint8_t* stage = s_len + 256;
-
-  const uint32_t e = blockIdx.x;
-  if (g.k_hint) {  // device-planned read: nothing selected here, or few enough rows for k_str_lengths_sparse
-    const uint32_t kh = g.k_hint[2u * e];
-    if (kh == 0u || kh <= g.sparse_max || g.plan->overflow) return;
-  }
+// One entry: selected keys, decoded lengths, local offsets. `phase` is the parity of the staging barrier (flipped by every
+// staged entry of the CTA), `table_cache` the symbol table already in shared memory.
+__device__ __forceinline__ void str_lengths_entry(const StrGatherIo& g, uint32_t e, uint32_t stage_cap, ScanSmem* sm, uint64_t* s_sym,
+                                                  uint8_t* s_len, uint8_t* stage, uint32_t& phase, uint64_t& table_cache) {
   const EntryRef ref = g.io.refs[e];
   const EntryIo w = resolve_io(g.io, e);
   const bool staged = ref.head_bytes <= stage_cap;
   scan_smem_init(sm);
   if (threadIdx.x == 0 && staged) {
-    mbar_init(&sm->bar[0], 1);
-    fence_mbar_init();
     mbar_expect_tx(&sm->bar[0], ref.head_bytes);
     tma_bulk_g2s(stage, ref.blob, ref.head_bytes, &sm->bar[0]);
   }
   __syncthreads();
   const uint8_t* head = ref.blob;
   if (staged) {
-    mbar_wait(&sm->bar[0], 0);
+    mbar_wait(&sm->bar[0], phase);
+    phase ^= 1u;
     head = stage;
   }
   const StrView v = make_view(head, ref.blob);
-  load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
+  if (v.h->table_ptr != table_cache) {
+    load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
+    table_cache = v.h->table_ptr;
+  }
   const uint32_t U = v.h->n_unique, spl = v.h->shared_prefix_len, n = v.h->n;
   uint32_t* row_off = g.row_off_base + g.row_base[e] + e;
   uint32_t* row_key = g.row_key_base + g.row_base[e];
@@ -1355,6 +1349,37 @@ __global__ void __launch_bounds__(256) k_str_lengths(StrGatherIo g, uint32_t sta
   if (threadIdx.x == 0) {
     row_off[k] = carry;
     w.counts[2] = carry;
+  }
+}
+
+// Host-planned gets launch one CTA per entry (per_cta = 1, no k_hint). Device-planned reads do not know on the host which
+// entries have rows, so a CTA takes a RANGE of entries, looks at their survivor counts in one coalesced round and leaves
+// at once when none of them is its business — the common case of a selective scan, where every batch with survivors has a
+// handful and belongs to k_str_lengths_sparse (12 207 one-entry CTAs that only exit cost 15 us of a 115 us read).
+__global__ void __launch_bounds__(256) k_str_lengths(StrGatherIo g, uint32_t stage_cap, uint32_t n_entries, uint32_t per_cta) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanSmem* sm = reinterpret_cast<ScanSmem*>(smem_raw);
+  uint64_t* s_sym = reinterpret_cast<uint64_t*>(smem_raw + kScanFixedSmem);
+  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_sym + 256);
+  uint8_t* stage = s_len + 256;
+
+  const uint32_t e_lo = blockIdx.x * per_cta, e_hi = min(n_entries, e_lo + per_cta);
+  if (g.k_hint) {
+    bool mine = false;
+    for (uint32_t e = e_lo + threadIdx.x; e < e_hi; e += 256u) mine |= g.k_hint[2u * e] > g.sparse_max;
+    if (!__syncthreads_or(mine) || g.plan->overflow) return;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&sm->bar[0], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  uint64_t table_cache = 0;
+  for (uint32_t e = e_lo; e < e_hi; ++e) {
+    if (g.k_hint && g.k_hint[2u * e] <= g.sparse_max) continue;  // nothing selected, or k_str_lengths_sparse's
+    str_lengths_entry(g, e, stage_cap, sm, s_sym, s_len, stage, phase, table_cache);
+    __syncthreads();  // shared state (counters, staged head) is reused by the next entry
   }
 }
 
@@ -1454,7 +1479,8 @@ cudaError_t launch_str_lengths(uint32_t n_entries, const StrGatherIo& g, uint32_
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_str_lengths<<<n_entries, 256, smem, s>>>(g, stage);
+  const uint32_t per_cta = g.k_hint ? (n_entries + 2367u) / 2368u : 1u;  // device-planned reads: entry ranges (see the kernel)
+  k_str_lengths<<<(n_entries + per_cta - 1u) / per_cta, 256, smem, s>>>(g, stage, n_entries, per_cta);
   return cudaGetLastError();
 }
 
@@ -1496,15 +1522,15 @@ __device__ __forceinline__ uint32_t warp_decode(const uint8_t* __restrict__ c, u
   return produced;
 }
 
-__global__ void __launch_bounds__(256) k_str_decode(StrGatherIo g) {
-  __shared__ uint64_t s_sym[256];
-  __shared__ __align__(16) uint8_t s_len[256];
-  const uint32_t e = blockIdx.x;
+__device__ __forceinline__ void str_decode_entry(const StrGatherIo& g, uint32_t e, uint64_t* s_sym, uint8_t* s_len, uint32_t* s_wtot,
+                                                 uint64_t& table_cache) {
   const uint32_t k = g.io.counts[static_cast<size_t>(e) * g.io.counts_stride];
-  if (g.k_hint && (k == 0u || g.plan->overflow)) return;  // device-planned read: nothing selected here (counts zeroed first)
   const EntryRef ref = g.io.refs[e];
   const StrView v = make_view(ref.blob, ref.blob);
-  load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
+  if (v.h->table_ptr != table_cache) {
+    load_fsst_table(reinterpret_cast<const FsstTable*>(v.h->table_ptr), s_sym, s_len);
+    table_cache = v.h->table_ptr;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t rb = g.row_base[e];
@@ -1517,7 +1543,6 @@ __global__ void __launch_bounds__(256) k_str_decode(StrGatherIo g) {
   if (g.dict_scratch && g.dict_base[e] != ~0ull) {
     // Dense get: decode every dictionary value once (the FSST work: ~35 codes per URL), then the rows are plain copies out
     // of the decoded dictionary — 8192 rows over ~1 750 values means 4-5 x less decoding than a decode per row.
-    __shared__ uint32_t s_wtot[8];
     const uint32_t U = v.h->n_unique;
     uint32_t* ulen = g.ulen_base + g.ulen_off[e];  // pass 1 left every value's decoded length here: lengths -> offsets, in place
     uint32_t total = 0;
@@ -1555,9 +1580,88 @@ __global__ void __launch_bounds__(256) k_str_decode(StrGatherIo g) {
   }
 }
 
+
+// One CTA per entry for host-planned gets; a range of entries per CTA for device-planned reads, for the reason given at
+// k_str_lengths. Entries with up to sparse_max survivors belong to k_str_decode_sparse there.
+__global__ void __launch_bounds__(256) k_str_decode(StrGatherIo g, uint32_t n_entries, uint32_t per_cta) {
+  __shared__ uint64_t s_sym[256];
+  __shared__ __align__(16) uint8_t s_len[256];
+  __shared__ uint32_t s_wtot[8];
+  const uint32_t e_lo = blockIdx.x * per_cta, e_hi = min(n_entries, e_lo + per_cta);
+  if (g.k_hint) {
+    bool mine = false;
+    for (uint32_t e = e_lo + threadIdx.x; e < e_hi; e += 256u) mine |= g.k_hint[2u * e] > g.sparse_max;
+    if (!__syncthreads_or(mine) || g.plan->overflow) return;
+  }
+  uint64_t table_cache = 0;
+  for (uint32_t e = e_lo; e < e_hi; ++e) {
+    if (g.k_hint && g.k_hint[2u * e] <= g.sparse_max) continue;
+    str_decode_entry(g, e, s_sym, s_len, s_wtot, table_cache);
+    __syncthreads();
+  }
+}
+
+// The rows k_str_lengths_sparse sized: one warp per entry again. The eight entries of a CTA nearly always share their
+// compressor (one per column or row group), so its symbol table is loaded into shared memory once per CTA; a warp whose entry
+// uses another table reads that one from global memory.
+__global__ void __launch_bounds__(256) k_str_decode_sparse(StrGatherIo g, uint32_t n_entries) {
+  __shared__ uint64_t s_sym[256];
+  __shared__ __align__(16) uint8_t s_len[256];
+  __shared__ uint64_t s_tab[8];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t e = blockIdx.x * 8u + warp;
+  const uint32_t k = e < n_entries ? g.k_hint[2u * e] : 0u;
+  const bool mine = k != 0u && k <= g.sparse_max;
+  if (!__syncthreads_or(mine) || g.plan->overflow) return;
+  const uint8_t* blob = nullptr;
+  uint32_t resid_off = 0, fsst_off = 0;
+  uint64_t table_ptr = 0;
+  if (mine) {
+    blob = g.io.refs[e].blob;
+    const uint32_t hw = __ldg(reinterpret_cast<const uint32_t*>(blob) + lane);
+    resid_off = __shfl_sync(kFullMask, hw, 11);
+    fsst_off = __shfl_sync(kFullMask, hw, 13);
+    table_ptr = static_cast<uint64_t>(__shfl_sync(kFullMask, hw, 20)) | (static_cast<uint64_t>(__shfl_sync(kFullMask, hw, 21)) << 32);
+  }
+  if (lane == 0) s_tab[warp] = table_ptr;
+  __syncthreads();
+  uint64_t cta_table = 0;
+#pragma unroll
+  for (int w = 7; w >= 0; --w)
+    if (s_tab[w]) cta_table = s_tab[w];
+  load_fsst_table(reinterpret_cast<const FsstTable*>(cta_table), s_sym, s_len);
+  __syncthreads();
+  if (!mine) return;
+  const FsstTable* gt = reinterpret_cast<const FsstTable*>(table_ptr);
+  const uint64_t* sym = table_ptr == cta_table ? s_sym : gt->symbols;
+  const uint8_t* len = table_ptr == cta_table ? s_len : gt->lens;
+  StrView v{};
+  v.h = reinterpret_cast<const StrHeader*>(blob);
+  v.resid = blob + resid_off;
+  v.fsst = blob + fsst_off;
+  const uint64_t rb = g.row_base[e];
+  const uint32_t* row_off = g.row_off_base + rb + e;
+  const uint32_t* row_key = g.row_key_base + rb;
+  const uint32_t byte_base = static_cast<uint32_t>(g.byte_base[e]);
+  int32_t* out_offsets = g.out_offsets + rb;
+  for (uint32_t j = lane; j < k; j += 32u) out_offsets[j] = static_cast<int32_t>(byte_base + row_off[j]);
+  for (uint32_t j = 0; j < k; ++j) {
+    const uint32_t key = row_key[j];
+    const uint32_t start = dict_offset(v, key), end = dict_offset(v, key + 1u);
+    if (start == end) continue;
+    warp_decode(v.fsst + start, end - start, g.out_bytes + byte_base + row_off[j], sym, len, static_cast<int>(lane));
+  }
+}
+
+// grid of the two gather kernels: one CTA per entry when the host planned the get; for device-planned reads about sixteen
+// CTAs per SM's worth of entry ranges, so that a list whose entries all have rows still fills the machine
+static inline uint32_t gather_per_cta(uint32_t n_entries, const StrGatherIo& g) { return g.k_hint ? (n_entries + 2367u) / 2368u : 1u; }
+
 cudaError_t launch_str_decode(uint32_t n_entries, const StrGatherIo& g, cudaStream_t s) {
   if (n_entries == 0) return cudaSuccess;
-  k_str_decode<<<n_entries, 256, 0, s>>>(g);
+  if (g.k_hint && g.sparse_max) k_str_decode_sparse<<<(n_entries + 7u) / 8u, 256, 0, s>>>(g, n_entries);
+  const uint32_t per_cta = gather_per_cta(n_entries, g);
+  k_str_decode<<<(n_entries + per_cta - 1u) / per_cta, 256, 0, s>>>(g, n_entries, per_cta);
   return cudaGetLastError();
 }
 

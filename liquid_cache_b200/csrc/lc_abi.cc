@@ -1,5 +1,7 @@
 // lc_abi.cc — extern "C" entry points declared in include/lc_gpu.h.
 #include <algorithm>
+#include <cstddef>
+#include <cstring>
 
 #include "host_common.h"
 
@@ -89,6 +91,8 @@ struct lc_scan {
   // filters over the same columns cost a hash of the array instead of 12k pointer chases
   struct Validated {
     uint64_t key = 0, epoch = 0;
+    bool any_squeezed = false;
+    std::vector<lc_handle> handles;  // the list itself: the key only pre-filters, the match is exact
     std::vector<Entry*> es;
   };
   std::vector<Validated> validated;
@@ -109,14 +113,8 @@ struct ScanGuard {
   }
 };
 
-static uint64_t hash_handles(const lc_handle* h, uint64_t n) {
-  uint64_t x = 0x9E3779B97F4A7C15ull ^ n;
-  for (uint64_t i = 0; i < n; ++i) {
-    x = (x ^ h[i]) * 0xff51afd7ed558ccdull;
-    x ^= x >> 32;
-  }
-  return x;
-}
+static_assert(sizeof(lc_handle) == sizeof(uint64_t), "handle lists hash as 64-bit words");
+static uint64_t hash_handles(const lc_handle* h, uint64_t n) { return hash_words(reinterpret_cast<const uint64_t*>(h), n); }
 
 // Batched calls outside a scan: same idea, cached on the context (call with the context lock held).
 static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Entry* const** out) {
@@ -135,7 +133,7 @@ static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Ent
   }
   const uint64_t key = hash_handles(handles, n);
   for (auto& v : ctx->L()->validated) {
-    if (v.key == key && v.n == n && v.epoch == ctx->epoch) {
+    if (v.key == key && v.n == n && v.epoch == ctx->epoch && std::memcmp(v.handles.data(), handles, n * sizeof(lc_handle)) == 0) {
       *out = v.es.data();
       return LC_OK;
     }
@@ -144,6 +142,7 @@ static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Ent
   v.key = key;
   v.n = n;
   v.epoch = ctx->epoch;
+  v.handles.assign(handles, handles + n);
   v.es.resize(n);
   for (uint64_t i = 0; i < n; ++i) {
     v.es[i] = entry_of(handles[i]);
@@ -158,17 +157,19 @@ static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Ent
   return LC_OK;
 }
 
-static int scan_entries_cached(lc_scan* scan, const lc_handle* handles, Entry* const** out) {
+static int scan_entries_cached(lc_scan* scan, const lc_handle* handles, Entry* const** out, bool* any_squeezed = nullptr) {
   const uint64_t key = hash_handles(handles, scan->n);
   for (auto& v : scan->validated) {
-    if (v.key == key && v.epoch == scan->ctx->epoch) {
+    if (v.key == key && v.epoch == scan->ctx->epoch && std::memcmp(v.handles.data(), handles, scan->n * sizeof(lc_handle)) == 0) {
       *out = v.es.data();
+      if (any_squeezed) *any_squeezed = v.any_squeezed;
       return LC_OK;
     }
   }
   lc_scan::Validated v;
   v.key = key;
   v.epoch = scan->ctx->epoch;
+  v.handles.assign(handles, handles + scan->n);
   v.es.resize(scan->n);
   for (uint64_t i = 0; i < scan->n; ++i) {
     v.es[i] = entry_of(handles[i]);
@@ -177,6 +178,8 @@ static int scan_entries_cached(lc_scan* scan, const lc_handle* handles, Entry* c
       return LC_ERR_INVALID;
     }
   }
+  for (uint64_t i = 0; i < scan->n && !v.any_squeezed; ++i) v.any_squeezed = v.es[i]->squeeze_kind != 0;  // squeezing bumps the epoch
+  if (any_squeezed) *any_squeezed = v.any_squeezed;
   if (scan->validated.size() >= 8) scan->validated.erase(scan->validated.begin());
   scan->validated.push_back(std::move(v));
   *out = scan->validated.back().es.data();
@@ -832,9 +835,8 @@ int lc_scan_filter(lc_scan* scan, const lc_handle* handles, const lc_predicate* 
   lc_ctx* ctx = scan->ctx;
   ScanGuard g(scan);
   Entry* const* es = nullptr;
-  LC_TRY(scan_entries_cached(scan, handles, &es));
   bool any_squeezed = false;
-  for (uint64_t i = 0; i < scan->n && !any_squeezed; ++i) any_squeezed = es[i]->squeeze_kind != 0;
+  LC_TRY(scan_entries_cached(scan, handles, &es, &any_squeezed));
   if (any_squeezed) LC_TRY(scan_filter_squeezed(scan, es, pred));
   else LC_TRY(refine_batch(ctx, es, scan->n, pred, scan->d_sel, scan->d_word_off, scan->all_rows, scan->d_counts));
   scan->all_rows = false;
@@ -1048,6 +1050,31 @@ int lc_scan_read_borrowed(lc_scan* scan, const lc_handle* handles, void** d_valu
   *out_rows = out.rows;
   *out_value_bytes = out.value_bytes;
   return LC_OK;
+}
+
+static_assert(sizeof(lc_read_header) == sizeof(ScanPlanHdr) && offsetof(lc_read_header, rows) == offsetof(ScanPlanHdr, rows) &&
+                  offsetof(lc_read_header, value_bytes) == offsetof(ScanPlanHdr, bytes) &&
+                  offsetof(lc_read_header, overflow) == offsetof(ScanPlanHdr, overflow),
+              "lc_read_header is the plan header the kernels write");
+
+int lc_scan_read_async(lc_scan* scan, const lc_handle* handles, void* d_values, uint64_t values_cap, void* d_offsets,
+                       uint64_t rows_cap, void* d_header) {
+  if (!scan || !handles || !d_values || !d_header) return LC_ERR_INVALID;
+  lc_ctx* ctx = scan->ctx;
+  ScanGuard g(scan);
+  Entry* const* esp = nullptr;
+  LC_TRY(scan_entries_cached(scan, handles, &esp));
+  if (!scan->counts_on_device || scan->all_rows) {
+    set_error("lc_scan_read_async: no filter has run on this scan yet");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  const int rc = scan_read_async(ctx, &scan->fused, esp, scan->n, scan->d_sel, scan->d_word_off, scan->d_counts, d_values, values_cap,
+                                 d_offsets, rows_cap, d_header);
+  if (rc == LC_INTERNAL_FALLBACK) {
+    set_error("lc_scan_read_async: this column is not read by the device-planned path (nulls, views, dictionaries, floats, decimals)");
+    return LC_ERR_UNSUPPORTED_EXPR;
+  }
+  return rc;
 }
 
 void lc_scan_end(lc_scan* scan) {

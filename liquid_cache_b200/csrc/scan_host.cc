@@ -4,6 +4,7 @@
 // Reference call sites: LiquidCache::read_arrow_array / eval_predicate_internal
 // (/root/reference/src/core/src/cache/core.rs:595-634, 862-930).
 #include <algorithm>
+#include <cstring>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -291,6 +292,7 @@ struct RefList {
   // instead of chasing 10^4 Entry pointers (each a cache miss)
   std::shared_ptr<std::vector<uint32_t>> rows;      // rows per entry
   std::shared_ptr<std::vector<uint32_t>> n_unique;  // dictionary size per entry (byte views)
+  std::shared_ptr<std::vector<const Entry*>> entries;  // the list itself: the key only pre-filters, the match is exact
   bool same_liquid_type = true, same_arrow_type = true, same_width = true, any_nulls = false, any_fixed = false;
   // did the last predicate over this list produce nearly-empty masks? (0 unknown, 1 sparse, 2 dense) — picks between
   // the sparse mask download and the chunked dense one before the answer is known
@@ -319,16 +321,12 @@ void drop_ref_cache(lc_ctx* ctx) {
 }
 
 static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const RefList** out) {
-  uint64_t h = 0xcbf29ce484222325ull ^ n;
-  for (uint64_t i = 0; i < n; ++i) {
-    h ^= reinterpret_cast<uintptr_t>(entries[i]);
-    h *= 0x100000001b3ull;
-    h ^= h >> 29;
-  }
+  static_assert(sizeof(Entry*) == sizeof(uint64_t), "entry lists hash as 64-bit words");
+  const uint64_t h = hash_words(reinterpret_cast<const uint64_t*>(entries), n);
   RefCache& rc = ref_cache_of(ctx);
   rc.tick++;
   for (auto& l : rc.lists) {
-    if (l.key == h && l.n == n && l.epoch == ctx->epoch) {
+    if (l.key == h && l.n == n && l.epoch == ctx->epoch && std::memcmp(l.entries->data(), entries, n * sizeof(Entry*)) == 0) {
       l.last_use = rc.tick;
       *out = &l;
       return LC_OK;
@@ -343,6 +341,7 @@ static int get_ref_list(lc_ctx* ctx, Entry* const* entries, uint64_t n, const Re
   nl.last_use = rc.tick;
   nl.rows = std::make_shared<std::vector<uint32_t>>(n);
   nl.n_unique = std::make_shared<std::vector<uint32_t>>(n, 0);
+  nl.entries = std::make_shared<std::vector<const Entry*>>(entries, entries + n);
   const Entry* proto = entries[0];
   for (uint64_t i = 0; i < n; ++i) {
     const Entry* e = entries[i];
@@ -1684,6 +1683,92 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
   return LC_OK;
 }
 
+// The same device-planned read, FULLY ASYNCHRONOUS: the result lands in caller-owned device buffers of stated capacities
+// and the 64-byte plan header (rows, bytes, overflow) in caller-owned device memory; nothing is downloaded and the stream is
+// not synchronised. This is what a consumer on the device wants — the NCCL gather of every rank's filtered batch runs right
+// behind it on the same stream and one tiny header download ends the step (bench.py, dist.py::DeviceGather).
+int scan_read_async(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t n, const uint32_t* d_sel, const uint64_t* d_word_off,
+                    const uint32_t* d_counts2, void* d_values, uint64_t values_cap, void* d_offsets, uint64_t rows_cap, void* d_header) {
+  const RefList* rl;
+  LC_TRY(get_ref_list(ctx, entries, n, &rl));
+  const Entry* proto = entries[0];
+  if (!rl->same_liquid_type || !rl->same_arrow_type || rl->any_nulls || rl->any_fixed) return LC_INTERNAL_FALLBACK;
+  const bool is_int = proto->liquid_type == LC_LIQUID_INTEGER;
+  const bool is_str = proto->liquid_type == LC_LIQUID_BYTE_VIEW &&
+                      (proto->sh.arrow_type == BT_UTF8 || proto->sh.arrow_type == BT_BINARY);
+  if ((!is_int && !is_str) || (is_int && !rl->same_width) || (is_str && !d_offsets) || !d_values || !d_header) return LC_INTERNAL_FALLBACK;
+  const uint32_t tb = is_int ? proto->ih.tbits / 8 : 0;
+  cudaStream_t s = ctx->L()->stream;
+  const uint64_t cap_rows = is_int ? std::min<uint64_t>(rows_cap, values_cap / tb) : rows_cap;
+  const uint64_t cap_bytes = is_int ? 0 : std::min<uint64_t>(values_cap, 0x7fffffffull);
+  // dictionary-length scratch: at most min(n, cap_rows) entries have survivors, each at most the list's largest dictionary
+  const uint64_t cap_ulen = is_int ? 0 : std::min<uint64_t>(n, cap_rows) * round_up(rl->max_unique, 4);
+  uint64_t o = 0;
+  auto take = [&](uint64_t bytes) { const uint64_t at = o; o += round_up(bytes, 256); return at; };
+  const uint64_t o_rowb = take(n * 8), o_vw = take(n * 8), o_ul = take(n * 8), o_bb = take(n * 8), o_cnt = take(n * 16);
+  const uint64_t o_rowoff = is_str ? take((cap_rows + n) * 4 + 16) : 0, o_rowkey = is_str ? take(cap_rows * 4 + 16) : 0;
+  const uint64_t o_ulen = is_str ? take(cap_ulen * 4 + 16) : 0;
+  if (o > fr->a_cap) {
+    if (fr->a_buf) {
+      LC_CUDA_OK(cudaStreamSynchronize(s));
+      cudaFree(fr->a_buf);
+      fr->a_buf = nullptr;
+      fr->a_cap = 0;
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&fr->a_buf), o + o / 8) != cudaSuccess) {
+      cudaGetLastError();
+      return LC_INTERNAL_FALLBACK;
+    }
+    fr->a_cap = o + o / 8;
+  }
+  uint8_t* d = fr->a_buf;
+  ScanPlanHdr* d_hdr = static_cast<ScanPlanHdr*>(d_header);
+  uint64_t* d_rowb = reinterpret_cast<uint64_t*>(d + o_rowb);
+  uint64_t* d_vw = reinterpret_cast<uint64_t*>(d + o_vw);
+  uint64_t* d_ul = reinterpret_cast<uint64_t*>(d + o_ul);
+  uint64_t* d_bb = reinterpret_cast<uint64_t*>(d + o_bb);
+  uint32_t* d_cnt = reinterpret_cast<uint32_t*>(d + o_cnt);
+  LC_CUDA_OK(cudaMemsetAsync(d_cnt, 0, n * 16, s));
+  LC_CUDA_OK(launch_scan_plan_rows(d_counts2, is_str ? rl->d_n_unique : nullptr, static_cast<uint32_t>(n), cap_rows, cap_ulen, d_rowb,
+                                   d_vw, d_ul, d_hdr, s));
+  ctx->kernel_launches++;
+  ScanIo io{};
+  io.refs = rl->d_refs;
+  io.sel_base = d_sel;
+  io.sel_off = d_word_off;
+  io.out_off = d_rowb;
+  io.valid_off = d_vw;
+  io.counts = d_cnt;
+  io.counts_stride = 4;
+  if (is_int) {
+    io.out_base = d_values;
+    io.abort_flag = &d_hdr->overflow;
+    IntPredDesc ip{};
+    LC_CUDA_OK(launch_int_scan(MODE_DECODE, static_cast<uint32_t>(n), io, ip, rl->max_blob, s));
+    ctx->kernel_launches++;
+  } else {
+    StrGatherIo g{};
+    g.io = io;
+    g.row_off_base = reinterpret_cast<uint32_t*>(d + o_rowoff);
+    g.row_key_base = reinterpret_cast<uint32_t*>(d + o_rowkey);
+    g.ulen_base = reinterpret_cast<uint32_t*>(d + o_ulen);
+    g.row_base = d_rowb;
+    g.ulen_off = d_ul;
+    g.byte_base = d_bb;
+    g.k_hint = d_counts2;
+    g.plan = d_hdr;
+    g.sparse_max = 64;
+    g.out_offsets = static_cast<int32_t*>(d_offsets);
+    g.out_bytes = static_cast<uint8_t*>(d_values);
+    LC_CUDA_OK(launch_str_lengths_sparse(static_cast<uint32_t>(n), g, s));
+    LC_CUDA_OK(launch_str_lengths(static_cast<uint32_t>(n), g, rl->max_head, s));
+    LC_CUDA_OK(launch_scan_plan_bytes(d_cnt, static_cast<uint32_t>(n), cap_bytes, d_bb, g.out_offsets, d_hdr, s));
+    LC_CUDA_OK(launch_str_decode(static_cast<uint32_t>(n), g, s));
+    ctx->kernel_launches += 4;
+  }
+  return LC_OK;
+}
+
 void fused_read_learn(FusedRead* fr, const ArrowArray* arr, int64_t value_bytes, uint64_t ulen_words) {
   fr->spec_rows = static_cast<uint64_t>(arr->length);
   fr->spec_bytes = value_bytes > 0 ? static_cast<uint64_t>(value_bytes) : 0;
@@ -1692,6 +1777,7 @@ void fused_read_learn(FusedRead* fr, const ArrowArray* arr, int64_t value_bytes,
 }
 
 void fused_read_free(FusedRead* fr) {
+  if (fr->a_buf) cudaFree(fr->a_buf);
   if (fr->d_buf) cudaFree(fr->d_buf);
   if (fr->h_hdr) cudaFreeHost(fr->h_hdr);
   *fr = FusedRead();

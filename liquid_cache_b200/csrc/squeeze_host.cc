@@ -211,6 +211,7 @@ int squeeze_date_entry(lc_ctx* ctx, Entry* full, uint32_t field, lc_backing_read
   e->orig_format = full->arrow_format;
   e->ih = h;
   e->squeeze_kind = 3;
+  ctx->epoch++;  // cached entry lists remember whether they hold squeezed entries
   e->date_field = field;
   e->backing_read = read;
   e->backing_user = user;
@@ -377,6 +378,7 @@ int squeeze_entry(lc_ctx* ctx, Entry* full, int32_t policy, int32_t hint, lc_bac
   e->arrow_format = full->arrow_format;
   e->ih = h;
   e->squeeze_kind = policy + 1;
+  ctx->epoch++;  // cached entry lists remember whether they hold squeezed entries
   e->bucket_width = bucket_width;
   e->backing_read = read;
   e->backing_user = user;

@@ -156,98 +156,98 @@ def gather_device_result_to_rank0(values, offsets, validity, rows: int, nulls: i
     return pa.concat_arrays(parts)
 
 
-class StepGather:
-    """The gather of `gather_device_result_to_rank0`, shaped for use INSIDE a timed loop: buffers are allocated once and
-    grown geometrically, the per-rank sizes travel in one small all_gather, every part lands at its final position in rank
-    0's buffers (no per-part host bounce), string offsets are rebased on the device, and rank 0 downloads the finished
-    Arrow buffers once into page-locked memory that the returned array references directly.
+class DeviceGather:
+    """The one exchange of the path, shaped for use INSIDE a timed loop: every rank's filtered batch goes from its HBM into
+    rank 0's HBM (into every rank's, it is one all_gather) with ONE collective and ONE host synchronisation per step.
 
-    One host synchronisation on every rank (the sizes), one more on rank 0 (the result)."""
+    Each rank owns a fixed-capacity slot `[header 64 B | int32 offsets[rows_cap + 1] | value bytes]` in device memory;
+    `lc_scan_read_async` (Scan.read_async) plans and writes the survivors of the filter straight into it without touching the
+    host. `exchange()` all-gathers the slots over NCCL (NVLink / NVSwitch), downloads the `world` headers — 64 bytes each —
+    and synchronises: that is the only point where the host waits. The gathered batches stay in HBM as `world` Arrow-layout
+    parts (what a device consumer reads); `to_arrow()` materialises them on the host for checking, outside any clock.
 
-    def __init__(self, arrow_type: pa.DataType, rank: int, world: int, device):
+    The library must run on torch's current stream (`LiquidCache.set_stream(torch.cuda.current_stream().cuda_stream)`) so
+    that the collective and the header download are ordered behind the read without an event.
+
+    Capacities are equal on every rank (all_gather needs equal slots) and every rank sees every header, so growing after an
+    overflow is decided identically everywhere without another message."""
+
+    HDR = 64
+
+    def __init__(self, arrow_type: pa.DataType, rank: int, world: int, device, rows_cap: int = 1 << 12, values_cap: int = 1 << 18):
         import torch
 
-        self.t, self.rank, self.world, self.dev = arrow_type, rank, world, device
+        self.torch, self.t, self.rank, self.world, self.dev = torch, arrow_type, rank, world, device
         self.is_bytes = pa.types.is_string(arrow_type) or pa.types.is_binary(arrow_type)
         self.width = 0 if self.is_bytes else arrow_type.bit_width // 8
-        self.torch = torch
-        self.sizes = torch.zeros(2, dtype=torch.int64, device=device)
-        self.all_sizes = torch.zeros(2 * world, dtype=torch.int64, device=device)
-        self.vals = self.offs = self.offs_packed = None
-        self.h_vals = self.h_offs = None
         self.pin = device.type == "cuda"
+        self.grows = 0
+        self._alloc(rows_cap, values_cap)
 
-    def _grow(self, name: str, n: int, dtype, host: bool):
-        cur = getattr(self, name)
-        if cur is None or cur.numel() < n:
-            cap = max(n + n // 2, 1 << 16)
-            t = (self.torch.empty(cap, dtype=dtype, pin_memory=self.pin) if host
-                 else self.torch.empty(cap, dtype=dtype, device=self.dev))
-            setattr(self, name, t)
-        return getattr(self, name)
+    def _alloc(self, rows_cap: int, values_cap: int):
+        torch = self.torch
+        self.rows_cap = int(rows_cap)
+        self.values_cap = int(values_cap) if self.is_bytes else self.rows_cap * self.width
+        self.off_at = self.HDR
+        self.val_at = self.HDR + (((self.rows_cap + 1) * 4 + 255) // 256 * 256 if self.is_bytes else 0)
+        self.slot = (self.val_at + self.values_cap + 255) // 256 * 256
+        self.send = torch.zeros(self.slot, dtype=torch.uint8, device=self.dev)
+        self.recv = self.send if self.world == 1 else torch.zeros(self.world * self.slot, dtype=torch.uint8, device=self.dev)
+        self.h_hdr = torch.zeros((self.world, self.HDR), dtype=torch.uint8, pin_memory=self.pin)
+        self.headers = None
 
-    def gather(self, values, offsets, rows: int) -> Optional[pa.Array]:
-        """values: u8 tensor of this rank's value bytes (ints: rows * width bytes); offsets: i32 tensor [rows + 1] for byte
-        types, else None. No nulls (the bench columns have none). Returns the concatenation on rank 0."""
+    def addresses(self):
+        """(d_values, values_cap, d_offsets, rows_cap, d_header): the arguments of Scan.read_async for this rank's slot."""
+        base = self.send.data_ptr()
+        return base + self.val_at, self.values_cap, (base + self.off_at) if self.is_bytes else 0, self.rows_cap, base
+
+    def exchange(self):
+        """All-gather the slots, download the headers, synchronise. Returns [(rows, value_bytes, overflow)] per rank."""
         import torch.distributed as dist
 
-        torch = self.torch
-        nbytes = int(values.numel())
-        if self.world == 1:
-            all_sizes = [rows, nbytes]
-        else:
-            self.sizes[0] = rows
-            self.sizes[1] = nbytes
-            dist.all_gather_into_tensor(self.all_sizes, self.sizes)
-            all_sizes = self.all_sizes.cpu().tolist()  # the one synchronisation every rank pays
-        rows_r = [int(all_sizes[2 * r]) for r in range(self.world)]
-        bytes_r = [int(all_sizes[2 * r + 1]) for r in range(self.world)]
-        if self.rank != 0:
-            ops = []
-            if nbytes:
-                ops.append(dist.P2POp(dist.isend, values, 0))
-            if self.is_bytes and rows:
-                ops.append(dist.P2POp(dist.isend, offsets[: rows + 1].view(torch.uint8), 0))
-            for w in (dist.batch_isend_irecv(ops) if ops else []):
-                w.wait()
-            return None
-        tot_rows, tot_bytes = sum(rows_r), sum(bytes_r)
-        vals = self._grow("vals", max(tot_bytes, 1), torch.uint8, False)
-        vals[:nbytes].copy_(values, non_blocking=True)
-        offs = None
-        if self.is_bytes:
-            offs = self._grow("offs", tot_rows + self.world + 1, torch.int32, False)
-            offs[: rows + 1].copy_(offsets[: rows + 1], non_blocking=True)
-        ops, places = [], []
-        vb, ob = nbytes, rows + 1
-        for r in range(1, self.world):
-            if bytes_r[r]:
-                ops.append(dist.P2POp(dist.irecv, vals[vb: vb + bytes_r[r]], r))
-            if self.is_bytes and rows_r[r]:
-                # each part arrives with its own rows + 1 offsets; they are rebased and packed below
-                ops.append(dist.P2POp(dist.irecv, offs[ob: ob + rows_r[r] + 1].view(torch.uint8), r))
-            places.append((r, vb, ob))
-            vb += bytes_r[r]
-            ob += rows_r[r] + 1
-        for w in (dist.batch_isend_irecv(ops) if ops else []):
-            w.wait()
-        h_vals = self._grow("h_vals", max(tot_bytes, 1), torch.uint8, True)
-        if self.is_bytes:
-            # pack the offsets: part r's rows start at byte vb_r of the concatenation; its first offset (0) is dropped
-            packed = self._grow("offs_packed", tot_rows + 1, torch.int32, False)
-            packed[: rows + 1].copy_(offs[: rows + 1])
-            at = rows + 1
-            for r, vb_r, ob_r in places:
-                if rows_r[r]:
-                    packed[at: at + rows_r[r]] = offs[ob_r + 1: ob_r + 1 + rows_r[r]] + vb_r
-                    at += rows_r[r]
-            h_offs = self._grow("h_offs", tot_rows + 1, torch.int32, True)
-            h_offs[: tot_rows + 1].copy_(packed[: tot_rows + 1], non_blocking=True)
-        h_vals[:tot_bytes].copy_(vals[:tot_bytes], non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.recv, self.send)
+        self.h_hdr.copy_(self.recv.view(self.world, self.slot)[:, : self.HDR], non_blocking=True)
         if self.pin:
-            torch.cuda.current_stream().synchronize()
-        data = pa.foreign_buffer(h_vals.data_ptr(), tot_bytes, base=h_vals)
+            self.torch.cuda.current_stream().synchronize()  # the step's one synchronisation
+        h = self.h_hdr.numpy()
+        u32, u64 = h.view(np.uint32), h.view(np.uint64)
+        self.headers = [(int(u64[r, 1]), int(u64[r, 2]) if self.is_bytes else int(u64[r, 1]) * self.width, int(u32[r, 1]))
+                        for r in range(self.world)]
+        return self.headers
+
+    def overflowed(self) -> bool:
+        return any(o for _r, _b, o in self.headers)
+
+    def grow(self):
+        """After an overflow: new equal capacities from what the headers say every rank needs (rows are always reported;
+        the byte total is only known once the rows fit, so it doubles until then)."""
+        rows = max(r for r, _b, _o in self.headers)
+        rows_cap = max(self.rows_cap, rows + rows // 4 + 1024)
+        values_cap = self.values_cap
         if self.is_bytes:
-            ofb = pa.foreign_buffer(h_offs.data_ptr(), (tot_rows + 1) * 4, base=h_offs)
-            return pa.Array.from_buffers(self.t, tot_rows, [None, ofb, data], null_count=0)
-        return pa.Array.from_buffers(self.t, tot_rows, [None, data], null_count=0)
+            known = max((b for _r, b, o in self.headers if o != 1), default=0)
+            values_cap = max(values_cap, known + known // 4 + 4096)
+            if any(o == 1 for _r, _b, o in self.headers):  # rows did not fit: bytes unknown there, scale with the rows
+                values_cap = max(values_cap, self.values_cap * -(-rows_cap // self.rows_cap))
+        self.grows += 1
+        self._alloc(rows_cap, values_cap)
+
+    def part(self, r: int):
+        """(values u8 view, offsets i32 view | None, rows) of rank r's batch in THIS rank's HBM after exchange()."""
+        rows, nbytes, _o = self.headers[r]
+        slot = self.recv[r * self.slot:(r + 1) * self.slot]
+        offs = slot[self.off_at: self.off_at + (rows + 1) * 4].view(self.torch.int32) if self.is_bytes else None
+        return slot[self.val_at: self.val_at + nbytes], offs, rows
+
+    def to_arrow(self, ranks=None) -> pa.Array:
+        """The gathered batches as one host Arrow array (rank order). For checking: downloads, not part of a timed step."""
+        parts = []
+        for r in (range(self.world) if ranks is None else ranks):
+            v, o, rows = self.part(r)
+            data = pa.py_buffer(v.cpu().numpy().tobytes())
+            if self.is_bytes:
+                parts.append(pa.Array.from_buffers(self.t, rows, [None, pa.py_buffer(o.cpu().numpy().tobytes()), data], null_count=0))
+            else:
+                parts.append(pa.Array.from_buffers(self.t, rows, [None, data], null_count=0))
+        return pa.concat_arrays(parts) if parts else pa.array([], type=self.t)

@@ -102,59 +102,88 @@ def test_sharding_keeps_all_columns_of_a_batch_together():
             assert min(len(p) for p in parts) > 0.5 * len(ids) / world
 
 
-def _step_gather_worker(rank, world, port, q):
+def _fill_slot(g, arr):
+    """What lc_scan_read_async does on the device, done with numpy on a CPU slot: header (rows at byte 8, value bytes at 16,
+    overflow at 4), int32 offsets and value bytes — or only the header with the overflow code when a capacity is short."""
+    from liquid_cache_b200.dist import _buffers_of
+
+    _v, off, data = _buffers_of(arr)
+    buf = g.send.numpy()
+    d_values, values_cap, d_offsets, rows_cap, _d_hdr = g.addresses()
+    base = g.send.data_ptr()
+    hdr64, hdr32 = buf[:64].view(np.uint64), buf[:64].view(np.uint32)
+    hdr64[:] = 0
+    hdr64[1] = len(arr)
+    if len(arr) > rows_cap:
+        hdr32[1] = 1
+        return
+    hdr64[2] = len(data)
+    if g.is_bytes and len(data) > values_cap:
+        hdr32[1] = 2
+        return
+    if g.is_bytes:
+        at = d_offsets - base
+        buf[at: at + 4 * (len(arr) + 1)] = (off if len(arr) else np.zeros(1, np.int32)).view(np.uint8)
+    at = d_values - base
+    buf[at: at + len(data)] = data
+
+
+def _device_gather_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
 
-    from liquid_cache_b200.dist import StepGather, _buffers_of
+    from liquid_cache_b200.dist import DeviceGather
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         dev = torch.device("cpu")
-        gs = StepGather(pa.string(), rank, world, dev)
-        gi = StepGather(pa.int32(), rank, world, dev)
+        gs = DeviceGather(pa.string(), rank, world, dev, rows_cap=64, values_cap=512)
+        gi = DeviceGather(pa.int32(), rank, world, dev, rows_cap=64)
         local, got = [], []
-        for step in range(4):  # sizes change from step to step, one rank is empty in step 2: buffers are reused / grown
+        for step in range(4):  # sizes change from step to step, one rank is empty in step 2: slots are reused / grown
             rng = np.random.default_rng(1000 * step + rank)
             n = 0 if (step == 2 and rank == 1) else int(rng.integers(1, 200)) * (step + 1)
             strs = pa.array([f"http://r{rank}/s{step}/{i}" * int(rng.integers(1, 4)) for i in range(n)], pa.string())
             ints = pa.array(rng.integers(-1000, 1000, size=n).astype(np.int32), pa.int32())
-            _v, off, data = _buffers_of(strs)
-            v = torch.from_numpy(data.copy()) if len(data) else torch.zeros(0, dtype=torch.uint8)
-            o = torch.from_numpy(off.copy()) if n else torch.zeros(1, dtype=torch.int32)
-            g = gs.gather(v, o, n)
-            _v, _o, idata = _buffers_of(ints)
-            iv = torch.from_numpy(idata.copy()) if n else torch.zeros(0, dtype=torch.uint8)
-            h = gi.gather(iv, None, n)
+            for g, arr in ((gs, strs), (gi, ints)):
+                for _ in range(8):
+                    _fill_slot(g, arr)
+                    g.exchange()
+                    if not g.overflowed():
+                        break
+                    g.grow()  # every rank sees every header: all of them grow to the same capacities
+                assert not g.overflowed()
             local.append((strs.to_pylist(), ints.to_pylist()))
-            got.append((None if g is None else g.to_pylist(), None if h is None else h.to_pylist()))
-        q.put((rank, local, got))
+            got.append((gs.to_arrow().to_pylist(), gi.to_arrow().to_pylist(), [h[0] for h in gs.headers]))
+        q.put((rank, local, got, gs.grows))
     finally:
         dist.destroy_process_group()
 
 
-def test_step_gather_world2_matches_concatenation():
-    """StepGather (the gather bench.py times inside its step at N > 1): every step's concatenation on rank 0 equals the
-    ranks' arrays in rank order, with buffers reused across steps."""
+def test_device_gather_world2_matches_concatenation():
+    """DeviceGather (the exchange bench.py times inside its step): after every step EVERY rank holds the ranks' batches in
+    rank order; slots are reused across steps and grown, identically on all ranks, when a capacity was short."""
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_step_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_device_gather_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = {}
     for _ in range(2):
-        rank, local, got = q.get(timeout=120)
-        res[rank] = (local, got)
+        rank, local, got, grows = q.get(timeout=120)
+        res[rank] = (local, got, grows)
     for p in procs:
         p.join(timeout=60)
+    assert res[0][2] == res[1][2] and res[0][2] > 0
     for step in range(4):
         want_s = res[0][0][step][0] + res[1][0][step][0]
         want_i = res[0][0][step][1] + res[1][0][step][1]
-        assert res[0][1][step][0] == want_s
-        assert res[0][1][step][1] == want_i
-        assert res[1][1][step] == (None, None)
+        for r in range(2):
+            assert res[r][1][step][0] == want_s
+            assert res[r][1][step][1] == want_i
+            assert res[r][1][step][2] == [len(res[0][0][step][0]), len(res[1][0][step][0])]

@@ -78,3 +78,56 @@ def test_selective_like_then_get_of_the_hits(cache):
             assert_arrays_equal(got_i, pa.concat_arrays([a.filter(m) for a, m in zip(ints, masks)]), pattern + " ints")
             counts, total = scan.counts()
             assert total == len(got_s) and [int(c) for c in counts] == [int(pc.sum(m).as_py() or 0) for m in masks]
+
+
+def test_async_read_into_caller_buffers_matches_arrow_and_reports_short_capacities(cache):
+    """lc_scan_read_async (scan_host.cc scan_read_async): the same get, with no host synchronisation — result and the
+    64-byte header land in caller-owned device memory. DeviceGather is the caller bench.py uses; with world = 1 its
+    exchange() is only the header download. Short capacities are reported in the header (rows stay valid), nothing else is
+    written, and growing from the headers converges."""
+    import torch
+
+    from liquid_cache_b200.dist import DeviceGather
+
+    rng = np.random.default_rng(13)
+    n_batches, rows = 30, 4096
+    ints, strs, li, ls = _columns(cache, rng, n_batches, rows, 8803)
+    hi = np.array([l.handle for l in li], dtype=np.uint64)
+    hs = np.array([l.handle for l in ls], dtype=np.uint64)
+    sizes = [len(a) for a in ints]
+    dev = torch.device("cuda", 0)
+    gi = DeviceGather(pa.int64(), 0, 1, dev, rows_cap=256)
+    gs = DeviceGather(pa.string(), 0, 1, dev, rows_cap=256, values_cap=1024)
+    with cache.scan(sizes) as scan:
+        for thr in (990, 500, 0, 2000, 700):
+            scan.reset()
+            scan.filter(hi, _bin(">=", thr), pa.int64())
+            want_i = pa.concat_arrays([a.filter(pc.greater_equal(a, thr)) for a in ints])
+            want_s = pa.concat_arrays([s.filter(pc.greater_equal(a, thr)) for a, s in zip(ints, strs)])
+            for g, h, want in ((gi, hi, want_i), (gs, hs, want_s)):
+                for _ in range(8):
+                    assert scan.read_async(h, *g.addresses())
+                    cache.synchronize()  # the session cache runs on its own stream, not torch's (bench.py shares one stream)
+                    (n_rows, _nbytes, overflow), = g.exchange()
+                    assert n_rows == len(want)  # rows are reported even when nothing could be written
+                    if not overflow:
+                        break
+                    g.grow()
+                assert not g.overflowed()
+                assert_arrays_equal(g.to_arrow(), want, f"async >= {thr}")
+    assert gi.grows > 0 and gs.grows > 0
+
+
+def test_async_read_refuses_what_the_device_plan_does_not_cover(cache):
+    import torch
+
+    from liquid_cache_b200.dist import DeviceGather
+
+    vals = pa.array([1, None, 3, 4] * 512, pa.int64())
+    l = cache.transcode(vals)
+    h = np.array([l.handle], dtype=np.uint64)
+    g = DeviceGather(pa.int64(), 0, 1, torch.device("cuda", 0), rows_cap=4096)
+    with cache.scan([len(vals)]) as scan:
+        scan.filter(h, _bin(">=", 2), pa.int64())
+        assert scan.read_async(h, *g.addresses()) is False  # nulls: the caller takes lc_scan_read / lc_scan_read_device
+        assert_arrays_equal(scan.read(h), vals.filter(pc.fill_null(pc.greater_equal(vals, 2), False)), "fallback")
