@@ -800,18 +800,19 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
     # Algorithmic bytes of one predicate launch, SURVEY.md §8d "string predicate, fingerprint path", counted by the kernel's
     # own counters in the untimed launch above:  R = keys 2n + staged head (header, shared prefix, fingerprints 4U, ALL offset
     # residuals (U+1)*res_bytes) + compressed bytes of the walked candidates;  W = selection words n/8.
-    # That is the reference's data for this predicate; roofline.achieved is quoted on it. Two more figures say what THIS
-    # build moves: `with_private_filter` adds the 32-byte trigram set of every value the reference gate lets through (the
-    # only ones whose set is fetched), and `kernel_reads` replaces the 2n of keys by the keys of the batches whose
-    # dictionary had a match (the others are answered without their keys: k_str.cu, k_str_like).
-    ref_pass, meta_bytes, rows_phase_entries = int(prof[12]), int(prof[13]), int(prof[3])
+    # That is the reference's data for this predicate; roofline.achieved is quoted on it. `kernel_reads` says what THIS build
+    # moves instead: the header, the needle's planes of the private trigram filter (entry_layout.h: k * ceil(U/32) words per
+    # entry; fingerprints and residuals of values that are not walked are never read), the walked values, the keys of
+    # the batches whose dictionary had a match (the others are answered without their keys: k_str.cu, k_str_like), and
+    # the selection words.
+    ref_pass, meta_bytes, rows_phase_entries, gate_bytes = int(prof[12]), int(prof[13]), int(prof[3]), int(prof[14])
     if meta_bytes == 0:  # the launch did not take the streaming LIKE kernel
         meta_bytes = 4 * uniques + 2 * uniques
         ref_pass = uniques
         rows_phase_entries = n_entries
+        gate_bytes = 4 * uniques
     algo_bytes = 2 * rows_local + meta_bytes + cand_bytes + rows_local // 8
-    algo_bytes_private = algo_bytes + 32 * ref_pass
-    kernel_reads = meta_bytes + 32 * ref_pass + cand_bytes + rows_phase_entries * 2 * ROWS_PER_ENTRY + rows_local // 8
+    kernel_reads = 128 * n_entries + gate_bytes + cand_bytes + rows_phase_entries * 2 * ROWS_PER_ENTRY + rows_local // 8
 
     k_start = torch.cuda.Event(enable_timing=True)
     k_stop = torch.cuda.Event(enable_timing=True)
@@ -994,7 +995,7 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
                          "frac": achieved / peak, "traffic": recorded_traffic(rows_local, n_entries) if source == "synthetic" else None,
                          "traffic_source": "replayed from profiles/r02_k_str_like_traffic.json (ncu --set full of this seeded workload), not measured in this run",
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "algorithmic_bytes_with_private_filter": algo_bytes_private,
+                         "gate_bytes_read": gate_bytes,
                          "bytes_this_kernel_must_move": kernel_reads,
                          "achieved_on_bytes_moved": kernel_reads / (kern_ms / 1e3) / 1e9,
                          "reference_gate_pass_frac": ref_pass / max(1, uniques),

@@ -28,7 +28,7 @@ struct StrView {
   const uint8_t* sp;
   const uint64_t* pk;
   const uint32_t* fp;
-  const unsigned long long* bloom;  // always in global memory (read once, coalesced)
+  const uint32_t* planes;  // trigram filter planes (entry_layout.h), always in global memory
   const uint8_t* resid;
   const uint32_t* valid;
   const uint16_t* keys;
@@ -46,7 +46,7 @@ __device__ __forceinline__ StrView make_view(const uint8_t* head, const uint8_t*
   v.valid = v.h->has_nulls ? reinterpret_cast<const uint32_t*>(head + v.h->validity_off) : nullptr;
   v.keys = reinterpret_cast<const uint16_t*>(head + v.h->keys_off);
   v.fsst = blob + v.h->fsst_off;
-  v.bloom = v.h->bloom_off ? reinterpret_cast<const unsigned long long*>(blob + v.h->bloom_off) : nullptr;
+  v.planes = v.h->bloom_off ? reinterpret_cast<const uint32_t*>(blob + v.h->bloom_off) : nullptr;
   return v;
 }
 
@@ -487,26 +487,21 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
     // the survivors to the queue. (An earlier version also ordered the queue by length class — worth 3 % with ~700
     // candidates per entry, nothing with the handful the trigram filter leaves, at the price of a second pass.)
     uint32_t* cand_cnt = sm->warp_tot;  // [0] queue length (unused scratch in this phase)
+    const uint32_t pw = bloom_plane_words(U);
     if (threadIdx.x == 0) cand_cnt[0] = 0;
     __syncthreads();
     for (uint32_t g0 = (threadIdx.x & ~31u); g0 < U; g0 += 1024u) {
-      // four stripes in flight: fingerprint (staged head) + the value's 256-bit trigram set (two 16-byte loads from
-      // global memory, 1 KB per warp and stripe, coalesced)
-      ulonglong2 blo[4], bhi[4];
-      uint32_t fpv[4];
+      // four stripes in flight: fingerprint (staged head) + the stripe's word of each of the needle's filter planes (lane t
+      // fetches plane t's word; their AND over the warp is the stripe's candidate word)
+      uint32_t fpv[4], pwd[4];
 #pragma unroll
       for (uint32_t t = 0; t < 4; ++t) {
-        const uint32_t i = g0 + t * 256u + lane;
-        const bool act = i < U;
-        fpv[t] = (act && v.fp) ? v.fp[i] : 0u;
-        if (act && v.bloom) {
-          const ulonglong2* src = reinterpret_cast<const ulonglong2*>(v.bloom + static_cast<size_t>(i) * kBloomWords);
-          blo[t] = src[0];
-          bhi[t] = src[1];
-        } else {
-          blo[t] = make_ulonglong2(~0ull, ~0ull);
-          bhi[t] = make_ulonglong2(~0ull, ~0ull);
-        }
+        const uint32_t i0 = g0 + t * 256u;
+        const uint32_t i = i0 + lane;
+        fpv[t] = (i < U && v.fp) ? v.fp[i] : 0u;
+        pwd[t] = kFullMask;
+        if (i0 < U && v.planes && static_cast<uint32_t>(lane) < pred.n_planes)
+          pwd[t] = __ldg(v.planes + static_cast<size_t>(pred.planes[lane]) * pw + (i0 >> 5));
       }
 #pragma unroll
       for (uint32_t t = 0; t < 4; ++t) {
@@ -514,10 +509,8 @@ __device__ __forceinline__ void str_scan_body(const StrView& v, const EntryIo& w
         if (i0 >= U) break;  // warp-uniform
         const uint32_t i = i0 + lane;
         const bool ref_ok = (i < U) && (v.fp ? ((fpv[t] & pred.needle_fp) == pred.needle_fp) : true);
-        const bool cand = ref_ok && ((blo[t].x & pred.needle_bloom[0]) == pred.needle_bloom[0]) &&
-                          ((blo[t].y & pred.needle_bloom[1]) == pred.needle_bloom[1]) &&
-                          ((bhi[t].x & pred.needle_bloom[2]) == pred.needle_bloom[2]) &&
-                          ((bhi[t].y & pred.needle_bloom[3]) == pred.needle_bloom[3]);
+        const uint32_t cwd = __reduce_and_sync(kFullMask, pwd[t]);  // every lane takes part (not behind ref_ok)
+        const bool cand = ref_ok && ((cwd >> lane) & 1u);
         const uint32_t rw = __ballot_sync(kFullMask, ref_ok);
         const uint32_t cw = __ballot_sync(kFullMask, cand);
         uint32_t base = 0;
@@ -887,20 +880,9 @@ k_str_like(ScanIo io, StrPredDesc pred_in, uint32_t dict_words, uint32_t n_entri
   for (uint32_t i = lane; i < dict_words; i += 32u) s_dict[i] = 0;
   if (lane == 0) s_queue[0] = 0;
   __syncwarp();
-  // The needle's 256 trigram bits as eight 32-bit words; the words that carry a bit at all (at most four for needles of up to
-  // six bytes) are what the gate fetches and tests.
-  uint32_t nw = 0, widx[4] = {0, 0, 0, 0}, wbits[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (uint32_t q = 0; q < 8; ++q) {
-    const uint32_t bits = static_cast<uint32_t>(pred.needle_bloom[q >> 1] >> ((q & 1u) * 32u));
-    if (bits) {
-      if (nw < 4u) {
-        widx[nw] = q;
-        wbits[nw] = bits;
-      }
-      ++nw;
-    }
-  }
+  // the needle's filter planes, one per lane (broadcast by shuffle where the gate walks them)
+  const uint32_t n_planes = pred.n_planes;
+  const uint32_t my_plane = lane < n_planes ? pred_in.planes[lane] : 0u;
   const uint32_t e0 = blockIdx.x * per_cta;
   const uint32_t e_end = e0 + per_cta < n_entries ? e0 + per_cta : n_entries;
   uint32_t e = e0 + warp;
@@ -921,7 +903,6 @@ k_str_like(ScanIo io, StrPredDesc pred_in, uint32_t dict_words, uint32_t n_entri
     const bool has_fp = (hw_lo >> 16) & 0xffu;
     const uint32_t bloom_off = __shfl_sync(kFullMask, hw0, 25);
     const uint32_t* fp = has_fp ? reinterpret_cast<const uint32_t*>(blob + __shfl_sync(kFullMask, hw0, 10)) : nullptr;
-    const unsigned long long* bloom = bloom_off ? reinterpret_cast<const unsigned long long*>(blob + bloom_off) : nullptr;
 
     // ---- gate + walk ----
     uint32_t ncand = 0, n_ref = 0, walked = 0;
@@ -942,105 +923,68 @@ k_str_like(ScanIo io, StrPredDesc pred_in, uint32_t dict_words, uint32_t n_entri
       ncand = 0;
       __syncwarp();
     };
-    auto append = [&](bool cand, bool ok, uint32_t i0) {  // survivors of one stripe join the candidate list
-      const uint32_t cw = __ballot_sync(kFullMask, cand);
-      if (neg || pred.prof) n_ref += __popc(__ballot_sync(kFullMask, ok));
-      if (cw) {
-        if (ncand + 32u > kLikeCandCap) walk();
-        if (cand) s_cand[ncand + __popc(cw & lanemask_lt())] = static_cast<uint16_t>(i0 + lane);
-        ncand += __popc(cw);
-        __syncwarp();
+    // The candidate bitmap of the dictionary, 32 values per word, lane l holding words l, l + 32, ...
+    //   with the private filter: the AND of the needle's planes (entry_layout.h) — n_planes coalesced words per lane, all
+    //     requested before the first AND; fingerprints are not read at all (a value that fails them cannot match, and the
+    //     walk is exact, so the answer is the reference's with or without them);
+    //   without it (needles below three bytes, entries loaded from LQDA): the reference gate, one ballot per 32 values.
+    const uint32_t n_cw = (U + 31u) >> 5;
+    const uint32_t* planes = bloom_off ? reinterpret_cast<const uint32_t*>(blob + bloom_off) : nullptr;
+    const bool by_planes = planes != nullptr && n_planes != 0u;
+    auto push = [&](uint32_t bits, uint32_t idx0) {  // set bits -> candidate list; at most 16 per lane, so a walked list has room
+      const uint32_t cnt = __popc(bits);
+      const uint32_t incl = warp_incl_scan(cnt, lane);
+      const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+      if (total == 0u) return;
+      if (ncand + total > kLikeCandCap) walk();
+      uint32_t pos = ncand + incl - cnt;
+      while (bits) {
+        const uint32_t b = __ffs(bits) - 1u;
+        bits &= bits - 1u;
+        s_cand[pos++] = static_cast<uint16_t>(idx0 + b);
+      }
+      ncand += total;
+      __syncwarp();
+    };
+    auto emit = [&](uint32_t acc, uint32_t w) {
+      if (__any_sync(kFullMask, acc != 0u)) {
+        push(acc & 0xffffu, w * 32u);
+        push(acc >> 16, w * 32u + 16u);
       }
     };
-    if (nw <= 4u) {
-      // The needle's trigram bits sit in at most four of the filter's eight 32-bit words (every needle of up to six bytes):
-      // only those words are fetched — still one 32-byte sector per surviving value, but four registers per stripe instead
-      // of eight, which is what lets the gate run as a software pipeline: while the four stripes of group g are tested,
-      // the filter words of group g+1 and the fingerprints of group g+2 are already in flight.
-      const uint32_t* bloom32 = reinterpret_cast<const uint32_t*>(bloom);
-      auto load_fp = [&](uint32_t g0, uint32_t (&f)[4]) {
-#pragma unroll
-        for (uint32_t t = 0; t < 4; ++t) {
-          const uint32_t i = g0 + t * 32u + lane;
-          f[t] = (fp && i < U) ? __ldg(fp + i) : 0xffffffffu;
+    if (by_planes) {
+      for (uint32_t w0 = 0; w0 < n_cw; w0 += 64u) {
+        const uint32_t wa = w0 + lane, wb = w0 + 32u + lane;
+        const bool in_a = wa < n_cw, in_b = wb < n_cw;
+        uint32_t a = in_a ? kFullMask : 0u, b = in_b ? kFullMask : 0u;
+#pragma unroll 4
+        for (uint32_t t = 0; t < n_planes; ++t) {
+          const uint32_t* pl = planes + static_cast<size_t>(__shfl_sync(kFullMask, my_plane, t)) * n_cw;
+          if (in_a) a &= __ldg(pl + wa);
+          if (in_b) b &= __ldg(pl + wb);
         }
-      };
-      auto issue = [&](uint32_t g0, const uint32_t (&f)[4], uint32_t (&bl)[4][4], bool (&ok)[4]) {
-#pragma unroll
-        for (uint32_t t = 0; t < 4; ++t) {
-          const uint32_t i = g0 + t * 32u + lane;
-          ok[t] = (i < U) && ((f[t] & pred.needle_fp) == pred.needle_fp);
-          if (ok[t] && bloom32) {  // lanes the fingerprint rejected fetch nothing
-            const uint32_t* src = bloom32 + static_cast<size_t>(i) * (2u * kBloomWords);
-#pragma unroll
-            for (uint32_t q = 0; q < 4; ++q) bl[t][q] = __ldg(src + widx[q]);
-          } else {
-#pragma unroll
-            for (uint32_t q = 0; q < 4; ++q) bl[t][q] = 0xffffffffu;
-          }
-        }
-      };
-      auto test = [&](uint32_t g0, const uint32_t (&bl)[4][4], const bool (&ok)[4]) {
-#pragma unroll
-        for (uint32_t t = 0; t < 4; ++t) {
-          const uint32_t i0 = g0 + t * 32u;
-          if (i0 >= U) break;  // warp-uniform
-          const uint32_t miss = (~bl[t][0] & wbits[0]) | (~bl[t][1] & wbits[1]) | (~bl[t][2] & wbits[2]) | (~bl[t][3] & wbits[3]);
-          append(ok[t] && miss == 0u, ok[t], i0);
-        }
-      };
-      // fingerprints run one group ahead of the filter words that hang off them
-      uint32_t fc[4], fn[4], bl[4][4];
-      bool ok[4];
-      load_fp(0, fc);
-      for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
-        issue(g0, fc, bl, ok);
-        if (g0 + 128u < U) load_fp(g0 + 128u, fn);
-        test(g0, bl, ok);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) fc[t] = fn[t];
+        emit(a, wa);
+        if (w0 + 32u < n_cw) emit(b, wb);
+      }
+      if ((neg || pred.prof) && fp) {  // NOT LIKE's inversion rule / the counters want the passes of the reference gate
+        for (uint32_t i = lane; i < U; i += 32u) n_ref += ((__ldg(fp + i) & pred.needle_fp) == pred.needle_fp) ? 1u : 0u;
+        n_ref = warp_sum(n_ref);
       }
     } else {
-      for (uint32_t g0 = 0; g0 < U; g0 += 128u) {
-        ulonglong2 blo[4], bhi[4];
-        bool ok[4];
-        uint32_t fpv[4];
-#pragma unroll
-        for (uint32_t t = 0; t < 4; ++t) {
-          const uint32_t i = g0 + t * 32u + lane;
-          fpv[t] = (fp && i < U) ? __ldg(fp + i) : 0xffffffffu;
+      for (uint32_t w0 = 0; w0 < n_cw; w0 += 32u) {
+        uint32_t acc = 0;
+#pragma unroll 4
+        for (uint32_t j = 0; j < 32u; ++j) {
+          const uint32_t i = (w0 + j) * 32u + lane;
+          if (i - lane >= U) break;  // warp-uniform
+          const bool ok = (i < U) && (!fp || ((__ldg(fp + (i < U ? i : 0u)) & pred.needle_fp) == pred.needle_fp));
+          const uint32_t bw = __ballot_sync(kFullMask, ok);
+          if (lane == j) acc = bw;
+          if (neg || pred.prof) n_ref += (lane == 0u) ? __popc(bw) : 0u;
         }
-#pragma unroll
-        for (uint32_t t = 0; t < 4; ++t) {
-          const uint32_t i = g0 + t * 32u + lane;
-          ok[t] = (i < U) && ((fpv[t] & pred.needle_fp) == pred.needle_fp);
-          if (ok[t] && bloom) {  // one 32-byte sector per surviving value; lanes the fingerprint rejected fetch nothing
-            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(bloom + static_cast<size_t>(i) * kBloomWords);
-            blo[t] = __ldg(src);
-            bhi[t] = __ldg(src + 1);
-          } else {
-            blo[t] = make_ulonglong2(~0ull, ~0ull);
-            bhi[t] = make_ulonglong2(~0ull, ~0ull);
-          }
-        }
-#pragma unroll
-        for (uint32_t t = 0; t < 4; ++t) {
-          const uint32_t i0 = g0 + t * 32u;
-          if (i0 >= U) break;  // warp-uniform
-          // needle bits the value lacks, over the eight words (one LOP3 each)
-          uint32_t nb[8];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            nb[2 * q] = static_cast<uint32_t>(pred.needle_bloom[q]);
-            nb[2 * q + 1] = static_cast<uint32_t>(pred.needle_bloom[q] >> 32);
-          }
-          const uint32_t miss = (~static_cast<uint32_t>(blo[t].x) & nb[0]) | (~static_cast<uint32_t>(blo[t].x >> 32) & nb[1]) |
-                                (~static_cast<uint32_t>(blo[t].y) & nb[2]) | (~static_cast<uint32_t>(blo[t].y >> 32) & nb[3]) |
-                                (~static_cast<uint32_t>(bhi[t].x) & nb[4]) | (~static_cast<uint32_t>(bhi[t].x >> 32) & nb[5]) |
-                                (~static_cast<uint32_t>(bhi[t].y) & nb[6]) | (~static_cast<uint32_t>(bhi[t].y >> 32) & nb[7]);
-          append(ok[t] && miss == 0u, ok[t], i0);
-        }
+        emit(acc, w0 + lane);
       }
+      if (neg || pred.prof) n_ref = __shfl_sync(kFullMask, n_ref, 0);
     }
     if (pred.prof) {  // measurement aid, never on in a timed run
       unsigned long long bytes = 0;
@@ -1065,6 +1009,8 @@ k_str_like(ScanIo io, StrPredDesc pred_in, uint32_t dict_words, uint32_t n_entri
       atomicAdd(&pred.prof[12], static_cast<unsigned long long>(n_ref));
       // what the reference's data for this predicate is besides the keys: header, fingerprints, all offset residuals
       atomicAdd(&pred.prof[13], static_cast<unsigned long long>(128u + (has_fp ? 4u * U : 0u) + (hw_lo >> 24) * (U + 1u)));
+      // ... and what THIS gate read: the needle's planes, or the fingerprints where an entry has no filter
+      atomicAdd(&pred.prof[14], static_cast<unsigned long long>(by_planes ? 4u * n_planes * n_cw : (has_fp ? 4u * U : 0u)));
       if (any) atomicAdd(&pred.prof[3], 1ull);
     }
     // NOT LIKE inverts every dictionary answer — but, as in the reference, only inside apply_like_match_on_candidates,

@@ -433,6 +433,45 @@ cudaError_t launch_str_encode_many(const StrEncIo* d_ios, uint32_t n_batches, ui
   return cudaGetLastError();
 }
 
+// The trigram sets are built one 256-bit row per dictionary value (k_uniq_pass1) and stored as 256 planes over the dictionary
+// (entry_layout.h): a 32 x 256 bit transposition per stripe of 32 values, done with ballots — lane j holds value j's row, the
+// ballot over bit t of the rows IS plane t's word for the stripe. One CTA per entry, a warp per stripe.
+__device__ __forceinline__ void bloom_rows_to_planes(const unsigned long long* __restrict__ rows, uint32_t U, uint32_t* __restrict__ planes) {
+  const uint32_t pw = bloom_plane_words(U);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_warps = blockDim.x >> 5;
+  for (uint32_t s = warp; s < pw; s += n_warps) {
+    const uint32_t i = s * 32u + lane;
+    ulonglong2 lo = make_ulonglong2(0ull, 0ull), hi = lo;
+    if (i < U) {
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(rows + static_cast<size_t>(i) * kBloomWords);
+      lo = src[0];
+      hi = src[1];
+    }
+    const unsigned long long r[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+    for (uint32_t q = 0; q < 8; ++q) {
+      const uint32_t w = static_cast<uint32_t>(r[q >> 1] >> ((q & 1u) * 32u));
+      uint32_t mine = 0;
+#pragma unroll
+      for (uint32_t b = 0; b < 32; ++b) {
+        const uint32_t bw = __ballot_sync(kFullMask, (w >> b) & 1u);
+        if (lane == b) mine = bw;
+      }
+      planes[static_cast<size_t>(q * 32u + lane) * pw + s] = mine;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bloom_planes(const unsigned long long* __restrict__ rows, const StrEncResult* __restrict__ res,
+                                                      uint32_t* __restrict__ planes) {
+  bloom_rows_to_planes(rows, res->n_unique, planes);
+}
+
+cudaError_t launch_bloom_planes(const unsigned long long* d_rows, const StrEncResult* d_res, uint32_t* d_planes, cudaStream_t s) {
+  k_bloom_planes<<<1, 256, 0, s>>>(d_rows, d_res, d_planes);
+  return cudaGetLastError();
+}
+
 // Entry blob of one batch from the pipeline's work areas (see StrAsmWork). 16-byte copies where source and length allow.
 __global__ void __launch_bounds__(256) k_str_assemble(const StrAsmWork* __restrict__ works) {
   const StrAsmWork& w = works[blockIdx.x];
@@ -447,7 +486,9 @@ __global__ void __launch_bounds__(256) k_str_assemble(const StrAsmWork* __restri
     if (last) break;
     const uint8_t* src = w.segs[q].src;
     const uint32_t bytes = w.segs[q].bytes;
-    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    if (w.hdr.bloom_off != 0u && dst == w.hdr.bloom_off) {  // the trigram sets: rows in the work area, planes in the blob
+      bloom_rows_to_planes(reinterpret_cast<const unsigned long long*>(src), w.hdr.n_unique, reinterpret_cast<uint32_t*>(blob + dst));
+    } else if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
       const uint32_t v16 = bytes >> 4;
       const uint4* s4 = reinterpret_cast<const uint4*>(src);
       uint4* d4 = reinterpret_cast<uint4*>(blob + dst);

@@ -177,8 +177,9 @@ struct alignas(16) StrPredDesc {
   int32_t op;            // lc_op (EQ..GE, LIKE, NOT_LIKE)
   uint32_t needle_len;   // full needle (for LIKE: the inner pattern without the % signs)
   uint32_t needle_fp;    // fingerprint of the LIKE needle (fingerprint.rs:19-26)
-  uint32_t pad;
-  unsigned long long needle_bloom[4];  // trigram bits of the LIKE needle (entry_layout.h trigram_bit); all zero below 3 bytes
+  uint32_t n_planes;     // distinct trigram bits of the LIKE needle (0 below three bytes): the filter planes the gate ANDs
+  unsigned long long needle_bloom[4];  // the same bits as a 256-bit set (entry_layout.h trigram_bit)
+  uint8_t planes[32];    // ... and as a list, ascending (needles on the streaming path have at most 29 trigrams)
   const uint8_t* needle; // device: needle bytes padded to 4, then needle_len x u16 KMP failure links
   unsigned long long* prof;  // optional device counters {uniques, candidates, candidate bytes}; nullptr = off
   // streaming LIKE kernel (k_str_like): the needle's Shift-And step table of every FSST symbol table the list uses
@@ -309,6 +310,8 @@ struct alignas(16) StrAsmWork {
   StrAsmSeg segs[9];  // ascending dst_off
 };
 cudaError_t launch_str_assemble(const StrAsmWork* d_works, uint32_t n_batches, cudaStream_t s);
+// single-batch insert: the trigram rows of the work area (n_unique read from d_res) -> the blob's plane-major section
+cudaError_t launch_bloom_planes(const unsigned long long* d_rows, const StrEncResult* d_res, uint32_t* d_planes, cudaStream_t s);
 
 // ---- bit utilities -----------------------------------------------------------------------------
 // boolean_buffer_and_then: out[p] = left[p] & right[rank_left(p)]  (datafusion/src/utils.rs:62-236)

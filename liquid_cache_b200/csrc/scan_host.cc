@@ -253,6 +253,10 @@ static int prepare_str_pred(const lc_predicate* pred, StrLaunch* L) {
       }
     }
     L->desc.needle_fp = fp;
+    // the same bits as a list of filter planes; a long needle keeps its first 32 (any subset is a necessary condition)
+    L->desc.n_planes = 0;
+    for (uint32_t t = 0; t < kBloomPlanes && L->desc.n_planes < 32u; ++t)
+      if ((L->desc.needle_bloom[t >> 6] >> (t & 63u)) & 1ull) L->desc.planes[L->desc.n_planes++] = static_cast<uint8_t>(t);
   }
   if (m > kMaxNeedle) {
     set_error("needle longer than %u bytes", kMaxNeedle);

@@ -448,7 +448,7 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   o += round_up(2ull * n, 16);
   h.head_bytes = static_cast<uint32_t>(o);
   h.bloom_off = (build_fp && U) ? static_cast<uint32_t>(o) : 0;
-  if (h.bloom_off) o += round_up(8ull * kBloomWords * U, 16);
+  if (h.bloom_off) o += bloom_section_bytes(U);
   h.fsst_off = static_cast<uint32_t>(o);
   h.fsst_bytes = static_cast<uint32_t>(co);
   o += round_up(co, 16) + 16;
@@ -481,7 +481,10 @@ int str_encode(lc_ctx* ctx, const ArrowIn& in, int32_t hint, uint64_t scope, Ent
   };
   if (spl) LC_CUDA_OK(d2d(h.shared_prefix_off, d_pool + row_off[first_valid], spl));
   if (build_fp) LC_CUDA_OK(d2d(h.fp_off, d_fps, 4ull * U));
-  if (h.bloom_off) LC_CUDA_OK(d2d(h.bloom_off, d_blooms, 8ull * kBloomWords * U));
+  if (h.bloom_off) {  // rows of the work area -> planes of the blob (entry_layout.h)
+    LC_CUDA_OK(launch_bloom_planes(d_blooms, d_res, reinterpret_cast<uint32_t*>(d_blob + h.bloom_off), s));
+    ctx->kernel_launches++;
+  }
   LC_CUDA_OK(d2d(h.resid_off, d_resid, static_cast<uint64_t>(ob) * (U + 1)));
   LC_CUDA_OK(d2d(h.prefix_keys_off, d_pkeys, 8ull * U));
   if (h.has_nulls) LC_CUDA_OK(d2d(h.validity_off, d_up + 2 * off_len, (n + 7) / 8));
@@ -833,7 +836,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       o += round_up(2ull * n, 16);
       hd.head_bytes = static_cast<uint32_t>(o);
       hd.bloom_off = (build_fp && U) ? static_cast<uint32_t>(o) : 0;
-      if (hd.bloom_off) o += round_up(8ull * kBloomWords * U, 16);
+      if (hd.bloom_off) o += bloom_section_bytes(U);
       hd.fsst_off = static_cast<uint32_t>(o);
       hd.fsst_bytes = static_cast<uint32_t>(co);
       o += round_up(co, 16) + 16;
@@ -876,7 +879,7 @@ int str_encode_many(lc_ctx* ctx, const std::vector<ArrowIn>& ins, int32_t hint, 
       seg(hd.prefix_keys_off, d + of.pkeys, 8ull * U);
       if (hd.has_nulls) seg(hd.validity_off, d + of.up + 2 * of.off_len, (n + 7) / 8);
       seg(hd.keys_off, d + of.keys, 2ull * n);
-      if (hd.bloom_off) seg(hd.bloom_off, d + of.blooms, 8ull * kBloomWords * U);
+      if (hd.bloom_off) seg(hd.bloom_off, d + of.blooms, bloom_section_bytes(U));  // transposed into planes by k_str_assemble
       seg(hd.fsst_off, d + of.comp, co);
       Entry* e = new Entry();
       e->liquid_type = LC_LIQUID_BYTE_VIEW;

@@ -42,7 +42,16 @@ def parse_str_image(img: bytes):
     dt = {1: np.int8, 2: np.int16, 4: np.int32}[offset_bytes]
     h["resid"] = np.frombuffer(img, dtype=dt, count=n_unique + 1, offset=resid_off).astype(np.int64)
     h["comp"] = img[fsst_off:fsst_off + fsst_bytes]
-    h["blooms"] = np.frombuffer(img, dtype=np.uint64, count=4 * n_unique, offset=bloom_off).tolist() if bloom_off else None
+    h["blooms"] = None
+    if bloom_off:
+        # entry_layout.h: the trigram sets are stored as 256 PLANES over the dictionary (plane t, bit i = value i has trigram
+        # bit t), ceil(U / 32) words per plane; read back here as one 256-bit row per value, four u64 words each
+        pw = (n_unique + 31) // 32
+        planes = np.frombuffer(img, dtype="<u4", count=256 * pw, offset=bloom_off).reshape(256, pw)
+        bits = np.unpackbits(planes.view(np.uint8).reshape(256, pw * 4), axis=1, bitorder="little")  # [plane, value]
+        assert not bits[:, n_unique:].any(), "plane padding beyond the dictionary must be zero"
+        rows = np.packbits(bits[:, :n_unique].T, axis=1, bitorder="little")                           # [value, 32 bytes]
+        h["blooms"] = rows.view("<u8").reshape(-1).tolist()
     return h
 
 
