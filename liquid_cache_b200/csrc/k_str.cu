@@ -434,6 +434,73 @@ __device__ __forceinline__ void like_candidates(const View& v, const uint16_t* s
   }
 }
 
+// A FEW candidates per entry (what the trigram filter leaves of a selective needle): the 32-lane queue above would walk one
+// value on one lane, a chain of ~50 dependent table steps, with 31 lanes idle. A step is S' = ((S << L) & A) | B with the hit
+// test (S & H) != 0 (bit 31 of S is a constant 1, bit 31 of H means "hits whatever the state"), and two steps in a row are
+// again one step of the same form:
+//     L = L1 + L2,  A = (A1 << L2) & A2,  B = ((B1 << L2) & A2) | B2,  H = H1 | ((A1 & H2) >> L1) | (B1 & H2 ? bit 31 : 0)
+// so the warp takes 32 codes of the value at once, one per lane (escape markers and the literal behind them are told apart
+// as in warp_decode), combines the 32 steps in order with five shuffle rounds and applies the result to the running state.
+struct StepC {
+  uint32_t L, A, B, H;
+};
+__device__ __forceinline__ uint32_t shl_sat(uint32_t x, uint32_t n) { return n >= 32u ? 0u : x << n; }
+__device__ __forceinline__ uint32_t shr_sat(uint32_t x, uint32_t n) { return n >= 32u ? 0u : x >> n; }
+__device__ __forceinline__ StepC step_then(const StepC& f, const StepC& g) {  // f first, then g
+  StepC r;
+  r.L = f.L + g.L > 32u ? 32u : f.L + g.L;
+  r.A = shl_sat(f.A, g.L) & g.A;
+  r.B = (shl_sat(f.B, g.L) & g.A) | g.B;
+  r.H = f.H | shr_sat(f.A & g.H, f.L) | ((f.B & g.H) ? kStateOne : 0u);
+  return r;
+}
+
+template <typename View>
+__device__ __forceinline__ void like_candidates_warp(const View& v, const uint16_t* s_cand, uint32_t ncand, const SymStep* steps,
+                                                     uint32_t* s_dict) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t c = 0; c < ncand; ++c) {
+    const uint32_t i = s_cand[c];
+    const uint32_t start = dict_offset(v, i), end = dict_offset(v, i + 1u);
+    const uint8_t* code = v.fsst + start;
+    const uint32_t clen = end - start;
+    uint32_t S = kStateOne, carry_lit = 0;
+    bool hit = false;
+    for (uint32_t base = 0; base < clen && !hit; base += 32u) {
+      const uint32_t idx = base + lane;
+      const bool in = idx < clen;
+      const uint32_t b = in ? code[idx] : 0u;
+      const uint32_t F = __ballot_sync(kFullMask, in && b == 255u);
+      const uint32_t Fp = carry_lit ? (F & ~1u) : F;
+      const uint32_t zeros = ~Fp & lanemask_lt();
+      const uint32_t run = zeros ? (lane - 1u - (31u - __clz(zeros))) : lane;
+      const bool lit = (lane == 0u) ? (carry_lit != 0u) : ((run & 1u) != 0u);
+      const bool esc = in && (b == 255u) && !lit;
+      StepC st{0u, kFullMask, 0u, 0u};  // identity: lanes past the end and escape markers
+      if (in && !esc) {
+        const SymStep e = steps[b + (lit ? 256u : 0u)];
+        st = StepC{e.L, e.A, e.B, e.H};
+      }
+#pragma unroll
+      for (uint32_t d = 1; d < 32u; d <<= 1) {
+        StepC o;
+        o.L = __shfl_down_sync(kFullMask, st.L, d);
+        o.A = __shfl_down_sync(kFullMask, st.A, d);
+        o.B = __shfl_down_sync(kFullMask, st.B, d);
+        o.H = __shfl_down_sync(kFullMask, st.H, d);
+        if ((lane & (2u * d - 1u)) == 0u) st = step_then(st, o);
+      }
+      const uint32_t Lc = __shfl_sync(kFullMask, st.L, 0), Ac = __shfl_sync(kFullMask, st.A, 0);
+      const uint32_t Bc = __shfl_sync(kFullMask, st.B, 0), Hc = __shfl_sync(kFullMask, st.H, 0);
+      hit = (S & Hc) != 0u;
+      S = (shl_sat(S, Lc) & Ac) | Bc | kStateOne;
+      carry_lit = __shfl_sync(kFullMask, esc ? 1u : 0u, 31);
+    }
+    if (hit && lane == 0u) s_dict[i >> 5] |= 1u << (i & 31u);
+    __syncwarp();
+  }
+}
+
 // The body of the predicate kernel, instantiated per address space of the staged sections so that the
 // compiler emits LDS / LDG instead of generic loads.
 template <int MODE>
@@ -829,6 +896,7 @@ k_str_scan(ScanIo io, StrPredDesc pred, uint32_t stage_cap, uint32_t dict_words,
 // trigram sets stream from global memory with coalesced / sector-sized loads, four stripes of 32 values in flight.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kLikeCandCap = 512;  // per-warp candidate list (u16); a full list is walked and reused
+constexpr uint32_t kWarpWalkMax = 12;   // up to this many candidates are walked by the whole warp, one value at a time
 
 static_assert(offsetof(StrHeader, shared_prefix_len) == 24 && offsetof(StrHeader, prefix_keys_off) == 36, "header words");
 static_assert(offsetof(StrHeader, n) == 8 && offsetof(StrHeader, n_unique) == 12 && offsetof(StrHeader, slope) == 16 &&
@@ -915,7 +983,8 @@ k_str_like(ScanIo io, StrPredDesc pred_in, uint32_t dict_words, uint32_t n_entri
       v.resid = blob + __shfl_sync(kFullMask, hw0, 11);
       v.fsst = blob + __shfl_sync(kFullMask, hw0, 13);
       const SymStep* steps = steps_all + static_cast<size_t>(pred.entry_table[e]) * 512u;
-      like_candidates(v, s_cand, ncand, s_queue, steps, s_dict);
+      if (ncand <= kWarpWalkMax) like_candidates_warp(v, s_cand, ncand, steps, s_dict);  // a handful: the warp takes each value together
+      else like_candidates(v, s_cand, ncand, s_queue, steps, s_dict);
       __syncwarp();
       if (lane == 0) s_queue[0] = 0;
       walked += ncand;
@@ -997,10 +1066,11 @@ k_str_like(ScanIo io, StrPredDesc pred_in, uint32_t dict_words, uint32_t n_entri
     }
     if (ncand) walk();
     bool any = false;
-    if (walked_any) {  // did any candidate match? (the walk set its bit)
-      uint32_t acc_bits = 0;
-      for (uint32_t i = lane; i < ((U + 31u) >> 5); i += 32u) acc_bits |= s_dict[i];
-      any = __any_sync(kFullMask, acc_bits != 0u);
+    uint32_t n_match = 0;  // dictionary values that matched (the walk set their bits)
+    if (walked_any) {
+      for (uint32_t i = lane; i < n_cw; i += 32u) n_match += __popc(s_dict[i]);
+      n_match = warp_sum(n_match);
+      any = n_match != 0u;
     }
     if (pred.prof && lane == 0) {
       atomicAdd(&pred.prof[0], static_cast<unsigned long long>(U));
@@ -1051,6 +1121,82 @@ k_str_like(ScanIo io, StrPredDesc pred_in, uint32_t dict_words, uint32_t n_entri
       const uint32_t flip = invert ? kFullMask : 0u;
       const uint16_t* keys = reinterpret_cast<const uint16_t*>(blob + keys_off);
       const uint32_t n_chunks = (n + 1023u) >> 10;
+      if (n_match <= 4u) {
+        // The usual case of a selective needle — one or two dictionary values matched: their ids sit in registers (both
+        // halves of a word, so a 32-bit word of two keys is tested with a handful of logic ops) and the keys come as
+        // 16-byte loads, eight rows per lane and load. Lane l's eight answers of load j are a byte of the mask word of rows
+        // [256 j + 32 (l / 4), + 32); two shuffles assemble the word in the four lanes of the group, and the lane with
+        // l % 4 == j keeps it — so a chunk of 1024 rows costs 4 loads and 8 shuffles per lane instead of 32 loads, 32
+        // shared-memory lookups and 32 ballots.
+        uint32_t mid[4] = {0u, 0u, 0u, 0u};
+        {
+          uint32_t got = 0;
+          for (uint32_t i0 = 0; i0 < n_cw; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            uint32_t bits = i < n_cw ? s_dict[i] : 0u;
+            uint32_t have;
+            while ((have = __ballot_sync(kFullMask, bits != 0u)) != 0u) {
+              const uint32_t leader = __ffs(have) - 1u;
+              const uint32_t id = __shfl_sync(kFullMask, i * 32u + (bits ? __ffs(bits) - 1u : 0u), leader);
+              if (lane == leader) bits &= bits - 1u;
+              if (got == 0u) mid[0] = mid[1] = mid[2] = mid[3] = id * 0x10001u;  // unused slots repeat the first id
+              else if (got == 1u) mid[1] = id * 0x10001u;
+              else if (got == 2u) mid[2] = id * 0x10001u;
+              else mid[3] = id * 0x10001u;
+              ++got;
+            }
+          }
+        }
+        auto pair_eq = [&](uint32_t x) -> uint32_t {  // bit 0 / bit 1: the low / high key of the word is a matched id
+          uint32_t e = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t == 0 || static_cast<uint32_t>(t) < n_match) {
+              const uint32_t r = x ^ mid[t];  // a zero half = equal
+              e |= ~(r | ((r & 0x7fff7fffu) + 0x7fff7fffu)) & 0x80008000u;
+            }
+          }
+          return ((e >> 15) & 1u) | ((e >> 30) & 2u);
+        };
+        const uint32_t grp = lane & 3u;
+        uint4 q[4], qn[4];
+        auto load_keys = [&](uint32_t c, uint4 (&dst)[4]) {
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t row0 = c * 1024u + j * 256u + lane * 8u;
+            // a load that starts inside the rows may run into the section's padding (16-byte aligned), never past it
+            dst[j] = row0 < n ? __ldg(reinterpret_cast<const uint4*>(keys + row0)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        };
+        load_keys(0u, qn);
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+          const uint32_t wi = c * 32u + grp * 8u + (lane >> 2);  // the mask word this lane ends up with
+          uint32_t sw = kFullMask, vw = kFullMask;
+          if (wi < n_words) {
+            if (sel) sw = sel[wi];
+            if (valid) vw = __ldg(valid + wi);
+          }
+          // this chunk's keys were requested while the previous one was being tested; the next chunk's go out now
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) q[j] = qn[j];
+          if (c + 1u < n_chunks) load_keys(c + 1u, qn);
+          uint32_t mine = 0;
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            uint32_t x = (pair_eq(q[j].x) | (pair_eq(q[j].y) << 2) | (pair_eq(q[j].z) << 4) | (pair_eq(q[j].w) << 6)) << (8u * grp);
+            x |= __shfl_xor_sync(kFullMask, x, 1);
+            x |= __shfl_xor_sync(kFullMask, x, 2);
+            if (grp == j) mine = x;
+          }
+          if (wi < n_words) {
+            if (wi == n_words - 1u && tail) vw &= (1u << tail) - 1u;
+            const uint32_t cw = (mine ^ flip) & vw & sw;
+            out_bits[wi] = cw;
+            if (out_valid) out_valid[wi] = vw;
+            survivors += __popc(cw);
+          }
+        }
+      } else
       for (uint32_t c = 0; c < n_chunks; ++c) {
         const uint32_t wi = c * 32u + lane;
         uint32_t sw = kFullMask, vw = kFullMask;
@@ -1601,6 +1747,318 @@ __global__ void __launch_bounds__(256) k_str_decode_sparse(StrGatherIo g, uint32
 
 // grid of the two gather kernels: one CTA per entry when the host planned the get; for device-planned reads about sixteen
 // CTAs per SM's worth of entry ranges, so that a list whose entries all have rows still fills the machine
+// ------------------------------------------------------------------------------------------------
+// get / filter of a SELECTIVE scan in one pass: the survivors of every entry, their offsets and their decoded bytes, written
+// at their final positions of the concatenated Arrow array by ONE kernel.
+//
+// The device-planned read above is six dependent launches (row plan, lengths x 2, byte plan, decode x 2): right for reads
+// that move data, but a selective LIKE leaves a handful of rows per batch and the read then costs more than the predicate
+// (measured: 0.102 ms of launches and drains behind a 0.093 ms k_str_like). Where each entry's rows and bytes start is a
+// prefix sum over the entries; here it is a single-pass chained scan (decoupled look-back) across the CTAs of the same
+// kernel that decodes: a CTA takes eight entries (a warp each), sizes their survivors, publishes its (rows, bytes)
+// aggregate, reads its predecessors' until it meets an inclusive prefix, and writes. CTAs take their position from a ticket
+// so that every predecessor a CTA waits for is already running. Any number of survivors per entry is handled — up to 64 are
+// kept in shared memory between the two phases, more are sized and then decoded again by the lane that owns them — but the
+// host only picks this kernel when the previous read of the scan was sparse.
+// Status word: flag (2 bits: 1 = aggregate, 2 = inclusive prefix) | rows (30 bits) | bytes (32 bits), both saturating —
+// a saturated total is over every capacity and reported as such.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kOnePassKeep = 64;
+constexpr unsigned long long kOpRowsMax = (1ull << 30) - 1ull, kOpBytesMax = 0xffffffffull;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long op_pack(uint32_t flag, unsigned long long rows, unsigned long long bytes) {
+  rows = rows > kOpRowsMax ? kOpRowsMax : rows;
+  bytes = bytes > kOpBytesMax ? kOpBytesMax : bytes;
+  return (static_cast<unsigned long long>(flag) << 62) | (rows << 32) | bytes;
+}
+
+// One entry as the read sees it (header words pulled apart once per phase).
+struct OpEntry {
+  StrView v;
+  const uint16_t* keys;
+  const uint64_t* pk;
+  const uint32_t* sel;
+  const FsstTable* table;
+  uint32_t n_words, per, tail, spl;
+};
+__device__ __forceinline__ OpEntry op_entry(const uint8_t* blob, const uint32_t* sel, uint32_t lane) {
+  OpEntry x{};
+  const uint32_t hw = __ldg(reinterpret_cast<const uint32_t*>(blob) + lane);
+  const uint32_t n = __shfl_sync(kFullMask, hw, 2);
+  x.spl = __shfl_sync(kFullMask, hw, 6);
+  x.table = reinterpret_cast<const FsstTable*>(static_cast<uint64_t>(__shfl_sync(kFullMask, hw, 20)) |
+                                               (static_cast<uint64_t>(__shfl_sync(kFullMask, hw, 21)) << 32));
+  x.v.h = reinterpret_cast<const StrHeader*>(blob);
+  x.v.resid = blob + __shfl_sync(kFullMask, hw, 11);
+  x.v.fsst = blob + __shfl_sync(kFullMask, hw, 13);
+  x.keys = reinterpret_cast<const uint16_t*>(blob + __shfl_sync(kFullMask, hw, 8));
+  x.pk = reinterpret_cast<const uint64_t*>(blob + __shfl_sync(kFullMask, hw, 9));
+  x.sel = sel;
+  // lane L owns the selection words [L * per, (L + 1) * per): set bits in order = rows in order
+  x.n_words = (n + 31u) >> 5;
+  x.per = (x.n_words + 31u) / 32u;
+  x.tail = n & 31u;
+  return x;
+}
+__device__ __forceinline__ uint32_t op_sel_word(const OpEntry& x, uint32_t wi) {
+  uint32_t sw = x.sel[wi];
+  if (wi == x.n_words - 1u && x.tail) sw &= (1u << x.tail) - 1u;
+  return sw;
+}
+__device__ __forceinline__ uint32_t op_value_len(const OpEntry& x, uint32_t key, uint32_t* start_out, uint32_t* end_out) {
+  const uint32_t l = static_cast<uint32_t>(x.pk[key] >> 56);
+  const uint32_t start = dict_offset(x.v, key), end = dict_offset(x.v, key + 1u);
+  *start_out = start;
+  *end_out = end;
+  if (start == end) return 0u;  // empty value (fsst_buffer.rs:100-113)
+  return l == 255u ? decoded_length(x.v.fsst, start, end, x.table->lens) : x.spl + l;
+}
+// Visits the lane's surviving rows in order: f(row position inside the entry, key).
+template <typename F>
+__device__ __forceinline__ void op_lane_rows(const OpEntry& x, uint32_t lane, uint32_t first_pos, F&& f) {
+  uint32_t pos = first_pos;
+  for (uint32_t q = 0; q < x.per; ++q) {
+    const uint32_t wi = lane * x.per + q;
+    if (wi >= x.n_words) break;
+    uint32_t sw = op_sel_word(x, wi);
+    while (sw) {
+      const uint32_t b = __ffs(sw) - 1u;
+      sw &= sw - 1u;
+      f(pos++, static_cast<uint32_t>(x.keys[wi * 32u + b]));
+    }
+  }
+}
+__device__ __forceinline__ uint32_t op_lane_count(const OpEntry& x, uint32_t lane) {
+  uint32_t c = 0;
+  for (uint32_t q = 0; q < x.per; ++q) {
+    const uint32_t wi = lane * x.per + q;
+    if (wi >= x.n_words) break;
+    c += __popc(op_sel_word(x, wi));
+  }
+  return c;
+}
+__device__ __forceinline__ unsigned long long warp_excl_scan64(unsigned long long v, uint32_t lane, unsigned long long* total) {
+  unsigned long long incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long y = __shfl_up_sync(kFullMask, incl, d);
+    if (lane >= static_cast<uint32_t>(d)) incl += y;
+  }
+  *total = __shfl_sync(kFullMask, incl, 31);
+  return incl - v;
+}
+
+// A CTA takes 32 consecutive entries, four per warp: a selective scan leaves most of them without a survivor, and a warp
+// that steps over its empty entries keeps the grid within ONE wave of the GPU for a 12 k-entry list (382 CTAs). That matters
+// because nothing can be written before every predecessor has sized its survivors — with one entry per warp the kernel ran
+// as three waves of 25 us, each waiting for its slowest chain of dependent loads (ncu: 2.1 M polls of predecessors' words).
+constexpr uint32_t kOpPerWarp = 4, kOpPerCta = 8u * kOpPerWarp;
+
+__global__ void __launch_bounds__(256) k_str_read_onepass(StrGatherIo g, uint32_t n_entries, unsigned long long cap_rows,
+                                                          unsigned long long cap_bytes, ScanPlanHdr* hdr,
+                                                          unsigned long long* status, uint32_t* ticket) {
+  __shared__ uint32_t s_off[8][kOpPerWarp][kOnePassKeep + 1], s_key[8][kOpPerWarp][kOnePassKeep];
+  __shared__ uint32_t s_rows[kOpPerCta], s_bytes[kOpPerCta];
+  __shared__ uint32_t s_cta;
+  __shared__ unsigned long long s_lb_rows[8], s_lb_bytes[8];
+  __shared__ uint32_t s_lb_has[8];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_cta = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t cta = s_cta, n_cta = gridDim.x;
+  const uint32_t e0 = cta * kOpPerCta + warp * kOpPerWarp;
+  // what the warp's entries start from, requested together: lane j < 4 holds entry e0 + j
+  uint32_t my_k = 0;
+  const uint8_t* my_blob = nullptr;
+  uint64_t my_sel_off = 0;
+  if (lane < kOpPerWarp && e0 + lane < n_entries) {
+    my_k = g.k_hint[2u * (e0 + lane)];
+    my_blob = g.io.refs[e0 + lane].blob;
+    my_sel_off = g.io.sel_off[e0 + lane];
+  }
+  uint32_t k[kOpPerWarp];
+  unsigned long long total[kOpPerWarp];
+
+  // ---- phase 1: the survivors of each entry and their decoded lengths ----
+#pragma unroll
+  for (uint32_t t = 0; t < kOpPerWarp; ++t) {
+    k[t] = __shfl_sync(kFullMask, my_k, t);
+    total[t] = 0;
+    if (k[t]) {  // warp-uniform
+      const uint8_t* blob = reinterpret_cast<const uint8_t*>(__shfl_sync(kFullMask, reinterpret_cast<unsigned long long>(my_blob), t));
+      const OpEntry x = op_entry(blob, g.io.sel_base + __shfl_sync(kFullMask, static_cast<unsigned long long>(my_sel_off), t), lane);
+      const uint32_t lane_rows = op_lane_count(x, lane);
+      const uint32_t lane_row0 = warp_incl_scan(lane_rows, static_cast<int>(lane)) - lane_rows;
+      const bool keep = k[t] <= kOnePassKeep;
+      unsigned long long lane_bytes = 0;
+      if (lane_rows)
+        op_lane_rows(x, lane, lane_row0, [&](uint32_t pos, uint32_t key) {
+          uint32_t st, en;
+          const uint32_t len = op_value_len(x, key, &st, &en);
+          if (keep && pos < kOnePassKeep) {
+            s_off[warp][t][pos] = len;
+            s_key[warp][t][pos] = key;
+          }
+          lane_bytes += len;
+        });
+      __syncwarp();
+      if (keep) {  // lengths -> offsets inside the entry
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < k[t]; base += 32u) {
+          const uint32_t j = base + lane;
+          const uint32_t len = j < k[t] ? s_off[warp][t][j] : 0u;
+          const uint32_t incl = warp_incl_scan(len, static_cast<int>(lane));
+          if (j < k[t]) s_off[warp][t][j] = carry + incl - len;
+          carry += __shfl_sync(kFullMask, incl, 31);
+        }
+        total[t] = carry;
+      } else {
+        warp_excl_scan64(lane_bytes, lane, &total[t]);
+      }
+    }
+    if (lane == 0) {
+      s_rows[warp * kOpPerWarp + t] = k[t];
+      s_bytes[warp * kOpPerWarp + t] = total[t] > kOpBytesMax ? 0xffffffffu : static_cast<uint32_t>(total[t]);
+    }
+  }
+  __syncthreads();
+
+  // ---- the chained scan across CTAs ----
+  // Every thread looks at one predecessor per round (256 status words at a time, nearest first); all threads compute the same
+  // sums from the same shared words, so nothing is broadcast afterwards.
+  unsigned long long agg_rows = 0, agg_bytes = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < kOpPerCta; ++w) {
+    agg_rows += s_rows[w];
+    agg_bytes += s_bytes[w];
+  }
+  if (threadIdx.x == 0 && cta != 0u) st_relaxed_gpu(status + cta, op_pack(1u, agg_rows, agg_bytes));
+  unsigned long long ex_rows = 0, ex_bytes = 0;
+  for (int64_t j = static_cast<int64_t>(cta) - 1; j >= 0; j -= 256) {
+    const int64_t idx = j - static_cast<int64_t>(threadIdx.x);
+    unsigned long long w = 2ull << 62;  // before the first CTA: an inclusive prefix of nothing
+    if (idx >= 0) {
+      w = ld_relaxed_gpu(status + idx);
+      while ((w >> 62) == 0ull) {  // a predecessor still sizing its entries
+        __nanosleep(32);
+        w = ld_relaxed_gpu(status + idx);
+      }
+    }
+    const uint32_t m2 = __ballot_sync(kFullMask, (w >> 62) == 2ull);
+    const uint32_t first = m2 ? static_cast<uint32_t>(__ffs(m2)) - 1u : 32u;  // the nearest predecessor of this warp's 32 holding a prefix
+    unsigned long long r = lane <= first ? ((w >> 32) & kOpRowsMax) : 0ull, b = lane <= first ? (w & kOpBytesMax) : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      r += __shfl_xor_sync(kFullMask, r, d);
+      b += __shfl_xor_sync(kFullMask, b, d);
+    }
+    if (lane == 0) {
+      s_lb_rows[warp] = r;
+      s_lb_bytes[warp] = b;
+      s_lb_has[warp] = m2 != 0u;
+    }
+    __syncthreads();
+    bool found = false;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) {
+      if (!found) {
+        ex_rows += s_lb_rows[w8];
+        ex_bytes += s_lb_bytes[w8];
+        found = s_lb_has[w8] != 0u;
+      }
+    }
+    __syncthreads();  // the shared words are rewritten by the next round
+    if (found) break;
+  }
+  if (threadIdx.x == 0) {
+    st_relaxed_gpu(status + cta, op_pack(2u, ex_rows + agg_rows, ex_bytes + agg_bytes));
+    if (cta == n_cta - 1u) {  // the grand totals: header and closing offset
+      const unsigned long long rows = ex_rows + agg_rows, bytes = ex_bytes + agg_bytes;
+      hdr->n_hit = 0;
+      hdr->rows = rows;
+      hdr->bytes = bytes;
+      hdr->nulls = 0;
+      hdr->ulen_words = 0;
+      hdr->vwords = 0;
+      if (rows > cap_rows || rows >= kOpRowsMax) atomicMax(&hdr->overflow, 1u);
+      else if (bytes > cap_bytes || bytes > 0x7fffffffull) atomicMax(&hdr->overflow, 2u);
+      else g.out_offsets[rows] = static_cast<int32_t>(bytes);
+    }
+  }
+
+  // ---- phase 2: offsets and bytes at their final positions ----
+  unsigned long long row_base = ex_rows, byte_base = ex_bytes;
+  for (uint32_t w = 0; w < warp * kOpPerWarp; ++w) {
+    row_base += s_rows[w];
+    byte_base += s_bytes[w];
+  }
+#pragma unroll
+  for (uint32_t t = 0; t < kOpPerWarp; ++t) {
+    if (!k[t]) continue;
+    const unsigned long long rb = row_base, bb = byte_base;
+    row_base += k[t];
+    byte_base += s_bytes[warp * kOpPerWarp + t];
+    if (rb + k[t] > cap_rows || bb + total[t] > cap_bytes || bb + total[t] > 0x7fffffffull) continue;  // the last CTA reports it
+    const uint8_t* blob = reinterpret_cast<const uint8_t*>(__shfl_sync(kFullMask, reinterpret_cast<unsigned long long>(my_blob), t));
+    const OpEntry x = op_entry(blob, g.io.sel_base + __shfl_sync(kFullMask, static_cast<unsigned long long>(my_sel_off), t), lane);
+    int32_t* out_offsets = g.out_offsets + rb;
+    uint8_t* out_bytes = g.out_bytes + bb;
+    if (k[t] <= kOnePassKeep) {
+      // (the symbol table is read through L1: neighbouring entries share it)
+      for (uint32_t j = lane; j < k[t]; j += 32u) out_offsets[j] = static_cast<int32_t>(bb + s_off[warp][t][j]);
+      for (uint32_t j = 0; j < k[t]; ++j) {
+        const uint32_t key = s_key[warp][t][j];
+        const uint32_t start = dict_offset(x.v, key), end = dict_offset(x.v, key + 1u);
+        if (start == end) continue;
+        warp_decode(x.v.fsst + start, end - start, out_bytes + s_off[warp][t][j], x.table->symbols, x.table->lens, static_cast<int>(lane));
+      }
+    } else {
+      // more survivors than the warp keeps: each lane sizes its own rows again, then decodes them itself
+      const uint32_t lane_rows = op_lane_count(x, lane);
+      const uint32_t lane_row0 = warp_incl_scan(lane_rows, static_cast<int>(lane)) - lane_rows;
+      unsigned long long lane_bytes = 0, unused;
+      op_lane_rows(x, lane, lane_row0, [&](uint32_t, uint32_t key) {
+        uint32_t st, en;
+        lane_bytes += op_value_len(x, key, &st, &en);
+      });
+      unsigned long long off = warp_excl_scan64(lane_bytes, lane, &unused);
+      op_lane_rows(x, lane, lane_row0, [&](uint32_t pos, uint32_t key) {
+        uint32_t st, en;
+        const uint32_t len = op_value_len(x, key, &st, &en);
+        out_offsets[pos] = static_cast<int32_t>(bb + off);
+        uint8_t* o = out_bytes + off;
+        if (len) decode_visit(x.v.fsst, st, en, x.table->symbols, x.table->lens, [&](uint32_t byte) {
+          *o++ = static_cast<uint8_t>(byte);
+          return true;
+        });
+        off += len;
+      });
+    }
+  }
+}
+
+// `d_status`: (grid + 1) 64-bit words of scratch owned by the caller's read state (status words, then the ticket).
+cudaError_t launch_str_read_onepass(uint32_t n_entries, const StrGatherIo& g, uint64_t cap_rows, uint64_t cap_bytes, ScanPlanHdr* d_hdr,
+                                    unsigned long long* d_status, cudaStream_t s) {
+  if (n_entries == 0) return cudaErrorInvalidValue;
+  const uint32_t grid = (n_entries + kOpPerCta - 1u) / kOpPerCta;
+  cudaError_t e = cudaMemsetAsync(d_status, 0, (static_cast<size_t>(grid) + 1u) * 8u, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(d_hdr, 0, sizeof(ScanPlanHdr), s);
+  if (e != cudaSuccess) return e;
+  k_str_read_onepass<<<grid, 256, 0, s>>>(g, n_entries, cap_rows, cap_bytes, d_hdr, d_status,
+                                          reinterpret_cast<uint32_t*>(d_status + grid));
+  return cudaGetLastError();
+}
+
 static inline uint32_t gather_per_cta(uint32_t n_entries, const StrGatherIo& g) { return g.k_hint ? (n_entries + 2367u) / 2368u : 1u; }
 
 cudaError_t launch_str_decode(uint32_t n_entries, const StrGatherIo& g, cudaStream_t s) {

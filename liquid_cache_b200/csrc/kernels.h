@@ -238,6 +238,11 @@ cudaError_t launch_str_decode(uint32_t n_entries, const StrGatherIo& g, cudaStre
 // pass 1 for entries with a handful of survivors (device-planned reads of lists without nulls): one warp per entry, straight
 // from global memory — no staging of the entry's head for one or two rows
 cudaError_t launch_str_lengths_sparse(uint32_t n_entries, const StrGatherIo& g, cudaStream_t s);
+// the whole device-planned read of a selective scan as ONE kernel (chained scan across its CTAs; k_str.cu): uses g.io.refs /
+// sel_base / sel_off, g.k_hint, g.out_offsets, g.out_bytes; writes *d_hdr (rows, bytes, overflow); d_status is
+// (ceil(n_entries / 8) + 1) x 8 bytes of scratch
+cudaError_t launch_str_read_onepass(uint32_t n_entries, const StrGatherIo& g, uint64_t cap_rows, uint64_t cap_bytes, ScanPlanHdr* d_hdr,
+                                    unsigned long long* d_status, cudaStream_t s);
 
 // ---- FSST compression at insert ----------------------------------------------------------------
 struct alignas(16) FsstEncTable {

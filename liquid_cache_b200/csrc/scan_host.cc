@@ -301,6 +301,10 @@ struct RefList {
   // did the last predicate over this list produce nearly-empty masks? (0 unknown, 1 sparse, 2 dense) — picks between
   // the sparse mask download and the chunked dense one before the answer is known
   mutable int mask_hint = 0;
+  // the needle whose Shift-And step tables d_like_steps holds (and the stream that wrote them): the same LIKE over the same
+  // list — the next query of a session, the next step of a bench — launches no k_like_steps
+  mutable std::string steps_needle;
+  mutable cudaStream_t steps_stream = nullptr;
 };
 
 struct RefCache {
@@ -846,8 +850,14 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   const bool like = !is_int && (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
   if (like && sl.desc.needle_len >= 1 && sl.desc.needle_len <= 31 && rl->n_tables) {
     // the streaming LIKE kernel walks candidates through one Shift-And step table per FSST symbol table of the list
-    LC_CUDA_OK(launch_like_steps(rl->d_tables, rl->n_tables, sl.desc, rl->d_like_steps, s));
-    ctx->kernel_launches++;
+    // (kept from the previous call over this list when the needle is the same)
+    const std::string needle_key(reinterpret_cast<const char*>(sl.needle_blob.data()), sl.needle_blob.size());
+    if (rl->steps_needle != needle_key || rl->steps_stream != s) {
+      LC_CUDA_OK(launch_like_steps(rl->d_tables, rl->n_tables, sl.desc, rl->d_like_steps, s));
+      ctx->kernel_launches++;
+      rl->steps_needle = needle_key;
+      rl->steps_stream = s;
+    }
     sl.desc.like_steps = rl->d_like_steps;
     sl.desc.entry_table = rl->d_entry_table;
   }
@@ -1055,14 +1065,23 @@ int refine_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const lc_predic
       }
     }
     uint8_t* d_nd = ctx->L()->d_needle;
-    LC_CUDA_OK(cudaMemcpyAsync(d_nd, sl.needle_blob.data(), sl.needle_blob.size(), cudaMemcpyHostToDevice, s));
-    ctx->h2d_bytes += sl.needle_blob.size();
+    const std::string needle_key(reinterpret_cast<const char*>(sl.needle_blob.data()), sl.needle_blob.size());
+    if (ctx->L()->needle_in_buffer != needle_key || ctx->L()->needle_stream != s) {  // the buffer already holds it otherwise
+      LC_CUDA_OK(cudaMemcpyAsync(d_nd, sl.needle_blob.data(), sl.needle_blob.size(), cudaMemcpyHostToDevice, s));
+      ctx->h2d_bytes += sl.needle_blob.size();
+      ctx->L()->needle_in_buffer = needle_key;
+      ctx->L()->needle_stream = s;
+    }
     sl.desc.needle = d_nd;
     sl.desc.prof = ctx->prof_on ? ctx->d_prof : nullptr;
     const bool like = (pred->op == LC_OP_LIKE || pred->op == LC_OP_NOT_LIKE);
     if (like && sl.desc.needle_len >= 1 && sl.desc.needle_len <= 31 && rl->n_tables) {
-      LC_CUDA_OK(launch_like_steps(rl->d_tables, rl->n_tables, sl.desc, rl->d_like_steps, s));
-      ctx->kernel_launches++;
+      if (rl->steps_needle != needle_key || rl->steps_stream != s) {
+        LC_CUDA_OK(launch_like_steps(rl->d_tables, rl->n_tables, sl.desc, rl->d_like_steps, s));
+        ctx->kernel_launches++;
+        rl->steps_needle = needle_key;
+        rl->steps_stream = s;
+      }
       sl.desc.like_steps = rl->d_like_steps;
       sl.desc.entry_table = rl->d_entry_table;
     }
@@ -1520,10 +1539,13 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
   // one device allocation, carved: header | 4 offset arrays | counts4 | scratch | result
   uint64_t o = 0;
   auto take = [&](uint64_t bytes) { const uint64_t at = o; o += round_up(bytes, 256); return at; };
+  // the previous read of this scan left a handful of survivors per entry: one kernel does the whole read (k_str_read_onepass)
+  const bool onepass = is_str && fr->spec_rows <= 8ull * n;
   const uint64_t o_hdr = take(256), o_rowb = take(n * 8), o_vw = take(n * 8), o_ul = take(n * 8), o_bb = take(n * 8);
   const uint64_t o_cnt = take(n * 16);
-  const uint64_t o_rowoff = is_str ? take((cap_rows + n) * 4 + 16) : 0, o_rowkey = is_str ? take(cap_rows * 4 + 16) : 0;
-  const uint64_t o_ulen = is_str ? take(cap_ulen * 4 + 16) : 0;
+  const uint64_t o_status = onepass ? take(((n + 7) / 8 + 2) * 8) : 0;
+  const uint64_t o_rowoff = (is_str && !onepass) ? take((cap_rows + n) * 4 + 16) : 0, o_rowkey = (is_str && !onepass) ? take(cap_rows * 4 + 16) : 0;
+  const uint64_t o_ulen = (is_str && !onepass) ? take(cap_ulen * 4 + 16) : 0;
   const uint64_t o_off = is_str ? take((cap_rows + 1) * 4) : 0;
   const uint64_t o_val = take(is_int ? cap_rows * tb + 16 : cap_bytes + 16);
   if (o > fr->d_cap) {
@@ -1551,10 +1573,12 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
   uint64_t* d_ul = reinterpret_cast<uint64_t*>(d + o_ul);
   uint64_t* d_bb = reinterpret_cast<uint64_t*>(d + o_bb);
   uint32_t* d_cnt = reinterpret_cast<uint32_t*>(d + o_cnt);
-  LC_CUDA_OK(cudaMemsetAsync(d_cnt, 0, n * 16, s));
-  LC_CUDA_OK(launch_scan_plan_rows(d_counts2, is_str ? rl->d_n_unique : nullptr, static_cast<uint32_t>(n), cap_rows, cap_ulen, d_rowb,
-                                   d_vw, d_ul, d_hdr, s));
-  ctx->kernel_launches++;
+  if (!onepass) {
+    LC_CUDA_OK(cudaMemsetAsync(d_cnt, 0, n * 16, s));
+    LC_CUDA_OK(launch_scan_plan_rows(d_counts2, is_str ? rl->d_n_unique : nullptr, static_cast<uint32_t>(n), cap_rows, cap_ulen, d_rowb,
+                                     d_vw, d_ul, d_hdr, s));
+    ctx->kernel_launches++;
+  }
   ScanIo io{};
   io.refs = rl->d_refs;
   io.sel_base = d_sel;
@@ -1593,11 +1617,17 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
     g.sparse_max = 64;  // entries with up to 64 survivors: one warp each, no staging (k_str_lengths_sparse)
     g.out_offsets = reinterpret_cast<int32_t*>(d + o_off);
     g.out_bytes = d + o_val;
-    LC_CUDA_OK(launch_str_lengths_sparse(static_cast<uint32_t>(n), g, s));
-    LC_CUDA_OK(launch_str_lengths(static_cast<uint32_t>(n), g, rl->max_head, s));
-    LC_CUDA_OK(launch_scan_plan_bytes(d_cnt, static_cast<uint32_t>(n), cap_bytes, d_bb, g.out_offsets, d_hdr, s));
-    LC_CUDA_OK(launch_str_decode(static_cast<uint32_t>(n), g, s));
-    ctx->kernel_launches += 4;
+    if (onepass) {
+      LC_CUDA_OK(launch_str_read_onepass(static_cast<uint32_t>(n), g, cap_rows, cap_bytes, d_hdr,
+                                         reinterpret_cast<unsigned long long*>(d + o_status), s));
+      ctx->kernel_launches++;
+    } else {
+      LC_CUDA_OK(launch_str_lengths_sparse(static_cast<uint32_t>(n), g, s));
+      LC_CUDA_OK(launch_str_lengths(static_cast<uint32_t>(n), g, rl->max_head, s));
+      LC_CUDA_OK(launch_scan_plan_bytes(d_cnt, static_cast<uint32_t>(n), cap_bytes, d_bb, g.out_offsets, d_hdr, s));
+      LC_CUDA_OK(launch_str_decode(static_cast<uint32_t>(n), g, s));
+      ctx->kernel_launches += 4;
+    }
     LC_CUDA_OK(cudaMemcpyAsync(fr->h_hdr, d_hdr, sizeof(ScanPlanHdr), cudaMemcpyDeviceToHost, s));
     if (!dev_out) {
       offsets = HostBuf{host_alloc((spec_rows + 1) * 4 + 64, true), (spec_rows + 1) * 4};
@@ -1635,7 +1665,7 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
     ctx->d2h_bytes += sizeof(ScanPlanHdr);
     fr->spec_rows = rows;
     fr->spec_bytes = is_int ? 0 : bytes;
-    fr->spec_ulen = hdr.ulen_words;
+    if (!onepass) fr->spec_ulen = hdr.ulen_words;
     fr->fused_reads++;
     dev_out->d_values = d + o_val;
     dev_out->d_offsets = is_int ? nullptr : d + o_off;
@@ -1668,7 +1698,7 @@ int scan_read_fused(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
   }
   fr->spec_rows = rows;
   fr->spec_bytes = is_int ? 0 : bytes;
-  fr->spec_ulen = hdr.ulen_words;
+  if (!onepass) fr->spec_ulen = hdr.ulen_words;  // the one-pass kernel uses no dictionary-length scratch: keep what the general path learnt
   fr->fused_reads++;
   export_schema(proto->arrow_format, "", out_schema);
   std::vector<HostBuf> bufs;
@@ -1709,9 +1739,13 @@ int scan_read_async(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
   const uint64_t cap_ulen = is_int ? 0 : std::min<uint64_t>(n, cap_rows) * round_up(rl->max_unique, 4);
   uint64_t o = 0;
   auto take = [&](uint64_t bytes) { const uint64_t at = o; o += round_up(bytes, 256); return at; };
+  // A selective scan (the caller's row capacity says so: at most a handful of survivors per entry on average) is read by
+  // ONE kernel — sizes, chained scan across its CTAs, decode (k_str_read_onepass) — instead of the six launches below.
+  const bool onepass = is_str && rows_cap <= 16ull * n;
+  const uint64_t o_status = onepass ? take(((n + 7) / 8 + 2) * 8) : 0;
   const uint64_t o_rowb = take(n * 8), o_vw = take(n * 8), o_ul = take(n * 8), o_bb = take(n * 8), o_cnt = take(n * 16);
-  const uint64_t o_rowoff = is_str ? take((cap_rows + n) * 4 + 16) : 0, o_rowkey = is_str ? take(cap_rows * 4 + 16) : 0;
-  const uint64_t o_ulen = is_str ? take(cap_ulen * 4 + 16) : 0;
+  const uint64_t o_rowoff = (is_str && !onepass) ? take((cap_rows + n) * 4 + 16) : 0, o_rowkey = (is_str && !onepass) ? take(cap_rows * 4 + 16) : 0;
+  const uint64_t o_ulen = (is_str && !onepass) ? take(cap_ulen * 4 + 16) : 0;
   if (o > fr->a_cap) {
     if (fr->a_buf) {
       LC_CUDA_OK(cudaStreamSynchronize(s));
@@ -1727,6 +1761,19 @@ int scan_read_async(lc_ctx* ctx, FusedRead* fr, Entry* const* entries, uint64_t 
   }
   uint8_t* d = fr->a_buf;
   ScanPlanHdr* d_hdr = static_cast<ScanPlanHdr*>(d_header);
+  if (onepass) {
+    StrGatherIo g{};
+    g.io.refs = rl->d_refs;
+    g.io.sel_base = d_sel;
+    g.io.sel_off = d_word_off;
+    g.k_hint = d_counts2;
+    g.out_offsets = static_cast<int32_t*>(d_offsets);
+    g.out_bytes = static_cast<uint8_t*>(d_values);
+    LC_CUDA_OK(launch_str_read_onepass(static_cast<uint32_t>(n), g, cap_rows, cap_bytes, d_hdr,
+                                       reinterpret_cast<unsigned long long*>(d + o_status), s));
+    ctx->kernel_launches++;
+    return LC_OK;
+  }
   uint64_t* d_rowb = reinterpret_cast<uint64_t*>(d + o_rowb);
   uint64_t* d_vw = reinterpret_cast<uint64_t*>(d + o_vw);
   uint64_t* d_ul = reinterpret_cast<uint64_t*>(d + o_ul);

@@ -131,3 +131,63 @@ def test_async_read_refuses_what_the_device_plan_does_not_cover(cache):
         scan.filter(h, _bin(">=", 2), pa.int64())
         assert scan.read_async(h, *g.addresses()) is False  # nulls: the caller takes lc_scan_read / lc_scan_read_device
         assert_arrays_equal(scan.read(h), vals.filter(pc.fill_null(pc.greater_equal(vals, 2), False)), "fallback")
+
+
+def test_one_pass_read_of_a_selective_scan(cache):
+    """k_str_read_onepass (k_str.cu): when few rows survive per batch the whole read — sizes, the prefix sums across entries
+    (a chained scan over the kernel's own CTAs), decode — is one kernel. Survivors are skewed on purpose: most batches keep
+    none or a couple, one keeps hundreds (more than the 64 a warp holds in shared memory, so the lane-owned second pass
+    runs), some surviving values are empty and some are longer than 254 bytes (their length is not in the PrefixKey)."""
+    import torch
+
+    from liquid_cache_b200.dist import DeviceGather
+
+    rng = np.random.default_rng(14)
+    n_batches, rows = 128, 1024
+    ints, strs, li, ls = [], [], [], []  # li / ls keep the transcoded arrays (and with them their handles) alive
+    for b in range(n_batches):
+        n = rows if b % 5 else rows - 13
+        iv = rng.integers(0, 1000, size=n)
+        if b == 77:
+            iv[rng.random(n) < 0.6] = 999  # one dense batch
+        if b in (3, 4, 5, 90):
+            iv[:] = 0                      # batches without survivors, some of them neighbours (a CTA with nothing to do)
+        vals = []
+        for i in range(n):
+            r = int(rng.integers(0, 40))
+            vals.append("" if r == 0 else ("x" * 300 + str(i % 7)) if r == 1 else f"http://h{int(rng.integers(0, 9))}.example/p/{int(rng.integers(0, 300))}")
+        ints.append(pa.array(iv, pa.int64()))
+        strs.append(pa.array(vals))
+        li.append(cache.transcode(ints[-1]))
+        ls.append(cache.transcode(strs[-1], compressor_scope=8804))
+    hi, hs = np.array([l.handle for l in li], dtype=np.uint64), np.array([l.handle for l in ls], dtype=np.uint64)
+    sizes = [len(a) for a in ints]
+    thr = 998
+    want_s = pa.concat_arrays([s.filter(pc.greater_equal(a, thr)) for a, s in zip(ints, strs)])
+    assert 64 < int(pc.sum(pc.greater_equal(ints[77], thr)).as_py()) and len(want_s) <= 8 * n_batches
+    dev = torch.device("cuda", 0)
+    with cache.scan(sizes) as scan:
+        for _ in range(3):  # the first read is planned on the host and teaches the sizes; the next ones take the one-pass kernel
+            scan.reset()
+            scan.filter(hi, _bin(">=", thr), pa.int64())
+            assert_arrays_equal(scan.read(hs), want_s, "one-pass read, host result")
+        # the asynchronous form: row capacity within 16 per batch selects the one-pass kernel; a short byte capacity is reported
+        g = DeviceGather(pa.string(), 0, 1, dev, rows_cap=16 * n_batches, values_cap=2048)
+        for attempt in range(6):
+            assert scan.read_async(hs, *g.addresses())
+            cache.synchronize()
+            (n_rows, n_bytes, overflow), = g.exchange()
+            assert n_rows == len(want_s)
+            if not overflow:
+                break
+            assert overflow == 2 and n_bytes == sum(len(v) for v in want_s.to_pylist())  # both totals are reported
+            g.grow()
+        assert attempt > 0 and not g.overflowed()
+        assert_arrays_equal(g.to_arrow(), want_s, "one-pass read, device result")
+        # nothing survives: an empty array, closing offset 0
+        scan.reset()
+        scan.filter(hi, _bin(">=", 5000), pa.int64())
+        assert scan.read_async(hs, *g.addresses())
+        cache.synchronize()
+        assert g.exchange() == [(0, 0, 0)]
+        assert len(g.to_arrow()) == 0
