@@ -914,7 +914,9 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
     np.cumsum(sizes[:-1], out=offs[1:])
     total_mask_bytes = int(sizes.sum())
     pin = lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, pin_memory=True).numpy()  # noqa: E731
-    out_bufs = (pin(total_mask_bytes), pin(total_mask_bytes), offs, np.zeros(n_entries, dtype=np.uint64),
+    # no validity buffer: `hits.URL` is declared NOT NULL, a BooleanArray over it carries no null bitmap (lc_gpu.h: out_validity
+    # may be NULL; the null counts still come back and are checked to be zero below)
+    out_bufs = (pin(total_mask_bytes), None, offs, np.zeros(n_entries, dtype=np.uint64),
                 np.zeros(n_entries, dtype=np.uint64), np.zeros(n_entries, dtype=np.uint64))
 
     vals_addr = np.uint64(out_bufs[0].ctypes.data)
@@ -923,6 +925,7 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
         t0 = time.perf_counter()
         vals, valid, offs, out_len, out_nulls, true_counts = cache._eval_many_native(handles, rows_arr, pred, None, out_bufs)
         t1 = time.perf_counter()
+        assert not out_nulls.any()
         # like LiquidCacheReader::read_from_cache: only batches with surviving rows are read
         hit = np.flatnonzero(true_counts)
         if len(hit) == 0:

@@ -576,7 +576,8 @@ class LiquidCache:
             sel_ptrs = arr
         N.check(
             N.lib().lc_eval_predicate_many(
-                self._ctx, handles.ctypes.data, n, C.byref(pred), sel_ptrs, vals.ctypes.data, valid.ctypes.data,
+                self._ctx, handles.ctypes.data, n, C.byref(pred), sel_ptrs, vals.ctypes.data,
+                valid.ctypes.data if valid is not None else None,  # NULL: the caller does not want validity (lc_gpu.h)
                 offs.ctypes.data, out_len.ctypes.data, out_nulls.ctypes.data,
                 true_counts.ctypes.data if true_counts is not None else None,
             )

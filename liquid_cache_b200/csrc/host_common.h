@@ -188,6 +188,7 @@ struct lc_lane {
   uint8_t* d_needle = nullptr;   // small device buffer for predicate needles (lc_scan_filter)
   std::string needle_in_buffer;  // ... what it holds, and the stream the upload was ordered on
   cudaStream_t needle_stream = nullptr;
+  double onepass_bytes_per_row = 96.0;  // decoded bytes per row of the last sparse string read (sizes the speculative download)
   cudaStream_t copy_stream = nullptr;  // results of chunk c travel to the host while chunk c+1 is computed
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
   void* ref_cache = nullptr;     // scan_host.cc: device-side entry lists cached per handle list

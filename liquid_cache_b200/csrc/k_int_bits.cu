@@ -149,13 +149,13 @@ static_assert(offsetof(IntHeader, n) == 8 && offsetof(IntHeader, reference) == 1
                   offsetof(IntHeader, patch_val_off) == 56 && offsetof(IntHeader, squeeze_kind) == 60,
               "k_int_bits reads the header by word offset");
 
-// Tasks: (entry e, group g of four chunks) = (t >> gshift, t & (gpe - 1)) for t = global warp id, + total warps, ...;
-// gpe = groups of the longest entry of the list rounded up to a power of two (2 for 8192-row batches), shorter entries
-// have idle tasks. The warps of a CTA take consecutive tasks, i.e. the groups of neighbouring entries. Per task the
+// Tasks: (entry e, group g of `1 << cshift` chunks) = (t >> gshift, t & (gpe - 1)) for t = global warp id, + total warps, ...;
+// gpe = groups of the longest entry of the list rounded up to a power of two (2 for 8192-row batches in groups of four
+// chunks), shorter entries have idle tasks. The warps of a CTA take consecutive tasks, i.e. the groups of neighbouring entries. Per task the
 // header is read once and the predicate planned once; the header of the warp's next task and the blob pointer of the
 // one after are already in flight (software pipeline in registers).
 template <int OCC>
-__global__ void __launch_bounds__(256, OCC) k_int_bits(ScanIo io, IntPredDesc pred, uint32_t n_entries, uint32_t gshift, int mode) {
+__global__ void __launch_bounds__(256, OCC) k_int_bits(ScanIo io, IntPredDesc pred, uint32_t n_entries, uint32_t gshift, uint32_t cshift, int mode) {
   __shared__ uint32_t s_strip[8][32];  // per warp: the 32 ballots of a chunk, transposed through shared memory
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t* strip = s_strip[threadIdx.x >> 5];
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(256, OCC) k_int_bits(ScanIo io, IntPredDesc pr
 
     const uint32_t tbits = (h0.w1 >> 8) & 0xffu, W = (h0.w1 >> 16) & 0xffu, n = h0.n;
     const uint32_t n_chunks = (n + 1023u) >> 10;
-    const uint32_t c0 = grp * 4u, c1 = c0 + 4u < n_chunks ? c0 + 4u : n_chunks;
+    const uint32_t gsz = 1u << cshift;
+    const uint32_t c0 = grp * gsz, c1 = c0 + gsz < n_chunks ? c0 + gsz : n_chunks;
     if (c0 < n_chunks) {
       const uint32_t ordl = tbits >= 32u ? breg_out_word<32>(lane) : (tbits == 16u ? breg_out_word<16>(lane) : lane);
       const uint32_t* sel = nullptr;
@@ -258,10 +259,6 @@ cudaError_t launch_int_bits(int mode, uint32_t n_entries, const ScanIo& io, cons
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
   const uint32_t cpe = max_rows ? (max_rows + 1023u) / 1024u : 1u;
-  uint32_t gshift = 0;
-  while ((4u << gshift) < cpe) ++gshift;  // groups of four chunks per entry, a power of two
-  const uint64_t n_tasks = static_cast<uint64_t>(n_entries) << gshift;
-  if (n_tasks > 0x7fffffffull) return cudaErrorInvalidValue;
   // register budget: 3 CTAs per SM (80 registers) by default; LC_INT_OCC=4 selects the 64-register build (experiments)
   static const int occ_pref = [] {
     const char* e = std::getenv("LC_INT_OCC");
@@ -275,10 +272,22 @@ cudaError_t launch_int_bits(int mode, uint32_t n_entries, const ScanIo& io, cons
     if (per_sm < 1) per_sm = 1;
   }
   uint32_t grid = static_cast<uint32_t>(n_sm * per_sm);  // persistent: every resident warp loops over the tasks
+  // groups of four chunks. (Groups of two spread a 75 M-row column more evenly over the resident warps — 10.3 tasks per
+  // warp instead of 5.15 — and were measured SLOWER, 0.053 against 0.045 ms: every task re-reads its header and re-plans
+  // the predicate. LC_INT_GROUP=2 / 8 select groups of two / eight for experiments.)
+  static const uint32_t cshift_pref = [] {
+    const char* e = std::getenv("LC_INT_GROUP");
+    return (e && e[0] == '2') ? 1u : ((e && e[0] == '8') ? 3u : 2u);
+  }();
+  const uint32_t cshift = cpe >= 4u ? cshift_pref : 2u;
+  uint32_t gshift = 0;
+  while (((1u << cshift) << gshift) < cpe) ++gshift;
+  const uint64_t n_tasks = static_cast<uint64_t>(n_entries) << gshift;
+  if (n_tasks > 0x7fffffffull) return cudaErrorInvalidValue;
   const uint32_t need = static_cast<uint32_t>((n_tasks + 7u) / 8u);
   if (grid > need) grid = need;
-  if (occ_pref == 4) k_int_bits<4><<<grid, 256, 0, s>>>(io, pred, n_entries, gshift, mode);
-  else k_int_bits<3><<<grid, 256, 0, s>>>(io, pred, n_entries, gshift, mode);
+  if (occ_pref == 4) k_int_bits<4><<<grid, 256, 0, s>>>(io, pred, n_entries, gshift, cshift, mode);
+  else k_int_bits<3><<<grid, 256, 0, s>>>(io, pred, n_entries, gshift, cshift, mode);
   return cudaGetLastError();
 }
 

@@ -301,6 +301,7 @@ struct RefList {
   // did the last predicate over this list produce nearly-empty masks? (0 unknown, 1 sparse, 2 dense) — picks between
   // the sparse mask download and the chunked dense one before the answer is known
   mutable int mask_hint = 0;
+  mutable uint64_t pairs_hint = 4096;  // non-zero mask words of the last sparse download over this list
   // the needle whose Shift-And step tables d_like_steps holds (and the stream that wrote them): the same LIKE over the same
   // list — the next query of a session, the next step of a bench — launches no k_like_steps
   mutable std::string steps_needle;
@@ -921,41 +922,50 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
     unsigned long long* d_counter = reinterpret_cast<unsigned long long*>(ctx->L()->d_pairs);
     unsigned long long* d_pairs = d_counter + 2;
     unsigned long long* h_counter = reinterpret_cast<unsigned long long*>(h_up);  // pinned, its upload is long done
+    // staging for the pairs: room for the whole budget, so that nothing is allocated once the results are known
+    if (budget * 8 + 64 > ctx->L()->sel_stage_cap) {
+      LC_CUDA_OK(cudaStreamSynchronize(s));  // the selection upload may still be reading the old block
+      if (ctx->L()->sel_stage) cudaFreeHost(ctx->L()->sel_stage);
+      ctx->L()->sel_stage = nullptr;
+      ctx->L()->sel_stage_cap = 0;
+      uint64_t cap = 1ull << 20;
+      while (cap < budget * 8 + 64) cap *= 2;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->L()->sel_stage), cap, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostAlloc of %llu bytes failed", (unsigned long long)cap);
+        return LC_ERR_OOM;
+      }
+      ctx->L()->sel_stage_cap = cap;
+    }
     LC_CUDA_OK(cudaMemsetAsync(d_counter, 0, 16, s));
     LC_CUDA_OK(launch_gather_nonzero(reinterpret_cast<const uint32_t*>(d_dn + dn_counts), out_words, d_pairs, budget, d_counter, s));
     ctx->kernel_launches++;
     LC_CUDA_OK(cudaMemcpyAsync(h_dn, d_dn, dn_counts, cudaMemcpyDeviceToHost, s));
     LC_CUDA_OK(cudaMemcpyAsync(h_counter, d_counter, 8, cudaMemcpyDeviceToHost, s));
+    // The pairs come down SPECULATIVELY with the counts — as many as the last predicate over this list produced, and a
+    // margin — so that the call waits for the device once; and the caller's mask area is zero-filled on the host while the
+    // kernels are still running, not after them (neither depends on the answer).
+    const uint64_t spec_pairs = std::min<uint64_t>(budget, rl->pairs_hint + rl->pairs_hint / 4 + 512);
+    if (spec_pairs) LC_CUDA_OK(cudaMemcpyAsync(ctx->L()->sel_stage, d_pairs, spec_pairs * 8, cudaMemcpyDeviceToHost, s));
+    parallel_for(span, 1u << 20, [&](uint64_t b, uint64_t e) { std::memset(out.values + first_off + b, 0, e - b); });
     LC_CUDA_OK(cudaStreamSynchronize(s));
     const uint64_t found = *h_counter;
-    ctx->d2h_bytes += dn_counts + 8;
+    ctx->d2h_bytes += dn_counts + 8 + spec_pairs * 8;
     if (found <= budget) {
-      const uint64_t bytes = found * 8;
-      if (bytes + 64 > ctx->L()->sel_stage_cap) {  // nothing is in flight on it after the sync above
-        if (ctx->L()->sel_stage) cudaFreeHost(ctx->L()->sel_stage);
-        ctx->L()->sel_stage = nullptr;
-        ctx->L()->sel_stage_cap = 0;
-        uint64_t cap = 1ull << 20;
-        while (cap < bytes + 64) cap *= 2;
-        if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->L()->sel_stage), cap, cudaHostAllocDefault) != cudaSuccess) {
-          cudaGetLastError();
-          set_error("cudaHostAlloc of %llu bytes failed", (unsigned long long)cap);
-          return LC_ERR_OOM;
-        }
-        ctx->L()->sel_stage_cap = cap;
+      if (found > spec_pairs) {  // more non-zero words than last time: fetch the rest (a second round trip)
+        LC_CUDA_OK(cudaMemcpyAsync(ctx->L()->sel_stage + spec_pairs * 8, d_pairs + spec_pairs, (found - spec_pairs) * 8,
+                                   cudaMemcpyDeviceToHost, s));
+        LC_CUDA_OK(cudaStreamSynchronize(s));
+        ctx->d2h_bytes += (found - spec_pairs) * 8;
       }
-      if (bytes) LC_CUDA_OK(cudaMemcpyAsync(ctx->L()->sel_stage, d_pairs, bytes, cudaMemcpyDeviceToHost, s));
-      // zero-fill the caller's mask area while the pairs travel
-      parallel_for(span, 1u << 20, [&](uint64_t b, uint64_t e) { std::memset(out.values + first_off + b, 0, e - b); });
-      LC_CUDA_OK(cudaStreamSynchronize(s));
       const unsigned long long* hp = reinterpret_cast<const unsigned long long*>(ctx->L()->sel_stage);
       uint32_t* dst = reinterpret_cast<uint32_t*>(out.values + first_off);
       for (uint64_t i = 0; i < found; ++i) dst[hp[i] >> 32] = static_cast<uint32_t>(hp[i]);
-      ctx->d2h_bytes += bytes;
+      rl->pairs_hint = found;
       rl->mask_hint = 1;
       sparse_done = true;
     } else {
-      rl->mask_hint = 2;  // dense after all: plain download now, chunked overlap next time
+      rl->mask_hint = 2;  // dense after all: plain download now (over the zeros), chunked overlap next time
     }
   }
   if (sparse_done) {
@@ -1316,6 +1326,111 @@ int to_arrow_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const uint8_t
     bufs.push_back(values);
     export_array(static_cast<int64_t>(rows), static_cast<int64_t>(nulls), std::move(bufs), nullptr, out_array);
     return LC_OK;
+  }
+
+  // ---------------- byte-view, a handful of rows per batch: ONE kernel, ONE synchronisation ----------------
+  // What the reader does after a selective predicate (liquid_cache_reader.rs:342-391: only batches with survivors, each with
+  // its mask as the selection): the row counts are known here, the decoded bytes are not — k_str_read_onepass sizes, places
+  // (chained scan across its CTAs) and decodes in one launch, and the host downloads the 64-byte header together with the
+  // offsets and a speculative prefix of the bytes (sized by what such reads have needed so far).
+  {
+    bool sparse_ok = !dev_sel && !dev_out && rows != 0 && rows <= 16ull * n && !rl->any_nulls && !rl->any_fixed &&
+                     (proto->sh.arrow_type == BT_UTF8 || proto->sh.arrow_type == BT_BINARY);
+    uint64_t bound = 0;
+    for (uint64_t i = 0; i < n && sparse_ok; ++i) {
+      if (!sp.bits[i]) sparse_ok = false;  // an all-ones selection takes every row of the batch
+      bound += static_cast<uint64_t>(sp.k[i]) * entries[i]->sh.max_value_len;
+    }
+    if (sparse_ok && bound <= (256ull << 20)) {
+      const uint64_t cap_bytes = bound;
+      const uint64_t up_tab = round_up(n * 16, 256);  // word_off[n] (u64) | k[n] at stride 2 (u32 pairs)
+      const uint64_t up_sel1 = round_up(sp.sel_words * 4, 256);
+      const uint64_t dv_status = round_up(((n + 7) / 8 + 2) * 8, 256);
+      const uint64_t dv_off = round_up((rows + 1) * 4, 256), dv_val = round_up(cap_bytes + 16, 256);
+      LC_TRY(sc.reserve(up_tab + up_sel1 + dv_status + 256 + dv_off + dv_val + 1024, up_tab + 256 + 1024));
+      uint8_t* h_up = sc.host(up_tab);
+      ScanPlanHdr* h_hdr = reinterpret_cast<ScanPlanHdr*>(sc.host(256));
+      uint8_t* d_up = sc.dev(up_tab + up_sel1);
+      uint8_t* d_status = sc.dev(dv_status);
+      ScanPlanHdr* d_hdr = reinterpret_cast<ScanPlanHdr*>(sc.dev(256));
+      uint8_t* d_off = sc.dev(dv_off);
+      uint8_t* d_val = sc.dev(dv_val);
+      if (!h_up || !h_hdr || !d_up || !d_status || !d_hdr || !d_off || !d_val) {
+        set_error("to_arrow: scratch exhausted");
+        return LC_ERR_OOM;
+      }
+      uint64_t* h_word_off = reinterpret_cast<uint64_t*>(h_up);
+      uint32_t* h_k2 = reinterpret_cast<uint32_t*>(h_up + n * 8);
+      for (uint64_t i = 0; i < n; ++i) {
+        h_word_off[i] = sp.word_off[i];
+        h_k2[2 * i] = sp.k[i];
+        h_k2[2 * i + 1] = 0;
+      }
+      LC_CUDA_OK(cudaMemcpyAsync(d_up, h_up, n * 16, cudaMemcpyHostToDevice, s));
+      ctx->h2d_bytes += n * 16;
+      LC_TRY(upload_selection(ctx, sp, d_up + up_tab, s));
+      StrGatherIo g{};
+      g.io.refs = rl->d_refs;
+      g.io.sel_base = reinterpret_cast<const uint32_t*>(d_up + up_tab);
+      g.io.sel_off = reinterpret_cast<const uint64_t*>(d_up);
+      g.k_hint = reinterpret_cast<const uint32_t*>(d_up + n * 8);
+      g.out_offsets = reinterpret_cast<int32_t*>(d_off);
+      g.out_bytes = d_val;
+      LC_CUDA_OK(launch_str_read_onepass(static_cast<uint32_t>(n), g, rows, cap_bytes, d_hdr, reinterpret_cast<unsigned long long*>(d_status), s));
+      ctx->kernel_launches++;
+      double& ratio = ctx->L()->onepass_bytes_per_row;
+      const uint64_t spec = std::min<uint64_t>(cap_bytes, static_cast<uint64_t>(static_cast<double>(rows) * ratio * 1.25) + 4096);
+      HostBuf offsets{host_alloc((rows + 1) * 4 + 64, true), (rows + 1) * 4};
+      HostBuf data{host_alloc(spec + 64, true), spec};
+      auto drop = [&]() {
+        host_free(offsets.p);
+        host_free(data.p);
+      };
+      if (!offsets.p || !data.p) {
+        drop();
+        set_error("host allocation failed");
+        return LC_ERR_OOM;
+      }
+      cudaError_t ce = cudaMemcpyAsync(h_hdr, d_hdr, sizeof(ScanPlanHdr), cudaMemcpyDeviceToHost, s);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(offsets.p, d_off, (rows + 1) * 4, cudaMemcpyDeviceToHost, s);
+      if (ce == cudaSuccess && spec) ce = cudaMemcpyAsync(data.p, d_val, spec, cudaMemcpyDeviceToHost, s);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+      tr.mark("one-pass read + the one synchronisation");
+      if (ce != cudaSuccess) {
+        drop();
+        set_error("CUDA error in the one-pass read: %s", cudaGetErrorString(ce));
+        return LC_ERR_CUDA;
+      }
+      const ScanPlanHdr hdr = *h_hdr;
+      if (hdr.overflow || hdr.rows != rows) {  // cannot happen with an upper bound as the capacity: refuse rather than guess
+        drop();
+        set_error("internal: one-pass read reported rows %llu (expected %llu), overflow %u", (unsigned long long)hdr.rows,
+                  (unsigned long long)rows, hdr.overflow);
+        return LC_ERR_INVALID;
+      }
+      const uint64_t bytes = hdr.bytes;
+      ctx->d2h_bytes += sizeof(ScanPlanHdr) + (rows + 1) * 4 + spec;
+      if (bytes > spec) {  // larger than the speculative download: fetch the values whole (a second round trip, rare)
+        host_free(data.p);
+        data = HostBuf{host_alloc(bytes + 64, true), bytes};
+        if (!data.p) {
+          drop();
+          set_error("host allocation failed");
+          return LC_ERR_OOM;
+        }
+        ce = cudaMemcpyAsync(data.p, d_val, bytes, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) {
+          drop();
+          set_error("CUDA error in the one-pass read: %s", cudaGetErrorString(ce));
+          return LC_ERR_CUDA;
+        }
+        ctx->d2h_bytes += bytes;
+      }
+      data.bytes = bytes;
+      ratio = std::max(8.0, static_cast<double>(bytes) / static_cast<double>(rows));
+      return finish_bytes_array(proto, rows, 0, HostBuf{}, offsets, HostBuf{}, data, out_schema, out_array);
+    }
   }
 
   // ---------------- byte-view: pass 1 (lengths), host prefix sums, pass 2 (decode) ----------------
