@@ -150,7 +150,7 @@ static_assert(offsetof(IntHeader, n) == 8 && offsetof(IntHeader, reference) == 1
               "k_int_bits reads the header by word offset");
 
 // Tasks: (entry e, group g of `1 << cshift` chunks) = (t >> gshift, t & (gpe - 1)) for t = global warp id, + total warps, ...;
-// gpe = groups of the longest entry of the list rounded up to a power of two (2 for 8192-row batches in groups of four
+// gpe = groups of the longest entry of the list rounded up to a power of two (1 for 8192-row batches in groups of eight
 // chunks), shorter entries have idle tasks. The warps of a CTA take consecutive tasks, i.e. the groups of neighbouring entries. Per task the
 // header is read once and the predicate planned once; the header of the warp's next task and the blob pointer of the
 // one after are already in flight (software pipeline in registers).
@@ -272,14 +272,14 @@ cudaError_t launch_int_bits(int mode, uint32_t n_entries, const ScanIo& io, cons
     if (per_sm < 1) per_sm = 1;
   }
   uint32_t grid = static_cast<uint32_t>(n_sm * per_sm);  // persistent: every resident warp loops over the tasks
-  // groups of four chunks. (Groups of two spread a 75 M-row column more evenly over the resident warps — 10.3 tasks per
-  // warp instead of 5.15 — and were measured SLOWER, 0.053 against 0.045 ms: every task re-reads its header and re-plans
-  // the predicate. LC_INT_GROUP=2 / 8 select groups of two / eight for experiments.)
+  // A task is a group of eight chunks — a whole 8192-row batch: header read and predicate planned once per batch. Measured
+  // on 100 M rows at W = 17: groups of four 0.069 ms, of eight 0.062 ms; at W = 12 (75 M rows) 0.045 ms either way, and groups
+  // of two — which spread the tasks more evenly over the resident warps — 0.053 ms. LC_INT_GROUP=2 / 4 select the others.
   static const uint32_t cshift_pref = [] {
     const char* e = std::getenv("LC_INT_GROUP");
-    return (e && e[0] == '2') ? 1u : ((e && e[0] == '8') ? 3u : 2u);
+    return (e && e[0] == '2') ? 1u : ((e && e[0] == '4') ? 2u : 3u);
   }();
-  const uint32_t cshift = cpe >= 4u ? cshift_pref : 2u;
+  const uint32_t cshift = cshift_pref;
   uint32_t gshift = 0;
   while (((1u << cshift) << gshift) < cpe) ++gshift;
   const uint64_t n_tasks = static_cast<uint64_t>(n_entries) << gshift;

@@ -94,7 +94,20 @@ int plan_selection(lc_ctx* ctx, const uint32_t* entry_rows, uint64_t n, const ui
       const uint32_t* w32 = reinterpret_cast<const uint32_t*>(dst);
       uint32_t k = 0;
       const bool note = !too_many.load(std::memory_order_relaxed);
-      for (uint64_t w = 0; w < words; ++w) {
+      // `words` is a multiple of four and the staging area is 16-byte aligned per entry: look at 64 bytes at a time and
+      // go word by word only where something is set (a selection behind a selective predicate is nearly all zero)
+      uint64_t w = 0;
+      for (; w + 16 <= words; w += 16) {
+        const uint64_t* q = reinterpret_cast<const uint64_t*>(w32 + w);
+        if ((q[0] | q[1] | q[2] | q[3] | q[4] | q[5] | q[6] | q[7]) == 0) continue;
+        for (uint64_t t = w; t < w + 16; ++t) {
+          const uint32_t v = w32[t];
+          if (v == 0) continue;
+          k += static_cast<uint32_t>(__builtin_popcount(v));
+          if (note) local.push_back(((p->word_off[i] + t) << 32) | v);
+        }
+      }
+      for (; w < words; ++w) {
         const uint32_t v = w32[w];  // padding is zero
         if (v == 0) continue;
         k += static_cast<uint32_t>(__builtin_popcount(v));
