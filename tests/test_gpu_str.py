@@ -306,3 +306,39 @@ def test_differential_spec_hypothesis_gpu(cache):
                 assert_masks_equal(got, pc.match_substring(filt, inner), f"like {inner!r} fp={fp}")
 
     run()
+
+
+@pytest.mark.parametrize("with_fp", [False, True])
+def test_streaming_like_walks_agree_with_arrow(cache, with_fp):
+    """k_str_like (full-length outputs: no selection, or a scan's refine) walks the candidates the gate leaves on their FSST
+    codes in two ways — a handful of candidates: the warp takes 32 codes of one value at once and composes their Shift-And
+    steps (k_str.cu like_candidates_warp); many: 32 values at once, a lane each. Both must give Arrow's match_substring for
+    needles planted at every offset around the 32-code block boundary, in values full of bytes the symbol table has to
+    escape, for LIKE and NOT LIKE, with the private filter (planes) and without it (no fingerprints: every value walks)."""
+    rng = np.random.default_rng(77 + with_fp)
+    alphabet = [chr(c) for c in range(0x21, 0x7f)] + ["é", "ß", "й", "中", " "]  # rare code points end up escaped
+    needle = "Zq~mark§x"
+    vals = []
+    for i in range(3000):
+        body = "".join(alphabet[int(x)] for x in rng.integers(0, len(alphabet), size=int(rng.integers(5, 120))))
+        if i % 17 == 0:
+            at = int(rng.integers(0, len(body) + 1)) if i % 34 else (i // 34) % 70  # every offset 0..69 once
+            body = body[:at] + needle + body[at:]
+        if i % 97 == 0:
+            body = body + needle[:-1]  # a near miss at the very end
+        vals.append(body)
+    vals += [needle, "", needle * 3, "x" * 400 + needle, needle + "y" * 400]
+    vals = vals * 2  # dictionary of ~3000 values, each key twice
+    arr = pa.array(vals)
+    liquid = cache.transcode(arr, hint=_hint() if with_fp else None, compressor_scope=4600 + with_fp)
+    for nd in (needle, needle[:3], needle[2:], "q~", "§", "中", "no such thing in here", needle + "y"):
+        want = pc.match_substring(arr, nd)
+        assert_masks_equal(liquid.try_eval_predicate(_like(f"%{nd}%"), None), want, f"like {nd!r} fp={with_fp}")
+        assert_masks_equal(liquid.try_eval_predicate(_like(f"%{nd}%", True), None), pc.invert(want), f"not like {nd!r} fp={with_fp}")
+    # the same through a scan (MODE_REFINE), after another conjunct has thinned the selection
+    h = np.array([liquid.handle], dtype=np.uint64)
+    with cache.scan([len(vals)]) as scan:
+        scan.filter(h, _bin(">=", "P"), pa.string())
+        scan.filter(h, _like(f"%{needle}%"), pa.string())
+        keep = pc.and_(pc.greater_equal(arr, pa.scalar("P")), pc.match_substring(arr, needle))
+        assert_arrays_equal(scan.read(h), arr.filter(keep), "refine + read")
