@@ -95,6 +95,12 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # the sampler must be up and running BEFORE the clock starts: nvidia-smi's start-up (NVML initialisation, its
+            # first device queries) takes driver locks that CUDA calls wait behind — with 20 steps of 0.16 ms in the timed
+            # region, one such stall (9.5 ms was measured) is three times the region
+            t_end = time.perf_counter() + 3.0
+            while not self.rows and time.perf_counter() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -586,6 +592,8 @@ def run_shipdate(args, rank, world, local_rank, emit=True):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(3):  # back to the steady state after the sampler's start-up
+        hdrs = step(False)
     barrier()
     st_a = cache.stats()
     grows_before = gather.grows
@@ -697,6 +705,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if world > 1 and "LC_HOST_THREADS" not in os.environ:
+        # the library's host pool (selection staging, mask zero-fill of the host-buffer calls) defaults to 8 threads per
+        # process; N ranks share one container's CPU quota (16 CPUs on the round-2 box), and threads beyond it are throttled
+        import bench_cpu
+
+        cpus, _ = bench_cpu.usable_cpus()
+        os.environ["LC_HOST_THREADS"] = str(max(1, min(8, cpus // world)))
     if args.workload == "int_filter":
         run_int_filter(args, rank, world, local_rank)
         return
@@ -860,10 +875,12 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
     last = None
     for _ in range(max(3, args.warmup)):
         last = step(False)
-    cache.kernel_timing(True)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(3):  # the sampler's start-up left the GPU idle for a moment: back to the steady state before the clock
+        last = step(False)
+    cache.kernel_timing(True)
     barrier()
     st_a = cache.stats()
     grows_before = gather.grows
