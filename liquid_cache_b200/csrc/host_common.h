@@ -181,6 +181,8 @@ inline uint64_t hash_words(const uint64_t* p, uint64_t n) {
   return x;
 }
 
+extern std::atomic<uint64_t> g_validated_gen;  // lc_ctx.cc
+
 struct lc_lane {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
@@ -194,6 +196,15 @@ struct lc_lane {
   void* ref_cache = nullptr;     // scan_host.cc: device-side entry lists cached per handle list
   // handle arrays already validated (hash of the array -> entries) for the batched calls: a repeated call over the same
   // column costs a hash of the array instead of one pointer chase per handle; any release bumps `epoch` and voids them
+  // Entry lists handed out by the validation caches (lc_abi.cc) are immutable while they live. `tok_*` names the one the
+  // current call was given and the value of g_validated_gen at that moment; `fast_*` remembers the hash scan_host.cc
+  // computed for exactly that (pointer, n, generation) — so the SAME list on the NEXT call finds its device-side list
+  // without hashing and comparing 12 k pointers again. Any creation or destruction of a validated list anywhere bumps
+  // the generation, which voids both.
+  const void* tok_ptr = nullptr;
+  uint64_t tok_n = 0, tok_gen = 0;
+  const void* fast_ptr = nullptr;
+  uint64_t fast_n = 0, fast_gen = 0, fast_key = 0, fast_epoch = 0;
   struct ValidatedHandles {
     uint64_t key = 0, n = 0, epoch = 0;
     std::vector<lc_handle> handles;  // the list itself: the key only pre-filters, the match is exact

@@ -132,9 +132,15 @@ static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Ent
     return LC_OK;
   }
   const uint64_t key = hash_handles(handles, n);
+  auto token = [&](const void* p) {  // the list this call works on, for scan_host.cc's lookup of its device-side twin
+    ctx->L()->tok_ptr = p;
+    ctx->L()->tok_n = n;
+    ctx->L()->tok_gen = g_validated_gen.load(std::memory_order_acquire);
+  };
   for (auto& v : ctx->L()->validated) {
     if (v.key == key && v.n == n && v.epoch == ctx->epoch && std::memcmp(v.handles.data(), handles, n * sizeof(lc_handle)) == 0) {
       *out = v.es.data();
+      token(*out);
       return LC_OK;
     }
   }
@@ -151,18 +157,27 @@ static int entries_cached(lc_ctx* ctx, const lc_handle* handles, uint64_t n, Ent
       return LC_ERR_INVALID;
     }
   }
+  g_validated_gen.fetch_add(1, std::memory_order_acq_rel);  // a list is born (and maybe one dropped): older tokens are void
   if (ctx->L()->validated.size() >= 8) ctx->L()->validated.erase(ctx->L()->validated.begin());
   ctx->L()->validated.push_back(std::move(v));
   *out = ctx->L()->validated.back().es.data();
+  token(*out);
   return LC_OK;
 }
 
 static int scan_entries_cached(lc_scan* scan, const lc_handle* handles, Entry* const** out, bool* any_squeezed = nullptr) {
   const uint64_t key = hash_handles(handles, scan->n);
+  auto token = [&](const void* p) {
+    lc_lane* L = scan->ctx->L();
+    L->tok_ptr = p;
+    L->tok_n = scan->n;
+    L->tok_gen = g_validated_gen.load(std::memory_order_acquire);
+  };
   for (auto& v : scan->validated) {
     if (v.key == key && v.epoch == scan->ctx->epoch && std::memcmp(v.handles.data(), handles, scan->n * sizeof(lc_handle)) == 0) {
       *out = v.es.data();
       if (any_squeezed) *any_squeezed = v.any_squeezed;
+      token(*out);
       return LC_OK;
     }
   }
@@ -180,9 +195,11 @@ static int scan_entries_cached(lc_scan* scan, const lc_handle* handles, Entry* c
   }
   for (uint64_t i = 0; i < scan->n && !v.any_squeezed; ++i) v.any_squeezed = v.es[i]->squeeze_kind != 0;  // squeezing bumps the epoch
   if (any_squeezed) *any_squeezed = v.any_squeezed;
+  g_validated_gen.fetch_add(1, std::memory_order_acq_rel);
   if (scan->validated.size() >= 8) scan->validated.erase(scan->validated.begin());
   scan->validated.push_back(std::move(v));
   *out = scan->validated.back().es.data();
+  token(*out);
   return LC_OK;
 }
 
@@ -1090,6 +1107,7 @@ void lc_scan_end(lc_scan* scan) {
     if (scan->d_word_off) cudaFree(scan->d_word_off);
     fused_read_free(&scan->fused);
   }
+  g_validated_gen.fetch_add(1, std::memory_order_acq_rel);  // the scan's validated lists go with it
   delete scan;
 }
 

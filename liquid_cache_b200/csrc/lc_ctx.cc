@@ -7,6 +7,8 @@
 
 #include "host_common.h"
 
+std::atomic<uint64_t> g_validated_gen{1};  // see lc_lane::tok_* (host_common.h)
+
 namespace lc {
 
 // Debugging aid (LC_DEBUG_SEGV=1): print the native stack of a crashing thread before dying.
