@@ -19,6 +19,7 @@
 #include "../../include/lc_gpu.h"
 #include "device_utils.cuh"
 #include "kernels.h"
+#include "like_math.cuh"
 #include "scan_rows.cuh"
 
 namespace lc {
@@ -275,11 +276,6 @@ __device__ __forceinline__ void plan_str_pred(const StrView& v, const StrPredDes
 // compare, branch). Values are never decompressed: this IS the predicate evaluated on the encoded bytes.
 // Bit 31 of the state is a constant 1 (needles are <= 31 bytes on this path, B always re-sets it), so "completed
 // at the symbol's first bytes regardless of the state" (hit0) is just bit 31 of H and the hit test is one AND.
-struct SymStep {
-  uint32_t A, B, H;  // B has bit 31 set; H bit 31 = hit0
-  uint32_t L;        // symbol length = shift
-};
-constexpr uint32_t kStateOne = 0x80000000u;
 constexpr uint32_t kLikeWarps = 8;     // warps of the CTA that may walk the candidate queue
 constexpr uint32_t kCandPerWarp = 32;  // ... one more warp for every 32 candidates (measured: 96 and 192 are slower)
 
@@ -292,27 +288,12 @@ __device__ __forceinline__ void build_sym_steps(const uint64_t* s_sym, const uin
     s_M[b] = bits;
   }
   __syncthreads();
-  const uint32_t acc = 1u << (m - 1u);
   // entries 0..254: FSST codes; 255: the escape marker (identity, the next byte is a literal);
   // entries 256..511: a literal byte b (what follows an escape) = a one-byte symbol
   for (uint32_t c = threadIdx.x; c < 512u; c += blockDim.x) {
-    uint64_t sym = c < 256u ? s_sym[c] : static_cast<uint64_t>(c - 256u);
+    const uint64_t sym = c < 256u ? s_sym[c] : static_cast<uint64_t>(c - 256u);
     const uint32_t L = c < 255u ? s_len[c] : (c == 255u ? 0u : 1u);
-    uint32_t A = 0xffffffffu, B = 0, H = 0, hit0 = 0;
-    for (uint32_t k = 0; k < L; ++k) {
-      const uint32_t Mb = s_M[static_cast<uint32_t>(sym & 0xffu)];
-      sym >>= 8;
-      A = (A << 1) & Mb;
-      B = ((B << 1) | 1u) & Mb;
-      H |= (A & acc) >> (k + 1u);
-      hit0 |= (B & acc) ? 1u : 0u;
-    }
-    SymStep st;
-    st.A = A;
-    st.B = B | kStateOne;
-    st.H = H | (hit0 << 31);
-    st.L = L;
-    s_step[c] = st;
+    s_step[c] = like_sym_step(sym, L, s_M, m);
   }
 }
 
@@ -441,20 +422,6 @@ __device__ __forceinline__ void like_candidates(const View& v, const uint16_t* s
 //     L = L1 + L2,  A = (A1 << L2) & A2,  B = ((B1 << L2) & A2) | B2,  H = H1 | ((A1 & H2) >> L1) | (B1 & H2 ? bit 31 : 0)
 // so the warp takes 32 codes of the value at once, one per lane (escape markers and the literal behind them are told apart
 // as in warp_decode), combines the 32 steps in order with five shuffle rounds and applies the result to the running state.
-struct StepC {
-  uint32_t L, A, B, H;
-};
-__device__ __forceinline__ uint32_t shl_sat(uint32_t x, uint32_t n) { return n >= 32u ? 0u : x << n; }
-__device__ __forceinline__ uint32_t shr_sat(uint32_t x, uint32_t n) { return n >= 32u ? 0u : x >> n; }
-__device__ __forceinline__ StepC step_then(const StepC& f, const StepC& g) {  // f first, then g
-  StepC r;
-  r.L = f.L + g.L > 32u ? 32u : f.L + g.L;
-  r.A = shl_sat(f.A, g.L) & g.A;
-  r.B = (shl_sat(f.B, g.L) & g.A) | g.B;
-  r.H = f.H | shr_sat(f.A & g.H, f.L) | ((f.B & g.H) ? kStateOne : 0u);
-  return r;
-}
-
 template <typename View>
 __device__ __forceinline__ void like_candidates_warp(const View& v, const uint16_t* s_cand, uint32_t ncand, const SymStep* steps,
                                                      uint32_t* s_dict) {
@@ -476,14 +443,11 @@ __device__ __forceinline__ void like_candidates_warp(const View& v, const uint16
       const uint32_t run = zeros ? (lane - 1u - (31u - __clz(zeros))) : lane;
       const bool lit = (lane == 0u) ? (carry_lit != 0u) : ((run & 1u) != 0u);
       const bool esc = in && (b == 255u) && !lit;
-      StepC st{0u, kFullMask, 0u, 0u};  // identity: lanes past the end and escape markers
-      if (in && !esc) {
-        const SymStep e = steps[b + (lit ? 256u : 0u)];
-        st = StepC{e.L, e.A, e.B, e.H};
-      }
+      SymStep st = step_identity();  // lanes past the end and escape markers
+      if (in && !esc) st = steps[b + (lit ? 256u : 0u)];
 #pragma unroll
       for (uint32_t d = 1; d < 32u; d <<= 1) {
-        StepC o;
+        SymStep o;
         o.L = __shfl_down_sync(kFullMask, st.L, d);
         o.A = __shfl_down_sync(kFullMask, st.A, d);
         o.B = __shfl_down_sync(kFullMask, st.B, d);
