@@ -711,7 +711,7 @@ def main():
         import bench_cpu
 
         cpus, _ = bench_cpu.usable_cpus()
-        os.environ["LC_HOST_THREADS"] = str(max(1, min(8, cpus // world)))
+        os.environ["LC_HOST_THREADS"] = str(max(1, min(8, cpus // world - 1)))  # one CPU per rank is the Python thread's
     if args.workload == "int_filter":
         run_int_filter(args, rank, world, local_rank)
         return

@@ -108,6 +108,8 @@ Pool& pool() {
 
 }  // namespace
 
+unsigned host_pool_threads() { return pool().threads(); }
+
 void parallel_for(uint64_t n, uint64_t min_grain, const std::function<void(uint64_t, uint64_t)>& fn) {
   if (n == 0) return;
   if (min_grain == 0) min_grain = 1;

@@ -11,5 +11,7 @@ namespace lc {
 // plus the pool's workers; returns when every range is done. Thread count: LC_HOST_THREADS (default
 // min(8, hardware threads / 2)); 1 disables the pool. One parallel_for at a time per process (internally serialised).
 void parallel_for(uint64_t n, uint64_t min_grain, const std::function<void(uint64_t, uint64_t)>& fn);
+// Threads parallel_for runs on (the caller included).
+unsigned host_pool_threads();
 
 }  // namespace lc

@@ -872,7 +872,10 @@ int eval_predicate_batch(lc_ctx* ctx, Entry* const* entries, uint64_t n, const l
   // Nearly-empty masks (a selective predicate) are downloaded as {word index, word} pairs: the mask area is zeroed
   // first, a gather kernel collects the non-zero words, and the host zero-fills the caller's buffer and drops them
   // in. Whether that pays is only known afterwards, so the list remembers how the last predicate turned out.
-  const bool try_sparse = direct && !want_valid && span >= (1u << 16) && rl->mask_hint != 2;
+  // ... and it has the host zero-fill the whole mask area (12.5 MB for a 100 M-row column): with fewer than four host
+  // threads to spread that over — ranks sharing one container's CPU quota — the plain download, which costs the host
+  // nothing and overlaps the kernel chunk by chunk, is the better deal.
+  const bool try_sparse = direct && !want_valid && span >= (1u << 16) && rl->mask_hint != 2 && host_pool_threads() >= 4u;
   const int n_chunks = (direct && n >= 2048 && span && !try_sparse) ? chunk_pref : 1;
   if (try_sparse) LC_CUDA_OK(cudaMemsetAsync(d_dn + dn_counts, 0, span, s));
   if (n_chunks > 1 && !ctx->L()->copy_stream) {
