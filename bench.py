@@ -340,9 +340,9 @@ def run_int_filter(args, rank, world, local_rank, emit=True):
                    "liquid_bytes_per_gpu": int(cache.stats().hbm_bytes_used)},
         "gpu_launches": int(st_b.kernel_launches - st_a.kernel_launches),
         "roofline": [
-            {"kernel": "k_int_scan<REFINE> EventTime>=lo (dense selection in)", "bound": "hbm", "achieved": b_ge / (med(k_ms[0]) / 1e3) / 1e9, "peak": peak,
+            {"kernel": "k_int_bits<REFINE> EventTime>=lo (W=17, dense selection in)", "bound": "hbm", "achieved": b_ge / (med(k_ms[0]) / 1e3) / 1e9, "peak": peak,
              "unit": "GB/s", "frac": b_ge / (med(k_ms[0]) / 1e3) / 1e9 / peak, "kernel_ms": med(k_ms[0]), "algorithmic_bytes_per_launch": b_ge},
-            {"kernel": "k_int_scan<REFINE> EventTime<hi (selection in+out)", "bound": "hbm", "achieved": b_lt / (med(k_ms[1]) / 1e3) / 1e9, "peak": peak,
+            {"kernel": "k_int_bits<REFINE> EventTime<hi (W=17, selection in+out)", "bound": "hbm", "achieved": b_lt / (med(k_ms[1]) / 1e3) / 1e9, "peak": peak,
              "unit": "GB/s", "frac": b_lt / (med(k_ms[1]) / 1e3) / 1e9 / peak, "kernel_ms": med(k_ms[1]), "algorithmic_bytes_per_launch": b_lt},
             {"kernel": "k_int_scan<REFINE> UserID=k (W=64)", "bound": "hbm", "achieved": b_eq / (med(k_ms[2]) / 1e3) / 1e9, "peak": peak,
              "unit": "GB/s", "frac": b_eq / (med(k_ms[2]) / 1e3) / 1e9 / peak, "kernel_ms": med(k_ms[2]), "algorithmic_bytes_per_launch": b_eq},
@@ -665,10 +665,10 @@ def run_shipdate(args, rank, world, local_rank, emit=True):
                     "d2h_bytes_per_step": int((st_d.d2h_bytes - st_c.d2h_bytes) / e2e_steps)},
             "gpu_launches": int(st_b.kernel_launches - st_a.kernel_launches),
             "roofline": [
-                {"kernel": "k_int_scan<REFINE> l_shipdate>=lo (dense selection in)", "bound": "hbm", "achieved": b_ge / (med(k_ms[0]) / 1e3) / 1e9,
+                {"kernel": "k_int_bits<REFINE> l_shipdate>=lo (W=12, dense selection in)", "bound": "hbm", "achieved": b_ge / (med(k_ms[0]) / 1e3) / 1e9,
                  "peak": peak, "unit": "GB/s", "frac": b_ge / (med(k_ms[0]) / 1e3) / 1e9 / peak, "kernel_ms": med(k_ms[0]),
                  "algorithmic_bytes_per_launch": b_ge, "traffic": None},
-                {"kernel": "k_int_scan<REFINE> l_shipdate<hi (selection in+out)", "bound": "hbm", "achieved": b_lt / (med(k_ms[1]) / 1e3) / 1e9,
+                {"kernel": "k_int_bits<REFINE> l_shipdate<hi (W=12, selection in+out)", "bound": "hbm", "achieved": b_lt / (med(k_ms[1]) / 1e3) / 1e9,
                  "peak": peak, "unit": "GB/s", "frac": b_lt / (med(k_ms[1]) / 1e3) / 1e9 / peak, "kernel_ms": med(k_ms[1]),
                  "algorithmic_bytes_per_launch": b_lt, "traffic": None},
             ],
