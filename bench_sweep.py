@@ -210,24 +210,36 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
                 pos += k
                 scan.set_selection(b, new)
             return
-        words = scan.store_selections()
+        words = np.array(scan.store_selections(), dtype=np.uint32)  # a private copy: the surviving words are edited below
+        nz = np.flatnonzero(words)
+        if len(nz) == 0:
+            return  # nothing selected any more: nothing to decode or evaluate (liquid_cache_reader.rs:308-311)
         vals = scan.read(handles[column])  # rows in batch order, then row order: the order of the set bits below
         mask = np.asarray(arrow_mask(vals, op, lit).fill_null(False).to_numpy(zero_copy_only=False), dtype=bool)
-        bits = np.unpackbits(words.view(np.uint8), bitorder="little")
+        # only the words that still have a bit set are unpacked (a selection behind earlier conjuncts is mostly zero words;
+        # unpacking all 16.8 M bits cost 30 ms per call)
+        bits = np.unpackbits(words[nz].view(np.uint8).reshape(len(nz), 4), axis=1, bitorder="little").reshape(-1)
         set_pos = np.flatnonzero(bits)
         assert len(set_pos) == len(mask)
         bits[set_pos[~mask]] = 0
-        scan.load_selections(np.packbits(bits, bitorder="little").view(np.uint32))
+        words[nz] = np.packbits(bits.reshape(len(nz), 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+        scan.load_selections(words)
 
-    def run_query(conj, proj, to_host, want_counts=False):
+    trace_q = os.environ.get("LC_SWEEP_TRACE")  # diagnosis: wall clock per conjunct of one query (synchronises after each)
+
+    def run_query(conj, proj, to_host, want_counts=False, q=None):
         scan.reset()
         for column, op, lit in conj:
             lit = conjunct_literal(lit)
+            t_c = time.perf_counter()
             if op == "in":
                 host_fallback(column, op, lit)
-                continue
-            expr = LiquidExpr.try_new(make_expr(column, op, lit, types[column]), types[column], CacheExpression.SubstringSearch)
-            scan.filter(handles[column], expr, types[column])
+            else:
+                expr = LiquidExpr.try_new(make_expr(column, op, lit, types[column]), types[column], CacheExpression.SubstringSearch)
+                scan.filter(handles[column], expr, types[column])
+            if trace_q is not None and q is not None and str(q) == trace_q:
+                cache.synchronize()
+                print(f"[sweep trace] q{q} {column} {op}: {1e3 * (time.perf_counter() - t_c):.3f} ms, {scan.counts()[1]} rows left", file=sys.stderr)
         out = []
         counts, total = None, None
         if want_counts or not proj or not conj:
@@ -256,7 +268,7 @@ def run_sweep(cache, rows: int, steps: int, warmup: int, rank: int = 0, world: i
         if not conj and not proj:
             results.append({"q": q, "ms": 0.0, "e2e_ms": 0.0, "rows_out": rows_local, "note": "no column touched"})
             continue
-        first, err = safe(lambda: run_query(conj, proj, False, want_counts=True))
+        first, err = safe(lambda: run_query(conj, proj, False, want_counts=True, q=q))
         if err:
             results.append({"q": q, "ms": 0.0, "e2e_ms": 0.0, "rows_out": 0, "note": "not run: " + err})
             continue
