@@ -1000,6 +1000,7 @@ def run_url_like(args, rank, world, local_rank, emit=True, source=None, rows=Non
                 "parallelism": f"entries sharded by EntryID over {world} GPU(s), no collective in the scan; every step ends with ONE NCCL all_gather of the filtered batches (HBM to HBM) inside the clock" if world > 1 else "one GPU",
                 "result": "Arrow-layout buffers in HBM (lc_scan_read_async): value; host Arrow arrays through the host-buffer ABI: e2e",
                 "host_syncs_per_step": 1, "gather_slot_bytes": gather.slot, "slot_regrown_in_timed_steps": grows_in_timed,
+                "untimed_steps_before_the_clock": max(3, args.warmup) + 3,  # --warmup, then 3 more once the clock sampler is up
                 "step_phases": step_phases,
                 "step_ms_rank0": {"min": min(step_wall), "median": float(np.median(step_wall)), "max": max(step_wall)}, "numa": numa_pin,
                 "l2": "inputs (liquid column) larger than the 126 MB L2, no flush needed",
