@@ -79,9 +79,39 @@ class FakeScan:
         pass
 
 
+class FakeScanWords(FakeScan):
+    """The double with the bulk selection transfer of the real scan (lc_scan_store_selections / lc_scan_load_selections):
+    uint32 words, LSB first, every batch padded to a multiple of four words — what the sweep's caller-evaluated conjuncts
+    (the IN list) go through on a GPU."""
+
+    def _layout(self):
+        offs, tot = [], 0
+        for r in self.rows:
+            offs.append(tot)
+            tot += ((r + 31) // 32 + 3) // 4 * 4
+        return offs, tot
+
+    def store_selections(self):
+        offs, tot = self._layout()
+        out = np.zeros(tot, dtype=np.uint32)
+        for o, s in zip(offs, self.sel):
+            w = np.packbits(s, bitorder="little")
+            w = np.concatenate([w, np.zeros((-len(w)) % 4, dtype=np.uint8)]).view(np.uint32)
+            out[o:o + len(w)] = w
+        return out
+
+    def load_selections(self, words):
+        offs, _tot = self._layout()
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        for b, (o, r) in enumerate(zip(offs, self.rows)):
+            n_w = (r + 31) // 32
+            self.sel[b] = np.unpackbits(words[o:o + n_w].view(np.uint8), bitorder="little")[:r].astype(bool)
+
+
 class FakeCache:
-    def __init__(self):
+    def __init__(self, bulk_selections=False):
         self.store = {}
+        self.bulk_selections = bulk_selections
 
     def insert(self, eid, arr):
         return _Insert(self, eid, arr)
@@ -94,7 +124,7 @@ class FakeCache:
         return np.asarray(ids, dtype=np.uint64)
 
     def scan(self, rows):
-        return FakeScan(self, rows)
+        return FakeScanWords(self, rows) if self.bulk_selections else FakeScan(self, rows)
 
     def stats(self):
         return _Stats()

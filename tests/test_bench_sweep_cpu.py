@@ -4,6 +4,7 @@ fallback. No GPU needed (the CUDA path runs the same harness through bench.py --
 import time
 
 import pyarrow as pa
+import pytest
 
 import bench_sweep as S
 from tests.fake_cache import FakeCache
@@ -32,8 +33,9 @@ def test_query_table_is_complete_and_well_formed():
                 assert pa.types.is_string(sample.cols[column].type)
 
 
-def test_sweep_runs_and_matches_arrow_on_the_test_double():
-    res = S.run_sweep(FakeCache(), rows=8192 * 24, steps=1, warmup=1, timer=_timer, check_batches=24)
+@pytest.mark.parametrize("bulk", [False, True])  # True: the IN conjunct edits the selection words in bulk, as on a GPU
+def test_sweep_runs_and_matches_arrow_on_the_test_double(bulk):
+    res = S.run_sweep(FakeCache(bulk_selections=bulk), rows=8192 * 24, steps=1, warmup=1, timer=_timer, check_batches=24)
     assert res["all_counts_match_arrow"] and len(res["queries"]) == 43
     by_q = {r["q"]: r for r in res["queries"]}
     assert by_q[0]["note"] == "no column touched"
